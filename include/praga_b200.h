@@ -1,0 +1,220 @@
+/*
+ * praga_b200.h — C ABI of libpraga_b200.so, the B200 (sm_100a) gridding engine that replaces the
+ * hot path of ARPA-SIMC/PRAGA's agrolib/interpolation behind the reference's own C++ API.
+ *
+ * The reference has no FFI for this path: it is reached through statically linked C++ free
+ * functions.  Every entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  The C++ shim in praga_b200/host/ keeps the reference
+ * signatures (interpolationRaster(), preInterpolation(), computeResiduals(), kriging*) and only
+ * flattens the reference objects into the POD descriptors declared here.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no C++ types, no exceptions across the ABI;
+ *  - every function returns a pb_status (0 = ok); pb_last_error() gives the message;
+ *  - all pointers are HOST pointers unless the name says "device"; the caller owns all of them;
+ *  - rasters are row-major, row 0 = northernmost row, exactly like gis::Crit3DRasterGrid::value
+ *    (agrolib/gis/gis.h:157-166); either one contiguous block (`data`) or the reference's
+ *    per-row allocation (`rows`, a float**) may be passed;
+ *  - there is NO CPU fallback: without a usable CUDA device every compute call fails with
+ *    PB_ERR_CUDA.
+ */
+#ifndef PRAGA_B200_H
+#define PRAGA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_NODATA (-9999)            /* agrolib/mathFunctions/commonConstants.h:31 */
+#define PB_MAX_PROXY 8
+#define PB_MAX_FIT_PARAMS 6          /* lapseRatePiecewise_three_free has 6 (furtherMathFunctions.cpp:149) */
+#define PB_MAX_FIRST_GUESS 64        /* calculateFirstGuessCombinations yields 16 or 31 (interpolation.cpp:1556) */
+
+typedef enum pb_status {
+    PB_OK = 0,
+    PB_ERR_INVALID = 1,        /* bad argument / inconsistent descriptor */
+    PB_ERR_CUDA = 2,           /* no device, launch or copy failure (reference-side: return false) */
+    PB_ERR_NO_VALID_CELL = 3,  /* gis::updateMinMaxRasterGrid returned false (gis.cpp:601-603) */
+    PB_ERR_NOMEM = 4,
+    PB_ERR_UNSUPPORTED = 5,    /* option combination outside the hot-path scope */
+    PB_ERR_FIT = 6             /* preInterpolation returned false (interpolation.cpp:2476) */
+} pb_status;
+
+/* --- enums copied BY VALUE from the reference (checked by static_assert in oracle/ref_driver.cpp) --- */
+/* TInterpolationMethod, agrolib/interpolation/interpolationConstants.h:18 */
+enum { PB_METHOD_IDW = 0, PB_METHOD_SHEPARD = 1, PB_METHOD_SHEPARD_MODIFIED = 2 };
+/* TProxyVar, interpolationConstants.h:26 */
+enum { PB_PROXY_HEIGHT = 0, PB_PROXY_URBAN_FRACTION = 1, PB_PROXY_OROG_INDEX = 2, PB_PROXY_SEA_DISTANCE = 3,
+       PB_PROXY_ASPECT = 4, PB_PROXY_SLOPE = 5, PB_PROXY_WATER_INDEX = 6, PB_PROXY_NONE = 7 };
+/* TFittingFunction, interpolationConstants.h:41 */
+enum { PB_FIT_PIECEWISE_TWO = 0, PB_FIT_PIECEWISE_THREE_FREE = 1, PB_FIT_PIECEWISE_THREE = 2, PB_FIT_LINEAR = 3,
+       PB_FIT_NONE = 4 };
+/* lapseRateCodeType, agrolib/meteo/meteo.h:84 */
+enum { PB_LAPSE_PRIMARY = 0, PB_LAPSE_SECONDARY = 1, PB_LAPSE_SUPPLEMENTAL = 2 };
+/* TkrigingMode, interpolationConstants.h:51 */
+enum { PB_KRIGING_SPHERICAL = 1, PB_KRIGING_EXPONENTIAL = 2, PB_KRIGING_GAUSSIAN = 3, PB_KRIGING_LINEAR = 4 };
+/* meteoVariable, agrolib/meteo/meteo.h:91-108 (only the values the gridding path distinguishes) */
+enum {
+    PB_VAR_AIR_TEMPERATURE = 0, PB_VAR_DAILY_TMIN = 1, PB_VAR_DAILY_TMAX = 3, PB_VAR_DAILY_TAVG = 5,
+    PB_VAR_DAILY_TRANGE = 7, PB_VAR_PRECIPITATION = 8, PB_VAR_DAILY_PRECIPITATION = 9,
+    PB_VAR_AIR_REL_HUMIDITY = 11, PB_VAR_AIR_DEW_TEMPERATURE = 12, PB_VAR_DAILY_RH_MIN = 13,
+    PB_VAR_DAILY_RH_MAX = 14, PB_VAR_DAILY_RH_AVG = 15, PB_VAR_GLOBAL_IRRADIANCE = 23,
+    PB_VAR_ATM_TRANSMISSIVITY = 28, PB_VAR_DAILY_GLOBAL_RADIATION = 29, PB_VAR_WIND_SCALAR_INTENSITY = 34,
+    PB_VAR_WIND_VECTOR_INTENSITY = 35, PB_VAR_WIND_VECTOR_X = 37, PB_VAR_WIND_VECTOR_Y = 38,
+    PB_VAR_DAILY_WIND_VECTOR_INT_AVG = 39, PB_VAR_DAILY_WIND_VECTOR_INT_MAX = 40,
+    PB_VAR_DAILY_WIND_SCALAR_INT_AVG = 42, PB_VAR_DAILY_WIND_SCALAR_INT_MAX = 43, PB_VAR_LEAF_WETNESS = 44,
+    PB_VAR_DAILY_LEAF_WETNESS = 45, PB_VAR_ATM_PRESSURE = 46, PB_VAR_DAILY_ET0_HS = 48,
+    PB_VAR_DAILY_WATER_TABLE_DEPTH = 67, PB_VAR_ELABORATION = 72, PB_VAR_NONE = 73
+};
+
+/* gis::Crit3DRasterHeader, agrolib/gis/gis.h:112-127 */
+typedef struct pb_raster_header {
+    int32_t nrRows, nrCols;
+    double cellSize, invCellSize;
+    double llx, lly;               /* llCorner.x / llCorner.y (lower-left corner, metres UTM) */
+    float flag;                    /* no-data marker of THIS raster */
+    int32_t reserved;
+} pb_raster_header;
+
+/* host view of a gis::Crit3DRasterGrid (gis.h:157-199): give `data` (contiguous) or `rows` (float**) */
+typedef struct pb_raster {
+    pb_raster_header h;
+    const float* data;             /* nrRows*nrCols contiguous, or NULL */
+    float* const* rows;            /* Crit3DRasterGrid::value, used when data == NULL */
+} pb_raster;
+
+/* std::vector<Crit3DInterpolationDataPoint> (agrolib/interpolation/interpolationPoint.h:14-31), SoA */
+typedef struct pb_stations {
+    int32_t n;                     /* number of points */
+    int32_t nProxy;                /* row stride of proxyValues == settings.nProxy */
+    const double* x;               /* point->utm.x */
+    const double* y;               /* point->utm.y */
+    const double* z;               /* point->z */
+    float* value;                  /* value (in/out for pb_pre_interpolation: detrended in place) */
+    const float* regressionWeight; /* may be NULL => all NODATA */
+    const int32_t* lapseRateCode;  /* PB_LAPSE_*; may be NULL => all primary */
+    const uint8_t* isActive;       /* may be NULL => all active */
+    const float* proxyValues;      /* n*nProxy, station-major; NODATA where missing */
+    const int32_t* index;          /* Crit3DInterpolationDataPoint::index; may be NULL */
+} pb_stations;
+
+/* Crit3DProxy (interpolationSettings.h:18-102) — fields the path reads or writes */
+typedef struct pb_proxy {
+    int32_t kind;                  /* PB_PROXY_* = getProxyPragaName(name) */
+    int32_t gridIndex;             /* index into the proxyGrids[] argument; -1: no loaded grid */
+    int32_t fittingFunction;       /* PB_FIT_* (fittingFunctionName) */
+    int32_t inversionIsSignificative;
+    float regressionR2, regressionSlope, regressionIntercept;
+    float lapseRateH0, lapseRateH1, lapseRateT0, lapseRateT1, inversionLapseRate;
+    float stdDevThreshold;
+    int32_t nFitParams;            /* fittingParametersRange.size()/2 */
+    double fitMin[PB_MAX_FIT_PARAMS];   /* fittingParametersRange[0..n)   */
+    double fitMax[PB_MAX_FIT_PARAMS];   /* fittingParametersRange[n..2n)  */
+    int32_t fitFirstGuess[PB_MAX_FIT_PARAMS];
+    int32_t nFirstGuessCombinations;    /* set by setMultipleDetrendingHeightTemperatureRange */
+    double firstGuessCombinations[PB_MAX_FIRST_GUESS][PB_MAX_FIT_PARAMS];
+} pb_proxy;
+
+/* Crit3DInterpolationSettings (interpolationSettings.h:185-391) + the two scalars the path reads from
+ * Crit3DMeteoSettings (rainfallThreshold) — in/out where the reference mutates its settings */
+typedef struct pb_settings {
+    int32_t method;                /* PB_METHOD_* */
+    int32_t useThermalInversion, useTD, useLocalDetrending, useGlocalDetrending;
+    int32_t useLapseRateCode, useBestDetrending, useMultipleDetrending;
+    int32_t useDoNotRetrend, useRetrendOnly, precipitationAllZero;
+    int32_t minPointsLocalDetrending, topoDist_Kh, topoDist_maxKh;
+    float minRegressionR2, maxHeightInversion, pointsBoundingBoxArea, localRadius;
+    float rainfallThreshold;       /* Crit3DMeteoSettings::getRainfallThreshold (meteo.h:48) */
+    float climateLapseRate;        /* Crit3DClimateParameters::getClimateLapseRate(var, time) (meteo.cpp:184) */
+    int32_t hasPointsRange;
+    double pointsRangeMin, pointsRangeMax;
+    int32_t nProxy;
+    int32_t selectedUseThermalInversion, currentUseThermalInversion;
+    uint8_t selectedActive[PB_MAX_PROXY];      /* selectedCombination._isActiveList */
+    uint8_t currentActive[PB_MAX_PROXY];       /* currentCombination */
+    uint8_t currentSignificant[PB_MAX_PROXY];
+    pb_proxy proxy[PB_MAX_PROXY];
+    /* fitted multiple-detrending model: fittingFunction / fittingParameters, elevation first
+     * (interpolation.cpp:1298-1313, 2563-2617) */
+    int32_t nFit;                              /* fittingParameters.size() */
+    int32_t nFitFunctions;                     /* fittingFunction.size() (can exceed nFit, interpolation.cpp:1506-1553) */
+    int32_t fitFunction[PB_MAX_PROXY];         /* PB_FIT_* */
+    int32_t fitNrParams[PB_MAX_PROXY];
+    double fitParams[PB_MAX_PROXY][PB_MAX_FIT_PARAMS];
+} pb_settings;
+
+/* output of a raster call: gis::Crit3DRasterGrid* outputGrid after interpolationRaster */
+typedef struct pb_raster_out {
+    float* data;                   /* nrRows*nrCols contiguous, or NULL */
+    float* const* rows;            /* row pointers (Crit3DRasterGrid::value), used when data == NULL */
+    float minimum, maximum;        /* gis::updateMinMaxRasterGrid (gis.cpp:569-614) */
+    int64_t nValid;                /* cells with DEM != flag (the metric's "gridded cells") */
+} pb_raster_out;
+
+/* cross-validation statistics: Project::computeStatisticsCrossValidation (project/project.cpp:2935-2969) */
+typedef struct pb_cv_stats {
+    int32_t n;
+    float meanAbsoluteError, meanBiasError, rootMeanSquareError, nashSutcliffe, R2;
+} pb_cv_stats;
+
+typedef struct pb_context pb_context;
+
+/* --- context ------------------------------------------------------------------------------------ */
+int pb_device_count(void);
+int pb_create(int device, pb_context** out);
+void pb_destroy(pb_context* ctx);
+const char* pb_last_error(const pb_context* ctx);   /* ctx may be NULL: last creation error */
+const char* pb_version(void);
+size_t pb_abi_sizeof(const char* structName);       /* sizeof of a descriptor in THIS build (binding self-check) */
+/* run on a caller-owned CUDA stream (a cudaStream_t passed as void*), e.g. torch's current stream */
+int pb_set_stream(pb_context* ctx, void* cudaStream);
+
+/* --- device-resident raster cache (DEM / proxy grids are reused by every time step) -------------- */
+typedef int32_t pb_raster_id;
+int pb_raster_upload(pb_context* ctx, const pb_raster* r, pb_raster_id* id);
+int pb_raster_free(pb_context* ctx, pb_raster_id id);
+/* number of cells with !isEqual(value, flag) (interpolationCmd.cpp:377): the metric's "gridded cells" */
+int pb_raster_valid_cells(pb_context* ctx, pb_raster_id id, int64_t* nValid);
+
+/* --- interpolationRaster (agrolib/project/interpolationCmd.h:73-75, .cpp:353-394) ---------------
+ * stations are the already pre-interpolated (detrended) points, settings carry the fitted model.
+ * `variable` is the reference meteoVariable value. rowBegin/rowEnd select a row band (multi-GPU
+ * sharding; 0,-1 = whole raster); cells outside the band are left untouched in `out`.
+ * Host-raster form (uploads, computes, downloads; the drop-in call): */
+int pb_interpolation_raster(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                            const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids,
+                            int rowBegin, int rowEnd, pb_raster_out* out);
+/* resident form: rasters were uploaded once with pb_raster_upload */
+int pb_interpolation_raster_resident(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                     pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids,
+                                     int rowBegin, int rowEnd, pb_raster_out* out);
+/* device-only step (no D2H of the grid; min/max/nValid still returned): used by bench `value` */
+int pb_interpolation_raster_device(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                   pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids,
+                                   int rowBegin, int rowEnd, pb_raster_out* out);
+
+/* --- interpolate() at explicit targets (agrolib/interpolation/interpolation.h:77-79, .cpp:2502-2560) -------
+ * The building block of computeResiduals (spatialControl.cpp:97-155): x, y are the f32 target coordinates,
+ * proxyValues holds m * settings.nProxy doubles (the targets' own proxy values, NODATA where missing).
+ * Stations whose distance to the target is 0 weigh nothing (interpolation.cpp:1039) => leave-one-out. */
+int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
+                          const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result);
+
+/* --- timing of the last call (device time measured with CUDA events on the engine's stream) ------ */
+typedef struct pb_timing {
+    float h2d_ms, kernel_ms, d2h_ms, total_ms;
+    int32_t launches;              /* kernels launched by the last call */
+    int64_t h2d_bytes, d2h_bytes;
+} pb_timing;
+int pb_last_timing(const pb_context* ctx, pb_timing* t);
+/* live ceilings of the two pipes that bound the IDW station loop: FP32 FMA (TFLOP/s, FFMA2 chain) and
+ * MUFU.RSQ (G op/s). Used by bench.py as roofline denominators (MEASURED_PEAKS.json has no FP32 figure). */
+int pb_measure_pipe_peaks(pb_context* ctx, float* fp32Tflops, float* mufuGops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRAGA_B200_H */

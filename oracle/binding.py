@@ -1,0 +1,135 @@
+"""ctypes binding of the CPU checkers (TEST INFRASTRUCTURE: imported by tests/, smoke() and bench.py's CPU legs only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from praga_b200 import _abi as A
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(HERE, "_ref", "libpraga_ref.so")
+PORT_LIB = os.path.join(HERE, "liboracle_port.so")
+_libs = {}
+
+
+def build(target="all"):
+    """Run oracle/Makefile (compiles the restatement; the reference only where /root/reference exists)."""
+    res = subprocess.run(["make", "-s", "-C", HERE, "-j8", target], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+
+
+def have_ref():
+    return os.path.exists(REF_LIB)
+
+
+def have_port():
+    return os.path.exists(PORT_LIB)
+
+
+def _load(path, prefix):
+    if path in _libs:
+        return _libs[path]
+    lib = C.CDLL(path)
+    P = C.POINTER
+    fn = getattr(lib, prefix + "_interpolation_raster")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_raster), P(A.pb_raster), C.c_int, C.c_int,
+                   P(A.pb_raster_out), P(C.c_double)]
+    fn = getattr(lib, prefix + "_pre_interpolation")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_uint8), P(A.pb_raster), C.c_int]
+    fn = getattr(lib, prefix + "_interpolate_points")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_float), P(C.c_float),
+                   P(C.c_double), C.c_int, C.c_int, P(C.c_float)]
+    fn = getattr(lib, prefix + "_compute_residuals")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_uint8), P(C.c_float),
+                   P(A.pb_cv_stats)]
+    fn = getattr(lib, prefix + "_kriging_points")
+    fn.argtypes = [P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                   P(C.c_double), C.c_int, P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_double)]
+    getattr(lib, prefix + "_max_threads").restype = C.c_int
+    _libs[path] = lib
+    return lib
+
+
+class Oracle:
+    """One of the two CPU checkers behind the same Python calls. kind = 'reference' | 'port'."""
+
+    def __init__(self, kind="reference"):
+        self.kind = kind
+        if kind == "reference":
+            if not have_ref():
+                raise RuntimeError("oracle/_ref/libpraga_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+            self.lib, self.p = _load(REF_LIB, "ref"), "ref"
+        else:
+            if not have_port():
+                build("port")
+            self.lib, self.p = _load(PORT_LIB, "port"), "port"
+
+    def _f(self, name):
+        return getattr(self.lib, f"{self.p}_{name}")
+
+    def max_threads(self):
+        return self._f("max_threads")()
+
+    def interpolation_raster(self, stations, settings, variable, dem, proxy_grids=(), threads=0):
+        """interpolationRaster (interpolationCmd.cpp:353-394). Returns (ok, grid, min, max, nValid, seconds)."""
+        st = stations.as_pb()
+        d = dem.as_pb()
+        grids = (A.pb_raster * max(1, len(proxy_grids)))()
+        for i, g in enumerate(proxy_grids):
+            grids[i] = g.as_pb()
+        out = np.empty(dem.shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        sec = C.c_double(0)
+        rc = self._f("interpolation_raster")(C.byref(st), C.byref(settings), variable, C.byref(d), grids,
+                                             len(proxy_grids), threads, C.byref(o), C.byref(sec))
+        return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid, sec.value
+
+    def pre_interpolation(self, stations, settings, variable, proxy_grids=()):
+        """preInterpolation (interpolation.cpp:2444): detrends stations.value IN PLACE, mutates settings.
+        Returns (ok, keep mask)."""
+        st = stations.as_pb()
+        grids = (A.pb_raster * max(1, len(proxy_grids)))()
+        for i, g in enumerate(proxy_grids):
+            grids[i] = g.as_pb()
+        keep = np.zeros(stations.n, dtype=np.uint8)
+        rc = self._f("pre_interpolation")(C.byref(st), C.byref(settings), variable, A.u8ptr(keep), grids,
+                                          len(proxy_grids))
+        return rc == A.PB_OK, keep.astype(bool)
+
+    def interpolate_points(self, stations, settings, variable, x, y, z, proxy_values, exclude_supplemental=False):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        z = np.ascontiguousarray(z, dtype=np.float32)
+        m = x.shape[0]
+        pv = np.ascontiguousarray(proxy_values, dtype=np.float64).reshape(m, -1)
+        res = np.empty(m, dtype=np.float32)
+        st = stations.as_pb()
+        self._f("interpolate_points")(C.byref(st), C.byref(settings), variable, A.fptr(x), A.fptr(y), A.fptr(z),
+                                      A.dptr(pv) if pv.size else None, m, int(exclude_supplemental), A.fptr(res))
+        return res
+
+    def compute_residuals(self, stations, settings, variable, observed, use_for_cv=None):
+        obs = np.ascontiguousarray(observed, dtype=np.float32)
+        res = np.empty(stations.n, dtype=np.float32)
+        stats = A.pb_cv_stats()
+        st = stations.as_pb()
+        use = None if use_for_cv is None else np.ascontiguousarray(use_for_cv, dtype=np.uint8)
+        self._f("compute_residuals")(C.byref(st), C.byref(settings), variable, A.fptr(obs),
+                                     None if use is None else A.u8ptr(use), A.fptr(res), C.byref(stats))
+        return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}
+
+    def kriging_points(self, pos, val, mode, rng, nugget, sill, slope, xy, want_rmse=True):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1)
+        m = xy.shape[0] // 2
+        res = np.empty(m, dtype=np.float64)
+        rm = np.empty(m, dtype=np.float64)
+        t_setup, t_eval = C.c_double(0), C.c_double(0)
+        rc = self._f("kriging_points")(A.dptr(pos), A.dptr(val), val.shape[0], mode, rng, nugget, sill, slope,
+                                       A.dptr(xy), m, A.dptr(res), A.dptr(rm) if want_rmse else None,
+                                       C.byref(t_setup), C.byref(t_eval))
+        return rc == A.PB_OK, res, rm, t_setup.value, t_eval.value

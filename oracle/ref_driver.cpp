@@ -1,0 +1,455 @@
+/*
+ * oracle/ref_driver.cpp — TEST INFRASTRUCTURE, never shipped, never on the product path.
+ *
+ * A thin C-ABI wrapper around the UNMODIFIED reference (ARPA-SIMC/PRAGA agrolib) so that the tests and
+ * bench.py's cpu_baseline / --impl reference leg can run the reference's own CPU code on the same POD
+ * descriptors the product's C ABI (include/praga_b200.h) takes.  It is compiled by oracle/Makefile
+ * against the reference headers and linked with the reference's five Qt-free libraries, which are
+ * compiled from the sources where they lie under /root/reference (nothing is copied into this repo);
+ * the output goes to oracle/_ref/libpraga_ref.so.
+ *
+ * What runs reference code verbatim:
+ *   ref_interpolation_raster  -> interpolationRaster()  agrolib/project/interpolationCmd.cpp:353-394
+ *                                (that file needs Qt; the Makefile extracts exactly that function body
+ *                                 into oracle/_ref/ at build time and compiles it with Qt-free includes)
+ *   ref_pre_interpolation     -> preInterpolation()     agrolib/interpolation/interpolation.cpp:2444
+ *   ref_compute_residuals     -> computeResiduals()     agrolib/interpolation/spatialControl.cpp:97
+ *   ref_kriging_*             -> kriging.cpp:97-295
+ *   ref_interpolate_points    -> interpolate()          interpolation.cpp:2502
+ * What is restated here because its only copy lives in Qt-bound code:
+ *   ref_local_detrending_raster  <- loop of Project::interpolationDemLocalDetrending, project.cpp:3208-3253
+ *   cv statistics                <- Project::computeStatisticsCrossValidation, project.cpp:2935-2969
+ */
+#include <omp.h>
+#include <math.h>
+#include <string.h>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "commonConstants.h"
+#include "basicMath.h"
+#include "furtherMathFunctions.h"
+#include "statistics.h"
+#include "gis.h"
+#include "meteo.h"
+#include "meteoPoint.h"
+#include "interpolation.h"
+#include "interpolationSettings.h"
+#include "interpolationPoint.h"
+#include "spatialControl.h"
+#include "kriging.h"
+
+#include "../include/praga_b200.h"
+
+/* extracted at build time from agrolib/project/interpolationCmd.cpp (see Makefile) */
+bool interpolationRaster(std::vector<Crit3DInterpolationDataPoint>& dataPoints,
+                         Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                         gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster, meteoVariable variable,
+                         bool isParallelComputing);
+
+/* ---- the enum values the C ABI copies by value must match the reference ---- */
+static_assert(int(idw) == PB_METHOD_IDW && int(shepard) == PB_METHOD_SHEPARD &&
+                  int(shepard_modified) == PB_METHOD_SHEPARD_MODIFIED, "TInterpolationMethod");
+static_assert(int(proxyHeight) == PB_PROXY_HEIGHT && int(proxyUrbanFraction) == PB_PROXY_URBAN_FRACTION &&
+                  int(proxyOrogIndex) == PB_PROXY_OROG_INDEX && int(proxySeaDistance) == PB_PROXY_SEA_DISTANCE &&
+                  int(proxyAspect) == PB_PROXY_ASPECT && int(proxySlope) == PB_PROXY_SLOPE &&
+                  int(proxyWaterIndex) == PB_PROXY_WATER_INDEX && int(noProxy) == PB_PROXY_NONE, "TProxyVar");
+static_assert(int(piecewiseTwo) == PB_FIT_PIECEWISE_TWO && int(piecewiseThreeFree) == PB_FIT_PIECEWISE_THREE_FREE &&
+                  int(piecewiseThree) == PB_FIT_PIECEWISE_THREE && int(linear) == PB_FIT_LINEAR &&
+                  int(noFunction) == PB_FIT_NONE, "TFittingFunction");
+static_assert(int(primary) == PB_LAPSE_PRIMARY && int(secondary) == PB_LAPSE_SECONDARY &&
+                  int(supplemental) == PB_LAPSE_SUPPLEMENTAL, "lapseRateCodeType");
+static_assert(int(KRIGING_SPHERICAL) == PB_KRIGING_SPHERICAL && int(KRIGING_LINEAR) == PB_KRIGING_LINEAR, "TkrigingMode");
+static_assert(int(airTemperature) == PB_VAR_AIR_TEMPERATURE && int(dailyAirTemperatureMin) == PB_VAR_DAILY_TMIN &&
+                  int(dailyAirTemperatureMax) == PB_VAR_DAILY_TMAX && int(dailyAirTemperatureAvg) == PB_VAR_DAILY_TAVG &&
+                  int(dailyAirTemperatureRange) == PB_VAR_DAILY_TRANGE && int(precipitation) == PB_VAR_PRECIPITATION &&
+                  int(dailyPrecipitation) == PB_VAR_DAILY_PRECIPITATION && int(airRelHumidity) == PB_VAR_AIR_REL_HUMIDITY &&
+                  int(airDewTemperature) == PB_VAR_AIR_DEW_TEMPERATURE && int(dailyAirRelHumidityMin) == PB_VAR_DAILY_RH_MIN &&
+                  int(dailyAirRelHumidityMax) == PB_VAR_DAILY_RH_MAX && int(dailyAirRelHumidityAvg) == PB_VAR_DAILY_RH_AVG &&
+                  int(globalIrradiance) == PB_VAR_GLOBAL_IRRADIANCE && int(atmTransmissivity) == PB_VAR_ATM_TRANSMISSIVITY &&
+                  int(dailyGlobalRadiation) == PB_VAR_DAILY_GLOBAL_RADIATION &&
+                  int(windScalarIntensity) == PB_VAR_WIND_SCALAR_INTENSITY &&
+                  int(windVectorIntensity) == PB_VAR_WIND_VECTOR_INTENSITY && int(windVectorX) == PB_VAR_WIND_VECTOR_X &&
+                  int(windVectorY) == PB_VAR_WIND_VECTOR_Y &&
+                  int(dailyWindVectorIntensityAvg) == PB_VAR_DAILY_WIND_VECTOR_INT_AVG &&
+                  int(dailyWindVectorIntensityMax) == PB_VAR_DAILY_WIND_VECTOR_INT_MAX &&
+                  int(dailyWindScalarIntensityAvg) == PB_VAR_DAILY_WIND_SCALAR_INT_AVG &&
+                  int(dailyWindScalarIntensityMax) == PB_VAR_DAILY_WIND_SCALAR_INT_MAX &&
+                  int(leafWetness) == PB_VAR_LEAF_WETNESS && int(dailyLeafWetness) == PB_VAR_DAILY_LEAF_WETNESS &&
+                  int(atmPressure) == PB_VAR_ATM_PRESSURE && int(dailyReferenceEvapotranspirationHS) == PB_VAR_DAILY_ET0_HS &&
+                  int(dailyWaterTableDepth) == PB_VAR_DAILY_WATER_TABLE_DEPTH && int(elaborationVar) == PB_VAR_ELABORATION &&
+                  int(noMeteoVar) == PB_VAR_NONE, "meteoVariable");
+static_assert(NODATA == PB_NODATA, "NODATA");
+
+namespace {
+
+const char* proxyNameOf(int kind)
+{
+    switch (kind) {
+    case PB_PROXY_HEIGHT: return "elevation";
+    case PB_PROXY_URBAN_FRACTION: return "urbanFraction";
+    case PB_PROXY_OROG_INDEX: return "orogIndex";
+    case PB_PROXY_SEA_DISTANCE: return "seaDistance";
+    case PB_PROXY_ASPECT: return "aspect";
+    case PB_PROXY_SLOPE: return "slope";
+    case PB_PROXY_WATER_INDEX: return "water_index";
+    default: return "unknown";
+    }
+}
+
+typedef double (*fit1d_t)(double, std::vector<double>&);
+
+fit1d_t fitFunctionOf(int f)
+{
+    switch (f) {
+    case PB_FIT_PIECEWISE_TWO: return lapseRatePiecewise_two;
+    case PB_FIT_PIECEWISE_THREE_FREE: return lapseRatePiecewise_three_free;
+    case PB_FIT_PIECEWISE_THREE: return lapseRatePiecewise_three;
+    case PB_FIT_LINEAR: return functionLinear_intercept;
+    default: return nullptr;
+    }
+}
+
+int fitFunctionId(const std::function<double(double, std::vector<double>&)>& f)
+{
+    auto t = f.target<fit1d_t>();
+    if (t == nullptr) return PB_FIT_NONE;
+    if (*t == lapseRatePiecewise_two) return PB_FIT_PIECEWISE_TWO;
+    if (*t == lapseRatePiecewise_three_free) return PB_FIT_PIECEWISE_THREE_FREE;
+    if (*t == lapseRatePiecewise_three) return PB_FIT_PIECEWISE_THREE;
+    if (*t == functionLinear_intercept) return PB_FIT_LINEAR;
+    return PB_FIT_NONE;
+}
+
+/* gis::Crit3DRasterGrid owning its rows, filled from a pb_raster */
+void fillGrid(gis::Crit3DRasterGrid& g, const pb_raster& r)
+{
+    gis::Crit3DRasterHeader h;
+    h.nrRows = r.h.nrRows; h.nrCols = r.h.nrCols; h.cellSize = r.h.cellSize; h.invCellSize = r.h.invCellSize;
+    h.flag = r.h.flag; h.llCorner.x = r.h.llx; h.llCorner.y = r.h.lly;
+    g.initializeGrid(h);
+    for (int row = 0; row < h.nrRows; row++) {
+        const float* src = r.data ? r.data + size_t(row) * h.nrCols : r.rows[row];
+        memcpy(g.value[row], src, sizeof(float) * h.nrCols);
+    }
+    g.isLoaded = true;
+}
+
+struct Scenario {
+    Crit3DInterpolationSettings settings;
+    Crit3DMeteoSettings meteoSettings;
+    Crit3DClimateParameters climate;
+    Crit3DTime time;
+    std::vector<Crit3DInterpolationDataPoint> points;
+    std::vector<gis::Crit3DRasterGrid*> grids;   // proxy grids (owned)
+    ~Scenario()
+    {
+        for (auto& p : points) delete p.point;          // the reference never frees these (interpolationPoint.cpp:49)
+        for (auto g : grids) delete g;
+    }
+};
+
+void buildSettings(Scenario& sc, const pb_settings& s, const pb_raster* proxyGrids, int nProxyGrids)
+{
+    Crit3DInterpolationSettings& st = sc.settings;
+    st.initialize();
+    st.setInterpolationMethod(TInterpolationMethod(s.method));
+    st.setUseThermalInversion(s.useThermalInversion != 0);
+    st.setUseTD(s.useTD != 0);
+    st.setUseLocalDetrending(s.useLocalDetrending != 0);
+    st.setUseGlocalDetrending(s.useGlocalDetrending != 0);
+    st.setUseLapseRateCode(s.useLapseRateCode != 0);
+    st.setUseBestDetrending(s.useBestDetrending != 0);
+    st.setUseMultipleDetrending(s.useMultipleDetrending != 0);
+    st.setUseDoNotRetrend(s.useDoNotRetrend != 0);
+    st.setUseRetrendOnly(s.useRetrendOnly != 0);
+    st.setPrecipitationAllZero(s.precipitationAllZero != 0);
+    st.setMinPointsLocalDetrending(s.minPointsLocalDetrending);
+    st.setTopoDist_Kh(s.topoDist_Kh);
+    st.setTopoDist_maxKh(s.topoDist_maxKh);
+    st.setMinRegressionR2(s.minRegressionR2);
+    st.setPointsBoundingBoxArea(s.pointsBoundingBoxArea);
+    st.setLocalRadius(s.localRadius);
+    if (s.hasPointsRange) st.setPointsRange(s.pointsRangeMin, s.pointsRangeMax);
+    sc.meteoSettings.setRainfallThreshold(s.rainfallThreshold);
+
+    for (int g = 0; g < nProxyGrids; g++) {
+        gis::Crit3DRasterGrid* grid = new gis::Crit3DRasterGrid();
+        fillGrid(*grid, proxyGrids[g]);
+        sc.grids.push_back(grid);
+    }
+
+    for (int i = 0; i < s.nProxy; i++) {
+        const pb_proxy& p = s.proxy[i];
+        Crit3DProxy proxy;
+        proxy.setName(proxyNameOf(p.kind));
+        if (p.gridIndex >= 0 && p.gridIndex < nProxyGrids) proxy.setGrid(sc.grids[p.gridIndex]);
+        proxy.setFittingFunctionName(TFittingFunction(p.fittingFunction));
+        proxy.setInversionIsSignificative(p.inversionIsSignificative != 0);
+        proxy.setRegressionR2(p.regressionR2);
+        proxy.setRegressionSlope(p.regressionSlope);
+        proxy.setRegressionIntercept(p.regressionIntercept);
+        proxy.setLapseRateH0(p.lapseRateH0);
+        proxy.setLapseRateH1(p.lapseRateH1);
+        proxy.setLapseRateT0(p.lapseRateT0);
+        proxy.setLapseRateT1(p.lapseRateT1);
+        proxy.setInversionLapseRate(p.inversionLapseRate);
+        proxy.setStdDevThreshold(p.stdDevThreshold);
+        std::vector<double> range;
+        for (int j = 0; j < p.nFitParams; j++) range.push_back(p.fitMin[j]);
+        for (int j = 0; j < p.nFitParams; j++) range.push_back(p.fitMax[j]);
+        proxy.setFittingParametersRange(range);
+        std::vector<int> fg;
+        for (int j = 0; j < p.nFitParams; j++) fg.push_back(p.fitFirstGuess[j]);
+        proxy.setFittingFirstGuess(fg);
+        std::vector<std::vector<double>> combos;
+        for (int k = 0; k < p.nFirstGuessCombinations; k++)
+            combos.push_back(std::vector<double>(p.firstGuessCombinations[k], p.firstGuessCombinations[k] + p.nFitParams));
+        proxy.setFirstGuessCombinations(combos);
+        st.addProxy(proxy, s.selectedActive[i] != 0);
+    }
+
+    Crit3DProxyCombination sel, cur;
+    for (int i = 0; i < s.nProxy; i++) {
+        sel.addProxyActive(s.selectedActive[i] != 0);
+        sel.addProxySignificant(false);
+        cur.addProxyActive(s.currentActive[i] != 0);
+        cur.addProxySignificant(s.currentSignificant[i] != 0);
+    }
+    sel.setUseThermalInversion(s.selectedUseThermalInversion != 0);
+    cur.setUseThermalInversion(s.currentUseThermalInversion != 0);
+    st.setSelectedCombination(sel);
+    st.setCurrentCombination(cur);
+
+    st.clearFitting();
+    std::vector<std::vector<double>> params;
+    for (int i = 0; i < s.nFit; i++) {
+        fit1d_t f = fitFunctionOf(s.fitFunction[i]);
+        if (f) st.addFittingFunction(f);
+        params.push_back(std::vector<double>(s.fitParams[i], s.fitParams[i] + s.fitNrParams[i]));
+    }
+    st.setFittingParameters(params);
+
+    /* climate: one lapse rate for every month; 06:00 makes the hourly blend return it exactly (meteo.cpp:173-222) */
+    sc.climate.tminLapseRate.assign(12, s.climateLapseRate);
+    sc.climate.tmaxLapseRate.assign(12, s.climateLapseRate);
+    sc.climate.tdMinLapseRate.assign(12, s.climateLapseRate);
+    sc.climate.tdMaxLapseRate.assign(12, s.climateLapseRate);
+    sc.time = Crit3DTime(Crit3DDate(15, 1, 2023), 6 * 3600);
+}
+
+void exportSettings(Scenario& sc, pb_settings& s)
+{
+    Crit3DInterpolationSettings& st = sc.settings;
+    s.precipitationAllZero = st.getPrecipitationAllZero() ? 1 : 0;
+    s.topoDist_Kh = st.getTopoDist_Kh();
+    s.localRadius = st.getLocalRadius();
+    Crit3DProxyCombination cur = st.getCurrentCombination();
+    s.currentUseThermalInversion = cur.getUseThermalInversion() ? 1 : 0;
+    for (int i = 0; i < s.nProxy; i++) {
+        s.currentActive[i] = cur.isProxyActive(i) ? 1 : 0;
+        s.currentSignificant[i] = cur.isProxySignificant(i) ? 1 : 0;
+        Crit3DProxy* p = st.getProxy(i);
+        pb_proxy& q = s.proxy[i];
+        q.inversionIsSignificative = p->getInversionIsSignificative() ? 1 : 0;
+        q.regressionR2 = p->getRegressionR2();
+        q.regressionSlope = p->getRegressionSlope();
+        q.regressionIntercept = p->getRegressionIntercept();
+        q.lapseRateH0 = p->getLapseRateH0();
+        q.lapseRateH1 = p->getLapseRateH1();
+        q.lapseRateT0 = p->getLapseRateT0();
+        q.lapseRateT1 = p->getLapseRateT1();
+        q.inversionLapseRate = p->getInversionLapseRate();
+        std::vector<double> range = p->getFittingParametersRange();
+        int np = int(range.size() / 2);
+        q.nFitParams = np;
+        for (int j = 0; j < np && j < PB_MAX_FIT_PARAMS; j++) { q.fitMin[j] = range[j]; q.fitMax[j] = range[np + j]; }
+        std::vector<std::vector<double>> combos = p->getFirstGuessCombinations();
+        q.nFirstGuessCombinations = int(combos.size());
+        for (size_t k = 0; k < combos.size() && k < PB_MAX_FIRST_GUESS; k++)
+            for (size_t j = 0; j < combos[k].size() && j < PB_MAX_FIT_PARAMS; j++) q.firstGuessCombinations[k][j] = combos[k][j];
+    }
+    auto funcs = st.getFittingFunction();
+    auto params = st.getFittingParameters();
+    s.nFit = int(params.size());
+    for (int i = 0; i < s.nFit && i < PB_MAX_PROXY; i++) {
+        s.fitFunction[i] = i < int(funcs.size()) ? fitFunctionId(funcs[i]) : PB_FIT_NONE;
+        s.fitNrParams[i] = int(params[i].size());
+        for (size_t j = 0; j < params[i].size() && j < PB_MAX_FIT_PARAMS; j++) s.fitParams[i][j] = params[i][j];
+    }
+    s.nFitFunctions = int(funcs.size());
+}
+
+void buildPoints(Scenario& sc, const pb_stations& st)
+{
+    sc.points.resize(st.n);
+    for (int i = 0; i < st.n; i++) {
+        Crit3DInterpolationDataPoint& p = sc.points[i];
+        p.point->utm.x = st.x[i];
+        p.point->utm.y = st.y[i];
+        p.point->z = st.z[i];
+        p.index = st.index ? st.index[i] : i;
+        p.isActive = st.isActive ? st.isActive[i] != 0 : true;
+        p.value = st.value[i];
+        p.regressionWeight = st.regressionWeight ? st.regressionWeight[i] : float(NODATA);
+        p.lapseRateCode = st.lapseRateCode ? lapseRateCodeType(st.lapseRateCode[i]) : primary;
+        p.proxyValues.assign(st.proxyValues + size_t(i) * st.nProxy, st.proxyValues + size_t(i + 1) * st.nProxy);
+    }
+}
+
+void copyOut(const gis::Crit3DRasterGrid& g, pb_raster_out* out)
+{
+    for (int row = 0; row < g.header->nrRows; row++) {
+        float* dst = out->data ? out->data + size_t(row) * g.header->nrCols : out->rows[row];
+        memcpy(dst, g.value[row], sizeof(float) * g.header->nrCols);
+    }
+    out->minimum = g.minimum;
+    out->maximum = g.maximum;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_max_threads(void) { return omp_get_max_threads(); }
+
+/* interpolationRaster, verbatim reference code. nThreads <= 0: all cores (the reference forces that anyway,
+ * interpolationCmd.cpp:362-367; OMP_NUM_THREADS / omp_set_num_threads before the call is how we time 1 thread).
+ * elapsed_s (optional) = wall time of the interpolationRaster call alone. */
+int ref_interpolation_raster(const pb_stations* st, const pb_settings* s, int variable, const pb_raster* dem,
+                             const pb_raster* proxyGrids, int nProxyGrids, int nThreads, pb_raster_out* out,
+                             double* elapsed_s)
+{
+    Scenario sc;
+    buildSettings(sc, *s, proxyGrids, nProxyGrids);
+    buildPoints(sc, *st);
+    gis::Crit3DRasterGrid demGrid, outGrid;
+    fillGrid(demGrid, *dem);
+    sc.settings.setCurrentDEM(&demGrid);
+    if (nThreads > 0) omp_set_num_threads(nThreads);
+    auto t0 = std::chrono::steady_clock::now();
+    bool ok = interpolationRaster(sc.points, sc.settings, &sc.meteoSettings, &outGrid, demGrid, meteoVariable(variable),
+                                  nThreads != 1);
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    int64_t nValid = 0;
+    for (int row = 0; row < demGrid.header->nrRows; row++)
+        for (int col = 0; col < demGrid.header->nrCols; col++)
+            if (!isEqual(demGrid.value[row][col], demGrid.header->flag)) nValid++;
+    out->nValid = nValid;
+    if (outGrid.isLoaded) copyOut(outGrid, out);
+    return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
+/* preInterpolation, verbatim reference code; station values and settings are written back.
+ * keep[i] = 1 if point i is still in myPoints afterwards (multiple detrending erases points, interpolation.cpp:2230). */
+int ref_pre_interpolation(pb_stations* st, pb_settings* s, int variable, uint8_t* keep, const pb_raster* proxyGrids,
+                          int nProxyGrids)
+{
+    Scenario sc;
+    buildSettings(sc, *s, proxyGrids, nProxyGrids);
+    buildPoints(sc, *st);
+    for (int i = 0; i < st->n; i++) sc.points[i].index = i;   // used to map survivors back
+    std::vector<Crit3DMeteoPoint> meteoPoints;                // only read by optimalDetrending / TD optimisation
+    std::string err;
+    bool ok = preInterpolation(sc.points, sc.settings, &sc.meteoSettings, &sc.climate, meteoPoints,
+                               meteoVariable(variable), sc.time, err);
+    if (keep) memset(keep, 0, st->n);
+    for (auto& p : sc.points) {
+        st->value[p.index] = p.value;
+        if (keep) keep[p.index] = 1;
+    }
+    exportSettings(sc, *s);
+    return ok ? PB_OK : PB_ERR_FIT;
+}
+
+/* interpolate() at arbitrary targets (x, y, z, proxyValues[nProxy]) — interpolation.cpp:2502 */
+int ref_interpolate_points(const pb_stations* st, const pb_settings* s, int variable, const float* x, const float* y,
+                           const float* z, const double* proxyValues, int m, int excludeSupplemental, float* result)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    std::vector<double> pv(s->nProxy);
+    for (int i = 0; i < m; i++) {
+        for (int k = 0; k < s->nProxy; k++) pv[k] = proxyValues[size_t(i) * s->nProxy + k];
+        result[i] = interpolate(sc.points, sc.settings, &sc.meteoSettings, meteoVariable(variable), x[i], y[i], z[i], pv,
+                                excludeSupplemental != 0);
+    }
+    return PB_OK;
+}
+
+/* computeResiduals (spatialControl.cpp:97-155) + Project::computeStatisticsCrossValidation (project.cpp:2935-2969,
+ * restated: that copy needs Qt). One Crit3DMeteoPoint per station: active, quality accepted, currentValue =
+ * observed[i], position/proxy values of the station. */
+int ref_compute_residuals(const pb_stations* st, const pb_settings* s, int variable, const float* observed,
+                          const uint8_t* useForCv, float* residual, pb_cv_stats* stats)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    std::vector<Crit3DMeteoPoint> mp(st->n);
+    for (int i = 0; i < st->n; i++) {
+        mp[i].active = useForCv ? useForCv[i] != 0 : true;
+        mp[i].quality = quality::accepted;
+        mp[i].currentValue = observed[i];
+        mp[i].point.utm.x = st->x[i];
+        mp[i].point.utm.y = st->y[i];
+        mp[i].point.z = st->z[i];
+        mp[i].isInsideDem = true;
+        mp[i].lapseRateCode = st->lapseRateCode ? lapseRateCodeType(st->lapseRateCode[i]) : primary;
+        for (int k = 0; k < st->nProxy; k++) mp[i].proxyValues.push_back(st->proxyValues[size_t(i) * st->nProxy + k]);
+        sc.points[i].index = i;
+    }
+    bool ok = computeResiduals(meteoVariable(variable), mp, sc.points, sc.settings, &sc.meteoSettings, false, false);
+    std::vector<float> obs, pre;
+    for (int i = 0; i < st->n; i++) {
+        residual[i] = mp[i].residual;
+        if (mp[i].active) {
+            float value = mp[i].currentValue;
+            if (!isEqual(value, NODATA) && !isEqual(mp[i].residual, NODATA)) {
+                obs.push_back(value);
+                pre.push_back(value - mp[i].residual);
+            }
+        }
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n = int(obs.size());
+        stats->meanAbsoluteError = stats->meanBiasError = stats->rootMeanSquareError = stats->nashSutcliffe = stats->R2 = NODATA;
+        if (obs.size() > 0) {
+            stats->meanAbsoluteError = statistics::meanAbsoluteError(obs, pre);
+            stats->meanBiasError = statistics::meanError(obs, pre);
+            stats->rootMeanSquareError = statistics::rootMeanSquareError(obs, pre);
+            stats->nashSutcliffe = statistics::NashSutcliffeEfficiency(obs, pre);
+            float intercept, slope, r2;
+            statistics::linearRegression(obs, pre, int(obs.size()), false, &intercept, &slope, &r2);
+            stats->R2 = r2;
+        }
+    }
+    return ok ? PB_OK : PB_ERR_INVALID;
+}
+
+/* kriging.cpp:97-295. File-static state => single threaded, one system at a time. */
+int ref_kriging_points(const double* pos, const double* val, int n, int mode, double range, double nugget, double sill,
+                       double slope, const double* xy, int m, double* result, double* rmse, double* setup_s,
+                       double* eval_s)
+{
+    std::vector<double> p(pos, pos + 2 * size_t(n)), v(val, val + n);
+    auto t0 = std::chrono::steady_clock::now();
+    if (!krigingVariogram(p.data(), v.data(), n, TkrigingMode(mode), range, nugget, sill, slope)) return PB_ERR_INVALID;
+    auto t1 = std::chrono::steady_clock::now();
+    for (int i = 0; i < m; i++) {
+        krigingSetWeight(xy[2 * i], xy[2 * i + 1]);
+        result[i] = krigingResult();
+        if (rmse) rmse[i] = krigingRMSE();
+    }
+    auto t2 = std::chrono::steady_clock::now();
+    krigingFreeMemory();
+    if (setup_s) *setup_s = std::chrono::duration<double>(t1 - t0).count();
+    if (eval_s) *eval_s = std::chrono::duration<double>(t2 - t1).count();
+    return PB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,707 @@
+// engine.cu — C ABI of libpraga_b200.so (include/praga_b200.h): context, device-resident raster cache,
+// flattening of the POD settings into the kernel model, staging and launches.  No CPU fallback: every compute
+// entry point needs a CUDA device and fails with PB_ERR_CUDA otherwise.
+#include <math.h>
+#include <omp.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pb {
+// idw_kernels.cu
+cudaError_t launchCompactValid(const float* dem, long long n, float flag, int* blockCount, long long* dTotal,
+                               int* validIdx, int phase, cudaStream_t s);
+int compactBlocks(long long n);
+int tileStations();
+cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevGrid& dem, const int* validIdx,
+                            int nTargets, float* out, unsigned* minmax, cudaStream_t s);
+cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty,
+                            const double* tproxy, int nTargets, float* out, cudaStream_t s);
+cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);
+cudaError_t launchFillValid(float* out, const int* validIdx, int n, float v, cudaStream_t s);
+// peaks.cu
+cudaError_t measurePipePeaks(cudaStream_t s, int sms, float* fp32Tflops, float* mufuGops);
+}  // namespace pb
+
+using namespace pb;
+
+namespace {
+
+std::string g_createError;
+
+struct RasterEntry {
+    bool used = false;
+    pb_raster_header h{};
+    float* d = nullptr;
+    size_t n = 0;
+    // DEM role (built lazily): ascending list of valid cells + per-row offsets into it
+    int* validIdx = nullptr;
+    long long nValid = -1;
+    std::vector<long long> rowStart;   // nrRows + 1 prefix counts (host)
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinnedBuf {
+    unsigned char* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, n);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct pb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = true;
+    std::string err;
+    std::vector<RasterEntry> rasters;
+    DevBuf<unsigned char> dStations;
+    PinnedBuf hStations;
+    DevBuf<float> dOut;
+    int outInitRaster = -1;             // dOut currently holds the flag pattern of this raster id
+    DevBuf<unsigned char> dScratch;     // point targets
+    PinnedBuf hStage;                   // raster staging (H2D / D2H)
+    unsigned* dMinMax = nullptr;
+    unsigned* hMinMax = nullptr;        // pinned
+    cudaEvent_t ev[4]{};
+    pb_timing timing{};
+};
+
+namespace {
+
+int fail(pb_context* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->err = msg;
+    else g_createError = msg;
+    return code;
+}
+#define CUDA_TRY(ctx, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, PB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+// ---- meteoVariable classification (interpolation.cpp:1190-1234, 2540-2558) ----
+bool useDetrendingVar(int v)
+{
+    return v == PB_VAR_AIR_TEMPERATURE || v == PB_VAR_AIR_DEW_TEMPERATURE || v == PB_VAR_DAILY_TAVG ||
+           v == PB_VAR_DAILY_TMAX || v == PB_VAR_DAILY_TMIN || v == PB_VAR_DAILY_ET0_HS || v == PB_VAR_ATM_PRESSURE ||
+           v == PB_VAR_ELABORATION;
+}
+bool useTdVar(int v)
+{
+    return !(v == PB_VAR_PRECIPITATION || v == PB_VAR_DAILY_PRECIPITATION || v == PB_VAR_GLOBAL_IRRADIANCE ||
+             v == PB_VAR_ATM_TRANSMISSIVITY || v == PB_VAR_DAILY_GLOBAL_RADIATION || v == PB_VAR_ATM_PRESSURE ||
+             v == PB_VAR_DAILY_WATER_TABLE_DEPTH);
+}
+bool isPrecVar(int v) { return v == PB_VAR_PRECIPITATION || v == PB_VAR_DAILY_PRECIPITATION; }
+int clampModeOf(int v)
+{
+    switch (v) {
+    case PB_VAR_PRECIPITATION: case PB_VAR_DAILY_PRECIPITATION: return CLAMP_PREC;
+    case PB_VAR_AIR_REL_HUMIDITY: case PB_VAR_DAILY_RH_AVG: case PB_VAR_DAILY_RH_MIN: case PB_VAR_DAILY_RH_MAX:
+        return CLAMP_RH;
+    case PB_VAR_DAILY_TRANGE: case PB_VAR_LEAF_WETNESS: case PB_VAR_DAILY_LEAF_WETNESS: case PB_VAR_GLOBAL_IRRADIANCE:
+    case PB_VAR_DAILY_GLOBAL_RADIATION: case PB_VAR_ATM_TRANSMISSIVITY: case PB_VAR_WIND_SCALAR_INTENSITY:
+    case PB_VAR_WIND_VECTOR_INTENSITY: case PB_VAR_DAILY_WIND_SCALAR_INT_AVG: case PB_VAR_DAILY_WIND_SCALAR_INT_MAX:
+    case PB_VAR_DAILY_WIND_VECTOR_INT_AVG: case PB_VAR_DAILY_WIND_VECTOR_INT_MAX: case PB_VAR_ATM_PRESSURE:
+        return CLAMP_POS;
+    default: return CLAMP_NONE;
+    }
+}
+// checkLapseRateCode (meteo/meteo.cpp:1127-1133)
+bool checkLapseRateCode(int code, bool useLapseRateCode, bool useSupplemental)
+{
+    if (useSupplemental) return !useLapseRateCode || code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SUPPLEMENTAL;
+    return !useLapseRateCode || code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SECONDARY;
+}
+
+DevGrid devGridOf(const RasterEntry& r)
+{
+    DevGrid g{};
+    g.data = r.d;
+    g.nrRows = r.h.nrRows; g.nrCols = r.h.nrCols;
+    g.llx = r.h.llx; g.lly = r.h.lly; g.cellSize = r.h.cellSize; g.invCellSize = r.h.invCellSize;
+    g.flag = r.h.flag;
+    return g;
+}
+
+// pb_settings -> DevModel. proxyGridIds: raster ids for settings.proxy[i].gridIndex (resident form).
+int buildModel(pb_context* ctx, const pb_settings* s, int variable, const pb_raster_id* proxyGridIds, int nProxyGrids,
+               DevModel& m)
+{
+    memset(&m, 0, sizeof(m));
+    if (s->nProxy < 0 || s->nProxy > PB_MAX_PROXY) return fail(ctx, PB_ERR_INVALID, "settings.nProxy out of range");
+    if (s->method != PB_METHOD_IDW)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the GPU path (shepard: DESIGN.md)");
+    if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending is out of scope (DESIGN.md)");
+    // getUseTD() is useTD && !useLocalDetrending (interpolationSettings.h:251)
+    if (s->useTD && !s->useLocalDetrending && useTdVar(variable) && s->topoDist_Kh != 0)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "topographic distance with kh != 0 is not implemented yet (DESIGN.md)");
+    m.nProxy = s->nProxy;
+    m.useDetrendingVar = useDetrendingVar(variable);
+    m.useMultipleDetrending = s->useMultipleDetrending;
+    m.useThermalInversion = s->useThermalInversion;
+    m.useDoNotRetrend = s->useDoNotRetrend;
+    m.useRetrendOnly = s->useRetrendOnly;
+    m.clampMode = clampModeOf(variable);
+    m.rainfallThreshold = s->rainfallThreshold;
+    m.minRegressionR2 = s->minRegressionR2;
+    int slots = 0;
+    for (int i = 0; i < s->nProxy; i++) {
+        const pb_proxy& p = s->proxy[i];
+        DevProxy& d = m.proxy[i];
+        d.kind = p.kind;
+        d.active = s->currentActive[i];
+        d.significant = s->currentSignificant[i];
+        d.slope = p.regressionSlope;
+        d.r2 = p.regressionR2;
+        d.H0 = p.lapseRateH0; d.H1 = p.lapseRateH1; d.invLapseRate = p.inversionLapseRate;
+        d.inversionIsSignificative = p.inversionIsSignificative;
+        d.gridSlot = -1;
+        if (p.gridIndex >= 0 && proxyGridIds) {
+            if (p.gridIndex >= nProxyGrids) return fail(ctx, PB_ERR_INVALID, "proxy.gridIndex >= nProxyGrids");
+            const pb_raster_id id = proxyGridIds[p.gridIndex];
+            if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used)
+                return fail(ctx, PB_ERR_INVALID, "proxy grid id is not a live raster");
+            d.gridSlot = slots;
+            m.grid[slots++] = devGridOf(ctx->rasters[id]);
+        }
+    }
+    if (s->useMultipleDetrending && m.useDetrendingVar) {
+        // getMultipleDetrendingValues order (interpolation.cpp:2563-2617): elevation, then the others
+        int elevationPos = -1;
+        for (int i = 0; i < s->nProxy; i++)
+            if (s->proxy[i].kind == PB_PROXY_HEIGHT && s->currentActive[i] && s->currentSignificant[i]) {
+                elevationPos = i;
+                m.activeSigPos[m.nActiveSig++] = i;
+            }
+        for (int i = 0; i < s->nProxy; i++)
+            if (i != elevationPos && s->currentActive[i] && s->currentSignificant[i]) m.activeSigPos[m.nActiveSig++] = i;
+        // functionSum walks fittingFunction and indexes values/parameters with the same counter
+        // (furtherMathFunctions.cpp:181-191); more functions than values/parameters is out of bounds in the reference
+        m.nFit = s->nFitFunctions;
+        if (s->nFit == 0) m.nFit = 0;   // retrend: fittingParameters.size() > 0 required (interpolation.cpp:1310)
+        if (m.nFit > m.nActiveSig || m.nFit > s->nFit || m.nFit > PB_MAX_PROXY)
+            return fail(ctx, PB_ERR_INVALID, "fitting functions/parameters/significant proxies are inconsistent");
+        for (int k = 0; k < m.nFit; k++) {
+            m.fitFunction[k] = s->fitFunction[k];
+            for (int j = 0; j < PB_MAX_FIT_PARAMS; j++) m.fitParams[k][j] = j < s->fitNrParams[k] ? s->fitParams[k][j] : 0.;
+        }
+    }
+    return PB_OK;
+}
+
+// pack the stations the estimator uses into the device layout. `excludeSupplemental` as in computeDistances
+// (interpolation.cpp:217-220): excluded points get distance 0 => never weigh => dropped here.
+int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, DevStations& ds,
+                  double& valueOffset)
+{
+    if (st->n < 0) return fail(ctx, PB_ERR_INVALID, "stations.n < 0");
+    std::vector<int> use;
+    use.reserve(st->n);
+    for (int i = 0; i < st->n; i++) {
+        const int code = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        if (excludeSupplemental && !checkLapseRateCode(code, s->useLapseRateCode != 0, false)) continue;
+        use.push_back(i);
+    }
+    const int n = (int)use.size();
+    const int T = tileStations();
+    const int nPadded = ((n + T - 1) / T) * T;
+    double mean = 0.;
+    for (int k = 0; k < n; k++) mean += double(st->value[use[k]]);
+    mean = n ? mean / n : 0.;
+    valueOffset = mean;
+
+    const size_t offXY = 0, offV = offXY + size_t(nPadded) * 16, offX = offV + size_t(nPadded) * 8;
+    const size_t nAl = (size_t(n) + 3) / 4 * 4;
+    const size_t offY = offX + nAl * 4, offVal = offY + nAl * 4, total = offVal + nAl * 4 + 16;
+    CUDA_TRY(ctx, ctx->hStations.reserve(total));
+    CUDA_TRY(ctx, ctx->dStations.reserve(total));
+    unsigned char* h = ctx->hStations.p;
+    float4* xy = reinterpret_cast<float4*>(h + offXY);
+    float2* v = reinterpret_cast<float2*>(h + offV);
+    float* px = reinterpret_cast<float*>(h + offX);
+    float* py = reinterpret_cast<float*>(h + offY);
+    float* pv = reinterpret_cast<float*>(h + offVal);
+    for (int k = 0; k < n; k++) {
+        const int i = use[k];
+        const float x = float(st->x[i]), y = float(st->y[i]);           // float(point->utm.x) (interpolation.cpp:222)
+        const float c = float(double(st->value[i]) - mean);
+        xy[k] = make_float4(x, x, y, y);
+        v[k] = make_float2(c, c);
+        px[k] = x; py[k] = y; pv[k] = c;
+    }
+    for (int k = n; k < nPadded; k++) {   // zero-weight padding: rsqrt(2e36)^3 underflows to 0
+        xy[k] = make_float4(1e18f, 1e18f, 1e18f, 1e18f);
+        v[k] = make_float2(0.f, 0.f);
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dStations.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)total;
+    unsigned char* d = ctx->dStations.p;
+    ds.xy = reinterpret_cast<const float4*>(d + offXY);
+    ds.v = reinterpret_cast<const float2*>(d + offV);
+    ds.x = reinterpret_cast<const float*>(d + offX);
+    ds.y = reinterpret_cast<const float*>(d + offY);
+    ds.val = reinterpret_cast<const float*>(d + offVal);
+    ds.n = n;
+    ds.nPadded = nPadded;
+    return PB_OK;
+}
+
+// gather a host raster (contiguous or float**) into pinned staging with all host cores, then one H2D
+int uploadRaster(pb_context* ctx, const pb_raster* r, RasterEntry& e)
+{
+    if (r->h.nrRows <= 0 || r->h.nrCols <= 0) return fail(ctx, PB_ERR_INVALID, "raster has no cells");
+    if (!r->data && !r->rows) return fail(ctx, PB_ERR_INVALID, "raster has neither data nor rows");
+    const size_t n = size_t(r->h.nrRows) * r->h.nrCols;
+    if (n > size_t(0x7fffffff)) return fail(ctx, PB_ERR_UNSUPPORTED, "raster larger than 2^31-1 cells");
+    CUDA_TRY(ctx, ctx->hStage.reserve(n * sizeof(float)));
+    float* stage = reinterpret_cast<float*>(ctx->hStage.p);
+    const int rows = r->h.nrRows, cols = r->h.nrCols;
+#pragma omp parallel for schedule(static)
+    for (int row = 0; row < rows; row++) {
+        const float* src = r->data ? r->data + size_t(row) * cols : r->rows[row];
+        memcpy(stage + size_t(row) * cols, src, sizeof(float) * cols);
+    }
+    e.h = r->h;
+    e.n = n;
+    CUDA_TRY(ctx, cudaMalloc(&e.d, n * sizeof(float)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(e.d, stage, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // staging buffer is reused by the next upload
+    ctx->timing.h2d_bytes += (int64_t)(n * sizeof(float));
+    e.used = true;
+    e.nValid = -1;
+    return PB_OK;
+}
+
+void freeEntry(RasterEntry& e)
+{
+    if (e.d) cudaFree(e.d);
+    if (e.validIdx) cudaFree(e.validIdx);
+    e = RasterEntry();
+}
+
+// valid-cell list of a DEM (cells with !isEqual(z, flag), interpolationCmd.cpp:377), built once per upload
+int ensureValidList(pb_context* ctx, RasterEntry& e)
+{
+    if (e.nValid >= 0) return PB_OK;
+    const long long n = (long long)e.n;
+    const int nb = compactBlocks(n);
+    int* blockCount = nullptr;
+    long long* dTotal = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&blockCount, sizeof(int) * nb));
+    CUDA_TRY(ctx, cudaMalloc(&dTotal, sizeof(long long)));
+    CUDA_TRY(ctx, launchCompactValid(e.d, n, e.h.flag, blockCount, dTotal, nullptr, 0, ctx->stream));
+    long long total = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&total, dTotal, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMalloc(&e.validIdx, sizeof(int) * std::max<long long>(total, 1)));
+    CUDA_TRY(ctx, launchCompactValid(e.d, n, e.h.flag, blockCount, dTotal, e.validIdx, 1, ctx->stream));
+    ctx->timing.launches += 3;
+    // per-row offsets (row bands for multi-GPU sharding): binary search of each row start on the host copy
+    std::vector<int> idx((size_t)total);
+    if (total)
+        CUDA_TRY(ctx, cudaMemcpyAsync(idx.data(), e.validIdx, sizeof(int) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    e.rowStart.assign(size_t(e.h.nrRows) + 1, 0);
+    for (int row = 0; row <= e.h.nrRows; row++) {
+        const long long first = (long long)row * e.h.nrCols;
+        e.rowStart[row] = std::lower_bound(idx.begin(), idx.end(), first,
+                                           [](int a, long long b) { return (long long)a < b; }) - idx.begin();
+    }
+    cudaFree(blockCount);
+    cudaFree(dTotal);
+    e.nValid = total;
+    return PB_OK;
+}
+
+float keyToFloat(unsigned k)
+{
+    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+enum OutMode { OUT_HOST = 0, OUT_DEVICE_ONLY = 1 };
+
+int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, pb_raster_id demId,
+               const pb_raster_id* proxyIds, int nProxyGrids, int rowBegin, int rowEnd, pb_raster_out* out, OutMode mode)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s || !out) return fail(ctx, PB_ERR_INVALID, "null argument");
+    if (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used)
+        return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
+    RasterEntry& dem = ctx->rasters[demId];
+    if (rowEnd < 0) rowEnd = dem.h.nrRows;
+    if (rowBegin < 0 || rowBegin > rowEnd || rowEnd > dem.h.nrRows) return fail(ctx, PB_ERR_INVALID, "bad row band");
+    int rc = ensureValidList(ctx, dem);
+    if (rc) return rc;
+
+    DevModel m;
+    rc = buildModel(ctx, s, variable, proxyIds, nProxyGrids, m);
+    if (rc) return rc;
+
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    const bool precZero = isPrecVar(variable) && s->precipitationAllZero;
+    DevStations ds{};
+    if (!precZero) {
+        rc = stageStations(ctx, st, s, true, ds, m.valueOffset);
+        if (rc) return rc;
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+
+    // output = DEM header, every cell = flag (initializeGrid(raster), gis.cpp:357-363); valid cells overwritten below
+    CUDA_TRY(ctx, ctx->dOut.reserve(dem.n));
+    if (ctx->outInitRaster != demId) {
+        CUDA_TRY(ctx, launchFill(ctx->dOut.p, (long long)dem.n, dem.h.flag, ctx->stream));
+        ctx->timing.launches++;
+        ctx->outInitRaster = demId;
+    }
+    ctx->hMinMax[0] = 0xffffffffu;
+    ctx->hMinMax[1] = 0u;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+
+    const long long t0 = dem.rowStart[rowBegin], t1 = dem.rowStart[rowEnd];
+    const int nTargets = (int)(t1 - t0);
+    const DevGrid dg = devGridOf(dem);
+    if (precZero) {
+        // interpolate() returns exactly 0.f for every cell (interpolation.cpp:2506-2507)
+        CUDA_TRY(ctx, launchFillValid(ctx->dOut.p, dem.validIdx + t0, nTargets, 0.f, ctx->stream));
+        if (nTargets > 0) { ctx->hMinMax[0] = 0x80000000u; ctx->hMinMax[1] = 0x80000000u; }
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CUDA_TRY(ctx, launchIdwRaster(ds, m, dg, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax, ctx->stream));
+    }
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t bandOff = size_t(rowBegin) * dem.h.nrCols, bandN = size_t(rowEnd - rowBegin) * dem.h.nrCols;
+    if (mode == OUT_HOST) {
+        if (!out->data && !out->rows) return fail(ctx, PB_ERR_INVALID, "output has neither data nor rows");
+        CUDA_TRY(ctx, ctx->hStage.reserve(dem.n * sizeof(float)));
+        float* stage = reinterpret_cast<float*>(ctx->hStage.p);
+        // D2H in row chunks, each chunk scattered into the caller's rows by the host cores while the next one flies
+        const int cols = dem.h.nrCols;
+        const int chunkRows = std::max(1, (int)((size_t(8) << 20) / (sizeof(float) * cols)));
+        std::vector<cudaEvent_t> done;
+        for (int r0 = rowBegin; r0 < rowEnd; r0 += chunkRows) {
+            const int r1 = std::min(rowEnd, r0 + chunkRows);
+            CUDA_TRY(ctx, cudaMemcpyAsync(stage + size_t(r0) * cols, ctx->dOut.p + size_t(r0) * cols,
+                                          size_t(r1 - r0) * cols * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            cudaEventRecord(e, ctx->stream);
+            done.push_back(e);
+        }
+        cudaEventRecord(ctx->ev[3], ctx->stream);
+        int ci = 0;
+        for (int r0 = rowBegin; r0 < rowEnd; r0 += chunkRows, ci++) {
+            const int r1 = std::min(rowEnd, r0 + chunkRows);
+            cudaError_t e = cudaEventSynchronize(done[ci]);
+            cudaEventDestroy(done[ci]);
+            if (e != cudaSuccess) return fail(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(e));
+#pragma omp parallel for schedule(static)
+            for (int row = r0; row < r1; row++) {
+                float* dst = out->data ? out->data + size_t(row) * cols : out->rows[row];
+                memcpy(dst, stage + size_t(row) * cols, sizeof(float) * cols);
+            }
+        }
+        ctx->timing.d2h_bytes += (int64_t)(bandN * sizeof(float));
+        (void)bandOff;
+    } else {
+        cudaEventRecord(ctx->ev[3], ctx->stream);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.d2h_bytes += 8;
+
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
+
+    out->nValid = nTargets;
+    if (ctx->hMinMax[0] == 0xffffffffu) {   // no valid output value: updateMinMaxRasterGrid returns false
+        out->minimum = kNoData;
+        out->maximum = kNoData;
+        return fail(ctx, PB_ERR_NO_VALID_CELL, "no valid cell in the output raster");
+    }
+    out->minimum = keyToFloat(ctx->hMinMax[0]);
+    out->maximum = keyToFloat(ctx->hMinMax[1]);
+    return PB_OK;
+}
+
+void resetTiming(pb_context* ctx) { memset(&ctx->timing, 0, sizeof(ctx->timing)); }
+
+}  // namespace
+
+extern "C" {
+
+const char* pb_version(void) { return "praga_b200 0.1 (sm_100a)"; }
+
+int pb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pb_create(int device, pb_context** out)
+{
+    if (!out) return PB_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PB_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                              " (praga_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, PB_ERR_INVALID, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, PB_ERR_CUDA, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10)
+        return fail(nullptr, PB_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                              ", this library is built for sm_100a only");
+    pb_context* ctx = new pb_context();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->dMinMax, 2 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMallocHost(&ctx->hMinMax, 2 * sizeof(unsigned)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, PB_ERR_CUDA, "context allocation failed");
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return PB_OK;
+}
+
+void pb_destroy(pb_context* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& r : ctx->rasters) if (r.used) freeEntry(r);
+    ctx->dStations.release(); ctx->hStations.release(); ctx->dOut.release(); ctx->dScratch.release(); ctx->hStage.release();
+    if (ctx->dMinMax) cudaFree(ctx->dMinMax);
+    if (ctx->hMinMax) cudaFreeHost(ctx->hMinMax);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* pb_last_error(const pb_context* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int pb_set_stream(pb_context* ctx, void* cudaStream)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cudaStream;
+    ctx->ownStream = false;
+    return PB_OK;
+}
+
+int pb_last_timing(const pb_context* ctx, pb_timing* t)
+{
+    if (!ctx || !t) return PB_ERR_INVALID;
+    *t = ctx->timing;
+    return PB_OK;
+}
+
+int pb_raster_upload(pb_context* ctx, const pb_raster* r, pb_raster_id* id)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!r || !id) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    int slot = -1;
+    for (size_t i = 0; i < ctx->rasters.size(); i++) if (!ctx->rasters[i].used) { slot = (int)i; break; }
+    if (slot < 0) { ctx->rasters.emplace_back(); slot = (int)ctx->rasters.size() - 1; }
+    int rc = uploadRaster(ctx, r, ctx->rasters[slot]);
+    if (rc) { freeEntry(ctx->rasters[slot]); return rc; }
+    if (ctx->outInitRaster == slot) ctx->outInitRaster = -1;
+    *id = slot;
+    return PB_OK;
+}
+
+int pb_raster_free(pb_context* ctx, pb_raster_id id)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used) return fail(ctx, PB_ERR_INVALID, "bad raster id");
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    freeEntry(ctx->rasters[id]);
+    if (ctx->outInitRaster == id) ctx->outInitRaster = -1;
+    return PB_OK;
+}
+
+int pb_raster_valid_cells(pb_context* ctx, pb_raster_id id, int64_t* nValid)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used) return fail(ctx, PB_ERR_INVALID, "bad raster id");
+    cudaSetDevice(ctx->device);
+    int rc = ensureValidList(ctx, ctx->rasters[id]);
+    if (rc) return rc;
+    if (nValid) *nValid = ctx->rasters[id].nValid;
+    return PB_OK;
+}
+
+int pb_interpolation_raster_resident(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                     pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin,
+                                     int rowEnd, pb_raster_out* out)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    resetTiming(ctx);
+    return rasterCore(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, OUT_HOST);
+}
+
+int pb_interpolation_raster_device(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                   pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin,
+                                   int rowEnd, pb_raster_out* out)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    resetTiming(ctx);
+    return rasterCore(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, OUT_DEVICE_ONLY);
+}
+
+int pb_interpolation_raster(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                            const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
+                            pb_raster_out* out)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!dem || (nProxyGrids > 0 && !proxyGrids)) return fail(ctx, PB_ERR_INVALID, "null raster argument");
+    if (nProxyGrids > PB_MAX_PROXY) return fail(ctx, PB_ERR_INVALID, "too many proxy grids");
+    cudaSetDevice(ctx->device);
+    resetTiming(ctx);
+    pb_raster_id demId = -1, ids[PB_MAX_PROXY];
+    int nUp = 0;
+    int rc = pb_raster_upload(ctx, dem, &demId);
+    for (int g = 0; rc == PB_OK && g < nProxyGrids; g++) {
+        // a proxy grid that IS the DEM (same buffer and header: setProxyDEM, project.cpp:184-211) is uploaded once
+        const bool same = proxyGrids[g].data == dem->data && proxyGrids[g].rows == dem->rows &&
+                          memcmp(&proxyGrids[g].h, &dem->h, sizeof(pb_raster_header)) == 0;
+        if (same) ids[g] = demId;
+        else rc = pb_raster_upload(ctx, &proxyGrids[g], &ids[g]);
+        if (rc == PB_OK) nUp = g + 1;
+    }
+    const pb_timing up = ctx->timing;
+    if (rc == PB_OK) rc = rasterCore(ctx, st, s, variable, demId, ids, nProxyGrids, rowBegin, rowEnd, out, OUT_HOST);
+    ctx->timing.h2d_bytes += 0;
+    std::string keep = ctx->err;
+    for (int g = 0; g < nUp; g++) if (ids[g] != demId) pb_raster_free(ctx, ids[g]);
+    if (demId >= 0) pb_raster_free(ctx, demId);
+    ctx->err = keep;
+    (void)up;
+    return rc;
+}
+
+/* interpolate() at explicit targets (interpolation.cpp:2502): the building block of computeResiduals.
+ * proxyValues: m * settings.nProxy doubles (the target's own proxy values). */
+int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
+                          const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s || !x || !y || !result || m < 0) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    resetTiming(ctx);
+    DevModel mod;
+    int rc = buildModel(ctx, s, variable, nullptr, 0, mod);
+    if (rc) return rc;
+    if (isPrecVar(variable) && s->precipitationAllZero) {
+        for (int i = 0; i < m; i++) result[i] = 0.f;
+        return PB_OK;
+    }
+    if (mod.nProxy > 0 && !proxyValues) return fail(ctx, PB_ERR_INVALID, "proxyValues required");
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    DevStations ds{};
+    rc = stageStations(ctx, st, s, excludeSupplemental != 0, ds, mod.valueOffset);
+    if (rc) return rc;
+    const size_t mAl = (size_t(m) + 3) / 4 * 4;
+    const size_t offX = 0, offY = mAl * 4, offP = offY + mAl * 4, offO = offP + size_t(m) * mod.nProxy * 8;
+    const size_t total = offO + mAl * 4;
+    CUDA_TRY(ctx, ctx->dScratch.reserve(total));
+    unsigned char* d = ctx->dScratch.p;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + offX, x, size_t(m) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + offY, y, size_t(m) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (mod.nProxy > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(d + offP, proxyValues, size_t(m) * mod.nProxy * 8, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    CUDA_TRY(ctx, launchIdwPoints(ds, mod, reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
+                                  reinterpret_cast<const double*>(d + offP), m, reinterpret_cast<float*>(d + offO), ctx->stream));
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(result, d + offO, size_t(m) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)(size_t(m) * (8 + mod.nProxy * 8));
+    ctx->timing.d2h_bytes += (int64_t)(size_t(m) * 4);
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
+    return PB_OK;
+}
+
+}  // extern "C"
+
+/* live pipe ceilings for the K1 roofline (FP32 FMA TFLOP/s, G MUFU.RSQ/s) */
+extern "C" int pb_measure_pipe_peaks(pb_context* ctx, float* fp32Tflops, float* mufuGops)
+{
+    if (!ctx || !fp32Tflops || !mufuGops) return PB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, ctx->device);
+    CUDA_TRY(ctx, measurePipePeaks(ctx->stream, prop.multiProcessorCount, fp32Tflops, mufuGops));
+    return PB_OK;
+}
+
+/* ABI self-description: lets bindings check that their struct layouts match this build */
+extern "C" size_t pb_abi_sizeof(const char* name)
+{
+    if (!name) return 0;
+    if (!strcmp(name, "pb_raster_header")) return sizeof(pb_raster_header);
+    if (!strcmp(name, "pb_raster")) return sizeof(pb_raster);
+    if (!strcmp(name, "pb_stations")) return sizeof(pb_stations);
+    if (!strcmp(name, "pb_proxy")) return sizeof(pb_proxy);
+    if (!strcmp(name, "pb_settings")) return sizeof(pb_settings);
+    if (!strcmp(name, "pb_raster_out")) return sizeof(pb_raster_out);
+    if (!strcmp(name, "pb_cv_stats")) return sizeof(pb_cv_stats);
+    if (!strcmp(name, "pb_timing")) return sizeof(pb_timing);
+    return 0;
+}

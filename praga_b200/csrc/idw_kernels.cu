@@ -1,0 +1,524 @@
+// idw_kernels.cu — K1: detrended inverse-distance-weighting estimator for raster cells and for point targets.
+//
+// Replaces, per target, the reference chain (paths relative to the reference tree, agrolib/):
+//   gis::getUtmXYFromRowColSinglePrecision      gis/gis.cpp:799-804
+//   getProxyValuesXY / getValueFromXY           interpolation/interpolation.cpp:2620-2647, gis/gis.cpp:533-546
+//   interpolate                                 interpolation/interpolation.cpp:2502-2560
+//     computeDistances                          interpolation.cpp:208-256   (no topographic distance here)
+//     inverseDistanceWeighted                   interpolation.cpp:1031-1051
+//     retrend                                   interpolation.cpp:1288-1351 (+ getMultipleDetrendingValues :2563-2617,
+//                                               functionSum / lapseRatePiecewise_* mathFunctions/furtherMathFunctions.cpp:115-201)
+//     per-variable clamp                        interpolation.cpp:2540-2558
+//   gis::updateMinMaxRasterGrid                 gis/gis.cpp:569-614 (fused min/max)
+//
+// B200 mapping (measured with tools/ubench_fp32.cu, profiles/r01_ubench_fp32.jsonl): the station loop costs
+// 8 FP32 ops + 1 MUFU.RSQ per (cell, station) pair; 128 FP32 lanes/clk/SM and 16 MUFU/clk/SM make both pipes
+// limit at 0.0625 clk/pair/SM.  Packed FFMA2/FADD2/FMUL2 (two cells per lane) halve the issue slots so that the
+// LDS and MUFU issue fit beside them.  Station tiles arrive in shared memory through 1-D bulk async copies
+// (TMA engine) double-buffered on mbarriers; every lane reads the same station (LDS broadcast).
+// Accumulation: FP32 inside a 512-station tile, FP64 across tiles; station values are centred on the host
+// (IDW is affine invariant), so the FP32 error scales with the spread of the residuals, not their level.
+#include "common.cuh"
+
+namespace pb {
+
+constexpr int kTileStations = 512;   // stations per shared-memory tile (12 KiB)
+constexpr int kThreads = 256;
+constexpr int kChunk = 32;           // stations per f32 accumulation chain
+constexpr int kTileBytes = kTileStations * (int)(sizeof(float4) + sizeof(float2));
+
+// ---------------------------------------------------------------------------------------------------------
+// valid-cell compaction: ascending list of linear indices of cells with !isEqual(z, flag)
+// (interpolationCmd.cpp:377).  Built once per DEM upload; deterministic order.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCompactChunk = 4096;  // cells per block
+
+__global__ void __launch_bounds__(256) count_valid_kernel(const float* __restrict__ dem, long long n, float flag,
+                                                          int* __restrict__ blockCount)
+{
+    long long base = (long long)blockIdx.x * kCompactChunk;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < kCompactChunk; i += 256) {
+        long long k = base + i;
+        if (k < n && !isEqualF(dem[k], flag)) cnt++;
+    }
+    __shared__ int red[8];
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; w++) s += red[w];
+        blockCount[blockIdx.x] = s;
+    }
+}
+
+// single-block exclusive scan of blockCount (nBlocks <= a few 10^5); total written to *total
+__global__ void __launch_bounds__(1024) scan_counts_kernel(int* __restrict__ blockCount, int nBlocks,
+                                                           long long* __restrict__ total)
+{
+    __shared__ long long carry;
+    __shared__ int warpSum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nBlocks; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < nBlocks ? blockCount[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warpSum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warpSum[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            warpSum[threadIdx.x] = w;
+        }
+        __syncthreads();
+        int prefix = (threadIdx.x >> 5) ? warpSum[(threadIdx.x >> 5) - 1] : 0;
+        long long excl = carry + prefix + x - v;
+        if (i < nBlocks) blockCount[i] = (int)excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += prefix + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(256) write_valid_kernel(const float* __restrict__ dem, long long n, float flag,
+                                                          const int* __restrict__ blockOffset,
+                                                          int* __restrict__ validIdx)
+{
+    // one warp handles 32 consecutive cells per step so the output order stays ascending
+    long long base = (long long)blockIdx.x * kCompactChunk;
+    __shared__ int warpBase[8];
+    __shared__ int warpCnt[8];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // each warp owns a contiguous 512-cell slice of the chunk
+    long long wbase = base + warp * (kCompactChunk / 8);
+    int cnt = 0;
+    for (int s = 0; s < kCompactChunk / 8; s += 32) {
+        long long k = wbase + s + lane;
+        bool ok = k < n && !isEqualF(dem[k], flag);
+        cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0) warpCnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = blockOffset[blockIdx.x];
+        for (int w = 0; w < 8; w++) { warpBase[w] = acc; acc += warpCnt[w]; }
+    }
+    __syncthreads();
+    int pos = warpBase[warp];
+    for (int s = 0; s < kCompactChunk / 8; s += 32) {
+        long long k = wbase + s + lane;
+        bool ok = k < n && !isEqualF(dem[k], flag);
+        unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (ok) validIdx[pos + __popc(b & ((1u << lane) - 1u))] = (int)k;
+        pos += __popc(b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-target epilogue pieces
+// ---------------------------------------------------------------------------------------------------------
+
+// Crit3DRasterGrid::getValueFromXY (gis.cpp:533-546): nearest cell by truncation, flag when outside
+__device__ __forceinline__ float gridValueFromXY(const DevGrid& g, double x, double y)
+{
+    const int r = int(__dmul_rn(__dsub_rn(y, g.lly), g.invCellSize));
+    const int row = (g.nrRows - 1) - r;
+    const int col = int(__dmul_rn(__dsub_rn(x, g.llx), g.invCellSize));
+    if (unsigned(row) >= unsigned(g.nrRows) || unsigned(col) >= unsigned(g.nrCols)) return g.flag;
+    return __ldg(g.data + (size_t)row * g.nrCols + col);
+}
+
+// lapseRatePiecewise_two / _three / _three_free / functionLinear_intercept
+// (mathFunctions/furtherMathFunctions.cpp:115-201); evaluated without FMA contraction like the x86-64 reference build
+__device__ __forceinline__ double evalFitFunction(int f, double x, const double* par)
+{
+    switch (f) {
+    case PB_FIT_PIECEWISE_TWO: {
+        const double slope = (x < par[0]) ? par[2] : par[3];
+        return __dadd_rn(__dmul_rn(slope, __dsub_rn(x, par[0])), par[1]);
+    }
+    case PB_FIT_PIECEWISE_THREE: {
+        const double p2 = par[2] > 10. ? par[2] : 10.;   // MAXVALUE(10, par[2])
+        const double xb = __dadd_rn(p2, par[0]);
+        if (x < par[0]) return __dadd_rn(__dsub_rn(__dmul_rn(par[4], x), __dmul_rn(par[0], par[4])), par[1]);
+        if (x > xb)
+            return __dadd_rn(__dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(par[4], x), __dmul_rn(par[4], par[0])),
+                                                 __dmul_rn(par[4], p2)),
+                                       __dmul_rn(par[3], p2)),
+                             par[1]);
+        return __dadd_rn(__dsub_rn(__dmul_rn(par[3], x), __dmul_rn(par[3], par[0])), par[1]);
+    }
+    case PB_FIT_PIECEWISE_THREE_FREE: {
+        const double p2 = par[2] > 10. ? par[2] : 10.;
+        const double xb = __dadd_rn(par[0], p2);
+        if (x < par[0]) return __dadd_rn(__dsub_rn(__dmul_rn(par[4], x), __dmul_rn(par[0], par[4])), par[1]);
+        if (x > xb)
+            return __dadd_rn(__dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(par[5], x), __dmul_rn(par[5], par[0])),
+                                                 __dmul_rn(par[5], p2)),
+                                       __dmul_rn(par[3], p2)),
+                             par[1]);
+        return __dadd_rn(__dsub_rn(__dmul_rn(par[3], x), __dmul_rn(par[3], par[0])), par[1]);
+    }
+    case PB_FIT_LINEAR:
+        return __dadd_rn(__dmul_rn(par[0], x), par[1]);
+    default:
+        return 0.;
+    }
+}
+
+// retrend (interpolation.cpp:1288-1351); proxyValues[i] as filled by getProxyValuesXY (NODATA when missing)
+__device__ __forceinline__ float retrendValue(const DevModel& m, const double* proxyValues)
+{
+    if (!m.useDetrendingVar) return 0.f;
+    double retrend = 0.;
+    if (m.useMultipleDetrending) {
+        // getMultipleDetrendingValues: elevation first, then the others; ANY active&&significant NODATA -> 0
+        if (m.nActiveSig == 0 || m.nFit == 0) return 0.f;
+        for (int k = 0; k < m.nActiveSig; k++)
+            if (proxyValues[m.activeSigPos[k]] == double(kNoData)) return 0.f;
+        double sum = 0.;
+        for (int k = 0; k < m.nFit; k++)
+            sum = __dadd_rn(sum, evalFitFunction(m.fitFunction[k], proxyValues[m.activeSigPos[k]], m.fitParams[k]));
+        retrend = double(float(sum));
+    } else {
+        for (int pos = 0; pos < m.nProxy; pos++) {
+            const DevProxy& p = m.proxy[pos];
+            if (!(p.active && p.significant)) continue;
+            const double v = proxyValues[pos];
+            if (v == double(kNoData)) continue;
+            const float slope = p.slope;
+            if (p.kind == PB_PROXY_HEIGHT) {
+                if (m.useThermalInversion && p.inversionIsSignificative) {
+                    const float H0 = p.H0, H1 = p.H1, below = p.invLapseRate;
+                    if (v <= double(H1)) {
+                        double t = __dsub_rn(v, double(H0));
+                        t = t > 0. ? t : 0.;
+                        retrend = __dadd_rn(retrend, __dmul_rn(t, double(below)));
+                    } else {
+                        // ((LR_H1 - LR_H0) * LR_Below) is float arithmetic in the reference, the rest double
+                        const float a = __fmul_rn(__fsub_rn(H1, H0), below);
+                        const double b = __dmul_rn(__dsub_rn(v, double(H1)), double(slope));
+                        retrend = __dadd_rn(retrend, __dadd_rn(double(a), b));
+                    }
+                } else {
+                    const double t = v > 0. ? v : 0.;
+                    retrend = __dadd_rn(retrend, __dmul_rn(t, double(slope)));
+                }
+            } else {
+                retrend = __dadd_rn(retrend, __dmul_rn(v, double(slope)));
+            }
+        }
+    }
+    return float(retrend);
+}
+
+// tail of interpolate(): NODATA passthrough, retrend, clamp (interpolation.cpp:2532-2558)
+__device__ __forceinline__ float finishEstimate(const DevModel& m, float result, const double* proxyValues)
+{
+    if (isEqualF(result, kNoData)) return kNoData;
+    if (!m.useDoNotRetrend) result = __fadd_rn(result, retrendValue(m, proxyValues));
+    switch (m.clampMode) {
+    case CLAMP_PREC: return (result < m.rainfallThreshold) ? 0.f : result;
+    case CLAMP_RH: return fmaxf(0.f, fminf(result, 100.f));
+    case CLAMP_POS: return fmaxf(result, 0.f);
+    default: return result;
+    }
+}
+
+// exact evaluation of computeDistances + inverseDistanceWeighted for ONE target, reference operation order
+// (f32 distance, f64 weights). Used when the fast path saw a zero distance (station on the target).
+__device__ __noinline__ void idwExact(const DevStations& st, float x, float y, double& sw, double& swv)
+{
+    sw = 0.;
+    swv = 0.;
+    for (int i = 0; i < st.n; i++) {
+        const float dx = __fsub_rn(st.x[i], x), dy = __fsub_rn(st.y[i], y);
+        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        if (d > 0.f) {
+            const double dk = double(d) / 10000.;
+            const double w = 1.0 / (dk * dk * dk);
+            sw += w;
+            swv += double(st.val[i]) * w;
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned orderedKey(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 kernel. POINTS = false: targets are DEM cells listed in validIdx; POINTS = true: explicit targets.
+// Each thread owns 2*P targets (P packed pairs).
+// ---------------------------------------------------------------------------------------------------------
+template <int P, bool POINTS>
+__global__ void __launch_bounds__(kThreads)
+idw_kernel(DevStations st, DevModel m, DevGrid dem, const int* __restrict__ validIdx, int nTargets,
+           const float* __restrict__ tx, const float* __restrict__ ty, const double* __restrict__ tproxy,
+           float* __restrict__ out, unsigned* __restrict__ minmax /* [0]=min key, [1]=max key */)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar[2];
+    float4* sxy0 = reinterpret_cast<float4*>(smem);
+    float2* sv0 = reinterpret_cast<float2*>(smem + kTileStations * sizeof(float4));
+    float4* sxy1 = reinterpret_cast<float4*>(smem + kTileBytes);
+    float2* sv1 = reinterpret_cast<float2*>(smem + kTileBytes + kTileStations * sizeof(float4));
+
+    const int tid = threadIdx.x;
+    const int nTiles = st.nPadded / kTileStations;
+    constexpr int C = 2 * P;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < 2 && t < nTiles; t++) {
+            mbar_expect_tx(&bar[t], kTileBytes);
+            bulk_g2s(t ? sxy1 : sxy0, st.xy + (size_t)t * kTileStations, kTileStations * sizeof(float4), &bar[t]);
+            bulk_g2s(t ? sv1 : sv0, st.v + (size_t)t * kTileStations, kTileStations * sizeof(float2), &bar[t]);
+        }
+    }
+
+    // ---- this thread's targets ----
+    const long long t0 = (long long)blockIdx.x * (kThreads * C) + tid;
+    float x[C], y[C];
+    int cell[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const long long t = t0 + (long long)c * kThreads;
+        if (t < nTargets) {
+            if (POINTS) {
+                cell[c] = (int)t;
+                x[c] = tx[t];
+                y[c] = ty[t];
+            } else {
+                const int idx = validIdx[t];
+                const int row = idx / dem.nrCols, col = idx - row * dem.nrCols;
+                cell[c] = idx;
+                // getUtmXYFromRowColSinglePrecision(header,...) gis.cpp:799-804: corner + (0.5 m, -0.5 m), f64 -> f32
+                x[c] = float(__dadd_rn(__dadd_rn(dem.llx, __dmul_rn(dem.cellSize, double(col))), 0.5));
+                y[c] = float(__dsub_rn(__dadd_rn(dem.lly, __dmul_rn(dem.cellSize, double(dem.nrRows - row))), 0.5));
+            }
+        } else {
+            cell[c] = -1;
+            x[c] = 0.f;
+            y[c] = 0.f;
+        }
+    }
+    f32x2 nx[P], ny[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        nx[p] = pack2(-x[2 * p], -x[2 * p + 1]);
+        ny[p] = pack2(-y[2 * p], -y[2 * p + 1]);
+    }
+
+    double SW[C], SWV[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) { SW[c] = 0.; SWV[c] = 0.; }
+
+    // ---- station loop ----
+    for (int t = 0; t < nTiles; t++) {
+        const int b = t & 1;
+        mbar_wait(&bar[b], (t >> 1) & 1);
+        const float4* __restrict__ sxy = b ? sxy1 : sxy0;
+        const float2* __restrict__ sv = b ? sv1 : sv0;
+        // three-level accumulation (measured against the reference's f64 sums, tests/test_accumulation.py):
+        // f32 over a 32-station chunk, f32 over the 16 chunks of a tile, f64 across tiles -> max error ~1.5e-5
+        // where one f32 chain over 512 stations reaches 1.5e-4.
+        f32x2 tsw[P], tswv[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) { tsw[p] = pack2(0.f, 0.f); tswv[p] = pack2(0.f, 0.f); }
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTileStations; c0 += kChunk) {
+            f32x2 sw[P], swv[P];
+#pragma unroll
+            for (int s = 0; s < kChunk; s++) {
+                const float4 pxy = sxy[c0 + s];
+                const float2 pv = sv[c0 + s];
+                const f32x2 px = pack2(pxy.x, pxy.y), py = pack2(pxy.z, pxy.w), pvv = pack2(pv.x, pv.y);
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    const f32x2 dx = add2(px, nx[p]), dy = add2(py, ny[p]);
+                    const f32x2 d2 = fma2(dx, dx, mul2(dy, dy));
+                    float a, bq;
+                    unpack2(d2, a, bq);
+                    if (POINTS) {   // leave-one-out: the target IS a station, its zero distance must weigh nothing (:1039)
+                        a = a > 0.f ? a : __int_as_float(0x7f800000);
+                        bq = bq > 0.f ? bq : __int_as_float(0x7f800000);
+                    }
+                    const f32x2 r = pack2(rsqrt_approx(a), rsqrt_approx(bq));
+                    const f32x2 w = mul2(mul2(r, r), r);       // 1/d^3 (the 1/10000 scale cancels in the ratio)
+                    if (s == 0) {
+                        sw[p] = w;
+                        swv[p] = mul2(w, pvv);
+                    } else {
+                        sw[p] = add2(sw[p], w);
+                        swv[p] = fma2(w, pvv, swv[p]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < P; p++) { tsw[p] = add2(tsw[p], sw[p]); tswv[p] = add2(tswv[p], swv[p]); }
+        }
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            float a, bq, va, vb;
+            unpack2(tsw[p], a, bq);
+            unpack2(tswv[p], va, vb);
+            SW[2 * p] += double(a);
+            SW[2 * p + 1] += double(bq);
+            SWV[2 * p] += double(va);
+            SWV[2 * p + 1] += double(vb);
+        }
+        __syncthreads();   // everyone is done with buffer b
+        if (tid == 0 && t + 2 < nTiles) {
+            mbar_expect_tx(&bar[b], kTileBytes);
+            bulk_g2s(b ? sxy1 : sxy0, st.xy + (size_t)(t + 2) * kTileStations, kTileStations * sizeof(float4), &bar[b]);
+            bulk_g2s(b ? sv1 : sv0, st.v + (size_t)(t + 2) * kTileStations, kTileStations * sizeof(float2), &bar[b]);
+        }
+    }
+
+    // ---- epilogue ----
+    float vmin = INFINITY, vmax = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < C; c++) {
+        if (cell[c] < 0) continue;
+        double sw = SW[c], swv = SWV[c];
+        if (!(sw <= 1.0e300) || !(fabs(swv) <= 1.0e300)) idwExact(st, x[c], y[c], sw, swv);   // inf/NaN: zero distance seen
+
+        double pv[PB_MAX_PROXY];
+        if (POINTS) {
+            for (int i = 0; i < m.nProxy; i++) pv[i] = tproxy[(size_t)cell[c] * m.nProxy + i];
+        } else if (m.useDetrendingVar) {
+            // getProxyValuesXY (interpolation.cpp:2620-2647)
+            for (int i = 0; i < m.nProxy; i++) {
+                pv[i] = double(kNoData);
+                const DevProxy& p = m.proxy[i];
+                if (p.active && p.gridSlot >= 0) {
+                    const DevGrid& g = m.grid[p.gridSlot];
+                    const float v = gridValueFromXY(g, double(x[c]), double(y[c]));
+                    if (v != g.flag) pv[i] = double(v);
+                }
+            }
+        } else {
+            for (int i = 0; i < m.nProxy; i++) pv[i] = double(kNoData);
+        }
+
+        float result;
+        if (m.useRetrendOnly) result = 0.f;
+        else result = (sw > 0.0) ? float(swv / sw + m.valueOffset) : kNoData;
+        const float o = finishEstimate(m, result, pv);
+        out[cell[c]] = o;
+        if (!isEqualF(o, dem.flag) && !isEqualF(o, kNoData)) {
+            vmin = fminf(vmin, o);
+            vmax = fmaxf(vmax, o);
+        }
+    }
+    if (minmax) {
+        for (int o = 16; o; o >>= 1) {
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        }
+        if ((tid & 31) == 0) {
+            if (vmin != INFINITY) atomicMin(&minmax[0], orderedKey(vmin));
+            if (vmax != -INFINITY) atomicMax(&minmax[1], orderedKey(vmax));
+        }
+    }
+}
+
+// constant fill of valid cells (precipitationAllZero short-circuit, interpolation.cpp:2506-2507) and
+// flag initialisation of the output (Crit3DRasterGrid::initializeGrid(raster), gis.cpp:357-363)
+__global__ void fill_kernel(float* __restrict__ out, long long n, float v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = v;
+}
+__global__ void fill_valid_kernel(float* __restrict__ out, const int* __restrict__ validIdx, int n, float v)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[validIdx[i]] = v;
+}
+
+// ---- host-side launchers (called from engine.cu) ----
+cudaError_t launchCompactValid(const float* dem, long long n, float flag, int* blockCount, long long* dTotal,
+                               int* validIdx, int phase, cudaStream_t s)
+{
+    const int nBlocks = (int)((n + kCompactChunk - 1) / kCompactChunk);
+    if (phase == 0) {
+        count_valid_kernel<<<nBlocks, 256, 0, s>>>(dem, n, flag, blockCount);
+        scan_counts_kernel<<<1, 1024, 0, s>>>(blockCount, nBlocks, dTotal);
+    } else {
+        write_valid_kernel<<<nBlocks, 256, 0, s>>>(dem, n, flag, blockCount, validIdx);
+    }
+    return cudaGetLastError();
+}
+
+int compactBlocks(long long n) { return (int)((n + kCompactChunk - 1) / kCompactChunk); }
+int tileStations() { return kTileStations; }
+
+cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevGrid& dem, const int* validIdx,
+                            int nTargets, float* out, unsigned* minmax, cudaStream_t s)
+{
+    if (nTargets <= 0) return cudaSuccess;
+    constexpr int P = 2;
+    const int per = kThreads * 2 * P;
+    const int grid = (nTargets + per - 1) / per;
+    auto k = idw_kernel<P, false>;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileBytes);
+        attr = true;
+    }
+    k<<<grid, kThreads, 2 * kTileBytes, s>>>(st, m, dem, validIdx, nTargets, nullptr, nullptr, nullptr, out, minmax);
+    return cudaGetLastError();
+}
+
+cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty,
+                            const double* tproxy, int nTargets, float* out, cudaStream_t s)
+{
+    if (nTargets <= 0) return cudaSuccess;
+    constexpr int P = 1;
+    const int per = kThreads * 2 * P;
+    const int grid = (nTargets + per - 1) / per;
+    auto k = idw_kernel<P, true>;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileBytes);
+        attr = true;
+    }
+    DevGrid none{};
+    none.flag = kNoData;
+    k<<<grid, kThreads, 2 * kTileBytes, s>>>(st, m, none, nullptr, nTargets, tx, ty, tproxy, out, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    fill_kernel<<<148 * 8, 256, 0, s>>>(out, n, v);
+    return cudaGetLastError();
+}
+cudaError_t launchFillValid(float* out, const int* validIdx, int n, float v, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    fill_valid_kernel<<<(n + 255) / 256, 256, 0, s>>>(out, validIdx, n, v);
+    return cudaGetLastError();
+}
+
+}  // namespace pb

@@ -1,0 +1,172 @@
+"""Python binding of libpraga_b200.so (ctypes over the C ABI of include/praga_b200.h).
+
+This is plumbing for tests and bench.py; the product is the shared library. There is no CPU fallback: if the
+library is missing or no B200 is visible, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+
+_LIB = None
+
+
+class PragaB200Error(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{A.STATUS_NAMES[status] if 0 <= status < len(A.STATUS_NAMES) else status}: {message}")
+        self.status = status
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpraga_b200.so")
+
+
+def load_library():
+    """dlopen libpraga_b200.so (built by praga_b200/build.py). Fails loudly when it is absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise PragaB200Error(A.PB_ERR_CUDA, f"{path} is missing: run `python -m praga_b200.build` "
+                                            "(the CUDA extension is mandatory, there is no CPU fallback)")
+    lib = C.CDLL(path)
+    P = C.POINTER
+    lib.pb_version.restype = C.c_char_p
+    lib.pb_abi_sizeof.restype = C.c_size_t
+    lib.pb_abi_sizeof.argtypes = [C.c_char_p]
+    lib.pb_device_count.restype = C.c_int
+    lib.pb_create.argtypes = [C.c_int, P(C.c_void_p)]
+    lib.pb_destroy.argtypes = [C.c_void_p]
+    lib.pb_destroy.restype = None
+    lib.pb_last_error.argtypes = [C.c_void_p]
+    lib.pb_last_error.restype = C.c_char_p
+    lib.pb_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pb_last_timing.argtypes = [C.c_void_p, P(A.pb_timing)]
+    lib.pb_raster_upload.argtypes = [C.c_void_p, P(A.pb_raster), P(C.c_int32)]
+    lib.pb_raster_free.argtypes = [C.c_void_p, C.c_int32]
+    lib.pb_raster_valid_cells.argtypes = [C.c_void_p, C.c_int32, P(C.c_int64)]
+    raster_args = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int]
+    lib.pb_interpolation_raster.argtypes = raster_args + [P(A.pb_raster), P(A.pb_raster), C.c_int, C.c_int, C.c_int,
+                                                          P(A.pb_raster_out)]
+    for name in ("pb_interpolation_raster_resident", "pb_interpolation_raster_device"):
+        getattr(lib, name).argtypes = raster_args + [C.c_int32, P(C.c_int32), C.c_int, C.c_int, C.c_int,
+                                                     P(A.pb_raster_out)]
+    lib.pb_interpolate_points.argtypes = raster_args + [P(C.c_float), P(C.c_float), P(C.c_double), C.c_int, C.c_int,
+                                                        P(C.c_float)]
+    lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
+    for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
+                 "pb_cv_stats", "pb_timing"):
+        got, want = lib.pb_abi_sizeof(name.encode()), C.sizeof(getattr(A, name))
+        if got != want:
+            raise PragaB200Error(A.PB_ERR_INVALID, f"ABI mismatch for {name}: library {got} B, binding {want} B")
+    _LIB = lib
+    return lib
+
+
+class Engine:
+    """One engine (CUDA context + stream + device-resident raster cache) on one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.pb_create(device, C.byref(h))
+        if rc != A.PB_OK:
+            raise PragaB200Error(rc, self.lib.pb_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow=()):
+        if rc != A.PB_OK and rc not in allow:
+            raise PragaB200Error(rc, self.lib.pb_last_error(self.h).decode())
+        return rc
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.pb_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def timing(self):
+        t = A.pb_timing()
+        self.lib.pb_last_timing(self.h, C.byref(t))
+        return {k: getattr(t, k) for k, _ in A.pb_timing._fields_}
+
+    def measure_pipe_peaks(self):
+        """(FP32 TFLOP/s, G MUFU.RSQ/s) measured live on this GPU."""
+        a, b = C.c_float(0), C.c_float(0)
+        self._check(self.lib.pb_measure_pipe_peaks(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ---- raster cache ----
+    def upload(self, raster):
+        rid = C.c_int32(-1)
+        r = raster.as_pb()
+        self._check(self.lib.pb_raster_upload(self.h, C.byref(r), C.byref(rid)))
+        return rid.value
+
+    def free(self, rid):
+        self._check(self.lib.pb_raster_free(self.h, rid))
+
+    def valid_cells(self, rid):
+        n = C.c_int64(0)
+        self._check(self.lib.pb_raster_valid_cells(self.h, rid, C.byref(n)))
+        return n.value
+
+    # ---- interpolationRaster (interpolationCmd.cpp:353-394) ----
+    def interpolation_raster(self, stations, settings, variable, dem, proxy_grids=(), row_begin=0, row_end=-1,
+                             out=None, rows=None):
+        """Drop-in call with HOST rasters. Returns (ok, grid, minimum, maximum, nValid); ok False <=> the reference
+        returns false (no valid output cell)."""
+        st = stations.as_pb()
+        d = dem.as_pb()
+        grids = (A.pb_raster * max(1, len(proxy_grids)))()
+        for i, g in enumerate(proxy_grids):
+            grids[i] = d if g is dem else g.as_pb()
+        o = A.pb_raster_out()
+        if rows is not None:
+            o.rows = rows
+        else:
+            if out is None:
+                out = np.empty(dem.shape, dtype=np.float32)
+            o.data = A.fptr(out)
+        rc = self._check(self.lib.pb_interpolation_raster(self.h, C.byref(st), C.byref(settings), variable, C.byref(d),
+                                                          grids, len(proxy_grids), row_begin, row_end, C.byref(o)),
+                         allow=(A.PB_ERR_NO_VALID_CELL,))
+        return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid
+
+    def interpolation_raster_resident(self, stations, settings, variable, dem_id, proxy_ids=(), row_begin=0, row_end=-1,
+                                      out=None, device_only=False):
+        st = stations.as_pb()
+        ids = (C.c_int32 * max(1, len(proxy_ids)))(*proxy_ids)
+        o = A.pb_raster_out()
+        if not device_only:
+            assert out is not None
+            o.data = A.fptr(out)
+        fn = self.lib.pb_interpolation_raster_device if device_only else self.lib.pb_interpolation_raster_resident
+        rc = self._check(fn(self.h, C.byref(st), C.byref(settings), variable, dem_id, ids, len(proxy_ids), row_begin,
+                            row_end, C.byref(o)), allow=(A.PB_ERR_NO_VALID_CELL,))
+        return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid
+
+    # ---- interpolate() at explicit targets (interpolation.cpp:2502) ----
+    def interpolate_points(self, stations, settings, variable, x, y, proxy_values, exclude_supplemental=False):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        m = x.shape[0]
+        pv = np.ascontiguousarray(proxy_values, dtype=np.float64).reshape(m, -1)
+        res = np.empty(m, dtype=np.float32)
+        st = stations.as_pb()
+        self._check(self.lib.pb_interpolate_points(self.h, C.byref(st), C.byref(settings), variable, A.fptr(x), A.fptr(y),
+                                                   A.dptr(pv) if pv.size else None, m, int(exclude_supplemental),
+                                                   A.fptr(res)))
+        return res

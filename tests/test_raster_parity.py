@@ -1,0 +1,203 @@
+"""GPU parity of interpolationRaster (interpolationCmd.cpp:353-394) against the reference's own CPU code.
+
+Bar (BASELINE.json north_star): |GPU - reference| <= 1e-4 in the variable's units on every valid cell,
+NODATA/flag masks bit-exact."""
+import copy
+
+import numpy as np
+import pytest
+
+from praga_b200 import _abi as A
+from praga_b200 import synthetic as syn
+
+TOL = 1e-4
+pytestmark = pytest.mark.gpu
+
+
+def assert_grid_parity(gpu, cpu, flag=-9999.0, tol=TOL):
+    assert gpu.shape == cpu.shape
+    mg, mc = gpu == np.float32(flag), cpu == np.float32(flag)
+    assert np.array_equal(mg, mc), f"NODATA masks differ on {np.count_nonzero(mg != mc)} cells"
+    d = np.abs(gpu[~mc].astype(np.float64) - cpu[~mc].astype(np.float64))
+    assert d.size == 0 or d.max() <= tol, f"max |gpu-ref| = {d.max():.3e} > {tol}"
+    return 0.0 if d.size == 0 else float(d.max())
+
+
+def run_both(engine, ref, st, s, var, dem, grids):
+    okc, gc, mnc, mxc, nvc, _ = ref.interpolation_raster(st, s, var, dem, grids)
+    okg, gg, mng, mxg, nvg = engine.interpolation_raster(st, s, var, dem, grids)
+    assert okg == okc
+    assert nvg == nvc
+    err = assert_grid_parity(gg, gc, dem.flag)
+    if okc:
+        assert abs(mng - mnc) <= TOL and abs(mxg - mxc) <= TOL
+    return err, gg, gc
+
+
+def test_multiple_detrending_idw_temperature(engine, ref):
+    """config 2 shape (scaled down): IDW + multipleDetrending, elevation (piecewise two) + urban fraction."""
+    dem = syn.make_dem(300, 400)
+    urban = syn.make_urban(300, 400)
+    st = syn.make_stations(dem, 200, proxies=(dem, urban))
+    s = syn.settings_multiple_detrending()
+    syn.set_points_range(s, st)
+    ok, keep = ref.pre_interpolation(st, s, A.airTemperature, (dem, urban))
+    assert ok and s.nFit == 2
+    run_both(engine, ref, st.subset(keep), s, A.airTemperature, dem, (dem, urban))
+
+
+def test_foreign_geometry_proxy_grid(engine, ref):
+    """urban proxy on a coarser 250 m grid that does not cover the whole DEM: lookups fall outside -> retrend 0."""
+    dem = syn.make_dem(240, 260)
+    urban = syn.make_urban(80, 90, cell_size=250.0, llx=syn.LLX + 1300.0, lly=syn.LLY + 700.0, nodata_frac=0.03)
+    st = syn.make_stations(dem, 150, proxies=(dem, urban))
+    s = syn.settings_multiple_detrending()
+    syn.set_points_range(s, st)
+    ok, keep = ref.pre_interpolation(st, s, A.airTemperature, (dem, urban))
+    assert ok
+    run_both(engine, ref, st.subset(keep), s, A.airTemperature, dem, (dem, urban))
+
+
+@pytest.mark.parametrize("inversion", [False, True])
+def test_classic_detrending_idw(engine, ref, inversion):
+    """classic detrending(): elevation regression (with/without thermal inversion heuristic) + urban regression."""
+    dem = syn.make_dem(200, 300, seed=3)
+    urban = syn.make_urban(200, 300)
+    st = syn.make_stations(dem, 180, proxies=(dem, urban), seed=5)
+    if inversion:   # cold-air pool below 600 m
+        st.value[:] = np.where(st.z < 600, st.value - 0.01 * (600 - st.z), st.value).astype(np.float32)
+    s = syn.settings_classic_detrending(2)
+    s.useThermalInversion = int(inversion)
+    s.selectedUseThermalInversion = s.currentUseThermalInversion = int(inversion)
+    ok, keep = ref.pre_interpolation(st, s, A.dailyAirTemperatureMax, (dem, urban))
+    assert ok
+    assert s.currentSignificant[0] == 1
+    run_both(engine, ref, st.subset(keep), s, A.dailyAirTemperatureMax, dem, (dem, urban))
+
+
+def test_no_detrending_humidity_clamped(engine, ref):
+    dem = syn.make_dem(180, 220, seed=9)
+    st = syn.make_stations(dem, 120, variable="humidity", seed=6)
+    st.value[:10] = 100.0
+    s = A.default_settings()
+    _, gg, _ = run_both(engine, ref, st, s, A.airRelHumidity, dem, ())
+    v = gg[gg != np.float32(dem.flag)]
+    assert v.min() >= 0.0 and v.max() <= 100.0
+
+
+def test_precipitation_threshold_and_all_zero(engine, ref):
+    dem = syn.make_dem(150, 170, seed=4)
+    st = syn.make_stations(dem, 90, variable="precipitation", seed=8)
+    s = A.default_settings()
+    ok, _ = ref.pre_interpolation(st, s, A.precipitation, ())
+    assert ok and s.precipitationAllZero == 0
+    _, gg, _ = run_both(engine, ref, st, s, A.precipitation, dem, ())
+    v = gg[gg != np.float32(dem.flag)]
+    assert np.all((v == 0.0) | (v >= s.rainfallThreshold))
+    # all observations below the threshold -> interpolate() short-circuits to exactly 0.f (interpolation.cpp:2506)
+    st0 = st.copy()
+    st0.value[:] = 0.1
+    s0 = A.default_settings()
+    ok, _ = ref.pre_interpolation(st0, s0, A.precipitation, ())
+    assert ok and s0.precipitationAllZero == 1
+    _, gg0, _ = run_both(engine, ref, st0, s0, A.precipitation, dem, ())
+    assert np.all(gg0[gg0 != np.float32(dem.flag)] == 0.0)
+
+
+def test_lapse_rate_code_excludes_supplemental(engine, ref):
+    dem = syn.make_dem(120, 140, seed=2)
+    st = syn.make_stations(dem, 100, variable="humidity", seed=3, supplemental_frac=0.2)
+    s = A.default_settings()
+    s.useLapseRateCode = 1
+    run_both(engine, ref, st, s, A.airRelHumidity, dem, ())
+
+
+def test_station_exactly_on_cell_coordinate(engine, ref):
+    """a station sitting exactly on a cell's (x, y) has distance 0 and is ignored (interpolation.cpp:1039)."""
+    dem = syn.make_dem(64, 64, nodata_frac=0.0, border=False)
+    st = syn.make_stations(dem, 40, variable="humidity", seed=1)
+    # cell (row 10, col 20): x = llx + cs*col + 0.5, y = lly + cs*(rows-row) - 0.5 (gis.cpp:799-804), both exact in f32
+    st.x[0] = dem.llx + dem.cell_size * 20 + 0.5
+    st.y[0] = dem.lly + dem.cell_size * (64 - 10) - 0.5
+    st.value[0] = 5.0
+    s = A.default_settings()
+    _, gg, gc = run_both(engine, ref, st, s, A.airRelHumidity, dem, ())
+    assert abs(gg[10, 20] - gc[10, 20]) <= TOL
+
+
+def test_all_flag_dem_returns_false(engine, ref):
+    dem = syn.make_dem(32, 32)
+    dem.data[:] = dem.flag
+    st = syn.make_stations(syn.make_dem(32, 32), 20, variable="humidity")
+    s = A.default_settings()
+    okc, gc, *_ = ref.interpolation_raster(st, s, A.airRelHumidity, dem, ())
+    okg, gg, *_ = engine.interpolation_raster(st, s, A.airRelHumidity, dem, ())
+    assert okc is False and okg is False
+    assert np.all(gg == np.float32(dem.flag))
+
+
+def test_empty_station_set_writes_nodata(engine, ref):
+    dem = syn.make_dem(40, 40)
+    st = syn.make_stations(dem, 5, variable="humidity").subset(np.zeros(5, dtype=bool))
+    s = A.default_settings()
+    okc, gc, *_ = ref.interpolation_raster(st, s, A.airRelHumidity, dem, ())
+    okg, gg, *_ = engine.interpolation_raster(st, s, A.airRelHumidity, dem, ())
+    assert okg == okc
+    assert np.array_equal(gg, gc)
+
+
+def test_ragged_shapes_and_many_stations(engine, ref):
+    """non-multiple-of-tile station count (> 1 tile) and a raster whose size is not a multiple of anything."""
+    dem = syn.make_dem(97, 131, seed=12)
+    st = syn.make_stations(dem, 1037, variable="humidity", seed=13)
+    s = A.default_settings()
+    run_both(engine, ref, st, s, A.dailyAirRelHumidityAvg, dem, ())
+
+
+def test_row_band_matches_full_raster(engine, ref):
+    dem = syn.make_dem(120, 90, seed=21)
+    st = syn.make_stations(dem, 77, variable="humidity", seed=22)
+    s = A.default_settings()
+    _, full, *_ = engine.interpolation_raster(st, s, A.airRelHumidity, dem, ())
+    parts = np.full(dem.shape, np.float32(123.0), dtype=np.float32)
+    for b0, b1 in ((0, 37), (37, 80), (80, 120)):
+        engine.interpolation_raster(st, s, A.airRelHumidity, dem, (), row_begin=b0, row_end=b1, out=parts)
+    assert np.array_equal(parts, full)
+
+
+def test_float_row_pointer_rasters(engine, ref):
+    """the reference's own layout: one allocation per row (float**), gis.cpp:301-317."""
+    import ctypes as C
+    dem = syn.make_dem(50, 60, seed=31)
+    st = syn.make_stations(dem, 33, variable="humidity", seed=32)
+    s = A.default_settings()
+    _, want, *_ = engine.interpolation_raster(st, s, A.airRelHumidity, dem, ())
+    rows_in = [np.ascontiguousarray(dem.data[r]).copy() for r in range(50)]
+    rows_out = [np.zeros(60, dtype=np.float32) for _ in range(50)]
+    RowPtrs = C.POINTER(C.c_float) * 50
+    d = A.pb_raster()
+    d.h = dem.header()
+    d.rows = RowPtrs(*[A.fptr(r) for r in rows_in])
+    o = A.pb_raster_out()
+    o.rows = RowPtrs(*[A.fptr(r) for r in rows_out])
+    stp = st.as_pb()
+    rc = engine.lib.pb_interpolation_raster(engine.h, C.byref(stp), C.byref(s), A.airRelHumidity, C.byref(d), None, 0, 0, -1,
+                                            C.byref(o))
+    assert rc == A.PB_OK
+    assert np.array_equal(np.stack(rows_out), want)
+
+
+def test_points_leave_one_out(engine, ref):
+    """interpolate() at the stations themselves: the station's own zero distance is skipped (computeResiduals)."""
+    dem = syn.make_dem(200, 200, seed=41)
+    urban = syn.make_urban(200, 200)
+    st = syn.make_stations(dem, 300, proxies=(dem, urban), seed=42)
+    s = syn.settings_multiple_detrending()
+    syn.set_points_range(s, st)
+    ok, keep = ref.pre_interpolation(st, s, A.airTemperature, (dem, urban))
+    st = st.subset(keep)
+    x, y, z = st.x.astype(np.float32), st.y.astype(np.float32), st.z.astype(np.float32)
+    pv = st.proxy_values.astype(np.float64)
+    want = ref.interpolate_points(st, s, A.airTemperature, x, y, z, pv, False)
+    got = engine.interpolate_points(st, s, A.airTemperature, x, y, pv, False)
+    assert np.abs(got.astype(np.float64) - want).max() <= TOL
