@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference (oracle/_ref, built from
+/root/reference) in this container. Re-run with:  python tests/golden/make_golden.py
+
+  c1_demo.npz   BASELINE.json configs[0]: the bundled DATA/ demo — DEM_ER_450m (635x337 @450 m) and the stations of
+                DATA/METEOPOINT/test.db for DAILY_TMIN 2023-01-05 and DAILY_TMAX 2023-01-10 — gridded with
+                algorithm=idw (override of the demo's shepard_modified), classic elevation detrending with thermal
+                inversion, optimalDetrending=false, climate lapse rates of January from parameters.ini.
+  synth_*.npz   small seeded synthetic cases (praga_b200/synthetic.py) with the reference's outputs.
+Each file stores the inputs, the settings AFTER preInterpolation (raw bytes of pb_settings), the detrended station
+values, the keep mask and the reference output grid.
+"""
+import os
+import sqlite3
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.binding import Oracle  # noqa: E402
+from praga_b200 import _abi as A  # noqa: E402
+from praga_b200 import synthetic as syn  # noqa: E402
+
+REF_DATA = "/root/reference/DATA"
+
+
+def read_flt(base):
+    hdr = {}
+    for line in open(base + ".hdr"):
+        k, v = line.split()
+        hdr[k.lower()] = v
+    rows, cols = int(hdr["nrows"]), int(hdr["ncols"])
+    data = np.fromfile(base + ".flt", dtype="<f4").reshape(rows, cols)
+    return A.Raster(data, float(hdr["xllcorner"]), float(hdr["yllcorner"]), float(hdr["cellsize"]), float(hdr["nodata_value"]))
+
+
+def demo_stations(var_id, date):
+    con = sqlite3.connect(f"file:{REF_DATA}/METEOPOINT/test.db?mode=ro", uri=True)
+    cur = con.cursor()
+    pts = cur.execute("select id_point, utm_x, utm_y, altitude from point_properties where is_active=1 order by id_point").fetchall()
+    xs, ys, zs, vs = [], [], [], []
+    for pid, x, y, z in pts:
+        try:
+            row = cur.execute(f"select value from '{pid}_D' where id_variable=? and date(date_time)=?", (var_id, date)).fetchone()
+        except sqlite3.OperationalError:
+            continue
+        if row is None or row[0] is None:
+            continue
+        xs.append(x); ys.append(y); zs.append(z); vs.append(row[0])
+    z = np.array(zs, dtype=np.float64)
+    return A.Stations(xs, ys, z, vs, z.astype(np.float32).reshape(-1, 1))
+
+
+def save(name, dem, grids, st_raw, st_det, keep, s, var, out, ok, mn, mx, nv):
+    arrs = dict(dem=dem.data, dem_hdr=np.array([dem.llx, dem.lly, dem.cell_size, dem.flag]),
+                x=st_raw.x, y=st_raw.y, z=st_raw.z, value_raw=st_raw.value, value_detrended=st_det.value, keep=keep,
+                proxy_values=st_raw.proxy_values, settings=np.frombuffer(bytes(s), dtype=np.uint8), variable=np.int32(var),
+                out=out, ok=np.bool_(ok), minimum=np.float32(mn), maximum=np.float32(mx), n_valid=np.int64(nv))
+    if st_raw.lapse_rate_code is not None:
+        arrs["lapse_rate_code"] = st_raw.lapse_rate_code
+    for i, g in enumerate(grids):
+        if g is not dem:
+            arrs[f"grid{i}"] = g.data
+            arrs[f"grid{i}_hdr"] = np.array([g.llx, g.lly, g.cell_size, g.flag])
+    np.savez_compressed(os.path.join(HERE, name), **arrs)
+    print(name, os.path.getsize(os.path.join(HERE, name)) // 1024, "KiB", "ok" if ok else "FALSE", mn, mx, nv)
+
+
+def run_case(ref, name, dem, grids, st, s, var):
+    raw = st.copy()
+    ok_pre, keep = ref.pre_interpolation(st, s, var, grids)
+    assert ok_pre
+    ok, out, mn, mx, nv, _ = ref.interpolation_raster(st.subset(keep), s, var, dem, grids)
+    save(name, dem, grids, raw, st, keep, s, var, out, ok, mn, mx, nv)
+
+
+def main():
+    ref = Oracle("reference")
+    # ---- C1: bundled demo ----
+    dem = read_flt(f"{REF_DATA}/DEM/DEM_ER_450m")
+    for tag, var_id, var, date, lapse in (("tmin_20230105", 151, A.dailyAirTemperatureMin, "2023-01-05", -0.001),
+                                          ("tmax_20230110", 152, A.dailyAirTemperatureMax, "2023-01-10", -0.001)):
+        st = demo_stations(var_id, date)
+        s = syn.settings_classic_detrending(1)
+        s.climateLapseRate = lapse         # [climate] tmin_lapserate / tmax_lapserate, January (parameters.ini)
+        run_case(ref, f"c1_demo_{tag}.npz", dem, (dem,), st, s, var)
+    # ---- synthetic ----
+    d = syn.make_dem(60, 70, seed=101)
+    u = syn.make_urban(60, 70)
+    st = syn.make_stations(d, 90, proxies=(d, u), seed=102, supplemental_frac=0.1)
+    s = syn.settings_multiple_detrending()
+    s.useLapseRateCode = 1
+    syn.set_points_range(s, st)
+    run_case(ref, "synth_multiple.npz", d, (d, u), st, s, A.airTemperature)
+    st = syn.make_stations(d, 70, variable="precipitation", seed=103)
+    run_case(ref, "synth_precipitation.npz", d, (), st, A.default_settings(), A.dailyPrecipitation)
+    st = syn.make_stations(d, 70, variable="humidity", seed=104)
+    run_case(ref, "synth_humidity.npz", d, (), st, A.default_settings(), A.airRelHumidity)
+
+
+if __name__ == "__main__":
+    main()
