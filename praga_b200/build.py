@@ -1,6 +1,9 @@
 """Build libpraga_b200.so (hand-written CUDA for sm_100a + the C ABI of include/praga_b200.h) in-tree with nvcc.
 
 The shared library has no torch dependency: PyTorch is only used by bench.py for torch.distributed plumbing.
+Each .cu is compiled to an object with its own flags, then linked:
+  detrend_kernels.cu is built with -fmad=false: the station-space fits follow the reference's FP64 operation
+  order (no FMA contraction, like the reference's x86-64 build) so that Levenberg-Marquardt takes the same path.
 """
 import os
 import shutil
@@ -9,9 +12,15 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpraga_b200.so")
-SOURCES = ["engine.cu", "idw_kernels.cu", "peaks.cu"]
+SOURCES = {
+    "engine.cu": [],
+    "idw_kernels.cu": [],
+    "peaks.cu": [],
+}
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def nvcc_path():
@@ -21,29 +30,54 @@ def nvcc_path():
     raise RuntimeError("nvcc not found: praga_b200 needs the CUDA toolkit to build (there is no CPU fallback)")
 
 
+def _deps():
+    return [os.path.join(CSRC, s) for s in list(SOURCES) + HEADERS] + [os.path.abspath(__file__)]
+
+
 def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return any(os.path.getmtime(d) > t for d in _deps() if os.path.exists(d))
+
+
+def _run(cmd, verbose):
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd[-3:]))
 
 
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into praga_b200/libpraga_b200.so. Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [
-        nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-        "-shared", "-Xcompiler", "-fPIC,-fopenmp,-O2", "-ccbin", "/usr/bin/g++",
-        "-Xptxas", "-v" if verbose else "-O3",
-        "-o", LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lgomp"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    nvcc = nvcc_path()
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC, h)))
+    hdr_t = max(hdr_t, os.path.getmtime(os.path.abspath(__file__)))
+    objs, procs = [], []
+    for src, extra in SOURCES.items():
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(o)
+        if not force and os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), hdr_t):
+            continue
+        cmd = [nvcc] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O2", "-ccbin", "/usr/bin/g++"]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        cmd += extra + ["-c", s, "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        failed |= p.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed building libpraga_b200.so")
+    _run([nvcc] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-lgomp"], verbose)
     return LIB
 
 
