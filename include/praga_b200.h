@@ -196,12 +196,36 @@ int pb_interpolation_raster_device(pb_context* ctx, const pb_stations* st, const
                                    pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids,
                                    int rowBegin, int rowEnd, pb_raster_out* out);
 
+/* --- local-detrending raster: the loop of Project::interpolationDemLocalDetrending (agrolib/project/project.cpp:3208-3253),
+ * which the reference inlines in its Qt-bound Project class instead of going through interpolationRaster. Per valid
+ * cell: localSelection (interpolation.cpp:1087-1170), preInterpolation on the subset (multipleDetrendingMain :1832,
+ * weighted Levenberg-Marquardt fits), interpolate (idw) and retrend. `st` holds the NOT yet detrended points of
+ * checkAndPassDataToInterpolation in their original order; `s` needs useLocalDetrending, useMultipleDetrending,
+ * minPointsLocalDetrending, the selected combination, the proxies' fitting ranges and the points range
+ * (setPointsRange, spatialControl.cpp:564). Same three forms as interpolationRaster. */
+int pb_local_detrending_raster(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                               const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids,
+                               int rowBegin, int rowEnd, pb_raster_out* out);
+int pb_local_detrending_raster_resident(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                        pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids,
+                                        int rowBegin, int rowEnd, pb_raster_out* out);
+int pb_local_detrending_raster_device(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                      pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids,
+                                      int rowBegin, int rowEnd, pb_raster_out* out);
+
 /* --- interpolate() at explicit targets (agrolib/interpolation/interpolation.h:77-79, .cpp:2502-2560) -------
  * The building block of computeResiduals (spatialControl.cpp:97-155): x, y are the f32 target coordinates,
  * proxyValues holds m * settings.nProxy doubles (the targets' own proxy values, NODATA where missing).
  * Stations whose distance to the target is 0 weigh nothing (interpolation.cpp:1039) => leave-one-out. */
 int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
                           const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result);
+
+/* --- leave-one-out cross-validation: computeResiduals (agrolib/interpolation/spatialControl.cpp:97-155) followed by
+ * Project::computeStatisticsCrossValidation (agrolib/project/project.cpp:2935-2969). One meteo point per station:
+ * observed[i] = its currentValue (NOT detrended), useForCv[i] = active && accepted && valid (NULL = all);
+ * residual[i] = observed - interpolate() at the station (NODATA where not computed). `stats` may be NULL. */
+int pb_compute_residuals(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* observed,
+                         const uint8_t* useForCv, float* residual, pb_cv_stats* stats);
 
 /* --- timing of the last call (device time measured with CUDA events on the engine's stream) ------ */
 typedef struct pb_timing {

@@ -48,6 +48,12 @@ def _load(path, prefix):
     fn.argtypes = [P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                    P(C.c_double), C.c_int, P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_double)]
     getattr(lib, prefix + "_max_threads").restype = C.c_int
+    fn = getattr(lib, prefix + "_local_detrending_raster")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_raster), P(A.pb_raster), C.c_int, C.c_int,
+                   C.c_int, C.c_int, P(A.pb_raster_out), P(C.c_double)]
+    fn = getattr(lib, prefix + "_local_detrending_point")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, C.c_double, C.c_double, C.c_float, P(C.c_double),
+                   P(C.c_int), P(C.c_float), P(C.c_float), P(C.c_int), P(C.c_float)]
     _libs[path] = lib
     return lib
 
@@ -86,6 +92,36 @@ class Oracle:
         rc = self._f("interpolation_raster")(C.byref(st), C.byref(settings), variable, C.byref(d), grids,
                                              len(proxy_grids), threads, C.byref(o), C.byref(sec))
         return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid, sec.value
+
+    def local_detrending_raster(self, stations, settings, variable, dem, proxy_grids=(), threads=0, row_begin=0,
+                                row_end=-1):
+        """loop of Project::interpolationDemLocalDetrending (project.cpp:3208-3253).
+        Returns (ok, grid, min, max, nValid, seconds)."""
+        st = stations.as_pb()
+        d = dem.as_pb()
+        grids = (A.pb_raster * max(1, len(proxy_grids)))()
+        for i, g in enumerate(proxy_grids):
+            grids[i] = g.as_pb()
+        out = np.empty(dem.shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        sec = C.c_double(0)
+        rc = self._f("local_detrending_raster")(C.byref(st), C.byref(settings), variable, C.byref(d), grids,
+                                                len(proxy_grids), threads, row_begin, row_end, C.byref(o), C.byref(sec))
+        return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid, sec.value
+
+    def local_detrending_point(self, stations, settings, variable, x, y, z, proxy_values):
+        """one cell of the local-detrending loop; returns dict(sel, weight, value, result); settings get the fit."""
+        st = stations.as_pb()
+        pv = np.ascontiguousarray(proxy_values, dtype=np.float64)
+        sel = np.zeros(stations.n, dtype=np.int32)
+        w = np.zeros(stations.n, dtype=np.float32)
+        v = np.zeros(stations.n, dtype=np.float32)
+        n = C.c_int(0)
+        res = C.c_float(0)
+        rc = self._f("local_detrending_point")(C.byref(st), C.byref(settings), variable, x, y, z, A.dptr(pv), A.iptr(sel),
+                                               A.fptr(w), A.fptr(v), C.byref(n), C.byref(res))
+        return dict(ok=rc == A.PB_OK, sel=sel[:n.value], weight=w[:n.value], value=v[:n.value], result=res.value)
 
     def pre_interpolation(self, stations, settings, variable, proxy_grids=()):
         """preInterpolation (interpolation.cpp:2444): detrends stations.value IN PLACE, mutates settings.

@@ -1194,6 +1194,68 @@ bool preInterpolation(Work& w)
     return true;
 }
 
+// localSelection, interpolation.cpp:1087-1170 (computeShepardInitialRadius :800-803)
+bool localSelection(const std::vector<Point>& in, std::vector<Point>& out, float x, float y, pb_settings& s, bool excludeSupplemental)
+{
+    const float ratioMinPoints = 1.2f;
+    const unsigned minPoints = unsigned(s.minPointsLocalDetrending * ratioMinPoints);
+    if (in.size() <= minPoints) {
+        out = in;
+        s.localRadius = float(sqrt((minPoints * s.pointsBoundingBoxArea) / (float(3.141592653589793238462643383) * unsigned(in.size()))));
+        return true;
+    }
+    std::vector<float> distances(in.size());
+    for (size_t i = 0; i < in.size(); i++) {
+        const float dx = float(in[i].x) - x, dy = float(in[i].y) - y;     // gis::computeDistance, gis.cpp:685-691
+        distances[i] = sqrtf(dx * dx + dy * dy);
+    }
+    unsigned nrValid = 0, nrPrimaries = 0;
+    float maxDistance = 0, stepRadius = 7500, r0 = 0, r1 = stepRadius;
+    bool beyondLastPoint = false;
+    const bool useCode = s.useLapseRateCode != 0;
+    std::vector<float> selD;
+    out.clear();
+    while (((!useCode && nrValid < minPoints) || (useCode && nrPrimaries < minPoints)) && !beyondLastPoint) {
+        beyondLastPoint = true;
+        for (unsigned i = 0; i < in.size(); i++) {
+            const bool excl = useCode && excludeSupplemental && in[i].lapseRateCode == PB_LAPSE_SUPPLEMENTAL;
+            if ((!isEqualF(distances[i], NODATA_F) && distances[i] > r0 && distances[i] <= r1) && !excl) {
+                out.push_back(in[i]);
+                selD.push_back(distances[i]);
+                nrValid++;
+                if (distances[i] > maxDistance) maxDistance = distances[i];
+                if (checkLapseRateCode(in[i].lapseRateCode, useCode, true)) nrPrimaries++;
+            }
+            if (beyondLastPoint && distances[i] > r1 && !excl) beyondLastPoint = false;
+        }
+        if (nrValid > unsigned(minPoints * 0.8)) stepRadius = 1000;
+        r0 = r1;
+        r1 += stepRadius;
+    }
+    if (!isEqualF(maxDistance, 0))
+        for (size_t i = 0; i < out.size(); i++) out[i].regressionWeight = std::max(1.f - selD[i] / maxDistance, float(EPSILON));
+    s.localRadius = maxDistance;
+    return !out.empty();
+}
+
+// one cell of the loop of Project::interpolationDemLocalDetrending, project/project.cpp:3225-3249
+float localCell(const std::vector<Point>& pts, pb_settings& s, int var, double x, double y, const double* pv, std::vector<Point>* subsetOut)
+{
+    Work w{{}, &s, var};
+    localSelection(pts, w.pts, float(x), float(y), s, false);
+    if (subsetOut) *subsetOut = w.pts;
+    preInterpolation(w);
+    const float r = interpolate(w.pts, s, var, float(x), float(y), pv, true);
+    if (subsetOut) {
+        for (auto& q : *subsetOut) {
+            float v = NODATA_F;
+            for (auto& p : w.pts) if (p.index == q.index) v = p.value;
+            q.value = v;
+        }
+    }
+    return r;
+}
+
 Grid gridOf(const pb_raster& r) { return Grid{r.h, r.data, r.rows}; }
 
 }  // namespace
@@ -1345,6 +1407,90 @@ int port_compute_residuals(const pb_stations* st, const pb_settings* s, int vari
             linearRegression(obs.data(), pre.data(), long(obs.size()), false, &q, &m, &r2);
             stats->R2 = r2;
         }
+    }
+    return PB_OK;
+}
+
+// loop of Project::interpolationDemLocalDetrending, project/project.cpp:3208-3253 (+ updateMinMaxRasterGrid)
+int port_local_detrending_raster(const pb_stations* st, const pb_settings* s0, int variable, const pb_raster* dem,
+                                 const pb_raster* proxyGrids, int nProxyGrids, int nThreads, int rowBegin, int rowEnd,
+                                 pb_raster_out* out, double* elapsed_s)
+{
+    if (!useDetrendingVar(variable) || !s0->useLocalDetrending) return PB_ERR_INVALID;
+    std::vector<Point> pts = loadPoints(st);
+    Grid d = gridOf(*dem);
+    std::vector<Grid> grids;
+    for (int g = 0; g < nProxyGrids; g++) grids.push_back(gridOf(proxyGrids[g]));
+    const int rows = d.h.nrRows, cols = d.h.nrCols;
+    if (rowEnd < 0) rowEnd = rows;
+    if (nThreads > 0) omp_set_num_threads(nThreads);
+    pb_settings base = *s0;
+    for (int i = 0; i < base.nProxy; i++) { base.currentActive[i] = base.selectedActive[i]; base.currentSignificant[i] = 0; }
+    base.currentUseThermalInversion = base.selectedUseThermalInversion;
+    if (!setMultipleDetrendingHeightTemperatureRange(base)) return PB_ERR_FIT;
+    for (int row = 0; row < rows; row++) {
+        float* orow = out->data ? out->data + size_t(row) * cols : out->rows[row];
+        for (int col = 0; col < cols; col++) orow[col] = d.h.flag;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    int64_t nValid = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nValid)
+    for (int row = rowBegin; row < rowEnd; row++) {
+        pb_settings s = base;
+        double pv[PB_MAX_PROXY];
+        float* orow = out->data ? out->data + size_t(row) * cols : out->rows[row];
+        for (int col = 0; col < cols; col++) {
+            const float z = d.at(row, col);
+            if (isEqualF(z, d.h.flag)) continue;
+            nValid++;
+            const double x = d.h.llx + d.h.cellSize * (col + 0.5);            // getUtmXYFromRowCol, gis.cpp:806-810
+            const double y = d.h.lly + d.h.cellSize * (rows - row - 0.5);
+            for (int i = 0; i < s.nProxy; i++) {                              // getProxyValuesXY(float x, float y, ...)
+                pv[i] = -9999;
+                if (!s.currentActive[i]) continue;
+                const int gi = s.proxy[i].gridIndex;
+                if (gi < 0 || gi >= nProxyGrids) continue;
+                const float v = grids[gi].valueFromXY(float(x), float(y));
+                if (v != grids[gi].h.flag) pv[i] = v;
+            }
+            orow[col] = localCell(pts, s, variable, x, y, pv, nullptr);
+            s.nFit = s.nFitFunctions = 0;                                     // clearFitting + setCurrentCombination(selected)
+            for (int i = 0; i < s.nProxy; i++) { s.currentActive[i] = s.selectedActive[i]; s.currentSignificant[i] = 0; }
+            s.currentUseThermalInversion = s.selectedUseThermalInversion;
+        }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    bool first = true;
+    float mn = NODATA_F, mx = NODATA_F;
+    for (int row = 0; row < rows; row++) {
+        const float* orow = out->data ? out->data + size_t(row) * cols : out->rows[row];
+        for (int col = 0; col < cols; col++) {
+            const float v = orow[col];
+            if (!isEqualF(v, d.h.flag) && !isEqualF(v, NODATA_F)) {
+                if (first) { mn = mx = v; first = false; }
+                else if (v < mn) mn = v;
+                else if (v > mx) mx = v;
+            }
+        }
+    }
+    out->minimum = mn; out->maximum = mx; out->nValid = nValid;
+    return first ? PB_ERR_NO_VALID_CELL : PB_OK;
+}
+
+int port_local_detrending_point(const pb_stations* st, pb_settings* s, int variable, double x, double y, float,
+                                const double* proxyValuesIn, int* selIndex, float* selWeight, float* selValue, int* nSel,
+                                float* result)
+{
+    std::vector<Point> pts = loadPoints(st);
+    for (int i = 0; i < s->nProxy; i++) { s->currentActive[i] = s->selectedActive[i]; s->currentSignificant[i] = 0; }
+    s->currentUseThermalInversion = s->selectedUseThermalInversion;
+    if (!setMultipleDetrendingHeightTemperatureRange(*s)) return PB_ERR_FIT;
+    std::vector<Point> subset;
+    *result = localCell(pts, *s, variable, x, y, proxyValuesIn, &subset);
+    *nSel = int(subset.size());
+    for (size_t k = 0; k < subset.size(); k++) {
+        selIndex[k] = subset[k].index; selWeight[k] = subset[k].regressionWeight; selValue[k] = subset[k].value;
     }
     return PB_OK;
 }

@@ -431,6 +431,117 @@ int ref_compute_residuals(const pb_stations* st, const pb_settings* s, int varia
     return ok ? PB_OK : PB_ERR_INVALID;
 }
 
+/* Local-detrending raster: the loop of Project::interpolationDemLocalDetrending (project/project.cpp:3208-3253) restated
+ * (its only copy is a method of the Qt-bound Project class); every call inside it is the reference's own code:
+ * setMultipleDetrendingHeightTemperatureRange, getUtmXYFromRowCol, getProxyValuesXY, localSelection, preInterpolation,
+ * interpolate, clearFitting/setCurrentCombination, updateMinMaxRasterGrid. Rows outside [rowBegin,rowEnd) keep the flag
+ * (bounded samples for timing). */
+int ref_local_detrending_raster(const pb_stations* st, const pb_settings* s, int variable, const pb_raster* dem,
+                                const pb_raster* proxyGrids, int nProxyGrids, int nThreads, int rowBegin, int rowEnd,
+                                pb_raster_out* out, double* elapsed_s)
+{
+    Scenario sc;
+    buildSettings(sc, *s, proxyGrids, nProxyGrids);
+    buildPoints(sc, *st);
+    gis::Crit3DRasterGrid demGrid, outGrid;
+    fillGrid(demGrid, *dem);
+    sc.settings.setCurrentDEM(&demGrid);
+    const meteoVariable myVar = meteoVariable(variable);
+    if (!getUseDetrendingVar(myVar) || !sc.settings.getUseLocalDetrending()) return PB_ERR_INVALID;   // project.cpp:3155
+    if (rowEnd < 0) rowEnd = demGrid.header->nrRows;
+    if (nThreads > 0) omp_set_num_threads(nThreads);
+
+    Crit3DProxyCombination myCombination = sc.settings.getSelectedCombination();
+    sc.settings.setCurrentCombination(myCombination);
+
+    gis::Crit3DRasterHeader myHeader = *(demGrid.header);
+    outGrid.initializeGrid(myHeader);
+    if (!setMultipleDetrendingHeightTemperatureRange(sc.settings)) return PB_ERR_FIT;
+
+    Crit3DInterpolationSettings myInterpolationSettings = sc.settings;
+    std::vector<double> proxyValues(myInterpolationSettings.getProxyNr());
+    std::vector<Crit3DMeteoPoint> meteoPoints;
+    std::vector<Crit3DInterpolationDataPoint>& interpolationPoints = sc.points;
+    Crit3DMeteoSettings* meteoSettings = &sc.meteoSettings;
+    Crit3DClimateParameters* climateParameters = &sc.climate;
+    const Crit3DTime myTime = sc.time;
+    int64_t nValid = 0;
+
+    auto t0 = std::chrono::steady_clock::now();
+    #pragma omp parallel for if(nThreads != 1) firstprivate(myInterpolationSettings, proxyValues) reduction(+ : nValid) schedule(dynamic, 1)
+    for (long row = rowBegin; row < rowEnd; row++)
+    {
+        std::string errorStdStr;
+        for (long col = 0; col < myHeader.nrCols; col++)
+        {
+            float z = demGrid.value[row][col];
+            if (isEqual(z, myHeader.flag))
+                continue;
+            nValid++;
+
+            double x, y;
+            gis::getUtmXYFromRowCol(myHeader, row, col, &x, &y);
+
+            if (getUseDetrendingVar(myVar))
+            {
+                getProxyValuesXY(x, y, myInterpolationSettings, proxyValues);
+            }
+
+            std::vector <Crit3DInterpolationDataPoint> subsetInterpolationPoints;
+            localSelection(interpolationPoints, subsetInterpolationPoints, x, y, myInterpolationSettings, false);
+
+            preInterpolation(subsetInterpolationPoints, myInterpolationSettings, meteoSettings, climateParameters,
+                             meteoPoints, myVar, myTime, errorStdStr);
+
+            outGrid.value[row][col] = interpolate(subsetInterpolationPoints, myInterpolationSettings, meteoSettings,
+                                                  myVar, x, y, z, proxyValues, true);
+            myInterpolationSettings.clearFitting();
+            myInterpolationSettings.setCurrentCombination(myInterpolationSettings.getSelectedCombination());
+
+            subsetInterpolationPoints.clear();
+        }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    bool ok = gis::updateMinMaxRasterGrid(&outGrid);
+    out->nValid = nValid;
+    copyOut(outGrid, out);
+    return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
+/* One cell of the loop above with everything the fit produced exported (debugging aid for the parity tests):
+ * selected station indices in selection order, their regression weights, the detrended values, fitted settings. */
+int ref_local_detrending_point(const pb_stations* st, pb_settings* s, int variable, double x, double y, float z,
+                               const double* proxyValuesIn, int* selIndex, float* selWeight, float* selValue, int* nSel,
+                               float* result)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    for (int i = 0; i < st->n; i++) sc.points[i].index = i;
+    const meteoVariable myVar = meteoVariable(variable);
+    sc.settings.setCurrentCombination(sc.settings.getSelectedCombination());
+    if (!setMultipleDetrendingHeightTemperatureRange(sc.settings)) return PB_ERR_FIT;
+    std::vector<double> proxyValues(proxyValuesIn, proxyValuesIn + s->nProxy);
+    std::vector<Crit3DMeteoPoint> meteoPoints;
+    std::string err;
+    std::vector<Crit3DInterpolationDataPoint> subset;
+    localSelection(sc.points, subset, x, y, sc.settings, false);
+    const size_t n0 = subset.size();
+    std::vector<int> order;
+    for (auto& p : subset) order.push_back(p.index);
+    std::vector<float> w0;
+    for (auto& p : subset) w0.push_back(p.regressionWeight);
+    preInterpolation(subset, sc.settings, &sc.meteoSettings, &sc.climate, meteoPoints, myVar, sc.time, err);
+    *result = interpolate(subset, sc.settings, &sc.meteoSettings, myVar, x, y, z, proxyValues, true);
+    *nSel = int(n0);
+    for (size_t k = 0; k < n0; k++) { selIndex[k] = order[k]; selWeight[k] = w0[k]; selValue[k] = NODATA; }
+    for (auto& p : subset)
+        for (size_t k = 0; k < n0; k++) if (order[k] == p.index) selValue[k] = p.value;
+    exportSettings(sc, *s);
+    return PB_OK;
+}
+
 /* kriging.cpp:97-295. File-static state => single threaded, one system at a time. */
 int ref_kriging_points(const double* pos, const double* val, int n, int mode, double range, double nugget, double sill,
                        double slope, const double* xy, int m, double* result, double* rmse, double* setup_s,

@@ -18,8 +18,9 @@ SOURCES = {
     "engine.cu": [],
     "idw_kernels.cu": [],
     "peaks.cu": [],
+    "local_kernels.cu": ["-fmad=false"],
 }
-HEADERS = ["common.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
+HEADERS = ["common.cuh", "local.cuh", "detrend_device.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

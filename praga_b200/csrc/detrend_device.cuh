@@ -1,0 +1,427 @@
+// detrend_device.cuh — device side of multiple detrending: the reference's Levenberg-Marquardt proxy fits, run by a
+// GROUP of G lanes (16 or 32) per problem (a raster cell with its locally selected stations, or a whole time step).
+//
+// Reference (paths relative to agrolib/):
+//   multipleDetrendingMain                interpolation/interpolation.cpp:1832-1859
+//   multipleDetrendingElevationFitting    :1862-1953   (setFittingParameters_elevation :1625-1677)
+//   detrendingElevation                   :1956-1972
+//   multipleDetrendingOtherProxiesFitting :1975-2171   (setFittingParameters_otherProxies :1680-1728)
+//   detrendingOtherProxies                :2173-2236
+//   proxyValidity                         :1418-1457
+//   bestFittingMarquardt_nDimension       mathFunctions/furtherMathFunctions.cpp:1360-1427 (elevation, weighted)
+//   fittingMarquardt_nDimension           :1954-2118 (1-D weighted), :1740-1947 (multi-proxy weighted)
+//   computeWeighted_R2 / _RMSE            :1245-1275, :1301-1322
+//   lapseRatePiecewise_* / functionLinear_intercept / functionSum   :115-201
+//
+// Mapping: bestFittingMarquardt runs one INDEPENDENT Levenberg-Marquardt descent per first guess (16 for the
+// two-piece lapse rate, 30/31 for the three-piece ones): lane g of the group runs first guess g, sequentially over
+// the data points in the reference's order, in FP64, with every accumulator in registers. Nothing is reduced across
+// lanes inside a fit, so each descent follows the reference's operation order exactly (this TU is compiled with
+// -fmad=false: no FMA contraction, like the reference's x86-64 build) and takes the same accept/reject path.
+// The winner is then picked with the reference's sequential rule (R2 > best + deltaR2) through warp shuffles.
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+// ---- group helpers (G = 16: two problems per warp, G = 32: one) ----
+template <int G> __device__ __forceinline__ unsigned grpShift() { return G == 32 ? 0u : (threadIdx.x & 16u); }
+template <int G> __device__ __forceinline__ unsigned grpMask() { return G == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16u)); }
+template <int G> __device__ __forceinline__ int grpLane() { return threadIdx.x & (G - 1); }
+template <int G> __device__ __forceinline__ unsigned grpBallot(bool p) { return __ballot_sync(grpMask<G>(), p) >> grpShift<G>(); }
+template <int G> __device__ __forceinline__ double grpBcast(double v, int src) { return __shfl_sync(grpMask<G>(), v, src, G); }
+template <int G> __device__ __forceinline__ void grpSync() { __syncwarp(grpMask<G>()); }
+
+__device__ __forceinline__ bool isEqualD(double a, double b) { return fabs(a - b) < kEpsilon; }
+
+// checkLapseRateCode, meteo/meteo.cpp:1127-1133
+__device__ __forceinline__ bool checkLapseRateCodeDev(int code, bool useLapseRateCode, bool useSupplemental)
+{
+    if (useSupplemental) return !useLapseRateCode || code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SUPPLEMENTAL;
+    return !useLapseRateCode || code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SECONDARY;
+}
+
+// ---- model functions with the reference's in-place clamp of par[2] (furtherMathFunctions.cpp:138, 158) ----
+template <int F> struct Fit;
+template <> struct Fit<PB_FIT_PIECEWISE_TWO> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void clamp(double*) {}
+    static __device__ __forceinline__ double eval(double x, const double* p)
+    {
+        if (x < p[0]) return p[2] * (x - p[0]) + p[1];
+        return p[3] * (x - p[0]) + p[1];
+    }
+};
+template <> struct Fit<PB_FIT_PIECEWISE_THREE> {
+    static constexpr int N = 5;
+    static __device__ __forceinline__ void clamp(double* p) { p[2] = (10. > p[2]) ? 10. : p[2]; }
+    static __device__ __forceinline__ double eval(double x, const double* p)
+    {
+        const double xb = p[2] + p[0];
+        if (x < p[0]) return p[4] * x - p[0] * p[4] + p[1];
+        else if (x > xb) return p[4] * x - p[4] * p[0] - p[4] * p[2] + p[3] * p[2] + p[1];
+        else return p[3] * x - p[3] * p[0] + p[1];
+    }
+};
+template <> struct Fit<PB_FIT_PIECEWISE_THREE_FREE> {
+    static constexpr int N = 6;
+    static __device__ __forceinline__ void clamp(double* p) { p[2] = (10. > p[2]) ? 10. : p[2]; }
+    static __device__ __forceinline__ double eval(double x, const double* p)
+    {
+        const double xb = p[0] + p[2];
+        if (x < p[0]) return p[4] * x - p[0] * p[4] + p[1];
+        else if (x > xb) return p[5] * x - p[5] * p[0] - p[5] * p[2] + p[3] * p[2] + p[1];
+        else return p[3] * x - p[3] * p[0] + p[1];
+    }
+};
+
+// run-time dispatched evaluation on a private copy of the parameters (detrend / retrend)
+__device__ __forceinline__ double evalFitRt(int f, double x, const double* par)
+{
+    double p[PB_MAX_FIT_PARAMS];
+#pragma unroll
+    for (int j = 0; j < PB_MAX_FIT_PARAMS; j++) p[j] = par[j];
+    switch (f) {
+    case PB_FIT_PIECEWISE_TWO: return Fit<PB_FIT_PIECEWISE_TWO>::eval(x, p);
+    case PB_FIT_PIECEWISE_THREE: Fit<PB_FIT_PIECEWISE_THREE>::clamp(p); return Fit<PB_FIT_PIECEWISE_THREE>::eval(x, p);
+    case PB_FIT_PIECEWISE_THREE_FREE:
+        Fit<PB_FIT_PIECEWISE_THREE_FREE>::clamp(p);
+        return Fit<PB_FIT_PIECEWISE_THREE_FREE>::eval(x, p);
+    case PB_FIT_LINEAR: return p[0] * x + p[1];
+    default: return 0.;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fittingMarquardt_nDimension, 1-D weighted (furtherMathFunctions.cpp:1954-2118): ONE descent, run by one lane.
+// The reference builds P[k][j] = (f(x_j; p + delta_k) - f(x_j; p)) / delta_k for k outer, j inner, then a = P^T W P
+// and g = P^T W (y - f). Here j is the outer loop and every accumulator lives in registers; each accumulator still
+// receives its terms in ascending j, so the sums are bit-identical. The perturb/restore sequence of the reference
+// (par[k] += delta; ...; par[k] -= delta, which does not always restore the same bits) is reproduced: column k is
+// evaluated with the already "restored" entries below k, and the restored vector is what the step is added to.
+// ---------------------------------------------------------------------------------------------------------
+template <int F>
+__device__ __noinline__ void lmElevation(const double* __restrict__ pmin, const double* __restrict__ pmax,
+                                         const double* __restrict__ delta, double* par, int maxIter, double eps,
+                                         const double* X, const double* Y, const double* W, int nData)
+{
+    constexpr int N = Fit<F>::N;
+    const double VFACTOR = 10;
+    double lambda[N], dl[N], lo[N], hi[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) { lambda[k] = 0.01; dl[k] = delta[k]; lo[k] = pmin[k]; hi[k] = pmax[k]; }
+    double p[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) p[k] = par[k];
+
+    double mySSE = 0;
+    if (nData > 0) Fit<F>::clamp(p);
+    for (int i = 0; i < nData; i++) {
+        const double error = Y[i] - Fit<F>::eval(X[i], p);
+        const double w = W[i];
+        mySSE += error * error * w * w;
+    }
+    int iter = 0;
+    double diffSSE;
+    do {
+        // perturbed parameter vectors: up[k] = value of par[k] while column k is evaluated; rs[k] = after the restore
+        double p0[N], up[N], rs[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) p0[k] = p[k];
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            p[k] += dl[k];
+            if (nData > 0) Fit<F>::clamp(p);       // the model function clamps par[2] in place when it is evaluated
+            up[k] = p[k];
+            p[k] -= dl[k];
+            rs[k] = p[k];
+        }
+        if (nData > 0) Fit<F>::clamp(p);           // evaluations of the following columns / of newPar see it clamped
+        // for the three-piece forms p[2] may have been re-clamped after its own restore: columns k > 2 see p[2]
+        double g[N], a[N][N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            g[i] = 0;
+#pragma unroll
+            for (int j = 0; j < N; j++) a[i][j] = 0;
+        }
+        for (int j = 0; j < nData; j++) {
+            const double x = X[j], y = Y[j], w = W[j];
+            const double f0 = Fit<F>::eval(x, p0);
+            double P[N], WP[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                double q[N];
+#pragma unroll
+                for (int c = 0; c < N; c++) q[c] = (c < k) ? ((F != PB_FIT_PIECEWISE_TWO && c == 2) ? p[2] : rs[c]) : p0[c];
+                q[k] = up[k];
+                P[k] = (Fit<F>::eval(x, q) - f0) / dl[k];
+                WP[k] = w * P[k];
+            }
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+#pragma unroll
+                for (int c = i; c < N; c++) a[i][c] += (P[i] * WP[c]);
+                g[i] += P[i] * w * (y - f0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            a[k][k] += lambda[k] * a[k][k];
+#pragma unroll
+            for (int j = k + 1; j < N; j++) a[j][k] = a[k][j];
+        }
+#pragma unroll
+        for (int j = 0; j < N - 1; j++) {
+            const double pivot = (a[j][j] > kEpsilon) ? a[j][j] : kEpsilon;     // MAXVALUE(a[j][j], EPSILON)
+#pragma unroll
+            for (int i = j + 1; i < N; i++) {
+                const double mult = a[i][j] / pivot;
+#pragma unroll
+                for (int k = j + 1; k < N; k++) a[i][k] -= mult * a[j][k];
+                g[i] -= mult * g[j];
+            }
+        }
+        double change[N];
+        change[N - 1] = g[N - 1] / ((a[N - 1][N - 1] > kEpsilon) ? a[N - 1][N - 1] : kEpsilon);
+#pragma unroll
+        for (int i = N - 2; i >= 0; i--) {
+            double top = g[i];
+#pragma unroll
+            for (int k = i + 1; k < N; k++) top -= a[i][k] * change[k];
+            change[i] = top / ((a[i][i] > kEpsilon) ? a[i][i] : kEpsilon);
+        }
+        double np[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            np[j] = p[j] + change[j];
+            if (np[j] > hi[j] && lambda[j] < 1000) {
+                np[j] = hi[j];
+                if (lambda[j] < 1000) lambda[j] *= VFACTOR;
+            }
+            if (np[j] < lo[j]) {
+                np[j] = lo[j];
+                if (lambda[j] < 1000) lambda[j] *= VFACTOR;
+            }
+        }
+        double newSSE = 0;
+        if (nData > 0) Fit<F>::clamp(np);
+        for (int i = 0; i < nData; i++) {
+            const double error = Y[i] - Fit<F>::eval(X[i], np);
+            const double w = W[i];
+            newSSE += error * error * w * w;
+        }
+        diffSSE = mySSE - newSSE;
+        if (diffSSE > 0) {
+            mySSE = newSSE;
+#pragma unroll
+            for (int j = 0; j < N; j++) { p[j] = np[j]; lambda[j] /= VFACTOR; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; j++) lambda[j] *= VFACTOR;
+        }
+        iter++;
+    } while (fabs(diffSSE) > eps && iter <= maxIter);
+#pragma unroll
+    for (int k = 0; k < N; k++) par[k] = p[k];
+}
+
+// computeWeighted_R2 (:1245-1275) and computeWeighted_RMSE (:1301-1322) of one fitted curve
+template <int F>
+__device__ __forceinline__ void weightedScores(double* par, const double* X, const double* Y, const double* W, int nData,
+                                               double& R2, double& RMSE)
+{
+    double mean = 0, sw = 0;
+    for (int i = 0; i < nData; i++) { mean += Y[i] * W[i]; sw += W[i]; }
+    mean /= sw;
+    if (nData > 0) Fit<F>::clamp(par);
+    double ssr = 0, sst = 0, s = 0;
+    for (int i = 0; i < nData; i++) {
+        const double sim = Fit<F>::eval(X[i], par);
+        const double r = W[i] * (Y[i] - sim);
+        ssr += r * r;
+        const double t = W[i] * (Y[i] - mean);
+        sst += t * t;
+        s += W[i] * (Y[i] - sim) * (Y[i] - sim);
+    }
+    R2 = 1.0 - (ssr / sst);
+    RMSE = sqrt(s / (sw * nData));
+}
+
+// bestFittingMarquardt_nDimension (:1360-1427): all first guesses of the group in parallel, reference pick order.
+// firstGuess: nGuess x PB_MAX_FIT_PARAMS doubles. par (out, group-uniform) = chosen parameters. Returns bestR2.
+template <int G, int F>
+__device__ double bestFitElevation(const double* __restrict__ pmin, const double* __restrict__ pmax,
+                                   const double* __restrict__ delta, const double* __restrict__ firstGuess, int nGuess,
+                                   double* par, int maxIter, double eps, double deltaR2, const double* X, const double* Y,
+                                   const double* W, int nData)
+{
+    constexpr int N = Fit<F>::N;
+    const int lane = grpLane<G>();
+    double best[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) best[j] = 0;
+    double bestR2 = -9999, bestRMSE = -9999;
+    int rmseIndex = -9999;
+    for (int c0 = 0; c0 < nGuess; c0 += G) {
+        const int k = c0 + lane;
+        double q[N], R2 = 0, RMSE = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) q[j] = 0;
+        if (k < nGuess) {
+#pragma unroll
+            for (int j = 0; j < N; j++) q[j] = firstGuess[k * PB_MAX_FIT_PARAMS + j];
+            lmElevation<F>(pmin, pmax, delta, q, maxIter, eps, X, Y, W, nData);
+            weightedScores<F>(q, X, Y, W, nData, R2, RMSE);
+        }
+        grpSync<G>();
+        const int nk = (nGuess - c0 < G) ? nGuess - c0 : G;
+        for (int kk = 0; kk < nk; kk++) {
+            const double r2 = grpBcast<G>(R2, kk), rmse = grpBcast<G>(RMSE, kk);
+            double cand[N];
+#pragma unroll
+            for (int j = 0; j < N; j++) cand[j] = grpBcast<G>(q[j], kk);
+            if (isEqualD(bestRMSE, -9999) || rmse < bestRMSE) { bestRMSE = rmse; rmseIndex = c0 + kk; }
+            if (isEqualD(bestR2, -9999) || r2 > (bestR2 + deltaR2)) {
+#pragma unroll
+                for (int j = 0; j < N; j++) best[j] = cand[j];
+                bestR2 = r2;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) par[j] = best[j];
+    if (bestR2 < 0 && rmseIndex >= 0) {     // refit from the best-RMSE guess (every lane computes the same descent)
+        double q[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) q[j] = firstGuess[rmseIndex * PB_MAX_FIT_PARAMS + j];
+        lmElevation<F>(pmin, pmax, delta, q, maxIter, eps, X, Y, W, nData);
+#pragma unroll
+        for (int j = 0; j < N; j++) par[j] = q[j];
+    }
+    return bestR2;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fittingMarquardt_nDimension for the other proxies (furtherMathFunctions.cpp:1740-1947): functionSum of nPred
+// functionLinear_intercept terms, 2*nPred parameters, weighted, no pivot clamp. One descent, group-uniform (every lane
+// computes it). Predictor c of data point j is pred(j, c).
+// ---------------------------------------------------------------------------------------------------------
+template <int NP, class PredFn>
+__device__ __noinline__ void lmOthers(int nPredRt, double (*pmin)[2], double (*pmax)[2], double (*par)[2],
+                                      double (*delta)[2], int maxIter, double eps, PredFn pred, const double* Y,
+                                      const double* W, int nData)
+{
+    constexpr int MT = NP > 0 ? 2 * NP : 2 * PB_MAX_PROXY;     // NP > 0: compile-time size, everything in registers
+    const double VFACTOR = 10;
+    const int nPred = NP > 0 ? NP : nPredRt;
+    const int nTot = 2 * nPred;
+    double lambda[MT], change[MT], np[MT], p[MT], dl[MT];
+    #pragma unroll
+    for (int t = 0; t < nTot; t++) { lambda[t] = 0.01; p[t] = par[t >> 1][t & 1]; dl[t] = delta[t >> 1][t & 1]; }
+    auto fsum = [&](int j, const double* q) {
+        double r = 0.0;
+        #pragma unroll
+        for (int c = 0; c < nPred; c++) r += q[2 * c] * pred(j, c) + q[2 * c + 1];
+        return r;
+    };
+    auto norm = [&](const double* q) {
+        double n = 0;
+        for (int i = 0; i < nData; i++) {
+            const double e = Y[i] - fsum(i, q);
+            n += e * e * W[i] * W[i];
+        }
+        return n;
+    };
+    double mySSE = norm(p), diffSSE;
+    int iter = 0;
+    do {
+        double g[MT], a[MT][MT], p0[MT], up[MT], rs[MT];
+        #pragma unroll
+        for (int i = 0; i < nTot; i++) {
+            g[i] = 0;
+            p0[i] = p[i];
+            #pragma unroll
+            for (int j = 0; j < nTot; j++) a[i][j] = 0;
+        }
+        #pragma unroll
+        for (int t = 0; t < nTot; t++) {
+            p[t] += dl[t];
+            up[t] = p[t];
+            p[t] -= dl[t];
+            rs[t] = p[t];
+        }
+        for (int j = 0; j < nData; j++) {
+            const double f0 = fsum(j, p0);
+            double P[MT], WP[MT];
+            #pragma unroll
+            for (int t = 0; t < nTot; t++) {
+                double q[MT];
+                #pragma unroll
+                for (int c = 0; c < nTot; c++) q[c] = (c < t) ? rs[c] : p0[c];
+                q[t] = up[t];
+                P[t] = (fsum(j, q) - f0) / dl[t];
+                WP[t] = W[j] * P[t];
+            }
+            #pragma unroll
+            for (int i = 0; i < nTot; i++) {
+                #pragma unroll
+                for (int c = i; c < nTot; c++) a[i][c] += (P[i] * WP[c]);
+                g[i] += P[i] * W[j] * (Y[j] - f0);
+            }
+        }
+        #pragma unroll
+        for (int t = 0; t < nTot; t++) {
+            a[t][t] += lambda[t] * a[t][t];
+            #pragma unroll
+            for (int j = t + 1; j < nTot; j++) a[j][t] = a[t][j];
+        }
+        #pragma unroll
+        for (int j = 0; j < nTot - 1; j++) {
+            const double pivot = a[j][j];
+            #pragma unroll
+            for (int i = j + 1; i < nTot; i++) {
+                const double mult = a[i][j] / pivot;
+                #pragma unroll
+                for (int k = j + 1; k < nTot; k++) a[i][k] -= mult * a[j][k];
+                g[i] -= mult * g[j];
+            }
+        }
+        change[nTot - 1] = g[nTot - 1] / a[nTot - 1][nTot - 1];
+        #pragma unroll
+        for (int i = nTot - 2; i >= 0; i--) {
+            double top = g[i];
+            #pragma unroll
+            for (int k = i + 1; k < nTot; k++) top -= a[i][k] * change[k];
+            change[i] = top / a[i][i];
+        }
+        #pragma unroll
+        for (int t = 0; t < nTot; t++) {
+            const double hi = pmax[t >> 1][t & 1], lo = pmin[t >> 1][t & 1];
+            np[t] = p[t] + change[t];
+            if (np[t] > hi && lambda[t] < 1000) {
+                np[t] = hi;
+                if (lambda[t] < 1000) lambda[t] *= VFACTOR;
+            }
+            if (np[t] < lo) {
+                np[t] = lo;
+                if (lambda[t] < 1000) lambda[t] *= VFACTOR;
+            }
+        }
+        const double newSSE = norm(np);
+        diffSSE = mySSE - newSSE;
+        if (diffSSE > 0) {
+            mySSE = newSSE;
+            #pragma unroll
+            for (int t = 0; t < nTot; t++) { p[t] = np[t]; lambda[t] /= VFACTOR; }
+        } else {
+            #pragma unroll
+            for (int t = 0; t < nTot; t++) lambda[t] *= VFACTOR;
+        }
+        iter++;
+    } while (fabs(diffSSE) > eps && iter <= maxIter);
+    #pragma unroll
+    for (int t = 0; t < nTot; t++) par[t >> 1][t & 1] = p[t];
+}
+
+}  // namespace pb

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "local.cuh"
 
 namespace pb {
 // idw_kernels.cu
@@ -89,6 +90,10 @@ struct pb_context {
     DevBuf<float> dOut;
     int outInitRaster = -1;             // dOut currently holds the flag pattern of this raster id
     DevBuf<unsigned char> dScratch;     // point targets
+    DevBuf<unsigned char> dLocalStations, dLocalScratch, dLocalModel;   // local-detrending raster (K2)
+    PinnedBuf hLocal;
+    int* dLocalError = nullptr;
+    int* hLocalError = nullptr;         // pinned
     PinnedBuf hStage;                   // raster staging (H2D / D2H)
     unsigned* dMinMax = nullptr;
     unsigned* hMinMax = nullptr;        // pinned
@@ -354,10 +359,205 @@ float keyToFloat(unsigned k)
     return f;
 }
 
+// ---- host side of the local-detrending raster (what Project::interpolationDemLocalDetrending does before its loop) ----
+
+// calculateFirstGuessCombinations (interpolation.cpp:1556-1622): 15 steps along parameter 0 (and 2 for the three-piece
+// functions) around the first-guess position; NB the reference indexes firstGuessPosition with the loop counter.
+int firstGuessCombinations(const pb_proxy& p, double out[PB_MAX_FIRST_GUESS][PB_MAX_FIT_PARAMS])
+{
+    const int numSteps = 15;
+    const int n = p.nFitParams;
+    double stepSize[PB_MAX_FIT_PARAMS], first[PB_MAX_FIT_PARAMS], tmp[PB_MAX_FIT_PARAMS];
+    for (int j = 0; j < n; j++) {
+        const double mn = p.fitMin[j], mx = p.fitMax[j];
+        stepSize[j] = (mx - mn) / numSteps;
+        first[j] = p.fitFirstGuess[j] == 0 ? mn : (p.fitFirstGuess[j] == 1 ? (mn + mx) / 2 : mx);
+    }
+    int count = 0;
+    auto push = [&](const double* v) {
+        if (count < PB_MAX_FIRST_GUESS) memcpy(out[count], v, sizeof(double) * n);
+        count++;
+    };
+    push(first);
+    const int paramIndex[2] = {0, 2};
+    const int nIdx = (p.fittingFunction == PB_FIT_PIECEWISE_TWO) ? 1 : 2;
+    for (int k = 0; k < nIdx; k++) {
+        const int pi = paramIndex[k];
+        for (int m = 1; m < numSteps + 1; m++) {
+            memcpy(tmp, first, sizeof(double) * n);
+            if (p.fitFirstGuess[k] == 0) {
+                tmp[pi] = first[pi] + m * stepSize[pi];
+                push(tmp);
+            } else if (p.fitFirstGuess[k] == 2) {
+                tmp[pi] = first[pi] - m * stepSize[pi];
+                push(tmp);
+            } else if (m < int(numSteps / 2) + 1) {
+                tmp[pi] = std::min(first[pi] + m * stepSize[pi], p.fitMax[pi]);
+                push(tmp);
+                memcpy(tmp, first, sizeof(double) * n);
+                tmp[pi] = std::max(first[pi] - m * stepSize[pi], p.fitMin[pi]);
+                push(tmp);
+            }
+        }
+    }
+    return std::min(count, PB_MAX_FIRST_GUESS);
+}
+
+// pb_settings -> LocalModel: selected combination, setMultipleDetrendingHeightTemperatureRange (interpolation.cpp:1506-1553),
+// setFittingParameters_elevation / _otherProxies (:1625-1728), localSelection constants (:1092-1099, :1152)
+int buildLocalModel(pb_context* ctx, const pb_settings* s, int variable, int nStations, const pb_raster_id* proxyGridIds,
+                    int nProxyGrids, LocalModel& m)
+{
+    memset(&m, 0, sizeof(m));
+    if (s->nProxy < 0 || s->nProxy > PB_MAX_PROXY) return fail(ctx, PB_ERR_INVALID, "settings.nProxy out of range");
+    if (!useDetrendingVar(variable) || !s->useLocalDetrending)      // project.cpp:3155
+        return fail(ctx, PB_ERR_INVALID, "local detrending needs useLocalDetrending and a detrending variable");
+    if (!s->useMultipleDetrending)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "local detrending without multiple detrending is outside the hot-path scope (DESIGN.md)");
+    if (s->method != PB_METHOD_IDW)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the GPU path (shepard: DESIGN.md)");
+    if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending is out of scope (DESIGN.md)");
+    if (!s->hasPointsRange)     // setMultipleDetrendingHeightTemperatureRange returns false (:1508)
+        return fail(ctx, PB_ERR_FIT, "couldn't set temperature ranges for height proxy (points range not set)");
+    m.nProxy = s->nProxy;
+    m.elevationPos = -1;
+    for (int i = 0; i < s->nProxy; i++) if (s->proxy[i].kind == PB_PROXY_HEIGHT) m.elevationPos = i;
+    m.useLapseRateCode = s->useLapseRateCode;
+    m.minPointsLocal = s->minPointsLocalDetrending;
+    const float ratioMinPoints = 1.2f;
+    m.minPoints = unsigned(s->minPointsLocalDetrending * ratioMinPoints);
+    m.thr80 = unsigned(m.minPoints * 0.8);
+    m.shepardRadius = nStations > 0 ? float(sqrt((m.minPoints * s->pointsBoundingBoxArea) / (float(3.141592653589793238462643383) * unsigned(nStations)))) : 0.f;
+    m.clampMode = clampModeOf(variable);
+    m.rainfallThreshold = s->rainfallThreshold;
+    m.useDoNotRetrend = s->useDoNotRetrend;
+    m.useRetrendOnly = s->useRetrendOnly;
+    int slots = 0;
+    m.elevFunction = PB_FIT_PIECEWISE_TWO;
+    for (int i = 0; i < s->nProxy; i++) {
+        const pb_proxy& p = s->proxy[i];
+        m.selectedActive[i] = s->selectedActive[i];
+        m.kind[i] = p.kind;
+        m.stdDevThreshold[i] = p.stdDevThreshold;
+        m.gridSlot[i] = -1;
+        if (p.gridIndex >= 0 && proxyGridIds) {
+            if (p.gridIndex >= nProxyGrids) return fail(ctx, PB_ERR_INVALID, "proxy.gridIndex >= nProxyGrids");
+            const pb_raster_id id = proxyGridIds[p.gridIndex];
+            if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used)
+                return fail(ctx, PB_ERR_INVALID, "proxy grid id is not a live raster");
+            m.gridSlot[i] = slots;
+            m.grid[slots++] = devGridOf(ctx->rasters[id]);
+        }
+        if (!s->selectedActive[i]) continue;
+        if (i == m.elevationPos) {
+            pb_proxy e = p;
+            const int f = e.fittingFunction;
+            if (!(f == PB_FIT_PIECEWISE_TWO || f == PB_FIT_PIECEWISE_THREE || f == PB_FIT_PIECEWISE_THREE_FREE))
+                return fail(ctx, PB_ERR_FIT, "elevation proxy needs a piecewise fitting function (interpolation.cpp:1640-1660)");
+            const int want = f == PB_FIT_PIECEWISE_TWO ? 4 : (f == PB_FIT_PIECEWISE_THREE ? 5 : 6);
+            if (e.nFitParams != want) return fail(ctx, PB_ERR_FIT, "wrong number of fitting parameters for the elevation proxy");
+            e.fitMin[1] = s->pointsRangeMin - 2;     // MIN_T - 2 / MAX_T + 6 (:1520-1545)
+            e.fitMax[1] = s->pointsRangeMax + 6;
+            m.elevFunction = f;
+            m.elevNPar = want;
+            for (int j = 0; j < want; j++) {
+                m.elevMin[j] = e.fitMin[j];
+                m.elevMax[j] = e.fitMax[j];
+                m.elevDelta[j] = (e.fitMax[j] - e.fitMin[j]) / 800;
+            }
+            m.nFirstGuess = firstGuessCombinations(e, m.firstGuess);
+            if (m.nFirstGuess < 1) return fail(ctx, PB_ERR_FIT, "no first-guess combination for the elevation proxy");
+        } else {
+            if (p.nFitParams < 2) return fail(ctx, PB_ERR_FIT, "wrong number of parameters for one of the proxies (interpolation.cpp:1700)");
+            for (int j = 0; j < 2; j++) {
+                m.otherMin[i][j] = p.fitMin[j];
+                m.otherMax[i][j] = p.fitMax[j];
+                m.otherDelta[i][j] = std::max((p.fitMax[j] - p.fitMin[j]) / 1000, kEpsilon);
+                m.otherStart[i][j] = (p.fitMax[j] + p.fitMin[j]) / 2;
+            }
+        }
+    }
+    return PB_OK;
+}
+
+// all stations in index order -> device (LocalStations)
+int stageLocalStations(pb_context* ctx, const pb_stations* st, LocalStations& ds)
+{
+    const int n = st->n, P = st->nProxy;
+    if (n < 0) return fail(ctx, PB_ERR_INVALID, "stations.n < 0");
+    if (P > 0 && !st->proxyValues) return fail(ctx, PB_ERR_INVALID, "stations.proxyValues required");
+    const size_t nAl = (size_t(n) + 3) / 4 * 4;
+    const size_t offXY = 0, offVal = offXY + nAl * 8, offW = offVal + nAl * 4, offCode = offW + nAl * 4,
+                 offProxy = offCode + nAl * 4, offAct = offProxy + (size_t(n) * P + 3) / 4 * 16, total = offAct + nAl + 16;
+    CUDA_TRY(ctx, ctx->hLocal.reserve(total));
+    CUDA_TRY(ctx, ctx->dLocalStations.reserve(total));
+    unsigned char* h = ctx->hLocal.p;
+    float2* xy = reinterpret_cast<float2*>(h + offXY);
+    float* val = reinterpret_cast<float*>(h + offVal);
+    float* w = reinterpret_cast<float*>(h + offW);
+    int* code = reinterpret_cast<int*>(h + offCode);
+    float* proxy = reinterpret_cast<float*>(h + offProxy);
+    unsigned char* act = h + offAct;
+    for (int i = 0; i < n; i++) {
+        xy[i] = make_float2(float(st->x[i]), float(st->y[i]));
+        val[i] = st->value[i];
+        w[i] = st->regressionWeight ? st->regressionWeight[i] : kNoData;
+        code[i] = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        act[i] = st->isActive ? (st->isActive[i] != 0) : 1;
+    }
+    if (P > 0) memcpy(proxy, st->proxyValues, sizeof(float) * size_t(n) * P);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dLocalStations.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)total;
+    unsigned char* d = ctx->dLocalStations.p;
+    ds.xy = reinterpret_cast<const float2*>(d + offXY);
+    ds.value = reinterpret_cast<const float*>(d + offVal);
+    ds.weight = reinterpret_cast<const float*>(d + offW);
+    ds.code = reinterpret_cast<const int*>(d + offCode);
+    ds.proxy = reinterpret_cast<const float*>(d + offProxy);
+    ds.active = d + offAct;
+    ds.n = n;
+    return PB_OK;
+}
+
+// stage + launch K2 on the targets [t0, t0 + nTargets) of the DEM's valid list
+int launchLocal(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const pb_raster_id* proxyIds,
+                int nProxyGrids, RasterEntry& dem, long long t0, int nTargets)
+{
+    LocalModel m;
+    int rc = buildLocalModel(ctx, s, variable, st->n, proxyIds, nProxyGrids, m);
+    if (rc) return rc;
+    LocalStations ds{};
+    rc = stageLocalStations(ctx, st, ds);
+    if (rc) return rc;
+    CUDA_TRY(ctx, ctx->dLocalModel.reserve(sizeof(LocalModel)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dLocalModel.p, &m, sizeof(m), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // `m` lives on this stack frame
+    ctx->timing.h2d_bytes += (int64_t)sizeof(m);
+    const int groupLanes = m.nFirstGuess <= 16 ? 16 : 32;
+    LocalScratch scr{};
+    scr.cap = std::max(std::min(st->n, 2048), 1);
+    scr.perGroup = localScratchBytesPerGroup(scr.cap);
+    CUDA_TRY(ctx, ctx->dLocalScratch.reserve(scr.perGroup * size_t(localGroupsTotal(groupLanes))));
+    scr.base = ctx->dLocalScratch.p;
+    if (!ctx->dLocalError) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dLocalError, sizeof(int)));
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->hLocalError, sizeof(int)));
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->dLocalError, 0, sizeof(int), ctx->stream));
+    scr.error = ctx->dLocalError;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    CUDA_TRY(ctx, launchLocalDetrendingRaster(reinterpret_cast<const LocalModel*>(ctx->dLocalModel.p), ds, devGridOf(dem),
+                                              dem.validIdx + t0, nTargets, scr, groupLanes, m.elevFunction, ctx->dOut.p,
+                                              ctx->dMinMax, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hLocalError, ctx->dLocalError, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return PB_OK;
+}
+
 enum OutMode { OUT_HOST = 0, OUT_DEVICE_ONLY = 1 };
 
 int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, pb_raster_id demId,
-               const pb_raster_id* proxyIds, int nProxyGrids, int rowBegin, int rowEnd, pb_raster_out* out, OutMode mode)
+               const pb_raster_id* proxyIds, int nProxyGrids, int rowBegin, int rowEnd, pb_raster_out* out, OutMode mode,
+               bool local = false)
 {
     if (!ctx) return PB_ERR_INVALID;
     if (!st || !s || !out) return fail(ctx, PB_ERR_INVALID, "null argument");
@@ -370,13 +570,15 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     if (rc) return rc;
 
     DevModel m;
-    rc = buildModel(ctx, s, variable, proxyIds, nProxyGrids, m);
-    if (rc) return rc;
+    if (!local) {
+        rc = buildModel(ctx, s, variable, proxyIds, nProxyGrids, m);
+        if (rc) return rc;
+    }
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    const bool precZero = isPrecVar(variable) && s->precipitationAllZero;
+    const bool precZero = !local && isPrecVar(variable) && s->precipitationAllZero;
     DevStations ds{};
-    if (!precZero) {
+    if (!precZero && !local) {
         rc = stageStations(ctx, st, s, true, ds, m.valueOffset);
         if (rc) return rc;
     }
@@ -396,7 +598,10 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     const long long t0 = dem.rowStart[rowBegin], t1 = dem.rowStart[rowEnd];
     const int nTargets = (int)(t1 - t0);
     const DevGrid dg = devGridOf(dem);
-    if (precZero) {
+    if (local) {
+        rc = launchLocal(ctx, st, s, variable, proxyIds, nProxyGrids, dem, t0, nTargets);
+        if (rc) return rc;
+    } else if (precZero) {
         // interpolate() returns exactly 0.f for every cell (interpolation.cpp:2506-2507)
         CUDA_TRY(ctx, launchFillValid(ctx->dOut.p, dem.validIdx + t0, nTargets, 0.f, ctx->stream));
         if (nTargets > 0) { ctx->hMinMax[0] = 0x80000000u; ctx->hMinMax[1] = 0x80000000u; }
@@ -446,6 +651,8 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->timing.d2h_bytes += 8;
+    if (local && ctx->hLocalError && *ctx->hLocalError)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "a local selection exceeded 2048 stations (dense first ring): outside the supported range");
 
     cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
@@ -516,6 +723,9 @@ void pb_destroy(pb_context* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& r : ctx->rasters) if (r.used) freeEntry(r);
+    ctx->dLocalStations.release(); ctx->dLocalScratch.release(); ctx->dLocalModel.release(); ctx->hLocal.release();
+    if (ctx->dLocalError) cudaFree(ctx->dLocalError);
+    if (ctx->hLocalError) cudaFreeHost(ctx->hLocalError);
     ctx->dStations.release(); ctx->hStations.release(); ctx->dOut.release(); ctx->dScratch.release(); ctx->hStage.release();
     if (ctx->dMinMax) cudaFree(ctx->dMinMax);
     if (ctx->hMinMax) cudaFreeHost(ctx->hMinMax);
@@ -600,9 +810,29 @@ int pb_interpolation_raster_device(pb_context* ctx, const pb_stations* st, const
     return rasterCore(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, OUT_DEVICE_ONLY);
 }
 
-int pb_interpolation_raster(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
-                            const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
-                            pb_raster_out* out)
+/* Local-detrending raster: the loop of Project::interpolationDemLocalDetrending (project/project.cpp:3208-3253). */
+int pb_local_detrending_raster_resident(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                        pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin,
+                                        int rowEnd, pb_raster_out* out)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    resetTiming(ctx);
+    return rasterCore(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, OUT_HOST, true);
+}
+
+int pb_local_detrending_raster_device(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                      pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin,
+                                      int rowEnd, pb_raster_out* out)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    resetTiming(ctx);
+    return rasterCore(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, OUT_DEVICE_ONLY, true);
+}
+
+static int hostRasterCall(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const pb_raster* dem,
+                          const pb_raster* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd, pb_raster_out* out, bool local)
 {
     if (!ctx) return PB_ERR_INVALID;
     if (!dem || (nProxyGrids > 0 && !proxyGrids)) return fail(ctx, PB_ERR_INVALID, "null raster argument");
@@ -620,15 +850,26 @@ int pb_interpolation_raster(pb_context* ctx, const pb_stations* st, const pb_set
         else rc = pb_raster_upload(ctx, &proxyGrids[g], &ids[g]);
         if (rc == PB_OK) nUp = g + 1;
     }
-    const pb_timing up = ctx->timing;
-    if (rc == PB_OK) rc = rasterCore(ctx, st, s, variable, demId, ids, nProxyGrids, rowBegin, rowEnd, out, OUT_HOST);
-    ctx->timing.h2d_bytes += 0;
+    if (rc == PB_OK) rc = rasterCore(ctx, st, s, variable, demId, ids, nProxyGrids, rowBegin, rowEnd, out, OUT_HOST, local);
     std::string keep = ctx->err;
     for (int g = 0; g < nUp; g++) if (ids[g] != demId) pb_raster_free(ctx, ids[g]);
     if (demId >= 0) pb_raster_free(ctx, demId);
     ctx->err = keep;
-    (void)up;
     return rc;
+}
+
+int pb_interpolation_raster(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                            const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
+                            pb_raster_out* out)
+{
+    return hostRasterCall(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, false);
+}
+
+int pb_local_detrending_raster(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                               const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
+                               pb_raster_out* out)
+{
+    return hostRasterCall(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, true);
 }
 
 /* interpolate() at explicit targets (interpolation.cpp:2502): the building block of computeResiduals.
@@ -679,6 +920,114 @@ int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_setti
 }
 
 }  // extern "C"
+
+// statistics::linearRegression (mathFunctions/statistics.cpp:1030-1092): f64 sums of float products, float results
+static void linearRegressionHost(const std::vector<float>& x, const std::vector<float>& y, float* intercept, float* slope, float* r2)
+{
+    double SUMx = 0, SUMy = 0, SUMxy = 0, SUMxx = 0, SUM_dy = 0, SUMres = 0;
+    long nrValid = 0;
+    *slope = 0; *intercept = 0; *r2 = 0;
+    for (size_t i = 0; i < x.size(); i++)
+        if (x[i] != kNoData && y[i] != kNoData) {
+            nrValid++;
+            SUMx += x[i];
+            SUMy += y[i];
+            SUMxy += x[i] * y[i];
+            SUMxx += x[i] * x[i];
+        }
+    const double AVGy = SUMy / nrValid, AVGx = SUMx / nrValid;
+    *slope = float((SUMxy - SUMx * SUMy / nrValid) / (SUMxx - SUMx * SUMx / nrValid));
+    *intercept = float(AVGy - *slope * AVGx);
+    for (size_t i = 0; i < x.size(); i++)
+        if (x[i] != kNoData && y[i] != kNoData) {
+            double dy = y[i] - (*intercept + *slope * x[i]);
+            dy *= dy;
+            SUM_dy += dy;
+            double res = y[i] - AVGy;
+            res *= res;
+            SUMres += res;
+        }
+    *r2 = float((SUMres - SUM_dy) / SUMres);
+}
+
+/* computeResiduals (interpolation/spatialControl.cpp:97-155) + Project::computeStatisticsCrossValidation
+ * (project/project.cpp:2935-2969; statistics::meanAbsoluteError / meanError / rootMeanSquareError /
+ * NashSutcliffeEfficiency, mathFunctions/statistics.cpp:180-268). The S x S leave-one-out estimates run on the GPU
+ * (K1 point kernel: a station's own zero distance weighs nothing); the O(S) statistics are host arithmetic. */
+extern "C" int pb_compute_residuals(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                    const float* observed, const uint8_t* useForCv, float* residual, pb_cv_stats* stats)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s || !observed || !residual) return fail(ctx, PB_ERR_INVALID, "null argument");
+    const int n = st->n, P = s->nProxy;
+    std::vector<float> x(n), y(n), est(n);
+    std::vector<double> pv(size_t(n) * std::max(P, 1), double(kNoData));
+    for (int i = 0; i < n; i++) {
+        x[i] = float(st->x[i]);
+        y[i] = float(st->y[i]);
+        for (int k = 0; k < P && k < st->nProxy; k++) pv[size_t(i) * P + k] = double(st->proxyValues[size_t(i) * st->nProxy + k]);
+    }
+    int rc = pb_interpolate_points(ctx, st, s, variable, x.data(), y.data(), pv.data(), n, 0, est.data());
+    if (rc) return rc;
+    const bool prec = isPrecVar(variable);
+    std::vector<float> obs, pre;
+    for (int i = 0; i < n; i++) {
+        residual[i] = kNoData;
+        if (useForCv && !useForCv[i]) continue;
+        float myValue = observed[i], e = est[i];
+        if (prec) {
+            if (myValue != kNoData && myValue < s->rainfallThreshold) myValue = 0.f;
+            if (e != kNoData && e < s->rainfallThreshold) e = 0.f;
+        }
+        if (e != kNoData && myValue != kNoData) residual[i] = myValue - e;
+        const float value = observed[i];
+        if (!isEqualF(value, kNoData) && !isEqualF(residual[i], kNoData)) {
+            obs.push_back(value);
+            pre.push_back(value - residual[i]);
+        }
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n = int(obs.size());
+        stats->meanAbsoluteError = stats->meanBiasError = stats->rootMeanSquareError = stats->nashSutcliffe = stats->R2 = kNoData;
+        if (!obs.empty()) {
+            double sumAbs = 0, sigma = 0;
+            float sumErr = 0.f;
+            long cnt = 0;
+            for (size_t i = 0; i < obs.size(); i++)
+                if (obs[i] != kNoData && pre[i] != kNoData) {
+                    sumAbs += fabs(obs[i] - pre[i]);
+                    sumErr += obs[i] - pre[i];
+                    const double diff = obs[i] - pre[i];
+                    sigma += diff * diff;
+                    cnt++;
+                }
+            if (cnt) {
+                stats->meanAbsoluteError = float(sumAbs / cnt);
+                stats->meanBiasError = sumErr / cnt;
+                stats->rootMeanSquareError = float(sqrt(sigma / cnt));
+            }
+            double s0 = 0;
+            int nv = 0;
+            for (float v : obs) if (!isEqualF(v, kNoData)) { s0 += double(v); nv++; }
+            if (nv) {
+                const float obsAvg = float(s0 / double(nv));
+                float sumDev = 0, sumError = 0;
+                for (size_t i = 0; i < obs.size(); i++)
+                    if (!isEqualF(obs[i], kNoData)) sumDev += (obs[i] - obsAvg) * (obs[i] - obsAvg);
+                if (sumDev != 0) {
+                    for (size_t i = 0; i < obs.size(); i++)
+                        if (!isEqualF(obs[i], kNoData) && !isEqualF(pre[i], kNoData)) sumError += (pre[i] - obs[i]) * (pre[i] - obs[i]);
+                    stats->nashSutcliffe = float(1 - (sumError / sumDev));
+                }
+            }
+            float q, m, r2;
+            linearRegressionHost(obs, pre, &q, &m, &r2);
+            stats->R2 = r2;
+        }
+    }
+    return PB_OK;
+}
 
 /* live pipe ceilings for the K1 roofline (FP32 FMA TFLOP/s, G MUFU.RSQ/s) */
 extern "C" int pb_measure_pipe_peaks(pb_context* ctx, float* fp32Tflops, float* mufuGops)

@@ -1,0 +1,59 @@
+// local.cuh — descriptors of the local-detrending raster kernel (K2), shared by engine.cu and local_kernels.cu
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+// everything multipleDetrendingMain + localSelection + interpolate + retrend read from Crit3DInterpolationSettings
+// (interpolation/interpolationSettings.h:185-391), flattened once per call on the host. Lives in global memory.
+struct LocalModel {
+    int nProxy;
+    int elevationPos;              // last proxy whose name is elevation (multipleDetrendingMain :1838-1842), -1 = none
+    int useLapseRateCode;
+    int minPointsLocal;            // getMinPointsLocalDetrending()
+    unsigned minPoints;            // unsigned(minPointsLocal * 1.2f)   (localSelection :1092-1093)
+    unsigned thr80;                // unsigned(minPoints * 0.8)         (:1152)
+    float shepardRadius;           // computeShepardInitialRadius(bboxArea, S, minPoints) when S <= minPoints (:1098)
+    int clampMode;
+    float rainfallThreshold;
+    int useDoNotRetrend, useRetrendOnly;
+    uint8_t selectedActive[PB_MAX_PROXY];
+    int kind[PB_MAX_PROXY];
+    float stdDevThreshold[PB_MAX_PROXY];
+    int gridSlot[PB_MAX_PROXY];
+    // elevation fit (setFittingParameters_elevation :1625-1677 after setMultipleDetrendingHeightTemperatureRange :1506-1553)
+    int elevFunction, elevNPar, nFirstGuess;
+    double elevMin[PB_MAX_FIT_PARAMS], elevMax[PB_MAX_FIT_PARAMS], elevDelta[PB_MAX_FIT_PARAMS];
+    double firstGuess[PB_MAX_FIRST_GUESS][PB_MAX_FIT_PARAMS];
+    // other proxies (setFittingParameters_otherProxies :1680-1728): linear, 2 parameters each
+    double otherMin[PB_MAX_PROXY][2], otherMax[PB_MAX_PROXY][2], otherDelta[PB_MAX_PROXY][2], otherStart[PB_MAX_PROXY][2];
+    DevGrid grid[PB_MAX_PROXY];
+};
+
+// all stations in index order (the selection order of localSelection depends on it)
+struct LocalStations {
+    const float2* xy;              // float(point->utm.x), float(point->utm.y)
+    const float* value;
+    const float* weight;           // regressionWeight as passed in (only used when S <= minPoints)
+    const float* proxy;            // n * nProxy
+    const int* code;               // lapseRateCode
+    const uint8_t* active;
+    int n;
+};
+
+// per-group scratch in global memory (capacity `cap` entries per group), used for the selection list and, when a
+// selection is larger than the shared-memory tile, for the working arrays
+struct LocalScratch {
+    unsigned char* base;
+    size_t perGroup;               // bytes
+    int cap;
+    int* error;                    // != 0: a selection exceeded cap
+};
+
+size_t localScratchBytesPerGroup(int cap);
+int localGroupsTotal(int groupLanes);
+cudaError_t launchLocalDetrendingRaster(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem,
+                                        const int* validIdx, int nTargets, const LocalScratch& scratch, int groupLanes,
+                                        int elevFunction, float* out, unsigned* minmax, cudaStream_t s);
+
+}  // namespace pb

@@ -51,11 +51,14 @@ def load_library():
     raster_args = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int]
     lib.pb_interpolation_raster.argtypes = raster_args + [P(A.pb_raster), P(A.pb_raster), C.c_int, C.c_int, C.c_int,
                                                           P(A.pb_raster_out)]
-    for name in ("pb_interpolation_raster_resident", "pb_interpolation_raster_device"):
+    lib.pb_local_detrending_raster.argtypes = lib.pb_interpolation_raster.argtypes
+    for name in ("pb_interpolation_raster_resident", "pb_interpolation_raster_device",
+                 "pb_local_detrending_raster_resident", "pb_local_detrending_raster_device"):
         getattr(lib, name).argtypes = raster_args + [C.c_int32, P(C.c_int32), C.c_int, C.c_int, C.c_int,
                                                      P(A.pb_raster_out)]
     lib.pb_interpolate_points.argtypes = raster_args + [P(C.c_float), P(C.c_float), P(C.c_double), C.c_int, C.c_int,
                                                         P(C.c_float)]
+    lib.pb_compute_residuals.argtypes = raster_args + [P(C.c_float), P(C.c_uint8), P(C.c_float), P(A.pb_cv_stats)]
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
                  "pb_cv_stats", "pb_timing"):
@@ -125,7 +128,7 @@ class Engine:
 
     # ---- interpolationRaster (interpolationCmd.cpp:353-394) ----
     def interpolation_raster(self, stations, settings, variable, dem, proxy_grids=(), row_begin=0, row_end=-1,
-                             out=None, rows=None):
+                             out=None, rows=None, local=False):
         """Drop-in call with HOST rasters. Returns (ok, grid, minimum, maximum, nValid); ok False <=> the reference
         returns false (no valid output cell)."""
         st = stations.as_pb()
@@ -140,20 +143,25 @@ class Engine:
             if out is None:
                 out = np.empty(dem.shape, dtype=np.float32)
             o.data = A.fptr(out)
-        rc = self._check(self.lib.pb_interpolation_raster(self.h, C.byref(st), C.byref(settings), variable, C.byref(d),
-                                                          grids, len(proxy_grids), row_begin, row_end, C.byref(o)),
-                         allow=(A.PB_ERR_NO_VALID_CELL,))
+        fn = self.lib.pb_local_detrending_raster if local else self.lib.pb_interpolation_raster
+        rc = self._check(fn(self.h, C.byref(st), C.byref(settings), variable, C.byref(d), grids, len(proxy_grids),
+                            row_begin, row_end, C.byref(o)), allow=(A.PB_ERR_NO_VALID_CELL,))
         return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid
 
+    def local_detrending_raster(self, stations, settings, variable, dem, proxy_grids=(), row_begin=0, row_end=-1, out=None):
+        """loop of Project::interpolationDemLocalDetrending (project.cpp:3208-3253) with HOST rasters."""
+        return self.interpolation_raster(stations, settings, variable, dem, proxy_grids, row_begin, row_end, out, local=True)
+
     def interpolation_raster_resident(self, stations, settings, variable, dem_id, proxy_ids=(), row_begin=0, row_end=-1,
-                                      out=None, device_only=False):
+                                      out=None, device_only=False, local=False):
         st = stations.as_pb()
         ids = (C.c_int32 * max(1, len(proxy_ids)))(*proxy_ids)
         o = A.pb_raster_out()
         if not device_only:
             assert out is not None
             o.data = A.fptr(out)
-        fn = self.lib.pb_interpolation_raster_device if device_only else self.lib.pb_interpolation_raster_resident
+        name = "pb_local_detrending_raster" if local else "pb_interpolation_raster"
+        fn = getattr(self.lib, name + ("_device" if device_only else "_resident"))
         rc = self._check(fn(self.h, C.byref(st), C.byref(settings), variable, dem_id, ids, len(proxy_ids), row_begin,
                             row_end, C.byref(o)), allow=(A.PB_ERR_NO_VALID_CELL,))
         return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid
@@ -170,3 +178,14 @@ class Engine:
                                                    A.dptr(pv) if pv.size else None, m, int(exclude_supplemental),
                                                    A.fptr(res)))
         return res
+
+    # ---- computeResiduals + computeStatisticsCrossValidation (spatialControl.cpp:97, project.cpp:2935) ----
+    def compute_residuals(self, stations, settings, variable, observed, use_for_cv=None):
+        obs = np.ascontiguousarray(observed, dtype=np.float32)
+        res = np.empty(stations.n, dtype=np.float32)
+        stats = A.pb_cv_stats()
+        st = stations.as_pb()
+        use = None if use_for_cv is None else np.ascontiguousarray(use_for_cv, dtype=np.uint8)
+        self._check(self.lib.pb_compute_residuals(self.h, C.byref(st), C.byref(settings), variable, A.fptr(obs),
+                                                  None if use is None else A.u8ptr(use), A.fptr(res), C.byref(stats)))
+        return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}

@@ -201,3 +201,39 @@ def test_points_leave_one_out(engine, ref):
     want = ref.interpolate_points(st, s, A.airTemperature, x, y, z, pv, False)
     got = engine.interpolate_points(st, s, A.airTemperature, x, y, pv, False)
     assert np.abs(got.astype(np.float64) - want).max() <= TOL
+
+
+@pytest.mark.parametrize("variable", ["temperature", "precipitation"])
+def test_compute_residuals_and_cv_statistics(engine, ref, variable):
+    """computeResiduals (spatialControl.cpp:97-155) + computeStatisticsCrossValidation (project.cpp:2935-2969)."""
+    dem = syn.make_dem(200, 200, seed=51)
+    urban = syn.make_urban(200, 200)
+    if variable == "temperature":
+        st = syn.make_stations(dem, 400, proxies=(dem, urban), seed=52)
+        raw = st.value.copy()
+        s = syn.settings_multiple_detrending()
+        syn.set_points_range(s, st)
+        var = A.airTemperature
+        ok, keep = ref.pre_interpolation(st, s, var, (dem, urban))
+        assert ok and keep.all()
+    else:
+        st = syn.make_stations(dem, 300, variable="precipitation", seed=53)
+        raw = st.value.copy()
+        s = A.default_settings()
+        var = A.dailyPrecipitation
+        ok, _ = ref.pre_interpolation(st, s, var, ())
+    use = np.ones(st.n, dtype=np.uint8)
+    use[::7] = 0
+    want, ws = ref.compute_residuals(st, s, var, raw, use)
+    got, gs = engine.compute_residuals(st, s, var, raw, use)
+    assert np.array_equal(got == np.float32(-9999), want == np.float32(-9999))
+    m = want != np.float32(-9999)
+    if variable == "precipitation":
+        # the rain threshold is a discontinuity: an estimate within 1e-4 of it may fall on the other side
+        close = np.abs(got[m].astype(np.float64) - want[m]) <= TOL
+        assert close.mean() > 0.99
+    else:
+        assert np.abs(got[m].astype(np.float64) - want[m]).max() <= TOL
+        assert gs["n"] == ws["n"]
+        for k in ("meanAbsoluteError", "meanBiasError", "rootMeanSquareError", "nashSutcliffe", "R2"):
+            assert abs(gs[k] - ws[k]) <= 1e-4, (k, gs[k], ws[k])
