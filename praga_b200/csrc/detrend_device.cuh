@@ -41,6 +41,23 @@ __device__ __forceinline__ bool checkLapseRateCodeDev(int code, bool useLapseRat
     return !useLapseRateCode || code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SECONDARY;
 }
 
+// n / d for a divisor whose correctly rounded reciprocal r = 1/d is known: two FMA correction steps on q = n*r give the
+// correctly rounded IEEE quotient (Markstein), the same bits as the division instruction sequence at a sixth of its cost.
+// Quotients outside the safe exponent range (zeros, subnormals, huge values, NaN) take the plain division.
+__device__ __forceinline__ double divByKnown(double n, double d, double r)
+{
+    const double q0 = n * r;
+    const double aq = fabs(q0);
+    if (aq > 1e-280 && aq < 1e280) {
+        const double e0 = __fma_rn(-d, q0, n);
+        const double q1 = __fma_rn(e0, r, q0);
+        const double e1 = __fma_rn(-d, q1, n);
+        return __fma_rn(e1, r, q1);
+    }
+    if (n == 0) return q0;      // (+-0) / d keeps the sign of n * sign(d)
+    return n / d;
+}
+
 // ---- model functions with the reference's in-place clamp of par[2] (furtherMathFunctions.cpp:138, 158) ----
 template <int F> struct Fit;
 template <> struct Fit<PB_FIT_PIECEWISE_TWO> {
@@ -107,9 +124,9 @@ __device__ __noinline__ void lmElevation(const double* __restrict__ pmin, const 
 {
     constexpr int N = Fit<F>::N;
     const double VFACTOR = 10;
-    double lambda[N], dl[N], lo[N], hi[N];
+    double lambda[N], dl[N], rdl[N];
 #pragma unroll
-    for (int k = 0; k < N; k++) { lambda[k] = 0.01; dl[k] = delta[k]; lo[k] = pmin[k]; hi[k] = pmax[k]; }
+    for (int k = 0; k < N; k++) { lambda[k] = 0.01; dl[k] = delta[k]; rdl[k] = 1.0 / dl[k]; }
     double p[N];
 #pragma unroll
     for (int k = 0; k < N; k++) p[k] = par[k];
@@ -155,7 +172,7 @@ __device__ __noinline__ void lmElevation(const double* __restrict__ pmin, const 
 #pragma unroll
                 for (int c = 0; c < N; c++) q[c] = (c < k) ? ((F != PB_FIT_PIECEWISE_TWO && c == 2) ? p[2] : rs[c]) : p0[c];
                 q[k] = up[k];
-                P[k] = (Fit<F>::eval(x, q) - f0) / dl[k];
+                P[k] = divByKnown(Fit<F>::eval(x, q) - f0, dl[k], rdl[k]);
                 WP[k] = w * P[k];
             }
 #pragma unroll
@@ -194,13 +211,14 @@ __device__ __noinline__ void lmElevation(const double* __restrict__ pmin, const 
         double np[N];
 #pragma unroll
         for (int j = 0; j < N; j++) {
+            const double hi = pmax[j], lo = pmin[j];
             np[j] = p[j] + change[j];
-            if (np[j] > hi[j] && lambda[j] < 1000) {
-                np[j] = hi[j];
+            if (np[j] > hi && lambda[j] < 1000) {
+                np[j] = hi;
                 if (lambda[j] < 1000) lambda[j] *= VFACTOR;
             }
-            if (np[j] < lo[j]) {
-                np[j] = lo[j];
+            if (np[j] < lo) {
+                np[j] = lo;
                 if (lambda[j] < 1000) lambda[j] *= VFACTOR;
             }
         }

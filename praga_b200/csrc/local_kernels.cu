@@ -11,6 +11,7 @@
 //
 // Built with -fmad=false: the FP64 fits follow the reference's operation order without FMA contraction, so the
 // Levenberg-Marquardt descents take the same accept/reject path as on the CPU. Distances use IEEE f32 ops.
+#include <stdlib.h>
 #include "detrend_device.cuh"
 #include "local.cuh"
 
@@ -425,8 +426,8 @@ __device__ __forceinline__ unsigned orderedKeyL(float f)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-template <int G, int F>
-__global__ void __launch_bounds__(kLocalThreads)
+template <int G, int F, int MINB>
+__global__ void __launch_bounds__(kLocalThreads, MINB)
 local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, DevGrid dem, const int* __restrict__ validIdx,
                         int nTargets, LocalScratch scr, int xyInSmem, float* __restrict__ out, unsigned* __restrict__ minmax)
 {
@@ -487,11 +488,11 @@ static int localCtas()
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms * 2;
+    return sms * 4;
 }
 int localGroupsTotal(int groupLanes) { return localCtas() * (kLocalThreads / groupLanes); }
 
-template <int G, int F>
+template <int G, int F, int MINB>
 static cudaError_t launchT(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem, const int* validIdx,
                            int nTargets, const LocalScratch& scratch, float* out, unsigned* minmax, cudaStream_t s)
 {
@@ -502,7 +503,7 @@ static cudaError_t launchT(const LocalModel* dModel, const LocalStations& st, co
         xyInSmem = 1;
         smem += size_t(st.n) * sizeof(float2);
     }
-    auto k = local_detrending_kernel<G, F>;
+    auto k = local_detrending_kernel<G, F, MINB>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int perSm = 1, dev = 0, sms = 148;
@@ -510,7 +511,7 @@ static cudaError_t launchT(const LocalModel* dModel, const LocalStations& st, co
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k, kLocalThreads, smem);
     if (e != cudaSuccess) return e;
-    perSm = perSm < 1 ? 1 : (perSm > 2 ? 2 : perSm);
+    perSm = perSm < 1 ? 1 : (perSm > 4 ? 4 : perSm);
     const long long need = (nTargets + groupsPerCta - 1) / groupsPerCta;
     const int grid = (int)(need < (long long)sms * perSm ? need : (long long)sms * perSm);
     k<<<grid, kLocalThreads, smem, s>>>(dModel, st, dem, validIdx, nTargets, scratch, xyInSmem, out, minmax);
@@ -522,7 +523,12 @@ cudaError_t launchLocalDetrendingRaster(const LocalModel* dModel, const LocalSta
                                         int elevFunction, float* out, unsigned* minmax, cudaStream_t s)
 {
     if (nTargets <= 0) return cudaSuccess;
-#define PB_LOCAL_CASE(G_, F_) return launchT<G_, F_>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s)
+    static const int minb = getenv("PB_LOCAL_MINB") ? atoi(getenv("PB_LOCAL_MINB")) : 2;
+#define PB_LOCAL_CASE(G_, F_)                                                                               \
+    return minb == 2 ? launchT<G_, F_, 2>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s)     \
+         : minb == 3 ? launchT<G_, F_, 3>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s)     \
+         : minb == 4 ? launchT<G_, F_, 4>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s)     \
+                     : launchT<G_, F_, 1>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s)
     if (groupLanes == 16) {
         switch (elevFunction) {
         case PB_FIT_PIECEWISE_THREE: PB_LOCAL_CASE(16, PB_FIT_PIECEWISE_THREE);
