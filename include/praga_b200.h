@@ -227,6 +227,25 @@ int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_setti
 int pb_compute_residuals(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* observed,
                          const uint8_t* useForCv, float* residual, pb_cv_stats* stats);
 
+/* --- ordinary kriging (agrolib/interpolation/kriging.h:4-15, kriging.cpp). The reference keeps ONE system in file-static
+ * globals; here every krigingVariogram call yields a handle and many systems can live on a device.
+ *   pb_kriging_setup   <- krigingVariogram(pos[2n], val[n], n, mode, range, nugget, sill, slope)   kriging.cpp:97-202
+ *   pb_kriging_points  <- per target: krigingSetWeight(x, y) :211-264, krigingResult() :271-279, krigingRMSE() :287-295
+ *   pb_kriging_raster  <- the same over the valid cells (cell centres) of a resident DEM; estimate + RMSE grids
+ *   pb_kriging_free    <- krigingFreeMemory() :299-331
+ * The variogram parameters are inputs (their fit stays on the host; the reference declares krigingEstimateVariogram,
+ * interpolation.h:65-68, but never defines it). flags: PB_KRIGING_FLAG_FP64_DIRECT forces the exact FP64 formulation
+ * (reference elimination order); default = tensor-core variance path for the bounded models, FP64 for the linear one. */
+typedef int32_t pb_kriging_id;
+enum { PB_KRIGING_FLAG_FP64_DIRECT = 1 };
+int pb_kriging_setup(pb_context* ctx, const double* pos, const double* val, int n, int mode, double range, double nugget,
+                     double sill, double slope, int flags, pb_kriging_id* id);
+int pb_kriging_free(pb_context* ctx, pb_kriging_id id);
+int pb_kriging_uses_tensor_path(pb_context* ctx, pb_kriging_id id);      /* 1 tensor, 0 FP64 direct, -1 bad id */
+int pb_kriging_points(pb_context* ctx, pb_kriging_id id, const double* xy, int m, double* result, double* rmse /* may be NULL */);
+int pb_kriging_raster(pb_context* ctx, pb_kriging_id id, pb_raster_id dem, int rowBegin, int rowEnd,
+                      pb_raster_out* estimate, pb_raster_out* rmse /* may be NULL */);
+
 /* --- timing of the last call (device time measured with CUDA events on the engine's stream) ------ */
 typedef struct pb_timing {
     float h2d_ms, kernel_ms, d2h_ms, total_ms;

@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "common.cuh"
+#include "context.cuh"
 #include "local.cuh"
 
 namespace pb {
@@ -31,90 +31,21 @@ cudaError_t measurePipePeaks(cudaStream_t s, int sms, float* fp32Tflops, float* 
 using namespace pb;
 
 namespace {
-
 std::string g_createError;
-
-struct RasterEntry {
-    bool used = false;
-    pb_raster_header h{};
-    float* d = nullptr;
-    size_t n = 0;
-    // DEM role (built lazily): ascending list of valid cells + per-row offsets into it
-    int* validIdx = nullptr;
-    long long nValid = -1;
-    std::vector<long long> rowStart;   // nrRows + 1 prefix counts (host)
-};
-
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n)
-    {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-        if (e == cudaSuccess) cap = n;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-struct PinnedBuf {
-    unsigned char* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n)
-    {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMallocHost(&p, n);
-        if (e == cudaSuccess) cap = n;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
 }  // namespace
 
-struct pb_context {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool ownStream = true;
-    std::string err;
-    std::vector<RasterEntry> rasters;
-    DevBuf<unsigned char> dStations;
-    PinnedBuf hStations;
-    DevBuf<float> dOut;
-    int outInitRaster = -1;             // dOut currently holds the flag pattern of this raster id
-    DevBuf<unsigned char> dScratch;     // point targets
-    DevBuf<unsigned char> dLocalStations, dLocalScratch, dLocalModel;   // local-detrending raster (K2)
-    PinnedBuf hLocal;
-    int* dLocalError = nullptr;
-    int* hLocalError = nullptr;         // pinned
-    PinnedBuf hStage;                   // raster staging (H2D / D2H)
-    unsigned* dMinMax = nullptr;
-    unsigned* hMinMax = nullptr;        // pinned
-    cudaEvent_t ev[4]{};
-    pb_timing timing{};
-};
-
-namespace {
-
-int fail(pb_context* ctx, int code, const std::string& msg)
+namespace pb {
+int failCtx(pb_context* ctx, int code, const std::string& msg)
 {
     if (ctx) ctx->err = msg;
     else g_createError = msg;
     return code;
 }
-#define CUDA_TRY(ctx, call)                                                                              \
-    do {                                                                                                 \
-        cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(ctx, PB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
-    } while (0)
+}  // namespace pb
+
+namespace {
+
+int fail(pb_context* ctx, int code, const std::string& msg) { return pb::failCtx(ctx, code, msg); }
 
 // ---- meteoVariable classification (interpolation.cpp:1190-1234, 2540-2558) ----
 bool useDetrendingVar(int v)
@@ -318,7 +249,7 @@ void freeEntry(RasterEntry& e)
 }
 
 // valid-cell list of a DEM (cells with !isEqual(z, flag), interpolationCmd.cpp:377), built once per upload
-int ensureValidList(pb_context* ctx, RasterEntry& e)
+int ensureValidListImpl(pb_context* ctx, RasterEntry& e)
 {
     if (e.nValid >= 0) return PB_OK;
     const long long n = (long long)e.n;
@@ -566,7 +497,7 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     RasterEntry& dem = ctx->rasters[demId];
     if (rowEnd < 0) rowEnd = dem.h.nrRows;
     if (rowBegin < 0 || rowBegin > rowEnd || rowEnd > dem.h.nrRows) return fail(ctx, PB_ERR_INVALID, "bad row band");
-    int rc = ensureValidList(ctx, dem);
+    int rc = ensureValidListImpl(ctx, dem);
     if (rc) return rc;
 
     DevModel m;
@@ -674,6 +605,10 @@ void resetTiming(pb_context* ctx) { memset(&ctx->timing, 0, sizeof(ctx->timing))
 
 }  // namespace
 
+namespace pb {
+int ensureValidList(pb_context* ctx, RasterEntry& e) { return ensureValidListImpl(ctx, e); }
+}  // namespace pb
+
 extern "C" {
 
 const char* pb_version(void) { return "praga_b200 0.1 (sm_100a)"; }
@@ -723,6 +658,7 @@ void pb_destroy(pb_context* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& r : ctx->rasters) if (r.used) freeEntry(r);
+    pb::krigingDestroyAll(ctx->kriging);
     ctx->dLocalStations.release(); ctx->dLocalScratch.release(); ctx->dLocalModel.release(); ctx->hLocal.release();
     if (ctx->dLocalError) cudaFree(ctx->dLocalError);
     if (ctx->hLocalError) cudaFreeHost(ctx->hLocalError);
@@ -784,7 +720,7 @@ int pb_raster_valid_cells(pb_context* ctx, pb_raster_id id, int64_t* nValid)
     if (!ctx) return PB_ERR_INVALID;
     if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used) return fail(ctx, PB_ERR_INVALID, "bad raster id");
     cudaSetDevice(ctx->device);
-    int rc = ensureValidList(ctx, ctx->rasters[id]);
+    int rc = ensureValidListImpl(ctx, ctx->rasters[id]);
     if (rc) return rc;
     if (nValid) *nValid = ctx->rasters[id].nValid;
     return PB_OK;

@@ -1,0 +1,564 @@
+// kriging.cu — ordinary kriging: host set-up of the system, FP64 estimate kernel, FP64 direct variance path and the
+// C-ABI entry points. The tensor-core variance path lives in kriging_tc.cu.
+//
+// Reference (agrolib/interpolation/kriging.cpp; file-static state, one system at a time, not thread safe):
+//   krigingVariogram  :97-202   V = [[gamma(|s_i - s_j|), 1], [1^T, 0]], then matrixInversion(V) :28-81 (Gauss-Jordan, no pivoting)
+//   krigingSetWeight  :211-264  D_j = gamma(|p - s_j|), D_n = 1;  weight_i = sum_j Vinv[i][j] D_j   (i < n)
+//   krigingResult     :271-279  sum_i weight_i val_i
+//   krigingRMSE       :287-295  sqrt|sum_i weight_i D_i|   (the Lagrange term is NOT added)
+//   krigingFreeMemory :299-331
+//
+// What runs where:
+//   estimate  = u . D with u = Vinv[:, 0:n] val  (V is symmetric)  -> O(n) per cell, FP64 on the CUDA cores: the sum
+//               cancels from ~1e4 down to ~1e1, FP32 variogram values would already cost 2e-4.
+//   variance  = D^T Vinv[0:n, :] D, the only dense contraction. Two implementations:
+//     TENSOR (default, bounded variogram models): with the covariance C = sill - Gamma = L L^T (Cholesky, SPD thanks
+//        to the nugget), c = sill - D, M = L^-1, y = M c, z = M 1:
+//            sum_i weight_i D_i = sill - ( |y|^2 - (z.y)(z.y - 1) / |z|^2 )
+//        Whitening removes the cancellation of the raw form (sum|M c| ~ 40 against 6e4), so FP16x2-split operands with
+//        FP32 accumulation on tcgen05 hold ~4e-6 on the RMSE (measured); the raw form loses 2e-3 in FP32.
+//     DIRECT (FP64, exact reference formula): Vinv by the reference's own elimination order on the host, W = A D with a
+//        tiled FP64 kernel. Used for the linear model (no sill, C is not SPD), on request, and as the anchor in tests.
+#include <math.h>
+#include <omp.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "context.cuh"
+#include "kriging.cuh"
+
+namespace pb {
+
+// ---------------------------------------------------------------------------------------------------------
+// device: variogram models (kriging.cpp:160-192, 228-253)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double variogram(const KrigingParams& k, double h)
+{
+    const double tmp = h / k.range;
+    switch (k.mode) {
+    case PB_KRIGING_SPHERICAL:
+        return (h < k.range) ? k.nugget + k.sillNugget * (1.5 * tmp - 0.5 * tmp * tmp * tmp) : k.nugget + k.sillNugget;
+    case PB_KRIGING_EXPONENTIAL: return k.nugget + k.sillNugget * (1. - exp(-3. * tmp));
+    case PB_KRIGING_GAUSSIAN: return k.nugget + k.sillNugget * (1. - exp(-4. * tmp * tmp));
+    default: return k.nugget + k.slope * h;
+    }
+}
+
+__device__ __forceinline__ void targetXY(const KrigingTargets& t, long long c, double& x, double& y)
+{
+    if (t.xy) {
+        x = t.xy[2 * c];
+        y = t.xy[2 * c + 1];
+    } else {      // raster cell centre, gis::getUtmXYFromRowCol (gis/gis.cpp:806-810)
+        const int cell = t.validIdx[c];
+        const int row = cell / t.grid.nrCols, col = cell - row * t.grid.nrCols;
+        x = t.grid.llx + t.grid.cellSize * (col + 0.5);
+        y = t.grid.lly + t.grid.cellSize * (t.grid.nrRows - row - 0.5);
+    }
+}
+
+constexpr int kEstThreads = 128;
+constexpr int kEstTile = 1024;      // stations per shared-memory tile (x, y, u: 24 KiB)
+
+// estimate_c = sum_j u_j gamma(|p_c - s_j|) + u_n ; optionally stores D[j][c] (direct variance path)
+__global__ void __launch_bounds__(kEstThreads)
+kriging_estimate_kernel(KrigingParams k, const double* __restrict__ pos, const double* __restrict__ u, KrigingTargets t,
+                        long long c0, int m, double* __restrict__ est, double* __restrict__ D, int ldD)
+{
+    __shared__ double sx[kEstTile], sy[kEstTile], su[kEstTile];
+    const int c = blockIdx.x * kEstThreads + threadIdx.x;
+    double x = 0, y = 0;
+    if (c < m) targetXY(t, c0 + c, x, y);
+    double acc = 0;
+    for (int j0 = 0; j0 < k.n; j0 += kEstTile) {
+        const int nj = min(kEstTile, k.n - j0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < nj; j += kEstThreads) {
+            sx[j] = pos[2 * (j0 + j)];
+            sy[j] = pos[2 * (j0 + j) + 1];
+            su[j] = u[j0 + j];
+        }
+        __syncthreads();
+        if (c < m) {
+            for (int j = 0; j < nj; j++) {
+                const double dx = sx[j] - x, dy = sy[j] - y;
+                const double g = variogram(k, sqrt(dx * dx + dy * dy));
+                acc += su[j] * g;
+                if (D) D[(size_t)(j0 + j) * ldD + c] = g;
+            }
+        }
+    }
+    if (c < m) {
+        est[c] = acc + u[k.n];
+        if (D) D[(size_t)k.n * ldD + c] = 1.;
+    }
+}
+
+// direct variance: q_c = sum_i D[i][c] * (sum_j A[i][j] D[j][c]), i < n, j <= n. 64 x 64 output tile, K step 16,
+// 16 x 16 threads with a 4 x 4 register block each; the i-reduction is finished with one atomicAdd per (thread, cell).
+constexpr int kQT = 64, kQK = 16;
+__global__ void __launch_bounds__(256)
+kriging_quadform_kernel(const double* __restrict__ A, int n, int ldA, const double* __restrict__ D, int ldD, int m,
+                        double* __restrict__ q)
+{
+    __shared__ double sA[kQK][kQT + 1], sD[kQK][kQT + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = blockIdx.y * kQT, c0 = blockIdx.x * kQT;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0;
+    const int K = n + 1;
+    for (int k0 = 0; k0 < K; k0 += kQK) {
+        for (int e = threadIdx.x; e < kQK * kQT; e += 256) {
+            const int kk = e & (kQK - 1), ii = e >> 4;      // A tile: consecutive threads walk along j (contiguous)
+            const int i = i0 + ii, j = k0 + kk;
+            sA[kk][ii] = (i < n && j < K) ? A[(size_t)i * ldA + j] : 0.;
+            const int cc = e & (kQT - 1), k2 = e >> 6;      // D tile: consecutive threads walk along the cells
+            const int c = c0 + cc, j2 = k0 + k2;
+            sD[k2][cc] = (c < m && j2 < K) ? D[(size_t)j2 * ldD + c] : 0.;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kQK; kk++) {
+            double av[4], dv[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) av[a] = sA[kk][ty * 4 + a];
+#pragma unroll
+            for (int b = 0; b < 4; b++) dv[b] = sD[kk][tx * 4 + b];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b] += av[a] * dv[b];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const int c = c0 + tx * 4 + b;
+        if (c >= m) continue;
+        double s = 0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int i = i0 + ty * 4 + a;
+            if (i < n) s += acc[a][b] * D[(size_t)i * ldD + c];
+        }
+        atomicAdd(&q[c], s);
+    }
+}
+
+// epilogue shared by both variance paths: rmse = sqrt|q|; scatter to raster grids or to the point arrays
+__global__ void kriging_finish_kernel(KrigingTargets t, long long c0, int m, const double* __restrict__ est,
+                                      const double* __restrict__ q, double* __restrict__ outEst, double* __restrict__ outRmse,
+                                      float* __restrict__ gridEst, float* __restrict__ gridRmse)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const double r = q ? sqrt(fabs(q[c])) : 0.;
+    if (t.xy) {
+        outEst[c0 + c] = est[c];
+        if (outRmse) outRmse[c0 + c] = r;
+    } else {
+        const int cell = t.validIdx[c0 + c];
+        gridEst[cell] = float(est[c]);
+        if (gridRmse) gridRmse[cell] = float(r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host set-up
+// ---------------------------------------------------------------------------------------------------------
+static double variogramHost(const KrigingParams& k, double h)
+{
+    const double tmp = h / k.range;
+    switch (k.mode) {
+    case PB_KRIGING_SPHERICAL:
+        return (h < k.range) ? k.nugget + k.sillNugget * (1.5 * tmp - 0.5 * tmp * tmp * tmp) : k.nugget + k.sillNugget;
+    case PB_KRIGING_EXPONENTIAL: return k.nugget + k.sillNugget * (1. - exp(-3. * tmp));
+    case PB_KRIGING_GAUSSIAN: return k.nugget + k.sillNugget * (1. - exp(-4. * tmp * tmp));
+    default: return k.nugget + k.slope * h;
+    }
+}
+
+// matrixInversion (kriging.cpp:28-81): Gauss-Jordan without pivoting in the reference's elimination order; the row
+// loops are independent inside one elimination step, so they are spread over the host cores without changing a bit.
+static bool gaussJordanNoPivot(std::vector<double>& V, std::vector<double>& I, int dim)
+{
+    double* A = V.data();
+    double* inv = I.data();
+    std::fill(I.begin(), I.end(), 0.);
+    for (int i = 0; i < dim; i++) inv[size_t(i) * dim + i] = 1.;
+    for (int iter = 0; iter < dim - 1; iter++) {
+        const int first = iter + 1;
+        const double piv = A[size_t(iter) * dim + iter];
+#pragma omp parallel for schedule(static)
+        for (int i = first; i < dim; i++) {
+            const double r = A[size_t(i) * dim + iter] / piv;
+            A[size_t(i) * dim + iter] = 0.;
+            for (int j = first; j < dim; j++) A[size_t(i) * dim + j] -= r * A[size_t(iter) * dim + j];
+            for (int j = 0; j <= iter; j++) inv[size_t(i) * dim + j] -= r * inv[size_t(iter) * dim + j];
+        }
+    }
+    for (int iter = dim - 1; iter > 0; iter--) {
+        const double piv = A[size_t(iter) * dim + iter];
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < iter; i++) {
+            const double r = A[size_t(i) * dim + iter] / piv;
+            A[size_t(i) * dim + iter] = 0.;
+            for (int j = 0; j < dim; j++) inv[size_t(i) * dim + j] -= r * inv[size_t(iter) * dim + j];
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < dim; i++) {
+        const double d = A[size_t(i) * dim + i];
+        for (int j = 0; j < dim; j++) inv[size_t(i) * dim + j] /= d;
+    }
+    for (size_t e = 0; e < I.size(); e++)
+        if (!std::isfinite(inv[e])) return false;      // zero pivot (nugget == 0): the reference returns NaN estimates
+    return true;
+}
+
+// lower Cholesky factor in place (row-major, lower triangle); false if the matrix is not positive definite
+static bool choleskyLower(std::vector<double>& C, int n)
+{
+    double* a = C.data();
+    for (int k = 0; k < n; k++) {
+        const double d = a[size_t(k) * n + k];
+        if (!(d > 0.)) return false;
+        const double l = sqrt(d);
+        a[size_t(k) * n + k] = l;
+#pragma omp parallel for schedule(static)
+        for (int i = k + 1; i < n; i++) a[size_t(i) * n + k] /= l;
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int i = k + 1; i < n; i++) {
+            const double lik = a[size_t(i) * n + k];
+            double* ri = a + size_t(i) * n;
+            for (int j = k + 1; j <= i; j++) ri[j] -= lik * a[size_t(j) * n + k];
+        }
+    }
+    return true;
+}
+
+// M = L^-1 (lower triangular), row-major
+static void invertLower(const std::vector<double>& L, std::vector<double>& M, int n)
+{
+    std::fill(M.begin(), M.end(), 0.);
+    // column c of M solves L m = e_c by forward substitution; columns are independent
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int c = 0; c < n; c++) {
+        std::vector<double> m(n, 0.);
+        m[c] = 1. / L[size_t(c) * n + c];
+        for (int i = c + 1; i < n; i++) {
+            double s = 0;
+            const double* li = L.data() + size_t(i) * n;
+            for (int j = c; j < i; j++) s += li[j] * m[j];
+            m[i] = -s / li[i];
+        }
+        for (int i = c; i < n; i++) M[size_t(i) * n + c] = m[i];
+    }
+}
+
+void krigingFree(KrigingSystem* k)
+{
+    if (!k) return;
+    if (k->dPos) cudaFree(k->dPos);
+    if (k->dU) cudaFree(k->dU);
+    if (k->dA) cudaFree(k->dA);
+    if (k->dMhi) cudaFree(k->dMhi);
+    if (k->dMlo) cudaFree(k->dMlo);
+    if (k->dZ) cudaFree(k->dZ);
+    if (k->dWork) cudaFree(k->dWork);
+    delete k;
+}
+
+void krigingDestroyAll(std::vector<KrigingSystem*>& v)
+{
+    for (auto k : v) krigingFree(k);
+    v.clear();
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+namespace {
+
+int fail(pb_context* ctx, int code, const std::string& msg) { return pb::failCtx(ctx, code, msg); }
+
+KrigingSystem* systemOf(pb_context* ctx, pb_kriging_id id)
+{
+    if (id < 0 || id >= (int)ctx->kriging.size()) return nullptr;
+    return ctx->kriging[id];
+}
+
+// run estimate + variance over targets [0, m) in chunks; results to host doubles (points) or device grids (raster)
+int evaluate(pb_context* ctx, KrigingSystem* k, const KrigingTargets& t, long long m, bool wantRmse, double* dOutEst,
+             double* dOutRmse, float* gridEst, float* gridRmse)
+{
+    const int chunk = k->tensor ? kTcChunk : 8192;
+    const size_t ldD = chunk;
+    const size_t needD = (!k->tensor && wantRmse) ? size_t(k->n + 1) * ldD * sizeof(double) : 0;
+    const size_t need = needD + 2 * size_t(chunk) * sizeof(double);
+    if (k->workBytes < need) {
+        if (k->dWork) cudaFree(k->dWork);
+        k->dWork = nullptr;
+        k->workBytes = 0;
+        CUDA_TRY(ctx, cudaMalloc(&k->dWork, need));
+        k->workBytes = need;
+    }
+    double* dEst = reinterpret_cast<double*>(k->dWork);
+    double* dQ = dEst + chunk;
+    double* dD = needD ? dQ + chunk : nullptr;
+    for (long long c0 = 0; c0 < m; c0 += chunk) {
+        const int mc = (int)std::min<long long>(chunk, m - c0);
+        kriging_estimate_kernel<<<(mc + kEstThreads - 1) / kEstThreads, kEstThreads, 0, ctx->stream>>>(
+            k->params, k->dPos, k->dU, t, c0, mc, dEst, dD, (int)ldD);
+        ctx->timing.launches++;
+        if (wantRmse) {
+            if (k->tensor) {
+                CUDA_TRY(ctx, launchKrigingVarianceTc(*k, t, c0, mc, dQ, ctx->stream));
+                ctx->timing.launches++;
+            } else {
+                CUDA_TRY(ctx, cudaMemsetAsync(dQ, 0, sizeof(double) * mc, ctx->stream));
+                dim3 grid((mc + kQT - 1) / kQT, (k->n + kQT - 1) / kQT);
+                kriging_quadform_kernel<<<grid, 256, 0, ctx->stream>>>(k->dA, k->n, k->n + 1, dD, (int)ldD, mc, dQ);
+                ctx->timing.launches++;
+            }
+        }
+        kriging_finish_kernel<<<(mc + 255) / 256, 256, 0, ctx->stream>>>(t, c0, mc, dEst, wantRmse ? dQ : nullptr, dOutEst,
+                                                                          dOutRmse, gridEst, gridRmse);
+        ctx->timing.launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+/* krigingVariogram (kriging.cpp:97-202): builds and factorises the system for one set of stations and values */
+int pb_kriging_setup(pb_context* ctx, const double* pos, const double* val, int n, int mode, double range, double nugget,
+                     double sill, double slope, int flags, pb_kriging_id* id)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!pos || !val || !id || n < 1) return fail(ctx, PB_ERR_INVALID, "null argument / no stations");
+    cudaSetDevice(ctx->device);
+    KrigingSystem* k = new KrigingSystem();
+    k->n = n;
+    k->params.n = n;
+    k->params.mode = (mode >= PB_KRIGING_SPHERICAL && mode <= PB_KRIGING_GAUSSIAN) ? mode : PB_KRIGING_LINEAR;
+    k->params.range = range;
+    k->params.nugget = nugget;
+    k->params.sillNugget = sill - nugget;
+    k->params.slope = slope;
+    k->params.sill = nugget + (sill - nugget);          // the value the reference's bounded models reach (:171)
+    const int dim = n + 1;
+    std::vector<double> G(size_t(n) * n);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int i = 0; i < n; i++)
+        for (int j = i; j < n; j++) {
+            const double dx = pos[i * 2] - pos[j * 2], dy = pos[i * 2 + 1] - pos[j * 2 + 1];
+            const double g = variogramHost(k->params, sqrt(dx * dx + dy * dy));
+            G[size_t(i) * n + j] = g;
+            G[size_t(j) * n + i] = g;
+        }
+    std::vector<double> u(dim);
+    bool tensor = !(flags & PB_KRIGING_FLAG_FP64_DIRECT) && k->params.mode != PB_KRIGING_LINEAR;
+    std::vector<double> M;
+    if (tensor) {
+        // covariance form: C = sill - Gamma = L L^T
+        std::vector<double> C(size_t(n) * n);
+        const double c0 = k->params.sill;
+        for (size_t e = 0; e < C.size(); e++) C[e] = c0 - G[e];
+        double normC = 0;
+        for (size_t e = 0; e < C.size(); e++) normC += C[e] * C[e];
+        if (!choleskyLower(C, n)) tensor = false;     // not SPD (nugget 0, degenerate model): exact path instead
+        else {
+            M.resize(size_t(n) * n);
+            invertLower(C, M, n);
+            // condition guard: cond_F(C) <= |C|_F |M|_F^2. An ill-conditioned system (Gaussian model: the reference puts
+            // the nugget on gamma(0), so C is a pure Gaussian correlation matrix) makes the reference's own no-pivot
+            // elimination result rounding-dependent; only the same elimination order reproduces it -> exact path.
+            double normM = 0;
+            for (size_t e = 0; e < M.size(); e++) normM += M[e] * M[e];
+            if (!(sqrt(normC) * normM < 1.0e8)) tensor = false;
+        }
+        if (tensor) {
+            // z = M 1, t = M val; u1 = C^-1 (1 u2 - val), u2 = (1^T C^-1 val) / (1^T C^-1 1)   [V u = (val; 0)]
+            std::vector<double> z(n), tv(n);
+#pragma omp parallel for schedule(static)
+            for (int i = 0; i < n; i++) {
+                double sz = 0, st = 0;
+                const double* mi = M.data() + size_t(i) * n;
+                for (int j = 0; j <= i; j++) { sz += mi[j]; st += mi[j] * val[j]; }
+                z[i] = sz;
+                tv[i] = st;
+            }
+            double zz = 0, zt = 0;
+            for (int i = 0; i < n; i++) { zz += z[i] * z[i]; zt += z[i] * tv[i]; }
+            const double u2 = zt / zz;
+            // u1 = M^T (z u2 - t)
+#pragma omp parallel for schedule(static)
+            for (int j = 0; j < n; j++) {
+                double s = 0;
+                for (int i = j; i < n; i++) s += M[size_t(i) * n + j] * (z[i] * u2 - tv[i]);
+                u[j] = s;
+            }
+            u[n] = u2;
+            int rc = krigingUploadWhitened(*k, M, z, zz);
+            if (rc != 0) { krigingFree(k); return fail(ctx, PB_ERR_CUDA, "kriging: upload of the whitened system failed"); }
+        }
+    }
+    if (!tensor) {
+        std::vector<double> V(size_t(dim) * dim, 0.), I(size_t(dim) * dim);
+        for (int i = 0; i < n; i++) {
+            memcpy(&V[size_t(i) * dim], &G[size_t(i) * n], sizeof(double) * n);
+            V[size_t(i) * dim + n] = 1.;
+            V[size_t(n) * dim + i] = 1.;
+        }
+        if (!gaussJordanNoPivot(V, I, dim)) {
+            krigingFree(k);
+            return fail(ctx, PB_ERR_FIT, "kriging: singular system (zero pivot; the reference needs nugget > 0)");
+        }
+        // u_j = sum_i val_i Vinv[i][j]
+        for (int j = 0; j < dim; j++) {
+            double s = 0;
+            for (int i = 0; i < n; i++) s += val[i] * I[size_t(i) * dim + j];
+            u[j] = s;
+        }
+        if (cudaMalloc(&k->dA, sizeof(double) * size_t(n) * dim) != cudaSuccess ||
+            cudaMemcpy(k->dA, I.data(), sizeof(double) * size_t(n) * dim, cudaMemcpyHostToDevice) != cudaSuccess) {
+            krigingFree(k);
+            return fail(ctx, PB_ERR_CUDA, "kriging: device allocation failed");
+        }
+    }
+    k->tensor = tensor;
+    if (cudaMalloc(&k->dPos, sizeof(double) * 2 * n) != cudaSuccess || cudaMalloc(&k->dU, sizeof(double) * dim) != cudaSuccess ||
+        cudaMemcpy(k->dPos, pos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(k->dU, u.data(), sizeof(double) * dim, cudaMemcpyHostToDevice) != cudaSuccess) {
+        krigingFree(k);
+        return fail(ctx, PB_ERR_CUDA, "kriging: device allocation failed");
+    }
+    int slot = -1;
+    for (size_t i = 0; i < ctx->kriging.size(); i++) if (!ctx->kriging[i]) { slot = (int)i; break; }
+    if (slot < 0) { ctx->kriging.push_back(nullptr); slot = (int)ctx->kriging.size() - 1; }
+    ctx->kriging[slot] = k;
+    *id = slot;
+    return PB_OK;
+}
+
+/* krigingFreeMemory (kriging.cpp:299-331) */
+int pb_kriging_free(pb_context* ctx, pb_kriging_id id)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    KrigingSystem* k = systemOf(ctx, id);
+    if (!k) return fail(ctx, PB_ERR_INVALID, "bad kriging id");
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    krigingFree(k);
+    ctx->kriging[id] = nullptr;
+    return PB_OK;
+}
+
+int pb_kriging_uses_tensor_path(pb_context* ctx, pb_kriging_id id)
+{
+    KrigingSystem* k = ctx ? systemOf(ctx, id) : nullptr;
+    return k ? (k->tensor ? 1 : 0) : -1;
+}
+
+/* krigingSetWeight + krigingResult + krigingRMSE (kriging.cpp:211-295) for m target points (x0, y0, x1, y1, ...) */
+int pb_kriging_points(pb_context* ctx, pb_kriging_id id, const double* xy, int m, double* result, double* rmse)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    KrigingSystem* k = systemOf(ctx, id);
+    if (!k) return fail(ctx, PB_ERR_INVALID, "bad kriging id");
+    if (!xy || !result || m < 0) return fail(ctx, PB_ERR_INVALID, "null argument");
+    if (m == 0) return PB_OK;
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    double *dXY = nullptr, *dRes = nullptr, *dRm = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&dXY, sizeof(double) * 2 * m));
+    CUDA_TRY(ctx, cudaMalloc(&dRes, sizeof(double) * 2 * m));
+    dRm = dRes + m;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dXY, xy, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, ctx->stream));
+    KrigingTargets t{};
+    t.xy = dXY;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    int rc = evaluate(ctx, k, t, m, rmse != nullptr, dRes, dRm, nullptr, nullptr);
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (rc == PB_OK) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(result, dRes, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        if (rmse) CUDA_TRY(ctx, cudaMemcpyAsync(rmse, dRm, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    }
+    cudaFree(dXY);
+    cudaFree(dRes);
+    return rc;
+}
+
+/* kriging over the valid cells of a resident DEM (cell centres): estimate and (optionally) RMSE grids.
+ * estimate->data / rmse->data (or ->rows) receive the host grids; NULL data and rows = keep on the device only. */
+int pb_kriging_raster(pb_context* ctx, pb_kriging_id id, pb_raster_id demId, int rowBegin, int rowEnd,
+                      pb_raster_out* estimate, pb_raster_out* rmse)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    KrigingSystem* k = systemOf(ctx, id);
+    if (!k) return fail(ctx, PB_ERR_INVALID, "bad kriging id");
+    if (!estimate) return fail(ctx, PB_ERR_INVALID, "null argument");
+    if (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used)
+        return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    RasterEntry& dem = ctx->rasters[demId];
+    if (rowEnd < 0) rowEnd = dem.h.nrRows;
+    if (rowBegin < 0 || rowBegin > rowEnd || rowEnd > dem.h.nrRows) return fail(ctx, PB_ERR_INVALID, "bad row band");
+    int rc = ensureValidList(ctx, dem);
+    if (rc) return rc;
+    const size_t N = dem.n;
+    CUDA_TRY(ctx, ctx->dOut.reserve(2 * N));
+    ctx->outInitRaster = -1;
+    float* gEst = ctx->dOut.p;
+    float* gRm = rmse ? ctx->dOut.p + N : nullptr;
+    // both grids start as the DEM's flag
+    CUDA_TRY(ctx, launchFill(gEst, (long long)(rmse ? 2 * N : N), dem.h.flag, ctx->stream));
+    const long long t0 = dem.rowStart[rowBegin], t1 = dem.rowStart[rowEnd];
+    KrigingTargets t{};
+    t.validIdx = dem.validIdx + t0;
+    t.grid.data = dem.d;
+    t.grid.nrRows = dem.h.nrRows; t.grid.nrCols = dem.h.nrCols;
+    t.grid.llx = dem.h.llx; t.grid.lly = dem.h.lly; t.grid.cellSize = dem.h.cellSize; t.grid.invCellSize = dem.h.invCellSize;
+    t.grid.flag = dem.h.flag;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    rc = evaluate(ctx, k, t, t1 - t0, rmse != nullptr, nullptr, nullptr, gEst, gRm);
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (rc) return rc;
+    pb_raster_out* outs[2] = {estimate, rmse};
+    float* grids[2] = {gEst, gRm};
+    const int cols = dem.h.nrCols;
+    for (int g = 0; g < 2; g++) {
+        pb_raster_out* o = outs[g];
+        if (!o) continue;
+        o->nValid = t1 - t0;
+        if (o->data) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(o->data + size_t(rowBegin) * cols, grids[g] + size_t(rowBegin) * cols,
+                                          sizeof(float) * size_t(rowEnd - rowBegin) * cols, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->timing.d2h_bytes += (int64_t)(sizeof(float) * size_t(rowEnd - rowBegin) * cols);
+        } else if (o->rows) {
+            for (int r = rowBegin; r < rowEnd; r++)
+                CUDA_TRY(ctx, cudaMemcpyAsync(o->rows[r], grids[g] + size_t(r) * cols, sizeof(float) * cols,
+                                              cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->timing.d2h_bytes += (int64_t)(sizeof(float) * size_t(rowEnd - rowBegin) * cols);
+        }
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    ctx->timing.total_ms = ctx->timing.kernel_ms;
+    return PB_OK;
+}
+
+}  // extern "C"

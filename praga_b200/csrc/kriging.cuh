@@ -1,0 +1,56 @@
+// kriging.cuh — shared declarations of the ordinary-kriging path (kriging.cu: set-up, FP64 kernels, C ABI;
+// kriging_tc.cu: tcgen05 variance contraction)
+#pragma once
+#include <cuda_fp16.h>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pb {
+
+struct KrigingParams {
+    int n, mode;                       // mode = PB_KRIGING_*
+    double range, nugget, sillNugget, slope;
+    double sill;                       // nugget + sillNugget
+};
+
+// targets: explicit points (xy != NULL: x0, y0, x1, y1, ...) or cells of a resident raster (validIdx + grid)
+struct KrigingTargets {
+    const double* xy;
+    const int* validIdx;
+    DevGrid grid;
+};
+
+// geometry of the tcgen05 variance kernel (kriging_tc.cu)
+constexpr int kTcCells = 128;          // cells per CTA = MMA M
+constexpr int kTcNT = 128;             // stations i per MMA N tile
+constexpr int kTcBK = 64;              // stations j per K block
+constexpr int kTcPass = 512;           // stations i per pass = TMEM columns
+constexpr int kTcTileBytes = kTcNT * kTcBK * 2;     // one FP16 piece of one (i-tile, k-block) tile, canonical UMMA layout
+constexpr int kTcChunk = 1 << 19;      // targets per evaluate() chunk on the tensor path
+
+struct KrigingSystem {
+    int n = 0;
+    KrigingParams params{};
+    bool tensor = false;
+    double* dPos = nullptr;            // 2n
+    double* dU = nullptr;              // n + 1: estimate = sum_j u_j D_j + u_n
+    double* dA = nullptr;              // direct path: Vinv rows 0..n-1, n x (n+1)
+    // whitened system (tensor path): M = L^-1 of C = sill - Gamma, FP16 hi/lo pieces pre-tiled for bulk copies
+    unsigned char* dMhi = nullptr;     // tiles[(it * nKb + kb) * 2 + piece][kTcTileBytes]   (dMlo unused: pieces are interleaved)
+    unsigned char* dMlo = nullptr;
+    float* dZ = nullptr;               // z = M 1, padded to nPad
+    float2* dPosF = nullptr;           // not owned separately (inside dZ allocation)
+    int nPad = 0, nIt = 0, nKb = 0;
+    double zz = 0;                     // |z|^2
+    unsigned char* dWork = nullptr;
+    size_t workBytes = 0;
+};
+
+void krigingFree(KrigingSystem* k);
+int krigingUploadWhitened(KrigingSystem& k, const std::vector<double>& M, const std::vector<double>& z, double zz);
+cudaError_t launchKrigingVarianceTc(const KrigingSystem& k, const KrigingTargets& t, long long c0, int m, double* q,
+                                    cudaStream_t s);
+cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);     // idw_kernels.cu
+
+}  // namespace pb

@@ -59,6 +59,13 @@ def load_library():
     lib.pb_interpolate_points.argtypes = raster_args + [P(C.c_float), P(C.c_float), P(C.c_double), C.c_int, C.c_int,
                                                         P(C.c_float)]
     lib.pb_compute_residuals.argtypes = raster_args + [P(C.c_float), P(C.c_uint8), P(C.c_float), P(A.pb_cv_stats)]
+    lib.pb_kriging_setup.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double,
+                                     C.c_double, C.c_double, C.c_int, P(C.c_int32)]
+    lib.pb_kriging_free.argtypes = [C.c_void_p, C.c_int32]
+    lib.pb_kriging_uses_tensor_path.argtypes = [C.c_void_p, C.c_int32]
+    lib.pb_kriging_points.argtypes = [C.c_void_p, C.c_int32, P(C.c_double), C.c_int, P(C.c_double), P(C.c_double)]
+    lib.pb_kriging_raster.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_int, P(A.pb_raster_out),
+                                      P(A.pb_raster_out)]
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
                  "pb_cv_stats", "pb_timing"):
@@ -189,3 +196,42 @@ class Engine:
         self._check(self.lib.pb_compute_residuals(self.h, C.byref(st), C.byref(settings), variable, A.fptr(obs),
                                                   None if use is None else A.u8ptr(use), A.fptr(res), C.byref(stats)))
         return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}
+
+    # ---- ordinary kriging (kriging.h:4-15) ----
+    def kriging_setup(self, pos, val, mode, rng, nugget, sill, slope=0.0, fp64_direct=False):
+        """krigingVariogram (kriging.cpp:97-202). Returns a system id."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        kid = C.c_int32(-1)
+        self._check(self.lib.pb_kriging_setup(self.h, A.dptr(pos), A.dptr(val), val.shape[0], mode, rng, nugget, sill, slope,
+                                              1 if fp64_direct else 0, C.byref(kid)))
+        return kid.value
+
+    def kriging_free(self, kid):
+        self._check(self.lib.pb_kriging_free(self.h, kid))
+
+    def kriging_uses_tensor_path(self, kid):
+        return self.lib.pb_kriging_uses_tensor_path(self.h, kid) == 1
+
+    def kriging_points(self, kid, xy, want_rmse=True):
+        """krigingSetWeight + krigingResult + krigingRMSE (kriging.cpp:211-295) at m points."""
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1)
+        m = xy.shape[0] // 2
+        res = np.empty(m, dtype=np.float64)
+        rm = np.empty(m, dtype=np.float64)
+        self._check(self.lib.pb_kriging_points(self.h, kid, A.dptr(xy), m, A.dptr(res), A.dptr(rm) if want_rmse else None))
+        return res, (rm if want_rmse else None)
+
+    def kriging_raster(self, kid, dem_id, shape, row_begin=0, row_end=-1, want_rmse=True, device_only=False):
+        est = A.pb_raster_out()
+        rm = A.pb_raster_out()
+        e = r = None
+        if not device_only:
+            e = np.empty(shape, dtype=np.float32)
+            est.data = A.fptr(e)
+            if want_rmse:
+                r = np.empty(shape, dtype=np.float32)
+                rm.data = A.fptr(r)
+        self._check(self.lib.pb_kriging_raster(self.h, kid, dem_id, row_begin, row_end, C.byref(est),
+                                               C.byref(rm) if want_rmse else None))
+        return e, r, est.nValid
