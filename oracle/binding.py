@@ -24,6 +24,25 @@ def have_ref():
     return os.path.exists(REF_LIB)
 
 
+SHIM_LIB = os.path.join(HERE, "_ref", "libpraga_shim_test.so")
+
+
+def have_shim():
+    return os.path.exists(SHIM_LIB)
+
+
+def load_shim():
+    """oracle/_ref/libpraga_shim_test.so: the C++ host shim driven with reference objects (needs a B200 to run)."""
+    lib = C.CDLL(SHIM_LIB)
+    P = C.POINTER
+    lib.shim_raster.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_raster), P(A.pb_raster), C.c_int, C.c_int,
+                                P(A.pb_raster_out), C.c_char_p, C.c_int]
+    lib.shim_compute_residuals.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_uint8), P(C.c_float)]
+    lib.shim_kriging_points.argtypes = [P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, P(C.c_double), C.c_int, P(C.c_double), P(C.c_double)]
+    return lib
+
+
 def have_port():
     return os.path.exists(PORT_LIB)
 

@@ -1,0 +1,342 @@
+/* praga_b200_host.cpp — see praga_b200_host.h. Only flattening + C-ABI calls; no arithmetic of the path lives here. */
+#include "praga_b200_host.h"
+
+#include <string.h>
+#include <map>
+
+#include "commonConstants.h"
+#include "basicMath.h"
+#include "furtherMathFunctions.h"
+#include "interpolation.h"
+#include "interpolationConstants.h"
+
+#include "../../include/praga_b200.h"
+
+namespace pragab200 {
+namespace {
+
+int g_device = 0;
+std::map<int, pb_context*> g_ctx;
+std::string g_error;
+
+pb_context* context()
+{
+    auto it = g_ctx.find(g_device);
+    if (it != g_ctx.end()) return it->second;
+    pb_context* ctx = nullptr;
+    if (pb_create(g_device, &ctx) != PB_OK) {
+        g_error = pb_last_error(nullptr);
+        return nullptr;
+    }
+    g_ctx[g_device] = ctx;
+    return ctx;
+}
+
+bool failed(pb_context* ctx, int rc)
+{
+    if (rc == PB_OK) return false;
+    g_error = ctx ? pb_last_error(ctx) : "no context";
+    return true;
+}
+
+typedef double (*fit1d_t)(double, std::vector<double>&);
+int fitFunctionId(const std::function<double(double, std::vector<double>&)>& f)
+{
+    auto t = f.target<fit1d_t>();
+    if (t == nullptr) return PB_FIT_NONE;
+    if (*t == lapseRatePiecewise_two) return PB_FIT_PIECEWISE_TWO;
+    if (*t == lapseRatePiecewise_three_free) return PB_FIT_PIECEWISE_THREE_FREE;
+    if (*t == lapseRatePiecewise_three) return PB_FIT_PIECEWISE_THREE;
+    if (*t == functionLinear_intercept) return PB_FIT_LINEAR;
+    return PB_FIT_NONE;
+}
+
+pb_raster rasterOf(const gis::Crit3DRasterGrid& g)
+{
+    pb_raster r;
+    memset(&r, 0, sizeof(r));
+    r.h.nrRows = g.header->nrRows;
+    r.h.nrCols = g.header->nrCols;
+    r.h.cellSize = g.header->cellSize;
+    r.h.invCellSize = g.header->invCellSize;
+    r.h.llx = g.header->llCorner.x;
+    r.h.lly = g.header->llCorner.y;
+    r.h.flag = g.header->flag;
+    r.rows = g.value;
+    return r;
+}
+
+/* Crit3DInterpolationSettings (+ rainfall threshold) -> pb_settings; proxy grids collected into `grids` */
+bool flattenSettings(Crit3DInterpolationSettings& st, Crit3DMeteoSettings* meteoSettings, pb_settings& s,
+                     std::vector<pb_raster>& grids, const gis::Crit3DRasterGrid* dem)
+{
+    memset(&s, 0, sizeof(s));
+    const unsigned P = unsigned(st.getProxyNr());
+    if (P > PB_MAX_PROXY) { g_error = "more than PB_MAX_PROXY proxies"; return false; }
+    s.method = int(st.getInterpolationMethod());
+    s.useThermalInversion = st.getUseThermalInversion();
+    s.useTD = st.getUseTD();
+    s.useLocalDetrending = st.getUseLocalDetrending();
+    s.useGlocalDetrending = st.getUseGlocalDetrending();
+    s.useLapseRateCode = st.getUseLapseRateCode();
+    s.useBestDetrending = st.getUseBestDetrending();
+    s.useMultipleDetrending = st.getUseMultipleDetrending();
+    s.useDoNotRetrend = st.getUseDoNotRetrend();
+    s.useRetrendOnly = st.getUseRetrendOnly();
+    s.precipitationAllZero = st.getPrecipitationAllZero();
+    s.minPointsLocalDetrending = st.getMinPointsLocalDetrending();
+    s.topoDist_Kh = st.getTopoDist_Kh();
+    s.topoDist_maxKh = st.getTopoDist_maxKh();
+    s.minRegressionR2 = st.getMinRegressionR2();
+    s.maxHeightInversion = st.getMaxHeightInversion();
+    s.pointsBoundingBoxArea = st.getPointsBoundingBoxArea();
+    s.localRadius = st.getLocalRadius();
+    s.rainfallThreshold = meteoSettings ? meteoSettings->getRainfallThreshold() : 0.f;
+    s.climateLapseRate = float(NODATA);
+    std::vector<double> range = st.getPointsRange();
+    s.hasPointsRange = range.size() >= 2;
+    if (s.hasPointsRange) { s.pointsRangeMin = range[0]; s.pointsRangeMax = range[1]; }
+    s.nProxy = int(P);
+    Crit3DProxyCombination sel = st.getSelectedCombination(), cur = st.getCurrentCombination();
+    s.selectedUseThermalInversion = sel.getUseThermalInversion();
+    s.currentUseThermalInversion = cur.getUseThermalInversion();
+    for (unsigned i = 0; i < P; i++) {
+        s.selectedActive[i] = i < sel.getProxySize() && sel.isProxyActive(i);
+        s.currentActive[i] = i < cur.getProxySize() && cur.isProxyActive(i);
+        s.currentSignificant[i] = i < cur.getProxySize() && cur.isProxySignificant(i);
+        Crit3DProxy* p = st.getProxy(i);
+        pb_proxy& q = s.proxy[i];
+        q.kind = int(getProxyPragaName(p->getName()));
+        q.gridIndex = -1;
+        gis::Crit3DRasterGrid* g = p->getGrid();
+        if (g != nullptr && g->isLoaded) {
+            q.gridIndex = int(grids.size());
+            grids.push_back(rasterOf(*g));
+            if (dem != nullptr && g == dem) grids.back().rows = dem->value;    // same buffer => uploaded once
+        }
+        q.fittingFunction = int(p->getFittingFunctionName());
+        q.inversionIsSignificative = p->getInversionIsSignificative();
+        q.regressionR2 = p->getRegressionR2();
+        q.regressionSlope = p->getRegressionSlope();
+        q.regressionIntercept = p->getRegressionIntercept();
+        q.lapseRateH0 = p->getLapseRateH0();
+        q.lapseRateH1 = p->getLapseRateH1();
+        q.lapseRateT0 = p->getLapseRateT0();
+        q.lapseRateT1 = p->getLapseRateT1();
+        q.inversionLapseRate = p->getInversionLapseRate();
+        q.stdDevThreshold = p->getStdDevThreshold();
+        std::vector<double> fr = p->getFittingParametersRange();
+        const int np = int(fr.size() / 2);
+        if (np > PB_MAX_FIT_PARAMS) { g_error = "too many fitting parameters"; return false; }
+        q.nFitParams = np;
+        for (int j = 0; j < np; j++) { q.fitMin[j] = fr[j]; q.fitMax[j] = fr[np + j]; }
+        std::vector<int> fg = p->getFittingFirstGuess();
+        for (int j = 0; j < np && j < int(fg.size()); j++) q.fitFirstGuess[j] = fg[j];
+        std::vector<std::vector<double>> combos = p->getFirstGuessCombinations();
+        q.nFirstGuessCombinations = int(std::min<size_t>(combos.size(), PB_MAX_FIRST_GUESS));
+        for (int k = 0; k < q.nFirstGuessCombinations; k++)
+            for (size_t j = 0; j < combos[k].size() && j < PB_MAX_FIT_PARAMS; j++) q.firstGuessCombinations[k][j] = combos[k][j];
+    }
+    auto funcs = st.getFittingFunction();
+    auto params = st.getFittingParameters();
+    s.nFit = int(params.size());
+    s.nFitFunctions = int(funcs.size());
+    if (s.nFit > PB_MAX_PROXY || s.nFitFunctions > PB_MAX_PROXY) { g_error = "too many fitted functions"; return false; }
+    for (int i = 0; i < s.nFitFunctions; i++) s.fitFunction[i] = fitFunctionId(funcs[i]);
+    for (int i = 0; i < s.nFit; i++) {
+        s.fitNrParams[i] = int(std::min<size_t>(params[i].size(), PB_MAX_FIT_PARAMS));
+        for (int j = 0; j < s.fitNrParams[i]; j++) s.fitParams[i][j] = params[i][j];
+    }
+    return true;
+}
+
+struct FlatPoints {
+    std::vector<double> x, y, z;
+    std::vector<float> value, weight, proxy;
+    std::vector<int32_t> code, index;
+    std::vector<uint8_t> active;
+    pb_stations st;
+};
+
+void flattenPoints(const std::vector<Crit3DInterpolationDataPoint>& pts, int nProxy, FlatPoints& f)
+{
+    const size_t n = pts.size();
+    f.x.resize(n); f.y.resize(n); f.z.resize(n); f.value.resize(n); f.weight.resize(n); f.code.resize(n);
+    f.index.resize(n); f.active.resize(n);
+    f.proxy.assign(n * size_t(std::max(nProxy, 1)), float(NODATA));
+    for (size_t i = 0; i < n; i++) {
+        const Crit3DInterpolationDataPoint& p = pts[i];
+        f.x[i] = p.point->utm.x; f.y[i] = p.point->utm.y; f.z[i] = p.point->z;
+        f.value[i] = p.value;
+        f.weight[i] = p.regressionWeight;
+        f.code[i] = int(p.lapseRateCode);
+        f.index[i] = p.index;
+        f.active[i] = p.isActive;
+        for (int k = 0; k < nProxy && k < int(p.proxyValues.size()); k++) f.proxy[i * nProxy + k] = p.proxyValues[k];
+    }
+    memset(&f.st, 0, sizeof(f.st));
+    f.st.n = int(n);
+    f.st.nProxy = nProxy;
+    f.st.x = f.x.data(); f.st.y = f.y.data(); f.st.z = f.z.data();
+    f.st.value = f.value.data(); f.st.regressionWeight = f.weight.data(); f.st.lapseRateCode = f.code.data();
+    f.st.isActive = f.active.data(); f.st.proxyValues = f.proxy.data(); f.st.index = f.index.data();
+}
+
+bool rasterCall(bool local, std::vector<Crit3DInterpolationDataPoint>& points, Crit3DInterpolationSettings& settings,
+                Crit3DMeteoSettings* meteoSettings, gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster,
+                meteoVariable variable)
+{
+    // output = DEM header, every cell = flag (interpolationCmd.cpp:357 -> gis.cpp:357-363)
+    if (!outputGrid->initializeGrid(raster)) return false;
+    pb_context* ctx = context();
+    if (!ctx) return false;
+    pb_settings s;
+    std::vector<pb_raster> grids;
+    if (!flattenSettings(settings, meteoSettings, s, grids, &raster)) return false;
+    FlatPoints fp;
+    flattenPoints(points, s.nProxy, fp);
+    pb_raster dem = rasterOf(raster);
+    pb_raster_out out;
+    memset(&out, 0, sizeof(out));
+    out.rows = outputGrid->value;
+    const int rc = local ? pb_local_detrending_raster(ctx, &fp.st, &s, int(variable), &dem, grids.data(), int(grids.size()), 0, -1, &out)
+                         : pb_interpolation_raster(ctx, &fp.st, &s, int(variable), &dem, grids.data(), int(grids.size()), 0, -1, &out);
+    if (failed(ctx, rc)) return false;       // incl. PB_ERR_NO_VALID_CELL <=> updateMinMaxRasterGrid false (gis.cpp:601-603)
+    outputGrid->minimum = out.minimum;
+    outputGrid->maximum = out.maximum;
+    if (!outputGrid->colorScale->isFixedRange()) outputGrid->colorScale->setRange(out.minimum, out.maximum);   // gis.cpp:606-611
+    return true;
+}
+
+/* kriging: the reference API is stateful (one system, file-static); keep that shape */
+pb_kriging_id g_kriging = -1;
+std::vector<double> g_lastXY(2);
+double g_lastResult = NODATA, g_lastRmse = NODATA;
+
+}  // namespace
+
+bool setDevice(int device)
+{
+    if (device < 0 || device >= pb_device_count()) { g_error = "device out of range"; return false; }
+    g_device = device;
+    return true;
+}
+const std::string& lastError() { return g_error; }
+
+bool interpolationRaster(std::vector<Crit3DInterpolationDataPoint>& dataPoints,
+                         Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                         gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster, meteoVariable variable,
+                         bool /*isParallelComputing*/)
+{
+    return rasterCall(false, dataPoints, interpolationSettings, meteoSettings, outputGrid, raster, variable);
+}
+
+bool interpolationRasterLocalDetrending(std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                                        Crit3DInterpolationSettings& interpolationSettings,
+                                        Crit3DMeteoSettings* meteoSettings, gis::Crit3DRasterGrid* outputGrid,
+                                        gis::Crit3DRasterGrid& raster, meteoVariable variable)
+{
+    // Project::interpolationDemLocalDetrending: current combination = selected combination before the loop (project.cpp:3172-3173)
+    interpolationSettings.setCurrentCombination(interpolationSettings.getSelectedCombination());
+    return rasterCall(true, interpolationPoints, interpolationSettings, meteoSettings, outputGrid, raster, variable);
+}
+
+bool computeResiduals(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoPoints,
+                      const std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                      Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                      bool excludeOutsideDem, bool excludeSupplemental)
+{
+    if (myVar == noMeteoVar) return false;
+    pb_context* ctx = context();
+    if (!ctx) return false;
+    pb_settings s;
+    std::vector<pb_raster> grids;
+    if (!flattenSettings(interpolationSettings, meteoSettings, s, grids, nullptr)) return false;
+    FlatPoints fp;
+    flattenPoints(interpolationPoints, s.nProxy, fp);
+    // targets = the meteo points that computeResiduals would evaluate (spatialControl.cpp:113-121)
+    std::vector<float> x, y, est;
+    std::vector<double> pv;
+    std::vector<size_t> who;
+    for (size_t i = 0; i < meteoPoints.size(); i++) {
+        meteoPoints[i].residual = NODATA;
+        if (!meteoPoints[i].active) continue;
+        bool isValid = (!excludeSupplemental || checkLapseRateCode(meteoPoints[i].lapseRateCode, interpolationSettings.getUseLapseRateCode(), false));
+        isValid = (isValid && (!excludeOutsideDem || meteoPoints[i].isInsideDem));
+        if (!(isValid && meteoPoints[i].quality == quality::accepted)) continue;
+        who.push_back(i);
+        x.push_back(float(meteoPoints[i].point.utm.x));
+        y.push_back(float(meteoPoints[i].point.utm.y));
+        std::vector<double> v = meteoPoints[i].getProxyValues();
+        for (int k = 0; k < s.nProxy; k++) pv.push_back(k < int(v.size()) ? v[k] : double(NODATA));
+    }
+    est.resize(who.size());
+    if (!who.empty()) {
+        const int rc = pb_interpolate_points(ctx, &fp.st, &s, int(myVar), x.data(), y.data(), pv.data(), int(who.size()), 0, est.data());
+        if (failed(ctx, rc)) return false;
+    }
+    for (size_t k = 0; k < who.size(); k++) {
+        Crit3DMeteoPoint& mp = meteoPoints[who[k]];
+        float myValue = mp.currentValue, interpolatedValue = est[k];
+        if (myVar == precipitation || myVar == dailyPrecipitation) {
+            if (myValue != NODATA && myValue < meteoSettings->getRainfallThreshold()) myValue = 0.;
+            if (interpolatedValue != NODATA && interpolatedValue < meteoSettings->getRainfallThreshold()) interpolatedValue = 0.;
+        }
+        if ((interpolatedValue != NODATA) && (myValue != NODATA)) mp.residual = myValue - interpolatedValue;
+    }
+    return true;
+}
+
+bool krigingVariogram(double* myPos, double* myVal, int nrItems, short myMode, double myRange, double myNugget,
+                      double mySill, double mySlope)
+{
+    pb_context* ctx = context();
+    if (!ctx) return false;
+    krigingFreeMemory();
+    return !failed(ctx, pb_kriging_setup(ctx, myPos, myVal, nrItems, myMode, myRange, myNugget, mySill, mySlope, 0, &g_kriging));
+}
+
+bool krigingSetWeight(double x_p, double y_p)
+{
+    pb_context* ctx = context();
+    if (!ctx || g_kriging < 0) return false;
+    g_lastXY[0] = x_p;
+    g_lastXY[1] = y_p;
+    return !failed(ctx, pb_kriging_points(ctx, g_kriging, g_lastXY.data(), 1, &g_lastResult, &g_lastRmse));
+}
+
+double krigingResult() { return g_lastResult; }
+double krigingRMSE() { return g_lastRmse; }
+
+void krigingFreeMemory()
+{
+    if (g_kriging >= 0) {
+        pb_context* ctx = context();
+        if (ctx) pb_kriging_free(ctx, g_kriging);
+        g_kriging = -1;
+    }
+}
+
+bool krigingRaster(gis::Crit3DRasterGrid& raster, gis::Crit3DRasterGrid* estimateGrid, gis::Crit3DRasterGrid* rmseGrid)
+{
+    pb_context* ctx = context();
+    if (!ctx || g_kriging < 0 || estimateGrid == nullptr) return false;
+    if (!estimateGrid->initializeGrid(raster)) return false;
+    if (rmseGrid && !rmseGrid->initializeGrid(raster)) return false;
+    pb_raster dem = rasterOf(raster);
+    pb_raster_id id = -1;
+    if (failed(ctx, pb_raster_upload(ctx, &dem, &id))) return false;
+    pb_raster_out e, r;
+    memset(&e, 0, sizeof(e));
+    memset(&r, 0, sizeof(r));
+    e.rows = estimateGrid->value;
+    if (rmseGrid) r.rows = rmseGrid->value;
+    const int rc = pb_kriging_raster(ctx, g_kriging, id, 0, -1, &e, rmseGrid ? &r : nullptr);
+    pb_raster_free(ctx, id);
+    if (failed(ctx, rc)) return false;
+    gis::updateMinMaxRasterGrid(estimateGrid);
+    if (rmseGrid) gis::updateMinMaxRasterGrid(rmseGrid);
+    return true;
+}
+
+}  // namespace pragab200

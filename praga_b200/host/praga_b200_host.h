@@ -1,0 +1,62 @@
+/*
+ * praga_b200_host.h — the C++ host side of the drop-in: the reference's own signatures for the gridding hot path,
+ * implemented by flattening the reference objects into the POD descriptors of include/praga_b200.h and calling
+ * libpraga_b200.so. Compiled against the reference's headers (agrolib/{gis,meteo,interpolation,mathFunctions}); a
+ * maintainer links this translation unit instead of the reference bodies.
+ *
+ * Same names, argument meaning and error behaviour as the reference:
+ *   pragab200::interpolationRaster            <- agrolib/project/interpolationCmd.h:73-75 (.cpp:353-394)
+ *   pragab200::interpolationRasterLocalDetrending <- loop of Project::interpolationDemLocalDetrending, project.cpp:3208-3253
+ *   pragab200::computeResiduals               <- agrolib/interpolation/spatialControl.h:30 (.cpp:97-155)
+ *   pragab200::krigingVariogram / krigingSetWeight / krigingResult / krigingRMSE / krigingFreeMemory
+ *                                             <- agrolib/interpolation/kriging.h:4-15
+ *   pragab200::krigingRaster                  (new: the reference never wired kriging into a raster loop)
+ * A GPU failure returns false (there is no CPU fallback); pragab200::lastError() gives the message.
+ */
+#ifndef PRAGA_B200_HOST_H
+#define PRAGA_B200_HOST_H
+
+#include <string>
+#include <vector>
+
+#include "gis.h"
+#include "meteo.h"
+#include "meteoPoint.h"
+#include "interpolationSettings.h"
+#include "interpolationPoint.h"
+
+namespace pragab200 {
+
+/* device used by the calls below (default 0); one engine context per device is created lazily and kept */
+bool setDevice(int device);
+const std::string& lastError();
+
+bool interpolationRaster(std::vector<Crit3DInterpolationDataPoint>& dataPoints,
+                         Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                         gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster, meteoVariable variable,
+                         bool isParallelComputing);
+
+/* interpolationPoints are the points of checkAndPassDataToInterpolation (NOT detrended); settings need
+ * useLocalDetrending + useMultipleDetrending and the points range (setPointsRange) */
+bool interpolationRasterLocalDetrending(std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                                        Crit3DInterpolationSettings& interpolationSettings,
+                                        Crit3DMeteoSettings* meteoSettings, gis::Crit3DRasterGrid* outputGrid,
+                                        gis::Crit3DRasterGrid& raster, meteoVariable variable);
+
+bool computeResiduals(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoPoints,
+                      const std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                      Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                      bool excludeOutsideDem, bool excludeSupplemental);
+
+bool krigingVariogram(double* myPos, double* myVal, int nrItems, short myMode, double myRange, double myNugget,
+                      double mySill, double mySlope);
+bool krigingSetWeight(double x_p, double y_p);
+double krigingResult();
+double krigingRMSE();
+void krigingFreeMemory();
+/* batched form: estimate and RMSE for every valid cell (cell centres) of `raster` with the current system */
+bool krigingRaster(gis::Crit3DRasterGrid& raster, gis::Crit3DRasterGrid* estimateGrid, gis::Crit3DRasterGrid* rmseGrid);
+
+}  // namespace pragab200
+
+#endif

@@ -1,0 +1,111 @@
+"""The C++ host shim (praga_b200/host/praga_b200_host.cpp) keeps the reference's own signatures — interpolationRaster(),
+computeResiduals(), kriging.h — on top of the C ABI. oracle/_ref/libpraga_shim_test.so drives it with REAL reference
+objects (Crit3DInterpolationSettings, Crit3DInterpolationDataPoint, gis::Crit3DRasterGrid, Crit3DMeteoPoint) and the
+results are compared with the reference's CPU code: this is the drop-in as a PRAGA maintainer would use it."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from praga_b200 import _abi as A
+from praga_b200 import synthetic as syn
+
+TOL = 1e-4
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def shim(built_lib):
+    from oracle import binding
+    import os
+    if os.path.isdir("/root/reference/agrolib"):
+        binding.build("shim")
+    if not binding.have_shim():
+        pytest.skip("oracle/_ref/libpraga_shim_test.so not available")
+    return binding.load_shim()
+
+
+def shim_raster(shim, st, s, var, dem, grids, local=False):
+    stp, d = st.as_pb(), dem.as_pb()
+    g = (A.pb_raster * max(1, len(grids)))()
+    for i, r in enumerate(grids):
+        g[i] = r.as_pb()
+    out = np.empty(dem.shape, dtype=np.float32)
+    o = A.pb_raster_out()
+    o.data = A.fptr(out)
+    err = C.create_string_buffer(512)
+    rc = shim.shim_raster(C.byref(stp), C.byref(s), var, C.byref(d), g, len(grids), int(local), C.byref(o), err, 512)
+    return rc == A.PB_OK, out, o.minimum, o.maximum, err.value.decode()
+
+
+def test_shim_interpolation_raster_multiple_detrending(shim, ref):
+    dem = syn.make_dem(160, 190)
+    urban = syn.make_urban(160, 190)
+    st = syn.make_stations(dem, 150, proxies=(dem, urban))
+    s = syn.settings_multiple_detrending()
+    syn.set_points_range(s, st)
+    ok, keep = ref.pre_interpolation(st, s, A.airTemperature, (dem, urban))
+    st = st.subset(keep)
+    okc, gc, mnc, mxc, _, _ = ref.interpolation_raster(st, s, A.airTemperature, dem, (dem, urban))
+    okg, gg, mng, mxg, err = shim_raster(shim, st, s, A.airTemperature, dem, (dem, urban))
+    assert okg == okc, err
+    assert np.array_equal(gg == np.float32(dem.flag), gc == np.float32(dem.flag))
+    m = gc != np.float32(dem.flag)
+    assert np.abs(gg[m].astype(np.float64) - gc[m]).max() <= TOL
+    assert abs(mng - mnc) <= TOL and abs(mxg - mxc) <= TOL
+
+
+def test_shim_local_detrending_raster(shim, ref):
+    dem = syn.make_dem(50, 60, cell_size=8000.0)
+    urban = syn.make_urban(50, 60, cell_size=8000.0)
+    st = syn.make_stations(dem, 1100, proxies=(dem, urban))
+    s = syn.settings_multiple_detrending()
+    s.useLocalDetrending = 1
+    s.minPointsLocalDetrending = 20
+    syn.set_points_range(s, st)
+    okc, gc, *_ = ref.local_detrending_raster(st, s, A.airTemperature, dem, (dem, urban), threads=8)
+    okg, gg, _, _, err = shim_raster(shim, st, s, A.airTemperature, dem, (dem, urban), local=True)
+    assert okg == okc, err
+    assert np.array_equal(gg == np.float32(dem.flag), gc == np.float32(dem.flag))
+    m = gc != np.float32(dem.flag)
+    assert np.abs(gg[m].astype(np.float64) - gc[m]).max() <= TOL
+
+
+def test_shim_all_flag_dem_returns_false(shim, ref):
+    dem = syn.make_dem(24, 24)
+    dem.data[:] = dem.flag
+    st = syn.make_stations(syn.make_dem(24, 24), 20, variable="humidity")
+    ok, gg, *_ = shim_raster(shim, st, A.default_settings(), A.airRelHumidity, dem, ())
+    assert ok is False and np.all(gg == np.float32(dem.flag))
+
+
+def test_shim_compute_residuals(shim, ref):
+    dem = syn.make_dem(150, 150, seed=61)
+    urban = syn.make_urban(150, 150)
+    st = syn.make_stations(dem, 250, proxies=(dem, urban), seed=62)
+    raw = st.value.copy()
+    s = syn.settings_multiple_detrending()
+    syn.set_points_range(s, st)
+    ok, keep = ref.pre_interpolation(st, s, A.airTemperature, (dem, urban))
+    assert keep.all()
+    want, _ = ref.compute_residuals(st, s, A.airTemperature, raw)
+    got = np.empty(st.n, dtype=np.float32)
+    stp = st.as_pb()
+    rc = shim.shim_compute_residuals(C.byref(stp), C.byref(s), A.airTemperature, A.fptr(raw), None, A.fptr(got))
+    assert rc == A.PB_OK
+    assert np.abs(got.astype(np.float64) - want).max() <= TOL
+
+
+def test_shim_kriging_stateful_api(shim, ref):
+    rng = np.random.default_rng(8)
+    n, m = 120, 40
+    pos = rng.random((n, 2)) * 2.0e5 + np.array([5.0e5, 4.8e6])
+    val = rng.normal(10, 3, n)
+    xy = rng.random((m, 2)) * 2.0e5 + np.array([5.0e5, 4.8e6])
+    ok, want, want_rm, _, _ = ref.kriging_points(pos, val, A.KRIGING_SPHERICAL, 7.0e4, 0.1, 4.0, 0.0, xy)
+    res, rm = np.empty(m), np.empty(m)
+    p, v, q = pos.reshape(-1).copy(), val.copy(), xy.reshape(-1).copy()
+    rc = shim.shim_kriging_points(A.dptr(p), A.dptr(v), n, A.KRIGING_SPHERICAL, 7.0e4, 0.1, 4.0, 0.0, A.dptr(q), m, A.dptr(res),
+                                  A.dptr(rm))
+    assert rc == A.PB_OK
+    assert np.abs(res - want).max() <= TOL and np.abs(rm - want_rm).max() <= TOL
