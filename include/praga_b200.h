@@ -196,6 +196,18 @@ int pb_interpolation_raster_device(pb_context* ctx, const pb_stations* st, const
                                    pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids,
                                    int rowBegin, int rowEnd, pb_raster_out* out);
 
+/* --- preInterpolation (agrolib/interpolation/interpolation.cpp:2444-2499): the per-time-step station-space fit.
+ * GPU branch: multipleDetrendingMain (:1832-1859; weighted Levenberg-Marquardt fits of the elevation function from
+ * 16-31 first guesses and of the other proxies) and checkPrecipitationZero (:1173). One time step cannot fill a GPU, so
+ * the batched form runs T independent time steps (the reference's hourly/daily batch drivers) that share the station set
+ * st (positions, proxies, codes): values = T x st->n; pointsRange = T x {min, max} as setPointsRange would receive
+ * (NULL: float min/max of each row, spatialControl.cpp:533-564); outputs: detrended T x n, keep T x n (1 = the point
+ * is still in myPoints, interpolation.cpp:2230), fitted[T] = the settings as the reference leaves them. */
+int pb_pre_interpolation_batch(pb_context* ctx, const pb_stations* st, const float* values, int T, const pb_settings* s,
+                               int variable, const double* pointsRange, float* detrended, uint8_t* keep, pb_settings* fitted);
+/* one time step, in place: st->value is detrended, *s receives the fit (same contract as the reference call) */
+int pb_pre_interpolation(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, uint8_t* keep);
+
 /* --- local-detrending raster: the loop of Project::interpolationDemLocalDetrending (agrolib/project/project.cpp:3208-3253),
  * which the reference inlines in its Qt-bound Project class instead of going through interpolationRaster. Per valid
  * cell: localSelection (interpolation.cpp:1087-1170), preInterpolation on the subset (multipleDetrendingMain :1832,

@@ -11,6 +11,7 @@
 
 #include "context.cuh"
 #include "local.cuh"
+#include "pre.cuh"
 
 namespace pb {
 // idw_kernels.cu
@@ -337,19 +338,22 @@ int firstGuessCombinations(const pb_proxy& p, double out[PB_MAX_FIRST_GUESS][PB_
 // pb_settings -> LocalModel: selected combination, setMultipleDetrendingHeightTemperatureRange (interpolation.cpp:1506-1553),
 // setFittingParameters_elevation / _otherProxies (:1625-1728), localSelection constants (:1092-1099, :1152)
 int buildLocalModel(pb_context* ctx, const pb_settings* s, int variable, int nStations, const pb_raster_id* proxyGridIds,
-                    int nProxyGrids, LocalModel& m)
+                    int nProxyGrids, LocalModel& m, bool isLocal = true, const double* range = nullptr)
 {
     memset(&m, 0, sizeof(m));
     if (s->nProxy < 0 || s->nProxy > PB_MAX_PROXY) return fail(ctx, PB_ERR_INVALID, "settings.nProxy out of range");
-    if (!useDetrendingVar(variable) || !s->useLocalDetrending)      // project.cpp:3155
-        return fail(ctx, PB_ERR_INVALID, "local detrending needs useLocalDetrending and a detrending variable");
-    if (!s->useMultipleDetrending)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "local detrending without multiple detrending is outside the hot-path scope (DESIGN.md)");
-    if (s->method != PB_METHOD_IDW)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the GPU path (shepard: DESIGN.md)");
+    if (isLocal) {
+        if (!useDetrendingVar(variable) || !s->useLocalDetrending)      // project.cpp:3155
+            return fail(ctx, PB_ERR_INVALID, "local detrending needs useLocalDetrending and a detrending variable");
+        if (!s->useMultipleDetrending)
+            return fail(ctx, PB_ERR_UNSUPPORTED, "local detrending without multiple detrending is outside the hot-path scope (DESIGN.md)");
+        if (s->method != PB_METHOD_IDW)
+            return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the GPU path (shepard: DESIGN.md)");
+    }
     if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending is out of scope (DESIGN.md)");
-    if (!s->hasPointsRange)     // setMultipleDetrendingHeightTemperatureRange returns false (:1508)
+    if (!s->hasPointsRange && !range)     // setMultipleDetrendingHeightTemperatureRange returns false (:1508)
         return fail(ctx, PB_ERR_FIT, "couldn't set temperature ranges for height proxy (points range not set)");
+    const double rangeMin = range ? range[0] : s->pointsRangeMin, rangeMax = range ? range[1] : s->pointsRangeMax;
     m.nProxy = s->nProxy;
     m.elevationPos = -1;
     for (int i = 0; i < s->nProxy; i++) if (s->proxy[i].kind == PB_PROXY_HEIGHT) m.elevationPos = i;
@@ -387,8 +391,8 @@ int buildLocalModel(pb_context* ctx, const pb_settings* s, int variable, int nSt
                 return fail(ctx, PB_ERR_FIT, "elevation proxy needs a piecewise fitting function (interpolation.cpp:1640-1660)");
             const int want = f == PB_FIT_PIECEWISE_TWO ? 4 : (f == PB_FIT_PIECEWISE_THREE ? 5 : 6);
             if (e.nFitParams != want) return fail(ctx, PB_ERR_FIT, "wrong number of fitting parameters for the elevation proxy");
-            e.fitMin[1] = s->pointsRangeMin - 2;     // MIN_T - 2 / MAX_T + 6 (:1520-1545)
-            e.fitMax[1] = s->pointsRangeMax + 6;
+            e.fitMin[1] = rangeMin - 2;     // MIN_T - 2 / MAX_T + 6 (:1520-1545)
+            e.fitMax[1] = rangeMax + 6;
             m.elevFunction = f;
             m.elevNPar = want;
             for (int j = 0; j < want; j++) {
@@ -481,6 +485,135 @@ int launchLocal(pb_context* ctx, const pb_stations* st, const pb_settings* s, in
                                               dem.validIdx + t0, nTargets, scr, groupLanes, m.elevFunction, ctx->dOut.p,
                                               ctx->dMinMax, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hLocalError, ctx->dLocalError, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return PB_OK;
+}
+
+void resetTiming(pb_context* ctx) { memset(&ctx->timing, 0, sizeof(ctx->timing)); }
+
+// ---- preInterpolation on the device (K3), multiple-detrending branch ----
+struct PreBatchBuffers {
+    std::vector<LocalModel> models;
+    std::vector<PreFit> fits;
+};
+
+int preInterpolationBatchImpl(pb_context* ctx, const pb_stations* st, const float* values, int T, const pb_settings* s,
+                              int variable, const double* pointsRange, float* detrended, uint8_t* keep, pb_settings* fitted)
+{
+    if (!st || !values || !s || !detrended || T < 0) return fail(ctx, PB_ERR_INVALID, "null argument");
+    const int n = st->n;
+    if (T == 0 || n == 0) return PB_OK;
+    if (!useDetrendingVar(variable)) return fail(ctx, PB_ERR_INVALID, "not a detrending variable (interpolation.cpp:1205)");
+    if (!s->useMultipleDetrending)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "batched preInterpolation covers multiple detrending; classic detrending: pb_pre_interpolation");
+    if (s->useLocalDetrending) return fail(ctx, PB_ERR_INVALID, "local detrending fits per cell (pb_local_detrending_raster)");
+    if (s->useBestDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "optimalDetrending is not on the GPU path (DESIGN.md)");
+    resetTiming(ctx);
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    std::vector<LocalModel> models(T);
+    for (int t = 0; t < T; t++) {
+        double range[2];
+        if (pointsRange) { range[0] = pointsRange[2 * t]; range[1] = pointsRange[2 * t + 1]; }
+        else {      // passDataToInterpolation (spatialControl.cpp:533-551): float min / max of the values
+            float mn = values[size_t(t) * n], mx = mn;
+            for (int i = 1; i < n; i++) {
+                const float v = values[size_t(t) * n + i];
+                mn = v < mn ? v : mn;
+                mx = v > mx ? v : mx;
+            }
+            range[0] = mn; range[1] = mx;
+        }
+        int rc = buildLocalModel(ctx, s, variable, n, nullptr, 0, models[t], false, range);
+        if (rc) return rc;
+    }
+    LocalStations ds{};
+    int rc = stageLocalStations(ctx, st, ds);
+    if (rc) return rc;
+    const int groupLanes = models[0].nFirstGuess <= 16 ? 16 : 32;
+    LocalScratch scr{};
+    scr.cap = n;
+    scr.perGroup = preScratchBytesPerGroup(scr.cap);
+    const size_t groups = size_t(preGroupsTotal(groupLanes, T));
+    const size_t offModels = 0, offFits = offModels + sizeof(LocalModel) * T, offVal = (offFits + sizeof(PreFit) * T + 15) / 16 * 16,
+                 offDet = offVal + sizeof(float) * size_t(T) * n, offKeep = offDet + sizeof(float) * size_t(T) * n,
+                 offScr = (offKeep + size_t(T) * n + 255) / 256 * 256, total = offScr + scr.perGroup * groups;
+    CUDA_TRY(ctx, ctx->dLocalScratch.reserve(total));
+    unsigned char* d = ctx->dLocalScratch.p;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + offModels, models.data(), sizeof(LocalModel) * T, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + offVal, values, sizeof(float) * size_t(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)(sizeof(LocalModel) * T + sizeof(float) * size_t(T) * n);
+    scr.base = d + offScr;
+    scr.error = nullptr;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    CUDA_TRY(ctx, launchPreInterpolationBatch(reinterpret_cast<const LocalModel*>(d + offModels), ds,
+                                              reinterpret_cast<const float*>(d + offVal), T, scr, groupLanes, models[0].elevFunction,
+                                              reinterpret_cast<float*>(d + offDet), d + offKeep,
+                                              reinterpret_cast<PreFit*>(d + offFits), ctx->stream));
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    std::vector<PreFit> fits(T);
+    std::vector<uint8_t> keepTmp;
+    if (!keep) { keepTmp.resize(size_t(T) * n); keep = keepTmp.data(); }
+    CUDA_TRY(ctx, cudaMemcpyAsync(detrended, d + offDet, sizeof(float) * size_t(T) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(keep, d + offKeep, size_t(T) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(fits.data(), d + offFits, sizeof(PreFit) * T, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.d2h_bytes += (int64_t)(size_t(T) * n * 5 + sizeof(PreFit) * T);
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
+    if (fitted) {
+        // what preInterpolation leaves in Crit3DInterpolationSettings (interpolation.cpp:1506-1553, 1832-2171)
+        for (int t = 0; t < T; t++) {
+            pb_settings& o = fitted[t];
+            if (&o != s) o = *s;
+            const LocalModel& m = models[t];
+            const PreFit& f = fits[t];
+            o.hasPointsRange = 1;
+            o.pointsRangeMin = m.elevationPos >= 0 && s->selectedActive[m.elevationPos] ? m.elevMin[1] + 2 : o.pointsRangeMin;
+            o.pointsRangeMax = m.elevationPos >= 0 && s->selectedActive[m.elevationPos] ? m.elevMax[1] - 6 : o.pointsRangeMax;
+            if (pointsRange) { o.pointsRangeMin = pointsRange[2 * t]; o.pointsRangeMax = pointsRange[2 * t + 1]; }
+            else if (s->hasPointsRange && T == 1 && !pointsRange) { o.pointsRangeMin = s->pointsRangeMin; o.pointsRangeMax = s->pointsRangeMax; }
+            for (int i = 0; i < o.nProxy; i++) {
+                o.currentActive[i] = o.selectedActive[i];
+                o.currentSignificant[i] = 0;
+            }
+            o.currentUseThermalInversion = o.selectedUseThermalInversion;
+            o.nFit = o.nFitFunctions = 0;
+            const int e = m.elevationPos;
+            for (int i = 0; i < o.nProxy; i++)
+                if (o.selectedActive[i] && o.proxy[i].kind == PB_PROXY_HEIGHT) {
+                    pb_proxy& p = o.proxy[i];
+                    if (i == e) {
+                        p.fitMin[1] = m.elevMin[1];
+                        p.fitMax[1] = m.elevMax[1];
+                        p.nFirstGuessCombinations = m.nFirstGuess;
+                        memcpy(p.firstGuessCombinations, m.firstGuess, sizeof(m.firstGuess));
+                    }
+                }
+            if (e >= 0 && o.selectedActive[e]) {
+                o.proxy[e].regressionR2 = f.elevR2;
+                if (f.elevR2 != kNoData || f.elevSig) {
+                    o.fitFunction[o.nFitFunctions++] = m.elevFunction;
+                    if (f.elevSig) {
+                        o.fitNrParams[o.nFit] = m.elevNPar;
+                        for (int j = 0; j < m.elevNPar; j++) o.fitParams[o.nFit][j] = f.elevPar[j];
+                        o.nFit++;
+                    }
+                }
+                o.currentSignificant[e] = f.elevSig ? 1 : 0;
+            }
+            for (int c = 0; c < f.nPred; c++) {
+                o.currentSignificant[f.sigPos[c]] = 1;
+                o.fitFunction[o.nFitFunctions++] = PB_FIT_LINEAR;
+                o.fitNrParams[o.nFit] = 2;
+                o.fitParams[o.nFit][0] = f.othPar[c][0];
+                o.fitParams[o.nFit][1] = f.othPar[c][1];
+                o.nFit++;
+            }
+        }
+    }
     return PB_OK;
 }
 
@@ -600,8 +733,6 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     out->maximum = keyToFloat(ctx->hMinMax[1]);
     return PB_OK;
 }
-
-void resetTiming(pb_context* ctx) { memset(&ctx->timing, 0, sizeof(ctx->timing)); }
 
 }  // namespace
 
@@ -765,6 +896,41 @@ int pb_local_detrending_raster_device(pb_context* ctx, const pb_stations* st, co
     cudaSetDevice(ctx->device);
     resetTiming(ctx);
     return rasterCore(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, OUT_DEVICE_ONLY, true);
+}
+
+/* preInterpolation (interpolation/interpolation.cpp:2444-2499) for T independent time steps sharing one station set */
+int pb_pre_interpolation_batch(pb_context* ctx, const pb_stations* st, const float* values, int T, const pb_settings* s,
+                               int variable, const double* pointsRange, float* detrended, uint8_t* keep, pb_settings* fitted)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return preInterpolationBatchImpl(ctx, st, values, T, s, variable, pointsRange, detrended, keep, fitted);
+}
+
+/* preInterpolation for one time step, in place like the reference: st->value is detrended, *s receives the fit */
+int pb_pre_interpolation(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, uint8_t* keep)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    if (isPrecVar(variable)) {      // checkPrecipitationZero (interpolation.cpp:1173-1186): a count, host arithmetic
+        int nrValid = 0;
+        for (int i = 0; i < st->n; i++) {
+            const bool active = st->isActive ? st->isActive[i] != 0 : true;
+            if (active && !isEqualF(st->value[i], kNoData) && st->value[i] >= s->rainfallThreshold) nrValid++;
+        }
+        s->precipitationAllZero = nrValid == 0;
+        if (keep) memset(keep, 1, st->n);
+        return PB_OK;
+    }
+    if (!useDetrendingVar(variable)) {
+        if (keep) memset(keep, 1, st->n);
+        return PB_OK;
+    }
+    std::vector<float> in(st->value, st->value + st->n);
+    const double range[2] = {s->pointsRangeMin, s->pointsRangeMax};
+    pb_settings tmpl = *s;
+    return preInterpolationBatchImpl(ctx, st, in.data(), 1, &tmpl, variable, s->hasPointsRange ? range : nullptr, st->value, keep, s);
 }
 
 static int hostRasterCall(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const pb_raster* dem,

@@ -58,6 +58,9 @@ def load_library():
                                                      P(A.pb_raster_out)]
     lib.pb_interpolate_points.argtypes = raster_args + [P(C.c_float), P(C.c_float), P(C.c_double), C.c_int, C.c_int,
                                                         P(C.c_float)]
+    lib.pb_pre_interpolation.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_uint8)]
+    lib.pb_pre_interpolation_batch.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), C.c_int, P(A.pb_settings), C.c_int,
+                                               P(C.c_double), P(C.c_float), P(C.c_uint8), P(A.pb_settings)]
     lib.pb_compute_residuals.argtypes = raster_args + [P(C.c_float), P(C.c_uint8), P(C.c_float), P(A.pb_cv_stats)]
     lib.pb_kriging_setup.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_int, P(C.c_int32)]
@@ -235,3 +238,25 @@ class Engine:
         self._check(self.lib.pb_kriging_raster(self.h, kid, dem_id, row_begin, row_end, C.byref(est),
                                                C.byref(rm) if want_rmse else None))
         return e, r, est.nValid
+
+    # ---- preInterpolation (interpolation.cpp:2444) ----
+    def pre_interpolation(self, stations, settings, variable):
+        """one time step, in place (stations.value detrended, settings get the fit). Returns the keep mask."""
+        st = stations.as_pb()
+        keep = np.zeros(stations.n, dtype=np.uint8)
+        self._check(self.lib.pb_pre_interpolation(self.h, C.byref(st), C.byref(settings), variable, A.u8ptr(keep)))
+        return keep.astype(bool)
+
+    def pre_interpolation_batch(self, stations, values, settings, variable, points_range=None):
+        """T time steps sharing the station set. values: (T, n). Returns (detrended (T, n), keep (T, n), [settings] * T)."""
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        T, n = values.shape
+        assert n == stations.n
+        st = stations.as_pb()
+        det = np.empty((T, n), dtype=np.float32)
+        keep = np.zeros((T, n), dtype=np.uint8)
+        fitted = (A.pb_settings * T)()
+        pr = None if points_range is None else np.ascontiguousarray(points_range, dtype=np.float64)
+        self._check(self.lib.pb_pre_interpolation_batch(self.h, C.byref(st), A.fptr(values), T, C.byref(settings), variable,
+                                                        None if pr is None else A.dptr(pr), A.fptr(det), A.u8ptr(keep), fitted))
+        return det, keep.astype(bool), fitted
