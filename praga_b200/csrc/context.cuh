@@ -14,9 +14,9 @@ struct RasterEntry {
     float* d = nullptr;
     size_t n = 0;
     // DEM role (built lazily): ascending list of valid cells + per-row offsets into it
-    int* validIdx = nullptr;
+    int* validIdx = nullptr;           // capacity n
     long long nValid = -1;
-    std::vector<long long> rowStart;   // nrRows + 1 prefix counts (host)
+    std::vector<long long> rowStart;   // nrRows + 1 prefix counts (host), built on first row-band request
 };
 
 template <typename T>
@@ -51,6 +51,86 @@ struct PinnedBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// ring of pinned staging slots: host gather/scatter of one slot overlaps the PCIe copy of the others
+struct PinnedRing {
+    static constexpr int kSlots = 8;
+    unsigned char* p = nullptr;
+    size_t slotBytes = 0;
+    cudaEvent_t ev[kSlots]{};
+    bool pending[kSlots]{};
+    int next = 0;
+    cudaError_t init(size_t bytesPerSlot)
+    {
+        if (p && slotBytes >= bytesPerSlot) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMallocHost(&p, bytesPerSlot * kSlots);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        slotBytes = bytesPerSlot;
+        for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+        return cudaSuccess;
+    }
+    // next slot, waiting for the copy that last used it
+    unsigned char* acquire(int* slot)
+    {
+        const int s = next;
+        next = (next + 1) % kSlots;
+        if (pending[s]) { cudaEventSynchronize(ev[s]); pending[s] = false; }
+        *slot = s;
+        return p + size_t(s) * slotBytes;
+    }
+    void submitted(int slot, cudaStream_t stream) { cudaEventRecord(ev[slot], stream); pending[slot] = true; }
+    cudaError_t wait(int slot)
+    {
+        cudaError_t e = cudaSuccess;
+        if (pending[slot]) { e = cudaEventSynchronize(ev[slot]); pending[slot] = false; }
+        return e;
+    }
+    void release()
+    {
+        if (p) {
+            for (int s = 0; s < kSlots; s++) if (pending[s]) cudaEventSynchronize(ev[s]);
+            cudaFreeHost(p);
+            for (auto& x : ev) if (x) cudaEventDestroy(x);
+        }
+        p = nullptr; slotBytes = 0; next = 0;
+        for (auto& x : ev) x = nullptr;
+        for (auto& x : pending) x = false;
+    }
+};
+
+// device buffers recycled by size: the drop-in call uploads and frees rasters every time step, cudaMalloc/cudaFree would
+// cost more than the kernel
+struct DevicePool {
+    struct Buf { void* p; size_t bytes; bool used; };
+    std::vector<Buf> bufs;
+    cudaError_t acquire(size_t bytes, void** out)
+    {
+        for (auto& b : bufs)
+            if (!b.used && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 + 4096) { b.used = true; *out = b.p; return cudaSuccess; }
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {     // give cached memory back and retry once
+            trim();
+            e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) return e;
+        }
+        bufs.push_back({p, bytes, true});
+        *out = p;
+        return cudaSuccess;
+    }
+    void release(void* p)
+    {
+        for (auto& b : bufs) if (b.p == p) { b.used = false; return; }
+    }
+    void trim()
+    {
+        for (size_t i = 0; i < bufs.size();)
+            if (!bufs[i].used) { cudaFree(bufs[i].p); bufs.erase(bufs.begin() + i); }
+            else i++;
+    }
+    void destroy() { for (auto& b : bufs) cudaFree(b.p); bufs.clear(); }
+};
+
 struct KrigingSystem;                       // kriging.cu
 void krigingDestroyAll(std::vector<KrigingSystem*>& v);
 
@@ -71,7 +151,10 @@ struct pb_context {
     pb::PinnedBuf hLocal;
     int* dLocalError = nullptr;
     int* hLocalError = nullptr;         // pinned
-    pb::PinnedBuf hStage;                   // raster staging (H2D / D2H)
+    pb::PinnedRing ring;                    // raster staging (H2D / D2H), 8 slots
+    pb::DevicePool pool;                    // raster-sized device buffers
+    long long* dTotal = nullptr;            // valid-cell count of the last compaction
+    long long* hTotal = nullptr;            // pinned
     unsigned* dMinMax = nullptr;
     unsigned* hMinMax = nullptr;        // pinned
     cudaEvent_t ev[4]{};
@@ -83,6 +166,7 @@ namespace pb {
 
 int failCtx(pb_context* ctx, int code, const std::string& msg);     // engine.cu
 int ensureValidList(pb_context* ctx, RasterEntry& e);               // engine.cu
+int ensureRowStart(pb_context* ctx, RasterEntry& e);                // engine.cu
 
 }  // namespace pb
 

@@ -24,6 +24,7 @@ cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevG
 cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty,
                             const double* tproxy, int nTargets, float* out, cudaStream_t s);
 cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);
+cudaError_t launchRowStart(const int* validIdx, long long total, int nrRows, int nrCols, long long* rowStart, cudaStream_t s);
 cudaError_t launchFillValid(float* out, const int* validIdx, int n, float v, cudaStream_t s);
 // peaks.cu
 cudaError_t measurePipePeaks(cudaStream_t s, int sms, float* fp32Tflops, float* mufuGops);
@@ -216,36 +217,52 @@ int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, 
     return PB_OK;
 }
 
-// gather a host raster (contiguous or float**) into pinned staging with all host cores, then one H2D
+constexpr size_t kStageSlotBytes = size_t(8) << 20;
+
+// host raster (contiguous or float**) -> device: row chunks gathered into pinned ring slots by the host cores while the
+// previous chunks cross PCIe
 int uploadRaster(pb_context* ctx, const pb_raster* r, RasterEntry& e)
 {
     if (r->h.nrRows <= 0 || r->h.nrCols <= 0) return fail(ctx, PB_ERR_INVALID, "raster has no cells");
     if (!r->data && !r->rows) return fail(ctx, PB_ERR_INVALID, "raster has neither data nor rows");
     const size_t n = size_t(r->h.nrRows) * r->h.nrCols;
     if (n > size_t(0x7fffffff)) return fail(ctx, PB_ERR_UNSUPPORTED, "raster larger than 2^31-1 cells");
-    CUDA_TRY(ctx, ctx->hStage.reserve(n * sizeof(float)));
-    float* stage = reinterpret_cast<float*>(ctx->hStage.p);
     const int rows = r->h.nrRows, cols = r->h.nrCols;
-#pragma omp parallel for schedule(static)
-    for (int row = 0; row < rows; row++) {
-        const float* src = r->data ? r->data + size_t(row) * cols : r->rows[row];
-        memcpy(stage + size_t(row) * cols, src, sizeof(float) * cols);
-    }
+    if (size_t(cols) * sizeof(float) > kStageSlotBytes) return fail(ctx, PB_ERR_UNSUPPORTED, "raster row larger than a staging slot");
+    CUDA_TRY(ctx, ctx->ring.init(kStageSlotBytes));
+    void* dptr = nullptr;
+    CUDA_TRY(ctx, ctx->pool.acquire(n * sizeof(float), &dptr));
+    e.d = static_cast<float*>(dptr);
     e.h = r->h;
     e.n = n;
-    CUDA_TRY(ctx, cudaMalloc(&e.d, n * sizeof(float)));
-    CUDA_TRY(ctx, cudaMemcpyAsync(e.d, stage, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // staging buffer is reused by the next upload
+    const int chunkRows = std::max(1, (int)(kStageSlotBytes / (sizeof(float) * cols)));
+    for (int r0 = 0; r0 < rows; r0 += chunkRows) {
+        const int r1 = std::min(rows, r0 + chunkRows);
+        int slot;
+        float* stage = reinterpret_cast<float*>(ctx->ring.acquire(&slot));
+        if (r->data && r1 - r0 < 64) memcpy(stage, r->data + size_t(r0) * cols, sizeof(float) * size_t(r1 - r0) * cols);
+        else {
+#pragma omp parallel for schedule(static)
+            for (int row = r0; row < r1; row++) {
+                const float* src = r->data ? r->data + size_t(row) * cols : r->rows[row];
+                memcpy(stage + size_t(row - r0) * cols, src, sizeof(float) * cols);
+            }
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(e.d + size_t(r0) * cols, stage, sizeof(float) * size_t(r1 - r0) * cols,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        ctx->ring.submitted(slot, ctx->stream);
+    }
     ctx->timing.h2d_bytes += (int64_t)(n * sizeof(float));
     e.used = true;
     e.nValid = -1;
+    e.rowStart.clear();
     return PB_OK;
 }
 
-void freeEntry(RasterEntry& e)
+void freeEntry(pb_context* ctx, RasterEntry& e)
 {
-    if (e.d) cudaFree(e.d);
-    if (e.validIdx) cudaFree(e.validIdx);
+    if (e.d) ctx->pool.release(e.d);
+    if (e.validIdx) ctx->pool.release(e.validIdx);
     e = RasterEntry();
 }
 
@@ -255,31 +272,38 @@ int ensureValidListImpl(pb_context* ctx, RasterEntry& e)
     if (e.nValid >= 0) return PB_OK;
     const long long n = (long long)e.n;
     const int nb = compactBlocks(n);
-    int* blockCount = nullptr;
-    long long* dTotal = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&blockCount, sizeof(int) * nb));
-    CUDA_TRY(ctx, cudaMalloc(&dTotal, sizeof(long long)));
-    CUDA_TRY(ctx, launchCompactValid(e.d, n, e.h.flag, blockCount, dTotal, nullptr, 0, ctx->stream));
-    long long total = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&total, dTotal, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(ctx, cudaMalloc(&e.validIdx, sizeof(int) * std::max<long long>(total, 1)));
-    CUDA_TRY(ctx, launchCompactValid(e.d, n, e.h.flag, blockCount, dTotal, e.validIdx, 1, ctx->stream));
-    ctx->timing.launches += 3;
-    // per-row offsets (row bands for multi-GPU sharding): binary search of each row start on the host copy
-    std::vector<int> idx((size_t)total);
-    if (total)
-        CUDA_TRY(ctx, cudaMemcpyAsync(idx.data(), e.validIdx, sizeof(int) * total, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    e.rowStart.assign(size_t(e.h.nrRows) + 1, 0);
-    for (int row = 0; row <= e.h.nrRows; row++) {
-        const long long first = (long long)row * e.h.nrCols;
-        e.rowStart[row] = std::lower_bound(idx.begin(), idx.end(), first,
-                                           [](int a, long long b) { return (long long)a < b; }) - idx.begin();
+    void* blockCount = nullptr;
+    void* idx = nullptr;
+    CUDA_TRY(ctx, ctx->pool.acquire(sizeof(int) * size_t(nb), &blockCount));
+    CUDA_TRY(ctx, ctx->pool.acquire(sizeof(int) * size_t(n), &idx));
+    e.validIdx = static_cast<int*>(idx);
+    if (!ctx->dTotal) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dTotal, sizeof(long long)));
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->hTotal, sizeof(long long)));
     }
-    cudaFree(blockCount);
-    cudaFree(dTotal);
-    e.nValid = total;
+    CUDA_TRY(ctx, launchCompactValid(e.d, n, e.h.flag, static_cast<int*>(blockCount), ctx->dTotal, nullptr, 0, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hTotal, ctx->dTotal, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, launchCompactValid(e.d, n, e.h.flag, static_cast<int*>(blockCount), ctx->dTotal, e.validIdx, 1, ctx->stream));
+    ctx->timing.launches += 3;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->pool.release(blockCount);
+    e.nValid = *ctx->hTotal;
+    return PB_OK;
+}
+
+// per-row offsets into the valid list (row bands for multi-GPU sharding), computed on the device on first use
+int ensureRowStartImpl(pb_context* ctx, RasterEntry& e)
+{
+    if (!e.rowStart.empty()) return PB_OK;
+    const int rows = e.h.nrRows;
+    void* d = nullptr;
+    CUDA_TRY(ctx, ctx->pool.acquire(sizeof(long long) * size_t(rows + 1), &d));
+    CUDA_TRY(ctx, launchRowStart(e.validIdx, e.nValid, rows, e.h.nrCols, static_cast<long long*>(d), ctx->stream));
+    ctx->timing.launches++;
+    e.rowStart.assign(size_t(rows) + 1, 0);
+    CUDA_TRY(ctx, cudaMemcpyAsync(e.rowStart.data(), d, sizeof(long long) * size_t(rows + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->pool.release(d);
     return PB_OK;
 }
 
@@ -659,7 +683,13 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     ctx->hMinMax[1] = 0u;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
 
-    const long long t0 = dem.rowStart[rowBegin], t1 = dem.rowStart[rowEnd];
+    long long t0 = 0, t1 = dem.nValid;
+    if (rowBegin != 0 || rowEnd != dem.h.nrRows) {
+        rc = ensureRowStartImpl(ctx, dem);
+        if (rc) return rc;
+        t0 = dem.rowStart[rowBegin];
+        t1 = dem.rowStart[rowEnd];
+    }
     const int nTargets = (int)(t1 - t0);
     const DevGrid dg = devGridOf(dem);
     if (local) {
@@ -680,33 +710,42 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     const size_t bandOff = size_t(rowBegin) * dem.h.nrCols, bandN = size_t(rowEnd - rowBegin) * dem.h.nrCols;
     if (mode == OUT_HOST) {
         if (!out->data && !out->rows) return fail(ctx, PB_ERR_INVALID, "output has neither data nor rows");
-        CUDA_TRY(ctx, ctx->hStage.reserve(dem.n * sizeof(float)));
-        float* stage = reinterpret_cast<float*>(ctx->hStage.p);
-        // D2H in row chunks, each chunk scattered into the caller's rows by the host cores while the next one flies
+        // D2H in row chunks through the pinned ring; each chunk is scattered into the caller's rows by the host cores
+        // while the following ones are still in flight
         const int cols = dem.h.nrCols;
-        const int chunkRows = std::max(1, (int)((size_t(8) << 20) / (sizeof(float) * cols)));
-        std::vector<cudaEvent_t> done;
+        CUDA_TRY(ctx, ctx->ring.init(kStageSlotBytes));
+        const int chunkRows = std::max(1, (int)(kStageSlotBytes / (sizeof(float) * cols)));
+        struct Chunk { int r0, r1, slot; float* stage; };
+        std::vector<Chunk> inflight;
+        size_t head = 0;
+        auto scatter = [&](const Chunk& c) -> cudaError_t {
+            cudaError_t e = ctx->ring.wait(c.slot);
+            if (e != cudaSuccess) return e;
+#pragma omp parallel for schedule(static)
+            for (int row = c.r0; row < c.r1; row++) {
+                float* dst = out->data ? out->data + size_t(row) * cols : out->rows[row];
+                memcpy(dst, c.stage + size_t(row - c.r0) * cols, sizeof(float) * cols);
+            }
+            return cudaSuccess;
+        };
         for (int r0 = rowBegin; r0 < rowEnd; r0 += chunkRows) {
-            const int r1 = std::min(rowEnd, r0 + chunkRows);
-            CUDA_TRY(ctx, cudaMemcpyAsync(stage + size_t(r0) * cols, ctx->dOut.p + size_t(r0) * cols,
-                                          size_t(r1 - r0) * cols * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-            cudaEvent_t e;
-            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-            cudaEventRecord(e, ctx->stream);
-            done.push_back(e);
+            if (inflight.size() - head >= size_t(PinnedRing::kSlots - 1)) {     // the next acquire would reuse this slot
+                cudaError_t e = scatter(inflight[head++]);
+                if (e != cudaSuccess) return fail(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(e));
+            }
+            Chunk c;
+            c.r0 = r0;
+            c.r1 = std::min(rowEnd, r0 + chunkRows);
+            c.stage = reinterpret_cast<float*>(ctx->ring.acquire(&c.slot));
+            CUDA_TRY(ctx, cudaMemcpyAsync(c.stage, ctx->dOut.p + size_t(r0) * cols, size_t(c.r1 - r0) * cols * sizeof(float),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->ring.submitted(c.slot, ctx->stream);
+            inflight.push_back(c);
         }
         cudaEventRecord(ctx->ev[3], ctx->stream);
-        int ci = 0;
-        for (int r0 = rowBegin; r0 < rowEnd; r0 += chunkRows, ci++) {
-            const int r1 = std::min(rowEnd, r0 + chunkRows);
-            cudaError_t e = cudaEventSynchronize(done[ci]);
-            cudaEventDestroy(done[ci]);
+        for (; head < inflight.size(); head++) {
+            cudaError_t e = scatter(inflight[head]);
             if (e != cudaSuccess) return fail(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(e));
-#pragma omp parallel for schedule(static)
-            for (int row = r0; row < r1; row++) {
-                float* dst = out->data ? out->data + size_t(row) * cols : out->rows[row];
-                memcpy(dst, stage + size_t(row) * cols, sizeof(float) * cols);
-            }
         }
         ctx->timing.d2h_bytes += (int64_t)(bandN * sizeof(float));
         (void)bandOff;
@@ -738,6 +777,7 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
 
 namespace pb {
 int ensureValidList(pb_context* ctx, RasterEntry& e) { return ensureValidListImpl(ctx, e); }
+int ensureRowStart(pb_context* ctx, RasterEntry& e) { return ensureRowStartImpl(ctx, e); }
 }  // namespace pb
 
 extern "C" {
@@ -788,12 +828,14 @@ void pb_destroy(pb_context* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& r : ctx->rasters) if (r.used) freeEntry(r);
+    for (auto& r : ctx->rasters) if (r.used) freeEntry(ctx, r);
     pb::krigingDestroyAll(ctx->kriging);
     ctx->dLocalStations.release(); ctx->dLocalScratch.release(); ctx->dLocalModel.release(); ctx->hLocal.release();
     if (ctx->dLocalError) cudaFree(ctx->dLocalError);
     if (ctx->hLocalError) cudaFreeHost(ctx->hLocalError);
-    ctx->dStations.release(); ctx->hStations.release(); ctx->dOut.release(); ctx->dScratch.release(); ctx->hStage.release();
+    ctx->dStations.release(); ctx->hStations.release(); ctx->dOut.release(); ctx->dScratch.release(); ctx->ring.release(); ctx->pool.destroy();
+    if (ctx->dTotal) cudaFree(ctx->dTotal);
+    if (ctx->hTotal) cudaFreeHost(ctx->hTotal);
     if (ctx->dMinMax) cudaFree(ctx->dMinMax);
     if (ctx->hMinMax) cudaFreeHost(ctx->hMinMax);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -829,7 +871,7 @@ int pb_raster_upload(pb_context* ctx, const pb_raster* r, pb_raster_id* id)
     for (size_t i = 0; i < ctx->rasters.size(); i++) if (!ctx->rasters[i].used) { slot = (int)i; break; }
     if (slot < 0) { ctx->rasters.emplace_back(); slot = (int)ctx->rasters.size() - 1; }
     int rc = uploadRaster(ctx, r, ctx->rasters[slot]);
-    if (rc) { freeEntry(ctx->rasters[slot]); return rc; }
+    if (rc) { freeEntry(ctx, ctx->rasters[slot]); return rc; }
     if (ctx->outInitRaster == slot) ctx->outInitRaster = -1;
     *id = slot;
     return PB_OK;
@@ -841,7 +883,7 @@ int pb_raster_free(pb_context* ctx, pb_raster_id id)
     if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used) return fail(ctx, PB_ERR_INVALID, "bad raster id");
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    freeEntry(ctx->rasters[id]);
+    freeEntry(ctx, ctx->rasters[id]);
     if (ctx->outInitRaster == id) ctx->outInitRaster = -1;
     return PB_OK;
 }

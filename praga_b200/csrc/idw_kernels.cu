@@ -455,7 +455,29 @@ __global__ void fill_valid_kernel(float* __restrict__ out, const int* __restrict
     if (i < n) out[validIdx[i]] = v;
 }
 
+// first position in the ascending valid list whose cell lies in row >= `row` (lower_bound), for every row boundary
+__global__ void row_start_kernel(const int* __restrict__ validIdx, long long total, int nrRows, int nrCols,
+                                 long long* __restrict__ rowStart)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row > nrRows) return;
+    const long long first = (long long)row * nrCols;
+    long long lo = 0, hi = total;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if ((long long)validIdx[mid] < first) lo = mid + 1;
+        else hi = mid;
+    }
+    rowStart[row] = lo;
+}
+
 // ---- host-side launchers (called from engine.cu) ----
+cudaError_t launchRowStart(const int* validIdx, long long total, int nrRows, int nrCols, long long* rowStart, cudaStream_t s)
+{
+    row_start_kernel<<<(nrRows + 1 + 255) / 256, 256, 0, s>>>(validIdx, total, nrRows, nrCols, rowStart);
+    return cudaGetLastError();
+}
+
 cudaError_t launchCompactValid(const float* dem, long long n, float flag, int* blockCount, long long* dTotal,
                                int* validIdx, int phase, cudaStream_t s)
 {

@@ -526,7 +526,13 @@ int pb_kriging_raster(pb_context* ctx, pb_kriging_id id, pb_raster_id demId, int
     float* gRm = rmse ? ctx->dOut.p + N : nullptr;
     // both grids start as the DEM's flag
     CUDA_TRY(ctx, launchFill(gEst, (long long)(rmse ? 2 * N : N), dem.h.flag, ctx->stream));
-    const long long t0 = dem.rowStart[rowBegin], t1 = dem.rowStart[rowEnd];
+    long long t0 = 0, t1 = dem.nValid;
+    if (rowBegin != 0 || rowEnd != dem.h.nrRows) {
+        rc = ensureRowStart(ctx, dem);
+        if (rc) return rc;
+        t0 = dem.rowStart[rowBegin];
+        t1 = dem.rowStart[rowEnd];
+    }
     KrigingTargets t{};
     t.validIdx = dem.validIdx + t0;
     t.grid.data = dem.d;
