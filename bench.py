@@ -201,6 +201,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # torchrun pins OMP_NUM_THREADS=1; the drop-in call gathers/scatters host rasters with the host cores, so every rank
+    # gets its share of them (must be set before libgomp starts, i.e. before the engine library runs a parallel region)
+    if world > 1:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
 
     if args.impl == "reference":
         run_reference(args, rank, world)

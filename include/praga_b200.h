@@ -232,6 +232,12 @@ int pb_local_detrending_raster_device(pb_context* ctx, const pb_stations* st, co
 int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
                           const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result);
 
+/* interpolate() with topographic distance (computeDistances :226-251 + gis::topographicDistance, gis/gis.cpp:1595-1647):
+ * z = the targets' elevation (float(point.z)), dem = the resident DEM the ray march samples (getCurrentDEM()). */
+int pb_interpolate_points_td(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
+                             const float* y, const float* z, const double* proxyValues, int m, int excludeSupplemental,
+                             pb_raster_id dem, float* result);
+
 /* --- leave-one-out cross-validation: computeResiduals (agrolib/interpolation/spatialControl.cpp:97-155) followed by
  * Project::computeStatisticsCrossValidation (agrolib/project/project.cpp:2935-2969). One meteo point per station:
  * observed[i] = its currentValue (NOT detrended), useForCv[i] = active && accepted && valid (NULL = all);

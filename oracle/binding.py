@@ -60,6 +60,9 @@ def _load(path, prefix):
     fn = getattr(lib, prefix + "_interpolate_points")
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_float), P(C.c_float),
                    P(C.c_double), C.c_int, C.c_int, P(C.c_float)]
+    fn = getattr(lib, prefix + "_interpolate_points_td")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_float), P(C.c_float),
+                   P(C.c_double), C.c_int, C.c_int, P(A.pb_raster), P(C.c_float)]
     fn = getattr(lib, prefix + "_compute_residuals")
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_uint8), P(C.c_float),
                    P(A.pb_cv_stats)]
@@ -164,6 +167,20 @@ class Oracle:
         st = stations.as_pb()
         self._f("interpolate_points")(C.byref(st), C.byref(settings), variable, A.fptr(x), A.fptr(y), A.fptr(z),
                                       A.dptr(pv) if pv.size else None, m, int(exclude_supplemental), A.fptr(res))
+        return res
+
+    def interpolate_points_td(self, stations, settings, variable, x, y, z, proxy_values, dem, exclude_supplemental=False):
+        """interpolate() with the current DEM set (topographic distance available)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        z = np.ascontiguousarray(z, dtype=np.float32)
+        m = x.shape[0]
+        pv = np.ascontiguousarray(proxy_values, dtype=np.float64).reshape(m, -1)
+        res = np.empty(m, dtype=np.float32)
+        st = stations.as_pb()
+        d = dem.as_pb()
+        self._f("interpolate_points_td")(C.byref(st), C.byref(settings), variable, A.fptr(x), A.fptr(y), A.fptr(z),
+                                         A.dptr(pv) if pv.size else None, m, int(exclude_supplemental), C.byref(d), A.fptr(res))
         return res
 
     def compute_residuals(self, stations, settings, variable, observed, use_for_cv=None):

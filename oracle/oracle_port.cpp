@@ -166,10 +166,41 @@ float retrend(const pb_settings& s, int var, const double* proxyValues)
     return float(retrendValue);
 }
 
-// interpolate, interpolation.cpp:2502-2560 with computeDistances :208-256 (no TD) and inverseDistanceWeighted :1031-1051
-float interpolate(const std::vector<Point>& pts, const pb_settings& s, int var, float x, float y, const double* proxyValues,
-                  bool excludeSupplemental)
+// getUseTdVar, interpolation.cpp:1220-1234
+inline bool useTdVar(int v)
 {
+    return !(v == PB_VAR_PRECIPITATION || v == PB_VAR_DAILY_PRECIPITATION || v == PB_VAR_GLOBAL_IRRADIANCE ||
+             v == PB_VAR_ATM_TRANSMISSIVITY || v == PB_VAR_DAILY_GLOBAL_RADIATION || v == PB_VAR_ATM_PRESSURE ||
+             v == PB_VAR_DAILY_WATER_TABLE_DEPTH);
+}
+
+// gis::topographicDistance, gis/gis.cpp:1595-1647
+float topographicDistance(float x1, float y1, float z1, float x2, float y2, float z2, float distance, const Grid& dem)
+{
+    const float stepMeter = float(dem.h.cellSize);
+    if (distance < stepMeter) return 0;
+    const int nrStep = int(distance / stepMeter);
+    float Xi, Yi, Zi, Xf, Yf;
+    if (z1 < z2) { Xi = x1; Yi = y1; Zi = z1; Xf = x2; Yf = y2; }
+    else { Xi = x2; Yi = y2; Zi = z2; Xf = x1; Yf = y1; }
+    const float dx = (Xf - Xi) / float(nrStep), dy = (Yf - Yi) / float(nrStep);
+    float x = Xi, y = Yi, maxDeltaZ = 0;
+    for (int i = 1; i <= nrStep; i++) {
+        x = x + dx;
+        y = y + dy;
+        const float demValue = dem.valueFromXY(x, y);
+        if (!isEqualF(demValue, dem.h.flag))
+            if (demValue > Zi) maxDeltaZ = std::max(maxDeltaZ, demValue - Zi);
+    }
+    return maxDeltaZ;
+}
+
+// interpolate, interpolation.cpp:2502-2560 with computeDistances :208-256 (topographic distance when a DEM is given
+// and getUseTD() holds; no per-station TD rasters) and inverseDistanceWeighted :1031-1051
+float interpolate(const std::vector<Point>& pts, const pb_settings& s, int var, float x, float y, const double* proxyValues,
+                  bool excludeSupplemental, float z = 0.f, const Grid* dem = nullptr)
+{
+    const bool td = dem && s.useTD && !s.useLocalDetrending && useTdVar(var) && s.topoDist_Kh != 0;
     if (isPrec(var) && s.precipitationAllZero) return 0.f;
     float result = NODATA_F;
     if (!s.useRetrendOnly) {
@@ -180,6 +211,10 @@ float interpolate(const std::vector<Point>& pts, const pb_settings& s, int var, 
             else {
                 const float dx = float(pts[i].x) - x, dy = float(pts[i].y) - y;     // gis::computeDistance, gis.cpp:685-691
                 d = sqrtf(dx * dx + dy * dy);
+                if (td) {
+                    const float topo = topographicDistance(x, y, z, float(pts[i].x), float(pts[i].y), float(pts[i].z), d, *dem);
+                    d += (s.topoDist_Kh * topo);
+                }
             }
             if (d > 0.f) {
                 const double dist_km = double(d) / 10000.;
@@ -1298,7 +1333,7 @@ int port_interpolation_raster(const pb_stations* st, const pb_settings* s, int v
                     if (v != grids[gi].h.flag) pv[i] = v;
                 }
             }
-            orow[col] = interpolate(pts, *s, variable, x, y, pv, true);
+            orow[col] = interpolate(pts, *s, variable, x, y, pv, true, z, &d);
         }
     }
     auto t1 = std::chrono::steady_clock::now();
@@ -1341,6 +1376,20 @@ int port_interpolate_points(const pb_stations* st, const pb_settings* s, int var
     for (int i = 0; i < m; i++)
         result[i] = interpolate(pts, *s, variable, x[i], y[i], proxyValues ? proxyValues + size_t(i) * s->nProxy : none,
                                 excludeSupplemental != 0);
+    return PB_OK;
+}
+
+int port_interpolate_points_td(const pb_stations* st, const pb_settings* s, int variable, const float* x, const float* y,
+                               const float* z, const double* proxyValues, int m, int excludeSupplemental, const pb_raster* dem,
+                               float* result)
+{
+    std::vector<Point> pts = loadPoints(st);
+    Grid d = gridOf(*dem);
+    double none[PB_MAX_PROXY];
+    for (auto& v : none) v = -9999;
+    for (int i = 0; i < m; i++)
+        result[i] = interpolate(pts, *s, variable, x[i], y[i], proxyValues ? proxyValues + size_t(i) * s->nProxy : none,
+                                excludeSupplemental != 0, z[i], &d);
     return PB_OK;
 }
 

@@ -380,6 +380,26 @@ int ref_interpolate_points(const pb_stations* st, const pb_settings* s, int vari
     return PB_OK;
 }
 
+/* interpolate() with a current DEM set, so that topographic distance (computeDistances :226-251) is available */
+int ref_interpolate_points_td(const pb_stations* st, const pb_settings* s, int variable, const float* x, const float* y,
+                              const float* z, const double* proxyValues, int m, int excludeSupplemental, const pb_raster* dem,
+                              float* result)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    gis::Crit3DRasterGrid demGrid;
+    fillGrid(demGrid, *dem);
+    sc.settings.setCurrentDEM(&demGrid);
+    std::vector<double> pv(s->nProxy);
+    for (int i = 0; i < m; i++) {
+        for (int k = 0; k < s->nProxy; k++) pv[k] = proxyValues[size_t(i) * s->nProxy + k];
+        result[i] = interpolate(sc.points, sc.settings, &sc.meteoSettings, meteoVariable(variable), x[i], y[i], z[i], pv,
+                                excludeSupplemental != 0);
+    }
+    return PB_OK;
+}
+
 /* computeResiduals (spatialControl.cpp:97-155) + Project::computeStatisticsCrossValidation (project.cpp:2935-2969,
  * restated: that copy needs Qt). One Crit3DMeteoPoint per station: active, quality accepted, currentValue =
  * observed[i], position/proxy values of the station. */

@@ -20,10 +20,11 @@ SOURCES = {
     "peaks.cu": [],
     "local_kernels.cu": ["-fmad=false"],
     "pre_kernels.cu": ["-fmad=false"],
+    "td_kernels.cu": ["-fmad=false"],
     "kriging.cu": [],
     "kriging_tc.cu": [],
 }
-HEADERS = ["common.cuh", "context.cuh", "local.cuh", "pre.cuh", "multiple_detrend.cuh", "detrend_device.cuh", "kriging.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
+HEADERS = ["common.cuh", "epilogue.cuh", "context.cuh", "local.cuh", "pre.cuh", "multiple_detrend.cuh", "detrend_device.cuh", "kriging.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

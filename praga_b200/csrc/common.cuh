@@ -122,6 +122,7 @@ struct DevStations {
     const float* x;           // plain SoA copies for the exact slow path (cell coincides with a station)
     const float* y;
     const float* val;
+    const float* z;           // float(point->z), topographic distance only
     int n;                    // real stations
     int nPadded;              // multiple of the tile size
 };

@@ -24,6 +24,12 @@ cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevG
 cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty,
                             const double* tproxy, int nTargets, float* out, cudaStream_t s);
 cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);
+// td_kernels.cu
+cudaError_t launchIdwTdRaster(const DevStations& st, const float* sz, const DevModel& m, const DevGrid& dem, int kh,
+                              const int* validIdx, int nTargets, float* out, unsigned* minmax, cudaStream_t s);
+cudaError_t launchIdwTdPoints(const DevStations& st, const float* sz, const DevModel& m, const DevGrid& dem, int kh,
+                              const float* tx, const float* ty, const float* tz, const double* tproxy, int nTargets, float* out,
+                              cudaStream_t s);
 cudaError_t launchRowStart(const int* validIdx, long long total, int nrRows, int nrCols, long long* rowStart, cudaStream_t s);
 cudaError_t launchFillValid(float* out, const int* validIdx, int n, float v, cudaStream_t s);
 // peaks.cu
@@ -61,6 +67,12 @@ bool useTdVar(int v)
     return !(v == PB_VAR_PRECIPITATION || v == PB_VAR_DAILY_PRECIPITATION || v == PB_VAR_GLOBAL_IRRADIANCE ||
              v == PB_VAR_ATM_TRANSMISSIVITY || v == PB_VAR_DAILY_GLOBAL_RADIATION || v == PB_VAR_ATM_PRESSURE ||
              v == PB_VAR_DAILY_WATER_TABLE_DEPTH);
+}
+// computeDistances adds kh * topographicDistance when getUseTD() (= useTD && !useLocalDetrending,
+// interpolationSettings.h:251) && getUseTdVar(var) && kh != 0 (interpolation.cpp:226-251)
+bool usesTopographicDistance(const pb_settings* s, int v)
+{
+    return s->useTD && !s->useLocalDetrending && useTdVar(v) && s->topoDist_Kh != 0;
 }
 bool isPrecVar(int v) { return v == PB_VAR_PRECIPITATION || v == PB_VAR_DAILY_PRECIPITATION; }
 int clampModeOf(int v)
@@ -103,9 +115,6 @@ int buildModel(pb_context* ctx, const pb_settings* s, int variable, const pb_ras
     if (s->method != PB_METHOD_IDW)
         return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the GPU path (shepard: DESIGN.md)");
     if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending is out of scope (DESIGN.md)");
-    // getUseTD() is useTD && !useLocalDetrending (interpolationSettings.h:251)
-    if (s->useTD && !s->useLocalDetrending && useTdVar(variable) && s->topoDist_Kh != 0)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "topographic distance with kh != 0 is not implemented yet (DESIGN.md)");
     m.nProxy = s->nProxy;
     m.useDetrendingVar = useDetrendingVar(variable);
     m.useMultipleDetrending = s->useMultipleDetrending;
@@ -183,7 +192,7 @@ int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, 
 
     const size_t offXY = 0, offV = offXY + size_t(nPadded) * 16, offX = offV + size_t(nPadded) * 8;
     const size_t nAl = (size_t(n) + 3) / 4 * 4;
-    const size_t offY = offX + nAl * 4, offVal = offY + nAl * 4, total = offVal + nAl * 4 + 16;
+    const size_t offY = offX + nAl * 4, offVal = offY + nAl * 4, offZ = offVal + nAl * 4, total = offZ + nAl * 4 + 16;
     CUDA_TRY(ctx, ctx->hStations.reserve(total));
     CUDA_TRY(ctx, ctx->dStations.reserve(total));
     unsigned char* h = ctx->hStations.p;
@@ -192,6 +201,7 @@ int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, 
     float* px = reinterpret_cast<float*>(h + offX);
     float* py = reinterpret_cast<float*>(h + offY);
     float* pv = reinterpret_cast<float*>(h + offVal);
+    float* pz = reinterpret_cast<float*>(h + offZ);
     for (int k = 0; k < n; k++) {
         const int i = use[k];
         const float x = float(st->x[i]), y = float(st->y[i]);           // float(point->utm.x) (interpolation.cpp:222)
@@ -199,6 +209,7 @@ int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, 
         xy[k] = make_float4(x, x, y, y);
         v[k] = make_float2(c, c);
         px[k] = x; py[k] = y; pv[k] = c;
+        pz[k] = float(st->z[i]);
     }
     for (int k = n; k < nPadded; k++) {   // zero-weight padding: rsqrt(2e36)^3 underflows to 0
         xy[k] = make_float4(1e18f, 1e18f, 1e18f, 1e18f);
@@ -212,6 +223,7 @@ int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, 
     ds.x = reinterpret_cast<const float*>(d + offX);
     ds.y = reinterpret_cast<const float*>(d + offY);
     ds.val = reinterpret_cast<const float*>(d + offVal);
+    ds.z = reinterpret_cast<const float*>(d + offZ);
     ds.n = n;
     ds.nPadded = nPadded;
     return PB_OK;
@@ -700,6 +712,10 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
         CUDA_TRY(ctx, launchFillValid(ctx->dOut.p, dem.validIdx + t0, nTargets, 0.f, ctx->stream));
         if (nTargets > 0) { ctx->hMinMax[0] = 0x80000000u; ctx->hMinMax[1] = 0x80000000u; }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    } else if (usesTopographicDistance(s, variable)) {
+        // the march needs the whole DEM (a ray reaches any station): `dem` is the full resident raster also for a row band
+        CUDA_TRY(ctx, launchIdwTdRaster(ds, ds.z, m, dg, s->topoDist_Kh, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax,
+                                        ctx->stream));
     } else {
         CUDA_TRY(ctx, launchIdwRaster(ds, m, dg, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax, ctx->stream));
     }
@@ -1018,8 +1034,9 @@ int pb_local_detrending_raster(pb_context* ctx, const pb_stations* st, const pb_
 
 /* interpolate() at explicit targets (interpolation.cpp:2502): the building block of computeResiduals.
  * proxyValues: m * settings.nProxy doubles (the target's own proxy values). */
-int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
-                          const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result)
+static int interpolatePointsImpl(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
+                                 const float* y, const float* z, const double* proxyValues, int m, int excludeSupplemental,
+                                 pb_raster_id demId, float* result)
 {
     if (!ctx) return PB_ERR_INVALID;
     if (!st || !s || !x || !y || !result || m < 0) return fail(ctx, PB_ERR_INVALID, "null argument");
@@ -1033,22 +1050,35 @@ int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_setti
         return PB_OK;
     }
     if (mod.nProxy > 0 && !proxyValues) return fail(ctx, PB_ERR_INVALID, "proxyValues required");
+    const bool td = usesTopographicDistance(s, variable);
+    if (td) {
+        if (!z) return fail(ctx, PB_ERR_INVALID, "topographic distance needs the targets' elevation (pb_interpolate_points_td)");
+        if (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used)
+            return fail(ctx, PB_ERR_INVALID, "topographic distance needs the resident DEM (pb_interpolate_points_td)");
+    }
     cudaEventRecord(ctx->ev[0], ctx->stream);
     DevStations ds{};
     rc = stageStations(ctx, st, s, excludeSupplemental != 0, ds, mod.valueOffset);
     if (rc) return rc;
     const size_t mAl = (size_t(m) + 3) / 4 * 4;
     const size_t offX = 0, offY = mAl * 4, offP = offY + mAl * 4, offO = offP + size_t(m) * mod.nProxy * 8;
-    const size_t total = offO + mAl * 4;
+    const size_t offZ = offO + mAl * 4, total = offZ + mAl * 4;
     CUDA_TRY(ctx, ctx->dScratch.reserve(total));
     unsigned char* d = ctx->dScratch.p;
     CUDA_TRY(ctx, cudaMemcpyAsync(d + offX, x, size_t(m) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(d + offY, y, size_t(m) * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (mod.nProxy > 0)
         CUDA_TRY(ctx, cudaMemcpyAsync(d + offP, proxyValues, size_t(m) * mod.nProxy * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (td) CUDA_TRY(ctx, cudaMemcpyAsync(d + offZ, z, size_t(m) * 4, cudaMemcpyHostToDevice, ctx->stream));
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    CUDA_TRY(ctx, launchIdwPoints(ds, mod, reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
-                                  reinterpret_cast<const double*>(d + offP), m, reinterpret_cast<float*>(d + offO), ctx->stream));
+    if (td)
+        CUDA_TRY(ctx, launchIdwTdPoints(ds, ds.z, mod, devGridOf(ctx->rasters[demId]), s->topoDist_Kh,
+                                        reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
+                                        reinterpret_cast<const float*>(d + offZ), reinterpret_cast<const double*>(d + offP), m,
+                                        reinterpret_cast<float*>(d + offO), ctx->stream));
+    else
+        CUDA_TRY(ctx, launchIdwPoints(ds, mod, reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
+                                      reinterpret_cast<const double*>(d + offP), m, reinterpret_cast<float*>(d + offO), ctx->stream));
     ctx->timing.launches++;
     cudaEventRecord(ctx->ev[2], ctx->stream);
     CUDA_TRY(ctx, cudaMemcpyAsync(result, d + offO, size_t(m) * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1061,6 +1091,21 @@ int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_setti
     cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
     return PB_OK;
+}
+
+
+int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
+                          const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result)
+{
+    return interpolatePointsImpl(ctx, st, s, variable, x, y, nullptr, proxyValues, m, excludeSupplemental, -1, result);
+}
+
+/* the same with topographic distance available: z = the targets' elevation, dem = the resident DEM the march samples */
+int pb_interpolate_points_td(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
+                             const float* y, const float* z, const double* proxyValues, int m, int excludeSupplemental,
+                             pb_raster_id dem, float* result)
+{
+    return interpolatePointsImpl(ctx, st, s, variable, x, y, z, proxyValues, m, excludeSupplemental, dem, result);
 }
 
 }  // extern "C"

@@ -69,6 +69,8 @@ def load_library():
     lib.pb_kriging_points.argtypes = [C.c_void_p, C.c_int32, P(C.c_double), C.c_int, P(C.c_double), P(C.c_double)]
     lib.pb_kriging_raster.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_int, P(A.pb_raster_out),
                                       P(A.pb_raster_out)]
+    lib.pb_interpolate_points_td.argtypes = raster_args + [P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_double), C.c_int,
+                                                           C.c_int, C.c_int32, P(C.c_float)]
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
                  "pb_cv_stats", "pb_timing"):
@@ -177,13 +179,20 @@ class Engine:
         return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid
 
     # ---- interpolate() at explicit targets (interpolation.cpp:2502) ----
-    def interpolate_points(self, stations, settings, variable, x, y, proxy_values, exclude_supplemental=False):
+    def interpolate_points(self, stations, settings, variable, x, y, proxy_values, exclude_supplemental=False, z=None,
+                           dem_id=-1):
         x = np.ascontiguousarray(x, dtype=np.float32)
         y = np.ascontiguousarray(y, dtype=np.float32)
         m = x.shape[0]
         pv = np.ascontiguousarray(proxy_values, dtype=np.float64).reshape(m, -1)
         res = np.empty(m, dtype=np.float32)
         st = stations.as_pb()
+        if z is not None:
+            z = np.ascontiguousarray(z, dtype=np.float32)
+            self._check(self.lib.pb_interpolate_points_td(self.h, C.byref(st), C.byref(settings), variable, A.fptr(x),
+                                                          A.fptr(y), A.fptr(z), A.dptr(pv) if pv.size else None, m,
+                                                          int(exclude_supplemental), dem_id, A.fptr(res)))
+            return res
         self._check(self.lib.pb_interpolate_points(self.h, C.byref(st), C.byref(settings), variable, A.fptr(x), A.fptr(y),
                                                    A.dptr(pv) if pv.size else None, m, int(exclude_supplemental),
                                                    A.fptr(res)))

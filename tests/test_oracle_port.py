@@ -124,3 +124,23 @@ def test_kriging_bit_exact(ref, port):
         b = port.kriging_points(pos, val, mode, 4e4, 0.1, 4.0, 1e-4, xy)
         assert a[0] and b[0]
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), mode
+
+
+def test_topographic_distance_raster_and_points_bit_exact(ref, port):
+    """computeDistances with getUseTD() (interpolation.cpp:226-251) + gis::topographicDistance (gis.cpp:1595-1647)."""
+    dem = syn.make_dem(70, 80, seed=6, cell_size=400.0)
+    st = syn.make_stations(dem, 45, variable="humidity", seed=7)
+    s = A.default_settings()
+    s.useTD = 1
+    s.topoDist_Kh = 8
+    a = ref.interpolation_raster(st, s, A.airRelHumidity, dem, ())
+    b = port.interpolation_raster(st, s, A.airRelHumidity, dem, ())
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    s0 = A.default_settings()
+    c = ref.interpolation_raster(st, s0, A.airRelHumidity, dem, ())
+    assert not np.array_equal(a[1], c[1]), "topographic distance must change the result"
+    x, y, z = st.x.astype(np.float32), st.y.astype(np.float32), st.z.astype(np.float32)
+    pv = np.zeros((st.n, 0))
+    pa = ref.interpolate_points_td(st, s, A.airRelHumidity, x, y, z, pv, dem)
+    pb_ = port.interpolate_points_td(st, s, A.airRelHumidity, x, y, z, pv, dem)
+    assert np.array_equal(pa, pb_)

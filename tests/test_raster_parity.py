@@ -237,3 +237,32 @@ def test_compute_residuals_and_cv_statistics(engine, ref, variable):
         assert gs["n"] == ws["n"]
         for k in ("meanAbsoluteError", "meanBiasError", "rootMeanSquareError", "nashSutcliffe", "R2"):
             assert abs(gs[k] - ws[k]) <= 1e-4, (k, gs[k], ws[k])
+
+
+def test_topographic_distance_raster_and_points(engine, ref):
+    """IDW with topographic distance (kh != 0): the ray march through the DEM is reproduced step by step."""
+    dem = syn.make_dem(110, 130, seed=6, cell_size=400.0)
+    urban = syn.make_urban(110, 130, cell_size=400.0)
+    st = syn.make_stations(dem, 90, proxies=(dem, urban), seed=7)
+    s = syn.settings_classic_detrending(2)
+    ok, keep = ref.pre_interpolation(st, s, A.dailyAirTemperatureMax, (dem, urban))
+    st = st.subset(keep)
+    s.useTD = 1
+    s.topoDist_Kh = 12
+    err, gg, gc = run_both(engine, ref, st, s, A.dailyAirTemperatureMax, dem, (dem, urban))
+    s0 = copy.copy(s)
+    okc, g0, *_ = ref.interpolation_raster(st, A.pb_settings.from_buffer_copy(s), A.dailyAirTemperatureMax, dem, (dem, urban))
+    # points: leave-one-out at the stations with their own elevation
+    x, y, z = st.x.astype(np.float32), st.y.astype(np.float32), st.z.astype(np.float32)
+    pv = st.proxy_values.astype(np.float64)
+    want = ref.interpolate_points_td(st, s, A.dailyAirTemperatureMax, x, y, z, pv, dem)
+    did = engine.upload(dem)
+    got = engine.interpolate_points(st, s, A.dailyAirTemperatureMax, x, y, pv, False, z=z, dem_id=did)
+    engine.free(did)
+    assert np.abs(got.astype(np.float64) - want).max() <= TOL
+    # precipitation does not use topographic distance (getUseTdVar, interpolation.cpp:1220-1234)
+    stp = syn.make_stations(dem, 60, variable="precipitation", seed=9)
+    sp = A.default_settings()
+    sp.useTD = 1
+    sp.topoDist_Kh = 12
+    run_both(engine, ref, stp, sp, A.precipitation, dem, ())
