@@ -77,6 +77,24 @@ def run_case(ref, name, dem, grids, st, s, var):
     save(name, dem, grids, raw, st, keep, s, var, out, ok, mn, mx, nv)
 
 
+def run_local_case(ref, name, dem, grids, st, s, var):
+    """loop of Project::interpolationDemLocalDetrending: raw points in, no global preInterpolation."""
+    ok, out, mn, mx, nv, _ = ref.local_detrending_raster(st, s, var, dem, grids, threads=8)
+    save(name, dem, grids, st, st, np.ones(st.n, dtype=bool), s, var, out, ok, mn, mx, nv)
+
+
+def run_kriging_case(ref, name, mode, n, m, rng_a, nugget, sill, slope, seed):
+    rng = np.random.default_rng(seed)
+    pos = rng.random((n, 2)) * 2.5e5 + np.array([5.0e5, 4.8e6])
+    val = rng.normal(11.0, 3.0, n)
+    xy = rng.random((m, 2)) * 2.5e5 + np.array([5.0e5, 4.8e6])
+    ok, res, rm, _, _ = ref.kriging_points(pos, val, mode, rng_a, nugget, sill, slope, xy)
+    assert ok
+    np.savez_compressed(os.path.join(HERE, name), pos=pos, val=val, xy=xy, params=np.array([mode, rng_a, nugget, sill, slope]),
+                        result=res, rmse=rm)
+    print(name, os.path.getsize(os.path.join(HERE, name)) // 1024, "KiB")
+
+
 def main():
     ref = Oracle("reference")
     # ---- C1: bundled demo ----
@@ -99,6 +117,26 @@ def main():
     run_case(ref, "synth_precipitation.npz", d, (), st, A.default_settings(), A.dailyPrecipitation)
     st = syn.make_stations(d, 70, variable="humidity", seed=104)
     run_case(ref, "synth_humidity.npz", d, (), st, A.default_settings(), A.airRelHumidity)
+    # topographic distance (kh = 10) on a 400 m DEM
+    dt = syn.make_dem(60, 70, seed=105, cell_size=400.0)
+    st = syn.make_stations(dt, 50, variable="humidity", seed=106)
+    s = A.default_settings()
+    s.useTD = 1
+    s.topoDist_Kh = 10
+    run_case(ref, "synth_topographic_distance.npz", dt, (), st, s, A.airRelHumidity)
+    # local detrending at config-3 station density
+    dl = syn.make_dem(36, 44, seed=107, cell_size=9000.0)
+    ul = syn.make_urban(36, 44, cell_size=9000.0)
+    st = syn.make_stations(dl, 640, proxies=(dl, ul), seed=108)
+    s = syn.settings_multiple_detrending()
+    s.useLocalDetrending = 1
+    s.minPointsLocalDetrending = 20
+    syn.set_points_range(s, st)
+    run_local_case(ref, "local_detrending.npz", dl, (dl, ul), st, s, A.airTemperature)
+    # ordinary kriging (kriging.cpp), one fixture per variogram model
+    run_kriging_case(ref, "kriging_spherical.npz", A.KRIGING_SPHERICAL, 140, 200, 8.0e4, 0.1, 4.0, 0.0, 201)
+    run_kriging_case(ref, "kriging_exponential.npz", A.KRIGING_EXPONENTIAL, 120, 150, 9.0e4, 0.2, 3.0, 0.0, 202)
+    run_kriging_case(ref, "kriging_linear.npz", A.KRIGING_LINEAR, 100, 150, 8.0e4, 0.15, 4.0, 2.0e-5, 203)
 
 
 if __name__ == "__main__":

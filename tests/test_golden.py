@@ -9,7 +9,10 @@ import pytest
 
 from praga_b200 import _abi as A
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+ALL = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+KRIGING = [p for p in ALL if os.path.basename(p).startswith("kriging_")]
+LOCAL = [p for p in ALL if os.path.basename(p).startswith("local_")]
+GOLDEN = [p for p in ALL if p not in KRIGING and p not in LOCAL]
 
 
 def load(path):
@@ -63,3 +66,46 @@ def test_gpu_matches_reference_raster(engine, path):
     err = np.abs(out.astype(np.float64) - want.astype(np.float64)).max()
     assert err <= 1e-4, err
     assert abs(mn - g["minimum"]) <= 1e-4 and abs(mx - g["maximum"]) <= 1e-4
+
+
+@pytest.mark.parametrize("path", LOCAL, ids=[os.path.basename(p) for p in LOCAL])
+def test_port_reproduces_reference_local_detrending(path):
+    from oracle import binding
+    port = binding.Oracle("port")
+    g, dem, grids, raw, det, s = load(path)
+    ok, out, mn, mx, nv, _ = port.local_detrending_raster(raw, s, int(g["variable"]), dem, grids, threads=4)
+    assert ok == bool(g["ok"]) and nv == int(g["n_valid"])
+    assert np.array_equal(out, g["out"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", LOCAL, ids=[os.path.basename(p) for p in LOCAL])
+def test_gpu_matches_reference_local_detrending(engine, path):
+    g, dem, grids, raw, det, s = load(path)
+    ok, out, mn, mx, nv = engine.local_detrending_raster(raw, s, int(g["variable"]), dem, grids)
+    want = g["out"]
+    flag = np.float32(dem.flag)
+    assert ok == bool(g["ok"]) and nv == int(g["n_valid"])
+    assert np.array_equal(out == flag, want == flag)
+    assert np.abs(out.astype(np.float64) - want.astype(np.float64)).max() <= 1e-4
+
+
+@pytest.mark.parametrize("path", KRIGING, ids=[os.path.basename(p) for p in KRIGING])
+def test_port_reproduces_reference_kriging(path):
+    from oracle import binding
+    port = binding.Oracle("port")
+    g = np.load(path)
+    mode, rng_a, nugget, sill, slope = g["params"]
+    ok, res, rm, _, _ = port.kriging_points(g["pos"], g["val"], int(mode), rng_a, nugget, sill, slope, g["xy"])
+    assert ok and np.array_equal(res, g["result"]) and np.array_equal(rm, g["rmse"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", KRIGING, ids=[os.path.basename(p) for p in KRIGING])
+def test_gpu_matches_reference_kriging(engine, path):
+    g = np.load(path)
+    mode, rng_a, nugget, sill, slope = g["params"]
+    kid = engine.kriging_setup(g["pos"], g["val"], int(mode), rng_a, nugget, sill, slope)
+    res, rm = engine.kriging_points(kid, g["xy"])
+    engine.kriging_free(kid)
+    assert np.abs(res - g["result"]).max() <= 1e-4 and np.abs(rm - g["rmse"]).max() <= 1e-4
