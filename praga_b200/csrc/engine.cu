@@ -693,7 +693,9 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     }
     ctx->hMinMax[0] = 0xffffffffu;
     ctx->hMinMax[1] = 0u;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->hMinMax[2] = 0u;           // work-item counter of the persistent IDW kernel
+    ctx->hMinMax[3] = 0u;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 4 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
 
     long long t0 = 0, t1 = dem.nValid;
     if (rowBegin != 0 || rowEnd != dem.h.nrRows) {
@@ -829,8 +831,8 @@ int pb_create(int device, pb_context** out)
     pb_context* ctx = new pb_context();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->dMinMax, 2 * sizeof(unsigned)) != cudaSuccess ||
-        cudaMallocHost(&ctx->hMinMax, 2 * sizeof(unsigned)) != cudaSuccess) {
+        cudaMalloc(&ctx->dMinMax, 4 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMallocHost(&ctx->hMinMax, 4 * sizeof(unsigned)) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, PB_ERR_CUDA, "context allocation failed");
     }

@@ -18,6 +18,7 @@
 // (TMA engine) double-buffered on mbarriers; every lane reads the same station (LDS broadcast).
 // Accumulation: FP32 inside a 512-station tile, FP64 across tiles; station values are centred on the host
 // (IDW is affine invariant), so the FP32 error scales with the spread of the residuals, not their level.
+#include <algorithm>
 #include "epilogue.cuh"
 
 namespace pb {
@@ -330,6 +331,171 @@ idw_kernel(DevStations st, DevModel m, DevGrid dem, const int* __restrict__ vali
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K1, persistent form (the raster path whenever the whole padded station set fits in shared memory, i.e. up to
+// kResidentMaxStations stations): ONE CTA per SM stays resident, loads every station tile once (1-D bulk copies
+// on one mbarrier) and then each WARP pulls work items of 32 x 2P consecutive valid cells from a global counter.
+// No CTA-wide barrier in the loop: warps drift apart, so one warp's epilogue (dependent DEM / proxy-grid loads,
+// f64 retrend) overlaps the other warps' station loops, and the tail costs one 128-cell item instead of a wave
+// of 1024-cell CTAs. Arithmetic and accumulation order are those of idw_kernel (bit-identical results).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kResidentMaxStations = 9216;     // 18 tiles x 12 KiB = 216 KiB of the 227 KiB a CTA may own
+
+template <int P, int kPersistThreads>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+idw_persistent_kernel(DevStations st, DevModel m, DevGrid dem, const int* __restrict__ validIdx, int nTargets,
+                      float* __restrict__ out, unsigned* __restrict__ minmax, unsigned* __restrict__ workCounter)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const float4* __restrict__ sxyAll = reinterpret_cast<const float4*>(smem);
+    const float2* __restrict__ svAll = reinterpret_cast<const float2*>(smem + (size_t)st.nPadded * sizeof(float4));
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nTiles = st.nPadded / kTileStations;
+    constexpr int C = 2 * P;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, (uint32_t)st.nPadded * (uint32_t)(sizeof(float4) + sizeof(float2)));
+        for (int t = 0; t < nTiles; t++) {
+            bulk_g2s(smem + (size_t)t * kTileStations * sizeof(float4), st.xy + (size_t)t * kTileStations,
+                     kTileStations * sizeof(float4), &bar);
+            bulk_g2s(smem + (size_t)st.nPadded * sizeof(float4) + (size_t)t * kTileStations * sizeof(float2),
+                     st.v + (size_t)t * kTileStations, kTileStations * sizeof(float2), &bar);
+        }
+    }
+    mbar_wait(&bar, 0);
+
+    float vmin = INFINITY, vmax = -INFINITY;
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(workCounter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        const long long base = (long long)item * (32 * C);
+        if (base >= nTargets) break;
+
+        float x[C], y[C];
+        int cell[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const long long t = base + c * 32 + lane;
+            if (t < nTargets) {
+                const int idx = validIdx[t];
+                const int row = idx / dem.nrCols, col = idx - row * dem.nrCols;
+                cell[c] = idx;
+                // getUtmXYFromRowColSinglePrecision(header,...) gis.cpp:799-804: corner + (0.5 m, -0.5 m), f64 -> f32
+                x[c] = float(__dadd_rn(__dadd_rn(dem.llx, __dmul_rn(dem.cellSize, double(col))), 0.5));
+                y[c] = float(__dsub_rn(__dadd_rn(dem.lly, __dmul_rn(dem.cellSize, double(dem.nrRows - row))), 0.5));
+            } else {
+                cell[c] = -1;
+                x[c] = 0.f;
+                y[c] = 0.f;
+            }
+        }
+        f32x2 nx[P], ny[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            nx[p] = pack2(-x[2 * p], -x[2 * p + 1]);
+            ny[p] = pack2(-y[2 * p], -y[2 * p + 1]);
+        }
+        double SW[C], SWV[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) { SW[c] = 0.; SWV[c] = 0.; }
+
+#pragma unroll 1
+        for (int t = 0; t < nTiles; t++) {
+            const float4* __restrict__ sxy = sxyAll + (size_t)t * kTileStations;
+            const float2* __restrict__ sv = svAll + (size_t)t * kTileStations;
+            f32x2 tsw[P], tswv[P];
+#pragma unroll
+            for (int p = 0; p < P; p++) { tsw[p] = pack2(0.f, 0.f); tswv[p] = pack2(0.f, 0.f); }
+#pragma unroll 1
+            for (int c0 = 0; c0 < kTileStations; c0 += kChunk) {
+                f32x2 sw[P], swv[P];
+#pragma unroll
+                for (int s = 0; s < kChunk; s++) {
+                    const float4 pxy = sxy[c0 + s];
+                    const float2 pv = sv[c0 + s];
+                    const f32x2 px = pack2(pxy.x, pxy.y), py = pack2(pxy.z, pxy.w), pvv = pack2(pv.x, pv.y);
+#pragma unroll
+                    for (int p = 0; p < P; p++) {
+                        const f32x2 dx = add2(px, nx[p]), dy = add2(py, ny[p]);
+                        const f32x2 d2 = fma2(dx, dx, mul2(dy, dy));
+                        float a, bq;
+                        unpack2(d2, a, bq);
+                        const f32x2 r = pack2(rsqrt_approx(a), rsqrt_approx(bq));
+                        const f32x2 w = mul2(mul2(r, r), r);       // 1/d^3 (the 1/10000 scale cancels in the ratio)
+                        if (s == 0) {
+                            sw[p] = w;
+                            swv[p] = mul2(w, pvv);
+                        } else {
+                            sw[p] = add2(sw[p], w);
+                            swv[p] = fma2(w, pvv, swv[p]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < P; p++) { tsw[p] = add2(tsw[p], sw[p]); tswv[p] = add2(tswv[p], swv[p]); }
+            }
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                float a, bq, va, vb;
+                unpack2(tsw[p], a, bq);
+                unpack2(tswv[p], va, vb);
+                SW[2 * p] += double(a);
+                SW[2 * p + 1] += double(bq);
+                SWV[2 * p] += double(va);
+                SWV[2 * p + 1] += double(vb);
+            }
+        }
+
+#pragma unroll 1
+        for (int c = 0; c < C; c++) {
+            if (cell[c] < 0) continue;
+            double sw = SW[c], swv = SWV[c];
+            if (!(sw <= 1.0e300) || !(fabs(swv) <= 1.0e300)) idwExact(st, x[c], y[c], sw, swv);   // inf/NaN: zero distance seen
+            double pv[PB_MAX_PROXY];
+            if (m.useDetrendingVar) {
+                // getProxyValuesXY (interpolation.cpp:2620-2647)
+                for (int i = 0; i < m.nProxy; i++) {
+                    pv[i] = double(kNoData);
+                    const DevProxy& p = m.proxy[i];
+                    if (p.active && p.gridSlot >= 0) {
+                        const DevGrid& g = m.grid[p.gridSlot];
+                        const float v = gridValueFromXY(g, double(x[c]), double(y[c]));
+                        if (v != g.flag) pv[i] = double(v);
+                    }
+                }
+            } else {
+                for (int i = 0; i < m.nProxy; i++) pv[i] = double(kNoData);
+            }
+            float result;
+            if (m.useRetrendOnly) result = 0.f;
+            else result = (sw > 0.0) ? float(swv / sw + m.valueOffset) : kNoData;
+            const float o = finishEstimate(m, result, pv);
+            out[cell[c]] = o;
+            if (!isEqualF(o, dem.flag) && !isEqualF(o, kNoData)) {
+                vmin = fminf(vmin, o);
+                vmax = fmaxf(vmax, o);
+            }
+        }
+    }
+    if (minmax) {
+        for (int o = 16; o; o >>= 1) {
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        }
+        if (lane == 0) {
+            if (vmin != INFINITY) atomicMin(&minmax[0], orderedKey(vmin));
+            if (vmax != -INFINITY) atomicMax(&minmax[1], orderedKey(vmax));
+        }
+    }
+}
+
 // constant fill of valid cells (precipitationAllZero short-circuit, interpolation.cpp:2506-2507) and
 // flag initialisation of the output (Crit3DRasterGrid::initializeGrid(raster), gis.cpp:357-363)
 __global__ void fill_kernel(float* __restrict__ out, long long n, float v)
@@ -388,6 +554,23 @@ cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevG
 {
     if (nTargets <= 0) return cudaSuccess;
     constexpr int P = 2;
+    if (st.nPadded <= kResidentMaxStations) {
+        // persistent form: minmax[2] is the work-item counter (zeroed by the caller together with min/max)
+        constexpr int kPersistThreads = 1024;     // 32 warps/SM: measured best on B200 (512: -5 % at C2, equal at S = 5000)
+        auto k = idw_persistent_kernel<P, kPersistThreads>;
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentMaxStations * 24);
+        }
+        const size_t smem = (size_t)st.nPadded * (sizeof(float4) + sizeof(float2));
+        const int items = (nTargets + 64 * P - 1) / (64 * P);
+        const int grid = std::min(sms, (items + kPersistThreads / 32 - 1) / (kPersistThreads / 32));
+        k<<<grid, kPersistThreads, smem, s>>>(st, m, dem, validIdx, nTargets, out, minmax, minmax + 2);
+        return cudaGetLastError();
+    }
     const int per = kThreads * 2 * P;
     const int grid = (nTargets + per - 1) / per;
     auto k = idw_kernel<P, false>;
