@@ -208,6 +208,35 @@ int pb_pre_interpolation_batch(pb_context* ctx, const pb_stations* st, const flo
 /* one time step, in place: st->value is detrended, *s receives the fit (same contract as the reference call) */
 int pb_pre_interpolation(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, uint8_t* keep);
 
+/* preInterpolation with EVERY branch of interpolation.cpp:2444-2499, one time step, in place:
+ *   - checkPrecipitationZero :1173; multipleDetrendingMain :1832 (as above);
+ *   - classic detrending() :1380-1415 (regressionOrographyT :433-798 thermal-inversion heuristic, regressionSimpleT :368,
+ *     regressionGeneric :346, detrendPoints :1236), one device lane per (time step, proxy combination);
+ *   - optimalDetrending() :2395-2441 when settings.useBestDetrending: every combination of getCombination
+ *     (interpolationSettings.cpp:869-892) is detrended, cross-validated (computeResiduals, spatialControl.cpp:97-155, exact
+ *     f32-distance / f64-weight leave-one-out on the device) and the smallest MAE wins;
+ *   - topographicDistanceOptimize() :2356-2392 when getUseTD() && getUseTdVar(var): golden section on kh over the
+ *     MAE(kh) table of all integer kh in [0, topoDist_maxKh], built in one launch from the station-to-station topographic
+ *     distances (gis::topographicDistance, gis/gis.cpp:1595-1647, marched through the resident DEM `dem`).
+ * The reference walks std::vector<Crit3DMeteoPoint> for the cross-validation; here there is one meteo point per station of
+ * `st` in the same order (what passDataToInterpolation, spatialControl.cpp:500-566, builds the points from), described by
+ * pb_cv_points (NULL: currentValue = st->value at entry, every point inside the DEM). settings receives what the reference
+ * leaves behind: current combination and significance, the proxies' regression fields, topoDist_Kh, points range /
+ * bounding-box area (optimalDetrending re-runs passDataToInterpolation); khSeries (may be NULL) the Kh / error series. */
+typedef struct pb_cv_points {
+    const float* currentValue;     /* Crit3DMeteoPoint::currentValue; NULL => st->value at entry */
+    const uint8_t* isInsideDem;    /* Crit3DMeteoPoint::isInsideDem; NULL => all inside */
+    int32_t excludeOutsideDem;     /* getUseExcludeStationsOutsideDEM() */
+    int32_t reserved;
+} pb_cv_points;
+#define PB_MAX_KH_SERIES 64
+typedef struct pb_kh_series {      /* Crit3DInterpolationSettings::Kh_series / Kh_error_series (interpolationSettings.cpp:134) */
+    int32_t n;
+    float kh[PB_MAX_KH_SERIES], error[PB_MAX_KH_SERIES];
+} pb_kh_series;
+int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv,
+                            pb_raster_id dem /* -1: none */, uint8_t* keep, pb_kh_series* khSeries);
+
 /* --- local-detrending raster: the loop of Project::interpolationDemLocalDetrending (agrolib/project/project.cpp:3208-3253),
  * which the reference inlines in its Qt-bound Project class instead of going through interpolationRaster. Per valid
  * cell: localSelection (interpolation.cpp:1087-1170), preInterpolation on the subset (multipleDetrendingMain :1832,

@@ -57,6 +57,9 @@ def _load(path, prefix):
                    P(A.pb_raster_out), P(C.c_double)]
     fn = getattr(lib, prefix + "_pre_interpolation")
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_uint8), P(A.pb_raster), C.c_int]
+    fn = getattr(lib, prefix + "_pre_interpolation_ex")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_cv_points), P(A.pb_raster), P(C.c_uint8),
+                   P(A.pb_kh_series)]
     fn = getattr(lib, prefix + "_interpolate_points")
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_float), P(C.c_float),
                    P(C.c_double), C.c_int, C.c_int, P(C.c_float)]
@@ -156,6 +159,26 @@ class Oracle:
         rc = self._f("pre_interpolation")(C.byref(st), C.byref(settings), variable, A.u8ptr(keep), grids,
                                           len(proxy_grids))
         return rc == A.PB_OK, keep.astype(bool)
+
+    def pre_interpolation_ex(self, stations, settings, variable, current_value=None, inside_dem=None,
+                             exclude_outside_dem=False, dem=None):
+        """preInterpolation with its meteo points and current DEM (optimalDetrending, kh golden section).
+        Returns (ok, keep mask, [(kh, error), ...])."""
+        st = stations.as_pb()
+        keep = np.zeros(stations.n, dtype=np.uint8)
+        cv = A.pb_cv_points()
+        cur = None if current_value is None else np.ascontiguousarray(current_value, dtype=np.float32)
+        ins = None if inside_dem is None else np.ascontiguousarray(inside_dem, dtype=np.uint8)
+        if cur is not None:
+            cv.currentValue = A.fptr(cur)
+        if ins is not None:
+            cv.isInsideDem = A.u8ptr(ins)
+        cv.excludeOutsideDem = int(exclude_outside_dem)
+        series = A.pb_kh_series()
+        d = None if dem is None else dem.as_pb()
+        rc = self._f("pre_interpolation_ex")(C.byref(st), C.byref(settings), variable, C.byref(cv),
+                                             None if d is None else C.byref(d), A.u8ptr(keep), C.byref(series))
+        return rc == A.PB_OK, keep.astype(bool), [(series.kh[i], series.error[i]) for i in range(series.n)]
 
     def interpolate_points(self, stations, settings, variable, x, y, z, proxy_values, exclude_supplemental=False):
         x = np.ascontiguousarray(x, dtype=np.float32)

@@ -1367,6 +1367,226 @@ int port_pre_interpolation(pb_stations* st, pb_settings* s, int variable, uint8_
     return ok ? PB_OK : PB_ERR_FIT;
 }
 
+// ---- station-space cross-validation drivers: optimalDetrending, topographicDistanceOptimize ------------------------
+struct MeteoPt {        // the Crit3DMeteoPoint fields computeResiduals reads (meteo/meteoPoint.h)
+    double x, y, z;
+    float currentValue, residual;
+    int lapseRateCode;
+    bool isInsideDem;
+    std::vector<float> proxy;
+};
+
+// computeResiduals, interpolation/spatialControl.cpp:97-155 (every meteo point active and accepted)
+void computeResidualsMeteo(int var, std::vector<MeteoPt>& mp, const std::vector<Point>& pts, const pb_settings& s,
+                           bool excludeOutsideDem, bool excludeSupplemental, const Grid* dem)
+{
+    for (auto& m : mp) {
+        m.residual = NODATA_F;
+        bool valid = !excludeSupplemental || checkLapseRateCode(m.lapseRateCode, s.useLapseRateCode != 0, false);
+        valid = valid && (!excludeOutsideDem || m.isInsideDem);
+        if (!valid) continue;
+        double pv[PB_MAX_PROXY];
+        for (int k = 0; k < PB_MAX_PROXY; k++) pv[k] = k < int(m.proxy.size()) ? double(m.proxy[k]) : -9999.;
+        float myValue = m.currentValue;
+        float est = interpolate(pts, s, var, float(m.x), float(m.y), pv, false, float(m.z), dem);
+        if (isPrec(var)) {
+            if (myValue != NODATA_F && myValue < s.rainfallThreshold) myValue = 0.f;
+            if (est != NODATA_F && est < s.rainfallThreshold) est = 0.f;
+        }
+        if (est != NODATA_F && myValue != NODATA_F) m.residual = myValue - est;
+    }
+}
+
+// computeErrorCrossValidation, spatialControl.cpp:305-328 + statistics::meanAbsoluteError, statistics.cpp:201-220
+float computeErrorCrossValidation(const std::vector<MeteoPt>& mp)
+{
+    double sum = 0;
+    long n = 0;
+    bool any = false;
+    for (auto& m : mp) {
+        const float value = m.currentValue, residual = m.residual;
+        if (value != NODATA_F && residual != NODATA_F) {
+            any = true;
+            const float est = value - residual;
+            if (value != NODATA_F && est != NODATA_F) { sum += fabs(value - est); n++; }
+        }
+    }
+    if (!any || n == 0) return NODATA_F;
+    return float(sum / n);
+}
+
+// topographicDistanceInternalFunction :2338-2353, goldenSectionSearch :2297-2335, topographicDistanceOptimize :2356-2392
+double tdInternal(int var, std::vector<MeteoPt>& mp, const std::vector<Point>& pts, pb_settings& s, const Grid* dem, double khFloat)
+{
+    s.topoDist_Kh = int(khFloat);
+    computeResidualsMeteo(var, mp, pts, s, true, true, dem);
+    return double(computeErrorCrossValidation(mp));
+}
+void topographicDistanceOptimize(int var, std::vector<MeteoPt>& mp, const std::vector<Point>& pts, pb_settings& s, const Grid* dem,
+                                 pb_kh_series* series)
+{
+    if (series) series->n = 0;
+    auto add = [&](float kh, float e) {
+        if (series && series->n < PB_MAX_KH_SERIES) { series->kh[series->n] = kh; series->error[series->n] = e; series->n++; }
+    };
+    const double GOLDEN = 1.6180339887499;
+    double a = 0, b = double(s.topoDist_maxKh);
+    double x1 = b - (b - a) / GOLDEN, x2 = a + (b - a) / GOLDEN;
+    int counter = 0;
+    while (std::abs(b - a) > 1 && counter < 100) {
+        counter++;
+        if (tdInternal(var, mp, pts, s, dem, x1) < tdInternal(var, mp, pts, s, dem, x2)) {
+            b = x2; x2 = x1; x1 = b - (b - a) / GOLDEN;
+            add(float(x1), float(tdInternal(var, mp, pts, s, dem, x1)));
+        } else {
+            a = x1; x1 = x2; x2 = a + (b - a) / GOLDEN;
+            add(float(x2), float(tdInternal(var, mp, pts, s, dem, x2)));
+        }
+    }
+    add(float((a + b) / 2), float(tdInternal(var, mp, pts, s, dem, (a + b) / 2)));
+    s.topoDist_Kh = int((a + b) / 2);
+}
+
+// passDataToInterpolation, spatialControl.cpp:500-566 (every meteo point active, accepted, not a selection)
+bool passDataToInterpolation(const std::vector<MeteoPt>& mp, std::vector<Point>& pts, pb_settings& s)
+{
+    float xMin = 0, xMax = 0, yMin = 0, yMax = 0, vMin = 0, vMax = 0;
+    bool first = true;
+    int nrValid = 0;
+    pts.clear();
+    for (size_t i = 0; i < mp.size(); i++) {
+        Point p{};
+        p.index = int(i);
+        p.value = mp[i].currentValue;
+        p.x = mp[i].x; p.y = mp[i].y; p.z = mp[i].z;
+        p.lapseRateCode = mp[i].lapseRateCode;
+        p.isActive = true;
+        p.regressionWeight = NODATA_F;
+        p.nProxy = int(mp[i].proxy.size());
+        for (int k = 0; k < p.nProxy; k++) p.proxy[k] = mp[i].proxy[k];
+        if (first) {
+            xMin = xMax = float(p.x); yMin = yMax = float(p.y); vMin = vMax = p.value;
+            first = false;
+        } else {
+            xMin = std::min(xMin, float(p.x)); xMax = std::max(xMax, float(p.x));
+            yMin = std::min(yMin, float(p.y)); yMax = std::max(yMax, float(p.y));
+            vMin = std::min(vMin, p.value); vMax = std::max(vMax, p.value);
+        }
+        pts.push_back(p);
+        if (checkLapseRateCode(p.lapseRateCode, s.useLapseRateCode != 0, false)) nrValid++;
+    }
+    if (nrValid == 0) return false;
+    s.pointsBoundingBoxArea = (xMax - xMin) * (yMax - yMin);
+    s.hasPointsRange = 1;
+    s.pointsRangeMin = vMin;
+    s.pointsRangeMax = vMax;
+    return true;
+}
+
+// Crit3DInterpolationSettings::getCombination, interpolationSettings.cpp:869-892
+bool getCombination(const pb_settings& s, int k, uint8_t* active, int& inversion)
+{
+    const int digits = s.nProxy + 1, ih = indexHeight(s);
+    auto bit = [&](int pos) { return (k >> (digits - 1 - pos)) & 1; };
+    if (k % 2 == 1 && (ih < 0 || !bit(ih))) return false;
+    for (int i = 0; i < s.nProxy; i++) active[i] = (bit(i) && s.selectedActive[i]) ? 1 : 0;
+    inversion = (bit(digits - 1) && s.selectedUseThermalInversion) ? 1 : 0;
+    return true;
+}
+
+// detrending() with an explicit combination (interpolation.cpp:1380-1415)
+void detrendingCombination(Work& w, const uint8_t* active, int inversion)
+{
+    pb_settings& s = *w.s;
+    uint8_t selSave[PB_MAX_PROXY];
+    memcpy(selSave, s.selectedActive, sizeof(selSave));
+    const int invSave = s.selectedUseThermalInversion;
+    memcpy(s.selectedActive, active, PB_MAX_PROXY);
+    s.selectedUseThermalInversion = inversion;
+    detrendingClassic(w);
+    memcpy(s.selectedActive, selSave, sizeof(selSave));
+    s.selectedUseThermalInversion = invSave;
+}
+
+// optimalDetrending, interpolation.cpp:2395-2441
+void optimalDetrending(int var, std::vector<MeteoPt>& mp, std::vector<Point>& outPts, pb_settings& s, bool excludeOutsideDem,
+                       const Grid* dem)
+{
+    const int nrCombination = 1 << (s.nProxy + 1);
+    float minError = NODATA_F;
+    int best = 0;
+    const bool td = dem && s.useTD && !s.useLocalDetrending && useTdVar(var);
+    for (int i = 0; i < nrCombination; i++) {
+        uint8_t active[PB_MAX_PROXY] = {0};
+        int inversion = 0;
+        if (!getCombination(s, i, active, inversion)) continue;
+        Work w{{}, &s, var};
+        passDataToInterpolation(mp, w.pts, s);
+        detrendingCombination(w, active, inversion);
+        if (td) topographicDistanceOptimize(var, mp, w.pts, s, dem, nullptr);
+        computeResidualsMeteo(var, mp, w.pts, s, excludeOutsideDem, true, dem);
+        const float avgError = computeErrorCrossValidation(mp);
+        if (!isEqualF(avgError, NODATA_F) && (isEqualF(minError, NODATA_F) || avgError < minError)) {
+            minError = avgError;
+            best = i;
+        }
+    }
+    uint8_t active[PB_MAX_PROXY] = {0};
+    int inversion = 0;
+    if (getCombination(s, best, active, inversion)) {
+        Work w{{}, &s, var};
+        passDataToInterpolation(mp, w.pts, s);
+        detrendingCombination(w, active, inversion);
+        outPts = w.pts;
+    }
+}
+
+int port_pre_interpolation_ex(pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv, const pb_raster* dem,
+                              uint8_t* keep, pb_kh_series* khSeries)
+{
+    if (khSeries) khSeries->n = 0;
+    Work w{loadPoints(st), s, variable};
+    std::vector<MeteoPt> mp(st->n);
+    for (int i = 0; i < st->n; i++) {
+        mp[i].x = st->x[i]; mp[i].y = st->y[i]; mp[i].z = st->z[i];
+        mp[i].currentValue = (cv && cv->currentValue) ? cv->currentValue[i] : st->value[i];
+        mp[i].residual = NODATA_F;
+        mp[i].lapseRateCode = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        mp[i].isInsideDem = (cv && cv->isInsideDem) ? cv->isInsideDem[i] != 0 : true;
+        mp[i].proxy.assign(st->proxyValues ? st->proxyValues + size_t(i) * st->nProxy : nullptr,
+                           st->proxyValues ? st->proxyValues + size_t(i + 1) * st->nProxy : nullptr);
+    }
+    Grid g{};
+    const Grid* gp = nullptr;
+    if (dem) { g = gridOf(*dem); gp = &g; }
+    bool ok = true;
+    bool done = false;
+    if (isPrec(variable)) {
+        int nrValid = 0;
+        for (auto& p : w.pts)
+            if (p.isActive && !isEqualF(p.value, NODATA_F) && p.value >= s->rainfallThreshold) nrValid++;
+        if (nrValid == 0) { s->precipitationAllZero = 1; done = true; }
+        else s->precipitationAllZero = 0;
+    }
+    if (!done) {
+        if (useDetrendingVar(variable)) {
+            if (s->useMultipleDetrending) {
+                if (!s->useLocalDetrending) setMultipleDetrendingHeightTemperatureRange(*s);
+                if (!multipleDetrendingMain(w)) ok = false;
+            } else if (s->useBestDetrending) optimalDetrending(variable, mp, w.pts, *s, cv && cv->excludeOutsideDem, gp);
+            else detrendingClassic(w);
+        }
+        if (ok && gp && s->useTD && !s->useLocalDetrending && useTdVar(variable) && !s->useGlocalDetrending)
+            topographicDistanceOptimize(variable, mp, w.pts, *s, gp, khSeries);
+    }
+    if (keep) memset(keep, 0, st->n);
+    for (auto& p : w.pts) {
+        st->value[p.index] = p.value;
+        if (keep) keep[p.index] = 1;
+    }
+    return ok ? PB_OK : PB_ERR_FIT;
+}
+
 int port_interpolate_points(const pb_stations* st, const pb_settings* s, int variable, const float* x, const float* y,
                             const float*, const double* proxyValues, int m, int excludeSupplemental, float* result)
 {

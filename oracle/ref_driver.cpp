@@ -364,6 +364,54 @@ int ref_pre_interpolation(pb_stations* st, pb_settings* s, int variable, uint8_t
     return ok ? PB_OK : PB_ERR_FIT;
 }
 
+/* preInterpolation with the meteo points and the current DEM it needs for optimalDetrending (:2395-2441) and
+ * topographicDistanceOptimize (:2356-2392), verbatim reference code. One Crit3DMeteoPoint per station (active, accepted,
+ * currentValue = cv->currentValue or the station value at entry). optimalDetrending rebuilds the interpolation points from
+ * the meteo points (passDataToInterpolation), so their count can differ from st->n only if a point were inactive. */
+int ref_pre_interpolation_ex(pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv, const pb_raster* dem,
+                             uint8_t* keep, pb_kh_series* khSeries)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    gis::Crit3DRasterGrid demGrid;
+    if (dem) {
+        fillGrid(demGrid, *dem);
+        sc.settings.setCurrentDEM(&demGrid);
+    }
+    sc.settings.setUseExcludeStationsOutsideDEM(cv && cv->excludeOutsideDem);
+    std::vector<Crit3DMeteoPoint> mp(st->n);
+    for (int i = 0; i < st->n; i++) {
+        sc.points[i].index = i;
+        mp[i].active = true;
+        mp[i].quality = quality::accepted;
+        mp[i].currentValue = (cv && cv->currentValue) ? cv->currentValue[i] : st->value[i];
+        mp[i].point.utm.x = st->x[i];
+        mp[i].point.utm.y = st->y[i];
+        mp[i].point.z = st->z[i];
+        mp[i].isInsideDem = (cv && cv->isInsideDem) ? cv->isInsideDem[i] != 0 : true;
+        mp[i].lapseRateCode = st->lapseRateCode ? lapseRateCodeType(st->lapseRateCode[i]) : primary;
+        for (int k = 0; k < st->nProxy; k++) mp[i].proxyValues.push_back(st->proxyValues[size_t(i) * st->nProxy + k]);
+    }
+    std::string err;
+    bool ok = preInterpolation(sc.points, sc.settings, &sc.meteoSettings, &sc.climate, mp, meteoVariable(variable), sc.time, err);
+    if (keep) memset(keep, 0, st->n);
+    for (auto& p : sc.points) {
+        st->value[p.index] = p.value;
+        if (keep) keep[p.index] = 1;
+    }
+    exportSettings(sc, *s);
+    s->pointsBoundingBoxArea = sc.settings.getPointsBoundingBoxArea();
+    std::vector<double> pr = sc.settings.getPointsRange();
+    if (pr.size() == 2) { s->hasPointsRange = 1; s->pointsRangeMin = pr[0]; s->pointsRangeMax = pr[1]; }
+    if (khSeries) {
+        std::vector<float> kh = sc.settings.getKh_series(), e = sc.settings.getKh_error_series();
+        khSeries->n = int(std::min(kh.size(), size_t(PB_MAX_KH_SERIES)));
+        for (int i = 0; i < khSeries->n; i++) { khSeries->kh[i] = kh[i]; khSeries->error[i] = e[i]; }
+    }
+    return ok ? PB_OK : PB_ERR_FIT;
+}
+
 /* interpolate() at arbitrary targets (x, y, z, proxyValues[nProxy]) — interpolation.cpp:2502 */
 int ref_interpolate_points(const pb_stations* st, const pb_settings* s, int variable, const float* x, const float* y,
                            const float* z, const double* proxyValues, int m, int excludeSupplemental, float* result)

@@ -108,6 +108,18 @@ class pb_cv_stats(C.Structure):
                 ("rootMeanSquareError", C.c_float), ("nashSutcliffe", C.c_float), ("R2", C.c_float)]
 
 
+class pb_cv_points(C.Structure):
+    _fields_ = [("currentValue", C.POINTER(C.c_float)), ("isInsideDem", C.POINTER(C.c_uint8)),
+                ("excludeOutsideDem", C.c_int32), ("reserved", C.c_int32)]
+
+
+PB_MAX_KH_SERIES = 64
+
+
+class pb_kh_series(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kh", C.c_float * PB_MAX_KH_SERIES), ("error", C.c_float * PB_MAX_KH_SERIES)]
+
+
 class pb_timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]

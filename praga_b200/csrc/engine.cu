@@ -794,6 +794,25 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
 }  // namespace
 
 namespace pb {
+// used by station_space.cu
+int buildDevModel(pb_context* ctx, const pb_settings* s, int variable, DevModel& m) { return buildModel(ctx, s, variable, nullptr, 0, m); }
+int preInterpolationMultiple(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, uint8_t* keep)
+{
+    std::vector<float> in(st->value, st->value + st->n);
+    const double range[2] = {s->pointsRangeMin, s->pointsRangeMax};
+    pb_settings tmpl = *s;
+    return preInterpolationBatchImpl(ctx, st, in.data(), 1, &tmpl, variable, s->hasPointsRange ? range : nullptr, st->value, keep, s);
+}
+DevGrid devGridOfRaster(const RasterEntry& r) { return devGridOf(r); }
+bool varUsesDetrending(int v) { return useDetrendingVar(v); }
+bool varUsesTd(int v) { return useTdVar(v); }
+bool varIsPrec(int v) { return isPrecVar(v); }
+bool varIsThermal(int v)       // isThermal, interpolation.cpp:1190-1203
+{
+    return v == PB_VAR_AIR_TEMPERATURE || v == PB_VAR_AIR_DEW_TEMPERATURE || v == PB_VAR_DAILY_TAVG || v == PB_VAR_DAILY_TMAX ||
+           v == PB_VAR_DAILY_TMIN || v == PB_VAR_DAILY_ET0_HS || v == PB_VAR_ELABORATION;
+}
+int varClampMode(int v) { return clampModeOf(v); }
 int ensureValidList(pb_context* ctx, RasterEntry& e) { return ensureValidListImpl(ctx, e); }
 int ensureRowStart(pb_context* ctx, RasterEntry& e) { return ensureRowStartImpl(ctx, e); }
 }  // namespace pb
@@ -970,27 +989,9 @@ int pb_pre_interpolation_batch(pb_context* ctx, const pb_stations* st, const flo
 /* preInterpolation for one time step, in place like the reference: st->value is detrended, *s receives the fit */
 int pb_pre_interpolation(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, uint8_t* keep)
 {
-    if (!ctx) return PB_ERR_INVALID;
-    if (!st || !s) return fail(ctx, PB_ERR_INVALID, "null argument");
-    cudaSetDevice(ctx->device);
-    if (isPrecVar(variable)) {      // checkPrecipitationZero (interpolation.cpp:1173-1186): a count, host arithmetic
-        int nrValid = 0;
-        for (int i = 0; i < st->n; i++) {
-            const bool active = st->isActive ? st->isActive[i] != 0 : true;
-            if (active && !isEqualF(st->value[i], kNoData) && st->value[i] >= s->rainfallThreshold) nrValid++;
-        }
-        s->precipitationAllZero = nrValid == 0;
-        if (keep) memset(keep, 1, st->n);
-        return PB_OK;
-    }
-    if (!useDetrendingVar(variable)) {
-        if (keep) memset(keep, 1, st->n);
-        return PB_OK;
-    }
-    std::vector<float> in(st->value, st->value + st->n);
-    const double range[2] = {s->pointsRangeMin, s->pointsRangeMax};
-    pb_settings tmpl = *s;
-    return preInterpolationBatchImpl(ctx, st, in.data(), 1, &tmpl, variable, s->hasPointsRange ? range : nullptr, st->value, keep, s);
+    // every branch that needs neither the meteo points' extra fields nor the DEM; optimalDetrending's leave-one-out uses
+    // the stations themselves as meteo points (pb_pre_interpolation_ex, station_space.cu)
+    return pb_pre_interpolation_ex(ctx, st, s, variable, nullptr, -1, keep, nullptr);
 }
 
 static int hostRasterCall(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const pb_raster* dem,
@@ -1235,6 +1236,8 @@ extern "C" int pb_measure_pipe_peaks(pb_context* ctx, float* fp32Tflops, float* 
 extern "C" size_t pb_abi_sizeof(const char* name)
 {
     if (!name) return 0;
+    if (!strcmp(name, "pb_cv_points")) return sizeof(pb_cv_points);
+    if (!strcmp(name, "pb_kh_series")) return sizeof(pb_kh_series);
     if (!strcmp(name, "pb_raster_header")) return sizeof(pb_raster_header);
     if (!strcmp(name, "pb_raster")) return sizeof(pb_raster);
     if (!strcmp(name, "pb_stations")) return sizeof(pb_stations);

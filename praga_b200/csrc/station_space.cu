@@ -1,0 +1,441 @@
+// station_space.cu — C ABI of the per-time-step station-space pipeline: preInterpolation with every branch
+// (agrolib/interpolation/interpolation.cpp:2444-2499): checkPrecipitationZero, multipleDetrendingMain (K3, engine.cu),
+// classic detrending(), optimalDetrending() and topographicDistanceOptimize() (K7, classic_kernels.cu).
+// The host side only flattens settings, orders the launches and replays the reference's bookkeeping (which fields of
+// Crit3DProxy each combination wrote, the golden-section walk over the MAE(kh) table, the Kh series); every sum over
+// stations runs on the device.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "classic.cuh"
+#include "context.cuh"
+
+namespace pb {
+// engine.cu
+int buildDevModel(pb_context* ctx, const pb_settings* s, int variable, DevModel& m);
+int preInterpolationMultiple(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, uint8_t* keep);
+DevGrid devGridOfRaster(const RasterEntry& r);
+bool varUsesDetrending(int v);
+bool varUsesTd(int v);
+bool varIsPrec(int v);
+bool varIsThermal(int v);
+int varClampMode(int v);
+}  // namespace pb
+
+using namespace pb;
+
+namespace {
+
+int fail(pb_context* ctx, int code, const std::string& msg) { return pb::failCtx(ctx, code, msg); }
+
+template <typename T>
+T* carve(unsigned char*& p, size_t count)
+{
+    T* r = reinterpret_cast<T*>(p);
+    p += (count * sizeof(T) + 255) / 256 * 256;
+    return r;
+}
+
+void applyWrites(pb_proxy& dst, const ClassicProxyState& p)
+{
+    if (p.written & CF_SLOPE) dst.regressionSlope = p.slope;
+    if (p.written & CF_INTERCEPT) dst.regressionIntercept = p.intercept;
+    if (p.written & CF_R2) dst.regressionR2 = p.r2;
+    if (p.written & CF_H0) dst.lapseRateH0 = p.H0;
+    if (p.written & CF_H1) dst.lapseRateH1 = p.H1;
+    if (p.written & CF_T0) dst.lapseRateT0 = p.T0;
+    if (p.written & CF_T1) dst.lapseRateT1 = p.T1;
+    if (p.written & CF_INVLAPSE) dst.inversionLapseRate = p.invLapse;
+    if (p.written & CF_INVSIG) dst.inversionIsSignificative = p.invSig;
+}
+
+ClassicProxyState stateOf(const pb_proxy& p)
+{
+    ClassicProxyState s{};
+    s.slope = p.regressionSlope; s.intercept = p.regressionIntercept; s.r2 = p.regressionR2;
+    s.H0 = p.lapseRateH0; s.H1 = p.lapseRateH1; s.T0 = p.lapseRateT0; s.T1 = p.lapseRateT1;
+    s.invLapse = p.inversionLapseRate; s.invSig = p.inversionIsSignificative;
+    s.written = 0;
+    return s;
+}
+
+// Crit3DInterpolationSettings::getCombination (interpolationSettings.cpp:869-892): bit i of the (P+1)-digit binary string,
+// most significant first, switches proxy i; the last digit switches the thermal inversion
+bool getCombination(const pb_settings& s, int indexHeight, int k, uint8_t* active, int& useInversion)
+{
+    const int digits = s.nProxy + 1;
+    auto bit = [&](int pos) { return (k >> (digits - 1 - pos)) & 1; };
+    if (k % 2 == 1)
+        if (indexHeight < 0 || !bit(indexHeight)) return false;
+    for (int i = 0; i < s.nProxy; i++) active[i] = (bit(i) && s.selectedActive[i]) ? 1 : 0;
+    useInversion = (bit(digits - 1) && s.selectedUseThermalInversion) ? 1 : 0;
+    return true;
+}
+
+// goldenSectionSearch (interpolation.cpp:2297-2335) over f(kh) = MAE at kh = int(khFloat), read from the table
+double goldenSection(const float* maeOfKh, int maxKh, double a, double b, pb_kh_series* series)
+{
+    const double GOLDEN = 1.6180339887499;      // GOLDEN_SECTION, commonConstants.h:258
+    auto f = [&](double khFloat) -> double {
+        int kh = int(khFloat);
+        kh = std::max(0, std::min(kh, maxKh));
+        return double(maeOfKh[kh]);
+    };
+    auto add = [&](float kh, float err) {
+        if (series && series->n < PB_MAX_KH_SERIES) { series->kh[series->n] = kh; series->error[series->n] = err; series->n++; }
+    };
+    const double tol = 1;
+    double x1 = b - (b - a) / GOLDEN;
+    double x2 = a + (b - a) / GOLDEN;
+    int counter = 0;
+    while (fabs(b - a) > tol && counter < 100) {
+        counter++;
+        if (f(x1) < f(x2)) {
+            b = x2;
+            x2 = x1;
+            x1 = b - (b - a) / GOLDEN;
+            add(float(x1), float(f(x1)));
+        } else {
+            a = x1;
+            x1 = x2;
+            x2 = a + (b - a) / GOLDEN;
+            add(float(x2), float(f(x2)));
+        }
+    }
+    add(float((a + b) / 2), float(f((a + b) / 2)));
+    return (a + b) / 2;
+}
+
+}  // namespace
+
+/* preInterpolation with every branch; see include/praga_b200.h */
+extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv,
+                                       pb_raster_id demId, uint8_t* keep, pb_kh_series* khSeries)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    const int n = st->n, P = s->nProxy;
+    if (khSeries) khSeries->n = 0;
+    if (P < 0 || P > PB_MAX_PROXY || (P > 0 && st->nProxy < P)) return fail(ctx, PB_ERR_INVALID, "settings.nProxy / stations.nProxy mismatch");
+
+    // checkPrecipitationZero (interpolation.cpp:1173-1186): a count, host arithmetic
+    if (varIsPrec(variable)) {
+        int nrValid = 0;
+        for (int i = 0; i < n; i++) {
+            const bool active = st->isActive ? st->isActive[i] != 0 : true;
+            if (active && !isEqualF(st->value[i], kNoData) && st->value[i] >= s->rainfallThreshold) nrValid++;
+        }
+        s->precipitationAllZero = nrValid == 0;
+        if (keep) memset(keep, 1, n);
+        if (s->precipitationAllZero) return PB_OK;
+    }
+
+    const std::vector<float> raw(st->value, st->value + n);      // the meteo points' currentValue unless cv gives it
+    std::vector<uint8_t> keepTmp;
+    const bool detrendVar = varUsesDetrending(variable);
+    const bool useTD = s->useTD && !s->useLocalDetrending && varUsesTd(variable) && !s->useGlocalDetrending;
+    const bool classic = detrendVar && !s->useMultipleDetrending;
+    const bool optimal = classic && s->useBestDetrending;
+    if (detrendVar && s->useMultipleDetrending) {
+        if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending is out of scope (DESIGN.md)");
+        if (s->useLocalDetrending) {
+            // preInterpolation on the whole set with local detrending fits nothing the raster loop uses: the raster entry
+            // point fits per cell (pb_local_detrending_raster)
+            return fail(ctx, PB_ERR_INVALID, "local detrending fits per cell (pb_local_detrending_raster)");
+        }
+        if (!keep) { keepTmp.assign(n, 1); keep = keepTmp.data(); }
+        int rc = preInterpolationMultiple(ctx, st, s, variable, keep);
+        if (rc) return rc;
+    } else if (keep) memset(keep, 1, n);
+    if (!classic && !useTD) return PB_OK;
+    if ((optimal || useTD) && n == 0) return PB_OK;
+    if (useTD && (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used))
+        return fail(ctx, PB_ERR_INVALID, "topographic-distance optimisation needs the resident DEM (getCurrentDEM())");
+    if (useTD && s->method != PB_METHOD_IDW)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "leave-one-out for the kh search runs the idw estimator only");
+    if (optimal && s->method != PB_METHOD_IDW)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "leave-one-out for optimalDetrending runs the idw estimator only");
+
+    // interpolation points = survivors of multiple detrending (points with NODATA proxies are erased, :2230); the meteo
+    // points the leave-one-out walks stay ALL stations
+    std::vector<int> ip;
+    for (int i = 0; i < n; i++)
+        if (classic || !keep || keep[i]) ip.push_back(i);
+    const int m = (int)ip.size();
+
+    // ---- combinations ----
+    int indexHeight = -1;
+    for (int i = 0; i < P; i++) if (s->proxy[i].kind == PB_PROXY_HEIGHT) indexHeight = i;
+    std::vector<ClassicProblem> problems;
+    std::vector<int> comboId;
+    if (classic) {
+        if (optimal) {
+            // passDataToInterpolation side effects (spatialControl.cpp:533-564)
+            if (n > 0) {
+                float xMin = float(st->x[0]), xMax = xMin, yMin = float(st->y[0]), yMax = yMin;
+                const float* v0 = (cv && cv->currentValue) ? cv->currentValue : st->value;
+                float vMin = v0[0], vMax = v0[0];
+                int nrValid = 0;
+                for (int i = 0; i < n; i++) {
+                    const float x = float(st->x[i]), y = float(st->y[i]);
+                    xMin = std::min(xMin, x); xMax = std::max(xMax, x);
+                    yMin = std::min(yMin, y); yMax = std::max(yMax, y);
+                    vMin = std::min(vMin, v0[i]); vMax = std::max(vMax, v0[i]);
+                    const int code = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+                    const bool ok = !s->useLapseRateCode || code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SECONDARY;
+                    if (ok) nrValid++;
+                }
+                if (nrValid > 0) {
+                    s->pointsBoundingBoxArea = (xMax - xMin) * (yMax - yMin);
+                    s->hasPointsRange = 1;
+                    s->pointsRangeMin = vMin;
+                    s->pointsRangeMax = vMax;
+                }
+            }
+            const int nrCombination = 1 << (P + 1);
+            for (int k = 0; k < nrCombination; k++) {
+                ClassicProblem pr{};
+                if (!getCombination(*s, indexHeight, k, pr.active, pr.useThermalInversion)) continue;
+                problems.push_back(pr);
+                comboId.push_back(k);
+            }
+        } else {
+            ClassicProblem pr{};
+            for (int i = 0; i < P; i++) pr.active[i] = s->selectedActive[i];
+            pr.useThermalInversion = s->selectedUseThermalInversion;
+            problems.push_back(pr);
+            comboId.push_back(-1);
+        }
+        for (auto& pr : problems)
+            for (int i = 0; i < P; i++) pr.proxy[i] = stateOf(s->proxy[i]);
+    } else {
+        problems.push_back(ClassicProblem{});      // one problem: the (already detrended) points, model in settings
+        comboId.push_back(-1);
+    }
+    const int NP = (int)problems.size();
+    const int maxKh = std::max(0, s->topoDist_maxKh);
+    const int nKh = useTD ? maxKh + 1 : 1;
+
+    // ---- stage everything once: sources = interpolation points (m), targets = meteo points (n) ----
+    const size_t Pp = std::max(P, 1);
+    size_t bytes = 0;
+    auto add = [&](size_t count, size_t size) { bytes += (count * size + 255) / 256 * 256; };
+    add(m, 4); add(m, 4); add(m, 4); add(m * Pp, 4); add(m, 4); add(m, 8); add(m, 4); add(m, 1);
+    add(n, 4); add(n, 4); add(n, 4); add(n * Pp, 4); add(n, 4); add(n, 4); add(n, 1);
+    add(size_t(m) * NP, 4);                                  // work
+    add(NP, sizeof(ClassicProblem));
+    add(size_t(NP) * nKh * n, 4);                            // residuals
+    add(size_t(NP) * nKh, 4);                                // mae
+    add(nKh, 4);                                             // kh list
+    if (useTD) add(size_t(n) * m, 4);                        // target-to-station topographic distances
+    CUDA_TRY(ctx, ctx->dScratch.reserve(bytes + 4096));
+    unsigned char* d = ctx->dScratch.p;
+    float* dX = carve<float>(d, m);
+    float* dY = carve<float>(d, m);
+    float* dZf = carve<float>(d, m);
+    float* dProxy = carve<float>(d, m * Pp);
+    float* dValues = carve<float>(d, m);
+    double* dZ = carve<double>(d, m);
+    int* dCode = carve<int>(d, m);
+    uint8_t* dActive = carve<uint8_t>(d, m);
+    float* tX = carve<float>(d, n);
+    float* tY = carve<float>(d, n);
+    float* tZf = carve<float>(d, n);
+    float* tProxy = carve<float>(d, n * Pp);
+    float* tObserved = carve<float>(d, n);
+    int* tCode = carve<int>(d, n);
+    uint8_t* tInside = carve<uint8_t>(d, n);
+    float* dWork = carve<float>(d, size_t(m) * NP);
+    ClassicProblem* dProblems = carve<ClassicProblem>(d, NP);
+    float* dResidual = carve<float>(d, size_t(NP) * nKh * n);
+    float* dMae = carve<float>(d, size_t(NP) * nKh);
+    int* dKh = carve<int>(d, nKh);
+    float* dTopo = useTD ? carve<float>(d, size_t(n) * m) : nullptr;
+
+    std::vector<float> hx(m), hy(m), hzf(m), hproxy(m * Pp, kNoData), hval(m);
+    std::vector<double> hz(m);
+    std::vector<int> hcode(m);
+    std::vector<uint8_t> hact(m);
+    std::vector<float> gx(n), gy(n), gzf(n), gproxy(n * Pp, kNoData), gobs(n);
+    std::vector<int> gcode(n);
+    std::vector<uint8_t> gin(n);
+    for (int i = 0; i < n; i++) {
+        gx[i] = float(st->x[i]);
+        gy[i] = float(st->y[i]);
+        gzf[i] = float(st->z[i]);
+        for (int q = 0; q < P; q++) gproxy[size_t(i) * Pp + q] = st->proxyValues[size_t(i) * st->nProxy + q];
+        gcode[i] = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        gin[i] = (cv && cv->isInsideDem) ? cv->isInsideDem[i] : 1;
+        gobs[i] = (cv && cv->currentValue) ? cv->currentValue[i] : raw[i];
+    }
+    for (int k = 0; k < m; k++) {
+        const int i = ip[k];
+        hx[k] = gx[i];
+        hy[k] = gy[i];
+        hz[k] = st->z[i];
+        hzf[k] = gzf[i];
+        for (int q = 0; q < P; q++) hproxy[size_t(k) * Pp + q] = gproxy[size_t(i) * Pp + q];
+        hcode[k] = gcode[i];
+        // optimalDetrending rebuilds the points from the meteo points: every one active, value = currentValue
+        hact[k] = optimal ? 1 : (st->isActive ? st->isActive[i] : 1);
+        hval[k] = optimal ? gobs[i] : st->value[i];
+    }
+    cudaStream_t stream = ctx->stream;
+    auto up = [&](void* dst, const void* src, size_t b) { return cudaMemcpyAsync(dst, src, b, cudaMemcpyHostToDevice, stream); };
+    CUDA_TRY(ctx, up(dX, hx.data(), m * 4));
+    CUDA_TRY(ctx, up(dY, hy.data(), m * 4));
+    CUDA_TRY(ctx, up(dZf, hzf.data(), m * 4));
+    CUDA_TRY(ctx, up(dProxy, hproxy.data(), m * Pp * 4));
+    CUDA_TRY(ctx, up(dValues, hval.data(), m * 4));
+    CUDA_TRY(ctx, up(dZ, hz.data(), m * 8));
+    CUDA_TRY(ctx, up(dCode, hcode.data(), m * 4));
+    CUDA_TRY(ctx, up(dActive, hact.data(), m));
+    CUDA_TRY(ctx, up(tX, gx.data(), n * 4));
+    CUDA_TRY(ctx, up(tY, gy.data(), n * 4));
+    CUDA_TRY(ctx, up(tZf, gzf.data(), n * 4));
+    CUDA_TRY(ctx, up(tProxy, gproxy.data(), n * Pp * 4));
+    CUDA_TRY(ctx, up(tObserved, gobs.data(), n * 4));
+    CUDA_TRY(ctx, up(tCode, gcode.data(), n * 4));
+    CUDA_TRY(ctx, up(tInside, gin.data(), n));
+    CUDA_TRY(ctx, up(dProblems, problems.data(), sizeof(ClassicProblem) * NP));
+    std::vector<int> khList(nKh);
+    for (int k = 0; k < nKh; k++) khList[k] = useTD ? k : 0;
+    CUDA_TRY(ctx, up(dKh, khList.data(), nKh * 4));
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+
+    // ---- detrending() of every problem ----
+    CUDA_TRY(ctx, launchClassicInit(dValues, 1, NP, m, dWork, stream));
+    ctx->timing.launches++;
+    if (classic) {
+        ClassicSetup cs{};
+        cs.n = m; cs.nProxy = P; cs.nProblems = NP;
+        cs.isThermalVar = varIsThermal(variable);
+        cs.isElaborationVar = variable == PB_VAR_ELABORATION;
+        cs.useLapseRateCode = s->useLapseRateCode;
+        cs.indexHeight = indexHeight;
+        cs.minRegressionR2 = s->minRegressionR2;
+        cs.maxHeightInversion = s->maxHeightInversion;
+        cs.climateLapseRate = s->climateLapseRate;
+        for (int i = 0; i < P; i++) cs.kind[i] = s->proxy[i].kind;
+        ClassicStations cst{dZ, dProxy, dCode, dActive};
+        CUDA_TRY(ctx, launchClassicDetrend(cs, cst, dProblems, dWork, stream));
+        ctx->timing.launches++;
+        CUDA_TRY(ctx, cudaMemcpyAsync(problems.data(), dProblems, sizeof(ClassicProblem) * NP, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+        for (auto& pr : problems)
+            if (pr.error) return fail(ctx, PB_ERR_UNSUPPORTED, "regressionOrographyT: more than 192 height intervals");
+    }
+
+    // ---- leave-one-out tables ----
+    std::vector<float> mae;
+    auto runLoo = [&](int excludeOutsideDem) -> int {
+        LooSetup ls{};
+        ls.nS = m; ls.nT = n; ls.nProxy = P; ls.nProblems = NP; ls.nKh = nKh;
+        ls.useLapseRateCode = s->useLapseRateCode;
+        ls.excludeSupplemental = 1;
+        ls.excludeOutsideDem = excludeOutsideDem;
+        ls.useDetrendingVar = detrendVar;
+        ls.useThermalInversion = s->useThermalInversion;
+        ls.useDoNotRetrend = s->useDoNotRetrend;
+        ls.useRetrendOnly = s->useRetrendOnly;
+        ls.clampMode = varClampMode(variable);
+        ls.isPrecVar = varIsPrec(variable);
+        ls.rainfallThreshold = s->rainfallThreshold;
+        ls.useMultipleModel = 0;
+        for (int i = 0; i < P; i++) ls.kind[i] = s->proxy[i].kind;
+        if (!classic && detrendVar && s->useMultipleDetrending) {
+            int rc = buildDevModel(ctx, s, variable, ls.multiple);
+            if (rc) return rc;
+            ls.useMultipleModel = 1;
+        }
+        LooTargets lt{tX, tY, tProxy, tCode, tInside, tObserved};
+        CUDA_TRY(ctx, launchLooExact(ls, lt, dX, dY, dWork, dProblems, dTopo, dKh, dResidual, stream));
+        CUDA_TRY(ctx, launchCvMae(dResidual, tObserved, n, NP * nKh, dMae, stream));
+        ctx->timing.launches += 2;
+        mae.resize(size_t(NP) * nKh);
+        CUDA_TRY(ctx, cudaMemcpyAsync(mae.data(), dMae, mae.size() * 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+        return PB_OK;
+    };
+
+    if (useTD) {
+        const DevGrid dem = devGridOfRaster(ctx->rasters[demId]);
+        CUDA_TRY(ctx, launchTopoMatrix(tX, tY, tZf, n, dX, dY, dZf, m, dem, dTopo, stream));
+        ctx->timing.launches++;
+    }
+
+    int best = 0;
+    std::vector<int> khOf(NP, s->topoDist_Kh);
+    if (optimal || useTD) {
+        // topographicDistanceOptimize runs computeResiduals(..., excludeOutsideDem = true, excludeSupplemental = true)
+        int rc = runLoo(useTD ? 1 : (cv ? cv->excludeOutsideDem : 0));
+        if (rc) return rc;
+        std::vector<float> maeTd = mae;
+        if (useTD)
+            for (int p = 0; p < NP; p++) {
+                pb_kh_series tmp{};
+                const double bestKh = goldenSection(&maeTd[size_t(p) * nKh], maxKh, 0., double(maxKh), &tmp);
+                khOf[p] = int(bestKh);
+            }
+        if (optimal) {
+            // computeResiduals(..., getUseExcludeStationsOutsideDEM(), true) at each combination's kh
+            const int excl = cv ? cv->excludeOutsideDem : 0;
+            const bool sameFilter = !useTD || excl == 1 || !(cv && cv->isInsideDem);
+            if (!sameFilter) {
+                rc = runLoo(excl);
+                if (rc) return rc;
+            }
+            float minError = kNoData;
+            int bestCombinationIndex = 0;       // index into the reference's 0..2^(P+1) numbering
+            best = -1;
+            for (int p = 0; p < NP; p++) {
+                const int kh = useTD ? std::max(0, std::min(khOf[p], maxKh)) : 0;
+                const float avgError = mae[size_t(p) * nKh + kh];
+                if (!isEqualF(avgError, kNoData) && (isEqualF(minError, kNoData) || avgError < minError)) {
+                    minError = avgError;
+                    bestCombinationIndex = comboId[p];
+                    best = p;
+                }
+            }
+            if (best < 0) {
+                // no combination produced an error: the reference falls back to combination 0 (all proxies off)
+                for (int p = 0; p < NP; p++) if (comboId[p] == bestCombinationIndex) best = p;
+                if (best < 0) best = 0;
+            }
+        }
+        if (useTD) {
+            // the search preInterpolation runs last, on the final points (:2493-2496): same table row, series kept
+            if (khSeries) khSeries->n = 0;
+            const double bestKh = goldenSection(&maeTd[size_t(best) * nKh], maxKh, 0., double(maxKh), khSeries);
+            s->topoDist_Kh = int(bestKh);
+        }
+    }
+
+    // ---- what the reference leaves in the settings and the points ----
+    if (classic) {
+        // optimalDetrending walks the combinations in order on one settings object, then detrends with the best one again
+        std::vector<int> order;
+        if (optimal) { for (int p = 0; p < NP; p++) order.push_back(p); }
+        order.push_back(best);
+        for (int p : order)
+            for (int i = 0; i < P; i++)
+                if (problems[p].active[i]) applyWrites(s->proxy[i], problems[p].proxy[i]);
+        const ClassicProblem& fin = problems[best];
+        for (int i = 0; i < P; i++) {
+            s->currentActive[i] = fin.active[i];
+            s->currentSignificant[i] = fin.significant[i];
+        }
+        s->currentUseThermalInversion = fin.useThermalInversion;
+        CUDA_TRY(ctx, launchClassicGather(dWork, m, NP, best, dValues, stream));
+        ctx->timing.launches++;
+        std::vector<float> out(m);
+        CUDA_TRY(ctx, cudaMemcpyAsync(out.data(), dValues, m * 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+        for (int k = 0; k < m; k++) st->value[ip[k]] = out[k];
+    }
+    return PB_OK;
+}

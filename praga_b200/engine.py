@@ -59,6 +59,8 @@ def load_library():
     lib.pb_interpolate_points.argtypes = raster_args + [P(C.c_float), P(C.c_float), P(C.c_double), C.c_int, C.c_int,
                                                         P(C.c_float)]
     lib.pb_pre_interpolation.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_uint8)]
+    lib.pb_pre_interpolation_ex.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_cv_points), C.c_int32,
+                                            P(C.c_uint8), P(A.pb_kh_series)]
     lib.pb_pre_interpolation_batch.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), C.c_int, P(A.pb_settings), C.c_int,
                                                P(C.c_double), P(C.c_float), P(C.c_uint8), P(A.pb_settings)]
     lib.pb_compute_residuals.argtypes = raster_args + [P(C.c_float), P(C.c_uint8), P(C.c_float), P(A.pb_cv_stats)]
@@ -73,7 +75,7 @@ def load_library():
                                                            C.c_int, C.c_int32, P(C.c_float)]
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
-                 "pb_cv_stats", "pb_timing"):
+                 "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series"):
         got, want = lib.pb_abi_sizeof(name.encode()), C.sizeof(getattr(A, name))
         if got != want:
             raise PragaB200Error(A.PB_ERR_INVALID, f"ABI mismatch for {name}: library {got} B, binding {want} B")
@@ -255,6 +257,25 @@ class Engine:
         keep = np.zeros(stations.n, dtype=np.uint8)
         self._check(self.lib.pb_pre_interpolation(self.h, C.byref(st), C.byref(settings), variable, A.u8ptr(keep)))
         return keep.astype(bool)
+
+    def pre_interpolation_ex(self, stations, settings, variable, current_value=None, inside_dem=None, exclude_outside_dem=False,
+                             dem_id=-1):
+        """preInterpolation with every branch (classic detrending, optimalDetrending, kh golden section), in place.
+        Returns (keep mask, [(kh, error), ...])."""
+        st = stations.as_pb()
+        keep = np.zeros(stations.n, dtype=np.uint8)
+        cv = A.pb_cv_points()
+        cur = None if current_value is None else np.ascontiguousarray(current_value, dtype=np.float32)
+        ins = None if inside_dem is None else np.ascontiguousarray(inside_dem, dtype=np.uint8)
+        if cur is not None:
+            cv.currentValue = A.fptr(cur)
+        if ins is not None:
+            cv.isInsideDem = A.u8ptr(ins)
+        cv.excludeOutsideDem = int(exclude_outside_dem)
+        series = A.pb_kh_series()
+        self._check(self.lib.pb_pre_interpolation_ex(self.h, C.byref(st), C.byref(settings), variable, C.byref(cv), dem_id,
+                                                     A.u8ptr(keep), C.byref(series)))
+        return keep.astype(bool), [(series.kh[i], series.error[i]) for i in range(series.n)]
 
     def pre_interpolation_batch(self, stations, values, settings, variable, points_range=None):
         """T time steps sharing the station set. values: (T, n). Returns (detrended (T, n), keep (T, n), [settings] * T)."""
