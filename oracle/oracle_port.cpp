@@ -195,8 +195,130 @@ float topographicDistance(float x1, float y1, float z1, float x2, float y2, floa
     return maxDeltaZ;
 }
 
+// sortPointsByDistance, interpolation.cpp:121-160 (indices into the input list)
+std::vector<int> sortByDistance(unsigned maxNr, const std::vector<int>& list, const std::vector<float>& dist)
+{
+    std::vector<int> idx;
+    for (int i : list)
+        if (!isEqualF(dist[i], 0) && !isEqualF(dist[i], NODATA_F)) idx.push_back(i);
+    std::sort(idx.begin(), idx.end(), [&dist](int a, int b) { return dist[a] < dist[b]; });
+    if (idx.size() > maxNr) idx.resize(maxNr);
+    return idx;
+}
+
+// shepardSearchNeighbour, interpolation.cpp:806-868 (computeShepardInitialRadius :800-803)
+float shepardSearchNeighbour(const std::vector<Point>& pts, const std::vector<float>& dist, const pb_settings& s, std::vector<int>& sel)
+{
+    const unsigned nrPoints = unsigned(pts.size());
+    const unsigned avg = 8;                                        // SHEPARD_AVG_NRPOINTS
+    const float R0 = float(sqrt((avg * s.pointsBoundingBoxArea) / (float(3.1415926535898) * nrPoints)));
+    std::vector<int> first, all;
+    for (unsigned i = 0; i < nrPoints; i++) {
+        all.push_back(int(i));
+        if (dist[i] <= R0 && dist[i] > 0) first.push_back(int(i));
+    }
+    if (first.size() < 5) {
+        sel = sortByDistance(5, all, dist);
+        if (sel.empty()) return NODATA_F;
+        return dist[sel.back()] + float(EPSILON);
+    }
+    if (first.size() > 10) {
+        sel = sortByDistance(10, first, dist);
+        return dist[sel.back()] + float(EPSILON);
+    }
+    sel = first;
+    return R0;
+}
+
+// shepardIdw, interpolation.cpp:871-945
+float shepardIdw(const std::vector<Point>& pts, const std::vector<float>& dist, const pb_settings& s, float x, float y)
+{
+    std::vector<int> sel;
+    const float radius = shepardSearchNeighbour(pts, dist, s, sel);
+    const unsigned n = unsigned(sel.size());
+    std::vector<double> weight(n), t(n), S(n);
+    double weightSum = 0;
+    const double radius_3 = radius / 3.;
+    const double radius_27_4 = 6.75 / radius;
+    for (unsigned i = 0; i < n; i++) {
+        const float d = dist[sel[i]];
+        if (d > 0) {
+            if (d <= radius_3) S[i] = 1 / d;
+            else if (d <= radius) {
+                const double tmp = (d / radius) - 1;
+                S[i] = radius_27_4 * tmp * tmp;
+            } else S[i] = 0;
+            weightSum += S[i];
+        }
+    }
+    if (weightSum == 0) return NODATA_F;
+    for (unsigned i = 0; i < n; i++) {
+        t[i] = 0;
+        for (unsigned j = 0; j < n; j++)
+            if (i != j) {
+                const double cosine = ((x - pts[sel[i]].x) * (x - pts[sel[j]].x) + (y - pts[sel[i]].y) * (y - pts[sel[j]].y)) /
+                                      (dist[sel[i]] * dist[sel[j]]);
+                t[i] += S[j] * (1 - cosine);
+            }
+        if (weightSum != 0) t[i] /= weightSum;
+    }
+    weightSum = 0;
+    for (unsigned i = 0; i < n; i++) {
+        weight[i] = S[i] * S[i] * (1 + t[i]);
+        weightSum += weight[i];
+    }
+    for (unsigned i = 0; i < n; i++) weight[i] /= weightSum;
+    double result = 0;
+    for (unsigned i = 0; i < n; i++) result += weight[i] * pts[sel[i]].value;
+    return float(result);
+}
+
+// modifiedShepardIdw, interpolation.cpp:948-1028. The definition's parameters are (radius, y, x) while the declaration and
+// the call site use (radius, x, y): the caller's x arrives in `y` and vice versa. Kept.
+float modifiedShepardIdw(const std::vector<Point>& pts, const std::vector<float>& dist, const pb_settings& s, float radius,
+                         float y, float x)
+{
+    std::vector<int> sel;
+    if (isEqualF(radius, NODATA_F)) radius = shepardSearchNeighbour(pts, dist, s, sel);
+    else for (size_t i = 0; i < pts.size(); i++) sel.push_back(int(i));
+    if (sel.empty()) return NODATA_F;
+    const size_t n = sel.size();
+    std::vector<double> weight(n), t(n, 0.0), sv(n, 0.0);
+    double weightSum = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        const float d = dist[sel[i]];
+        if (d > 0.0 && d <= radius) {
+            sv[i] = (radius - d) / (radius * d);
+            weightSum += sv[i];
+        }
+    }
+    if (weightSum == 0.0) return NODATA_F;
+    const double invWeightSum = 1.0 / weightSum;
+    for (size_t i = 0; i < n; i++) {
+        if (sv[i] == 0.0 || dist[sel[i]] <= 0.0) continue;
+        const double xi = pts[sel[i]].x, yi = pts[sel[i]].y;
+        for (size_t j = 0; j < n; j++) {
+            if (i == j || sv[j] == 0.0 || dist[sel[j]] <= 0.0) continue;
+            const double xj = pts[sel[j]].x, yj = pts[sel[j]].y;
+            const double cosine = ((x - xi) * (x - xj) + (y - yi) * (y - yj)) / (dist[sel[i]] * dist[sel[j]]);
+            t[i] += sv[j] * (1.0 - cosine);
+        }
+        t[i] *= invWeightSum;
+    }
+    weightSum = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        weight[i] = sv[i] * sv[i] * (1.0 + t[i]);
+        weightSum += weight[i];
+    }
+    const double inv = 1.0 / weightSum;
+    for (size_t i = 0; i < n; i++) weight[i] *= inv;
+    double result = 0.0;
+    for (size_t i = 0; i < n; i++) result += weight[i] * pts[sel[i]].value;
+    return float(result);
+}
+
 // interpolate, interpolation.cpp:2502-2560 with computeDistances :208-256 (topographic distance when a DEM is given
-// and getUseTD() holds; no per-station TD rasters) and inverseDistanceWeighted :1031-1051
+// and getUseTD() holds; no per-station TD rasters), inverseDistanceWeighted :1031-1051 and the Shepard estimators
 float interpolate(const std::vector<Point>& pts, const pb_settings& s, int var, float x, float y, const double* proxyValues,
                   bool excludeSupplemental, float z = 0.f, const Grid* dem = nullptr)
 {
@@ -204,7 +326,7 @@ float interpolate(const std::vector<Point>& pts, const pb_settings& s, int var, 
     if (isPrec(var) && s.precipitationAllZero) return 0.f;
     float result = NODATA_F;
     if (!s.useRetrendOnly) {
-        double sum = 0, sumWeights = 0;
+        std::vector<float> dist(pts.size());
         for (size_t i = 0; i < pts.size(); i++) {
             float d;
             if (excludeSupplemental && !checkLapseRateCode(pts[i].lapseRateCode, s.useLapseRateCode != 0, false)) d = 0;
@@ -216,14 +338,26 @@ float interpolate(const std::vector<Point>& pts, const pb_settings& s, int var, 
                     d += (s.topoDist_Kh * topo);
                 }
             }
-            if (d > 0.f) {
-                const double dist_km = double(d) / 10000.;
-                const double weight = 1.0 / (dist_km * dist_km * dist_km);
-                sumWeights += weight;
-                sum += double(pts[i].value) * weight;
-            }
+            dist[i] = d;
         }
-        result = (sumWeights > 0.0) ? float(sum / sumWeights) : NODATA_F;
+        if (s.method == PB_METHOD_SHEPARD) result = shepardIdw(pts, dist, s, x, y);
+        else if (s.method == PB_METHOD_SHEPARD_MODIFIED) {
+            float radius = NODATA_F;
+            if (s.useLocalDetrending) radius = s.localRadius;
+            result = modifiedShepardIdw(pts, dist, s, radius, x, y);
+        } else {
+            double sum = 0, sumWeights = 0;
+            for (size_t i = 0; i < pts.size(); i++) {
+                const float d = dist[i];
+                if (d > 0.f) {
+                    const double dist_km = double(d) / 10000.;
+                    const double weight = 1.0 / (dist_km * dist_km * dist_km);
+                    sumWeights += weight;
+                    sum += double(pts[i].value) * weight;
+                }
+            }
+            result = (sumWeights > 0.0) ? float(sum / sumWeights) : NODATA_F;
+        }
     } else result = 0;
     if (isEqualF(result, NODATA_F)) return NODATA_F;
     if (!s.useDoNotRetrend) result += retrend(s, var, proxyValues);

@@ -22,11 +22,12 @@ SOURCES = {
     "pre_kernels.cu": ["-fmad=false"],
     "td_kernels.cu": ["-fmad=false"],
     "classic_kernels.cu": ["-fmad=false"],
+    "shepard_kernels.cu": ["-fmad=false"],
     "station_space.cu": [],
     "kriging.cu": [],
     "kriging_tc.cu": [],
 }
-HEADERS = ["common.cuh", "epilogue.cuh", "context.cuh", "local.cuh", "pre.cuh", "multiple_detrend.cuh", "detrend_device.cuh", "kriging.cuh", "classic.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
+HEADERS = ["common.cuh", "epilogue.cuh", "context.cuh", "local.cuh", "pre.cuh", "multiple_detrend.cuh", "detrend_device.cuh", "kriging.cuh", "classic.cuh", "shepard.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -12,6 +12,7 @@
 #include "context.cuh"
 #include "local.cuh"
 #include "pre.cuh"
+#include "shepard.cuh"
 
 namespace pb {
 // idw_kernels.cu
@@ -112,8 +113,8 @@ int buildModel(pb_context* ctx, const pb_settings* s, int variable, const pb_ras
 {
     memset(&m, 0, sizeof(m));
     if (s->nProxy < 0 || s->nProxy > PB_MAX_PROXY) return fail(ctx, PB_ERR_INVALID, "settings.nProxy out of range");
-    if (s->method != PB_METHOD_IDW)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the GPU path (shepard: DESIGN.md)");
+    if (s->method != PB_METHOD_IDW && s->method != PB_METHOD_SHEPARD && s->method != PB_METHOD_SHEPARD_MODIFIED)
+        return fail(ctx, PB_ERR_INVALID, "unknown TInterpolationMethod");
     if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending is out of scope (DESIGN.md)");
     m.nProxy = s->nProxy;
     m.useDetrendingVar = useDetrendingVar(variable);
@@ -226,6 +227,50 @@ int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, 
     ds.z = reinterpret_cast<const float*>(d + offZ);
     ds.n = n;
     ds.nPadded = nPadded;
+    return PB_OK;
+}
+
+// stations for the Shepard estimators (K8): original order, raw values, f32 + f64 coordinates; R0 =
+// computeShepardInitialRadius(pointsBoundingBoxArea, ALL points, SHEPARD_AVG_NRPOINTS = 8) (interpolation.cpp:800-803, 812)
+int stageShepardStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental,
+                         ShepardStations& ss, float& R0)
+{
+    if (st->n < 0) return fail(ctx, PB_ERR_INVALID, "stations.n < 0");
+    std::vector<int> use;
+    use.reserve(st->n);
+    for (int i = 0; i < st->n; i++) {
+        const int code = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        if (excludeSupplemental && !checkLapseRateCode(code, s->useLapseRateCode != 0, false)) continue;
+        use.push_back(i);
+    }
+    const size_t n = use.size(), nAl = (n + 3) / 4 * 4;
+    const unsigned nrPoints = unsigned(st->n), minPointsNr = 8;
+    R0 = float(sqrt((minPointsNr * s->pointsBoundingBoxArea) / (float(3.1415926535898) * nrPoints)));
+    const size_t offXd = 0, offYd = offXd + nAl * 8, offX = offYd + nAl * 8, offY = offX + nAl * 4, offV = offY + nAl * 4,
+                 total = offV + nAl * 4 + 16;
+    CUDA_TRY(ctx, ctx->hStations.reserve(total));
+    CUDA_TRY(ctx, ctx->dStations.reserve(total));
+    unsigned char* h = ctx->hStations.p;
+    double* xd = reinterpret_cast<double*>(h + offXd);
+    double* yd = reinterpret_cast<double*>(h + offYd);
+    float* px = reinterpret_cast<float*>(h + offX);
+    float* py = reinterpret_cast<float*>(h + offY);
+    float* pv = reinterpret_cast<float*>(h + offV);
+    for (size_t k = 0; k < n; k++) {
+        const int i = use[k];
+        xd[k] = st->x[i]; yd[k] = st->y[i];
+        px[k] = float(st->x[i]); py[k] = float(st->y[i]);
+        pv[k] = st->value[i];
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dStations.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)total;
+    unsigned char* d = ctx->dStations.p;
+    ss.xd = reinterpret_cast<const double*>(d + offXd);
+    ss.yd = reinterpret_cast<const double*>(d + offYd);
+    ss.x = reinterpret_cast<const float*>(d + offX);
+    ss.y = reinterpret_cast<const float*>(d + offY);
+    ss.value = reinterpret_cast<const float*>(d + offV);
+    ss.n = int(n);
     return PB_OK;
 }
 
@@ -678,8 +723,14 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     cudaEventRecord(ctx->ev[0], ctx->stream);
     const bool precZero = !local && isPrecVar(variable) && s->precipitationAllZero;
     DevStations ds{};
+    ShepardStations ss{};
+    float shepardR0 = 0.f;
+    const bool shepardMethod = !local && s->method != PB_METHOD_IDW;
+    if (shepardMethod && usesTopographicDistance(s, variable))
+        return fail(ctx, PB_ERR_UNSUPPORTED, "the Shepard estimators run without topographic distance on the GPU path");
     if (!precZero && !local) {
-        rc = stageStations(ctx, st, s, true, ds, m.valueOffset);
+        if (shepardMethod) rc = stageShepardStations(ctx, st, s, true, ss, shepardR0);
+        else rc = stageStations(ctx, st, s, true, ds, m.valueOffset);
         if (rc) return rc;
     }
     cudaEventRecord(ctx->ev[1], ctx->stream);
@@ -714,6 +765,9 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
         CUDA_TRY(ctx, launchFillValid(ctx->dOut.p, dem.validIdx + t0, nTargets, 0.f, ctx->stream));
         if (nTargets > 0) { ctx->hMinMax[0] = 0x80000000u; ctx->hMinMax[1] = 0x80000000u; }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    } else if (shepardMethod) {
+        CUDA_TRY(ctx, launchShepardRaster(ss, m, dg, shepardR0, s->method == PB_METHOD_SHEPARD_MODIFIED, dem.validIdx + t0,
+                                          nTargets, ctx->dOut.p, ctx->dMinMax, ctx->stream));
     } else if (usesTopographicDistance(s, variable)) {
         // the march needs the whole DEM (a ray reaches any station): `dem` is the full resident raster also for a row band
         CUDA_TRY(ctx, launchIdwTdRaster(ds, ds.z, m, dg, s->topoDist_Kh, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax,
@@ -1061,7 +1115,14 @@ static int interpolatePointsImpl(pb_context* ctx, const pb_stations* st, const p
     }
     cudaEventRecord(ctx->ev[0], ctx->stream);
     DevStations ds{};
-    rc = stageStations(ctx, st, s, excludeSupplemental != 0, ds, mod.valueOffset);
+    ShepardStations ss{};
+    float shepardR0 = 0.f;
+    const bool shepardMethod = s->method != PB_METHOD_IDW;
+    if (shepardMethod && td) return fail(ctx, PB_ERR_UNSUPPORTED, "the Shepard estimators run without topographic distance on the GPU path");
+    if (shepardMethod && s->method == PB_METHOD_SHEPARD_MODIFIED && s->useLocalDetrending)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "modified Shepard with the local radius is not on the GPU path");
+    if (shepardMethod) rc = stageShepardStations(ctx, st, s, excludeSupplemental != 0, ss, shepardR0);
+    else rc = stageStations(ctx, st, s, excludeSupplemental != 0, ds, mod.valueOffset);
     if (rc) return rc;
     const size_t mAl = (size_t(m) + 3) / 4 * 4;
     const size_t offX = 0, offY = mAl * 4, offP = offY + mAl * 4, offO = offP + size_t(m) * mod.nProxy * 8;
@@ -1074,7 +1135,12 @@ static int interpolatePointsImpl(pb_context* ctx, const pb_stations* st, const p
         CUDA_TRY(ctx, cudaMemcpyAsync(d + offP, proxyValues, size_t(m) * mod.nProxy * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (td) CUDA_TRY(ctx, cudaMemcpyAsync(d + offZ, z, size_t(m) * 4, cudaMemcpyHostToDevice, ctx->stream));
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    if (td)
+    if (shepardMethod)
+        CUDA_TRY(ctx, launchShepardPoints(ss, mod, shepardR0, s->method == PB_METHOD_SHEPARD_MODIFIED,
+                                          reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
+                                          reinterpret_cast<const double*>(d + offP), m, reinterpret_cast<float*>(d + offO),
+                                          ctx->stream));
+    else if (td)
         CUDA_TRY(ctx, launchIdwTdPoints(ds, ds.z, mod, devGridOf(ctx->rasters[demId]), s->topoDist_Kh,
                                         reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                         reinterpret_cast<const float*>(d + offZ), reinterpret_cast<const double*>(d + offP), m,
