@@ -56,6 +56,54 @@ int shim_compute_residuals(const pb_stations* st, const pb_settings* s, int vari
     return ok ? PB_OK : PB_ERR_INVALID;
 }
 
+/* pragab200::preInterpolation on reference objects (settings, points, meteo points, current DEM); same outputs as
+ * ref_pre_interpolation_ex so the two can be compared field by field */
+int shim_pre_interpolation(pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv, const pb_raster* dem,
+                           uint8_t* keep, pb_kh_series* khSeries, char* err, int errLen)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    gis::Crit3DRasterGrid demGrid;
+    if (dem) {
+        fillGrid(demGrid, *dem);
+        sc.settings.setCurrentDEM(&demGrid);
+    }
+    sc.settings.setUseExcludeStationsOutsideDEM(cv && cv->excludeOutsideDem);
+    std::vector<Crit3DMeteoPoint> mp(st->n);
+    for (int i = 0; i < st->n; i++) {
+        sc.points[i].index = i;
+        mp[i].active = true;
+        mp[i].quality = quality::accepted;
+        mp[i].currentValue = (cv && cv->currentValue) ? cv->currentValue[i] : st->value[i];
+        mp[i].point.utm.x = st->x[i];
+        mp[i].point.utm.y = st->y[i];
+        mp[i].point.z = st->z[i];
+        mp[i].isInsideDem = (cv && cv->isInsideDem) ? cv->isInsideDem[i] != 0 : true;
+        mp[i].lapseRateCode = st->lapseRateCode ? lapseRateCodeType(st->lapseRateCode[i]) : primary;
+        for (int k = 0; k < st->nProxy; k++) mp[i].proxyValues.push_back(st->proxyValues[size_t(i) * st->nProxy + k]);
+    }
+    std::string e;
+    bool ok = pragab200::preInterpolation(sc.points, sc.settings, &sc.meteoSettings, &sc.climate, mp, meteoVariable(variable),
+                                          sc.time, e);
+    if (err && errLen > 0) { strncpy(err, e.c_str(), errLen - 1); err[errLen - 1] = 0; }
+    if (keep) memset(keep, 0, st->n);
+    for (auto& p : sc.points) {
+        st->value[p.index] = p.value;
+        if (keep) keep[p.index] = 1;
+    }
+    exportSettings(sc, *s);
+    s->pointsBoundingBoxArea = sc.settings.getPointsBoundingBoxArea();
+    std::vector<double> pr = sc.settings.getPointsRange();
+    if (pr.size() == 2) { s->hasPointsRange = 1; s->pointsRangeMin = pr[0]; s->pointsRangeMax = pr[1]; }
+    if (khSeries) {
+        std::vector<float> kh = sc.settings.getKh_series(), ke = sc.settings.getKh_error_series();
+        khSeries->n = int(std::min(kh.size(), size_t(PB_MAX_KH_SERIES)));
+        for (int i = 0; i < khSeries->n; i++) { khSeries->kh[i] = kh[i]; khSeries->error[i] = ke[i]; }
+    }
+    return ok ? PB_OK : PB_ERR_FIT;
+}
+
 /* the stateful kriging API of kriging.h through the shim */
 int shim_kriging_points(const double* pos, const double* val, int n, int mode, double range, double nugget, double sill,
                         double slope, const double* xy, int m, double* result, double* rmse)

@@ -241,6 +241,124 @@ bool interpolationRasterLocalDetrending(std::vector<Crit3DInterpolationDataPoint
     return rasterCall(true, interpolationPoints, interpolationSettings, meteoSettings, outputGrid, raster, variable);
 }
 
+namespace {
+typedef double (*fit1d_t)(double, std::vector<double>&);
+fit1d_t fitFunctionPtr(int f)
+{
+    switch (f) {
+    case PB_FIT_PIECEWISE_TWO: return lapseRatePiecewise_two;
+    case PB_FIT_PIECEWISE_THREE_FREE: return lapseRatePiecewise_three_free;
+    case PB_FIT_PIECEWISE_THREE: return lapseRatePiecewise_three;
+    case PB_FIT_LINEAR: return functionLinear_intercept;
+    default: return nullptr;
+    }
+}
+
+/* pb_settings -> the fields preInterpolation mutates in Crit3DInterpolationSettings */
+void writeBackSettings(const pb_settings& s, Crit3DInterpolationSettings& st, const pb_kh_series& kh)
+{
+    st.setPrecipitationAllZero(s.precipitationAllZero != 0);
+    st.setTopoDist_Kh(s.topoDist_Kh);
+    st.setPointsBoundingBoxArea(s.pointsBoundingBoxArea);
+    if (s.hasPointsRange) st.setPointsRange(s.pointsRangeMin, s.pointsRangeMax);
+    Crit3DProxyCombination cur = st.getCurrentCombination();
+    while (int(cur.getProxySize()) < s.nProxy) { cur.addProxyActive(false); cur.addProxySignificant(false); }
+    for (int i = 0; i < s.nProxy; i++) {
+        cur.setProxyActive(i, s.currentActive[i] != 0);
+        cur.setProxySignificant(i, s.currentSignificant[i] != 0);
+        Crit3DProxy* p = st.getProxy(i);
+        const pb_proxy& q = s.proxy[i];
+        p->setInversionIsSignificative(q.inversionIsSignificative != 0);
+        p->setRegressionR2(q.regressionR2);
+        p->setRegressionSlope(q.regressionSlope);
+        p->setRegressionIntercept(q.regressionIntercept);
+        p->setLapseRateH0(q.lapseRateH0);
+        p->setLapseRateH1(q.lapseRateH1);
+        p->setLapseRateT0(q.lapseRateT0);
+        p->setLapseRateT1(q.lapseRateT1);
+        p->setInversionLapseRate(q.inversionLapseRate);
+        if (s.useMultipleDetrending) {
+            std::vector<double> range;
+            for (int j = 0; j < q.nFitParams; j++) range.push_back(q.fitMin[j]);
+            for (int j = 0; j < q.nFitParams; j++) range.push_back(q.fitMax[j]);
+            p->setFittingParametersRange(range);
+            std::vector<std::vector<double>> combos;
+            for (int k = 0; k < q.nFirstGuessCombinations; k++)
+                combos.push_back(std::vector<double>(q.firstGuessCombinations[k], q.firstGuessCombinations[k] + q.nFitParams));
+            p->setFirstGuessCombinations(combos);
+        }
+    }
+    cur.setUseThermalInversion(s.currentUseThermalInversion != 0);
+    st.setCurrentCombination(cur);
+    if (s.useMultipleDetrending) {
+        st.clearFitting();
+        for (int i = 0; i < s.nFitFunctions; i++)
+            if (fit1d_t f = fitFunctionPtr(s.fitFunction[i])) st.addFittingFunction(f);
+        std::vector<std::vector<double>> params;
+        for (int i = 0; i < s.nFit; i++) params.push_back(std::vector<double>(s.fitParams[i], s.fitParams[i] + s.fitNrParams[i]));
+        st.setFittingParameters(params);
+    }
+    if (kh.n > 0) {
+        st.initializeKhSeries();
+        for (int i = 0; i < kh.n; i++) st.addToKhSeries(kh.kh[i], kh.error[i]);
+    }
+}
+}  // namespace
+
+bool preInterpolation(std::vector<Crit3DInterpolationDataPoint>& myPoints, Crit3DInterpolationSettings& interpolationSettings,
+                      Crit3DMeteoSettings* meteoSettings, Crit3DClimateParameters* climateParameters,
+                      std::vector<Crit3DMeteoPoint>& meteoPoints, meteoVariable myVar, Crit3DTime myTime, std::string& errorStr)
+{
+    pb_context* ctx = context();
+    if (!ctx) { errorStr = g_error; return false; }
+    pb_settings s;
+    std::vector<pb_raster> grids;
+    gis::Crit3DRasterGrid* dem = interpolationSettings.getCurrentDEM();
+    if (!flattenSettings(interpolationSettings, meteoSettings, s, grids, dem)) { errorStr = g_error; return false; }
+    if (climateParameters) s.climateLapseRate = climateParameters->getClimateLapseRate(myVar, myTime);
+    else s.climateLapseRate = 0.f;
+    FlatPoints fp;
+    flattenPoints(myPoints, s.nProxy, fp);
+    const int n = fp.st.n;
+    // the meteo point behind each interpolation point: Crit3DInterpolationDataPoint::index (passDataToInterpolation :516)
+    std::vector<float> current(n);
+    std::vector<uint8_t> inside(n, 1);
+    bool haveMeteo = !meteoPoints.empty();
+    for (int i = 0; i < n && haveMeteo; i++) {
+        const int k = myPoints[i].index;
+        if (k < 0 || k >= int(meteoPoints.size())) { haveMeteo = false; break; }
+        current[i] = meteoPoints[k].currentValue;
+        inside[i] = meteoPoints[k].isInsideDem;
+    }
+    pb_cv_points cv;
+    memset(&cv, 0, sizeof(cv));
+    if (haveMeteo) { cv.currentValue = current.data(); cv.isInsideDem = inside.data(); }
+    cv.excludeOutsideDem = interpolationSettings.getUseExcludeStationsOutsideDEM();
+    pb_raster_id demId = -1;
+    const bool needDem = s.useTD && !s.useLocalDetrending && !s.useGlocalDetrending;
+    if (needDem && dem != nullptr && dem->isLoaded) {
+        pb_raster r = rasterOf(*dem);
+        if (failed(ctx, pb_raster_upload(ctx, &r, &demId))) { errorStr = g_error; return false; }
+    }
+    std::vector<uint8_t> keep(n, 1);
+    pb_kh_series kh;
+    memset(&kh, 0, sizeof(kh));
+    const int rc = pb_pre_interpolation_ex(ctx, &fp.st, &s, int(myVar), &cv, demId, keep.data(), &kh);
+    if (demId >= 0) pb_raster_free(ctx, demId);
+    if (rc == PB_ERR_FIT) { errorStr = "Error in function preInterpolation"; return false; }
+    if (failed(ctx, rc)) { errorStr = g_error; return false; }
+    writeBackSettings(s, interpolationSettings, kh);
+    std::vector<Crit3DInterpolationDataPoint> out;
+    out.reserve(n);
+    for (int i = 0; i < n; i++)
+        if (keep[i]) {
+            myPoints[i].value = fp.value[i];
+            out.push_back(myPoints[i]);
+        }
+    if (int(out.size()) != n) myPoints = out;
+    return true;
+}
+
 bool computeResiduals(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoPoints,
                       const std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
                       Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,

@@ -7,6 +7,8 @@
  * Same names, argument meaning and error behaviour as the reference:
  *   pragab200::interpolationRaster            <- agrolib/project/interpolationCmd.h:73-75 (.cpp:353-394)
  *   pragab200::interpolationRasterLocalDetrending <- loop of Project::interpolationDemLocalDetrending, project.cpp:3208-3253
+ *   pragab200::preInterpolation               <- agrolib/interpolation/interpolation.h (.cpp:2444-2499): precipitation check,
+ *                                                multiple detrending, classic detrending(), optimalDetrending(), kh search
  *   pragab200::computeResiduals               <- agrolib/interpolation/spatialControl.h:30 (.cpp:97-155)
  *   pragab200::krigingVariogram / krigingSetWeight / krigingResult / krigingRMSE / krigingFreeMemory
  *                                             <- agrolib/interpolation/kriging.h:4-15
@@ -42,6 +44,14 @@ bool interpolationRasterLocalDetrending(std::vector<Crit3DInterpolationDataPoint
                                         Crit3DInterpolationSettings& interpolationSettings,
                                         Crit3DMeteoSettings* meteoSettings, gis::Crit3DRasterGrid* outputGrid,
                                         gis::Crit3DRasterGrid& raster, meteoVariable variable);
+
+/* same contract as the reference: myPoints are detrended in place (points multiple detrending drops are erased), the
+ * settings receive the fit (current combination, proxies' regression fields or fitting functions/parameters, kh and the
+ * Kh series, points range / bounding box). meteoPoints: the points passDataToInterpolation built myPoints from (one per
+ * interpolation point with the same index order once inactive / not accepted ones are skipped). */
+bool preInterpolation(std::vector<Crit3DInterpolationDataPoint>& myPoints, Crit3DInterpolationSettings& interpolationSettings,
+                      Crit3DMeteoSettings* meteoSettings, Crit3DClimateParameters* climateParameters,
+                      std::vector<Crit3DMeteoPoint>& meteoPoints, meteoVariable myVar, Crit3DTime myTime, std::string& errorStr);
 
 bool computeResiduals(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoPoints,
                       const std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,

@@ -109,3 +109,30 @@ def test_shim_kriging_stateful_api(shim, ref):
                                   A.dptr(rm))
     assert rc == A.PB_OK
     assert np.abs(res - want).max() <= TOL and np.abs(rm - want_rm).max() <= TOL
+
+
+@pytest.mark.parametrize("case", ["optimal_inversion", "optimal_codes_warm_valley", "classic_td_kh64", "multiple_td", "td_humidity"])
+def test_shim_pre_interpolation(shim, ref, case):
+    """pragab200::preInterpolation with the reference's signature on reference objects: points, settings and Kh series
+    must come back exactly as the reference's own preInterpolation leaves them."""
+    from test_oracle_port import clone, describe_diff, settings_equal
+    from test_station_space import scenario
+    dem, urban, st, s, var = scenario(case)
+    raw = st.value.copy()
+    st_r, st_g, s_r, s_g = st.copy(), st.copy(), clone(s), clone(s)
+    ok, keep_r, series_r = ref.pre_interpolation_ex(st_r, s_r, var, current_value=raw, dem=dem if "td" in case else None)
+    assert ok
+    stp = st_g.as_pb()
+    cv = A.pb_cv_points()
+    cv.currentValue = A.fptr(raw)
+    keep_g = np.zeros(st.n, dtype=np.uint8)
+    series = A.pb_kh_series()
+    d = dem.as_pb()
+    err = C.create_string_buffer(512)
+    rc = shim.shim_pre_interpolation(C.byref(stp), C.byref(s_g), var, C.byref(cv), C.byref(d) if "td" in case else None,
+                                     A.u8ptr(keep_g), C.byref(series), err, 512)
+    assert rc == A.PB_OK, err.value.decode()
+    assert np.array_equal(keep_r, keep_g.astype(bool))
+    assert np.array_equal(st_r.value[keep_r], st_g.value[keep_r])
+    assert series_r == [(series.kh[i], series.error[i]) for i in range(series.n)]
+    assert settings_equal(s_r, s_g), describe_diff(s_r, s_g)
