@@ -66,7 +66,7 @@ enum {
     PB_VAR_WIND_VECTOR_INTENSITY = 35, PB_VAR_WIND_VECTOR_X = 37, PB_VAR_WIND_VECTOR_Y = 38,
     PB_VAR_DAILY_WIND_VECTOR_INT_AVG = 39, PB_VAR_DAILY_WIND_VECTOR_INT_MAX = 40,
     PB_VAR_DAILY_WIND_SCALAR_INT_AVG = 42, PB_VAR_DAILY_WIND_SCALAR_INT_MAX = 43, PB_VAR_LEAF_WETNESS = 44,
-    PB_VAR_DAILY_LEAF_WETNESS = 45, PB_VAR_ATM_PRESSURE = 46, PB_VAR_DAILY_ET0_HS = 48,
+    PB_VAR_DAILY_LEAF_WETNESS = 45, PB_VAR_ATM_PRESSURE = 46, PB_VAR_DAILY_ET0_HS = 48, PB_VAR_DAILY_BIC = 52,
     PB_VAR_DAILY_WATER_TABLE_DEPTH = 67, PB_VAR_ELABORATION = 72, PB_VAR_NONE = 73
 };
 
@@ -273,6 +273,28 @@ int pb_interpolate_points_td(pb_context* ctx, const pb_stations* st, const pb_se
  * residual[i] = observed - interpolate() at the station (NODATA where not computed). `stats` may be NULL. */
 int pb_compute_residuals(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* observed,
                          const uint8_t* useForCv, float* residual, pb_cv_stats* stats);
+
+/* computeResiduals with the EXACT arithmetic of the reference (f32 distances, f64 weights, sequential order) for any
+ * settings the station-space pipeline produces, topographic distance included (computeDistances :226-251 through the
+ * resident DEM). meteo = one entry per Crit3DMeteoPoint (active and accepted): position, lapse code, proxy values;
+ * observed[i] = currentValue (NULL: meteo->value); points = the interpolation points (already detrended, as
+ * preInterpolation leaves them; may be a subset of meteo); residual[meteo->n]. */
+int pb_compute_residuals_exact(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
+                               const pb_stations* points, const pb_settings* s, int variable, pb_raster_id dem /* -1: none */,
+                               int excludeOutsideDem, int excludeSupplemental, float* residual);
+
+/* --- spatialQualityControl (agrolib/interpolation/spatialControl.cpp:331-427), the check every
+ * checkAndPassDataToInterpolation runs before gridding (checkData :466-476; not for precipitation / wind vectors):
+ *   passDataToInterpolation :500-566 -> preInterpolation -> computeResiduals(…, false, false) -> per point
+ *   neighbourhoodVariability (interpolation.cpp:259-301: the 10 nearest interpolation points, stdDev of their values,
+ *   mean |dz|, smallest distance) -> |residual| > getSpatialThresholdVar(…, 2 stdDev) (:14-94) marks the point suspect;
+ *   the suspects are then re-estimated from the field WITHOUT them (second preInterpolation) and tested at 3 stdDev.
+ * st = one entry per accepted, active meteo point with its current (raw) value; s = the spatial-quality interpolation
+ * settings (mutated exactly like the reference mutates them: both preInterpolation fits, points range, bounding box);
+ * wrongSpatial[st->n] receives 1 where the reference leaves quality::wrong_spatial. The second pass keeps the
+ * reference's indexing of the proxy values (meteoPoints[i] with i = position in the suspect list, :393). */
+int pb_spatial_quality_control(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv,
+                               pb_raster_id dem /* -1: none */, uint8_t* wrongSpatial);
 
 /* --- ordinary kriging (agrolib/interpolation/kriging.h:4-15, kriging.cpp). The reference keeps ONE system in file-static
  * globals; here every krigingVariogram call yields a handle and many systems can live on a device.

@@ -62,6 +62,8 @@ def _load(path, prefix):
     fn = getattr(lib, prefix + "_pre_interpolation_ex")
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_cv_points), P(A.pb_raster), P(C.c_uint8),
                    P(A.pb_kh_series)]
+    fn = getattr(lib, prefix + "_spatial_quality_control")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_cv_points), P(A.pb_raster), P(C.c_uint8)]
     fn = getattr(lib, prefix + "_interpolate_points")
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_float), P(C.c_float),
                    P(C.c_double), C.c_int, C.c_int, P(C.c_float)]
@@ -181,6 +183,20 @@ class Oracle:
         rc = self._f("pre_interpolation_ex")(C.byref(st), C.byref(settings), variable, C.byref(cv),
                                              None if d is None else C.byref(d), A.u8ptr(keep), C.byref(series))
         return rc == A.PB_OK, keep.astype(bool), [(series.kh[i], series.error[i]) for i in range(series.n)]
+
+    def spatial_quality_control(self, stations, settings, variable, inside_dem=None, exclude_outside_dem=False, dem=None):
+        """spatialQualityControl (spatialControl.cpp:331-427). Returns (ok, wrong_spatial mask); settings are mutated."""
+        st = stations.as_pb()
+        cv = A.pb_cv_points()
+        ins = None if inside_dem is None else np.ascontiguousarray(inside_dem, dtype=np.uint8)
+        if ins is not None:
+            cv.isInsideDem = A.u8ptr(ins)
+        cv.excludeOutsideDem = int(exclude_outside_dem)
+        wrong = np.zeros(stations.n, dtype=np.uint8)
+        d = None if dem is None else dem.as_pb()
+        rc = self._f("spatial_quality_control")(C.byref(st), C.byref(settings), variable, C.byref(cv),
+                                                None if d is None else C.byref(d), A.u8ptr(wrong))
+        return rc == A.PB_OK, wrong.astype(bool)
 
     def interpolate_points(self, stations, settings, variable, x, y, z, proxy_values, exclude_supplemental=False):
         x = np.ascontiguousarray(x, dtype=np.float32)

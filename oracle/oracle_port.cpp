@@ -1675,11 +1675,33 @@ void optimalDetrending(int var, std::vector<MeteoPt>& mp, std::vector<Point>& ou
     }
 }
 
-int port_pre_interpolation_ex(pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv, const pb_raster* dem,
-                              uint8_t* keep, pb_kh_series* khSeries)
+// preInterpolation, interpolation.cpp:2444-2499, with its meteo points and current DEM
+bool preInterpolationEx(Work& w, std::vector<MeteoPt>& mp, bool excludeOutsideDem, const Grid* gp, pb_kh_series* khSeries)
 {
-    if (khSeries) khSeries->n = 0;
-    Work w{loadPoints(st), s, variable};
+    pb_settings* s = w.s;
+    const int variable = w.var;
+    bool ok = true;
+    if (isPrec(variable)) {
+        int nrValid = 0;
+        for (auto& p : w.pts)
+            if (p.isActive && !isEqualF(p.value, NODATA_F) && p.value >= s->rainfallThreshold) nrValid++;
+        if (nrValid == 0) { s->precipitationAllZero = 1; return true; }
+        s->precipitationAllZero = 0;
+    }
+    if (useDetrendingVar(variable)) {
+        if (s->useMultipleDetrending) {
+            if (!s->useLocalDetrending) setMultipleDetrendingHeightTemperatureRange(*s);
+            if (!multipleDetrendingMain(w)) ok = false;
+        } else if (s->useBestDetrending) optimalDetrending(variable, mp, w.pts, *s, excludeOutsideDem, gp);
+        else detrendingClassic(w);
+    }
+    if (ok && gp && s->useTD && !s->useLocalDetrending && useTdVar(variable) && !s->useGlocalDetrending)
+        topographicDistanceOptimize(variable, mp, w.pts, *s, gp, khSeries);
+    return ok;
+}
+
+std::vector<MeteoPt> loadMeteoPoints(const pb_stations* st, const pb_cv_points* cv)
+{
     std::vector<MeteoPt> mp(st->n);
     for (int i = 0; i < st->n; i++) {
         mp[i].x = st->x[i]; mp[i].y = st->y[i]; mp[i].z = st->z[i];
@@ -1690,35 +1712,203 @@ int port_pre_interpolation_ex(pb_stations* st, pb_settings* s, int variable, con
         mp[i].proxy.assign(st->proxyValues ? st->proxyValues + size_t(i) * st->nProxy : nullptr,
                            st->proxyValues ? st->proxyValues + size_t(i + 1) * st->nProxy : nullptr);
     }
+    return mp;
+}
+
+int port_pre_interpolation_ex(pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv, const pb_raster* dem,
+                              uint8_t* keep, pb_kh_series* khSeries)
+{
+    if (khSeries) khSeries->n = 0;
+    Work w{loadPoints(st), s, variable};
+    std::vector<MeteoPt> mp = loadMeteoPoints(st, cv);
     Grid g{};
     const Grid* gp = nullptr;
     if (dem) { g = gridOf(*dem); gp = &g; }
-    bool ok = true;
-    bool done = false;
-    if (isPrec(variable)) {
-        int nrValid = 0;
-        for (auto& p : w.pts)
-            if (p.isActive && !isEqualF(p.value, NODATA_F) && p.value >= s->rainfallThreshold) nrValid++;
-        if (nrValid == 0) { s->precipitationAllZero = 1; done = true; }
-        else s->precipitationAllZero = 0;
-    }
-    if (!done) {
-        if (useDetrendingVar(variable)) {
-            if (s->useMultipleDetrending) {
-                if (!s->useLocalDetrending) setMultipleDetrendingHeightTemperatureRange(*s);
-                if (!multipleDetrendingMain(w)) ok = false;
-            } else if (s->useBestDetrending) optimalDetrending(variable, mp, w.pts, *s, cv && cv->excludeOutsideDem, gp);
-            else detrendingClassic(w);
-        }
-        if (ok && gp && s->useTD && !s->useLocalDetrending && useTdVar(variable) && !s->useGlocalDetrending)
-            topographicDistanceOptimize(variable, mp, w.pts, *s, gp, khSeries);
-    }
+    const bool ok = preInterpolationEx(w, mp, cv && cv->excludeOutsideDem, gp, khSeries);
     if (keep) memset(keep, 0, st->n);
     for (auto& p : w.pts) {
         st->value[p.index] = p.value;
         if (keep) keep[p.index] = 1;
     }
     return ok ? PB_OK : PB_ERR_FIT;
+}
+
+// sortPointsByDistance :121-160 + neighbourhoodVariability :259-301 (computeDistances with excludeSupplemental = true)
+bool neighbourhoodVariability(int var, const std::vector<Point>& pts, const pb_settings& s, float x, float y, float z, int maxNrPoints,
+                              const Grid* dem, float& devSt, float& avgDeltaZ, float& minDistance)
+{
+    const bool td = dem && s.useTD && !s.useLocalDetrending && useTdVar(var) && s.topoDist_Kh != 0;
+    std::vector<float> dist(pts.size());
+    for (size_t i = 0; i < pts.size(); i++) {
+        float d;
+        if (!checkLapseRateCode(pts[i].lapseRateCode, s.useLapseRateCode != 0, false)) d = 0;
+        else {
+            const float dx = float(pts[i].x) - x, dy = float(pts[i].y) - y;
+            d = sqrtf(dx * dx + dy * dy);
+            if (td) d += (s.topoDist_Kh * topographicDistance(x, y, z, float(pts[i].x), float(pts[i].y), float(pts[i].z), d, *dem));
+        }
+        dist[i] = d;
+    }
+    std::vector<int> idx;
+    for (int i = 0; i < int(pts.size()); i++)
+        if (!isEqualF(dist[i], 0) && !isEqualF(dist[i], NODATA_F)) idx.push_back(i);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return dist[a] < dist[b]; });
+    const int n = std::min(maxNrPoints, int(idx.size()));
+    if (n <= 1) return false;
+    minDistance = dist[idx[0]];
+    // statistics::standardDeviation -> variance(vector<float>) :1189-1215 with mean(vector<float>) :1300-1321
+    double sum = 0;
+    int nv = 0;
+    for (int q = 0; q < n; q++) {
+        const float v = pts[idx[q]].value;
+        if (!isEqualF(v, NODATA_F)) { sum += double(v); nv++; }
+    }
+    const float myMean = nv ? float(sum / double(nv)) : NODATA_F;
+    float squareDiff = 0;
+    int nrValid = 0;
+    for (int q = 0; q < n; q++) {
+        const float v = pts[idx[q]].value;
+        if (v != NODATA_F) {
+            const float diff = v - myMean;
+            squareDiff += diff * diff;
+            nrValid++;
+        }
+    }
+    const float variance = nrValid > 1 ? squareDiff / (nrValid - 1) : NODATA_F;
+    devSt = isEqualF(variance, NODATA_F) ? NODATA_F : sqrtf(variance);
+    if (z != NODATA_F) {
+        double s2 = 0;
+        int nz = 0;
+        for (int q = 0; q < n; q++) {
+            const double zi = pts[idx[q]].z;
+            if (!isEqualD(zi, double(NODATA_F))) {
+                const float dz = float(fabs(zi - z));
+                if (!isEqualF(dz, NODATA_F)) { s2 += double(dz); nz++; }
+            }
+        }
+        avgDeltaZ = nz ? float(s2 / double(nz)) : NODATA_F;
+    } else avgDeltaZ = NODATA_F;
+    return true;
+}
+
+// getSpatialThresholdVar, spatialControl.cpp:14-94
+float getSpatialThresholdVar(int v, float rainfallThreshold, float value, float stdDev, int nrStdDev, float avgDeltaZ, float minDistance)
+{
+    const float PREC_THRESHOLD = 1000.f;
+    float zWeight, distWeight, threshold;
+    switch (v) {
+    case PB_VAR_PRECIPITATION: case PB_VAR_DAILY_PRECIPITATION:
+        distWeight = std::max(1.f, minDistance / 2000.f);
+        if (value <= rainfallThreshold) threshold = std::max(5.f, distWeight + stdDev * (nrStdDev + 1));
+        else return PREC_THRESHOLD;
+        break;
+    case PB_VAR_AIR_TEMPERATURE: case PB_VAR_AIR_DEW_TEMPERATURE: case PB_VAR_DAILY_TMAX: case PB_VAR_DAILY_TMIN: case PB_VAR_DAILY_TAVG:
+        threshold = 1.f;
+        zWeight = avgDeltaZ / 100.f;
+        distWeight = minDistance / 1000.f;
+        threshold = std::min(std::min(distWeight + threshold + zWeight, 12.f) + stdDev * nrStdDev, 15.f);
+        break;
+    case PB_VAR_AIR_REL_HUMIDITY: case PB_VAR_DAILY_RH_MAX: case PB_VAR_DAILY_RH_MIN: case PB_VAR_DAILY_RH_AVG:
+        threshold = 20.f;
+        zWeight = avgDeltaZ / 10.f;
+        distWeight = minDistance / 1000.f;
+        threshold += zWeight + distWeight + stdDev * nrStdDev;
+        break;
+    case PB_VAR_WIND_SCALAR_INTENSITY: case PB_VAR_WIND_VECTOR_INTENSITY: case PB_VAR_DAILY_WIND_SCALAR_INT_AVG:
+    case PB_VAR_DAILY_WIND_SCALAR_INT_MAX: case PB_VAR_DAILY_WIND_VECTOR_INT_AVG: case PB_VAR_DAILY_WIND_VECTOR_INT_MAX:
+        threshold = 1.f;
+        zWeight = avgDeltaZ / 50.f;
+        distWeight = minDistance / 2000.f;
+        threshold += zWeight + distWeight + stdDev * nrStdDev;
+        break;
+    case PB_VAR_GLOBAL_IRRADIANCE:
+        threshold = 500;
+        distWeight = minDistance / 5000.f;
+        threshold += distWeight + stdDev * (nrStdDev + 1);
+        break;
+    case PB_VAR_DAILY_GLOBAL_RADIATION:
+        threshold = 10;
+        distWeight = minDistance / 5000.f;
+        threshold += distWeight + stdDev * (nrStdDev + 1);
+        break;
+    case PB_VAR_ATM_TRANSMISSIVITY:
+        distWeight = minDistance / 20000.f;
+        threshold = std::min(std::max(distWeight + stdDev * nrStdDev, 0.3f), 0.8f);
+        break;
+    case PB_VAR_ATM_PRESSURE:
+        zWeight = avgDeltaZ / 10.f;
+        threshold = zWeight + stdDev * nrStdDev;
+        break;
+    case PB_VAR_DAILY_BIC: threshold = PREC_THRESHOLD; break;
+    default: threshold = stdDev * nrStdDev;
+    }
+    return threshold;
+}
+
+// spatialQualityControl, spatialControl.cpp:331-427 (every meteo point of st active and accepted at entry)
+int port_spatial_quality_control(const pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv, const pb_raster* dem,
+                                 uint8_t* wrongSpatial)
+{
+    const int n = st->n;
+    memset(wrongSpatial, 0, n);
+    std::vector<MeteoPt> all = loadMeteoPoints(st, cv);
+    Grid g{};
+    const Grid* gp = nullptr;
+    if (dem) { g = gridOf(*dem); gp = &g; }
+    const bool exclOut = cv && cv->excludeOutsideDem;
+    // meteo points still accepted -> the vector the reference's loops walk (indices into `all`)
+    auto accepted = [&]() {
+        std::vector<int> idx;
+        for (int i = 0; i < n; i++) if (!wrongSpatial[i]) idx.push_back(i);
+        return idx;
+    };
+    auto subset = [&](const std::vector<int>& idx) {
+        std::vector<MeteoPt> mp;
+        for (int i : idx) mp.push_back(all[i]);
+        return mp;
+    };
+    std::vector<int> idxA = accepted();
+    std::vector<MeteoPt> mpA = subset(idxA);
+    Work w{{}, s, variable};
+    if (!passDataToInterpolation(mpA, w.pts, *s)) return PB_OK;
+    if (!preInterpolationEx(w, mpA, exclOut, gp, nullptr)) return PB_ERR_FIT;
+    computeResidualsMeteo(variable, mpA, w.pts, *s, false, false, gp);
+    std::vector<int> listIndex;
+    for (int i = 0; i < n; i++) {
+        float stdDev, avgDeltaZ, minDist;
+        if (neighbourhoodVariability(variable, w.pts, *s, float(all[i].x), float(all[i].y), float(all[i].z), 10, gp, stdDev, avgDeltaZ, minDist)) {
+            const float myValue = all[i].currentValue, myResidual = mpA[i].residual;
+            stdDev = std::max(stdDev, myValue / 100.f);
+            if (fabs(myResidual) > getSpatialThresholdVar(variable, s->rainfallThreshold, myValue, stdDev, 2, avgDeltaZ, minDist)) {
+                listIndex.push_back(i);
+                wrongSpatial[i] = 1;
+            }
+        }
+    }
+    if (listIndex.empty()) return PB_OK;
+    std::vector<int> idxB = accepted();
+    std::vector<MeteoPt> mpB = subset(idxB);
+    Work w2{{}, s, variable};
+    if (!passDataToInterpolation(mpB, w2.pts, *s)) return PB_OK;
+    if (!preInterpolationEx(w2, mpB, exclOut, gp, nullptr)) return PB_ERR_FIT;
+    std::vector<float> listResiduals;
+    for (size_t k = 0; k < listIndex.size(); k++) {
+        const MeteoPt& m = all[listIndex[k]];
+        double pv[PB_MAX_PROXY];
+        // meteoPoints[i].getProxyValues() with i = position in the list (spatialControl.cpp:393)
+        for (int q = 0; q < PB_MAX_PROXY; q++) pv[q] = q < int(all[k].proxy.size()) ? double(all[k].proxy[q]) : -9999.;
+        const float est = interpolate(w2.pts, *s, variable, float(m.x), float(m.y), pv, false, float(m.z), gp);
+        listResiduals.push_back(est - m.currentValue);
+    }
+    for (size_t k = 0; k < listIndex.size(); k++) {
+        const int i = listIndex[k];
+        float stdDev, avgDeltaZ, minDist;
+        if (neighbourhoodVariability(variable, w2.pts, *s, float(all[i].x), float(all[i].y), float(all[i].z), 10, gp, stdDev, avgDeltaZ, minDist))
+            wrongSpatial[i] = fabs(listResiduals[k]) > getSpatialThresholdVar(variable, s->rainfallThreshold, all[i].currentValue, stdDev, 3,
+                                                                             avgDeltaZ, minDist) ? 1 : 0;
+        else wrongSpatial[i] = 0;
+    }
+    return PB_OK;
 }
 
 int port_interpolate_points(const pb_stations* st, const pb_settings* s, int variable, const float* x, const float* y,

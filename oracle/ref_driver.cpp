@@ -79,7 +79,7 @@ static_assert(int(airTemperature) == PB_VAR_AIR_TEMPERATURE && int(dailyAirTempe
                   int(leafWetness) == PB_VAR_LEAF_WETNESS && int(dailyLeafWetness) == PB_VAR_DAILY_LEAF_WETNESS &&
                   int(atmPressure) == PB_VAR_ATM_PRESSURE && int(dailyReferenceEvapotranspirationHS) == PB_VAR_DAILY_ET0_HS &&
                   int(dailyWaterTableDepth) == PB_VAR_DAILY_WATER_TABLE_DEPTH && int(elaborationVar) == PB_VAR_ELABORATION &&
-                  int(noMeteoVar) == PB_VAR_NONE, "meteoVariable");
+                  int(noMeteoVar) == PB_VAR_NONE && int(dailyBIC) == PB_VAR_DAILY_BIC, "meteoVariable");
 static_assert(NODATA == PB_NODATA, "NODATA");
 
 namespace {
@@ -409,6 +409,40 @@ int ref_pre_interpolation_ex(pb_stations* st, pb_settings* s, int variable, cons
         khSeries->n = int(std::min(kh.size(), size_t(PB_MAX_KH_SERIES)));
         for (int i = 0; i < khSeries->n; i++) { khSeries->kh[i] = kh[i]; khSeries->error[i] = e[i]; }
     }
+    return ok ? PB_OK : PB_ERR_FIT;
+}
+
+/* spatialQualityControl (spatialControl.cpp:331-427) on one accepted, active Crit3DMeteoPoint per station */
+int ref_spatial_quality_control(const pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv, const pb_raster* dem,
+                                uint8_t* wrongSpatial)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    gis::Crit3DRasterGrid demGrid;
+    if (dem) {
+        fillGrid(demGrid, *dem);
+        sc.settings.setCurrentDEM(&demGrid);
+    }
+    sc.settings.setUseExcludeStationsOutsideDEM(cv && cv->excludeOutsideDem);
+    std::vector<Crit3DMeteoPoint> mp(st->n);
+    for (int i = 0; i < st->n; i++) {
+        mp[i].active = true;
+        mp[i].quality = quality::accepted;
+        mp[i].currentValue = (cv && cv->currentValue) ? cv->currentValue[i] : st->value[i];
+        mp[i].point.utm.x = st->x[i];
+        mp[i].point.utm.y = st->y[i];
+        mp[i].point.z = st->z[i];
+        mp[i].isInsideDem = (cv && cv->isInsideDem) ? cv->isInsideDem[i] != 0 : true;
+        mp[i].lapseRateCode = st->lapseRateCode ? lapseRateCodeType(st->lapseRateCode[i]) : primary;
+        for (int k = 0; k < st->nProxy; k++) mp[i].proxyValues.push_back(st->proxyValues[size_t(i) * st->nProxy + k]);
+    }
+    std::string err;
+    bool ok = spatialQualityControl(meteoVariable(variable), mp, sc.settings, &sc.meteoSettings, &sc.climate, sc.time, err);
+    for (int i = 0; i < st->n; i++) wrongSpatial[i] = mp[i].quality == quality::wrong_spatial ? 1 : 0;
+    exportSettings(sc, *s);
+    s->pointsBoundingBoxArea = sc.settings.getPointsBoundingBoxArea();
+    std::vector<double> pr = sc.settings.getPointsRange();
+    if (pr.size() == 2) { s->hasPointsRange = 1; s->pointsRangeMin = pr[0]; s->pointsRangeMax = pr[1]; }
     return ok ? PB_OK : PB_ERR_FIT;
 }
 

@@ -75,7 +75,17 @@ cudaError_t launchClassicGather(const float* work, int n, int NP, int problem, f
 cudaError_t launchTopoMatrix(const float* tx, const float* ty, const float* tz, int nT, const float* sx, const float* sy,
                              const float* sz, int nS, const DevGrid& dem, float* topo, cudaStream_t s);
 cudaError_t launchLooExact(const LooSetup& ls, const LooTargets& t, const float* sx, const float* sy, const float* work,
-                           const ClassicProblem* problems, const float* topo, const int* khList, float* residual, cudaStream_t s);
+                           const ClassicProblem* problems, const float* topo, const int* khList, float* residual, cudaStream_t s,
+                           float* estimate = nullptr);
+
+// neighbourhoodVariability (interpolation.cpp:259-301) for nT targets over the nS interpolation points
+struct NeighbourOut {
+    int ok;                                // nrValidPoints > 1
+    float devSt, avgDeltaZ, minDistance;
+};
+cudaError_t launchNeighbourhood(const float* tx, const float* ty, const float* tz, int nT, const float* sx, const float* sy,
+                                const double* sz, const int* scode, const float* svalue, int nS, int useLapseRateCode,
+                                const float* topo, int kh, int maxNrPoints, NeighbourOut* out, cudaStream_t s);
 cudaError_t launchCvMae(const float* residual, const float* observed, int n, int nJobs, float* mae, cudaStream_t s);
 
 }  // namespace pb

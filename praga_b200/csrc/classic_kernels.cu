@@ -623,7 +623,7 @@ __device__ float retrendClassicDev(const LooSetup& ls, const ClassicProblem& pr,
 __global__ void __launch_bounds__(128)
 loo_exact_kernel(LooSetup ls, LooTargets tg, const float* __restrict__ sx, const float* __restrict__ sy,
                  const float* __restrict__ work, const ClassicProblem* __restrict__ problems, const float* __restrict__ topo,
-                 const int* __restrict__ khList, float* __restrict__ residual)
+                 const int* __restrict__ khList, float* __restrict__ residual, float* __restrict__ estimate)
 {
     const int nS = ls.nS, nT = ls.nT, NP = ls.nProblems;
     const long long tIdx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -637,7 +637,10 @@ loo_exact_kernel(LooSetup ls, LooTargets tg, const float* __restrict__ sx, const
     if (ls.excludeSupplemental) valid = checkLapseRateCodeDev(tg.code[j], ls.useLapseRateCode, false);
     if (valid && ls.excludeOutsideDem && tg.insideDem) valid = tg.insideDem[j] != 0;
     if (!valid) {
-        for (int q = 0; q < np; q++) residual[((size_t)(p0 + q) * ls.nKh + k) * nT + j] = kNoData;
+        for (int q = 0; q < np; q++) {
+            residual[((size_t)(p0 + q) * ls.nKh + k) * nT + j] = kNoData;
+            if (estimate) estimate[((size_t)(p0 + q) * ls.nKh + k) * nT + j] = kNoData;
+        }
         return;
     }
 
@@ -690,7 +693,81 @@ loo_exact_kernel(LooSetup ls, LooTargets tg, const float* __restrict__ sx, const
         float res = kNoData;
         if (est != kNoData && myValue != kNoData) res = myValue - est;
         residual[((size_t)(p0 + q) * ls.nKh + k) * nT + j] = res;
+        if (estimate) estimate[((size_t)(p0 + q) * ls.nKh + k) * nT + j] = est;
     }
+}
+
+// neighbourhoodVariability, interpolation.cpp:259-301: computeDistances(..., excludeSupplemental = true), the maxNrPoints
+// nearest points with |d| >= EPSILON (sortPointsByDistance :121-160; equal distances in station order), then
+// statistics::standardDeviation (float accumulators, statistics.cpp:1189-1215, 1383-1391) and statistics::mean of |dz|
+constexpr int kMaxNeighbours = 16;
+__global__ void __launch_bounds__(128)
+neighbourhood_kernel(const float* __restrict__ tx, const float* __restrict__ ty, const float* __restrict__ tz, int nT,
+                     const float* __restrict__ sx, const float* __restrict__ sy, const double* __restrict__ sz,
+                     const int* __restrict__ scode, const float* __restrict__ svalue, int nS, int useLapseRateCode,
+                     const float* __restrict__ topo, int kh, int maxNrPoints, NeighbourOut* __restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nT) return;
+    const float x = tx[j], y = ty[j], z = tz[j];
+    float nd[kMaxNeighbours];
+    int ni[kMaxNeighbours];
+    int n = 0;
+    for (int i = 0; i < nS; i++) {
+        float d;
+        if (!checkLapseRateCodeDev(scode[i], useLapseRateCode, false)) d = 0.f;
+        else {
+            const float dx = sx[i] - x, dy = sy[i] - y;
+            d = sqrtf(dx * dx + dy * dy);
+            if (topo && kh != 0) d += (float(kh) * topo[(size_t)j * nS + i]);
+        }
+        if (isEqualF(d, 0.f) || isEqualF(d, kNoData)) continue;
+        if (n == maxNrPoints && !(d < nd[n - 1])) continue;
+        int pos = n < maxNrPoints ? n : maxNrPoints - 1;
+        while (pos > 0 && d < nd[pos - 1]) { nd[pos] = nd[pos - 1]; ni[pos] = ni[pos - 1]; pos--; }
+        nd[pos] = d;
+        ni[pos] = i;
+        if (n < maxNrPoints) n++;
+    }
+    NeighbourOut o;
+    o.ok = n > 1;
+    o.devSt = o.avgDeltaZ = o.minDistance = kNoData;
+    if (n > 1) {
+        o.minDistance = nd[0];
+        // mean (double sum) then variance (float accumulators)
+        double sum = 0.;
+        int nv = 0;
+        for (int q = 0; q < n; q++) {
+            const float v = svalue[ni[q]];
+            if (!isEqualF(v, kNoData)) { sum += double(v); nv++; }
+        }
+        const float myMean = nv ? float(sum / double(nv)) : kNoData;
+        float squareDiff = 0.f;
+        int nrValid = 0;
+        for (int q = 0; q < n; q++) {
+            const float v = svalue[ni[q]];
+            if (v != kNoData) {
+                const float diff = v - myMean;
+                squareDiff += diff * diff;
+                nrValid++;
+            }
+        }
+        const float variance = nrValid > 1 ? squareDiff / float(nrValid - 1) : kNoData;
+        o.devSt = isEqualF(variance, kNoData) ? kNoData : sqrtf(variance);
+        if (z != kNoData) {
+            double s2 = 0.;
+            int nz = 0;
+            for (int q = 0; q < n; q++) {
+                const double zi = sz[ni[q]];
+                if (!(fabs(zi - double(kNoData)) < kEpsilon)) {
+                    const float dz = float(fabs(zi - double(z)));
+                    if (!isEqualF(dz, kNoData)) { s2 += double(dz); nz++; }
+                }
+            }
+            o.avgDeltaZ = nz ? float(s2 / double(nz)) : kNoData;
+        }
+    }
+    out[j] = o;
 }
 
 // computeErrorCrossValidation (spatialControl.cpp:305-328) + statistics::meanAbsoluteError (statistics.cpp:201-220):
@@ -749,13 +826,25 @@ cudaError_t launchTopoMatrix(const float* tx, const float* ty, const float* tz, 
     return cudaGetLastError();
 }
 
+cudaError_t launchNeighbourhood(const float* tx, const float* ty, const float* tz, int nT, const float* sx, const float* sy,
+                                const double* sz, const int* scode, const float* svalue, int nS, int useLapseRateCode,
+                                const float* topo, int kh, int maxNrPoints, NeighbourOut* out, cudaStream_t s)
+{
+    if (nT <= 0) return cudaSuccess;
+    if (maxNrPoints > kMaxNeighbours) maxNrPoints = kMaxNeighbours;
+    neighbourhood_kernel<<<(nT + 127) / 128, 128, 0, s>>>(tx, ty, tz, nT, sx, sy, sz, scode, svalue, nS, useLapseRateCode, topo, kh,
+                                                        maxNrPoints, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launchLooExact(const LooSetup& ls, const LooTargets& t, const float* sx, const float* sy, const float* work,
-                           const ClassicProblem* problems, const float* topo, const int* khList, float* residual, cudaStream_t s)
+                           const ClassicProblem* problems, const float* topo, const int* khList, float* residual, cudaStream_t s,
+                           float* estimate)
 {
     if (ls.nT <= 0 || ls.nProblems <= 0 || ls.nKh <= 0) return cudaSuccess;
     const long long threads = (long long)ls.nT * ls.nKh;
     dim3 grid((unsigned)((threads + 127) / 128), (unsigned)((ls.nProblems + kLooProblemsPerThread - 1) / kLooProblemsPerThread));
-    loo_exact_kernel<<<grid, 128, 0, s>>>(ls, t, sx, sy, work, problems, topo, khList, residual);
+    loo_exact_kernel<<<grid, 128, 0, s>>>(ls, t, sx, sy, work, problems, topo, khList, residual, estimate);
     return cudaGetLastError();
 }
 

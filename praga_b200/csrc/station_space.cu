@@ -439,3 +439,368 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     }
     return PB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// exact computeResiduals / interpolate at explicit targets with the FITTED settings, and neighbourhoodVariability:
+// the building blocks of spatialQualityControl (spatialControl.cpp:331-427)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct LooArrays {
+    // targets (meteo points)
+    std::vector<float> tx, ty, tz, tproxy, tobs;
+    std::vector<int> tcode;
+    std::vector<uint8_t> tin;
+    // sources (interpolation points, detrended values)
+    std::vector<float> sx, sy, szf, sval;
+    std::vector<double> sz;
+    std::vector<int> scode;
+};
+
+// problem = what the settings say about classic detrending (current combination + the proxies' regression fields)
+ClassicProblem problemOfSettings(const pb_settings& s)
+{
+    ClassicProblem pr{};
+    for (int i = 0; i < s.nProxy; i++) {
+        pr.active[i] = s.currentActive[i];
+        pr.significant[i] = s.currentSignificant[i];
+        pr.proxy[i] = stateOf(s.proxy[i]);
+    }
+    pr.useThermalInversion = s.currentUseThermalInversion;
+    return pr;
+}
+
+int exactLoo(pb_context* ctx, const LooArrays& a, const pb_settings* s, int variable, pb_raster_id demId, int excludeOutsideDem,
+             int excludeSupplemental, float* residual, float* estimate, NeighbourOut* nb)
+{
+    const int nT = (int)a.tx.size(), nS = (int)a.sx.size(), P = s->nProxy;
+    if (nT == 0) return PB_OK;
+    const size_t Pp = std::max(P, 1);
+    const bool detrendVar = varUsesDetrending(variable);
+    const bool useTD = s->useTD && !s->useLocalDetrending && varUsesTd(variable) && s->topoDist_Kh != 0;
+    if (useTD && (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used))
+        return fail(ctx, PB_ERR_INVALID, "topographic distance needs the resident DEM (getCurrentDEM())");
+    if (s->method != PB_METHOD_IDW) return fail(ctx, PB_ERR_UNSUPPORTED, "the exact leave-one-out runs the idw estimator only");
+    size_t bytes = 0;
+    auto add = [&](size_t count, size_t size) { bytes += (count * size + 255) / 256 * 256; };
+    add(nT, 4); add(nT, 4); add(nT, 4); add(nT * Pp, 4); add(nT, 4); add(nT, 4); add(nT, 1);
+    add(nS, 4); add(nS, 4); add(nS, 4); add(nS, 4); add(nS, 8); add(nS, 4);
+    add(1, sizeof(ClassicProblem)); add(nT, 4); add(nT, 4); add(1, 4); add(nT, sizeof(NeighbourOut));
+    if (useTD) add(size_t(nT) * nS, 4);
+    CUDA_TRY(ctx, ctx->dScratch.reserve(bytes + 4096));
+    unsigned char* d = ctx->dScratch.p;
+    float* tX = carve<float>(d, nT);
+    float* tY = carve<float>(d, nT);
+    float* tZ = carve<float>(d, nT);
+    float* tProxy = carve<float>(d, nT * Pp);
+    float* tObs = carve<float>(d, nT);
+    int* tCode = carve<int>(d, nT);
+    uint8_t* tIn = carve<uint8_t>(d, nT);
+    float* sX = carve<float>(d, nS);
+    float* sY = carve<float>(d, nS);
+    float* sZf = carve<float>(d, nS);
+    float* sVal = carve<float>(d, nS);
+    double* sZ = carve<double>(d, nS);
+    int* sCode = carve<int>(d, nS);
+    ClassicProblem* dProblem = carve<ClassicProblem>(d, 1);
+    float* dRes = carve<float>(d, nT);
+    float* dEst = carve<float>(d, nT);
+    int* dKh = carve<int>(d, 1);
+    NeighbourOut* dNb = carve<NeighbourOut>(d, nT);
+    float* dTopo = useTD ? carve<float>(d, size_t(nT) * nS) : nullptr;
+    cudaStream_t stream = ctx->stream;
+    auto up = [&](void* dst, const void* src, size_t b) { return b ? cudaMemcpyAsync(dst, src, b, cudaMemcpyHostToDevice, stream) : cudaSuccess; };
+    CUDA_TRY(ctx, up(tX, a.tx.data(), nT * 4));
+    CUDA_TRY(ctx, up(tY, a.ty.data(), nT * 4));
+    CUDA_TRY(ctx, up(tZ, a.tz.data(), nT * 4));
+    CUDA_TRY(ctx, up(tProxy, a.tproxy.data(), a.tproxy.size() * 4));
+    CUDA_TRY(ctx, up(tObs, a.tobs.data(), nT * 4));
+    CUDA_TRY(ctx, up(tCode, a.tcode.data(), nT * 4));
+    CUDA_TRY(ctx, up(tIn, a.tin.data(), nT));
+    CUDA_TRY(ctx, up(sX, a.sx.data(), nS * 4));
+    CUDA_TRY(ctx, up(sY, a.sy.data(), nS * 4));
+    CUDA_TRY(ctx, up(sZf, a.szf.data(), nS * 4));
+    CUDA_TRY(ctx, up(sVal, a.sval.data(), nS * 4));
+    CUDA_TRY(ctx, up(sZ, a.sz.data(), nS * 8));
+    CUDA_TRY(ctx, up(sCode, a.scode.data(), nS * 4));
+    const ClassicProblem pr = problemOfSettings(*s);
+    CUDA_TRY(ctx, up(dProblem, &pr, sizeof(pr)));
+    const int kh = useTD ? s->topoDist_Kh : 0;
+    CUDA_TRY(ctx, up(dKh, &kh, 4));
+    if (useTD) {
+        CUDA_TRY(ctx, launchTopoMatrix(tX, tY, tZ, nT, sX, sY, sZf, nS, devGridOfRaster(ctx->rasters[demId]), dTopo, stream));
+        ctx->timing.launches++;
+    }
+    if (residual || estimate) {
+        LooSetup ls{};
+        ls.nS = nS; ls.nT = nT; ls.nProxy = P; ls.nProblems = 1; ls.nKh = 1;
+        ls.useLapseRateCode = s->useLapseRateCode;
+        ls.excludeSupplemental = excludeSupplemental;
+        ls.excludeOutsideDem = excludeOutsideDem;
+        ls.useDetrendingVar = detrendVar;
+        ls.useThermalInversion = s->useThermalInversion;
+        ls.useDoNotRetrend = s->useDoNotRetrend;
+        ls.useRetrendOnly = s->useRetrendOnly;
+        ls.clampMode = varClampMode(variable);
+        ls.isPrecVar = varIsPrec(variable);
+        ls.rainfallThreshold = s->rainfallThreshold;
+        for (int i = 0; i < P; i++) ls.kind[i] = s->proxy[i].kind;
+        if (detrendVar && s->useMultipleDetrending) {
+            int rc = buildDevModel(ctx, s, variable, ls.multiple);
+            if (rc) return rc;
+            ls.useMultipleModel = 1;
+        }
+        if (ls.isPrecVar && s->precipitationAllZero) {
+            // interpolate() returns 0 for every target (interpolation.cpp:2506): retrend-only with nothing to retrend
+            ls.useRetrendOnly = 1;
+            ls.useDoNotRetrend = 1;
+        }
+        LooTargets lt{tX, tY, tProxy, tCode, tIn, tObs};
+        CUDA_TRY(ctx, launchLooExact(ls, lt, sX, sY, sVal /* NP = 1: work[i] = value i */, dProblem, dTopo, dKh, dRes, stream, dEst));
+        ctx->timing.launches++;
+        if (residual) CUDA_TRY(ctx, cudaMemcpyAsync(residual, dRes, nT * 4, cudaMemcpyDeviceToHost, stream));
+        if (estimate) CUDA_TRY(ctx, cudaMemcpyAsync(estimate, dEst, nT * 4, cudaMemcpyDeviceToHost, stream));
+    }
+    if (nb) {
+        CUDA_TRY(ctx, launchNeighbourhood(tX, tY, tZ, nT, sX, sY, sZ, sCode, sVal, nS, s->useLapseRateCode, dTopo, kh, 10, dNb, stream));
+        ctx->timing.launches++;
+        CUDA_TRY(ctx, cudaMemcpyAsync(nb, dNb, nT * sizeof(NeighbourOut), cudaMemcpyDeviceToHost, stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+    return PB_OK;
+}
+
+// getSpatialThresholdVar, spatialControl.cpp:14-94
+float spatialThreshold(int v, float rainfallThreshold, float value, float stdDev, int nrStdDev, float avgDeltaZ, float minDistance)
+{
+    const float PREC_THRESHOLD = 1000.f;
+    float zWeight, distWeight, threshold;
+    if (v == PB_VAR_PRECIPITATION || v == PB_VAR_DAILY_PRECIPITATION) {
+        distWeight = std::max(1.f, minDistance / 2000.f);
+        if (value <= rainfallThreshold) threshold = std::max(5.f, distWeight + stdDev * (nrStdDev + 1));
+        else return PREC_THRESHOLD;
+    } else if (v == PB_VAR_AIR_TEMPERATURE || v == PB_VAR_AIR_DEW_TEMPERATURE || v == PB_VAR_DAILY_TMAX || v == PB_VAR_DAILY_TMIN ||
+               v == PB_VAR_DAILY_TAVG) {
+        threshold = 1.f;
+        zWeight = avgDeltaZ / 100.f;
+        distWeight = minDistance / 1000.f;
+        threshold = std::min(std::min(distWeight + threshold + zWeight, 12.f) + stdDev * nrStdDev, 15.f);
+    } else if (v == PB_VAR_AIR_REL_HUMIDITY || v == PB_VAR_DAILY_RH_MAX || v == PB_VAR_DAILY_RH_MIN || v == PB_VAR_DAILY_RH_AVG) {
+        threshold = 20.f;
+        zWeight = avgDeltaZ / 10.f;
+        distWeight = minDistance / 1000.f;
+        threshold += zWeight + distWeight + stdDev * nrStdDev;
+    } else if (v == PB_VAR_WIND_SCALAR_INTENSITY || v == PB_VAR_WIND_VECTOR_INTENSITY || v == PB_VAR_DAILY_WIND_SCALAR_INT_AVG ||
+               v == PB_VAR_DAILY_WIND_SCALAR_INT_MAX || v == PB_VAR_DAILY_WIND_VECTOR_INT_AVG || v == PB_VAR_DAILY_WIND_VECTOR_INT_MAX) {
+        threshold = 1.f;
+        zWeight = avgDeltaZ / 50.f;
+        distWeight = minDistance / 2000.f;
+        threshold += zWeight + distWeight + stdDev * nrStdDev;
+    } else if (v == PB_VAR_GLOBAL_IRRADIANCE) {
+        threshold = 500;
+        distWeight = minDistance / 5000.f;
+        threshold += distWeight + stdDev * (nrStdDev + 1);
+    } else if (v == PB_VAR_DAILY_GLOBAL_RADIATION) {
+        threshold = 10;
+        distWeight = minDistance / 5000.f;
+        threshold += distWeight + stdDev * (nrStdDev + 1);
+    } else if (v == PB_VAR_ATM_TRANSMISSIVITY) {
+        distWeight = minDistance / 20000.f;
+        threshold = std::min(std::max(distWeight + stdDev * nrStdDev, 0.3f), 0.8f);
+    } else if (v == PB_VAR_ATM_PRESSURE) {
+        zWeight = avgDeltaZ / 10.f;
+        threshold = zWeight + stdDev * nrStdDev;
+    } else if (v == PB_VAR_DAILY_BIC) threshold = PREC_THRESHOLD;
+    else threshold = stdDev * nrStdDev;
+    return threshold;
+}
+
+void fillTargets(LooArrays& a, const pb_stations* st, const std::vector<int>& tIdx, const std::vector<int>& proxyFrom,
+                 const float* observed, const uint8_t* insideDem, int P)
+{
+    const size_t nT = tIdx.size(), Pp = std::max(P, 1);
+    a.tx.resize(nT); a.ty.resize(nT); a.tz.resize(nT); a.tobs.resize(nT); a.tcode.resize(nT); a.tin.resize(nT);
+    a.tproxy.assign(nT * Pp, kNoData);
+    for (size_t k = 0; k < nT; k++) {
+        const int i = tIdx[k], pi = proxyFrom[k];
+        a.tx[k] = float(st->x[i]);
+        a.ty[k] = float(st->y[i]);
+        a.tz[k] = float(st->z[i]);
+        a.tobs[k] = observed[i];
+        a.tcode[k] = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        a.tin[k] = insideDem ? insideDem[i] : 1;
+        for (int q = 0; q < P; q++) a.tproxy[k * Pp + q] = st->proxyValues[size_t(pi) * st->nProxy + q];
+    }
+}
+
+void fillSources(LooArrays& a, const pb_stations* pts, const uint8_t* keep)
+{
+    a.sx.clear(); a.sy.clear(); a.szf.clear(); a.sval.clear(); a.sz.clear(); a.scode.clear();
+    for (int i = 0; i < pts->n; i++) {
+        if (keep && !keep[i]) continue;
+        a.sx.push_back(float(pts->x[i]));
+        a.sy.push_back(float(pts->y[i]));
+        a.szf.push_back(float(pts->z[i]));
+        a.sz.push_back(pts->z[i]);
+        a.sval.push_back(pts->value[i]);
+        a.scode.push_back(pts->lapseRateCode ? pts->lapseRateCode[i] : PB_LAPSE_PRIMARY);
+    }
+}
+
+// a pb_stations view over the entries `idx` of st (host copies owned by the struct)
+struct SubStations {
+    std::vector<double> x, y, z;
+    std::vector<float> value, weight, proxy;
+    std::vector<int32_t> code;
+    pb_stations st{};
+    SubStations(const pb_stations* src, const std::vector<int>& idx, const float* values)
+    {
+        const size_t n = idx.size(), P = size_t(std::max(src->nProxy, 0));
+        x.resize(n); y.resize(n); z.resize(n); value.resize(n); code.resize(n);
+        proxy.resize(n * std::max<size_t>(P, 1));
+        for (size_t k = 0; k < n; k++) {
+            const int i = idx[k];
+            x[k] = src->x[i]; y[k] = src->y[i]; z[k] = src->z[i];
+            value[k] = values[i];
+            code[k] = src->lapseRateCode ? src->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+            for (size_t q = 0; q < P; q++) proxy[k * P + q] = src->proxyValues[size_t(i) * P + q];
+        }
+        st.n = int(n);
+        st.nProxy = src->nProxy;
+        st.x = x.data(); st.y = y.data(); st.z = z.data();
+        st.value = value.data();
+        st.lapseRateCode = code.data();
+        st.proxyValues = proxy.data();
+    }
+};
+
+// passDataToInterpolation's writes into the settings (spatialControl.cpp:560-565)
+void passDataSideEffects(const pb_stations* st, pb_settings* s)
+{
+    const int n = st->n;
+    if (n == 0) return;
+    float xMin = float(st->x[0]), xMax = xMin, yMin = float(st->y[0]), yMax = yMin, vMin = st->value[0], vMax = vMin;
+    for (int i = 1; i < n; i++) {
+        const float x = float(st->x[i]), y = float(st->y[i]);
+        xMin = std::min(xMin, x); xMax = std::max(xMax, x);
+        yMin = std::min(yMin, y); yMax = std::max(yMax, y);
+        vMin = std::min(vMin, st->value[i]); vMax = std::max(vMax, st->value[i]);
+    }
+    s->pointsBoundingBoxArea = (xMax - xMin) * (yMax - yMin);
+    s->hasPointsRange = 1;
+    s->pointsRangeMin = vMin;
+    s->pointsRangeMax = vMax;
+}
+
+}  // namespace
+
+/* computeResiduals (spatialControl.cpp:97-155), exact arithmetic, with topographic distance when the settings ask for it */
+extern "C" int pb_compute_residuals_exact(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
+                                          const pb_stations* points, const pb_settings* s, int variable, pb_raster_id dem,
+                                          int excludeOutsideDem, int excludeSupplemental, float* residual)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!meteo || !points || !s || !residual) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    LooArrays a;
+    std::vector<int> all(meteo->n);
+    for (int i = 0; i < meteo->n; i++) all[i] = i;
+    fillTargets(a, meteo, all, all, observed ? observed : meteo->value, cv ? cv->isInsideDem : nullptr, s->nProxy);
+    fillSources(a, points, nullptr);
+    return exactLoo(ctx, a, s, variable, dem, excludeOutsideDem, excludeSupplemental, residual, nullptr, nullptr);
+}
+
+/* spatialQualityControl (spatialControl.cpp:331-427); see include/praga_b200.h */
+extern "C" int pb_spatial_quality_control(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv,
+                                          pb_raster_id dem, uint8_t* wrongSpatial)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s || !wrongSpatial) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    const int n = st->n, P = s->nProxy;
+    memset(wrongSpatial, 0, n);
+    if (n == 0) return PB_OK;
+    const float* observed = (cv && cv->currentValue) ? cv->currentValue : st->value;
+    const uint8_t* inside = cv ? cv->isInsideDem : nullptr;
+    std::vector<int> all(n);
+    for (int i = 0; i < n; i++) all[i] = i;
+    auto nrValidOf = [&](const std::vector<int>& idx) {
+        int c = 0;
+        for (int i : idx) {
+            const int code = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+            if (!s->useLapseRateCode || code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SECONDARY) c++;
+        }
+        return c;
+    };
+    if (nrValidOf(all) == 0) return PB_OK;           // passDataToInterpolation returns false
+
+    // ---- first pass: every accepted point ----
+    SubStations ptsA(st, all, observed);
+    passDataSideEffects(&ptsA.st, s);
+    std::vector<uint8_t> keepA(n, 1);
+    pb_cv_points cvA{};
+    cvA.currentValue = observed;
+    cvA.isInsideDem = inside;
+    cvA.excludeOutsideDem = cv ? cv->excludeOutsideDem : 0;
+    int rc = pb_pre_interpolation_ex(ctx, &ptsA.st, s, variable, &cvA, dem, keepA.data(), nullptr);
+    if (rc) return rc;
+    LooArrays a;
+    fillTargets(a, st, all, all, observed, inside, P);
+    fillSources(a, &ptsA.st, keepA.data());
+    std::vector<float> residual(n);
+    std::vector<NeighbourOut> nb(n);
+    rc = exactLoo(ctx, a, s, variable, dem, 0, 0, residual.data(), nullptr, nb.data());
+    if (rc) return rc;
+    std::vector<int> listIndex;
+    for (int i = 0; i < n; i++) {
+        if (!nb[i].ok) continue;
+        const float myValue = observed[i], myResidual = residual[i];
+        const float stdDev = std::max(nb[i].devSt, myValue / 100.f);
+        if (fabs(myResidual) > spatialThreshold(variable, s->rainfallThreshold, myValue, stdDev, 2, nb[i].avgDeltaZ, nb[i].minDistance)) {
+            listIndex.push_back(i);
+            wrongSpatial[i] = 1;
+        }
+    }
+    if (listIndex.empty()) return PB_OK;
+
+    // ---- second pass: the suspects against the field interpolated without them ----
+    std::vector<int> rest;
+    for (int i = 0; i < n; i++) if (!wrongSpatial[i]) rest.push_back(i);
+    if (rest.empty() || nrValidOf(rest) == 0) return PB_OK;
+    SubStations ptsB(st, rest, observed);
+    passDataSideEffects(&ptsB.st, s);
+    std::vector<uint8_t> keepB(rest.size(), 1);
+    std::vector<float> obsB(rest.size());
+    std::vector<uint8_t> inB(rest.size(), 1);
+    for (size_t k = 0; k < rest.size(); k++) { obsB[k] = observed[rest[k]]; if (inside) inB[k] = inside[rest[k]]; }
+    pb_cv_points cvB{};
+    cvB.currentValue = obsB.data();
+    cvB.isInsideDem = inB.data();
+    cvB.excludeOutsideDem = cvA.excludeOutsideDem;
+    rc = pb_pre_interpolation_ex(ctx, &ptsB.st, s, variable, &cvB, dem, keepB.data(), nullptr);
+    if (rc) return rc;
+    // interpolate() at the suspects; the reference passes meteoPoints[i].getProxyValues() with i = position in the list,
+    // not the suspect's own index (spatialControl.cpp:393): kept
+    std::vector<int> proxyFrom(listIndex.size());
+    for (size_t k = 0; k < listIndex.size(); k++) proxyFrom[k] = int(k);
+    LooArrays b;
+    fillTargets(b, st, listIndex, proxyFrom, observed, inside, P);
+    fillSources(b, &ptsB.st, keepB.data());
+    std::vector<float> est(listIndex.size());
+    std::vector<float> dummy(listIndex.size());
+    std::vector<NeighbourOut> nbB(listIndex.size());
+    rc = exactLoo(ctx, b, s, variable, dem, 0, 0, dummy.data(), est.data(), nbB.data());
+    if (rc) return rc;
+    for (size_t k = 0; k < listIndex.size(); k++) {
+        const int i = listIndex[k];
+        if (nbB[k].ok) {
+            const float myValue = observed[i];
+            const float myResidual = est[k] - myValue;
+            wrongSpatial[i] = fabs(myResidual) > spatialThreshold(variable, s->rainfallThreshold, myValue, nbB[k].devSt, 3,
+                                                                  nbB[k].avgDeltaZ, nbB[k].minDistance)
+                                  ? 1 : 0;
+        } else wrongSpatial[i] = 0;
+    }
+    return PB_OK;
+}

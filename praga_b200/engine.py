@@ -61,6 +61,10 @@ def load_library():
     lib.pb_pre_interpolation.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_uint8)]
     lib.pb_pre_interpolation_ex.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_cv_points), C.c_int32,
                                             P(C.c_uint8), P(A.pb_kh_series)]
+    lib.pb_spatial_quality_control.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_cv_points),
+                                               C.c_int32, P(C.c_uint8)]
+    lib.pb_compute_residuals_exact.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), P(A.pb_cv_points), P(A.pb_stations),
+                                               P(A.pb_settings), C.c_int, C.c_int32, C.c_int, C.c_int, P(C.c_float)]
     lib.pb_pre_interpolation_batch.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), C.c_int, P(A.pb_settings), C.c_int,
                                                P(C.c_double), P(C.c_float), P(C.c_uint8), P(A.pb_settings)]
     lib.pb_compute_residuals.argtypes = raster_args + [P(C.c_float), P(C.c_uint8), P(C.c_float), P(A.pb_cv_stats)]
@@ -276,6 +280,35 @@ class Engine:
         self._check(self.lib.pb_pre_interpolation_ex(self.h, C.byref(st), C.byref(settings), variable, C.byref(cv), dem_id,
                                                      A.u8ptr(keep), C.byref(series)))
         return keep.astype(bool), [(series.kh[i], series.error[i]) for i in range(series.n)]
+
+    def spatial_quality_control(self, stations, settings, variable, inside_dem=None, exclude_outside_dem=False, dem_id=-1):
+        """spatialQualityControl (spatialControl.cpp:331-427): stations carry the raw current values of the accepted meteo
+        points; settings (the spatial-quality settings) are mutated like the reference does. Returns the wrong_spatial mask."""
+        st = stations.as_pb()
+        cv = A.pb_cv_points()
+        ins = None if inside_dem is None else np.ascontiguousarray(inside_dem, dtype=np.uint8)
+        if ins is not None:
+            cv.isInsideDem = A.u8ptr(ins)
+        cv.excludeOutsideDem = int(exclude_outside_dem)
+        wrong = np.zeros(stations.n, dtype=np.uint8)
+        self._check(self.lib.pb_spatial_quality_control(self.h, C.byref(st), C.byref(settings), variable, C.byref(cv), dem_id,
+                                                        A.u8ptr(wrong)))
+        return wrong.astype(bool)
+
+    def compute_residuals_exact(self, meteo, points, settings, variable, observed=None, inside_dem=None, dem_id=-1,
+                                exclude_outside_dem=False, exclude_supplemental=False):
+        """computeResiduals (spatialControl.cpp:97-155) in the reference's exact arithmetic, topographic distance included."""
+        m, p = meteo.as_pb(), points.as_pb()
+        cv = A.pb_cv_points()
+        ins = None if inside_dem is None else np.ascontiguousarray(inside_dem, dtype=np.uint8)
+        if ins is not None:
+            cv.isInsideDem = A.u8ptr(ins)
+        obs = None if observed is None else np.ascontiguousarray(observed, dtype=np.float32)
+        res = np.empty(meteo.n, dtype=np.float32)
+        self._check(self.lib.pb_compute_residuals_exact(self.h, C.byref(m), None if obs is None else A.fptr(obs), C.byref(cv),
+                                                        C.byref(p), C.byref(settings), variable, dem_id, int(exclude_outside_dem),
+                                                        int(exclude_supplemental), A.fptr(res)))
+        return res
 
     def pre_interpolation_batch(self, stations, values, settings, variable, points_range=None):
         """T time steps sharing the station set. values: (T, n). Returns (detrended (T, n), keep (T, n), [settings] * T)."""
