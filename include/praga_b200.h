@@ -274,6 +274,17 @@ int pb_interpolate_points_td(pb_context* ctx, const pb_stations* st, const pb_se
 int pb_compute_residuals(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* observed,
                          const uint8_t* useForCv, float* residual, pb_cv_stats* stats);
 
+/* local-detrending chain at explicit targets (K2 in point form): per target localSelection (interpolation.cpp:1087-1170),
+ * preInterpolation on the subset (multipleDetrendingMain :1832), interpolate(…, excludeSupplemental) with the targets' own
+ * proxy values (m * settings.nProxy doubles). `st` = the NOT detrended interpolation points. */
+int pb_local_detrending_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
+                               const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result);
+/* computeResidualsLocalDetrending (agrolib/interpolation/spatialControl.cpp:158-228) as Project::interpolationCv calls it
+ * (agrolib/project/project.cpp:3086-3097) + computeStatisticsCrossValidation (:2935-2969): same contract as
+ * pb_compute_residuals, `s` as for pb_local_detrending_raster. Supplemental stations are not cross-validated. */
+int pb_compute_residuals_local(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* observed,
+                               const uint8_t* useForCv, float* residual, pb_cv_stats* stats);
+
 /* computeResiduals with the EXACT arithmetic of the reference (f32 distances, f64 weights, sequential order) for any
  * settings the station-space pipeline produces, topographic distance included (computeDistances :226-251 through the
  * resident DEM). meteo = one entry per Crit3DMeteoPoint (active and accepted): position, lapse code, proxy values;
@@ -295,6 +306,26 @@ int pb_compute_residuals_exact(pb_context* ctx, const pb_stations* meteo, const 
  * reference's indexing of the proxy values (meteoPoints[i] with i = position in the suspect list, :393). */
 int pb_spatial_quality_control(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv,
                                pb_raster_id dem /* -1: none */, uint8_t* wrongSpatial);
+
+/* --- one time step of one variable, raw station values -> DEM raster: Project::interpolationDem
+ * (agrolib/project/project.cpp:3106-3150), the unit of work of the reference's hourly/daily batch drivers:
+ *   checkAndPassDataToInterpolation (spatialControl.cpp:479-497): spatialQualityControl with qualitySettings (NULL or a
+ *   variable checkData :466 exempts: skipped), passDataToInterpolation of the accepted points (points range, bounding box);
+ *   preInterpolation (every branch, as pb_pre_interpolation_ex); interpolationRaster over the resident DEM / proxy grids.
+ * meteo = one entry per active meteo point holding data for this time step (raw values). step (may be NULL) selects the
+ * optional outputs: wrongSpatial[n]; residual[n] + stats = the leave-one-out of Project::interpolationCv (:3012-3104:
+ * computeResiduals(…, excludeOutsideDem, excludeSupplemental = true) on the same fitted points, then
+ * computeStatisticsCrossValidation :2935-2969); khSeries. deviceOnly != 0: the raster stays in HBM (min/max/nValid only).
+ * Both settings are mutated as the reference mutates them. pb_last_timing sums the launches of the whole step. */
+typedef struct pb_dem_step {
+    uint8_t* wrongSpatial;         /* may be NULL */
+    float* residual;               /* may be NULL: no cross-validation */
+    pb_cv_stats* stats;            /* may be NULL */
+    pb_kh_series* khSeries;        /* may be NULL */
+} pb_dem_step;
+int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, pb_settings* qualitySettings, pb_settings* s, int variable,
+                         pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
+                         int deviceOnly, pb_raster_out* out, pb_dem_step* step);
 
 /* --- ordinary kriging (agrolib/interpolation/kriging.h:4-15, kriging.cpp). The reference keeps ONE system in file-static
  * globals; here every krigingVariogram call yields a handle and many systems can live on a device.

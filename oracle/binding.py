@@ -45,6 +45,15 @@ def load_shim():
     return lib
 
 
+def load_ref_extra():
+    """entry points only the reference driver has (composites of reference calls)."""
+    lib = _load(REF_LIB, "ref")
+    P = C.POINTER
+    lib.ref_interpolation_dem.argtypes = [P(A.pb_stations), P(A.pb_settings), P(A.pb_settings), C.c_int, P(A.pb_raster),
+                                          P(A.pb_raster), C.c_int, C.c_int, P(A.pb_raster_out), P(A.pb_dem_step)]
+    return lib
+
+
 def have_port():
     return os.path.exists(PORT_LIB)
 
@@ -71,6 +80,9 @@ def _load(path, prefix):
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_float), P(C.c_float),
                    P(C.c_double), C.c_int, C.c_int, P(A.pb_raster), P(C.c_float)]
     fn = getattr(lib, prefix + "_compute_residuals")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_uint8), P(C.c_float),
+                   P(A.pb_cv_stats)]
+    fn = getattr(lib, prefix + "_compute_residuals_local")
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_uint8), P(C.c_float),
                    P(A.pb_cv_stats)]
     fn = getattr(lib, prefix + "_kriging_points")
@@ -198,6 +210,38 @@ class Oracle:
                                                 None if d is None else C.byref(d), A.u8ptr(wrong))
         return rc == A.PB_OK, wrong.astype(bool)
 
+    def interpolation_dem(self, meteo, settings, variable, dem, proxy_grids=(), quality_settings=None, cross_validate=False,
+                          threads=0):
+        """Project::interpolationDem for one time step out of reference calls (reference oracle only); mirrors
+        Engine.interpolation_dem."""
+        assert self.kind == "reference"
+        lib = load_ref_extra()
+        st = meteo.as_pb()
+        d = dem.as_pb()
+        grids = (A.pb_raster * max(1, len(proxy_grids)))()
+        for i, g in enumerate(proxy_grids):
+            grids[i] = g.as_pb()
+        out = np.empty(dem.shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        wrong = np.zeros(meteo.n, dtype=np.uint8)
+        res = np.empty(meteo.n, dtype=np.float32)
+        stats = A.pb_cv_stats()
+        series = A.pb_kh_series()
+        step = A.pb_dem_step()
+        step.wrongSpatial = A.u8ptr(wrong)
+        step.khSeries = C.pointer(series)
+        if cross_validate:
+            step.residual = A.fptr(res)
+            step.stats = C.pointer(stats)
+        rc = lib.ref_interpolation_dem(C.byref(st), None if quality_settings is None else C.byref(quality_settings),
+                                       C.byref(settings), variable, C.byref(d), grids, len(proxy_grids), threads, C.byref(o),
+                                       C.byref(step))
+        return dict(ok=rc == A.PB_OK, rc=rc, grid=out, min=o.minimum, max=o.maximum, n_valid=o.nValid,
+                    wrong_spatial=wrong.astype(bool), residual=res if cross_validate else None,
+                    stats={k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_} if cross_validate else None,
+                    kh_series=[(series.kh[i], series.error[i]) for i in range(series.n)])
+
     def interpolate_points(self, stations, settings, variable, x, y, z, proxy_values, exclude_supplemental=False):
         x = np.ascontiguousarray(x, dtype=np.float32)
         y = np.ascontiguousarray(y, dtype=np.float32)
@@ -224,13 +268,14 @@ class Oracle:
                                          A.dptr(pv) if pv.size else None, m, int(exclude_supplemental), C.byref(d), A.fptr(res))
         return res
 
-    def compute_residuals(self, stations, settings, variable, observed, use_for_cv=None):
+    def compute_residuals(self, stations, settings, variable, observed, use_for_cv=None, local=False):
+        """computeResiduals (local=True: computeResidualsLocalDetrending) + the cross-validation statistics."""
         obs = np.ascontiguousarray(observed, dtype=np.float32)
         res = np.empty(stations.n, dtype=np.float32)
         stats = A.pb_cv_stats()
         st = stations.as_pb()
         use = None if use_for_cv is None else np.ascontiguousarray(use_for_cv, dtype=np.uint8)
-        self._f("compute_residuals")(C.byref(st), C.byref(settings), variable, A.fptr(obs),
+        self._f("compute_residuals_local" if local else "compute_residuals")(C.byref(st), C.byref(settings), variable, A.fptr(obs),
                                      None if use is None else A.u8ptr(use), A.fptr(res), C.byref(stats))
         return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}
 

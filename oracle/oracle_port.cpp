@@ -1937,6 +1937,49 @@ int port_interpolate_points_td(const pb_stations* st, const pb_settings* s, int 
     return PB_OK;
 }
 
+// Project::computeStatisticsCrossValidation, project/project.cpp:2935-2969 (statistics.cpp:180-268, 1030-1092)
+void cvStatistics(const std::vector<float>& obs, const std::vector<float>& pre, pb_cv_stats* stats)
+{
+    if (!stats) return;
+    memset(stats, 0, sizeof(*stats));
+    stats->n = int(obs.size());
+    stats->meanAbsoluteError = stats->meanBiasError = stats->rootMeanSquareError = stats->nashSutcliffe = stats->R2 = NODATA_F;
+    if (!obs.empty()) {
+        double sumAbs = 0, sigma = 0;
+        float sumErr = 0.f;
+        long n = 0;
+        for (size_t i = 0; i < obs.size(); i++)
+            if (obs[i] != NODATA_F && pre[i] != NODATA_F) {
+                sumAbs += fabs(obs[i] - pre[i]);
+                sumErr += obs[i] - pre[i];
+                const double diff = obs[i] - pre[i];
+                sigma += diff * diff;
+                n++;
+            }
+        if (n) {
+            stats->meanAbsoluteError = float(sumAbs / n);
+            stats->meanBiasError = sumErr / n;
+            stats->rootMeanSquareError = float(sqrt(sigma / n));
+        }
+        // NashSutcliffeEfficiency (statistics.cpp:243-268): float accumulators
+        double s0 = 0; int nv = 0;
+        for (float v : obs) if (!isEqualF(v, NODATA_F)) { s0 += double(v); nv++; }
+        if (nv) {
+            const float obsAvg = float(s0 / double(nv));
+            float sumDev = 0, sumError = 0;
+            for (size_t i = 0; i < obs.size(); i++) if (!isEqualF(obs[i], NODATA_F)) sumDev += (obs[i] - obsAvg) * (obs[i] - obsAvg);
+            if (sumDev != 0) {
+                for (size_t i = 0; i < obs.size(); i++)
+                    if (!isEqualF(obs[i], NODATA_F) && !isEqualF(pre[i], NODATA_F)) sumError += (pre[i] - obs[i]) * (pre[i] - obs[i]);
+                stats->nashSutcliffe = float(1 - (sumError / sumDev));
+            }
+        }
+        float q, m, r2;
+        linearRegression(obs.data(), pre.data(), long(obs.size()), false, &q, &m, &r2);
+        stats->R2 = r2;
+    }
+}
+
 // computeResiduals, interpolation/spatialControl.cpp:97-155 + Project::computeStatisticsCrossValidation, project/project.cpp:2935-2969
 // with statistics::meanAbsoluteError / meanError / rootMeanSquareError / NashSutcliffeEfficiency, mathFunctions/statistics.cpp:180-268
 int port_compute_residuals(const pb_stations* st, const pb_settings* s, int variable, const float* observed,
@@ -1962,45 +2005,7 @@ int port_compute_residuals(const pb_stations* st, const pb_settings* s, int vari
             pre.push_back(value - residual[i]);
         }
     }
-    if (stats) {
-        memset(stats, 0, sizeof(*stats));
-        stats->n = int(obs.size());
-        stats->meanAbsoluteError = stats->meanBiasError = stats->rootMeanSquareError = stats->nashSutcliffe = stats->R2 = NODATA_F;
-        if (!obs.empty()) {
-            double sumAbs = 0, sigma = 0;
-            float sumErr = 0.f;
-            long n = 0;
-            for (size_t i = 0; i < obs.size(); i++)
-                if (obs[i] != NODATA_F && pre[i] != NODATA_F) {
-                    sumAbs += fabs(obs[i] - pre[i]);
-                    sumErr += obs[i] - pre[i];
-                    const double diff = obs[i] - pre[i];
-                    sigma += diff * diff;
-                    n++;
-                }
-            if (n) {
-                stats->meanAbsoluteError = float(sumAbs / n);
-                stats->meanBiasError = sumErr / n;
-                stats->rootMeanSquareError = float(sqrt(sigma / n));
-            }
-            // NashSutcliffeEfficiency (statistics.cpp:243-268): float accumulators
-            double s0 = 0; int nv = 0;
-            for (float v : obs) if (!isEqualF(v, NODATA_F)) { s0 += double(v); nv++; }
-            if (nv) {
-                const float obsAvg = float(s0 / double(nv));
-                float sumDev = 0, sumError = 0;
-                for (size_t i = 0; i < obs.size(); i++) if (!isEqualF(obs[i], NODATA_F)) sumDev += (obs[i] - obsAvg) * (obs[i] - obsAvg);
-                if (sumDev != 0) {
-                    for (size_t i = 0; i < obs.size(); i++)
-                        if (!isEqualF(obs[i], NODATA_F) && !isEqualF(pre[i], NODATA_F)) sumError += (pre[i] - obs[i]) * (pre[i] - obs[i]);
-                    stats->nashSutcliffe = float(1 - (sumError / sumDev));
-                }
-            }
-            float q, m, r2;
-            linearRegression(obs.data(), pre.data(), long(obs.size()), false, &q, &m, &r2);
-            stats->R2 = r2;
-        }
-    }
+    cvStatistics(obs, pre, stats);
     return PB_OK;
 }
 
@@ -2069,6 +2074,45 @@ int port_local_detrending_raster(const pb_stations* st, const pb_settings* s0, i
     }
     out->minimum = mn; out->maximum = mx; out->nValid = nValid;
     return first ? PB_ERR_NO_VALID_CELL : PB_OK;
+}
+
+// computeResidualsLocalDetrending, spatialControl.cpp:158-228, called as in Project::interpolationCv (project.cpp:3086-3097)
+int port_compute_residuals_local(const pb_stations* st, const pb_settings* s0, int variable, const float* observed,
+                                 const uint8_t* useForCv, float* residual, pb_cv_stats* stats)
+{
+    std::vector<Point> pts = loadPoints(st);
+    pb_settings s = *s0;
+    for (int i = 0; i < s.nProxy; i++) { s.currentActive[i] = s.selectedActive[i]; s.currentSignificant[i] = 0; }
+    s.currentUseThermalInversion = s.selectedUseThermalInversion;
+    if (!setMultipleDetrendingHeightTemperatureRange(s)) return PB_ERR_FIT;
+    std::vector<float> obs, pre;
+    for (int i = 0; i < st->n; i++) {
+        residual[i] = NODATA_F;
+        if (useForCv && !useForCv[i]) continue;
+        if (!checkLapseRateCode(pts[i].lapseRateCode, s.useLapseRateCode != 0, false)) continue;   // excludeSupplemental = true
+        double pv[PB_MAX_PROXY];
+        for (int k = 0; k < PB_MAX_PROXY; k++) pv[k] = k < st->nProxy ? double(pts[i].proxy[k]) : -9999.;
+        float myValue = observed[i];
+        Work w{{}, &s, variable};
+        if (!localSelection(pts, w.pts, float(st->x[i]), float(st->y[i]), s, false)) return PB_ERR_INVALID;
+        if (!preInterpolation(w)) return PB_ERR_FIT;
+        float est = interpolate(w.pts, s, variable, float(st->x[i]), float(st->y[i]), pv, false);
+        if (isPrec(variable)) {
+            if (myValue != NODATA_F && myValue < s.rainfallThreshold) myValue = 0.f;
+            if (est != NODATA_F && est < s.rainfallThreshold) est = 0.f;
+        }
+        if (est != NODATA_F && myValue != NODATA_F) residual[i] = myValue - est;
+    }
+    for (int i = 0; i < st->n; i++) {
+        if (useForCv && !useForCv[i]) continue;
+        const float value = observed[i];
+        if (!isEqualF(value, NODATA_F) && !isEqualF(residual[i], NODATA_F)) {
+            obs.push_back(value);
+            pre.push_back(value - residual[i]);
+        }
+    }
+    cvStatistics(obs, pre, stats);
+    return PB_OK;
 }
 
 int port_local_detrending_point(const pb_stations* st, pb_settings* s, int variable, double x, double y, float,

@@ -446,6 +446,95 @@ int ref_spatial_quality_control(const pb_stations* st, pb_settings* s, int varia
     return ok ? PB_OK : PB_ERR_FIT;
 }
 
+/* One time step as Project::interpolationDem runs it (project/project.cpp:3106-3150; the method lives in the Qt-bound
+ * Project class, every call inside is reference code): spatialQualityControl (the part of checkData :466-476 that is
+ * not a time-series lookup), passDataToInterpolation, preInterpolation, interpolationRaster; with step->residual also the
+ * cross-validation of Project::interpolationCv (:3063-3067 computeResiduals + computeStatisticsCrossValidation :2935). */
+int ref_interpolation_dem(const pb_stations* meteo, pb_settings* sq, pb_settings* s, int variable, const pb_raster* dem,
+                          const pb_raster* proxyGrids, int nProxyGrids, int nThreads, pb_raster_out* out, pb_dem_step* step)
+{
+    const meteoVariable myVar = meteoVariable(variable);
+    Scenario sc, scq;
+    buildSettings(sc, *s, proxyGrids, nProxyGrids);
+    gis::Crit3DRasterGrid demGrid, outGrid;
+    fillGrid(demGrid, *dem);
+    sc.settings.setCurrentDEM(&demGrid);
+    std::vector<Crit3DMeteoPoint> mp(meteo->n);
+    for (int i = 0; i < meteo->n; i++) {
+        mp[i].active = true;
+        mp[i].quality = quality::accepted;
+        mp[i].currentValue = meteo->value[i];
+        mp[i].point.utm.x = meteo->x[i];
+        mp[i].point.utm.y = meteo->y[i];
+        mp[i].point.z = meteo->z[i];
+        mp[i].isInsideDem = true;
+        mp[i].lapseRateCode = meteo->lapseRateCode ? lapseRateCodeType(meteo->lapseRateCode[i]) : primary;
+        for (int k = 0; k < meteo->nProxy; k++) mp[i].proxyValues.push_back(meteo->proxyValues[size_t(i) * meteo->nProxy + k]);
+    }
+    std::string err;
+    if (sq && myVar != precipitation && myVar != dailyPrecipitation && myVar != windVectorX && myVar != windVectorY &&
+        myVar != windVectorDirection && myVar != dailyWindVectorDirectionPrevailing) {
+        buildSettings(scq, *sq, nullptr, 0);
+        scq.settings.setCurrentDEM(&demGrid);
+        if (!spatialQualityControl(myVar, mp, scq.settings, &scq.meteoSettings, &scq.climate, scq.time, err)) return PB_ERR_FIT;
+        exportSettings(scq, *sq);
+        sq->pointsBoundingBoxArea = scq.settings.getPointsBoundingBoxArea();
+        std::vector<double> pr = scq.settings.getPointsRange();
+        if (pr.size() == 2) { sq->hasPointsRange = 1; sq->pointsRangeMin = pr[0]; sq->pointsRangeMax = pr[1]; }
+    }
+    if (step && step->wrongSpatial)
+        for (int i = 0; i < meteo->n; i++) step->wrongSpatial[i] = mp[i].quality == quality::wrong_spatial ? 1 : 0;
+    std::vector<Crit3DInterpolationDataPoint> points;
+    if (!passDataToInterpolation(mp, points, sc.settings)) return PB_ERR_INVALID;
+    if (sc.settings.getUseMultipleDetrending()) sc.settings.clearFitting();
+    if (!preInterpolation(points, sc.settings, &sc.meteoSettings, &sc.climate, mp, myVar, sc.time, err)) return PB_ERR_FIT;
+    if (nThreads > 0) omp_set_num_threads(nThreads);
+    bool ok = interpolationRaster(points, sc.settings, &sc.meteoSettings, &outGrid, demGrid, myVar, nThreads != 1);
+    int64_t nValid = 0;
+    for (int row = 0; row < demGrid.header->nrRows; row++)
+        for (int col = 0; col < demGrid.header->nrCols; col++)
+            if (!isEqual(demGrid.value[row][col], demGrid.header->flag)) nValid++;
+    out->nValid = nValid;
+    if (outGrid.isLoaded) copyOut(outGrid, out);
+    if (step && step->residual) {
+        computeResiduals(myVar, mp, points, sc.settings, &sc.meteoSettings, sc.settings.getUseExcludeStationsOutsideDEM(), true);
+        std::vector<float> obs, pre;
+        for (int i = 0; i < meteo->n; i++) {
+            step->residual[i] = mp[i].residual;
+            float value = mp[i].currentValue;
+            if (!isEqual(value, NODATA) && !isEqual(mp[i].residual, NODATA)) {
+                obs.push_back(value);
+                pre.push_back(value - mp[i].residual);
+            }
+        }
+        if (step->stats) {
+            pb_cv_stats* stats = step->stats;
+            memset(stats, 0, sizeof(*stats));
+            stats->n = int(obs.size());
+            stats->meanAbsoluteError = stats->meanBiasError = stats->rootMeanSquareError = stats->nashSutcliffe = stats->R2 = NODATA;
+            if (obs.size() > 0) {
+                stats->meanAbsoluteError = statistics::meanAbsoluteError(obs, pre);
+                stats->meanBiasError = statistics::meanError(obs, pre);
+                stats->rootMeanSquareError = statistics::rootMeanSquareError(obs, pre);
+                stats->nashSutcliffe = statistics::NashSutcliffeEfficiency(obs, pre);
+                float intercept, slope, r2;
+                statistics::linearRegression(obs, pre, int(obs.size()), false, &intercept, &slope, &r2);
+                stats->R2 = r2;
+            }
+        }
+    }
+    if (step && step->khSeries) {
+        std::vector<float> kh = sc.settings.getKh_series(), e = sc.settings.getKh_error_series();
+        step->khSeries->n = int(std::min(kh.size(), size_t(PB_MAX_KH_SERIES)));
+        for (int i = 0; i < step->khSeries->n; i++) { step->khSeries->kh[i] = kh[i]; step->khSeries->error[i] = e[i]; }
+    }
+    exportSettings(sc, *s);
+    s->pointsBoundingBoxArea = sc.settings.getPointsBoundingBoxArea();
+    std::vector<double> pr = sc.settings.getPointsRange();
+    if (pr.size() == 2) { s->hasPointsRange = 1; s->pointsRangeMin = pr[0]; s->pointsRangeMax = pr[1]; }
+    return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
 /* interpolate() at arbitrary targets (x, y, z, proxyValues[nProxy]) — interpolation.cpp:2502 */
 int ref_interpolate_points(const pb_stations* st, const pb_settings* s, int variable, const float* x, const float* y,
                            const float* z, const double* proxyValues, int m, int excludeSupplemental, float* result)
@@ -505,6 +594,58 @@ int ref_compute_residuals(const pb_stations* st, const pb_settings* s, int varia
         sc.points[i].index = i;
     }
     bool ok = computeResiduals(meteoVariable(variable), mp, sc.points, sc.settings, &sc.meteoSettings, false, false);
+    std::vector<float> obs, pre;
+    for (int i = 0; i < st->n; i++) {
+        residual[i] = mp[i].residual;
+        if (mp[i].active) {
+            float value = mp[i].currentValue;
+            if (!isEqual(value, NODATA) && !isEqual(mp[i].residual, NODATA)) {
+                obs.push_back(value);
+                pre.push_back(value - mp[i].residual);
+            }
+        }
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n = int(obs.size());
+        stats->meanAbsoluteError = stats->meanBiasError = stats->rootMeanSquareError = stats->nashSutcliffe = stats->R2 = NODATA;
+        if (obs.size() > 0) {
+            stats->meanAbsoluteError = statistics::meanAbsoluteError(obs, pre);
+            stats->meanBiasError = statistics::meanError(obs, pre);
+            stats->rootMeanSquareError = statistics::rootMeanSquareError(obs, pre);
+            stats->nashSutcliffe = statistics::NashSutcliffeEfficiency(obs, pre);
+            float intercept, slope, r2;
+            statistics::linearRegression(obs, pre, int(obs.size()), false, &intercept, &slope, &r2);
+            stats->R2 = r2;
+        }
+    }
+    return ok ? PB_OK : PB_ERR_INVALID;
+}
+
+/* computeResidualsLocalDetrending (spatialControl.cpp:158-228) called like Project::interpolationCv does
+ * (project/project.cpp:3086-3097) + the statistics of computeStatisticsCrossValidation (:2935-2969) */
+int ref_compute_residuals_local(const pb_stations* st, const pb_settings* s, int variable, const float* observed,
+                                const uint8_t* useForCv, float* residual, pb_cv_stats* stats)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    std::vector<Crit3DMeteoPoint> mp(st->n);
+    for (int i = 0; i < st->n; i++) {
+        mp[i].active = useForCv ? useForCv[i] != 0 : true;
+        mp[i].quality = quality::accepted;
+        mp[i].currentValue = observed[i];
+        mp[i].point.utm.x = st->x[i];
+        mp[i].point.utm.y = st->y[i];
+        mp[i].point.z = st->z[i];
+        mp[i].isInsideDem = true;
+        mp[i].lapseRateCode = st->lapseRateCode ? lapseRateCodeType(st->lapseRateCode[i]) : primary;
+        for (int k = 0; k < st->nProxy; k++) mp[i].proxyValues.push_back(st->proxyValues[size_t(i) * st->nProxy + k]);
+        sc.points[i].index = i;
+    }
+    if (!setMultipleDetrendingHeightTemperatureRange(sc.settings)) return PB_ERR_FIT;
+    bool ok = computeResidualsLocalDetrending(meteoVariable(variable), sc.time, mp, sc.points, sc.settings, &sc.meteoSettings,
+                                              &sc.climate, true, true);
     std::vector<float> obs, pre;
     for (int i = 0; i < st->n; i++) {
         residual[i] = mp[i].residual;

@@ -120,6 +120,11 @@ class pb_kh_series(C.Structure):
     _fields_ = [("n", C.c_int32), ("kh", C.c_float * PB_MAX_KH_SERIES), ("error", C.c_float * PB_MAX_KH_SERIES)]
 
 
+class pb_dem_step(C.Structure):
+    _fields_ = [("wrongSpatial", C.POINTER(C.c_uint8)), ("residual", C.POINTER(C.c_float)),
+                ("stats", C.POINTER(pb_cv_stats)), ("khSeries", C.POINTER(pb_kh_series))]
+
+
 class pb_timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]

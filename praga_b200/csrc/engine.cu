@@ -1208,6 +1208,54 @@ static void linearRegressionHost(const std::vector<float>& x, const std::vector<
     *r2 = float((SUMres - SUM_dy) / SUMres);
 }
 
+// Project::computeStatisticsCrossValidation (project/project.cpp:2935-2969) over the (observed, predicted) pairs
+static void cvStatistics(const std::vector<float>& obs, const std::vector<float>& pre, pb_cv_stats* stats);
+namespace pb {
+void cvStatisticsHost(const std::vector<float>& obs, const std::vector<float>& pre, pb_cv_stats* stats) { cvStatistics(obs, pre, stats); }
+}
+static void cvStatistics(const std::vector<float>& obs, const std::vector<float>& pre, pb_cv_stats* stats)
+{
+    if (!stats) return;
+    memset(stats, 0, sizeof(*stats));
+    stats->n = int(obs.size());
+    stats->meanAbsoluteError = stats->meanBiasError = stats->rootMeanSquareError = stats->nashSutcliffe = stats->R2 = kNoData;
+    if (!obs.empty()) {
+        double sumAbs = 0, sigma = 0;
+        float sumErr = 0.f;
+        long cnt = 0;
+        for (size_t i = 0; i < obs.size(); i++)
+            if (obs[i] != kNoData && pre[i] != kNoData) {
+                sumAbs += fabs(obs[i] - pre[i]);
+                sumErr += obs[i] - pre[i];
+                const double diff = obs[i] - pre[i];
+                sigma += diff * diff;
+                cnt++;
+            }
+        if (cnt) {
+            stats->meanAbsoluteError = float(sumAbs / cnt);
+            stats->meanBiasError = sumErr / cnt;
+            stats->rootMeanSquareError = float(sqrt(sigma / cnt));
+        }
+        double s0 = 0;
+        int nv = 0;
+        for (float v : obs) if (!isEqualF(v, kNoData)) { s0 += double(v); nv++; }
+        if (nv) {
+            const float obsAvg = float(s0 / double(nv));
+            float sumDev = 0, sumError = 0;
+            for (size_t i = 0; i < obs.size(); i++)
+                if (!isEqualF(obs[i], kNoData)) sumDev += (obs[i] - obsAvg) * (obs[i] - obsAvg);
+            if (sumDev != 0) {
+                for (size_t i = 0; i < obs.size(); i++)
+                    if (!isEqualF(obs[i], kNoData) && !isEqualF(pre[i], kNoData)) sumError += (pre[i] - obs[i]) * (pre[i] - obs[i]);
+                stats->nashSutcliffe = float(1 - (sumError / sumDev));
+            }
+        }
+        float q, m, r2;
+        linearRegressionHost(obs, pre, &q, &m, &r2);
+        stats->R2 = r2;
+    }
+}
+
 /* computeResiduals (interpolation/spatialControl.cpp:97-155) + Project::computeStatisticsCrossValidation
  * (project/project.cpp:2935-2969; statistics::meanAbsoluteError / meanError / rootMeanSquareError /
  * NashSutcliffeEfficiency, mathFunctions/statistics.cpp:180-268). The S x S leave-one-out estimates run on the GPU
@@ -1244,46 +1292,123 @@ extern "C" int pb_compute_residuals(pb_context* ctx, const pb_stations* st, cons
             pre.push_back(value - residual[i]);
         }
     }
-    if (stats) {
-        memset(stats, 0, sizeof(*stats));
-        stats->n = int(obs.size());
-        stats->meanAbsoluteError = stats->meanBiasError = stats->rootMeanSquareError = stats->nashSutcliffe = stats->R2 = kNoData;
-        if (!obs.empty()) {
-            double sumAbs = 0, sigma = 0;
-            float sumErr = 0.f;
-            long cnt = 0;
-            for (size_t i = 0; i < obs.size(); i++)
-                if (obs[i] != kNoData && pre[i] != kNoData) {
-                    sumAbs += fabs(obs[i] - pre[i]);
-                    sumErr += obs[i] - pre[i];
-                    const double diff = obs[i] - pre[i];
-                    sigma += diff * diff;
-                    cnt++;
-                }
-            if (cnt) {
-                stats->meanAbsoluteError = float(sumAbs / cnt);
-                stats->meanBiasError = sumErr / cnt;
-                stats->rootMeanSquareError = float(sqrt(sigma / cnt));
-            }
-            double s0 = 0;
-            int nv = 0;
-            for (float v : obs) if (!isEqualF(v, kNoData)) { s0 += double(v); nv++; }
-            if (nv) {
-                const float obsAvg = float(s0 / double(nv));
-                float sumDev = 0, sumError = 0;
-                for (size_t i = 0; i < obs.size(); i++)
-                    if (!isEqualF(obs[i], kNoData)) sumDev += (obs[i] - obsAvg) * (obs[i] - obsAvg);
-                if (sumDev != 0) {
-                    for (size_t i = 0; i < obs.size(); i++)
-                        if (!isEqualF(obs[i], kNoData) && !isEqualF(pre[i], kNoData)) sumError += (pre[i] - obs[i]) * (pre[i] - obs[i]);
-                    stats->nashSutcliffe = float(1 - (sumError / sumDev));
-                }
-            }
-            float q, m, r2;
-            linearRegressionHost(obs, pre, &q, &m, &r2);
-            stats->R2 = r2;
+    cvStatistics(obs, pre, stats);
+    return PB_OK;
+}
+
+/* interpolate() through the local-detrending chain at explicit targets: localSelection at the target, preInterpolation on
+ * the subset (multipleDetrendingMain), interpolate with the targets' own proxy values. K2 in point form. */
+extern "C" int pb_local_detrending_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
+                                          const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s || (m > 0 && (!x || !y || !result))) return fail(ctx, PB_ERR_INVALID, "null argument");
+    if (m <= 0) return PB_OK;
+    cudaSetDevice(ctx->device);
+    resetTiming(ctx);
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    LocalModel lm;
+    int rc = buildLocalModel(ctx, s, variable, st->n, nullptr, 0, lm);
+    if (rc) return rc;
+    LocalStations ds{};
+    rc = stageLocalStations(ctx, st, ds);
+    if (rc) return rc;
+    const int P = s->nProxy, Pp = std::max(P, 1);
+    const size_t offModel = 0, offX = (sizeof(LocalModel) + 255) / 256 * 256, offY = offX + (size_t(m) * 4 + 255) / 256 * 256,
+                 offPv = offY + (size_t(m) * 4 + 255) / 256 * 256, offOut = offPv + (size_t(m) * Pp * 8 + 255) / 256 * 256,
+                 total = offOut + size_t(m) * 4;
+    CUDA_TRY(ctx, ctx->dScratch.reserve(total + 256));
+    unsigned char* d = ctx->dScratch.p;
+    std::vector<double> none;
+    if (!proxyValues) { none.assign(size_t(m) * Pp, double(kNoData)); proxyValues = none.data(); }
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + offModel, &lm, sizeof(lm), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + offX, x, size_t(m) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + offY, y, size_t(m) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (P > 0) CUDA_TRY(ctx, cudaMemcpyAsync(d + offPv, proxyValues, size_t(m) * P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // `lm` and `none` live on this stack frame
+    ctx->timing.h2d_bytes += (int64_t)(sizeof(lm) + size_t(m) * (8 + 8 * P));
+    const int groupLanes = lm.nFirstGuess <= 16 ? 16 : 32;
+    LocalScratch scr{};
+    scr.cap = std::max(std::min(st->n, 2048), 1);
+    scr.perGroup = localScratchBytesPerGroup(scr.cap);
+    CUDA_TRY(ctx, ctx->dLocalScratch.reserve(scr.perGroup * size_t(localGroupsTotal(groupLanes))));
+    scr.base = ctx->dLocalScratch.p;
+    if (!ctx->dLocalError) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dLocalError, sizeof(int)));
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->hLocalError, sizeof(int)));
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->dLocalError, 0, sizeof(int), ctx->stream));
+    scr.error = ctx->dLocalError;
+    LocalPointTargets pt{reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
+                         reinterpret_cast<const double*>(d + offPv), excludeSupplemental};
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    CUDA_TRY(ctx, launchLocalDetrendingRaster(reinterpret_cast<const LocalModel*>(d + offModel), ds, DevGrid{}, nullptr, m, scr,
+                                              groupLanes, lm.elevFunction, reinterpret_cast<float*>(d + offOut), nullptr, ctx->stream,
+                                              &pt));
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hLocalError, ctx->dLocalError, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(result, d + offOut, size_t(m) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.d2h_bytes += (int64_t)(size_t(m) * 4);
+    if (*ctx->hLocalError)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "a local selection exceeded 2048 stations (dense first ring): outside the supported range");
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
+    return PB_OK;
+}
+
+/* computeResidualsLocalDetrending (interpolation/spatialControl.cpp:158-228) as Project::interpolationCv calls it
+ * (project/project.cpp:3086-3097: excludeOutsideDem = excludeSupplemental = true for the choice of targets; the inner
+ * localSelection / interpolate run with excludeSupplemental = false, :186-200) + computeStatisticsCrossValidation. */
+extern "C" int pb_compute_residuals_local(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
+                                          const float* observed, const uint8_t* useForCv, float* residual, pb_cv_stats* stats)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s || !observed || !residual) return fail(ctx, PB_ERR_INVALID, "null argument");
+    const int n = st->n, P = s->nProxy;
+    std::vector<int> target;
+    for (int i = 0; i < n; i++) {
+        residual[i] = kNoData;
+        if (useForCv && !useForCv[i]) continue;
+        const int code = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        if (s->useLapseRateCode && !(code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SECONDARY)) continue;   // checkLapseRateCode(…, false)
+        target.push_back(i);
+    }
+    const int m = int(target.size());
+    std::vector<float> x(m), y(m), est(m);
+    std::vector<double> pv(size_t(m) * std::max(P, 1), double(kNoData));
+    for (int k = 0; k < m; k++) {
+        const int i = target[k];
+        x[k] = float(st->x[i]);
+        y[k] = float(st->y[i]);
+        for (int q = 0; q < P && q < st->nProxy; q++) pv[size_t(k) * P + q] = double(st->proxyValues[size_t(i) * st->nProxy + q]);
+    }
+    int rc = pb_local_detrending_points(ctx, st, s, variable, x.data(), y.data(), pv.data(), m, 0, est.data());
+    if (rc) return rc;
+    const bool prec = isPrecVar(variable);
+    std::vector<float> obs, pre;
+    for (int k = 0; k < m; k++) {
+        const int i = target[k];
+        float myValue = observed[i], e = est[k];
+        if (prec) {
+            if (myValue != kNoData && myValue < s->rainfallThreshold) myValue = 0.f;
+            if (e != kNoData && e < s->rainfallThreshold) e = 0.f;
+        }
+        if (e != kNoData && myValue != kNoData) residual[i] = myValue - e;
+    }
+    for (int i = 0; i < n; i++) {
+        if (useForCv && !useForCv[i]) continue;
+        const float value = observed[i];
+        if (!isEqualF(value, kNoData) && !isEqualF(residual[i], kNoData)) {
+            obs.push_back(value);
+            pre.push_back(value - residual[i]);
         }
     }
+    cvStatistics(obs, pre, stats);
     return PB_OK;
 }
 
@@ -1312,5 +1437,6 @@ extern "C" size_t pb_abi_sizeof(const char* name)
     if (!strcmp(name, "pb_raster_out")) return sizeof(pb_raster_out);
     if (!strcmp(name, "pb_cv_stats")) return sizeof(pb_cv_stats);
     if (!strcmp(name, "pb_timing")) return sizeof(pb_timing);
+    if (!strcmp(name, "pb_dem_step")) return sizeof(pb_dem_step);
     return 0;
 }

@@ -50,10 +50,19 @@ struct LocalScratch {
     int* error;                    // != 0: a selection exceeded cap
 };
 
+// point form (computeResidualsLocalDetrending, spatialControl.cpp:158-228): explicit targets instead of DEM cells
+struct LocalPointTargets {
+    const float* x;                // float(point.utm.x); nullptr = raster form
+    const float* y;
+    const double* pv;              // n * nProxy: the targets' own proxy values (getProxyValues())
+    int excludeSupplemental;       // the flag interpolate() receives (raster loop: true; leave-one-out: false)
+};
+
 size_t localScratchBytesPerGroup(int cap);
 int localGroupsTotal(int groupLanes);
 cudaError_t launchLocalDetrendingRaster(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem,
                                         const int* validIdx, int nTargets, const LocalScratch& scratch, int groupLanes,
-                                        int elevFunction, float* out, unsigned* minmax, cudaStream_t s);
+                                        int elevFunction, float* out, unsigned* minmax, cudaStream_t s,
+                                        const LocalPointTargets* points = nullptr);
 
 }  // namespace pb

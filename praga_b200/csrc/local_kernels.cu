@@ -18,7 +18,8 @@ namespace pb {
 
 template <int G, int F>
 __device__ float localCell(const LocalModel& m, const LocalStations& st, const float2* __restrict__ xy, float xf, float yf,
-                           const double* pv, const WorkPtrs& gw, int gcap, unsigned char* tile, int* errFlag)
+                           const double* pv, const WorkPtrs& gw, int gcap, unsigned char* tile, int* errFlag,
+                           bool excludeSupplemental)
 {
     constexpr int N = Fit<F>::N;
     const int lane = grpLane<G>();
@@ -121,7 +122,7 @@ __device__ float localCell(const LocalModel& m, const LocalStations& st, const f
         double sum = 0, sumWeights = 0;
         for (int k = 0; k < n; k++) {
             if (!(w.flg[k] & 1)) continue;
-            if (!checkLapseRateCodeDev(st.code[w.idx[k]], useCode, false)) continue;      // excludeSupplemental = true
+            if (excludeSupplemental && !checkLapseRateCodeDev(st.code[w.idx[k]], useCode, false)) continue;
             const float d = w.d[k];
             if (d > 0.f) {
                 const double dk = double(d) / 10000.;
@@ -178,7 +179,8 @@ __device__ __forceinline__ unsigned orderedKeyL(float f)
 template <int G, int F, int MINB>
 __global__ void __launch_bounds__(kLocalThreads, MINB)
 local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, DevGrid dem, const int* __restrict__ validIdx,
-                        int nTargets, LocalScratch scr, int xyInSmem, float* __restrict__ out, unsigned* __restrict__ minmax)
+                        int nTargets, LocalScratch scr, int xyInSmem, float* __restrict__ out, unsigned* __restrict__ minmax,
+                        LocalPointTargets pt)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int groupsPerCta = kLocalThreads / G;
@@ -199,6 +201,13 @@ local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, Dev
 
     float vmin = INFINITY, vmax = -INFINITY;
     for (long long t = gid; t < nTargets; t += groupsTotal) {
+        if (pt.x) {       // point form: the target's own coordinates and proxy values, result t
+            double pv[PB_MAX_PROXY];
+            for (int i = 0; i < m.nProxy; i++) pv[i] = pt.pv[t * m.nProxy + i];
+            const float o = localCell<G, F>(m, st, xy, pt.x[t], pt.y[t], pv, gw, scr.cap, tile, scr.error, pt.excludeSupplemental != 0);
+            if (lane == 0) out[t] = o;
+            continue;
+        }
         const int cell = validIdx[t];
         const int row = cell / dem.nrCols, col = cell - row * dem.nrCols;
         // gis::getUtmXYFromRowCol (gis.cpp:806-810), then narrowed to float by the callee signatures (interpolation.h:77-95,162)
@@ -214,7 +223,7 @@ local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, Dev
                 if (v != g.flag) pv[i] = double(v);
             }
         }
-        const float o = localCell<G, F>(m, st, xy, xf, yf, pv, gw, scr.cap, tile, scr.error);
+        const float o = localCell<G, F>(m, st, xy, xf, yf, pv, gw, scr.cap, tile, scr.error, true);
         if (lane == 0) {
             out[cell] = o;
             if (!isEqualF(o, dem.flag) && !isEqualF(o, kNoData)) {
@@ -243,7 +252,8 @@ int localGroupsTotal(int groupLanes) { return localCtas() * (kLocalThreads / gro
 
 template <int G, int F, int MINB>
 static cudaError_t launchT(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem, const int* validIdx,
-                           int nTargets, const LocalScratch& scratch, float* out, unsigned* minmax, cudaStream_t s)
+                           int nTargets, const LocalScratch& scratch, float* out, unsigned* minmax, cudaStream_t s,
+                           const LocalPointTargets& pt)
 {
     constexpr int groupsPerCta = kLocalThreads / G;
     size_t smem = groupsPerCta * workBytes(kCap);
@@ -263,21 +273,23 @@ static cudaError_t launchT(const LocalModel* dModel, const LocalStations& st, co
     perSm = perSm < 1 ? 1 : (perSm > 4 ? 4 : perSm);
     const long long need = (nTargets + groupsPerCta - 1) / groupsPerCta;
     const int grid = (int)(need < (long long)sms * perSm ? need : (long long)sms * perSm);
-    k<<<grid, kLocalThreads, smem, s>>>(dModel, st, dem, validIdx, nTargets, scratch, xyInSmem, out, minmax);
+    k<<<grid, kLocalThreads, smem, s>>>(dModel, st, dem, validIdx, nTargets, scratch, xyInSmem, out, minmax, pt);
     return cudaGetLastError();
 }
 
 cudaError_t launchLocalDetrendingRaster(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem,
                                         const int* validIdx, int nTargets, const LocalScratch& scratch, int groupLanes,
-                                        int elevFunction, float* out, unsigned* minmax, cudaStream_t s)
+                                        int elevFunction, float* out, unsigned* minmax, cudaStream_t s,
+                                        const LocalPointTargets* points)
 {
     if (nTargets <= 0) return cudaSuccess;
+    const LocalPointTargets pt = points ? *points : LocalPointTargets{nullptr, nullptr, nullptr, 1};
     static const int minb = getenv("PB_LOCAL_MINB") ? atoi(getenv("PB_LOCAL_MINB")) : 2;
 #define PB_LOCAL_CASE(G_, F_)                                                                               \
-    return minb == 2 ? launchT<G_, F_, 2>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s)     \
-         : minb == 3 ? launchT<G_, F_, 3>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s)     \
-         : minb == 4 ? launchT<G_, F_, 4>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s)     \
-                     : launchT<G_, F_, 1>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s)
+    return minb == 2 ? launchT<G_, F_, 2>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)   \
+         : minb == 3 ? launchT<G_, F_, 3>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)   \
+         : minb == 4 ? launchT<G_, F_, 4>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)   \
+                     : launchT<G_, F_, 1>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)
     if (groupLanes == 16) {
         switch (elevFunction) {
         case PB_FIT_PIECEWISE_THREE: PB_LOCAL_CASE(16, PB_FIT_PIECEWISE_THREE);

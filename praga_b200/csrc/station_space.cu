@@ -23,6 +23,7 @@ bool varUsesTd(int v);
 bool varIsPrec(int v);
 bool varIsThermal(int v);
 int varClampMode(int v);
+void cvStatisticsHost(const std::vector<float>& obs, const std::vector<float>& pre, pb_cv_stats* stats);
 }  // namespace pb
 
 using namespace pb;
@@ -802,5 +803,88 @@ extern "C" int pb_spatial_quality_control(pb_context* ctx, const pb_stations* st
                                   ? 1 : 0;
         } else wrongSpatial[i] = 0;
     }
+    return PB_OK;
+}
+
+/* Project::interpolationDem (project/project.cpp:3106-3150) [+ the leave-one-out of Project::interpolationCv :3012-3104]:
+ * one time step of one variable, from raw station values to the DEM raster; see include/praga_b200.h */
+extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, pb_settings* qualitySettings, pb_settings* s, int variable,
+                                    pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
+                                    int deviceOnly, pb_raster_out* out, pb_dem_step* step)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!meteo || !s || !out) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    const int n = meteo->n;
+    int launches = 0;
+    float kernelMs = 0.f;
+    int64_t h2d = 0, d2h = 0;
+    auto account = [&]() { launches += ctx->timing.launches; kernelMs += ctx->timing.kernel_ms; h2d += ctx->timing.h2d_bytes; d2h += ctx->timing.d2h_bytes; };
+    std::vector<uint8_t> wrong(std::max(n, 1), 0);
+    // checkData (spatialControl.cpp:466-476): the spatial check is skipped for precipitation and the wind vector components
+    const bool spatialVar = variable != PB_VAR_PRECIPITATION && variable != PB_VAR_DAILY_PRECIPITATION && variable != PB_VAR_WIND_VECTOR_X &&
+                            variable != PB_VAR_WIND_VECTOR_Y && variable != 36 /* windVectorDirection */ &&
+                            variable != 41 /* dailyWindVectorDirectionPrevailing */;
+    if (qualitySettings && spatialVar && n > 0) {
+        int rc = pb_spatial_quality_control(ctx, meteo, qualitySettings, variable, nullptr, dem, wrong.data());
+        if (rc) return rc;
+        account();
+    }
+    if (step && step->wrongSpatial) memcpy(step->wrongSpatial, wrong.data(), n);
+    // passDataToInterpolation (spatialControl.cpp:500-566)
+    std::vector<int> accepted;
+    int nrValid = 0;
+    for (int i = 0; i < n; i++) {
+        if (wrong[i]) continue;
+        accepted.push_back(i);
+        const int code = meteo->lapseRateCode ? meteo->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        if (!s->useLapseRateCode || code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SECONDARY) nrValid++;
+    }
+    if (nrValid == 0) return fail(ctx, PB_ERR_INVALID, "No data available");
+    SubStations pts(meteo, accepted, meteo->value);
+    passDataSideEffects(&pts.st, s);
+    if (s->useMultipleDetrending) s->nFit = s->nFitFunctions = 0;       // clearFitting (project.cpp:3540)
+    std::vector<float> raw(pts.value);
+    std::vector<uint8_t> keep(accepted.size(), 1);
+    pb_cv_points cv{};
+    cv.currentValue = raw.data();
+    int rc = pb_pre_interpolation_ex(ctx, &pts.st, s, variable, &cv, dem, keep.data(), step ? step->khSeries : nullptr);
+    if (rc) return rc;
+    account();
+    std::vector<int> kept;
+    for (size_t k = 0; k < accepted.size(); k++) if (keep[k]) kept.push_back(int(k));
+    SubStations ipts(&pts.st, kept, pts.st.value);
+    rc = deviceOnly ? pb_interpolation_raster_device(ctx, &ipts.st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out)
+                    : pb_interpolation_raster_resident(ctx, &ipts.st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out);
+    if (rc) return rc;
+    account();
+    if (step && step->residual) {
+        // computeResiduals(…, getUseExcludeStationsOutsideDEM(), true) over the accepted meteo points (project.cpp:3063-3067)
+        SubStations mp(meteo, accepted, meteo->value);
+        std::vector<float> res(accepted.size());
+        LooArrays a;
+        std::vector<int> all(accepted.size());
+        for (size_t k = 0; k < all.size(); k++) all[k] = int(k);
+        fillTargets(a, &mp.st, all, all, raw.data(), nullptr, s->nProxy);
+        fillSources(a, &ipts.st, nullptr);
+        rc = exactLoo(ctx, a, s, variable, dem, 0, 1, res.data(), nullptr, nullptr);
+        if (rc) return rc;
+        launches += ctx->timing.launches;
+        std::vector<float> obs, pre;
+        for (int i = 0; i < n; i++) step->residual[i] = kNoData;
+        for (size_t k = 0; k < accepted.size(); k++) {
+            step->residual[accepted[k]] = res[k];
+            const float value = raw[k];
+            if (!(fabs(double(value) - double(kNoData)) < kEpsilon) && !(fabs(double(res[k]) - double(kNoData)) < kEpsilon)) {
+                obs.push_back(value);
+                pre.push_back(value - res[k]);
+            }
+        }
+        cvStatisticsHost(obs, pre, step->stats);
+    }
+    ctx->timing.launches = launches;
+    ctx->timing.kernel_ms = kernelMs;
+    ctx->timing.h2d_bytes = h2d;
+    ctx->timing.d2h_bytes = d2h;
     return PB_OK;
 }

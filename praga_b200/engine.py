@@ -68,6 +68,10 @@ def load_library():
     lib.pb_pre_interpolation_batch.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), C.c_int, P(A.pb_settings), C.c_int,
                                                P(C.c_double), P(C.c_float), P(C.c_uint8), P(A.pb_settings)]
     lib.pb_compute_residuals.argtypes = raster_args + [P(C.c_float), P(C.c_uint8), P(C.c_float), P(A.pb_cv_stats)]
+    lib.pb_compute_residuals_local.argtypes = lib.pb_compute_residuals.argtypes
+    lib.pb_local_detrending_points.argtypes = lib.pb_interpolate_points.argtypes
+    lib.pb_interpolation_dem.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), P(A.pb_settings), C.c_int, C.c_int32,
+                                         P(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, P(A.pb_raster_out), P(A.pb_dem_step)]
     lib.pb_kriging_setup.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_int, P(C.c_int32)]
     lib.pb_kriging_free.argtypes = [C.c_void_p, C.c_int32]
@@ -79,7 +83,7 @@ def load_library():
                                                            C.c_int, C.c_int32, P(C.c_float)]
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
-                 "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series"):
+                 "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series", "pb_dem_step"):
         got, want = lib.pb_abi_sizeof(name.encode()), C.sizeof(getattr(A, name))
         if got != want:
             raise PragaB200Error(A.PB_ERR_INVALID, f"ABI mismatch for {name}: library {got} B, binding {want} B")
@@ -205,14 +209,16 @@ class Engine:
         return res
 
     # ---- computeResiduals + computeStatisticsCrossValidation (spatialControl.cpp:97, project.cpp:2935) ----
-    def compute_residuals(self, stations, settings, variable, observed, use_for_cv=None):
+    def compute_residuals(self, stations, settings, variable, observed, use_for_cv=None, local=False):
+        """computeResiduals (local=True: computeResidualsLocalDetrending, stations NOT detrended) + CV statistics."""
         obs = np.ascontiguousarray(observed, dtype=np.float32)
         res = np.empty(stations.n, dtype=np.float32)
         stats = A.pb_cv_stats()
         st = stations.as_pb()
         use = None if use_for_cv is None else np.ascontiguousarray(use_for_cv, dtype=np.uint8)
-        self._check(self.lib.pb_compute_residuals(self.h, C.byref(st), C.byref(settings), variable, A.fptr(obs),
-                                                  None if use is None else A.u8ptr(use), A.fptr(res), C.byref(stats)))
+        fn = self.lib.pb_compute_residuals_local if local else self.lib.pb_compute_residuals
+        self._check(fn(self.h, C.byref(st), C.byref(settings), variable, A.fptr(obs), None if use is None else A.u8ptr(use),
+                       A.fptr(res), C.byref(stats)))
         return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}
 
     # ---- ordinary kriging (kriging.h:4-15) ----
@@ -309,6 +315,37 @@ class Engine:
                                                         C.byref(p), C.byref(settings), variable, dem_id, int(exclude_outside_dem),
                                                         int(exclude_supplemental), A.fptr(res)))
         return res
+
+    def interpolation_dem(self, meteo, settings, variable, dem_id, shape, proxy_ids=(), quality_settings=None, cross_validate=False,
+                          row_begin=0, row_end=-1, out=None, device_only=False):
+        """Project::interpolationDem (project.cpp:3106-3150) for one time step: spatial quality control, preInterpolation,
+        interpolationRaster over resident rasters [+ the leave-one-out of Project::interpolationCv]. meteo: RAW values.
+        Returns dict(ok, grid, min, max, n_valid, wrong_spatial, residual, stats, kh_series)."""
+        st = meteo.as_pb()
+        ids = (C.c_int32 * max(1, len(proxy_ids)))(*proxy_ids)
+        o = A.pb_raster_out()
+        if not device_only:
+            if out is None:
+                out = np.empty(shape, dtype=np.float32)
+            o.data = A.fptr(out)
+        wrong = np.zeros(meteo.n, dtype=np.uint8)
+        res = np.empty(meteo.n, dtype=np.float32)
+        stats = A.pb_cv_stats()
+        series = A.pb_kh_series()
+        step = A.pb_dem_step()
+        step.wrongSpatial = A.u8ptr(wrong)
+        step.khSeries = C.pointer(series)
+        if cross_validate:
+            step.residual = A.fptr(res)
+            step.stats = C.pointer(stats)
+        rc = self.lib.pb_interpolation_dem(self.h, C.byref(st), None if quality_settings is None else C.byref(quality_settings),
+                                           C.byref(settings), variable, dem_id, ids, len(proxy_ids), row_begin, row_end,
+                                           int(device_only), C.byref(o), C.byref(step))
+        self._check(rc, allow=(A.PB_ERR_NO_VALID_CELL,))
+        return dict(ok=rc == A.PB_OK, grid=out, min=o.minimum, max=o.maximum, n_valid=o.nValid, wrong_spatial=wrong.astype(bool),
+                    residual=res if cross_validate else None,
+                    stats={k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_} if cross_validate else None,
+                    kh_series=[(series.kh[i], series.error[i]) for i in range(series.n)])
 
     def pre_interpolation_batch(self, stations, values, settings, variable, points_range=None):
         """T time steps sharing the station set. values: (T, n). Returns (detrended (T, n), keep (T, n), [settings] * T)."""

@@ -96,3 +96,34 @@ def test_local_detrending_rejects_non_detrending_variable(engine):
     s = local_settings(st, use_urban=False)
     with pytest.raises(pb.PragaB200Error):
         engine.local_detrending_raster(st, s, A.precipitation, dem, (dem,))
+
+
+# ---- leave-one-out in local mode: computeResidualsLocalDetrending (spatialControl.cpp:158-228) ------------------------
+def loo_cases():
+    dem = syn.make_dem(120, 140, cell_size=5000.0)
+    urban = syn.make_urban(120, 140, cell_size=5000.0)
+    st = syn.make_stations(dem, 1200, proxies=(dem, urban), seed=11)
+    yield "c3_density", st, local_settings(st), A.airTemperature
+    dem2 = syn.make_dem(60, 70, cell_size=500.0, seed=3)
+    urban2 = syn.make_urban(60, 70, cell_size=500.0)
+    st2 = syn.make_stations(dem2, 300, proxies=(dem2, urban2), seed=9, supplemental_frac=0.15)
+    s2 = local_settings(st2, min_points=25)
+    s2.useLapseRateCode = 1
+    yield "codes_dense", st2, s2, A.dailyAirTemperatureMax
+    st3 = syn.make_stations(dem2, 22, proxies=(dem2, urban2), seed=4)
+    yield "takes_all", st3, local_settings(st3), A.airTemperature
+
+
+def test_local_residuals_identical_to_reference(engine, ref):
+    for name, st, s, var in loo_cases():
+        use = np.ones(st.n, dtype=np.uint8)
+        use[::17] = 0
+        res_r, stats_r = ref.compute_residuals(st, s, var, st.value, use_for_cv=use, local=True)
+        res_g, stats_g = engine.compute_residuals(st, s, var, st.value, use_for_cv=use, local=True)
+        assert np.array_equal(res_r == np.float32(-9999), res_g == np.float32(-9999)), name
+        d = np.abs(res_r.astype(np.float64) - res_g.astype(np.float64))
+        assert d.max() <= TOL, f"{name}: max |gpu-ref| residual = {d.max():.3e}"
+        assert stats_r["n"] == stats_g["n"], name
+        for k in ("meanAbsoluteError", "meanBiasError", "rootMeanSquareError", "nashSutcliffe", "R2"):
+            assert abs(stats_r[k] - stats_g[k]) <= TOL, f"{name}: {k} {stats_r[k]} vs {stats_g[k]}"
+        print(f"{name}: max |gpu-ref| = {d.max():.2e}, bit-identical: {100 * np.mean(d == 0):.1f} %, MAE = {stats_g['meanAbsoluteError']:.4f}")

@@ -144,3 +144,23 @@ def test_topographic_distance_raster_and_points_bit_exact(ref, port):
     pa = ref.interpolate_points_td(st, s, A.airRelHumidity, x, y, z, pv, dem)
     pb_ = port.interpolate_points_td(st, s, A.airRelHumidity, x, y, z, pv, dem)
     assert np.array_equal(pa, pb_)
+
+
+def test_local_residuals_port_bit_exact(ref, port):
+    """computeResidualsLocalDetrending (spatialControl.cpp:158-228) + CV statistics: restatement == reference."""
+    dem = syn.make_dem(60, 70, cell_size=3000.0, seed=3)
+    urban = syn.make_urban(60, 70, cell_size=3000.0)
+    for n, codes in ((260, 0.15), (22, 0.0)):
+        st = syn.make_stations(dem, n, proxies=(dem, urban), seed=9, supplemental_frac=codes)
+        s = syn.settings_multiple_detrending()
+        s.useLocalDetrending = 1
+        s.minPointsLocalDetrending = 20
+        s.useLapseRateCode = 1 if codes else 0
+        syn.set_points_range(s, st)
+        use = np.ones(st.n, dtype=np.uint8)
+        use[::13] = 0
+        ra, sa = ref.compute_residuals(st, clone(s), A.airTemperature, st.value, use_for_cv=use, local=True)
+        rb, sb = port.compute_residuals(st, clone(s), A.airTemperature, st.value, use_for_cv=use, local=True)
+        assert np.array_equal(ra, rb), np.abs(ra - rb).max()
+        assert sa == sb
+        assert sa["n"] > 10
