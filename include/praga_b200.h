@@ -356,6 +356,8 @@ int pb_last_timing(const pb_context* ctx, pb_timing* t);
 /* live ceilings of the two pipes that bound the IDW station loop: FP32 FMA (TFLOP/s, FFMA2 chain) and
  * MUFU.RSQ (G op/s). Used by bench.py as roofline denominators (MEASURED_PEAKS.json has no FP32 figure). */
 int pb_measure_pipe_peaks(pb_context* ctx, float* fp32Tflops, float* mufuGops);
+/* FP64 FMA ceiling (TFLOP/s, DFMA chain): roofline denominator of the local-detrending and kriging-estimate kernels */
+int pb_measure_fp64_peak(pb_context* ctx, float* fp64Tflops);
 
 #ifdef __cplusplus
 }

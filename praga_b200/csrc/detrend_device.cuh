@@ -48,14 +48,33 @@ __device__ __forceinline__ double divByKnown(double n, double d, double r)
 {
     const double q0 = n * r;
     const double aq = fabs(q0);
-    if (aq > 1e-280 && aq < 1e280) {
-        const double e0 = __fma_rn(-d, q0, n);
-        const double q1 = __fma_rn(e0, r, q0);
-        const double e1 = __fma_rn(-d, q1, n);
-        return __fma_rn(e1, r, q1);
+    // the corrected quotient is computed unconditionally (straight-line code: the lanes of a group sit on different data
+    // points of different descents, a branch here diverges on every zero derivative); the rare cases select afterwards
+    const double e0 = __fma_rn(-d, q0, n);
+    const double q1 = __fma_rn(e0, r, q0);
+    const double e1 = __fma_rn(-d, q1, n);
+    double q = __fma_rn(e1, r, q1);
+    if (!(aq > 1e-280 && aq < 1e280)) {
+        q = q0;                     // n == 0: (+-0) / d keeps the sign of n * sign(d)
+        if (n != 0) q = n / d;      // subnormal / huge / NaN quotients: the division instruction sequence
     }
-    if (n == 0) return q0;      // (+-0) / d keeps the sign of n * sign(d)
-    return n / d;
+    return q;
+}
+
+// straight-line form of divByKnown for the inner loops: the corrected quotient is always computed, a zero numerator
+// selects q0 = (+-0) (same value and sign as the division), and the quotients outside the safe exponent range only raise
+// `slow`, so that the caller redoes them with divByKnown after the loop body. No branch => the independent columns of a
+// Jacobian row interleave instead of being serialised by reconvergence barriers.
+__device__ __forceinline__ double divFast(double n, double d, double r, bool& slow)
+{
+    const double q0 = n * r;
+    const double aq = fabs(q0);
+    const double e0 = __fma_rn(-d, q0, n);
+    const double q1 = __fma_rn(e0, r, q0);
+    const double e1 = __fma_rn(-d, q1, n);
+    const double q = __fma_rn(e1, r, q1);
+    slow |= !(aq > 1e-280 && aq < 1e280) && (n != 0);
+    return (n == 0) ? q0 : q;
 }
 
 // ---- model functions with the reference's in-place clamp of par[2] (furtherMathFunctions.cpp:138, 158) ----
@@ -65,8 +84,8 @@ template <> struct Fit<PB_FIT_PIECEWISE_TWO> {
     static __device__ __forceinline__ void clamp(double*) {}
     static __device__ __forceinline__ double eval(double x, const double* p)
     {
-        if (x < p[0]) return p[2] * (x - p[0]) + p[1];
-        return p[3] * (x - p[0]) + p[1];
+        const double slope = (x < p[0]) ? p[2] : p[3];      // same products and sums as the two returns, no branch
+        return slope * (x - p[0]) + p[1];
     }
 };
 template <> struct Fit<PB_FIT_PIECEWISE_THREE> {
@@ -165,16 +184,23 @@ __device__ __noinline__ void lmElevation(const double* __restrict__ pmin, const 
         for (int j = 0; j < nData; j++) {
             const double x = X[j], y = Y[j], w = W[j];
             const double f0 = Fit<F>::eval(x, p0);
-            double P[N], WP[N];
+            double P[N], WP[N], num[N];
+            bool slow = false;
 #pragma unroll
             for (int k = 0; k < N; k++) {
                 double q[N];
 #pragma unroll
                 for (int c = 0; c < N; c++) q[c] = (c < k) ? ((F != PB_FIT_PIECEWISE_TWO && c == 2) ? p[2] : rs[c]) : p0[c];
                 q[k] = up[k];
-                P[k] = divByKnown(Fit<F>::eval(x, q) - f0, dl[k], rdl[k]);
-                WP[k] = w * P[k];
+                num[k] = Fit<F>::eval(x, q) - f0;
+                P[k] = divFast(num[k], dl[k], rdl[k], slow);
             }
+            if (slow) {
+#pragma unroll
+                for (int k = 0; k < N; k++) P[k] = divByKnown(num[k], dl[k], rdl[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < N; k++) WP[k] = w * P[k];
 #pragma unroll
             for (int i = 0; i < N; i++) {
 #pragma unroll

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <omp.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -535,6 +536,27 @@ int stageLocalStations(pb_context* ctx, const pb_stations* st, LocalStations& ds
     return PB_OK;
 }
 
+// radius within which the ring search of localSelection is expected to end, with margin: the kernel keeps the stations
+// inside it as a per-cell candidate list (a speed knob only: rings beyond it fall back to full scans)
+float candidateRadius(const pb_stations* st, const LocalModel& m)
+{
+    if (getenv("PB_LOCAL_NO_CANDIDATES")) return 0.f;
+    const int n = st->n;
+    if (n <= 0 || unsigned(n) <= m.minPoints) return 0.f;
+    double xMin = st->x[0], xMax = xMin, yMin = st->y[0], yMax = yMin;
+    int counted = 0;
+    for (int i = 0; i < n; i++) {
+        xMin = std::min(xMin, st->x[i]); xMax = std::max(xMax, st->x[i]);
+        yMin = std::min(yMin, st->y[i]); yMax = std::max(yMax, st->y[i]);
+        const int code = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        if (!m.useLapseRateCode || code == PB_LAPSE_PRIMARY || code == PB_LAPSE_SUPPLEMENTAL) counted++;
+    }
+    const double area = (xMax - xMin) * (yMax - yMin);
+    if (!(area > 0) || counted == 0) return 0.f;
+    const double rStar = sqrt(double(m.minPoints) * area / (3.141592653589793 * counted));
+    return float(std::max(1.5 * rStar, rStar + 7500.0) + 1000.0);
+}
+
 // stage + launch K2 on the targets [t0, t0 + nTargets) of the DEM's valid list
 int launchLocal(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const pb_raster_id* proxyIds,
                 int nProxyGrids, RasterEntry& dem, long long t0, int nTargets)
@@ -542,6 +564,7 @@ int launchLocal(pb_context* ctx, const pb_stations* st, const pb_settings* s, in
     LocalModel m;
     int rc = buildLocalModel(ctx, s, variable, st->n, proxyIds, nProxyGrids, m);
     if (rc) return rc;
+    m.candRadius = candidateRadius(st, m);
     LocalStations ds{};
     rc = stageLocalStations(ctx, st, ds);
     if (rc) return rc;
@@ -1310,6 +1333,7 @@ extern "C" int pb_local_detrending_points(pb_context* ctx, const pb_stations* st
     LocalModel lm;
     int rc = buildLocalModel(ctx, s, variable, st->n, nullptr, 0, lm);
     if (rc) return rc;
+    lm.candRadius = candidateRadius(st, lm);
     LocalStations ds{};
     rc = stageLocalStations(ctx, st, ds);
     if (rc) return rc;
@@ -1424,6 +1448,17 @@ extern "C" int pb_measure_pipe_peaks(pb_context* ctx, float* fp32Tflops, float* 
 }
 
 /* ABI self-description: lets bindings check that their struct layouts match this build */
+namespace pb { cudaError_t measureFp64Peak(cudaStream_t s, int sms, float* fp64Tflops); }
+extern "C" int pb_measure_fp64_peak(pb_context* ctx, float* fp64Tflops)
+{
+    if (!ctx || !fp64Tflops) return PB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, ctx->device);
+    CUDA_TRY(ctx, measureFp64Peak(ctx->stream, prop.multiProcessorCount, fp64Tflops));
+    return PB_OK;
+}
+
 extern "C" size_t pb_abi_sizeof(const char* name)
 {
     if (!name) return 0;

@@ -13,6 +13,7 @@ struct LocalModel {
     int minPointsLocal;            // getMinPointsLocalDetrending()
     unsigned minPoints;            // unsigned(minPointsLocal * 1.2f)   (localSelection :1092-1093)
     unsigned thr80;                // unsigned(minPoints * 0.8)         (:1152)
+    float candRadius;              // radius of the per-cell candidate list of the ring search (0 = scan all stations)
     float shepardRadius;           // computeShepardInitialRadius(bboxArea, S, minPoints) when S <= minPoints (:1098)
     int clampMode;
     float rainfallThreshold;

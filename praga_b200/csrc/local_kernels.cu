@@ -42,21 +42,65 @@ __device__ float localCell(const LocalModel& m, const LocalStations& st, const f
         n = S < gcap ? S : gcap;
         if (S > gcap && lane == 0) *errFlag = 1;
     } else {
+        // Candidate pass: ONE scan of all stations keeps, in station order, those within the candidate radius (so that the
+        // rings below walk a few dozen entries instead of all S) and the largest distance (the `beyond last point` test).
+        // d2 <= rcap2 is conservative (slack >> the rounding of sqrtf), so every station of a ring with r1 <= rcap is a
+        // candidate; rings beyond rcap (raster borders, sparse corners) scan the full list as before.
+        float rcap = m.candRadius;
+        int nc = 0;
+        float dmax = 0.f;
+        if (rcap > 0.f) {
+            const float rcap2 = rcap * rcap * 1.0001f;
+            float dmax2 = 0.f;
+            for (int base = 0; base < S; base += G) {
+                const int i = base + lane;
+                bool c = false;
+                float d2 = 0.f;
+                if (i < S) {
+                    const float2 p = xy[i];
+                    const float dx = p.x - xf, dy = p.y - yf;
+                    d2 = dx * dx + dy * dy;
+                    c = d2 <= rcap2;
+                    dmax2 = fmaxf(dmax2, d2);
+                }
+                const unsigned b = grpBallot<G>(c);
+                if (b) {
+                    if (c) {
+                        const int pos = nc + __popc(b & ltMask);
+                        if (pos < gcap) { gw.oi[pos] = i; gw.w[pos] = sqrtf(d2); }
+                    }
+                    nc += __popc(b);
+                }
+            }
+#pragma unroll
+            for (int o = G / 2; o; o >>= 1) dmax2 = fmaxf(dmax2, __shfl_xor_sync(grpMask<G>(), dmax2, o, G));
+            dmax = sqrtf(dmax2);                  // sqrtf is monotonic: max of the distances
+            if (nc > gcap) rcap = 0.f;            // too dense for the candidate list: full scans
+            grpSync<G>();
+        }
         unsigned nrValid = 0, nrPrimaries = 0;
         float stepRadius = 7500.f, r0 = 0.f, r1 = 7500.f;
         bool beyondLastPoint = false;
         while (((!useCode && nrValid < m.minPoints) || (useCode && nrPrimaries < m.minPoints)) && !beyondLastPoint) {
+            const bool compact = rcap > 0.f && r1 <= rcap;
+            const int L = compact ? nc : S;
             bool farther = false;
-            for (int base = 0; base < S; base += G) {
-                const int i = base + lane;
+            for (int base = 0; base < L; base += G) {
+                const int k = base + lane;
                 bool in = false, prim = false;
                 float d = 0.f;
-                if (i < S) {
-                    const float2 p = xy[i];
-                    const float dx = p.x - xf, dy = p.y - yf;       // gis::computeDistance(x, y, px, py), gis.cpp:685-691
-                    d = sqrtf(dx * dx + dy * dy);
+                int i = k;
+                if (k < L) {
+                    if (compact) {
+                        i = gw.oi[k];
+                        d = gw.w[k];
+                    } else {
+                        const float2 p = xy[i];
+                        const float dx = p.x - xf, dy = p.y - yf;       // gis::computeDistance(x, y, px, py), gis.cpp:685-691
+                        d = sqrtf(dx * dx + dy * dy);
+                        farther |= d > r1;
+                    }
                     in = d > r0 && d <= r1;
-                    farther |= d > r1;
                     if (in) prim = checkLapseRateCodeDev(st.code[i], useCode, true);
                 }
                 const unsigned b = grpBallot<G>(in);
@@ -72,7 +116,7 @@ __device__ float localCell(const LocalModel& m, const LocalStations& st, const f
                 }
             }
             nrValid = unsigned(n);
-            beyondLastPoint = grpBallot<G>(farther) == 0u;
+            beyondLastPoint = compact ? !(dmax > r1) : grpBallot<G>(farther) == 0u;
             if (nrValid > m.thr80) stepRadius = 1000.f;
             r0 = r1;
             r1 += stepRadius;

@@ -39,6 +39,49 @@ __global__ void __launch_bounds__(256) rsq_chain_kernel(float* out)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+__global__ void __launch_bounds__(256) dfma_chain_kernel(double* out, double b, double c)
+{
+    double a[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; i++) a[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < kIters / 4; it++) {
+#pragma unroll
+        for (int i = 0; i < kChains; i++) a[i] = fma(a[i], b, c);
+    }
+    double s = 0.;
+#pragma unroll
+    for (int i = 0; i < kChains; i++) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// FP64 FMA ceiling (TFLOP/s, DFMA chain): the denominator of the K2 (local detrending) and K5-estimate rooflines
+cudaError_t measureFp64Peak(cudaStream_t s, int sms, float* fp64Tflops)
+{
+    const int blocks = sms * 8, threads = 256;
+    double* out = nullptr;
+    cudaError_t e = cudaMalloc(&out, sizeof(double) * blocks * threads);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, s);
+        dfma_chain_kernel<<<blocks, threads, 0, s>>>(out, 1.0000001, 1e-9);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const double lanes = double(blocks) * threads * double(kIters / 4) * kChains;
+    *fp64Tflops = float(lanes * 2.0 / (best * 1e-3) * 1e-12);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return cudaGetLastError();
+}
+
 // returns best-of-`reps` TFLOP/s (FMA = 2 flop) and G MUFU.RSQ/s
 cudaError_t measurePipePeaks(cudaStream_t s, int sms, float* fp32Tflops, float* mufuGops)
 {

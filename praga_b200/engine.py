@@ -82,6 +82,7 @@ def load_library():
     lib.pb_interpolate_points_td.argtypes = raster_args + [P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_double), C.c_int,
                                                            C.c_int, C.c_int32, P(C.c_float)]
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
+    lib.pb_measure_fp64_peak.argtypes = [C.c_void_p, P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
                  "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series", "pb_dem_step"):
         got, want = lib.pb_abi_sizeof(name.encode()), C.sizeof(getattr(A, name))
@@ -132,6 +133,12 @@ class Engine:
         a, b = C.c_float(0), C.c_float(0)
         self._check(self.lib.pb_measure_pipe_peaks(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def measure_fp64_peak(self):
+        """FP64 FMA TFLOP/s measured live on this GPU (DFMA chain)."""
+        a = C.c_float(0)
+        self._check(self.lib.pb_measure_fp64_peak(self.h, C.byref(a)))
+        return a.value
 
     # ---- raster cache ----
     def upload(self, raster):
