@@ -136,138 +136,162 @@ __device__ __forceinline__ double evalFitRt(int f, double x, const double* par)
 // (par[k] += delta; ...; par[k] -= delta, which does not always restore the same bits) is reproduced: column k is
 // evaluated with the already "restored" entries below k, and the restored vector is what the step is added to.
 // ---------------------------------------------------------------------------------------------------------
+// state of one descent: lmElevation = lmInit + lmIter until it reports the end
+template <int F>
+struct LmState {
+    double p[Fit<F>::N], lambda[Fit<F>::N];
+    double mySSE;
+    int iter;
+};
+
+template <int F>
+__device__ __forceinline__ void lmInit(LmState<F>& s, const double* par, const double* X, const double* Y, const double* W,
+                                       int nData)
+{
+    constexpr int N = Fit<F>::N;
+#pragma unroll
+    for (int k = 0; k < N; k++) { s.lambda[k] = 0.01; s.p[k] = par[k]; }
+    s.mySSE = 0;
+    if (nData > 0) Fit<F>::clamp(s.p);
+    for (int i = 0; i < nData; i++) {
+        const double error = Y[i] - Fit<F>::eval(X[i], s.p);
+        const double w = W[i];
+        s.mySSE += error * error * w * w;
+    }
+    s.iter = 0;
+}
+
+// one Levenberg-Marquardt iteration; true when the descent is over (the reference's do-while condition turned false)
+template <int F>
+__device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__ pmin, const double* __restrict__ pmax,
+                                       const double* dl, const double* rdl, int maxIter, double eps, const double* X,
+                                       const double* Y, const double* W, int nData)
+{
+    constexpr int N = Fit<F>::N;
+    const double VFACTOR = 10;
+    double diffSSE;
+    // perturbed parameter vectors: up[k] = value of par[k] while column k is evaluated; rs[k] = after the restore
+    double p0[N], up[N], rs[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) p0[k] = s.p[k];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        s.p[k] += dl[k];
+        if (nData > 0) Fit<F>::clamp(s.p);       // the model function clamps par[2] in place when it is evaluated
+        up[k] = s.p[k];
+        s.p[k] -= dl[k];
+        rs[k] = s.p[k];
+    }
+    if (nData > 0) Fit<F>::clamp(s.p);           // evaluations of the following columns / of newPar see it clamped
+    // for the three-piece forms s.p[2] may have been re-clamped after its own restore: columns k > 2 see s.p[2]
+    double g[N], a[N][N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        g[i] = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) a[i][j] = 0;
+    }
+    for (int j = 0; j < nData; j++) {
+        const double x = X[j], y = Y[j], w = W[j];
+        const double f0 = Fit<F>::eval(x, p0);
+        double P[N], WP[N], num[N];
+        bool slow = false;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            double q[N];
+#pragma unroll
+            for (int c = 0; c < N; c++) q[c] = (c < k) ? ((F != PB_FIT_PIECEWISE_TWO && c == 2) ? s.p[2] : rs[c]) : p0[c];
+            q[k] = up[k];
+            num[k] = Fit<F>::eval(x, q) - f0;
+            P[k] = divFast(num[k], dl[k], rdl[k], slow);
+        }
+        if (slow) {
+#pragma unroll
+            for (int k = 0; k < N; k++) P[k] = divByKnown(num[k], dl[k], rdl[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) WP[k] = w * P[k];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+#pragma unroll
+            for (int c = i; c < N; c++) a[i][c] += (P[i] * WP[c]);
+            g[i] += P[i] * w * (y - f0);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        a[k][k] += s.lambda[k] * a[k][k];
+#pragma unroll
+        for (int j = k + 1; j < N; j++) a[j][k] = a[k][j];
+    }
+#pragma unroll
+    for (int j = 0; j < N - 1; j++) {
+        const double pivot = (a[j][j] > kEpsilon) ? a[j][j] : kEpsilon;     // MAXVALUE(a[j][j], EPSILON)
+#pragma unroll
+        for (int i = j + 1; i < N; i++) {
+            const double mult = a[i][j] / pivot;
+#pragma unroll
+            for (int k = j + 1; k < N; k++) a[i][k] -= mult * a[j][k];
+            g[i] -= mult * g[j];
+        }
+    }
+    double change[N];
+    change[N - 1] = g[N - 1] / ((a[N - 1][N - 1] > kEpsilon) ? a[N - 1][N - 1] : kEpsilon);
+#pragma unroll
+    for (int i = N - 2; i >= 0; i--) {
+        double top = g[i];
+#pragma unroll
+        for (int k = i + 1; k < N; k++) top -= a[i][k] * change[k];
+        change[i] = top / ((a[i][i] > kEpsilon) ? a[i][i] : kEpsilon);
+    }
+    double np[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const double hi = pmax[j], lo = pmin[j];
+        np[j] = s.p[j] + change[j];
+        if (np[j] > hi && s.lambda[j] < 1000) {
+            np[j] = hi;
+            if (s.lambda[j] < 1000) s.lambda[j] *= VFACTOR;
+        }
+        if (np[j] < lo) {
+            np[j] = lo;
+            if (s.lambda[j] < 1000) s.lambda[j] *= VFACTOR;
+        }
+    }
+    double newSSE = 0;
+    if (nData > 0) Fit<F>::clamp(np);
+    for (int i = 0; i < nData; i++) {
+        const double error = Y[i] - Fit<F>::eval(X[i], np);
+        const double w = W[i];
+        newSSE += error * error * w * w;
+    }
+    diffSSE = s.mySSE - newSSE;
+    if (diffSSE > 0) {
+        s.mySSE = newSSE;
+#pragma unroll
+        for (int j = 0; j < N; j++) { s.p[j] = np[j]; s.lambda[j] /= VFACTOR; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) s.lambda[j] *= VFACTOR;
+    }
+    s.iter++;
+    return !(fabs(diffSSE) > eps && s.iter <= maxIter);
+}
+
 template <int F>
 __device__ __noinline__ void lmElevation(const double* __restrict__ pmin, const double* __restrict__ pmax,
                                          const double* __restrict__ delta, double* par, int maxIter, double eps,
                                          const double* X, const double* Y, const double* W, int nData)
 {
     constexpr int N = Fit<F>::N;
-    const double VFACTOR = 10;
-    double lambda[N], dl[N], rdl[N];
+    double dl[N], rdl[N];
 #pragma unroll
-    for (int k = 0; k < N; k++) { lambda[k] = 0.01; dl[k] = delta[k]; rdl[k] = 1.0 / dl[k]; }
-    double p[N];
+    for (int k = 0; k < N; k++) { dl[k] = delta[k]; rdl[k] = 1.0 / dl[k]; }
+    LmState<F> s;
+    lmInit<F>(s, par, X, Y, W, nData);
+    while (!lmIter<F>(s, pmin, pmax, dl, rdl, maxIter, eps, X, Y, W, nData)) {}
 #pragma unroll
-    for (int k = 0; k < N; k++) p[k] = par[k];
-
-    double mySSE = 0;
-    if (nData > 0) Fit<F>::clamp(p);
-    for (int i = 0; i < nData; i++) {
-        const double error = Y[i] - Fit<F>::eval(X[i], p);
-        const double w = W[i];
-        mySSE += error * error * w * w;
-    }
-    int iter = 0;
-    double diffSSE;
-    do {
-        // perturbed parameter vectors: up[k] = value of par[k] while column k is evaluated; rs[k] = after the restore
-        double p0[N], up[N], rs[N];
-#pragma unroll
-        for (int k = 0; k < N; k++) p0[k] = p[k];
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            p[k] += dl[k];
-            if (nData > 0) Fit<F>::clamp(p);       // the model function clamps par[2] in place when it is evaluated
-            up[k] = p[k];
-            p[k] -= dl[k];
-            rs[k] = p[k];
-        }
-        if (nData > 0) Fit<F>::clamp(p);           // evaluations of the following columns / of newPar see it clamped
-        // for the three-piece forms p[2] may have been re-clamped after its own restore: columns k > 2 see p[2]
-        double g[N], a[N][N];
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-            g[i] = 0;
-#pragma unroll
-            for (int j = 0; j < N; j++) a[i][j] = 0;
-        }
-        for (int j = 0; j < nData; j++) {
-            const double x = X[j], y = Y[j], w = W[j];
-            const double f0 = Fit<F>::eval(x, p0);
-            double P[N], WP[N], num[N];
-            bool slow = false;
-#pragma unroll
-            for (int k = 0; k < N; k++) {
-                double q[N];
-#pragma unroll
-                for (int c = 0; c < N; c++) q[c] = (c < k) ? ((F != PB_FIT_PIECEWISE_TWO && c == 2) ? p[2] : rs[c]) : p0[c];
-                q[k] = up[k];
-                num[k] = Fit<F>::eval(x, q) - f0;
-                P[k] = divFast(num[k], dl[k], rdl[k], slow);
-            }
-            if (slow) {
-#pragma unroll
-                for (int k = 0; k < N; k++) P[k] = divByKnown(num[k], dl[k], rdl[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < N; k++) WP[k] = w * P[k];
-#pragma unroll
-            for (int i = 0; i < N; i++) {
-#pragma unroll
-                for (int c = i; c < N; c++) a[i][c] += (P[i] * WP[c]);
-                g[i] += P[i] * w * (y - f0);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            a[k][k] += lambda[k] * a[k][k];
-#pragma unroll
-            for (int j = k + 1; j < N; j++) a[j][k] = a[k][j];
-        }
-#pragma unroll
-        for (int j = 0; j < N - 1; j++) {
-            const double pivot = (a[j][j] > kEpsilon) ? a[j][j] : kEpsilon;     // MAXVALUE(a[j][j], EPSILON)
-#pragma unroll
-            for (int i = j + 1; i < N; i++) {
-                const double mult = a[i][j] / pivot;
-#pragma unroll
-                for (int k = j + 1; k < N; k++) a[i][k] -= mult * a[j][k];
-                g[i] -= mult * g[j];
-            }
-        }
-        double change[N];
-        change[N - 1] = g[N - 1] / ((a[N - 1][N - 1] > kEpsilon) ? a[N - 1][N - 1] : kEpsilon);
-#pragma unroll
-        for (int i = N - 2; i >= 0; i--) {
-            double top = g[i];
-#pragma unroll
-            for (int k = i + 1; k < N; k++) top -= a[i][k] * change[k];
-            change[i] = top / ((a[i][i] > kEpsilon) ? a[i][i] : kEpsilon);
-        }
-        double np[N];
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            const double hi = pmax[j], lo = pmin[j];
-            np[j] = p[j] + change[j];
-            if (np[j] > hi && lambda[j] < 1000) {
-                np[j] = hi;
-                if (lambda[j] < 1000) lambda[j] *= VFACTOR;
-            }
-            if (np[j] < lo) {
-                np[j] = lo;
-                if (lambda[j] < 1000) lambda[j] *= VFACTOR;
-            }
-        }
-        double newSSE = 0;
-        if (nData > 0) Fit<F>::clamp(np);
-        for (int i = 0; i < nData; i++) {
-            const double error = Y[i] - Fit<F>::eval(X[i], np);
-            const double w = W[i];
-            newSSE += error * error * w * w;
-        }
-        diffSSE = mySSE - newSSE;
-        if (diffSSE > 0) {
-            mySSE = newSSE;
-#pragma unroll
-            for (int j = 0; j < N; j++) { p[j] = np[j]; lambda[j] /= VFACTOR; }
-        } else {
-#pragma unroll
-            for (int j = 0; j < N; j++) lambda[j] *= VFACTOR;
-        }
-        iter++;
-    } while (fabs(diffSSE) > eps && iter <= maxIter);
-#pragma unroll
-    for (int k = 0; k < N; k++) par[k] = p[k];
+    for (int k = 0; k < N; k++) par[k] = s.p[k];
 }
 
 // computeWeighted_R2 (:1245-1275) and computeWeighted_RMSE (:1301-1322) of one fitted curve

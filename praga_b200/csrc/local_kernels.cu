@@ -16,15 +16,14 @@
 
 namespace pb {
 
-template <int G, int F>
-__device__ float localCell(const LocalModel& m, const LocalStations& st, const float2* __restrict__ xy, float xf, float yf,
-                           const double* pv, const WorkPtrs& gw, int gcap, unsigned char* tile, int* errFlag,
-                           bool excludeSupplemental)
+// localSelection (:1087-1170) for the target (xf, yf) by one group: returns n and the working arrays w (the shared-memory
+// tile when n <= tileCap, else the group's global scratch) with idx, d, w (regression weight), val, flg filled
+template <int G>
+__device__ int localSelect(const LocalModel& m, const LocalStations& st, const float2* __restrict__ xy, float xf, float yf,
+                           const WorkPtrs& gw, int gcap, unsigned char* tile, int tileCap, int* errFlag, WorkPtrs& w)
 {
-    constexpr int N = Fit<F>::N;
     const int lane = grpLane<G>();
     const int S = st.n;
-    const int nProxy = m.nProxy;
     const bool useCode = m.useLapseRateCode != 0;
     const unsigned ltMask = (1u << lane) - 1u;
 
@@ -131,9 +130,9 @@ __device__ float localCell(const LocalModel& m, const LocalStations& st, const f
     }
     grpSync<G>();
 
-    WorkPtrs w = gw;
-    if (n <= kCap) {
-        w = carve(tile, kCap);
+    w = gw;
+    if (n <= tileCap) {
+        w = carve(tile, tileCap);
         for (int k = lane; k < n; k += G) { w.idx[k] = gw.idx[k]; w.d[k] = gw.d[k]; }
     }
     for (int k = lane; k < n; k += G) {
@@ -148,10 +147,16 @@ __device__ float localCell(const LocalModel& m, const LocalStations& st, const f
         w.flg[k] = 1;
     }
     grpSync<G>();
+    return n;
+}
 
-    // ------------------------------------------------------------------ multipleDetrendingMain (:1832-1859)
-    MdFit<N> fit;
-    multipleDetrendingGroup<G, F>(m, st, w, n, true, fit);
+// interpolate (:2502-2560: idw over the detrended subset, retrend with the fit, clamp) for one target, group-uniform
+template <int G, int F>
+__device__ float localFinish(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, const double* pv,
+                             const MdFit<Fit<F>::N>& fit, bool excludeSupplemental)
+{
+    constexpr int N = Fit<F>::N;
+    const bool useCode = m.useLapseRateCode != 0;
     const int ePos = m.elevationPos;
     const bool elevSig = fit.elevSig;
     const int nPred = fit.nPred;
@@ -214,6 +219,19 @@ __device__ float localCell(const LocalModel& m, const LocalStations& st, const f
     }
 }
 
+// one cell of the loop of Project::interpolationDemLocalDetrending: selection, multipleDetrendingMain (:1832-1859), estimate
+template <int G, int F>
+__device__ float localCell(const LocalModel& m, const LocalStations& st, const float2* __restrict__ xy, float xf, float yf,
+                           const double* pv, const WorkPtrs& gw, int gcap, unsigned char* tile, int tileCap, int* errFlag,
+                           bool excludeSupplemental)
+{
+    WorkPtrs w;
+    const int n = localSelect<G>(m, st, xy, xf, yf, gw, gcap, tile, tileCap, errFlag, w);
+    MdFit<Fit<F>::N> fit;
+    multipleDetrendingGroup<G, F>(m, st, w, n, true, fit);
+    return localFinish<G, F>(m, st, w, n, pv, fit, excludeSupplemental);
+}
+
 __device__ __forceinline__ unsigned orderedKeyL(float f)
 {
     unsigned u = __float_as_uint(f);
@@ -248,7 +266,7 @@ local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, Dev
         if (pt.x) {       // point form: the target's own coordinates and proxy values, result t
             double pv[PB_MAX_PROXY];
             for (int i = 0; i < m.nProxy; i++) pv[i] = pt.pv[t * m.nProxy + i];
-            const float o = localCell<G, F>(m, st, xy, pt.x[t], pt.y[t], pv, gw, scr.cap, tile, scr.error, pt.excludeSupplemental != 0);
+            const float o = localCell<G, F>(m, st, xy, pt.x[t], pt.y[t], pv, gw, scr.cap, tile, kCap, scr.error, pt.excludeSupplemental != 0);
             if (lane == 0) out[t] = o;
             continue;
         }
@@ -267,7 +285,7 @@ local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, Dev
                 if (v != g.flag) pv[i] = double(v);
             }
         }
-        const float o = localCell<G, F>(m, st, xy, xf, yf, pv, gw, scr.cap, tile, scr.error, true);
+        const float o = localCell<G, F>(m, st, xy, xf, yf, pv, gw, scr.cap, tile, kCap, scr.error, true);
         if (lane == 0) {
             out[cell] = o;
             if (!isEqualF(o, dem.flag) && !isEqualF(o, kNoData)) {
@@ -328,7 +346,9 @@ cudaError_t launchLocalDetrendingRaster(const LocalModel* dModel, const LocalSta
 {
     if (nTargets <= 0) return cudaSuccess;
     const LocalPointTargets pt = points ? *points : LocalPointTargets{nullptr, nullptr, nullptr, 1};
-    static const int minb = getenv("PB_LOCAL_MINB") ? atoi(getenv("PB_LOCAL_MINB")) : 2;
+    // 1 resident CTA per SM (255 registers, no spills in the Levenberg-Marquardt loop) measured faster than 2 CTAs at 128
+    // registers (155 vs 164 ms on 925k cells / 5000 stations): the loop is latency bound and spills sit on its critical path
+    static const int minb = getenv("PB_LOCAL_MINB") ? atoi(getenv("PB_LOCAL_MINB")) : 1;
 #define PB_LOCAL_CASE(G_, F_)                                                                               \
     return minb == 2 ? launchT<G_, F_, 2>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)   \
          : minb == 3 ? launchT<G_, F_, 3>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)   \

@@ -21,7 +21,7 @@ struct WorkPtrs {
     unsigned char* act;       // isActive of compact elevation entry
 };
 
-__host__ __device__ inline size_t workBytes(int cap) { return (size_t(cap) * (3 * 8 + 5 * 4 + 2) + 15) / 16 * 16; }
+__host__ __device__ constexpr size_t workBytes(int cap) { return (size_t(cap) * (3 * 8 + 5 * 4 + 2) + 15) / 16 * 16; }
 
 __device__ __forceinline__ WorkPtrs carve(unsigned char* base, int cap)
 {
@@ -90,11 +90,93 @@ struct MdFit {
     double othPar[PB_MAX_PROXY][2];
 };
 
+// multipleDetrendingElevationFitting (:1862-1953), first half: the points with a usable lapse-rate code and an elevation
+// value go to X (height), Y (value), W (regression weight), act; then proxyValidity (:1418-1457) and the local
+// minimum-points rule (:1885). Returns nE; isValid = the elevation function is to be fitted.
+template <int G>
+__device__ int mdStageElevation(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, bool isLocal, bool& isValid)
+{
+    const int lane = grpLane<G>();
+    const int nProxy = m.nProxy;
+    const bool useCode = m.useLapseRateCode != 0;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int ePos = m.elevationPos;
+    int nE = 0;
+    for (int base = 0; base < n; base += G) {
+        const int k = base + lane;
+        bool ok = false;
+        float h = 0.f;
+        int i = 0;
+        if (k < n) {
+            i = w.idx[k];
+            h = st.proxy[(size_t)i * nProxy + ePos];
+            ok = checkLapseRateCodeDev(st.code[i], useCode, true) && h != kNoData;
+        }
+        const unsigned b = grpBallot<G>(ok);
+        if (ok) {
+            const int pos = nE + __popc(b & ltMask);
+            w.X[pos] = double(h);
+            w.Y[pos] = double(w.val[k]);
+            w.W[pos] = (w.w[k] != kNoData) ? double(w.w[k]) : 1.;
+            w.act[pos] = st.active[i];
+        }
+        nE += __popc(b);
+    }
+    grpSync<G>();
+    isValid = false;
+    {
+        double sum = 0;
+        unsigned cnt = 0;
+        for (int j = 0; j < nE; j++)
+            if (w.act[j]) { sum += w.X[j]; cnt++; }
+        if (cnt >= 5) {
+            const double avg = sum / cnt;
+            sum = 0;
+            for (int j = 0; j < nE; j++)
+                if (w.act[j]) sum += (w.X[j] - avg) * (w.X[j] - avg);
+            const double stdDev = sqrt(sum / (cnt - 1));
+            const float thr = m.stdDevThreshold[ePos];
+            isValid = (thr != kNoData) ? (stdDev > thr) : true;
+        }
+    }
+    if (isLocal) isValid = isValid && unsigned(nE) >= unsigned(m.minPointsLocal);          // local detrending (:1885)
+    return nE;
+}
+
+template <int G, int F>
+__device__ void mdFinish(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, bool isLocal, bool fitRan,
+                         double R2, const double* elevParIn, MdFit<Fit<F>::N>& fit);
+
 // w: idx (station index), w (regressionWeight), val (value, detrended in place), flg (bit0 = still in myPoints) of the
 // n points; X, Y, W, oi, act are scratch. isLocal adds the minPointsLocalDetrending conditions (:1885, :2100).
 template <int G, int F>
 __device__ void multipleDetrendingGroup(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, bool isLocal,
                                         MdFit<Fit<F>::N>& fit)
+{
+    constexpr int N = Fit<F>::N;
+    const int ePos = m.elevationPos;
+    double elevPar[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) elevPar[j] = 0;
+    bool fitRan = false;
+    double R2 = 0;
+    if (ePos >= 0 && m.selectedActive[ePos]) {
+        bool isValid;
+        const int nE = mdStageElevation<G>(m, st, w, n, isLocal, isValid);
+        if (isValid) {
+            R2 = bestFitElevation<G, F>(m.elevMin, m.elevMax, m.elevDelta, &m.firstGuess[0][0], m.nFirstGuess, elevPar, 1000,
+                                        0.002, 0.005, w.X, w.Y, w.W, nE);
+            fitRan = true;
+        }
+    }
+    mdFinish<G, F>(m, st, w, n, isLocal, fitRan, R2, elevPar, fit);
+}
+
+// the rest of multipleDetrendingMain once the elevation parameters are chosen (fitRan: a fit ran and gave R2, elevParIn):
+// significance of the elevation proxy, detrendingElevation, the other proxies' fit and detrendingOtherProxies
+template <int G, int F>
+__device__ void mdFinish(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, bool isLocal, bool fitRan,
+                         double R2, const double* elevParIn, MdFit<Fit<F>::N>& fit)
 {
     constexpr int N = Fit<F>::N;
     const int lane = grpLane<G>();
@@ -105,74 +187,28 @@ __device__ void multipleDetrendingGroup(const LocalModel& m, const LocalStations
     bool elevSig = false;
     double elevPar[N];
 #pragma unroll
-    for (int j = 0; j < N; j++) elevPar[j] = 0;
+    for (int j = 0; j < N; j++) elevPar[j] = elevParIn[j];
     fit.elevR2 = kNoData;
-
-    if (ePos >= 0 && m.selectedActive[ePos]) {
-        // multipleDetrendingElevationFitting (:1862-1953): points with a usable lapse-rate code and an elevation value
-        int nE = 0;
-        for (int base = 0; base < n; base += G) {
-            const int k = base + lane;
-            bool ok = false;
-            float h = 0.f;
-            int i = 0;
-            if (k < n) {
-                i = w.idx[k];
-                h = st.proxy[(size_t)i * nProxy + ePos];
-                ok = checkLapseRateCodeDev(st.code[i], useCode, true) && h != kNoData;
-            }
-            const unsigned b = grpBallot<G>(ok);
-            if (ok) {
-                const int pos = nE + __popc(b & ltMask);
-                w.X[pos] = double(h);
-                w.Y[pos] = double(w.val[k]);
-                w.W[pos] = (w.w[k] != kNoData) ? double(w.w[k]) : 1.;
-                w.act[pos] = st.active[i];
-            }
-            nE += __popc(b);
+    if (fitRan) {
+        fit.elevR2 = float(R2);
+        bool nodataOrZero = false;                                         // isVectorNodataOrZero (:2696-2705)
+#pragma unroll
+        for (int j = 0; j < N; j++) nodataOrZero |= isEqualD(elevPar[j], -9999) || isEqualD(elevPar[j], 0);
+        elevSig = !isEqualD(R2, -9999) || !nodataOrZero;
+    }
+    grpSync<G>();
+    if (elevSig) {
+        // detrendingElevation (:1956-1972): every point of myPoints, including those without an elevation value
+        double pc[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) pc[j] = elevPar[j];
+        Fit<F>::clamp(pc);
+        for (int k = lane; k < n; k += G) {
+            const float h = st.proxy[(size_t)w.idx[k] * nProxy + ePos];
+            const float detrendValue = float(Fit<F>::eval(double(h), pc));
+            w.val[k] -= detrendValue;
         }
         grpSync<G>();
-        // proxyValidity (:1418-1457) on those points
-        bool isValid = false;
-        {
-            double sum = 0;
-            unsigned cnt = 0;
-            for (int j = 0; j < nE; j++)
-                if (w.act[j]) { sum += w.X[j]; cnt++; }
-            if (cnt >= 5) {
-                const double avg = sum / cnt;
-                sum = 0;
-                for (int j = 0; j < nE; j++)
-                    if (w.act[j]) sum += (w.X[j] - avg) * (w.X[j] - avg);
-                const double stdDev = sqrt(sum / (cnt - 1));
-                const float thr = m.stdDevThreshold[ePos];
-                isValid = (thr != kNoData) ? (stdDev > thr) : true;
-            }
-        }
-        if (isLocal) isValid = isValid && unsigned(nE) >= unsigned(m.minPointsLocal);          // local detrending (:1885)
-        if (isValid) {
-            const double R2 = bestFitElevation<G, F>(m.elevMin, m.elevMax, m.elevDelta, &m.firstGuess[0][0], m.nFirstGuess,
-                                                     elevPar, 1000, 0.002, 0.005, w.X, w.Y, w.W, nE);
-            fit.elevR2 = float(R2);
-            bool nodataOrZero = false;                                         // isVectorNodataOrZero (:2696-2705)
-#pragma unroll
-            for (int j = 0; j < N; j++) nodataOrZero |= isEqualD(elevPar[j], -9999) || isEqualD(elevPar[j], 0);
-            elevSig = !isEqualD(R2, -9999) || !nodataOrZero;
-        }
-        grpSync<G>();
-        if (elevSig) {
-            // detrendingElevation (:1956-1972): every point of myPoints, including those without an elevation value
-            double pc[N];
-#pragma unroll
-            for (int j = 0; j < N; j++) pc[j] = elevPar[j];
-            Fit<F>::clamp(pc);
-            for (int k = lane; k < n; k += G) {
-                const float h = st.proxy[(size_t)w.idx[k] * nProxy + ePos];
-                const float detrendValue = float(Fit<F>::eval(double(h), pc));
-                w.val[k] -= detrendValue;
-            }
-            grpSync<G>();
-        }
     }
 
     // multipleDetrendingOtherProxiesFitting (:1975-2171)

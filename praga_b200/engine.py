@@ -20,7 +20,8 @@ class PragaB200Error(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpraga_b200.so")
+    """the in-tree library; PRAGA_B200_LIB selects another BUILD of the same CUDA library (instrumented debug builds)."""
+    return os.environ.get("PRAGA_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpraga_b200.so")
 
 
 def load_library():
