@@ -22,10 +22,13 @@ struct KrigingTargets {
 };
 
 // geometry of the tcgen05 variance kernel (kriging_tc.cu)
-constexpr int kTcCells = 128;          // cells per CTA = MMA M
+constexpr int kTcM = 128;              // MMA M = TMEM lanes
+constexpr int kTcMTiles = 2;           // M tiles per CTA: 256 cells share every L^-1 tile that is loaded
+constexpr int kTcCells = kTcM * kTcMTiles;
 constexpr int kTcNT = 128;             // stations i per MMA N tile
-constexpr int kTcBK = 64;              // stations j per K block
-constexpr int kTcPass = 512;           // stations i per pass = TMEM columns
+constexpr int kTcBK = 32;              // stations j per pipeline stage
+constexpr int kTcPass = 256;           // stations i per pass: 2 M tiles x 256 columns = the 512 TMEM columns
+constexpr int kTcStages = 3;           // shared-memory pipeline depth
 constexpr int kTcTileBytes = kTcNT * kTcBK * 2;     // one FP16 piece of one (i-tile, k-block) tile, canonical UMMA layout
 constexpr int kTcChunk = 1 << 19;      // targets per evaluate() chunk on the tensor path
 

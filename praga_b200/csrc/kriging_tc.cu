@@ -7,14 +7,19 @@
 // c_j = sill - gamma(|p - s_j|);  sum_i weight_i D_i = sill - (|y|^2 - (z.y)(z.y - 1) / |z|^2),  z = M 1.
 //
 // GEMM mapping: D[cell][i] = sum_j A[cell][j] * B[i][j]
-//   A (MMA M = 128 cells x K): c values GENERATED on the fly by the CTA's threads (FP32 variogram of centred FP32
-//     distances), split into FP16 hi + lo, written to shared memory in the canonical K-major no-swizzle UMMA layout;
-//   B (MMA N = 128 stations i x K): M pre-split into FP16 hi + lo and pre-tiled on the host in the same canonical layout,
-//     one 1-D bulk async copy (TMA engine) per 16 KiB tile, completion on an mbarrier; only tiles on or below the
-//     diagonal exist (M is lower triangular) so half of the K range is skipped;
-//   D: FP32 accumulators in TMEM, 4 N-tiles = 512 columns = one pass over 512 stations i; three MMAs per K step
-//     (hi*hi + hi*lo + lo*hi) give ~22 mantissa bits on each product.
-//   Epilogue: tcgen05.ld, thread = cell (TMEM lane), per-thread sums of y^2 and z*y, no cross-lane reduction.
+//   A (2 M tiles x 128 cells x K): c values GENERATED on the fly by 8 generator warps (thread = cell; FP32 variogram of
+//     centred FP32 distances), split into FP16 hi + lo, written to shared memory in the canonical K-major no-swizzle UMMA
+//     layout;
+//   B (N = 128 stations i x K): M pre-split into FP16 hi + lo and pre-tiled on the host in the same canonical layout,
+//     one 1-D bulk async copy (TMA engine) per 16 KiB (hi + lo) tile, completion on an mbarrier; only tiles on or below the
+//     diagonal exist (M is lower triangular) so half of the K range is skipped; every tile that is loaded serves 256 cells
+//     (the L2 -> SM stream of L^-1 is what a 128-cell CTA would be bound by: ~6300 B/clk for the whole chip);
+//   D: FP32 accumulators in TMEM: 2 M tiles x 2 N tiles x 128 columns = 512 columns = one pass over 256 stations i; three
+//     MMAs per K step (hi*hi + hi*lo + lo*hi) give ~22 mantissa bits on each product;
+//   pipeline: kTcStages shared-memory stages of K = 32; warp 8 = loader (station coordinates of the stage + the bulk copies),
+//     warp 9 = MMA issuer (one elected lane, tcgen05.mma + tcgen05.commit on the stage's mbarrier), warps 0-7 generate the A
+//     tiles of stage s+1.. while the tensor core works on stage s; nobody waits for an MMA except to reuse its buffers;
+//   epilogue per pass: tcgen05.ld, thread = cell (TMEM lane), per-thread sums of y^2 and z*y, no cross-lane reduction.
 #include <stdlib.h>
 #include <string.h>
 
@@ -68,55 +73,83 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"): core matrix = 8 rows x 16 B contiguous;
-// LBO = 128 B between the two core matrices of one K = 16 step, SBO = 1024 B between 8-row groups; version 1 (Blackwell)
+// LBO = 128 B between the two core matrices of one K = 16 step, SBO = kTcBK * 16 B between 8-row groups; version 1 (Blackwell)
+constexpr uint32_t kTcSbo = kTcBK * 16;
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
 {
-    return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(128 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46);
+    return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(128 >> 4) << 16) | (uint64_t(kTcSbo >> 4) << 32) | (uint64_t(1) << 46);
 }
 // instruction descriptor: D = F32, A = B = F16, both K-major, N = 128, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (uint32_t(kTcNT >> 3) << 17) | (uint32_t(kTcCells >> 4) << 24);
+constexpr uint32_t kIdesc = (1u << 4) | (uint32_t(kTcNT >> 3) << 17) | (uint32_t(kTcM >> 4) << 24);
 
-__host__ __device__ inline size_t tileOffset(int r, int k) { return size_t(r >> 3) * 1024 + size_t(k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2; }
+__host__ __device__ inline size_t tileOffset(int r, int k) { return size_t(r >> 3) * (kTcBK * 16) + size_t(k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2; }
 
 struct TcParams {
     int n, nPad, nKb, mode;
-    float range, sn;            // sn = sill - nugget
+    float range, invRange, sn;  // sn = sill - nugget
     double sill, zz;
 };
 
-// covariance c = sill - gamma(h) in FP32 (kriging.cpp:160-192 rewritten for c)
+// covariance c = sill - gamma(h) in FP32 (kriging.cpp:160-192 rewritten for c); the model is a template parameter of the
+// kernel so that the generator loop carries no switch, and h / range is a multiplication by the precomputed reciprocal
+template <int MODE>
 __device__ __forceinline__ float covariance(const TcParams& p, float h)
 {
-    const float t = h / p.range;
+    const float t = h * p.invRange;
+    if (MODE == PB_KRIGING_SPHERICAL) return (h < p.range) ? p.sn * fmaf(fmaf(0.5f * t, t, -1.5f), t, 1.f) : 0.f;
+    if (MODE == PB_KRIGING_EXPONENTIAL) return p.sn * __expf(-3.f * t);
+    return p.sn * __expf(-4.f * t * t);
+}
+// run-time form for the CUDA-core check kernel
+__device__ __forceinline__ float covarianceRt(const TcParams& p, float h)
+{
     switch (p.mode) {
-    case PB_KRIGING_SPHERICAL: return (h < p.range) ? p.sn * (1.f - 1.5f * t + 0.5f * t * t * t) : 0.f;
-    case PB_KRIGING_EXPONENTIAL: return p.sn * __expf(-3.f * t);
-    default: return p.sn * __expf(-4.f * t * t);
+    case PB_KRIGING_SPHERICAL: return covariance<PB_KRIGING_SPHERICAL>(p, h);
+    case PB_KRIGING_EXPONENTIAL: return covariance<PB_KRIGING_EXPONENTIAL>(p, h);
+    default: return covariance<PB_KRIGING_GAUSSIAN>(p, h);
     }
 }
 
-constexpr int kTcThreads = 256;
-constexpr int kTcSmem = 2 * kTcTileBytes + 8 * kTcTileBytes + 64 * 8 + 512 * 4 + 2 * 2 * kTcCells * 8;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gen_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the 16 generator warps
 
+constexpr int kTcGenThreads = 2 * kTcCells;             // 512: two threads per cell, each half of a stage's K range / of the columns
+constexpr int kTcGenWarps = kTcGenThreads / 32;
+constexpr int kTcThreads = kTcGenThreads + 64;          // + loader warp + MMA warp
+constexpr int kTcStageA = kTcMTiles * 2 * kTcTileBytes; // 2 M tiles x (hi, lo)
+constexpr int kTcStageB = (kTcPass / kTcNT) * 2 * kTcTileBytes;
+constexpr int kTcStageBytes = kTcStageA + kTcStageB;
+constexpr int kTcSmem = kTcStages * kTcStageBytes + kTcStages * kTcBK * 8 + kTcPass * 4 + 2 * kTcCells * 8 + 1024;
+
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 kriging_variance_tc_kernel(TcParams p, const double* __restrict__ pos, const unsigned char* __restrict__ Mt,
                            const float* __restrict__ z, KrigingTargets t, long long c0, int m, double* __restrict__ q)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sA = smem;                                   // [2 pieces][16 KiB]
-    unsigned char* sB = smem + 2 * kTcTileBytes;                // [4 N tiles][2 pieces][16 KiB]
-    float2* sRel = reinterpret_cast<float2*>(sB + 8 * kTcTileBytes);
-    float* sZ = reinterpret_cast<float*>(sRel + 64);
-    double* sRed = reinterpret_cast<double*>(sZ + 512);         // [2 halves][2 sums][128 cells]
-    __shared__ __align__(8) uint64_t bBar, mmaBar;
+    // stage s: [A: M tile 0 hi, lo, M tile 1 hi, lo][B: N tile 0 hi, lo, N tile 1 hi, lo]
+    float2* sRel = reinterpret_cast<float2*>(smem + kTcStages * kTcStageBytes);       // [stage][kTcBK]
+    float* sZ = reinterpret_cast<float*>(sRel + kTcStages * kTcBK);                   // [kTcPass]
+    double* sRed = reinterpret_cast<double*>(sZ + kTcPass);                           // [2 sums][kTcCells]
+    __shared__ __align__(8) uint64_t relFull[kTcStages], aFull[kTcStages], bFull[kTcStages], mmaDone[kTcStages], passDone,
+        tmemFree;
     __shared__ uint32_t tmemBase;
     __shared__ double sCenter[2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long tile0 = (long long)blockIdx.x * kTcCells;
     if (tid == 0) {
-        mbar_init(&bBar, 1);
-        mbar_init(&mmaBar, 1);
+        for (int s = 0; s < kTcStages; s++) {
+            mbar_init(&relFull[s], 32);
+            mbar_init(&aFull[s], kTcGenThreads);
+            mbar_init(&bFull[s], 1);
+            mbar_init(&mmaDone[s], 1);
+        }
+        mbar_init(&passDone, 1);
+        mbar_init(&tmemFree, kTcGenThreads);
         mbar_fence_init();
         double cx, cy;
         // centre of the tile: its first target (the tile is spatially compact, station offsets reach ~1e6 m)
@@ -139,130 +172,186 @@ kriging_variance_tc_kernel(TcParams p, const double* __restrict__ pos, const uns
     tc_fence_after();
     const uint32_t tmem = tmemBase;
     const double cx = sCenter[0], cy = sCenter[1];
-
-    // this thread's cell (= MMA row = TMEM lane) and its half of the K block / of the accumulator columns
-    const int r = tid & (kTcCells - 1), half = tid >> 7;
-    const long long cidx = tile0 + r;
-    const bool valid = cidx < m;
-    float xr = 0.f, yr = 0.f;
-    if (valid) {
-        double x, y;
-        if (t.xy) { x = t.xy[2 * (c0 + cidx)]; y = t.xy[2 * (c0 + cidx) + 1]; }
-        else {
-            const int cell = t.validIdx[c0 + cidx];
-            const int row = cell / t.grid.nrCols, col = cell - row * t.grid.nrCols;
-            x = t.grid.llx + t.grid.cellSize * (col + 0.5);
-            y = t.grid.lly + t.grid.cellSize * (t.grid.nrRows - row - 0.5);
-        }
-        xr = float(x - cx);
-        yr = float(y - cy);
-    }
-    double accY2 = 0., accZY = 0.;
-    uint32_t it = 0;
     const int nPasses = (p.nPad + kTcPass - 1) / kTcPass;
 
-    for (int pass = 0; pass < nPasses; pass++) {
-        const int i0p = pass * kTcPass;
-        const int nT = min(kTcPass / kTcNT, (p.nPad - i0p) / kTcNT);
-        const int kbEnd = min(p.nKb, (i0p + nT * kTcNT) / kTcBK);
-        for (int i = tid; i < kTcPass; i += kTcThreads) sZ[i] = (i0p + i < p.nPad) ? z[i0p + i] : 0.f;
-
-        for (int kb = 0; kb < kbEnd; kb++) {
-            const int j0 = kb * kTcBK;
-            if (tid < kTcBK) {
-                const int j = j0 + tid;
-                sRel[tid] = (j < p.n) ? make_float2(float(pos[2 * j] - cx), float(pos[2 * j + 1] - cy))
-                                      : make_float2(1e18f, 1e18f);      // padding: covariance 0 against zero columns of M
-            }
-            if (tid == 0) {
-                int cnt = 0;
-                for (int tt = 0; tt < nT; tt++) cnt += (j0 <= i0p + tt * kTcNT + kTcNT - 1);
-                mbar_expect_tx(&bBar, uint32_t(cnt) * 2u * kTcTileBytes);
-                for (int tt = 0; tt < nT; tt++)
-                    if (j0 <= i0p + tt * kTcNT + kTcNT - 1) {
-                        const size_t itile = size_t(i0p / kTcNT + tt);
-                        bulk_g2s(sB + size_t(tt) * 2 * kTcTileBytes, Mt + (itile * p.nKb + kb) * 2 * kTcTileBytes,
-                                 2 * kTcTileBytes, &bBar);
-                    }
-            }
-            __syncthreads();
-            // ---- generate the A tile: 128 cells x 64 stations, this thread: row r, 32 stations of its half ----
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const int k0 = half * 32 + g * 8;
-                __half2 hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    float c2[2];
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const float2 s = sRel[k0 + 2 * e + u];
-                        const float dx = s.x - xr, dy = s.y - yr;
-                        c2[u] = covariance(p, sqrtf(dx * dx + dy * dy));
-                    }
-                    const __half2 h2 = __floats2half2_rn(c2[0], c2[1]);
-                    const float2 back = __half22float2(h2);
-                    hi[e] = h2;
-                    lo[e] = __floats2half2_rn(c2[0] - back.x, c2[1] - back.y);
+    if (warp == kTcGenWarps) {
+        // ------------------------------------------------------------ loader: station coordinates + L^-1 tiles of each stage
+        uint32_t it = 0;
+        for (int pass = 0; pass < nPasses; pass++) {
+            const int i0p = pass * kTcPass;
+            const int nT = min(kTcPass / kTcNT, (p.nPad - i0p) / kTcNT);
+            const int kbEnd = min(p.nKb, (i0p + nT * kTcNT) / kTcBK);
+            for (int kb = 0; kb < kbEnd; kb++, it++) {
+                const int s = it % kTcStages;
+                const uint32_t u = it / kTcStages;
+                if (u > 0) mbar_wait(&mmaDone[s], (u - 1) & 1);            // the MMAs that read this stage's buffers are done
+                const int j0 = kb * kTcBK, j = j0 + lane;
+                // pairs of stations as {x0, x1, y0, y1}: the generators load a pair's x (y) as one packed FP32x2 operand;
+                // padding stations sit far away: covariance 0 against the zero columns of M
+                float* relS = reinterpret_cast<float*>(sRel + s * kTcBK) + (lane >> 1) * 4 + (lane & 1);
+                relS[0] = (j < p.n) ? float(pos[2 * j] - cx) : 1e18f;
+                relS[2] = (j < p.n) ? float(pos[2 * j + 1] - cy) : 1e18f;
+                mbar_arrive(&relFull[s]);
+                if (lane == 0) {
+                    unsigned char* sB = smem + s * kTcStageBytes + kTcStageA;
+                    int cnt = 0;
+                    for (int tt = 0; tt < nT; tt++) cnt += (j0 <= i0p + tt * kTcNT + kTcNT - 1);
+                    mbar_expect_tx(&bFull[s], uint32_t(cnt) * 2u * kTcTileBytes);
+                    for (int tt = 0; tt < nT; tt++)
+                        if (j0 <= i0p + tt * kTcNT + kTcNT - 1) {
+                            const size_t itile = size_t(i0p / kTcNT + tt);
+                            bulk_g2s(sB + size_t(tt) * 2 * kTcTileBytes, Mt + (itile * p.nKb + kb) * 2 * kTcTileBytes,
+                                     2 * kTcTileBytes, &bFull[s]);
+                        }
                 }
-                const size_t off = tileOffset(r, k0);
-                *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<const uint4*>(hi);
-                *reinterpret_cast<uint4*>(sA + kTcTileBytes + off) = *reinterpret_cast<const uint4*>(lo);
+                __syncwarp();
             }
-            fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
-            __syncthreads();
-            if (tid == 0) {
-                mbar_wait(&bBar, it & 1);
-                tc_fence_after();
-                const uint32_t aHi = smem_u32(sA), aLo = aHi + kTcTileBytes;
-                for (int tt = 0; tt < nT; tt++) {
-                    if (!(j0 <= i0p + tt * kTcNT + kTcNT - 1)) continue;
-                    const uint32_t bHi = smem_u32(sB) + uint32_t(tt) * 2 * kTcTileBytes, bLo = bHi + kTcTileBytes;
-                    const uint32_t d = tmem + uint32_t(tt * kTcNT);
-#pragma unroll
-                    for (int ks = 0; ks < kTcBK / 16; ks++) {
-                        const uint32_t o = ks * 256;
-                        umma_f16(d, umma_desc(aHi + o), umma_desc(bHi + o), kIdesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                        umma_f16(d, umma_desc(aHi + o), umma_desc(bLo + o), kIdesc, 1u);
-                        umma_f16(d, umma_desc(aLo + o), umma_desc(bHi + o), kIdesc, 1u);
-                    }
-                }
-                umma_commit(&mmaBar);
-            }
-            mbar_wait(&mmaBar, it & 1);     // every thread: the MMAs have consumed this block's shared memory
-            tc_fence_after();
-            it++;
         }
-
-        // ---- epilogue of the pass: thread = cell (TMEM lane), columns = stations i of this pass ----
+    } else if (warp == kTcGenWarps + 1) {
+        // ------------------------------------------------------------ MMA issuer (one elected lane)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int pass = 0; pass < nPasses; pass++) {
+                const int i0p = pass * kTcPass;
+                const int nT = min(kTcPass / kTcNT, (p.nPad - i0p) / kTcNT);
+                const int kbEnd = min(p.nKb, (i0p + nT * kTcNT) / kTcBK);
+                if (pass > 0) {
+                    mbar_wait(&tmemFree, (pass - 1) & 1);                  // the epilogue has read the accumulators
+                    tc_fence_after();
+                }
+                for (int kb = 0; kb < kbEnd; kb++, it++) {
+                    const int s = it % kTcStages;
+                    const uint32_t ph = (it / kTcStages) & 1;
+                    const int j0 = kb * kTcBK;
+                    mbar_wait(&aFull[s], ph);
+                    mbar_wait(&bFull[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * kTcStageBytes), sb = sa + kTcStageA;
+                    for (int mt = 0; mt < kTcMTiles; mt++) {
+                        const uint32_t aHi = sa + uint32_t(mt) * 2 * kTcTileBytes, aLo = aHi + kTcTileBytes;
+                        for (int tt = 0; tt < nT; tt++) {
+                            if (!(j0 <= i0p + tt * kTcNT + kTcNT - 1)) continue;
+                            const uint32_t bHi = sb + uint32_t(tt) * 2 * kTcTileBytes, bLo = bHi + kTcTileBytes;
+                            const uint32_t d = tmem + uint32_t(mt * kTcPass + tt * kTcNT);
+#pragma unroll
+                            for (int ks = 0; ks < kTcBK / 16; ks++) {
+                                const uint32_t o = ks * 256;
+                                umma_f16(d, umma_desc(aHi + o), umma_desc(bHi + o), kIdesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                                umma_f16(d, umma_desc(aHi + o), umma_desc(bLo + o), kIdesc, 1u);
+                                umma_f16(d, umma_desc(aLo + o), umma_desc(bHi + o), kIdesc, 1u);
+                            }
+                        }
+                    }
+                    umma_commit(&mmaDone[s]);                               // frees the stage once these MMAs have run
+                    if (kb == kbEnd - 1) umma_commit(&passDone);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ generators: two threads per cell (= MMA row = TMEM lane)
+        const int cellInCta = tid & (kTcCells - 1), kh = tid >> 8;        // kh: which half of the stage / of the columns
+        const int mt = cellInCta >> 7, r = cellInCta & (kTcM - 1);
+        const long long cidx = tile0 + cellInCta;
+        const bool valid = cidx < m;
+        float xr = 0.f, yr = 0.f;
+        if (valid) {
+            double x, y;
+            if (t.xy) { x = t.xy[2 * (c0 + cidx)]; y = t.xy[2 * (c0 + cidx) + 1]; }
+            else {
+                const int cell = t.validIdx[c0 + cidx];
+                const int row = cell / t.grid.nrCols, col = cell - row * t.grid.nrCols;
+                x = t.grid.llx + t.grid.cellSize * (col + 0.5);
+                y = t.grid.lly + t.grid.cellSize * (t.grid.nrRows - row - 0.5);
+            }
+            xr = float(x - cx);
+            yr = float(y - cy);
+        }
+        double accY2 = 0., accZY = 0.;
+        uint32_t it = 0;
         const uint32_t laneBase = uint32_t((warp & 3) * 32) << 16;
-        for (int cb = 0; cb < (kTcPass / 2) / 32; cb++) {
-            const int col = half * (kTcPass / 2) + cb * 32;
-            if (col >= nT * kTcNT) break;
-            uint32_t v[32];
-            tmem_ld32(tmem + laneBase + uint32_t(col), v);
-            float y2 = 0.f, zy = 0.f;
+        const f32x2 nxr2 = pack2(-xr, -xr), nyr2 = pack2(-yr, -yr);
+        const float sphA = 0.5f * p.sn * p.invRange * p.invRange * p.invRange, sphNB = -1.5f * p.sn * p.invRange;
+        const f32x2 sphA2 = pack2(sphA, sphA), sphNB2 = pack2(sphNB, sphNB), sn2 = pack2(p.sn, p.sn);
+        const float range2 = p.range * p.range;
+        for (int pass = 0; pass < nPasses; pass++) {
+            const int i0p = pass * kTcPass;
+            const int nT = min(kTcPass / kTcNT, (p.nPad - i0p) / kTcNT);
+            const int kbEnd = min(p.nKb, (i0p + nT * kTcNT) / kTcBK);
+            for (int kb = 0; kb < kbEnd; kb++, it++) {
+                const int s = it % kTcStages;
+                const uint32_t u = it / kTcStages;
+                if (u > 0) mbar_wait(&mmaDone[s], (u - 1) & 1);            // A[s] is free again
+                mbar_wait(&relFull[s], u & 1);
+                unsigned char* sA = smem + s * kTcStageBytes + size_t(mt) * 2 * kTcTileBytes;
+                const ulonglong2* rel = reinterpret_cast<const ulonglong2*>(sRel + s * kTcBK);     // [pair] = {x0 x1, y0 y1}
 #pragma unroll
-            for (int e = 0; e < 32; e++) {
-                const float y = __uint_as_float(v[e]);
-                y2 = fmaf(y, y, y2);
-                zy = fmaf(sZ[col + e], y, zy);
+                for (int g = 0; g < kTcBK / 16; g++) {
+                    const int k0 = kh * (kTcBK / 2) + g * 8;
+                    __half2 hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const ulonglong2 sxy = rel[(k0 >> 1) + e];
+                        const f32x2 dx = add2(sxy.x, nxr2), dy = add2(sxy.y, nyr2);
+                        const f32x2 d2p = fma2(dx, dx, mul2(dy, dy));
+                        float d2a, d2b, c0v, c1v;
+                        unpack2(d2p, d2a, d2b);
+                        if (MODE == PB_KRIGING_SPHERICAL) {
+                            // sn (1 - 1.5 t + 0.5 t^3), t = h / range, as h (h^2 A - B) + sn with h^2 = d2 already at hand
+                            const f32x2 rs = pack2(rsqrt_approx(fmaxf(d2a, 1e-30f)), rsqrt_approx(fmaxf(d2b, 1e-30f)));
+                            const f32x2 h = mul2(d2p, rs);
+                            const f32x2 c = fma2(h, fma2(d2p, sphA2, sphNB2), sn2);
+                            unpack2(c, c0v, c1v);
+                            c0v = (d2a < range2) ? c0v : 0.f;
+                            c1v = (d2b < range2) ? c1v : 0.f;
+                        } else {
+                            c0v = covariance<MODE>(p, d2a * rsqrt_approx(fmaxf(d2a, 1e-30f)));
+                            c1v = covariance<MODE>(p, d2b * rsqrt_approx(fmaxf(d2b, 1e-30f)));
+                        }
+                        const __half2 h2 = __floats2half2_rn(c0v, c1v);
+                        const float2 back = __half22float2(h2);
+                        hi[e] = h2;
+                        lo[e] = __floats2half2_rn(c0v - back.x, c1v - back.y);
+                    }
+                    const size_t off = tileOffset(r, k0);
+                    *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<const uint4*>(hi);
+                    *reinterpret_cast<uint4*>(sA + kTcTileBytes + off) = *reinterpret_cast<const uint4*>(lo);
+                }
+                fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+                mbar_arrive(&aFull[s]);
             }
-            accY2 += double(y2);
-            accZY += double(zy);
+            // ---- epilogue of the pass: columns = stations i of this pass, split between the two threads of a cell ----
+            if (tid < kTcPass) sZ[tid] = (i0p + tid < p.nPad) ? z[i0p + tid] : 0.f;
+            mbar_wait(&passDone, pass & 1);
+            tc_fence_after();
+            gen_bar_sync();
+            const int nCb = nT * kTcNT / 32;
+            for (int cb = kh; cb < nCb; cb += 2) {
+                uint32_t v[32];
+                tmem_ld32(tmem + laneBase + uint32_t(mt * kTcPass + cb * 32), v);
+                float y2 = 0.f, zy = 0.f;
+#pragma unroll
+                for (int e = 0; e < 32; e++) {
+                    const float y = __uint_as_float(v[e]);
+                    y2 = fmaf(y, y, y2);
+                    zy = fmaf(sZ[cb * 32 + e], y, zy);
+                }
+                accY2 += double(y2);
+                accZY += double(zy);
+            }
+            tc_fence_before();
+            gen_bar_sync();                     // sZ is rewritten for the next pass
+            mbar_arrive(&tmemFree);
         }
-        tc_fence_before();
-        __syncthreads();        // TMEM and sZ are rewritten by the next pass
+        if (kh == 1) { sRed[cellInCta] = accY2; sRed[kTcCells + cellInCta] = accZY; }
+        gen_bar_sync();
+        if (kh == 0 && valid) {
+            const double y2 = accY2 + sRed[cellInCta], zy = accZY + sRed[kTcCells + cellInCta];
+            q[cidx] = p.sill - (y2 - zy * (zy - 1.) / p.zz);      // = sum_i weight_i D_i of krigingRMSE
+        }
     }
-
-    sRed[(half * 2 + 0) * kTcCells + r] = accY2;
-    sRed[(half * 2 + 1) * kTcCells + r] = accZY;
+    tc_fence_before();
     __syncthreads();
-    if (half == 0 && valid) {
-        const double y2 = sRed[0 * kTcCells + r] + sRed[2 * kTcCells + r];
-        const double zy = sRed[1 * kTcCells + r] + sRed[3 * kTcCells + r];
-        q[cidx] = p.sill - (y2 - zy * (zy - 1.) / p.zz);      // = sum_i weight_i D_i of krigingRMSE
-    }
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -293,7 +382,7 @@ __global__ void kriging_variance_simple_kernel(TcParams p, const double* __restr
             const float mh = __half2float(*reinterpret_cast<const __half*>(tile + off));
             const float ml = __half2float(*reinterpret_cast<const __half*>(tile + kTcTileBytes + off));
             const float dx = float(pos[2 * j] - x), dy = float(pos[2 * j + 1] - y);
-            const float cj = covariance(p, sqrtf(dx * dx + dy * dy));
+            const float cj = covarianceRt(p, sqrtf(dx * dx + dy * dy));
             yi += (mh + ml) * cj;
         }
         y2 += double(yi) * yi;
@@ -358,6 +447,7 @@ cudaError_t launchKrigingVarianceTc(const KrigingSystem& k, const KrigingTargets
     p.nKb = k.nKb;
     p.mode = k.params.mode;
     p.range = float(k.params.range);
+    p.invRange = 1.f / p.range;
     p.sn = float(k.params.sillNugget);
     p.sill = k.params.sill;
     p.zz = k.zz;
@@ -366,14 +456,20 @@ cudaError_t launchKrigingVarianceTc(const KrigingSystem& k, const KrigingTargets
         kriging_variance_simple_kernel<<<(m + 127) / 128, 128, 0, s>>>(p, k.dPos, k.dMhi, k.dZ, t, c0, m, q);
         return cudaGetLastError();
     }
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(kriging_variance_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
     const int grid = (m + kTcCells - 1) / kTcCells;
-    kriging_variance_tc_kernel<<<grid, kTcThreads, kTcSmem, s>>>(p, k.dPos, k.dMhi, k.dZ, t, c0, m, q);
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, kTcThreads, kTcSmem, s>>>(p, k.dPos, k.dMhi, k.dZ, t, c0, m, q);
+        return cudaSuccess;
+    };
+    cudaError_t e;
+    switch (p.mode) {
+    case PB_KRIGING_SPHERICAL: e = launch(kriging_variance_tc_kernel<PB_KRIGING_SPHERICAL>); break;
+    case PB_KRIGING_EXPONENTIAL: e = launch(kriging_variance_tc_kernel<PB_KRIGING_EXPONENTIAL>); break;
+    default: e = launch(kriging_variance_tc_kernel<PB_KRIGING_GAUSSIAN>); break;
+    }
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

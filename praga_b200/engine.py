@@ -254,15 +254,17 @@ class Engine:
         self._check(self.lib.pb_kriging_points(self.h, kid, A.dptr(xy), m, A.dptr(res), A.dptr(rm) if want_rmse else None))
         return res, (rm if want_rmse else None)
 
-    def kriging_raster(self, kid, dem_id, shape, row_begin=0, row_end=-1, want_rmse=True, device_only=False):
+    def kriging_raster(self, kid, dem_id, shape, row_begin=0, row_end=-1, want_rmse=True, device_only=False, est_out=None,
+                       rmse_out=None):
+        """estimate (and RMSE) grids over the valid cells of a resident DEM. est_out / rmse_out: reusable host grids."""
         est = A.pb_raster_out()
         rm = A.pb_raster_out()
         e = r = None
         if not device_only:
-            e = np.empty(shape, dtype=np.float32)
+            e = est_out if est_out is not None else np.empty(shape, dtype=np.float32)
             est.data = A.fptr(e)
             if want_rmse:
-                r = np.empty(shape, dtype=np.float32)
+                r = rmse_out if rmse_out is not None else np.empty(shape, dtype=np.float32)
                 rm.data = A.fptr(r)
         self._check(self.lib.pb_kriging_raster(self.h, kid, dem_id, row_begin, row_end, C.byref(est),
                                                C.byref(rm) if want_rmse else None))
