@@ -607,7 +607,9 @@ def main():
     # torchrun pins OMP_NUM_THREADS=1; the drop-in call gathers/scatters host rasters with the host cores, so every rank
     # gets its share of them (must be set before libgomp starts, i.e. before the engine library runs a parallel region)
     if world > 1:
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
+        # the reference arm runs on rank 0 alone and gets every host core
+        share = 1 if args.impl == "reference" else world
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // share))
 
     if args.impl == "reference":
         if args.workload in GENERIC:

@@ -228,6 +228,10 @@ typedef struct pb_cv_points {
     const uint8_t* isInsideDem;    /* Crit3DMeteoPoint::isInsideDem; NULL => all inside */
     int32_t excludeOutsideDem;     /* getUseExcludeStationsOutsideDEM() */
     int32_t reserved;
+    /* pb_spatial_quality_control only: n * nProxy values, row k = what the reference passes for the k-th SUSPECT of the
+     * second pass: meteoPoints[k].getProxyValues() with k counted over the caller's FULL meteo-point vector, not the
+     * suspect's own entry (spatialControl.cpp:393). NULL => st->proxyValues (every meteo point active and accepted). */
+    const float* suspectProxyValues;
 } pb_cv_points;
 #define PB_MAX_KH_SERIES 64
 typedef struct pb_kh_series {      /* Crit3DInterpolationSettings::Kh_series / Kh_error_series (interpolationSettings.cpp:134) */

@@ -40,6 +40,9 @@ def load_shim():
     lib.shim_compute_residuals.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_uint8), P(C.c_float)]
     lib.shim_pre_interpolation.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_cv_points), P(A.pb_raster),
                                            P(C.c_uint8), P(A.pb_kh_series), C.c_char_p, C.c_int]
+    lib.shim_spatial_quality_control.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_cv_points), P(A.pb_raster),
+                                                 P(C.c_uint8)]
+    lib.shim_compute_residuals_local.argtypes = lib.shim_compute_residuals.argtypes
     lib.shim_kriging_points.argtypes = [P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                         C.c_double, P(C.c_double), C.c_int, P(C.c_double), P(C.c_double)]
     return lib

@@ -104,6 +104,67 @@ int shim_pre_interpolation(pb_stations* st, pb_settings* s, int variable, const 
     return ok ? PB_OK : PB_ERR_FIT;
 }
 
+/* pragab200::spatialQualityControl on reference Crit3DMeteoPoint objects; same outputs as ref_spatial_quality_control */
+int shim_spatial_quality_control(const pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv, const pb_raster* dem,
+                                 uint8_t* wrongSpatial)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    gis::Crit3DRasterGrid demGrid;
+    if (dem) {
+        fillGrid(demGrid, *dem);
+        sc.settings.setCurrentDEM(&demGrid);
+    }
+    sc.settings.setUseExcludeStationsOutsideDEM(cv && cv->excludeOutsideDem);
+    std::vector<Crit3DMeteoPoint> mp(st->n);
+    for (int i = 0; i < st->n; i++) {
+        mp[i].active = true;
+        mp[i].quality = quality::accepted;
+        mp[i].currentValue = (cv && cv->currentValue) ? cv->currentValue[i] : st->value[i];
+        mp[i].point.utm.x = st->x[i];
+        mp[i].point.utm.y = st->y[i];
+        mp[i].point.z = st->z[i];
+        mp[i].isInsideDem = (cv && cv->isInsideDem) ? cv->isInsideDem[i] != 0 : true;
+        mp[i].lapseRateCode = st->lapseRateCode ? lapseRateCodeType(st->lapseRateCode[i]) : primary;
+        for (int k = 0; k < st->nProxy; k++) mp[i].proxyValues.push_back(st->proxyValues[size_t(i) * st->nProxy + k]);
+    }
+    std::string err;
+    bool ok = pragab200::spatialQualityControl(meteoVariable(variable), mp, sc.settings, &sc.meteoSettings, &sc.climate, sc.time, err);
+    for (int i = 0; i < st->n; i++) wrongSpatial[i] = mp[i].quality == quality::wrong_spatial ? 1 : 0;
+    exportSettings(sc, *s);
+    s->pointsBoundingBoxArea = sc.settings.getPointsBoundingBoxArea();
+    std::vector<double> pr = sc.settings.getPointsRange();
+    if (pr.size() == 2) { s->hasPointsRange = 1; s->pointsRangeMin = pr[0]; s->pointsRangeMax = pr[1]; }
+    return ok ? PB_OK : PB_ERR_FIT;
+}
+
+/* pragab200::computeResidualsLocalDetrending on reference objects */
+int shim_compute_residuals_local(const pb_stations* st, const pb_settings* s, int variable, const float* observed,
+                                 const uint8_t* useForCv, float* residual)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    std::vector<Crit3DMeteoPoint> mp(st->n);
+    for (int i = 0; i < st->n; i++) {
+        mp[i].active = useForCv ? useForCv[i] != 0 : true;
+        mp[i].quality = quality::accepted;
+        mp[i].currentValue = observed[i];
+        mp[i].point.utm.x = st->x[i];
+        mp[i].point.utm.y = st->y[i];
+        mp[i].point.z = st->z[i];
+        mp[i].isInsideDem = true;
+        mp[i].lapseRateCode = st->lapseRateCode ? lapseRateCodeType(st->lapseRateCode[i]) : primary;
+        for (int k = 0; k < st->nProxy; k++) mp[i].proxyValues.push_back(st->proxyValues[size_t(i) * st->nProxy + k]);
+        sc.points[i].index = i;
+    }
+    if (!setMultipleDetrendingHeightTemperatureRange(sc.settings)) return PB_ERR_FIT;
+    bool ok = pragab200::computeResidualsLocalDetrending(meteoVariable(variable), sc.time, mp, sc.points, sc.settings,
+                                                         &sc.meteoSettings, &sc.climate, true, true);
+    for (int i = 0; i < st->n; i++) residual[i] = mp[i].residual;
+    return ok ? PB_OK : PB_ERR_INVALID;
+}
+
 /* the stateful kriging API of kriging.h through the shim */
 int shim_kriging_points(const double* pos, const double* val, int n, int mode, double range, double nugget, double sill,
                         double slope, const double* xy, int m, double* result, double* rmse)

@@ -110,7 +110,7 @@ class pb_cv_stats(C.Structure):
 
 class pb_cv_points(C.Structure):
     _fields_ = [("currentValue", C.POINTER(C.c_float)), ("isInsideDem", C.POINTER(C.c_uint8)),
-                ("excludeOutsideDem", C.c_int32), ("reserved", C.c_int32)]
+                ("excludeOutsideDem", C.c_int32), ("reserved", C.c_int32), ("suspectProxyValues", C.POINTER(C.c_float))]
 
 
 PB_MAX_KH_SERIES = 64

@@ -787,6 +787,9 @@ extern "C" int pb_spatial_quality_control(pb_context* ctx, const pb_stations* st
     for (size_t k = 0; k < listIndex.size(); k++) proxyFrom[k] = int(k);
     LooArrays b;
     fillTargets(b, st, listIndex, proxyFrom, observed, inside, P);
+    if (cv && cv->suspectProxyValues)
+        for (size_t k = 0; k < listIndex.size(); k++)
+            for (int q = 0; q < P; q++) b.tproxy[k * std::max(P, 1) + q] = cv->suspectProxyValues[k * size_t(st->nProxy) + q];
     fillSources(b, &ptsB.st, keepB.data());
     std::vector<float> est(listIndex.size());
     std::vector<float> dummy(listIndex.size());

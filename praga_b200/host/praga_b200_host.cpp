@@ -405,6 +405,116 @@ bool computeResiduals(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoP
     return true;
 }
 
+bool computeResidualsLocalDetrending(meteoVariable myVar, const Crit3DTime& myTime, std::vector<Crit3DMeteoPoint>& meteoPoints,
+                                     std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                                     Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                                     Crit3DClimateParameters* climateParameters, bool excludeOutsideDem, bool excludeSupplemental)
+{
+    (void)myTime; (void)climateParameters;
+    if (myVar == noMeteoVar) return false;
+    pb_context* ctx = context();
+    if (!ctx) return false;
+    pb_settings s;
+    std::vector<pb_raster> grids;
+    if (!flattenSettings(interpolationSettings, meteoSettings, s, grids, nullptr)) return false;
+    FlatPoints fp;
+    flattenPoints(interpolationPoints, s.nProxy, fp);
+    // targets = the meteo points computeResidualsLocalDetrending evaluates (spatialControl.cpp:176-183)
+    std::vector<float> x, y, est;
+    std::vector<double> pv;
+    std::vector<size_t> who;
+    for (size_t i = 0; i < meteoPoints.size(); i++) {
+        meteoPoints[i].residual = NODATA;
+        if (!meteoPoints[i].active) continue;
+        bool isValid = (!excludeSupplemental || checkLapseRateCode(meteoPoints[i].lapseRateCode, interpolationSettings.getUseLapseRateCode(), false));
+        isValid = (isValid && (!excludeOutsideDem || meteoPoints[i].isInsideDem));
+        if (!(isValid && meteoPoints[i].quality == quality::accepted)) continue;
+        who.push_back(i);
+        x.push_back(float(meteoPoints[i].point.utm.x));
+        y.push_back(float(meteoPoints[i].point.utm.y));
+        std::vector<double> v = meteoPoints[i].getProxyValues();
+        for (int k = 0; k < s.nProxy; k++) pv.push_back(k < int(v.size()) ? v[k] : double(NODATA));
+    }
+    est.resize(who.size());
+    if (!who.empty()) {
+        // the inner localSelection / interpolate run with excludeSupplemental = false (the shadowing local, :186)
+        const int rc = pb_local_detrending_points(ctx, &fp.st, &s, int(myVar), x.data(), y.data(), pv.data(), int(who.size()), 0, est.data());
+        if (failed(ctx, rc)) return false;
+    }
+    for (size_t k = 0; k < who.size(); k++) {
+        Crit3DMeteoPoint& mp = meteoPoints[who[k]];
+        float myValue = mp.currentValue, interpolatedValue = est[k];
+        if (myVar == precipitation || myVar == dailyPrecipitation) {
+            if (myValue != NODATA && myValue < meteoSettings->getRainfallThreshold()) myValue = 0.;
+            if (interpolatedValue != NODATA && interpolatedValue < meteoSettings->getRainfallThreshold()) interpolatedValue = 0.;
+        }
+        if ((interpolatedValue != NODATA) && (myValue != NODATA)) mp.residual = myValue - interpolatedValue;
+    }
+    return true;
+}
+
+bool spatialQualityControl(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoPoints,
+                           Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                           Crit3DClimateParameters* climateParameters, const Crit3DTime& myTime, std::string& errorStr)
+{
+    pb_context* ctx = context();
+    if (!ctx) { errorStr = g_error; return false; }
+    pb_settings s;
+    std::vector<pb_raster> grids;
+    gis::Crit3DRasterGrid* dem = interpolationSettings.getCurrentDEM();
+    if (!flattenSettings(interpolationSettings, meteoSettings, s, grids, dem)) { errorStr = g_error; return false; }
+    s.climateLapseRate = climateParameters ? climateParameters->getClimateLapseRate(myVar, myTime) : 0.f;
+    // the points passDataToInterpolation would take (spatialControl.cpp:510-516): active, accepted, selected if a selection exists
+    bool isSelection = false;
+    for (const auto& mp : meteoPoints) if (mp.selected) { isSelection = true; break; }
+    std::vector<size_t> who;
+    for (size_t i = 0; i < meteoPoints.size(); i++)
+        if (meteoPoints[i].active && meteoPoints[i].quality == quality::accepted && (!isSelection || meteoPoints[i].selected)) who.push_back(i);
+    const int n = int(who.size()), P = s.nProxy, Pp = std::max(P, 1);
+    if (n == 0) return true;
+    std::vector<double> x(n), y(n), z(n);
+    std::vector<float> value(n), proxy(size_t(n) * Pp, float(NODATA)), suspect(size_t(n) * Pp, float(NODATA));
+    std::vector<int32_t> code(n);
+    std::vector<uint8_t> inside(n), wrong(n, 0);
+    for (int k = 0; k < n; k++) {
+        const Crit3DMeteoPoint& mp = meteoPoints[who[k]];
+        x[k] = mp.point.utm.x; y[k] = mp.point.utm.y; z[k] = mp.point.z;
+        value[k] = mp.currentValue;
+        code[k] = int(mp.lapseRateCode);
+        inside[k] = mp.isInsideDem;
+        for (int q = 0; q < P && q < int(mp.proxyValues.size()); q++) proxy[size_t(k) * P + q] = mp.proxyValues[q];
+        // second pass: the reference reads meteoPoints[k] (k = position in the suspect list), spatialControl.cpp:393
+        if (size_t(k) < meteoPoints.size())
+            for (int q = 0; q < P && q < int(meteoPoints[k].proxyValues.size()); q++) suspect[size_t(k) * P + q] = meteoPoints[k].proxyValues[q];
+    }
+    pb_stations st;
+    memset(&st, 0, sizeof(st));
+    st.n = n; st.nProxy = P;
+    st.x = x.data(); st.y = y.data(); st.z = z.data(); st.value = value.data();
+    st.lapseRateCode = code.data(); st.proxyValues = proxy.data();
+    pb_cv_points cv;
+    memset(&cv, 0, sizeof(cv));
+    cv.isInsideDem = inside.data();
+    cv.excludeOutsideDem = interpolationSettings.getUseExcludeStationsOutsideDEM();
+    cv.suspectProxyValues = suspect.data();
+    pb_raster_id demId = -1;
+    const bool needDem = s.useTD && !s.useLocalDetrending && !s.useGlocalDetrending;
+    if (needDem && dem != nullptr && dem->isLoaded) {
+        pb_raster r = rasterOf(*dem);
+        if (failed(ctx, pb_raster_upload(ctx, &r, &demId))) { errorStr = g_error; return false; }
+    }
+    const int rc = pb_spatial_quality_control(ctx, &st, &s, int(myVar), &cv, demId, wrong.data());
+    if (demId >= 0) pb_raster_free(ctx, demId);
+    if (rc == PB_ERR_FIT) { errorStr = "Error in function preInterpolation"; return false; }
+    if (failed(ctx, rc)) { errorStr = g_error; return false; }
+    pb_kh_series kh;
+    memset(&kh, 0, sizeof(kh));
+    writeBackSettings(s, interpolationSettings, kh);
+    for (int k = 0; k < n; k++)
+        if (wrong[k]) meteoPoints[who[k]].quality = quality::wrong_spatial;
+    return true;
+}
+
 bool krigingVariogram(double* myPos, double* myVal, int nrItems, short myMode, double myRange, double myNugget,
                       double mySill, double mySlope)
 {

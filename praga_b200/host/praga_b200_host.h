@@ -10,6 +10,8 @@
  *   pragab200::preInterpolation               <- agrolib/interpolation/interpolation.h (.cpp:2444-2499): precipitation check,
  *                                                multiple detrending, classic detrending(), optimalDetrending(), kh search
  *   pragab200::computeResiduals               <- agrolib/interpolation/spatialControl.h:30 (.cpp:97-155)
+ *   pragab200::computeResidualsLocalDetrending <- agrolib/interpolation/spatialControl.h (.cpp:158-228)
+ *   pragab200::spatialQualityControl          <- agrolib/interpolation/spatialControl.h (.cpp:331-427)
  *   pragab200::krigingVariogram / krigingSetWeight / krigingResult / krigingRMSE / krigingFreeMemory
  *                                             <- agrolib/interpolation/kriging.h:4-15
  *   pragab200::krigingRaster                  (new: the reference never wired kriging into a raster loop)
@@ -57,6 +59,19 @@ bool computeResiduals(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoP
                       const std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
                       Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
                       bool excludeOutsideDem, bool excludeSupplemental);
+
+/* the interpolation points are the NOT detrended points of passDataToInterpolation; the caller has run
+ * setMultipleDetrendingHeightTemperatureRange like Project::interpolationCv does (project.cpp:3086-3097) */
+bool computeResidualsLocalDetrending(meteoVariable myVar, const Crit3DTime& myTime, std::vector<Crit3DMeteoPoint>& meteoPoints,
+                                     std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                                     Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                                     Crit3DClimateParameters* climateParameters, bool excludeOutsideDem, bool excludeSupplemental);
+
+/* marks meteoPoints[i].quality = quality::wrong_spatial exactly where the reference does; the settings (the project's
+ * qualityInterpolationSettings) receive both preInterpolation fits, points range and bounding box */
+bool spatialQualityControl(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoPoints,
+                           Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                           Crit3DClimateParameters* climateParameters, const Crit3DTime& myTime, std::string& errorStr);
 
 bool krigingVariogram(double* myPos, double* myVal, int nrItems, short myMode, double myRange, double myNugget,
                       double mySill, double mySlope);

@@ -136,3 +136,43 @@ def test_shim_pre_interpolation(shim, ref, case):
     assert np.array_equal(st_r.value[keep_r], st_g.value[keep_r])
     assert series_r == [(series.kh[i], series.error[i]) for i in range(series.n)]
     assert settings_equal(s_r, s_g), describe_diff(s_r, s_g)
+
+
+def test_shim_spatial_quality_control(shim, ref):
+    """pragab200::spatialQualityControl on reference meteo points: same flags and settings as the reference."""
+    from test_oracle_port import clone, describe_diff, settings_equal
+    from test_spatial_quality import sq_scenario
+    for case in ("classic_codes", "optimal", "classic_td_kh64", "humidity_plain"):
+        dem, urban, st, s, var, bad = sq_scenario(case)
+        s_r, s_g = clone(s), clone(s)
+        okr, wrong_r = ref.spatial_quality_control(st.copy(), s_r, var, dem=dem if "td" in case else None)
+        stp = st.as_pb()
+        cv = A.pb_cv_points()
+        wrong_g = np.zeros(st.n, dtype=np.uint8)
+        d = dem.as_pb()
+        rc = shim.shim_spatial_quality_control(C.byref(stp), C.byref(s_g), var, C.byref(cv), C.byref(d) if "td" in case else None,
+                                               A.u8ptr(wrong_g))
+        assert rc == A.PB_OK and okr, case
+        assert np.array_equal(wrong_r, wrong_g.astype(bool)), (case, np.flatnonzero(wrong_r), np.flatnonzero(wrong_g))
+        assert settings_equal(s_r, s_g), case + ": " + describe_diff(s_r, s_g)
+
+
+def test_shim_compute_residuals_local(shim, ref):
+    dem = syn.make_dem(60, 70, cell_size=3000.0, seed=3)
+    urban = syn.make_urban(60, 70, cell_size=3000.0)
+    st = syn.make_stations(dem, 260, proxies=(dem, urban), seed=9, supplemental_frac=0.15)
+    s = syn.settings_multiple_detrending()
+    s.useLocalDetrending = 1
+    s.minPointsLocalDetrending = 20
+    s.useLapseRateCode = 1
+    syn.set_points_range(s, st)
+    use = np.ones(st.n, dtype=np.uint8)
+    use[::11] = 0
+    res_r, _ = ref.compute_residuals(st, s, A.airTemperature, st.value, use_for_cv=use, local=True)
+    stp = st.as_pb()
+    res_g = np.empty(st.n, dtype=np.float32)
+    obs = st.value.copy()
+    rc = shim.shim_compute_residuals_local(C.byref(stp), C.byref(s), A.airTemperature, A.fptr(obs), A.u8ptr(use), A.fptr(res_g))
+    assert rc == A.PB_OK
+    assert np.array_equal(res_r == np.float32(-9999), res_g == np.float32(-9999))
+    assert np.abs(res_r.astype(np.float64) - res_g).max() <= TOL
