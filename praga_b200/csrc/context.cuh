@@ -152,6 +152,11 @@ struct pb_context {
     int* dLocalError = nullptr;
     int* hLocalError = nullptr;         // pinned
     pb::PinnedRing ring;                    // raster staging (H2D / D2H), 8 slots
+    pb::PinnedRing ringDn;                  // band pipeline of the drop-in call: D2H staging (ring is then H2D only)
+    cudaStream_t sUp = nullptr, sDn = nullptr;      // band pipeline: upload / download streams (kernels: stream)
+    cudaEvent_t evBand[2 * 16 + 1]{};       // per band: rows uploaded, band gridded; + one fence
+    unsigned char* dBand = nullptr;         // per band: valid-cell count (long long) and work-item counter (unsigned)
+    unsigned char* hBand = nullptr;         // pinned copy of the counts
     pb::DevicePool pool;                    // raster-sized device buffers
     long long* dTotal = nullptr;            // valid-cell count of the last compaction
     long long* hTotal = nullptr;            // pinned

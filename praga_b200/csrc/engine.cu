@@ -18,11 +18,15 @@
 namespace pb {
 // idw_kernels.cu
 cudaError_t launchCompactValid(const float* dem, long long n, float flag, int* blockCount, long long* dTotal,
-                               int* validIdx, int phase, cudaStream_t s);
+                               int* validIdx, int phase, cudaStream_t s, int indexBase = 0);
 int compactBlocks(long long n);
+bool idwResidentFits(int nPaddedStations);
+cudaError_t launchCompactFill(const float* dem, long long n, float flag, int* validIdx, int indexBase, long long* dCount,
+                              float* outBand, cudaStream_t s);
 int tileStations();
 cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevGrid& dem, const int* validIdx,
-                            int nTargets, float* out, unsigned* minmax, cudaStream_t s);
+                            int nTargets, float* out, unsigned* minmax, cudaStream_t s, const long long* nTargetsDev = nullptr,
+                            unsigned* workCounter = nullptr);
 cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty,
                             const double* tproxy, int nTargets, float* out, cudaStream_t s);
 cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);
@@ -950,6 +954,11 @@ void pb_destroy(pb_context* ctx)
     ctx->dStations.release(); ctx->hStations.release(); ctx->dOut.release(); ctx->dScratch.release(); ctx->ring.release(); ctx->pool.destroy();
     if (ctx->dTotal) cudaFree(ctx->dTotal);
     if (ctx->hTotal) cudaFreeHost(ctx->hTotal);
+    ctx->ringDn.release();
+    if (ctx->sUp) { cudaStreamDestroy(ctx->sUp); cudaStreamDestroy(ctx->sDn); }
+    for (auto& e : ctx->evBand) if (e) cudaEventDestroy(e);
+    if (ctx->dBand) cudaFree(ctx->dBand);
+    if (ctx->hBand) cudaFreeHost(ctx->hBand);
     if (ctx->dMinMax) cudaFree(ctx->dMinMax);
     if (ctx->hMinMax) cudaFreeHost(ctx->hMinMax);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -1071,6 +1080,265 @@ int pb_pre_interpolation(pb_context* ctx, pb_stations* st, pb_settings* s, int v
     return pb_pre_interpolation_ex(ctx, st, s, variable, nullptr, -1, keep, nullptr);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The drop-in call with HOST rasters as a band pipeline (K1 path): the rows are cut into bands; band b's DEM / proxy rows
+// go up on one stream while band b-1 is gridded on the engine's stream and band b-2's output comes down on a third one.
+// The valid cells of a band are compacted on the device and the kernel reads their number there, so the host never
+// waits inside the loop. Same kernel, same arithmetic as the resident form; only the schedule differs.
+// Not eligible (-> sequential form below): local detrending, Shepard, topographic distance (needs the whole DEM),
+// all-zero precipitation, more stations than the persistent kernel keeps in shared memory, small rasters.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxBands = 16;
+constexpr int kMinBandRows = 128;
+
+static bool sameGeometry(const pb_raster_header& a, const pb_raster_header& b)
+{
+    return a.nrRows == b.nrRows && a.nrCols == b.nrCols && a.cellSize == b.cellSize && a.llx == b.llx && a.lly == b.lly;
+}
+
+static int allocRasterEntry(pb_context* ctx, const pb_raster* r, pb_raster_id* id)
+{
+    if (r->h.nrRows <= 0 || r->h.nrCols <= 0) return fail(ctx, PB_ERR_INVALID, "raster has no cells");
+    if (!r->data && !r->rows) return fail(ctx, PB_ERR_INVALID, "raster has neither data nor rows");
+    const size_t n = size_t(r->h.nrRows) * r->h.nrCols;
+    if (n > size_t(0x7fffffff)) return fail(ctx, PB_ERR_UNSUPPORTED, "raster larger than 2^31-1 cells");
+    int slot = -1;
+    for (size_t i = 0; i < ctx->rasters.size(); i++) if (!ctx->rasters[i].used) { slot = (int)i; break; }
+    if (slot < 0) { ctx->rasters.emplace_back(); slot = (int)ctx->rasters.size() - 1; }
+    RasterEntry& e = ctx->rasters[slot];
+    void* dptr = nullptr;
+    CUDA_TRY(ctx, ctx->pool.acquire(n * sizeof(float), &dptr));
+    e = RasterEntry();
+    e.d = static_cast<float*>(dptr);
+    e.h = r->h;
+    e.n = n;
+    e.used = true;
+    if (ctx->outInitRaster == slot) ctx->outInitRaster = -1;
+    *id = slot;
+    return PB_OK;
+}
+
+// rows [r0, r1) of several host rasters (same column count) -> the same rows of their device buffers, through the pinned
+// ring, on `stream`. One parallel region gathers the rows of all rasters of a chunk: the regions' fork/join latency, not
+// the copy bandwidth, is what limits the host side of the band pipeline.
+struct RowsJob { const pb_raster* r; float* dst; };
+
+static int uploadRows(pb_context* ctx, const RowsJob* jobs, int nJobs, int r0, int r1, cudaStream_t stream)
+{
+    if (nJobs <= 0) return PB_OK;
+    const int cols = jobs[0].r->h.nrCols;
+    const int chunkRows = std::max(1, (int)(kStageSlotBytes / (sizeof(float) * cols)));
+    for (int a = r0; a < r1; a += chunkRows) {
+        const int b = std::min(r1, a + chunkRows);
+        int slot[PB_MAX_PROXY + 1];
+        float* stage[PB_MAX_PROXY + 1];
+        for (int j = 0; j < nJobs; j++) stage[j] = reinterpret_cast<float*>(ctx->ring.acquire(&slot[j]));
+        const int nr = b - a;
+#pragma omp parallel for schedule(static)
+        for (int k = 0; k < nJobs * nr; k++) {
+            const int j = k / nr, row = a + (k - j * nr);
+            const pb_raster* r = jobs[j].r;
+            const float* src = r->data ? r->data + size_t(row) * cols : r->rows[row];
+            memcpy(stage[j] + size_t(row - a) * cols, src, sizeof(float) * cols);
+        }
+        for (int j = 0; j < nJobs; j++) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(jobs[j].dst + size_t(a) * cols, stage[j], sizeof(float) * size_t(nr) * cols,
+                                          cudaMemcpyHostToDevice, stream));
+            ctx->ring.submitted(slot[j], stream);
+            ctx->timing.h2d_bytes += (int64_t)(sizeof(float) * size_t(nr) * cols);
+        }
+    }
+    return PB_OK;
+}
+
+static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const pb_raster* dem,
+                               const pb_raster* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd, pb_raster_out* out,
+                               bool* handled)
+{
+    *handled = false;
+    const int rows = dem->h.nrRows, cols = dem->h.nrCols;
+    if (rowEnd < 0) rowEnd = rows;
+    if (rowBegin < 0 || rowBegin > rowEnd || rowEnd > rows) return PB_OK;          // the sequential form reports it
+    const int nRows = rowEnd - rowBegin;
+    static const bool off = getenv("PB_NO_BAND_PIPELINE") != nullptr;
+    if (off || nRows < 2 * kMinBandRows || s->method != PB_METHOD_IDW || usesTopographicDistance(s, variable) ||
+        (isPrecVar(variable) && s->precipitationAllZero) || !idwResidentFits(st->n + tileStations()) ||
+        size_t(cols) * sizeof(float) > kStageSlotBytes || (!out->data && !out->rows))
+        return PB_OK;
+    *handled = true;
+
+    if (!ctx->sUp) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->sUp, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->sDn, cudaStreamNonBlocking));
+        for (auto& e : ctx->evBand) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dBand, kMaxBands * (sizeof(long long) + sizeof(unsigned))));
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->hBand, kMaxBands * sizeof(long long)));
+    }
+    CUDA_TRY(ctx, ctx->ring.init(kStageSlotBytes));
+    CUDA_TRY(ctx, ctx->ringDn.init(kStageSlotBytes));
+
+    // device buffers (no data yet) registered as rasters so that the model can refer to the proxy grids
+    pb_raster_id demId = -1, ids[PB_MAX_PROXY];
+    std::vector<pb_raster_id> owned;
+    auto cleanup = [&]() {
+        std::string keep = ctx->err;
+        for (pb_raster_id id : owned) pb_raster_free(ctx, id);
+        ctx->err = keep;
+    };
+    int rc = allocRasterEntry(ctx, dem, &demId);
+    if (rc) return rc;
+    owned.push_back(demId);
+    bool banded[PB_MAX_PROXY];
+    for (int g = 0; g < nProxyGrids; g++) {
+        const bool same = proxyGrids[g].data == dem->data && proxyGrids[g].rows == dem->rows &&
+                          memcmp(&proxyGrids[g].h, &dem->h, sizeof(pb_raster_header)) == 0;
+        banded[g] = false;
+        if (same) { ids[g] = demId; continue; }
+        rc = allocRasterEntry(ctx, &proxyGrids[g], &ids[g]);
+        if (rc) { cleanup(); return rc; }
+        owned.push_back(ids[g]);
+        banded[g] = sameGeometry(proxyGrids[g].h, dem->h);       // a cell looks up itself: band-local rows are enough
+    }
+    DevModel m;
+    rc = buildModel(ctx, s, variable, ids, nProxyGrids, m);
+    if (rc) { cleanup(); return rc; }
+    cudaStream_t sK = ctx->stream, sUp = ctx->sUp, sDn = ctx->sDn;
+    cudaEventRecord(ctx->ev[0], sK);
+    DevStations ds{};
+    rc = stageStations(ctx, st, s, true, ds, m.valueOffset);
+    if (rc) { cleanup(); return rc; }
+    if (!idwResidentFits(ds.nPadded)) { cleanup(); *handled = false; return PB_OK; }
+    cudaEventRecord(ctx->ev[1], sK);
+
+    RasterEntry& eDem = ctx->rasters[demId];
+    const size_t n = eDem.n;
+    CUDA_TRY(ctx, ctx->dOut.reserve(n));
+    ctx->outInitRaster = -1;
+    void* vIdx = nullptr;
+    CUDA_TRY(ctx, ctx->pool.acquire(sizeof(int) * n, &vIdx));
+    eDem.validIdx = static_cast<int*>(vIdx);          // released with the entry
+    static const int wantBands = getenv("PB_BANDS") ? atoi(getenv("PB_BANDS")) : 8;
+    const int nBands = std::max(2, std::min(std::min(kMaxBands, wantBands), nRows / kMinBandRows));
+    const int bandRows = (nRows + nBands - 1) / nBands;
+    long long* dTotals = reinterpret_cast<long long*>(ctx->dBand);
+    unsigned* dCounters = reinterpret_cast<unsigned*>(dTotals + kMaxBands);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->dBand, 0, kMaxBands * (sizeof(long long) + sizeof(unsigned)), sK));
+    ctx->hMinMax[0] = 0xffffffffu;
+    ctx->hMinMax[1] = 0u;
+    ctx->hMinMax[2] = 0u;
+    ctx->hMinMax[3] = 0u;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 4 * sizeof(unsigned), cudaMemcpyHostToDevice, sK));
+    // the uploads must not overtake work of a previous call that still reads the recycled buffers
+    cudaEventRecord(ctx->evBand[2 * kMaxBands], sK);
+    cudaStreamWaitEvent(sUp, ctx->evBand[2 * kMaxBands], 0);
+
+    const DevGrid dg = devGridOf(eDem);
+    const int chunkRows = std::max(1, (int)(kStageSlotBytes / (sizeof(float) * cols)));
+    struct Chunk { int r0, r1, slot; float* stage; };
+    std::vector<Chunk> inflight;
+    size_t head = 0;
+    auto scatter = [&](const Chunk& c) -> cudaError_t {
+        cudaError_t e = ctx->ringDn.wait(c.slot);
+        if (e != cudaSuccess) return e;
+#pragma omp parallel for schedule(static)
+        for (int row = c.r0; row < c.r1; row++) {
+            float* dst = out->data ? out->data + size_t(row) * cols : out->rows[row];
+            memcpy(dst, c.stage + size_t(row - c.r0) * cols, sizeof(float) * cols);
+        }
+        return cudaSuccess;
+    };
+    auto fail2 = [&](int code) { cudaStreamSynchronize(sUp); cudaStreamSynchronize(sK); cudaStreamSynchronize(sDn); cleanup(); return code; };
+
+    // ---- up: a band's rows of the DEM and of the proxy grids that share its geometry (others: whole, with band 0)
+    auto issueUpload = [&](int b) -> int {
+        const int r0 = rowBegin + b * bandRows, r1 = std::min(rowEnd, r0 + bandRows);
+        if (r0 >= r1) return PB_OK;
+        RowsJob jobs[PB_MAX_PROXY + 1];
+        int nJobs = 0;
+        jobs[nJobs++] = RowsJob{dem, eDem.d};
+        int rcu = PB_OK;
+        for (int g = 0; rcu == PB_OK && g < nProxyGrids; g++) {
+            if (ids[g] == demId) continue;
+            if (banded[g]) jobs[nJobs++] = RowsJob{&proxyGrids[g], ctx->rasters[ids[g]].d};
+            else if (b == 0) {
+                const RowsJob whole{&proxyGrids[g], ctx->rasters[ids[g]].d};
+                rcu = uploadRows(ctx, &whole, 1, 0, proxyGrids[g].h.nrRows, sUp);
+            }
+        }
+        if (rcu == PB_OK) rcu = uploadRows(ctx, jobs, nJobs, r0, r1, sUp);
+        if (rcu) return rcu;
+        cudaEventRecord(ctx->evBand[b], sUp);
+        return PB_OK;
+    };
+    rc = issueUpload(0);
+    if (rc) return fail2(rc);
+    for (int b = 0; b < nBands; b++) {
+        const int r0 = rowBegin + b * bandRows, r1 = std::min(rowEnd, r0 + bandRows);
+        if (r0 >= r1) continue;
+        const long long bandCells = (long long)(r1 - r0) * cols;
+        // the next band's uploads are queued BEFORE this band's kernels: the upload engine is the busiest resource of the
+        // pipeline and must never wait for the host
+        if (b + 1 < nBands) {
+            rc = issueUpload(b + 1);
+            if (rc) return fail2(rc);
+        }
+        cudaStreamWaitEvent(sK, ctx->evBand[b], 0);
+        // ---- grid: one pass writes the flag into the output band and lists the band's valid cells; K1 over that list
+        //      (its length is read on the device)
+        cudaError_t ce = launchCompactFill(eDem.d + size_t(r0) * cols, bandCells, eDem.h.flag, eDem.validIdx + size_t(r0) * cols,
+                                           int(size_t(r0) * cols), dTotals + b, ctx->dOut.p + size_t(r0) * cols, sK);
+        if (ce == cudaSuccess)
+            ce = launchIdwRaster(ds, m, dg, eDem.validIdx + size_t(r0) * cols, (int)bandCells, ctx->dOut.p, ctx->dMinMax, sK,
+                                 dTotals + b, dCounters + b);
+        if (ce != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, std::string("band pipeline: ") + cudaGetErrorString(ce)); return fail2(PB_ERR_CUDA); }
+        ctx->timing.launches += 2;
+        cudaEventRecord(ctx->evBand[kMaxBands + b], sK);
+        cudaStreamWaitEvent(sDn, ctx->evBand[kMaxBands + b], 0);
+        // ---- down: the band's output rows; chunks are scattered into the caller's grid while later ones are in flight
+        for (int a = r0; a < r1; a += chunkRows) {
+            if (inflight.size() - head >= size_t(PinnedRing::kSlots - 1)) {
+                if (scatter(inflight[head++]) != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, "D2H failed"); return fail2(PB_ERR_CUDA); }
+            }
+            Chunk c;
+            c.r0 = a;
+            c.r1 = std::min(r1, a + chunkRows);
+            c.stage = reinterpret_cast<float*>(ctx->ringDn.acquire(&c.slot));
+            ce = cudaMemcpyAsync(c.stage, ctx->dOut.p + size_t(a) * cols, size_t(c.r1 - a) * cols * sizeof(float),
+                                 cudaMemcpyDeviceToHost, sDn);
+            if (ce != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(ce)); return fail2(PB_ERR_CUDA); }
+            ctx->ringDn.submitted(c.slot, sDn);
+            inflight.push_back(c);
+        }
+        // no host wait here: the upload engine is the busiest resource of the pipeline, every band's uploads are issued as
+        // early as the staging ring allows; finished output chunks are scattered after the loop (or above, under slot pressure)
+    }
+    cudaEventRecord(ctx->ev[2], sK);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, sK));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hBand, dTotals, kMaxBands * sizeof(long long), cudaMemcpyDeviceToHost, sK));
+    for (; head < inflight.size(); head++)
+        if (scatter(inflight[head]) != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, "D2H failed"); return fail2(PB_ERR_CUDA); }
+    cudaEventRecord(ctx->ev[3], sK);
+    cudaStreamSynchronize(sUp);
+    cudaStreamSynchronize(sDn);
+    CUDA_TRY(ctx, cudaStreamSynchronize(sK));
+    ctx->timing.d2h_bytes += (int64_t)(size_t(nRows) * cols * sizeof(float)) + 8;
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
+    long long nValid = 0;
+    for (int b = 0; b < nBands; b++) nValid += reinterpret_cast<long long*>(ctx->hBand)[b];
+    out->nValid = nValid;
+    cleanup();
+    if (ctx->hMinMax[0] == 0xffffffffu) {   // no valid output value: updateMinMaxRasterGrid returns false
+        out->minimum = kNoData;
+        out->maximum = kNoData;
+        return fail(ctx, PB_ERR_NO_VALID_CELL, "no valid cell in the output raster");
+    }
+    out->minimum = keyToFloat(ctx->hMinMax[0]);
+    out->maximum = keyToFloat(ctx->hMinMax[1]);
+    return PB_OK;
+}
+
 static int hostRasterCall(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const pb_raster* dem,
                           const pb_raster* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd, pb_raster_out* out, bool local)
 {
@@ -1079,6 +1347,12 @@ static int hostRasterCall(pb_context* ctx, const pb_stations* st, const pb_setti
     if (nProxyGrids > PB_MAX_PROXY) return fail(ctx, PB_ERR_INVALID, "too many proxy grids");
     cudaSetDevice(ctx->device);
     resetTiming(ctx);
+    if (!local && st && s && out) {
+        bool handled = false;
+        const int rcp = hostRasterPipelined(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, &handled);
+        if (handled || rcp != PB_OK) return rcp;
+        resetTiming(ctx);
+    }
     pb_raster_id demId = -1, ids[PB_MAX_PROXY];
     int nUp = 0;
     int rc = pb_raster_upload(ctx, dem, &demId);

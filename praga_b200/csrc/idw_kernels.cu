@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(int* __restrict__ blo
 
 __global__ void __launch_bounds__(256) write_valid_kernel(const float* __restrict__ dem, long long n, float flag,
                                                           const int* __restrict__ blockOffset,
-                                                          int* __restrict__ validIdx)
+                                                          int* __restrict__ validIdx, int indexBase)
 {
     // one warp handles 32 consecutive cells per step so the output order stays ascending
     long long base = (long long)blockIdx.x * kCompactChunk;
@@ -120,7 +120,42 @@ __global__ void __launch_bounds__(256) write_valid_kernel(const float* __restric
         long long k = wbase + s + lane;
         bool ok = k < n && !isEqualF(dem[k], flag);
         unsigned b = __ballot_sync(0xffffffffu, ok);
-        if (ok) validIdx[pos + __popc(b & ((1u << lane) - 1u))] = (int)k;
+        if (ok) validIdx[pos + __popc(b & ((1u << lane) - 1u))] = indexBase + (int)k;
+        pos += __popc(b);
+    }
+}
+
+// Band pipeline of the drop-in call: ONE pass over a band of the DEM writes the flag into the band of the output grid
+// and appends the band's valid cells to its list (slots reserved with one atomicAdd per warp: the list is ascending inside
+// every 512-cell slice, the slices land in arrival order, which the kernels do not care about). *count must be zero.
+__global__ void __launch_bounds__(256) compact_fill_kernel(const float* __restrict__ dem, long long n, float flag,
+                                                           int* __restrict__ validIdx, int indexBase,
+                                                           unsigned long long* __restrict__ count, float* __restrict__ outBand)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long wbase = (long long)blockIdx.x * kCompactChunk + warp * (kCompactChunk / 8);
+    unsigned masks[kCompactChunk / 8 / 32];
+    int cnt = 0;
+#pragma unroll
+    for (int s = 0; s < kCompactChunk / 8 / 32; s++) {
+        const long long k = wbase + s * 32 + lane;
+        bool ok = false;
+        if (k < n) {
+            ok = !isEqualF(dem[k], flag);
+            outBand[k] = flag;
+        }
+        masks[s] = __ballot_sync(0xffffffffu, ok);
+        cnt += __popc(masks[s]);
+    }
+    if (cnt == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    int pos = 0;
+#pragma unroll
+    for (int s = 0; s < kCompactChunk / 8 / 32; s++) {
+        const unsigned b = masks[s];
+        if (b & (1u << lane)) validIdx[base + pos + __popc(b & ((1u << lane) - 1u))] = indexBase + int(wbase + s * 32 + lane);
         pos += __popc(b);
     }
 }
@@ -343,9 +378,12 @@ constexpr int kResidentMaxStations = 9216;     // 18 tiles x 12 KiB = 216 KiB of
 
 template <int P, int kPersistThreads>
 __global__ void __launch_bounds__(kPersistThreads, 1)
-idw_persistent_kernel(DevStations st, DevModel m, DevGrid dem, const int* __restrict__ validIdx, int nTargets,
-                      float* __restrict__ out, unsigned* __restrict__ minmax, unsigned* __restrict__ workCounter)
+idw_persistent_kernel(DevStations st, DevModel m, DevGrid dem, const int* __restrict__ validIdx, int nTargetsHost,
+                      float* __restrict__ out, unsigned* __restrict__ minmax, unsigned* __restrict__ workCounter,
+                      const long long* __restrict__ nTargetsDev)
 {
+    // band pipeline of the drop-in call: the number of valid cells of a band is only known on the device
+    const int nTargets = nTargetsDev ? int(*nTargetsDev) : nTargetsHost;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     const float4* __restrict__ sxyAll = reinterpret_cast<const float4*>(smem);
@@ -534,25 +572,37 @@ cudaError_t launchRowStart(const int* validIdx, long long total, int nrRows, int
 }
 
 cudaError_t launchCompactValid(const float* dem, long long n, float flag, int* blockCount, long long* dTotal,
-                               int* validIdx, int phase, cudaStream_t s)
+                               int* validIdx, int phase, cudaStream_t s, int indexBase)
 {
     const int nBlocks = (int)((n + kCompactChunk - 1) / kCompactChunk);
     if (phase == 0) {
         count_valid_kernel<<<nBlocks, 256, 0, s>>>(dem, n, flag, blockCount);
         scan_counts_kernel<<<1, 1024, 0, s>>>(blockCount, nBlocks, dTotal);
     } else {
-        write_valid_kernel<<<nBlocks, 256, 0, s>>>(dem, n, flag, blockCount, validIdx);
+        write_valid_kernel<<<nBlocks, 256, 0, s>>>(dem, n, flag, blockCount, validIdx, indexBase);
     }
     return cudaGetLastError();
 }
 
+cudaError_t launchCompactFill(const float* dem, long long n, float flag, int* validIdx, int indexBase, long long* dCount,
+                              float* outBand, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    const int nBlocks = (int)((n + kCompactChunk - 1) / kCompactChunk);
+    compact_fill_kernel<<<nBlocks, 256, 0, s>>>(dem, n, flag, validIdx, indexBase, reinterpret_cast<unsigned long long*>(dCount), outBand);
+    return cudaGetLastError();
+}
+
 int compactBlocks(long long n) { return (int)((n + kCompactChunk - 1) / kCompactChunk); }
+bool idwResidentFits(int nPaddedStations) { return nPaddedStations <= 9216; }
 int tileStations() { return kTileStations; }
 
 cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevGrid& dem, const int* validIdx,
-                            int nTargets, float* out, unsigned* minmax, cudaStream_t s)
+                            int nTargets, float* out, unsigned* minmax, cudaStream_t s, const long long* nTargetsDev,
+                            unsigned* workCounter)
 {
     if (nTargets <= 0) return cudaSuccess;
+    if (nTargetsDev && st.nPadded > kResidentMaxStations) return cudaErrorInvalidValue;    // callers check idwResidentFits()
     constexpr int P = 2;
     if (st.nPadded <= kResidentMaxStations) {
         // persistent form: minmax[2] is the work-item counter (zeroed by the caller together with min/max)
@@ -568,7 +618,8 @@ cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevG
         const size_t smem = (size_t)st.nPadded * (sizeof(float4) + sizeof(float2));
         const int items = (nTargets + 64 * P - 1) / (64 * P);
         const int grid = std::min(sms, (items + kPersistThreads / 32 - 1) / (kPersistThreads / 32));
-        k<<<grid, kPersistThreads, smem, s>>>(st, m, dem, validIdx, nTargets, out, minmax, minmax + 2);
+        k<<<grid, kPersistThreads, smem, s>>>(st, m, dem, validIdx, nTargets, out, minmax, workCounter ? workCounter : minmax + 2,
+                                              nTargetsDev);
         return cudaGetLastError();
     }
     const int per = kThreads * 2 * P;
