@@ -734,7 +734,11 @@ def main():
             "wall_s_timed_region": wall_s,
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp32_peak, "traffic": None,
+                         "frac": achieved_tflops / fp32_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C2 from the ncu --set full capture
+                         # profiles/r01_idw_c2b.ncu_summary.json (46.9 MB + 10.2 MB; algorithmic 12 B/cell = 44.4 MB + the
+                         # 14.8 MB valid-cell list); other workloads: not captured
+                         "traffic": 57.09e6 if args.workload == "c2" else None,
                          "kernel": "pb::idw_kernel<2,false>", "kernel_ms_per_launch": kernel_s_per_launch * 1e3,
                          "algorithmic": f"11 flop x {S} stations x {n_valid} cells per launch (SURVEY.md 8d)",
                          "peak_source": "FFMA2 chain measured live on this GPU (MEASURED_PEAKS.json has no FP32 figure; "

@@ -350,6 +350,27 @@ int pb_kriging_points(pb_context* ctx, pb_kriging_id id, const double* xy, int m
 int pb_kriging_raster(pb_context* ctx, pb_kriging_id id, pb_raster_id dem, int rowBegin, int rowEnd,
                       pb_raster_out* estimate, pb_raster_out* rmse /* may be NULL */);
 
+/* --- raster map operators on either side of the gridding path. Inputs are resident rasters;
+ * the result goes to `out` (host grid: data or rows; may be NULL) and / or stays on the device as a new resident raster
+ * (*outId, to be released with pb_raster_free; NULL: not kept).
+ *   pb_raster_download              a resident raster back into a host grid
+ *   pb_relative_humidity_map     <- Crit3DHourlyMeteoMaps::computeRelativeHumidityMap (agrolib/project/meteoMaps.cpp:301-321)
+ *                                   with relHumFromTdew (agrolib/meteo/meteo.cpp:301-315); header = the air temperature map's
+ *   pb_fix_daily_thermal_consistency <- Crit3DDailyMeteoMaps::fixDailyThermalConsistency (meteoMaps.cpp:103-126): tmin is
+ *                                   lowered in place to tmax - 0.1 where it exceeds tmax; *nFixed = cells changed
+ *   pb_topographic_distance_map  <- gis::topographicDistanceMap (agrolib/gis/gis.cpp:1648-1672): the DEM ray march of
+ *                                   gis::topographicDistance (:1595-1647) from (x, y, z) to every valid cell
+ *   pb_resample_grid             <- gis::resampleGrid (gis.cpp:1722-1811), aggrAverage / aggrMedian / aggrCenter
+ *                                   (enum aggregationMethod, agrolib/mathFunctions/statistics.h:21) */
+enum { PB_AGGR_AVERAGE = 1, PB_AGGR_MEDIAN = 2, PB_AGGR_PREVAILING = 7, PB_AGGR_CENTER = 9 };
+int pb_raster_download(pb_context* ctx, pb_raster_id id, pb_raster_out* out);
+int pb_relative_humidity_map(pb_context* ctx, pb_raster_id airT, pb_raster_id dewT, pb_raster_out* out, pb_raster_id* outId);
+int pb_fix_daily_thermal_consistency(pb_context* ctx, pb_raster_id tmax, pb_raster_id tmin, int64_t* nFixed);
+int pb_topographic_distance_map(pb_context* ctx, pb_raster_id dem, double x, double y, double z, pb_raster_out* out,
+                                pb_raster_id* outId);
+int pb_resample_grid(pb_context* ctx, pb_raster_id src, const pb_raster_header* newHeader, int method, float nodataRatioThreshold,
+                     pb_raster_out* out, pb_raster_id* outId);
+
 /* --- timing of the last call (device time measured with CUDA events on the engine's stream) ------ */
 typedef struct pb_timing {
     float h2d_ms, kernel_ms, d2h_ms, total_ms;

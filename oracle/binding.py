@@ -88,6 +88,14 @@ def _load(path, prefix):
     fn = getattr(lib, prefix + "_compute_residuals_local")
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(C.c_float), P(C.c_uint8), P(C.c_float),
                    P(A.pb_cv_stats)]
+    fn = getattr(lib, prefix + "_relative_humidity_map")
+    fn.argtypes = [P(A.pb_raster), P(A.pb_raster), P(A.pb_raster_out)]
+    fn = getattr(lib, prefix + "_fix_daily_thermal_consistency")
+    fn.argtypes = [P(A.pb_raster), P(A.pb_raster), P(C.c_float), P(C.c_int64)]
+    fn = getattr(lib, prefix + "_topographic_distance_map")
+    fn.argtypes = [P(A.pb_raster), C.c_double, C.c_double, C.c_double, P(A.pb_raster_out)]
+    fn = getattr(lib, prefix + "_resample_grid")
+    fn.argtypes = [P(A.pb_raster), P(A.pb_raster_header), C.c_int, C.c_float, P(A.pb_raster_out)]
     fn = getattr(lib, prefix + "_kriging_points")
     fn.argtypes = [P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                    P(C.c_double), C.c_int, P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_double)]
@@ -281,6 +289,38 @@ class Oracle:
         self._f("compute_residuals_local" if local else "compute_residuals")(C.byref(st), C.byref(settings), variable, A.fptr(obs),
                                      None if use is None else A.u8ptr(use), A.fptr(res), C.byref(stats))
         return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}
+
+    # ---- raster map operators ----
+    def relative_humidity_map(self, air_t, dew_t):
+        a, b = air_t.as_pb(), dew_t.as_pb()
+        out = np.empty(air_t.shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        rc = self._f("relative_humidity_map")(C.byref(a), C.byref(b), C.byref(o))
+        return rc == A.PB_OK, out, o.minimum, o.maximum
+
+    def fix_daily_thermal_consistency(self, tmax, tmin):
+        a, b = tmax.as_pb(), tmin.as_pb()
+        out = np.empty(tmin.shape, dtype=np.float32)
+        n = C.c_int64(0)
+        self._f("fix_daily_thermal_consistency")(C.byref(a), C.byref(b), A.fptr(out), C.byref(n))
+        return out, n.value
+
+    def topographic_distance_map(self, dem, x, y, z):
+        d = dem.as_pb()
+        out = np.empty(dem.shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        self._f("topographic_distance_map")(C.byref(d), x, y, z, C.byref(o))
+        return out
+
+    def resample_grid(self, src, new_header, method, threshold=0.0):
+        s = src.as_pb()
+        out = np.empty((new_header.nrRows, new_header.nrCols), dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        rc = self._f("resample_grid")(C.byref(s), C.byref(new_header), method, threshold, C.byref(o))
+        return rc == A.PB_OK, out, o.minimum, o.maximum
 
     def kriging_points(self, pos, val, mode, rng, nugget, sill, slope, xy, want_rmse=True):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1)

@@ -2134,6 +2134,161 @@ int port_local_detrending_point(const pb_stations* st, pb_settings* s, int varia
 
 // kriging, interpolation/kriging.cpp: krigingVariogram :97-202, matrixInversion :28-81, krigingSetWeight :211-264,
 // krigingResult :271-279, krigingRMSE :287-295
+// ---- raster map operators around the gridding path ------------------------------------------------
+// updateMinMaxRasterGrid, gis/gis.cpp:569-614
+static bool minMaxOf(const float* v, size_t n, float flag, float* mn, float* mx)
+{
+    bool first = true;
+    *mn = *mx = NODATA_F;
+    for (size_t i = 0; i < n; i++)
+        if (!isEqualF(v[i], flag) && !isEqualF(v[i], NODATA_F)) {
+            if (first) { *mn = *mx = v[i]; first = false; }
+            else if (v[i] < *mn) *mn = v[i];
+            else if (v[i] > *mx) *mx = v[i];
+        }
+    return !first;
+}
+static float* outRow(pb_raster_out* out, int row, int cols) { return out->data ? out->data + size_t(row) * cols : out->rows[row]; }
+
+// relHumFromTdew(float, float), meteo/meteo.cpp:301-315
+static float relHumFromTdew(float Td, float T)
+{
+    if (isEqualF(Td, NODATA_F) || isEqualF(T, NODATA_F)) return NODATA_F;
+    double d = 237.3;
+    double c = 17.2693882;
+    double esp = 1 / (double(T) + d);
+    double rh = pow(exp((c * double(Td)) - ((c * double(T) / (double(T) + d))) * (double(Td) + d)), esp);
+    rh *= 100;
+    if (rh > 100) return 100;
+    return std::max(1.f, float(rh));
+}
+
+// Crit3DHourlyMeteoMaps::computeRelativeHumidityMap, project/meteoMaps.cpp:301-321
+int port_relative_humidity_map(const pb_raster* airT, const pb_raster* dewT, pb_raster_out* out)
+{
+    Grid t = gridOf(*airT), td = gridOf(*dewT);
+    const int rows = t.h.nrRows, cols = t.h.nrCols;
+    std::vector<float> flat(size_t(rows) * cols);
+    for (int row = 0; row < rows; row++)
+        for (int col = 0; col < cols; col++) {
+            float v = t.h.flag;                                      // emptyGrid()
+            const float a = t.at(row, col), b = td.at(row, col);
+            if (!isEqualF(a, t.h.flag) && !isEqualF(b, td.h.flag)) v = relHumFromTdew(b, a);
+            flat[size_t(row) * cols + col] = v;
+            outRow(out, row, cols)[col] = v;
+        }
+    out->nValid = int64_t(rows) * cols;
+    return minMaxOf(flat.data(), flat.size(), t.h.flag, &out->minimum, &out->maximum) ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
+// Crit3DDailyMeteoMaps::fixDailyThermalConsistency, project/meteoMaps.cpp:103-126
+int port_fix_daily_thermal_consistency(const pb_raster* tmax, const pb_raster* tmin, float* tminOut, int64_t* nFixed)
+{
+    Grid a = gridOf(*tmax), b = gridOf(*tmin);
+    int64_t n = 0;
+    for (int row = 0; row < a.h.nrRows; row++)
+        for (int col = 0; col < a.h.nrCols; col++) {
+            float v = b.at(row, col);
+            if (!isEqualF(a.at(row, col), a.h.flag) && !isEqualF(v, b.h.flag) && v > a.at(row, col)) {
+                v = a.at(row, col) - 0.1f;
+                n++;
+            }
+            tminOut[size_t(row) * a.h.nrCols + col] = v;
+        }
+    if (nFixed) *nFixed = n;
+    return PB_OK;
+}
+
+// gis::topographicDistanceMap, gis/gis.cpp:1648-1672
+int port_topographic_distance_map(const pb_raster* dem, double x, double y, double z, pb_raster_out* out)
+{
+    Grid d = gridOf(*dem);
+    const int rows = d.h.nrRows, cols = d.h.nrCols;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int row = 0; row < rows; row++)
+        for (int col = 0; col < cols; col++) {
+            const float demValue = d.at(row, col);
+            float v = d.h.flag;
+            if (!isEqualF(demValue, d.h.flag)) {
+                const double gx = d.h.llx + d.h.cellSize * (double(col) + 0.5);          // getXY, gis.cpp:473-477
+                const double gy = d.h.lly + d.h.cellSize * (double(rows - row) - 0.5);
+                const float dx = float(gx) - float(x), dy = float(gy) - float(y);          // computeDistance, gis.cpp:685-691
+                const float distance = sqrtf(dx * dx + dy * dy);
+                v = topographicDistance(float(gx), float(gy), demValue, float(x), float(y), float(z), distance, d);
+            }
+            outRow(out, row, cols)[col] = v;
+        }
+    out->nValid = int64_t(rows) * cols;
+    out->minimum = out->maximum = NODATA_F;
+    return PB_OK;
+}
+
+// gis::resampleGrid, gis/gis.cpp:1722-1811 (aggrAverage, aggrMedian, aggrCenter)
+int port_resample_grid(const pb_raster* src, const pb_raster_header* nh, int method, float nodataRatioThreshold, pb_raster_out* out)
+{
+    if (method != PB_AGGR_AVERAGE && method != PB_AGGR_MEDIAN && method != PB_AGGR_CENTER) return PB_ERR_UNSUPPORTED;
+    Grid o = gridOf(*src);
+    const int rows = nh->nrRows, cols = nh->nrCols;
+    const double resampleFactor = nh->cellSize / o.h.cellSize;
+    std::vector<float> flat(size_t(rows) * cols);
+    for (int row = 0; row < rows; row++)
+        for (int col = 0; col < cols; col++) {
+            float value = NODATA_F;
+            const double x0 = nh->llx + nh->cellSize * (double(col) + 0.5);
+            const double y0 = nh->lly + nh->cellSize * (double(rows - row) - 0.5);
+            if (resampleFactor <= 1. || method == PB_AGGR_CENTER) {
+                const float tmp = o.valueFromXY(x0, y0);                // getRowCol + isOutOfGridRowCol + value
+                if (!isEqualF(tmp, o.h.flag)) value = tmp;
+            } else {
+                const int nrStep = int(floor(resampleFactor)) + 1;
+                const double step = nh->cellSize / nrStep, halfStep = step * 0.5;
+                const double llx = x0 - (nh->cellSize / 2) + halfStep, lly = y0 - (nh->cellSize / 2) + halfStep;
+                std::vector<float> values;
+                int maxNrValues = 0;
+                for (int i = 0; i < nrStep; i++) {
+                    const double x = llx + step * i;
+                    for (int j = 0; j < nrStep; j++) {
+                        const double y = lly + step * j;
+                        const float tmp = o.valueFromXY(x, y);
+                        if (!isEqualF(tmp, o.h.flag)) values.push_back(tmp);
+                        maxNrValues++;
+                    }
+                }
+                const int nrValues = int(values.size());
+                if (maxNrValues > 0 && (float(nrValues) / float(maxNrValues)) > nodataRatioThreshold) {
+                    if (method == PB_AGGR_AVERAGE) {                    // statistics::mean, statistics.cpp:1300-1321
+                        double sum = 0;
+                        int nv = 0;
+                        for (float v : values) if (!isEqualF(v, NODATA_F)) { sum += double(v); nv++; }
+                        value = (values.empty() || nv == 0) ? NODATA_F : float(sum / double(nv));
+                    } else {                                           // sorting::percentile(values, n, 50, true), basicMath.cpp:327-366
+                        if (values.size() >= 3) {
+                            std::vector<float> list;
+                            for (float v : values) if (!isEqualF(v, NODATA_F)) list.push_back(v);
+                            std::sort(list.begin(), list.end());
+                            const int n = int(list.size());
+                            if (n >= 3) {
+                                const double rank = n * double(50.0 / 100.f) - 1.0;
+                                if (rank < 0.0) value = list[0];
+                                else {
+                                    const int low = int(rank);
+                                    if (low >= n - 1) value = list[n - 1];
+                                    else value = float(list[low] + (rank - low) * (list[low + 1] - list[low]));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            const float v = isEqualF(value, NODATA_F) ? nh->flag : value;
+            flat[size_t(row) * cols + col] = v;
+            outRow(out, row, cols)[col] = v;
+        }
+    out->nValid = int64_t(rows) * cols;
+    minMaxOf(flat.data(), flat.size(), nh->flag, &out->minimum, &out->maximum);
+    return PB_OK;
+}
+
 int port_kriging_points(const double* pos, const double* val, int n, int mode, double range, double nugget, double sill,
                         double slope, const double* xy, int m, double* result, double* rmse, double* setup_s, double* eval_s)
 {

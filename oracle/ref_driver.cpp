@@ -81,6 +81,8 @@ static_assert(int(airTemperature) == PB_VAR_AIR_TEMPERATURE && int(dailyAirTempe
                   int(dailyWaterTableDepth) == PB_VAR_DAILY_WATER_TABLE_DEPTH && int(elaborationVar) == PB_VAR_ELABORATION &&
                   int(noMeteoVar) == PB_VAR_NONE && int(dailyBIC) == PB_VAR_DAILY_BIC, "meteoVariable");
 static_assert(NODATA == PB_NODATA, "NODATA");
+static_assert(int(aggrAverage) == PB_AGGR_AVERAGE && int(aggrMedian) == PB_AGGR_MEDIAN && int(aggrPrevailing) == PB_AGGR_PREVAILING &&
+                  int(aggrCenter) == PB_AGGR_CENTER, "aggregationMethod");
 
 namespace {
 
@@ -533,6 +535,77 @@ int ref_interpolation_dem(const pb_stations* meteo, pb_settings* sq, pb_settings
     std::vector<double> pr = sc.settings.getPointsRange();
     if (pr.size() == 2) { s->hasPointsRange = 1; s->pointsRangeMin = pr[0]; s->pointsRangeMax = pr[1]; }
     return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
+/* Crit3DHourlyMeteoMaps::computeRelativeHumidityMap (project/meteoMaps.cpp:301-321; the class is Qt-bound, the loop is
+ * restated, relHumFromTdew and updateMinMaxRasterGrid are reference code) */
+int ref_relative_humidity_map(const pb_raster* airT, const pb_raster* dewT, pb_raster_out* out)
+{
+    gis::Crit3DRasterGrid tGrid, tdGrid, rh;
+    fillGrid(tGrid, *airT);
+    fillGrid(tdGrid, *dewT);
+    rh.initializeGrid(tGrid);
+    rh.emptyGrid();
+    for (long row = 0; row < rh.header->nrRows; row++)
+        for (long col = 0; col < rh.header->nrCols; col++) {
+            float myT = tGrid.value[row][col], dewPoint = tdGrid.value[row][col];
+            if (!isEqual(myT, tGrid.header->flag) && !isEqual(dewPoint, tdGrid.header->flag))
+                rh.value[row][col] = relHumFromTdew(dewPoint, myT);
+        }
+    bool ok = gis::updateMinMaxRasterGrid(&rh);
+    out->nValid = int64_t(rh.header->nrRows) * rh.header->nrCols;
+    copyOut(rh, out);
+    return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
+/* Crit3DDailyMeteoMaps::fixDailyThermalConsistency (project/meteoMaps.cpp:103-126), loop restated; tmin is rewritten */
+int ref_fix_daily_thermal_consistency(const pb_raster* tmax, const pb_raster* tmin, float* tminOut, int64_t* nFixed)
+{
+    gis::Crit3DRasterGrid a, b;
+    fillGrid(a, *tmax);
+    fillGrid(b, *tmin);
+    int64_t n = 0;
+    for (unsigned row = 0; row < unsigned(a.header->nrRows); row++)
+        for (unsigned col = 0; col < unsigned(a.header->nrCols); col++) {
+            if (!isEqual(a.value[row][col], a.header->flag) && !isEqual(b.value[row][col], b.header->flag))
+                if (b.value[row][col] > a.value[row][col]) {
+                    b.value[row][col] = a.value[row][col] - 0.1f;
+                    n++;
+                }
+            tminOut[size_t(row) * a.header->nrCols + col] = b.value[row][col];
+        }
+    if (nFixed) *nFixed = n;
+    return PB_OK;
+}
+
+/* gis::topographicDistanceMap, verbatim reference code */
+int ref_topographic_distance_map(const pb_raster* dem, double x, double y, double z, pb_raster_out* out)
+{
+    gis::Crit3DRasterGrid demGrid, map;
+    fillGrid(demGrid, *dem);
+    gis::Crit3DPoint p;
+    p.utm.x = x; p.utm.y = y; p.z = z;
+    bool ok = gis::topographicDistanceMap(p, demGrid, &map);
+    out->nValid = int64_t(demGrid.header->nrRows) * demGrid.header->nrCols;
+    copyOut(map, out);
+    return ok ? PB_OK : PB_ERR_INVALID;
+}
+
+/* gis::resampleGrid, verbatim reference code */
+int ref_resample_grid(const pb_raster* src, const pb_raster_header* newHeader, int method, float nodataRatioThreshold,
+                      pb_raster_out* out)
+{
+    gis::Crit3DRasterGrid oldGrid, newGrid;
+    fillGrid(oldGrid, *src);
+    gis::Crit3DRasterHeader h;
+    h.nrRows = newHeader->nrRows; h.nrCols = newHeader->nrCols;
+    h.cellSize = newHeader->cellSize; h.invCellSize = newHeader->invCellSize;
+    h.llCorner.x = newHeader->llx; h.llCorner.y = newHeader->lly;
+    h.flag = newHeader->flag;
+    gis::resampleGrid(oldGrid, &newGrid, &h, aggregationMethod(method), nodataRatioThreshold);
+    out->nValid = int64_t(h.nrRows) * h.nrCols;
+    copyOut(newGrid, out);
+    return PB_OK;
 }
 
 /* interpolate() at arbitrary targets (x, y, z, proxyValues[nProxy]) — interpolation.cpp:2502 */

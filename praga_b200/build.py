@@ -24,6 +24,7 @@ SOURCES = {
     "classic_kernels.cu": ["-fmad=false"],
     "shepard_kernels.cu": ["-fmad=false"],
     "station_space.cu": [],
+    "raster_ops.cu": ["-fmad=false"],
     "kriging.cu": [],
     "kriging_tc.cu": [],
 }

@@ -1,0 +1,514 @@
+// raster_ops.cu — K9: the raster map kernels on either side of the gridding path. All of them are
+// one pass over a grid (HBM bound: a few bytes read and 4 written per cell) except the topographic-distance map, which
+// is the DEM ray march of K6 from one point to every cell.
+//
+//   computeRelativeHumidityMap   agrolib/project/meteoMaps.cpp:301-321 with relHumFromTdew, agrolib/meteo/meteo.cpp:301-315
+//   fixDailyThermalConsistency   agrolib/project/meteoMaps.cpp:103-126
+//   gis::topographicDistanceMap  agrolib/gis/gis.cpp:1648-1672 (gis::topographicDistance :1595-1647)
+//   gis::resampleGrid            agrolib/gis/gis.cpp:1722-1811 (statistics::mean, sorting::percentile basicMath.cpp:327-366,
+//                                gis::prevailingValue gis.cpp:1513-1554)
+//
+// Built with -fmad=false: the ray march and the sampling coordinates follow the reference's operation order.
+#include <math.h>
+#include <string.h>
+#include <string>
+
+#include "context.cuh"
+
+namespace pb {
+
+// gis::topographicDistance (gis.cpp:1595-1647), same code as K6 (td_kernels.cu) for one pair
+__device__ __forceinline__ float topoDistancePair(const DevGrid& dem, float x1, float y1, float z1, float x2, float y2, float z2,
+                                                  float distance)
+{
+    const float stepMeter = float(dem.cellSize);
+    if (distance < stepMeter) return 0.f;
+    const int nrStep = int(distance / stepMeter);
+    float Xi, Yi, Zi, Xf, Yf;
+    if (z1 < z2) { Xi = x1; Yi = y1; Zi = z1; Xf = x2; Yf = y2; }
+    else { Xi = x2; Yi = y2; Zi = z2; Xf = x1; Yf = y1; }
+    const float dx = (Xf - Xi) / float(nrStep);
+    const float dy = (Yf - Yi) / float(nrStep);
+    float x = Xi, y = Yi, maxDeltaZ = 0.f;
+    for (int i = 1; i <= nrStep; i++) {
+        x = x + dx;
+        y = y + dy;
+        const int r = int((double(y) - dem.lly) * dem.invCellSize);
+        const int row = (dem.nrRows - 1) - r;
+        const int col = int((double(x) - dem.llx) * dem.invCellSize);
+        float demValue = dem.flag;
+        if (unsigned(row) < unsigned(dem.nrRows) && unsigned(col) < unsigned(dem.nrCols))
+            demValue = __ldg(dem.data + (size_t)row * dem.nrCols + col);
+        if (!isEqualF(demValue, dem.flag))
+            if (demValue > Zi) maxDeltaZ = (maxDeltaZ > demValue - Zi) ? maxDeltaZ : demValue - Zi;
+    }
+    return maxDeltaZ;
+}
+
+__device__ __forceinline__ unsigned orderedKeyR(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// block-wide min/max of the valid outputs -> two atomics per block (gis::updateMinMaxRasterGrid, gis.cpp:569-614)
+__device__ __forceinline__ void blockMinMax(float v, bool valid, unsigned* minmax)
+{
+    float vmin = valid ? v : INFINITY, vmax = valid ? v : -INFINITY;
+    for (int o = 16; o; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (vmin != INFINITY) atomicMin(&minmax[0], orderedKeyR(vmin));
+        if (vmax != -INFINITY) atomicMax(&minmax[1], orderedKeyR(vmax));
+    }
+}
+
+// relHumFromTdew(float Td, float T), meteo.cpp:301-315. The reference evaluates pow(exp(a), esp); exp(a * esp) is the same
+// number to ~1e-15 relative (far inside the float result's half ulp except at rounding ties, and the parity bar is 1e-4)
+// at a quarter of the FP64 instructions, which is what bounds this map.
+__device__ __forceinline__ float relHumFromTdewDev(float Td, float T)
+{
+    if (isEqualF(Td, kNoData) || isEqualF(T, kNoData)) return kNoData;
+    const double d = 237.3;
+    const double c = 17.2693882;
+    const double esp = 1 / (double(T) + d);
+    // c T / (T + d) as c T esp: one FP64 division per cell instead of two (same ~1e-16 argument as above)
+    double rh = exp(((c * double(Td)) - ((c * double(T)) * esp) * (double(Td) + d)) * esp);
+    rh *= 100;
+    if (rh > 100) return 100;
+    return fmaxf(1.f, float(rh));
+}
+
+// four cells per thread (128-bit loads / stores when the buffers allow it), scalar tail
+__global__ void __launch_bounds__(256) relative_humidity_map_kernel(const float* __restrict__ airT, float flagT,
+                                                                    const float* __restrict__ dewT, float flagTd, long long n,
+                                                                    float outFlag, float* __restrict__ out,
+                                                                    unsigned* __restrict__ minmax)
+{
+    const long long k0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    float tv[4], dv[4], ov[4];
+    const bool full = k0 + 3 < n;
+    if (full) {
+        *reinterpret_cast<float4*>(tv) = *reinterpret_cast<const float4*>(airT + k0);
+        *reinterpret_cast<float4*>(dv) = *reinterpret_cast<const float4*>(dewT + k0);
+    } else {
+        for (int q = 0; q < 4; q++) { tv[q] = (k0 + q < n) ? airT[k0 + q] : flagT; dv[q] = (k0 + q < n) ? dewT[k0 + q] : flagTd; }
+    }
+    float vmin = INFINITY, vmax = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        float o = outFlag;
+        if (!isEqualF(tv[q], flagT) && !isEqualF(dv[q], flagTd)) o = relHumFromTdewDev(dv[q], tv[q]);
+        ov[q] = o;
+        if (k0 + q < n && !isEqualF(o, outFlag) && !isEqualF(o, kNoData)) { vmin = fminf(vmin, o); vmax = fmaxf(vmax, o); }
+    }
+    if (full) *reinterpret_cast<float4*>(out + k0) = *reinterpret_cast<const float4*>(ov);
+    else for (int q = 0; q < 4; q++) if (k0 + q < n) out[k0 + q] = ov[q];
+    for (int o = 16; o; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (vmin != INFINITY) atomicMin(&minmax[0], orderedKeyR(vmin));
+        if (vmax != -INFINITY) atomicMax(&minmax[1], orderedKeyR(vmax));
+    }
+}
+
+__global__ void __launch_bounds__(256) thermal_consistency_kernel(const float* __restrict__ tmax, float flagMax,
+                                                                  float* __restrict__ tmin, float flagMin, long long n,
+                                                                  unsigned long long* __restrict__ nFixed)
+{
+    const long long k0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    float a[4], b[4];
+    const bool full = k0 + 3 < n;
+    if (full) {
+        *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(tmax + k0);
+        *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(tmin + k0);
+    } else {
+        for (int q = 0; q < 4; q++) { a[q] = (k0 + q < n) ? tmax[k0 + q] : flagMax; b[q] = (k0 + q < n) ? tmin[k0 + q] : flagMin; }
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (!isEqualF(a[q], flagMax) && !isEqualF(b[q], flagMin) && b[q] > a[q]) {
+            b[q] = a[q] - 0.1f;
+            cnt++;
+        }
+    if (cnt) {                                    // only the quads that changed are written back
+        if (full) *reinterpret_cast<float4*>(tmin + k0) = *reinterpret_cast<const float4*>(b);
+        else for (int q = 0; q < 4; q++) if (k0 + q < n) tmin[k0 + q] = b[q];
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(nFixed, (unsigned long long)cnt);
+}
+
+__global__ void __launch_bounds__(128) topographic_distance_map_kernel(DevGrid dem, float px, float py, float pz,
+                                                                       float* __restrict__ out)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)dem.nrRows * dem.nrCols;
+    if (k >= n) return;
+    const float demValue = dem.data[k];
+    if (isEqualF(demValue, dem.flag)) { out[k] = dem.flag; return; }
+    const int row = int(k / dem.nrCols), col = int(k - (long long)row * dem.nrCols);
+    // Crit3DRasterGrid::getXY (gis.cpp:473-477), narrowed to float at the calls
+    const double gx = dem.llx + dem.cellSize * (double(col) + 0.5);
+    const double gy = dem.lly + dem.cellSize * (double(dem.nrRows - row) - 0.5);
+    const float x = float(gx), y = float(gy);
+    const float dx = x - px, dy = y - py;                      // gis::computeDistance(x1, y1, x2, y2), gis.cpp:685-691
+    const float distance = sqrtf(dx * dx + dy * dy);
+    out[k] = topoDistancePair(dem, x, y, demValue, px, py, pz, distance);
+}
+
+constexpr int kResampleMax = 256;       // samples per new cell held for the median (nrStep <= 16)
+
+// one thread per cell of the new grid; METHOD: PB_AGGR_AVERAGE / _MEDIAN / _CENTER
+template <int METHOD>
+__global__ void __launch_bounds__(128) resample_grid_kernel(DevGrid oldGrid, DevGrid newGrid, float nodataRatioThreshold,
+                                                            float* __restrict__ out, unsigned* __restrict__ minmax)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = (long long)newGrid.nrRows * newGrid.nrCols;
+    float o = newGrid.flag;
+    bool valid = false;
+    if (k < n) {
+        const int row = int(k / newGrid.nrCols), col = int(k - (long long)row * newGrid.nrCols);
+        const double resampleFactor = newGrid.cellSize / oldGrid.cellSize;
+        float value = kNoData;
+        // Crit3DRasterGrid::getXY (gis.cpp:473-477)
+        const double x0 = newGrid.llx + newGrid.cellSize * (double(col) + 0.5);
+        const double y0 = newGrid.lly + newGrid.cellSize * (double(newGrid.nrRows - row) - 0.5);
+        if (resampleFactor <= 1. || METHOD == PB_AGGR_CENTER) {
+            // getRowCol (gis.cpp:486-493) + isOutOfGridRowCol
+            const int r = int((y0 - oldGrid.lly) * oldGrid.invCellSize);
+            const int tmpRow = (oldGrid.nrRows - 1) - r;
+            const int tmpCol = int((x0 - oldGrid.llx) * oldGrid.invCellSize);
+            if (unsigned(tmpRow) < unsigned(oldGrid.nrRows) && unsigned(tmpCol) < unsigned(oldGrid.nrCols)) {
+                const float tmpValue = oldGrid.data[(size_t)tmpRow * oldGrid.nrCols + tmpCol];
+                if (!isEqualF(tmpValue, oldGrid.flag)) value = tmpValue;
+            }
+        } else {
+            const int nrStep = int(floor(resampleFactor)) + 1;
+            const double step = newGrid.cellSize / nrStep;
+            const double halfStep = step * 0.5;
+            const double llxS = x0 - (newGrid.cellSize / 2) + halfStep;
+            const double llyS = y0 - (newGrid.cellSize / 2) + halfStep;
+            float values[METHOD == PB_AGGR_MEDIAN ? kResampleMax : 1];
+            int nrValues = 0, maxNrValues = 0, nrMean = 0;
+            double sum = 0.;
+            for (int i = 0; i < nrStep; i++) {
+                const double x = llxS + step * i;
+                for (int j = 0; j < nrStep; j++) {
+                    const double y = llyS + step * j;
+                    // gis::getValueFromXY (gis.cpp:533-546)
+                    const int r = int((y - oldGrid.lly) * oldGrid.invCellSize);
+                    const int sr = (oldGrid.nrRows - 1) - r;
+                    const int sc = int((x - oldGrid.llx) * oldGrid.invCellSize);
+                    float tmpValue = oldGrid.flag;
+                    if (unsigned(sr) < unsigned(oldGrid.nrRows) && unsigned(sc) < unsigned(oldGrid.nrCols))
+                        tmpValue = __ldg(oldGrid.data + (size_t)sr * oldGrid.nrCols + sc);
+                    if (!isEqualF(tmpValue, oldGrid.flag)) {
+                        if (METHOD == PB_AGGR_MEDIAN) values[nrValues] = tmpValue;
+                        nrValues++;
+                        if (!isEqualF(tmpValue, kNoData)) { sum += double(tmpValue); nrMean++; }     // statistics::mean skips NODATA
+                    }
+                    maxNrValues++;
+                }
+            }
+            if (maxNrValues > 0 && (float(nrValues) / float(maxNrValues)) > nodataRatioThreshold) {
+                if (METHOD == PB_AGGR_AVERAGE) {
+                    // statistics::mean(std::vector<float>) (statistics.cpp:1300-1321): double sum of the non-NODATA values
+                    value = (nrValues < 1 || nrMean == 0) ? kNoData : float(sum / double(nrMean));
+                } else if (METHOD == PB_AGGR_MEDIAN) {
+                    // sorting::percentile(values, n, 50, true) (basicMath.cpp:327-366): < 3 values -> NODATA; drop NODATA, sort
+                    // ascending, rank = n * 0.5 - 1, linear interpolation
+                    int m = 0;
+                    for (int q = 0; q < nrValues; q++) if (!isEqualF(values[q], kNoData)) values[m++] = values[q];
+                    if (nrValues >= 3 && m >= 3) {
+                        for (int a = 1; a < m; a++) {                     // insertion sort (a few dozen values)
+                            const float v = values[a];
+                            int b = a - 1;
+                            while (b >= 0 && values[b] > v) { values[b + 1] = values[b]; b--; }
+                            values[b + 1] = v;
+                        }
+                        const double rank = m * double(50.0 / 100.f) - 1.0;
+                        if (rank < 0.0) value = values[0];
+                        else {
+                            const int low = int(rank);
+                            if (low >= m - 1) value = values[m - 1];
+                            else {
+                                const double frac = rank - low;
+                                value = float(values[low] + frac * (values[low + 1] - values[low]));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!isEqualF(value, kNoData)) o = value;
+        out[k] = o;
+        valid = !isEqualF(o, newGrid.flag) && !isEqualF(o, kNoData);
+    }
+    blockMinMax(o, valid, minmax);
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+namespace {
+
+int fail(pb_context* ctx, int code, const std::string& msg) { return pb::failCtx(ctx, code, msg); }
+
+RasterEntry* entryOf(pb_context* ctx, pb_raster_id id)
+{
+    if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used) return nullptr;
+    return &ctx->rasters[id];
+}
+
+DevGrid gridOf(const RasterEntry& r)
+{
+    DevGrid g{};
+    g.data = r.d;
+    g.nrRows = r.h.nrRows; g.nrCols = r.h.nrCols;
+    g.llx = r.h.llx; g.lly = r.h.lly; g.cellSize = r.h.cellSize; g.invCellSize = r.h.invCellSize;
+    g.flag = r.h.flag;
+    return g;
+}
+
+float keyToFloatR(unsigned k)
+{
+    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// D2H of a device grid into a pb_raster_out (contiguous data or row pointers) + min / max / nValid bookkeeping
+int finishGrid(pb_context* ctx, const float* dGrid, int rows, int cols, bool wantMinMax, pb_raster_out* out)
+{
+    if (out && (out->data || out->rows)) {
+        if (out->data)
+            CUDA_TRY(ctx, cudaMemcpyAsync(out->data, dGrid, sizeof(float) * size_t(rows) * cols, cudaMemcpyDeviceToHost, ctx->stream));
+        else
+            for (int r = 0; r < rows; r++)
+                CUDA_TRY(ctx, cudaMemcpyAsync(out->rows[r], dGrid + size_t(r) * cols, sizeof(float) * cols, cudaMemcpyDeviceToHost,
+                                              ctx->stream));
+        ctx->timing.d2h_bytes += (int64_t)(sizeof(float) * size_t(rows) * cols);
+    }
+    if (wantMinMax) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[1], ctx->ev[3]);
+    if (out && wantMinMax) {
+        if (ctx->hMinMax[0] == 0xffffffffu) {
+            out->minimum = kNoData;
+            out->maximum = kNoData;
+            return fail(ctx, PB_ERR_NO_VALID_CELL, "no valid cell in the output raster");
+        }
+        out->minimum = keyToFloatR(ctx->hMinMax[0]);
+        out->maximum = keyToFloatR(ctx->hMinMax[1]);
+    }
+    return PB_OK;
+}
+
+int resetMinMax(pb_context* ctx)
+{
+    ctx->hMinMax[0] = 0xffffffffu;
+    ctx->hMinMax[1] = 0u;
+    ctx->hMinMax[2] = 0u;
+    ctx->hMinMax[3] = 0u;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 4 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    return PB_OK;
+}
+
+// a new resident raster (device buffer from the pool) with the given header; returns its id
+int newResident(pb_context* ctx, pb_raster_header h /* by value: the caller's may live in the vector that grows here */, pb_raster_id* id)
+{
+    const size_t n = size_t(h.nrRows) * h.nrCols;
+    if (h.nrRows <= 0 || h.nrCols <= 0) return fail(ctx, PB_ERR_INVALID, "raster has no cells");
+    if (n > size_t(0x7fffffff)) return fail(ctx, PB_ERR_UNSUPPORTED, "raster larger than 2^31-1 cells");
+    int slot = -1;
+    for (size_t i = 0; i < ctx->rasters.size(); i++) if (!ctx->rasters[i].used) { slot = (int)i; break; }
+    if (slot < 0) { ctx->rasters.emplace_back(); slot = (int)ctx->rasters.size() - 1; }
+    void* d = nullptr;
+    CUDA_TRY(ctx, ctx->pool.acquire(n * sizeof(float), &d));
+    RasterEntry& e = ctx->rasters[slot];
+    e = RasterEntry();
+    e.d = static_cast<float*>(d);
+    e.h = h;
+    e.n = n;
+    e.used = true;
+    if (ctx->outInitRaster == slot) ctx->outInitRaster = -1;
+    *id = slot;
+    return PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb_raster_download(pb_context* ctx, pb_raster_id id, pb_raster_out* out)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    RasterEntry* e = entryOf(ctx, id);
+    if (!e || !out) return fail(ctx, PB_ERR_INVALID, "bad raster id / null output");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    return finishGrid(ctx, e->d, e->h.nrRows, e->h.nrCols, false, out);
+}
+
+int pb_relative_humidity_map(pb_context* ctx, pb_raster_id airT, pb_raster_id dewT, pb_raster_out* out, pb_raster_id* outId)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    RasterEntry *t = entryOf(ctx, airT), *td = entryOf(ctx, dewT);
+    if (!t || !td) return fail(ctx, PB_ERR_INVALID, "bad raster id");
+    if (t->h.nrRows != td->h.nrRows || t->h.nrCols != td->h.nrCols)
+        return fail(ctx, PB_ERR_INVALID, "temperature and dew point maps differ in size");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    const long long n = (long long)t->n;
+    float* dOut = nullptr;
+    pb_raster_id nid = -1;
+    if (outId) {
+        int rc = newResident(ctx, t->h, &nid);
+        if (rc) return rc;
+        t = entryOf(ctx, airT);            // the raster vector may have grown
+        td = entryOf(ctx, dewT);
+        dOut = ctx->rasters[nid].d;
+        *outId = nid;
+    } else {
+        CUDA_TRY(ctx, ctx->dOut.reserve(size_t(n)));
+        ctx->outInitRaster = -1;
+        dOut = ctx->dOut.p;
+    }
+    int rc = resetMinMax(ctx);
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    // emptyGrid(): every cell = the output's own flag; the output header is the air temperature map's
+    relative_humidity_map_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, ctx->stream>>>(t->d, t->h.flag, td->d, td->h.flag, n, t->h.flag,
+                                                                                     dOut, ctx->dMinMax);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (out) out->nValid = n;
+    return finishGrid(ctx, dOut, t->h.nrRows, t->h.nrCols, true, out);
+}
+
+int pb_fix_daily_thermal_consistency(pb_context* ctx, pb_raster_id tmax, pb_raster_id tmin, int64_t* nFixed)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    RasterEntry *a = entryOf(ctx, tmax), *b = entryOf(ctx, tmin);
+    if (!a || !b) return fail(ctx, PB_ERR_INVALID, "bad raster id");
+    if (a->h.nrRows != b->h.nrRows || a->h.nrCols != b->h.nrCols) return fail(ctx, PB_ERR_INVALID, "maps differ in size");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    if (!ctx->dTotal) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dTotal, sizeof(long long)));
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->hTotal, sizeof(long long)));
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->dTotal, 0, sizeof(long long), ctx->stream));
+    const long long n = (long long)a->n;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    thermal_consistency_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, ctx->stream>>>(a->d, a->h.flag, b->d, b->h.flag, n,
+                                                                                   reinterpret_cast<unsigned long long*>(ctx->dTotal));
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hTotal, ctx->dTotal, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    if (nFixed) *nFixed = *ctx->hTotal;
+    b->nValid = -1;        // the list of valid cells does not change (flags are untouched), values do
+    return PB_OK;
+}
+
+int pb_topographic_distance_map(pb_context* ctx, pb_raster_id demId, double x, double y, double z, pb_raster_out* out,
+                                pb_raster_id* outId)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    RasterEntry* dem = entryOf(ctx, demId);
+    if (!dem) return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    const long long n = (long long)dem->n;
+    float* dOut = nullptr;
+    if (outId) {
+        pb_raster_id nid = -1;
+        int rc = newResident(ctx, dem->h, &nid);
+        if (rc) return rc;
+        dem = entryOf(ctx, demId);
+        dOut = ctx->rasters[nid].d;
+        *outId = nid;
+    } else {
+        CUDA_TRY(ctx, ctx->dOut.reserve(size_t(n)));
+        ctx->outInitRaster = -1;
+        dOut = ctx->dOut.p;
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    topographic_distance_map_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(gridOf(*dem), float(x), float(y), float(z), dOut);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (out) out->nValid = n;
+    return finishGrid(ctx, dOut, dem->h.nrRows, dem->h.nrCols, false, out);
+}
+
+int pb_resample_grid(pb_context* ctx, pb_raster_id srcId, const pb_raster_header* newHeader, int method, float nodataRatioThreshold,
+                     pb_raster_out* out, pb_raster_id* outId)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    RasterEntry* src = entryOf(ctx, srcId);
+    if (!src || !newHeader) return fail(ctx, PB_ERR_INVALID, "bad raster id / null header");
+    if (method != PB_AGGR_AVERAGE && method != PB_AGGR_MEDIAN && method != PB_AGGR_CENTER)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "resampleGrid: aggrAverage, aggrMedian and aggrCenter run on the GPU (aggrPrevailing does not)");
+    const double factor = newHeader->cellSize / src->h.cellSize;
+    if (factor > 1. && method == PB_AGGR_MEDIAN && int(floor(factor)) + 1 > 16)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "median resampling above factor 15 (more than 256 samples per cell)");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    pb_raster_header h = *newHeader;
+    const long long n = (long long)h.nrRows * h.nrCols;
+    if (n <= 0) return fail(ctx, PB_ERR_INVALID, "new grid has no cells");
+    float* dOut = nullptr;
+    if (outId) {
+        pb_raster_id nid = -1;
+        int rc = newResident(ctx, h, &nid);
+        if (rc) return rc;
+        src = entryOf(ctx, srcId);
+        dOut = ctx->rasters[nid].d;
+        *outId = nid;
+    } else {
+        CUDA_TRY(ctx, ctx->dOut.reserve(size_t(n)));
+        ctx->outInitRaster = -1;
+        dOut = ctx->dOut.p;
+    }
+    int rc = resetMinMax(ctx);
+    if (rc) return rc;
+    DevGrid ng{};
+    ng.data = nullptr;
+    ng.nrRows = h.nrRows; ng.nrCols = h.nrCols;
+    ng.llx = h.llx; ng.lly = h.lly; ng.cellSize = h.cellSize; ng.invCellSize = h.invCellSize;
+    ng.flag = h.flag;
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    const unsigned nb = (unsigned)((n + 127) / 128);
+    if (method == PB_AGGR_AVERAGE)
+        resample_grid_kernel<PB_AGGR_AVERAGE><<<nb, 128, 0, ctx->stream>>>(gridOf(*src), ng, nodataRatioThreshold, dOut, ctx->dMinMax);
+    else if (method == PB_AGGR_MEDIAN)
+        resample_grid_kernel<PB_AGGR_MEDIAN><<<nb, 128, 0, ctx->stream>>>(gridOf(*src), ng, nodataRatioThreshold, dOut, ctx->dMinMax);
+    else
+        resample_grid_kernel<PB_AGGR_CENTER><<<nb, 128, 0, ctx->stream>>>(gridOf(*src), ng, nodataRatioThreshold, dOut, ctx->dMinMax);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (out) out->nValid = n;
+    rc = finishGrid(ctx, dOut, h.nrRows, h.nrCols, true, out);
+    return rc == PB_ERR_NO_VALID_CELL ? PB_OK : rc;      // resampleGrid ignores updateMinMaxRasterGrid's result
+}
+
+}  // extern "C"

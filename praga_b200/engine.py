@@ -82,6 +82,13 @@ def load_library():
                                       P(A.pb_raster_out)]
     lib.pb_interpolate_points_td.argtypes = raster_args + [P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_double), C.c_int,
                                                            C.c_int, C.c_int32, P(C.c_float)]
+    lib.pb_raster_download.argtypes = [C.c_void_p, C.c_int32, P(A.pb_raster_out)]
+    lib.pb_relative_humidity_map.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(A.pb_raster_out), P(C.c_int32)]
+    lib.pb_fix_daily_thermal_consistency.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(C.c_int64)]
+    lib.pb_topographic_distance_map.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, P(A.pb_raster_out),
+                                                P(C.c_int32)]
+    lib.pb_resample_grid.argtypes = [C.c_void_p, C.c_int32, P(A.pb_raster_header), C.c_int, C.c_float, P(A.pb_raster_out),
+                                     P(C.c_int32)]
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
     lib.pb_measure_fp64_peak.argtypes = [C.c_void_p, P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
@@ -228,6 +235,42 @@ class Engine:
         self._check(fn(self.h, C.byref(st), C.byref(settings), variable, A.fptr(obs), None if use is None else A.u8ptr(use),
                        A.fptr(res), C.byref(stats)))
         return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}
+
+    # ---- raster map operators around the path ----
+    def _grid_call(self, fn, shape, keep, want_host, *args):
+        out = np.empty(shape, dtype=np.float32) if want_host else None
+        o = A.pb_raster_out()
+        if out is not None:
+            o.data = A.fptr(out)
+        rid = C.c_int32(-1)
+        rc = self._check(fn(self.h, *args, C.byref(o), C.byref(rid) if keep else None), allow=(A.PB_ERR_NO_VALID_CELL,))
+        return rc == A.PB_OK, out, o.minimum, o.maximum, (rid.value if keep else None)
+
+    def download(self, rid, shape):
+        out = np.empty(shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        self._check(self.lib.pb_raster_download(self.h, rid, C.byref(o)))
+        return out
+
+    def relative_humidity_map(self, air_t_id, dew_t_id, shape, keep=False, want_host=True):
+        """computeRelativeHumidityMap (meteoMaps.cpp:301-321). Returns (ok, grid, min, max, resident id or None)."""
+        return self._grid_call(self.lib.pb_relative_humidity_map, shape, keep, want_host, air_t_id, dew_t_id)
+
+    def fix_daily_thermal_consistency(self, tmax_id, tmin_id):
+        """fixDailyThermalConsistency (meteoMaps.cpp:103-126), in place on the resident tmin map. Returns cells changed."""
+        n = C.c_int64(0)
+        self._check(self.lib.pb_fix_daily_thermal_consistency(self.h, tmax_id, tmin_id, C.byref(n)))
+        return n.value
+
+    def topographic_distance_map(self, dem_id, shape, x, y, z, keep=False, want_host=True):
+        """gis::topographicDistanceMap (gis.cpp:1648-1672) for one point."""
+        return self._grid_call(self.lib.pb_topographic_distance_map, shape, keep, want_host, dem_id, x, y, z)
+
+    def resample_grid(self, src_id, new_header, method, threshold=0.0, keep=False, want_host=True):
+        """gis::resampleGrid (gis.cpp:1722-1811)."""
+        return self._grid_call(self.lib.pb_resample_grid, (new_header.nrRows, new_header.nrCols), keep, want_host, src_id,
+                               C.byref(new_header), method, threshold)
 
     # ---- ordinary kriging (kriging.h:4-15) ----
     def kriging_setup(self, pos, val, mode, rng, nugget, sill, slope=0.0, fp64_direct=False):

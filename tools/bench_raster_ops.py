@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""HBM roofline of the raster map kernels (K9) on a 10k x 10k grid: algorithmic bytes / device time vs the measured copy
+bandwidth of MEASURED_PEAKS.json. python tools/bench_raster_ops.py [rows cols] -> one JSON line per operator."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import praga_b200 as pb  # noqa: E402
+from praga_b200 import _abi as A, synthetic as syn  # noqa: E402
+
+rows, cols = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (10000, 10000)
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+dem = syn.make_dem(rows, cols)
+flag = np.float32(dem.flag)
+rng = np.random.default_rng(1)
+t = (15.0 - 0.0065 * np.where(dem.data == flag, 0, dem.data)).astype(np.float32)
+td = (t - 3.0).astype(np.float32)
+t[dem.data == flag] = flag
+td[dem.data == flag] = flag
+T = A.Raster(t, dem.llx, dem.lly, dem.cell_size, dem.flag)
+TD = A.Raster(td, dem.llx, dem.lly, dem.cell_size, dem.flag)
+eng = pb.Engine(0)
+d_id, t_id, td_id = eng.upload(dem), eng.upload(T), eng.upload(TD)
+n = rows * cols
+
+
+def timed(fn, reps=5):
+    best = 1e9
+    for _ in range(reps):
+        fn()
+        best = min(best, eng.timing()["kernel_ms"])
+    return best
+
+
+def line(name, ms, bytes_per_cell, cells, extra=None):
+    gbs = bytes_per_cell * cells / (ms * 1e-3) * 1e-9
+    out = {"kernel": name, "cells": cells, "kernel_ms": ms, "cells_per_s": cells / (ms * 1e-3),
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                        "algorithmic_bytes_per_cell": bytes_per_cell}}
+    if extra:
+        out.update(extra)
+    print(json.dumps(out), flush=True)
+
+
+ms = timed(lambda: eng.relative_humidity_map(t_id, td_id, dem.shape, want_host=False))
+line("relative_humidity_map_kernel", ms, 12, n)
+ms = timed(lambda: eng.fix_daily_thermal_consistency(t_id, td_id))
+line("thermal_consistency_kernel", ms, 8, n, {"note": "reads tmax and tmin; writes only the cells it fixes"})
+h = A.pb_raster_header()
+f = 5.0
+h.cellSize, h.invCellSize = dem.cell_size * f, 1.0 / (dem.cell_size * f)
+h.nrRows, h.nrCols, h.llx, h.lly, h.flag = int(rows / f), int(cols / f), dem.llx, dem.lly, dem.flag
+ms = timed(lambda: eng.resample_grid(d_id, h, A.PB_AGGR_AVERAGE, 0.0, want_host=False))
+line("resample_grid_kernel<average> 100 m -> 500 m", ms, 4.0 * 36 / 25 + 4.0 / 25, n,
+     {"note": "36 samples per new cell over 25 old cells: 5.8 B per OLD cell read + 0.16 written"})
+small = A.Raster(dem.data[:2000, :2000].copy(), dem.llx, dem.lly, dem.cell_size, dem.flag)
+s_id = eng.upload(small)
+ms = timed(lambda: eng.topographic_distance_map(s_id, small.shape, dem.llx + 70000.0, dem.lly + 90000.0, 600.0, want_host=False), reps=3)
+line("topographic_distance_map_kernel 2000x2000", ms, 8, 2000 * 2000,
+     {"note": "ray march: ~d/cellSize DEM samples per cell from L2, not an HBM-streaming kernel; bytes = DEM read + map written"})
