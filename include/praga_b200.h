@@ -331,6 +331,24 @@ int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, pb_settings*
                          pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
                          int deviceOnly, pb_raster_out* out, pb_dem_step* step);
 
+/* --- a batch of independent (time step, variable) units, the loop of the reference's hourly / daily batch drivers over
+ * Project::interpolationDemMain (agrolib/project/project.cpp:3526-3556): every item is one pb_interpolation_dem call (own
+ * station values and settings, same resident rasters); the units are spread over nLanes internal streams (0: 4) so that the
+ * raster kernel of one unit overlaps the station-space kernels of the others. items[i].status receives the unit's pb_status;
+ * results are identical to stand-alone calls. */
+typedef struct pb_dem_batch_item {
+    const pb_stations* meteo;
+    pb_settings* qualitySettings;  /* may be NULL */
+    pb_settings* settings;
+    int32_t variable;
+    int32_t status;                /* out */
+    pb_raster_out* out;
+    pb_dem_step* step;             /* may be NULL */
+} pb_dem_batch_item;
+int pb_interpolation_dem_batch(pb_context* ctx, pb_dem_batch_item* items, int nItems, pb_raster_id dem,
+                               const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd, int deviceOnly,
+                               int nLanes);
+
 /* --- ordinary kriging (agrolib/interpolation/kriging.h:4-15, kriging.cpp). The reference keeps ONE system in file-static
  * globals; here every krigingVariogram call yields a handle and many systems can live on a device.
  *   pb_kriging_setup   <- krigingVariogram(pos[2n], val[n], n, mode, range, nugget, sill, slope)   kriging.cpp:97-202

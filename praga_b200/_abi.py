@@ -126,6 +126,11 @@ class pb_dem_step(C.Structure):
                 ("stats", C.POINTER(pb_cv_stats)), ("khSeries", C.POINTER(pb_kh_series))]
 
 
+class pb_dem_batch_item(C.Structure):
+    _fields_ = [("meteo", C.POINTER(pb_stations)), ("qualitySettings", C.POINTER(pb_settings)), ("settings", C.POINTER(pb_settings)),
+                ("variable", C.c_int32), ("status", C.c_int32), ("out", C.POINTER(pb_raster_out)), ("step", C.POINTER(pb_dem_step))]
+
+
 class pb_timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]

@@ -17,6 +17,7 @@ struct RasterEntry {
     int* validIdx = nullptr;           // capacity n
     long long nValid = -1;
     std::vector<long long> rowStart;   // nrRows + 1 prefix counts (host), built on first row-band request
+    bool borrowed = false;             // a lane context's view of its parent's raster: never released here
 };
 
 template <typename T>
@@ -165,6 +166,7 @@ struct pb_context {
     cudaEvent_t ev[4]{};
     pb_timing timing{};
     std::vector<pb::KrigingSystem*> kriging;    // pb_kriging_id -> system (kriging.cu)
+    std::vector<pb_context*> lanes;             // child contexts (own stream and buffers) of pb_interpolation_dem_batch
 };
 
 namespace pb {

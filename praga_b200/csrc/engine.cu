@@ -323,8 +323,10 @@ int uploadRaster(pb_context* ctx, const pb_raster* r, RasterEntry& e)
 
 void freeEntry(pb_context* ctx, RasterEntry& e)
 {
-    if (e.d) ctx->pool.release(e.d);
-    if (e.validIdx) ctx->pool.release(e.validIdx);
+    if (!e.borrowed) {
+        if (e.d) ctx->pool.release(e.d);
+        if (e.validIdx) ctx->pool.release(e.validIdx);
+    }
     e = RasterEntry();
 }
 
@@ -946,6 +948,8 @@ void pb_destroy(pb_context* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (pb_context* lane : ctx->lanes) pb_destroy(lane);
+    ctx->lanes.clear();
     for (auto& r : ctx->rasters) if (r.used) freeEntry(ctx, r);
     pb::krigingDestroyAll(ctx->kriging);
     ctx->dLocalStations.release(); ctx->dLocalScratch.release(); ctx->dLocalModel.release(); ctx->hLocal.release();
@@ -1747,5 +1751,6 @@ extern "C" size_t pb_abi_sizeof(const char* name)
     if (!strcmp(name, "pb_cv_stats")) return sizeof(pb_cv_stats);
     if (!strcmp(name, "pb_timing")) return sizeof(pb_timing);
     if (!strcmp(name, "pb_dem_step")) return sizeof(pb_dem_step);
+    if (!strcmp(name, "pb_dem_batch_item")) return sizeof(pb_dem_batch_item);
     return 0;
 }

@@ -7,7 +7,9 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "classic.cuh"
@@ -24,6 +26,8 @@ bool varIsPrec(int v);
 bool varIsThermal(int v);
 int varClampMode(int v);
 void cvStatisticsHost(const std::vector<float>& obs, const std::vector<float>& pre, pb_cv_stats* stats);
+int ensureValidList(pb_context* ctx, RasterEntry& e);
+int ensureRowStart(pb_context* ctx, RasterEntry& e);
 }  // namespace pb
 
 using namespace pb;
@@ -889,5 +893,83 @@ extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, p
     ctx->timing.kernel_ms = kernelMs;
     ctx->timing.h2d_bytes = h2d;
     ctx->timing.d2h_bytes = d2h;
+    return PB_OK;
+}
+
+/* A batch of independent (time step, variable) units — what the reference's hourly / daily drivers loop over — run through
+ * pb_interpolation_dem on several LANES: child contexts of ctx with their own stream and buffers, each driven by its own
+ * host thread, all reading the parent's resident rasters. One step alone is latency bound (a dozen small station-space
+ * kernels and their host round trips around one raster kernel); with lanes the raster kernel of one step overlaps the
+ * station-space work of the others. Every unit gives exactly the result of a stand-alone pb_interpolation_dem call. */
+extern "C" int pb_interpolation_dem_batch(pb_context* ctx, pb_dem_batch_item* items, int nItems, pb_raster_id dem,
+                                          const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd, int deviceOnly,
+                                          int nLanes)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (nItems < 0 || (nItems > 0 && !items)) return fail(ctx, PB_ERR_INVALID, "null argument");
+    if (nItems == 0) return PB_OK;
+    if (dem < 0 || dem >= (int)ctx->rasters.size() || !ctx->rasters[dem].used) return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
+    cudaSetDevice(ctx->device);
+    if (nLanes <= 0) nLanes = 4;
+    nLanes = std::min(std::min(nLanes, nItems), 16);
+    // the lists the raster calls need are built once on the parent, then shared
+    int rc = ensureValidList(ctx, ctx->rasters[dem]);
+    if (rc) return rc;
+    if (rowBegin != 0 || (rowEnd >= 0 && rowEnd != ctx->rasters[dem].h.nrRows)) {
+        rc = ensureRowStart(ctx, ctx->rasters[dem]);
+        if (rc) return rc;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    while ((int)ctx->lanes.size() < nLanes) {
+        pb_context* lane = nullptr;
+        rc = pb_create(ctx->device, &lane);
+        if (rc) return fail(ctx, rc, "could not create a lane context");
+        ctx->lanes.push_back(lane);
+    }
+    for (int l = 0; l < nLanes; l++) {
+        pb_context* lane = ctx->lanes[l];
+        lane->rasters = ctx->rasters;                       // same ids, same device memory
+        for (auto& e : lane->rasters) e.borrowed = true;
+        lane->outInitRaster = -1;
+    }
+    std::atomic<int> next(0);
+    std::vector<int> launches(nLanes, 0);
+    std::vector<float> kernelMs(nLanes, 0.f);
+    std::vector<int64_t> h2d(nLanes, 0), d2h(nLanes, 0);
+    auto work = [&](int l) {
+        pb_context* lane = ctx->lanes[l];
+        cudaSetDevice(lane->device);
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= nItems) break;
+            pb_dem_batch_item& it = items[i];
+            if (!it.meteo || !it.settings || !it.out) { it.status = PB_ERR_INVALID; continue; }
+            it.status = pb_interpolation_dem(lane, it.meteo, it.qualitySettings, it.settings, it.variable, dem, proxyGrids, nProxyGrids,
+                                             rowBegin, rowEnd, deviceOnly, it.out, it.step);
+            launches[l] += lane->timing.launches;
+            kernelMs[l] += lane->timing.kernel_ms;
+            h2d[l] += lane->timing.h2d_bytes;
+            d2h[l] += lane->timing.d2h_bytes;
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int l = 1; l < nLanes; l++) threads.emplace_back(work, l);
+    work(0);
+    for (auto& th : threads) th.join();
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    int firstError = PB_OK;
+    for (int l = 0; l < nLanes; l++) {
+        pb_context* lane = ctx->lanes[l];
+        cudaStreamSynchronize(lane->stream);
+        for (auto& e : lane->rasters) e = RasterEntry();    // views only: nothing to release
+        lane->rasters.clear();
+        ctx->timing.launches += launches[l];
+        ctx->timing.kernel_ms += kernelMs[l];
+        ctx->timing.h2d_bytes += h2d[l];
+        ctx->timing.d2h_bytes += d2h[l];
+    }
+    for (int i = 0; i < nItems; i++)
+        if (items[i].status != PB_OK && items[i].status != PB_ERR_NO_VALID_CELL && firstError == PB_OK) firstError = items[i].status;
+    if (firstError != PB_OK) return fail(ctx, firstError, "a unit of the batch failed (see the items' status)");
     return PB_OK;
 }

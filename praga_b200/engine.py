@@ -73,6 +73,8 @@ def load_library():
     lib.pb_local_detrending_points.argtypes = lib.pb_interpolate_points.argtypes
     lib.pb_interpolation_dem.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), P(A.pb_settings), C.c_int, C.c_int32,
                                          P(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, P(A.pb_raster_out), P(A.pb_dem_step)]
+    lib.pb_interpolation_dem_batch.argtypes = [C.c_void_p, P(A.pb_dem_batch_item), C.c_int, C.c_int32, P(C.c_int32), C.c_int, C.c_int,
+                                               C.c_int, C.c_int, C.c_int]
     lib.pb_kriging_setup.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_int, P(C.c_int32)]
     lib.pb_kriging_free.argtypes = [C.c_void_p, C.c_int32]
@@ -92,7 +94,7 @@ def load_library():
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
     lib.pb_measure_fp64_peak.argtypes = [C.c_void_p, P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
-                 "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series", "pb_dem_step"):
+                 "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series", "pb_dem_step", "pb_dem_batch_item"):
         got, want = lib.pb_abi_sizeof(name.encode()), C.sizeof(getattr(A, name))
         if got != want:
             raise PragaB200Error(A.PB_ERR_INVALID, f"ABI mismatch for {name}: library {got} B, binding {want} B")
@@ -399,6 +401,47 @@ class Engine:
                     residual=res if cross_validate else None,
                     stats={k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_} if cross_validate else None,
                     kh_series=[(series.kh[i], series.error[i]) for i in range(series.n)])
+
+    def interpolation_dem_batch(self, units, dem_id, shape, proxy_ids=(), cross_validate=False, device_only=False, lanes=0,
+                                outs=None):
+        """pb_interpolation_dem_batch. units: list of (meteo stations, settings, quality settings or None, variable).
+        Returns a list of dicts like interpolation_dem (grid None when device_only)."""
+        n = len(units)
+        items = (A.pb_dem_batch_item * max(1, n))()
+        keep = []
+        for i, (meteo, s, sq, var) in enumerate(units):
+            st = meteo.as_pb()
+            o = A.pb_raster_out()
+            grid = None
+            if not device_only:
+                grid = outs[i] if outs is not None else np.empty(shape, dtype=np.float32)
+                o.data = A.fptr(grid)
+            wrong = np.zeros(meteo.n, dtype=np.uint8)
+            res = np.empty(meteo.n, dtype=np.float32)
+            stats, series, step = A.pb_cv_stats(), A.pb_kh_series(), A.pb_dem_step()
+            step.wrongSpatial = A.u8ptr(wrong)
+            step.khSeries = C.pointer(series)
+            if cross_validate:
+                step.residual = A.fptr(res)
+                step.stats = C.pointer(stats)
+            items[i].meteo = C.pointer(st)
+            items[i].settings = C.pointer(s)
+            if sq is not None:
+                items[i].qualitySettings = C.pointer(sq)
+            items[i].variable = var
+            items[i].out = C.pointer(o)
+            items[i].step = C.pointer(step)
+            keep.append((meteo, st, o, grid, wrong, res, stats, series, step))
+        ids = (C.c_int32 * max(1, len(proxy_ids)))(*proxy_ids)
+        rc = self.lib.pb_interpolation_dem_batch(self.h, items, n, dem_id, ids, len(proxy_ids), 0, -1, int(device_only), lanes)
+        self._check(rc, allow=(A.PB_ERR_NO_VALID_CELL,))
+        out = []
+        for i, (meteo, st, o, grid, wrong, res, stats, series, step) in enumerate(keep):
+            out.append(dict(ok=items[i].status == A.PB_OK, status=items[i].status, grid=grid, min=o.minimum, max=o.maximum,
+                            n_valid=o.nValid, wrong_spatial=wrong.astype(bool), residual=res if cross_validate else None,
+                            stats={k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_} if cross_validate else None,
+                            kh_series=[(series.kh[j], series.error[j]) for j in range(series.n)]))
+        return out
 
     def pre_interpolation_batch(self, stations, values, settings, variable, points_range=None):
         """T time steps sharing the station set. values: (T, n). Returns (detrended (T, n), keep (T, n), [settings] * T)."""

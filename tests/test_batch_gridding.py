@@ -119,3 +119,34 @@ def test_interpolation_dem_without_quality_control_and_device_only(engine, ref):
     finally:
         engine.free(dem_id)
         engine.free(urb_id)
+
+
+def test_batch_call_equals_stand_alone_calls(engine, ref):
+    """pb_interpolation_dem_batch (units spread over internal lanes / streams) returns, unit by unit, exactly what the
+    stand-alone call returns: rasters, flags, residuals, statistics and the settings written back."""
+    dem, urban, steps = batch_inputs(n=200, seed=71)
+    dem_id, urb_id = engine.upload(dem), engine.upload(urban)
+    try:
+        units, alone = [], []
+        for h, var, st in steps:
+            s_a, sq_a = settings_for(var)
+            alone.append((engine.interpolation_dem(st.copy(), s_a, var, dem_id, dem.shape, (dem_id, urb_id), quality_settings=sq_a,
+                                                   cross_validate=True), s_a, sq_a))
+            s_b, sq_b = settings_for(var)
+            units.append((st.copy(), s_b, sq_b, var))
+        for lanes in (1, 3, 5):
+            fresh = [(u[0].copy(), clone(settings_for(u[3])[0]), clone(settings_for(u[3])[1]), u[3]) for u in units]
+            got = engine.interpolation_dem_batch(fresh, dem_id, dem.shape, (dem_id, urb_id), cross_validate=True, lanes=lanes)
+            assert len(got) == len(steps)
+            for (a, s_a, sq_a), g, u in zip(alone, got, fresh):
+                assert g["ok"] == a["ok"]
+                assert np.array_equal(g["grid"], a["grid"]), lanes
+                assert np.array_equal(g["wrong_spatial"], a["wrong_spatial"])
+                assert np.array_equal(g["residual"], a["residual"])
+                assert g["stats"] == a["stats"] and g["n_valid"] == a["n_valid"] and g["min"] == a["min"] and g["max"] == a["max"]
+                assert settings_equal(u[1], s_a), describe_diff(u[1], s_a)
+                assert settings_equal(u[2], sq_a), describe_diff(u[2], sq_a)
+        assert engine.timing()["launches"] > len(steps)
+    finally:
+        engine.free(dem_id)
+        engine.free(urb_id)
