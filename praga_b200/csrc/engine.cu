@@ -1274,48 +1274,46 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
         cudaEventRecord(ctx->evBand[b], sUp);
         return PB_OK;
     };
-    rc = issueUpload(0);
-    if (rc) return fail2(rc);
-    for (int b = 0; b < nBands; b++) {
+    // ---- grid + down for one band: one pass writes the flag into the output band and lists the band's valid cells, K1 runs
+    //      over that list (its length is read on the device), then the band's output rows start their way down
+    auto issueBand = [&](int b, bool mayScatter) -> int {
         const int r0 = rowBegin + b * bandRows, r1 = std::min(rowEnd, r0 + bandRows);
-        if (r0 >= r1) continue;
+        if (r0 >= r1) return PB_OK;
         const long long bandCells = (long long)(r1 - r0) * cols;
-        // the next band's uploads are queued BEFORE this band's kernels: the upload engine is the busiest resource of the
-        // pipeline and must never wait for the host
-        if (b + 1 < nBands) {
-            rc = issueUpload(b + 1);
-            if (rc) return fail2(rc);
-        }
         cudaStreamWaitEvent(sK, ctx->evBand[b], 0);
-        // ---- grid: one pass writes the flag into the output band and lists the band's valid cells; K1 over that list
-        //      (its length is read on the device)
         cudaError_t ce = launchCompactFill(eDem.d + size_t(r0) * cols, bandCells, eDem.h.flag, eDem.validIdx + size_t(r0) * cols,
                                            int(size_t(r0) * cols), dTotals + b, ctx->dOut.p + size_t(r0) * cols, sK);
         if (ce == cudaSuccess)
             ce = launchIdwRaster(ds, m, dg, eDem.validIdx + size_t(r0) * cols, (int)bandCells, ctx->dOut.p, ctx->dMinMax, sK,
                                  dTotals + b, dCounters + b);
-        if (ce != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, std::string("band pipeline: ") + cudaGetErrorString(ce)); return fail2(PB_ERR_CUDA); }
+        if (ce != cudaSuccess) return failCtx(ctx, PB_ERR_CUDA, std::string("band pipeline: ") + cudaGetErrorString(ce));
         ctx->timing.launches += 2;
         cudaEventRecord(ctx->evBand[kMaxBands + b], sK);
         cudaStreamWaitEvent(sDn, ctx->evBand[kMaxBands + b], 0);
-        // ---- down: the band's output rows; chunks are scattered into the caller's grid while later ones are in flight
         for (int a = r0; a < r1; a += chunkRows) {
-            if (inflight.size() - head >= size_t(PinnedRing::kSlots - 1)) {
-                if (scatter(inflight[head++]) != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, "D2H failed"); return fail2(PB_ERR_CUDA); }
-            }
+            if (mayScatter && inflight.size() - head >= size_t(PinnedRing::kSlots - 1))
+                if (scatter(inflight[head++]) != cudaSuccess) return failCtx(ctx, PB_ERR_CUDA, "D2H failed");
             Chunk c;
             c.r0 = a;
             c.r1 = std::min(r1, a + chunkRows);
             c.stage = reinterpret_cast<float*>(ctx->ringDn.acquire(&c.slot));
             ce = cudaMemcpyAsync(c.stage, ctx->dOut.p + size_t(a) * cols, size_t(c.r1 - a) * cols * sizeof(float),
                                  cudaMemcpyDeviceToHost, sDn);
-            if (ce != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(ce)); return fail2(PB_ERR_CUDA); }
+            if (ce != cudaSuccess) return failCtx(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(ce));
             ctx->ringDn.submitted(c.slot, sDn);
             inflight.push_back(c);
         }
-        // no host wait here: the upload engine is the busiest resource of the pipeline, every band's uploads are issued as
-        // early as the staging ring allows; finished output chunks are scattered after the loop (or above, under slot pressure)
+        return PB_OK;
+    };
+    // The upload engine is the busiest resource of the pipeline and must never wait for the host: the next band's uploads are
+    // queued BEFORE this band's kernels. (A second host thread issuing the kernels / downloads was measured slower: the two
+    // threads contend for the driver and the spinning one disturbs the OpenMP team that gathers the rows.)
+    rc = issueUpload(0);
+    for (int b = 0; b < nBands && rc == PB_OK; b++) {
+        if (b + 1 < nBands) rc = issueUpload(b + 1);
+        if (rc == PB_OK) rc = issueBand(b, true);
     }
+    if (rc) return fail2(rc);
     cudaEventRecord(ctx->ev[2], sK);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, sK));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hBand, dTotals, kMaxBands * sizeof(long long), cudaMemcpyDeviceToHost, sK));
