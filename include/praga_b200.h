@@ -389,6 +389,18 @@ int pb_topographic_distance_map(pb_context* ctx, pb_raster_id dem, double x, dou
 int pb_resample_grid(pb_context* ctx, pb_raster_id src, const pb_raster_header* newHeader, int method, float nodataRatioThreshold,
                      pb_raster_out* out, pb_raster_id* outId);
 
+/* --- ESRI float grids (.hdr + .flt), the on-disk format at either end of the path, streamed between
+ * the file and HBM through pinned staging (no pageable full-size copy):
+ *   pb_raster_read_esri_header <- gis::readEsriGridHeader (agrolib/gis/gisIO.cpp:118-193)
+ *   pb_raster_read_esri        <- gis::readEsriGrid (:516-557: header, readRasterFloatData :347-422 for 4 / 2 / 1-byte values,
+ *                                 updateMinMaxRasterGrid); fileName with or without ".flt"; the grid becomes a resident raster
+ *   pb_raster_write_esri       <- gis::writeEsriGrid (:504-513; header text byte-identical to writeEsriGridHeader :432-467);
+ *                                 fileName without extension */
+int pb_raster_read_esri_header(pb_context* ctx, const char* fileName, pb_raster_header* header);
+int pb_raster_read_esri(pb_context* ctx, const char* fileName, pb_raster_id* id, pb_raster_header* header /* may be NULL */,
+                        float* minimum /* may be NULL */, float* maximum /* may be NULL */);
+int pb_raster_write_esri(pb_context* ctx, pb_raster_id id, const char* fileName);
+
 /* --- timing of the last call (device time measured with CUDA events on the engine's stream) ------ */
 typedef struct pb_timing {
     float h2d_ms, kernel_ms, d2h_ms, total_ms;

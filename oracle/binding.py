@@ -57,6 +57,16 @@ def load_ref_extra():
     return lib
 
 
+def load_ref_io():
+    """ESRI grid I/O of the reference (gis/gisIO.cpp), reference driver only."""
+    lib = _load(REF_LIB, "ref")
+    P = C.POINTER
+    lib.ref_write_esri.argtypes = [P(A.pb_raster), C.c_char_p]
+    lib.ref_read_esri_header.argtypes = [C.c_char_p, P(A.pb_raster_header)]
+    lib.ref_read_esri.argtypes = [C.c_char_p, P(A.pb_raster_out)]
+    return lib
+
+
 def have_port():
     return os.path.exists(PORT_LIB)
 
@@ -321,6 +331,26 @@ class Oracle:
         o.data = A.fptr(out)
         rc = self._f("resample_grid")(C.byref(s), C.byref(new_header), method, threshold, C.byref(o))
         return rc == A.PB_OK, out, o.minimum, o.maximum
+
+    # ---- ESRI float grids (reference oracle only) ----
+    def write_esri(self, raster, path):
+        assert self.kind == "reference"
+        r = raster.as_pb()
+        return load_ref_io().ref_write_esri(C.byref(r), path.encode()) == A.PB_OK
+
+    def read_esri(self, path):
+        """gis::readEsriGrid. Returns (header, grid, min, max) or None."""
+        assert self.kind == "reference"
+        lib = load_ref_io()
+        h = A.pb_raster_header()
+        if lib.ref_read_esri_header(path.encode(), C.byref(h)) != A.PB_OK:
+            return None
+        out = np.empty((h.nrRows, h.nrCols), dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        if lib.ref_read_esri(path.encode(), C.byref(o)) != A.PB_OK:
+            return None
+        return h, out, o.minimum, o.maximum
 
     def kriging_points(self, pos, val, mode, rng, nugget, sill, slope, xy, want_rmse=True):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1)

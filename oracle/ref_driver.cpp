@@ -608,6 +608,37 @@ int ref_resample_grid(const pb_raster* src, const pb_raster_header* newHeader, i
     return PB_OK;
 }
 
+/* gis::writeEsriGrid / gis::readEsriGrid, verbatim reference code (gis/gisIO.cpp) */
+}  // extern "C"
+namespace gis { bool readEsriGridHeader(const std::string& fileName, gis::Crit3DRasterHeader* header, std::string& errorStr); }   // gisIO.cpp:118, not in gis.h
+extern "C" {
+int ref_write_esri(const pb_raster* r, const char* fileName)
+{
+    gis::Crit3DRasterGrid g;
+    fillGrid(g, *r);
+    std::string err;
+    return gis::writeEsriGrid(fileName, &g, err) ? PB_OK : PB_ERR_INVALID;
+}
+int ref_read_esri_header(const char* fileName, pb_raster_header* h)
+{
+    gis::Crit3DRasterHeader header;
+    std::string err;
+    if (!gis::readEsriGridHeader(fileName, &header, err)) return PB_ERR_INVALID;
+    memset(h, 0, sizeof(*h));
+    h->nrRows = header.nrRows; h->nrCols = header.nrCols; h->cellSize = header.cellSize; h->invCellSize = header.invCellSize;
+    h->llx = header.llCorner.x; h->lly = header.llCorner.y; h->flag = header.flag;
+    return PB_OK;
+}
+int ref_read_esri(const char* fileName, pb_raster_out* out)
+{
+    gis::Crit3DRasterGrid g;
+    std::string err;
+    if (!gis::readEsriGrid(fileName, &g, err)) return PB_ERR_INVALID;
+    out->nValid = int64_t(g.header->nrRows) * g.header->nrCols;
+    copyOut(g, out);
+    return PB_OK;
+}
+
 /* interpolate() at arbitrary targets (x, y, z, proxyValues[nProxy]) — interpolation.cpp:2502 */
 int ref_interpolate_points(const pb_stations* st, const pb_settings* s, int variable, const float* x, const float* y,
                            const float* z, const double* proxyValues, int m, int excludeSupplemental, float* result)

@@ -25,6 +25,7 @@ SOURCES = {
     "shepard_kernels.cu": ["-fmad=false"],
     "station_space.cu": [],
     "raster_ops.cu": ["-fmad=false"],
+    "raster_io.cu": [],
     "kriging.cu": [],
     "kriging_tc.cu": [],
 }

@@ -84,6 +84,9 @@ def load_library():
                                       P(A.pb_raster_out)]
     lib.pb_interpolate_points_td.argtypes = raster_args + [P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_double), C.c_int,
                                                            C.c_int, C.c_int32, P(C.c_float)]
+    lib.pb_raster_read_esri_header.argtypes = [C.c_void_p, C.c_char_p, P(A.pb_raster_header)]
+    lib.pb_raster_read_esri.argtypes = [C.c_void_p, C.c_char_p, P(C.c_int32), P(A.pb_raster_header), P(C.c_float), P(C.c_float)]
+    lib.pb_raster_write_esri.argtypes = [C.c_void_p, C.c_int32, C.c_char_p]
     lib.pb_raster_download.argtypes = [C.c_void_p, C.c_int32, P(A.pb_raster_out)]
     lib.pb_relative_humidity_map.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(A.pb_raster_out), P(C.c_int32)]
     lib.pb_fix_daily_thermal_consistency.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(C.c_int64)]
@@ -247,6 +250,17 @@ class Engine:
         rid = C.c_int32(-1)
         rc = self._check(fn(self.h, *args, C.byref(o), C.byref(rid) if keep else None), allow=(A.PB_ERR_NO_VALID_CELL,))
         return rc == A.PB_OK, out, o.minimum, o.maximum, (rid.value if keep else None)
+
+    def read_esri(self, path):
+        """gis::readEsriGrid (gisIO.cpp:516-557) straight into a resident raster. Returns (id, header, min, max)."""
+        rid, h = C.c_int32(-1), A.pb_raster_header()
+        mn, mx = C.c_float(0), C.c_float(0)
+        self._check(self.lib.pb_raster_read_esri(self.h, path.encode(), C.byref(rid), C.byref(h), C.byref(mn), C.byref(mx)))
+        return rid.value, h, mn.value, mx.value
+
+    def write_esri(self, rid, path):
+        """gis::writeEsriGrid (gisIO.cpp:504-513) from a resident raster; path without extension."""
+        self._check(self.lib.pb_raster_write_esri(self.h, rid, path.encode()))
 
     def download(self, rid, shape):
         out = np.empty(shape, dtype=np.float32)
