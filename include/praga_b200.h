@@ -258,6 +258,53 @@ int pb_local_detrending_raster_device(pb_context* ctx, const pb_stations* st, co
                                       pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids,
                                       int rowBegin, int rowEnd, pb_raster_out* out);
 
+/* --- glocal detrending: one multiple-detrending fit per MACRO AREA, cells blended over the areas they belong to.
+ * pb_macro_area mirrors Crit3DMacroArea (agrolib/interpolation/interpolationSettings.h:149-182): meteoPoints = the
+ * Crit3DInterpolationDataPoint::index values of the area's stations (matched against st->index, or the position when that is
+ * NULL), areaCellsDEM = the reference's flat (cell index = row * nrCols + col, weight) pairs as floats (cell indices above
+ * 2^24 are not exact in that format; the reference has the same limit). The fit part is in/out.
+ *   pb_glocal_detrending_fitting <- glocalDetrendingFitting (agrolib/interpolation/interpolation.cpp:2239-2294) as
+ *       preInterpolation :2471-2474 reaches it (after setMultipleDetrendingHeightTemperatureRange): per area with stations,
+ *       the UNWEIGHTED elevation fit (bestFittingMarquardt_nDimension, mathFunctions/furtherMathFunctions.cpp:1433-1529, over
+ *       fittingMarquardt_nDimension :2125-2283), detrendingElevation, the other proxies' fit; the area keeps parameters and
+ *       combination. All areas are fitted in ONE launch (one lane group per area). st = the NOT detrended points; *s receives
+ *       what the reference leaves in the settings (the last fitted area's combination / parameters, the height ranges).
+ *   pb_glocal_detrending_raster  <- the loop of Project::interpolationDemGlocalDetrending (agrolib/project/project.cpp:3262-3375)
+ *       after checkAndPassDataToInterpolation: preInterpolation (= the fitting above), then per area macroAreaDetrending
+ *       (interpolation.cpp:1759-1829: the area's stations detrended with the area's fit), and for each of its cells
+ *       getUtmXYFromRowCol (cell centre, gis/gis.cpp:806-810), getSignificantProxyValuesXY (:2650-2677; incomplete => the
+ *       cell is set to NODATA), interpolate() over the area's stations, out[cell] (+)= value * weight. Areas are applied in
+ *       index order (the reference's order when isParallelComputing is off; with OpenMP it is unordered, same sum up to
+ *       float rounding). Returns PB_ERR_NO_VALID_CELL where the reference returns false (an interpolate() gave NODATA); the
+ *       grid is still written. out->minimum / maximum as gis::updateMinMaxRasterGrid would set them. Topographic distance
+ *       inside macro areas is not on the GPU path (PB_ERR_UNSUPPORTED).
+ *   pb_compute_residuals_glocal  <- Project::computeResidualsAndStatisticsGlocalDetrending (project.cpp:6525-6565) over
+ *       computeResidualsGlocalDetrending (agrolib/interpolation/spatialControl.cpp:231-302), areas already fitted: meteo =
+ *       one entry per Crit3DMeteoPoint (position, lapse code, proxy values; meteo->isActive = active), area.meteoPoints index
+ *       this array AND are matched against points->index; residual[meteo->n] = sum over the areas holding the point of
+ *       (observed - interpolate()), NODATA where never computed. */
+typedef struct pb_macro_area {
+    int32_t nMeteoPoints;
+    int32_t reserved;
+    const int32_t* meteoPoints;    /* Crit3DMacroArea::getMeteoPoints() */
+    int64_t nAreaCells;            /* number of FLOATS in areaCellsDEM (2 per cell) */
+    const float* areaCellsDEM;     /* Crit3DMacroArea::getAreaCellsDEM() */
+    /* fit (in/out): areaCombination, areaParameters (elevation first when significant) */
+    uint8_t active[PB_MAX_PROXY], significant[PB_MAX_PROXY];
+    int32_t useThermalInversion;
+    int32_t nParameters;
+    int32_t nrParams[PB_MAX_PROXY];
+    double parameters[PB_MAX_PROXY][PB_MAX_FIT_PARAMS];
+} pb_macro_area;
+int pb_glocal_detrending_fitting(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
+                                 int nAreas);
+int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
+                                int nAreas, pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int deviceOnly,
+                                pb_raster_out* out);
+int pb_compute_residuals_glocal(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
+                                const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
+                                int excludeOutsideDem, int excludeSupplemental, float* residual);
+
 /* --- interpolate() at explicit targets (agrolib/interpolation/interpolation.h:77-79, .cpp:2502-2560) -------
  * The building block of computeResiduals (spatialControl.cpp:97-155): x, y are the f32 target coordinates,
  * proxyValues holds m * settings.nProxy doubles (the targets' own proxy values, NODATA where missing).

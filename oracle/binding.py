@@ -116,6 +116,14 @@ def _load(path, prefix):
     fn = getattr(lib, prefix + "_local_detrending_point")
     fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, C.c_double, C.c_double, C.c_float, P(C.c_double),
                    P(C.c_int), P(C.c_float), P(C.c_float), P(C.c_int), P(C.c_float)]
+    fn = getattr(lib, prefix + "_glocal_detrending_fitting")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int]
+    fn = getattr(lib, prefix + "_glocal_detrending_raster")
+    fn.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int, P(A.pb_raster), P(A.pb_raster),
+                   C.c_int, C.c_int, P(A.pb_raster_out), P(C.c_double)]
+    fn = getattr(lib, prefix + "_compute_residuals_glocal")
+    fn.argtypes = [P(A.pb_stations), P(C.c_float), P(A.pb_cv_points), P(A.pb_stations), P(A.pb_settings), C.c_int,
+                   P(A.pb_macro_area), C.c_int, P(A.pb_raster), C.c_int, C.c_int, P(C.c_float)]
     _libs[path] = lib
     return lib
 
@@ -299,6 +307,41 @@ class Oracle:
         self._f("compute_residuals_local" if local else "compute_residuals")(C.byref(st), C.byref(settings), variable, A.fptr(obs),
                                      None if use is None else A.u8ptr(use), A.fptr(res), C.byref(stats))
         return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}
+
+    # ---- glocal detrending (macro areas) ----
+    def glocal_detrending_fitting(self, stations, settings, variable, areas):
+        """preInterpolation with useGlocalDetrending (glocalDetrendingFitting, interpolation.cpp:2239-2294): the areas
+        (praga_b200._abi.MacroAreas) receive their fit, settings what the reference leaves behind."""
+        st = stations.as_pb()
+        rc = self._f("glocal_detrending_fitting")(C.byref(st), C.byref(settings), variable, areas.arr, areas.n)
+        return rc == A.PB_OK
+
+    def glocal_detrending_raster(self, stations, settings, variable, areas, dem, proxy_grids=(), threads=1):
+        """gridding part of Project::interpolationDemGlocalDetrending (project.cpp:3283-3375).
+        Returns (ok, grid, min, max, nValid, seconds)."""
+        st = stations.as_pb()
+        d = dem.as_pb()
+        grids = (A.pb_raster * max(1, len(proxy_grids)))()
+        for i, g in enumerate(proxy_grids):
+            grids[i] = g.as_pb()
+        out = np.empty(dem.shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        sec = C.c_double(0)
+        rc = self._f("glocal_detrending_raster")(C.byref(st), C.byref(settings), variable, areas.arr, areas.n, C.byref(d), grids,
+                                                 len(proxy_grids), threads, C.byref(o), C.byref(sec))
+        return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid, sec.value
+
+    def compute_residuals_glocal(self, meteo, observed, points, settings, variable, areas, dem, exclude_outside_dem=True,
+                                 exclude_supplemental=True):
+        """computeResidualsAndStatisticsGlocalDetrending (project.cpp:6525-6565), areas already fitted."""
+        obs = np.ascontiguousarray(observed, dtype=np.float32)
+        res = np.empty(meteo.n, dtype=np.float32)
+        mp, pt, d = meteo.as_pb(), points.as_pb(), dem.as_pb()
+        rc = self._f("compute_residuals_glocal")(C.byref(mp), A.fptr(obs), None, C.byref(pt), C.byref(settings), variable,
+                                                 areas.arr, areas.n, C.byref(d), int(exclude_outside_dem),
+                                                 int(exclude_supplemental), A.fptr(res))
+        return rc == A.PB_OK, res
 
     # ---- raster map operators (SURVEY 8f rows 2-3) ----
     def relative_humidity_map(self, air_t, dew_t):

@@ -50,6 +50,7 @@ struct Point {            // Crit3DInterpolationDataPoint, interpolation/interpo
     double x, y, z;
     float value, regressionWeight;
     int lapseRateCode, index;
+    int meteoIndex;           // Crit3DInterpolationDataPoint::index as the caller gave it (macro areas refer to it)
     bool isActive;
     float proxy[PB_MAX_PROXY];
     int nProxy;
@@ -67,6 +68,7 @@ std::vector<Point> loadPoints(const pb_stations* st)
         p.lapseRateCode = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
         p.isActive = st->isActive ? st->isActive[i] != 0 : true;
         p.index = i;
+        p.meteoIndex = st->index ? st->index[i] : i;
         p.nProxy = st->nProxy;
         for (int k = 0; k < st->nProxy && k < PB_MAX_PROXY; k++) p.proxy[k] = st->proxyValues[size_t(i) * st->nProxy + k];
     }
@@ -1047,6 +1049,69 @@ double bestFittingMarquardt1D(int f, const double* pmin, const double* pmax, dou
     return bestR2;
 }
 
+// computeR2adjusted :1175-1194, computeRMSE :1324-1340
+double r2Adjusted(const std::vector<double>& obs, const std::vector<double>& sim)
+{
+    double meanObs = 0, RSS = 0, TSS = 0;
+    for (size_t i = 0; i < obs.size(); i++) meanObs += obs[i];
+    meanObs /= obs.size();
+    for (size_t i = 0; i < obs.size(); i++) {
+        RSS += (obs[i] - sim[i]) * (obs[i] - sim[i]);
+        TSS += (obs[i] - meanObs) * (obs[i] - meanObs);
+    }
+    return 1 - RSS / TSS;
+}
+double rmsePlain(const std::vector<double>& obs, const std::vector<double>& pred)
+{
+    double sum = 0.0;
+    for (size_t i = 0; i < obs.size(); i++) {
+        const double residual = (obs[i] - pred[i]) * (obs[i] - pred[i]);
+        sum += residual;
+    }
+    return sqrt(sum / obs.size());
+}
+
+// bestFittingMarquardt_nDimension, elevation, NO weights (glocal detrending): furtherMathFunctions.cpp:1433-1529. The descent
+// fittingMarquardt_nDimension :2125-2283 is the weighted one :1954-2118 with every weight dropped; with weights of exactly
+// 1.0 each product it drops is exact, so the weighted restatement above run on unit weights takes the same steps bit for bit.
+double bestFittingMarquardt1DUnweighted(int f, const double* pmin, const double* pmax, double* par, const double* delta, int nPar,
+                                        int maxIter, double eps, double deltaR2, const std::vector<double>& x,
+                                        const std::vector<double>& y, const pb_proxy& proxy)
+{
+    const int nData = int(y.size());
+    const std::vector<double> ones(nData, 1.0);
+    double best[PB_MAX_FIT_PARAMS] = {0};
+    double bestR2 = -9999, bestRMSE = -9999;
+    int rmseIndex = -9999;
+    std::vector<double> ySim(nData);
+    double maxZ = x.front();
+    for (size_t k = 0; k < x.size(); k++) if (x[k] > maxZ) maxZ = x[k];
+    bool isValid = true;
+    for (int k = 0; k < proxy.nFirstGuessCombinations; k++) {
+        memcpy(par, proxy.firstGuessCombinations[k], sizeof(double) * nPar);
+        fittingMarquardt1D(f, pmin, pmax, par, delta, nPar, maxIter, eps, x, y, ones);
+        bool rangeFlag = true;
+        for (int i = 0; i < nPar; i++)
+            if (par[i] < pmin[i] || par[i] > pmax[i]) { rangeFlag = false; break; }
+        if (!rangeFlag) continue;
+        for (int i = 0; i < nData; i++) ySim[i] = evalFit(f, x[i], par);
+        const double R2 = r2Adjusted(y, ySim);
+        const double RMSE = rmsePlain(y, ySim);
+        if (isEqualD(bestRMSE, -9999) || RMSE < bestRMSE) { bestRMSE = RMSE; rmseIndex = k; }
+        if (nPar > 4) isValid = (par[0] + par[2]) < maxZ;
+        if (isEqualD(bestR2, -9999) || (R2 > (bestR2 + deltaR2) && isValid)) {
+            memcpy(best, par, sizeof(double) * nPar);
+            bestR2 = R2;
+        }
+    }
+    memcpy(par, best, sizeof(double) * nPar);
+    if (bestR2 < 0 && rmseIndex != -9999) {
+        memcpy(par, proxy.firstGuessCombinations[rmseIndex], sizeof(double) * nPar);
+        fittingMarquardt1D(f, pmin, pmax, par, delta, nPar, maxIter, eps, x, y, ones);
+    }
+    return bestR2;
+}
+
 bool isVectorNodataOrZero(const double* v, int n)   // interpolation.cpp:2696-2705
 {
     bool flag = false;
@@ -1055,7 +1120,7 @@ bool isVectorNodataOrZero(const double* v, int n)   // interpolation.cpp:2696-27
 }
 
 // multipleDetrendingElevationFitting, interpolation.cpp:1862-1953 (isWeighted = true from multipleDetrendingMain :1848)
-bool multipleDetrendingElevationFitting(Work& w, int elevationPos)
+bool multipleDetrendingElevationFitting(Work& w, int elevationPos, bool isWeighted = true)
 {
     pb_settings& s = *w.s;
     s.proxy[elevationPos].regressionR2 = NODATA_F;
@@ -1088,7 +1153,8 @@ bool multipleDetrendingElevationFitting(Work& w, int elevationPos)
         delta[j] = (pmax[j] - pmin[j]) / 800;
         par[j] = (pmax[j] + pmin[j]) / 2;
     }
-    const double R2 = bestFittingMarquardt1D(f, pmin, pmax, par, delta, nPar, 1000, 0.002, 0.005, x, y, wgt, p);
+    const double R2 = isWeighted ? bestFittingMarquardt1D(f, pmin, pmax, par, delta, nPar, 1000, 0.002, 0.005, x, y, wgt, p)
+                                 : bestFittingMarquardt1DUnweighted(f, pmin, pmax, par, delta, nPar, 1000, 0.002, 0.005, x, y, p);
     s.proxy[elevationPos].regressionR2 = float(R2);
     if (!isEqualD(R2, -9999) || !isVectorNodataOrZero(par, nPar)) addFittingParameters(s, par, nPar);
     else s.currentSignificant[elevationPos] = 0;
@@ -1425,6 +1491,86 @@ float localCell(const std::vector<Point>& pts, pb_settings& s, int var, double x
     return r;
 }
 
+// ---- glocal detrending (macro areas) ---------------------------------------------------------------------------
+// glocalDetrendingFitting, interpolation.cpp:2239-2294
+bool glocalDetrendingFitting(const std::vector<Point>& myPoints, pb_settings& s, int var, pb_macro_area* areas, int nAreas)
+{
+    int elevationPos = -9999;
+    for (int pos = 0; pos < s.nProxy; pos++) if (s.proxy[pos].kind == PB_PROXY_HEIGHT) elevationPos = pos;
+    for (int i = 0; i < nAreas; i++) {
+        pb_macro_area& A = areas[i];
+        if (A.nMeteoPoints <= 0) continue;
+        Work w{{}, &s, var};
+        for (int l = 0; l < A.nMeteoPoints; l++)
+            for (size_t k = 0; k < myPoints.size(); k++)
+                if (myPoints[k].meteoIndex == A.meteoPoints[l]) { w.pts.push_back(myPoints[k]); break; }
+        for (int p = 0; p < s.nProxy; p++) { s.currentActive[p] = s.selectedActive[p]; s.currentSignificant[p] = 0; }
+        s.currentUseThermalInversion = s.selectedUseThermalInversion;
+        s.nFit = s.nFitFunctions = 0;    // clearFitting
+        if (elevationPos != -9999 && s.selectedActive[elevationPos]) {
+            if (!multipleDetrendingElevationFitting(w, elevationPos, false)) return false;
+            if (s.currentSignificant[elevationPos]) detrendingElevation(w, elevationPos);
+        }
+        if (!multipleDetrendingOtherProxiesFitting(w, elevationPos)) return false;
+        memset(A.active, 0, sizeof(A.active));
+        memset(A.significant, 0, sizeof(A.significant));
+        for (int p = 0; p < s.nProxy; p++) { A.active[p] = s.currentActive[p]; A.significant[p] = s.currentSignificant[p]; }
+        A.useThermalInversion = s.currentUseThermalInversion;
+        A.nParameters = s.nFit;
+        for (int p = 0; p < PB_MAX_PROXY; p++) {
+            A.nrParams[p] = p < s.nFit ? s.fitNrParams[p] : 0;
+            for (int j = 0; j < PB_MAX_FIT_PARAMS; j++) A.parameters[p][j] = (p < s.nFit && j < s.fitNrParams[p]) ? s.fitParams[p][j] : 0.;
+        }
+    }
+    return true;
+}
+
+// macroAreaDetrending, interpolation.cpp:1759-1829 (topographic-distance optimisation inside an area: not restated)
+void macroAreaDetrending(const pb_macro_area& A, pb_settings& s, int var, const std::vector<Point>& pts, std::vector<Point>& subset,
+                         int elevationPos)
+{
+    s.nFit = A.nParameters;
+    for (int p = 0; p < A.nParameters; p++) {
+        s.fitNrParams[p] = A.nrParams[p];
+        memcpy(s.fitParams[p], A.parameters[p], sizeof(s.fitParams[p]));
+    }
+    for (int p = 0; p < s.nProxy; p++) { s.currentActive[p] = A.active[p]; s.currentSignificant[p] = A.significant[p]; }
+    s.currentUseThermalInversion = A.useThermalInversion;
+    s.nFitFunctions = 0;
+    for (int l = 0; l < A.nParameters; l++) {
+        const int n = A.nrParams[l];
+        if (n == 2) s.fitFunction[s.nFitFunctions++] = PB_FIT_LINEAR;
+        else if (n == 4) s.fitFunction[s.nFitFunctions++] = PB_FIT_PIECEWISE_TWO;
+        else if (n == 5) s.fitFunction[s.nFitFunctions++] = PB_FIT_PIECEWISE_THREE;
+        else if (n == 6) s.fitFunction[s.nFitFunctions++] = PB_FIT_PIECEWISE_THREE_FREE;
+    }
+    Work w{{}, &s, var};
+    for (int l = 0; l < A.nMeteoPoints; l++)
+        for (size_t k = 0; k < pts.size(); k++)
+            if (pts[k].meteoIndex == A.meteoPoints[l]) w.pts.push_back(pts[k]);
+    if (elevationPos != -9999 && A.active[elevationPos] && A.significant[elevationPos]) detrendingElevation(w, elevationPos);
+    detrendingOtherProxies(w, elevationPos);
+    subset.swap(w.pts);
+}
+
+// getSignificantProxyValuesXY, interpolation.cpp:2650-2677
+bool getSignificantProxyValuesXY(float x, float y, const pb_settings& s, const std::vector<Grid>& grids, double* pv)
+{
+    bool complete = true;
+    for (int i = 0; i < s.nProxy; i++) {
+        pv[i] = -9999;
+        if (s.currentActive[i] && s.currentSignificant[i]) {
+            const int gi = s.proxy[i].gridIndex;
+            if (gi >= 0 && gi < int(grids.size())) {
+                const float v = grids[gi].valueFromXY(x, y);
+                if (v != grids[gi].h.flag) pv[i] = v;
+                else complete = false;
+            }
+        }
+    }
+    return complete;
+}
+
 Grid gridOf(const pb_raster& r) { return Grid{r.h, r.data, r.rows}; }
 
 }  // namespace
@@ -1507,6 +1653,7 @@ struct MeteoPt {        // the Crit3DMeteoPoint fields computeResiduals reads (m
     float currentValue, residual;
     int lapseRateCode;
     bool isInsideDem;
+    bool active = true;
     std::vector<float> proxy;
 };
 
@@ -2353,6 +2500,130 @@ int port_kriging_points(const double* pos, const double* val, int n, int mode, d
     auto t2 = std::chrono::steady_clock::now();
     if (setup_s) *setup_s = std::chrono::duration<double>(t1 - t0).count();
     if (eval_s) *eval_s = std::chrono::duration<double>(t2 - t1).count();
+    return PB_OK;
+}
+
+}  // extern "C"
+
+// ---- glocal detrending entry points ------------------------------------------------------------------------------
+extern "C" {
+
+// preInterpolation :2444-2499 with useGlocalDetrending: height ranges, then glocalDetrendingFitting
+int port_glocal_detrending_fitting(const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas)
+{
+    std::vector<Point> pts = loadPoints(st);
+    if (!useDetrendingVar(variable) || !s->useMultipleDetrending) return PB_OK;
+    if (!s->useLocalDetrending) setMultipleDetrendingHeightTemperatureRange(*s);
+    glocalDetrendingFitting(pts, *s, variable, areas, nAreas);        // the result is ignored by preInterpolation (:2473)
+    return PB_OK;
+}
+
+// the gridding part of Project::interpolationDemGlocalDetrending, project/project.cpp:3283-3375 (areas in index order)
+int port_glocal_detrending_raster(const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas,
+                                  const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int, pb_raster_out* out,
+                                  double* elapsed_s)
+{
+    if (!useDetrendingVar(variable) || !s->useGlocalDetrending) return PB_ERR_INVALID;
+    std::vector<Point> pts = loadPoints(st);
+    Grid d = gridOf(*dem);
+    std::vector<Grid> grids;
+    for (int g = 0; g < nProxyGrids; g++) grids.push_back(gridOf(proxyGrids[g]));
+    const int rows = d.h.nrRows, cols = d.h.nrCols;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int p = 0; p < s->nProxy; p++) { s->currentActive[p] = s->selectedActive[p]; s->currentSignificant[p] = 0; }
+    int rc = port_glocal_detrending_fitting(st, s, variable, areas, nAreas);
+    if (rc) return rc;
+    bool isOk = true;
+    for (int row = 0; row < rows; row++) {
+        float* orow = out->data ? out->data + size_t(row) * cols : out->rows[row];
+        for (int col = 0; col < cols; col++) orow[col] = d.h.flag;           // initializeGrid(header)
+    }
+    if (!setMultipleDetrendingHeightTemperatureRange(*s)) return PB_ERR_FIT;
+    int elevationPos = -9999;
+    for (int pos = 0; pos < s->nProxy; pos++) if (s->proxy[pos].kind == PB_PROXY_HEIGHT) elevationPos = pos;
+    pb_settings my = *s;
+    for (int a = 0; a < nAreas && isOk; a++) {
+        const pb_macro_area& A = areas[a];
+        if (A.nAreaCells <= 0) continue;
+        std::vector<Point> subset;
+        macroAreaDetrending(A, my, variable, pts, subset, elevationPos);
+        for (int64_t c = 0; c + 1 < A.nAreaCells; c += 2) {
+            if (!isOk) break;
+            const int row = int(A.areaCellsDEM[c] / cols);
+            const int col = int(A.areaCellsDEM[c]) % cols;
+            const float z = d.at(row, col);
+            if (isEqualF(z, d.h.flag)) continue;
+            const double x = d.h.llx + d.h.cellSize * (col + 0.5);              // getUtmXYFromRowCol, gis.cpp:806-810
+            const double y = d.h.lly + d.h.cellSize * (rows - row - 0.5);
+            float* cell = (out->data ? out->data + size_t(row) * cols : out->rows[row]) + col;
+            double pv[PB_MAX_PROXY];
+            if (!getSignificantProxyValuesXY(float(x), float(y), my, grids, pv)) { *cell = NODATA_F; continue; }
+            const double v = interpolate(subset, my, variable, float(x), float(y), pv, true, z, nullptr);
+            if (isEqualD(v, -9999)) isOk = false;
+            if (isEqualF(*cell, NODATA_F)) *cell = float(v * A.areaCellsDEM[c + 1]);
+            else *cell += v * A.areaCellsDEM[c + 1];
+        }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    int64_t nValid = 0;
+    bool first = true;
+    float mn = NODATA_F, mx = NODATA_F;
+    for (int row = 0; row < rows; row++) {
+        const float* orow = out->data ? out->data + size_t(row) * cols : out->rows[row];
+        for (int col = 0; col < cols; col++) {
+            if (!isEqualF(d.at(row, col), d.h.flag)) nValid++;
+            const float v = orow[col];
+            if (!isEqualF(v, d.h.flag) && !isEqualF(v, NODATA_F)) {
+                if (first) { mn = mx = v; first = false; }
+                else if (v < mn) mn = v;
+                else if (v > mx) mx = v;
+            }
+        }
+    }
+    out->minimum = mn; out->maximum = mx; out->nValid = nValid;
+    return isOk ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
+// Project::computeResidualsAndStatisticsGlocalDetrending (project.cpp:6525-6565) over computeResidualsGlocalDetrending
+// (spatialControl.cpp:231-302)
+int port_compute_residuals_glocal(const pb_stations* meteo, const float* observed, const pb_cv_points* cv, const pb_stations* points,
+                                  pb_settings* s, int variable, const pb_macro_area* areas, int nAreas, const pb_raster*,
+                                  int excludeOutsideDem, int excludeSupplemental, float* residual)
+{
+    std::vector<Point> pts = loadPoints(points);
+    std::vector<MeteoPt> mp = loadMeteoPoints(meteo, cv);
+    for (int i = 0; i < meteo->n; i++) {
+        if (observed) mp[i].currentValue = observed[i];
+        mp[i].active = meteo->isActive ? meteo->isActive[i] != 0 : true;
+        mp[i].residual = NODATA_F;
+    }
+    if (!setMultipleDetrendingHeightTemperatureRange(*s)) return PB_ERR_FIT;
+    int elevationPos = -9999;
+    for (int pos = 0; pos < s->nProxy; pos++) if (s->proxy[pos].kind == PB_PROXY_HEIGHT) elevationPos = pos;
+    for (int k = 0; k < nAreas; k++) {
+        const pb_macro_area& A = areas[k];
+        if (A.nAreaCells <= 0 || A.nMeteoPoints <= 0) continue;
+        std::vector<Point> subset;
+        macroAreaDetrending(A, *s, variable, pts, subset, elevationPos);
+        for (int i = 0; i < A.nMeteoPoints; i++) {
+            MeteoPt& m = mp[A.meteoPoints[i]];
+            if (!m.active) continue;
+            const float weight = 1;
+            bool isValid = !excludeSupplemental || checkLapseRateCode(m.lapseRateCode, s->useLapseRateCode != 0, false);
+            isValid = isValid && (!excludeOutsideDem || m.isInsideDem);
+            if (!isValid) continue;
+            double pv[PB_MAX_PROXY];
+            for (int q = 0; q < PB_MAX_PROXY; q++) pv[q] = q < int(m.proxy.size()) ? double(m.proxy[q]) : -9999.;
+            const float myValue = m.currentValue;
+            const float est = interpolate(subset, *s, variable, float(m.x), float(m.y), pv, false, float(m.z), nullptr);
+            if (!isEqualF(est, NODATA_F) && !isEqualF(myValue, NODATA_F)) {
+                if (isEqualF(m.residual, NODATA_F)) m.residual = (myValue - est) * weight;
+                else m.residual += (myValue - est) * weight;
+            }
+        }
+    }
+    for (int i = 0; i < meteo->n; i++) residual[i] = mp[i].residual;
     return PB_OK;
 }
 

@@ -275,6 +275,7 @@ void exportSettings(Scenario& sc, pb_settings& s)
     auto funcs = st.getFittingFunction();
     auto params = st.getFittingParameters();
     s.nFit = int(params.size());
+    for (int i = s.nFit; i < int(funcs.size()) && i < PB_MAX_PROXY; i++) s.fitFunction[i] = fitFunctionId(funcs[i]);
     for (int i = 0; i < s.nFit && i < PB_MAX_PROXY; i++) {
         s.fitFunction[i] = i < int(funcs.size()) ? fitFunctionId(funcs[i]) : PB_FIT_NONE;
         s.fitNrParams[i] = int(params[i].size());
@@ -854,6 +855,217 @@ int ref_local_detrending_raster(const pb_stations* st, const pb_settings* s, int
     out->nValid = nValid;
     copyOut(outGrid, out);
     return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
+/* ---- glocal detrending (macro areas) ------------------------------------------------------------------------------ */
+namespace {
+std::vector<Crit3DMacroArea> buildAreas(const pb_macro_area* areas, int nAreas, int nProxy)
+{
+    std::vector<Crit3DMacroArea> v(nAreas);
+    for (int a = 0; a < nAreas; a++) {
+        const pb_macro_area& A = areas[a];
+        v[a].setMeteoPoints(std::vector<int>(A.meteoPoints, A.meteoPoints + A.nMeteoPoints));
+        v[a].setAreaCellsDEM(std::vector<float>(A.areaCellsDEM, A.areaCellsDEM + A.nAreaCells));
+        Crit3DProxyCombination c;
+        for (int i = 0; i < nProxy; i++) { c.addProxyActive(A.active[i] != 0); c.addProxySignificant(A.significant[i] != 0); }
+        c.setUseThermalInversion(A.useThermalInversion != 0);
+        v[a].setCombination(c);
+        std::vector<std::vector<double>> par;
+        for (int i = 0; i < A.nParameters; i++) par.push_back(std::vector<double>(A.parameters[i], A.parameters[i] + A.nrParams[i]));
+        v[a].setParameters(par);
+    }
+    return v;
+}
+
+void exportAreas(const std::vector<Crit3DMacroArea>& v, pb_macro_area* areas, int nProxy)
+{
+    for (size_t a = 0; a < v.size(); a++) {
+        pb_macro_area& A = areas[a];
+        Crit3DProxyCombination c = v[a].getCombination();
+        for (int i = 0; i < PB_MAX_PROXY; i++) {
+            A.active[i] = (i < nProxy && i < int(c.getProxySize()) && c.isProxyActive(i)) ? 1 : 0;
+            A.significant[i] = (i < nProxy && i < int(c.getProxySize()) && c.isProxySignificant(i)) ? 1 : 0;
+        }
+        A.useThermalInversion = c.getUseThermalInversion() ? 1 : 0;
+        std::vector<std::vector<double>> par = v[a].getParameters();
+        A.nParameters = int(par.size());
+        for (int i = 0; i < PB_MAX_PROXY; i++) {
+            A.nrParams[i] = i < int(par.size()) ? int(par[i].size()) : 0;
+            for (int j = 0; j < PB_MAX_FIT_PARAMS; j++) A.parameters[i][j] = (i < int(par.size()) && j < int(par[i].size())) ? par[i][j] : 0.;
+        }
+    }
+}
+
+void buildMeteoPoints(std::vector<Crit3DMeteoPoint>& mp, const pb_stations* meteo, const float* observed, const pb_cv_points* cv)
+{
+    mp.resize(meteo->n);
+    for (int i = 0; i < meteo->n; i++) {
+        mp[i].active = meteo->isActive ? meteo->isActive[i] != 0 : true;
+        mp[i].quality = quality::accepted;
+        mp[i].currentValue = observed ? observed[i] : meteo->value[i];
+        mp[i].point.utm.x = meteo->x[i];
+        mp[i].point.utm.y = meteo->y[i];
+        mp[i].point.z = meteo->z[i];
+        mp[i].isInsideDem = (cv && cv->isInsideDem) ? cv->isInsideDem[i] != 0 : true;
+        mp[i].lapseRateCode = meteo->lapseRateCode ? lapseRateCodeType(meteo->lapseRateCode[i]) : primary;
+        for (int k = 0; k < meteo->nProxy; k++) mp[i].proxyValues.push_back(meteo->proxyValues[size_t(i) * meteo->nProxy + k]);
+    }
+}
+}  // namespace
+
+/* preInterpolation with useGlocalDetrending: setMultipleDetrendingHeightTemperatureRange + glocalDetrendingFitting
+ * (interpolation.cpp:2466-2474, 2239-2294), verbatim reference code; the areas receive their fit. */
+int ref_glocal_detrending_fitting(const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    sc.settings.setMacroAreas(buildAreas(areas, nAreas, s->nProxy));
+    std::vector<Crit3DMeteoPoint> meteoPoints;
+    std::string err;
+    bool ok = preInterpolation(sc.points, sc.settings, &sc.meteoSettings, &sc.climate, meteoPoints, meteoVariable(variable),
+                               sc.time, err);
+    exportSettings(sc, *s);
+    exportAreas(sc.settings.getMacroAreas(), areas, s->nProxy);
+    return ok ? PB_OK : PB_ERR_FIT;
+}
+
+/* The gridding part of Project::interpolationDemGlocalDetrending (project/project.cpp:3262-3375) restated (a method of the
+ * Qt-bound Project class), from `setCurrentCombination(selected)` on: preInterpolation, the second
+ * setMultipleDetrendingHeightTemperatureRange, the loop over macro areas. Every call inside is the reference's own code
+ * (macroAreaDetrending, getUtmXYFromRowCol, getSignificantProxyValuesXY, interpolate). updateMinMaxRasterGrid is what the
+ * callers of interpolationDemMain run on the result. */
+int ref_glocal_detrending_raster(const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas,
+                                 const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int nThreads,
+                                 pb_raster_out* out, double* elapsed_s)
+{
+    Scenario sc;
+    buildSettings(sc, *s, proxyGrids, nProxyGrids);
+    buildPoints(sc, *st);
+    gis::Crit3DRasterGrid DEM, outGrid;
+    fillGrid(DEM, *dem);
+    sc.settings.setCurrentDEM(&DEM);
+    sc.settings.setMacroAreas(buildAreas(areas, nAreas, s->nProxy));
+    const meteoVariable myVar = meteoVariable(variable);
+    Crit3DInterpolationSettings& interpolationSettings = sc.settings;
+    if (!getUseDetrendingVar(myVar) || !interpolationSettings.getUseGlocalDetrending()) return PB_ERR_INVALID;
+    std::vector<Crit3DMeteoPoint> meteoPoints;
+    std::vector<Crit3DInterpolationDataPoint>& interpolationPoints = sc.points;
+    Crit3DMeteoSettings* meteoSettings = &sc.meteoSettings;
+    gis::Crit3DRasterGrid* myRaster = &outGrid;
+    const bool _isParallelComputing = nThreads != 1;
+    if (nThreads > 0) omp_set_num_threads(nThreads);
+    auto t0 = std::chrono::steady_clock::now();
+
+    Crit3DProxyCombination myCombination = interpolationSettings.getSelectedCombination();
+    interpolationSettings.setCurrentCombination(myCombination);
+    std::string errorStdStr;
+    if (!preInterpolation(interpolationPoints, interpolationSettings, meteoSettings, &sc.climate, meteoPoints, myVar, sc.time,
+                          errorStdStr))
+        return PB_ERR_FIT;
+    exportSettings(sc, *s);
+    exportAreas(interpolationSettings.getMacroAreas(), areas, s->nProxy);
+
+    bool isOk = true;
+    gis::Crit3DRasterHeader myHeader = *(DEM.header);
+    myRaster->initializeGrid(myHeader);
+    if (!setMultipleDetrendingHeightTemperatureRange(interpolationSettings)) return PB_ERR_FIT;
+    exportSettings(sc, *s);     // the state Project::interpolationSettings is left in (the loop works on a copy)
+
+    int elevationPos = NODATA;
+    for (unsigned int pos = 0; pos < interpolationSettings.getCurrentCombination().getProxySize(); pos++)
+        if (getProxyPragaName(interpolationSettings.getProxy(pos)->getName()) == proxyHeight) elevationPos = pos;
+
+    Crit3DInterpolationSettings myInterpolationSettings = interpolationSettings;
+    std::vector<double> proxyValues(myInterpolationSettings.getProxyNr());
+
+    #pragma omp parallel for if (_isParallelComputing) firstprivate(myInterpolationSettings, proxyValues) shared(isOk)
+    for (int areaIndex = 0; areaIndex < myInterpolationSettings.getMacroAreasSize(); areaIndex++)
+    {
+        if (!isOk) continue;
+        Crit3DMacroArea macroArea = myInterpolationSettings.getMacroArea(areaIndex);
+        std::vector<float> areaCells = macroArea.getAreaCellsDEM();
+        std::vector<Crit3DInterpolationDataPoint> subsetInterpolationPoints;
+        double interpolatedValue = NODATA;
+        if (areaCells.empty()) continue;
+
+        macroAreaDetrending(macroArea, myVar, myInterpolationSettings, meteoSettings, meteoPoints, interpolationPoints,
+                            subsetInterpolationPoints, elevationPos);
+
+        for (std::size_t cellIndex = 0; cellIndex < areaCells.size(); cellIndex = cellIndex + 2)
+        {
+            if (!isOk) break;
+            int row = int(areaCells[cellIndex] / DEM.header->nrCols);
+            int col = int(areaCells[cellIndex]) % DEM.header->nrCols;
+            float z = DEM.value[row][col];
+            if (isEqual(z, myHeader.flag)) continue;
+            double x, y;
+            gis::getUtmXYFromRowCol(myHeader, row, col, &x, &y);
+            if (!getSignificantProxyValuesXY(x, y, myInterpolationSettings, proxyValues))
+            {
+                myRaster->value[row][col] = NODATA;
+                continue;
+            }
+            interpolatedValue = interpolate(subsetInterpolationPoints, myInterpolationSettings, meteoSettings, myVar, x, y, z,
+                                            proxyValues, true);
+            if (isEqual(interpolatedValue, NODATA)) isOk = false;
+            #pragma omp critical
+            {
+                if (isEqual(myRaster->value[row][col], NODATA))
+                    myRaster->value[row][col] = interpolatedValue * areaCells[cellIndex + 1];
+                else
+                    myRaster->value[row][col] += interpolatedValue * areaCells[cellIndex + 1];
+            }
+        }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    gis::updateMinMaxRasterGrid(&outGrid);
+    int64_t nValid = 0;
+    for (int row = 0; row < DEM.header->nrRows; row++)
+        for (int col = 0; col < DEM.header->nrCols; col++)
+            if (!isEqual(DEM.value[row][col], DEM.header->flag)) nValid++;
+    out->nValid = nValid;
+    copyOut(outGrid, out);
+    return isOk ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
+/* Project::computeResidualsAndStatisticsGlocalDetrending (project/project.cpp:6525-6565) restated around the reference's
+ * computeResidualsGlocalDetrending (spatialControl.cpp:231-302); the areas carry their fit. The per-area statistics
+ * (computeStatisticsGlocalCrossValidation) are not part of the residuals and are left out. */
+int ref_compute_residuals_glocal(const pb_stations* meteo, const float* observed, const pb_cv_points* cv, const pb_stations* points,
+                                 pb_settings* s, int variable, const pb_macro_area* areas, int nAreas, const pb_raster* dem,
+                                 int excludeOutsideDem, int excludeSupplemental, float* residual)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *points);
+    gis::Crit3DRasterGrid DEM;
+    fillGrid(DEM, *dem);
+    sc.settings.setCurrentDEM(&DEM);
+    sc.settings.setMacroAreas(buildAreas(areas, nAreas, s->nProxy));
+    std::vector<Crit3DMeteoPoint> meteoPoints;
+    buildMeteoPoints(meteoPoints, meteo, observed, cv);
+    Crit3DInterpolationSettings& interpolationSettings = sc.settings;
+    const meteoVariable myVar = meteoVariable(variable);
+    if (!setMultipleDetrendingHeightTemperatureRange(interpolationSettings)) return PB_ERR_FIT;      // project.cpp:3069
+
+    int elevationPos = NODATA;
+    for (unsigned int pos = 0; pos < interpolationSettings.getCurrentCombination().getProxySize(); pos++)
+        if (getProxyPragaName(interpolationSettings.getProxy(pos)->getName()) == proxyHeight) elevationPos = pos;
+    for (size_t j = 0; j < meteoPoints.size(); j++) meteoPoints[j].residual = NODATA;
+    for (int k = 0; k < interpolationSettings.getMacroAreasSize(); k++)
+    {
+        Crit3DMacroArea myArea = interpolationSettings.getMacroArea(k);
+        std::vector<int> meteoPointsList = myArea.getMeteoPoints();
+        if (myArea.getAreaCellsDEM().empty() || meteoPointsList.empty()) continue;
+        interpolationSettings.pushMacroAreaNumber(k);
+        if (!computeResidualsGlocalDetrending(myVar, myArea, elevationPos, meteoPoints, sc.points, interpolationSettings,
+                                              &sc.meteoSettings, excludeOutsideDem != 0, excludeSupplemental != 0))
+            return PB_ERR_INVALID;
+    }
+    for (int i = 0; i < meteo->n; i++) residual[i] = meteoPoints[i].residual;
+    return PB_OK;
 }
 
 /* One cell of the loop above with everything the fit produced exported (debugging aid for the parity tests):

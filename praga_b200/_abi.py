@@ -131,6 +131,41 @@ class pb_dem_batch_item(C.Structure):
                 ("variable", C.c_int32), ("status", C.c_int32), ("out", C.POINTER(pb_raster_out)), ("step", C.POINTER(pb_dem_step))]
 
 
+class pb_macro_area(C.Structure):
+    _fields_ = [("nMeteoPoints", C.c_int32), ("reserved", C.c_int32), ("meteoPoints", C.POINTER(C.c_int32)),
+                ("nAreaCells", C.c_int64), ("areaCellsDEM", C.POINTER(C.c_float)),
+                ("active", C.c_uint8 * PB_MAX_PROXY), ("significant", C.c_uint8 * PB_MAX_PROXY),
+                ("useThermalInversion", C.c_int32), ("nParameters", C.c_int32), ("nrParams", C.c_int32 * PB_MAX_PROXY),
+                ("parameters", (C.c_double * PB_MAX_FIT_PARAMS) * PB_MAX_PROXY)]
+
+
+class MacroAreas:
+    """std::vector<Crit3DMacroArea> (interpolationSettings.h:149-182): per area the station indices and the flat
+    (cell index, weight) float pairs; keeps the numpy buffers alive behind the pb_macro_area array."""
+
+    def __init__(self, meteo_points, area_cells):
+        assert len(meteo_points) == len(area_cells)
+        self.meteo_points = [np.ascontiguousarray(m, dtype=np.int32) for m in meteo_points]
+        self.area_cells = [np.ascontiguousarray(c, dtype=np.float32).ravel() for c in area_cells]
+        self.n = len(self.meteo_points)
+        self.arr = (pb_macro_area * max(1, self.n))()
+        for i in range(self.n):
+            a = self.arr[i]
+            a.nMeteoPoints = self.meteo_points[i].size
+            a.meteoPoints = iptr(self.meteo_points[i]) if self.meteo_points[i].size else None
+            a.nAreaCells = self.area_cells[i].size
+            a.areaCellsDEM = fptr(self.area_cells[i]) if self.area_cells[i].size else None
+
+    def fit(self, i):
+        """(active, significant, parameters) of area i as the last fitting call left them."""
+        a = self.arr[i]
+        pars = [[a.parameters[k][j] for j in range(a.nrParams[k])] for k in range(a.nParameters)]
+        return list(a.active), list(a.significant), pars
+
+    def fits(self):
+        return [self.fit(i) for i in range(self.n)]
+
+
 class pb_timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]

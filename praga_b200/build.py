@@ -24,6 +24,7 @@ SOURCES = {
     "classic_kernels.cu": ["-fmad=false"],
     "shepard_kernels.cu": ["-fmad=false"],
     "station_space.cu": [],
+    "glocal.cu": ["-fmad=false"],
     "raster_ops.cu": ["-fmad=false"],
     "raster_io.cu": [],
     "kriging.cu": [],

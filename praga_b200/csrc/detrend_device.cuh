@@ -316,13 +316,35 @@ __device__ __forceinline__ void weightedScores(double* par, const double* X, con
     RMSE = sqrt(s / (sw * nData));
 }
 
+// computeR2adjusted (:1175-1194) and computeRMSE (:1324-1340) of one fitted curve (the unweighted best fit of glocal detrending)
+template <int F>
+__device__ __forceinline__ void plainScores(double* par, const double* X, const double* Y, int nData, double& R2, double& RMSE)
+{
+    double mean = 0;
+    for (int i = 0; i < nData; i++) mean += Y[i];
+    mean /= double(nData);
+    if (nData > 0) Fit<F>::clamp(par);
+    double rss = 0, tss = 0;
+    for (int i = 0; i < nData; i++) {
+        const double sim = Fit<F>::eval(X[i], par);
+        rss += (Y[i] - sim) * (Y[i] - sim);
+        tss += (Y[i] - mean) * (Y[i] - mean);
+    }
+    R2 = 1 - rss / tss;
+    RMSE = sqrt(rss / double(nData));
+}
+
 // bestFittingMarquardt_nDimension (:1360-1427): all first guesses of the group in parallel, reference pick order.
 // firstGuess: nGuess x PB_MAX_FIT_PARAMS doubles. par (out, group-uniform) = chosen parameters. Returns bestR2.
+// unweighted: the form without weights (:1433-1529, glocal detrending) — W must hold 1.0 everywhere (the descent :2125-2283
+// is the weighted one with the weights dropped: every product by exactly 1.0 is exact); a fit that ends outside its
+// parameter ranges is skipped, the scores are computeR2adjusted / computeRMSE, and the three-piece forms are only taken
+// while their second inversion point stays below the highest station.
 template <int G, int F>
 __device__ double bestFitElevation(const double* __restrict__ pmin, const double* __restrict__ pmax,
                                    const double* __restrict__ delta, const double* __restrict__ firstGuess, int nGuess,
                                    double* par, int maxIter, double eps, double deltaR2, const double* X, const double* Y,
-                                   const double* W, int nData)
+                                   const double* W, int nData, bool unweighted = false)
 {
     constexpr int N = Fit<F>::N;
     const int lane = grpLane<G>();
@@ -331,26 +353,41 @@ __device__ double bestFitElevation(const double* __restrict__ pmin, const double
     for (int j = 0; j < N; j++) best[j] = 0;
     double bestR2 = -9999, bestRMSE = -9999;
     int rmseIndex = -9999;
+    double maxZ = 0;
+    if (unweighted && nData > 0) {
+        maxZ = X[0];
+        for (int i = 0; i < nData; i++) if (X[i] > maxZ) maxZ = X[i];
+    }
     for (int c0 = 0; c0 < nGuess; c0 += G) {
         const int k = c0 + lane;
         double q[N], R2 = 0, RMSE = 0;
+        bool inRange = true, secondBelow = true;
 #pragma unroll
         for (int j = 0; j < N; j++) q[j] = 0;
         if (k < nGuess) {
 #pragma unroll
             for (int j = 0; j < N; j++) q[j] = firstGuess[k * PB_MAX_FIT_PARAMS + j];
             lmElevation<F>(pmin, pmax, delta, q, maxIter, eps, X, Y, W, nData);
-            weightedScores<F>(q, X, Y, W, nData, R2, RMSE);
+            if (unweighted) {
+#pragma unroll
+                for (int j = 0; j < N; j++) inRange = inRange && !(q[j] < pmin[j] || q[j] > pmax[j]);
+                plainScores<F>(q, X, Y, nData, R2, RMSE);
+                if (N > 4) secondBelow = (q[0] + q[2]) < maxZ;
+            } else {
+                weightedScores<F>(q, X, Y, W, nData, R2, RMSE);
+            }
         }
         grpSync<G>();
         const int nk = (nGuess - c0 < G) ? nGuess - c0 : G;
+        const unsigned okMask = grpBallot<G>(inRange), belowMask = grpBallot<G>(secondBelow);
         for (int kk = 0; kk < nk; kk++) {
             const double r2 = grpBcast<G>(R2, kk), rmse = grpBcast<G>(RMSE, kk);
             double cand[N];
 #pragma unroll
             for (int j = 0; j < N; j++) cand[j] = grpBcast<G>(q[j], kk);
+            if (!((okMask >> kk) & 1u)) continue;                // rangeFlag false: `continue` (:1481-1482)
             if (isEqualD(bestRMSE, -9999) || rmse < bestRMSE) { bestRMSE = rmse; rmseIndex = c0 + kk; }
-            if (isEqualD(bestR2, -9999) || r2 > (bestR2 + deltaR2)) {
+            if (isEqualD(bestR2, -9999) || (r2 > (bestR2 + deltaR2) && ((belowMask >> kk) & 1u))) {
 #pragma unroll
                 for (int j = 0; j < N; j++) best[j] = cand[j];
                 bestR2 = r2;

@@ -606,6 +606,56 @@ struct PreBatchBuffers {
     std::vector<PreFit> fits;
 };
 
+// what preInterpolation leaves in Crit3DInterpolationSettings (interpolation.cpp:1506-1553, 1832-2171) after the
+// multiple-detrending fit `f` of one unit (time step or macro area) run with model `m`
+void applyPreFit(const pb_settings& s, const LocalModel& m, const PreFit& f, const double* pointsRange, bool singleStep,
+                 pb_settings& o)
+{
+    if (&o != &s) o = s;
+    o.hasPointsRange = 1;
+    o.pointsRangeMin = m.elevationPos >= 0 && s.selectedActive[m.elevationPos] ? m.elevMin[1] + 2 : o.pointsRangeMin;
+    o.pointsRangeMax = m.elevationPos >= 0 && s.selectedActive[m.elevationPos] ? m.elevMax[1] - 6 : o.pointsRangeMax;
+    if (pointsRange) { o.pointsRangeMin = pointsRange[0]; o.pointsRangeMax = pointsRange[1]; }
+    else if (s.hasPointsRange && singleStep) { o.pointsRangeMin = s.pointsRangeMin; o.pointsRangeMax = s.pointsRangeMax; }
+    for (int i = 0; i < o.nProxy; i++) {
+        o.currentActive[i] = o.selectedActive[i];
+        o.currentSignificant[i] = 0;
+    }
+    o.currentUseThermalInversion = o.selectedUseThermalInversion;
+    o.nFit = o.nFitFunctions = 0;
+    const int e = m.elevationPos;
+    for (int i = 0; i < o.nProxy; i++)
+        if (o.selectedActive[i] && o.proxy[i].kind == PB_PROXY_HEIGHT) {
+            pb_proxy& p = o.proxy[i];
+            if (i == e) {
+                p.fitMin[1] = m.elevMin[1];
+                p.fitMax[1] = m.elevMax[1];
+                p.nFirstGuessCombinations = m.nFirstGuess;
+                memcpy(p.firstGuessCombinations, m.firstGuess, sizeof(m.firstGuess));
+            }
+        }
+    if (e >= 0 && o.selectedActive[e]) {
+        o.proxy[e].regressionR2 = f.elevR2;
+        if (f.elevR2 != kNoData || f.elevSig) {
+            o.fitFunction[o.nFitFunctions++] = m.elevFunction;
+            if (f.elevSig) {
+                o.fitNrParams[o.nFit] = m.elevNPar;
+                for (int j = 0; j < m.elevNPar; j++) o.fitParams[o.nFit][j] = f.elevPar[j];
+                o.nFit++;
+            }
+        }
+        o.currentSignificant[e] = f.elevSig ? 1 : 0;
+    }
+    for (int c = 0; c < f.nPred; c++) {
+        o.currentSignificant[f.sigPos[c]] = 1;
+        o.fitFunction[o.nFitFunctions++] = PB_FIT_LINEAR;
+        o.fitNrParams[o.nFit] = 2;
+        o.fitParams[o.nFit][0] = f.othPar[c][0];
+        o.fitParams[o.nFit][1] = f.othPar[c][1];
+        o.nFit++;
+    }
+}
+
 int preInterpolationBatchImpl(pb_context* ctx, const pb_stations* st, const float* values, int T, const pb_settings* s,
                               int variable, const double* pointsRange, float* detrended, uint8_t* keep, pb_settings* fitted)
 {
@@ -673,57 +723,9 @@ int preInterpolationBatchImpl(pb_context* ctx, const pb_stations* st, const floa
     cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
-    if (fitted) {
-        // what preInterpolation leaves in Crit3DInterpolationSettings (interpolation.cpp:1506-1553, 1832-2171)
-        for (int t = 0; t < T; t++) {
-            pb_settings& o = fitted[t];
-            if (&o != s) o = *s;
-            const LocalModel& m = models[t];
-            const PreFit& f = fits[t];
-            o.hasPointsRange = 1;
-            o.pointsRangeMin = m.elevationPos >= 0 && s->selectedActive[m.elevationPos] ? m.elevMin[1] + 2 : o.pointsRangeMin;
-            o.pointsRangeMax = m.elevationPos >= 0 && s->selectedActive[m.elevationPos] ? m.elevMax[1] - 6 : o.pointsRangeMax;
-            if (pointsRange) { o.pointsRangeMin = pointsRange[2 * t]; o.pointsRangeMax = pointsRange[2 * t + 1]; }
-            else if (s->hasPointsRange && T == 1 && !pointsRange) { o.pointsRangeMin = s->pointsRangeMin; o.pointsRangeMax = s->pointsRangeMax; }
-            for (int i = 0; i < o.nProxy; i++) {
-                o.currentActive[i] = o.selectedActive[i];
-                o.currentSignificant[i] = 0;
-            }
-            o.currentUseThermalInversion = o.selectedUseThermalInversion;
-            o.nFit = o.nFitFunctions = 0;
-            const int e = m.elevationPos;
-            for (int i = 0; i < o.nProxy; i++)
-                if (o.selectedActive[i] && o.proxy[i].kind == PB_PROXY_HEIGHT) {
-                    pb_proxy& p = o.proxy[i];
-                    if (i == e) {
-                        p.fitMin[1] = m.elevMin[1];
-                        p.fitMax[1] = m.elevMax[1];
-                        p.nFirstGuessCombinations = m.nFirstGuess;
-                        memcpy(p.firstGuessCombinations, m.firstGuess, sizeof(m.firstGuess));
-                    }
-                }
-            if (e >= 0 && o.selectedActive[e]) {
-                o.proxy[e].regressionR2 = f.elevR2;
-                if (f.elevR2 != kNoData || f.elevSig) {
-                    o.fitFunction[o.nFitFunctions++] = m.elevFunction;
-                    if (f.elevSig) {
-                        o.fitNrParams[o.nFit] = m.elevNPar;
-                        for (int j = 0; j < m.elevNPar; j++) o.fitParams[o.nFit][j] = f.elevPar[j];
-                        o.nFit++;
-                    }
-                }
-                o.currentSignificant[e] = f.elevSig ? 1 : 0;
-            }
-            for (int c = 0; c < f.nPred; c++) {
-                o.currentSignificant[f.sigPos[c]] = 1;
-                o.fitFunction[o.nFitFunctions++] = PB_FIT_LINEAR;
-                o.fitNrParams[o.nFit] = 2;
-                o.fitParams[o.nFit][0] = f.othPar[c][0];
-                o.fitParams[o.nFit][1] = f.othPar[c][1];
-                o.nFit++;
-            }
-        }
-    }
+    if (fitted)
+        for (int t = 0; t < T; t++)
+            applyPreFit(*s, models[t], fits[t], pointsRange ? pointsRange + 2 * t : nullptr, T == 1, fitted[t]);
     return PB_OK;
 }
 
@@ -896,6 +898,25 @@ bool varIsThermal(int v)       // isThermal, interpolation.cpp:1190-1203
            v == PB_VAR_DAILY_TMIN || v == PB_VAR_DAILY_ET0_HS || v == PB_VAR_ELABORATION;
 }
 int varClampMode(int v) { return clampModeOf(v); }
+// used by glocal.cu
+int buildDevModelGrids(pb_context* ctx, const pb_settings* s, int variable, const pb_raster_id* proxyIds, int nProxyGrids, DevModel& m)
+{
+    return buildModel(ctx, s, variable, proxyIds, nProxyGrids, m);
+}
+int stageIdwStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, DevStations& ds,
+                     double& valueOffset)
+{
+    return stageStations(ctx, st, s, excludeSupplemental, ds, valueOffset);
+}
+int buildPreModel(pb_context* ctx, const pb_settings* s, int variable, int nStations, LocalModel& m)
+{
+    return buildLocalModel(ctx, s, variable, nStations, nullptr, 0, m, false, nullptr);
+}
+int stageAllStations(pb_context* ctx, const pb_stations* st, LocalStations& ds) { return stageLocalStations(ctx, st, ds); }
+void applyPreFitToSettings(const pb_settings& s, const LocalModel& m, const PreFit& f, pb_settings& o)
+{
+    applyPreFit(s, m, f, nullptr, true, o);
+}
 int ensureValidList(pb_context* ctx, RasterEntry& e) { return ensureValidListImpl(ctx, e); }
 int ensureRowStart(pb_context* ctx, RasterEntry& e) { return ensureRowStartImpl(ctx, e); }
 }  // namespace pb
@@ -1750,5 +1771,6 @@ extern "C" size_t pb_abi_sizeof(const char* name)
     if (!strcmp(name, "pb_timing")) return sizeof(pb_timing);
     if (!strcmp(name, "pb_dem_step")) return sizeof(pb_dem_step);
     if (!strcmp(name, "pb_dem_batch_item")) return sizeof(pb_dem_batch_item);
+    if (!strcmp(name, "pb_macro_area")) return sizeof(pb_macro_area);
     return 0;
 }

@@ -1,0 +1,631 @@
+// glocal.cu — glocal detrending: one multiple-detrending fit per MACRO AREA, cells blended over the
+// areas they belong to. Reference (paths relative to agrolib/):
+//   glocalDetrendingFitting                          interpolation/interpolation.cpp:2239-2294 (from preInterpolation :2471-2474)
+//   macroAreaDetrending                              :1759-1829
+//   getSignificantProxyValuesXY                      :2650-2677
+//   loop of Project::interpolationDemGlocalDetrending project/project.cpp:3299-3375
+//   computeResidualsGlocalDetrending                 interpolation/spatialControl.cpp:231-302
+//   Project::computeResidualsAndStatisticsGlocalDetrending  project/project.cpp:6525-6565
+//
+// Mapping:
+//   * FIT: all areas in ONE launch of the batched preInterpolation kernel (K3, pre_kernels.cu): a unit is an area = a station
+//     subset of the same time step, one lane group per area, lane g = first guess g of the UNWEIGHTED elevation fit
+//     (bestFittingMarquardt_nDimension, mathFunctions/furtherMathFunctions.cpp:1433-1529). Parameters bit-identical.
+//   * RASTER: per area, in index order on one stream: the area's (cell, weight) pairs become explicit targets
+//     (glocal_targets_kernel: cell centre of getUtmXYFromRowCol rounded to f32, significant proxies looked up), the IDW
+//     station loop of K1 in point form grids them over the area's detrended stations, glocal_blend_kernel accumulates
+//     value * weight into the output (first touch replaces NODATA). The few-hundred-station detrend of an area
+//     (detrendingElevation :1956-1972, detrendingOtherProxies :2173-2236) is host arithmetic in the reference's float/double
+//     mix (this TU is built without FMA contraction on either side).
+//   * LOO: per area the exact leave-one-out kernel (pb_compute_residuals_exact) on the area's stations; sums over areas on
+//     the host like the reference's `residual +=`.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "context.cuh"
+#include "pre.cuh"
+
+namespace pb {
+// engine.cu
+int buildDevModelGrids(pb_context* ctx, const pb_settings* s, int variable, const pb_raster_id* proxyIds, int nProxyGrids, DevModel& m);
+int stageIdwStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, DevStations& ds,
+                     double& valueOffset);
+int buildPreModel(pb_context* ctx, const pb_settings* s, int variable, int nStations, LocalModel& m);
+int stageAllStations(pb_context* ctx, const pb_stations* st, LocalStations& ds);
+void applyPreFitToSettings(const pb_settings& s, const LocalModel& m, const PreFit& f, pb_settings& o);
+DevGrid devGridOfRaster(const RasterEntry& r);
+bool varUsesDetrending(int v);
+bool varUsesTd(int v);
+// idw_kernels.cu
+cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty, const double* tproxy,
+                            int nTargets, float* out, cudaStream_t s);
+cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);
+
+// which proxies getSignificantProxyValuesXY looks up (active && significant, grid loaded)
+struct GlocalLookup {
+    int nProxy;
+    int slot[PB_MAX_PROXY];          // -1: value stays NODATA
+    DevGrid grid[PB_MAX_PROXY];
+};
+
+enum : unsigned char { CELL_SKIP = 0, CELL_NODATA = 1, CELL_OK = 2 };
+
+// Crit3DRasterGrid::getValueFromXY (gis.cpp:533-546)
+__device__ __forceinline__ float glocalGridValueXY(const DevGrid& g, double x, double y)
+{
+    const int r = int((y - g.lly) * g.invCellSize);
+    const int row = (g.nrRows - 1) - r;
+    const int col = int((x - g.llx) * g.invCellSize);
+    if (unsigned(row) >= unsigned(g.nrRows) || unsigned(col) >= unsigned(g.nrCols)) return g.flag;
+    return __ldg(g.data + (size_t)row * g.nrCols + col);
+}
+
+// row / col of an areaCells entry exactly as project.cpp:3337-3338 computes them: a FLOAT division for the row, an integer
+// remainder for the column
+__device__ __forceinline__ void glocalRowCol(float idxf, int nrCols, int& row, int& col)
+{
+    row = int(__fdiv_rn(idxf, float(nrCols)));
+    col = int(idxf) % nrCols;
+}
+
+// the area's cells -> explicit targets: getUtmXYFromRowCol (gis.cpp:806-810) rounded to f32 (the float parameters of
+// getSignificantProxyValuesXY and interpolate), the significant proxies' values
+__global__ void __launch_bounds__(256)
+glocal_targets_kernel(const float* __restrict__ cells, int nCells, DevGrid dem, GlocalLookup lk, float* __restrict__ tx,
+                      float* __restrict__ ty, double* __restrict__ pv, unsigned char* __restrict__ state)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    int row, col;
+    glocalRowCol(cells[2 * c], dem.nrCols, row, col);
+    unsigned char st = CELL_SKIP;
+    float xf = 0.f, yf = 0.f;
+    double v[PB_MAX_PROXY];
+#pragma unroll
+    for (int i = 0; i < PB_MAX_PROXY; i++) v[i] = -9999.;
+    if (unsigned(row) < unsigned(dem.nrRows) && unsigned(col) < unsigned(dem.nrCols)) {
+        const float z = __ldg(dem.data + (size_t)row * dem.nrCols + col);
+        if (!isEqualF(z, dem.flag)) {
+            const double x = dem.llx + dem.cellSize * (col + 0.5);
+            const double y = dem.lly + dem.cellSize * (dem.nrRows - row - 0.5);
+            xf = float(x);
+            yf = float(y);
+            bool complete = true;
+#pragma unroll
+            for (int i = 0; i < PB_MAX_PROXY; i++)
+                if (i < lk.nProxy && lk.slot[i] >= 0) {
+                    const DevGrid& g = lk.grid[lk.slot[i]];
+                    const float gv = glocalGridValueXY(g, double(xf), double(yf));
+                    if (gv != g.flag) v[i] = double(gv);
+                    else complete = false;
+                }
+            st = complete ? CELL_OK : CELL_NODATA;
+        }
+    }
+    tx[c] = xf;
+    ty[c] = yf;
+    state[c] = st;
+    for (int i = 0; i < lk.nProxy; i++) pv[(size_t)c * lk.nProxy + i] = v[i];
+}
+
+// out[cell] (+)= interpolate() * weight (project.cpp:3361-3369); an incomplete proxy set leaves NODATA (:3350-3354)
+__global__ void __launch_bounds__(256)
+glocal_blend_kernel(const float* __restrict__ cells, int nCells, int nrCols, const unsigned char* __restrict__ state,
+                    const float* __restrict__ res, float* __restrict__ out, int* __restrict__ notOk)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    const unsigned char st = state[c];
+    if (st == CELL_SKIP) return;
+    int row, col;
+    glocalRowCol(cells[2 * c], nrCols, row, col);
+    float* cell = out + (size_t)row * nrCols + col;
+    if (st == CELL_NODATA) { *cell = kNoData; return; }
+    const double interpolatedValue = double(res[c]);
+    if (fabs(interpolatedValue - (-9999.)) < kEpsilon) *notOk = 1;
+    const double prod = interpolatedValue * double(cells[2 * c + 1]);
+    const float cur = *cell;
+    *cell = isEqualF(cur, kNoData) ? float(prod) : float(double(cur) + prod);
+}
+
+__device__ __forceinline__ unsigned orderedKeyG(float f)
+{
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// gis::updateMinMaxRasterGrid (gis.cpp:569-614) over the blended grid
+__global__ void __launch_bounds__(256) glocal_minmax_kernel(const float* __restrict__ v, long long n, float flag, unsigned* __restrict__ minmax)
+{
+    float vmin = INFINITY, vmax = -INFINITY;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const float x = v[k];
+        if (!isEqualF(x, flag) && !isEqualF(x, kNoData)) { vmin = fminf(vmin, x); vmax = fmaxf(vmax, x); }
+    }
+    for (int o = 16; o; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (vmin != INFINITY) atomicMin(&minmax[0], orderedKeyG(vmin));
+        if (vmax != -INFINITY) atomicMax(&minmax[1], orderedKeyG(vmax));
+    }
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+namespace {
+
+int fail(pb_context* ctx, int code, const std::string& msg) { return pb::failCtx(ctx, code, msg); }
+
+float keyToFloatG(unsigned k)
+{
+    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+bool isEqualDh(double a, double b) { return fabs(a - b) < kEpsilon; }
+
+// model functions (mathFunctions/furtherMathFunctions.cpp:115-201) on the host, for the per-area detrend of a few hundred
+// stations; par is mutated by the three-piece forms like in the reference
+double evalFitHost(int f, double x, double* par)
+{
+    switch (f) {
+    case PB_FIT_PIECEWISE_TWO:
+        if (x < par[0]) return par[2] * (x - par[0]) + par[1];
+        return par[3] * (x - par[0]) + par[1];
+    case PB_FIT_PIECEWISE_THREE: {
+        par[2] = std::max(10., par[2]);
+        const double xb = par[2] + par[0];
+        if (x < par[0]) return par[4] * x - par[0] * par[4] + par[1];
+        else if (x > xb) return par[4] * x - par[4] * par[0] - par[4] * par[2] + par[3] * par[2] + par[1];
+        else return par[3] * x - par[3] * par[0] + par[1];
+    }
+    case PB_FIT_PIECEWISE_THREE_FREE: {
+        par[2] = std::max(10., par[2]);
+        const double xb = par[0] + par[2];
+        if (x < par[0]) return par[4] * x - par[0] * par[4] + par[1];
+        else if (x > xb) return par[5] * x - par[5] * par[0] - par[5] * par[2] + par[3] * par[2] + par[1];
+        else return par[3] * x - par[3] * par[0] + par[1];
+    }
+    case PB_FIT_LINEAR: return par[0] * x + par[1];
+    default: return 0.;
+    }
+}
+
+int elevationPosOf(const pb_settings& s)
+{
+    int e = -1;
+    for (int pos = 0; pos < s.nProxy; pos++) if (s.proxy[pos].kind == PB_PROXY_HEIGHT) e = pos;
+    return e;
+}
+
+// the stations of one area after macroAreaDetrending (:1759-1829), with the settings interpolate() then sees
+struct AreaStations {
+    std::vector<double> x, y, z;
+    std::vector<float> value, weight, proxy;
+    std::vector<int32_t> code, index;
+    std::vector<uint8_t> active;
+    pb_stations st{};
+    pb_settings s{};
+};
+
+void macroAreaDetrendingHost(const pb_macro_area& A, const pb_settings& base, const pb_stations* pts, AreaStations& out)
+{
+    pb_settings& s = out.s;
+    s = base;
+    s.useGlocalDetrending = 0;     // interpolate() itself never looks at it
+    // setFittingParameters(area), setCurrentCombination(area), fitting functions by parameter count (:1766-1785)
+    s.nFit = A.nParameters;
+    for (int p = 0; p < PB_MAX_PROXY; p++) {
+        s.fitNrParams[p] = p < A.nParameters ? A.nrParams[p] : 0;
+        for (int j = 0; j < PB_MAX_FIT_PARAMS; j++) s.fitParams[p][j] = p < A.nParameters ? A.parameters[p][j] : 0.;
+    }
+    for (int p = 0; p < s.nProxy; p++) { s.currentActive[p] = A.active[p]; s.currentSignificant[p] = A.significant[p]; }
+    s.currentUseThermalInversion = A.useThermalInversion;
+    s.nFitFunctions = 0;
+    for (int l = 0; l < A.nParameters; l++) {
+        const int n = A.nrParams[l];
+        if (n == 2) s.fitFunction[s.nFitFunctions++] = PB_FIT_LINEAR;
+        else if (n == 4) s.fitFunction[s.nFitFunctions++] = PB_FIT_PIECEWISE_TWO;
+        else if (n == 5) s.fitFunction[s.nFitFunctions++] = PB_FIT_PIECEWISE_THREE;
+        else if (n == 6) s.fitFunction[s.nFitFunctions++] = PB_FIT_PIECEWISE_THREE_FREE;
+    }
+    // the area's interpolation points, in the area's order (:1794-1803: every match, no break)
+    const int P = std::max(pts->nProxy, 0);
+    std::vector<int> sel;
+    for (int l = 0; l < A.nMeteoPoints; l++)
+        for (int k = 0; k < pts->n; k++)
+            if ((pts->index ? pts->index[k] : k) == A.meteoPoints[l]) sel.push_back(k);
+    const int e = elevationPosOf(s);
+    auto proxyOf = [&](int k, int pos) { return pos < P ? pts->proxyValues[size_t(k) * P + pos] : kNoData; };
+    std::vector<float> value(sel.size());
+    for (size_t q = 0; q < sel.size(); q++) value[q] = pts->value[sel[q]];
+    // detrendingElevation (:1956-1972)
+    if (e >= 0 && A.active[e] && A.significant[e] && s.nFitFunctions > 0 && s.nFit > 0) {
+        double par[PB_MAX_FIT_PARAMS];
+        memcpy(par, s.fitParams[0], sizeof(par));
+        for (size_t q = 0; q < sel.size(); q++) {
+            const float proxyValue = proxyOf(sel[q], e);
+            const float detrendValue = float(evalFitHost(s.fitFunction[0], proxyValue, par));
+            value[q] -= detrendValue;
+        }
+    }
+    // detrendingOtherProxies (:2173-2236)
+    std::vector<uint8_t> kept(sel.size(), 1);
+    if (s.nFit > 0) {
+        const int first = s.fitNrParams[0] > 2 ? 1 : 0;
+        if (s.nFit - first > 0) {
+            const int nF = s.nFitFunctions - first;
+            for (size_t q = 0; q < sel.size(); q++) {
+                double pvv[PB_MAX_PROXY];
+                int n = 0;
+                bool complete = true;
+                for (int pos = 0; pos < s.nProxy; pos++)
+                    if (pos != e && s.currentActive[pos] && s.currentSignificant[pos] && complete) {
+                        const double v = proxyOf(sel[q], pos);
+                        if (!isEqualDh(v, -9999)) pvv[n++] = v;
+                        else complete = false;
+                    }
+                if (complete) {
+                    double r = 0.0;
+                    for (int c = 0; c < nF && c < n; c++) {
+                        double par[PB_MAX_FIT_PARAMS];
+                        memcpy(par, s.fitParams[first + c], sizeof(par));
+                        r += evalFitHost(s.fitFunction[first + c], pvv[c], par);
+                    }
+                    value[q] -= float(r);
+                } else kept[q] = 0;
+            }
+        }
+    }
+    for (size_t q = 0; q < sel.size(); q++) {
+        if (!kept[q]) continue;
+        const int k = sel[q];
+        out.x.push_back(pts->x[k]); out.y.push_back(pts->y[k]); out.z.push_back(pts->z[k]);
+        out.value.push_back(value[q]);
+        out.weight.push_back(pts->regressionWeight ? pts->regressionWeight[k] : kNoData);
+        out.code.push_back(pts->lapseRateCode ? pts->lapseRateCode[k] : PB_LAPSE_PRIMARY);
+        out.active.push_back(pts->isActive ? pts->isActive[k] : 1);
+        out.index.push_back(pts->index ? pts->index[k] : k);
+        for (int pos = 0; pos < P; pos++) out.proxy.push_back(pts->proxyValues[size_t(k) * P + pos]);
+    }
+    if (out.proxy.empty()) out.proxy.push_back(0.f);
+    pb_stations& st = out.st;
+    st.n = int(out.x.size());
+    st.nProxy = pts->nProxy;
+    st.x = out.x.data(); st.y = out.y.data(); st.z = out.z.data();
+    st.value = out.value.data();
+    st.regressionWeight = out.weight.data();
+    st.lapseRateCode = out.code.data();
+    st.isActive = out.active.data();
+    st.proxyValues = out.proxy.data();
+    st.index = out.index.data();
+}
+
+// setMultipleDetrendingHeightTemperatureRange (:1506-1553) as far as it shows in pb_settings beyond what the fit already
+// wrote: one more fitting function per active height proxy with parameter ranges
+void secondHeightRangeCall(pb_settings& s)
+{
+    if (!s.hasPointsRange || !s.useMultipleDetrending) return;
+    for (int i = 0; i < s.nProxy; i++)
+        if (s.selectedActive[i] && s.proxy[i].kind == PB_PROXY_HEIGHT && s.proxy[i].nFitParams > 0) {
+            const int f = s.proxy[i].fittingFunction;
+            if ((f == PB_FIT_PIECEWISE_TWO || f == PB_FIT_PIECEWISE_THREE_FREE || f == PB_FIT_PIECEWISE_THREE) &&
+                s.nFitFunctions < PB_MAX_PROXY)
+                s.fitFunction[s.nFitFunctions++] = f;
+        }
+}
+
+// glocalDetrendingFitting on the device: every area with stations is one unit of the batched preInterpolation kernel
+int glocalFit(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas)
+{
+    if (!varUsesDetrending(variable) || !s->useMultipleDetrending) return PB_OK;      // preInterpolation :2464-2467
+    if (s->useLocalDetrending) return fail(ctx, PB_ERR_INVALID, "glocal and local detrending are exclusive (project.cpp:3546-3552)");
+    if (s->useTD && varUsesTd(variable))
+        return fail(ctx, PB_ERR_UNSUPPORTED, "topographic distance inside macro areas is not on the GPU path (DESIGN.md)");
+    if (!s->hasPointsRange) return fail(ctx, PB_ERR_FIT, "couldn't set temperature ranges for height proxy (points range not set)");
+    pb_settings s0 = *s;
+    s0.useGlocalDetrending = 0;
+    LocalModel m;
+    int rc = buildPreModel(ctx, &s0, variable, st->n, m);
+    if (rc) return rc;
+    // the subsets, in each area's order (first match only, :2259-2266)
+    std::vector<int> idx, off(nAreas + 1, 0), unitArea;
+    int cap = 1;
+    for (int a = 0; a < nAreas; a++) {
+        const pb_macro_area& A = areas[a];
+        if (A.nMeteoPoints <= 0) continue;
+        if (!A.meteoPoints) return fail(ctx, PB_ERR_INVALID, "macro area without meteoPoints");
+        const int begin = int(idx.size());
+        for (int l = 0; l < A.nMeteoPoints; l++)
+            for (int k = 0; k < st->n; k++)
+                if ((st->index ? st->index[k] : k) == A.meteoPoints[l]) { idx.push_back(k); break; }
+        unitArea.push_back(a);
+        off[unitArea.size()] = int(idx.size());
+        cap = std::max(cap, int(idx.size()) - begin);
+    }
+    const int T = int(unitArea.size());
+    // the state glocalDetrendingFitting starts every area from, kept when no area has stations
+    for (int i = 0; i < s->nProxy; i++) { s->currentActive[i] = s->selectedActive[i]; }
+    if (T == 0) {
+        // no area has stations: only setMultipleDetrendingHeightTemperatureRange acted (:2466-2469): height ranges, first
+        // guesses and one more fitting function
+        pb_settings o;
+        PreFit none{};
+        none.elevR2 = kNoData;
+        applyPreFitToSettings(s0, m, none, o);
+        for (int i = 0; i < s->nProxy; i++)
+            if (i == m.elevationPos && s->selectedActive[i]) {
+                const float r2 = s->proxy[i].regressionR2;
+                s->proxy[i] = o.proxy[i];
+                s->proxy[i].regressionR2 = r2;
+            }
+        secondHeightRangeCall(*s);
+        return PB_OK;
+    }
+    LocalStations ds{};
+    rc = stageAllStations(ctx, st, ds);
+    if (rc) return rc;
+    const int groupLanes = m.nFirstGuess <= 16 ? 16 : 32;
+    LocalScratch scr{};
+    scr.cap = cap;
+    scr.perGroup = preScratchBytesPerGroup(scr.cap);
+    const size_t groups = size_t(preGroupsTotal(groupLanes, T));
+    const size_t offModel = 0, offFits = (sizeof(LocalModel) + 15) / 16 * 16, offIdx = (offFits + sizeof(PreFit) * T + 15) / 16 * 16,
+                 offOff = offIdx + (idx.size() * 4 + 15) / 16 * 16, offScr = (offOff + size_t(T + 1) * 4 + 255) / 256 * 256,
+                 total = offScr + scr.perGroup * groups;
+    CUDA_TRY(ctx, ctx->dLocalScratch.reserve(total));
+    unsigned char* d = ctx->dLocalScratch.p;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + offModel, &m, sizeof(LocalModel), cudaMemcpyHostToDevice, ctx->stream));
+    if (!idx.empty()) CUDA_TRY(ctx, cudaMemcpyAsync(d + offIdx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d + offOff, off.data(), size_t(T + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)(sizeof(LocalModel) + idx.size() * 4 + size_t(T + 1) * 4);
+    scr.base = d + offScr;
+    scr.error = nullptr;
+    PreSubsets sub{};
+    sub.idx = reinterpret_cast<const int*>(d + offIdx);
+    sub.off = reinterpret_cast<const int*>(d + offOff);
+    sub.unweightedElevation = 1;
+    CUDA_TRY(ctx, launchPreInterpolationBatch(reinterpret_cast<const LocalModel*>(d + offModel), ds, ds.value, T, scr, groupLanes,
+                                              m.elevFunction, nullptr, nullptr, reinterpret_cast<PreFit*>(d + offFits), ctx->stream,
+                                              &sub));
+    ctx->timing.launches++;
+    std::vector<PreFit> fits(T);
+    CUDA_TRY(ctx, cudaMemcpyAsync(fits.data(), d + offFits, sizeof(PreFit) * T, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.d2h_bytes += (int64_t)(sizeof(PreFit) * T);
+    pb_settings o = *s;
+    for (int u = 0; u < T; u++) {
+        applyPreFitToSettings(s0, m, fits[u], o);
+        pb_macro_area& A = areas[unitArea[u]];
+        memset(A.active, 0, sizeof(A.active));
+        memset(A.significant, 0, sizeof(A.significant));
+        for (int p = 0; p < o.nProxy; p++) { A.active[p] = o.currentActive[p]; A.significant[p] = o.currentSignificant[p]; }
+        A.useThermalInversion = o.currentUseThermalInversion;
+        A.nParameters = o.nFit;
+        for (int p = 0; p < PB_MAX_PROXY; p++) {
+            A.nrParams[p] = p < o.nFit ? o.fitNrParams[p] : 0;
+            for (int j = 0; j < PB_MAX_FIT_PARAMS; j++) A.parameters[p][j] = (p < o.nFit && j < o.fitNrParams[p]) ? o.fitParams[p][j] : 0.;
+        }
+    }
+    o.useGlocalDetrending = s->useGlocalDetrending;      // the settings keep the last fitted area's state
+    *s = o;
+    return PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb_glocal_detrending_fitting(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
+                                 int nAreas)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s || (!areas && nAreas > 0) || nAreas < 0) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    return glocalFit(ctx, st, s, variable, areas, nAreas);
+}
+
+int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
+                                int nAreas, pb_raster_id demId, const pb_raster_id* proxyGrids, int nProxyGrids, int deviceOnly,
+                                pb_raster_out* out)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!st || !s || !out || (!areas && nAreas > 0) || nAreas < 0) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    if (!varUsesDetrending(variable) || !s->useGlocalDetrending)       // project.cpp:3264
+        return fail(ctx, PB_ERR_INVALID, "glocal detrending needs useGlocalDetrending and a detrending variable");
+    if (s->method != PB_METHOD_IDW)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the glocal GPU path");
+    if (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used)
+        return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
+    if (!deviceOnly && !out->data && !out->rows) return fail(ctx, PB_ERR_INVALID, "output has neither data nor rows");
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    for (int i = 0; i < s->nProxy; i++) { s->currentActive[i] = s->selectedActive[i]; s->currentSignificant[i] = 0; }
+    s->currentUseThermalInversion = s->selectedUseThermalInversion;
+    int rc = glocalFit(ctx, st, s, variable, areas, nAreas);     // preInterpolation (:3283)
+    if (rc) return rc;
+    secondHeightRangeCall(*s);                                   // :3300
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+
+    RasterEntry& dem = ctx->rasters[demId];
+    rc = ensureValidList(ctx, dem);
+    if (rc) return rc;
+    const DevGrid dg = devGridOfRaster(dem);
+    long long maxCells = 1;
+    for (int a = 0; a < nAreas; a++) {
+        if (areas[a].nAreaCells > 0 && !areas[a].areaCellsDEM) return fail(ctx, PB_ERR_INVALID, "macro area without areaCellsDEM");
+        if (areas[a].nAreaCells / 2 > 0x7fffff00LL) return fail(ctx, PB_ERR_INVALID, "macro area with too many cells");
+        maxCells = std::max<long long>(maxCells, areas[a].nAreaCells / 2);
+    }
+    const int P = std::max(s->nProxy, 0);
+    const size_t mAl = (size_t(maxCells) + 3) / 4 * 4;
+    const size_t offCells = 0, offX = offCells + mAl * 8, offY = offX + mAl * 4, offRes = offY + mAl * 4,
+                 offPv = offRes + mAl * 4, offState = offPv + mAl * 8 * std::max(P, 1), offFlag = (offState + mAl + 15) / 16 * 16,
+                 total = offFlag + 16;
+    CUDA_TRY(ctx, ctx->dScratch.reserve(total));
+    unsigned char* d = ctx->dScratch.p;
+    int* dNotOk = reinterpret_cast<int*>(d + offFlag);
+    CUDA_TRY(ctx, cudaMemsetAsync(dNotOk, 0, sizeof(int), ctx->stream));
+    CUDA_TRY(ctx, ctx->dOut.reserve(dem.n));
+    CUDA_TRY(ctx, launchFill(ctx->dOut.p, (long long)dem.n, dem.h.flag, ctx->stream));      // initializeGrid(header) :3297
+    ctx->outInitRaster = -1;
+    ctx->timing.launches++;
+
+    for (int a = 0; a < nAreas; a++) {
+        const pb_macro_area& A = areas[a];
+        const int nCells = int(A.nAreaCells / 2);
+        if (nCells <= 0) continue;
+        AreaStations sub;
+        macroAreaDetrendingHost(A, *s, st, sub);
+        DevModel mod;
+        rc = buildDevModelGrids(ctx, &sub.s, variable, proxyGrids, nProxyGrids, mod);
+        if (rc) return rc;
+        GlocalLookup lk{};
+        lk.nProxy = P;
+        for (int i = 0; i < PB_MAX_PROXY; i++) {
+            lk.slot[i] = (i < P && sub.s.currentActive[i] && sub.s.currentSignificant[i]) ? mod.proxy[i].gridSlot : -1;
+            lk.grid[i] = mod.grid[i];
+        }
+        // the pinned station staging buffer is reused: the previous area's copy must have left it
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        DevStations ds{};
+        rc = stageIdwStations(ctx, &sub.st, &sub.s, true, ds, mod.valueOffset);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d + offCells, A.areaCellsDEM, size_t(nCells) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->timing.h2d_bytes += (int64_t)(size_t(nCells) * 8);
+        const int grid = (nCells + 255) / 256;
+        glocal_targets_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(d + offCells), nCells, dg, lk,
+                                                             reinterpret_cast<float*>(d + offX), reinterpret_cast<float*>(d + offY),
+                                                             reinterpret_cast<double*>(d + offPv), d + offState);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, launchIdwPoints(ds, mod, reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
+                                      reinterpret_cast<const double*>(d + offPv), nCells, reinterpret_cast<float*>(d + offRes),
+                                      ctx->stream));
+        glocal_blend_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(d + offCells), nCells, dem.h.nrCols,
+                                                           d + offState, reinterpret_cast<const float*>(d + offRes), ctx->dOut.p,
+                                                           dNotOk);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->timing.launches += 3;
+    }
+    ctx->hMinMax[0] = 0xffffffffu;
+    ctx->hMinMax[1] = 0u;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        const int grid = int(std::min<long long>((long long)sms * 8, ((long long)dem.n + 255) / 256));
+        glocal_minmax_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->dOut.p, (long long)dem.n, dem.h.flag, ctx->dMinMax);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->timing.launches++;
+    }
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    int notOk = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&notOk, dNotOk, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!deviceOnly) {
+        const int cols = dem.h.nrCols, rows = dem.h.nrRows;
+        if (out->data) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(out->data, ctx->dOut.p, dem.n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            for (int row = 0; row < rows; row++)
+                CUDA_TRY(ctx, cudaMemcpyAsync(out->rows[row], ctx->dOut.p + size_t(row) * cols, size_t(cols) * sizeof(float),
+                                              cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        ctx->timing.d2h_bytes += (int64_t)(dem.n * sizeof(float));
+    }
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
+    out->nValid = dem.nValid;
+    if (ctx->hMinMax[0] == 0xffffffffu) {
+        out->minimum = kNoData;
+        out->maximum = kNoData;
+    } else {
+        out->minimum = keyToFloatG(ctx->hMinMax[0]);
+        out->maximum = keyToFloatG(ctx->hMinMax[1]);
+    }
+    if (notOk) return fail(ctx, PB_ERR_NO_VALID_CELL, "interpolate() returned NODATA inside a macro area (project.cpp:3358-3359)");
+    return PB_OK;
+}
+
+int pb_compute_residuals_glocal(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
+                                const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
+                                int excludeOutsideDem, int excludeSupplemental, float* residual)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!meteo || !points || !s || !residual || (!areas && nAreas > 0)) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    if (!s->hasPointsRange || !s->useMultipleDetrending)        // setMultipleDetrendingHeightTemperatureRange false (project.cpp:3069)
+        return fail(ctx, PB_ERR_FIT, "couldn't set temperature ranges for height proxy");
+    if (s->useTD && varUsesTd(variable))
+        return fail(ctx, PB_ERR_UNSUPPORTED, "topographic distance inside macro areas is not on the GPU path (DESIGN.md)");
+    for (int i = 0; i < meteo->n; i++) residual[i] = kNoData;
+    const float* obs = observed ? observed : meteo->value;
+    const int P = std::max(meteo->nProxy, 0);
+    pb_timing sum{};
+    for (int k = 0; k < nAreas; k++) {
+        const pb_macro_area& A = areas[k];
+        if (A.nAreaCells <= 0 || A.nMeteoPoints <= 0) continue;
+        AreaStations sub;
+        macroAreaDetrendingHost(A, *s, points, sub);
+        // the area's active meteo points, in the area's order
+        std::vector<int> who;
+        for (int i = 0; i < A.nMeteoPoints; i++) {
+            const int j = A.meteoPoints[i];
+            if (j < 0 || j >= meteo->n) return fail(ctx, PB_ERR_INVALID, "macro area meteo point out of range");
+            if (meteo->isActive && !meteo->isActive[j]) continue;
+            who.push_back(j);
+        }
+        if (who.empty()) continue;
+        const size_t m = who.size();
+        std::vector<double> x(m), y(m), z(m);
+        std::vector<float> val(m), proxy(std::max<size_t>(m * P, 1)), res(m);
+        std::vector<int32_t> code(m);
+        std::vector<uint8_t> inside(m, 1);
+        for (size_t q = 0; q < m; q++) {
+            const int j = who[q];
+            x[q] = meteo->x[j]; y[q] = meteo->y[j]; z[q] = meteo->z[j];
+            val[q] = obs[j];
+            code[q] = meteo->lapseRateCode ? meteo->lapseRateCode[j] : PB_LAPSE_PRIMARY;
+            if (cv && cv->isInsideDem) inside[q] = cv->isInsideDem[j];
+            for (int p = 0; p < P; p++) proxy[q * P + p] = meteo->proxyValues[size_t(j) * P + p];
+        }
+        pb_stations mp{};
+        mp.n = int(m);
+        mp.nProxy = meteo->nProxy;
+        mp.x = x.data(); mp.y = y.data(); mp.z = z.data();
+        mp.value = val.data();
+        mp.lapseRateCode = code.data();
+        mp.proxyValues = proxy.data();
+        pb_cv_points cva{};
+        cva.isInsideDem = inside.data();
+        int rc = pb_compute_residuals_exact(ctx, &mp, val.data(), &cva, &sub.st, &sub.s, variable, -1, excludeOutsideDem,
+                                            excludeSupplemental, res.data());
+        if (rc) return rc;
+        sum.kernel_ms += ctx->timing.kernel_ms; sum.total_ms += ctx->timing.total_ms; sum.launches += ctx->timing.launches;
+        for (size_t q = 0; q < m; q++) {
+            if (isEqualF(res[q], kNoData)) continue;
+            float& r = residual[who[q]];
+            if (isEqualF(r, kNoData)) r = res[q] * 1.f;
+            else r += res[q] * 1.f;
+        }
+    }
+    ctx->timing = sum;
+    return PB_OK;
+}
+
+}  // extern "C"

@@ -149,9 +149,10 @@ __device__ void mdFinish(const LocalModel& m, const LocalStations& st, const Wor
 
 // w: idx (station index), w (regressionWeight), val (value, detrended in place), flg (bit0 = still in myPoints) of the
 // n points; X, Y, W, oi, act are scratch. isLocal adds the minPointsLocalDetrending conditions (:1885, :2100).
+// unweightedElevation: the elevation fit of glocalDetrendingFitting (:2273: isWeighted = false).
 template <int G, int F>
 __device__ void multipleDetrendingGroup(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, bool isLocal,
-                                        MdFit<Fit<F>::N>& fit)
+                                        MdFit<Fit<F>::N>& fit, bool unweightedElevation = false)
 {
     constexpr int N = Fit<F>::N;
     const int ePos = m.elevationPos;
@@ -164,8 +165,12 @@ __device__ void multipleDetrendingGroup(const LocalModel& m, const LocalStations
         bool isValid;
         const int nE = mdStageElevation<G>(m, st, w, n, isLocal, isValid);
         if (isValid) {
+            if (unweightedElevation) {
+                for (int j = grpLane<G>(); j < nE; j += G) w.W[j] = 1.;
+                grpSync<G>();
+            }
             R2 = bestFitElevation<G, F>(m.elevMin, m.elevMax, m.elevDelta, &m.firstGuess[0][0], m.nFirstGuess, elevPar, 1000,
-                                        0.002, 0.005, w.X, w.Y, w.W, nE);
+                                        0.002, 0.005, w.X, w.Y, w.W, nE, unweightedElevation);
             fitRan = true;
         }
     }

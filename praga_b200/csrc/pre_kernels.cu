@@ -11,10 +11,13 @@
 
 namespace pb {
 
+// Units: time steps of one station set (sub.idx == nullptr: unit t = all stations with values[t * n + k]) or, for glocal
+// detrending, MACRO AREAS of one time step (unit t = the stations sub.idx[sub.off[t] .. sub.off[t + 1]) with the shared
+// values[k], one model for all units, the unweighted elevation fit of glocalDetrendingFitting :2239-2294).
 template <int G, int F>
 __global__ void __launch_bounds__(kLocalThreads, 2)
 pre_interpolation_batch_kernel(const LocalModel* __restrict__ models, LocalStations st, const float* __restrict__ values, int T,
-                               LocalScratch scr, float* __restrict__ detrended, unsigned char* __restrict__ keep,
+                               LocalScratch scr, PreSubsets sub, float* __restrict__ detrended, unsigned char* __restrict__ keep,
                                PreFit* __restrict__ fits)
 {
     constexpr int groupsPerCta = kLocalThreads / G;
@@ -23,23 +26,27 @@ pre_interpolation_batch_kernel(const LocalModel* __restrict__ models, LocalStati
     const long long groupsTotal = (long long)gridDim.x * groupsPerCta;
     const long long gid = (long long)blockIdx.x * groupsPerCta + grp;
     const WorkPtrs w = carve(scr.base + gid * scr.perGroup, scr.cap);
-    const int n = st.n;
     for (long long t = gid; t < T; t += groupsTotal) {
-        const LocalModel& m = models[t];
+        const LocalModel& m = models[sub.idx ? 0 : t];
+        const int first = sub.idx ? sub.off[t] : 0;
+        const int n = sub.idx ? sub.off[t + 1] - first : st.n;
+        const float* val = sub.idx ? values : values + (size_t)t * st.n;
         for (int k = lane; k < n; k += G) {
-            w.idx[k] = k;
-            w.w[k] = st.weight ? st.weight[k] : kNoData;
-            w.val[k] = values[(size_t)t * n + k];
+            const int i = sub.idx ? sub.idx[first + k] : k;
+            w.idx[k] = i;
+            w.w[k] = st.weight ? st.weight[i] : kNoData;
+            w.val[k] = val[i];
             w.flg[k] = 1;
         }
         grpSync<G>();
         MdFit<N> fit;
-        multipleDetrendingGroup<G, F>(m, st, w, n, false, fit);
+        multipleDetrendingGroup<G, F>(m, st, w, n, false, fit, sub.unweightedElevation != 0);
         grpSync<G>();
-        for (int k = lane; k < n; k += G) {
-            detrended[(size_t)t * n + k] = w.val[k];
-            keep[(size_t)t * n + k] = w.flg[k] & 1;
-        }
+        if (detrended)
+            for (int k = lane; k < n; k += G) {
+                detrended[(size_t)t * st.n + k] = w.val[k];
+                keep[(size_t)t * st.n + k] = w.flg[k] & 1;
+            }
         if (lane == 0) {
             PreFit& o = fits[t];
             o.elevSig = fit.elevSig;
@@ -70,20 +77,23 @@ size_t preScratchBytesPerGroup(int cap) { return workBytes(cap); }
 
 template <int G, int F>
 static cudaError_t launchPreT(const LocalModel* models, const LocalStations& st, const float* values, int T,
-                              const LocalScratch& scr, float* detrended, unsigned char* keep, PreFit* fits, cudaStream_t s)
+                              const LocalScratch& scr, const PreSubsets& sub, float* detrended, unsigned char* keep, PreFit* fits,
+                              cudaStream_t s)
 {
     const int perCta = kLocalThreads / G;
     const int grid = preGroupsTotal(G, T) / perCta;
-    pre_interpolation_batch_kernel<G, F><<<grid, kLocalThreads, 0, s>>>(models, st, values, T, scr, detrended, keep, fits);
+    pre_interpolation_batch_kernel<G, F><<<grid, kLocalThreads, 0, s>>>(models, st, values, T, scr, sub, detrended, keep, fits);
     return cudaGetLastError();
 }
 
 cudaError_t launchPreInterpolationBatch(const LocalModel* models, const LocalStations& st, const float* values, int T,
                                         const LocalScratch& scr, int groupLanes, int elevFunction, float* detrended,
-                                        unsigned char* keep, PreFit* fits, cudaStream_t s)
+                                        unsigned char* keep, PreFit* fits, cudaStream_t s, const PreSubsets* subsets)
 {
     if (T <= 0) return cudaSuccess;
-#define PB_PRE_CASE(G_, F_) return launchPreT<G_, F_>(models, st, values, T, scr, detrended, keep, fits, s)
+    PreSubsets sub{};
+    if (subsets) sub = *subsets;
+#define PB_PRE_CASE(G_, F_) return launchPreT<G_, F_>(models, st, values, T, scr, sub, detrended, keep, fits, s)
     if (groupLanes == 16) {
         switch (elevFunction) {
         case PB_FIT_PIECEWISE_THREE: PB_PRE_CASE(16, PB_FIT_PIECEWISE_THREE);

@@ -94,10 +94,17 @@ def load_library():
                                                 P(C.c_int32)]
     lib.pb_resample_grid.argtypes = [C.c_void_p, C.c_int32, P(A.pb_raster_header), C.c_int, C.c_float, P(A.pb_raster_out),
                                      P(C.c_int32)]
+    lib.pb_glocal_detrending_fitting.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int]
+    lib.pb_glocal_detrending_raster.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int,
+                                                C.c_int32, P(C.c_int32), C.c_int, C.c_int, P(A.pb_raster_out)]
+    lib.pb_compute_residuals_glocal.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), P(A.pb_cv_points), P(A.pb_stations),
+                                                P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int, C.c_int, C.c_int,
+                                                P(C.c_float)]
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
     lib.pb_measure_fp64_peak.argtypes = [C.c_void_p, P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
-                 "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series", "pb_dem_step", "pb_dem_batch_item"):
+                 "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series", "pb_dem_step", "pb_dem_batch_item",
+                 "pb_macro_area"):
         got, want = lib.pb_abi_sizeof(name.encode()), C.sizeof(getattr(A, name))
         if got != want:
             raise PragaB200Error(A.PB_ERR_INVALID, f"ABI mismatch for {name}: library {got} B, binding {want} B")
@@ -470,3 +477,40 @@ class Engine:
         self._check(self.lib.pb_pre_interpolation_batch(self.h, C.byref(st), A.fptr(values), T, C.byref(settings), variable,
                                                         None if pr is None else A.dptr(pr), A.fptr(det), A.u8ptr(keep), fitted))
         return det, keep.astype(bool), fitted
+
+    # ---- glocal detrending (macro areas) ----
+    def glocal_detrending_fitting(self, stations, settings, variable, areas):
+        """glocalDetrendingFitting (interpolation.cpp:2239-2294) as preInterpolation reaches it: every area of `areas`
+        (_abi.MacroAreas) is fitted in one launch and keeps its parameters / combination; settings is mutated like the reference's."""
+        st = stations.as_pb()
+        self._check(self.lib.pb_glocal_detrending_fitting(self.h, C.byref(st), C.byref(settings), variable, areas.arr, areas.n))
+
+    def glocal_detrending_raster(self, stations, settings, variable, areas, dem_id, shape, proxy_ids=(), device_only=False):
+        """gridding part of Project::interpolationDemGlocalDetrending (project.cpp:3283-3375).
+        Returns (ok, grid or None, min, max, nValid); ok False where the reference returns false."""
+        st = stations.as_pb()
+        ids = (C.c_int32 * max(1, len(proxy_ids)))(*proxy_ids)
+        grid = None if device_only else np.empty(shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        if grid is not None:
+            o.data = A.fptr(grid)
+        rc = self._check(self.lib.pb_glocal_detrending_raster(self.h, C.byref(st), C.byref(settings), variable, areas.arr, areas.n,
+                                                              dem_id, ids, len(proxy_ids), int(device_only), C.byref(o)),
+                         allow=(A.PB_ERR_NO_VALID_CELL,))
+        return rc == A.PB_OK, grid, o.minimum, o.maximum, o.nValid
+
+    def compute_residuals_glocal(self, meteo, observed, points, settings, variable, areas, exclude_outside_dem=True,
+                                 exclude_supplemental=True, inside_dem=None):
+        """computeResidualsAndStatisticsGlocalDetrending (project.cpp:6525-6565) over computeResidualsGlocalDetrending
+        (spatialControl.cpp:231-302); the areas carry their fit."""
+        mp, pt = meteo.as_pb(), points.as_pb()
+        obs = np.ascontiguousarray(observed, dtype=np.float32)
+        cv = A.pb_cv_points()
+        ins = None if inside_dem is None else np.ascontiguousarray(inside_dem, dtype=np.uint8)
+        if ins is not None:
+            cv.isInsideDem = A.u8ptr(ins)
+        res = np.empty(meteo.n, dtype=np.float32)
+        self._check(self.lib.pb_compute_residuals_glocal(self.h, C.byref(mp), A.fptr(obs), C.byref(cv), C.byref(pt), C.byref(settings),
+                                                         variable, areas.arr, areas.n, int(exclude_outside_dem),
+                                                         int(exclude_supplemental), A.fptr(res)))
+        return res

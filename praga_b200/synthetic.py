@@ -140,3 +140,47 @@ def set_points_range(settings, stations):
     settings.hasPointsRange = 1
     settings.pointsRangeMin = float(stations.value.min())
     settings.pointsRangeMax = float(stations.value.max())
+
+
+def make_macro_areas(dem, stations, n_side=2, blend_cells=8, margin_m=None):
+    """Synthetic macro areas for glocal detrending: the DEM split into n_side x n_side tiles whose weights ramp linearly
+    across a band of `blend_cells` cells around every internal border (weights of a cell sum to 1, like the reference's
+    glocalWeight_<i> maps, project.cpp:2592-2700); an area's cells are the flat (row * nrCols + col, weight) float pairs of
+    every DEM-valid cell with weight > 0; its stations are those inside the tile grown by `margin_m` (default: the blend
+    band), in station order. Returns _abi.MacroAreas."""
+    rows, cols = dem.shape
+    cs = dem.cell_size
+    if margin_m is None:
+        margin_m = blend_cells * cs
+
+    def ramps(n):
+        edges = np.linspace(0, n, n_side + 1)
+        c = np.arange(n) + 0.5
+        w = np.zeros((n_side, n))
+        for k in range(n_side):
+            lo, hi = edges[k], edges[k + 1]
+            up = np.ones(n) if k == 0 else np.clip((c - (lo - blend_cells / 2)) / blend_cells, 0, 1)
+            dn = np.ones(n) if k == n_side - 1 else np.clip(((hi + blend_cells / 2) - c) / blend_cells, 0, 1)
+            w[k] = np.minimum(up, dn)
+        return w / w.sum(axis=0), edges
+
+    wr, er = ramps(rows)
+    wc, ec = ramps(cols)
+    valid = dem.data != np.float32(dem.flag)
+    meteo, cells = [], []
+    for i in range(n_side):
+        for j in range(n_side):
+            w = np.outer(wr[i], wc[j]).astype(np.float32)
+            sel = valid & (w > 0)
+            idx = np.flatnonzero(sel.ravel())
+            pairs = np.empty((idx.size, 2), dtype=np.float32)
+            pairs[:, 0] = idx.astype(np.float32)
+            pairs[:, 1] = w.ravel()[idx]
+            cells.append(pairs.ravel())
+            y_hi = dem.lly + (rows - er[i]) * cs + margin_m
+            y_lo = dem.lly + (rows - er[i + 1]) * cs - margin_m
+            x_lo = dem.llx + ec[j] * cs - margin_m
+            x_hi = dem.llx + ec[j + 1] * cs + margin_m
+            inside = (stations.x >= x_lo) & (stations.x <= x_hi) & (stations.y >= y_lo) & (stations.y <= y_hi)
+            meteo.append(np.flatnonzero(inside).astype(np.int32))
+    return A.MacroAreas(meteo, cells)
