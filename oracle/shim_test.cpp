@@ -180,4 +180,42 @@ int shim_kriging_points(const double* pos, const double* val, int n, int mode, d
     return PB_OK;
 }
 
+/* pragab200::interpolationRasterGlocalDetrending + computeResidualsGlocalDetrending on reference objects (the macro areas live
+ * in the Crit3DInterpolationSettings, like Project keeps them): grid, the areas' fit, the settings and the summed residuals */
+int shim_glocal(const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas, const pb_raster* dem,
+                const pb_raster* proxyGrids, int nProxyGrids, pb_raster_out* out, float* residual, char* err, int errLen)
+{
+    Scenario sc;
+    buildSettings(sc, *s, proxyGrids, nProxyGrids);
+    buildPoints(sc, *st);
+    gis::Crit3DRasterGrid demGrid, outGrid;
+    fillGrid(demGrid, *dem);
+    sc.settings.setCurrentDEM(&demGrid);
+    for (int i = 0; i < s->nProxy; i++)
+        if (s->proxy[i].kind == PB_PROXY_HEIGHT && s->proxy[i].gridIndex >= 0) sc.settings.getProxy(i)->setGrid(&demGrid);
+    sc.settings.setMacroAreas(buildAreas(areas, nAreas, s->nProxy));
+    bool ok = pragab200::interpolationRasterGlocalDetrending(sc.points, sc.settings, &sc.meteoSettings, &outGrid, demGrid,
+                                                             meteoVariable(variable));
+    if (err && errLen > 0) { strncpy(err, pragab200::lastError().c_str(), errLen - 1); err[errLen - 1] = 0; }
+    exportSettings(sc, *s);
+    exportAreas(sc.settings.getMacroAreas(), areas, s->nProxy);
+    if (outGrid.isLoaded) copyOut(outGrid, out);
+    if (residual) {
+        std::vector<Crit3DMeteoPoint> mp;
+        buildMeteoPoints(mp, st, nullptr, nullptr);
+        for (auto& m : mp) m.residual = NODATA;
+        int elevationPos = NODATA;
+        for (int pos = 0; pos < s->nProxy; pos++) if (s->proxy[pos].kind == PB_PROXY_HEIGHT) elevationPos = pos;
+        for (int k = 0; k < sc.settings.getMacroAreasSize(); k++) {          // project.cpp:6545-6562
+            Crit3DMacroArea myArea = sc.settings.getMacroArea(k);
+            if (myArea.getAreaCellsDEM().empty() || myArea.getMeteoPoints().empty()) continue;
+            if (!pragab200::computeResidualsGlocalDetrending(meteoVariable(variable), myArea, elevationPos, mp, sc.points, sc.settings,
+                                                             &sc.meteoSettings, true, true))
+                return PB_ERR_INVALID;
+        }
+        for (int i = 0; i < st->n; i++) residual[i] = mp[i].residual;
+    }
+    return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
 }  // extern "C"

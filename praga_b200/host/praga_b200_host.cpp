@@ -305,6 +305,65 @@ void writeBackSettings(const pb_settings& s, Crit3DInterpolationSettings& st, co
 }
 }  // namespace
 
+namespace {
+/* std::vector<Crit3DMacroArea> <-> pb_macro_area[] (interpolationSettings.h:149-182) */
+struct FlatAreas {
+    std::vector<pb_macro_area> a;
+    std::vector<std::vector<int32_t>> pts;
+    std::vector<std::vector<float>> cells;
+};
+
+void flattenArea(const Crit3DMacroArea& area, int nProxy, pb_macro_area& A, std::vector<int32_t>& pts, std::vector<float>& cells)
+{
+    memset(&A, 0, sizeof(A));
+    std::vector<int> mp = area.getMeteoPoints();
+    pts.assign(mp.begin(), mp.end());
+    cells = area.getAreaCellsDEM();
+    A.nMeteoPoints = int(pts.size());
+    A.meteoPoints = pts.empty() ? nullptr : pts.data();
+    A.nAreaCells = int64_t(cells.size());
+    A.areaCellsDEM = cells.empty() ? nullptr : cells.data();
+    Crit3DProxyCombination c = area.getCombination();
+    for (int i = 0; i < nProxy && i < int(c.getProxySize()) && i < PB_MAX_PROXY; i++) {
+        A.active[i] = c.isProxyActive(i);
+        A.significant[i] = c.isProxySignificant(i);
+    }
+    A.useThermalInversion = c.getUseThermalInversion();
+    std::vector<std::vector<double>> par = area.getParameters();
+    A.nParameters = int(std::min(par.size(), size_t(PB_MAX_PROXY)));
+    for (int i = 0; i < A.nParameters; i++) {
+        A.nrParams[i] = int(std::min(par[i].size(), size_t(PB_MAX_FIT_PARAMS)));
+        for (int j = 0; j < A.nrParams[i]; j++) A.parameters[i][j] = par[i][j];
+    }
+}
+
+void flattenAreas(const Crit3DInterpolationSettings& st, int nProxy, FlatAreas& f)
+{
+    const std::vector<Crit3DMacroArea>& areas = st.getMacroAreas();
+    const size_t n = areas.size();
+    f.a.resize(n); f.pts.resize(n); f.cells.resize(n);
+    for (size_t i = 0; i < n; i++) flattenArea(areas[i], nProxy, f.a[i], f.pts[i], f.cells[i]);
+}
+
+/* what glocalDetrendingFitting stores in the areas it fitted (interpolation.cpp:2283-2285, 2291) */
+void writeBackAreas(const FlatAreas& f, int nProxy, Crit3DInterpolationSettings& st)
+{
+    std::vector<Crit3DMacroArea> areas = st.getMacroAreas();
+    for (size_t i = 0; i < areas.size() && i < f.a.size(); i++) {
+        const pb_macro_area& A = f.a[i];
+        if (A.nMeteoPoints <= 0) continue;
+        std::vector<std::vector<double>> par;
+        for (int k = 0; k < A.nParameters; k++) par.push_back(std::vector<double>(A.parameters[k], A.parameters[k] + A.nrParams[k]));
+        areas[i].setParameters(par);
+        Crit3DProxyCombination c;
+        for (int k = 0; k < nProxy; k++) { c.addProxyActive(A.active[k] != 0); c.addProxySignificant(A.significant[k] != 0); }
+        c.setUseThermalInversion(A.useThermalInversion != 0);
+        areas[i].setCombination(c);
+    }
+    st.setMacroAreas(areas);
+}
+}  // namespace
+
 bool preInterpolation(std::vector<Crit3DInterpolationDataPoint>& myPoints, Crit3DInterpolationSettings& interpolationSettings,
                       Crit3DMeteoSettings* meteoSettings, Crit3DClimateParameters* climateParameters,
                       std::vector<Crit3DMeteoPoint>& meteoPoints, meteoVariable myVar, Crit3DTime myTime, std::string& errorStr)
@@ -343,6 +402,17 @@ bool preInterpolation(std::vector<Crit3DInterpolationDataPoint>& myPoints, Crit3
     std::vector<uint8_t> keep(n, 1);
     pb_kh_series kh;
     memset(&kh, 0, sizeof(kh));
+    if (s.useGlocalDetrending && s.useMultipleDetrending && getUseDetrendingVar(myVar)) {
+        // glocalDetrendingFitting (:2471-2474): the points stay as they are, the macro areas receive their fit
+        FlatAreas fa;
+        flattenAreas(interpolationSettings, s.nProxy, fa);
+        const int rcg = pb_glocal_detrending_fitting(ctx, &fp.st, &s, int(myVar), fa.a.data(), int(fa.a.size()));
+        if (demId >= 0) pb_raster_free(ctx, demId);
+        if (failed(ctx, rcg)) { errorStr = g_error; return false; }
+        writeBackSettings(s, interpolationSettings, kh);
+        writeBackAreas(fa, s.nProxy, interpolationSettings);
+        return true;
+    }
     const int rc = pb_pre_interpolation_ex(ctx, &fp.st, &s, int(myVar), &cv, demId, keep.data(), &kh);
     if (demId >= 0) pb_raster_free(ctx, demId);
     if (rc == PB_ERR_FIT) { errorStr = "Error in function preInterpolation"; return false; }
@@ -356,6 +426,104 @@ bool preInterpolation(std::vector<Crit3DInterpolationDataPoint>& myPoints, Crit3
             out.push_back(myPoints[i]);
         }
     if (int(out.size()) != n) myPoints = out;
+    return true;
+}
+
+bool interpolationRasterGlocalDetrending(std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                                         Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                                         gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster, meteoVariable variable)
+{
+    if (!getUseDetrendingVar(variable) || !interpolationSettings.getUseGlocalDetrending()) return false;     // project.cpp:3264
+    interpolationSettings.setCurrentCombination(interpolationSettings.getSelectedCombination());               // :3279-3280
+    gis::Crit3DRasterHeader header = *(raster.header);
+    if (!outputGrid->initializeGrid(header)) return false;                                                     // :3296-3297
+    pb_context* ctx = context();
+    if (!ctx) return false;
+    pb_settings s;
+    std::vector<pb_raster> grids;
+    if (!flattenSettings(interpolationSettings, meteoSettings, s, grids, &raster)) return false;
+    FlatPoints fp;
+    flattenPoints(interpolationPoints, s.nProxy, fp);
+    FlatAreas fa;
+    flattenAreas(interpolationSettings, s.nProxy, fa);
+    pb_raster dem = rasterOf(raster);
+    pb_raster_id demId = -1;
+    std::vector<pb_raster_id> ids(grids.size(), -1);
+    auto release = [&]() {
+        if (demId >= 0) pb_raster_free(ctx, demId);
+        for (pb_raster_id id : ids) if (id >= 0 && id != demId) pb_raster_free(ctx, id);
+    };
+    if (failed(ctx, pb_raster_upload(ctx, &dem, &demId))) return false;
+    for (size_t g = 0; g < grids.size(); g++) {
+        if (grids[g].rows == dem.rows && grids[g].data == dem.data) { ids[g] = demId; continue; }     // the elevation proxy IS the DEM
+        if (failed(ctx, pb_raster_upload(ctx, &grids[g], &ids[g]))) { release(); return false; }
+    }
+    pb_raster_out out;
+    memset(&out, 0, sizeof(out));
+    out.rows = outputGrid->value;
+    const int rc = pb_glocal_detrending_raster(ctx, &fp.st, &s, int(variable), fa.a.data(), int(fa.a.size()), demId, ids.data(),
+                                               int(ids.size()), 0, &out);
+    release();
+    if (rc != PB_OK && rc != PB_ERR_NO_VALID_CELL) { failed(ctx, rc); return false; }
+    pb_kh_series kh;
+    memset(&kh, 0, sizeof(kh));
+    writeBackSettings(s, interpolationSettings, kh);
+    writeBackAreas(fa, s.nProxy, interpolationSettings);
+    outputGrid->minimum = out.minimum;
+    outputGrid->maximum = out.maximum;
+    if (rc == PB_ERR_NO_VALID_CELL) { failed(ctx, rc); return false; }       // isOk = false (:3358-3359)
+    return true;
+}
+
+bool computeResidualsGlocalDetrending(meteoVariable myVar, const Crit3DMacroArea& myArea, int /*elevationPos*/,
+                                      std::vector<Crit3DMeteoPoint>& meteoPoints,
+                                      std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                                      Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                                      bool excludeOutsideDem, bool excludeSupplemental)
+{
+    pb_context* ctx = context();
+    if (!ctx) return false;
+    pb_settings s;
+    std::vector<pb_raster> grids;
+    if (!flattenSettings(interpolationSettings, meteoSettings, s, grids, interpolationSettings.getCurrentDEM())) return false;
+    FlatPoints fp;
+    flattenPoints(interpolationPoints, s.nProxy, fp);
+    pb_macro_area A;
+    std::vector<int32_t> pts;
+    std::vector<float> cells;
+    flattenArea(myArea, s.nProxy, A, pts, cells);
+    if (A.nAreaCells <= 0) { A.nAreaCells = 2; static const float one[2] = {0.f, 1.f}; A.areaCellsDEM = one; }   // this call never reads the cells
+    // one Crit3DMeteoPoint per entry: position, lapse code, proxy values, current value; only accepted points are cross-validated
+    const int n = int(meteoPoints.size()), P = s.nProxy;
+    std::vector<double> x(n), y(n), z(n);
+    std::vector<float> val(n), proxy(size_t(n) * std::max(P, 1), float(NODATA)), res(n);
+    std::vector<int32_t> code(n);
+    std::vector<uint8_t> active(n), inside(n);
+    for (int i = 0; i < n; i++) {
+        const Crit3DMeteoPoint& m = meteoPoints[i];
+        x[i] = m.point.utm.x; y[i] = m.point.utm.y; z[i] = m.point.z;
+        val[i] = m.currentValue;
+        code[i] = int(m.lapseRateCode);
+        active[i] = m.active && m.quality == quality::accepted;
+        inside[i] = m.isInsideDem;
+        for (int k = 0; k < P && k < int(m.proxyValues.size()); k++) proxy[size_t(i) * P + k] = m.proxyValues[k];
+    }
+    pb_stations mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.n = n; mp.nProxy = P;
+    mp.x = x.data(); mp.y = y.data(); mp.z = z.data(); mp.value = val.data(); mp.lapseRateCode = code.data();
+    mp.isActive = active.data(); mp.proxyValues = proxy.data();
+    pb_cv_points cv;
+    memset(&cv, 0, sizeof(cv));
+    cv.isInsideDem = inside.data();
+    if (failed(ctx, pb_compute_residuals_glocal(ctx, &mp, val.data(), &cv, &fp.st, &s, int(myVar), &A, 1, excludeOutsideDem,
+                                                excludeSupplemental, res.data())))
+        return false;
+    for (int i = 0; i < n; i++) {
+        if (isEqual(res[i], NODATA)) continue;
+        if (isEqual(meteoPoints[i].residual, NODATA)) meteoPoints[i].residual = res[i];
+        else meteoPoints[i].residual += res[i];
+    }
     return true;
 }
 

@@ -9,6 +9,10 @@
  *   pragab200::interpolationRasterLocalDetrending <- loop of Project::interpolationDemLocalDetrending, project.cpp:3208-3253
  *   pragab200::preInterpolation               <- agrolib/interpolation/interpolation.h (.cpp:2444-2499): precipitation check,
  *                                                multiple detrending, classic detrending(), optimalDetrending(), kh search
+ *                                                with useGlocalDetrending: glocalDetrendingFitting (.cpp:2239-2294), the macro
+ *                                                areas of the settings receive their fit
+ *   pragab200::interpolationRasterGlocalDetrending <- loop of Project::interpolationDemGlocalDetrending, project.cpp:3283-3375
+ *   pragab200::computeResidualsGlocalDetrending <- agrolib/interpolation/spatialControl.h:42 (.cpp:231-302)
  *   pragab200::computeResiduals               <- agrolib/interpolation/spatialControl.h:30 (.cpp:97-155)
  *   pragab200::computeResidualsLocalDetrending <- agrolib/interpolation/spatialControl.h (.cpp:158-228)
  *   pragab200::spatialQualityControl          <- agrolib/interpolation/spatialControl.h (.cpp:331-427)
@@ -46,6 +50,22 @@ bool interpolationRasterLocalDetrending(std::vector<Crit3DInterpolationDataPoint
                                         Crit3DInterpolationSettings& interpolationSettings,
                                         Crit3DMeteoSettings* meteoSettings, gis::Crit3DRasterGrid* outputGrid,
                                         gis::Crit3DRasterGrid& raster, meteoVariable variable);
+
+/* glocal detrending: interpolationPoints are the points of checkAndPassDataToInterpolation (NOT detrended); the settings carry
+ * the macro areas (setMacroAreas), useGlocalDetrending + useMultipleDetrending and the points range. Does what
+ * Project::interpolationDemGlocalDetrending does from preInterpolation on: fits every area (the areas in the settings keep
+ * parameters and combination), grids each area's cells over the area's stations and blends them by weight into outputGrid.
+ * Returns false where the reference does (an interpolate() inside an area gave NODATA). */
+bool interpolationRasterGlocalDetrending(std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                                         Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                                         gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster, meteoVariable variable);
+
+/* same signature and side effects as the reference (residuals are ADDED to meteoPoints[].residual, one area per call) */
+bool computeResidualsGlocalDetrending(meteoVariable myVar, const Crit3DMacroArea& myArea, int elevationPos,
+                                      std::vector<Crit3DMeteoPoint>& meteoPoints,
+                                      std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
+                                      Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
+                                      bool excludeOutsideDem, bool excludeSupplemental);
 
 /* same contract as the reference: myPoints are detrended in place (points multiple detrending drops are erased), the
  * settings receive the fit (current combination, proxies' regression fields or fitting functions/parameters, kh and the

@@ -176,3 +176,36 @@ def test_shim_compute_residuals_local(shim, ref):
     assert rc == A.PB_OK
     assert np.array_equal(res_r == np.float32(-9999), res_g == np.float32(-9999))
     assert np.abs(res_r.astype(np.float64) - res_g).max() <= TOL
+
+
+def test_shim_glocal_detrending_raster_and_residuals(shim, ref):
+    """pragab200::interpolationRasterGlocalDetrending / computeResidualsGlocalDetrending / preInterpolation(glocal) on
+    reference objects (the macro areas live in Crit3DInterpolationSettings) against the reference's own loop."""
+    from test_oracle_port import clone, describe_diff, settings_equal
+    dem = syn.make_dem(100, 120, seed=5)
+    urban = syn.make_urban(100, 120)
+    st = syn.make_stations(dem, 400, proxies=(dem, urban), seed=17)
+    s = syn.settings_multiple_detrending()
+    s.useGlocalDetrending = 1
+    syn.set_points_range(s, st)
+    a_r, s_r = syn.make_macro_areas(dem, st, 2, 8), clone(s)
+    ok_r, grid_r, mn_r, mx_r, _, _ = ref.glocal_detrending_raster(st.copy(), s_r, A.airTemperature, a_r, dem, (dem, urban), threads=1)
+    ok2, res_r = ref.compute_residuals_glocal(st, st.value, st, clone(s_r), A.airTemperature, a_r, dem)
+    a_g, s_g = syn.make_macro_areas(dem, st, 2, 8), clone(s)
+    stp, d = st.as_pb(), dem.as_pb()
+    g = (A.pb_raster * 2)(dem.as_pb(), urban.as_pb())
+    grid_g = np.empty(dem.shape, dtype=np.float32)
+    o = A.pb_raster_out()
+    o.data = A.fptr(grid_g)
+    res_g = np.empty(st.n, dtype=np.float32)
+    err = C.create_string_buffer(512)
+    rc = shim.shim_glocal(C.byref(stp), C.byref(s_g), A.airTemperature, a_g.arr, a_g.n, C.byref(d), g, 2, C.byref(o), A.fptr(res_g),
+                          err, 512)
+    assert (rc == A.PB_OK) == ok_r, err.value.decode()
+    assert a_g.fits() == a_r.fits()
+    assert settings_equal(s_r, s_g), describe_diff(s_r, s_g)
+    nod = grid_r == np.float32(dem.flag)
+    assert np.array_equal(nod, grid_g == np.float32(dem.flag))
+    assert np.abs(grid_g[~nod].astype(np.float64) - grid_r[~nod]).max() <= TOL
+    assert abs(o.minimum - mn_r) <= TOL and abs(o.maximum - mx_r) <= TOL
+    assert ok2 and np.array_equal(res_r, res_g)
