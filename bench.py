@@ -51,12 +51,15 @@ WORKLOADS = {
     "c4": dict(rows=10000, cols=10000, stations=2000, band_rows=1000,
                desc="synthetic 10000x10000 DEM @100 m, 2000 stations, ordinary kriging (spherical, range 2e5 m, nugget 0.1, "
                     "sill 4), estimate + RMSE grids"),
+    "c2g": dict(rows=2000, cols=2000, stations=500, areas_side=3, blend_cells=100, margin_m=30000.0,
+                desc="synthetic 2000x2000 DEM @100 m, 500 stations, glocal detrending: 3x3 macro areas with 10 km blended borders, "
+                     "per-area multipleDetrending (elevation + urbanFraction) + IDW over the area's stations, airTemperature"),
     "c5": dict(rows=2000, cols=2000, stations=500,
                desc="hourly batch on the synthetic 2000x2000 DEM @100 m, 500 stations: airTemperature (multipleDetrending), "
                     "airRelHumidity, precipitation; per step spatial quality control + preInterpolation + raster + "
                     "leave-one-out cross-validation (Project::interpolationDem / interpolationCv)"),
 }
-GENERIC = ("c3", "c4", "c5")
+GENERIC = ("c3", "c4", "c5", "c2g")
 
 
 def build_workload(name, n_steps, first_step=0):
@@ -454,11 +457,76 @@ class HourlyBatchWorkload:
         return cells, sec, threads, "3 whole steps (one per variable) of the same chain out of the reference's functions"
 
 
-GENERIC_CLASSES = {"c3": LocalDetrendingWorkload, "c4": KrigingWorkload, "c5": HourlyBatchWorkload}
+class GlocalWorkload:
+    """c2g: G1. unit = one glocal gridding call on the 2000 x 2000 raster (fit of every macro area + per-area IDW + blend);
+    ranks take different time steps."""
+    kernel = "pb::idw_kernel<1,true> per macro area (+ pre_interpolation_batch_kernel, glocal_targets / glocal_blend)"
+    ROOFLINE_ON_STEP_TIME = True
+
+    def __init__(self, eng, w, rank, world, n_total):
+        self.eng, self.w, self.var = eng, w, A.airTemperature
+        self.dem = syn.make_dem(w["rows"], w["cols"])
+        self.urban = syn.make_urban(w["rows"], w["cols"])
+        self.base = syn.make_stations(self.dem, w["stations"], proxies=(self.dem, self.urban))
+        self.s = syn.settings_multiple_detrending()
+        self.s.useGlocalDetrending = 1
+        self.areas = syn.make_macro_areas(self.dem, self.base, w["areas_side"], w["blend_cells"], w["margin_m"])
+        self.pairs = float(sum(len(m) * (c.size // 2) for m, c in zip(self.areas.meteo_points, self.areas.area_cells)))
+        self.area_cells = int(sum(c.size // 2 for c in self.areas.area_cells))
+        self.rank, self.world = rank, world
+        if eng is not None and getattr(eng, "h", None):
+            self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
+
+    def _step_inputs(self, k):
+        st = self.base.copy()
+        st.value[:] = (self.base.value + np.random.default_rng(700 + self.rank + k * self.world).normal(0, 0.3, st.n)).astype(np.float32)
+        s = A.pb_settings.from_buffer_copy(bytes(self.s))
+        syn.set_points_range(s, st)
+        return st, s
+
+    def _run(self, k, device_only):
+        st, s = self._step_inputs(k)
+        ok, grid, mn, mx, nv = self.eng.glocal_detrending_raster(st, s, self.var, self.areas, self.dem_id, self.dem.shape,
+                                                                 (self.dem_id, self.urb_id), device_only=device_only)
+        assert ok
+        return nv
+
+    def device_step(self, k):
+        return self._run(k, True)
+
+    def e2e_step(self, k):
+        return self._run(k, False)
+
+    def roofline(self, cells_per_launch, step_s, peaks):
+        fp32, mufu = self.eng.measure_pipe_peaks()
+        ach = 11.0 * self.pairs / step_s * 1e-12
+        return {"bound": "fp32", "achieved": ach, "peak": fp32, "unit": "TFLOP/s", "frac": ach / fp32, "traffic": None,
+                "kernel": self.kernel, "kernel_ms_per_launch": step_s * 1e3,
+                "algorithmic": f"11 flop x {self.pairs:.4g} (cell, station) pairs per step = sum over areas of stations x cells "
+                               f"({self.area_cells} (cell, area) entries for {int(cells_per_launch)} cells); taken against the whole "
+                               "device time of the step (fit + 3 kernels per area + min/max)",
+                "peak_source": "FFMA2 chain measured live on this GPU (MEASURED_PEAKS.json has no FP32 figure)",
+                "mufu_bound": {"pairs_per_s": self.pairs / step_s, "mufu_peak_per_s": mufu * 1e9, "frac": self.pairs / step_s / (mufu * 1e9)}}
+
+    def config(self):
+        return {"unit_of_work": "one glocal gridding call (all macro areas) per step", "macro_areas": self.areas.n,
+                "cell_area_entries": self.area_cells, "stations_per_area": [int(len(m)) for m in self.areas.meteo_points],
+                "sharding": "time steps over ranks, no collective"}
+
+    def cpu_sample(self, orc, seconds_hint):
+        threads = orc.max_threads()
+        st, s = self._step_inputs(0)
+        ok, grid, mn, mx, nv, sec = orc.glocal_detrending_raster(st, s, self.var, self.areas, self.dem, (self.dem, self.urban), threads=0)
+        return nv, sec, threads, (f"the whole {self.w['rows']}x{self.w['cols']} raster ({nv} valid cells), 1 pass; the reference "
+                                  f"parallelises over the {self.areas.n} macro areas (project.cpp:3317)")
+
+
+GENERIC_CLASSES = {"c3": LocalDetrendingWorkload, "c4": KrigingWorkload, "c5": HourlyBatchWorkload, "c2g": GlocalWorkload}
 GENERIC_DTYPE = {"c3": "f64 (LM fits, IDW weights) / f32 distances", "c4": "f64 estimate / fp16x2-split tensor-core variance, f32 accumulate",
-                 "c5": "f32 (f64 cross-tile accumulation, f64 fits)"}
+                 "c5": "f32 (f64 cross-tile accumulation, f64 fits)", "c2g": "f32 (f64 fits, f64 cross-tile accumulation and blend)"}
 GENERIC_METRIC = {"c3": "gridded cells/sec (localDetrending + IDW)", "c4": "gridded cells/sec (ordinary kriging, estimate + RMSE)",
-                  "c5": "gridded cells/sec (hourly batch: QC + detrending + IDW + LOO)"}
+                  "c5": "gridded cells/sec (hourly batch: QC + detrending + IDW + LOO)",
+                  "c2g": "gridded cells/sec (glocal detrending + IDW)"}
 
 
 def run_generic(args, rank, local_rank, world):

@@ -415,6 +415,21 @@ int pb_kriging_points(pb_context* ctx, pb_kriging_id id, const double* xy, int m
 int pb_kriging_raster(pb_context* ctx, pb_kriging_id id, pb_raster_id dem, int rowBegin, int rowEnd,
                       pb_raster_out* estimate, pb_raster_out* rmse /* may be NULL */);
 
+/* --- variogram estimation for ordinary kriging, HOST side (north_star: "the variogram fit stays on the host"; no context,
+ * no GPU needed). The reference declares krigingEstimateVariogram(myDist, mySemiVar, sizeMyVar, nrMyPoints, myMaxDistance,
+ * mySill, myNugget, myRange, mySlope, myMode, nrPointData) (agrolib/interpolation/interpolation.h:65-68) and never defines it
+ * (SURVEY.md 3.5): these two calls are the engine's own definition — parity UNPINNED by construction — for the model family of
+ * krigingVariogram (kriging.cpp:97-202).
+ *   pb_kriging_empirical_variogram  Matheron estimator over all pairs closer than maxDistance (<= 0: half the bounding-box
+ *                                   diagonal; *maxDistanceUsed may be NULL): nBins distance bins, binDist = mean pair distance,
+ *                                   binSemiVar = sum (vi - vj)^2 / (2 N) (PB_NODATA for an empty bin), binCount = N
+ *   pb_kriging_fit_variogram        weighted (N) least squares of the bins; mode = PB_KRIGING_* or 0 = best of spherical /
+ *                                   exponential / gaussian; outputs feed pb_kriging_setup (nugget floored at 1e-4 sill: > 0) */
+int pb_kriging_empirical_variogram(const double* pos, const double* val, int n, int nBins, double maxDistance, float* binDist,
+                                   float* binSemiVar, int32_t* binCount, double* maxDistanceUsed);
+int pb_kriging_fit_variogram(const float* binDist, const float* binSemiVar, const int32_t* binCount, int nBins, int mode,
+                             double* range, double* nugget, double* sill, double* slope, int* modeOut, double* weightedSse);
+
 /* --- raster map operators on either side of the gridding path. Inputs are resident rasters;
  * the result goes to `out` (host grid: data or rows; may be NULL) and / or stays on the device as a new resident raster
  * (*outId, to be released with pb_raster_free; NULL: not kept).

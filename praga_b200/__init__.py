@@ -5,6 +5,7 @@ This package only holds the build script, the ctypes binding and the synthetic-s
 """
 from . import _abi as abi  # noqa: F401
 from ._abi import Raster, Stations, default_proxy, default_settings  # noqa: F401
-from .engine import Engine, PragaB200Error, load_library  # noqa: F401
+from .engine import Engine, PragaB200Error, empirical_variogram, fit_variogram, load_library  # noqa: F401
 
-__all__ = ["abi", "Raster", "Stations", "default_proxy", "default_settings", "Engine", "PragaB200Error", "load_library"]
+__all__ = ["abi", "Raster", "Stations", "default_proxy", "default_settings", "Engine", "PragaB200Error", "load_library",
+           "empirical_variogram", "fit_variogram"]

@@ -29,6 +29,7 @@ SOURCES = {
     "raster_io.cu": [],
     "kriging.cu": [],
     "kriging_tc.cu": [],
+    "variogram.cu": [],
 }
 HEADERS = ["common.cuh", "epilogue.cuh", "context.cuh", "local.cuh", "pre.cuh", "multiple_detrend.cuh", "detrend_device.cuh", "kriging.cuh", "classic.cuh", "shepard.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

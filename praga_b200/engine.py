@@ -100,6 +100,10 @@ def load_library():
     lib.pb_compute_residuals_glocal.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), P(A.pb_cv_points), P(A.pb_stations),
                                                 P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int, C.c_int, C.c_int,
                                                 P(C.c_float)]
+    lib.pb_kriging_empirical_variogram.argtypes = [P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, P(C.c_float),
+                                                   P(C.c_float), P(C.c_int32), P(C.c_double)]
+    lib.pb_kriging_fit_variogram.argtypes = [P(C.c_float), P(C.c_float), P(C.c_int32), C.c_int, C.c_int, P(C.c_double),
+                                             P(C.c_double), P(C.c_double), P(C.c_double), P(C.c_int), P(C.c_double)]
     lib.pb_measure_pipe_peaks.argtypes = [C.c_void_p, P(C.c_float), P(C.c_float)]
     lib.pb_measure_fp64_peak.argtypes = [C.c_void_p, P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
@@ -110,6 +114,35 @@ def load_library():
             raise PragaB200Error(A.PB_ERR_INVALID, f"ABI mismatch for {name}: library {got} B, binding {want} B")
     _LIB = lib
     return lib
+
+
+def empirical_variogram(pos, val, n_bins=30, max_distance=0.0):
+    """Host-side Matheron estimator (pb_kriging_empirical_variogram). pos: (n, 2). Returns (dist, semivar, count, max_distance)."""
+    lib = load_library()
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    d, g, c = np.empty(n_bins, np.float32), np.empty(n_bins, np.float32), np.empty(n_bins, np.int32)
+    used = C.c_double(0)
+    rc = lib.pb_kriging_empirical_variogram(A.dptr(pos), A.dptr(val), val.size, n_bins, float(max_distance), A.fptr(d), A.fptr(g),
+                                            A.iptr(c), C.byref(used))
+    if rc != A.PB_OK:
+        raise PragaB200Error(rc, "pb_kriging_empirical_variogram failed")
+    return d, g, c, used.value
+
+
+def fit_variogram(dist, semivar, count=None, mode=0):
+    """Host-side weighted least-squares variogram fit (pb_kriging_fit_variogram). Returns a dict with mode, range, nugget, sill,
+    slope, sse: the inputs of Engine.kriging_setup."""
+    lib = load_library()
+    d = np.ascontiguousarray(dist, dtype=np.float32)
+    g = np.ascontiguousarray(semivar, dtype=np.float32)
+    c = None if count is None else np.ascontiguousarray(count, dtype=np.int32)
+    rng, nug, sill, slope, sse, m = C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0), C.c_int(0)
+    rc = lib.pb_kriging_fit_variogram(A.fptr(d), A.fptr(g), None if c is None else A.iptr(c), d.size, mode, C.byref(rng),
+                                      C.byref(nug), C.byref(sill), C.byref(slope), C.byref(m), C.byref(sse))
+    if rc != A.PB_OK:
+        raise PragaB200Error(rc, "pb_kriging_fit_variogram failed")
+    return {"mode": m.value, "range": rng.value, "nugget": nug.value, "sill": sill.value, "slope": slope.value, "sse": sse.value}
 
 
 class Engine:

@@ -713,6 +713,24 @@ void krigingFreeMemory()
     }
 }
 
+bool krigingEstimateVariogram(float* myDist, float* mySemiVar, int sizeMyVar, int /*nrMyPoints*/, float myMaxDistance,
+                              double* mySill, double* myNugget, double* myRange, double* mySlope, TkrigingMode* myMode,
+                              int /*nrPointData*/)
+{
+    if (!myDist || !mySemiVar || !mySill || !myNugget || !myRange || !mySlope || !myMode) return false;
+    // bins beyond myMaxDistance do not take part (count 0)
+    std::vector<int32_t> count(size_t(std::max(sizeMyVar, 0)), 1);
+    for (int i = 0; i < sizeMyVar; i++) if (myMaxDistance > 0 && myDist[i] > myMaxDistance) count[i] = 0;
+    int mode = int(*myMode);
+    if (mode < int(KRIGING_SPHERICAL) || mode > int(KRIGING_LINEAR)) mode = 0;
+    int modeOut = 0;
+    const int rc = pb_kriging_fit_variogram(myDist, mySemiVar, count.data(), sizeMyVar, mode, myRange, myNugget, mySill, mySlope,
+                                            &modeOut, nullptr);
+    if (rc != PB_OK) { g_error = "variogram fit failed"; return false; }
+    *myMode = TkrigingMode(modeOut);
+    return true;
+}
+
 bool krigingRaster(gis::Crit3DRasterGrid& raster, gis::Crit3DRasterGrid* estimateGrid, gis::Crit3DRasterGrid* rmseGrid)
 {
     pb_context* ctx = context();

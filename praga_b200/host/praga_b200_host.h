@@ -99,6 +99,11 @@ bool krigingSetWeight(double x_p, double y_p);
 double krigingResult();
 double krigingRMSE();
 void krigingFreeMemory();
+/* the variogram fit the reference declares but never defines (agrolib/interpolation/interpolation.h:65-68), same parameter
+ * list: myDist / mySemiVar = the sizeMyVar bins of the empirical variogram; *myMode in: the model to fit (an invalid value:
+ * the best of spherical / exponential / gaussian), out: the model fitted. Host arithmetic (pb_kriging_fit_variogram). */
+bool krigingEstimateVariogram(float* myDist, float* mySemiVar, int sizeMyVar, int nrMyPoints, float myMaxDistance, double* mySill,
+                              double* myNugget, double* myRange, double* mySlope, TkrigingMode* myMode, int nrPointData);
 /* batched form: estimate and RMSE for every valid cell (cell centres) of `raster` with the current system */
 bool krigingRaster(gis::Crit3DRasterGrid& raster, gis::Crit3DRasterGrid* estimateGrid, gis::Crit3DRasterGrid* rmseGrid);
 
