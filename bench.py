@@ -476,6 +476,7 @@ class GlocalWorkload:
         self.rank, self.world = rank, world
         if eng is not None and getattr(eng, "h", None):
             self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
+            self.cells_id = eng.macro_areas_upload(self.areas)       # static like the DEM: the glocal weight maps
 
     def _step_inputs(self, k):
         st = self.base.copy()
@@ -487,7 +488,8 @@ class GlocalWorkload:
     def _run(self, k, device_only):
         st, s = self._step_inputs(k)
         ok, grid, mn, mx, nv = self.eng.glocal_detrending_raster(st, s, self.var, self.areas, self.dem_id, self.dem.shape,
-                                                                 (self.dem_id, self.urb_id), device_only=device_only)
+                                                                 (self.dem_id, self.urb_id), device_only=device_only,
+                                                                 cells_id=self.cells_id)
         assert ok
         return nv
 

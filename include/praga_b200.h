@@ -301,6 +301,14 @@ int pb_glocal_detrending_fitting(pb_context* ctx, const pb_stations* st, pb_sett
 int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
                                 int nAreas, pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int deviceOnly,
                                 pb_raster_out* out);
+/* the areas' (cell, weight) pairs only change with the glocal weight maps: upload them once (like the DEM) and give the id
+ * to the resident form, which then moves only the stations per time step; areas[] must describe the same areas. */
+typedef int32_t pb_macro_areas_id;
+int pb_macro_areas_upload(pb_context* ctx, const pb_macro_area* areas, int nAreas, pb_macro_areas_id* id);
+int pb_macro_areas_free(pb_context* ctx, pb_macro_areas_id id);
+int pb_glocal_detrending_raster_resident(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
+                                         int nAreas, pb_macro_areas_id cells, pb_raster_id dem, const pb_raster_id* proxyGrids,
+                                         int nProxyGrids, int deviceOnly, pb_raster_out* out);
 int pb_compute_residuals_glocal(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
                                 const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
                                 int excludeOutsideDem, int excludeSupplemental, float* residual);
@@ -450,6 +458,23 @@ int pb_topographic_distance_map(pb_context* ctx, pb_raster_id dem, double x, dou
                                 pb_raster_id* outId);
 int pb_resample_grid(pb_context* ctx, pb_raster_id src, const pb_raster_header* newHeader, int method, float nodataRatioThreshold,
                      pb_raster_out* out, pb_raster_id* outId);
+
+/* --- DEM -> meteo-grid aggregation, the step right after the gridding path in the batch drivers:
+ * Crit3DMeteoGrid::spatialAggregateMeteoGrid (agrolib/meteo/meteoGrid.cpp:1135-1190) + spatialAggregateMeteoGridPoint
+ * (:1193-1240). The geometry — every active meteo-grid cell's aggregationPoints (utm x, y) and aggregationPointsMaxNr, built by
+ * Crit3DMeteoGrid::findGridAggregationPoints (:655-760) on the host — is uploaded once (first[c] .. first[c + 1] index x / y for
+ * cell c); then every gridded map resident on the device is reduced to one value per cell: nearest-cell samples
+ * (gis::getValueFromXY), coverage test against GRID_MIN_COVERAGE (= 0: at least one valid sample), aggrAverage / aggrMedian /
+ * aggrStdDeviation in the reference's float arithmetic and list order (other methods: NODATA, like the reference).
+ * value[c] = what the reference stores in the cell's currentValue (NODATA where it leaves the cell untouched). Each call
+ * starts from fresh aggregation points (z = NODATA); the reference keeps a stale z where a later map has no data. Only the
+ * nCells values cross PCIe (instead of the whole raster). */
+enum { PB_AGGR_STDDEV = 3 };
+typedef int32_t pb_aggregation_id;
+int pb_aggregation_upload(pb_context* ctx, const double* x, const double* y, const int64_t* first, const int32_t* maxNr, int nCells,
+                          pb_aggregation_id* id);
+int pb_aggregation_free(pb_context* ctx, pb_aggregation_id id);
+int pb_spatial_aggregate_meteo_grid(pb_context* ctx, pb_raster_id raster, pb_aggregation_id aggregation, int method, float* value);
 
 /* --- ESRI float grids (.hdr + .flt), the on-disk format at either end of the path, streamed between
  * the file and HBM through pinned staging (no pageable full-size copy):

@@ -126,6 +126,8 @@ def _load(path, prefix):
     fn = getattr(lib, prefix + "_compute_residuals_glocal")
     fn.argtypes = [P(A.pb_stations), P(C.c_float), P(A.pb_cv_points), P(A.pb_stations), P(A.pb_settings), C.c_int,
                    P(A.pb_macro_area), C.c_int, P(A.pb_raster), C.c_int, C.c_int, P(C.c_float)]
+    fn = getattr(lib, prefix + "_spatial_aggregate_meteo_grid")
+    fn.argtypes = [P(A.pb_raster), P(C.c_double), P(C.c_double), P(C.c_int64), P(C.c_int32), C.c_int, C.c_int, P(C.c_float)]
     _libs[path] = lib
     return lib
 
@@ -309,6 +311,18 @@ class Oracle:
         self._f("compute_residuals_local" if local else "compute_residuals")(C.byref(st), C.byref(settings), variable, A.fptr(obs),
                                      None if use is None else A.u8ptr(use), A.fptr(res), C.byref(stats))
         return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}
+
+    def spatial_aggregate_meteo_grid(self, raster, x, y, first, max_nr, method):
+        """Crit3DMeteoGrid::spatialAggregateMeteoGrid (meteoGrid.cpp:1135-1190): one value per meteo-grid cell."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        first = np.ascontiguousarray(first, dtype=np.int64)
+        max_nr = np.ascontiguousarray(max_nr, dtype=np.int32)
+        val = np.empty(max_nr.size, dtype=np.float32)
+        r = raster.as_pb()
+        self._f("spatial_aggregate_meteo_grid")(C.byref(r), A.dptr(x), A.dptr(y), first.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                A.iptr(max_nr), max_nr.size, method, A.fptr(val))
+        return val
 
     # ---- glocal detrending (macro areas) ----
     def glocal_detrending_fitting(self, stations, settings, variable, areas):

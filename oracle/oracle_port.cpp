@@ -2628,3 +2628,68 @@ int port_compute_residuals_glocal(const pb_stations* meteo, const float* observe
 }
 
 }  // extern "C"
+
+// Crit3DMeteoGrid::spatialAggregateMeteoGrid (meteo/meteoGrid.cpp:1135-1190) + spatialAggregateMeteoGridPoint (:1193-1240) with
+// statistics::mean / variance / standardDeviation (mathFunctions/statistics.cpp:1274-1297, 1160-1186, 1373-1381) and
+// sorting::percentile (basicMath.cpp:327-366); fresh aggregation points (z = NODATA)
+extern "C" int port_spatial_aggregate_meteo_grid(const pb_raster* raster, const double* x, const double* y, const int64_t* first,
+                                                 const int32_t* maxNr, int nCells, int method, float* value)
+{
+    const Grid g = gridOf(*raster);
+    for (int c = 0; c < nCells; c++) {
+        value[c] = NODATA_F;
+        const int64_t n = first[c + 1] - first[c];
+        std::vector<double> z(size_t(n), -9999.);
+        double validValues = 0;
+        for (int64_t i = 0; i < n; i++) {
+            const float v = g.valueFromXY(x[first[c] + i], y[first[c] + i]);
+            if (!isEqualF(v, g.h.flag)) { z[size_t(i)] = double(v); validValues = validValues + 1; }
+        }
+        if (n == 0) continue;
+        if (!((validValues / maxNr[c]) > (0 / 100))) continue;
+        std::vector<float> vals;
+        for (double q : z) if (q != -9999) vals.push_back(float(q));
+        double myValue = -9999;
+        if (!vals.empty() && !((double(vals.size()) / maxNr[c]) < (0 / 100.0))) {
+            if (method == PB_AGGR_AVERAGE) {
+                float sum = 0.;
+                int nv = 0;
+                for (float v : vals) if (v != NODATA_F) { sum += v; nv++; }
+                myValue = nv > 0 ? sum / float(nv) : NODATA_F;
+            } else if (method == PB_AGGR_STDDEV) {
+                float var = NODATA_F;
+                if (vals.size() > 1) {
+                    float sum = 0.;
+                    int nv = 0;
+                    for (float v : vals) if (v != NODATA_F) { sum += v; nv++; }
+                    const float mean = nv > 0 ? sum / float(nv) : NODATA_F;
+                    float squareDiff = 0;
+                    int m = 0;
+                    for (float v : vals) if (v != NODATA_F) { const float d = v - mean; squareDiff += d * d; m++; }
+                    if (m > 1) var = squareDiff / (m - 1);
+                }
+                myValue = isEqualF(var, NODATA_F) ? NODATA_F : sqrtf(var);
+            } else if (method == PB_AGGR_MEDIAN) {
+                float r = NODATA_F;
+                if (vals.size() >= 3) {
+                    std::vector<float> l;
+                    for (float v : vals) if (!isEqualF(v, NODATA_F)) l.push_back(v);
+                    std::sort(l.begin(), l.end());
+                    const int nl = int(l.size());
+                    if (nl >= 3) {
+                        const double rank = nl * double(50.0 / 100.f) - 1.0;
+                        if (rank < 0.0) r = l[0];
+                        else {
+                            const int low = int(rank);
+                            if (low >= nl - 1) r = l[nl - 1];
+                            else { const double frac = rank - low; r = float(l[low] + frac * (l[low + 1] - l[low])); }
+                        }
+                    }
+                }
+                myValue = r;
+            }
+        }
+        value[c] = float(myValue);
+    }
+    return PB_OK;
+}

@@ -35,6 +35,7 @@
 #include "meteo.h"
 #include "meteoPoint.h"
 #include "interpolation.h"
+#include "meteoGrid.h"
 #include "interpolationSettings.h"
 #include "interpolationPoint.h"
 #include "spatialControl.h"
@@ -1123,3 +1124,35 @@ int ref_kriging_points(const double* pos, const double* val, int n, int mode, do
 }
 
 }  // extern "C"
+
+/* Crit3DMeteoGrid::spatialAggregateMeteoGrid (meteo/meteoGrid.cpp:1135-1190), verbatim reference code, on a 1 x nCells meteo
+ * grid whose cells carry the given aggregation points (what findGridAggregationPoints would have built); value[c] = the
+ * cell's currentValue afterwards (NODATA where the reference leaves the cell untouched). */
+extern "C" int ref_spatial_aggregate_meteo_grid(const pb_raster* raster, const double* x, const double* y, const int64_t* first,
+                                                const int32_t* maxNr, int nCells, int method, float* value)
+{
+    gis::Crit3DRasterGrid grid;
+    fillGrid(grid, *raster);
+    Crit3DMeteoGrid mg;
+    Crit3DMeteoGridStructure gs;
+    gis::Crit3DLatLonHeader h;
+    h.nrRows = 1; h.nrCols = nCells; h.dx = 1; h.dy = 1; h.llCorner.latitude = 0; h.llCorner.longitude = 0;
+    gs.setHeader(h);
+    mg.setGridStructure(gs);
+    mg.initMeteoPoints(1, nCells);
+    for (int c = 0; c < nCells; c++) {
+        Crit3DMeteoPoint* mp = mg.meteoPointPointer(0, c);
+        mp->active = true;
+        mp->currentValue = NODATA;
+        mp->aggregationPointsMaxNr = maxNr[c];
+        for (int64_t i = first[c]; i < first[c + 1]; i++) {
+            gis::Crit3DPoint p;
+            p.utm.x = x[i]; p.utm.y = y[i]; p.z = NODATA;
+            mp->aggregationPoints.push_back(p);
+        }
+    }
+    mg.setIsAggregationDefined(true);
+    mg.spatialAggregateMeteoGrid(airTemperature, hourly, Crit3DDate(15, 1, 2023), 6, 0, &grid, &grid, aggregationMethod(method));
+    for (int c = 0; c < nCells; c++) value[c] = mg.meteoPointPointer(0, c)->currentValue;
+    return PB_OK;
+}

@@ -113,7 +113,7 @@ class pb_cv_points(C.Structure):
                 ("excludeOutsideDem", C.c_int32), ("reserved", C.c_int32), ("suspectProxyValues", C.POINTER(C.c_float))]
 
 
-PB_AGGR_AVERAGE, PB_AGGR_MEDIAN, PB_AGGR_PREVAILING, PB_AGGR_CENTER = 1, 2, 7, 9
+PB_AGGR_AVERAGE, PB_AGGR_MEDIAN, PB_AGGR_STDDEV, PB_AGGR_PREVAILING, PB_AGGR_CENTER = 1, 2, 3, 7, 9
 PB_MAX_KH_SERIES = 64
 
 

@@ -132,6 +132,28 @@ struct DevicePool {
     void destroy() { for (auto& b : bufs) cudaFree(b.p); bufs.clear(); }
 };
 
+// aggregation geometry of a meteo grid (Crit3DMeteoPoint::aggregationPoints of every cell, meteo/meteoPoint.h:86-87),
+// resident on the device: the batch drivers aggregate every gridded map onto the same cells (raster_ops.cu)
+struct AggregationGeometry {
+    bool used = false;
+    double* x = nullptr;
+    double* y = nullptr;
+    long long* first = nullptr;        // nCells + 1
+    int* maxNr = nullptr;              // aggregationPointsMaxNr
+    float* scratch = nullptr;          // one float per point
+    float* value = nullptr;            // nCells
+    int nCells = 0;
+    long long nPoints = 0;
+};
+
+// the (cell, weight) pairs of a set of macro areas, resident on the device (glocal.cu): they only change when the
+// glocal weight maps do, every time step reuses them
+struct ResidentMacroAreas {
+    bool used = false;
+    float* cells = nullptr;                // concatenated areaCellsDEM
+    std::vector<long long> firstFloat;     // nAreas + 1 offsets (in floats) into cells
+};
+
 struct KrigingSystem;                       // kriging.cu
 void krigingDestroyAll(std::vector<KrigingSystem*>& v);
 
@@ -166,6 +188,8 @@ struct pb_context {
     cudaEvent_t ev[4]{};
     pb_timing timing{};
     std::vector<pb::KrigingSystem*> kriging;    // pb_kriging_id -> system (kriging.cu)
+    std::vector<pb::AggregationGeometry> aggregations;   // pb_aggregation_id -> geometry (raster_ops.cu)
+    std::vector<pb::ResidentMacroAreas> macroAreas;      // pb_macro_areas_id -> resident cells (glocal.cu)
     std::vector<pb_context*> lanes;             // child contexts (own stream and buffers) of pb_interpolation_dem_batch
 };
 

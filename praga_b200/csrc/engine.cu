@@ -177,10 +177,18 @@ int buildModel(pb_context* ctx, const pb_settings* s, int variable, const pb_ras
 
 // pack the stations the estimator uses into the device layout. `excludeSupplemental` as in computeDistances
 // (interpolation.cpp:217-220): excluded points get distance 0 => never weigh => dropped here.
-int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, DevStations& ds,
-                  double& valueOffset)
+// Layout of one packed station set; h / d = host staging and its device twin (same offsets).
+size_t idwStationsBytes(int nStations)
 {
-    if (st->n < 0) return fail(ctx, PB_ERR_INVALID, "stations.n < 0");
+    const int T = tileStations();
+    const size_t nPadded = size_t((nStations + T - 1) / T) * T;
+    const size_t nAl = (size_t(nStations) + 3) / 4 * 4;
+    return (nPadded * 24 + nAl * 16 + 16 + 255) / 256 * 256;
+}
+
+void packIdwStations(const pb_stations* st, const pb_settings* s, bool excludeSupplemental, unsigned char* h, unsigned char* d,
+                     DevStations& ds, double& valueOffset)
+{
     std::vector<int> use;
     use.reserve(st->n);
     for (int i = 0; i < st->n; i++) {
@@ -195,13 +203,9 @@ int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, 
     for (int k = 0; k < n; k++) mean += double(st->value[use[k]]);
     mean = n ? mean / n : 0.;
     valueOffset = mean;
-
     const size_t offXY = 0, offV = offXY + size_t(nPadded) * 16, offX = offV + size_t(nPadded) * 8;
     const size_t nAl = (size_t(n) + 3) / 4 * 4;
-    const size_t offY = offX + nAl * 4, offVal = offY + nAl * 4, offZ = offVal + nAl * 4, total = offZ + nAl * 4 + 16;
-    CUDA_TRY(ctx, ctx->hStations.reserve(total));
-    CUDA_TRY(ctx, ctx->dStations.reserve(total));
-    unsigned char* h = ctx->hStations.p;
+    const size_t offY = offX + nAl * 4, offVal = offY + nAl * 4, offZ = offVal + nAl * 4;
     float4* xy = reinterpret_cast<float4*>(h + offXY);
     float2* v = reinterpret_cast<float2*>(h + offV);
     float* px = reinterpret_cast<float*>(h + offX);
@@ -221,9 +225,6 @@ int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, 
         xy[k] = make_float4(1e18f, 1e18f, 1e18f, 1e18f);
         v[k] = make_float2(0.f, 0.f);
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dStations.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->timing.h2d_bytes += (int64_t)total;
-    unsigned char* d = ctx->dStations.p;
     ds.xy = reinterpret_cast<const float4*>(d + offXY);
     ds.v = reinterpret_cast<const float2*>(d + offV);
     ds.x = reinterpret_cast<const float*>(d + offX);
@@ -232,6 +233,18 @@ int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, 
     ds.z = reinterpret_cast<const float*>(d + offZ);
     ds.n = n;
     ds.nPadded = nPadded;
+}
+
+int stageStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, DevStations& ds,
+                  double& valueOffset)
+{
+    if (st->n < 0) return fail(ctx, PB_ERR_INVALID, "stations.n < 0");
+    const size_t total = idwStationsBytes(st->n);
+    CUDA_TRY(ctx, ctx->hStations.reserve(total));
+    CUDA_TRY(ctx, ctx->dStations.reserve(total));
+    packIdwStations(st, s, excludeSupplemental, ctx->hStations.p, ctx->dStations.p, ds, valueOffset);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dStations.p, ctx->hStations.p, total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)total;
     return PB_OK;
 }
 
@@ -903,10 +916,11 @@ int buildDevModelGrids(pb_context* ctx, const pb_settings* s, int variable, cons
 {
     return buildModel(ctx, s, variable, proxyIds, nProxyGrids, m);
 }
-int stageIdwStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, DevStations& ds,
-                     double& valueOffset)
+size_t idwStationsStagingBytes(int nStations) { return idwStationsBytes(nStations); }
+void packIdwStationsAt(const pb_stations* st, const pb_settings* s, bool excludeSupplemental, unsigned char* h, unsigned char* d,
+                       DevStations& ds, double& valueOffset)
 {
-    return stageStations(ctx, st, s, excludeSupplemental, ds, valueOffset);
+    packIdwStations(st, s, excludeSupplemental, h, d, ds, valueOffset);
 }
 int buildPreModel(pb_context* ctx, const pb_settings* s, int variable, int nStations, LocalModel& m)
 {
@@ -973,6 +987,9 @@ void pb_destroy(pb_context* ctx)
     ctx->lanes.clear();
     for (auto& r : ctx->rasters) if (r.used) freeEntry(ctx, r);
     pb::krigingDestroyAll(ctx->kriging);
+    for (auto& g : ctx->aggregations)
+        if (g.used) { cudaFree(g.x); cudaFree(g.y); cudaFree(g.first); cudaFree(g.maxNr); cudaFree(g.scratch); cudaFree(g.value); }
+    for (auto& m : ctx->macroAreas) if (m.used) cudaFree(m.cells);
     ctx->dLocalStations.release(); ctx->dLocalScratch.release(); ctx->dLocalModel.release(); ctx->hLocal.release();
     if (ctx->dLocalError) cudaFree(ctx->dLocalError);
     if (ctx->hLocalError) cudaFreeHost(ctx->hLocalError);

@@ -31,8 +31,9 @@
 namespace pb {
 // engine.cu
 int buildDevModelGrids(pb_context* ctx, const pb_settings* s, int variable, const pb_raster_id* proxyIds, int nProxyGrids, DevModel& m);
-int stageIdwStations(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, DevStations& ds,
-                     double& valueOffset);
+size_t idwStationsStagingBytes(int nStations);
+void packIdwStationsAt(const pb_stations* st, const pb_settings* s, bool excludeSupplemental, unsigned char* h, unsigned char* d,
+                       DevStations& ds, double& valueOffset);
 int buildPreModel(pb_context* ctx, const pb_settings* s, int variable, int nStations, LocalModel& m);
 int stageAllStations(pb_context* ctx, const pb_stations* st, LocalStations& ds);
 void applyPreFitToSettings(const pb_settings& s, const LocalModel& m, const PreFit& f, pb_settings& o);
@@ -435,11 +436,10 @@ int pb_glocal_detrending_fitting(pb_context* ctx, const pb_stations* st, pb_sett
     return glocalFit(ctx, st, s, variable, areas, nAreas);
 }
 
-int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
-                                int nAreas, pb_raster_id demId, const pb_raster_id* proxyGrids, int nProxyGrids, int deviceOnly,
-                                pb_raster_out* out)
+static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas,
+                            const ResidentMacroAreas* resident, pb_raster_id demId, const pb_raster_id* proxyGrids, int nProxyGrids,
+                            int deviceOnly, pb_raster_out* out)
 {
-    if (!ctx) return PB_ERR_INVALID;
     if (!st || !s || !out || (!areas && nAreas > 0) || nAreas < 0) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
     memset(&ctx->timing, 0, sizeof(ctx->timing));
@@ -450,6 +450,7 @@ int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_setti
     if (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used)
         return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
     if (!deviceOnly && !out->data && !out->rows) return fail(ctx, PB_ERR_INVALID, "output has neither data nor rows");
+    if (resident && int(resident->firstFloat.size()) != nAreas + 1) return fail(ctx, PB_ERR_INVALID, "resident cells describe other areas");
     cudaEventRecord(ctx->ev[0], ctx->stream);
     for (int i = 0; i < s->nProxy; i++) { s->currentActive[i] = s->selectedActive[i]; s->currentSignificant[i] = 0; }
     s->currentUseThermalInversion = s->selectedUseThermalInversion;
@@ -464,13 +465,39 @@ int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_setti
     const DevGrid dg = devGridOfRaster(dem);
     long long maxCells = 1;
     for (int a = 0; a < nAreas; a++) {
-        if (areas[a].nAreaCells > 0 && !areas[a].areaCellsDEM) return fail(ctx, PB_ERR_INVALID, "macro area without areaCellsDEM");
+        if (areas[a].nAreaCells > 0 && !areas[a].areaCellsDEM && !resident) return fail(ctx, PB_ERR_INVALID, "macro area without areaCellsDEM");
         if (areas[a].nAreaCells / 2 > 0x7fffff00LL) return fail(ctx, PB_ERR_INVALID, "macro area with too many cells");
+        if (resident && resident->firstFloat[a + 1] - resident->firstFloat[a] != areas[a].nAreaCells)
+            return fail(ctx, PB_ERR_INVALID, "resident cells describe other areas");
         maxCells = std::max<long long>(maxCells, areas[a].nAreaCells / 2);
     }
+    // every area's stations (macroAreaDetrending on the host), packed behind each other in ONE staging buffer: one copy, no
+    // synchronisation between the areas
+    std::vector<AreaStations> subs(nAreas);
+    std::vector<size_t> stOff(nAreas + 1, 0);
+    for (int a = 0; a < nAreas; a++) {
+        if (areas[a].nAreaCells / 2 > 0) macroAreaDetrendingHost(areas[a], *s, st, subs[a]);
+        stOff[a + 1] = stOff[a] + (areas[a].nAreaCells / 2 > 0 ? idwStationsStagingBytes(subs[a].st.n) : 0);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));           // nothing in flight may still read the staging buffer
+    CUDA_TRY(ctx, ctx->hStations.reserve(stOff[nAreas] + 256));
+    CUDA_TRY(ctx, ctx->dStations.reserve(stOff[nAreas] + 256));
+    std::vector<DevStations> dss(nAreas);
+    std::vector<DevModel> mods(nAreas);
+    for (int a = 0; a < nAreas; a++) {
+        if (areas[a].nAreaCells / 2 <= 0) continue;
+        rc = buildDevModelGrids(ctx, &subs[a].s, variable, proxyGrids, nProxyGrids, mods[a]);
+        if (rc) return rc;
+        packIdwStationsAt(&subs[a].st, &subs[a].s, true, ctx->hStations.p + stOff[a], ctx->dStations.p + stOff[a], dss[a],
+                          mods[a].valueOffset);
+    }
+    if (stOff[nAreas] > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dStations.p, ctx->hStations.p, stOff[nAreas], cudaMemcpyHostToDevice, ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)stOff[nAreas];
+
     const int P = std::max(s->nProxy, 0);
     const size_t mAl = (size_t(maxCells) + 3) / 4 * 4;
-    const size_t offCells = 0, offX = offCells + mAl * 8, offY = offX + mAl * 4, offRes = offY + mAl * 4,
+    const size_t offCells = 0, offX = offCells + (resident ? 0 : mAl * 8), offY = offX + mAl * 4, offRes = offY + mAl * 4,
                  offPv = offRes + mAl * 4, offState = offPv + mAl * 8 * std::max(P, 1), offFlag = (offState + mAl + 15) / 16 * 16,
                  total = offFlag + 16;
     CUDA_TRY(ctx, ctx->dScratch.reserve(total));
@@ -486,35 +513,29 @@ int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_setti
         const pb_macro_area& A = areas[a];
         const int nCells = int(A.nAreaCells / 2);
         if (nCells <= 0) continue;
-        AreaStations sub;
-        macroAreaDetrendingHost(A, *s, st, sub);
-        DevModel mod;
-        rc = buildDevModelGrids(ctx, &sub.s, variable, proxyGrids, nProxyGrids, mod);
-        if (rc) return rc;
         GlocalLookup lk{};
         lk.nProxy = P;
         for (int i = 0; i < PB_MAX_PROXY; i++) {
-            lk.slot[i] = (i < P && sub.s.currentActive[i] && sub.s.currentSignificant[i]) ? mod.proxy[i].gridSlot : -1;
-            lk.grid[i] = mod.grid[i];
+            lk.slot[i] = (i < P && subs[a].s.currentActive[i] && subs[a].s.currentSignificant[i]) ? mods[a].proxy[i].gridSlot : -1;
+            lk.grid[i] = mods[a].grid[i];
         }
-        // the pinned station staging buffer is reused: the previous area's copy must have left it
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        DevStations ds{};
-        rc = stageIdwStations(ctx, &sub.st, &sub.s, true, ds, mod.valueOffset);
-        if (rc) return rc;
-        CUDA_TRY(ctx, cudaMemcpyAsync(d + offCells, A.areaCellsDEM, size_t(nCells) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->timing.h2d_bytes += (int64_t)(size_t(nCells) * 8);
+        const float* dCells;
+        if (resident) dCells = resident->cells + resident->firstFloat[a];
+        else {
+            CUDA_TRY(ctx, cudaMemcpyAsync(d + offCells, A.areaCellsDEM, size_t(nCells) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->timing.h2d_bytes += (int64_t)(size_t(nCells) * 8);
+            dCells = reinterpret_cast<const float*>(d + offCells);
+        }
         const int grid = (nCells + 255) / 256;
-        glocal_targets_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(d + offCells), nCells, dg, lk,
-                                                             reinterpret_cast<float*>(d + offX), reinterpret_cast<float*>(d + offY),
-                                                             reinterpret_cast<double*>(d + offPv), d + offState);
+        glocal_targets_kernel<<<grid, 256, 0, ctx->stream>>>(dCells, nCells, dg, lk, reinterpret_cast<float*>(d + offX),
+                                                             reinterpret_cast<float*>(d + offY), reinterpret_cast<double*>(d + offPv),
+                                                             d + offState);
         CUDA_TRY(ctx, cudaGetLastError());
-        CUDA_TRY(ctx, launchIdwPoints(ds, mod, reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
+        CUDA_TRY(ctx, launchIdwPoints(dss[a], mods[a], reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                       reinterpret_cast<const double*>(d + offPv), nCells, reinterpret_cast<float*>(d + offRes),
                                       ctx->stream));
-        glocal_blend_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(d + offCells), nCells, dem.h.nrCols,
-                                                           d + offState, reinterpret_cast<const float*>(d + offRes), ctx->dOut.p,
-                                                           dNotOk);
+        glocal_blend_kernel<<<grid, 256, 0, ctx->stream>>>(dCells, nCells, dem.h.nrCols, d + offState,
+                                                           reinterpret_cast<const float*>(d + offRes), ctx->dOut.p, dNotOk);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->timing.launches += 3;
     }
@@ -531,8 +552,7 @@ int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_setti
     }
     cudaEventRecord(ctx->ev[2], ctx->stream);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-    int notOk = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&notOk, dNotOk, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hMinMax + 2, dNotOk, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (!deviceOnly) {
         const int cols = dem.h.nrCols, rows = dem.h.nrRows;
         if (out->data) {
@@ -546,6 +566,7 @@ int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_setti
     }
     cudaEventRecord(ctx->ev[3], ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const int notOk = int(ctx->hMinMax[2]);
     cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
@@ -559,6 +580,62 @@ int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_setti
         out->maximum = keyToFloatG(ctx->hMinMax[1]);
     }
     if (notOk) return fail(ctx, PB_ERR_NO_VALID_CELL, "interpolate() returned NODATA inside a macro area (project.cpp:3358-3359)");
+    return PB_OK;
+}
+
+int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
+                                int nAreas, pb_raster_id demId, const pb_raster_id* proxyGrids, int nProxyGrids, int deviceOnly,
+                                pb_raster_out* out)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    return glocalRasterImpl(ctx, st, s, variable, areas, nAreas, nullptr, demId, proxyGrids, nProxyGrids, deviceOnly, out);
+}
+
+int pb_glocal_detrending_raster_resident(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
+                                         int nAreas, pb_macro_areas_id cells, pb_raster_id demId, const pb_raster_id* proxyGrids,
+                                         int nProxyGrids, int deviceOnly, pb_raster_out* out)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (cells < 0 || cells >= (int)ctx->macroAreas.size() || !ctx->macroAreas[cells].used)
+        return fail(ctx, PB_ERR_INVALID, "macro areas id is not live");
+    return glocalRasterImpl(ctx, st, s, variable, areas, nAreas, &ctx->macroAreas[cells], demId, proxyGrids, nProxyGrids, deviceOnly,
+                            out);
+}
+
+int pb_macro_areas_upload(pb_context* ctx, const pb_macro_area* areas, int nAreas, pb_macro_areas_id* id)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!areas || nAreas <= 0 || !id) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    ResidentMacroAreas r;
+    r.firstFloat.assign(nAreas + 1, 0);
+    for (int a = 0; a < nAreas; a++) {
+        if (areas[a].nAreaCells < 0 || (areas[a].nAreaCells > 0 && !areas[a].areaCellsDEM))
+            return fail(ctx, PB_ERR_INVALID, "macro area without areaCellsDEM");
+        r.firstFloat[a + 1] = r.firstFloat[a] + areas[a].nAreaCells;
+    }
+    CUDA_TRY(ctx, cudaMalloc(&r.cells, std::max<size_t>(size_t(r.firstFloat[nAreas]), 1) * sizeof(float)));
+    for (int a = 0; a < nAreas; a++)
+        if (areas[a].nAreaCells > 0)
+            CUDA_TRY(ctx, cudaMemcpyAsync(r.cells + r.firstFloat[a], areas[a].areaCellsDEM, size_t(areas[a].nAreaCells) * sizeof(float),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    r.used = true;
+    int slot = -1;
+    for (size_t i = 0; i < ctx->macroAreas.size(); i++) if (!ctx->macroAreas[i].used) { slot = int(i); break; }
+    if (slot < 0) { ctx->macroAreas.emplace_back(); slot = int(ctx->macroAreas.size()) - 1; }
+    ctx->macroAreas[slot] = r;
+    *id = slot;
+    return PB_OK;
+}
+
+int pb_macro_areas_free(pb_context* ctx, pb_macro_areas_id id)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (id < 0 || id >= (int)ctx->macroAreas.size() || !ctx->macroAreas[id].used) return fail(ctx, PB_ERR_INVALID, "bad macro areas id");
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->macroAreas[id].cells);
+    ctx->macroAreas[id] = ResidentMacroAreas();
     return PB_OK;
 }
 

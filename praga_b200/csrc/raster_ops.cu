@@ -254,6 +254,99 @@ __global__ void __launch_bounds__(128) resample_grid_kernel(DevGrid oldGrid, Dev
     blockMinMax(o, valid, minmax);
 }
 
+// ---- Crit3DMeteoGrid::spatialAggregateMeteoGrid (meteo/meteoGrid.cpp:1135-1190) + spatialAggregateMeteoGridPoint (:1193-1240):
+// one WARP per meteo-grid cell. The lanes sample the raster at the cell's aggregation points (gis::getValueFromXY, nearest
+// cell); lane 0 then reduces them in the list's order with the reference's FLOAT arithmetic (statistics::mean / variance,
+// mathFunctions/statistics.cpp:1274-1297, 1160-1186) or sorts them for sorting::percentile (basicMath.cpp:327-366).
+__device__ void heapSortAscending(float* v, int n)
+{
+    auto sift = [&](int root, int end) {
+        const float t = v[root];
+        int child;
+        while ((child = 2 * root + 1) < end) {
+            if (child + 1 < end && v[child + 1] > v[child]) child++;
+            if (!(v[child] > t)) break;
+            v[root] = v[child];
+            root = child;
+        }
+        v[root] = t;
+    };
+    for (int i = n / 2 - 1; i >= 0; i--) sift(i, n);
+    for (int end = n - 1; end > 0; end--) {
+        const float t = v[0]; v[0] = v[end]; v[end] = t;
+        sift(0, end);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+spatial_aggregate_kernel(DevGrid raster, const double* __restrict__ px, const double* __restrict__ py,
+                         const long long* __restrict__ first, const int* __restrict__ maxNr, int nCells, int method,
+                         float* __restrict__ scratch, float* __restrict__ value)
+{
+    const int lane = threadIdx.x & 31;
+    const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cell >= nCells) return;
+    const long long p0 = first[cell];
+    const int n = int(first[cell + 1] - p0);
+    float* z = scratch + p0;
+    int valid = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double x = px[p0 + i], y = py[p0 + i];
+        const int r = int((y - raster.lly) * raster.invCellSize);
+        const int row = (raster.nrRows - 1) - r;
+        const int col = int((x - raster.llx) * raster.invCellSize);
+        float v = raster.flag;
+        if (unsigned(row) < unsigned(raster.nrRows) && unsigned(col) < unsigned(raster.nrCols))
+            v = __ldg(raster.data + (size_t)row * raster.nrCols + col);
+        const bool ok = !isEqualF(v, raster.flag);
+        z[i] = ok ? v : kNoData;          // a fresh Crit3DPoint::z is NODATA (meteoGrid.cpp:703)
+        valid += ok;
+    }
+    for (int o = 16; o; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    __syncwarp();
+    if (lane != 0) return;
+    float result = kNoData;
+    // (validValues / aggregationPointsMaxNr) > (GRID_MIN_COVERAGE / 100), GRID_MIN_COVERAGE = 0 (meteoGrid.h:8)
+    if (n > 0 && (double(valid) / double(maxNr[cell])) > 0) {
+        // validValues: z != NODATA, as floats, in list order
+        int m = 0;
+        if (method == PB_AGGR_AVERAGE) {
+            float sum = 0.f;
+            for (int i = 0; i < n; i++) { const float v = z[i]; if (double(v) != -9999.) { if (v != kNoData) sum += v; m++; } }
+            // statistics::mean(float*, n): the NODATA test is redundant here (they were dropped above)
+            if (m > 0) result = sum / float(m);
+        } else if (method == PB_AGGR_STDDEV) {
+            float sum = 0.f;
+            for (int i = 0; i < n; i++) { const float v = z[i]; if (v != kNoData) { sum += v; m++; } }
+            if (m > 1) {
+                const float mean = sum / float(m);
+                float squareDiff = 0.f;
+                for (int i = 0; i < n; i++) {
+                    const float v = z[i];
+                    if (v != kNoData) { const float d = v - mean; squareDiff += d * d; }
+                }
+                result = sqrtf(squareDiff / (m - 1));
+            }
+        } else if (method == PB_AGGR_MEDIAN) {
+            for (int i = 0; i < n; i++) { const float v = z[i]; if (v != kNoData) z[m++] = v; }
+            if (m >= 3) {                                   // MINIMUM_PERCENTILE_DATA
+                heapSortAscending(z, m);
+                const double rank = m * double(50.0 / 100.f) - 1.0;
+                if (rank < 0.0) result = z[0];
+                else {
+                    const int low = int(rank);
+                    if (low >= m - 1) result = z[m - 1];
+                    else {
+                        const double frac = rank - low;
+                        result = float(z[low] + frac * (z[low + 1] - z[low]));
+                    }
+                }
+            }
+        }
+    }
+    value[cell] = result;
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -509,6 +602,80 @@ int pb_resample_grid(pb_context* ctx, pb_raster_id srcId, const pb_raster_header
     if (out) out->nValid = n;
     rc = finishGrid(ctx, dOut, h.nrRows, h.nrCols, true, out);
     return rc == PB_ERR_NO_VALID_CELL ? PB_OK : rc;      // resampleGrid ignores updateMinMaxRasterGrid's result
+}
+
+int pb_aggregation_upload(pb_context* ctx, const double* x, const double* y, const int64_t* first, const int32_t* maxNr, int nCells,
+                          pb_aggregation_id* id)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!x || !y || !first || !maxNr || nCells <= 0 || !id) return fail(ctx, PB_ERR_INVALID, "null argument");
+    if (first[0] != 0) return fail(ctx, PB_ERR_INVALID, "first[0] must be 0");
+    for (int c = 0; c < nCells; c++) if (first[c + 1] < first[c]) return fail(ctx, PB_ERR_INVALID, "first[] must not decrease");
+    cudaSetDevice(ctx->device);
+    const long long nPoints = first[nCells];
+    int slot = -1;
+    for (size_t i = 0; i < ctx->aggregations.size(); i++) if (!ctx->aggregations[i].used) { slot = int(i); break; }
+    if (slot < 0) { ctx->aggregations.emplace_back(); slot = int(ctx->aggregations.size()) - 1; }
+    AggregationGeometry g;
+    g.nCells = nCells;
+    g.nPoints = nPoints;
+    const size_t np = size_t(std::max<long long>(nPoints, 1));
+    CUDA_TRY(ctx, cudaMalloc(&g.x, np * 8));
+    CUDA_TRY(ctx, cudaMalloc(&g.y, np * 8));
+    CUDA_TRY(ctx, cudaMalloc(&g.first, size_t(nCells + 1) * 8));
+    CUDA_TRY(ctx, cudaMalloc(&g.maxNr, size_t(nCells) * 4));
+    CUDA_TRY(ctx, cudaMalloc(&g.scratch, np * 4));
+    CUDA_TRY(ctx, cudaMalloc(&g.value, size_t(nCells) * 4));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g.x, x, size_t(nPoints) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g.y, y, size_t(nPoints) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g.first, first, size_t(nCells + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g.maxNr, maxNr, size_t(nCells) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    g.used = true;
+    ctx->aggregations[slot] = g;
+    *id = slot;
+    return PB_OK;
+}
+
+int pb_aggregation_free(pb_context* ctx, pb_aggregation_id id)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (id < 0 || id >= (int)ctx->aggregations.size() || !ctx->aggregations[id].used) return fail(ctx, PB_ERR_INVALID, "bad aggregation id");
+    cudaSetDevice(ctx->device);
+    AggregationGeometry& g = ctx->aggregations[id];
+    cudaFree(g.x); cudaFree(g.y); cudaFree(g.first); cudaFree(g.maxNr); cudaFree(g.scratch); cudaFree(g.value);
+    g = AggregationGeometry();
+    return PB_OK;
+}
+
+int pb_spatial_aggregate_meteo_grid(pb_context* ctx, pb_raster_id rasterId, pb_aggregation_id aggId, int method, float* value)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    RasterEntry* src = entryOf(ctx, rasterId);
+    if (!src || !value) return fail(ctx, PB_ERR_INVALID, "bad raster id / null output");
+    if (aggId < 0 || aggId >= (int)ctx->aggregations.size() || !ctx->aggregations[aggId].used)
+        return fail(ctx, PB_ERR_INVALID, "bad aggregation id");
+    if (method != PB_AGGR_AVERAGE && method != PB_AGGR_MEDIAN && method != PB_AGGR_STDDEV) {
+        // spatialAggregateMeteoGridPoint returns NODATA for every other method (meteoGrid.cpp:1234-1237)
+        for (int c = 0; c < ctx->aggregations[aggId].nCells; c++) value[c] = kNoData;
+        return PB_OK;
+    }
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    AggregationGeometry& g = ctx->aggregations[aggId];
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    const unsigned nb = (unsigned)((size_t(g.nCells) * 32 + 255) / 256);
+    spatial_aggregate_kernel<<<nb, 256, 0, ctx->stream>>>(gridOf(*src), g.x, g.y, g.first, g.maxNr, g.nCells, method, g.scratch, g.value);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(value, g.value, size_t(g.nCells) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.d2h_bytes = (int64_t)(size_t(g.nCells) * 4);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[1], ctx->ev[3]);
+    return PB_OK;
 }
 
 }  // extern "C"

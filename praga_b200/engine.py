@@ -97,6 +97,14 @@ def load_library():
     lib.pb_glocal_detrending_fitting.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int]
     lib.pb_glocal_detrending_raster.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int,
                                                 C.c_int32, P(C.c_int32), C.c_int, C.c_int, P(A.pb_raster_out)]
+    lib.pb_glocal_detrending_raster_resident.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area),
+                                                         C.c_int, C.c_int32, C.c_int32, P(C.c_int32), C.c_int, C.c_int,
+                                                         P(A.pb_raster_out)]
+    lib.pb_macro_areas_upload.argtypes = [C.c_void_p, P(A.pb_macro_area), C.c_int, P(C.c_int32)]
+    lib.pb_macro_areas_free.argtypes = [C.c_void_p, C.c_int32]
+    lib.pb_aggregation_upload.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_int64), P(C.c_int32), C.c_int, P(C.c_int32)]
+    lib.pb_aggregation_free.argtypes = [C.c_void_p, C.c_int32]
+    lib.pb_spatial_aggregate_meteo_grid.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int, P(C.c_float)]
     lib.pb_compute_residuals_glocal.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), P(A.pb_cv_points), P(A.pb_stations),
                                                 P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int, C.c_int, C.c_int,
                                                 P(C.c_float)]
@@ -518,8 +526,18 @@ class Engine:
         st = stations.as_pb()
         self._check(self.lib.pb_glocal_detrending_fitting(self.h, C.byref(st), C.byref(settings), variable, areas.arr, areas.n))
 
-    def glocal_detrending_raster(self, stations, settings, variable, areas, dem_id, shape, proxy_ids=(), device_only=False):
-        """gridding part of Project::interpolationDemGlocalDetrending (project.cpp:3283-3375).
+    def macro_areas_upload(self, areas):
+        """The areas' (cell, weight) pairs resident on the device (they only change with the glocal weight maps)."""
+        mid = C.c_int32(-1)
+        self._check(self.lib.pb_macro_areas_upload(self.h, areas.arr, areas.n, C.byref(mid)))
+        return mid.value
+
+    def macro_areas_free(self, mid):
+        self._check(self.lib.pb_macro_areas_free(self.h, mid))
+
+    def glocal_detrending_raster(self, stations, settings, variable, areas, dem_id, shape, proxy_ids=(), device_only=False,
+                                 cells_id=None):
+        """gridding part of Project::interpolationDemGlocalDetrending (project.cpp:3283-3375). cells_id: macro_areas_upload id.
         Returns (ok, grid or None, min, max, nValid); ok False where the reference returns false."""
         st = stations.as_pb()
         ids = (C.c_int32 * max(1, len(proxy_ids)))(*proxy_ids)
@@ -527,9 +545,13 @@ class Engine:
         o = A.pb_raster_out()
         if grid is not None:
             o.data = A.fptr(grid)
-        rc = self._check(self.lib.pb_glocal_detrending_raster(self.h, C.byref(st), C.byref(settings), variable, areas.arr, areas.n,
-                                                              dem_id, ids, len(proxy_ids), int(device_only), C.byref(o)),
-                         allow=(A.PB_ERR_NO_VALID_CELL,))
+        if cells_id is None:
+            rc = self.lib.pb_glocal_detrending_raster(self.h, C.byref(st), C.byref(settings), variable, areas.arr, areas.n, dem_id, ids,
+                                                      len(proxy_ids), int(device_only), C.byref(o))
+        else:
+            rc = self.lib.pb_glocal_detrending_raster_resident(self.h, C.byref(st), C.byref(settings), variable, areas.arr, areas.n,
+                                                               cells_id, dem_id, ids, len(proxy_ids), int(device_only), C.byref(o))
+        self._check(rc, allow=(A.PB_ERR_NO_VALID_CELL,))
         return rc == A.PB_OK, grid, o.minimum, o.maximum, o.nValid
 
     def compute_residuals_glocal(self, meteo, observed, points, settings, variable, areas, exclude_outside_dem=True,
@@ -547,3 +569,26 @@ class Engine:
                                                          variable, areas.arr, areas.n, int(exclude_outside_dem),
                                                          int(exclude_supplemental), A.fptr(res)))
         return res
+
+    # ---- DEM -> meteo-grid aggregation ----
+    def aggregation_upload(self, x, y, first, max_nr):
+        """Aggregation points of every meteo-grid cell (Crit3DMeteoPoint::aggregationPoints): x, y concatenated, first[c]..first[c+1]."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        first = np.ascontiguousarray(first, dtype=np.int64)
+        max_nr = np.ascontiguousarray(max_nr, dtype=np.int32)
+        aid = C.c_int32(-1)
+        self._check(self.lib.pb_aggregation_upload(self.h, A.dptr(x), A.dptr(y), first.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                   A.iptr(max_nr), max_nr.size, C.byref(aid)))
+        self._agg_cells = getattr(self, "_agg_cells", {})
+        self._agg_cells[aid.value] = int(max_nr.size)
+        return aid.value
+
+    def aggregation_free(self, aid):
+        self._check(self.lib.pb_aggregation_free(self.h, aid))
+
+    def spatial_aggregate_meteo_grid(self, raster_id, aid, method):
+        """Crit3DMeteoGrid::spatialAggregateMeteoGrid (meteoGrid.cpp:1135-1190) of a resident raster: one value per cell."""
+        val = np.empty(self._agg_cells[aid], dtype=np.float32)
+        self._check(self.lib.pb_spatial_aggregate_meteo_grid(self.h, raster_id, aid, method, A.fptr(val)))
+        return val

@@ -106,6 +106,15 @@ def test_gpu_glocal_matches_reference(engine, ref, case):
             err = np.abs(grid_g.astype(np.float64) - grid_r.astype(np.float64))[~nod_r].max()
             assert err <= 1e-4, err          # north_star tolerance, in the variable's units
             assert abs(mn_g - mn_r) <= 1e-4 and abs(mx_g - mx_r) <= 1e-4
+        # resident (cell, weight) pairs: same grid, bit for bit
+        cid = engine.macro_areas_upload(a_g)
+        try:
+            a_c, s_c = areas(), clone(s)
+            ok_c, grid_c, *_ = engine.glocal_detrending_raster(st.copy(), s_c, A.airTemperature, a_c, dem_id, dem.shape,
+                                                               (dem_id, urb_id), cells_id=cid)
+            assert ok_c == ok_g and np.array_equal(grid_c, grid_g) and a_c.fits() == a_g.fits()
+        finally:
+            engine.macro_areas_free(cid)
         # fitting alone (preInterpolation with useGlocalDetrending)
         a_f, s_f = areas(), clone(s)
         engine.glocal_detrending_fitting(st.copy(), s_f, A.airTemperature, a_f)
