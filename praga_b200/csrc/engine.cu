@@ -120,7 +120,7 @@ int buildModel(pb_context* ctx, const pb_settings* s, int variable, const pb_ras
     if (s->nProxy < 0 || s->nProxy > PB_MAX_PROXY) return fail(ctx, PB_ERR_INVALID, "settings.nProxy out of range");
     if (s->method != PB_METHOD_IDW && s->method != PB_METHOD_SHEPARD && s->method != PB_METHOD_SHEPARD_MODIFIED)
         return fail(ctx, PB_ERR_INVALID, "unknown TInterpolationMethod");
-    if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending is out of scope (DESIGN.md)");
+    if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending runs through pb_glocal_detrending_fitting / pb_glocal_detrending_raster (macro areas needed)");
     m.nProxy = s->nProxy;
     m.useDetrendingVar = useDetrendingVar(variable);
     m.useMultipleDetrending = s->useMultipleDetrending;
@@ -451,7 +451,7 @@ int buildLocalModel(pb_context* ctx, const pb_settings* s, int variable, int nSt
         if (s->method != PB_METHOD_IDW)
             return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the GPU path (shepard: DESIGN.md)");
     }
-    if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending is out of scope (DESIGN.md)");
+    if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending runs through pb_glocal_detrending_fitting / pb_glocal_detrending_raster (macro areas needed)");
     if (!s->hasPointsRange && !range)     // setMultipleDetrendingHeightTemperatureRange returns false (:1508)
         return fail(ctx, PB_ERR_FIT, "couldn't set temperature ranges for height proxy (points range not set)");
     const double rangeMin = range ? range[0] : s->pointsRangeMin, rangeMax = range ? range[1] : s->pointsRangeMax;

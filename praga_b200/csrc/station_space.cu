@@ -146,7 +146,7 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     const bool classic = detrendVar && !s->useMultipleDetrending;
     const bool optimal = classic && s->useBestDetrending;
     if (detrendVar && s->useMultipleDetrending) {
-        if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending is out of scope (DESIGN.md)");
+        if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending runs through pb_glocal_detrending_fitting / pb_glocal_detrending_raster (macro areas needed)");
         if (s->useLocalDetrending) {
             // preInterpolation on the whole set with local detrending fits nothing the raster loop uses: the raster entry
             // point fits per cell (pb_local_detrending_raster)

@@ -63,3 +63,21 @@ s_id = eng.upload(small)
 ms = timed(lambda: eng.topographic_distance_map(s_id, small.shape, dem.llx + 70000.0, dem.lly + 90000.0, 600.0, want_host=False), reps=3)
 line("topographic_distance_map_kernel 2000x2000", ms, 8, 2000 * 2000,
      {"note": "ray march: ~d/cellSize DEM samples per cell from L2, not an HBM-streaming kernel; bytes = DEM read + map written"})
+
+# DEM -> meteo-grid aggregation (spatialAggregateMeteoGrid): 5 km cells over the 100 m raster, every DEM cell sampled once
+cell = 5000.0
+k = int(cell / dem.cell_size)
+ncx, ncy = cols // k, rows // k
+gx = dem.llx + (np.arange(cols // k * k) + 0.5) * dem.cell_size
+gy = dem.lly + (np.arange(rows // k * k) + 0.5) * dem.cell_size
+X, Y = np.meshgrid(gx, gy, indexing="xy")
+X = X.reshape(ncy, k, ncx, k).transpose(0, 2, 1, 3).reshape(-1)
+Y = Y.reshape(ncy, k, ncx, k).transpose(0, 2, 1, 3).reshape(-1)
+first = np.arange(ncx * ncy + 1, dtype=np.int64) * (k * k)
+aid = eng.aggregation_upload(X, Y, first, np.full(ncx * ncy, k * k, np.int32))
+for name, m in (("average", A.PB_AGGR_AVERAGE), ("median", A.PB_AGGR_MEDIAN), ("stdDeviation", A.PB_AGGR_STDDEV)):
+    ms = timed(lambda: eng.spatial_aggregate_meteo_grid(t_id, aid, m), reps=3)
+    line(f"spatial_aggregate_kernel<{name}> 100 m -> 5 km meteo grid", ms, 4 + 16 + 4, ncx * ncy * k * k,
+         {"meteo_grid_cells": ncx * ncy, "samples_per_cell": k * k, "d2h_bytes": 4 * ncx * ncy,
+          "note": "24 B per sample (x, y doubles + raster value + scratch); one warp per meteo-grid cell, lane 0 reduces in list "
+                  "order (float arithmetic of the reference): latency bound, not an HBM-streaming kernel"})
