@@ -203,6 +203,7 @@ idw_kernel(DevStations st, DevModel m, DevGrid dem, const int* __restrict__ vali
 
     const int tid = threadIdx.x;
     const int nTiles = st.nPadded / kTileStations;
+    const int usedPadded = (st.n + kChunk - 1) / kChunk * kChunk;     // stations rounded up to whole accumulation chunks
     constexpr int C = 2 * P;
 
     if (tid == 0) {
@@ -268,8 +269,10 @@ idw_kernel(DevStations st, DevModel m, DevGrid dem, const int* __restrict__ vali
         f32x2 tsw[P], tswv[P];
 #pragma unroll
         for (int p = 0; p < P; p++) { tsw[p] = pack2(0.f, 0.f); tswv[p] = pack2(0.f, 0.f); }
+        // chunks that hold only padding (zero-weight stations) add +0 to every sum: skipped, same bits
+        const int tileLim = min(kTileStations, usedPadded - t * kTileStations);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kTileStations; c0 += kChunk) {
+        for (int c0 = 0; c0 < tileLim; c0 += kChunk) {
             f32x2 sw[P], swv[P];
 #pragma unroll
             for (int s = 0; s < kChunk; s++) {
@@ -390,6 +393,7 @@ idw_persistent_kernel(DevStations st, DevModel m, DevGrid dem, const int* __rest
     const float2* __restrict__ svAll = reinterpret_cast<const float2*>(smem + (size_t)st.nPadded * sizeof(float4));
     const int tid = threadIdx.x, lane = tid & 31;
     const int nTiles = st.nPadded / kTileStations;
+    const int usedPadded = (st.n + kChunk - 1) / kChunk * kChunk;
     constexpr int C = 2 * P;
 
     if (tid == 0) {
@@ -451,8 +455,9 @@ idw_persistent_kernel(DevStations st, DevModel m, DevGrid dem, const int* __rest
             f32x2 tsw[P], tswv[P];
 #pragma unroll
             for (int p = 0; p < P; p++) { tsw[p] = pack2(0.f, 0.f); tswv[p] = pack2(0.f, 0.f); }
+            const int tileLim = min(kTileStations, usedPadded - t * kTileStations);      // padding-only chunks add +0: skipped
 #pragma unroll 1
-            for (int c0 = 0; c0 < kTileStations; c0 += kChunk) {
+            for (int c0 = 0; c0 < tileLim; c0 += kChunk) {
                 f32x2 sw[P], swv[P];
 #pragma unroll
                 for (int s = 0; s < kChunk; s++) {
@@ -634,11 +639,10 @@ cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevG
     return cudaGetLastError();
 }
 
-cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty,
-                            const double* tproxy, int nTargets, float* out, cudaStream_t s)
+template <int P>
+static cudaError_t launchIdwPointsT(const DevStations& st, const DevModel& m, const float* tx, const float* ty,
+                                    const double* tproxy, int nTargets, float* out, cudaStream_t s)
 {
-    if (nTargets <= 0) return cudaSuccess;
-    constexpr int P = 1;
     const int per = kThreads * 2 * P;
     const int grid = (nTargets + per - 1) / per;
     auto k = idw_kernel<P, true>;
@@ -651,6 +655,16 @@ cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const floa
     none.flag = kNoData;
     k<<<grid, kThreads, 2 * kTileBytes, s>>>(st, m, none, nullptr, nTargets, tx, ty, tproxy, out, nullptr);
     return cudaGetLastError();
+}
+
+cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty,
+                            const double* tproxy, int nTargets, float* out, cudaStream_t s)
+{
+    if (nTargets <= 0) return cudaSuccess;
+    // leave-one-out sets (a few thousand targets) spread over more CTAs with 2 targets per thread; raster-sized target
+    // lists (glocal areas) amortise each station load over 4 targets like the raster kernel. Same arithmetic per target.
+    if (nTargets >= 148 * kThreads * 8) return launchIdwPointsT<2>(st, m, tx, ty, tproxy, nTargets, out, s);
+    return launchIdwPointsT<1>(st, m, tx, ty, tproxy, nTargets, out, s);
 }
 
 cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s)
