@@ -161,6 +161,32 @@ __device__ __forceinline__ void lmInit(LmState<F>& s, const double* par, const d
     s.iter = 0;
 }
 
+// one data point of the forward-difference Jacobian: P[k] = (f(x; p + delta_k) - f(x; p)) / delta_k with the reference's
+// perturb / restore sequence (see above); returns f(x; p). Shared by the lane-per-descent and the warp-per-descent forms.
+template <int F>
+__device__ __forceinline__ double lmPointJacobian(double x, const double* p0, const double* up, const double* rs, double sp2,
+                                                  const double* dl, const double* rdl, double* P)
+{
+    constexpr int N = Fit<F>::N;
+    const double f0 = Fit<F>::eval(x, p0);
+    double num[N];
+    bool slow = false;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        double q[N];
+#pragma unroll
+        for (int c = 0; c < N; c++) q[c] = (c < k) ? ((F != PB_FIT_PIECEWISE_TWO && c == 2) ? sp2 : rs[c]) : p0[c];
+        q[k] = up[k];
+        num[k] = Fit<F>::eval(x, q) - f0;
+        P[k] = divFast(num[k], dl[k], rdl[k], slow);
+    }
+    if (slow) {
+#pragma unroll
+        for (int k = 0; k < N; k++) P[k] = divByKnown(num[k], dl[k], rdl[k]);
+    }
+    return f0;
+}
+
 // one Levenberg-Marquardt iteration; true when the descent is over (the reference's do-while condition turned false)
 template <int F>
 __device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__ pmin, const double* __restrict__ pmax,
@@ -193,22 +219,8 @@ __device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__
     }
     for (int j = 0; j < nData; j++) {
         const double x = X[j], y = Y[j], w = W[j];
-        const double f0 = Fit<F>::eval(x, p0);
-        double P[N], WP[N], num[N];
-        bool slow = false;
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            double q[N];
-#pragma unroll
-            for (int c = 0; c < N; c++) q[c] = (c < k) ? ((F != PB_FIT_PIECEWISE_TWO && c == 2) ? s.p[2] : rs[c]) : p0[c];
-            q[k] = up[k];
-            num[k] = Fit<F>::eval(x, q) - f0;
-            P[k] = divFast(num[k], dl[k], rdl[k], slow);
-        }
-        if (slow) {
-#pragma unroll
-            for (int k = 0; k < N; k++) P[k] = divByKnown(num[k], dl[k], rdl[k]);
-        }
+        double P[N], WP[N];
+        const double f0 = lmPointJacobian<F>(x, p0, up, rs, s.p[2], dl, rdl, P);
 #pragma unroll
         for (int k = 0; k < N; k++) WP[k] = w * P[k];
 #pragma unroll
@@ -292,6 +304,162 @@ __device__ __noinline__ void lmElevation(const double* __restrict__ pmin, const 
     while (!lmIter<F>(s, pmin, pmax, dl, rdl, maxIter, eps, X, Y, W, nData)) {}
 #pragma unroll
     for (int k = 0; k < N; k++) par[k] = s.p[k];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same descent run by a whole WARP (single time step / a handful of macro areas: the GPU is otherwise idle and the
+// latency of one descent is what counts). The data points of an iteration are spread over the lanes for everything that is
+// independent per point (model evaluations, the four divisions, the products); every SUM is then taken in ascending point
+// order by ONE lane per accumulator (lane t owns accumulator t; the terms of a 32-point chunk go through shared memory), so
+// each accumulator receives exactly the terms, in exactly the order, of the sequential form: same bits, same accept /
+// reject path. The small N x N solve and the step are computed redundantly by every lane (uniform data).
+// sm: kLmWarpTerms x kLmWarpStride doubles of shared memory owned by this warp.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kLmWarpTerms = 6 * 7 / 2 + 6 + 1;        // upper triangle + gradient (+ 1 spare) for N = 6
+constexpr int kLmWarpStride = 33;                       // doubles per term row (32 lanes + 1: the row readers hit different banks)
+
+template <int F>
+__device__ __forceinline__ double lmWarpSse(const double* p /* clamped */, const double* X, const double* Y, const double* W, int nData,
+                                            double* sm)
+{
+    const int lane = threadIdx.x & 31;
+    double sse = 0;
+    for (int base = 0; base < nData; base += 32) {
+        const int j = base + lane;
+        if (j < nData) {
+            const double error = Y[j] - Fit<F>::eval(X[j], p);
+            const double w = W[j];
+            sm[lane] = error * error * w * w;
+        }
+        __syncwarp();
+        const int cnt = min(32, nData - base);
+        for (int l = 0; l < cnt; l++) sse += sm[l];      // every lane: the same ordered sum (broadcast reads)
+        __syncwarp();
+    }
+    return sse;
+}
+
+template <int F>
+__device__ __noinline__ void lmElevationWarp(const double* __restrict__ pmin, const double* __restrict__ pmax,
+                                             const double* __restrict__ delta, double* par, int maxIter, double eps,
+                                             const double* X, const double* Y, const double* W, int nData, double* sm)
+{
+    constexpr int N = Fit<F>::N;
+    constexpr int NA = N * (N + 1) / 2;
+    const double VFACTOR = 10;
+    const int lane = threadIdx.x & 31;
+    double dl[N], rdl[N], p[N], lambda[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) { dl[k] = delta[k]; rdl[k] = 1.0 / dl[k]; lambda[k] = 0.01; p[k] = par[k]; }
+    if (nData > 0) Fit<F>::clamp(p);
+    double mySSE = lmWarpSse<F>(p, X, Y, W, nData, sm);
+    int iter = 0;
+    double diffSSE;
+    do {
+        double p0[N], up[N], rs[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) p0[k] = p[k];
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            p[k] += dl[k];
+            if (nData > 0) Fit<F>::clamp(p);
+            up[k] = p[k];
+            p[k] -= dl[k];
+            rs[k] = p[k];
+        }
+        if (nData > 0) Fit<F>::clamp(p);
+        double acc = 0;                          // lane t < NA: a[i][c] (row-major upper triangle); NA <= t < NA + N: g[t - NA]
+        for (int base = 0; base < nData; base += 32) {
+            const int j = base + lane;
+            if (j < nData) {
+                const double x = X[j], y = Y[j], w = W[j];
+                double P[N], WP[N];
+                const double f0 = lmPointJacobian<F>(x, p0, up, rs, p[2 < N ? 2 : 0], dl, rdl, P);
+#pragma unroll
+                for (int k = 0; k < N; k++) WP[k] = w * P[k];
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+#pragma unroll
+                    for (int c = i; c < N; c++) sm[(t++) * kLmWarpStride + lane] = (P[i] * WP[c]);
+                }
+#pragma unroll
+                for (int i = 0; i < N; i++) sm[(NA + i) * kLmWarpStride + lane] = P[i] * w * (y - f0);
+            }
+            __syncwarp();
+            const int cnt = min(32, nData - base);
+            if (lane < NA + N) {
+                const double* src = sm + lane * kLmWarpStride;
+                for (int l = 0; l < cnt; l++) acc += src[l];
+            }
+            __syncwarp();
+        }
+        double g[N], a[N][N];
+        {
+            int t = 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+#pragma unroll
+                for (int c = i; c < N; c++) a[i][c] = __shfl_sync(0xffffffffu, acc, t++);
+            }
+#pragma unroll
+            for (int i = 0; i < N; i++) g[i] = __shfl_sync(0xffffffffu, acc, NA + i);
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            a[k][k] += lambda[k] * a[k][k];
+#pragma unroll
+            for (int j = k + 1; j < N; j++) a[j][k] = a[k][j];
+        }
+#pragma unroll
+        for (int j = 0; j < N - 1; j++) {
+            const double pivot = (a[j][j] > kEpsilon) ? a[j][j] : kEpsilon;
+#pragma unroll
+            for (int i = j + 1; i < N; i++) {
+                const double mult = a[i][j] / pivot;
+#pragma unroll
+                for (int k = j + 1; k < N; k++) a[i][k] -= mult * a[j][k];
+                g[i] -= mult * g[j];
+            }
+        }
+        double change[N];
+        change[N - 1] = g[N - 1] / ((a[N - 1][N - 1] > kEpsilon) ? a[N - 1][N - 1] : kEpsilon);
+#pragma unroll
+        for (int i = N - 2; i >= 0; i--) {
+            double top = g[i];
+#pragma unroll
+            for (int k = i + 1; k < N; k++) top -= a[i][k] * change[k];
+            change[i] = top / ((a[i][i] > kEpsilon) ? a[i][i] : kEpsilon);
+        }
+        double np[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const double hi = pmax[j], lo = pmin[j];
+            np[j] = p[j] + change[j];
+            if (np[j] > hi && lambda[j] < 1000) {
+                np[j] = hi;
+                if (lambda[j] < 1000) lambda[j] *= VFACTOR;
+            }
+            if (np[j] < lo) {
+                np[j] = lo;
+                if (lambda[j] < 1000) lambda[j] *= VFACTOR;
+            }
+        }
+        if (nData > 0) Fit<F>::clamp(np);
+        const double newSSE = lmWarpSse<F>(np, X, Y, W, nData, sm);
+        diffSSE = mySSE - newSSE;
+        if (diffSSE > 0) {
+            mySSE = newSSE;
+#pragma unroll
+            for (int j = 0; j < N; j++) { p[j] = np[j]; lambda[j] /= VFACTOR; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; j++) lambda[j] *= VFACTOR;
+        }
+        iter++;
+    } while (fabs(diffSSE) > eps && iter <= maxIter);
+#pragma unroll
+    for (int k = 0; k < N; k++) par[k] = p[k];
 }
 
 // computeWeighted_R2 (:1245-1275) and computeWeighted_RMSE (:1301-1322) of one fitted curve

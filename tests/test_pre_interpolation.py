@@ -45,11 +45,12 @@ def test_pre_interpolation_single_step_bit_exact(engine, ref, case):
     assert settings_equal(s_r, s_g), describe_diff(s_r, s_g)
 
 
-def test_pre_interpolation_batch_matches_per_step_reference(engine, ref):
-    """24 'hours' sharing one station set: every step bit-identical to the reference run on that step alone."""
+@pytest.mark.parametrize("T", [24, 70])
+def test_pre_interpolation_batch_matches_per_step_reference(engine, ref, T):
+    """T 'hours' sharing one station set: every step bit-identical to the reference run on that step alone. Up to 64 steps run
+    on the warp-per-descent kernel (one CTA per step), more on the lane-per-descent batch kernel: both are covered."""
     dem, urban, st, s = scenario(n=300, seed=3)
     rng = np.random.default_rng(11)
-    T = 24
     values = np.stack([st.value + np.float32(3.0 * np.sin(2 * np.pi * t / 24)) + rng.normal(0, 0.4, st.n).astype(np.float32)
                        for t in range(T)]).astype(np.float32)
     det, keep, fitted = engine.pre_interpolation_batch(st, values, s, A.airTemperature)
