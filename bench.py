@@ -381,7 +381,7 @@ class HourlyBatchWorkload:
         self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
         self.rank, self.world = rank, world
         self.outs = []
-        self.lanes = int(os.environ.get("PB_BENCH_LANES", "8"))
+        self.lanes = int(os.environ.get("PB_BENCH_LANES", "16"))
 
     def _settings(self, var):
         if var == A.airTemperature:
