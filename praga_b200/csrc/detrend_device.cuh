@@ -697,4 +697,150 @@ __device__ __noinline__ void lmOthers(int nPredRt, double (*pmin)[2], double (*p
     for (int t = 0; t < nTot; t++) par[t >> 1][t & 1] = p[t];
 }
 
+// lmOthers run by a whole warp (few units, see lmElevationWarp): data points over the lanes, every sum in ascending point
+// order by one lane per accumulator through shared memory; NP = 1..3 predictors (at most 27 accumulators). Same bits.
+template <int NP, class PredFn>
+__device__ __noinline__ void lmOthersWarp(double (*pmin)[2], double (*pmax)[2], double (*par)[2], double (*delta)[2], int maxIter,
+                                          double eps, PredFn pred, const double* Y, const double* W, int nData, double* sm)
+{
+    constexpr int MT = 2 * NP;
+    constexpr int NA = MT * (MT + 1) / 2;
+    static_assert(NA + MT <= kLmWarpTerms, "too many accumulators for the warp form");
+    const double VFACTOR = 10;
+    const int lane = threadIdx.x & 31;
+    double lambda[MT], change[MT], np[MT], p[MT], dl[MT];
+#pragma unroll
+    for (int t = 0; t < MT; t++) { lambda[t] = 0.01; p[t] = par[t >> 1][t & 1]; dl[t] = delta[t >> 1][t & 1]; }
+    auto fsum = [&](int j, const double* q) {
+        double r = 0.0;
+#pragma unroll
+        for (int c = 0; c < NP; c++) r += q[2 * c] * pred(j, c) + q[2 * c + 1];
+        return r;
+    };
+    auto norm = [&](const double* q) {
+        double n = 0;
+        for (int base = 0; base < nData; base += 32) {
+            const int j = base + lane;
+            if (j < nData) {
+                const double e = Y[j] - fsum(j, q);
+                sm[lane] = e * e * W[j] * W[j];
+            }
+            __syncwarp();
+            const int cnt = min(32, nData - base);
+            for (int l = 0; l < cnt; l++) n += sm[l];
+            __syncwarp();
+        }
+        return n;
+    };
+    double mySSE = norm(p), diffSSE;
+    int iter = 0;
+    do {
+        double g[MT], a[MT][MT], p0[MT], up[MT], rs[MT];
+#pragma unroll
+        for (int t = 0; t < MT; t++) {
+            p0[t] = p[t];
+        }
+#pragma unroll
+        for (int t = 0; t < MT; t++) {
+            p[t] += dl[t];
+            up[t] = p[t];
+            p[t] -= dl[t];
+            rs[t] = p[t];
+        }
+        double acc = 0;
+        for (int base = 0; base < nData; base += 32) {
+            const int j = base + lane;
+            if (j < nData) {
+                const double f0 = fsum(j, p0);
+                double P[MT], WP[MT];
+#pragma unroll
+                for (int t = 0; t < MT; t++) {
+                    double q[MT];
+#pragma unroll
+                    for (int c = 0; c < MT; c++) q[c] = (c < t) ? rs[c] : p0[c];
+                    q[t] = up[t];
+                    P[t] = (fsum(j, q) - f0) / dl[t];
+                    WP[t] = W[j] * P[t];
+                }
+                int k = 0;
+#pragma unroll
+                for (int i = 0; i < MT; i++) {
+#pragma unroll
+                    for (int c = i; c < MT; c++) sm[(k++) * kLmWarpStride + lane] = (P[i] * WP[c]);
+                }
+#pragma unroll
+                for (int i = 0; i < MT; i++) sm[(NA + i) * kLmWarpStride + lane] = P[i] * W[j] * (Y[j] - f0);
+            }
+            __syncwarp();
+            const int cnt = min(32, nData - base);
+            if (lane < NA + MT) {
+                const double* src = sm + lane * kLmWarpStride;
+                for (int l = 0; l < cnt; l++) acc += src[l];
+            }
+            __syncwarp();
+        }
+        {
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < MT; i++) {
+#pragma unroll
+                for (int c = i; c < MT; c++) a[i][c] = __shfl_sync(0xffffffffu, acc, k++);
+            }
+#pragma unroll
+            for (int i = 0; i < MT; i++) g[i] = __shfl_sync(0xffffffffu, acc, NA + i);
+        }
+#pragma unroll
+        for (int t = 0; t < MT; t++) {
+            a[t][t] += lambda[t] * a[t][t];
+#pragma unroll
+            for (int j = t + 1; j < MT; j++) a[j][t] = a[t][j];
+        }
+#pragma unroll
+        for (int j = 0; j < MT - 1; j++) {
+            const double pivot = a[j][j];
+#pragma unroll
+            for (int i = j + 1; i < MT; i++) {
+                const double mult = a[i][j] / pivot;
+#pragma unroll
+                for (int k = j + 1; k < MT; k++) a[i][k] -= mult * a[j][k];
+                g[i] -= mult * g[j];
+            }
+        }
+        change[MT - 1] = g[MT - 1] / a[MT - 1][MT - 1];
+#pragma unroll
+        for (int i = MT - 2; i >= 0; i--) {
+            double top = g[i];
+#pragma unroll
+            for (int k = i + 1; k < MT; k++) top -= a[i][k] * change[k];
+            change[i] = top / a[i][i];
+        }
+#pragma unroll
+        for (int t = 0; t < MT; t++) {
+            const double hi = pmax[t >> 1][t & 1], lo = pmin[t >> 1][t & 1];
+            np[t] = p[t] + change[t];
+            if (np[t] > hi && lambda[t] < 1000) {
+                np[t] = hi;
+                if (lambda[t] < 1000) lambda[t] *= VFACTOR;
+            }
+            if (np[t] < lo) {
+                np[t] = lo;
+                if (lambda[t] < 1000) lambda[t] *= VFACTOR;
+            }
+        }
+        const double newSSE = norm(np);
+        diffSSE = mySSE - newSSE;
+        if (diffSSE > 0) {
+            mySSE = newSSE;
+#pragma unroll
+            for (int t = 0; t < MT; t++) { p[t] = np[t]; lambda[t] /= VFACTOR; }
+        } else {
+#pragma unroll
+            for (int t = 0; t < MT; t++) lambda[t] *= VFACTOR;
+        }
+        iter++;
+    } while (fabs(diffSSE) > eps && iter <= maxIter);
+#pragma unroll
+    for (int t = 0; t < MT; t++) par[t >> 1][t & 1] = p[t];
+}
+
 }  // namespace pb

@@ -145,7 +145,7 @@ __device__ int mdStageElevation(const LocalModel& m, const LocalStations& st, co
 
 template <int G, int F>
 __device__ void mdFinish(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, bool isLocal, bool fitRan,
-                         double R2, const double* elevParIn, MdFit<Fit<F>::N>& fit);
+                         double R2, const double* elevParIn, MdFit<Fit<F>::N>& fit, double* smWarp = nullptr);
 
 // w: idx (station index), w (regressionWeight), val (value, detrended in place), flg (bit0 = still in myPoints) of the
 // n points; X, Y, W, oi, act are scratch. isLocal adds the minPointsLocalDetrending conditions (:1885, :2100).
@@ -179,9 +179,10 @@ __device__ void multipleDetrendingGroup(const LocalModel& m, const LocalStations
 
 // the rest of multipleDetrendingMain once the elevation parameters are chosen (fitRan: a fit ran and gave R2, elevParIn):
 // significance of the elevation proxy, detrendingElevation, the other proxies' fit and detrendingOtherProxies
+// smWarp (G == 32 only): shared memory of lmOthersWarp; with it the other-proxies fit runs in its warp-cooperative form.
 template <int G, int F>
 __device__ void mdFinish(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, bool isLocal, bool fitRan,
-                         double R2, const double* elevParIn, MdFit<Fit<F>::N>& fit)
+                         double R2, const double* elevParIn, MdFit<Fit<F>::N>& fit, double* smWarp)
 {
     constexpr int N = Fit<F>::N;
     const int lane = grpLane<G>();
@@ -297,14 +298,21 @@ __device__ void mdFinish(const LocalModel& m, const LocalStations& st, const Wor
                             }
                         const float* proxy = st.proxy;
                         const int* oi = w.oi;
+                        const bool coop = G == 32 && smWarp != nullptr;
                         if (nPred == 1) {
                             const int p0 = sigPos[0];
                             auto pred = [=](int j, int) { return double(proxy[(size_t)oi[j] * nProxy + p0]); };
-                            lmOthers<1>(1, pmin, pmax, othPar, delta, 100, 0.005, pred, w.Y, w.W, nO);
+                            if (coop) lmOthersWarp<1>(pmin, pmax, othPar, delta, 100, 0.005, pred, w.Y, w.W, nO, smWarp);
+                            else lmOthers<1>(1, pmin, pmax, othPar, delta, 100, 0.005, pred, w.Y, w.W, nO);
                         } else if (nPred == 2) {
                             const int p0 = sigPos[0], p1 = sigPos[1];
                             auto pred = [=](int j, int c) { return double(proxy[(size_t)oi[j] * nProxy + (c == 0 ? p0 : p1)]); };
-                            lmOthers<2>(2, pmin, pmax, othPar, delta, 100, 0.005, pred, w.Y, w.W, nO);
+                            if (coop) lmOthersWarp<2>(pmin, pmax, othPar, delta, 100, 0.005, pred, w.Y, w.W, nO, smWarp);
+                            else lmOthers<2>(2, pmin, pmax, othPar, delta, 100, 0.005, pred, w.Y, w.W, nO);
+                        } else if (nPred == 3 && coop) {
+                            const int* sp = sigPos;
+                            auto pred = [=](int j, int c) { return double(proxy[(size_t)oi[j] * nProxy + sp[c]]); };
+                            lmOthersWarp<3>(pmin, pmax, othPar, delta, 100, 0.005, pred, w.Y, w.W, nO, smWarp);
                         } else {
                             const int* sp = sigPos;
                             auto pred = [=](int j, int c) { return double(proxy[(size_t)oi[j] * nProxy + sp[c]]); };

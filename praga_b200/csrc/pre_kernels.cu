@@ -182,7 +182,7 @@ pre_interpolation_coop_kernel(const LocalModel* __restrict__ models, LocalStatio
         R2best = bestR2;
     }
     MdFit<N> fit;
-    mdFinish<32, F>(m, st, w, n, false, fitRan, R2best, elevPar, fit);
+    mdFinish<32, F>(m, st, w, n, false, fitRan, R2best, elevPar, fit, smWarp);
     __syncwarp();
     if (detrended)
         for (int k = lane; k < n; k += 32) {
