@@ -2373,7 +2373,8 @@ int port_topographic_distance_map(const pb_raster* dem, double x, double y, doub
 // gis::resampleGrid, gis/gis.cpp:1722-1811 (aggrAverage, aggrMedian, aggrCenter)
 int port_resample_grid(const pb_raster* src, const pb_raster_header* nh, int method, float nodataRatioThreshold, pb_raster_out* out)
 {
-    if (method != PB_AGGR_AVERAGE && method != PB_AGGR_MEDIAN && method != PB_AGGR_CENTER) return PB_ERR_UNSUPPORTED;
+    if (method != PB_AGGR_AVERAGE && method != PB_AGGR_MEDIAN && method != PB_AGGR_CENTER && method != PB_AGGR_PREVAILING)
+        return PB_ERR_UNSUPPORTED;
     Grid o = gridOf(*src);
     const int rows = nh->nrRows, cols = nh->nrCols;
     const double resampleFactor = nh->cellSize / o.h.cellSize;
@@ -2408,6 +2409,23 @@ int port_resample_grid(const pb_raster* src, const pb_raster_header* nh, int met
                         int nv = 0;
                         for (float v : values) if (!isEqualF(v, NODATA_F)) { sum += double(v); nv++; }
                         value = (values.empty() || nv == 0) ? NODATA_F : float(sum / double(nv));
+                    } else if (method == PB_AGGR_PREVAILING) {          // gis::prevailingValue, gis.cpp:1513-1554 (:1794-1799)
+                        if (maxNrValues - nrValues < nrValues) {
+                            std::vector<float> distinct;
+                            std::vector<unsigned> counters;
+                            distinct.push_back(values[0]);
+                            counters.push_back(1);
+                            for (size_t i = 1; i < values.size(); i++) {
+                                bool found = false;
+                                for (size_t j = 0; j < distinct.size() && !found; j++)
+                                    if (isEqualF(values[i], distinct[j])) { found = true; counters[j]++; }
+                                if (!found) { distinct.push_back(values[i]); counters.push_back(1); }
+                            }
+                            unsigned maxCount = counters[0];
+                            value = distinct[0];
+                            for (size_t i = 1; i < distinct.size(); i++)
+                                if (counters[i] > maxCount) { maxCount = counters[i]; value = distinct[i]; }
+                        }
                     } else {                                           // sorting::percentile(values, n, 50, true), basicMath.cpp:327-366
                         if (values.size() >= 3) {
                             std::vector<float> list;

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(128) resample_grid_kernel(DevGrid oldGrid, Dev
             const double halfStep = step * 0.5;
             const double llxS = x0 - (newGrid.cellSize / 2) + halfStep;
             const double llyS = y0 - (newGrid.cellSize / 2) + halfStep;
-            float values[METHOD == PB_AGGR_MEDIAN ? kResampleMax : 1];
+            float values[(METHOD == PB_AGGR_MEDIAN || METHOD == PB_AGGR_PREVAILING) ? kResampleMax : 1];
             int nrValues = 0, maxNrValues = 0, nrMean = 0;
             double sum = 0.;
             for (int i = 0; i < nrStep; i++) {
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128) resample_grid_kernel(DevGrid oldGrid, Dev
                     if (unsigned(sr) < unsigned(oldGrid.nrRows) && unsigned(sc) < unsigned(oldGrid.nrCols))
                         tmpValue = __ldg(oldGrid.data + (size_t)sr * oldGrid.nrCols + sc);
                     if (!isEqualF(tmpValue, oldGrid.flag)) {
-                        if (METHOD == PB_AGGR_MEDIAN) values[nrValues] = tmpValue;
+                        if (METHOD == PB_AGGR_MEDIAN || METHOD == PB_AGGR_PREVAILING) values[nrValues] = tmpValue;
                         nrValues++;
                         if (!isEqualF(tmpValue, kNoData)) { sum += double(tmpValue); nrMean++; }     // statistics::mean skips NODATA
                     }
@@ -221,6 +221,25 @@ __global__ void __launch_bounds__(128) resample_grid_kernel(DevGrid oldGrid, Dev
                 if (METHOD == PB_AGGR_AVERAGE) {
                     // statistics::mean(std::vector<float>) (statistics.cpp:1300-1321): double sum of the non-NODATA values
                     value = (nrValues < 1 || nrMean == 0) ? kNoData : float(sum / double(nrMean));
+                } else if (METHOD == PB_AGGR_PREVAILING) {
+                    // gis::prevailingValue (gis.cpp:1513-1554) when fewer samples are missing than present (:1794-1799): the
+                    // first value (in sample order) with the largest number of isEqual matches; a value counts for the FIRST
+                    // distinct entry it is isEqual to, like the reference's linear search
+                    if (maxNrValues - nrValues < nrValues) {
+                        float distinct[kResampleMax];
+                        unsigned short counters[kResampleMax];
+                        int nd = 0;
+                        for (int q = 0; q < nrValues; q++) {
+                            bool found = false;
+                            for (int d = 0; d < nd && !found; d++)
+                                if (isEqualF(values[q], distinct[d])) { found = true; counters[d]++; }
+                            if (!found) { distinct[nd] = values[q]; counters[nd] = 1; nd++; }
+                        }
+                        unsigned maxCount = counters[0];
+                        value = distinct[0];
+                        for (int d = 1; d < nd; d++)
+                            if (counters[d] > maxCount) { maxCount = counters[d]; value = distinct[d]; }
+                    }
                 } else if (METHOD == PB_AGGR_MEDIAN) {
                     // sorting::percentile(values, n, 50, true) (basicMath.cpp:327-366): < 3 values -> NODATA; drop NODATA, sort
                     // ascending, rank = n * 0.5 - 1, linear interpolation
@@ -558,11 +577,11 @@ int pb_resample_grid(pb_context* ctx, pb_raster_id srcId, const pb_raster_header
     if (!ctx) return PB_ERR_INVALID;
     RasterEntry* src = entryOf(ctx, srcId);
     if (!src || !newHeader) return fail(ctx, PB_ERR_INVALID, "bad raster id / null header");
-    if (method != PB_AGGR_AVERAGE && method != PB_AGGR_MEDIAN && method != PB_AGGR_CENTER)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "resampleGrid: aggrAverage, aggrMedian and aggrCenter run on the GPU (aggrPrevailing does not)");
+    if (method != PB_AGGR_AVERAGE && method != PB_AGGR_MEDIAN && method != PB_AGGR_CENTER && method != PB_AGGR_PREVAILING)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "resampleGrid: aggrAverage, aggrMedian, aggrPrevailing and aggrCenter run on the GPU");
     const double factor = newHeader->cellSize / src->h.cellSize;
-    if (factor > 1. && method == PB_AGGR_MEDIAN && int(floor(factor)) + 1 > 16)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "median resampling above factor 15 (more than 256 samples per cell)");
+    if (factor > 1. && (method == PB_AGGR_MEDIAN || method == PB_AGGR_PREVAILING) && int(floor(factor)) + 1 > 16)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "median / prevailing resampling above factor 15 (more than 256 samples per cell)");
     cudaSetDevice(ctx->device);
     memset(&ctx->timing, 0, sizeof(ctx->timing));
     pb_raster_header h = *newHeader;
@@ -594,6 +613,8 @@ int pb_resample_grid(pb_context* ctx, pb_raster_id srcId, const pb_raster_header
         resample_grid_kernel<PB_AGGR_AVERAGE><<<nb, 128, 0, ctx->stream>>>(gridOf(*src), ng, nodataRatioThreshold, dOut, ctx->dMinMax);
     else if (method == PB_AGGR_MEDIAN)
         resample_grid_kernel<PB_AGGR_MEDIAN><<<nb, 128, 0, ctx->stream>>>(gridOf(*src), ng, nodataRatioThreshold, dOut, ctx->dMinMax);
+    else if (method == PB_AGGR_PREVAILING)
+        resample_grid_kernel<PB_AGGR_PREVAILING><<<nb, 128, 0, ctx->stream>>>(gridOf(*src), ng, nodataRatioThreshold, dOut, ctx->dMinMax);
     else
         resample_grid_kernel<PB_AGGR_CENTER><<<nb, 128, 0, ctx->stream>>>(gridOf(*src), ng, nodataRatioThreshold, dOut, ctx->dMinMax);
     CUDA_TRY(ctx, cudaGetLastError());

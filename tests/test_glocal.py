@@ -129,3 +129,68 @@ def test_gpu_glocal_matches_reference(engine, ref, case):
     finally:
         engine.free(dem_id)
         engine.free(urb_id)
+
+
+def _edge_areas(dem, st, kind):
+    a = syn.make_macro_areas(dem, st, 2, 8)
+    if kind == "no_stations_anywhere":          # no area is ever fitted: only the height ranges / first guesses are set
+        return A.MacroAreas([np.zeros(0, np.int32)] * a.n, [np.zeros(0, np.float32)] * a.n)
+    if kind == "cells_without_stations":        # interpolate() over no points gives NODATA: the reference returns false
+        return A.MacroAreas(a.meteo_points[:3] + [np.zeros(0, np.int32)], a.area_cells)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["no_stations_anywhere", "cells_without_stations"])
+def test_port_matches_reference_on_degenerate_areas(ref, port, kind):  # noqa: F811
+    dem, urban, st, s, _ = scenario("two_piece")
+    got = []
+    for o in (ref, port):
+        a, so = _edge_areas(dem, st, kind), clone(s)
+        ok, grid, mn, mx, nv, _ = o.glocal_detrending_raster(st.copy(), so, A.airTemperature, a, dem, (dem, urban), threads=1)
+        got.append((ok, a.fits(), so, grid))
+    assert got[0][0] == got[1][0] and got[0][1] == got[1][1]
+    assert settings_equal(got[0][2], got[1][2]), describe_diff(got[0][2], got[1][2])
+    if kind == "no_stations_anywhere":
+        assert got[0][0] and np.array_equal(got[0][3], got[1][3]) and (got[0][3] == np.float32(dem.flag)).all()
+    else:
+        assert not got[0][0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["no_stations_anywhere", "cells_without_stations"])
+def test_gpu_degenerate_areas(engine, ref, kind):
+    dem, urban, st, s, _ = scenario("two_piece")
+    a_r, s_r = _edge_areas(dem, st, kind), clone(s)
+    ok_r, grid_r, *_ = ref.glocal_detrending_raster(st.copy(), s_r, A.airTemperature, a_r, dem, (dem, urban), threads=1)
+    dem_id, urb_id = engine.upload(dem), engine.upload(urban)
+    try:
+        a_g, s_g = _edge_areas(dem, st, kind), clone(s)
+        ok_g, grid_g, *_ = engine.glocal_detrending_raster(st.copy(), s_g, A.airTemperature, a_g, dem_id, dem.shape, (dem_id, urb_id))
+        assert ok_g == ok_r
+        assert a_g.fits() == a_r.fits()
+        assert settings_equal(s_r, s_g), describe_diff(s_r, s_g)
+        if ok_r:
+            assert np.array_equal(grid_r, grid_g)
+    finally:
+        engine.free(dem_id)
+        engine.free(urb_id)
+
+
+@pytest.mark.gpu
+def test_gpu_glocal_rejects_what_it_does_not_cover(engine):
+    import praga_b200 as pb
+    dem, urban, st, s, areas = scenario("two_piece")
+    dem_id = engine.upload(dem)
+    try:
+        s_td = clone(s)
+        s_td.useTD = 1          # topographic distance inside macro areas: not on the GPU path, never silently ignored
+        with pytest.raises(pb.PragaB200Error) as e:
+            engine.glocal_detrending_raster(st.copy(), s_td, A.airTemperature, areas(), dem_id, dem.shape, (dem_id, dem_id))
+        assert e.value.status == A.PB_ERR_UNSUPPORTED
+        s_off = clone(s)
+        s_off.useGlocalDetrending = 0
+        with pytest.raises(pb.PragaB200Error) as e:
+            engine.glocal_detrending_raster(st.copy(), s_off, A.airTemperature, areas(), dem_id, dem.shape, (dem_id, dem_id))
+        assert e.value.status == A.PB_ERR_INVALID
+    finally:
+        engine.free(dem_id)

@@ -38,7 +38,16 @@ def new_header(src, factor, rows=None, cols=None, shift=(0.0, 0.0)):
 
 RESAMPLE_CASES = [("average", A.PB_AGGR_AVERAGE, 4.0, 0.0), ("average_thr", A.PB_AGGR_AVERAGE, 2.5, 0.5),
                   ("median", A.PB_AGGR_MEDIAN, 3.0, 0.0), ("center", A.PB_AGGR_CENTER, 5.0, 0.0),
-                  ("finer", A.PB_AGGR_AVERAGE, 0.5, 0.0)]
+                  ("finer", A.PB_AGGR_AVERAGE, 0.5, 0.0), ("prevailing", A.PB_AGGR_PREVAILING, 4.0, 0.0),
+                  ("prevailing_sparse", A.PB_AGGR_PREVAILING, 3.0, 0.3)]
+
+
+def categorical(r):
+    """a land-use-like raster (a few integer classes) on the header of r: what aggrPrevailing is for"""
+    d = r.data.copy()
+    ok = d != np.float32(r.flag)
+    d[ok] = np.floor(d[ok] / 150.0) % 7
+    return A.Raster(d, r.llx, r.lly, r.cell_size, r.flag)
 
 
 # ---------------------------------------------------------------- CPU: restatement == reference
@@ -61,7 +70,9 @@ def test_port_topographic_distance_map(ref, port):  # noqa: F811
 
 @pytest.mark.parametrize("name,method,factor,thr", RESAMPLE_CASES)
 def test_port_resample_grid(ref, port, name, method, factor, thr):  # noqa: F811
-    src = syn.make_dem(96, 128, seed=8)
+    src = syn.make_dem(96, 128, seed=8, nodata_frac=0.3 if name == "prevailing_sparse" else 0.05)
+    if method == A.PB_AGGR_PREVAILING:
+        src = categorical(src)
     h = new_header(src, factor, shift=(30.0, -20.0))
     a, b = ref.resample_grid(src, h, method, thr), port.resample_grid(src, h, method, thr)
     assert np.array_equal(a[1], b[1]), np.abs(a[1] - b[1]).max()
@@ -120,8 +131,10 @@ def test_gpu_topographic_distance_map_bit_exact(engine, ref):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,method,factor,thr", RESAMPLE_CASES)
 def test_gpu_resample_grid(engine, ref, name, method, factor, thr):
-    src = syn.make_dem(480, 640, seed=8)
+    src = syn.make_dem(480, 640, seed=8, nodata_frac=0.3 if name == "prevailing_sparse" else 0.05)
     urban = syn.make_urban(480, 640)
+    if method == A.PB_AGGR_PREVAILING:
+        src = categorical(src)
     for grid in (src, urban):
         h = new_header(grid, factor, shift=(30.0, -20.0))
         sid = engine.upload(grid)
