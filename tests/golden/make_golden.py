@@ -6,6 +6,9 @@
                 DATA/METEOPOINT/test.db for DAILY_TMIN 2023-01-05 and DAILY_TMAX 2023-01-10 — gridded with
                 algorithm=idw (override of the demo's shepard_modified), classic elevation detrending with thermal
                 inversion, optimalDetrending=false, climate lapse rates of January from parameters.ini.
+  c1_demo_shipped_*.npz  the same demo day with the settings AS SHIPPED (DATA/PROJECT/test/SETTINGS/parameters.ini):
+                algorithm=shepard_modified, optimalDetrending=true, thermalInversion=true, lapseRateCode=true; also stores the
+                settings before preInterpolation so that the fit itself (all combinations, leave-one-out, argmin) is checked.
   synth_*.npz   small seeded synthetic cases (praga_b200/synthetic.py) with the reference's outputs.
 Each file stores the inputs, the settings AFTER preInterpolation (raw bytes of pb_settings), the detrended station
 values, the keep mask and the reference output grid.
@@ -77,6 +80,20 @@ def run_case(ref, name, dem, grids, st, s, var):
     save(name, dem, grids, raw, st, keep, s, var, out, ok, mn, mx, nv)
 
 
+def run_case_ex(ref, name, dem, grids, st, s, var):
+    """preInterpolation with its meteo points (optimalDetrending re-runs passDataToInterpolation and cross-validates)."""
+    raw = st.copy()
+    pre = np.frombuffer(bytes(s), dtype=np.uint8).copy()
+    ok_pre, keep, _ = ref.pre_interpolation_ex(st, s, var, current_value=raw.value)
+    assert ok_pre
+    ok, out, mn, mx, nv, _ = ref.interpolation_raster(st.subset(keep), s, var, dem, grids)
+    save(name, dem, grids, raw, st, keep, s, var, out, ok, mn, mx, nv)
+    path = os.path.join(HERE, name)
+    g = dict(np.load(path))
+    g["settings_before"] = pre
+    np.savez_compressed(path, **g)
+
+
 def run_local_case(ref, name, dem, grids, st, s, var):
     """loop of Project::interpolationDemLocalDetrending: raw points in, no global preInterpolation."""
     ok, out, mn, mx, nv, _ = ref.local_detrending_raster(st, s, var, dem, grids, threads=8)
@@ -105,6 +122,14 @@ def main():
         s = syn.settings_classic_detrending(1)
         s.climateLapseRate = lapse         # [climate] tmin_lapserate / tmax_lapserate, January (parameters.ini)
         run_case(ref, f"c1_demo_{tag}.npz", dem, (dem,), st, s, var)
+    # ---- C1 as shipped: algorithm=shepard_modified, optimalDetrending=true, thermalInversion=true, lapseRateCode=true ----
+    st = demo_stations(151, "2023-01-05")
+    s = syn.settings_classic_detrending(1)
+    s.method = A.shepard_modified
+    s.useBestDetrending = 1
+    s.useLapseRateCode = 1
+    s.climateLapseRate = -0.001
+    run_case_ex(ref, "c1_demo_shipped_tmin_20230105.npz", dem, (dem,), st, s, A.dailyAirTemperatureMin)
     # ---- synthetic ----
     d = syn.make_dem(60, 70, seed=101)
     u = syn.make_urban(60, 70)

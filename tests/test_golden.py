@@ -109,3 +109,42 @@ def test_gpu_matches_reference_kriging(engine, path):
     res, rm = engine.kriging_points(kid, g["xy"])
     engine.kriging_free(kid)
     assert np.abs(res - g["result"]).max() <= 1e-4 and np.abs(rm - g["rmse"]).max() <= 1e-4
+
+
+# ---- the demo day with the settings AS SHIPPED (shepard_modified + optimalDetrending): the fit itself is part of the fixture
+SHIPPED = [p for p in GOLDEN if "shipped" in os.path.basename(p)]
+
+
+def _before(g):
+    s = A.pb_settings()
+    ctypes.memmove(ctypes.byref(s), g["settings_before"].tobytes(), ctypes.sizeof(s))
+    return s
+
+
+def test_shipped_fixture_present():
+    assert len(SHIPPED) >= 1
+
+
+@pytest.mark.parametrize("path", SHIPPED, ids=[os.path.basename(p) for p in SHIPPED])
+def test_port_reproduces_reference_optimal_detrending(path):
+    from oracle import binding
+    port = binding.Oracle("port")
+    g, dem, grids, raw, det, s_after = load(path)
+    s = _before(g)
+    st = raw.copy()
+    ok, keep, _ = port.pre_interpolation_ex(st, s, int(g["variable"]), current_value=raw.value)
+    assert ok and np.array_equal(keep, g["keep"].astype(bool))
+    assert np.array_equal(st.value, g["value_detrended"])
+    assert bytes(s) == bytes(s_after)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", SHIPPED, ids=[os.path.basename(p) for p in SHIPPED])
+def test_gpu_reproduces_reference_optimal_detrending(engine, path):
+    g, dem, grids, raw, det, s_after = load(path)
+    s = _before(g)
+    st = raw.copy()
+    keep, _ = engine.pre_interpolation_ex(st, s, int(g["variable"]), current_value=raw.value)
+    assert np.array_equal(keep, g["keep"].astype(bool))
+    assert np.array_equal(st.value, g["value_detrended"])
+    assert bytes(s) == bytes(s_after)
