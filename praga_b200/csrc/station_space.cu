@@ -44,6 +44,66 @@ T* carve(unsigned char*& p, size_t count)
     return r;
 }
 
+// interpolate() with a Shepard estimator (K8, bit-identical point form behind pb_interpolate_points) at the meteo points,
+// followed by the residual rules of computeResiduals (spatialControl.cpp:97-155): the leave-one-out of optimalDetrending,
+// spatialQualityControl and interpolationCv when TInterpolationMethod is shepard / shepard_modified (the demo's default).
+// Sources = the interpolation points (f64 coordinates, detrended values); targets = the meteo points. NOTE: the call goes
+// through the context's point-target scratch, so nothing staged there by the caller survives it.
+int shepardLoo(pb_context* ctx, const pb_settings* sp, int variable, int nS, const double* sx, const double* sy, const double* sz,
+               const float* sval, const int* scode, int nT, const float* tx, const float* ty, const float* tproxy /* nT * max(P,1) */,
+               const int* tcode, const uint8_t* tinside, const float* tobs, int excludeOutsideDem, int excludeSupplemental,
+               float* residual, float* estimate)
+{
+    const int P = sp->nProxy;
+    const size_t Pp = std::max(P, 1);
+    std::vector<float> val(sval, sval + nS), proxy(size_t(nS) * Pp, kNoData), est(nT);
+    std::vector<int32_t> code(scode, scode + nS);
+    pb_stations st{};
+    st.n = nS;
+    st.nProxy = P;
+    st.x = sx; st.y = sy; st.z = sz;
+    st.value = val.data();
+    st.lapseRateCode = code.data();
+    st.proxyValues = proxy.data();              // interpolate() never reads the points' own proxy values
+    std::vector<double> pv(size_t(nT) * Pp);
+    for (size_t k = 0; k < pv.size(); k++) pv[k] = double(tproxy[k]);
+    int rc = pb_interpolate_points(ctx, &st, sp, variable, tx, ty, pv.data(), nT, 0, est.data());
+    if (rc) return rc;
+    const bool isPrec = varIsPrec(variable);
+    for (int j = 0; j < nT; j++) {
+        bool valid = !excludeSupplemental || !sp->useLapseRateCode || tcode[j] == PB_LAPSE_PRIMARY || tcode[j] == PB_LAPSE_SECONDARY;
+        valid = valid && (!excludeOutsideDem || (tinside ? tinside[j] != 0 : true));
+        float res = kNoData, e = kNoData;
+        if (valid) {
+            float myValue = tobs[j];
+            e = est[j];
+            if (isPrec) {
+                if (myValue != kNoData && myValue < sp->rainfallThreshold) myValue = 0.f;
+                if (e != kNoData && e < sp->rainfallThreshold) e = 0.f;
+            }
+            if (e != kNoData && myValue != kNoData) res = myValue - e;
+        }
+        if (residual) residual[j] = res;
+        if (estimate) estimate[j] = e;
+    }
+    return PB_OK;
+}
+
+// computeErrorCrossValidation (spatialControl.cpp:305-328) + statistics::meanAbsoluteError (statistics.cpp:201-220) on the host
+float cvMaeHost(const float* residual, const float* observed, int n)
+{
+    double sum = 0.;
+    long cnt = 0;
+    for (int j = 0; j < n; j++) {
+        const float value = observed[j], res = residual[j];
+        if (value != kNoData && res != kNoData) {
+            const float e = value - res;
+            if (e != kNoData) { sum += fabs(double(value - e)); cnt++; }
+        }
+    }
+    return cnt == 0 ? kNoData : float(sum / double(cnt));
+}
+
 void applyWrites(pb_proxy& dst, const ClassicProxyState& p)
 {
     if (p.written & CF_SLOPE) dst.regressionSlope = p.slope;
@@ -162,8 +222,9 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
         return fail(ctx, PB_ERR_INVALID, "topographic-distance optimisation needs the resident DEM (getCurrentDEM())");
     if (useTD && s->method != PB_METHOD_IDW)
         return fail(ctx, PB_ERR_UNSUPPORTED, "leave-one-out for the kh search runs the idw estimator only");
-    if (optimal && s->method != PB_METHOD_IDW)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "leave-one-out for optimalDetrending runs the idw estimator only");
+    if (optimal && s->method != PB_METHOD_IDW && useTD)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "the Shepard estimators run without topographic distance on the GPU path");
+    const bool shepardCv = optimal && s->method != PB_METHOD_IDW;
 
     // interpolation points = survivors of multiple detrending (points with NODATA proxies are erased, :2230); the meteo
     // points the leave-one-out walks stay ALL stations
@@ -337,7 +398,38 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
 
     // ---- leave-one-out tables ----
     std::vector<float> mae;
+    std::vector<float> hWork;                 // host copy of the detrended values of every problem (Shepard cross-validation)
     auto runLoo = [&](int excludeOutsideDem) -> int {
+        if (shepardCv) {
+            // one K8 point-form call per combination over that combination's detrended points and regression fields
+            hWork.resize(size_t(m) * NP);
+            CUDA_TRY(ctx, cudaMemcpyAsync(hWork.data(), dWork, hWork.size() * 4, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+            mae.assign(size_t(NP) * nKh, kNoData);
+            std::vector<double> sxd(m), syd(m);
+            for (int k = 0; k < m; k++) { sxd[k] = st->x[ip[k]]; syd[k] = st->y[ip[k]]; }
+            std::vector<float> col(m), res(n);
+            pb_timing acc = ctx->timing;
+            for (int p = 0; p < NP; p++) {
+                pb_settings sp = *s;
+                for (int i = 0; i < P; i++) {
+                    applyWrites(sp.proxy[i], problems[p].proxy[i]);
+                    sp.currentActive[i] = problems[p].active[i];
+                    sp.currentSignificant[i] = problems[p].significant[i];
+                }
+                sp.currentUseThermalInversion = problems[p].useThermalInversion;
+                for (int k = 0; k < m; k++) col[k] = hWork[size_t(k) * NP + p];
+                int rc = shepardLoo(ctx, &sp, variable, m, sxd.data(), syd.data(), hz.data(), col.data(), hcode.data(), n, gx.data(),
+                                    gy.data(), gproxy.data(), gcode.data(), gin.data(), gobs.data(), excludeOutsideDem, 1, res.data(),
+                                    nullptr);
+                if (rc) return rc;
+                acc.launches += ctx->timing.launches;
+                acc.kernel_ms += ctx->timing.kernel_ms;
+                mae[p] = cvMaeHost(res.data(), gobs.data(), n);
+            }
+            ctx->timing = acc;
+            return PB_OK;
+        }
         LooSetup ls{};
         ls.nS = m; ls.nT = n; ls.nProxy = P; ls.nProblems = NP; ls.nKh = nKh;
         ls.useLapseRateCode = s->useLapseRateCode;
@@ -435,12 +527,16 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
             s->currentSignificant[i] = fin.significant[i];
         }
         s->currentUseThermalInversion = fin.useThermalInversion;
-        CUDA_TRY(ctx, launchClassicGather(dWork, m, NP, best, dValues, stream));
-        ctx->timing.launches++;
-        std::vector<float> out(m);
-        CUDA_TRY(ctx, cudaMemcpyAsync(out.data(), dValues, m * 4, cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(stream));
-        for (int k = 0; k < m; k++) st->value[ip[k]] = out[k];
+        if (!hWork.empty()) {       // the device staging did not survive the Shepard calls: the host copy has every problem
+            for (int k = 0; k < m; k++) st->value[ip[k]] = hWork[size_t(k) * NP + best];
+        } else {
+            CUDA_TRY(ctx, launchClassicGather(dWork, m, NP, best, dValues, stream));
+            ctx->timing.launches++;
+            std::vector<float> out(m);
+            CUDA_TRY(ctx, cudaMemcpyAsync(out.data(), dValues, m * 4, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+            for (int k = 0; k < m; k++) st->value[ip[k]] = out[k];
+        }
     }
     return PB_OK;
 }
@@ -460,6 +556,7 @@ struct LooArrays {
     std::vector<float> sx, sy, szf, sval;
     std::vector<double> sz;
     std::vector<int> scode;
+    std::vector<double> sxd, syd;           // the Shepard estimators take the direction cosines from the f64 coordinates
 };
 
 // problem = what the settings say about classic detrending (current combination + the proxies' regression fields)
@@ -485,7 +582,19 @@ int exactLoo(pb_context* ctx, const LooArrays& a, const pb_settings* s, int vari
     const bool useTD = s->useTD && !s->useLocalDetrending && varUsesTd(variable) && s->topoDist_Kh != 0;
     if (useTD && (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used))
         return fail(ctx, PB_ERR_INVALID, "topographic distance needs the resident DEM (getCurrentDEM())");
-    if (s->method != PB_METHOD_IDW) return fail(ctx, PB_ERR_UNSUPPORTED, "the exact leave-one-out runs the idw estimator only");
+    const bool shepardMethod = s->method != PB_METHOD_IDW;
+    if (shepardMethod && useTD)
+        return fail(ctx, PB_ERR_UNSUPPORTED, "the Shepard estimators run without topographic distance on the GPU path");
+    if (shepardMethod && (residual || estimate)) {
+        if (a.sxd.size() != size_t(nS)) return fail(ctx, PB_ERR_INVALID, "Shepard leave-one-out needs the f64 station coordinates");
+        if (nb) {       // the neighbourhood statistics do not depend on the estimator: device pass first, then the estimates
+            int rc = exactLoo(ctx, a, s, variable, demId, excludeOutsideDem, excludeSupplemental, nullptr, nullptr, nb);
+            if (rc) return rc;
+        }
+        return shepardLoo(ctx, s, variable, nS, a.sxd.data(), a.syd.data(), a.sz.data(), a.sval.data(), a.scode.data(), nT,
+                          a.tx.data(), a.ty.data(), a.tproxy.data(), a.tcode.data(), a.tin.data(), a.tobs.data(), excludeOutsideDem,
+                          excludeSupplemental, residual, estimate);
+    }
     size_t bytes = 0;
     auto add = [&](size_t count, size_t size) { bytes += (count * size + 255) / 256 * 256; };
     add(nT, 4); add(nT, 4); add(nT, 4); add(nT * Pp, 4); add(nT, 4); add(nT, 4); add(nT, 1);
@@ -640,9 +749,11 @@ void fillTargets(LooArrays& a, const pb_stations* st, const std::vector<int>& tI
 
 void fillSources(LooArrays& a, const pb_stations* pts, const uint8_t* keep)
 {
-    a.sx.clear(); a.sy.clear(); a.szf.clear(); a.sval.clear(); a.sz.clear(); a.scode.clear();
+    a.sx.clear(); a.sy.clear(); a.szf.clear(); a.sval.clear(); a.sz.clear(); a.scode.clear(); a.sxd.clear(); a.syd.clear();
     for (int i = 0; i < pts->n; i++) {
         if (keep && !keep[i]) continue;
+        a.sxd.push_back(pts->x[i]);
+        a.syd.push_back(pts->y[i]);
         a.sx.push_back(float(pts->x[i]));
         a.sy.push_back(float(pts->y[i]));
         a.szf.push_back(float(pts->z[i]));

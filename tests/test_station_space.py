@@ -34,6 +34,9 @@ def scenario(case, n=150, seed=19):
     if "td" in case:
         s.useTD = 1
         s.topoDist_maxKh = 64 if "kh64" in case else 128
+    if "shepard" in case:       # the demo's default estimator (parameters.ini: algorithm=shepard_modified)
+        s.method = A.shepard_modified if "modified" in case else A.shepard
+        s.pointsBoundingBoxArea = float((np.float32(st.x.max()) - np.float32(st.x.min())) * (np.float32(st.y.max()) - np.float32(st.y.min())))
     if "humidity" in case:
         st = syn.make_stations(dem, n, variable="humidity", seed=seed)
         s = A.default_settings()
@@ -53,7 +56,8 @@ def scenario(case, n=150, seed=19):
 
 CPU_CASES = ["classic_inversion", "classic_warm_valley", "classic_noinv", "classic_codes", "classic_pressure",
              "optimal", "optimal_inversion", "optimal_codes_warm_valley", "optimal_noinv",
-             "td_humidity", "classic_td_kh64", "optimal_td_kh64", "multiple_td"]
+             "td_humidity", "classic_td_kh64", "optimal_td_kh64", "multiple_td",
+             "optimal_shepard", "optimal_modified_shepard_codes_warm_valley", "optimal_modified_shepard_inversion"]
 
 
 def run_oracle(orc, case):
