@@ -150,3 +150,37 @@ def test_batch_call_equals_stand_alone_calls(engine, ref):
     finally:
         engine.free(dem_id)
         engine.free(urb_id)
+
+
+def test_interpolation_dem_with_the_demo_shipped_settings(engine, ref):
+    """Project::interpolationDem with the settings the bundled demo ships (parameters.ini: algorithm=shepard_modified,
+    optimalDetrending=true, thermalInversion=true, lapseRateCode=true) for the gridding AND the quality settings: spatial
+    quality control, optimalDetrending cross-validated with the Shepard estimator, Shepard raster, Shepard leave-one-out."""
+    dem, urban, steps = batch_inputs(n=180, seed=9)
+    dem_id, urb_id = engine.upload(dem), engine.upload(urban)
+    try:
+        for h, var, st in steps[:3]:
+            def shipped():
+                s = syn.settings_classic_detrending(2)
+                s.method = A.shepard_modified
+                s.useBestDetrending = 1
+                s.useLapseRateCode = 1
+                return s
+            s_g, sq_g = shipped(), shipped()
+            s_r, sq_r = clone(s_g), clone(sq_g)
+            g = engine.interpolation_dem(st.copy(), s_g, var, dem_id, dem.shape, (dem_id, urb_id), quality_settings=sq_g,
+                                         cross_validate=True)
+            r = ref.interpolation_dem(st.copy(), s_r, var, dem, (dem, urban), quality_settings=sq_r, cross_validate=True, threads=8)
+            tag = f"hour {h} var {var}"
+            assert g["ok"] == r["ok"], tag
+            assert np.array_equal(g["wrong_spatial"], r["wrong_spatial"]), tag
+            assert settings_equal(sq_g, sq_r), tag + ": quality settings: " + describe_diff(sq_g, sq_r)
+            assert settings_equal(s_g, s_r), tag + ": settings: " + describe_diff(s_g, s_r)
+            mr = r["grid"] == np.float32(dem.flag)
+            assert np.array_equal(g["grid"] == np.float32(dem.flag), mr), tag
+            assert np.abs(g["grid"][~mr].astype(np.float64) - r["grid"][~mr]).max() <= TOL, tag
+            assert np.array_equal(g["residual"] == np.float32(-9999), r["residual"] == np.float32(-9999)), tag
+            assert np.abs(g["residual"].astype(np.float64) - r["residual"]).max() <= TOL, tag
+    finally:
+        engine.free(dem_id)
+        engine.free(urb_id)
