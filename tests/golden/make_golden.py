@@ -123,13 +123,21 @@ def main():
         s.climateLapseRate = lapse         # [climate] tmin_lapserate / tmax_lapserate, January (parameters.ini)
         run_case(ref, f"c1_demo_{tag}.npz", dem, (dem,), st, s, var)
     # ---- C1 as shipped: algorithm=shepard_modified, optimalDetrending=true, thermalInversion=true, lapseRateCode=true ----
+    # two proxies like the shipped project: elevation (table field) + the orography-index raster of DATA/GEO (500 m grid, a
+    # geometry foreign to the 450 m DEM; station values sampled from the grid as Project::readProxyValues does, project.cpp:2066-2091)
+    ti = read_flt(f"{REF_DATA}/GEO/TI_DEM_ER_bacini_500m")
     st = demo_stations(151, "2023-01-05")
-    s = syn.settings_classic_detrending(1)
+    tiv = syn.sample_grid(ti, st.x, st.y)
+    tiv = np.where(tiv == np.float32(ti.flag), np.float32(A.NODATA), tiv)
+    st = A.Stations(st.x, st.y, st.z, st.value, np.stack([st.z.astype(np.float32), tiv], axis=1))
+    s = syn.settings_classic_detrending(2)
+    p1 = A.default_proxy(A.proxyOrogIndex, 1)
+    s.proxy[1] = p1
     s.method = A.shepard_modified
     s.useBestDetrending = 1
     s.useLapseRateCode = 1
     s.climateLapseRate = -0.001
-    run_case_ex(ref, "c1_demo_shipped_tmin_20230105.npz", dem, (dem,), st, s, A.dailyAirTemperatureMin)
+    run_case_ex(ref, "c1_demo_shipped_tmin_20230105.npz", dem, (dem, ti), st, s, A.dailyAirTemperatureMin)
     # ---- synthetic ----
     d = syn.make_dem(60, 70, seed=101)
     u = syn.make_urban(60, 70)
