@@ -476,6 +476,15 @@ int pb_aggregation_upload(pb_context* ctx, const double* x, const double* y, con
 int pb_aggregation_free(pb_context* ctx, pb_aggregation_id id);
 int pb_spatial_aggregate_meteo_grid(pb_context* ctx, pb_raster_id raster, pb_aggregation_id aggregation, int method, float* value);
 
+/* values of a resident raster at explicit points (nearest cell): Crit3DRasterGrid::getRowCol (agrolib/gis/gis.cpp:485-492),
+ * gis::isOutOfGridRowCol (:771-776), value[row][col] — the lookup of Project::passInterpolatedTemperatureToHumidityPoints
+ * (agrolib/project/project.cpp:2826-2848): stations with humidity but no temperature take the air temperature of the map just
+ * gridded, so that their dew point (tDewFromRelHum, host arithmetic of the meteo point) can be gridded next and turned into
+ * relative humidity by pb_relative_humidity_map. value[i] = the cell's value (the raster's flag included, like the
+ * reference), PB_NODATA outside the grid; inGrid[i] (may be NULL) = 1 inside. Only n values cross PCIe. */
+int pb_raster_sample_points(pb_context* ctx, pb_raster_id raster, const double* x, const double* y, int n, float* value,
+                            uint8_t* inGrid);
+
 /* --- ESRI float grids (.hdr + .flt), the on-disk format at either end of the path, streamed between
  * the file and HBM through pinned staging (no pageable full-size copy):
  *   pb_raster_read_esri_header <- gis::readEsriGridHeader (agrolib/gis/gisIO.cpp:118-193)

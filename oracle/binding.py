@@ -59,6 +59,14 @@ def load_ref_extra():
     return lib
 
 
+def load_ref_sample():
+    """reference driver only: the raster lookup of passInterpolatedTemperatureToHumidityPoints"""
+    lib = _load(REF_LIB, "ref")
+    lib.ref_raster_sample_points.argtypes = [C.POINTER(A.pb_raster), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
+                                             C.POINTER(C.c_float), C.POINTER(C.c_uint8)]
+    return lib
+
+
 def load_ref_io():
     """ESRI grid I/O of the reference (gis/gisIO.cpp), reference driver only."""
     lib = _load(REF_LIB, "ref")

@@ -1156,3 +1156,18 @@ extern "C" int ref_spatial_aggregate_meteo_grid(const pb_raster* raster, const d
     for (int c = 0; c < nCells; c++) value[c] = mg.meteoPointPointer(0, c)->currentValue;
     return PB_OK;
 }
+
+/* the raster lookup of Project::passInterpolatedTemperatureToHumidityPoints (project/project.cpp:2840-2845): reference calls only */
+extern "C" int ref_raster_sample_points(const pb_raster* raster, const double* x, const double* y, int n, float* value, uint8_t* inGrid)
+{
+    gis::Crit3DRasterGrid grid;
+    fillGrid(grid, *raster);
+    for (int i = 0; i < n; i++) {
+        int row, col;
+        grid.getRowCol(x[i], y[i], row, col);
+        const bool in = !gis::isOutOfGridRowCol(row, col, grid);
+        value[i] = in ? grid.value[row][col] : float(NODATA);
+        if (inGrid) inGrid[i] = in;
+    }
+    return PB_OK;
+}

@@ -366,6 +366,22 @@ spatial_aggregate_kernel(DevGrid raster, const double* __restrict__ px, const do
     value[cell] = result;
 }
 
+// values of a resident raster at explicit points: Crit3DRasterGrid::getRowCol (gis.cpp:485-492) + gis::isOutOfGridRowCol
+// (:771-776) + value[row][col], the lookup of Project::passInterpolatedTemperatureToHumidityPoints (project.cpp:2826-2848)
+__global__ void __launch_bounds__(256)
+sample_points_kernel(DevGrid g, const double* __restrict__ px, const double* __restrict__ py, int n, float* __restrict__ value,
+                     unsigned char* __restrict__ inGrid)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = int((py[i] - g.lly) * g.invCellSize);
+    const int row = (g.nrRows - 1) - r;
+    const int col = int((px[i] - g.llx) * g.invCellSize);
+    const bool in = unsigned(row) < unsigned(g.nrRows) && unsigned(col) < unsigned(g.nrCols);
+    value[i] = in ? __ldg(g.data + (size_t)row * g.nrCols + col) : kNoData;
+    inGrid[i] = in;
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -696,6 +712,37 @@ int pb_spatial_aggregate_meteo_grid(pb_context* ctx, pb_raster_id rasterId, pb_a
     ctx->timing.d2h_bytes = (int64_t)(size_t(g.nCells) * 4);
     cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[1], ctx->ev[3]);
+    return PB_OK;
+}
+
+int pb_raster_sample_points(pb_context* ctx, pb_raster_id rasterId, const double* x, const double* y, int n, float* value,
+                            uint8_t* inGrid)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    RasterEntry* src = entryOf(ctx, rasterId);
+    if (!src || !x || !y || !value || n < 0) return fail(ctx, PB_ERR_INVALID, "bad raster id / null argument");
+    if (n == 0) return PB_OK;
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    const size_t nAl = (size_t(n) + 1) / 2 * 2;
+    CUDA_TRY(ctx, ctx->dScratch.reserve(nAl * 8 * 2 + nAl * 4 + nAl + 64));
+    unsigned char* d = ctx->dScratch.p;
+    double* dX = reinterpret_cast<double*>(d);
+    double* dY = dX + nAl;
+    float* dV = reinterpret_cast<float*>(dY + nAl);
+    unsigned char* dIn = reinterpret_cast<unsigned char*>(dV + nAl);
+    CUDA_TRY(ctx, cudaMemcpyAsync(dX, x, size_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dY, y, size_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    sample_points_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(gridOf(*src), dX, dY, n, dV, dIn);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.launches++;
+    CUDA_TRY(ctx, cudaMemcpyAsync(value, dV, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint8_t> tmp;
+    if (!inGrid) { tmp.resize(n); inGrid = tmp.data(); }
+    CUDA_TRY(ctx, cudaMemcpyAsync(inGrid, dIn, size_t(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.h2d_bytes = int64_t(n) * 16;
+    ctx->timing.d2h_bytes = int64_t(n) * 5;
     return PB_OK;
 }
 

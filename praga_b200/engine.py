@@ -102,6 +102,7 @@ def load_library():
                                                          P(A.pb_raster_out)]
     lib.pb_macro_areas_upload.argtypes = [C.c_void_p, P(A.pb_macro_area), C.c_int, P(C.c_int32)]
     lib.pb_macro_areas_free.argtypes = [C.c_void_p, C.c_int32]
+    lib.pb_raster_sample_points.argtypes = [C.c_void_p, C.c_int32, P(C.c_double), P(C.c_double), C.c_int, P(C.c_float), P(C.c_uint8)]
     lib.pb_aggregation_upload.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_int64), P(C.c_int32), C.c_int, P(C.c_int32)]
     lib.pb_aggregation_free.argtypes = [C.c_void_p, C.c_int32]
     lib.pb_spatial_aggregate_meteo_grid.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int, P(C.c_float)]
@@ -592,3 +593,13 @@ class Engine:
         val = np.empty(self._agg_cells[aid], dtype=np.float32)
         self._check(self.lib.pb_spatial_aggregate_meteo_grid(self.h, raster_id, aid, method, A.fptr(val)))
         return val
+
+    def raster_sample_points(self, raster_id, x, y):
+        """Nearest-cell values of a resident raster at points (passInterpolatedTemperatureToHumidityPoints, project.cpp:2826-2848).
+        Returns (values, in_grid mask)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        val = np.empty(x.size, dtype=np.float32)
+        ins = np.zeros(x.size, dtype=np.uint8)
+        self._check(self.lib.pb_raster_sample_points(self.h, raster_id, A.dptr(x), A.dptr(y), x.size, A.fptr(val), A.u8ptr(ins)))
+        return val, ins.astype(bool)

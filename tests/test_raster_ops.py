@@ -183,3 +183,30 @@ def test_gpu_resampled_proxy_feeds_the_raster_call(engine, ref):
     finally:
         engine.free(cid)
         engine.free(did)
+
+
+@pytest.mark.gpu
+def test_gpu_raster_sample_points(engine, ref):
+    """pb_raster_sample_points = the lookup of Project::passInterpolatedTemperatureToHumidityPoints (project.cpp:2826-2848),
+    then the dew point of those stations (tDewFromRelHum) feeds the humidity-from-dew-point chain."""
+    import ctypes as C
+    from oracle import binding
+    lib = binding.load_ref_sample()
+    dem, t, td = temperature_maps()
+    rng = np.random.default_rng(4)
+    n = 5000
+    x = dem.llx + (rng.random(n) * 1.2 - 0.1) * dem.shape[1] * dem.cell_size          # some points fall outside the grid
+    y = dem.lly + (rng.random(n) * 1.2 - 0.1) * dem.shape[0] * dem.cell_size
+    x[:3] = [dem.llx, dem.llx + dem.shape[1] * dem.cell_size, dem.llx - 1e-9]          # the edges
+    y[:3] = [dem.lly, dem.lly + dem.shape[0] * dem.cell_size, dem.lly]
+    want = np.empty(n, dtype=np.float32)
+    win = np.zeros(n, dtype=np.uint8)
+    r = t.as_pb()
+    lib.ref_raster_sample_points(C.byref(r), A.dptr(x), A.dptr(y), n, A.fptr(want), A.u8ptr(win))
+    tid = engine.upload(t)
+    try:
+        got, gin = engine.raster_sample_points(tid, x, y)
+    finally:
+        engine.free(tid)
+    assert np.array_equal(gin, win.astype(bool)) and np.array_equal(got, want)
+    assert 0 < gin.sum() < n and (got[gin] == np.float32(t.flag)).any()
