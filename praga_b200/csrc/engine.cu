@@ -448,8 +448,8 @@ int buildLocalModel(pb_context* ctx, const pb_settings* s, int variable, int nSt
             return fail(ctx, PB_ERR_INVALID, "local detrending needs useLocalDetrending and a detrending variable");
         if (!s->useMultipleDetrending)
             return fail(ctx, PB_ERR_UNSUPPORTED, "local detrending without multiple detrending is outside the hot-path scope (DESIGN.md)");
-        if (s->method != PB_METHOD_IDW)
-            return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the GPU path (shepard: DESIGN.md)");
+        if (s->method != PB_METHOD_IDW && s->method != PB_METHOD_SHEPARD_MODIFIED)
+            return fail(ctx, PB_ERR_UNSUPPORTED, "local detrending runs with idw or shepard_modified on the GPU path (shepard: DESIGN.md)");
     }
     if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending runs through pb_glocal_detrending_fitting / pb_glocal_detrending_raster (macro areas needed)");
     if (!s->hasPointsRange && !range)     // setMultipleDetrendingHeightTemperatureRange returns false (:1508)
@@ -468,6 +468,7 @@ int buildLocalModel(pb_context* ctx, const pb_settings* s, int variable, int nSt
     m.rainfallThreshold = s->rainfallThreshold;
     m.useDoNotRetrend = s->useDoNotRetrend;
     m.useRetrendOnly = s->useRetrendOnly;
+    m.method = s->method;
     int slots = 0;
     m.elevFunction = PB_FIT_PIECEWISE_TWO;
     for (int i = 0; i < s->nProxy; i++) {
@@ -524,7 +525,8 @@ int stageLocalStations(pb_context* ctx, const pb_stations* st, LocalStations& ds
     if (P > 0 && !st->proxyValues) return fail(ctx, PB_ERR_INVALID, "stations.proxyValues required");
     const size_t nAl = (size_t(n) + 3) / 4 * 4;
     const size_t offXY = 0, offVal = offXY + nAl * 8, offW = offVal + nAl * 4, offCode = offW + nAl * 4,
-                 offProxy = offCode + nAl * 4, offAct = offProxy + (size_t(n) * P + 3) / 4 * 16, total = offAct + nAl + 16;
+                 offProxy = offCode + nAl * 4, offAct = offProxy + (size_t(n) * P + 3) / 4 * 16, offXd = (offAct + nAl + 15) / 16 * 16,
+                 offYd = offXd + nAl * 8, total = offYd + nAl * 8 + 16;
     CUDA_TRY(ctx, ctx->hLocal.reserve(total));
     CUDA_TRY(ctx, ctx->dLocalStations.reserve(total));
     unsigned char* h = ctx->hLocal.p;
@@ -534,7 +536,11 @@ int stageLocalStations(pb_context* ctx, const pb_stations* st, LocalStations& ds
     int* code = reinterpret_cast<int*>(h + offCode);
     float* proxy = reinterpret_cast<float*>(h + offProxy);
     unsigned char* act = h + offAct;
+    double* xd = reinterpret_cast<double*>(h + offXd);
+    double* yd = reinterpret_cast<double*>(h + offYd);
     for (int i = 0; i < n; i++) {
+        xd[i] = st->x[i];
+        yd[i] = st->y[i];
         xy[i] = make_float2(float(st->x[i]), float(st->y[i]));
         val[i] = st->value[i];
         w[i] = st->regressionWeight ? st->regressionWeight[i] : kNoData;
@@ -551,6 +557,8 @@ int stageLocalStations(pb_context* ctx, const pb_stations* st, LocalStations& ds
     ds.code = reinterpret_cast<const int*>(d + offCode);
     ds.proxy = reinterpret_cast<const float*>(d + offProxy);
     ds.active = d + offAct;
+    ds.xd = reinterpret_cast<const double*>(d + offXd);
+    ds.yd = reinterpret_cast<const double*>(d + offYd);
     ds.n = n;
     return PB_OK;
 }

@@ -18,6 +18,7 @@ struct LocalModel {
     int clampMode;
     float rainfallThreshold;
     int useDoNotRetrend, useRetrendOnly;
+    int method;                    // PB_METHOD_IDW or PB_METHOD_SHEPARD_MODIFIED (interpolate :2513-2530; the demo's default estimator)
     uint8_t selectedActive[PB_MAX_PROXY];
     int kind[PB_MAX_PROXY];
     float stdDevThreshold[PB_MAX_PROXY];
@@ -39,6 +40,8 @@ struct LocalStations {
     const float* proxy;            // n * nProxy
     const int* code;               // lapseRateCode
     const uint8_t* active;
+    const double* xd;              // point->utm.x / y in f64: the direction term of modifiedShepardIdw (:994-1003)
+    const double* yd;
     int n;
 };
 

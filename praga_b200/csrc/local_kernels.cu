@@ -20,7 +20,8 @@ namespace pb {
 // tile when n <= tileCap, else the group's global scratch) with idx, d, w (regression weight), val, flg filled
 template <int G>
 __device__ int localSelect(const LocalModel& m, const LocalStations& st, const float2* __restrict__ xy, float xf, float yf,
-                           const WorkPtrs& gw, int gcap, unsigned char* tile, int tileCap, int* errFlag, WorkPtrs& w)
+                           const WorkPtrs& gw, int gcap, unsigned char* tile, int tileCap, int* errFlag, WorkPtrs& w,
+                           float& localRadius)
 {
     const int lane = grpLane<G>();
     const int S = st.n;
@@ -129,6 +130,7 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
         }
     }
     grpSync<G>();
+    localRadius = takeAll ? m.shepardRadius : maxDistance;        // setLocalRadius (:1098, :1167)
 
     w = gw;
     if (n <= tileCap) {
@@ -153,7 +155,7 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
 // interpolate (:2502-2560: idw over the detrended subset, retrend with the fit, clamp) for one target, group-uniform
 template <int G, int F>
 __device__ float localFinish(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, const double* pv,
-                             const MdFit<Fit<F>::N>& fit, bool excludeSupplemental)
+                             const MdFit<Fit<F>::N>& fit, bool excludeSupplemental, float xf, float yf, float localRadius)
 {
     constexpr int N = Fit<F>::N;
     const bool useCode = m.useLapseRateCode != 0;
@@ -167,7 +169,53 @@ __device__ float localFinish(const LocalModel& m, const LocalStations& st, const
     // ------------------------------------------------------------------ interpolate (:2502-2560), idw over the subset
     float result;
     if (m.useRetrendOnly) result = 0.f;
-    else {
+    else if (m.method == PB_METHOD_SHEPARD_MODIFIED) {
+        // modifiedShepardIdw (:948-1028) over the whole subset with radius = getLocalRadius() (:2525-2527). The points still in
+        // myPoints (flag bit 0) are the vector; a point computeDistances excludes has distance 0 and weighs nothing. The lanes
+        // share the O(n^2) direction term (one row each); every sum over points is taken in point order. s -> w.X, t -> w.Y.
+        const int lane = grpLane<G>();
+        const float radius = localRadius;
+        for (int k = lane; k < n; k += G) {
+            float d = w.d[k];
+            if (!(w.flg[k] & 1) || (excludeSupplemental && !checkLapseRateCodeDev(st.code[w.idx[k]], useCode, false))) d = 0.f;
+            w.d[k] = d;
+            w.X[k] = (d > 0.f && d <= radius) ? double((radius - d) / (radius * d)) : 0.;
+            w.Y[k] = 0.;
+        }
+        grpSync<G>();
+        double weightSum = 0.0;
+        for (int k = 0; k < n; k++) {
+            const float d = w.d[k];
+            if ((w.flg[k] & 1) && d > 0.f && d <= radius) weightSum += w.X[k];
+        }
+        result = kNoData;
+        if (weightSum != 0.0) {
+            const double invWeightSum = 1.0 / weightSum;
+            // parameter order of the definition (:948-949): inside, "x" is the caller's y and "y" the caller's x
+            const double X = double(yf), Y = double(xf);
+            for (int a = lane; a < n; a += G) {
+                if (!(w.flg[a] & 1) || w.X[a] == 0.0 || w.d[a] <= 0.f) continue;
+                const double xa = st.xd[w.idx[a]], ya = st.yd[w.idx[a]];
+                double tt = 0.;
+                for (int b = 0; b < n; b++) {
+                    if (a == b || !(w.flg[b] & 1) || w.X[b] == 0.0 || w.d[b] <= 0.f) continue;
+                    const double cosine = ((X - xa) * (X - st.xd[w.idx[b]]) + (Y - ya) * (Y - st.yd[w.idx[b]])) /
+                                          double(w.d[a] * w.d[b]);
+                    tt += w.X[b] * (1.0 - cosine);
+                }
+                w.Y[a] = tt * invWeightSum;
+            }
+            grpSync<G>();
+            double wsum = 0.0;
+            for (int k = 0; k < n; k++)
+                if (w.flg[k] & 1) wsum += w.X[k] * w.X[k] * (1.0 + w.Y[k]);
+            const double inv = 1.0 / wsum;
+            double r = 0.0;
+            for (int k = 0; k < n; k++)
+                if (w.flg[k] & 1) r += ((w.X[k] * w.X[k] * (1.0 + w.Y[k])) * inv) * double(w.val[k]);
+            result = float(r);
+        }
+    } else {
         double sum = 0, sumWeights = 0;
         for (int k = 0; k < n; k++) {
             if (!(w.flg[k] & 1)) continue;
@@ -226,10 +274,11 @@ __device__ float localCell(const LocalModel& m, const LocalStations& st, const f
                            bool excludeSupplemental)
 {
     WorkPtrs w;
-    const int n = localSelect<G>(m, st, xy, xf, yf, gw, gcap, tile, tileCap, errFlag, w);
+    float localRadius = 0.f;
+    const int n = localSelect<G>(m, st, xy, xf, yf, gw, gcap, tile, tileCap, errFlag, w, localRadius);
     MdFit<Fit<F>::N> fit;
     multipleDetrendingGroup<G, F>(m, st, w, n, true, fit);
-    return localFinish<G, F>(m, st, w, n, pv, fit, excludeSupplemental);
+    return localFinish<G, F>(m, st, w, n, pv, fit, excludeSupplemental, xf, yf, localRadius);
 }
 
 __device__ __forceinline__ unsigned orderedKeyL(float f)

@@ -127,3 +127,53 @@ def test_local_residuals_identical_to_reference(engine, ref):
         for k in ("meanAbsoluteError", "meanBiasError", "rootMeanSquareError", "nashSutcliffe", "R2"):
             assert abs(stats_r[k] - stats_g[k]) <= TOL, f"{name}: {k} {stats_r[k]} vs {stats_g[k]}"
         print(f"{name}: max |gpu-ref| = {d.max():.2e}, bit-identical: {100 * np.mean(d == 0):.1f} %, MAE = {stats_g['meanAbsoluteError']:.4f}")
+
+
+# ---- the demo's default estimator in local mode: modifiedShepardIdw over the selected stations with radius = getLocalRadius()
+# (interpolation.cpp:2521-2527, 948-1028)
+def shepard_local(st, **kw):
+    s = local_settings(st, **kw)
+    s.method = A.shepard_modified
+    s.pointsBoundingBoxArea = float((np.float32(st.x.max()) - np.float32(st.x.min())) * (np.float32(st.y.max()) - np.float32(st.y.min())))
+    return s
+
+
+def test_local_detrending_modified_shepard(engine, ref):
+    dem = syn.make_dem(90, 100, cell_size=5000.0)
+    urban = syn.make_urban(90, 100, cell_size=5000.0)
+    st = syn.make_stations(dem, 1900, proxies=(dem, urban), seed=21)
+    err, exact = compare(engine, ref, st, shepard_local(st), A.airTemperature, dem, (dem, urban))
+    print(f"max |gpu-ref| = {err:.2e}, bit-identical cells: {100 * exact:.1f} %")
+    # lapse-rate codes: supplemental stations take part in the fit but weigh nothing in the estimate
+    dem2 = syn.make_dem(60, 70, cell_size=500.0, seed=3)
+    urban2 = syn.make_urban(60, 70, cell_size=500.0)
+    st2 = syn.make_stations(dem2, 400, proxies=(dem2, urban2), seed=9, supplemental_frac=0.15)
+    s2 = shepard_local(st2, min_points=25)
+    s2.useLapseRateCode = 1
+    compare(engine, ref, st2, s2, A.dailyAirTemperatureMax, dem2, (dem2, urban2))
+    # fewer stations than minPoints * 1.2: every station, radius = computeShepardInitialRadius (:1098)
+    st3 = syn.make_stations(dem2, 22, proxies=(dem2, urban2), seed=4)
+    compare(engine, ref, st3, shepard_local(st3), A.airTemperature, dem2, (dem2, urban2))
+
+
+def test_local_residuals_modified_shepard(engine, ref):
+    dem = syn.make_dem(120, 140, cell_size=5000.0)
+    urban = syn.make_urban(120, 140, cell_size=5000.0)
+    st = syn.make_stations(dem, 1200, proxies=(dem, urban), seed=11)
+    s = shepard_local(st)
+    res_r, stats_r = ref.compute_residuals(st, s, A.airTemperature, st.value, local=True)
+    res_g, stats_g = engine.compute_residuals(st, s, A.airTemperature, st.value, local=True)
+    assert np.array_equal(res_r == np.float32(-9999), res_g == np.float32(-9999))
+    assert np.abs(res_r.astype(np.float64) - res_g.astype(np.float64)).max() <= TOL
+    assert stats_r["n"] == stats_g["n"] and abs(stats_r["meanAbsoluteError"] - stats_g["meanAbsoluteError"]) <= TOL
+
+
+def test_local_detrending_plain_shepard_is_rejected(engine):
+    import praga_b200 as pb
+    dem = syn.make_dem(20, 20)
+    st = syn.make_stations(dem, 50, proxies=(dem,))
+    s = local_settings(st, use_urban=False)
+    s.method = A.shepard
+    with pytest.raises(pb.PragaB200Error) as e:
+        engine.local_detrending_raster(st, s, A.airTemperature, dem, (dem,))
+    assert e.value.status == A.PB_ERR_UNSUPPORTED
