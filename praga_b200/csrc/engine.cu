@@ -930,6 +930,11 @@ void packIdwStationsAt(const pb_stations* st, const pb_settings* s, bool exclude
 {
     packIdwStations(st, s, excludeSupplemental, h, d, ds, valueOffset);
 }
+int stageShepardStationsFor(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental,
+                            ShepardStations& ss, float& R0)
+{
+    return stageShepardStations(ctx, st, s, excludeSupplemental, ss, R0);
+}
 int buildPreModel(pb_context* ctx, const pb_settings* s, int variable, int nStations, LocalModel& m)
 {
     return buildLocalModel(ctx, s, variable, nStations, nullptr, 0, m, false, nullptr);

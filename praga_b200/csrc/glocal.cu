@@ -27,6 +27,7 @@
 
 #include "context.cuh"
 #include "pre.cuh"
+#include "shepard.cuh"
 
 namespace pb {
 // engine.cu
@@ -35,6 +36,8 @@ size_t idwStationsStagingBytes(int nStations);
 void packIdwStationsAt(const pb_stations* st, const pb_settings* s, bool excludeSupplemental, unsigned char* h, unsigned char* d,
                        DevStations& ds, double& valueOffset);
 int buildPreModel(pb_context* ctx, const pb_settings* s, int variable, int nStations, LocalModel& m);
+int stageShepardStationsFor(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental,
+                            ShepardStations& ss, float& R0);
 int stageAllStations(pb_context* ctx, const pb_stations* st, LocalStations& ds);
 void applyPreFitToSettings(const pb_settings& s, const LocalModel& m, const PreFit& f, pb_settings& o);
 DevGrid devGridOfRaster(const RasterEntry& r);
@@ -445,8 +448,7 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
     memset(&ctx->timing, 0, sizeof(ctx->timing));
     if (!varUsesDetrending(variable) || !s->useGlocalDetrending)       // project.cpp:3264
         return fail(ctx, PB_ERR_INVALID, "glocal detrending needs useGlocalDetrending and a detrending variable");
-    if (s->method != PB_METHOD_IDW)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "only TInterpolationMethod idw runs on the glocal GPU path");
+    const bool shepardMethod = s->method != PB_METHOD_IDW;      // K8 point form per area (one staging copy and sync per area)
     if (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used)
         return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
     if (!deviceOnly && !out->data && !out->rows) return fail(ctx, PB_ERR_INVALID, "output has neither data nor rows");
@@ -488,10 +490,11 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
         if (areas[a].nAreaCells / 2 <= 0) continue;
         rc = buildDevModelGrids(ctx, &subs[a].s, variable, proxyGrids, nProxyGrids, mods[a]);
         if (rc) return rc;
-        packIdwStationsAt(&subs[a].st, &subs[a].s, true, ctx->hStations.p + stOff[a], ctx->dStations.p + stOff[a], dss[a],
-                          mods[a].valueOffset);
+        if (!shepardMethod)
+            packIdwStationsAt(&subs[a].st, &subs[a].s, true, ctx->hStations.p + stOff[a], ctx->dStations.p + stOff[a], dss[a],
+                              mods[a].valueOffset);
     }
-    if (stOff[nAreas] > 0)
+    if (stOff[nAreas] > 0 && !shepardMethod)
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dStations.p, ctx->hStations.p, stOff[nAreas], cudaMemcpyHostToDevice, ctx->stream));
     ctx->timing.h2d_bytes += (int64_t)stOff[nAreas];
 
@@ -531,6 +534,19 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
                                                              reinterpret_cast<float*>(d + offY), reinterpret_cast<double*>(d + offPv),
                                                              d + offState);
         CUDA_TRY(ctx, cudaGetLastError());
+        if (shepardMethod) {
+            // shepardIdw / modifiedShepardIdw over the area's points: neighbourhood radius from the settings' bounding box and
+            // the AREA's point count (computeShepardInitialRadius :800-803 inside shepardSearchNeighbour :812)
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));           // the station staging buffer is reused per area
+            ShepardStations ss{};
+            float R0 = 0.f;
+            rc = stageShepardStationsFor(ctx, &subs[a].st, &subs[a].s, true, ss, R0);
+            if (rc) return rc;
+            CUDA_TRY(ctx, launchShepardPoints(ss, mods[a], R0, s->method == PB_METHOD_SHEPARD_MODIFIED,
+                                              reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
+                                              reinterpret_cast<const double*>(d + offPv), nCells,
+                                              reinterpret_cast<float*>(d + offRes), ctx->stream));
+        } else
         CUDA_TRY(ctx, launchIdwPoints(dss[a], mods[a], reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                       reinterpret_cast<const double*>(d + offPv), nCells, reinterpret_cast<float*>(d + offRes),
                                       ctx->stream));

@@ -17,7 +17,7 @@ def scenario(case):
     dem = syn.make_dem(rows, cols, seed=5)
     urban = syn.make_urban(rows, cols, nodata_frac=0.02 if case == "urban_nodata" else 0.0)
     n = 400 if case != "big" else 1500
-    codes = 0.1 if case == "lapse_codes" else 0.0
+    codes = 0.1 if "lapse_codes" in case else 0.0
     st = syn.make_stations(dem, n, proxies=(dem, urban), seed=17, supplemental_frac=codes)
     s = syn.settings_multiple_detrending()
     s.useGlocalDetrending = 1
@@ -30,6 +30,9 @@ def scenario(case):
         for j, (lo, hi, fg) in enumerate(zip((0, -30, 100, -0.01, -0.015), (1500, 50, 1000, 0.01, -0.002), (0, 1, 1, 1, 1))):
             el.fitMin[j], el.fitMax[j], el.fitFirstGuess[j] = lo, hi, fg
         s.proxy[0] = el
+    if "shepard" in case:       # the demo's default estimator inside every macro area
+        s.method = A.shepard_modified if "modified" in case else A.shepard
+        s.pointsBoundingBoxArea = float((np.float32(st.x.max()) - np.float32(st.x.min())) * (np.float32(st.y.max()) - np.float32(st.y.min())))
     if case == "missing_proxies":
         st.proxy_values[::9, 1] = A.NODATA
         st.proxy_values[5::13, 0] = A.NODATA
@@ -44,7 +47,8 @@ def scenario(case):
     return dem, urban, st, s, areas
 
 
-CASES = ["two_piece", "three_piece", "lapse_codes", "missing_proxies", "three_by_three", "urban_nodata", "empty_area"]
+CASES = ["two_piece", "three_piece", "lapse_codes", "missing_proxies", "three_by_three", "urban_nodata", "empty_area",
+         "modified_shepard", "shepard_lapse_codes"]
 
 
 @pytest.mark.parametrize("case", CASES)
