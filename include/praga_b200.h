@@ -476,6 +476,14 @@ int pb_aggregation_upload(pb_context* ctx, const double* x, const double* y, con
 int pb_aggregation_free(pb_context* ctx, pb_aggregation_id id);
 int pb_spatial_aggregate_meteo_grid(pb_context* ctx, pb_raster_id raster, pb_aggregation_id aggregation, int method, float* value);
 
+/* topographicIndex (agrolib/project/interpolationCmd.cpp:397-482), the orography-index proxy raster of the detrending (the demo
+ * ships one, DATA/GEO/TI_DEM_ER_bacini_500m): for every valid DEM cell and window width, over the disc of round(width / cellSize)
+ * cells around it (its own row and column excluded, :438) the distance-weighted share of lower minus higher minus half the equal
+ * neighbours; the widths add up. Same float accumulation order as the reference: bit-identical. The result (header = the DEM's)
+ * goes to `out` and / or stays resident as *outId, ready to be used as a proxy grid of the raster calls. */
+int pb_topographic_index(pb_context* ctx, pb_raster_id dem, const float* windowWidths, int nWidths, pb_raster_out* out,
+                         pb_raster_id* outId);
+
 /* values of a resident raster at explicit points (nearest cell): Crit3DRasterGrid::getRowCol (agrolib/gis/gis.cpp:485-492),
  * gis::isOutOfGridRowCol (:771-776), value[row][col] — the lookup of Project::passInterpolatedTemperatureToHumidityPoints
  * (agrolib/project/project.cpp:2826-2848): stations with humidity but no temperature take the air temperature of the map just

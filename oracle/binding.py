@@ -136,6 +136,8 @@ def _load(path, prefix):
                    P(A.pb_macro_area), C.c_int, P(A.pb_raster), C.c_int, C.c_int, P(C.c_float)]
     fn = getattr(lib, prefix + "_spatial_aggregate_meteo_grid")
     fn.argtypes = [P(A.pb_raster), P(C.c_double), P(C.c_double), P(C.c_int64), P(C.c_int32), C.c_int, C.c_int, P(C.c_float)]
+    fn = getattr(lib, prefix + "_topographic_index")
+    fn.argtypes = [P(A.pb_raster), P(C.c_float), C.c_int, P(A.pb_raster_out)]
     _libs[path] = lib
     return lib
 
@@ -319,6 +321,16 @@ class Oracle:
         self._f("compute_residuals_local" if local else "compute_residuals")(C.byref(st), C.byref(settings), variable, A.fptr(obs),
                                      None if use is None else A.u8ptr(use), A.fptr(res), C.byref(stats))
         return res, {k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_}
+
+    def topographic_index(self, dem, widths):
+        """topographicIndex (interpolationCmd.cpp:397-482). Returns (ok, grid, min, max)."""
+        w = np.ascontiguousarray(widths, dtype=np.float32)
+        d = dem.as_pb()
+        out = np.empty(dem.shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        rc = self._f("topographic_index")(C.byref(d), A.fptr(w), w.size, C.byref(o))
+        return rc == A.PB_OK, out, o.minimum, o.maximum
 
     def spatial_aggregate_meteo_grid(self, raster, x, y, first, max_nr, method):
         """Crit3DMeteoGrid::spatialAggregateMeteoGrid (meteoGrid.cpp:1135-1190): one value per meteo-grid cell."""

@@ -2711,3 +2711,51 @@ extern "C" int port_spatial_aggregate_meteo_grid(const pb_raster* raster, const 
     }
     return PB_OK;
 }
+
+// topographicIndex, project/interpolationCmd.cpp:397-482: per window width, the weighted share of lower minus higher (minus half
+// the equal) neighbours inside a disc of cellNr cells, the centre's own row and column excluded (:438); widths add up
+extern "C" int port_topographic_index(const pb_raster* dem, const float* windowWidths, int nWidths, pb_raster_out* out)
+{
+    const Grid d = gridOf(*dem);
+    const int rows = d.h.nrRows, cols = d.h.nrCols;
+    if (nWidths == 0) return PB_ERR_INVALID;
+    std::vector<float> flat(size_t(rows) * cols, d.h.flag);
+    const float threshold = float(EPSILON);
+    for (int w = 0; w < nWidths; w++) {
+        const float cellNr = float(round(windowWidths[w] / d.h.cellSize));
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int row = 0; row < rows; row++)
+            for (int col = 0; col < cols; col++) {
+                const float z = d.at(row, col);
+                if (isEqualF(z, d.h.flag)) continue;
+                const int r1 = int(row - cellNr), r2 = int(row + cellNr), c1 = int(col - cellNr), c2 = int(col + cellNr);
+                float higherSum = 0, lowerSum = 0, equalSum = 0, weightSum = 0;
+                for (int wr = r1; wr <= r2; wr++)
+                    for (int wc = c1; wc <= c2; wc++) {
+                        if (unsigned(wr) >= unsigned(rows) || unsigned(wc) >= unsigned(cols)) continue;
+                        const float value = d.at(wr, wc);
+                        if (isEqualF(value, d.h.flag)) continue;
+                        if (wr != row && wc != col) {
+                            const float dx = float(row - wr), dy = float(col - wc);
+                            const float cellDelta = sqrtf(dx * dx + dy * dy);
+                            if (cellDelta <= cellNr) {
+                                const float weight = 1 - (cellDelta / cellNr);
+                                if (value - z > threshold) higherSum += weight;
+                                else if (value - z < -threshold) lowerSum += weight;
+                                else equalSum += weight;
+                                weightSum += weight;
+                            }
+                        }
+                    }
+                if (weightSum > 0) {
+                    float& o = flat[size_t(row) * cols + col];
+                    if (isEqualF(o, d.h.flag)) o = (lowerSum - higherSum - equalSum * 0.5) / weightSum;
+                    else o += (lowerSum - higherSum - equalSum * 0.5) / weightSum;
+                }
+            }
+    }
+    for (int row = 0; row < rows; row++) memcpy(outRow(out, row, cols), &flat[size_t(row) * cols], sizeof(float) * cols);
+    out->nValid = int64_t(rows) * cols;
+    minMaxOf(flat.data(), flat.size(), d.h.flag, &out->minimum, &out->maximum);
+    return PB_OK;
+}

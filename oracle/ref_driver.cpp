@@ -1171,3 +1171,16 @@ extern "C" int ref_raster_sample_points(const pb_raster* raster, const double* x
     }
     return PB_OK;
 }
+
+/* topographicIndex (project/interpolationCmd.cpp:397-482), verbatim reference code (extracted at build time like
+ * interpolationRaster): the orography-index proxy raster (the demo's TI_DEM_ER_bacini_500m is one) */
+bool topographicIndex(const gis::Crit3DRasterGrid& DEM, std::vector <float> windowWidths, gis::Crit3DRasterGrid& outGrid);
+extern "C" int ref_topographic_index(const pb_raster* dem, const float* windowWidths, int nWidths, pb_raster_out* out)
+{
+    gis::Crit3DRasterGrid DEM, outGrid;
+    fillGrid(DEM, *dem);
+    bool ok = topographicIndex(DEM, std::vector<float>(windowWidths, windowWidths + nWidths), outGrid);
+    if (outGrid.isLoaded) copyOut(outGrid, out);
+    out->nValid = int64_t(DEM.header->nrRows) * DEM.header->nrCols;
+    return ok ? PB_OK : PB_ERR_INVALID;
+}

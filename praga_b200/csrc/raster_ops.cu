@@ -382,6 +382,88 @@ sample_points_kernel(DevGrid g, const double* __restrict__ px, const double* __r
     inGrid[i] = in;
 }
 
+__global__ void fill_flag_kernel(float* __restrict__ out, long long n, float v)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = v;
+}
+
+// gis::updateMinMaxRasterGrid (gis.cpp:569-614) as a separate pass over a finished grid
+__global__ void __launch_bounds__(256) raster_minmax_ops_kernel(const float* __restrict__ v, long long n, float flag, unsigned* __restrict__ minmax)
+{
+    float x = flag;
+    bool any = false;
+    float vmin = INFINITY, vmax = -INFINITY;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        x = v[k];
+        if (!isEqualF(x, flag) && !isEqualF(x, kNoData)) { vmin = fminf(vmin, x); vmax = fmaxf(vmax, x); any = true; }
+    }
+    (void)any;
+    for (int o = 16; o; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (vmin != INFINITY) atomicMin(&minmax[0], orderedKeyR(vmin));
+        if (vmax != -INFINITY) atomicMax(&minmax[1], orderedKeyR(vmax));
+    }
+}
+
+// ---- topographicIndex (project/interpolationCmd.cpp:397-482): the orography-index proxy. Per window width: over the disc of
+// cellNr cells around a cell — its own row and column excluded (:438) — the weights 1 - delta / cellNr of the lower, higher and
+// equal (|dz| <= EPSILON) neighbours; index = (lower - higher - equal / 2) / total; the widths add up. One thread per cell walks
+// its window in the reference's row-major order with FLOAT accumulators (same sums, same bits); the weights only depend on
+// the offset and come from a shared-memory table built once per CTA (IEEE sqrtf, float division like the reference).
+__global__ void __launch_bounds__(256)
+topographic_index_kernel(DevGrid dem, int k /* cellNr */, int useTable, float* __restrict__ out)
+{
+    extern __shared__ float wTable[];          // (k + 1) x (k + 1): weight of offset (|dr|, |dc|), < 0 outside the disc
+    const float cellNr = float(k);
+    if (useTable) {
+        for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (k + 1) * (k + 1); i += blockDim.x * blockDim.y) {
+            const float dx = float(i / (k + 1)), dy = float(i % (k + 1));
+            const float cellDelta = sqrtf(dx * dx + dy * dy);
+            wTable[i] = cellDelta <= cellNr ? 1 - (cellDelta / cellNr) : -1.f;
+        }
+        __syncthreads();
+    }
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y * blockDim.y + threadIdx.y;
+    if (row >= dem.nrRows || col >= dem.nrCols) return;
+    const float z = __ldg(dem.data + (size_t)row * dem.nrCols + col);
+    if (isEqualF(z, dem.flag)) return;
+    const float threshold = float(kEpsilon);
+    float higherSum = 0, lowerSum = 0, equalSum = 0, weightSum = 0;
+    const int r1 = max(row - k, 0), r2 = min(row + k, dem.nrRows - 1), c1 = max(col - k, 0), c2 = min(col + k, dem.nrCols - 1);
+    for (int wr = r1; wr <= r2; wr++) {
+        if (wr == row) continue;
+        const float* __restrict__ line = dem.data + (size_t)wr * dem.nrCols;
+        const int adr = abs(wr - row);
+        for (int wc = c1; wc <= c2; wc++) {
+            if (wc == col) continue;
+            float weight;
+            if (useTable) {
+                weight = wTable[adr * (k + 1) + abs(wc - col)];
+                if (weight < 0.f) continue;
+            } else {
+                const float dx = float(row - wr), dy = float(col - wc);
+                const float cellDelta = sqrtf(dx * dx + dy * dy);
+                if (!(cellDelta <= cellNr)) continue;
+                weight = 1 - (cellDelta / cellNr);
+            }
+            const float value = __ldg(line + wc);
+            if (isEqualF(value, dem.flag)) continue;
+            if (value - z > threshold) higherSum += weight;
+            else if (value - z < -threshold) lowerSum += weight;
+            else equalSum += weight;
+            weightSum += weight;
+        }
+    }
+    if (weightSum > 0) {
+        float* o = out + (size_t)row * dem.nrCols + col;
+        const double v = (double(lowerSum - higherSum) - double(equalSum) * 0.5) / double(weightSum);
+        *o = isEqualF(*o, dem.flag) ? float(v) : float(double(*o) + v);
+    }
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -744,6 +826,61 @@ int pb_raster_sample_points(pb_context* ctx, pb_raster_id rasterId, const double
     ctx->timing.h2d_bytes = int64_t(n) * 16;
     ctx->timing.d2h_bytes = int64_t(n) * 5;
     return PB_OK;
+}
+
+int pb_topographic_index(pb_context* ctx, pb_raster_id demId, const float* windowWidths, int nWidths, pb_raster_out* out,
+                         pb_raster_id* outId)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    RasterEntry* src = entryOf(ctx, demId);
+    if (!src || !windowWidths) return fail(ctx, PB_ERR_INVALID, "bad raster id / null widths");
+    if (nWidths <= 0) return fail(ctx, PB_ERR_INVALID, "no window width (interpolationCmd.cpp:403)");
+    cudaSetDevice(ctx->device);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    pb_raster_header h = src->h;
+    const long long n = (long long)h.nrRows * h.nrCols;
+    float* dOut = nullptr;
+    if (outId) {
+        pb_raster_id nid = -1;
+        int rc = newResident(ctx, h, &nid);
+        if (rc) return rc;
+        src = entryOf(ctx, demId);
+        dOut = ctx->rasters[nid].d;
+        *outId = nid;
+    } else {
+        CUDA_TRY(ctx, ctx->dOut.reserve(size_t(n)));
+        ctx->outInitRaster = -1;
+        dOut = ctx->dOut.p;
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    {   // initializeGrid(DEM): every cell = flag
+        const unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148 * 32);
+        fill_flag_kernel<<<nb, 256, 0, ctx->stream>>>(dOut, n, h.flag);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->timing.launches++;
+    }
+    const dim3 block(32, 8), grid((h.nrCols + 31) / 32, (h.nrRows + 7) / 8);
+    for (int w = 0; w < nWidths; w++) {
+        const float cellNr = float(round(windowWidths[w] / h.cellSize));        // :413
+        if (!(cellNr >= 0.f) || cellNr > 1.0e6f) return fail(ctx, PB_ERR_INVALID, "window width out of range");
+        const int k = int(cellNr);
+        const size_t table = size_t(k + 1) * (k + 1) * sizeof(float);
+        const int useTable = table <= 200 * 1024;
+        if (useTable && table > 48 * 1024)
+            CUDA_TRY(ctx, cudaFuncSetAttribute(topographic_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table));
+        topographic_index_kernel<<<grid, block, useTable ? table : 0, ctx->stream>>>(gridOf(*src), k, useTable, dOut);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->timing.launches++;
+    }
+    int rc = resetMinMax(ctx);
+    if (rc) return rc;
+    raster_minmax_ops_kernel<<<148 * 8, 256, 0, ctx->stream>>>(dOut, n, h.flag, ctx->dMinMax);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.launches++;
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (out) out->nValid = n;
+    rc = finishGrid(ctx, dOut, h.nrRows, h.nrCols, true, out);
+    return rc == PB_ERR_NO_VALID_CELL ? PB_OK : rc;      // topographicIndex ignores updateMinMaxRasterGrid's result
 }
 
 }  // extern "C"

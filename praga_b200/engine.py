@@ -102,6 +102,7 @@ def load_library():
                                                          P(A.pb_raster_out)]
     lib.pb_macro_areas_upload.argtypes = [C.c_void_p, P(A.pb_macro_area), C.c_int, P(C.c_int32)]
     lib.pb_macro_areas_free.argtypes = [C.c_void_p, C.c_int32]
+    lib.pb_topographic_index.argtypes = [C.c_void_p, C.c_int32, P(C.c_float), C.c_int, P(A.pb_raster_out), P(C.c_int32)]
     lib.pb_raster_sample_points.argtypes = [C.c_void_p, C.c_int32, P(C.c_double), P(C.c_double), C.c_int, P(C.c_float), P(C.c_uint8)]
     lib.pb_aggregation_upload.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_int64), P(C.c_int32), C.c_int, P(C.c_int32)]
     lib.pb_aggregation_free.argtypes = [C.c_void_p, C.c_int32]
@@ -336,6 +337,11 @@ class Engine:
         """gis::resampleGrid (gis.cpp:1722-1811)."""
         return self._grid_call(self.lib.pb_resample_grid, (new_header.nrRows, new_header.nrCols), keep, want_host, src_id,
                                C.byref(new_header), method, threshold)
+
+    def topographic_index(self, dem_id, shape, widths, keep=False, want_host=True):
+        """topographicIndex (interpolationCmd.cpp:397-482): the orography-index proxy of a resident DEM."""
+        w = np.ascontiguousarray(widths, dtype=np.float32)
+        return self._grid_call(self.lib.pb_topographic_index, shape, keep, want_host, dem_id, A.fptr(w), w.size)
 
     # ---- ordinary kriging (kriging.h:4-15) ----
     def kriging_setup(self, pos, val, mode, rng, nugget, sill, slope=0.0, fp64_direct=False):

@@ -210,3 +210,38 @@ def test_gpu_raster_sample_points(engine, ref):
         engine.free(tid)
     assert np.array_equal(gin, win.astype(bool)) and np.array_equal(got, want)
     assert 0 < gin.sum() < n and (got[gin] == np.float32(t.flag)).any()
+
+
+# ---- topographicIndex (interpolationCmd.cpp:397-482): the orography-index proxy raster
+TI_CASES = [("one_width", [1500.0]), ("two_widths", [1500.0, 3100.0]), ("narrow", [520.0]), ("one_cell", [260.0]),
+            ("zero_cells", [100.0])]
+
+
+@pytest.mark.parametrize("name,widths", TI_CASES)
+def test_port_topographic_index(ref, port, name, widths):  # noqa: F811
+    dem = syn.make_dem(70, 90, seed=6, cell_size=250.0, nodata_frac=0.08)
+    a, b = ref.topographic_index(dem, widths), port.topographic_index(dem, widths)
+    assert a[0] and b[0] and np.array_equal(a[1], b[1]) and a[2:] == b[2:]
+    valid = a[1] != np.float32(dem.flag)
+    if name in ("zero_cells", "one_cell"):   # 0 cells, or 1 cell (only the diagonal neighbours, sqrt(2) > 1 away): nothing is written
+        assert not valid.any()
+    else:
+        assert valid.any() and np.abs(a[1][valid]).max() <= len(widths) + 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,widths", TI_CASES + [("wide", [9000.0])])
+def test_gpu_topographic_index(engine, ref, name, widths):
+    dem = syn.make_dem(140, 180, seed=6, cell_size=250.0, nodata_frac=0.08)
+    ok, want, mn, mx = ref.topographic_index(dem, widths)
+    did = engine.upload(dem)
+    try:
+        okg, got, mng, mxg, rid = engine.topographic_index(did, dem.shape, widths, keep=True)
+        assert np.array_equal(got, want), np.abs(got - want).max()
+        if (want != np.float32(dem.flag)).any():
+            assert (mng, mxg) == (mn, mx)
+        back = engine.download(rid, dem.shape)          # the resident copy can serve as a proxy grid
+        assert np.array_equal(back[1] if isinstance(back, tuple) else back, want)
+        engine.free(rid)
+    finally:
+        engine.free(did)
