@@ -81,3 +81,22 @@ for name, m in (("average", A.PB_AGGR_AVERAGE), ("median", A.PB_AGGR_MEDIAN), ("
          {"meteo_grid_cells": ncx * ncy, "samples_per_cell": k * k, "d2h_bytes": 4 * ncx * ncy,
           "note": "24 B per sample (x, y doubles + raster value + scratch); one warp per meteo-grid cell, lane 0 reduces in list "
                   "order (float arithmetic of the reference): latency bound, not an HBM-streaming kernel"})
+
+# topographicIndex: 2000 x 2000 cells @100 m, 5 km window (cellNr = 50: 10 201 offsets per cell, ~7 800 inside the disc)
+import time  # noqa: E402
+ms = timed(lambda: eng.topographic_index(s_id, small.shape, [5000.0], want_host=False), reps=2)
+visits = 4.0e6 * 101 * 101
+line("topographic_index_kernel 2000x2000, 5 km window", ms, 8, 2000 * 2000,
+     {"window_visits_per_s": visits / (ms * 1e-3),
+      "note": "stencil: 10 201 window offsets per cell from L1/L2, float accumulators in the reference's order; compute bound, not HBM"})
+try:
+    from oracle import binding  # noqa: E402
+    orc = binding.Oracle("reference" if binding.have_ref() else "port")
+    sub = A.Raster(dem.data[4000:4300, 4000:4300].copy(), dem.llx, dem.lly, dem.cell_size, dem.flag)
+    t0 = time.perf_counter()
+    orc.topographic_index(sub, [5000.0])
+    dt = time.perf_counter() - t0
+    print(json.dumps({"kernel": "topographicIndex reference (single thread, as shipped)", "cells": 300 * 300, "seconds": dt,
+                      "cells_per_s": 300 * 300 / dt, "note": "300x300 sample, same 5 km window (border cells see smaller windows)"}), flush=True)
+except Exception as e:  # noqa: BLE001
+    print(json.dumps({"kernel": "topographicIndex reference", "error": str(e)[:100]}))
