@@ -24,9 +24,9 @@
 
 namespace pb {
 
-// ---- group helpers (G = 16: two problems per warp, G = 32: one) ----
-template <int G> __device__ __forceinline__ unsigned grpShift() { return G == 32 ? 0u : (threadIdx.x & 16u); }
-template <int G> __device__ __forceinline__ unsigned grpMask() { return G == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16u)); }
+// ---- group helpers (G lanes per problem, a power of two: 32 = one problem per warp, 16 = two, 4 = eight) ----
+template <int G> __device__ __forceinline__ unsigned grpShift() { return G == 32 ? 0u : ((threadIdx.x & 31u) & ~(unsigned(G) - 1u)); }
+template <int G> __device__ __forceinline__ unsigned grpMask() { return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << grpShift<G>()); }
 template <int G> __device__ __forceinline__ int grpLane() { return threadIdx.x & (G - 1); }
 template <int G> __device__ __forceinline__ unsigned grpBallot(bool p) { return __ballot_sync(grpMask<G>(), p) >> grpShift<G>(); }
 template <int G> __device__ __forceinline__ double grpBcast(double v, int src) { return __shfl_sync(grpMask<G>(), v, src, G); }
@@ -502,6 +502,9 @@ __device__ __forceinline__ void plainScores(double* par, const double* X, const 
     RMSE = sqrt(rss / double(nData));
 }
 
+constexpr int kFitResultStride = PB_MAX_FIT_PARAMS + 3;       // parameters, R2, RMSE, flags of one first guess
+constexpr int kFitResultDoubles = PB_MAX_FIRST_GUESS * kFitResultStride;
+
 // bestFittingMarquardt_nDimension (:1360-1427): all first guesses of the group in parallel, reference pick order.
 // firstGuess: nGuess x PB_MAX_FIT_PARAMS doubles. par (out, group-uniform) = chosen parameters. Returns bestR2.
 // unweighted: the form without weights (:1433-1529, glocal detrending) — W must hold 1.0 everywhere (the descent :2125-2283
@@ -512,7 +515,7 @@ template <int G, int F>
 __device__ double bestFitElevation(const double* __restrict__ pmin, const double* __restrict__ pmax,
                                    const double* __restrict__ delta, const double* __restrict__ firstGuess, int nGuess,
                                    double* par, int maxIter, double eps, double deltaR2, const double* X, const double* Y,
-                                   const double* W, int nData, bool unweighted = false)
+                                   const double* W, int nData, bool unweighted = false, double* results = nullptr)
 {
     constexpr int N = Fit<F>::N;
     const int lane = grpLane<G>();
@@ -526,6 +529,59 @@ __device__ double bestFitElevation(const double* __restrict__ pmin, const double
         maxZ = X[0];
         for (int i = 0; i < nData; i++) if (X[i] > maxZ) maxZ = X[i];
     }
+    if (results && nGuess > G) {
+        // More first guesses than lanes (small groups: more problems per warp). Every lane owns the guesses lane, lane + G, ...
+        // and walks them as ONE loop of Levenberg-Marquardt iterations: a lane whose descent ends scores it, stores it and
+        // starts its next guess while the others keep iterating, so the lanes' totals (sums of 2-60 iterations each) even
+        // out instead of every round waiting for its longest descent. Results go to `results` (kFitResultStride doubles
+        // per guess); the pick below reads them in guess order: same rule, same winner.
+        double dl[N], rdl[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) { dl[j] = delta[j]; rdl[j] = 1.0 / dl[j]; }
+        LmState<F> st;
+        int k = lane;
+        bool active = k < nGuess;
+        if (active) lmInit<F>(st, firstGuess + k * PB_MAX_FIT_PARAMS, X, Y, W, nData);
+        while (grpBallot<G>(active)) {
+            if (active && lmIter<F>(st, pmin, pmax, dl, rdl, maxIter, eps, X, Y, W, nData)) {
+                double q[N], R2 = 0, RMSE = 0;
+                bool inRange = true, secondBelow = true;
+#pragma unroll
+                for (int j = 0; j < N; j++) q[j] = st.p[j];
+                if (unweighted) {
+#pragma unroll
+                    for (int j = 0; j < N; j++) inRange = inRange && !(q[j] < pmin[j] || q[j] > pmax[j]);
+                    plainScores<F>(q, X, Y, nData, R2, RMSE);
+                    if (N > 4) secondBelow = (q[0] + q[2]) < maxZ;
+                } else {
+                    weightedScores<F>(q, X, Y, W, nData, R2, RMSE);
+                }
+                double* r = results + (size_t)k * kFitResultStride;
+#pragma unroll
+                for (int j = 0; j < N; j++) r[j] = q[j];
+                r[PB_MAX_FIT_PARAMS] = R2;
+                r[PB_MAX_FIT_PARAMS + 1] = RMSE;
+                r[PB_MAX_FIT_PARAMS + 2] = double((inRange ? 1 : 0) | (secondBelow ? 2 : 0));
+                k += G;
+                active = k < nGuess;
+                if (active) lmInit<F>(st, firstGuess + k * PB_MAX_FIT_PARAMS, X, Y, W, nData);
+            }
+        }
+        grpSync<G>();
+        for (int kk = 0; kk < nGuess; kk++) {
+            const double* r = results + (size_t)kk * kFitResultStride;
+            const int flags = int(r[PB_MAX_FIT_PARAMS + 2]);
+            if (!(flags & 1)) continue;
+            const double r2 = r[PB_MAX_FIT_PARAMS], rmse = r[PB_MAX_FIT_PARAMS + 1];
+            if (isEqualD(bestRMSE, -9999) || rmse < bestRMSE) { bestRMSE = rmse; rmseIndex = kk; }
+            if (isEqualD(bestR2, -9999) || (r2 > (bestR2 + deltaR2) && (flags & 2))) {
+#pragma unroll
+                for (int j = 0; j < N; j++) best[j] = r[j];
+                bestR2 = r2;
+            }
+        }
+        grpSync<G>();
+    } else
     for (int c0 = 0; c0 < nGuess; c0 += G) {
         const int k = c0 + lane;
         double q[N], R2 = 0, RMSE = 0;

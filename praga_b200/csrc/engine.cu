@@ -599,7 +599,7 @@ int launchLocal(pb_context* ctx, const pb_stations* st, const pb_settings* s, in
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dLocalModel.p, &m, sizeof(m), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // `m` lives on this stack frame
     ctx->timing.h2d_bytes += (int64_t)sizeof(m);
-    const int groupLanes = m.nFirstGuess <= 16 ? 16 : 32;
+    const int groupLanes = localGroupLanes(m.nFirstGuess);
     LocalScratch scr{};
     scr.cap = std::max(std::min(st->n, 2048), 1);
     scr.perGroup = localScratchBytesPerGroup(scr.cap);
@@ -1678,7 +1678,7 @@ extern "C" int pb_local_detrending_points(pb_context* ctx, const pb_stations* st
     if (P > 0) CUDA_TRY(ctx, cudaMemcpyAsync(d + offPv, proxyValues, size_t(m) * P * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // `lm` and `none` live on this stack frame
     ctx->timing.h2d_bytes += (int64_t)(sizeof(lm) + size_t(m) * (8 + 8 * P));
-    const int groupLanes = lm.nFirstGuess <= 16 ? 16 : 32;
+    const int groupLanes = localGroupLanes(lm.nFirstGuess);
     LocalScratch scr{};
     scr.cap = std::max(std::min(st->n, 2048), 1);
     scr.perGroup = localScratchBytesPerGroup(scr.cap);

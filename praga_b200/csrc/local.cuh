@@ -64,6 +64,7 @@ struct LocalPointTargets {
 
 size_t localScratchBytesPerGroup(int cap);
 int localGroupsTotal(int groupLanes);
+int localGroupLanes(int nFirstGuess);      // lanes per cell chosen for a model (PB_LOCAL_G overrides)
 cudaError_t launchLocalDetrendingRaster(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem,
                                         const int* validIdx, int nTargets, const LocalScratch& scratch, int groupLanes,
                                         int elevFunction, float* out, unsigned* minmax, cudaStream_t s,

@@ -271,13 +271,13 @@ __device__ float localFinish(const LocalModel& m, const LocalStations& st, const
 template <int G, int F>
 __device__ float localCell(const LocalModel& m, const LocalStations& st, const float2* __restrict__ xy, float xf, float yf,
                            const double* pv, const WorkPtrs& gw, int gcap, unsigned char* tile, int tileCap, int* errFlag,
-                           bool excludeSupplemental)
+                           bool excludeSupplemental, double* fitResults)
 {
     WorkPtrs w;
     float localRadius = 0.f;
     const int n = localSelect<G>(m, st, xy, xf, yf, gw, gcap, tile, tileCap, errFlag, w, localRadius);
     MdFit<Fit<F>::N> fit;
-    multipleDetrendingGroup<G, F>(m, st, w, n, true, fit);
+    multipleDetrendingGroup<G, F>(m, st, w, n, true, fit, false, fitResults);
     return localFinish<G, F>(m, st, w, n, pv, fit, excludeSupplemental, xf, yf, localRadius);
 }
 
@@ -298,7 +298,8 @@ local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, Dev
     const LocalModel& m = *mp;
     const int grp = threadIdx.x / G;
     const int lane = grpLane<G>();
-    const size_t tileBytes = workBytes(kCap);
+    constexpr int tileCap = localTileCap(G);
+    const size_t tileBytes = workBytes(tileCap);
     unsigned char* tile = smem + grp * tileBytes;
     float2* sxy = reinterpret_cast<float2*>(smem + groupsPerCta * tileBytes);
     if (xyInSmem) {
@@ -309,13 +310,15 @@ local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, Dev
     const long long groupsTotal = (long long)gridDim.x * groupsPerCta;
     const long long gid = (long long)blockIdx.x * groupsPerCta + grp;
     const WorkPtrs gw = carve(scr.base + gid * scr.perGroup, scr.cap);
+    // per-guess results of the elevation fit when a group has fewer lanes than first guesses (behind the group's work arrays)
+    double* fitResults = reinterpret_cast<double*>(scr.base + gid * scr.perGroup + workBytes(scr.cap));
 
     float vmin = INFINITY, vmax = -INFINITY;
     for (long long t = gid; t < nTargets; t += groupsTotal) {
         if (pt.x) {       // point form: the target's own coordinates and proxy values, result t
             double pv[PB_MAX_PROXY];
             for (int i = 0; i < m.nProxy; i++) pv[i] = pt.pv[t * m.nProxy + i];
-            const float o = localCell<G, F>(m, st, xy, pt.x[t], pt.y[t], pv, gw, scr.cap, tile, kCap, scr.error, pt.excludeSupplemental != 0);
+            const float o = localCell<G, F>(m, st, xy, pt.x[t], pt.y[t], pv, gw, scr.cap, tile, tileCap, scr.error, pt.excludeSupplemental != 0, fitResults);
             if (lane == 0) out[t] = o;
             continue;
         }
@@ -334,7 +337,7 @@ local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, Dev
                 if (v != g.flag) pv[i] = double(v);
             }
         }
-        const float o = localCell<G, F>(m, st, xy, xf, yf, pv, gw, scr.cap, tile, kCap, scr.error, true);
+        const float o = localCell<G, F>(m, st, xy, xf, yf, pv, gw, scr.cap, tile, tileCap, scr.error, true, fitResults);
         if (lane == 0) {
             out[cell] = o;
             if (!isEqualF(o, dem.flag) && !isEqualF(o, kNoData)) {
@@ -349,7 +352,7 @@ local_detrending_kernel(const LocalModel* __restrict__ mp, LocalStations st, Dev
     }
 }
 
-size_t localScratchBytesPerGroup(int cap) { return workBytes(cap); }
+size_t localScratchBytesPerGroup(int cap) { return workBytes(cap) + sizeof(double) * kFitResultDoubles; }
 
 // persistent grid: every SM filled to the occupancy the fit kernel's registers allow (at most 2 CTAs per SM)
 static int localCtas()
@@ -360,6 +363,16 @@ static int localCtas()
     return sms * 4;
 }
 int localGroupsTotal(int groupLanes) { return localCtas() * (kLocalThreads / groupLanes); }
+// Lanes per cell. The descents of a cell end after 2-60 iterations: with one lane per first guess the group waits for its
+// longest descent (12 of 32 lanes busy on average); with fewer lanes each lane walks several guesses back to back and the
+// totals even out, the group-uniform parts (validity checks, the other proxies' fit, the estimate) are replicated on fewer
+// lanes, and a warp holds more cells. Measured on B200 at config-3 density (profiles/r01_local_groups.json).
+int localGroupLanes(int nFirstGuess)
+{
+    static const int forced = getenv("PB_LOCAL_G") ? atoi(getenv("PB_LOCAL_G")) : 0;
+    if (forced == 4 || forced == 8 || forced == 16) return forced;
+    return nFirstGuess <= 16 ? 4 : 8;       // 4 lanes x 4 guesses (two-piece), 8 lanes x 4 guesses (three-piece)
+}
 
 template <int G, int F, int MINB>
 static cudaError_t launchT(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem, const int* validIdx,
@@ -367,9 +380,9 @@ static cudaError_t launchT(const LocalModel* dModel, const LocalStations& st, co
                            const LocalPointTargets& pt)
 {
     constexpr int groupsPerCta = kLocalThreads / G;
-    size_t smem = groupsPerCta * workBytes(kCap);
+    size_t smem = groupsPerCta * workBytes(localTileCap(G));
     int xyInSmem = 0;
-    if (smem + size_t(st.n) * sizeof(float2) <= 100 * 1024) {
+    if (smem + size_t(st.n) * sizeof(float2) <= (G >= 16 ? 100 : 200) * 1024) {
         xyInSmem = 1;
         smem += size_t(st.n) * sizeof(float2);
     }
@@ -397,23 +410,25 @@ cudaError_t launchLocalDetrendingRaster(const LocalModel* dModel, const LocalSta
     const LocalPointTargets pt = points ? *points : LocalPointTargets{nullptr, nullptr, nullptr, 1};
     // 1 resident CTA per SM (255 registers, no spills in the Levenberg-Marquardt loop) measured faster than 2 CTAs at 128
     // registers (155 vs 164 ms on 925k cells / 5000 stations): the loop is latency bound and spills sit on its critical path
-    static const int minb = getenv("PB_LOCAL_MINB") ? atoi(getenv("PB_LOCAL_MINB")) : 1;
-#define PB_LOCAL_CASE(G_, F_)                                                                               \
-    return minb == 2 ? launchT<G_, F_, 2>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)   \
-         : minb == 3 ? launchT<G_, F_, 3>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)   \
-         : minb == 4 ? launchT<G_, F_, 4>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)   \
-                     : launchT<G_, F_, 1>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)
-    if (groupLanes == 16) {
+#define PB_LOCAL_CASE(G_, F_) return launchT<G_, F_, 1>(dModel, st, dem, validIdx, nTargets, scratch, out, minmax, s, pt)
+    if (groupLanes == 4) {
         switch (elevFunction) {
-        case PB_FIT_PIECEWISE_THREE: PB_LOCAL_CASE(16, PB_FIT_PIECEWISE_THREE);
-        case PB_FIT_PIECEWISE_THREE_FREE: PB_LOCAL_CASE(16, PB_FIT_PIECEWISE_THREE_FREE);
-        default: PB_LOCAL_CASE(16, PB_FIT_PIECEWISE_TWO);
+        case PB_FIT_PIECEWISE_THREE: PB_LOCAL_CASE(4, PB_FIT_PIECEWISE_THREE);
+        case PB_FIT_PIECEWISE_THREE_FREE: PB_LOCAL_CASE(4, PB_FIT_PIECEWISE_THREE_FREE);
+        default: PB_LOCAL_CASE(4, PB_FIT_PIECEWISE_TWO);
         }
     }
-    switch (elevFunction) {
-    case PB_FIT_PIECEWISE_THREE: PB_LOCAL_CASE(32, PB_FIT_PIECEWISE_THREE);
-    case PB_FIT_PIECEWISE_THREE_FREE: PB_LOCAL_CASE(32, PB_FIT_PIECEWISE_THREE_FREE);
-    default: PB_LOCAL_CASE(32, PB_FIT_PIECEWISE_TWO);
+    if (groupLanes == 8) {
+        switch (elevFunction) {
+        case PB_FIT_PIECEWISE_THREE: PB_LOCAL_CASE(8, PB_FIT_PIECEWISE_THREE);
+        case PB_FIT_PIECEWISE_THREE_FREE: PB_LOCAL_CASE(8, PB_FIT_PIECEWISE_THREE_FREE);
+        default: PB_LOCAL_CASE(8, PB_FIT_PIECEWISE_TWO);
+        }
+    }
+    switch (elevFunction) {     // 16 lanes: one lane per first guess of the two-piece function (the form measured before)
+    case PB_FIT_PIECEWISE_THREE: PB_LOCAL_CASE(16, PB_FIT_PIECEWISE_THREE);
+    case PB_FIT_PIECEWISE_THREE_FREE: PB_LOCAL_CASE(16, PB_FIT_PIECEWISE_THREE_FREE);
+    default: PB_LOCAL_CASE(16, PB_FIT_PIECEWISE_TWO);
     }
 #undef PB_LOCAL_CASE
 }

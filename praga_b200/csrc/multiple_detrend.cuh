@@ -11,6 +11,9 @@ namespace pb {
 
 constexpr int kLocalThreads = 256;
 constexpr int kCap = 64;      // stations per group held in shared memory; larger selections work from global scratch
+// smaller groups put more cells in flight per CTA: their shared-memory tiles shrink so that all of them (and the stations'
+// coordinates) still fit; config-3 density selects 24-35 stations per cell
+__host__ __device__ constexpr int localTileCap(int G) { return G >= 16 ? kCap : (G == 8 ? 56 : 40); }
 
 struct WorkPtrs {
     double *X, *Y, *W;        // LM data (compact)
@@ -152,7 +155,7 @@ __device__ void mdFinish(const LocalModel& m, const LocalStations& st, const Wor
 // unweightedElevation: the elevation fit of glocalDetrendingFitting (:2273: isWeighted = false).
 template <int G, int F>
 __device__ void multipleDetrendingGroup(const LocalModel& m, const LocalStations& st, const WorkPtrs& w, int n, bool isLocal,
-                                        MdFit<Fit<F>::N>& fit, bool unweightedElevation = false)
+                                        MdFit<Fit<F>::N>& fit, bool unweightedElevation = false, double* fitResults = nullptr)
 {
     constexpr int N = Fit<F>::N;
     const int ePos = m.elevationPos;
@@ -170,7 +173,7 @@ __device__ void multipleDetrendingGroup(const LocalModel& m, const LocalStations
                 grpSync<G>();
             }
             R2 = bestFitElevation<G, F>(m.elevMin, m.elevMax, m.elevDelta, &m.firstGuess[0][0], m.nFirstGuess, elevPar, 1000,
-                                        0.002, 0.005, w.X, w.Y, w.W, nE, unweightedElevation);
+                                        0.002, 0.005, w.X, w.Y, w.W, nE, unweightedElevation, fitResults);
             fitRan = true;
         }
     }
