@@ -231,10 +231,11 @@ def _band_raster(dem, r0, r1):
 
 class LocalDetrendingWorkload:
     """c3: K2. unit = a band of rows of the 10k x 10k raster; ranks take different bands (row-band sharding)."""
-    kernel = "pb::local_detrending_kernel<16,0,1>"
+    kernel = "pb::local_detrending_kernel<4,0,1>"
     # FP64 flop per cell executed by the LM fits + estimate at this station density, counted with ncu
-    # (thread-level DADD + DMUL + 2 DFMA of profiles/r01_local_k2c.ncu-rep / 925 224 cells; data dependent)
-    FP64_FLOP_PER_CELL = 4.22e5
+    # (thread-level DADD + DMUL + 2 DFMA of profiles/r01_local_k2e_flops.csv / 453 823 cells, 4 lanes per cell; data dependent;
+    # the 16-lane form executed 4.22e5: more lanes replicate the group-uniform parts)
+    FP64_FLOP_PER_CELL = 3.64e5
 
     def __init__(self, eng, w, rank, world, n_total):
         self.eng, self.w, self.var = eng, w, A.airTemperature
