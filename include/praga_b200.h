@@ -179,6 +179,13 @@ int pb_raster_free(pb_context* ctx, pb_raster_id id);
 /* number of cells with !isEqual(value, flag) (interpolationCmd.cpp:377): the metric's "gridded cells" */
 int pb_raster_valid_cells(pb_context* ctx, pb_raster_id id, int64_t* nValid);
 
+/* Optional: page-lock a long-lived CONTIGUOUS host buffer of the caller (a DEM or proxy grid given as pb_raster.data, an
+ * output grid given as pb_raster_out.data). The host-raster calls below then copy straight from / into it (no staging copy by
+ * the host cores): the drop-in call is otherwise bound by that memcpy, not by PCIe. The caller must unregister the buffer
+ * before freeing it. Buffers of the reference's per-row layout (float**) always go through the staging ring. */
+int pb_host_register(pb_context* ctx, void* ptr, size_t bytes);
+int pb_host_unregister(pb_context* ctx, void* ptr);
+
 /* --- interpolationRaster (agrolib/project/interpolationCmd.h:73-75, .cpp:353-394) ---------------
  * stations are the already pre-interpolated (detrended) points, settings carry the fitted model.
  * `variable` is the reference meteoVariable value. rowBegin/rowEnd select a row band (multi-GPU

@@ -1178,10 +1178,32 @@ static int allocRasterEntry(pb_context* ctx, const pb_raster* r, pb_raster_id* i
 // the copy bandwidth, is what limits the host side of the band pipeline.
 struct RowsJob { const pb_raster* r; float* dst; };
 
-static int uploadRows(pb_context* ctx, const RowsJob* jobs, int nJobs, int r0, int r1, cudaStream_t stream)
+// page-locked host memory (cudaHostAlloc'd, or registered through pb_host_register) can be the source / target of an
+// asynchronous copy itself: no gather into the staging ring, no host memcpy at all
+static bool isPinnedHost(const void* p)
 {
-    if (nJobs <= 0) return PB_OK;
-    const int cols = jobs[0].r->h.nrCols;
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int uploadRows(pb_context* ctx, const RowsJob* jobsIn, int nJobsIn, int r0, int r1, cudaStream_t stream)
+{
+    if (nJobsIn <= 0) return PB_OK;
+    const int cols = jobsIn[0].r->h.nrCols;
+    // contiguous page-locked rasters go up straight from the caller's memory
+    RowsJob jobs[PB_MAX_PROXY + 1];
+    int nJobs = 0;
+    for (int j = 0; j < nJobsIn; j++) {
+        const pb_raster* r = jobsIn[j].r;
+        if (r->data && r1 > r0 && isPinnedHost(r->data)) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(jobsIn[j].dst + size_t(r0) * cols, r->data + size_t(r0) * cols,
+                                          sizeof(float) * size_t(r1 - r0) * cols, cudaMemcpyHostToDevice, stream));
+            ctx->timing.h2d_bytes += (int64_t)(sizeof(float) * size_t(r1 - r0) * cols);
+        } else jobs[nJobs++] = jobsIn[j];
+    }
+    if (nJobs == 0) return PB_OK;
     const int chunkRows = std::max(1, (int)(kStageSlotBytes / (sizeof(float) * cols)));
     for (int a = r0; a < r1; a += chunkRows) {
         const int b = std::min(r1, a + chunkRows);
@@ -1292,6 +1314,7 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
     struct Chunk { int r0, r1, slot; float* stage; };
     std::vector<Chunk> inflight;
     size_t head = 0;
+    const bool outPinned = out->data && isPinnedHost(out->data);     // the band comes down straight into the caller's grid
     auto scatter = [&](const Chunk& c) -> cudaError_t {
         cudaError_t e = ctx->ringDn.wait(c.slot);
         if (e != cudaSuccess) return e;
@@ -1341,6 +1364,12 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
         ctx->timing.launches += 2;
         cudaEventRecord(ctx->evBand[kMaxBands + b], sK);
         cudaStreamWaitEvent(sDn, ctx->evBand[kMaxBands + b], 0);
+        if (outPinned) {
+            ce = cudaMemcpyAsync(out->data + size_t(r0) * cols, ctx->dOut.p + size_t(r0) * cols, size_t(r1 - r0) * cols * sizeof(float),
+                                 cudaMemcpyDeviceToHost, sDn);
+            if (ce != cudaSuccess) return failCtx(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(ce));
+            return PB_OK;
+        }
         for (int a = r0; a < r1; a += chunkRows) {
             if (mayScatter && inflight.size() - head >= size_t(PinnedRing::kSlots - 1))
                 if (scatter(inflight[head++]) != cudaSuccess) return failCtx(ctx, PB_ERR_CUDA, "D2H failed");
@@ -1764,6 +1793,24 @@ extern "C" int pb_compute_residuals_local(pb_context* ctx, const pb_stations* st
 }
 
 /* live pipe ceilings for the K1 roofline (FP32 FMA TFLOP/s, G MUFU.RSQ/s) */
+extern "C" int pb_host_register(pb_context* ctx, void* ptr, size_t bytes)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!ptr || bytes == 0) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return PB_OK;
+}
+
+extern "C" int pb_host_unregister(pb_context* ctx, void* ptr)
+{
+    if (!ctx) return PB_ERR_INVALID;
+    if (!ptr) return fail(ctx, PB_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(ctx, cudaHostUnregister(ptr));
+    return PB_OK;
+}
+
 extern "C" int pb_measure_pipe_peaks(pb_context* ctx, float* fp32Tflops, float* mufuGops)
 {
     if (!ctx || !fp32Tflops || !mufuGops) return PB_ERR_INVALID;

@@ -102,6 +102,8 @@ def load_library():
                                                          P(A.pb_raster_out)]
     lib.pb_macro_areas_upload.argtypes = [C.c_void_p, P(A.pb_macro_area), C.c_int, P(C.c_int32)]
     lib.pb_macro_areas_free.argtypes = [C.c_void_p, C.c_int32]
+    lib.pb_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.pb_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
     lib.pb_topographic_index.argtypes = [C.c_void_p, C.c_int32, P(C.c_float), C.c_int, P(A.pb_raster_out), P(C.c_int32)]
     lib.pb_raster_sample_points.argtypes = [C.c_void_p, C.c_int32, P(C.c_double), P(C.c_double), C.c_int, P(C.c_float), P(C.c_uint8)]
     lib.pb_aggregation_upload.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_int64), P(C.c_int32), C.c_int, P(C.c_int32)]
@@ -204,6 +206,13 @@ class Engine:
         return a.value
 
     # ---- raster cache ----
+    def host_register(self, array):
+        """Page-lock a long-lived contiguous numpy buffer (DEM / proxy / output grid of the host-raster calls)."""
+        self._check(self.lib.pb_host_register(self.h, array.ctypes.data, array.nbytes))
+
+    def host_unregister(self, array):
+        self._check(self.lib.pb_host_unregister(self.h, array.ctypes.data))
+
     def upload(self, raster):
         rid = C.c_int32(-1)
         r = raster.as_pb()

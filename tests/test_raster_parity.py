@@ -266,3 +266,30 @@ def test_topographic_distance_raster_and_points(engine, ref):
     sp.useTD = 1
     sp.topoDist_Kh = 12
     run_both(engine, ref, stp, sp, A.precipitation, dem, ())
+
+
+@pytest.mark.gpu
+def test_registered_host_buffers_give_the_same_grid(engine, ref):
+    """pb_host_register: page-locked DEM / proxy / output buffers are copied straight from / into the caller's memory by the
+    band pipeline of the drop-in call; the grid must be bit-identical to the one that went through the staging ring."""
+    dem = syn.make_dem(900, 1000)
+    urban = syn.make_urban(900, 1000)
+    st = syn.make_stations(dem, 300, proxies=(dem, urban))
+    s = syn.settings_multiple_detrending()
+    syn.set_points_range(s, st)
+    ok, keep = ref.pre_interpolation(st, s, A.airTemperature, (dem, urban))
+    st = st.subset(keep)
+    out_a = np.empty(dem.shape, dtype=np.float32)
+    out_b = np.full(dem.shape, 123.0, dtype=np.float32)
+    ra = engine.interpolation_raster(st, s, A.airTemperature, dem, (dem, urban), out=out_a)
+    for a in (dem.data, urban.data, out_b):
+        engine.host_register(a)
+    try:
+        rb = engine.interpolation_raster(st, s, A.airTemperature, dem, (dem, urban), out=out_b)
+        rc = engine.interpolation_raster(st, s, A.airTemperature, dem, (dem, urban), out=out_b, row_begin=100, row_end=650)
+    finally:
+        for a in (dem.data, urban.data, out_b):
+            engine.host_unregister(a)
+    assert ra[0] and rb[0] and ra[2:] == rb[2:]
+    assert np.array_equal(out_a, out_b)
+    assert rc[0]
