@@ -45,6 +45,10 @@ def load_shim():
     lib.shim_compute_residuals_local.argtypes = lib.shim_compute_residuals.argtypes
     lib.shim_kriging_points.argtypes = [P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                         C.c_double, P(C.c_double), C.c_int, P(C.c_double), P(C.c_double)]
+    lib.shim_estimate_variogram.argtypes = [P(C.c_float), P(C.c_float), C.c_int, C.c_float, P(C.c_int), P(C.c_double), P(C.c_double),
+                                            P(C.c_double), P(C.c_double)]
+    lib.shim_pre_interpolation_glocal.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int, C.c_char_p,
+                                                  C.c_int]
     lib.shim_glocal.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int, P(A.pb_raster),
                                 P(A.pb_raster), C.c_int, P(A.pb_raster_out), P(C.c_float), C.c_char_p, C.c_int]
     return lib

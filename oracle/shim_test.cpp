@@ -218,4 +218,31 @@ int shim_glocal(const pb_stations* st, pb_settings* s, int variable, pb_macro_ar
     return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
 }
 
+/* pragab200::krigingEstimateVariogram (the signature the reference declares, interpolation.h:65-68) and
+ * pragab200::preInterpolation with useGlocalDetrending on reference objects */
+int shim_estimate_variogram(float* dist, float* semiVar, int n, float maxDistance, int* mode, double* sill, double* nugget,
+                            double* range, double* slope)
+{
+    TkrigingMode m = TkrigingMode(*mode);
+    bool ok = pragab200::krigingEstimateVariogram(dist, semiVar, n, n, maxDistance, sill, nugget, range, slope, &m, n);
+    *mode = int(m);
+    return ok ? PB_OK : PB_ERR_FIT;
+}
+
+int shim_pre_interpolation_glocal(pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas, char* err, int errLen)
+{
+    Scenario sc;
+    buildSettings(sc, *s, nullptr, 0);
+    buildPoints(sc, *st);
+    sc.settings.setMacroAreas(buildAreas(areas, nAreas, s->nProxy));
+    std::vector<Crit3DMeteoPoint> meteoPoints;
+    std::string e;
+    bool ok = pragab200::preInterpolation(sc.points, sc.settings, &sc.meteoSettings, &sc.climate, meteoPoints, meteoVariable(variable),
+                                          sc.time, e);
+    if (err && errLen > 0) { strncpy(err, e.c_str(), errLen - 1); err[errLen - 1] = 0; }
+    exportSettings(sc, *s);
+    exportAreas(sc.settings.getMacroAreas(), areas, s->nProxy);
+    return ok ? PB_OK : PB_ERR_FIT;
+}
+
 }  // extern "C"

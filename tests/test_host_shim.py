@@ -209,3 +209,37 @@ def test_shim_glocal_detrending_raster_and_residuals(shim, ref):
     assert np.abs(grid_g[~nod].astype(np.float64) - grid_r[~nod]).max() <= TOL
     assert abs(o.minimum - mn_r) <= TOL and abs(o.maximum - mx_r) <= TOL
     assert ok2 and np.array_equal(res_r, res_g)
+
+
+def test_shim_variogram_and_glocal_pre_interpolation(shim, ref):
+    """pragab200::krigingEstimateVariogram (the signature the reference declares and never defines) and the glocal branch of
+    pragab200::preInterpolation on reference objects."""
+    import praga_b200 as pb
+    from test_oracle_port import clone, describe_diff, settings_equal
+    h = ((np.arange(40) + 0.5) * 3.0e3).astype(np.float32)
+    r = h.astype(np.float64) / 8.0e4
+    g = np.where(h < 8.0e4, 0.1 + 3.9 * (1.5 * r - 0.5 * r ** 3), 4.0).astype(np.float32)
+    mode = C.c_int(A.KRIGING_SPHERICAL)
+    sill, nug, rng, slope = C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0)
+    rc = shim.shim_estimate_variogram(A.fptr(h), A.fptr(g), h.size, 0.0, C.byref(mode), C.byref(sill), C.byref(nug), C.byref(rng),
+                                      C.byref(slope))
+    want = pb.fit_variogram(h, g, None, A.KRIGING_SPHERICAL)
+    assert rc == A.PB_OK and mode.value == A.KRIGING_SPHERICAL
+    assert (sill.value, nug.value, rng.value) == (want["sill"], want["nugget"], want["range"])
+    assert abs(rng.value - 8.0e4) / 8.0e4 < 5e-3
+
+    dem = syn.make_dem(100, 120, seed=5)
+    urban = syn.make_urban(100, 120)
+    st = syn.make_stations(dem, 400, proxies=(dem, urban), seed=17)
+    s = syn.settings_multiple_detrending()
+    s.useGlocalDetrending = 1
+    syn.set_points_range(s, st)
+    a_r, s_r = syn.make_macro_areas(dem, st, 2, 8), clone(s)
+    assert ref.glocal_detrending_fitting(st.copy(), s_r, A.airTemperature, a_r)
+    a_g, s_g = syn.make_macro_areas(dem, st, 2, 8), clone(s)
+    stp = st.copy().as_pb()
+    err = C.create_string_buffer(256)
+    rc = shim.shim_pre_interpolation_glocal(C.byref(stp), C.byref(s_g), A.airTemperature, a_g.arr, a_g.n, err, 256)
+    assert rc == A.PB_OK, err.value.decode()
+    assert a_g.fits() == a_r.fits()
+    assert settings_equal(s_r, s_g), describe_diff(s_r, s_g)
