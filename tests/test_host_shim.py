@@ -237,7 +237,8 @@ def test_shim_variogram_and_glocal_pre_interpolation(shim, ref):
     a_r, s_r = syn.make_macro_areas(dem, st, 2, 8), clone(s)
     assert ref.glocal_detrending_fitting(st.copy(), s_r, A.airTemperature, a_r)
     a_g, s_g = syn.make_macro_areas(dem, st, 2, 8), clone(s)
-    stp = st.copy().as_pb()
+    st_g = st.copy()                      # keep the buffers behind the descriptor alive
+    stp = st_g.as_pb()
     err = C.create_string_buffer(256)
     rc = shim.shim_pre_interpolation_glocal(C.byref(stp), C.byref(s_g), A.airTemperature, a_g.arr, a_g.n, err, 256)
     assert rc == A.PB_OK, err.value.decode()
