@@ -17,6 +17,7 @@
 // the weight of a (target, station) pair does not depend on the combination, so it is computed once and applied to the
 // detrended values of 8 problems per pass. kh only takes the integer values 0..maxKh, so the golden section runs on the
 // host over a table of MAE(problem, kh) built in one launch instead of ~35 sequential leave-one-out passes.
+#include <stdlib.h>
 #include "classic.cuh"
 #include "epilogue.cuh"
 
@@ -39,45 +40,67 @@ struct Ctx {
     const ClassicStations& st;
     float* val;        // this problem's column of the working values: val[i * NP]
     int NP;
+    bool warp;         // a whole warp runs this problem (few problems: latency form), else one lane
     __device__ __forceinline__ float value(int i) const { return val[(size_t)i * NP]; }
     __device__ __forceinline__ bool active(int i) const { return st.active ? st.active[i] != 0 : true; }
     __device__ __forceinline__ float proxy(int i, int pos) const { return st.proxy[(size_t)i * cs.nProxy + pos]; }
 };
 
+// The items of an ordered sum. One lane: a plain loop. A whole warp (few problems, the latency of ONE problem is the cost):
+// the lanes evaluate 32 items at a time (loads and predicates in parallel), then every lane receives the accepted ones in
+// index order through shuffles and feeds its own copy of the accumulators: the float / double sums see exactly the
+// reference's sequence.
+template <class Eval, class Acc>
+__device__ __forceinline__ void orderedItems(bool warp, int n, Eval eval, Acc acc)
+{
+    if (!warp) {
+        for (int i = 0; i < n; i++) {
+            float a, b;
+            if (eval(i, a, b)) acc(a, b);
+        }
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        float a = 0.f, b = 0.f;
+        const bool ok = i < n && eval(i, a, b);
+        unsigned mm = __ballot_sync(0xffffffffu, ok);
+        while (mm) {
+            const int l = __ffs(mm) - 1;
+            mm &= mm - 1;
+            acc(__shfl_sync(0xffffffffu, a, l), __shfl_sync(0xffffffffu, b, l));
+        }
+    }
+}
+
 // statistics::linearRegression over the items `get` yields (x, y as float; returns false to skip the item)
 template <class G>
-__device__ void linearRegressionDev(int n, G get, float& q, float& m, float& r2)
+__device__ void linearRegressionDev(int n, G get, float& q, float& m, float& r2, bool warp = false)
 {
     double SUMx = 0, SUMy = 0, SUMxy = 0, SUMxx = 0;
     long nrValid = 0;
-    for (int i = 0; i < n; i++) {
-        float x, y;
-        if (!get(i, x, y)) continue;
-        if (x != kNoData && y != kNoData) {
-            nrValid++;
-            SUMx += x;
-            SUMy += y;
-            SUMxy += x * y;
-            SUMxx += x * x;
-        }
-    }
+    auto valid = [&](int i, float& x, float& y) -> bool { return get(i, x, y) && x != kNoData && y != kNoData; };
+    orderedItems(warp, n, valid, [&](float x, float y) {
+        nrValid++;
+        SUMx += x;
+        SUMy += y;
+        SUMxy += x * y;
+        SUMxx += x * x;
+    });
     const double AVGy = SUMy / double(nrValid);
     const double AVGx = SUMx / double(nrValid);
     m = float((SUMxy - SUMx * SUMy / double(nrValid)) / (SUMxx - SUMx * SUMx / double(nrValid)));
     q = float(AVGy - double(m) * AVGx);
     double SUM_dy = 0, SUMres = 0;
-    for (int i = 0; i < n; i++) {
-        float x, y;
-        if (!get(i, x, y)) continue;
-        if (x != kNoData && y != kNoData) {
-            double dy = double(y - (q + m * x));
-            dy *= dy;
-            SUM_dy += dy;
-            double res = double(y) - AVGy;
-            res *= res;
-            SUMres += res;
-        }
-    }
+    orderedItems(warp, n, valid, [&](float x, float y) {
+        double dy = double(y - (q + m * x));
+        dy *= dy;
+        SUM_dy += dy;
+        double res = double(y) - AVGy;
+        res *= res;
+        SUMres += res;
+    });
     r2 = float((SUMres - SUM_dy) / SUMres);
 }
 
@@ -85,17 +108,32 @@ __device__ void linearRegressionDev(int n, G get, float& q, float& m, float& r2)
 __device__ float maxHeightDev(const Ctx& c)
 {
     float zMax = kNoData;
-    for (int i = 0; i < c.cs.n; i++)
-        if (c.value(i) != kNoData && c.active(i) && checkLapseRateCodeDev(c.st.code[i], c.cs.useLapseRateCode, true))
-            if (zMax == kNoData || c.st.z[i] > double(zMax)) zMax = float(c.st.z[i]);
+    // the f64 elevation travels as its two 32-bit halves
+    orderedItems(c.warp, c.cs.n, [&](int i, float& hi, float& lo) -> bool {
+        if (!(c.value(i) != kNoData && c.active(i) && checkLapseRateCodeDev(c.st.code[i], c.cs.useLapseRateCode, true))) return false;
+        const double z = c.st.z[i];
+        hi = __int_as_float(__double2hiint(z));
+        lo = __int_as_float(__double2loint(z));
+        return true;
+    }, [&](float hi, float lo) {
+        const double z = __hiloint2double(__float_as_int(hi), __float_as_int(lo));
+        if (zMax == kNoData || z > double(zMax)) zMax = float(z);
+    });
     return zMax;
 }
 __device__ float minHeightDev(const Ctx& c)
 {
     float zMin = kNoData;
-    for (int i = 0; i < c.cs.n; i++)
-        if (c.st.z[i] != double(kNoData) && c.active(i) && checkLapseRateCodeDev(c.st.code[i], c.cs.useLapseRateCode, true))
-            if (zMin == kNoData || c.st.z[i] < double(zMin)) zMin = float(c.st.z[i]);
+    orderedItems(c.warp, c.cs.n, [&](int i, float& hi, float& lo) -> bool {
+        const double z = c.st.z[i];
+        if (!(z != double(kNoData) && c.active(i) && checkLapseRateCodeDev(c.st.code[i], c.cs.useLapseRateCode, true))) return false;
+        hi = __int_as_float(__double2hiint(z));
+        lo = __int_as_float(__double2loint(z));
+        return true;
+    }, [&](float hi, float lo) {
+        const double z = __hiloint2double(__float_as_int(hi), __float_as_int(lo));
+        if (zMin == kNoData || z < double(zMin)) zMin = float(z);
+    });
     return zMin;
 }
 
@@ -114,12 +152,9 @@ __device__ bool regressionSimpleDev(const Ctx& c, int pos, float& coeff, float& 
         return true;
     };
     int cnt = 0;
-    for (int i = 0; i < c.cs.n; i++) {
-        float x, y;
-        if (get(i, x, y)) cnt++;
-    }
+    orderedItems(c.warp, c.cs.n, get, [&](float, float) { cnt++; });
     if (cnt < kMinRegressionPoints) return false;
-    linearRegressionDev(c.cs.n, get, intercept, coeff, r2);
+    linearRegressionDev(c.cs.n, get, intercept, coeff, r2, c.warp);
     return true;
 }
 
@@ -182,14 +217,13 @@ __device__ bool regressionSimpleTDev(const Ctx& c, int pos, ClassicProxyState& p
 __device__ float heightIntervalAvgDev(const Ctx& c, float heightInf, float heightSup, float maxPointsZ)
 {
     float sum = 0.f, nValues = 0.f;
-    for (int i = 0; i < c.cs.n; i++) {
+    orderedItems(c.warp, c.cs.n, [&](int i, float& v, float&) -> bool {
         const double z = c.st.z[i];
-        if (z != double(kNoData) && c.active(i) && checkLapseRateCodeDev(c.st.code[i], c.cs.useLapseRateCode, true))
-            if (z >= double(heightInf) && z <= double(heightSup)) {
-                const float v = c.value(i);
-                if (v != kNoData) { sum += v; nValues += 1.f; }
-            }
-    }
+        if (!(z != double(kNoData) && c.active(i) && checkLapseRateCodeDev(c.st.code[i], c.cs.useLapseRateCode, true))) return false;
+        if (!(z >= double(heightInf) && z <= double(heightSup))) return false;
+        v = c.value(i);
+        return v != kNoData;
+    }, [&](float v, float) { sum += v; nValues += 1.f; });
     if (nValues > 1 || (nValues > 0 && heightSup >= maxPointsZ)) return sum / nValues;
     return kNoData;
 }
@@ -282,10 +316,7 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
         return true;
     };
     int n2 = 0;
-    for (int i = 0; i < cs.n; i++) {
-        float a, b;
-        if (above(i, a, b)) n2++;
-    }
+    orderedItems(c.warp, cs.n, above, [&](float, float) { n2++; });
     int nI1 = 0;
     for (int i = 0; i < nI; i++)
         if (ih[i] <= H1split) nI1++;
@@ -312,7 +343,7 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
             PB_SET(p, T0, CF_T0, q);
             PB_SET(p, T1, CF_T1, q + m * p.H1);
         } else {
-            linearRegressionDev(nI, int1, q, m, r2);
+            linearRegressionDev(nI, int1, q, m, r2, c.warp);
             PB_SET(p, r2, CF_R2, kNoData);
             if (r2 >= sigR2) {
                 PB_SET(p, T0, CF_T0, q);
@@ -327,8 +358,8 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
     }
 
     // check inversion significance
-    linearRegressionDev(cs.n, below, q1, m1, r2_values);
-    if (nI1 > 2) linearRegressionDev(nI, int1, q, m, r2_intervals);
+    linearRegressionDev(cs.n, below, q1, m1, r2_values, c.warp);
+    if (nI1 > 2) linearRegressionDev(nI, int1, q, m, r2_intervals, c.warp);
     else r2_intervals = 0.f;
 
     if (r2_values < sigR2Inv && r2_intervals < sigR2Inv) {
@@ -345,7 +376,7 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
         }
         // case 1: analysis only above inversion, flat lapse rate below
         PB_SET(p, invLapse, CF_INVLAPSE, 0.f);
-        linearRegressionDev(cs.n, above, q2, m2, r2);
+        linearRegressionDev(cs.n, above, q2, m2, r2, c.warp);
         if (n2 >= kMinRegressionPoints) {
             if (r2 >= sigR2) {
                 PB_SET(p, slope, CF_SLOPE, m2 < 0.f ? m2 : 0.f);
@@ -354,7 +385,7 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
                 PB_SET(p, r2, CF_R2, r2);
                 return true;
             } else {
-                linearRegressionDev(nI, int2, q2, m2, r2);
+                linearRegressionDev(nI, int2, q2, m2, r2, c.warp);
                 if (r2 >= sigR2) {
                     PB_SET(p, slope, CF_SLOPE, m2 < 0.f ? m2 : 0.f);
                     PB_SET(p, T0, CF_T0, q2 + p.H1 * p.slope);
@@ -385,8 +416,8 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
     }
 
     // significance analysis
-    linearRegressionDev(cs.n, below, q1, m1, r21);
-    linearRegressionDev(cs.n, above, q2, m2, r22);
+    linearRegressionDev(cs.n, below, q1, m1, r21, c.warp);
+    linearRegressionDev(cs.n, above, q2, m2, r22, c.warp);
     if (m1 <= 0) r21 = 0;
     PB_SET(p, r2, CF_R2, r22);
 
@@ -406,7 +437,7 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
         return true;
     } else if (r21 < sigR2Inv && r22 >= sigR2) {
         if (n2 < kMinRegressionPoints && double(m2) > 0.) { m2 = 0.f; q2 = p.T1; }
-        linearRegressionDev(nI, int1, q, m, r2);
+        linearRegressionDev(nI, int1, q, m, r2, c.warp);
         PB_SET(p, slope, CF_SLOPE, m2);
         if (r2 >= sigR2Inv) {
             if (linesIntersectionAboveDev(q, m, q2, m2, 40.f, x, y)) {
@@ -430,7 +461,7 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
     } else if (r21 >= sigR2Inv && r22 < sigR2) {
         PB_SET(p, T0, CF_T0, q1);
         PB_SET(p, invLapse, CF_INVLAPSE, m1);
-        linearRegressionDev(nI, int2, q, m, r2);
+        linearRegressionDev(nI, int2, q, m, r2, c.warp);
         if (r2 >= sigR2) {
             PB_SET(p, slope, CF_SLOPE, m < 0.f ? m : 0.f);
             linesIntersectionDev(p.T0, p.invLapse, q, p.slope, x, y);
@@ -444,7 +475,7 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
         }
         return true;
     } else if (r21 < sigR2Inv && r22 < sigR2) {
-        linearRegressionDev(nI, int1, q, m, r2);
+        linearRegressionDev(nI, int1, q, m, r2, c.warp);
         if (r2 >= sigR2Inv) {
             PB_SET(p, T0, CF_T0, q);
             PB_SET(p, invLapse, CF_INVLAPSE, m);
@@ -454,7 +485,7 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
             PB_SET(p, T0, CF_T0, iv[0]);
             PB_SET(p, T1, CF_T1, p.T0);
         }
-        linearRegressionDev(nI, int2, q, m, r2);
+        linearRegressionDev(nI, int2, q, m, r2, c.warp);
         if (r2 >= sigR2) {
             PB_SET(p, slope, CF_SLOPE, m < 0.f ? m : 0.f);
             if (linesIntersectionAboveDev(p.T0, p.invLapse, q, p.slope, 40.f, x, y)) {
@@ -478,7 +509,7 @@ __device__ bool regressionOrographyTDev(const Ctx& c, int pos, ClassicProxyState
 __device__ void detrendPointsDev(const Ctx& c, int pos, const ClassicProxyState& p)
 {
     const bool isHeight = c.cs.kind[pos] == PB_PROXY_HEIGHT;
-    for (int i = 0; i < c.cs.n; i++) {
+    for (int i = c.warp ? int(threadIdx.x & 31) : 0; i < c.cs.n; i += c.warp ? 32 : 1) {      // independent per point
         float detrendValue = 0.f;
         const float proxyValue = c.proxy(i, pos);
         if (isHeight) {
@@ -498,6 +529,7 @@ __device__ void detrendPointsDev(const Ctx& c, int pos, const ClassicProxyState&
         }
         c.val[(size_t)i * c.NP] -= detrendValue;
     }
+    if (c.warp) __syncwarp();
 }
 
 __global__ void __launch_bounds__(64) classic_detrend_kernel(ClassicSetup cs, ClassicStations st, ClassicProblem* __restrict__ problems,
@@ -506,7 +538,7 @@ __global__ void __launch_bounds__(64) classic_detrend_kernel(ClassicSetup cs, Cl
     const int pIdx = blockIdx.x * blockDim.x + threadIdx.x;
     if (pIdx >= cs.nProblems) return;
     ClassicProblem& pr = problems[pIdx];
-    Ctx c{cs, st, work + pIdx, cs.nProblems};
+    Ctx c{cs, st, work + pIdx, cs.nProblems, false};
     int error = 0;
     for (int pos = 0; pos < cs.nProxy; pos++) {
         pr.significant[pos] = 0;
@@ -525,6 +557,39 @@ __global__ void __launch_bounds__(64) classic_detrend_kernel(ClassicSetup cs, Cl
         }
     }
     pr.error = error;
+}
+
+// the same with one WARP per problem (a single time step and its handful of combinations: the GPU is otherwise idle): every
+// station loop runs through orderedItems, so the lanes share the loads while each sum keeps the reference's order. Every lane
+// holds the same state; lane 0 writes it back.
+__global__ void __launch_bounds__(128) classic_detrend_warp_kernel(ClassicSetup cs, ClassicStations st, ClassicProblem* __restrict__ problems,
+                                                                   float* __restrict__ work)
+{
+    const int pIdx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pIdx >= cs.nProblems) return;
+    const bool writer = (threadIdx.x & 31) == 0;
+    ClassicProblem& pr = problems[pIdx];
+    Ctx c{cs, st, work + pIdx, cs.nProblems, true};
+    int error = 0;
+    for (int pos = 0; pos < cs.nProxy; pos++) {
+        if (writer) pr.significant[pos] = 0;
+        if (!pr.active[pos]) continue;
+        ClassicProxyState p = pr.proxy[pos];
+        p.written = 0;
+        bool ok;
+        if (cs.kind[pos] == PB_PROXY_HEIGHT) {
+            if (cs.isThermalVar) ok = pr.useThermalInversion ? regressionOrographyTDev(c, pos, p, error) : regressionSimpleTDev(c, pos, p);
+            else ok = regressionGenericDev(c, pos, p);
+        } else ok = regressionGenericDev(c, pos, p);
+        __syncwarp();
+        if (writer) pr.proxy[pos] = p;
+        if (ok) {
+            if (writer) pr.significant[pos] = 1;
+            detrendPointsDev(c, pos, p);
+        }
+        __syncwarp();
+    }
+    if (writer) pr.error = error;
 }
 
 // work[i * NP + (t * nCombos + c)] = values[t * n + i]
@@ -806,7 +871,11 @@ cudaError_t launchClassicDetrend(const ClassicSetup& cs, const ClassicStations& 
                                  cudaStream_t s)
 {
     if (cs.nProblems <= 0) return cudaSuccess;
-    classic_detrend_kernel<<<(cs.nProblems + 63) / 64, 64, 0, s>>>(cs, st, problems, work);
+    static const bool noWarp = getenv("PB_CLASSIC_NO_WARP") != nullptr;
+    if (cs.nProblems <= 64 && !noWarp)
+        classic_detrend_warp_kernel<<<(cs.nProblems * 32 + 127) / 128, 128, 0, s>>>(cs, st, problems, work);
+    else
+        classic_detrend_kernel<<<(cs.nProblems + 63) / 64, 64, 0, s>>>(cs, st, problems, work);
     return cudaGetLastError();
 }
 
