@@ -478,6 +478,8 @@ class GlocalWorkload:
         if eng is not None and getattr(eng, "h", None):
             self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
             self.cells_id = eng.macro_areas_upload(self.areas)       # static like the DEM: the glocal weight maps
+            self.out = np.empty(self.dem.shape, dtype=np.float32)    # the host's output grid, page-locked once by its owner
+            eng.host_register(self.out)
 
     def _step_inputs(self, k):
         st = self.base.copy()
@@ -490,7 +492,7 @@ class GlocalWorkload:
         st, s = self._step_inputs(k)
         ok, grid, mn, mx, nv = self.eng.glocal_detrending_raster(st, s, self.var, self.areas, self.dem_id, self.dem.shape,
                                                                  (self.dem_id, self.urb_id), device_only=device_only,
-                                                                 cells_id=self.cells_id)
+                                                                 cells_id=self.cells_id, out=None if device_only else self.out)
         assert ok
         return nv
 

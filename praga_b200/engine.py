@@ -552,12 +552,12 @@ class Engine:
         self._check(self.lib.pb_macro_areas_free(self.h, mid))
 
     def glocal_detrending_raster(self, stations, settings, variable, areas, dem_id, shape, proxy_ids=(), device_only=False,
-                                 cells_id=None):
+                                 cells_id=None, out=None):
         """gridding part of Project::interpolationDemGlocalDetrending (project.cpp:3283-3375). cells_id: macro_areas_upload id.
         Returns (ok, grid or None, min, max, nValid); ok False where the reference returns false."""
         st = stations.as_pb()
         ids = (C.c_int32 * max(1, len(proxy_ids)))(*proxy_ids)
-        grid = None if device_only else np.empty(shape, dtype=np.float32)
+        grid = None if device_only else (out if out is not None else np.empty(shape, dtype=np.float32))
         o = A.pb_raster_out()
         if grid is not None:
             o.data = A.fptr(grid)
