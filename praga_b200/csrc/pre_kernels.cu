@@ -210,12 +210,9 @@ static cudaError_t launchCoopT(const LocalModel* models, const LocalStations& st
     constexpr int N = Fit<F>::N;
     const size_t smem = sizeof(double) * kCoopWarps * kLmWarpTerms * kLmWarpStride + sizeof(CoopResult<N>) * PB_MAX_FIRST_GUESS;
     auto k = pre_interpolation_coop_kernel<F>;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    // set on every launch: the attribute is per device and a host may drive several devices from one process
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     k<<<T, kCoopWarps * 32, smem, s>>>(models, st, values, T, scr, sub, detrended, keep, fits);
     return cudaGetLastError();
 }
