@@ -50,26 +50,35 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
         int nc = 0;
         float dmax = 0.f;
         if (rcap > 0.f) {
+            // every lane scans ONE contiguous block of the station list: counts first, then (offsets from a prefix over the
+            // group's lanes) writes its candidates — station order is kept without a vote per chunk of G stations, which
+            // with 4 lanes per cell was a third of the kernel's stall samples
             const float rcap2 = rcap * rcap * 1.0001f;
             float dmax2 = 0.f;
-            for (int base = 0; base < S; base += G) {
-                const int i = base + lane;
-                bool c = false;
-                float d2 = 0.f;
-                if (i < S) {
+            const int per = (S + G - 1) / G;
+            const int i0 = lane * per, i1 = (i0 + per < S) ? i0 + per : S;
+            int mine = 0;
+            for (int i = i0; i < i1; i++) {
+                const float2 p = xy[i];
+                const float dx = p.x - xf, dy = p.y - yf;
+                const float d2 = dx * dx + dy * dy;
+                mine += d2 <= rcap2;
+                dmax2 = fmaxf(dmax2, d2);
+            }
+            int offset = 0;
+#pragma unroll
+            for (int l = 0; l < G; l++) {
+                const int cl = __shfl_sync(grpMask<G>(), mine, l, G);
+                offset += (l < lane) ? cl : 0;
+                nc += cl;
+            }
+            if (nc <= gcap) {
+                int pos = offset;
+                for (int i = i0; i < i1; i++) {
                     const float2 p = xy[i];
                     const float dx = p.x - xf, dy = p.y - yf;
-                    d2 = dx * dx + dy * dy;
-                    c = d2 <= rcap2;
-                    dmax2 = fmaxf(dmax2, d2);
-                }
-                const unsigned b = grpBallot<G>(c);
-                if (b) {
-                    if (c) {
-                        const int pos = nc + __popc(b & ltMask);
-                        if (pos < gcap) { gw.oi[pos] = i; gw.w[pos] = sqrtf(d2); }
-                    }
-                    nc += __popc(b);
+                    const float d2 = dx * dx + dy * dy;
+                    if (d2 <= rcap2) { gw.oi[pos] = i; gw.w[pos] = sqrtf(d2); pos++; }
                 }
             }
 #pragma unroll
