@@ -94,35 +94,53 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
             const bool compact = rcap > 0.f && r1 <= rcap;
             const int L = compact ? nc : S;
             bool farther = false;
-            for (int base = 0; base < L; base += G) {
-                const int k = base + lane;
-                bool in = false, prim = false;
-                float d = 0.f;
+            // one contiguous block of the list per lane: count the ring's members, prefix over the group, write in place —
+            // ring-major / index order without a vote per chunk
+            const int per = (L + G - 1) / G;
+            const int k0 = lane * per, k1 = (k0 + per < L) ? k0 + per : L;
+            int mine = 0, minePrim = 0;
+            for (int k = k0; k < k1; k++) {
+                float d;
                 int i = k;
-                if (k < L) {
-                    if (compact) {
-                        i = gw.oi[k];
-                        d = gw.w[k];
-                    } else {
-                        const float2 p = xy[i];
-                        const float dx = p.x - xf, dy = p.y - yf;       // gis::computeDistance(x, y, px, py), gis.cpp:685-691
-                        d = sqrtf(dx * dx + dy * dy);
-                        farther |= d > r1;
-                    }
-                    in = d > r0 && d <= r1;
-                    if (in) prim = checkLapseRateCodeDev(st.code[i], useCode, true);
+                if (compact) { i = gw.oi[k]; d = gw.w[k]; }
+                else {
+                    const float2 p = xy[i];
+                    const float dx = p.x - xf, dy = p.y - yf;       // gis::computeDistance(x, y, px, py), gis.cpp:685-691
+                    d = sqrtf(dx * dx + dy * dy);
+                    farther |= d > r1;
                 }
-                const unsigned b = grpBallot<G>(in);
-                if (b) {
-                    const unsigned bp = grpBallot<G>(prim);
-                    if (in) {
-                        const int pos = n + __popc(b & ltMask);
+                if (d > r0 && d <= r1) {
+                    mine++;
+                    minePrim += checkLapseRateCodeDev(st.code[i], useCode, true);
+                }
+            }
+            int offset = 0, total = 0, totalPrim = 0;
+#pragma unroll
+            for (int l = 0; l < G; l++) {
+                const int cl = __shfl_sync(grpMask<G>(), mine, l, G);
+                offset += (l < lane) ? cl : 0;
+                total += cl;
+                totalPrim += __shfl_sync(grpMask<G>(), minePrim, l, G);
+            }
+            if (total) {
+                int pos = n + offset;
+                for (int k = k0; k < k1 && mine; k++) {
+                    float d;
+                    int i = k;
+                    if (compact) { i = gw.oi[k]; d = gw.w[k]; }
+                    else {
+                        const float2 p = xy[i];
+                        const float dx = p.x - xf, dy = p.y - yf;
+                        d = sqrtf(dx * dx + dy * dy);
+                    }
+                    if (d > r0 && d <= r1) {
                         if (pos < gcap) { gw.idx[pos] = i; gw.d[pos] = d; }
                         maxDistance = fmaxf(maxDistance, d);
+                        pos++;
                     }
-                    n += __popc(b);
-                    nrPrimaries += __popc(bp);
                 }
+                n += total;
+                nrPrimaries += totalPrim;
             }
             nrValid = unsigned(n);
             beyondLastPoint = compact ? !(dmax > r1) : grpBallot<G>(farther) == 0u;
