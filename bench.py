@@ -479,7 +479,10 @@ class GlocalWorkload:
             self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
             self.cells_id = eng.macro_areas_upload(self.areas)       # static like the DEM: the glocal weight maps
             self.out = np.empty(self.dem.shape, dtype=np.float32)    # the host's output grid, page-locked once by its owner
-            eng.host_register(self.out)
+            try:
+                eng.host_register(self.out)
+            except Exception:  # noqa: BLE001 - pageable output: slower download, same result
+                pass
 
     def _step_inputs(self, k):
         st = self.base.copy()
@@ -779,8 +782,13 @@ def main():
         eng.interpolation_raster(steps[k], s, var, dem, (dem, urban), out=out_host)
         pageable_s += time.perf_counter() - t1
     barrier()
-    for a in (dem.data, urban.data, out_host):
-        eng.host_register(a)
+    registered = []
+    try:
+        for a in (dem.data, urban.data, out_host):
+            eng.host_register(a)
+            registered.append(a)
+    except Exception as e:  # noqa: BLE001 - a box that refuses to page-lock: the call then stages every byte itself
+        print(f"[bench] pb_host_register failed ({e}); e2e measured on pageable host buffers", file=sys.stderr)
     for k in range(min(2, args.warmup)):
         eng.interpolation_raster(steps[k], s, var, dem, (dem, urban), out=out_host)
     barrier()
@@ -796,7 +804,7 @@ def main():
         d2h_b += t["d2h_bytes"]
         e2e_cells += nv
     barrier()
-    for a in (dem.data, urban.data, out_host):
+    for a in registered:
         eng.host_unregister(a)
     # cached-raster variant (DEM/proxies resident, stations H2D + output D2H per step), reported as extra context
     res_s = 0.0
@@ -831,7 +839,8 @@ def main():
             "e2e": {"value": e2e_cells / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b / args.steps),
                     "d2h_bytes_per_step": int(d2h_b / args.steps), "ms_per_step": 1e3 * e2e_s / args.steps,
                     "what": "pb_interpolation_raster with host DEM/proxy/station buffers and host output grid; the three raster "
-                            "buffers are page-locked once by their owner (pb_host_register), every step copies them H2D / D2H",
+                            "buffers are page-locked once by their owner (pb_host_register), every step copies them H2D / D2H"
+                            if len(registered) == 3 else "pb_interpolation_raster with pageable host buffers (page-locking refused)",
                     "pageable_host_buffers_value": e2e_cells / pageable_s,
                     "resident_rasters_value": e2e_cells / res_s},
             "gpu_launches": int(launches),
