@@ -251,7 +251,8 @@ int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_settings* s, in
 /* --- local-detrending raster: the loop of Project::interpolationDemLocalDetrending (agrolib/project/project.cpp:3208-3253),
  * which the reference inlines in its Qt-bound Project class instead of going through interpolationRaster. Per valid
  * cell: localSelection (interpolation.cpp:1087-1170), preInterpolation on the subset (multipleDetrendingMain :1832,
- * weighted Levenberg-Marquardt fits), interpolate (idw) and retrend. `st` holds the NOT yet detrended points of
+ * weighted Levenberg-Marquardt fits), interpolate (idw, or modifiedShepardIdw with the local radius when method =
+ * shepard_modified) and retrend. `st` holds the NOT yet detrended points of
  * checkAndPassDataToInterpolation in their original order; `s` needs useLocalDetrending, useMultipleDetrending,
  * minPointsLocalDetrending, the selected combination, the proxies' fitting ranges and the points range
  * (setPointsRange, spatialControl.cpp:564). Same three forms as interpolationRaster. */
@@ -455,7 +456,7 @@ int pb_kriging_fit_variogram(const float* binDist, const float* binSemiVar, cons
  *                                   lowered in place to tmax - 0.1 where it exceeds tmax; *nFixed = cells changed
  *   pb_topographic_distance_map  <- gis::topographicDistanceMap (agrolib/gis/gis.cpp:1648-1672): the DEM ray march of
  *                                   gis::topographicDistance (:1595-1647) from (x, y, z) to every valid cell
- *   pb_resample_grid             <- gis::resampleGrid (gis.cpp:1722-1811), aggrAverage / aggrMedian / aggrCenter
+ *   pb_resample_grid             <- gis::resampleGrid (gis.cpp:1722-1811), aggrAverage / aggrMedian / aggrPrevailing / aggrCenter
  *                                   (enum aggregationMethod, agrolib/mathFunctions/statistics.h:21) */
 enum { PB_AGGR_AVERAGE = 1, PB_AGGR_MEDIAN = 2, PB_AGGR_PREVAILING = 7, PB_AGGR_CENTER = 9 };
 int pb_raster_download(pb_context* ctx, pb_raster_id id, pb_raster_out* out);
