@@ -484,6 +484,40 @@ __device__ __forceinline__ void weightedScores(double* par, const double* X, con
     RMSE = sqrt(s / (sw * nData));
 }
 
+// the parts of computeWeighted_R2 / _RMSE that do not depend on the fitted curve (weighted mean, sum of weights, total sum of
+// squares): the same for every first guess of a problem, so the queue form computes them once per lane instead of once per
+// descent. Same sums in the same order as weightedScores.
+struct ScoreBase { double mean, sw, sst; };
+__device__ __forceinline__ ScoreBase weightedScoreBase(const double* Y, const double* W, int nData)
+{
+    ScoreBase b;
+    double mean = 0, sw = 0;
+    for (int i = 0; i < nData; i++) { mean += Y[i] * W[i]; sw += W[i]; }
+    mean /= sw;
+    double sst = 0;
+    for (int i = 0; i < nData; i++) {
+        const double t = W[i] * (Y[i] - mean);
+        sst += t * t;
+    }
+    b.mean = mean; b.sw = sw; b.sst = sst;
+    return b;
+}
+template <int F>
+__device__ __forceinline__ void weightedScoresWith(const ScoreBase& b, double* par, const double* X, const double* Y, const double* W,
+                                                   int nData, double& R2, double& RMSE)
+{
+    if (nData > 0) Fit<F>::clamp(par);
+    double ssr = 0, s = 0;
+    for (int i = 0; i < nData; i++) {
+        const double sim = Fit<F>::eval(X[i], par);
+        const double r = W[i] * (Y[i] - sim);
+        ssr += r * r;
+        s += W[i] * (Y[i] - sim) * (Y[i] - sim);
+    }
+    R2 = 1.0 - (ssr / b.sst);
+    RMSE = sqrt(s / (b.sw * nData));
+}
+
 // computeR2adjusted (:1175-1194) and computeRMSE (:1324-1340) of one fitted curve (the unweighted best fit of glocal detrending)
 template <int F>
 __device__ __forceinline__ void plainScores(double* par, const double* X, const double* Y, int nData, double& R2, double& RMSE)
@@ -541,6 +575,8 @@ __device__ double bestFitElevation(const double* __restrict__ pmin, const double
         LmState<F> st;
         int k = lane;
         bool active = k < nGuess;
+        ScoreBase base{};
+        if (active && !unweighted) base = weightedScoreBase(Y, W, nData);
         if (active) lmInit<F>(st, firstGuess + k * PB_MAX_FIT_PARAMS, X, Y, W, nData);
         while (grpBallot<G>(active)) {
             if (active && lmIter<F>(st, pmin, pmax, dl, rdl, maxIter, eps, X, Y, W, nData)) {
@@ -554,7 +590,7 @@ __device__ double bestFitElevation(const double* __restrict__ pmin, const double
                     plainScores<F>(q, X, Y, nData, R2, RMSE);
                     if (N > 4) secondBelow = (q[0] + q[2]) < maxZ;
                 } else {
-                    weightedScores<F>(q, X, Y, W, nData, R2, RMSE);
+                    weightedScoresWith<F>(base, q, X, Y, W, nData, R2, RMSE);
                 }
                 double* r = results + (size_t)k * kFitResultStride;
 #pragma unroll
