@@ -119,6 +119,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first(self, seconds=5.0):
+        """nvidia-smi takes 0.1-1 s to print its first line (longer with 8 ranks starting it at once): the timed regions of the
+        fast workloads are shorter than that, so the caller waits here BEFORE the warm-up"""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < seconds:
+            time.sleep(0.02)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -143,7 +150,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "window": "100 ms samples from the warm-up through the device-timed and end-to-end regions"}
 
 
 def measured_peaks():
@@ -562,11 +570,12 @@ def run_generic(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first()
     for k in range(args.warmup):
         wl.device_step(k)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     dev_ms, kernel_ms, launches, cells = 0.0, 0.0, 0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
@@ -583,7 +592,6 @@ def run_generic(args, rank, local_rank, world):
         cells += nv
     barrier()
     wall_s = time.perf_counter() - wall0
-    clocks = sampler.stop()
 
     for k in range(min(1, args.warmup)):
         wl.e2e_step(k)
@@ -600,6 +608,7 @@ def run_generic(args, rank, local_rank, world):
         d2h_b += tm["d2h_bytes"]
         e2e_cells += nv
     barrier()
+    clocks = sampler.stop()
 
     if world > 1:
         tt = torch.tensor([dev_ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
@@ -744,11 +753,12 @@ def main():
     out_host = np.empty(dem.shape, dtype=np.float32)
 
     # ---------------- device-resident throughput (`value`) ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first()
     for k in range(args.warmup):
         eng.interpolation_raster_resident(steps[k], s, var, dem_id, (dem_id, urb_id), device_only=True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     dev_ms, kernel_ms, launches, cells = 0.0, 0.0, 0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
@@ -765,7 +775,6 @@ def main():
         cells += nv
     barrier()
     wall_s = time.perf_counter() - wall0
-    clocks = sampler.stop()
 
     # ---------------- end to end through the drop-in call with host buffers (`e2e`) ----------------
     # first with pageable host buffers (every byte passes through the engine's pinned staging ring: extra context), then — the
@@ -804,6 +813,7 @@ def main():
         d2h_b += t["d2h_bytes"]
         e2e_cells += nv
     barrier()
+    clocks = sampler.stop()
     for a in registered:
         eng.host_unregister(a)
     # cached-raster variant (DEM/proxies resident, stations H2D + output D2H per step), reported as extra context
