@@ -1,24 +1,29 @@
 #!/usr/bin/env python
 """bench.py — gridded cells/s of the interpolationRaster hot path on B200 (driver contract: one JSON line).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3idw|c3|c4|c5] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3idw|c3|c4|c5|c2g] [--impl reference] [--no-extras]
 
-Workload (default "c2" = BASELINE.json configs[1]): synthetic 2000x2000 DEM @100 m, 500 stations, IDW with
-multipleDetrending (elevation double-piecewise + urban fraction linear), airTemperature. A "step" = one time
-step = one interpolationRaster call over the whole raster with that step's station values.
+Primary workload (default "c2" = BASELINE.json configs[1]): synthetic 2000x2000 DEM @100 m, 500 stations, IDW with
+multipleDetrending (elevation double-piecewise + urban fraction linear), airTemperature. A "step" = one time step = one
+interpolationRaster call over the whole raster with that step's station values.
 
   value : valid cells gridded / device time, DEM + proxy rasters resident in HBM (pb_interpolation_raster_device).
   e2e   : the same through the drop-in C-ABI call with HOST buffers (pb_interpolation_raster): DEM + proxy H2D,
           station H2D, output raster D2H into host memory, all inside the timed region, every step.
   N > 1 : time steps are sharded over ranks (one process per GPU, no data-path collective); weak scaling.
-  --impl reference : the reference's own CPU interpolationRaster (oracle/_ref, built from the unmodified
-          sources) with all host threads, each step a bounded row-band sample of the same workload.
+  parity: before the line is printed a sample of the workload is gridded by the reference's own CPU code (oracle/_ref) and
+          compared with the GPU result of the same inputs: {"max_abs", "cells", "mask_equal", "ok"} (bar 1e-4).
+  --impl reference : the reference's own CPU interpolationRaster (oracle/_ref, built from the unmodified sources) with all
+          host threads, each step a bounded row-band sample of the same workload.
 
-Other BASELINE.json configs, same JSON line (not the driver's default; results under profiles/):
-  c3 : 10000x10000 DEM, 5000 stations, localDetrending + IDW (K2); a step = one band of rows, bands sharded over ranks.
-  c4 : 10000x10000 DEM, 2000 stations, ordinary kriging estimate + RMSE (K5); a step = one band of rows.
-  c5 : hourly batch on the 2000x2000 DEM, 500 stations: a step = Project::interpolationDem for one (hour, variable) of
-       air temperature / relative humidity / precipitation = spatial QC + preInterpolation + raster + leave-one-out.
+With the default workload the line also carries an "extra" block with the other BASELINE.json configs, each measured by the
+same harness (value / e2e / roofline / parity, cpu_baseline at N = 1) on fewer steps:
+  c3idw : 10000x10000 DEM, 5000 stations, IDW + multipleDetrending (the shape the >= 50x target is quoted on);
+  c3    : 10000x10000 DEM, 5000 stations, localDetrending + IDW (K2); a step = one band of rows, ROW BANDS sharded over ranks;
+  c4    : 10000x10000 DEM, 2000 stations, ordinary kriging estimate + RMSE (K5); a step = one band of rows (N = 1 only);
+  c5    : hourly batch on the 2000x2000 DEM, 500 stations: a step = 24 (hour, variable) units of Project::interpolationDem
+          (spatial QC + preInterpolation + raster + leave-one-out), TIME STEPS sharded over ranks.
+At N > 1 the extra block holds c3 and c5: the two partitions BASELINE.json's north_star names.
 """
 import argparse
 import json
@@ -36,8 +41,8 @@ sys.path.insert(0, ROOT)
 from praga_b200 import _abi as A  # noqa: E402
 from praga_b200 import synthetic as syn  # noqa: E402
 
-METRIC = "gridded cells/sec (detrended IDW)"
 UNIT = "cells/s"
+TOL = 1e-4
 
 WORKLOADS = {
     "c2": dict(rows=2000, cols=2000, stations=500, desc="synthetic 2000x2000 DEM @100 m, 500 stations, IDW + "
@@ -59,7 +64,40 @@ WORKLOADS = {
                     "airRelHumidity, precipitation; per step spatial quality control + preInterpolation + raster + "
                     "leave-one-out cross-validation (Project::interpolationDem / interpolationCv)"),
 }
-GENERIC = ("c3", "c4", "c5", "c2g")
+METRIC = {"c2": "gridded cells/sec (detrended IDW)", "c3idw": "gridded cells/sec (detrended IDW)",
+          "tiny": "gridded cells/sec (detrended IDW)",
+          "c3": "gridded cells/sec (localDetrending + IDW)", "c4": "gridded cells/sec (ordinary kriging, estimate + RMSE)",
+          "c5": "gridded cells/sec (hourly batch: QC + detrending + IDW + LOO)",
+          "c2g": "gridded cells/sec (glocal detrending + IDW)"}
+DTYPE = {"c2": "f32 (f64 cross-tile accumulation and retrend)", "c3idw": "f32 (f64 cross-tile accumulation and retrend)",
+         "tiny": "f32 (f64 cross-tile accumulation and retrend)",
+         "c3": "f64 (LM fits, IDW weights) / f32 distances", "c4": "f64 estimate / fp16x2-split tensor-core variance, f32 accumulate",
+         "c5": "f32 (f64 cross-tile accumulation, f64 fits)", "c2g": "f32 (f64 fits, f64 cross-tile accumulation and blend)"}
+SHARDING = {"c2": "time steps over ranks, no collective", "c3idw": "time steps over ranks, no collective",
+            "tiny": "time steps over ranks, no collective", "c3": "row bands over ranks, no collective",
+            "c4": "row bands over ranks, no collective", "c5": "time steps over ranks, no collective",
+            "c2g": "time steps over ranks, no collective"}
+
+
+def static_config(name):
+    """the `config` object of the JSON line: a pure function of the workload name, printed identically by both arms"""
+    w = WORKLOADS[name]
+    cfg = {"workload": f"{name}: {w['desc']}", "raster": f"{w['rows']}x{w['cols']}", "stations": w["stations"],
+           "sharding": SHARDING[name], "l2": "flushed (256 MiB write) between timed iterations"}
+    if "band_rows" in w:
+        cfg["unit_of_work"] = f"one band of {w['band_rows']} rows per step"
+    return cfg
+
+
+_RASTER_CACHE = {}
+
+
+def cached(kind, rows, cols):
+    """the 10k x 10k rasters are shared by c3idw / c3 / c4 (4 s of numpy each)"""
+    key = (kind, rows, cols)
+    if key not in _RASTER_CACHE:
+        _RASTER_CACHE[key] = syn.make_dem(rows, cols) if kind == "dem" else syn.make_urban(rows, cols)
+    return _RASTER_CACHE[key]
 
 
 def build_workload(name, n_steps, first_step=0):
@@ -69,8 +107,8 @@ def build_workload(name, n_steps, first_step=0):
     fitted model (project.cpp:3108-3150), so that is what a step is given. The fit itself is station-space work
     of a few ms; here the model parameters are fixed plausible values and the residuals are computed with numpy."""
     w = WORKLOADS[name]
-    dem = syn.make_dem(w["rows"], w["cols"])
-    urban = syn.make_urban(w["rows"], w["cols"])
+    dem = cached("dem", w["rows"], w["cols"])
+    urban = cached("urban", w["rows"], w["cols"])
     s = syn.settings_multiple_detrending()
     s.currentSignificant[0] = s.currentSignificant[1] = 1
     s.nFit = s.nFitFunctions = 2
@@ -96,20 +134,21 @@ def build_workload(name, n_steps, first_step=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe). ONE sampler per node (rank 0)
+    watches every GPU of the job: eight ranks each starting their own nvidia-smi loop cost host time inside the timed regions."""
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
+    def __init__(self, n_gpus):
+        self.n = n_gpus
         self.proc = None
         self.lines = []
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -120,38 +159,47 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def wait_first(self, seconds=5.0):
-        """nvidia-smi takes 0.1-1 s to print its first line (longer with 8 ranks starting it at once): the timed regions of the
-        fast workloads are shorter than that, so the caller waits here BEFORE the warm-up"""
+        """nvidia-smi takes 0.1-1 s to print its first line: the timed regions of the fast workloads are shorter than that,
+        so the caller waits here BEFORE the warm-up"""
         t0 = time.perf_counter()
         while self.proc and not self.lines and time.perf_counter() - t0 < seconds:
             time.sleep(0.02)
 
-    def stop(self):
+    def mark(self):
+        return len(self.lines)
+
+    def stats(self, since=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        time.sleep(0.12)
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[since:]:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                smax.append(float(f[1]))
+                if int(f[0]) >= self.n:
+                    continue
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
             except ValueError:
                 continue
-            for nme, val in zip(names, f[3:7]):
+            for nme, val in zip(names, f[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons),
-                "window": "100 ms samples from the warm-up through the device-timed and end-to-end regions"}
+                "samples": len(sm), "gpus_watched": self.n, "reasons": sorted(reasons),
+                "window": "100 ms samples of every GPU of the job from this workload's warm-up through its device-timed and "
+                          "end-to-end regions (one sampler per node)"}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
 
 
 def measured_peaks():
@@ -161,70 +209,11 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the unmodified reference's CPU interpolationRaster on the box's host cores."""
-    if rank != 0:
-        return
-    from oracle import binding
-    kind = "reference" if binding.have_ref() else "port"
-    orc = binding.Oracle(kind)
-    w = WORKLOADS[args.workload]
-    # bounded sample: a band of full rows sized for ~1 s per step at ~1e6 cells/s
-    sample_rows = max(8, min(w["rows"], int(1.0e6 * 500 / max(1, w["stations"]) / w["cols"])))
-    dem, urban, s, steps = build_workload(args.workload, args.steps + args.warmup)
-    r0 = (w["rows"] - sample_rows) // 2
-    band = A.Raster(dem.data[r0:r0 + sample_rows], dem.llx, dem.lly + (w["rows"] - r0 - sample_rows) * dem.cell_size,
-                    dem.cell_size, dem.flag)
-    threads = orc.max_threads()
-    total_cells, total_s = 0, 0.0
-    for k, st in enumerate(steps):
-        ok, grid, mn, mx, nv, sec = orc.interpolation_raster(st, s, A.airTemperature, band, (dem, urban), threads=0)
-        if k >= args.warmup:
-            total_cells += nv
-            total_s += sec
-    value = total_cells / total_s
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 distances / f64 weights (reference arithmetic)", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                             "sample": f"{sample_rows} full rows ({total_cells // args.steps} valid cells) of the "
-                                       f"{w['rows']}x{w['cols']} raster per step, {args.steps} steps"},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+def _band_raster(dem, r0, r1):
+    rows = dem.shape[0]
+    return A.Raster(dem.data[r0:r1], dem.llx, dem.lly + (rows - r1) * dem.cell_size, dem.cell_size, dem.flag)
 
 
-def cpu_baseline_leg(args):
-    """reference CPU path on a bounded sample (rank 0, N = 1 only): ~10-30 s of CPU work."""
-    try:
-        from oracle import binding
-        kind = "reference" if binding.have_ref() else "port"
-        orc = binding.Oracle(kind)
-    except Exception as e:  # noqa: BLE001
-        return {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:100]}
-    w = WORKLOADS[args.workload]
-    dem, urban, s, steps = build_workload(args.workload, 1)
-    threads = orc.max_threads()
-    target_cells = 1.2e7 * 500 / max(1, w["stations"])        # ~10-20 s at ~1e6 cells/s (500 stations)
-    sample_rows = int(max(8, min(w["rows"], target_cells / w["cols"])))
-    r0 = (w["rows"] - sample_rows) // 2
-    band = A.Raster(dem.data[r0:r0 + sample_rows], dem.llx, dem.lly + (w["rows"] - r0 - sample_rows) * dem.cell_size,
-                    dem.cell_size, dem.flag)
-    # repeat the pass until ~10 s of CPU work are timed (the reference is fast on many-core hosts); best pass reported
-    total, best, passes = 0.0, None, 0
-    while total < 10.0 and passes < 40:
-        ok, grid, mn, mx, nv, sec = orc.interpolation_raster(steps[0], s, A.airTemperature, band, (dem, urban), threads=0)
-        total += sec
-        passes += 1
-        best = sec if best is None else min(best, sec)
-    return {"value": nv / best, "unit": UNIT, "cores": threads, "kind": kind, "seconds": total,
-            "sample": f"{sample_rows} full rows ({nv} valid cells) of the {w['rows']}x{w['cols']} raster, best of {passes} "
-                      f"passes ({total:.1f} s of CPU work), all {threads} host threads"}
-
-
-# ---------------------------------------------------------------------------------------------------------------------
-# the other BASELINE configs (c3 local detrending, c4 kriging, c5 hourly batch): one harness, three workload objects
-# ---------------------------------------------------------------------------------------------------------------------
 def _bands(dem, band_rows):
     """interior row bands of band_rows rows (the masked north margin is skipped)."""
     rows = dem.shape[0]
@@ -232,23 +221,181 @@ def _bands(dem, band_rows):
     return [(r, min(rows, r + band_rows)) for r in range(first, rows - band_rows + 1, band_rows)]
 
 
-def _band_raster(dem, r0, r1):
-    rows = dem.shape[0]
-    return A.Raster(dem.data[r0:r1], dem.llx, dem.lly + (rows - r1) * dem.cell_size, dem.cell_size, dem.flag)
+def grid_parity(gpu, cpu, flag):
+    """{"max_abs", "cells", "mask_equal", "ok"} of two grids (bar: 1e-4 on every valid cell, NODATA masks equal)"""
+    f = np.float32(flag)
+    mg, mc = gpu == f, cpu == f
+    mask_equal = bool(np.array_equal(mg, mc))
+    both = ~mg & ~mc
+    d = np.abs(gpu[both].astype(np.float64) - cpu[both].astype(np.float64))
+    mx = float(d.max()) if d.size else 0.0
+    return {"max_abs": mx, "cells": int(both.sum()), "mask_equal": mask_equal, "ok": bool(mask_equal and mx <= TOL),
+            "tolerance": TOL}
+
+
+class _NoEngine:
+    """the reference arm builds the same workload objects without a GPU"""
+    h = None
+
+    def upload(self, r):
+        return -1
+
+    def free(self, rid):
+        pass
+
+    def kriging_setup(self, *a, **k):
+        return -1
+
+    def kriging_free(self, k):
+        pass
+
+    def kriging_uses_tensor_path(self, k):
+        return -1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workload objects: device_step / e2e_step / roofline / cpu_sample / parity, one harness (run_workload) for all of them
+# ---------------------------------------------------------------------------------------------------------------------
+class IdwWorkload:
+    """c2 / c3idw: K1. unit = one time step over the whole raster; ranks take different time steps."""
+    kernel = "pb::idw_persistent_kernel<2,1024>"
+
+    def __init__(self, eng, w, rank, world, n_total, name="c2"):
+        self.eng, self.w, self.name, self.var = eng, w, name, A.airTemperature
+        self.rank, self.world = rank, world
+        self.dem, self.urban, self.s, self.steps = build_workload(name, n_total, first_step=rank * n_total)
+        self.gpu = getattr(eng, "h", None) is not None
+        self.registered = []
+        if self.gpu:
+            t0 = time.perf_counter()
+            self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
+            self.n_valid = eng.valid_cells(self.dem_id)
+            self.upload_s = time.perf_counter() - t0
+            self.out_host = np.empty(self.dem.shape, dtype=np.float32)
+            self.fp32_peak, self.mufu_peak = eng.measure_pipe_peaks()
+
+    def device_step(self, k):
+        ok, _, mn, mx, nv = self.eng.interpolation_raster_resident(self.steps[k], self.s, self.var, self.dem_id,
+                                                                   (self.dem_id, self.urb_id), device_only=True)
+        return nv
+
+    def e2e_begin(self):
+        """the three long-lived host buffers (DEM, proxy grid, output grid) are page-locked once by their owner
+        (pb_host_register), which is what a host keeps loaded across time steps; the copies stay inside the timed region"""
+        try:
+            for a in (self.dem.data, self.urban.data, self.out_host):
+                self.eng.host_register(a)
+                self.registered.append(a)
+        except Exception as e:  # noqa: BLE001 - a box that refuses to page-lock: the call then stages every byte itself
+            print(f"[bench] pb_host_register failed ({e}); e2e measured on pageable host buffers", file=sys.stderr)
+
+    def e2e_step(self, k):
+        ok, _, mn, mx, nv = self.eng.interpolation_raster(self.steps[k], self.s, self.var, self.dem, (self.dem, self.urban),
+                                                          out=self.out_host)
+        return nv
+
+    def e2e_end(self):
+        for a in self.registered:
+            self.eng.host_unregister(a)
+        self.registered = []
+
+    def e2e_what(self):
+        if len(self.registered) == 3:
+            return ("pb_interpolation_raster with host DEM/proxy/station buffers and host output grid; the three raster buffers are "
+                    "page-locked once by their owner (pb_host_register), every step copies them H2D / D2H")
+        return "pb_interpolation_raster with pageable host buffers (page-locking refused)"
+
+    def e2e_context(self, k_range, sync):
+        """extra end-to-end variants of the same step (context for the e2e figure): pageable caller buffers (every byte passes
+        through the engine's pinned staging ring) and resident rasters (stations H2D + output D2H per step)"""
+        out = {}
+        for label, fn in (("pageable_host_buffers", lambda k: self.eng.interpolation_raster(self.steps[k], self.s, self.var, self.dem,
+                                                                                           (self.dem, self.urban), out=self.out_host)),
+                          ("resident_rasters", lambda k: self.eng.interpolation_raster_resident(self.steps[k], self.s, self.var,
+                                                                                               self.dem_id, (self.dem_id, self.urb_id),
+                                                                                               out=self.out_host))):
+            fn(k_range[0])
+            sync()
+            t = 0.0
+            for k in k_range:
+                t1 = time.perf_counter()
+                fn(k)
+                t += time.perf_counter() - t1
+            out[label] = t
+        return out
+
+    def roofline(self, cells_per_launch, kernel_s, step_s, peaks):
+        S = self.w["stations"]
+        pairs = cells_per_launch * S
+        ach = 11.0 * pairs / kernel_s * 1e-12
+        return {"bound": "fp32", "achieved": ach, "peak": self.fp32_peak, "unit": "TFLOP/s", "frac": ach / self.fp32_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C2 from the ncu --set full capture
+                # profiles/r01_idw_c2b.ncu_summary.json (46.9 MB + 10.2 MB; algorithmic 12 B/cell = 44.4 MB + the 14.8 MB
+                # valid-cell list); other workloads: not captured
+                "traffic": 57.09e6 if self.name == "c2" else None,
+                "kernel": self.kernel, "kernel_ms_per_launch": kernel_s * 1e3,
+                "algorithmic": f"11 flop x {S} stations x {int(cells_per_launch)} cells per launch (SURVEY.md 8d)",
+                "peak_source": "FFMA2 chain measured live on this GPU by the builder's own micro-kernel (pb_measure_pipe_peaks): "
+                               "MEASURED_PEAKS.json (driver-written) has no FP32 figure",
+                "mufu_bound": {"pairs_per_s": pairs / kernel_s, "mufu_peak_per_s": self.mufu_peak * 1e9,
+                               "frac": pairs / kernel_s / (self.mufu_peak * 1e9)},
+                "hbm": {"algorithmic_bytes_per_cell": 12, "achieved_gbs": 12.0 * cells_per_launch / kernel_s * 1e-9,
+                        "peak_gbs": peaks.get("hbm_gbs")}}
+
+    def details(self):
+        return {"valid_cells_per_step": self.n_valid, "static_raster_upload_s": self.upload_s}
+
+    def _sample_band(self, rows):
+        r0 = (self.w["rows"] - rows) // 2
+        return r0, r0 + rows
+
+    def cpu_sample(self, orc, seconds_hint):
+        """reference CPU path on a bounded row band: the pass is repeated until ~seconds_hint of CPU work are timed"""
+        threads = orc.max_threads()
+        target_cells = 1.2e6 * seconds_hint * 500 / max(1, self.w["stations"])   # ~1e6 cells/s at 500 stations on 16 threads
+        rows = int(max(8, min(self.w["rows"], target_cells / self.w["cols"])))
+        r0, r1 = self._sample_band(rows)
+        band = _band_raster(self.dem, r0, r1)
+        total, best, passes, nv = 0.0, None, 0, 0
+        while total < seconds_hint and passes < 40:
+            ok, grid, mn, mx, nv, sec = orc.interpolation_raster(self.steps[0], self.s, self.var, band, (self.dem, self.urban), threads=0)
+            total += sec
+            passes += 1
+            best = sec if best is None else min(best, sec)
+        return nv, best, threads, (f"{rows} full rows ({nv} valid cells) of the {self.w['rows']}x{self.w['cols']} raster, best of "
+                                   f"{passes} passes ({total:.1f} s of CPU work), all {threads} host threads")
+
+    def parity(self, orc):
+        rows = 16 if self.w["stations"] <= 1000 else 2
+        r0, r1 = self._sample_band(rows)
+        band = _band_raster(self.dem, r0, r1)
+        okc, gc, mnc, mxc, nvc, _ = orc.interpolation_raster(self.steps[0], self.s, self.var, band, (self.dem, self.urban), threads=0)
+        self.out_host[r0:r1] = 0
+        okg, _, mn, mx, nvg = self.eng.interpolation_raster_resident(self.steps[0], self.s, self.var, self.dem_id,
+                                                                     (self.dem_id, self.urb_id), row_begin=r0, row_end=r1,
+                                                                     out=self.out_host)
+        p = grid_parity(self.out_host[r0:r1], gc, self.dem.flag)
+        p["ok"] = bool(p["ok"] and nvc == nvg)
+        p["sample"] = f"rows {r0}-{r1} of step 0 against the {orc.kind} CPU interpolationRaster"
+        return p
+
+    def close(self):
+        if self.gpu:
+            self.eng.free(self.urb_id)
+            self.eng.free(self.dem_id)
 
 
 class LocalDetrendingWorkload:
     """c3: K2. unit = a band of rows of the 10k x 10k raster; ranks take different bands (row-band sharding)."""
-    kernel = "pb::local_detrending_kernel<4,0,1>"
+    kernel = "pb::local_detrending_kernel (selection + Levenberg-Marquardt fits + estimate)"
     # FP64 flop per cell executed by the LM fits + estimate at this station density, counted with ncu
-    # (thread-level DADD + DMUL + 2 DFMA of profiles/r01_local_k2e_flops.csv / 453 823 cells, 4 lanes per cell; data dependent;
-    # the 16-lane form executed 4.22e5: more lanes replicate the group-uniform parts)
+    # (thread-level DADD + DMUL + 2 DFMA of profiles/r01_local_k2e_flops.csv / 453 823 cells; data dependent)
     FP64_FLOP_PER_CELL = 3.64e5
 
-    def __init__(self, eng, w, rank, world, n_total):
+    def __init__(self, eng, w, rank, world, n_total, name="c3"):
         self.eng, self.w, self.var = eng, w, A.airTemperature
-        self.dem = syn.make_dem(w["rows"], w["cols"])
-        self.urban = syn.make_urban(w["rows"], w["cols"])
+        self.dem = cached("dem", w["rows"], w["cols"])
+        self.urban = cached("urban", w["rows"], w["cols"])
         self.base = syn.make_stations(self.dem, w["stations"], proxies=(self.dem, self.urban))
         self.s = syn.settings_multiple_detrending()
         self.s.useLocalDetrending = 1
@@ -256,9 +403,10 @@ class LocalDetrendingWorkload:
         syn.set_points_range(self.s, self.base)
         self.bands = _bands(self.dem, w["band_rows"])
         self.rank, self.world = rank, world
-        self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
-        self.out = np.empty(self.dem.shape, dtype=np.float32)
-        self.n_valid_ref = None
+        self.gpu = getattr(eng, "h", None) is not None
+        if self.gpu:
+            self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
+            self.out = np.empty(self.dem.shape, dtype=np.float32)
 
     def _step_inputs(self, k):
         r0, r1 = self.bands[(self.rank + k * self.world) % len(self.bands)]
@@ -278,54 +426,85 @@ class LocalDetrendingWorkload:
                                                           row_end=r1, out=self.out, local=True)
         return nv
 
-    def roofline(self, cells_per_launch, kernel_s, peaks):
+    def e2e_what(self):
+        return "pb_local_detrending_raster with host DEM / proxy grids (pageable) and host output grid, one band of rows per call"
+
+    def roofline(self, cells_per_launch, kernel_s, step_s, peaks):
         peak = self.eng.measure_fp64_peak()
         ach = self.FP64_FLOP_PER_CELL * cells_per_launch / kernel_s * 1e-12
         return {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "kernel": self.kernel, "kernel_ms_per_launch": kernel_s * 1e3,
                 "algorithmic": f"{self.FP64_FLOP_PER_CELL:.3g} FP64 flop per cell (ncu-counted at this station density, data "
                                f"dependent) x {int(cells_per_launch)} cells per launch",
-                "peak_source": "DFMA chain measured live on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
+                "peak_source": "DFMA chain measured live on this GPU by the builder's own micro-kernel (MEASURED_PEAKS.json has no "
+                               "FP64 figure); the TU is built with -fmad=false like the reference's x86-64 build, so no DFMA is "
+                               "formed: the reachable ceiling is half of this peak",
                 "selection_floor": {"fp32_flop_per_cell": 6 * self.w["stations"],
                                     "note": "6*S FP32 flop per cell for the selection distances (SURVEY 8d)"}}
 
-    def config(self):
-        return {"unit_of_work": f"one band of {self.w['band_rows']} rows per step", "bands": len(self.bands),
-                "sharding": "row bands over ranks, no collective"}
+    def details(self):
+        return {"bands": len(self.bands)}
 
     def cpu_sample(self, orc, seconds_hint):
         # ~2e-4 s per cell and thread in the reference: a few rows are ~10-30 s
         threads = orc.max_threads()
-        rows = max(2, int(seconds_hint * threads / 2.2e-4 / (0.925 * self.w["cols"])))
+        rows = max(1, int(seconds_hint * threads / 2.2e-4 / (0.925 * self.w["cols"])))
         r0 = self.bands[len(self.bands) // 2][0]
         st, _, _ = self._step_inputs(0)
         ok, grid, mn, mx, nv, sec = orc.local_detrending_raster(st, self.s, self.var, self.dem, (self.dem, self.urban), threads=0,
                                                                 row_begin=r0, row_end=r0 + rows)
+        self._cpu_grid = (r0, r0 + rows, st, grid[r0:r0 + rows].copy())
         return nv, sec, threads, f"{rows} full rows ({nv} valid cells) of the {self.w['rows']}x{self.w['cols']} raster, 1 pass"
+
+    def parity(self, orc):
+        if getattr(self, "_cpu_grid", None) is not None:      # N = 1: the rows the CPU baseline leg just gridded
+            r0, r1, st, gc = self._cpu_grid
+        else:
+            r0 = self.bands[len(self.bands) // 2][0]
+            r1 = r0 + 1
+            st, _, _ = self._step_inputs(0)
+            ok, grid, mn, mx, nv, sec = orc.local_detrending_raster(st, self.s, self.var, self.dem, (self.dem, self.urban), threads=0,
+                                                                    row_begin=r0, row_end=r1)
+            gc = grid[r0:r1]
+        self.out[r0:r1] = 0
+        self.eng.interpolation_raster_resident(st, self.s, self.var, self.dem_id, (self.dem_id, self.urb_id), row_begin=r0,
+                                               row_end=r1, out=self.out, local=True)
+        p = grid_parity(self.out[r0:r1], gc, self.dem.flag)
+        p["bit_identical"] = bool(np.array_equal(self.out[r0:r1], gc))
+        p["sample"] = f"rows {r0}-{r1} against the {orc.kind} CPU loop of interpolationDemLocalDetrending"
+        return p
+
+    def close(self):
+        if self.gpu:
+            self.eng.free(self.urb_id)
+            self.eng.free(self.dem_id)
 
 
 class KrigingWorkload:
     """c4: K5. unit = a band of rows; estimate + RMSE grids."""
     kernel = "pb::kriging_variance_tc_kernel (+ kriging_estimate_kernel)"
 
-    def __init__(self, eng, w, rank, world, n_total):
+    def __init__(self, eng, w, rank, world, n_total, name="c4"):
         self.eng, self.w = eng, w
-        self.dem = syn.make_dem(w["rows"], w["cols"])
+        self.dem = cached("dem", w["rows"], w["cols"])
         n = w["stations"]
         rng = np.random.default_rng(1)
         self.pos = np.stack([self.dem.llx + rng.random(n) * w["cols"] * self.dem.cell_size,
                              self.dem.lly + rng.random(n) * w["rows"] * self.dem.cell_size], axis=1)
         self.val = rng.normal(12.0, 3.0, n)
         self.vario = (A.KRIGING_SPHERICAL, 2.0e5, 0.1, 4.0, 0.0)
-        t0 = time.perf_counter()
-        self.kid = eng.kriging_setup(self.pos, self.val, *self.vario)
-        self.setup_s = time.perf_counter() - t0
-        self.tensor = eng.kriging_uses_tensor_path(self.kid)
-        self.dem_id = eng.upload(self.dem)
         self.bands = _bands(self.dem, w["band_rows"])
         self.rank, self.world = rank, world
-        self.est = np.empty(self.dem.shape, dtype=np.float32)
-        self.rmse = np.empty(self.dem.shape, dtype=np.float32)
+        self.gpu = getattr(eng, "h", None) is not None
+        self.setup_s, self.tensor = 0.0, -1
+        if self.gpu:
+            t0 = time.perf_counter()
+            self.kid = eng.kriging_setup(self.pos, self.val, *self.vario)
+            self.setup_s = time.perf_counter() - t0
+            self.tensor = eng.kriging_uses_tensor_path(self.kid)
+            self.dem_id = eng.upload(self.dem)
+            self.est = np.empty(self.dem.shape, dtype=np.float32)
+            self.rmse = np.empty(self.dem.shape, dtype=np.float32)
 
     def _band(self, k):
         return self.bands[(self.rank + k * self.world) % len(self.bands)]
@@ -341,7 +520,11 @@ class KrigingWorkload:
                                            rmse_out=self.rmse)
         return nv
 
-    def roofline(self, cells_per_launch, kernel_s, peaks):
+    def e2e_what(self):
+        return ("pb_kriging_raster: the DEM is resident by API (the call takes a raster id); per step both output grids of the band "
+                "come down to host memory")
+
+    def roofline(self, cells_per_launch, kernel_s, step_s, peaks):
         n = self.w["stations"]
         flop = 2.0 * n * (n + 1) + 4.0 * n
         ach = flop * cells_per_launch / kernel_s * 1e-12
@@ -353,44 +536,66 @@ class KrigingWorkload:
                                "(hi/lo operand split) on the lower triangle only",
                 "peak_source": "dense bf16 GEMM, sustained, MEASURED_PEAKS.json"}
 
-    def config(self):
-        return {"unit_of_work": f"one band of {self.w['band_rows']} rows per step", "bands": len(self.bands),
-                "sharding": "row bands over ranks, no collective", "kriging_setup_s": self.setup_s,
-                "tensor_path": bool(self.tensor == 1),
-                "e2e_note": "the DEM is resident by API (pb_kriging_raster takes a raster id); per step: both output grids D2H"}
+    def details(self):
+        return {"bands": len(self.bands), "kriging_setup_s": self.setup_s, "tensor_path": bool(self.tensor == 1)}
+
+    def _sample_xy(self, m, seed=3):
+        r0, r1 = self.bands[len(self.bands) // 2]
+        rng = np.random.default_rng(seed)
+        return np.stack([self.dem.llx + rng.random(m) * self.w["cols"] * self.dem.cell_size,
+                         self.dem.lly + (self.w["rows"] - r1 + rng.random(m) * (r1 - r0)) * self.dem.cell_size], axis=1)
 
     def cpu_sample(self, orc, seconds_hint):
         # krigingSetWeight is O(n^2) per cell (~3 ms at n = 2000) and the reference keeps its system in file statics: 1 thread
         m = max(200, int(seconds_hint / 3.2e-3))
-        r0, r1 = self.bands[len(self.bands) // 2]
-        rng = np.random.default_rng(3)
-        xy = np.stack([self.dem.llx + rng.random(m) * self.w["cols"] * self.dem.cell_size,
-                       self.dem.lly + (self.w["rows"] - r1 + rng.random(m) * (r1 - r0)) * self.dem.cell_size], axis=1)
+        xy = self._sample_xy(m)
         ok, res, rm, t_setup, t_eval = orc.kriging_points(self.pos, self.val, *self.vario, xy)
+        self._cpu_points = (xy, res, rm)
         return m, t_eval, 1, (f"{m} random cells of one band (krigingSetWeight + krigingResult + krigingRMSE each), single "
                               f"thread: kriging.cpp keeps one system in file-static globals; krigingVariogram setup "
                               f"{t_setup:.1f} s not included")
 
+    def parity(self, orc):
+        if getattr(self, "_cpu_points", None) is not None:
+            xy, res, rm = self._cpu_points
+        else:
+            xy = self._sample_xy(48)
+            ok, res, rm, _, _ = orc.kriging_points(self.pos, self.val, *self.vario, xy)
+        got, got_rm = self.eng.kriging_points(self.kid, xy)
+        e1, e2 = float(np.abs(got - res).max()), float(np.abs(got_rm - rm).max())
+        return {"max_abs": max(e1, e2), "max_abs_estimate": e1, "max_abs_rmse": e2, "cells": int(xy.shape[0]), "mask_equal": True,
+                "ok": bool(max(e1, e2) <= TOL), "tolerance": TOL,
+                "sample": f"{xy.shape[0]} random cells of one band against the {orc.kind} CPU krigingSetWeight / krigingResult / "
+                          f"krigingRMSE (n = {self.w['stations']}, tensor path = {bool(self.tensor == 1)})"}
+
+    def close(self):
+        if self.gpu:
+            self.eng.kriging_free(self.kid)
+            self.eng.free(self.dem_id)
+
 
 class HourlyBatchWorkload:
-    """c5: one (hour, variable) per step through pb_interpolation_dem (spatial QC + fit + raster + leave-one-out)."""
-    kernel = "pb::idw_kernel + station-space kernels (K3/K7, loo_exact, neighbourhood)"
+    """c5: 24 (hour, variable) units per step through pb_interpolation_dem_batch (spatial QC + fit + raster + leave-one-out)."""
+    kernel = "pb::idw_persistent_kernel<2,1024> + station-space kernels (K3/K7, loo_exact, neighbourhood)"
     VARS = (A.airTemperature, A.airRelHumidity, A.precipitation)
     ROOFLINE_ON_STEP_TIME = True
+    UNITS = int(os.environ.get("PB_BENCH_UNITS", "24"))      # (hour, variable) units per bench step (8 hours x 3 variables)
 
-    def __init__(self, eng, w, rank, world, n_total):
+    def __init__(self, eng, w, rank, world, n_total, name="c5"):
         self.eng, self.w = eng, w
-        self.dem = syn.make_dem(w["rows"], w["cols"])
-        self.urban = syn.make_urban(w["rows"], w["cols"])
+        self.dem = cached("dem", w["rows"], w["cols"])
+        self.urban = cached("urban", w["rows"], w["cols"])
         n = w["stations"]
         grids = (self.dem, self.urban)
         self.base = {A.airTemperature: syn.make_stations(self.dem, n, proxies=grids),
                      A.airRelHumidity: syn.make_stations(self.dem, n, proxies=grids, variable="humidity"),
                      A.precipitation: syn.make_stations(self.dem, n, proxies=grids, variable="precipitation")}
-        self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
         self.rank, self.world = rank, world
         self.outs = []
         self.lanes = int(os.environ.get("PB_BENCH_LANES", "16"))
+        self.gpu = getattr(eng, "h", None) is not None
+        if self.gpu:
+            self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
 
     def _settings(self, var):
         if var == A.airTemperature:
@@ -402,8 +607,8 @@ class HourlyBatchWorkload:
             s.proxy[1] = A.default_proxy(A.proxyUrbanFraction, 1)
         return s, syn.settings_classic_detrending(2)
 
-    def _step_inputs(self, k):
-        unit = self.rank + k * self.world                      # global (hour, variable) index: time steps over ranks
+    def _unit_inputs(self, unit):
+        """global (hour, variable) index -> that unit's raw station values"""
         hour, var = unit // 3, self.VARS[unit % 3]
         st = self.base[var].copy()
         rng = np.random.default_rng(9000 + hour)
@@ -416,12 +621,11 @@ class HourlyBatchWorkload:
             st.value[:] = np.maximum(st.value + 2 * anomaly, 0).astype(np.float32)
         return st, var
 
-    UNITS = int(os.environ.get("PB_BENCH_UNITS", "24"))      # (hour, variable) units per bench step (8 hours x 3 variables)
-
     def _run(self, k, device_only):
         units = []
         for j in range(self.UNITS):
-            st, var = self._step_inputs(k * self.UNITS + j)
+            # time steps over ranks: rank r takes the steps r, r + world, ... (a step = UNITS consecutive units)
+            st, var = self._unit_inputs((self.rank + k * self.world) * self.UNITS + j)
             s, sq = self._settings(var)
             units.append((st, s, sq, var))
         if not device_only and len(self.outs) < self.UNITS:
@@ -436,46 +640,81 @@ class HourlyBatchWorkload:
     def e2e_step(self, k):
         return self._run(k, False)
 
-    def roofline(self, cells_per_launch, kernel_s, peaks):
+    def e2e_what(self):
+        return ("pb_interpolation_dem_batch: DEM / proxy rasters resident by API (the call takes raster ids); per unit the station "
+                "arrays go up and the output raster comes down to host memory")
+
+    def roofline(self, cells_per_launch, kernel_s, step_s, peaks):
         fp32_peak, mufu_peak = self.eng.measure_pipe_peaks()
         S = self.w["stations"]
-        ach = 11.0 * S * cells_per_launch / kernel_s * 1e-12
+        ach = 11.0 * S * cells_per_launch / step_s * 1e-12
         return {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
-                "kernel": self.kernel, "kernel_ms_per_launch": kernel_s * 1e3,
+                "kernel": self.kernel, "kernel_ms_per_launch": step_s * 1e3,
                 "algorithmic": f"11 flop x {S} stations x {int(cells_per_launch)} cells per step (raster only; the station-space "
                                "kernels of the step are counted in the time, not in the flops; time = device time of the whole step)",
-                "peak_source": "FFMA2 chain measured live on this GPU"}
+                "peak_source": "FFMA2 chain measured live on this GPU by the builder's own micro-kernel"}
 
-    def config(self):
-        return {"unit_of_work": f"{self.UNITS} (hour, variable) units per step through pb_interpolation_dem_batch ({self.lanes} lanes); "
-                                "each unit: QC + preInterpolation + raster + leave-one-out",
-                "sharding": "time steps over ranks, no collective",
-                "e2e_note": "DEM / proxy rasters resident by API (pb_interpolation_dem takes raster ids); per step: station "
-                            "arrays H2D, output raster D2H"}
+    def details(self):
+        return {"units_per_step": self.UNITS, "lanes": self.lanes,
+                "unit_of_work": f"{self.UNITS} (hour, variable) units per step through pb_interpolation_dem_batch ({self.lanes} lanes); "
+                                "each unit: QC + preInterpolation + raster + leave-one-out"}
 
     def cpu_sample(self, orc, seconds_hint):
         threads = orc.max_threads()
         cells, sec = 0, 0.0
-        for k in range(3):                                      # one step per variable
-            st, var = self._step_inputs(k)
+        self._cpu_grids = []
+        for k in range(3):                                      # one unit per variable
+            st, var = self._unit_inputs(k)
             s, sq = self._settings(var)
             t0 = time.perf_counter()
             r = orc.interpolation_dem(st, s, var, self.dem, (self.dem, self.urban), quality_settings=sq, cross_validate=True)
             sec += time.perf_counter() - t0
             cells += r["n_valid"]
-        return cells, sec, threads, "3 whole steps (one per variable) of the same chain out of the reference's functions"
+            self._cpu_grids.append((k, r["grid"], r["residual"]))
+        return cells, sec, threads, "3 whole units (one per variable) of the same chain out of the reference's functions"
+
+    def parity(self, orc):
+        todo = getattr(self, "_cpu_grids", None)
+        if todo is None:
+            st, var = self._unit_inputs(0)
+            s, sq = self._settings(var)
+            r = orc.interpolation_dem(st, s, var, self.dem, (self.dem, self.urban), quality_settings=sq, cross_validate=True)
+            todo = [(0, r["grid"], r["residual"])]
+        worst = {"max_abs": 0.0, "cells": 0, "mask_equal": True, "ok": True, "tolerance": TOL, "max_abs_residual": 0.0}
+        for k, gc, res_c in todo:
+            st, var = self._unit_inputs(k)
+            s, sq = self._settings(var)
+            r = self.eng.interpolation_dem(st, s, var, self.dem_id, self.dem.shape, (self.dem_id, self.urb_id), quality_settings=sq,
+                                           cross_validate=True)
+            p = grid_parity(r["grid"], gc, self.dem.flag)
+            worst["max_abs"] = max(worst["max_abs"], p["max_abs"])
+            worst["cells"] += p["cells"]
+            worst["mask_equal"] = worst["mask_equal"] and p["mask_equal"]
+            both = (r["residual"] != np.float32(A.NODATA)) & (res_c != np.float32(A.NODATA))
+            same_mask = bool(np.array_equal(r["residual"] == np.float32(A.NODATA), res_c == np.float32(A.NODATA)))
+            dres = float(np.abs(r["residual"][both].astype(np.float64) - res_c[both]).max()) if both.any() else 0.0
+            worst["max_abs_residual"] = max(worst["max_abs_residual"], dres)
+            worst["ok"] = bool(worst["ok"] and p["ok"] and same_mask and dres <= TOL)
+        worst["sample"] = (f"{len(todo)} whole unit(s) (grid of 2000x2000 + leave-one-out residuals) against the {orc.kind} CPU chain "
+                           "spatialQualityControl / preInterpolation / interpolationRaster / computeResiduals")
+        return worst
+
+    def close(self):
+        if self.gpu:
+            self.eng.free(self.urb_id)
+            self.eng.free(self.dem_id)
 
 
 class GlocalWorkload:
     """c2g: G1. unit = one glocal gridding call on the 2000 x 2000 raster (fit of every macro area + per-area IDW + blend);
     ranks take different time steps."""
-    kernel = "pb::idw_kernel<1,true> per macro area (+ pre_interpolation_batch_kernel, glocal_targets / glocal_blend)"
+    kernel = "pb::idw_kernel<1,true> per macro area (+ pre_interpolation_coop_kernel, glocal_targets / glocal_blend)"
     ROOFLINE_ON_STEP_TIME = True
 
-    def __init__(self, eng, w, rank, world, n_total):
+    def __init__(self, eng, w, rank, world, n_total, name="c2g"):
         self.eng, self.w, self.var = eng, w, A.airTemperature
-        self.dem = syn.make_dem(w["rows"], w["cols"])
-        self.urban = syn.make_urban(w["rows"], w["cols"])
+        self.dem = cached("dem", w["rows"], w["cols"])
+        self.urban = cached("urban", w["rows"], w["cols"])
         self.base = syn.make_stations(self.dem, w["stations"], proxies=(self.dem, self.urban))
         self.s = syn.settings_multiple_detrending()
         self.s.useGlocalDetrending = 1
@@ -483,12 +722,15 @@ class GlocalWorkload:
         self.pairs = float(sum(len(m) * (c.size // 2) for m, c in zip(self.areas.meteo_points, self.areas.area_cells)))
         self.area_cells = int(sum(c.size // 2 for c in self.areas.area_cells))
         self.rank, self.world = rank, world
-        if eng is not None and getattr(eng, "h", None):
+        self.gpu = getattr(eng, "h", None) is not None
+        if self.gpu:
             self.dem_id, self.urb_id = eng.upload(self.dem), eng.upload(self.urban)
             self.cells_id = eng.macro_areas_upload(self.areas)       # static like the DEM: the glocal weight maps
             self.out = np.empty(self.dem.shape, dtype=np.float32)    # the host's output grid, page-locked once by its owner
+            self.registered = False
             try:
                 eng.host_register(self.out)
+                self.registered = True
             except Exception:  # noqa: BLE001 - pageable output: slower download, same result
                 pass
 
@@ -513,74 +755,89 @@ class GlocalWorkload:
     def e2e_step(self, k):
         return self._run(k, False)
 
-    def roofline(self, cells_per_launch, step_s, peaks):
+    def e2e_what(self):
+        return "pb_glocal_detrending_raster_resident: rasters and area cells resident, stations up, output grid down per step"
+
+    def roofline(self, cells_per_launch, kernel_s, step_s, peaks):
         fp32, mufu = self.eng.measure_pipe_peaks()
         ach = 11.0 * self.pairs / step_s * 1e-12
         return {"bound": "fp32", "achieved": ach, "peak": fp32, "unit": "TFLOP/s", "frac": ach / fp32, "traffic": None,
                 "kernel": self.kernel, "kernel_ms_per_launch": step_s * 1e3,
                 "algorithmic": f"11 flop x {self.pairs:.4g} (cell, station) pairs per step = sum over areas of stations x cells "
                                f"({self.area_cells} (cell, area) entries for {int(cells_per_launch)} cells); taken against the whole "
-                               "device time of the step (fit + 3 kernels per area + min/max)",
-                "peak_source": "FFMA2 chain measured live on this GPU (MEASURED_PEAKS.json has no FP32 figure)",
+                               "device time of the step (fit + kernels per area + min/max)",
+                "peak_source": "FFMA2 chain measured live on this GPU by the builder's own micro-kernel",
                 "mufu_bound": {"pairs_per_s": self.pairs / step_s, "mufu_peak_per_s": mufu * 1e9, "frac": self.pairs / step_s / (mufu * 1e9)}}
 
-    def config(self):
-        return {"unit_of_work": "one glocal gridding call (all macro areas) per step", "macro_areas": self.areas.n,
-                "cell_area_entries": self.area_cells, "stations_per_area": [int(len(m)) for m in self.areas.meteo_points],
-                "sharding": "time steps over ranks, no collective"}
+    def details(self):
+        return {"macro_areas": self.areas.n, "cell_area_entries": self.area_cells,
+                "stations_per_area": [int(len(m)) for m in self.areas.meteo_points]}
 
     def cpu_sample(self, orc, seconds_hint):
         threads = orc.max_threads()
         st, s = self._step_inputs(0)
         ok, grid, mn, mx, nv, sec = orc.glocal_detrending_raster(st, s, self.var, self.areas, self.dem, (self.dem, self.urban), threads=0)
+        self._cpu_grid = grid
         return nv, sec, threads, (f"the whole {self.w['rows']}x{self.w['cols']} raster ({nv} valid cells), 1 pass; the reference "
                                   f"parallelises over the {self.areas.n} macro areas (project.cpp:3317)")
 
+    def parity(self, orc):
+        gc = getattr(self, "_cpu_grid", None)
+        st, s = self._step_inputs(0)
+        if gc is None:
+            ok, gc, mn, mx, nv, sec = orc.glocal_detrending_raster(st, s, self.var, self.areas, self.dem, (self.dem, self.urban), threads=0)
+            st, s = self._step_inputs(0)
+        out = np.empty(self.dem.shape, dtype=np.float32)
+        self.eng.glocal_detrending_raster(st, s, self.var, self.areas, self.dem_id, self.dem.shape, (self.dem_id, self.urb_id),
+                                          cells_id=self.cells_id, out=out)
+        p = grid_parity(out, gc, self.dem.flag)
+        p["sample"] = f"the whole raster of step 0 against the {orc.kind} CPU loop of interpolationDemGlocalDetrending"
+        return p
 
-GENERIC_CLASSES = {"c3": LocalDetrendingWorkload, "c4": KrigingWorkload, "c5": HourlyBatchWorkload, "c2g": GlocalWorkload}
-GENERIC_DTYPE = {"c3": "f64 (LM fits, IDW weights) / f32 distances", "c4": "f64 estimate / fp16x2-split tensor-core variance, f32 accumulate",
-                 "c5": "f32 (f64 cross-tile accumulation, f64 fits)", "c2g": "f32 (f64 fits, f64 cross-tile accumulation and blend)"}
-GENERIC_METRIC = {"c3": "gridded cells/sec (localDetrending + IDW)", "c4": "gridded cells/sec (ordinary kriging, estimate + RMSE)",
-                  "c5": "gridded cells/sec (hourly batch: QC + detrending + IDW + LOO)",
-                  "c2g": "gridded cells/sec (glocal detrending + IDW)"}
+    def close(self):
+        if self.gpu:
+            if self.registered:
+                self.eng.host_unregister(self.out)
+            self.eng.free(self.urb_id)
+            self.eng.free(self.dem_id)
 
 
-def run_generic(args, rank, local_rank, world):
-    import torch
-    import torch.distributed as dist
-    import praga_b200 as pb
+CLASSES = {"c2": IdwWorkload, "c3idw": IdwWorkload, "tiny": IdwWorkload, "c3": LocalDetrendingWorkload, "c4": KrigingWorkload,
+           "c5": HourlyBatchWorkload, "c2g": GlocalWorkload}
+# extras run on fewer steps (warm-up stays >= 3): they are context for the primary line, not the driver's headline
+EXTRA_STEPS = {"c3idw": 4, "c3": 3, "c4": 4, "c5": 4}
+CPU_SECONDS = {"c2": 10.0, "c3idw": 8.0, "tiny": 1.0, "c3": 10.0, "c4": 8.0, "c5": 0.0, "c2g": 0.0}
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: praga_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    eng = pb.Engine(local_rank)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    w = WORKLOADS[args.workload]
-    n_total = args.warmup + args.steps
+
+def get_oracle():
+    from oracle import binding
+    kind = "reference" if binding.have_ref() else "port"
+    return binding.Oracle(kind), kind
+
+
+def run_workload(name, eng, torch, dist, rank, world, steps, warmup, sampler, flush, want_cpu):
+    """one workload through the contract: W untimed warm-up steps, K timed steps (CUDA events on the launching stream, L2
+    flushed between iterations), barrier + synchronize on both sides, max over ranks; then the same K steps end to end."""
+    n_total = warmup + steps
     t0 = time.perf_counter()
-    wl = GENERIC_CLASSES[args.workload](eng, w, rank, world, n_total)
+    wl = CLASSES[name](eng, WORKLOADS[name], rank, world, n_total, name=name)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    sampler.wait_first()
-    for k in range(args.warmup):
+    mark = sampler.mark() if sampler else 0
+    for k in range(warmup):
         wl.device_step(k)
     barrier()
     dev_ms, kernel_ms, launches, cells = 0.0, 0.0, 0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
-    for k in range(args.warmup, n_total):
-        flush.zero_()
+    for k in range(warmup, n_total):
+        flush.zero_()                                   # L2 flush between timed iterations (not timed)
         e0.record()
         nv = wl.device_step(k)
         e1.record()
@@ -593,11 +850,14 @@ def run_generic(args, rank, local_rank, world):
     barrier()
     wall_s = time.perf_counter() - wall0
 
-    for k in range(min(1, args.warmup)):
+    # ---------------- end to end through the C-ABI call with host buffers ----------------
+    if hasattr(wl, "e2e_begin"):
+        wl.e2e_begin()
+    for k in range(min(2, warmup)):
         wl.e2e_step(k)
     barrier()
     e2e_s, e2e_cells, h2d_b, d2h_b = 0.0, 0, 0, 0
-    for k in range(args.warmup, n_total):
+    for k in range(warmup, n_total):
         flush.zero_()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -608,81 +868,87 @@ def run_generic(args, rank, local_rank, world):
         d2h_b += tm["d2h_bytes"]
         e2e_cells += nv
     barrier()
-    clocks = sampler.stop()
+    e2e_what = wl.e2e_what()
+    if hasattr(wl, "e2e_end"):
+        wl.e2e_end()
+    ctx_s = {}
+    if name == "c2":
+        ctx_s = wl.e2e_context(range(warmup, n_total), torch.cuda.synchronize)
+        barrier()
+    clocks = sampler.stats(mark) if sampler else None
 
     if world > 1:
-        tt = torch.tensor([dev_ms, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
+        keys = sorted(ctx_s)
+        tt = torch.tensor([dev_ms, e2e_s, kernel_ms] + [ctx_s[k] for k in keys], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, kernel_ms = tt.tolist()
-        cc = torch.tensor([cells, e2e_cells, launches], dtype=torch.float64, device="cuda")
+        vals = tt.tolist()
+        dev_ms, e2e_s, kernel_ms = vals[:3]
+        ctx_s = dict(zip(keys, vals[3:]))
+        cc = torch.tensor([cells, e2e_cells, launches, h2d_b, d2h_b], dtype=torch.float64, device="cuda")
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
-        cells, e2e_cells, launches = cc.tolist()
+        cells, e2e_cells, launches, h2d_b, d2h_b = cc.tolist()
+        h2d_b /= world                                  # bytes per step of ONE rank's call
+        d2h_b /= world
 
+    res = None
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        line = {
-            "metric": GENERIC_METRIC[args.workload], "value": cells / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": GENERIC_DTYPE[args.workload], "data": "synthetic",
-            "config": dict({"workload": f"{args.workload}: {w['desc']}", "stations": w["stations"],
-                            "valid_cells_per_step": cells / (args.steps * world), "steps_per_rank": args.steps,
-                            "l2": "flushed (256 MiB write) between timed iterations", "setup_s": setup_s}, **wl.config()),
-            "e2e": {"value": e2e_cells / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b / args.steps),
-                    "d2h_bytes_per_step": int(d2h_b / args.steps), "ms_per_step": 1e3 * e2e_s / args.steps},
+        per_launch_cells = cells / (steps * world)
+        on_step = getattr(wl, "ROOFLINE_ON_STEP_TIME", False)
+        res = {
+            "metric": METRIC[name], "value": cells / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPE[name], "data": "synthetic", "config": static_config(name),
+            "details": dict({"valid_cells_per_step": per_launch_cells, "steps_per_rank": steps, "setup_s": setup_s,
+                             "peaks_file": peak_kind}, **wl.details()),
+            "e2e": {"value": e2e_cells / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b / steps),
+                    "d2h_bytes_per_step": int(d2h_b / steps), "ms_per_step": 1e3 * e2e_s / steps, "what": e2e_what},
             "gpu_launches": int(launches), "wall_s_timed_region": wall_s, "clocks": clocks,
-            # c5: many kernels on several lanes per step; its roofline is taken against the whole device time of the step
-            "roofline": wl.roofline(cells / (args.steps * world),
-                                    (dev_ms if getattr(wl, "ROOFLINE_ON_STEP_TIME", False) else kernel_ms) * 1e-3 / args.steps, peaks),
+            "roofline": wl.roofline(per_launch_cells, kernel_ms * 1e-3 / steps, dev_ms * 1e-3 / steps, peaks),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                from oracle import binding
-                kind = "reference" if binding.have_ref() else "port"
-                orc = binding.Oracle(kind)
-                n_cpu, sec, threads, sample = wl.cpu_sample(orc, 15.0)
-                line["cpu_baseline"] = {"value": n_cpu / sec, "unit": UNIT, "cores": threads, "kind": kind, "seconds": sec,
-                                        "sample": sample}
-            except Exception as e:  # noqa: BLE001
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:120]}
-        print(json.dumps(line), flush=True)
-    eng.close()
+        if on_step:
+            res["roofline"]["note"] = "taken against the device time of the whole step (many kernels on several lanes per step)"
+        for k, v in ctx_s.items():
+            res["e2e"][k + "_value"] = e2e_cells / v
+        # ---------------- CPU baseline (N = 1 only) and the parity gate (every N, rank 0) ----------------
+        try:
+            orc, kind = get_oracle()
+            if want_cpu and world == 1:
+                n_cpu, sec, threads, sample = wl.cpu_sample(orc, CPU_SECONDS.get(name, 8.0))
+                res["cpu_baseline"] = {"value": n_cpu / sec, "unit": UNIT, "cores": threads, "kind": kind, "seconds": sec,
+                                       "sample": sample}
+            res["parity"] = wl.parity(orc)
+        except Exception as e:  # noqa: BLE001
+            res.setdefault("cpu_baseline", {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:160]})
+            res["parity"] = {"ok": False, "error": f"{type(e).__name__}: {e}"[:200]}
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()                                  # the other ranks wait for rank 0's CPU legs before the next workload
+    wl.close()
+    return res
 
 
-def run_reference_generic(args, rank):
-    """--impl reference for c3 / c4 / c5: the reference's CPU functions on a bounded sample per step."""
+def run_reference(args, rank):
+    """--impl reference: the unmodified reference's CPU code on the box's host cores, rank 0 only, each step a bounded
+    sample of the workload (the same sample the GPU arm's cpu_baseline leg times)."""
     if rank != 0:
         return
-    from oracle import binding
-    kind = "reference" if binding.have_ref() else "port"
-    orc = binding.Oracle(kind)
-    w = WORKLOADS[args.workload]
-
-    class _NoEngine:                                           # the workload objects only need the engine for GPU steps
-        def upload(self, r):
-            return -1
-
-        def kriging_setup(self, *a, **k):
-            return -1
-
-        def kriging_uses_tensor_path(self, k):
-            return -1
-
-    wl = GENERIC_CLASSES[args.workload](_NoEngine(), w, 0, 1, args.steps + args.warmup)
+    orc, kind = get_oracle()
+    name = args.workload
+    wl = CLASSES[name](_NoEngine(), WORKLOADS[name], 0, 1, 1, name=name)
     cells, sec, threads, sample = 0, 0.0, 1, ""
-    budget = max(2.0, 60.0 / max(1, args.steps + args.warmup))
+    # the whole run ends within a few minutes: ~60 s of CPU work spread over the steps
+    budget = min(CPU_SECONDS.get(name, 8.0) or 8.0, max(1.0, 60.0 / max(1, args.steps + args.warmup)))
     for k in range(args.warmup + args.steps):
         n_cpu, s_cpu, threads, sample = wl.cpu_sample(orc, budget)
         if k >= args.warmup:
             cells += n_cpu
             sec += s_cpu
     value = cells / sec
-    line = {"impl": "reference", "metric": GENERIC_METRIC[args.workload], "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC[name], "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "reference arithmetic (f32 / f64 mix)", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample + " per step"},
+            "config": static_config(name),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample + ", per step"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -695,6 +961,9 @@ def main():
     ap.add_argument("--impl", default="praga_b200", choices=["praga_b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="primary workload only (no `extra` block)")
+    ap.add_argument("--extras", default=None, help="comma-separated workloads for the `extra` block (default: c3idw,c3,c4,c5 at "
+                                                   "N = 1; c3,c5 at N > 1)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -708,13 +977,7 @@ def main():
         os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // share))
 
     if args.impl == "reference":
-        if args.workload in GENERIC:
-            run_reference_generic(args, rank)
-        else:
-            run_reference(args, rank, world)
-        return
-    if args.workload in GENERIC:
-        run_generic(args, rank, local_rank, world)
+        run_reference(args, rank)
         return
 
     import torch
@@ -728,153 +991,39 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = pb.Engine(local_rank)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
-
-    w = WORKLOADS[args.workload]
-    n_total = args.warmup + args.steps
-    dem, urban, s, steps = build_workload(args.workload, n_total, first_step=rank * n_total)
-    var = A.airTemperature
-
-    # one-off upload of the static rasters (reported separately from the per-step numbers)
-    t0 = time.perf_counter()
-    dem_id = eng.upload(dem)
-    urb_id = eng.upload(urban)
-    n_valid = eng.valid_cells(dem_id)
-    torch.cuda.synchronize()
-    upload_s = time.perf_counter() - t0
-
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    fp32_peak, mufu_peak = eng.measure_pipe_peaks()
-    out_host = np.empty(dem.shape, dtype=np.float32)
-
-    # ---------------- device-resident throughput (`value`) ----------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    sampler.wait_first()
-    for k in range(args.warmup):
-        eng.interpolation_raster_resident(steps[k], s, var, dem_id, (dem_id, urb_id), device_only=True)
-    barrier()
-    dev_ms, kernel_ms, launches, cells = 0.0, 0.0, 0, 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    for k in range(args.warmup, n_total):
-        flush.zero_()                                   # L2 flush between timed iterations (not timed)
-        e0.record()
-        ok, _, mn, mx, nv = eng.interpolation_raster_resident(steps[k], s, var, dem_id, (dem_id, urb_id), device_only=True)
-        e1.record()
-        e1.synchronize()
-        dev_ms += e0.elapsed_time(e1)
-        t = eng.timing()
-        kernel_ms += t["kernel_ms"]
-        launches += t["launches"]
-        cells += nv
-    barrier()
-    wall_s = time.perf_counter() - wall0
-
-    # ---------------- end to end through the drop-in call with host buffers (`e2e`) ----------------
-    # first with pageable host buffers (every byte passes through the engine's pinned staging ring: extra context), then — the
-    # `e2e` figure — with the three long-lived host buffers (DEM, proxy grid, output grid) page-locked once by their owner
-    # (pb_host_register), which is what a host keeps loaded across time steps; the copies stay inside the timed region
-    for k in range(min(2, args.warmup)):
-        eng.interpolation_raster(steps[k], s, var, dem, (dem, urban), out=out_host)
-    barrier()
-    pageable_s = 0.0
-    for k in range(args.warmup, n_total):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        eng.interpolation_raster(steps[k], s, var, dem, (dem, urban), out=out_host)
-        pageable_s += time.perf_counter() - t1
-    barrier()
-    registered = []
-    try:
-        for a in (dem.data, urban.data, out_host):
-            eng.host_register(a)
-            registered.append(a)
-    except Exception as e:  # noqa: BLE001 - a box that refuses to page-lock: the call then stages every byte itself
-        print(f"[bench] pb_host_register failed ({e}); e2e measured on pageable host buffers", file=sys.stderr)
-    for k in range(min(2, args.warmup)):
-        eng.interpolation_raster(steps[k], s, var, dem, (dem, urban), out=out_host)
-    barrier()
-    e2e_s, e2e_cells, h2d_b, d2h_b = 0.0, 0, 0, 0
-    for k in range(args.warmup, n_total):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        ok, _, mn, mx, nv = eng.interpolation_raster(steps[k], s, var, dem, (dem, urban), out=out_host)
-        e2e_s += time.perf_counter() - t1
-        t = eng.timing()
-        h2d_b += t["h2d_bytes"]
-        d2h_b += t["d2h_bytes"]
-        e2e_cells += nv
-    barrier()
-    clocks = sampler.stop()
-    for a in registered:
-        eng.host_unregister(a)
-    # cached-raster variant (DEM/proxies resident, stations H2D + output D2H per step), reported as extra context
-    res_s = 0.0
-    for k in range(args.warmup, n_total):
-        t1 = time.perf_counter()
-        eng.interpolation_raster_resident(steps[k], s, var, dem_id, (dem_id, urb_id), out=out_host)
-        res_s += time.perf_counter() - t1
-    barrier()
-
-    if world > 1:
-        tt = torch.tensor([dev_ms, e2e_s, res_s, kernel_ms, pageable_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, res_s, kernel_ms, pageable_s = tt.tolist()
-        cc = torch.tensor([cells, e2e_cells, launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
-        cells, e2e_cells, launches = cc.tolist()
-
+    sampler = None
     if rank == 0:
-        peaks, peak_kind = measured_peaks()
-        S = w["stations"]
-        kernel_s_per_launch = kernel_ms * 1e-3 / args.steps
-        pairs_per_launch = n_valid * S
-        achieved_tflops = 11.0 * pairs_per_launch / kernel_s_per_launch * 1e-12
-        line = {
-            "metric": METRIC, "value": cells / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (f64 cross-tile accumulation and retrend)", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "valid_cells_per_step": n_valid,
-                       "stations": S, "steps_per_rank": args.steps, "sharding": "time steps over ranks, no collective",
-                       "l2": "flushed (256 MiB write) between timed iterations",
-                       "static_raster_upload_s": upload_s},
-            "e2e": {"value": e2e_cells / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b / args.steps),
-                    "d2h_bytes_per_step": int(d2h_b / args.steps), "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "what": "pb_interpolation_raster with host DEM/proxy/station buffers and host output grid; the three raster "
-                            "buffers are page-locked once by their owner (pb_host_register), every step copies them H2D / D2H"
-                            if len(registered) == 3 else "pb_interpolation_raster with pageable host buffers (page-locking refused)",
-                    "pageable_host_buffers_value": e2e_cells / pageable_s,
-                    "resident_rasters_value": e2e_cells / res_s},
-            "gpu_launches": int(launches),
-            "wall_s_timed_region": wall_s,
-            "clocks": clocks,
-            "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp32_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C2 from the ncu --set full capture
-                         # profiles/r01_idw_c2b.ncu_summary.json (46.9 MB + 10.2 MB; algorithmic 12 B/cell = 44.4 MB + the
-                         # 14.8 MB valid-cell list); other workloads: not captured
-                         "traffic": 57.09e6 if args.workload == "c2" else None,
-                         "kernel": "pb::idw_kernel<2,false>", "kernel_ms_per_launch": kernel_s_per_launch * 1e3,
-                         "algorithmic": f"11 flop x {S} stations x {n_valid} cells per launch (SURVEY.md 8d)",
-                         "peak_source": "FFMA2 chain measured live on this GPU (MEASURED_PEAKS.json has no FP32 figure; "
-                                        f"its hbm/bf16 numbers are '{peak_kind}')",
-                         "mufu_bound": {"pairs_per_s": pairs_per_launch / kernel_s_per_launch,
-                                        "mufu_peak_per_s": mufu_peak * 1e9,
-                                        "frac": pairs_per_launch / kernel_s_per_launch / (mufu_peak * 1e9)},
-                         "hbm": {"algorithmic_bytes_per_cell": 12,
-                                 "achieved_gbs": 12.0 * n_valid / kernel_s_per_launch * 1e-9,
-                                 "peak_gbs": peaks.get("hbm_gbs")}},
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_leg(args)
+        sampler = ClockSampler(world)
+        sampler.start()
+        sampler.wait_first()
+    if world > 1:
+        dist.barrier()
+
+    line = run_workload(args.workload, eng, torch, dist, rank, world, args.steps, args.warmup, sampler, flush,
+                        want_cpu=not args.no_cpu_baseline)
+    if args.workload == "c2" and not args.no_extras:
+        names = args.extras.split(",") if args.extras else (["c3idw", "c3", "c4", "c5"] if world == 1 else ["c3", "c5"])
+        extra = {}
+        for nme in names:
+            nme = nme.strip()
+            if nme not in CLASSES or nme == "c2":
+                continue
+            try:
+                r = run_workload(nme, eng, torch, dist, rank, world, EXTRA_STEPS.get(nme, 4), max(3, min(args.warmup, 3)), sampler,
+                                 flush, want_cpu=not args.no_cpu_baseline)
+            except Exception as e:  # noqa: BLE001 - an extra must never cost the primary line
+                if world > 1:
+                    raise
+                r = {"error": f"{type(e).__name__}: {e}"[:300]}
+            if rank == 0:
+                extra[nme] = r
+        if rank == 0:
+            line["extra"] = extra
+    if rank == 0:
+        if sampler:
+            sampler.stop()
         print(json.dumps(line), flush=True)
 
     eng.close()

@@ -2,8 +2,10 @@
 
 The shared library has no torch dependency: PyTorch is only used by bench.py for torch.distributed plumbing.
 Each .cu is compiled to an object with its own flags, then linked:
-  detrend_kernels.cu is built with -fmad=false: the station-space fits follow the reference's FP64 operation
-  order (no FMA contraction, like the reference's x86-64 build) so that Levenberg-Marquardt takes the same path.
+  the TUs on the bit-exact station-space / per-cell fit paths (local_kernels.cu, pre_kernels.cu, classic_kernels.cu,
+  station_space.cu, td_kernels.cu, shepard_kernels.cu, glocal.cu, raster_ops.cu) are built with -fmad=false: they follow
+  the reference's FP32 / FP64 operation order (no FMA contraction, like the reference's x86-64 build) so that
+  Levenberg-Marquardt takes the same accept / reject path and every decision falls the same way.
 """
 import os
 import shutil
@@ -23,7 +25,7 @@ SOURCES = {
     "td_kernels.cu": ["-fmad=false"],
     "classic_kernels.cu": ["-fmad=false"],
     "shepard_kernels.cu": ["-fmad=false"],
-    "station_space.cu": [],
+    "station_space.cu": ["-fmad=false"],
     "glocal.cu": ["-fmad=false"],
     "raster_ops.cu": ["-fmad=false"],
     "raster_io.cu": [],

@@ -1180,12 +1180,17 @@ struct RowsJob { const pb_raster* r; float* dst; };
 
 // page-locked host memory (cudaHostAlloc'd, or registered through pb_host_register) can be the source / target of an
 // asynchronous copy itself: no gather into the staging ring, no host memcpy at all
-static bool isPinnedHost(const void* p)
+// (both ends of the range are checked: a caller may have registered only part of a grid)
+static bool isPinnedHost(const void* p, size_t bytes)
 {
-    if (!p) return false;
-    cudaPointerAttributes a{};
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
+    if (!p || bytes == 0) return false;
+    const void* ends[2] = {p, static_cast<const unsigned char*>(p) + bytes - 1};
+    for (const void* q : ends) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (a.type != cudaMemoryTypeHost) return false;
+    }
+    return true;
 }
 
 static int uploadRows(pb_context* ctx, const RowsJob* jobsIn, int nJobsIn, int r0, int r1, cudaStream_t stream)
@@ -1197,7 +1202,7 @@ static int uploadRows(pb_context* ctx, const RowsJob* jobsIn, int nJobsIn, int r
     int nJobs = 0;
     for (int j = 0; j < nJobsIn; j++) {
         const pb_raster* r = jobsIn[j].r;
-        if (r->data && r1 > r0 && isPinnedHost(r->data)) {
+        if (r->data && r1 > r0 && isPinnedHost(r->data, sizeof(float) * size_t(r->h.nrRows) * cols)) {
             CUDA_TRY(ctx, cudaMemcpyAsync(jobsIn[j].dst + size_t(r0) * cols, r->data + size_t(r0) * cols,
                                           sizeof(float) * size_t(r1 - r0) * cols, cudaMemcpyHostToDevice, stream));
             ctx->timing.h2d_bytes += (int64_t)(sizeof(float) * size_t(r1 - r0) * cols);
@@ -1205,24 +1210,30 @@ static int uploadRows(pb_context* ctx, const RowsJob* jobsIn, int nJobsIn, int r
     }
     if (nJobs == 0) return PB_OK;
     const int chunkRows = std::max(1, (int)(kStageSlotBytes / (sizeof(float) * cols)));
+    // a group of jobs holds one ring slot each until its copies are submitted: never more than half the ring at once
+    // (PB_MAX_PROXY + 1 = 9 jobs would otherwise wrap around the 8 slots and share a staging buffer)
+    constexpr int kGroup = PinnedRing::kSlots / 2;
     for (int a = r0; a < r1; a += chunkRows) {
         const int b = std::min(r1, a + chunkRows);
-        int slot[PB_MAX_PROXY + 1];
-        float* stage[PB_MAX_PROXY + 1];
-        for (int j = 0; j < nJobs; j++) stage[j] = reinterpret_cast<float*>(ctx->ring.acquire(&slot[j]));
         const int nr = b - a;
+        for (int j0 = 0; j0 < nJobs; j0 += kGroup) {
+            const int nG = std::min(kGroup, nJobs - j0);
+            int slot[kGroup];
+            float* stage[kGroup];
+            for (int j = 0; j < nG; j++) stage[j] = reinterpret_cast<float*>(ctx->ring.acquire(&slot[j]));
 #pragma omp parallel for schedule(static)
-        for (int k = 0; k < nJobs * nr; k++) {
-            const int j = k / nr, row = a + (k - j * nr);
-            const pb_raster* r = jobs[j].r;
-            const float* src = r->data ? r->data + size_t(row) * cols : r->rows[row];
-            memcpy(stage[j] + size_t(row - a) * cols, src, sizeof(float) * cols);
-        }
-        for (int j = 0; j < nJobs; j++) {
-            CUDA_TRY(ctx, cudaMemcpyAsync(jobs[j].dst + size_t(a) * cols, stage[j], sizeof(float) * size_t(nr) * cols,
-                                          cudaMemcpyHostToDevice, stream));
-            ctx->ring.submitted(slot[j], stream);
-            ctx->timing.h2d_bytes += (int64_t)(sizeof(float) * size_t(nr) * cols);
+            for (int k = 0; k < nG * nr; k++) {
+                const int j = k / nr, row = a + (k - j * nr);
+                const pb_raster* r = jobs[j0 + j].r;
+                const float* src = r->data ? r->data + size_t(row) * cols : r->rows[row];
+                memcpy(stage[j] + size_t(row - a) * cols, src, sizeof(float) * cols);
+            }
+            for (int j = 0; j < nG; j++) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(jobs[j0 + j].dst + size_t(a) * cols, stage[j], sizeof(float) * size_t(nr) * cols,
+                                              cudaMemcpyHostToDevice, stream));
+                ctx->ring.submitted(slot[j], stream);
+                ctx->timing.h2d_bytes += (int64_t)(sizeof(float) * size_t(nr) * cols);
+            }
         }
     }
     return PB_OK;
@@ -1262,6 +1273,19 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
         for (pb_raster_id id : owned) pb_raster_free(ctx, id);
         ctx->err = keep;
     };
+    // every error exit after the first allocRasterEntry gives the temporary raster entries back (the three streams may
+    // still be reading / writing them: drained first)
+    auto abortPipeline = [&](int code) {
+        cudaStreamSynchronize(ctx->sUp); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->sDn);
+        cleanup();
+        return code;
+    };
+#define PIPE_TRY(call)                                                                                                  \
+    do {                                                                                                                \
+        cudaError_t e_ = (call);                                                                                        \
+        if (e_ != cudaSuccess)                                                                                          \
+            return abortPipeline(pb::failCtx(ctx, PB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)));    \
+    } while (0)
     int rc = allocRasterEntry(ctx, dem, &demId);
     if (rc) return rc;
     owned.push_back(demId);
@@ -1289,22 +1313,22 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
 
     RasterEntry& eDem = ctx->rasters[demId];
     const size_t n = eDem.n;
-    CUDA_TRY(ctx, ctx->dOut.reserve(n));
+    PIPE_TRY(ctx->dOut.reserve(n));
     ctx->outInitRaster = -1;
     void* vIdx = nullptr;
-    CUDA_TRY(ctx, ctx->pool.acquire(sizeof(int) * n, &vIdx));
+    PIPE_TRY(ctx->pool.acquire(sizeof(int) * n, &vIdx));
     eDem.validIdx = static_cast<int*>(vIdx);          // released with the entry
     static const int wantBands = getenv("PB_BANDS") ? atoi(getenv("PB_BANDS")) : 8;
     const int nBands = std::max(2, std::min(std::min(kMaxBands, wantBands), nRows / kMinBandRows));
     const int bandRows = (nRows + nBands - 1) / nBands;
     long long* dTotals = reinterpret_cast<long long*>(ctx->dBand);
     unsigned* dCounters = reinterpret_cast<unsigned*>(dTotals + kMaxBands);
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->dBand, 0, kMaxBands * (sizeof(long long) + sizeof(unsigned)), sK));
+    PIPE_TRY(cudaMemsetAsync(ctx->dBand, 0, kMaxBands * (sizeof(long long) + sizeof(unsigned)), sK));
     ctx->hMinMax[0] = 0xffffffffu;
     ctx->hMinMax[1] = 0u;
     ctx->hMinMax[2] = 0u;
     ctx->hMinMax[3] = 0u;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 4 * sizeof(unsigned), cudaMemcpyHostToDevice, sK));
+    PIPE_TRY(cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 4 * sizeof(unsigned), cudaMemcpyHostToDevice, sK));
     // the uploads must not overtake work of a previous call that still reads the recycled buffers
     cudaEventRecord(ctx->evBand[2 * kMaxBands], sK);
     cudaStreamWaitEvent(sUp, ctx->evBand[2 * kMaxBands], 0);
@@ -1314,7 +1338,7 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
     struct Chunk { int r0, r1, slot; float* stage; };
     std::vector<Chunk> inflight;
     size_t head = 0;
-    const bool outPinned = out->data && isPinnedHost(out->data);     // the band comes down straight into the caller's grid
+    const bool outPinned = out->data && isPinnedHost(out->data, sizeof(float) * size_t(rows) * cols);     // the band comes down straight into the caller's grid
     auto scatter = [&](const Chunk& c) -> cudaError_t {
         cudaError_t e = ctx->ringDn.wait(c.slot);
         if (e != cudaSuccess) return e;
@@ -1325,7 +1349,7 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
         }
         return cudaSuccess;
     };
-    auto fail2 = [&](int code) { cudaStreamSynchronize(sUp); cudaStreamSynchronize(sK); cudaStreamSynchronize(sDn); cleanup(); return code; };
+    auto fail2 = abortPipeline;
 
     // ---- up: a band's rows of the DEM and of the proxy grids that share its geometry (others: whole, with band 0)
     auto issueUpload = [&](int b) -> int {
@@ -1395,14 +1419,14 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
     }
     if (rc) return fail2(rc);
     cudaEventRecord(ctx->ev[2], sK);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, sK));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hBand, dTotals, kMaxBands * sizeof(long long), cudaMemcpyDeviceToHost, sK));
+    PIPE_TRY(cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, sK));
+    PIPE_TRY(cudaMemcpyAsync(ctx->hBand, dTotals, kMaxBands * sizeof(long long), cudaMemcpyDeviceToHost, sK));
     for (; head < inflight.size(); head++)
         if (scatter(inflight[head]) != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, "D2H failed"); return fail2(PB_ERR_CUDA); }
     cudaEventRecord(ctx->ev[3], sK);
     cudaStreamSynchronize(sUp);
     cudaStreamSynchronize(sDn);
-    CUDA_TRY(ctx, cudaStreamSynchronize(sK));
+    PIPE_TRY(cudaStreamSynchronize(sK));
     ctx->timing.d2h_bytes += (int64_t)(size_t(nRows) * cols * sizeof(float)) + 8;
     cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
@@ -1419,6 +1443,7 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
     out->minimum = keyToFloat(ctx->hMinMax[0]);
     out->maximum = keyToFloat(ctx->hMinMax[1]);
     return PB_OK;
+#undef PIPE_TRY
 }
 
 static int hostRasterCall(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const pb_raster* dem,

@@ -570,6 +570,14 @@ __global__ void row_start_kernel(const int* __restrict__ validIdx, long long tot
 }
 
 // ---- host-side launchers (called from engine.cu) ----
+static int currentSmCount()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
 cudaError_t launchRowStart(const int* validIdx, long long total, int nrRows, int nrCols, long long* rowStart, cudaStream_t s)
 {
     row_start_kernel<<<(nrRows + 1 + 255) / 256, 256, 0, s>>>(validIdx, total, nrRows, nrCols, rowStart);
@@ -613,13 +621,11 @@ cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevG
         // persistent form: minmax[2] is the work-item counter (zeroed by the caller together with min/max)
         constexpr int kPersistThreads = 1024;     // 32 warps/SM: measured best on B200 (512: -5 % at C2, equal at S = 5000)
         auto k = idw_persistent_kernel<P, kPersistThreads>;
-        static int sms = 0;
-        if (!sms) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentMaxStations * 24);
-        }
+        // the attribute is per device and this launcher runs on several lane threads / devices of one process: set on every
+        // launch (a microsecond against a kernel of hundreds), SM count of the CURRENT device
+        const int sms = currentSmCount();
+        cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentMaxStations * 24);
+        if (ea != cudaSuccess) return ea;
         const size_t smem = (size_t)st.nPadded * (sizeof(float4) + sizeof(float2));
         const int items = (nTargets + 64 * P - 1) / (64 * P);
         const int grid = std::min(sms, (items + kPersistThreads / 32 - 1) / (kPersistThreads / 32));
@@ -629,12 +635,7 @@ cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevG
     }
     const int per = kThreads * 2 * P;
     const int grid = (nTargets + per - 1) / per;
-    auto k = idw_kernel<P, false>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileBytes);
-        attr = true;
-    }
+    auto k = idw_kernel<P, false>;           // 2 * kTileBytes = 24 KiB of dynamic shared memory: no opt-in attribute needed
     k<<<grid, kThreads, 2 * kTileBytes, s>>>(st, m, dem, validIdx, nTargets, nullptr, nullptr, nullptr, out, minmax);
     return cudaGetLastError();
 }
@@ -646,11 +647,6 @@ static cudaError_t launchIdwPointsT(const DevStations& st, const DevModel& m, co
     const int per = kThreads * 2 * P;
     const int grid = (nTargets + per - 1) / per;
     auto k = idw_kernel<P, true>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileBytes);
-        attr = true;
-    }
     DevGrid none{};
     none.flag = kNoData;
     k<<<grid, kThreads, 2 * kTileBytes, s>>>(st, m, none, nullptr, nTargets, tx, ty, tproxy, out, nullptr);
@@ -663,14 +659,14 @@ cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const floa
     if (nTargets <= 0) return cudaSuccess;
     // leave-one-out sets (a few thousand targets) spread over more CTAs with 2 targets per thread; raster-sized target
     // lists (glocal areas) amortise each station load over 4 targets like the raster kernel. Same arithmetic per target.
-    if (nTargets >= 148 * kThreads * 8) return launchIdwPointsT<2>(st, m, tx, ty, tproxy, nTargets, out, s);
+    if (nTargets >= currentSmCount() * kThreads * 8) return launchIdwPointsT<2>(st, m, tx, ty, tproxy, nTargets, out, s);
     return launchIdwPointsT<1>(st, m, tx, ty, tproxy, nTargets, out, s);
 }
 
 cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    fill_kernel<<<148 * 8, 256, 0, s>>>(out, n, v);
+    fill_kernel<<<currentSmCount() * 8, 256, 0, s>>>(out, n, v);
     return cudaGetLastError();
 }
 cudaError_t launchFillValid(float* out, const int* validIdx, int n, float v, cudaStream_t s)

@@ -112,8 +112,42 @@ def run_kriging_case(ref, name, mode, n, m, rng_a, nugget, sill, slope, seed):
     print(name, os.path.getsize(os.path.join(HERE, name)) // 1024, "KiB")
 
 
+def run_kriging_c4(ref, name):
+    """BASELINE config 4's own system: 2000 stations in the 1000 km box, spherical, range 2e5 m, nugget 0.1, sill 4 (the
+    generator state of bench.py KrigingWorkload); 320 targets, 8 of them 30 m from a station."""
+    n, m = 2000, 320
+    rng = np.random.default_rng(1)
+    pos = np.stack([syn.LLX + rng.random(n) * 1.0e6, syn.LLY + rng.random(n) * 1.0e6], axis=1)
+    val = rng.normal(12.0, 3.0, n)
+    rq = np.random.default_rng(77)
+    xy = np.stack([syn.LLX + rq.random(m) * 1.0e6, syn.LLY + rq.random(m) * 1.0e6], axis=1)
+    xy[:8] = pos[:8] + 30.0
+    ok, res, rm, _, _ = ref.kriging_points(pos, val, A.KRIGING_SPHERICAL, 2.0e5, 0.1, 4.0, 0.0, xy)
+    assert ok
+    np.savez_compressed(os.path.join(HERE, name), pos=pos, val=val, xy=xy, params=np.array([A.KRIGING_SPHERICAL, 2.0e5, 0.1, 4.0, 0.0]),
+                        result=res, rmse=rm)
+    print(name, os.path.getsize(os.path.join(HERE, name)) // 1024, "KiB")
+
+
+def large_station_sets(ref):
+    """K1 where it is benchmarked: 5000 stations (10 tiles resident in the persistent kernel, the c3idw shape) and 9500
+    stations (more than the 9216 the persistent kernel holds: the tiled idw_kernel<2,false>), multiple detrending, on a
+    small DEM so that the fixture stays small."""
+    for n, seed in ((5000, 301), (9500, 302)):
+        d = syn.make_dem(72, 88, seed=seed, cell_size=1000.0)
+        u = syn.make_urban(72, 88, cell_size=1000.0)
+        st = syn.make_stations(d, n, proxies=(d, u), seed=seed + 10)
+        s = syn.settings_multiple_detrending()
+        syn.set_points_range(s, st)
+        run_case(ref, f"synth_idw_s{n}.npz", d, (d, u), st, s, A.airTemperature)
+
+
 def main():
     ref = Oracle("reference")
+    if "--round2" in sys.argv:          # only the fixtures added in round 2 (the others are unchanged)
+        run_kriging_c4(ref, "kriging_c4_n2000.npz")
+        large_station_sets(ref)
+        return
     # ---- C1: bundled demo ----
     dem = read_flt(f"{REF_DATA}/DEM/DEM_ER_450m")
     for tag, var_id, var, date, lapse in (("tmin_20230105", 151, A.dailyAirTemperatureMin, "2023-01-05", -0.001),
@@ -170,6 +204,8 @@ def main():
     run_kriging_case(ref, "kriging_spherical.npz", A.KRIGING_SPHERICAL, 140, 200, 8.0e4, 0.1, 4.0, 0.0, 201)
     run_kriging_case(ref, "kriging_exponential.npz", A.KRIGING_EXPONENTIAL, 120, 150, 9.0e4, 0.2, 3.0, 0.0, 202)
     run_kriging_case(ref, "kriging_linear.npz", A.KRIGING_LINEAR, 100, 150, 8.0e4, 0.15, 4.0, 2.0e-5, 203)
+    run_kriging_c4(ref, "kriging_c4_n2000.npz")
+    large_station_sets(ref)
 
 
 if __name__ == "__main__":

@@ -51,6 +51,29 @@ def test_kriging_points_tensor_path(engine, ref, mode, n):
     assert e1 <= TOL and e2 <= TOL
 
 
+def test_kriging_c4_shape_tensor_path(engine, ref):
+    """BASELINE config 4 itself: n = 2000 stations in the 1000 km box of the 10k x 10k @100 m DEM, spherical variogram with
+    range 2e5 m, nugget 0.1, sill 4 (bench.py KrigingWorkload): 8 accumulator passes of 256 stations, ||L^-1|| at its
+    largest. 320 targets (krigingSetWeight is O(n^2) per target on the CPU: ~3 ms each) against the reference's own
+    krigingSetWeight / krigingResult / krigingRMSE (kriging.cpp:211-295)."""
+    n, m = 2000, 320
+    rng = np.random.default_rng(1)                     # the generator state of bench.py KrigingWorkload
+    pos = np.stack([syn.LLX + rng.random(n) * 1.0e6, syn.LLY + rng.random(n) * 1.0e6], axis=1)
+    val = rng.normal(12.0, 3.0, n)
+    rq = np.random.default_rng(77)
+    xy = np.stack([syn.LLX + rq.random(m) * 1.0e6, syn.LLY + rq.random(m) * 1.0e6], axis=1)
+    xy[:8] = pos[:8] + 30.0                             # targets next to a station (largest weights, strongest cancellation)
+    ok, want, want_rm, _, _ = ref.kriging_points(pos, val, A.KRIGING_SPHERICAL, 2.0e5, 0.1, 4.0, 0.0, xy)
+    assert ok
+    kid = engine.kriging_setup(pos, val, A.KRIGING_SPHERICAL, 2.0e5, 0.1, 4.0, 0.0)
+    assert engine.kriging_uses_tensor_path(kid) == 1
+    got, got_rm = engine.kriging_points(kid, xy)
+    engine.kriging_free(kid)
+    e1, e2 = np.abs(got - want).max(), np.abs(got_rm - want_rm).max()
+    print(f"C4 shape n {n}: max |estimate - ref| = {e1:.2e}, max |rmse - ref| = {e2:.2e}")
+    assert e1 <= TOL and e2 <= TOL
+
+
 def test_kriging_linear_falls_back_to_fp64(engine, ref):
     pos, val, xy = scenario(120, 200, seed=3)
     kid = engine.kriging_setup(pos, val, A.KRIGING_LINEAR, 8.0e4, 0.2, 4.0, 1.0e-5)

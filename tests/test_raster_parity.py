@@ -293,3 +293,37 @@ def test_registered_host_buffers_give_the_same_grid(engine, ref):
     assert ra[0] and rb[0] and ra[2:] == rb[2:]
     assert np.array_equal(out_a, out_b)
     assert rc[0]
+
+
+@pytest.mark.gpu
+def test_eight_distinct_proxy_grids_through_the_band_pipeline(engine, ref):
+    """PB_MAX_PROXY = 8 proxies, every one with its own same-geometry grid that is NOT the DEM buffer, pageable buffers: the
+    band pipeline stages 9 rasters (DEM + 8 grids) per chunk through a ring of 8 pinned slots — they must never share a slot
+    (ADVICE r1). Fitted model given directly: elevation (piecewise two) + 7 linear terms."""
+    rows, cols = 640, 520
+    dem = syn.make_dem(rows, cols, seed=21)
+    elev = A.Raster(dem.data.copy(), dem.llx, dem.lly, dem.cell_size, dem.flag)      # the elevation proxy's own grid buffer
+    others = [syn.make_urban(rows, cols, seed=40 + k) for k in range(7)]
+    grids = (elev,) + tuple(others)
+    st = syn.make_stations(dem, 220, proxies=(dem,) + tuple(others), seed=9)
+    kinds = (A.proxyHeight, A.proxyUrbanFraction, A.proxyOrogIndex, A.proxySeaDistance, A.proxyAspect, A.proxySlope,
+             A.proxyWaterIndex, A.proxyUrbanFraction)
+    s = A.default_settings()
+    s.useMultipleDetrending = 1
+    s.nProxy = 8
+    for i, kind in enumerate(kinds):
+        p = A.default_proxy(kind, i)
+        p.fittingFunction = A.piecewiseTwo if i == 0 else A.linear
+        s.proxy[i] = p
+        s.selectedActive[i] = s.currentActive[i] = s.currentSignificant[i] = 1
+    s.nFit = s.nFitFunctions = 8
+    s.fitFunction[0], s.fitNrParams[0] = A.piecewiseTwo, 4
+    for j, v in enumerate((420.0, 12.5, 0.004, -0.0062)):
+        s.fitParams[0][j] = v
+    for k in range(1, 8):
+        s.fitFunction[k], s.fitNrParams[k] = A.linear, 2
+        s.fitParams[k][0], s.fitParams[k][1] = 0.3 * k, -0.1 * k
+    st.value[:] = (st.value - 12.0).astype(np.float32)
+    err, gg, gc = run_both(engine, ref, st, s, A.airTemperature, dem, grids)
+    # the retrend term of every proxy is visible in the result: a swapped / mixed staging buffer cannot hide below 1e-4
+    assert np.ptp(gc[gc != np.float32(dem.flag)]) > 1.0
