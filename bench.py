@@ -305,6 +305,48 @@ class IdwWorkload:
                     "page-locked once by their owner (pb_host_register), every step copies them H2D / D2H")
         return "pb_interpolation_raster with pageable host buffers (page-locking refused)"
 
+    # ---- the drop-in as a PRAGA host calls it: pragab200::interpolationRaster (praga_b200/host/praga_b200_host.cpp) on
+    # gis::Crit3DRasterGrid objects (float** rows) that live across time steps. oracle/_ref/libpraga_shim_test.so is only the
+    # harness that owns those reference objects (it links the reference's gis / interpolation classes, which cannot be built
+    # outside oracle/_ref); the code on the clock is the shim + libpraga_b200.so.
+    def shim_open(self):
+        from oracle import binding
+        if not binding.have_shim():
+            return False
+        import ctypes as C
+        self._C, self.shim = C, binding.load_shim()
+        d = self.dem.as_pb()
+        g = (A.pb_raster * 2)()
+        g[0], g[1] = d, self.urban.as_pb()
+        self.shim_h = self.shim.shim_session_open(C.byref(self.s), C.byref(d), g, 2)
+        return bool(self.shim_h)
+
+    def shim_step(self, k):
+        C = self._C
+        stp = self.steps[k].as_pb()
+        sec, mn, mx = C.c_double(0), C.c_float(0), C.c_float(0)
+        rc = self.shim.shim_session_step(self.shim_h, C.byref(stp), self.var, 0, C.byref(sec), C.byref(mn), C.byref(mx))
+        if rc != A.PB_OK:
+            raise RuntimeError(f"pragab200::interpolationRaster failed ({rc})")
+        t = A.pb_timing()
+        self.shim.shim_session_timing(C.byref(t))
+        return self.n_valid, sec.value, t.h2d_bytes, t.d2h_bytes
+
+    def shim_parity(self, orc):
+        """the session's output grid (float** rows) of step 0 against the reference CPU interpolationRaster on a row band"""
+        C = self._C
+        self.shim_step(0)
+        o = A.pb_raster_out()
+        o.data = A.fptr(self.out_host)
+        self.shim.shim_session_output(self.shim_h, C.byref(o))
+        rows = 16 if self.w["stations"] <= 1000 else 2
+        r0, r1 = self._sample_band(rows)
+        okc, gc, *_ = orc.interpolation_raster(self.steps[0], self.s, self.var, _band_raster(self.dem, r0, r1), (self.dem, self.urban), threads=0)
+        return grid_parity(self.out_host[r0:r1], gc, self.dem.flag)
+
+    def shim_close(self):
+        self.shim.shim_session_close(self.shim_h)
+
     def e2e_context(self, k_range, sync):
         """extra end-to-end variants of the same step (context for the e2e figure): pageable caller buffers (every byte passes
         through the engine's pinned staging ring) and resident rasters (stations H2D + output D2H per step)"""
@@ -875,20 +917,51 @@ def run_workload(name, eng, torch, dist, rank, world, steps, warmup, sampler, fl
     if name == "c2":
         ctx_s = wl.e2e_context(range(warmup, n_total), torch.cuda.synchronize)
         barrier()
+    # ---------------- end to end through the C++ drop-in itself (reference objects, float** rows, resident raster cache) ----
+    shim_s, shim_cells, shim_h2d, shim_d2h, shim_first_s, shim_ok = 0.0, 0, 0, 0, 0.0, 0.0
+    if hasattr(wl, "shim_open") and not os.environ.get("PB_BENCH_NO_SHIM"):
+        opened = False
+        try:
+            if wl.shim_open():
+                _, shim_first_s, _, _ = wl.shim_step(0)            # first call of the session: uploads DEM + proxy grid
+                for k in range(1, min(3, warmup)):
+                    wl.shim_step(k)
+                opened = True
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] shim leg unavailable: {e}", file=sys.stderr)
+        barrier()
+        if opened:
+            try:
+                for k in range(warmup, n_total):
+                    flush.zero_()
+                    torch.cuda.synchronize()
+                    nv, sec, hb, db = wl.shim_step(k)
+                    shim_s += sec
+                    shim_cells += nv
+                    shim_h2d += hb
+                    shim_d2h += db
+                shim_ok = 1.0
+            except Exception as e:  # noqa: BLE001
+                print(f"[bench] shim leg failed: {e}", file=sys.stderr)
+        barrier()
     clocks = sampler.stats(mark) if sampler else None
 
     if world > 1:
         keys = sorted(ctx_s)
-        tt = torch.tensor([dev_ms, e2e_s, kernel_ms] + [ctx_s[k] for k in keys], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dev_ms, e2e_s, kernel_ms, shim_s, shim_first_s, -shim_ok] + [ctx_s[k] for k in keys], dtype=torch.float64,
+                          device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         vals = tt.tolist()
-        dev_ms, e2e_s, kernel_ms = vals[:3]
-        ctx_s = dict(zip(keys, vals[3:]))
-        cc = torch.tensor([cells, e2e_cells, launches, h2d_b, d2h_b], dtype=torch.float64, device="cuda")
+        dev_ms, e2e_s, kernel_ms, shim_s, shim_first_s = vals[:5]
+        shim_ok = -vals[5]                              # 1 only if the leg ran on every rank
+        ctx_s = dict(zip(keys, vals[6:]))
+        cc = torch.tensor([cells, e2e_cells, launches, h2d_b, d2h_b, shim_cells, shim_h2d, shim_d2h], dtype=torch.float64, device="cuda")
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
-        cells, e2e_cells, launches, h2d_b, d2h_b = cc.tolist()
+        cells, e2e_cells, launches, h2d_b, d2h_b, shim_cells, shim_h2d, shim_d2h = cc.tolist()
         h2d_b /= world                                  # bytes per step of ONE rank's call
         d2h_b /= world
+        shim_h2d /= world
+        shim_d2h /= world
 
     res = None
     if rank == 0:
@@ -910,6 +983,20 @@ def run_workload(name, eng, torch, dist, rank, world, steps, warmup, sampler, fl
             res["roofline"]["note"] = "taken against the device time of the whole step (many kernels on several lanes per step)"
         for k, v in ctx_s.items():
             res["e2e"][k + "_value"] = e2e_cells / v
+        if shim_ok > 0 and shim_s > 0:
+            # the headline end-to-end figure is the drop-in as the reference's host calls it; the C-ABI call that uploads the
+            # rasters every step stays beside it
+            c_abi = res["e2e"]
+            res["e2e"] = {
+                "value": shim_cells / shim_s, "unit": UNIT, "h2d_bytes_per_step": int(shim_h2d / steps),
+                "d2h_bytes_per_step": int(shim_d2h / steps), "ms_per_step": 1e3 * shim_s / steps,
+                "what": "pragab200::interpolationRaster (the C++ drop-in with the reference's signature) on gis::Crit3DRasterGrid "
+                        "objects (float** rows) that live across time steps, as in a PRAGA session: the DEM / proxy grids are kept "
+                        "resident by the shim's raster cache after the session's first call, every step flattens that step's "
+                        "Crit3DInterpolationDataPoint vector + settings, copies the stations up and the output grid down into "
+                        "the caller's float** rows (pinned staging ring + host scatter), all inside the timed region",
+                "first_call_ms": 1e3 * shim_first_s,
+                "c_abi_host_rasters": {k: v for k, v in c_abi.items() if k != "unit"}}
         # ---------------- CPU baseline (N = 1 only) and the parity gate (every N, rank 0) ----------------
         try:
             orc, kind = get_oracle()
@@ -918,11 +1005,17 @@ def run_workload(name, eng, torch, dist, rank, world, steps, warmup, sampler, fl
                 res["cpu_baseline"] = {"value": n_cpu / sec, "unit": UNIT, "cores": threads, "kind": kind, "seconds": sec,
                                        "sample": sample}
             res["parity"] = wl.parity(orc)
+            if shim_ok > 0 and hasattr(wl, "shim_parity"):
+                ps = wl.shim_parity(orc)
+                res["parity"]["shim_max_abs"] = ps["max_abs"]
+                res["parity"]["ok"] = bool(res["parity"]["ok"] and ps["ok"])
         except Exception as e:  # noqa: BLE001
             res.setdefault("cpu_baseline", {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:160]})
             res["parity"] = {"ok": False, "error": f"{type(e).__name__}: {e}"[:200]}
     if world > 1:
         dist.barrier()                                  # the other ranks wait for rank 0's CPU legs before the next workload
+    if getattr(wl, "shim_h", None):
+        wl.shim_close()
     wl.close()
     return res
 

@@ -43,6 +43,17 @@ def load_shim():
     lib.shim_spatial_quality_control.argtypes = [P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_cv_points), P(A.pb_raster),
                                                  P(C.c_uint8)]
     lib.shim_compute_residuals_local.argtypes = lib.shim_compute_residuals.argtypes
+    lib.shim_session_open.argtypes = [P(A.pb_settings), P(A.pb_raster), P(A.pb_raster), C.c_int]
+    lib.shim_session_open.restype = C.c_void_p
+    lib.shim_session_step.argtypes = [C.c_void_p, P(A.pb_stations), C.c_int, C.c_int, P(C.c_double), P(C.c_float), P(C.c_float)]
+    lib.shim_session_output.argtypes = [C.c_void_p, P(A.pb_raster_out)]
+    lib.shim_session_poke_dem.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]
+    lib.shim_session_poke_dem.restype = None
+    lib.shim_session_timing.argtypes = [P(A.pb_timing)]
+    lib.shim_session_cache.argtypes = [C.c_int]
+    lib.shim_session_cache.restype = None
+    lib.shim_session_close.argtypes = [C.c_void_p]
+    lib.shim_session_close.restype = None
     lib.shim_kriging_points.argtypes = [P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                         C.c_double, P(C.c_double), C.c_int, P(C.c_double), P(C.c_double)]
     lib.shim_estimate_variogram.argtypes = [P(C.c_float), P(C.c_float), C.c_int, C.c_float, P(C.c_int), P(C.c_double), P(C.c_double),

@@ -245,4 +245,71 @@ int shim_pre_interpolation_glocal(pb_stations* st, pb_settings* s, int variable,
     return ok ? PB_OK : PB_ERR_FIT;
 }
 
+/* ---- a host SESSION as PRAGA runs one: the DEM, the proxy grids and the output grid are gis::Crit3DRasterGrid objects
+ * (float** rows) that live across time steps; every step brings new detrended points and settings and calls
+ * pragab200::interpolationRaster. Used by tests (cached vs uncached grids must agree) and by bench.py to time the drop-in
+ * through the reference's own data layout: the clock runs around the pragab200 call only; building the reference's point
+ * objects from the flat arrays is the harness' work, not the drop-in's. */
+struct ShimSession {
+    Scenario sc;
+    gis::Crit3DRasterGrid dem, out;
+    pb_settings flat;
+};
+
+void* shim_session_open(const pb_settings* s, const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids)
+{
+    ShimSession* ss = new ShimSession();
+    ss->flat = *s;
+    buildSettings(ss->sc, *s, proxyGrids, nProxyGrids);
+    fillGrid(ss->dem, *dem);
+    ss->sc.settings.setCurrentDEM(&ss->dem);
+    for (int i = 0; i < s->nProxy; i++)
+        if (s->proxy[i].kind == PB_PROXY_HEIGHT && s->proxy[i].gridIndex >= 0) ss->sc.settings.getProxy(i)->setGrid(&ss->dem);
+    return ss;
+}
+
+/* one time step: returns PB_OK / PB_ERR_NO_VALID_CELL; *elapsed_s = wall time of the pragab200::interpolationRaster call */
+int shim_session_step(void* session, const pb_stations* st, int variable, int local, double* elapsed_s, float* minimum, float* maximum)
+{
+    ShimSession* ss = static_cast<ShimSession*>(session);
+    for (auto& p : ss->sc.points) delete p.point;
+    ss->sc.points.clear();
+    buildPoints(ss->sc, *st);
+    auto t0 = std::chrono::steady_clock::now();
+    bool ok = local ? pragab200::interpolationRasterLocalDetrending(ss->sc.points, ss->sc.settings, &ss->sc.meteoSettings, &ss->out,
+                                                                    ss->dem, meteoVariable(variable))
+                    : pragab200::interpolationRaster(ss->sc.points, ss->sc.settings, &ss->sc.meteoSettings, &ss->out, ss->dem,
+                                                     meteoVariable(variable), true);
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    if (minimum) *minimum = ss->out.minimum;
+    if (maximum) *maximum = ss->out.maximum;
+    return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
+}
+
+/* the session's output grid -> a flat array; modifyDem != 0: the DEM cell (row, col) is overwritten IN PLACE first (tests of
+ * the cache's invalidation rules) */
+int shim_session_output(void* session, pb_raster_out* out)
+{
+    ShimSession* ss = static_cast<ShimSession*>(session);
+    if (!ss->out.isLoaded) return PB_ERR_INVALID;
+    copyOut(ss->out, out);
+    return PB_OK;
+}
+void shim_session_poke_dem(void* session, int row, int col, float value, int announce)
+{
+    ShimSession* ss = static_cast<ShimSession*>(session);
+    ss->dem.value[row][col] = value;
+    if (announce) pragab200::invalidate(&ss->dem);
+}
+int shim_session_timing(pb_timing* t) { return pragab200::lastTiming(t) ? PB_OK : PB_ERR_INVALID; }
+void shim_session_cache(int enabled) { pragab200::setRasterCache(enabled != 0); }
+void shim_session_close(void* session)
+{
+    ShimSession* ss = static_cast<ShimSession*>(session);
+    pragab200::invalidate(&ss->dem);
+    for (auto g : ss->sc.grids) pragab200::invalidate(g);
+    delete ss;
+}
+
 }  // extern "C"

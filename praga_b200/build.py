@@ -21,6 +21,7 @@ SOURCES = {
     "idw_kernels.cu": [],
     "peaks.cu": [],
     "local_kernels.cu": ["-fmad=false"],
+    "local_pipeline.cu": ["-fmad=false"],
     "pre_kernels.cu": ["-fmad=false"],
     "td_kernels.cu": ["-fmad=false"],
     "classic_kernels.cu": ["-fmad=false"],
@@ -33,7 +34,7 @@ SOURCES = {
     "kriging_tc.cu": [],
     "variogram.cu": [],
 }
-HEADERS = ["common.cuh", "epilogue.cuh", "context.cuh", "local.cuh", "pre.cuh", "multiple_detrend.cuh", "detrend_device.cuh", "kriging.cuh", "classic.cuh", "shepard.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
+HEADERS = ["common.cuh", "epilogue.cuh", "context.cuh", "local.cuh", "local_device.cuh", "pre.cuh", "multiple_detrend.cuh", "detrend_device.cuh", "kriging.cuh", "classic.cuh", "shepard.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

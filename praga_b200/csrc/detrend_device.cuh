@@ -142,6 +142,10 @@ struct LmState {
     double p[Fit<F>::N], lambda[Fit<F>::N];
     double mySSE;
     int iter;
+    // SCORED form of lmIter only: the curve-dependent sums of computeWeighted_R2 / _RMSE (:1245-1275, :1301-1322) for the
+    // CURRENT parameters p, i.e. ssr = sum (W (Y - f))^2 and sc = sum W (Y - f)^2, taken in the pass that evaluates the SSE of
+    // a candidate (same f, same terms, same order as weightedScoresWith) and kept when the candidate is accepted
+    double ssr, sc;
 };
 
 template <int F>
@@ -188,7 +192,7 @@ __device__ __forceinline__ double lmPointJacobian(double x, const double* p0, co
 }
 
 // one Levenberg-Marquardt iteration; true when the descent is over (the reference's do-while condition turned false)
-template <int F>
+template <int F, bool SCORED = false>
 __device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__ pmin, const double* __restrict__ pmax,
                                        const double* dl, const double* rdl, int maxIter, double eps, const double* X,
                                        const double* Y, const double* W, int nData)
@@ -270,16 +274,22 @@ __device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__
             if (s.lambda[j] < 1000) s.lambda[j] *= VFACTOR;
         }
     }
-    double newSSE = 0;
+    double newSSE = 0, newSsr = 0, newSc = 0;
     if (nData > 0) Fit<F>::clamp(np);
     for (int i = 0; i < nData; i++) {
         const double error = Y[i] - Fit<F>::eval(X[i], np);
         const double w = W[i];
         newSSE += error * error * w * w;
+        if (SCORED) {
+            const double r = w * error;          // W (Y - sim)
+            newSsr += r * r;
+            newSc += r * error;                  // W (Y - sim) (Y - sim), left to right
+        }
     }
     diffSSE = s.mySSE - newSSE;
     if (diffSSE > 0) {
         s.mySSE = newSSE;
+        if (SCORED) { s.ssr = newSsr; s.sc = newSc; }
 #pragma unroll
         for (int j = 0; j < N; j++) { s.p[j] = np[j]; s.lambda[j] /= VFACTOR; }
     } else {

@@ -612,9 +612,41 @@ int launchLocal(pb_context* ctx, const pb_stations* st, const pb_settings* s, in
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->dLocalError, 0, sizeof(int), ctx->stream));
     scr.error = ctx->dLocalError;
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    CUDA_TRY(ctx, launchLocalDetrendingRaster(reinterpret_cast<const LocalModel*>(ctx->dLocalModel.p), ds, devGridOf(dem),
-                                              dem.validIdx + t0, nTargets, scr, groupLanes, m.elevFunction, ctx->dOut.p,
-                                              ctx->dMinMax, ctx->stream));
+    const LocalModel* dModel = reinterpret_cast<const LocalModel*>(ctx->dLocalModel.p);
+    // Raster-sized target lists go through the three-kernel pipeline (local_pipeline.cu) in chunks of cells; each chunk's
+    // cells that do not fit a pipeline record are then gridded by the fused kernel (list form, count read on the device).
+    // PB_LOCAL_FUSED=1 forces the fused kernel for everything (A/B comparison of the two schedules: same bits).
+    // PB_LOCAL_PIPELINE_MIN: smallest target list that takes the pipeline (tests lower it to drive small rasters through it).
+    const char* forceFused = getenv("PB_LOCAL_FUSED");
+    const char* minEnv = getenv("PB_LOCAL_PIPELINE_MIN");
+    const int minCells = minEnv ? atoi(minEnv) : 4096;
+    const bool pipeline = !(forceFused && atoi(forceFused) != 0) && nTargets >= minCells;
+    if (!pipeline) {
+        CUDA_TRY(ctx, launchLocalDetrendingRaster(dModel, ds, devGridOf(dem), dem.validIdx + t0, nTargets, scr, groupLanes,
+                                                  m.elevFunction, ctx->dOut.p, ctx->dMinMax, ctx->stream));
+    } else {
+        const int chunkEnv = getenv("PB_LOCAL_CHUNK") ? atoi(getenv("PB_LOCAL_CHUNK")) : 0;
+        const int chunk = std::min(nTargets, chunkEnv > 0 ? chunkEnv : (512 << 10));
+        const size_t recStride = localRecordStride(m.nFirstGuess);
+        const int selCap = std::max(std::min(st->n, 2048), 1);
+        CUDA_TRY(ctx, ctx->dLocalRecords.reserve(recStride * size_t(chunk)));
+        CUDA_TRY(ctx, ctx->dLocalSel.reserve(localSelectScratchBytes(selCap)));
+        CUDA_TRY(ctx, ctx->dLocalOverflow.reserve(size_t(chunk) + 4));
+        unsigned* counters = reinterpret_cast<unsigned*>(ctx->dLocalOverflow.p);
+        int* overflowList = ctx->dLocalOverflow.p + 4;
+        for (long long c0 = 0; c0 < nTargets; c0 += chunk) {
+            const int nc = int(std::min<long long>(chunk, nTargets - c0));
+            int launches = 0;
+            CUDA_TRY(ctx, launchLocalPipelineChunk(dModel, ds, devGridOf(dem), dem.validIdx + t0 + c0, nc, m.elevFunction, m.nFirstGuess,
+                                                   ctx->dLocalRecords.p, recStride, ctx->dLocalSel.p, selCap, ctx->dLocalError, counters,
+                                                   overflowList, ctx->dOut.p, ctx->dMinMax, ctx->stream, &launches));
+            CUDA_TRY(ctx, launchLocalDetrendingRaster(dModel, ds, devGridOf(dem), overflowList, nc, scr, groupLanes, m.elevFunction,
+                                                      ctx->dOut.p, ctx->dMinMax, ctx->stream, nullptr,
+                                                      reinterpret_cast<const int*>(counters + 1)));
+            ctx->timing.launches += launches;        // the caller counts one more (the fused kernel's launch)
+            if (c0 + chunk < nTargets) ctx->timing.launches++;
+        }
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hLocalError, ctx->dLocalError, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return PB_OK;
 }
@@ -750,6 +782,152 @@ int preInterpolationBatchImpl(pb_context* ctx, const pb_stations* st, const floa
     return PB_OK;
 }
 
+constexpr int kMaxBands = 16;
+constexpr int kMinBandRows = 128;
+
+// page-locked host memory (cudaHostAlloc'd, or registered through pb_host_register) can be the source / target of an
+// asynchronous copy itself: no gather into the staging ring, no host memcpy at all
+// (both ends of the range are checked: a caller may have registered only part of a grid)
+static bool isPinnedHost(const void* p, size_t bytes)
+{
+    if (!p || bytes == 0) return false;
+    const void* ends[2] = {p, static_cast<const unsigned char*>(p) + bytes - 1};
+    for (const void* q : ends) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (a.type != cudaMemoryTypeHost) return false;
+    }
+    return true;
+}
+
+// streams, events and counters of the band pipelines (created on first use)
+static int ensurePipeline(pb_context* ctx)
+{
+    if (!ctx->sUp) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->sUp, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->sDn, cudaStreamNonBlocking));
+        for (auto& e : ctx->evBand) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->dBand, kMaxBands * (sizeof(long long) + sizeof(unsigned))));
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->hBand, kMaxBands * sizeof(long long)));
+    }
+    CUDA_TRY(ctx, ctx->ring.init(kStageSlotBytes));
+    CUDA_TRY(ctx, ctx->ringDn.init(kStageSlotBytes));
+    return PB_OK;
+}
+
+// rows of the device output grid -> the caller's grid on the download stream: straight into page-locked contiguous memory,
+// else in chunks through the pinned ring, each chunk scattered into the caller's rows (float** or contiguous) by the host
+// cores while the following ones are still in flight
+struct BandDownloader {
+    pb_context* ctx;
+    pb_raster_out* out;
+    int cols, chunkRows;
+    bool outPinned;
+    struct Chunk { int r0, r1, slot; float* stage; };
+    std::vector<Chunk> inflight;
+    size_t head = 0;
+    BandDownloader(pb_context* c, pb_raster_out* o, int rows, int cols_) : ctx(c), out(o), cols(cols_)
+    {
+        chunkRows = std::max(1, (int)(kStageSlotBytes / (sizeof(float) * cols)));
+        outPinned = out->data && isPinnedHost(out->data, sizeof(float) * size_t(rows) * cols);
+    }
+    cudaError_t scatter(const Chunk& c)
+    {
+        cudaError_t e = ctx->ringDn.wait(c.slot);
+        if (e != cudaSuccess) return e;
+        const int n = c.r1 - c.r0;
+        if (n < 32) {
+            for (int row = c.r0; row < c.r1; row++)
+                memcpy(out->data ? out->data + size_t(row) * cols : out->rows[row], c.stage + size_t(row - c.r0) * cols, sizeof(float) * cols);
+            return cudaSuccess;
+        }
+#pragma omp parallel for schedule(static)
+        for (int row = c.r0; row < c.r1; row++) {
+            float* dst = out->data ? out->data + size_t(row) * cols : out->rows[row];
+            memcpy(dst, c.stage + size_t(row - c.r0) * cols, sizeof(float) * cols);
+        }
+        return cudaSuccess;
+    }
+    // rows [r0, r1) of dOut start their way down on sDn (the caller has made sDn wait for the kernel that writes them)
+    cudaError_t issue(const float* dOut, int r0, int r1, bool mayScatter)
+    {
+        cudaStream_t sDn = ctx->sDn;
+        if (outPinned)
+            return cudaMemcpyAsync(out->data + size_t(r0) * cols, dOut + size_t(r0) * cols, size_t(r1 - r0) * cols * sizeof(float),
+                                   cudaMemcpyDeviceToHost, sDn);
+        for (int a = r0; a < r1; a += chunkRows) {
+            if (mayScatter && inflight.size() - head >= size_t(PinnedRing::kSlots - 1)) {
+                cudaError_t e = scatter(inflight[head++]);
+                if (e != cudaSuccess) return e;
+            }
+            Chunk c;
+            c.r0 = a;
+            c.r1 = std::min(r1, a + chunkRows);
+            c.stage = reinterpret_cast<float*>(ctx->ringDn.acquire(&c.slot));
+            cudaError_t e = cudaMemcpyAsync(c.stage, dOut + size_t(a) * cols, size_t(c.r1 - a) * cols * sizeof(float),
+                                            cudaMemcpyDeviceToHost, sDn);
+            if (e != cudaSuccess) return e;
+            ctx->ringDn.submitted(c.slot, sDn);
+            inflight.push_back(c);
+        }
+        return cudaSuccess;
+    }
+    cudaError_t finish()
+    {
+        for (; head < inflight.size(); head++) {
+            cudaError_t e = scatter(inflight[head]);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+};
+
+// K1 over RESIDENT rasters with the output grid coming down band by band while the following bands are still being gridded:
+// the per-step cost of a cached DEM is max(kernel, download) instead of their sum. Same kernel and arithmetic as one launch
+// over the whole valid list (a band is a slice of that list; every cell is independent).
+static int residentRasterPipelined(pb_context* ctx, const DevStations& ds, const DevModel& m, RasterEntry& dem, int rowBegin,
+                                   int rowEnd, pb_raster_out* out)
+{
+    int rc = ensurePipeline(ctx);
+    if (rc) return rc;
+    rc = ensureRowStartImpl(ctx, dem);
+    if (rc) return rc;
+    const int cols = dem.h.nrCols, nRows = rowEnd - rowBegin;
+    static const int wantBands = getenv("PB_BANDS") ? atoi(getenv("PB_BANDS")) : 8;
+    const int nBands = std::max(2, std::min(std::min(kMaxBands, wantBands), nRows / kMinBandRows));
+    const int bandRows = (nRows + nBands - 1) / nBands;
+    cudaStream_t sK = ctx->stream, sDn = ctx->sDn;
+    unsigned* dCounters = reinterpret_cast<unsigned*>(reinterpret_cast<long long*>(ctx->dBand) + kMaxBands);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->dBand, 0, kMaxBands * (sizeof(long long) + sizeof(unsigned)), sK));
+    const DevGrid dg = devGridOf(dem);
+    BandDownloader dl(ctx, out, dem.h.nrRows, cols);
+    auto drain = [&](int code) { cudaStreamSynchronize(sK); cudaStreamSynchronize(sDn); return code; };
+    for (int b = 0; b < nBands; b++) {
+        const int r0 = rowBegin + b * bandRows, r1 = std::min(rowEnd, r0 + bandRows);
+        if (r0 >= r1) break;
+        const long long t0 = dem.rowStart[r0], t1 = dem.rowStart[r1];
+        if (t1 > t0) {
+            cudaError_t ce = launchIdwRaster(ds, m, dg, dem.validIdx + t0, int(t1 - t0), ctx->dOut.p, ctx->dMinMax, sK, nullptr,
+                                             dCounters + b);
+            if (ce != cudaSuccess) return drain(failCtx(ctx, PB_ERR_CUDA, std::string("band launch: ") + cudaGetErrorString(ce)));
+            ctx->timing.launches++;
+        }
+        cudaEventRecord(ctx->evBand[kMaxBands + b], sK);
+        cudaStreamWaitEvent(sDn, ctx->evBand[kMaxBands + b], 0);
+        cudaError_t ce = dl.issue(ctx->dOut.p, r0, r1, true);
+        if (ce != cudaSuccess) return drain(failCtx(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(ce)));
+    }
+    cudaEventRecord(ctx->ev[2], sK);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, sK));
+    cudaError_t ce = dl.finish();
+    if (ce != cudaSuccess) return drain(failCtx(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(ce)));
+    CUDA_TRY(ctx, cudaStreamSynchronize(sDn));
+    cudaEventRecord(ctx->ev[3], sK);
+    CUDA_TRY(ctx, cudaStreamSynchronize(sK));
+    ctx->timing.d2h_bytes += (int64_t)(size_t(nRows) * cols * sizeof(float)) + 8;
+    return PB_OK;
+}
+
 enum OutMode { OUT_HOST = 0, OUT_DEVICE_ONLY = 1 };
 
 int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, pb_raster_id demId,
@@ -809,6 +987,26 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     }
     const int nTargets = (int)(t1 - t0);
     const DevGrid dg = devGridOf(dem);
+    // K1 with a host output grid: band by band, downloads overlapped with the following bands' kernels
+    static const bool noBands = getenv("PB_NO_BAND_PIPELINE") != nullptr;
+    if (mode == OUT_HOST && !local && !precZero && !shepardMethod && !usesTopographicDistance(s, variable) && !noBands &&
+        idwResidentFits(ds.nPadded) && rowEnd - rowBegin >= 2 * kMinBandRows && (out->data || out->rows)) {
+        rc = residentRasterPipelined(ctx, ds, m, dem, rowBegin, rowEnd, out);
+        if (rc) return rc;
+        cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[3]);
+        out->nValid = nTargets;
+        if (ctx->hMinMax[0] == 0xffffffffu) {
+            out->minimum = kNoData;
+            out->maximum = kNoData;
+            return fail(ctx, PB_ERR_NO_VALID_CELL, "no valid cell in the output raster");
+        }
+        out->minimum = keyToFloat(ctx->hMinMax[0]);
+        out->maximum = keyToFloat(ctx->hMinMax[1]);
+        return PB_OK;
+    }
     if (local) {
         rc = launchLocal(ctx, st, s, variable, proxyIds, nProxyGrids, dem, t0, nTargets);
         if (rc) return rc;
@@ -1004,6 +1202,7 @@ void pb_destroy(pb_context* ctx)
         if (g.used) { cudaFree(g.x); cudaFree(g.y); cudaFree(g.first); cudaFree(g.maxNr); cudaFree(g.scratch); cudaFree(g.value); }
     for (auto& m : ctx->macroAreas) if (m.used) cudaFree(m.cells);
     ctx->dLocalStations.release(); ctx->dLocalScratch.release(); ctx->dLocalModel.release(); ctx->hLocal.release();
+    ctx->dLocalRecords.release(); ctx->dLocalSel.release(); ctx->dLocalOverflow.release();
     if (ctx->dLocalError) cudaFree(ctx->dLocalError);
     if (ctx->hLocalError) cudaFreeHost(ctx->hLocalError);
     ctx->dStations.release(); ctx->hStations.release(); ctx->dOut.release(); ctx->dScratch.release(); ctx->ring.release(); ctx->pool.destroy();
@@ -1143,9 +1342,6 @@ int pb_pre_interpolation(pb_context* ctx, pb_stations* st, pb_settings* s, int v
 // Not eligible (-> sequential form below): local detrending, Shepard, topographic distance (needs the whole DEM),
 // all-zero precipitation, more stations than the persistent kernel keeps in shared memory, small rasters.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kMaxBands = 16;
-constexpr int kMinBandRows = 128;
-
 static bool sameGeometry(const pb_raster_header& a, const pb_raster_header& b)
 {
     return a.nrRows == b.nrRows && a.nrCols == b.nrCols && a.cellSize == b.cellSize && a.llx == b.llx && a.lly == b.lly;
@@ -1177,21 +1373,6 @@ static int allocRasterEntry(pb_context* ctx, const pb_raster* r, pb_raster_id* i
 // ring, on `stream`. One parallel region gathers the rows of all rasters of a chunk: the regions' fork/join latency, not
 // the copy bandwidth, is what limits the host side of the band pipeline.
 struct RowsJob { const pb_raster* r; float* dst; };
-
-// page-locked host memory (cudaHostAlloc'd, or registered through pb_host_register) can be the source / target of an
-// asynchronous copy itself: no gather into the staging ring, no host memcpy at all
-// (both ends of the range are checked: a caller may have registered only part of a grid)
-static bool isPinnedHost(const void* p, size_t bytes)
-{
-    if (!p || bytes == 0) return false;
-    const void* ends[2] = {p, static_cast<const unsigned char*>(p) + bytes - 1};
-    for (const void* q : ends) {
-        cudaPointerAttributes a{};
-        if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return false; }
-        if (a.type != cudaMemoryTypeHost) return false;
-    }
-    return true;
-}
 
 static int uploadRows(pb_context* ctx, const RowsJob* jobsIn, int nJobsIn, int r0, int r1, cudaStream_t stream)
 {
@@ -1255,15 +1436,10 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
         return PB_OK;
     *handled = true;
 
-    if (!ctx->sUp) {
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->sUp, cudaStreamNonBlocking));
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->sDn, cudaStreamNonBlocking));
-        for (auto& e : ctx->evBand) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CUDA_TRY(ctx, cudaMalloc(&ctx->dBand, kMaxBands * (sizeof(long long) + sizeof(unsigned))));
-        CUDA_TRY(ctx, cudaMallocHost(&ctx->hBand, kMaxBands * sizeof(long long)));
+    {
+        const int rcp = ensurePipeline(ctx);
+        if (rcp) return rcp;
     }
-    CUDA_TRY(ctx, ctx->ring.init(kStageSlotBytes));
-    CUDA_TRY(ctx, ctx->ringDn.init(kStageSlotBytes));
 
     // device buffers (no data yet) registered as rasters so that the model can refer to the proxy grids
     pb_raster_id demId = -1, ids[PB_MAX_PROXY];
@@ -1334,21 +1510,7 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
     cudaStreamWaitEvent(sUp, ctx->evBand[2 * kMaxBands], 0);
 
     const DevGrid dg = devGridOf(eDem);
-    const int chunkRows = std::max(1, (int)(kStageSlotBytes / (sizeof(float) * cols)));
-    struct Chunk { int r0, r1, slot; float* stage; };
-    std::vector<Chunk> inflight;
-    size_t head = 0;
-    const bool outPinned = out->data && isPinnedHost(out->data, sizeof(float) * size_t(rows) * cols);     // the band comes down straight into the caller's grid
-    auto scatter = [&](const Chunk& c) -> cudaError_t {
-        cudaError_t e = ctx->ringDn.wait(c.slot);
-        if (e != cudaSuccess) return e;
-#pragma omp parallel for schedule(static)
-        for (int row = c.r0; row < c.r1; row++) {
-            float* dst = out->data ? out->data + size_t(row) * cols : out->rows[row];
-            memcpy(dst, c.stage + size_t(row - c.r0) * cols, sizeof(float) * cols);
-        }
-        return cudaSuccess;
-    };
+    BandDownloader dl(ctx, out, rows, cols);      // the band comes down straight into a page-locked grid, else through the ring
     auto fail2 = abortPipeline;
 
     // ---- up: a band's rows of the DEM and of the proxy grids that share its geometry (others: whole, with band 0)
@@ -1388,25 +1550,8 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
         ctx->timing.launches += 2;
         cudaEventRecord(ctx->evBand[kMaxBands + b], sK);
         cudaStreamWaitEvent(sDn, ctx->evBand[kMaxBands + b], 0);
-        if (outPinned) {
-            ce = cudaMemcpyAsync(out->data + size_t(r0) * cols, ctx->dOut.p + size_t(r0) * cols, size_t(r1 - r0) * cols * sizeof(float),
-                                 cudaMemcpyDeviceToHost, sDn);
-            if (ce != cudaSuccess) return failCtx(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(ce));
-            return PB_OK;
-        }
-        for (int a = r0; a < r1; a += chunkRows) {
-            if (mayScatter && inflight.size() - head >= size_t(PinnedRing::kSlots - 1))
-                if (scatter(inflight[head++]) != cudaSuccess) return failCtx(ctx, PB_ERR_CUDA, "D2H failed");
-            Chunk c;
-            c.r0 = a;
-            c.r1 = std::min(r1, a + chunkRows);
-            c.stage = reinterpret_cast<float*>(ctx->ringDn.acquire(&c.slot));
-            ce = cudaMemcpyAsync(c.stage, ctx->dOut.p + size_t(a) * cols, size_t(c.r1 - a) * cols * sizeof(float),
-                                 cudaMemcpyDeviceToHost, sDn);
-            if (ce != cudaSuccess) return failCtx(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(ce));
-            ctx->ringDn.submitted(c.slot, sDn);
-            inflight.push_back(c);
-        }
+        ce = dl.issue(ctx->dOut.p, r0, r1, mayScatter);
+        if (ce != cudaSuccess) return failCtx(ctx, PB_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(ce));
         return PB_OK;
     };
     // The upload engine is the busiest resource of the pipeline and must never wait for the host: the next band's uploads are
@@ -1421,8 +1566,7 @@ static int hostRasterPipelined(pb_context* ctx, const pb_stations* st, const pb_
     cudaEventRecord(ctx->ev[2], sK);
     PIPE_TRY(cudaMemcpyAsync(ctx->hMinMax, ctx->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, sK));
     PIPE_TRY(cudaMemcpyAsync(ctx->hBand, dTotals, kMaxBands * sizeof(long long), cudaMemcpyDeviceToHost, sK));
-    for (; head < inflight.size(); head++)
-        if (scatter(inflight[head]) != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, "D2H failed"); return fail2(PB_ERR_CUDA); }
+    if (dl.finish() != cudaSuccess) { failCtx(ctx, PB_ERR_CUDA, "D2H failed"); return fail2(PB_ERR_CUDA); }
     cudaEventRecord(ctx->ev[3], sK);
     cudaStreamSynchronize(sUp);
     cudaStreamSynchronize(sDn);

@@ -68,6 +68,16 @@ int localGroupLanes(int nFirstGuess);      // lanes per cell chosen for a model 
 cudaError_t launchLocalDetrendingRaster(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem,
                                         const int* validIdx, int nTargets, const LocalScratch& scratch, int groupLanes,
                                         int elevFunction, float* out, unsigned* minmax, cudaStream_t s,
-                                        const LocalPointTargets* points = nullptr);
+                                        const LocalPointTargets* points = nullptr, const int* nTargetsDev = nullptr);
+
+// the raster form as a three-kernel pipeline over one chunk of cells (local_pipeline.cu): selection -> flat
+// Levenberg-Marquardt descents -> pick + estimate; cells that do not fit a record end up in overflowList (count in counters[1])
+size_t localRecordStride(int nGuess);
+int localSelectGroups();
+size_t localSelectScratchBytes(int cap);
+cudaError_t launchLocalPipelineChunk(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem, const int* validIdx,
+                                     int nCells, int elevFunction, int nFirstGuess, unsigned char* records, size_t recStride,
+                                     unsigned char* selScratch, int selCap, int* errFlag, unsigned* counters, int* overflowList,
+                                     float* out, unsigned* minmax, cudaStream_t s, int* launches);
 
 }  // namespace pb

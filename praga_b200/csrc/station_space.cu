@@ -937,7 +937,13 @@ extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, p
     int launches = 0;
     float kernelMs = 0.f;
     int64_t h2d = 0, d2h = 0;
-    auto account = [&]() { launches += ctx->timing.launches; kernelMs += ctx->timing.kernel_ms; h2d += ctx->timing.h2d_bytes; d2h += ctx->timing.d2h_bytes; };
+    // every stage below starts from a zeroed pb_timing (a stage that does not reset it would otherwise be counted with the
+    // totals of the stage before) and is added up here
+    auto account = [&]() {
+        launches += ctx->timing.launches; kernelMs += ctx->timing.kernel_ms; h2d += ctx->timing.h2d_bytes; d2h += ctx->timing.d2h_bytes;
+        memset(&ctx->timing, 0, sizeof(ctx->timing));
+    };
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
     std::vector<uint8_t> wrong(std::max(n, 1), 0);
     // checkData (spatialControl.cpp:466-476): the spatial check is skipped for precipitation and the wind vector components
     const bool spatialVar = variable != PB_VAR_PRECIPITATION && variable != PB_VAR_DAILY_PRECIPITATION && variable != PB_VAR_WIND_VECTOR_X &&
@@ -987,7 +993,7 @@ extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, p
         fillSources(a, &ipts.st, nullptr);
         rc = exactLoo(ctx, a, s, variable, dem, 0, 1, res.data(), nullptr, nullptr);
         if (rc) return rc;
-        launches += ctx->timing.launches;
+        account();
         std::vector<float> obs, pre;
         for (int i = 0; i < n; i++) step->residual[i] = kNoData;
         for (size_t k = 0; k < accepted.size(); k++) {

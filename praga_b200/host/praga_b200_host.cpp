@@ -182,12 +182,108 @@ void flattenPoints(const std::vector<Crit3DInterpolationDataPoint>& pts, int nPr
     f.st.isActive = f.active.data(); f.st.proxyValues = f.proxy.data(); f.st.index = f.index.data();
 }
 
+/* ---- resident raster cache -----------------------------------------------------------------------------------------
+ * The reference keeps its DEM and proxy grids loaded for the whole session (Project::loadDEM / loadProxyGrids) and every
+ * time step grids onto them; the drop-in therefore keeps one device copy per (device, grid): key = the grid's row-pointer
+ * array + header. A call with a cached grid moves only the stations up and the output grid down. A grid that is modified IN
+ * PLACE must be announced with pragab200::invalidate(&grid) (INTEGRATION.md shows the two hooks); as a safety net every hit
+ * also re-checks a fingerprint of 256 sampled cells and the row pointers, and a mismatch uploads the grid again. */
+struct CachedGrid {
+    const gis::Crit3DRasterGrid* owner;
+    float* const* rows;
+    pb_raster_header h;
+    pb_raster_id id;
+    std::vector<float> sample;
+    std::vector<const float*> rowPtr;
+    unsigned long long lastUse;
+    size_t bytes;
+};
+std::map<int, std::vector<CachedGrid>> g_cache;
+unsigned long long g_useClock = 0;
+bool g_cacheEnabled = true;
+size_t g_cacheLimit = size_t(16) << 30;
+
+bool sameHeader(const pb_raster_header& a, const pb_raster_header& b)
+{
+    return a.nrRows == b.nrRows && a.nrCols == b.nrCols && a.cellSize == b.cellSize && a.llx == b.llx && a.lly == b.lly &&
+           a.flag == b.flag;
+}
+
+void fingerprint(const pb_raster& r, std::vector<float>& sample, std::vector<const float*>& rowPtr)
+{
+    const int kSamples = 256;
+    sample.resize(kSamples);
+    unsigned long long x = 0x9E3779B97F4A7C15ull;
+    for (int k = 0; k < kSamples; k++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const int row = int((x >> 11) % (unsigned long long)r.h.nrRows), col = int((x >> 37) % (unsigned long long)r.h.nrCols);
+        sample[k] = r.rows[row][col];
+    }
+    const int rowsToCheck[4] = {0, r.h.nrRows / 3, (2 * r.h.nrRows) / 3, r.h.nrRows - 1};
+    rowPtr.clear();
+    for (int q : rowsToCheck) rowPtr.push_back(r.rows[q]);
+}
+
+void dropEntry(pb_context* ctx, std::vector<CachedGrid>& v, size_t i)
+{
+    pb_raster_free(ctx, v[i].id);
+    v.erase(v.begin() + long(i));
+}
+
+/* device id of a host grid: cached copy when it is still the same grid, else upload (evicting least-recently-used copies
+ * beyond the byte limit). *temporary = the caller frees it after the call (cache disabled). */
+bool residentId(pb_context* ctx, const gis::Crit3DRasterGrid* owner, const pb_raster& r, pb_raster_id* id, bool* temporary)
+{
+    *temporary = false;
+    if (!g_cacheEnabled) {
+        *temporary = true;
+        return !failed(ctx, pb_raster_upload(ctx, &r, id));
+    }
+    std::vector<CachedGrid>& v = g_cache[g_device];
+    std::vector<float> sample;
+    std::vector<const float*> rowPtr;
+    fingerprint(r, sample, rowPtr);
+    for (size_t i = 0; i < v.size(); i++) {
+        if (v[i].rows != r.rows) continue;
+        if (sameHeader(v[i].h, r.h) && v[i].rowPtr == rowPtr && memcmp(v[i].sample.data(), sample.data(), sample.size() * sizeof(float)) == 0) {
+            v[i].lastUse = ++g_useClock;
+            v[i].owner = owner;
+            *id = v[i].id;
+            return true;
+        }
+        dropEntry(ctx, v, i);       // same address, different grid: stale
+        break;
+    }
+    const size_t bytes = size_t(r.h.nrRows) * r.h.nrCols * sizeof(float);
+    size_t total = bytes;
+    for (const CachedGrid& c : v) total += c.bytes;
+    while (total > g_cacheLimit && !v.empty()) {
+        size_t lru = 0;
+        for (size_t i = 1; i < v.size(); i++) if (v[i].lastUse < v[lru].lastUse) lru = i;
+        total -= v[lru].bytes;
+        dropEntry(ctx, v, lru);
+    }
+    CachedGrid c;
+    c.owner = owner; c.rows = r.rows; c.h = r.h; c.sample.swap(sample); c.rowPtr.swap(rowPtr); c.lastUse = ++g_useClock; c.bytes = bytes;
+    if (failed(ctx, pb_raster_upload(ctx, &r, &c.id))) return false;
+    *id = c.id;
+    v.push_back(std::move(c));
+    return true;
+}
+
 bool rasterCall(bool local, std::vector<Crit3DInterpolationDataPoint>& points, Crit3DInterpolationSettings& settings,
                 Crit3DMeteoSettings* meteoSettings, gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster,
                 meteoVariable variable)
 {
-    // output = DEM header, every cell = flag (interpolationCmd.cpp:357 -> gis.cpp:357-363)
-    if (!outputGrid->initializeGrid(raster)) return false;
+    // output = DEM header, every cell = flag (interpolationCmd.cpp:357 -> gis.cpp:357-363). A grid that already has this
+    // geometry keeps its rows: every cell is overwritten below (valid cells by the estimate, the others by the flag).
+    const bool reuse = outputGrid->isLoaded && outputGrid->value != nullptr && outputGrid->header->nrRows == raster.header->nrRows &&
+                       outputGrid->header->nrCols == raster.header->nrCols;
+    if (reuse) {
+        outputGrid->mapTime.setNullTime();       // what clear() resets besides the rows (gis.cpp:265-288)
+        outputGrid->minimum = outputGrid->maximum = NODATA;
+        *outputGrid->header = *raster.header;
+    } else if (!outputGrid->initializeGrid(raster)) return false;
     pb_context* ctx = context();
     if (!ctx) return false;
     pb_settings s;
@@ -199,9 +295,27 @@ bool rasterCall(bool local, std::vector<Crit3DInterpolationDataPoint>& points, C
     pb_raster_out out;
     memset(&out, 0, sizeof(out));
     out.rows = outputGrid->value;
-    const int rc = local ? pb_local_detrending_raster(ctx, &fp.st, &s, int(variable), &dem, grids.data(), int(grids.size()), 0, -1, &out)
-                         : pb_interpolation_raster(ctx, &fp.st, &s, int(variable), &dem, grids.data(), int(grids.size()), 0, -1, &out);
-    if (failed(ctx, rc)) return false;       // incl. PB_ERR_NO_VALID_CELL <=> updateMinMaxRasterGrid false (gis.cpp:601-603)
+    // rasters: resident copies (cached across calls)
+    pb_raster_id demId = -1, ids[PB_MAX_PROXY];
+    std::vector<pb_raster_id> temporaries;
+    bool tmp = false;
+    bool ok = residentId(ctx, &raster, dem, &demId, &tmp);
+    if (ok && tmp) temporaries.push_back(demId);
+    for (size_t g = 0; ok && g < grids.size(); g++) {
+        if (grids[g].rows == dem.rows && sameHeader(grids[g].h, dem.h)) { ids[g] = demId; continue; }
+        ok = residentId(ctx, nullptr, grids[g], &ids[g], &tmp);
+        if (ok && tmp) temporaries.push_back(ids[g]);
+    }
+    int rc = PB_ERR_CUDA;
+    if (ok)
+        rc = local ? pb_local_detrending_raster_resident(ctx, &fp.st, &s, int(variable), demId, ids, int(grids.size()), 0, -1, &out)
+                   : pb_interpolation_raster_resident(ctx, &fp.st, &s, int(variable), demId, ids, int(grids.size()), 0, -1, &out);
+    const bool bad = ok ? failed(ctx, rc) : true;
+    for (pb_raster_id t : temporaries) pb_raster_free(ctx, t);
+    if (bad) {
+        if (reuse && rc != PB_ERR_NO_VALID_CELL) outputGrid->emptyGrid();      // the call failed before it wrote the grid
+        return false;                        // incl. PB_ERR_NO_VALID_CELL <=> updateMinMaxRasterGrid false (gis.cpp:601-603)
+    }
     outputGrid->minimum = out.minimum;
     outputGrid->maximum = out.maximum;
     if (!outputGrid->colorScale->isFixedRange()) outputGrid->colorScale->setRange(out.minimum, out.maximum);   // gis.cpp:606-611
@@ -222,6 +336,41 @@ bool setDevice(int device)
     return true;
 }
 const std::string& lastError() { return g_error; }
+
+bool lastTiming(pb_timing* t)
+{
+    auto it = g_ctx.find(g_device);
+    return it != g_ctx.end() && t && pb_last_timing(it->second, t) == PB_OK;
+}
+
+void setRasterCache(bool enabled, size_t limitBytes)
+{
+    g_cacheEnabled = enabled;
+    if (limitBytes) g_cacheLimit = limitBytes;
+    if (!enabled) invalidateAll();
+}
+
+void invalidate(const gis::Crit3DRasterGrid* grid)
+{
+    if (!grid) return;
+    for (auto& dev : g_cache) {
+        auto it = g_ctx.find(dev.first);
+        if (it == g_ctx.end()) continue;
+        std::vector<CachedGrid>& v = dev.second;
+        for (size_t i = 0; i < v.size();)
+            if (v[i].owner == grid || v[i].rows == grid->value) dropEntry(it->second, v, i);
+            else i++;
+    }
+}
+
+void invalidateAll()
+{
+    for (auto& dev : g_cache) {
+        auto it = g_ctx.find(dev.first);
+        if (it == g_ctx.end()) continue;
+        while (!dev.second.empty()) dropEntry(it->second, dev.second, dev.second.size() - 1);
+    }
+}
 
 bool interpolationRaster(std::vector<Crit3DInterpolationDataPoint>& dataPoints,
                          Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,

@@ -33,11 +33,25 @@
 #include "interpolationSettings.h"
 #include "interpolationPoint.h"
 
+#include "../../include/praga_b200.h"
+
 namespace pragab200 {
 
 /* device used by the calls below (default 0); one engine context per device is created lazily and kept */
 bool setDevice(int device);
 const std::string& lastError();
+
+/* Resident raster cache of the raster calls below. The reference keeps its DEM and proxy grids loaded for the whole session
+ * (Project::loadDEM, project.cpp:1050-1120; loadProxyGrids :1960-2060) and grids every time step onto them; the drop-in keeps
+ * one device copy per (device, grid) — key: the grid's `value` row-pointer array + header — so a time step moves only the
+ * stations up and the output grid down. A grid that is modified IN PLACE or freed must be announced with invalidate(); as a
+ * safety net every call re-checks a fingerprint of the grid (256 sampled cells, 4 row pointers) and uploads again on a
+ * mismatch. setRasterCache(false) restores upload-per-call; limitBytes (0 = keep) bounds the device memory held (LRU). */
+/* device time, launches and bytes moved by the last call on the current device (pb_last_timing of the shim's own context) */
+bool lastTiming(pb_timing* t);
+void setRasterCache(bool enabled, size_t limitBytes = 0);
+void invalidate(const gis::Crit3DRasterGrid* grid);
+void invalidateAll();
 
 bool interpolationRaster(std::vector<Crit3DInterpolationDataPoint>& dataPoints,
                          Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,

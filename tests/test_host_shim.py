@@ -244,3 +244,78 @@ def test_shim_variogram_and_glocal_pre_interpolation(shim, ref):
     assert rc == A.PB_OK, err.value.decode()
     assert a_g.fits() == a_r.fits()
     assert settings_equal(s_r, s_g), describe_diff(s_r, s_g)
+
+
+class ShimSession:
+    """a host session as PRAGA runs one: gis::Crit3DRasterGrid DEM / proxy / output objects that live across time steps"""
+
+    def __init__(self, shim, s, dem, grids):
+        self.shim, self.shape = shim, dem.shape
+        d = dem.as_pb()
+        g = (A.pb_raster * max(1, len(grids)))()
+        for i, r in enumerate(grids):
+            g[i] = r.as_pb()
+        self.h = shim.shim_session_open(C.byref(s), C.byref(d), g, len(grids))
+
+    def step(self, st, var, local=False):
+        stp = st.as_pb()
+        sec, mn, mx = C.c_double(0), C.c_float(0), C.c_float(0)
+        rc = self.shim.shim_session_step(self.h, C.byref(stp), var, int(local), C.byref(sec), C.byref(mn), C.byref(mx))
+        out = np.empty(self.shape, dtype=np.float32)
+        o = A.pb_raster_out()
+        o.data = A.fptr(out)
+        self.shim.shim_session_output(self.h, C.byref(o))
+        return rc == A.PB_OK, out, mn.value, mx.value, sec.value
+
+    def close(self):
+        self.shim.shim_session_close(self.h)
+
+
+def test_shim_session_keeps_rasters_resident_and_notices_changes(shim, ref):
+    """Time steps of one session: the DEM / proxy grids go up once (resident cache of the shim), every step must still equal
+    the reference's grid; an announced in-place change of the DEM (pragab200::invalidate) is seen by the next step; with the
+    cache switched off the grids are the same."""
+    dem = syn.make_dem(420, 380, seed=31)
+    urban = syn.make_urban(420, 380)
+    s = syn.settings_multiple_detrending()
+    s.currentSignificant[0] = s.currentSignificant[1] = 1
+    s.nFit = s.nFitFunctions = 2
+    s.fitFunction[0], s.fitNrParams[0] = A.piecewiseTwo, 4
+    s.fitFunction[1], s.fitNrParams[1] = A.linear, 2
+    for j, v in enumerate((400.0, 13.3, 0.0045, -0.0065)):
+        s.fitParams[0][j] = v
+    s.fitParams[1][0], s.fitParams[1][1] = 2.0, -0.6
+    base = syn.make_stations(dem, 160, proxies=(dem, urban))
+    sess = ShimSession(shim, s, dem, (dem, urban))
+    try:
+        for k in range(3):
+            st = base.copy()
+            st.value[:] = (base.value - 12.0 + np.random.default_rng(k).normal(0, 0.3, st.n)).astype(np.float32)
+            okc, gc, mnc, mxc, _, _ = ref.interpolation_raster(st, s, A.airTemperature, dem, (dem, urban))
+            okg, gg, mng, mxg, sec = sess.step(st, A.airTemperature)
+            assert okg == okc
+            assert np.array_equal(gg == np.float32(dem.flag), gc == np.float32(dem.flag))
+            m = gc != np.float32(dem.flag)
+            assert np.abs(gg[m].astype(np.float64) - gc[m]).max() <= TOL
+            assert abs(mng - mnc) <= TOL and abs(mxg - mxc) <= TOL
+        # the DEM changes in place: a valid cell becomes NODATA and an elevation changes by 800 m; the host announces it
+        rows, cols = np.nonzero(dem.data != np.float32(dem.flag))
+        r1, c1, r2, c2 = int(rows[1000]), int(cols[1000]), int(rows[5000]), int(cols[5000])
+        dem2 = A.Raster(dem.data.copy(), dem.llx, dem.lly, dem.cell_size, dem.flag)
+        dem2.data[r1, c1] = dem.flag
+        dem2.data[r2, c2] += 800.0
+        shim.shim_session_poke_dem(sess.h, r1, c1, float(dem.flag), 0)
+        shim.shim_session_poke_dem(sess.h, r2, c2, float(dem2.data[r2, c2]), 1)
+        okc, gc, *_ = ref.interpolation_raster(st, s, A.airTemperature, dem2, (dem2, urban))
+        okg, gg, *_ = sess.step(st, A.airTemperature)
+        assert gg[r1, c1] == np.float32(dem.flag)
+        assert np.array_equal(gg == np.float32(dem.flag), gc == np.float32(dem.flag))
+        m = gc != np.float32(dem.flag)
+        assert np.abs(gg[m].astype(np.float64) - gc[m]).max() <= TOL
+        # cache off: same grid
+        shim.shim_session_cache(0)
+        okg2, gg2, *_ = sess.step(st, A.airTemperature)
+        shim.shim_session_cache(1)
+        assert np.array_equal(gg, gg2)
+    finally:
+        sess.close()

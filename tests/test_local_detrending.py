@@ -13,6 +13,18 @@ TOL = 1e-4
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["pipeline", "fused"])
+def schedule(request, monkeypatch):
+    """every test of this module runs under both schedules of K2: the three-kernel pipeline (selection -> flat
+    Levenberg-Marquardt descents -> pick + estimate; forced here also for small rasters) and the fused kernel"""
+    if request.param == "pipeline":
+        monkeypatch.setenv("PB_LOCAL_PIPELINE_MIN", "1")
+        monkeypatch.delenv("PB_LOCAL_FUSED", raising=False)
+    else:
+        monkeypatch.setenv("PB_LOCAL_FUSED", "1")
+    return request.param
+
+
 def local_settings(st, min_points=20, use_urban=True):
     s = syn.settings_multiple_detrending(use_urban)
     s.useLocalDetrending = 1
@@ -177,3 +189,21 @@ def test_local_detrending_plain_shepard_is_rejected(engine):
     with pytest.raises(pb.PragaB200Error) as e:
         engine.local_detrending_raster(st, s, A.airTemperature, dem, (dem,))
     assert e.value.status == A.PB_ERR_UNSUPPORTED
+
+
+def test_pipeline_and_fused_schedules_give_the_same_bits(engine, monkeypatch):
+    """the same raster through both schedules of K2, the pipeline in chunks smaller than the raster: identical bits,
+    identical min / max"""
+    dem = syn.make_dem(150, 170, cell_size=5000.0, seed=17)
+    urban = syn.make_urban(150, 170, cell_size=5000.0)
+    st = syn.make_stations(dem, 5400, proxies=(dem, urban), seed=23)
+    s = local_settings(st)
+    monkeypatch.setenv("PB_LOCAL_FUSED", "1")
+    ra = engine.local_detrending_raster(st, s, A.airTemperature, dem, (dem, urban))
+    monkeypatch.delenv("PB_LOCAL_FUSED")
+    monkeypatch.setenv("PB_LOCAL_PIPELINE_MIN", "1")
+    monkeypatch.setenv("PB_LOCAL_CHUNK", "7000")
+    rb = engine.local_detrending_raster(st, s, A.airTemperature, dem, (dem, urban))
+    assert ra[0] and rb[0]
+    assert np.array_equal(ra[1], rb[1])
+    assert ra[2:] == rb[2:]
