@@ -171,8 +171,10 @@ struct pb_context {
     int outInitRaster = -1;             // dOut currently holds the flag pattern of this raster id
     pb::DevBuf<unsigned char> dScratch;     // point targets
     pb::DevBuf<unsigned char> dLocalStations, dLocalScratch, dLocalModel;   // local-detrending raster (K2)
-    pb::DevBuf<unsigned char> dLocalRecords, dLocalSel;                     // K2 pipeline: per-cell records of a chunk, selection scratch
-    pb::DevBuf<int> dLocalOverflow;                                         // K2 pipeline: cells left to the fused kernel + {cell counter, count}
+    pb::DevBuf<unsigned char> dLocalRecords;                                // K2 pipeline: per-cell records of the two chunks in flight
+    pb::DevBuf<int> dLocalWork, dLocalOverflow;                             // K2 pipeline: per-chunk counters / order; cells left to the fused kernel
+    cudaStream_t sPipe[2] = {nullptr, nullptr};                             // K2 pipeline: chunks alternate between two streams
+    cudaEvent_t evPipe[3] = {nullptr, nullptr, nullptr};
     pb::PinnedBuf hLocal;
     int* dLocalError = nullptr;
     int* hLocalError = nullptr;         // pinned

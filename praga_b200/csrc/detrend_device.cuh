@@ -68,13 +68,16 @@ __device__ __forceinline__ double divByKnown(double n, double d, double r)
 __device__ __forceinline__ double divFast(double n, double d, double r, bool& slow)
 {
     const double q0 = n * r;
-    const double aq = fabs(q0);
     const double e0 = __fma_rn(-d, q0, n);
     const double q1 = __fma_rn(e0, r, q0);
     const double e1 = __fma_rn(-d, q1, n);
     const double q = __fma_rn(e1, r, q1);
-    slow |= !(aq > 1e-280 && aq < 1e280) && (n != 0);
-    return (n == 0) ? q0 : q;
+    // the guards are integer tests on the operands' bits (the FP64 pipe is what bounds the descents: no DSETP here): biased
+    // exponent of q0 in [94, 1952] = |q0| within about (1e-280, 1e280); a zero numerator of either sign keeps q0
+    const unsigned ex = (unsigned(__double2hiint(q0)) >> 20) & 0x7ffu;
+    const bool nz = ((__double2hiint(n) & 0x7fffffff) | __double2loint(n)) != 0;
+    slow |= (ex - 94u > 1858u) && nz;
+    return nz ? q : q0;
 }
 
 // ---- model functions with the reference's in-place clamp of par[2] (furtherMathFunctions.cpp:138, 158) ----
@@ -136,6 +139,13 @@ __device__ __forceinline__ double evalFitRt(int f, double x, const double* par)
 // (par[k] += delta; ...; par[k] -= delta, which does not always restore the same bits) is reproduced: column k is
 // evaluated with the already "restored" entries below k, and the restored vector is what the step is added to.
 // ---------------------------------------------------------------------------------------------------------
+// unroll factor of the data loops of lmIter (each accumulator still receives its terms in ascending point order; the point
+// computations of consecutive iterations overlap). A TU may define PB_LM_UNROLL before including this header.
+#ifndef PB_LM_UNROLL
+#define PB_LM_UNROLL 1
+#endif
+constexpr int kLmUnroll = PB_LM_UNROLL;
+
 // state of one descent: lmElevation = lmInit + lmIter until it reports the end
 template <int F>
 struct LmState {
@@ -221,6 +231,7 @@ __device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__
 #pragma unroll
         for (int j = 0; j < N; j++) a[i][j] = 0;
     }
+#pragma unroll kLmUnroll
     for (int j = 0; j < nData; j++) {
         const double x = X[j], y = Y[j], w = W[j];
         double P[N], WP[N];
@@ -276,6 +287,7 @@ __device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__
     }
     double newSSE = 0, newSsr = 0, newSc = 0;
     if (nData > 0) Fit<F>::clamp(np);
+#pragma unroll kLmUnroll
     for (int i = 0; i < nData; i++) {
         const double error = Y[i] - Fit<F>::eval(X[i], np);
         const double w = W[i];

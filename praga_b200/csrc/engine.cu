@@ -628,24 +628,48 @@ int launchLocal(pb_context* ctx, const pb_stations* st, const pb_settings* s, in
         const int chunkEnv = getenv("PB_LOCAL_CHUNK") ? atoi(getenv("PB_LOCAL_CHUNK")) : 0;
         const int chunk = std::min(nTargets, chunkEnv > 0 ? chunkEnv : (512 << 10));
         const size_t recStride = localRecordStride(m.nFirstGuess);
-        const int selCap = std::max(std::min(st->n, 2048), 1);
-        CUDA_TRY(ctx, ctx->dLocalRecords.reserve(recStride * size_t(chunk)));
-        CUDA_TRY(ctx, ctx->dLocalSel.reserve(localSelectScratchBytes(selCap)));
-        CUDA_TRY(ctx, ctx->dLocalOverflow.reserve(size_t(chunk) + 4));
-        unsigned* counters = reinterpret_cast<unsigned*>(ctx->dLocalOverflow.p);
+        // Two chunks are in flight, each on its own stream with its own records: a few descents of a chunk run for hundreds of
+        // Levenberg-Marquardt iterations (maxIter = 1000) while every other lane has run out of work; the next chunk's kernels
+        // take the SMs those stragglers leave free instead of waiting for them.
+        const bool twoStreams = nTargets > chunk && !getenv("PB_LOCAL_ONE_STREAM") && !getenv("PB_LOCAL_TIMING");
+        const int nSlots = twoStreams ? 2 : 1;
+        const size_t workInts = (localPipelineWorkInts(chunk) + 63) / 64 * 64;
+        CUDA_TRY(ctx, ctx->dLocalRecords.reserve(recStride * size_t(chunk) * nSlots));
+        CUDA_TRY(ctx, ctx->dLocalWork.reserve(workInts * nSlots));
+        CUDA_TRY(ctx, ctx->dLocalOverflow.reserve(size_t(nTargets) + 4));
+        int* overflowCount = ctx->dLocalOverflow.p;
         int* overflowList = ctx->dLocalOverflow.p + 4;
-        for (long long c0 = 0; c0 < nTargets; c0 += chunk) {
-            const int nc = int(std::min<long long>(chunk, nTargets - c0));
-            int launches = 0;
-            CUDA_TRY(ctx, launchLocalPipelineChunk(dModel, ds, devGridOf(dem), dem.validIdx + t0 + c0, nc, m.elevFunction, m.nFirstGuess,
-                                                   ctx->dLocalRecords.p, recStride, ctx->dLocalSel.p, selCap, ctx->dLocalError, counters,
-                                                   overflowList, ctx->dOut.p, ctx->dMinMax, ctx->stream, &launches));
-            CUDA_TRY(ctx, launchLocalDetrendingRaster(dModel, ds, devGridOf(dem), overflowList, nc, scr, groupLanes, m.elevFunction,
-                                                      ctx->dOut.p, ctx->dMinMax, ctx->stream, nullptr,
-                                                      reinterpret_cast<const int*>(counters + 1)));
-            ctx->timing.launches += launches;        // the caller counts one more (the fused kernel's launch)
-            if (c0 + chunk < nTargets) ctx->timing.launches++;
+        CUDA_TRY(ctx, cudaMemsetAsync(overflowCount, 0, 4 * sizeof(int), ctx->stream));
+        cudaStream_t streams[2] = {ctx->stream, ctx->stream};
+        if (twoStreams) {
+            for (int k = 0; k < 2; k++)
+                if (!ctx->sPipe[k]) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->sPipe[k], cudaStreamNonBlocking));
+            for (auto& e : ctx->evPipe)
+                if (!e) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->evPipe[2], ctx->stream));
+            for (int k = 0; k < 2; k++) {
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->sPipe[k], ctx->evPipe[2], 0));
+                streams[k] = ctx->sPipe[k];
+            }
         }
+        int launches = 0, k = 0;
+        for (long long c0 = 0; c0 < nTargets; c0 += chunk, k++) {
+            const int nc = int(std::min<long long>(chunk, nTargets - c0));
+            const int slot = k % nSlots;
+            CUDA_TRY(ctx, launchLocalPipelineChunk(dModel, ds, devGridOf(dem), dem.validIdx + t0 + c0, nc, m.elevFunction, m.candRadius,
+                                                   ctx->dLocalRecords.p + recStride * size_t(chunk) * slot, recStride,
+                                                   ctx->dLocalWork.p + workInts * slot, overflowList, overflowCount, ctx->dOut.p,
+                                                   ctx->dMinMax, streams[slot], &launches));
+        }
+        if (twoStreams)
+            for (int q = 0; q < 2; q++) {
+                CUDA_TRY(ctx, cudaEventRecord(ctx->evPipe[q], ctx->sPipe[q]));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evPipe[q], 0));
+            }
+        // the cells no chunk could take, through the fused kernel (list form, count read on the device)
+        CUDA_TRY(ctx, launchLocalDetrendingRaster(dModel, ds, devGridOf(dem), overflowList, nTargets, scr, groupLanes, m.elevFunction,
+                                                  ctx->dOut.p, ctx->dMinMax, ctx->stream, nullptr, overflowCount));
+        ctx->timing.launches += launches;            // the caller counts one more (the fused kernel's launch)
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hLocalError, ctx->dLocalError, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return PB_OK;
@@ -1202,7 +1226,9 @@ void pb_destroy(pb_context* ctx)
         if (g.used) { cudaFree(g.x); cudaFree(g.y); cudaFree(g.first); cudaFree(g.maxNr); cudaFree(g.scratch); cudaFree(g.value); }
     for (auto& m : ctx->macroAreas) if (m.used) cudaFree(m.cells);
     ctx->dLocalStations.release(); ctx->dLocalScratch.release(); ctx->dLocalModel.release(); ctx->hLocal.release();
-    ctx->dLocalRecords.release(); ctx->dLocalSel.release(); ctx->dLocalOverflow.release();
+    ctx->dLocalRecords.release(); ctx->dLocalWork.release(); ctx->dLocalOverflow.release();
+    for (auto& sp : ctx->sPipe) if (sp) cudaStreamDestroy(sp);
+    for (auto& e : ctx->evPipe) if (e) cudaEventDestroy(e);
     if (ctx->dLocalError) cudaFree(ctx->dLocalError);
     if (ctx->hLocalError) cudaFreeHost(ctx->hLocalError);
     ctx->dStations.release(); ctx->hStations.release(); ctx->dOut.release(); ctx->dScratch.release(); ctx->ring.release(); ctx->pool.destroy();

@@ -73,11 +73,10 @@ cudaError_t launchLocalDetrendingRaster(const LocalModel* dModel, const LocalSta
 // the raster form as a three-kernel pipeline over one chunk of cells (local_pipeline.cu): selection -> flat
 // Levenberg-Marquardt descents -> pick + estimate; cells that do not fit a record end up in overflowList (count in counters[1])
 size_t localRecordStride(int nGuess);
-int localSelectGroups();
-size_t localSelectScratchBytes(int cap);
+size_t localPipelineWorkInts(int nCells);
 cudaError_t launchLocalPipelineChunk(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem, const int* validIdx,
-                                     int nCells, int elevFunction, int nFirstGuess, unsigned char* records, size_t recStride,
-                                     unsigned char* selScratch, int selCap, int* errFlag, unsigned* counters, int* overflowList,
-                                     float* out, unsigned* minmax, cudaStream_t s, int* launches);
+                                     int nCells, int elevFunction, float candRadius, unsigned char* records, size_t recStride,
+                                     int* work, int* overflowList, int* overflowCount, float* out, unsigned* minmax, cudaStream_t s,
+                                     int* launches);
 
 }  // namespace pb

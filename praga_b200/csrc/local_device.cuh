@@ -11,8 +11,16 @@ namespace pb {
 template <int G>
 __device__ int localSelect(const LocalModel& m, const LocalStations& st, const float2* __restrict__ xy, float xf, float yf,
                            const WorkPtrs& gw, int gcap, unsigned char* tile, int tileCap, int* errFlag, WorkPtrs& w,
-                           float& localRadius)
+                           float& localRadius, const int* __restrict__ sList = nullptr, int nList = 0, int ccap = -1,
+                           float listRadius = 0.f)
 {
+    // listRadius: every station within listRadius (>= the candidate radius) of the target is in sList: rings that end inside it
+    // but beyond the candidate radius (raster borders, sparse neighbourhoods) walk the list instead of all S stations
+    // ccap: capacity of the candidate arrays gw.oi / gw.w when it differs from gcap (the pipeline keeps them in shared
+    // memory). errFlag == nullptr: a selection larger than gcap is the caller's business — the true n is returned and the
+    // working arrays are left unfilled
+    // sList (optional): ascending station indices that contain EVERY station within the candidate radius of this target (a
+    // prefilter shared by the targets of a CTA, local_pipeline.cu); the candidate pass then walks the list instead of all S
     const int lane = grpLane<G>();
     const int S = st.n;
     const bool useCode = m.useLapseRateCode != 0;
@@ -22,6 +30,7 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
     int n = 0;
     float maxDistance = 0.f;
     const bool takeAll = unsigned(S) <= m.minPoints;
+    if (ccap < 0) ccap = gcap;
     if (takeAll) {
         for (int i = lane; i < S && i < gcap; i += G) {
             const float2 p = xy[i];
@@ -30,7 +39,7 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
             gw.d[i] = sqrtf(dx * dx + dy * dy);
         }
         n = S < gcap ? S : gcap;
-        if (S > gcap && lane == 0) *errFlag = 1;
+        if (S > gcap && lane == 0 && errFlag) *errFlag = 1;
     } else {
         // Candidate pass: ONE scan of all stations keeps, in station order, those within the candidate radius (so that the
         // rings below walk a few dozen entries instead of all S) and the largest distance (the `beyond last point` test).
@@ -45,10 +54,12 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
             // with 4 lanes per cell was a third of the kernel's stall samples
             const float rcap2 = rcap * rcap * 1.0001f;
             float dmax2 = 0.f;
-            const int per = (S + G - 1) / G;
-            const int i0 = lane * per, i1 = (i0 + per < S) ? i0 + per : S;
+            const int L0 = sList ? nList : S;
+            const int per = (L0 + G - 1) / G;
+            const int i0 = lane * per, i1 = (i0 + per < L0) ? i0 + per : L0;
             int mine = 0;
-            for (int i = i0; i < i1; i++) {
+            for (int k = i0; k < i1; k++) {
+                const int i = sList ? sList[k] : k;
                 const float2 p = xy[i];
                 const float dx = p.x - xf, dy = p.y - yf;
                 const float d2 = dx * dx + dy * dy;
@@ -62,9 +73,10 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
                 offset += (l < lane) ? cl : 0;
                 nc += cl;
             }
-            if (nc <= gcap) {
+            if (nc <= ccap) {
                 int pos = offset;
-                for (int i = i0; i < i1; i++) {
+                for (int k = i0; k < i1; k++) {
+                    const int i = sList ? sList[k] : k;
                     const float2 p = xy[i];
                     const float dx = p.x - xf, dy = p.y - yf;
                     const float d2 = dx * dx + dy * dy;
@@ -74,7 +86,8 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
 #pragma unroll
             for (int o = G / 2; o; o >>= 1) dmax2 = fmaxf(dmax2, __shfl_xor_sync(grpMask<G>(), dmax2, o, G));
             dmax = sqrtf(dmax2);                  // sqrtf is monotonic: max of the distances
-            if (nc > gcap) rcap = 0.f;            // too dense for the candidate list: full scans
+            if (sList && nList < S) dmax = INFINITY;      // a station outside the shared list lies beyond the candidate radius
+            if (nc > ccap) rcap = 0.f;            // too dense for the candidate list: full scans
             grpSync<G>();
         }
         unsigned nrValid = 0, nrPrimaries = 0;
@@ -82,7 +95,8 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
         bool beyondLastPoint = false;
         while (((!useCode && nrValid < m.minPoints) || (useCode && nrPrimaries < m.minPoints)) && !beyondLastPoint) {
             const bool compact = rcap > 0.f && r1 <= rcap;
-            const int L = compact ? nc : S;
+            const bool useList = !compact && sList != nullptr && r1 <= listRadius;
+            const int L = compact ? nc : (useList ? nList : S);
             bool farther = false;
             // one contiguous block of the list per lane: count the ring's members, prefix over the group, write in place —
             // ring-major / index order without a vote per chunk
@@ -94,6 +108,7 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
                 int i = k;
                 if (compact) { i = gw.oi[k]; d = gw.w[k]; }
                 else {
+                    if (useList) i = sList[k];
                     const float2 p = xy[i];
                     const float dx = p.x - xf, dy = p.y - yf;       // gis::computeDistance(x, y, px, py), gis.cpp:685-691
                     d = sqrtf(dx * dx + dy * dy);
@@ -119,6 +134,7 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
                     int i = k;
                     if (compact) { i = gw.oi[k]; d = gw.w[k]; }
                     else {
+                        if (useList) i = sList[k];
                         const float2 p = xy[i];
                         const float dx = p.x - xf, dy = p.y - yf;
                         d = sqrtf(dx * dx + dy * dy);
@@ -133,7 +149,10 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
                 nrPrimaries += totalPrim;
             }
             nrValid = unsigned(n);
-            beyondLastPoint = compact ? !(dmax > r1) : grpBallot<G>(farther) == 0u;
+            // a station outside the shared list lies beyond listRadius >= r1: it is "farther"
+            if (compact) beyondLastPoint = !(dmax > r1);
+            else if (useList && nList < S) beyondLastPoint = false;
+            else beyondLastPoint = grpBallot<G>(farther) == 0u;
             if (nrValid > m.thr80) stepRadius = 1000.f;
             r0 = r1;
             r1 += stepRadius;
@@ -142,6 +161,7 @@ __device__ int localSelect(const LocalModel& m, const LocalStations& st, const f
 #pragma unroll
         for (int o = G / 2; o; o >>= 1) maxDistance = fmaxf(maxDistance, __shfl_xor_sync(grpMask<G>(), maxDistance, o, G));
         if (n > gcap) {
+            if (!errFlag) { grpSync<G>(); return n; }
             if (lane == 0) *errFlag = 1;
             n = gcap;
         }

@@ -17,6 +17,7 @@
 // owned a cell from selection to estimate, and 18 of 32 lanes were busy because descents end after 2-60 iterations.
 // Cells whose selection does not fit a record (more than kRecCap stations, or more than kFitCap elevation points) are listed
 // and gridded by the fused kernel afterwards. Built with -fmad=false.
+#include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
 #include "local_device.cuh"
@@ -71,88 +72,196 @@ __device__ __forceinline__ void descentInit(const double* __restrict__ guess, co
 // A: selection + staging. One group of 4 lanes per cell, many cells in flight per SM (no LM code: few registers).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kSelG = 4;
-constexpr int kSelThreads = 256;
+constexpr int kSelThreads = 128;     // 32 cells in flight per CTA; 5 CTAs per SM (shared memory)
+constexpr int kSelSpanTilesMax = 8;  // tiles (of kSelThreads / kSelG consecutive targets) that share one prefilter list, at most
+constexpr int kSelListCap = 1024;    // stations the CTA-wide prefilter list holds (beyond: the groups scan all stations)
+constexpr int kCandCap = 80;         // per-cell candidate list (shared memory); denser neighbourhoods scan the prefilter list per ring
 
-// candidate / selection scratch of one group: only the arrays localSelect touches (candidate list oi / w, selection idx / d,
-// and val / flg, which it also fills when a selection is too large for the record)
-__host__ __device__ constexpr size_t selScratchBytes(int cap) { return (size_t(cap) * 21 + 15) / 16 * 16; }
-__device__ __forceinline__ WorkPtrs carveSel(unsigned char* base, int cap)
+// shared-memory scratch of one group: candidate list (oi, w: kCandCap) + selection (idx, d: kRecCap)
+constexpr int kSelGroupBytes = kCandCap * 8 + kRecCap * 8;
+__device__ __forceinline__ WorkPtrs carveSel(unsigned char* base)
 {
     WorkPtrs p{};
-    p.idx = reinterpret_cast<int*>(base);
-    p.d = reinterpret_cast<float*>(p.idx + cap);
-    p.oi = reinterpret_cast<int*>(p.d + cap);
-    p.w = reinterpret_cast<float*>(p.oi + cap);
-    p.val = p.w + cap;
-    p.flg = reinterpret_cast<unsigned char*>(p.val + cap);
+    p.oi = reinterpret_cast<int*>(base);
+    p.w = reinterpret_cast<float*>(p.oi + kCandCap);
+    p.idx = reinterpret_cast<int*>(p.w + kCandCap);
+    p.d = reinterpret_cast<float*>(p.idx + kRecCap);
     return p;
 }
 
-__global__ void __launch_bounds__(kSelThreads, 3)
-local_select_kernel(const LocalModel* __restrict__ mp, LocalStations st, DevGrid dem, const int* __restrict__ validIdx, int nCells,
-                    unsigned char* __restrict__ selScratch, int selCap, int* __restrict__ errFlag, int xyInSmem,
-                    unsigned char* __restrict__ records, size_t recStride, int* __restrict__ overflowList,
-                    int* __restrict__ overflowCount)
+__device__ __forceinline__ unsigned orderedKeyF(float f)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float keyToFloatF(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(kSelThreads, 5)
+local_select_kernel(const LocalModel* __restrict__ mp, LocalStations st, DevGrid dem, const int* __restrict__ validIdx, int nCells,
+                    unsigned char* __restrict__ records, size_t recStride, int* __restrict__ overflowList,
+                    int* __restrict__ overflowCount, unsigned* __restrict__ fitHist, int spanTiles, unsigned* __restrict__ spanCounter)
+{
+    __shared__ __align__(16) unsigned char sGroup[(kSelThreads / kSelG) * kSelGroupBytes];
+    __shared__ int sList[kSelListCap];
+    __shared__ unsigned sBox[4];            // ordered keys of min x, max x, min y, max y of the span's targets
+    __shared__ int sWarpCount[kSelThreads / 32];
+    __shared__ unsigned sSpan;
     constexpr int G = kSelG;
     constexpr int groupsPerCta = kSelThreads / G;
+    const int spanCells = groupsPerCta * spanTiles;
     const LocalModel& m = *mp;
     const int grp = threadIdx.x / G;
     const int lane = grpLane<G>();
-    float2* sxy = reinterpret_cast<float2*>(smem);
-    if (xyInSmem) {
-        for (int i = threadIdx.x; i < st.n; i += kSelThreads) sxy[i] = st.xy[i];
-        __syncthreads();
-    }
-    const float2* xy = xyInSmem ? sxy : st.xy;
-    const long long groupsTotal = (long long)gridDim.x * groupsPerCta;
-    const long long gid = (long long)blockIdx.x * groupsPerCta + grp;
-    const WorkPtrs gw = carveSel(selScratch + gid * selScratchBytes(selCap), selCap);
+    const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    const float2* xy = st.xy;
+    const WorkPtrs gw = carveSel(sGroup + grp * kSelGroupBytes);
     const int ePos = m.elevationPos;
     const bool hasElev = ePos >= 0 && m.selectedActive[ePos];
+    const int S = st.n;
+    // the prefilter pays when the candidate radius covers a small part of the station set
+    const bool prefilter = m.candRadius > 0.f && unsigned(S) > m.minPoints && S > 256;
 
-    for (long long t = gid; t < nCells; t += groupsTotal) {
-        const int cell = validIdx[t];
-        const int row = cell / dem.nrCols, col = cell - row * dem.nrCols;
-        // gis::getUtmXYFromRowCol (gis.cpp:806-810), then narrowed to float by the callee signatures (interpolation.h:77-95,162)
-        const double x = dem.llx + dem.cellSize * (col + 0.5);
-        const double y = dem.lly + dem.cellSize * (dem.nrRows - row - 0.5);
-        const float xf = float(x), yf = float(y);
-        unsigned char* rec = records + size_t(t) * recStride;
-        WorkPtrs w;
-        float localRadius = 0.f;
-        // the record's work area plays the role of the fused kernel's shared-memory tile (capacity kRecCap)
-        const int n = localSelect<G>(m, st, xy, xf, yf, gw, selCap, rec + recWorkOff(), kRecCap, errFlag, w, localRadius);
-        int nE = 0, flags = 0;
-        if (n > kRecCap) flags = CELL_OVERFLOW;
-        else if (hasElev) {
-            bool isValid;
-            nE = mdStageElevation<G>(m, st, w, n, true, isValid);
-            if (isValid) flags = (nE <= kFitCap) ? CELL_FIT : CELL_OVERFLOW;
-            if (flags == CELL_FIT) {
-                // starting point of every descent of this cell (the lanes share the first guesses)
-                double* init = reinterpret_cast<double*>(rec + recInitOff());
-                const int nGuess = m.nFirstGuess < kMaxGuess ? m.nFirstGuess : kMaxGuess;
-                for (int g = lane; g < nGuess; g += G) {
-                    const double* guess = &m.firstGuess[g][0];
-                    switch (m.elevFunction) {
-                    case PB_FIT_PIECEWISE_THREE: descentInit<PB_FIT_PIECEWISE_THREE>(guess, w.X, w.Y, w.W, nE, init + g * 3); break;
-                    case PB_FIT_PIECEWISE_THREE_FREE: descentInit<PB_FIT_PIECEWISE_THREE_FREE>(guess, w.X, w.Y, w.W, nE, init + g * 3); break;
-                    default: descentInit<PB_FIT_PIECEWISE_TWO>(guess, w.X, w.Y, w.W, nE, init + g * 3); break;
+    // a SPAN = spanTiles x groupsPerCta consecutive targets of the valid list (neighbouring cells of a row, a few rows at
+    // most): their candidate circles overlap almost entirely, so the CTA first lists, in station order, the stations inside the
+    // span's bounding box grown by the candidate radius (a superset of every target's candidates); each group's candidate pass
+    // then walks that list instead of all S stations. One barrier per span: the groups run their cells independently.
+    // the list reaches twice the candidate radius: the rings of targets with few stations around them (raster borders) go on
+    // beyond the candidate radius and would otherwise scan all S stations per ring
+    const float listRadius = 2.f * m.candRadius;
+    for (;;) {
+        __syncthreads();                     // every group is done with the previous span's list
+        if (threadIdx.x == 0) sSpan = atomicAdd(spanCounter, 1u);          // spans are handed out dynamically (uneven cost)
+        __syncthreads();
+        const long long first = (long long)sSpan * spanCells;
+        if (first >= nCells) break;
+        int nList = 0;
+        const int* list = nullptr;
+        if (prefilter) {
+            if (threadIdx.x == 0) { sBox[0] = 0xffffffffu; sBox[1] = 0u; sBox[2] = 0xffffffffu; sBox[3] = 0u; }
+            __syncthreads();
+            {
+                float bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
+                for (long long t = first + threadIdx.x; t < first + spanCells && t < nCells; t += kSelThreads) {
+                    const int cell = validIdx[t];
+                    const int row = cell / dem.nrCols, col = cell - row * dem.nrCols;
+                    const float xf = float(dem.llx + dem.cellSize * (col + 0.5));
+                    const float yf = float(dem.lly + dem.cellSize * (dem.nrRows - row - 0.5));
+                    bx0 = fminf(bx0, xf); bx1 = fmaxf(bx1, xf); by0 = fminf(by0, yf); by1 = fmaxf(by1, yf);
+                }
+                for (int o = 16; o; o >>= 1) {
+                    bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+                    by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+                }
+                if (wl == 0 && bx0 != INFINITY) {
+                    atomicMin(&sBox[0], orderedKeyF(bx0)); atomicMax(&sBox[1], orderedKeyF(bx1));
+                    atomicMin(&sBox[2], orderedKeyF(by0)); atomicMax(&sBox[3], orderedKeyF(by1));
+                }
+            }
+            __syncthreads();
+            // grown by more than the list radius (the per-target tests are d2 <= rcap^2 * 1.0001 and d <= r1 <= listRadius): a
+            // superset for sure
+            const float R = listRadius * 1.001f + 1.f;
+            const float x0 = keyToFloatF(sBox[0]) - R, x1 = keyToFloatF(sBox[1]) + R;
+            const float y0 = keyToFloatF(sBox[2]) - R, y1 = keyToFloatF(sBox[3]) + R;
+            // every warp owns one contiguous range of stations: count, prefix over the warps, write — station order is kept
+            const int per = ((S + kSelThreads / 32 - 1) / (kSelThreads / 32) + 31) / 32 * 32;
+            const int w0 = warp * per, w1 = min(S, w0 + per);
+            int cnt = 0;
+            for (int i = w0 + wl; i - wl < w1; i += 32) {
+                bool in = false;
+                if (i < w1) { const float2 p = xy[i]; in = p.x >= x0 && p.x <= x1 && p.y >= y0 && p.y <= y1; }
+                cnt += __popc(__ballot_sync(0xffffffffu, in));
+            }
+            if (wl == 0) sWarpCount[warp] = cnt;
+            __syncthreads();
+            int base = 0, total = 0;
+            for (int q = 0; q < kSelThreads / 32; q++) { const int c = sWarpCount[q]; if (q < warp) base += c; total += c; }
+            if (total <= kSelListCap) {
+                int pos = base;
+                for (int i = w0 + wl; i - wl < w1; i += 32) {
+                    bool in = false;
+                    if (i < w1) { const float2 p = xy[i]; in = p.x >= x0 && p.x <= x1 && p.y >= y0 && p.y <= y1; }
+                    const unsigned b = __ballot_sync(0xffffffffu, in);
+                    if (in) sList[pos + __popc(b & ((1u << wl) - 1u))] = i;
+                    pos += __popc(b);
+                }
+                nList = total;
+                list = sList;
+            }
+            __syncthreads();
+        }
+        for (int j = 0; j < spanTiles; j++) {
+            const long long t = first + (long long)j * groupsPerCta + grp;
+            if (t >= nCells) break;
+            const int cell = validIdx[t];
+            const int row = cell / dem.nrCols, col = cell - row * dem.nrCols;
+            // gis::getUtmXYFromRowCol (gis.cpp:806-810), then narrowed to float by the callee signatures (interpolation.h:77-95,162)
+            const double x = dem.llx + dem.cellSize * (col + 0.5);
+            const double y = dem.lly + dem.cellSize * (dem.nrRows - row - 0.5);
+            const float xf = float(x), yf = float(y);
+            unsigned char* rec = records + size_t(t) * recStride;
+            WorkPtrs w;
+            float localRadius = 0.f;
+            // the record's work area plays the role of the fused kernel's shared-memory tile (capacity kRecCap); a selection that
+            // does not fit it is left to the fused kernel
+            const int n = localSelect<G>(m, st, xy, xf, yf, gw, kRecCap, rec + recWorkOff(), kRecCap, nullptr, w, localRadius, list,
+                                         nList, kCandCap, listRadius);
+            int nE = 0, flags = 0;
+            if (n > kRecCap) flags = CELL_OVERFLOW;
+            else if (hasElev) {
+                bool isValid;
+                nE = mdStageElevation<G>(m, st, w, n, true, isValid);
+                if (isValid) flags = (nE <= kFitCap) ? CELL_FIT : CELL_OVERFLOW;
+                if (flags == CELL_FIT) {
+                    // starting point of every descent of this cell (the lanes share the first guesses)
+                    double* init = reinterpret_cast<double*>(rec + recInitOff());
+                    const int nGuess = m.nFirstGuess < kMaxGuess ? m.nFirstGuess : kMaxGuess;
+                    for (int g = lane; g < nGuess; g += G) {
+                        const double* guess = &m.firstGuess[g][0];
+                        switch (m.elevFunction) {
+                        case PB_FIT_PIECEWISE_THREE: descentInit<PB_FIT_PIECEWISE_THREE>(guess, w.X, w.Y, w.W, nE, init + g * 3); break;
+                        case PB_FIT_PIECEWISE_THREE_FREE: descentInit<PB_FIT_PIECEWISE_THREE_FREE>(guess, w.X, w.Y, w.W, nE, init + g * 3); break;
+                        default: descentInit<PB_FIT_PIECEWISE_TWO>(guess, w.X, w.Y, w.W, nE, init + g * 3); break;
+                        }
                     }
                 }
             }
+            if (lane == 0) {
+                CellHeader h;
+                h.n = n; h.nE = nE; h.flags = flags; h.cell = cell;
+                h.localRadius = localRadius; h.xf = xf; h.yf = yf; h.pad = 0;
+                *reinterpret_cast<CellHeader*>(rec) = h;
+                if (flags & CELL_OVERFLOW) overflowList[atomicAdd(overflowCount, 1)] = cell;
+                else if (flags & CELL_FIT) atomicAdd(&fitHist[nE], 1u);      // the descents are handed out by fit size (order kernel)
+            }
+            grpSync<G>();
         }
-        if (lane == 0) {
-            CellHeader h;
-            h.n = n; h.nE = nE; h.flags = flags; h.cell = cell;
-            h.localRadius = localRadius; h.xf = xf; h.yf = yf; h.pad = 0;
-            *reinterpret_cast<CellHeader*>(rec) = h;
-            if (flags & CELL_OVERFLOW) overflowList[atomicAdd(overflowCount, 1)] = cell;
-        }
-        grpSync<G>();
     }
+}
+
+// the cells of a chunk that run descents, ordered by the number of points of their elevation fit (largest first): the lanes
+// of a warp pull consecutive queue entries, so they work on fits of the same length and their data loops end together
+constexpr int kHistBins = kFitCap + 1;
+__global__ void local_order_scan_kernel(unsigned* __restrict__ hist /* in: counts, out: first position of each bin */,
+                                        unsigned* __restrict__ total)
+{
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int b = kHistBins - 1; b >= 0; b--) { const unsigned c = hist[b]; hist[b] = run; run += c; }
+        *total = run;
+    }
+}
+__global__ void __launch_bounds__(256)
+local_order_scatter_kernel(const unsigned char* __restrict__ records, size_t recStride, int nCells, unsigned* __restrict__ binPos,
+                           int* __restrict__ order)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nCells) return;
+    const CellHeader* h = reinterpret_cast<const CellHeader*>(records + size_t(t) * recStride);
+    if (h->flags == CELL_FIT) order[atomicAdd(&binPos[h->nE], 1u)] = t;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -196,8 +305,8 @@ __host__ __device__ constexpr int descentRegs(int warps)
 
 template <int F, int NCONS, int NPROD>
 __global__ void __maxnreg__(descentRegs(NCONS + NPROD))
-local_descent_kernel(const LocalModel* __restrict__ mp, unsigned char* __restrict__ records, size_t recStride, int nCells,
-                     unsigned* __restrict__ cellCounter)
+local_descent_kernel(const LocalModel* __restrict__ mp, unsigned char* __restrict__ records, size_t recStride,
+                     const int* __restrict__ order, const unsigned* __restrict__ nOrder, unsigned* __restrict__ cellCounter)
 {
     using P = Pipe<F>;
     constexpr int N = P::N;
@@ -230,12 +339,14 @@ local_descent_kernel(const LocalModel* __restrict__ mp, unsigned char* __restric
         // ------------------------------------------------------------------ producer warp
         for (;;) {
             unsigned t = 0;
-            if (lane == 0) t = atomicAdd(cellCounter, 1u);
+            if (lane == 0) {
+                t = atomicAdd(cellCounter, 1u);
+                t = t < *nOrder ? unsigned(order[t]) : 0xffffffffu;       // cells with a fit, largest fits first
+            }
             t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= unsigned(nCells)) break;
+            if (t == 0xffffffffu) break;
             unsigned char* rec = records + size_t(t) * recStride;
             const CellHeader h = *reinterpret_cast<const CellHeader*>(rec);
-            if (!(h.flags & CELL_FIT) || (h.flags & CELL_OVERFLOW)) continue;
             // a free slot
             unsigned fp = 0;
             if (lane == 0) fp = atomicAdd(&ctl->fHead, 1u);
@@ -447,23 +558,29 @@ static int smCount()
     return sms;
 }
 
-int localSelectGroups() { return smCount() * 4 * (kSelThreads / kSelG); }
-size_t localSelectScratchBytes(int cap) { return selScratchBytes(cap) * size_t(localSelectGroups()); }
 
-template <int F>
-static cudaError_t launchDescent(const LocalModel* dModel, unsigned char* records, size_t recStride, int nCells, unsigned* cellCounter,
-                                 cudaStream_t s)
+template <int F, int NCONS>
+static cudaError_t launchDescentT(const LocalModel* dModel, unsigned char* records, size_t recStride, int nCells, const int* order,
+                                  const unsigned* nOrder, unsigned* cellCounter, cudaStream_t s)
 {
-    // registers bound the CTA: each of the four SM sub-partitions owns 16 K registers and holds whole warps, so 12 warps (3 per
-    // sub-partition) may use 168 registers each; the two-piece descent needs 146, the three-piece ones 182 (a few spills at 168)
     constexpr int NPROD = 1;
-    constexpr int NCONS = 11;
     auto k = local_descent_kernel<F, NCONS, NPROD>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<F>::smemBytes);
     if (e != cudaSuccess) return e;
     const int grid = std::min(smCount(), std::max(1, nCells / 8));
-    k<<<grid, (NCONS + NPROD) * 32, Pipe<F>::smemBytes, s>>>(dModel, records, recStride, nCells, cellCounter);
+    k<<<grid, (NCONS + NPROD) * 32, Pipe<F>::smemBytes, s>>>(dModel, records, recStride, order, nOrder, cellCounter);
     return cudaGetLastError();
+}
+
+template <int F>
+static cudaError_t launchDescent(const LocalModel* dModel, unsigned char* records, size_t recStride, int nCells, const int* order,
+                                 const unsigned* nOrder, unsigned* cellCounter, cudaStream_t s)
+{
+    // registers bound the CTA: each of the four SM sub-partitions owns 16 K registers and holds whole warps, so 12 warps (3 per
+    // sub-partition) may use 168 registers each, 16 warps 128; the two-piece descent needs 146, the three-piece ones 182
+    static const int wide = getenv("PB_LOCAL_WARPS16") ? atoi(getenv("PB_LOCAL_WARPS16")) : 0;
+    if (F == PB_FIT_PIECEWISE_TWO && wide) return launchDescentT<F, 15>(dModel, records, recStride, nCells, order, nOrder, cellCounter, s);
+    return launchDescentT<F, 11>(dModel, records, recStride, nCells, order, nOrder, cellCounter, s);
 }
 
 template <int F>
@@ -477,46 +594,80 @@ static cudaError_t launchFinish(const LocalModel* dModel, const LocalStations& s
     return cudaGetLastError();
 }
 
-// one chunk of cells [validIdx, validIdx + nCells) through A, B, C. records: nCells * recStride bytes; selScratch:
-// localSelectScratchBytes(selCap); counters: {cellCounter, overflowCount} zeroed here; overflowList: nCells ints.
+// one chunk of cells [validIdx, validIdx + nCells) through A, (order), B, C on stream s. records: nCells * recStride bytes;
+// work: localPipelineWorkInts(nCells) ints = {cell counter, -, fit count, span counter, histogram[64], order[nCells]}, private
+// to the chunk; overflowList / overflowCount: the cells left to the fused kernel, appended to by every chunk of a call (the
+// caller zeroes the count once and runs the fused kernel over the list when all chunks are done).
+size_t localPipelineWorkInts(int nCells) { return 4 + 64 + size_t(nCells); }
+
 cudaError_t launchLocalPipelineChunk(const LocalModel* dModel, const LocalStations& st, const DevGrid& dem, const int* validIdx,
-                                     int nCells, int elevFunction, int nFirstGuess, unsigned char* records, size_t recStride,
-                                     unsigned char* selScratch, int selCap, int* errFlag, unsigned* counters, int* overflowList,
-                                     float* out, unsigned* minmax, cudaStream_t s, int* launches)
+                                     int nCells, int elevFunction, float candRadius, unsigned char* records, size_t recStride,
+                                     int* work, int* overflowList, int* overflowCount, float* out, unsigned* minmax, cudaStream_t s,
+                                     int* launches)
 {
     if (nCells <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), s);
+    static_assert(kHistBins <= 64, "histogram area too small");
+    unsigned* counters = reinterpret_cast<unsigned*>(work);
+    unsigned* hist = counters + 4;
+    int* order = work + 4 + 64;
+    cudaError_t e = cudaMemsetAsync(work, 0, (4 + 64) * sizeof(int), s);
     if (e != cudaSuccess) return e;
+    cudaEvent_t evStart = nullptr;
+    if (getenv("PB_LOCAL_TIMING")) { cudaEventCreate(&evStart); cudaEventRecord(evStart, s); }
     {
-        size_t smem = 0;
-        int xyInSmem = 0;
-        if (size_t(st.n) * sizeof(float2) <= 96 * 1024) { xyInSmem = 1; smem = size_t(st.n) * sizeof(float2); }
-        e = cudaFuncSetAttribute(local_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
-        if (e != cudaSuccess) return e;
+        // a span should not be much wider than the candidate radius, or its station list grows with it
         const int groupsPerCta = kSelThreads / kSelG;
-        const long long need = (nCells + groupsPerCta - 1) / groupsPerCta;
-        const int grid = int(std::min<long long>(need, (long long)smCount() * 4));
-        local_select_kernel<<<grid, kSelThreads, smem, s>>>(dModel, st, dem, validIdx, nCells, selScratch, selCap, errFlag, xyInSmem,
-                                                            records, recStride, overflowList, reinterpret_cast<int*>(counters + 1));
+        int spanTiles = candRadius > 0.f ? int(double(candRadius) / dem.cellSize / groupsPerCta) : 1;
+        spanTiles = std::max(1, std::min(kSelSpanTilesMax, spanTiles));
+        const int spanCells = groupsPerCta * spanTiles;
+        const long long need = (nCells + spanCells - 1) / spanCells;
+        const int grid = int(std::min<long long>(need, (long long)smCount() * 5));
+        local_select_kernel<<<grid, kSelThreads, 0, s>>>(dModel, st, dem, validIdx, nCells, records, recStride, overflowList,
+                                                         overflowCount, hist, spanTiles, counters + 3);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        local_order_scan_kernel<<<1, 32, 0, s>>>(hist, counters + 2);
+        local_order_scatter_kernel<<<(nCells + 255) / 256, 256, 0, s>>>(records, recStride, nCells, hist, order);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    (void)nFirstGuess;
+    // PB_LOCAL_TIMING=1: per-phase device times of this chunk on stderr (a diagnostic: it synchronises the stream)
+    static const bool timing = getenv("PB_LOCAL_TIMING") != nullptr;
+    cudaEvent_t ev[4] = {};
+    if (timing) {
+        for (auto& x : ev) cudaEventCreate(&x);
+        cudaEventDestroy(ev[0]);
+        ev[0] = evStart;
+        cudaEventRecord(ev[1], s);
+    }
     switch (elevFunction) {
     case PB_FIT_PIECEWISE_THREE:
-        e = launchDescent<PB_FIT_PIECEWISE_THREE>(dModel, records, recStride, nCells, counters, s);
+        e = launchDescent<PB_FIT_PIECEWISE_THREE>(dModel, records, recStride, nCells, order, counters + 2, counters, s);
+        if (timing) cudaEventRecord(ev[2], s);
         if (e == cudaSuccess) e = launchFinish<PB_FIT_PIECEWISE_THREE>(dModel, st, dem, records, recStride, nCells, out, minmax, s);
         break;
     case PB_FIT_PIECEWISE_THREE_FREE:
-        e = launchDescent<PB_FIT_PIECEWISE_THREE_FREE>(dModel, records, recStride, nCells, counters, s);
+        e = launchDescent<PB_FIT_PIECEWISE_THREE_FREE>(dModel, records, recStride, nCells, order, counters + 2, counters, s);
+        if (timing) cudaEventRecord(ev[2], s);
         if (e == cudaSuccess) e = launchFinish<PB_FIT_PIECEWISE_THREE_FREE>(dModel, st, dem, records, recStride, nCells, out, minmax, s);
         break;
     default:
-        e = launchDescent<PB_FIT_PIECEWISE_TWO>(dModel, records, recStride, nCells, counters, s);
+        e = launchDescent<PB_FIT_PIECEWISE_TWO>(dModel, records, recStride, nCells, order, counters + 2, counters, s);
+        if (timing) cudaEventRecord(ev[2], s);
         if (e == cudaSuccess) e = launchFinish<PB_FIT_PIECEWISE_TWO>(dModel, st, dem, records, recStride, nCells, out, minmax, s);
         break;
     }
-    if (launches) *launches += 3;
+    if (timing) {
+        cudaEventRecord(ev[3], s);
+        cudaEventSynchronize(ev[3]);
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        cudaEventElapsedTime(&c, ev[2], ev[3]);
+        fprintf(stderr, "[pb local pipeline] %d cells: select+order %.3f ms, descents %.3f ms, finish %.3f ms\n", nCells, a, b, c);
+        for (auto& x : ev) cudaEventDestroy(x);
+    }
+    if (launches) *launches += 5;
     return e;
 }
 

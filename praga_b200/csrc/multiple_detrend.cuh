@@ -269,7 +269,13 @@ __device__ void mdFinish(const LocalModel& m, const LocalStations& st, const Wor
                         if (othSig[pos]) validNr++;
                     }
                 if (validNr > 0) {
-                    // compact predictands / weights of othersPoints, in order
+                    // compact predictands / weights of othersPoints, in order. With a single significant proxy (the common
+                    // case) its values go to X as well (free once the elevation fit is over): the fit below then reads one
+                    // array instead of chasing oi -> proxy for every model evaluation (same values)
+                    int onlyPos = -1;
+                    if (validNr == 1)
+                        for (int i = 0; i < nProxy; i++)
+                            if (i != ePos && m.selectedActive[i] && othSig[i]) onlyPos = i;
                     int nO = 0;
                     for (int base = 0; base < n; base += G) {
                         const int k = base + lane;
@@ -280,6 +286,7 @@ __device__ void mdFinish(const LocalModel& m, const LocalStations& st, const Wor
                             w.oi[pos] = w.idx[k];
                             w.Y[pos] = double(w.val[k]);
                             w.W[pos] = !isEqualF(w.w[k], kNoData) ? double(w.w[k]) : 1.;
+                            if (onlyPos >= 0) w.X[pos] = double(st.proxy[(size_t)w.idx[k] * nProxy + onlyPos]);
                         }
                         nO += __popc(b);
                     }
@@ -303,8 +310,8 @@ __device__ void mdFinish(const LocalModel& m, const LocalStations& st, const Wor
                         const int* oi = w.oi;
                         const bool coop = G == 32 && smWarp != nullptr;
                         if (nPred == 1) {
-                            const int p0 = sigPos[0];
-                            auto pred = [=](int j, int) { return double(proxy[(size_t)oi[j] * nProxy + p0]); };
+                            const double* px = w.X;
+                            auto pred = [=](int j, int) { return px[j]; };
                             if (coop) lmOthersWarp<1>(pmin, pmax, othPar, delta, 100, 0.005, pred, w.Y, w.W, nO, smWarp);
                             else lmOthers<1>(1, pmin, pmax, othPar, delta, 100, 0.005, pred, w.Y, w.W, nO);
                         } else if (nPred == 2) {
