@@ -171,6 +171,9 @@ const char* pb_version(void);
 size_t pb_abi_sizeof(const char* structName);       /* sizeof of a descriptor in THIS build (binding self-check) */
 /* run on a caller-owned CUDA stream (a cudaStream_t passed as void*), e.g. torch's current stream */
 int pb_set_stream(pb_context* ctx, void* cudaStream);
+/* how the host threads of this process wait for the device (cudaSetDeviceFlags): blocking != 0 = sleep on a synchronisation
+ * primitive instead of spinning. For hosts that run more waiting threads (ranks x lanes of the batch drivers) than cores. */
+int pb_set_blocking_sync(pb_context* ctx, int blocking);
 
 /* --- device-resident raster cache (DEM / proxy grids are reused by every time step) -------------- */
 typedef int32_t pb_raster_id;
@@ -411,6 +414,49 @@ typedef struct pb_dem_batch_item {
 int pb_interpolation_dem_batch(pb_context* ctx, pb_dem_batch_item* items, int nItems, pb_raster_id dem,
                                const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd, int deviceOnly,
                                int nLanes);
+
+/* --- the hourly gridding driver kept on the device: PragaProject::interpolationMeteoGrid with getMeteoGridUpscaleFromDem()
+ * (src/pragaProject/pragaProject.cpp:2951-2990). Per hour and variable the reference runs interpolationDemMain (= one
+ * pb_interpolation_dem unit) and then Crit3DMeteoGrid::spatialAggregateMeteoGrid (agrolib/meteo/meteoGrid.cpp:1135-1240) of the
+ * gridded map onto the meteo grid; relative humidity with getUseDewPoint() goes through the dew point (:2967-2974):
+ *   passInterpolatedTemperatureToHumidityPoints (agrolib/project/project.cpp:2826-2848): a humidity station without air
+ *       temperature takes the value of the hour's air temperature MAP at its position;
+ *   the stations' dew point (Crit3DMeteoPoint::getMeteoPointValueH -> tDewFromRelHum, agrolib/meteo/meteo.cpp:275-285; host
+ *       arithmetic) is gridded like any other variable (interpolationDemMain(airDewTemperature, ...));
+ *   computeRelativeHumidityMap (agrolib/project/meteoMaps.cpp:301-321) turns the temperature and dew-point maps into the
+ *       relative humidity map, which is then aggregated.
+ * Here one HOUR is a list of variables worked through in order by one lane (stream + buffers of its own, like
+ * pb_interpolation_dem_batch): the gridded maps stay in HBM, the air temperature map of the hour is kept for the humidity
+ * chain, and only the meteo-grid cell values (nCells floats per variable, 160 kB instead of a 16 MB raster at the C5 shape)
+ * and the per-station outputs cross PCIe. Hours are independent and spread over nLanes lanes.
+ *   meteo           raw station values of the variable at this hour (humidity chain: relative humidity)
+ *   airTemperature  humidity chain only: the same stations' own air temperature (PB_NODATA where they have none)
+ *   cellValue       out, nCells of the aggregation geometry (pb_aggregation_upload); NULL: no aggregation
+ *   out             optional: the map itself (data / rows NULL: stays on the device; minimum / maximum / nValid always set)
+ *   step            optional per-station outputs as in pb_interpolation_dem (humidity chain: of the dew-point gridding, in the
+ *                   order of `meteo`, PB_NODATA / 0 for the stations without a dew point)
+ *   status          out: pb_status of this variable; a humidity chain without an air temperature map of the same hour before
+ *                   it is PB_ERR_INVALID */
+typedef struct pb_meteo_grid_var {
+    const pb_stations* meteo;
+    pb_settings* qualitySettings;  /* may be NULL */
+    pb_settings* settings;
+    int32_t variable;              /* PB_VAR_*; PB_VAR_AIR_REL_HUMIDITY with useDewPoint != 0: the dew-point chain */
+    int32_t useDewPoint;
+    const float* airTemperature;
+    int32_t aggrMethod;            /* PB_AGGR_AVERAGE / PB_AGGR_MEDIAN / PB_AGGR_STDDEV */
+    int32_t status;
+    float* cellValue;
+    pb_raster_out* out;            /* may be NULL */
+    pb_dem_step* step;             /* may be NULL */
+} pb_meteo_grid_var;
+typedef struct pb_meteo_grid_hour {
+    pb_meteo_grid_var* vars;
+    int32_t nVars;
+    int32_t reserved;
+} pb_meteo_grid_hour;
+int pb_meteo_grid_step_batch(pb_context* ctx, pb_meteo_grid_hour* hours, int nHours, pb_raster_id dem, const pb_raster_id* proxyGrids,
+                             int nProxyGrids, int32_t aggregation /* pb_aggregation_id, -1: none */, int nLanes);
 
 /* --- ordinary kriging (agrolib/interpolation/kriging.h:4-15, kriging.cpp). The reference keeps ONE system in file-static
  * globals; here every krigingVariogram call yields a handle and many systems can live on a device.

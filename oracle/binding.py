@@ -395,6 +395,16 @@ class Oracle:
         return rc == A.PB_OK, res
 
     # ---- raster map operators ----
+    def tdew_from_relhum(self, rh, t):
+        """tDewFromRelHum(float, float) (meteo.cpp:275-285) element-wise: the stations' dew point of the humidity chain."""
+        rh = np.ascontiguousarray(rh, dtype=np.float32)
+        t = np.ascontiguousarray(t, dtype=np.float32)
+        out = np.empty(rh.shape[0], dtype=np.float32)
+        f = self._f("tdew_from_relhum")
+        f.restype = None
+        f(A.fptr(rh), A.fptr(t), rh.shape[0], A.fptr(out))
+        return out
+
     def relative_humidity_map(self, air_t, dew_t):
         a, b = air_t.as_pb(), dew_t.as_pb()
         out = np.empty(air_t.shape, dtype=np.float32)

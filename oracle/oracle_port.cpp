@@ -2310,6 +2310,20 @@ static float relHumFromTdew(float Td, float T)
     return std::max(1.f, float(rh));
 }
 
+// tDewFromRelHum(float, float), meteo/meteo.cpp:275-285
+void port_tdew_from_relhum(const float* rh, const float* t, int n, float* tdew)
+{
+    for (int i = 0; i < n; i++) {
+        float RH = rh[i];
+        const float T = t[i];
+        if (isEqualF(RH, NODATA_F) || isEqualF(T, NODATA_F) || RH == 0) { tdew[i] = NODATA_F; continue; }
+        RH = (100 < RH) ? 100 : RH;
+        const double mySaturatedVaporPres = exp((16.78 * double(T) - 116.9) / (double(T) + 237.3));
+        const double actualVaporPres = double(RH) / 100. * mySaturatedVaporPres;
+        tdew[i] = float((log(actualVaporPres) * 237.3 + 116.9) / (16.78 - log(actualVaporPres)));
+    }
+}
+
 // Crit3DHourlyMeteoMaps::computeRelativeHumidityMap, project/meteoMaps.cpp:301-321
 int port_relative_humidity_map(const pb_raster* airT, const pb_raster* dewT, pb_raster_out* out)
 {

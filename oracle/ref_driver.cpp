@@ -539,6 +539,13 @@ int ref_interpolation_dem(const pb_stations* meteo, pb_settings* sq, pb_settings
     return ok ? PB_OK : PB_ERR_NO_VALID_CELL;
 }
 
+/* tDewFromRelHum(float, float) (meteo/meteo.cpp:275-285): what Crit3DMeteoPoint::getMeteoPointValueH returns as a station's
+ * airDewTemperature when none is stored (meteoPoint.cpp:967-972); reference code */
+void ref_tdew_from_relhum(const float* rh, const float* t, int n, float* tdew)
+{
+    for (int i = 0; i < n; i++) tdew[i] = tDewFromRelHum(rh[i], t[i]);
+}
+
 /* Crit3DHourlyMeteoMaps::computeRelativeHumidityMap (project/meteoMaps.cpp:301-321; the class is Qt-bound, the loop is
  * restated, relHumFromTdew and updateMinMaxRasterGrid are reference code) */
 int ref_relative_humidity_map(const pb_raster* airT, const pb_raster* dewT, pb_raster_out* out)

@@ -131,6 +131,17 @@ class pb_dem_batch_item(C.Structure):
                 ("variable", C.c_int32), ("status", C.c_int32), ("out", C.POINTER(pb_raster_out)), ("step", C.POINTER(pb_dem_step))]
 
 
+class pb_meteo_grid_var(C.Structure):
+    _fields_ = [("meteo", C.POINTER(pb_stations)), ("qualitySettings", C.POINTER(pb_settings)), ("settings", C.POINTER(pb_settings)),
+                ("variable", C.c_int32), ("useDewPoint", C.c_int32), ("airTemperature", C.POINTER(C.c_float)),
+                ("aggrMethod", C.c_int32), ("status", C.c_int32), ("cellValue", C.POINTER(C.c_float)),
+                ("out", C.POINTER(pb_raster_out)), ("step", C.POINTER(pb_dem_step))]
+
+
+class pb_meteo_grid_hour(C.Structure):
+    _fields_ = [("vars", C.POINTER(pb_meteo_grid_var)), ("nVars", C.c_int32), ("reserved", C.c_int32)]
+
+
 class pb_macro_area(C.Structure):
     _fields_ = [("nMeteoPoints", C.c_int32), ("reserved", C.c_int32), ("meteoPoints", C.POINTER(C.c_int32)),
                 ("nAreaCells", C.c_int64), ("areaCellsDEM", C.POINTER(C.c_float)),

@@ -1,6 +1,7 @@
 // context.cuh — the engine context behind the opaque pb_context of include/praga_b200.h, shared by the .cu files that
 // implement C-ABI entry points (engine.cu, kriging.cu).
 #pragma once
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -167,6 +168,7 @@ struct pb_context {
     std::vector<pb::RasterEntry> rasters;
     pb::DevBuf<unsigned char> dStations;
     pb::PinnedBuf hStations;
+    pb::PinnedBuf hUpload;                  // page-locked mirror of one stage's small uploads (station_space.cu UploadBatch)
     pb::DevBuf<float> dOut;
     int outInitRaster = -1;             // dOut currently holds the flag pattern of this raster id
     pb::DevBuf<unsigned char> dScratch;     // point targets
@@ -195,6 +197,16 @@ struct pb_context {
     std::vector<pb::AggregationGeometry> aggregations;   // pb_aggregation_id -> geometry (raster_ops.cu)
     std::vector<pb::ResidentMacroAreas> macroAreas;      // pb_macro_areas_id -> resident cells (glocal.cu)
     std::vector<pb_context*> lanes;             // child contexts (own stream and buffers) of pb_interpolation_dem_batch
+    // batch drivers: a lane's raster kernels leave `reserveSms` SMs to the station-space kernels of the other lanes and are
+    // chained one after the other across lanes (the persistent K1 kernel fills every SM it gets: two of them in flight, or one
+    // on all SMs, would make every small kernel of every other lane wait for a whole raster)
+    pb_context* parent = nullptr;
+    int reserveSms = 0;
+    std::mutex rasterMutex;                     // parent: guards lastRaster
+    cudaEvent_t lastRaster = nullptr;           // parent: completion of the raster kernel launched last by any lane
+    cudaEvent_t evRaster = nullptr;             // lane: completion of this lane's last raster kernel
+    pb::DevBuf<float> dMapT;                    // a lane's air temperature map of the hour (pb_meteo_grid_step_batch)
+    pb::DevBuf<float> dAgg;                     // a lane's aggregation scratch (one float per point) + cell values
 };
 
 namespace pb {

@@ -14,6 +14,7 @@
 #include "local.cuh"
 #include "pre.cuh"
 #include "shepard.cuh"
+#include "nvtx.cuh"
 
 namespace pb {
 // idw_kernels.cu
@@ -26,7 +27,7 @@ cudaError_t launchCompactFill(const float* dem, long long n, float flag, int* va
 int tileStations();
 cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevGrid& dem, const int* validIdx,
                             int nTargets, float* out, unsigned* minmax, cudaStream_t s, const long long* nTargetsDev = nullptr,
-                            unsigned* workCounter = nullptr);
+                            unsigned* workCounter = nullptr, int reserveSms = 0);
 cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty,
                             const double* tproxy, int nTargets, float* out, cudaStream_t s);
 cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);
@@ -1047,7 +1048,19 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
         CUDA_TRY(ctx, launchIdwTdRaster(ds, ds.z, m, dg, s->topoDist_Kh, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax,
                                         ctx->stream));
     } else {
-        CUDA_TRY(ctx, launchIdwRaster(ds, m, dg, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax, ctx->stream));
+        pb_context* par = ctx->parent;
+        if (par && ctx->reserveSms > 0) {
+            // a lane of a batch driver: raster kernels run one after the other across lanes on all SMs but `reserveSms`
+            std::lock_guard<std::mutex> lock(par->rasterMutex);
+            if (!ctx->evRaster) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->evRaster, cudaEventDisableTiming));
+            if (par->lastRaster && par->lastRaster != ctx->evRaster) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, par->lastRaster, 0));
+            CUDA_TRY(ctx, launchIdwRaster(ds, m, dg, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax, ctx->stream, nullptr, nullptr,
+                                          ctx->reserveSms));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->evRaster, ctx->stream));
+            par->lastRaster = ctx->evRaster;
+        } else {
+            CUDA_TRY(ctx, launchIdwRaster(ds, m, dg, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax, ctx->stream));
+        }
     }
     ctx->timing.launches++;
     cudaEventRecord(ctx->ev[2], ctx->stream);
@@ -1183,6 +1196,7 @@ int pb_device_count(void)
 
 int pb_create(int device, pb_context** out)
 {
+    PB_NVTX_RANGE();
     if (!out) return PB_ERR_INVALID;
     *out = nullptr;
     int n = 0;
@@ -1227,6 +1241,7 @@ void pb_destroy(pb_context* ctx)
     for (auto& m : ctx->macroAreas) if (m.used) cudaFree(m.cells);
     ctx->dLocalStations.release(); ctx->dLocalScratch.release(); ctx->dLocalModel.release(); ctx->hLocal.release();
     ctx->dLocalRecords.release(); ctx->dLocalWork.release(); ctx->dLocalOverflow.release();
+    ctx->dMapT.release(); ctx->dAgg.release(); ctx->hUpload.release();
     for (auto& sp : ctx->sPipe) if (sp) cudaStreamDestroy(sp);
     for (auto& e : ctx->evPipe) if (e) cudaEventDestroy(e);
     if (ctx->dLocalError) cudaFree(ctx->dLocalError);
@@ -1242,6 +1257,7 @@ void pb_destroy(pb_context* ctx)
     if (ctx->dMinMax) cudaFree(ctx->dMinMax);
     if (ctx->hMinMax) cudaFreeHost(ctx->hMinMax);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->evRaster) cudaEventDestroy(ctx->evRaster);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1250,11 +1266,21 @@ const char* pb_last_error(const pb_context* ctx) { return ctx ? ctx->err.c_str()
 
 int pb_set_stream(pb_context* ctx, void* cudaStream)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cudaStream;
     ctx->ownStream = false;
+    return PB_OK;
+}
+
+int pb_set_blocking_sync(pb_context* ctx, int blocking)
+{
+    PB_NVTX_RANGE();
+    if (!ctx) return PB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(ctx, cudaSetDeviceFlags(blocking ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
     return PB_OK;
 }
 
@@ -1267,6 +1293,7 @@ int pb_last_timing(const pb_context* ctx, pb_timing* t)
 
 int pb_raster_upload(pb_context* ctx, const pb_raster* r, pb_raster_id* id)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!r || !id) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -1282,6 +1309,7 @@ int pb_raster_upload(pb_context* ctx, const pb_raster* r, pb_raster_id* id)
 
 int pb_raster_free(pb_context* ctx, pb_raster_id id)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used) return fail(ctx, PB_ERR_INVALID, "bad raster id");
     cudaSetDevice(ctx->device);
@@ -1293,6 +1321,7 @@ int pb_raster_free(pb_context* ctx, pb_raster_id id)
 
 int pb_raster_valid_cells(pb_context* ctx, pb_raster_id id, int64_t* nValid)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used) return fail(ctx, PB_ERR_INVALID, "bad raster id");
     cudaSetDevice(ctx->device);
@@ -1306,6 +1335,7 @@ int pb_interpolation_raster_resident(pb_context* ctx, const pb_stations* st, con
                                      pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin,
                                      int rowEnd, pb_raster_out* out)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     cudaSetDevice(ctx->device);
     resetTiming(ctx);
@@ -1316,6 +1346,7 @@ int pb_interpolation_raster_device(pb_context* ctx, const pb_stations* st, const
                                    pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin,
                                    int rowEnd, pb_raster_out* out)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     cudaSetDevice(ctx->device);
     resetTiming(ctx);
@@ -1327,6 +1358,7 @@ int pb_local_detrending_raster_resident(pb_context* ctx, const pb_stations* st, 
                                         pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin,
                                         int rowEnd, pb_raster_out* out)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     cudaSetDevice(ctx->device);
     resetTiming(ctx);
@@ -1337,6 +1369,7 @@ int pb_local_detrending_raster_device(pb_context* ctx, const pb_stations* st, co
                                       pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin,
                                       int rowEnd, pb_raster_out* out)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     cudaSetDevice(ctx->device);
     resetTiming(ctx);
@@ -1347,6 +1380,7 @@ int pb_local_detrending_raster_device(pb_context* ctx, const pb_stations* st, co
 int pb_pre_interpolation_batch(pb_context* ctx, const pb_stations* st, const float* values, int T, const pb_settings* s,
                                int variable, const double* pointsRange, float* detrended, uint8_t* keep, pb_settings* fitted)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     cudaSetDevice(ctx->device);
     return preInterpolationBatchImpl(ctx, st, values, T, s, variable, pointsRange, detrended, keep, fitted);
@@ -1355,6 +1389,7 @@ int pb_pre_interpolation_batch(pb_context* ctx, const pb_stations* st, const flo
 /* preInterpolation for one time step, in place like the reference: st->value is detrended, *s receives the fit */
 int pb_pre_interpolation(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, uint8_t* keep)
 {
+    PB_NVTX_RANGE();
     // every branch that needs neither the meteo points' extra fields nor the DEM; optimalDetrending's leave-one-out uses
     // the stations themselves as meteo points (pb_pre_interpolation_ex, station_space.cu)
     return pb_pre_interpolation_ex(ctx, st, s, variable, nullptr, -1, keep, nullptr);
@@ -1653,6 +1688,7 @@ int pb_interpolation_raster(pb_context* ctx, const pb_stations* st, const pb_set
                             const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
                             pb_raster_out* out)
 {
+    PB_NVTX_RANGE();
     return hostRasterCall(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, false);
 }
 
@@ -1660,6 +1696,7 @@ int pb_local_detrending_raster(pb_context* ctx, const pb_stations* st, const pb_
                                const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
                                pb_raster_out* out)
 {
+    PB_NVTX_RANGE();
     return hostRasterCall(ctx, st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out, true);
 }
 
@@ -1740,6 +1777,7 @@ static int interpolatePointsImpl(pb_context* ctx, const pb_stations* st, const p
 int pb_interpolate_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
                           const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result)
 {
+    PB_NVTX_RANGE();
     return interpolatePointsImpl(ctx, st, s, variable, x, y, nullptr, proxyValues, m, excludeSupplemental, -1, result);
 }
 
@@ -1748,6 +1786,7 @@ int pb_interpolate_points_td(pb_context* ctx, const pb_stations* st, const pb_se
                              const float* y, const float* z, const double* proxyValues, int m, int excludeSupplemental,
                              pb_raster_id dem, float* result)
 {
+    PB_NVTX_RANGE();
     return interpolatePointsImpl(ctx, st, s, variable, x, y, z, proxyValues, m, excludeSupplemental, dem, result);
 }
 
@@ -1837,6 +1876,7 @@ static void cvStatistics(const std::vector<float>& obs, const std::vector<float>
 extern "C" int pb_compute_residuals(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
                                     const float* observed, const uint8_t* useForCv, float* residual, pb_cv_stats* stats)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!st || !s || !observed || !residual) return fail(ctx, PB_ERR_INVALID, "null argument");
     const int n = st->n, P = s->nProxy;
@@ -1875,6 +1915,7 @@ extern "C" int pb_compute_residuals(pb_context* ctx, const pb_stations* st, cons
 extern "C" int pb_local_detrending_points(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable, const float* x,
                                           const float* y, const double* proxyValues, int m, int excludeSupplemental, float* result)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!st || !s || (m > 0 && (!x || !y || !result))) return fail(ctx, PB_ERR_INVALID, "null argument");
     if (m <= 0) return PB_OK;
@@ -1942,6 +1983,7 @@ extern "C" int pb_local_detrending_points(pb_context* ctx, const pb_stations* st
 extern "C" int pb_compute_residuals_local(pb_context* ctx, const pb_stations* st, const pb_settings* s, int variable,
                                           const float* observed, const uint8_t* useForCv, float* residual, pb_cv_stats* stats)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!st || !s || !observed || !residual) return fail(ctx, PB_ERR_INVALID, "null argument");
     const int n = st->n, P = s->nProxy;
@@ -1990,6 +2032,7 @@ extern "C" int pb_compute_residuals_local(pb_context* ctx, const pb_stations* st
 /* live pipe ceilings for the K1 roofline (FP32 FMA TFLOP/s, G MUFU.RSQ/s) */
 extern "C" int pb_host_register(pb_context* ctx, void* ptr, size_t bytes)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!ptr || bytes == 0) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -1999,6 +2042,7 @@ extern "C" int pb_host_register(pb_context* ctx, void* ptr, size_t bytes)
 
 extern "C" int pb_host_unregister(pb_context* ctx, void* ptr)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!ptr) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -2008,6 +2052,7 @@ extern "C" int pb_host_unregister(pb_context* ctx, void* ptr)
 
 extern "C" int pb_measure_pipe_peaks(pb_context* ctx, float* fp32Tflops, float* mufuGops)
 {
+    PB_NVTX_RANGE();
     if (!ctx || !fp32Tflops || !mufuGops) return PB_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaDeviceProp prop;
@@ -2020,6 +2065,7 @@ extern "C" int pb_measure_pipe_peaks(pb_context* ctx, float* fp32Tflops, float* 
 namespace pb { cudaError_t measureFp64Peak(cudaStream_t s, int sms, float* fp64Tflops); }
 extern "C" int pb_measure_fp64_peak(pb_context* ctx, float* fp64Tflops)
 {
+    PB_NVTX_RANGE();
     if (!ctx || !fp64Tflops) return PB_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaDeviceProp prop;
@@ -2044,5 +2090,7 @@ extern "C" size_t pb_abi_sizeof(const char* name)
     if (!strcmp(name, "pb_dem_step")) return sizeof(pb_dem_step);
     if (!strcmp(name, "pb_dem_batch_item")) return sizeof(pb_dem_batch_item);
     if (!strcmp(name, "pb_macro_area")) return sizeof(pb_macro_area);
+    if (!strcmp(name, "pb_meteo_grid_var")) return sizeof(pb_meteo_grid_var);
+    if (!strcmp(name, "pb_meteo_grid_hour")) return sizeof(pb_meteo_grid_hour);
     return 0;
 }

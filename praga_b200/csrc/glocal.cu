@@ -28,6 +28,7 @@
 #include "context.cuh"
 #include "pre.cuh"
 #include "shepard.cuh"
+#include "nvtx.cuh"
 
 namespace pb {
 // engine.cu
@@ -432,6 +433,7 @@ extern "C" {
 int pb_glocal_detrending_fitting(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
                                  int nAreas)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!st || !s || (!areas && nAreas > 0) || nAreas < 0) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -603,6 +605,7 @@ int pb_glocal_detrending_raster(pb_context* ctx, const pb_stations* st, pb_setti
                                 int nAreas, pb_raster_id demId, const pb_raster_id* proxyGrids, int nProxyGrids, int deviceOnly,
                                 pb_raster_out* out)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     return glocalRasterImpl(ctx, st, s, variable, areas, nAreas, nullptr, demId, proxyGrids, nProxyGrids, deviceOnly, out);
 }
@@ -611,6 +614,7 @@ int pb_glocal_detrending_raster_resident(pb_context* ctx, const pb_stations* st,
                                          int nAreas, pb_macro_areas_id cells, pb_raster_id demId, const pb_raster_id* proxyGrids,
                                          int nProxyGrids, int deviceOnly, pb_raster_out* out)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (cells < 0 || cells >= (int)ctx->macroAreas.size() || !ctx->macroAreas[cells].used)
         return fail(ctx, PB_ERR_INVALID, "macro areas id is not live");
@@ -620,6 +624,7 @@ int pb_glocal_detrending_raster_resident(pb_context* ctx, const pb_stations* st,
 
 int pb_macro_areas_upload(pb_context* ctx, const pb_macro_area* areas, int nAreas, pb_macro_areas_id* id)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!areas || nAreas <= 0 || !id) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -647,6 +652,7 @@ int pb_macro_areas_upload(pb_context* ctx, const pb_macro_area* areas, int nArea
 
 int pb_macro_areas_free(pb_context* ctx, pb_macro_areas_id id)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (id < 0 || id >= (int)ctx->macroAreas.size() || !ctx->macroAreas[id].used) return fail(ctx, PB_ERR_INVALID, "bad macro areas id");
     cudaSetDevice(ctx->device);
@@ -659,6 +665,7 @@ int pb_compute_residuals_glocal(pb_context* ctx, const pb_stations* meteo, const
                                 const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
                                 int excludeOutsideDem, int excludeSupplemental, float* residual)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!meteo || !points || !s || !residual || (!areas && nAreas > 0)) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);

@@ -612,7 +612,7 @@ int tileStations() { return kTileStations; }
 
 cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevGrid& dem, const int* validIdx,
                             int nTargets, float* out, unsigned* minmax, cudaStream_t s, const long long* nTargetsDev,
-                            unsigned* workCounter)
+                            unsigned* workCounter, int reserveSms)
 {
     if (nTargets <= 0) return cudaSuccess;
     if (nTargetsDev && st.nPadded > kResidentMaxStations) return cudaErrorInvalidValue;    // callers check idwResidentFits()
@@ -623,7 +623,7 @@ cudaError_t launchIdwRaster(const DevStations& st, const DevModel& m, const DevG
         auto k = idw_persistent_kernel<P, kPersistThreads>;
         // the attribute is per device and this launcher runs on several lane threads / devices of one process: set on every
         // launch (a microsecond against a kernel of hundreds), SM count of the CURRENT device
-        const int sms = currentSmCount();
+        const int sms = std::max(1, currentSmCount() - std::max(0, reserveSms));      // batch lanes leave SMs to each other's small kernels
         cudaError_t ea = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentMaxStations * 24);
         if (ea != cudaSuccess) return ea;
         const size_t smem = (size_t)st.nPadded * (sizeof(float4) + sizeof(float2));

@@ -28,6 +28,7 @@
 
 #include "context.cuh"
 #include "kriging.cuh"
+#include "nvtx.cuh"
 
 namespace pb {
 
@@ -394,6 +395,7 @@ extern "C" {
 int pb_kriging_setup(pb_context* ctx, const double* pos, const double* val, int n, int mode, double range, double nugget,
                      double sill, double slope, int flags, pb_kriging_id* id)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!pos || !val || !id || n < 1) return fail(ctx, PB_ERR_INVALID, "null argument / no stations");
     cudaSetDevice(ctx->device);
@@ -504,6 +506,7 @@ int pb_kriging_setup(pb_context* ctx, const double* pos, const double* val, int 
 /* krigingFreeMemory (kriging.cpp:299-331) */
 int pb_kriging_free(pb_context* ctx, pb_kriging_id id)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     KrigingSystem* k = systemOf(ctx, id);
     if (!k) return fail(ctx, PB_ERR_INVALID, "bad kriging id");
@@ -516,6 +519,7 @@ int pb_kriging_free(pb_context* ctx, pb_kriging_id id)
 
 int pb_kriging_uses_tensor_path(pb_context* ctx, pb_kriging_id id)
 {
+    PB_NVTX_RANGE();
     KrigingSystem* k = ctx ? systemOf(ctx, id) : nullptr;
     return k ? (k->tensor ? 1 : 0) : -1;
 }
@@ -523,6 +527,7 @@ int pb_kriging_uses_tensor_path(pb_context* ctx, pb_kriging_id id)
 /* krigingSetWeight + krigingResult + krigingRMSE (kriging.cpp:211-295) for m target points (x0, y0, x1, y1, ...) */
 int pb_kriging_points(pb_context* ctx, pb_kriging_id id, const double* xy, int m, double* result, double* rmse)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     KrigingSystem* k = systemOf(ctx, id);
     if (!k) return fail(ctx, PB_ERR_INVALID, "bad kriging id");
@@ -556,6 +561,7 @@ int pb_kriging_points(pb_context* ctx, pb_kriging_id id, const double* xy, int m
 int pb_kriging_raster(pb_context* ctx, pb_kriging_id id, pb_raster_id demId, int rowBegin, int rowEnd,
                       pb_raster_out* estimate, pb_raster_out* rmse)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     KrigingSystem* k = systemOf(ctx, id);
     if (!k) return fail(ctx, PB_ERR_INVALID, "bad kriging id");

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "context.cuh"
+#include "nvtx.cuh"
 
 namespace pb {
 
@@ -130,6 +131,7 @@ extern "C" {
 
 int pb_raster_read_esri_header(pb_context* ctx, const char* fileName, pb_raster_header* header)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!fileName || !header) return fail(ctx, PB_ERR_INVALID, "null argument");
     int nrBytes;
@@ -139,6 +141,7 @@ int pb_raster_read_esri_header(pb_context* ctx, const char* fileName, pb_raster_
 int pb_raster_read_esri(pb_context* ctx, const char* fileName, pb_raster_id* id, pb_raster_header* header, float* minimum,
                         float* maximum)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!fileName || !id) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -222,6 +225,7 @@ int pb_raster_read_esri(pb_context* ctx, const char* fileName, pb_raster_id* id,
 
 int pb_raster_write_esri(pb_context* ctx, pb_raster_id id, const char* fileName)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!fileName) return fail(ctx, PB_ERR_INVALID, "null argument");
     if (id < 0 || id >= (int)ctx->rasters.size() || !ctx->rasters[id].used) return fail(ctx, PB_ERR_INVALID, "bad raster id");

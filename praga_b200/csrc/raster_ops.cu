@@ -14,6 +14,7 @@
 #include <string>
 
 #include "context.cuh"
+#include "nvtx.cuh"
 
 namespace pb {
 
@@ -559,10 +560,36 @@ int newResident(pb_context* ctx, pb_raster_header h /* by value: the caller's ma
 
 }  // namespace
 
+namespace pb {
+// device-pointer forms of three map operators for the batch drivers (station_space.cu: pb_meteo_grid_step_batch), which chain
+// them on a lane's stream without a host round trip; scratch / value: the caller's (one float per aggregation point / cell)
+cudaError_t launchSpatialAggregateDev(const DevGrid& raster, const AggregationGeometry& g, int method, float* scratch, float* value,
+                                      cudaStream_t s)
+{
+    const unsigned nb = (unsigned)((size_t(g.nCells) * 32 + 255) / 256);
+    spatial_aggregate_kernel<<<nb, 256, 0, s>>>(raster, g.x, g.y, g.first, g.maxNr, g.nCells, method, scratch, value);
+    return cudaGetLastError();
+}
+cudaError_t launchRelativeHumidityMapDev(const float* airT, float flagT, const float* dewT, float flagTd, long long n, float outFlag,
+                                         float* out, unsigned* minmax, cudaStream_t s)
+{
+    relative_humidity_map_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(airT, flagT, dewT, flagTd, n, outFlag, out, minmax);
+    return cudaGetLastError();
+}
+cudaError_t launchSamplePointsDev(const DevGrid& g, const double* x, const double* y, int n, float* value, unsigned char* inGrid,
+                                  cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    sample_points_kernel<<<(n + 255) / 256, 256, 0, s>>>(g, x, y, n, value, inGrid);
+    return cudaGetLastError();
+}
+}  // namespace pb
+
 extern "C" {
 
 int pb_raster_download(pb_context* ctx, pb_raster_id id, pb_raster_out* out)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     RasterEntry* e = entryOf(ctx, id);
     if (!e || !out) return fail(ctx, PB_ERR_INVALID, "bad raster id / null output");
@@ -575,6 +602,7 @@ int pb_raster_download(pb_context* ctx, pb_raster_id id, pb_raster_out* out)
 
 int pb_relative_humidity_map(pb_context* ctx, pb_raster_id airT, pb_raster_id dewT, pb_raster_out* out, pb_raster_id* outId)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     RasterEntry *t = entryOf(ctx, airT), *td = entryOf(ctx, dewT);
     if (!t || !td) return fail(ctx, PB_ERR_INVALID, "bad raster id");
@@ -612,6 +640,7 @@ int pb_relative_humidity_map(pb_context* ctx, pb_raster_id airT, pb_raster_id de
 
 int pb_fix_daily_thermal_consistency(pb_context* ctx, pb_raster_id tmax, pb_raster_id tmin, int64_t* nFixed)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     RasterEntry *a = entryOf(ctx, tmax), *b = entryOf(ctx, tmin);
     if (!a || !b) return fail(ctx, PB_ERR_INVALID, "bad raster id");
@@ -641,6 +670,7 @@ int pb_fix_daily_thermal_consistency(pb_context* ctx, pb_raster_id tmax, pb_rast
 int pb_topographic_distance_map(pb_context* ctx, pb_raster_id demId, double x, double y, double z, pb_raster_out* out,
                                 pb_raster_id* outId)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     RasterEntry* dem = entryOf(ctx, demId);
     if (!dem) return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
@@ -672,6 +702,7 @@ int pb_topographic_distance_map(pb_context* ctx, pb_raster_id demId, double x, d
 int pb_resample_grid(pb_context* ctx, pb_raster_id srcId, const pb_raster_header* newHeader, int method, float nodataRatioThreshold,
                      pb_raster_out* out, pb_raster_id* outId)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     RasterEntry* src = entryOf(ctx, srcId);
     if (!src || !newHeader) return fail(ctx, PB_ERR_INVALID, "bad raster id / null header");
@@ -726,6 +757,7 @@ int pb_resample_grid(pb_context* ctx, pb_raster_id srcId, const pb_raster_header
 int pb_aggregation_upload(pb_context* ctx, const double* x, const double* y, const int64_t* first, const int32_t* maxNr, int nCells,
                           pb_aggregation_id* id)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!x || !y || !first || !maxNr || nCells <= 0 || !id) return fail(ctx, PB_ERR_INVALID, "null argument");
     if (first[0] != 0) return fail(ctx, PB_ERR_INVALID, "first[0] must be 0");
@@ -758,6 +790,7 @@ int pb_aggregation_upload(pb_context* ctx, const double* x, const double* y, con
 
 int pb_aggregation_free(pb_context* ctx, pb_aggregation_id id)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (id < 0 || id >= (int)ctx->aggregations.size() || !ctx->aggregations[id].used) return fail(ctx, PB_ERR_INVALID, "bad aggregation id");
     cudaSetDevice(ctx->device);
@@ -769,6 +802,7 @@ int pb_aggregation_free(pb_context* ctx, pb_aggregation_id id)
 
 int pb_spatial_aggregate_meteo_grid(pb_context* ctx, pb_raster_id rasterId, pb_aggregation_id aggId, int method, float* value)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     RasterEntry* src = entryOf(ctx, rasterId);
     if (!src || !value) return fail(ctx, PB_ERR_INVALID, "bad raster id / null output");
@@ -800,6 +834,7 @@ int pb_spatial_aggregate_meteo_grid(pb_context* ctx, pb_raster_id rasterId, pb_a
 int pb_raster_sample_points(pb_context* ctx, pb_raster_id rasterId, const double* x, const double* y, int n, float* value,
                             uint8_t* inGrid)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     RasterEntry* src = entryOf(ctx, rasterId);
     if (!src || !x || !y || !value || n < 0) return fail(ctx, PB_ERR_INVALID, "bad raster id / null argument");
@@ -831,6 +866,7 @@ int pb_raster_sample_points(pb_context* ctx, pb_raster_id rasterId, const double
 int pb_topographic_index(pb_context* ctx, pb_raster_id demId, const float* windowWidths, int nWidths, pb_raster_out* out,
                          pb_raster_id* outId)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     RasterEntry* src = entryOf(ctx, demId);
     if (!src || !windowWidths) return fail(ctx, PB_ERR_INVALID, "bad raster id / null widths");

@@ -8,12 +8,14 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "classic.cuh"
 #include "context.cuh"
+#include "nvtx.cuh"
 
 namespace pb {
 // engine.cu
@@ -43,6 +45,36 @@ T* carve(unsigned char*& p, size_t count)
     p += (count * sizeof(T) + 255) / 256 * 256;
     return r;
 }
+
+// Many small host arrays -> their places in one device scratch buffer with ONE asynchronous copy: the arrays are gathered into a
+// page-locked mirror of the device range they span (gaps travel as they are: scratch the kernels write later). A stage of the
+// station-space chain stages 15 arrays; as separate pageable copies they were 15 driver calls, each taking the driver's lock
+// that the other lanes of a batch contend for.
+struct UploadBatch {
+    struct Item { void* dst; const void* src; size_t bytes; };
+    std::vector<Item> items;
+    cudaError_t add(void* dst, const void* src, size_t bytes)
+    {
+        if (bytes) items.push_back(Item{dst, src, bytes});
+        return cudaSuccess;
+    }
+    cudaError_t flush(pb_context* ctx, cudaStream_t stream)
+    {
+        if (items.empty()) return cudaSuccess;
+        unsigned char *lo = static_cast<unsigned char*>(items[0].dst), *hi = lo;
+        for (const Item& it : items) {
+            unsigned char* d = static_cast<unsigned char*>(it.dst);
+            lo = std::min(lo, d);
+            hi = std::max(hi, d + it.bytes);
+        }
+        cudaError_t e = ctx->hUpload.reserve(size_t(hi - lo));
+        if (e != cudaSuccess) return e;
+        for (const Item& it : items) memcpy(ctx->hUpload.p + (static_cast<unsigned char*>(it.dst) - lo), it.src, it.bytes);
+        items.clear();
+        return cudaMemcpyAsync(lo, ctx->hUpload.p, size_t(hi - lo), cudaMemcpyHostToDevice, stream);
+    }
+};
+
 
 // interpolate() with a Shepard estimator (K8, bit-identical point form behind pb_interpolate_points) at the meteo points,
 // followed by the residual rules of computeResiduals (spatialControl.cpp:97-155): the leave-one-out of optimalDetrending,
@@ -180,6 +212,7 @@ double goldenSection(const float* maeOfKh, int maxKh, double a, double b, pb_kh_
 extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv,
                                        pb_raster_id demId, uint8_t* keep, pb_kh_series* khSeries)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!st || !s) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -315,11 +348,11 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     float* tObserved = carve<float>(d, n);
     int* tCode = carve<int>(d, n);
     uint8_t* tInside = carve<uint8_t>(d, n);
+    ClassicProblem* dProblems = carve<ClassicProblem>(d, NP);       // (everything that is uploaded lies before the work areas)
+    int* dKh = carve<int>(d, nKh);
     float* dWork = carve<float>(d, size_t(m) * NP);
-    ClassicProblem* dProblems = carve<ClassicProblem>(d, NP);
     float* dResidual = carve<float>(d, size_t(NP) * nKh * n);
     float* dMae = carve<float>(d, size_t(NP) * nKh);
-    int* dKh = carve<int>(d, nKh);
     float* dTopo = useTD ? carve<float>(d, size_t(n) * m) : nullptr;
 
     std::vector<float> hx(m), hy(m), hzf(m), hproxy(m * Pp, kNoData), hval(m);
@@ -351,7 +384,8 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
         hval[k] = optimal ? gobs[i] : st->value[i];
     }
     cudaStream_t stream = ctx->stream;
-    auto up = [&](void* dst, const void* src, size_t b) { return cudaMemcpyAsync(dst, src, b, cudaMemcpyHostToDevice, stream); };
+    UploadBatch batch;
+    auto up = [&](void* dst, const void* src, size_t b) { return batch.add(dst, src, b); };
     CUDA_TRY(ctx, up(dX, hx.data(), m * 4));
     CUDA_TRY(ctx, up(dY, hy.data(), m * 4));
     CUDA_TRY(ctx, up(dZf, hzf.data(), m * 4));
@@ -371,6 +405,7 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     std::vector<int> khList(nKh);
     for (int k = 0; k < nKh; k++) khList[k] = useTD ? k : 0;
     CUDA_TRY(ctx, up(dKh, khList.data(), nKh * 4));
+    CUDA_TRY(ctx, batch.flush(ctx, stream));
     memset(&ctx->timing, 0, sizeof(ctx->timing));
 
     // ---- detrending() of every problem ----
@@ -623,7 +658,8 @@ int exactLoo(pb_context* ctx, const LooArrays& a, const pb_settings* s, int vari
     NeighbourOut* dNb = carve<NeighbourOut>(d, nT);
     float* dTopo = useTD ? carve<float>(d, size_t(nT) * nS) : nullptr;
     cudaStream_t stream = ctx->stream;
-    auto up = [&](void* dst, const void* src, size_t b) { return b ? cudaMemcpyAsync(dst, src, b, cudaMemcpyHostToDevice, stream) : cudaSuccess; };
+    UploadBatch batch;
+    auto up = [&](void* dst, const void* src, size_t b) { return batch.add(dst, src, b); };
     CUDA_TRY(ctx, up(tX, a.tx.data(), nT * 4));
     CUDA_TRY(ctx, up(tY, a.ty.data(), nT * 4));
     CUDA_TRY(ctx, up(tZ, a.tz.data(), nT * 4));
@@ -641,6 +677,7 @@ int exactLoo(pb_context* ctx, const LooArrays& a, const pb_settings* s, int vari
     CUDA_TRY(ctx, up(dProblem, &pr, sizeof(pr)));
     const int kh = useTD ? s->topoDist_Kh : 0;
     CUDA_TRY(ctx, up(dKh, &kh, 4));
+    CUDA_TRY(ctx, batch.flush(ctx, stream));
     if (useTD) {
         CUDA_TRY(ctx, launchTopoMatrix(tX, tY, tZ, nT, sX, sY, sZf, nS, devGridOfRaster(ctx->rasters[demId]), dTopo, stream));
         ctx->timing.launches++;
@@ -815,6 +852,7 @@ extern "C" int pb_compute_residuals_exact(pb_context* ctx, const pb_stations* me
                                           const pb_stations* points, const pb_settings* s, int variable, pb_raster_id dem,
                                           int excludeOutsideDem, int excludeSupplemental, float* residual)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!meteo || !points || !s || !residual) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -831,6 +869,7 @@ extern "C" int pb_compute_residuals_exact(pb_context* ctx, const pb_stations* me
 extern "C" int pb_spatial_quality_control(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, const pb_cv_points* cv,
                                           pb_raster_id dem, uint8_t* wrongSpatial)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!st || !s || !wrongSpatial) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -924,12 +963,31 @@ extern "C" int pb_spatial_quality_control(pb_context* ctx, const pb_stations* st
     return PB_OK;
 }
 
+// PB_STAGE_TIMING=1: wall time a lane spends in each stage of pb_interpolation_dem, summed over the batch and printed on stderr
+// when the batch returns (a diagnostic of where the lanes wait for each other)
+static std::atomic<long long> g_stageUs[5];
+static std::atomic<long long> g_stageCalls;
+static bool stageTiming()
+{
+    static const bool on = getenv("PB_STAGE_TIMING") != nullptr;
+    return on;
+}
+static void stageReport(const char* what, double wallMs, int nLanes)
+{
+    if (!stageTiming()) return;
+    const long long n = std::max<long long>(1, g_stageCalls.exchange(0));
+    fprintf(stderr, "[pb stages] %s: %lld griddings, %d lanes, wall %.2f ms; per gridding: qc %.3f pre %.3f raster %.3f loo %.3f other %.3f ms\n",
+            what, n, nLanes, wallMs, g_stageUs[0].exchange(0) / 1e3 / n, g_stageUs[1].exchange(0) / 1e3 / n,
+            g_stageUs[2].exchange(0) / 1e3 / n, g_stageUs[3].exchange(0) / 1e3 / n, g_stageUs[4].exchange(0) / 1e3 / n);
+}
+
 /* Project::interpolationDem (project/project.cpp:3106-3150) [+ the leave-one-out of Project::interpolationCv :3012-3104]:
  * one time step of one variable, from raw station values to the DEM raster; see include/praga_b200.h */
 extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, pb_settings* qualitySettings, pb_settings* s, int variable,
                                     pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd,
                                     int deviceOnly, pb_raster_out* out, pb_dem_step* step)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (!meteo || !s || !out) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -945,6 +1003,13 @@ extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, p
     };
     memset(&ctx->timing, 0, sizeof(ctx->timing));
     std::vector<uint8_t> wrong(std::max(n, 1), 0);
+    auto tStage = std::chrono::steady_clock::now();
+    auto lap = [&](int k) {
+        if (!stageTiming()) return;
+        const auto now = std::chrono::steady_clock::now();
+        g_stageUs[k] += std::chrono::duration_cast<std::chrono::microseconds>(now - tStage).count();
+        tStage = now;
+    };
     // checkData (spatialControl.cpp:466-476): the spatial check is skipped for precipitation and the wind vector components
     const bool spatialVar = variable != PB_VAR_PRECIPITATION && variable != PB_VAR_DAILY_PRECIPITATION && variable != PB_VAR_WIND_VECTOR_X &&
                             variable != PB_VAR_WIND_VECTOR_Y && variable != 36 /* windVectorDirection */ &&
@@ -955,6 +1020,7 @@ extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, p
         account();
     }
     if (step && step->wrongSpatial) memcpy(step->wrongSpatial, wrong.data(), n);
+    lap(0);
     // passDataToInterpolation (spatialControl.cpp:500-566)
     std::vector<int> accepted;
     int nrValid = 0;
@@ -975,6 +1041,7 @@ extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, p
     int rc = pb_pre_interpolation_ex(ctx, &pts.st, s, variable, &cv, dem, keep.data(), step ? step->khSeries : nullptr);
     if (rc) return rc;
     account();
+    lap(1);
     std::vector<int> kept;
     for (size_t k = 0; k < accepted.size(); k++) if (keep[k]) kept.push_back(int(k));
     SubStations ipts(&pts.st, kept, pts.st.value);
@@ -982,6 +1049,7 @@ extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, p
                     : pb_interpolation_raster_resident(ctx, &ipts.st, s, variable, dem, proxyGrids, nProxyGrids, rowBegin, rowEnd, out);
     if (rc) return rc;
     account();
+    lap(2);
     if (step && step->residual) {
         // computeResiduals(…, getUseExcludeStationsOutsideDEM(), true) over the accepted meteo points (project.cpp:3063-3067)
         SubStations mp(meteo, accepted, meteo->value);
@@ -1006,11 +1074,20 @@ extern "C" int pb_interpolation_dem(pb_context* ctx, const pb_stations* meteo, p
         }
         cvStatisticsHost(obs, pre, step->stats);
     }
+    lap(3);
+    if (stageTiming()) g_stageCalls++;
     ctx->timing.launches = launches;
     ctx->timing.kernel_ms = kernelMs;
     ctx->timing.h2d_bytes = h2d;
     ctx->timing.d2h_bytes = d2h;
     return PB_OK;
+}
+
+// SMs a lane's raster kernel leaves free for the other lanes' station-space kernels (PB_LANE_RESERVE_SMS overrides)
+static int laneReserveSms()
+{
+    static const int v = getenv("PB_LANE_RESERVE_SMS") ? atoi(getenv("PB_LANE_RESERVE_SMS")) : 16;
+    return v;
 }
 
 /* A batch of independent (time step, variable) units — what the reference's hourly / daily drivers loop over — run through
@@ -1022,6 +1099,7 @@ extern "C" int pb_interpolation_dem_batch(pb_context* ctx, pb_dem_batch_item* it
                                           const pb_raster_id* proxyGrids, int nProxyGrids, int rowBegin, int rowEnd, int deviceOnly,
                                           int nLanes)
 {
+    PB_NVTX_RANGE();
     if (!ctx) return PB_ERR_INVALID;
     if (nItems < 0 || (nItems > 0 && !items)) return fail(ctx, PB_ERR_INVALID, "null argument");
     if (nItems == 0) return PB_OK;
@@ -1048,7 +1126,10 @@ extern "C" int pb_interpolation_dem_batch(pb_context* ctx, pb_dem_batch_item* it
         lane->rasters = ctx->rasters;                       // same ids, same device memory
         for (auto& e : lane->rasters) e.borrowed = true;
         lane->outInitRaster = -1;
+        lane->parent = ctx;
+        lane->reserveSms = nLanes > 1 ? laneReserveSms() : 0;
     }
+    ctx->lastRaster = nullptr;
     std::atomic<int> next(0);
     std::vector<int> launches(nLanes, 0);
     std::vector<float> kernelMs(nLanes, 0.f);
@@ -1090,3 +1171,250 @@ extern "C" int pb_interpolation_dem_batch(pb_context* ctx, pb_dem_batch_item* it
     if (firstError != PB_OK) return fail(ctx, firstError, "a unit of the batch failed (see the items' status)");
     return PB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pb_meteo_grid_step_batch: the hourly driver kept on the device (see include/praga_b200.h)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace pb {
+cudaError_t launchSpatialAggregateDev(const DevGrid& raster, const AggregationGeometry& g, int method, float* scratch, float* value,
+                                      cudaStream_t s);
+cudaError_t launchRelativeHumidityMapDev(const float* airT, float flagT, const float* dewT, float flagTd, long long n, float outFlag,
+                                         float* out, unsigned* minmax, cudaStream_t s);
+cudaError_t launchSamplePointsDev(const DevGrid& g, const double* x, const double* y, int n, float* value, unsigned char* inGrid,
+                                  cudaStream_t s);
+}  // namespace pb
+
+namespace {
+
+// tDewFromRelHum(float RH, float T), agrolib/meteo/meteo.cpp:275-285 (host arithmetic of the meteo point, like the reference)
+float tDewFromRelHumHost(float RH, float T)
+{
+    auto isEq = [](float a, float b) { return fabs(double(a) - double(b)) < kEpsilon; };
+    if (isEq(RH, kNoData) || isEq(T, kNoData) || RH == 0) return kNoData;
+    RH = (100 < RH) ? 100 : RH;
+    const double mySaturatedVaporPres = exp((16.78 * double(T) - 116.9) / (double(T) + 237.3));
+    const double actualVaporPres = double(RH) / 100. * mySaturatedVaporPres;
+    return float((log(actualVaporPres) * 237.3 + 116.9) / (16.78 - log(actualVaporPres)));
+}
+
+float keyToFloatS(unsigned k)
+{
+    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// the map a lane has just gridded (lane->dOut, header of the DEM) -> the meteo-grid cells
+int aggregateLaneMap(pb_context* lane, const AggregationGeometry& g, const DevGrid& map, int method, float* cellValue)
+{
+    if (method != PB_AGGR_AVERAGE && method != PB_AGGR_MEDIAN && method != PB_AGGR_STDDEV) {
+        for (int c = 0; c < g.nCells; c++) cellValue[c] = kNoData;      // spatialAggregateMeteoGridPoint: NODATA (meteoGrid.cpp:1234-1237)
+        return PB_OK;
+    }
+    CUDA_TRY(lane, lane->dAgg.reserve(size_t(std::max<long long>(g.nPoints, 1)) + size_t(g.nCells)));
+    float* scratch = lane->dAgg.p;
+    float* value = scratch + std::max<long long>(g.nPoints, 1);
+    CUDA_TRY(lane, launchSpatialAggregateDev(map, g, method, scratch, value, lane->stream));
+    CUDA_TRY(lane, cudaMemcpyAsync(cellValue, value, size_t(g.nCells) * 4, cudaMemcpyDeviceToHost, lane->stream));
+    CUDA_TRY(lane, cudaStreamSynchronize(lane->stream));
+    return PB_OK;
+}
+
+// one variable of one hour on a lane; tMapValid: lane->dMapT holds the hour's air temperature map
+int meteoGridVar(pb_context* lane, pb_meteo_grid_var& v, pb_raster_id dem, const pb_raster_id* proxyGrids, int nProxyGrids,
+                 const AggregationGeometry* g, bool& tMapValid, int& launches, int64_t& h2d, int64_t& d2h)
+{
+    if (!v.meteo || !v.settings) return fail(lane, PB_ERR_INVALID, "null argument");
+    const RasterEntry& eDem = lane->rasters[dem];
+    const size_t nCellsDem = eDem.n;
+    DevGrid mapGrid = devGridOfRaster(eDem);
+    pb_raster_out localOut{};
+    pb_raster_out* out = v.out ? v.out : &localOut;
+    auto account = [&]() { launches += lane->timing.launches; h2d += lane->timing.h2d_bytes; d2h += lane->timing.d2h_bytes; };
+
+    if (v.variable == PB_VAR_AIR_REL_HUMIDITY && v.useDewPoint) {
+        if (!tMapValid) return fail(lane, PB_ERR_INVALID, "the dew-point chain needs the air temperature map of the same hour before it");
+        if (!v.airTemperature) return fail(lane, PB_ERR_INVALID, "the dew-point chain needs the stations' air temperature (PB_NODATA where missing)");
+        const pb_stations* st = v.meteo;
+        const int n = st->n;
+        DevGrid tGrid = mapGrid;
+        tGrid.data = lane->dMapT.p;
+        // passInterpolatedTemperatureToHumidityPoints (project.cpp:2826-2848)
+        std::vector<float> airT(v.airTemperature, v.airTemperature + n);
+        std::vector<int> need;
+        for (int i = 0; i < n; i++)
+            if (!(fabs(double(st->value[i]) - double(kNoData)) < kEpsilon) && (fabs(double(airT[i]) - double(kNoData)) < kEpsilon)) need.push_back(i);
+        if (!need.empty()) {
+            const size_t m = need.size(), mAl = (m + 1) / 2 * 2;
+            CUDA_TRY(lane, lane->dScratch.reserve(mAl * 16 + mAl * 4 + mAl + 64));
+            std::vector<double> xy(2 * mAl);
+            for (size_t k = 0; k < m; k++) { xy[k] = st->x[need[k]]; xy[mAl + k] = st->y[need[k]]; }
+            double* dX = reinterpret_cast<double*>(lane->dScratch.p);
+            double* dY = dX + mAl;
+            float* dV = reinterpret_cast<float*>(dY + mAl);
+            unsigned char* dIn = reinterpret_cast<unsigned char*>(dV + mAl);
+            std::vector<float> val(m);
+            std::vector<uint8_t> in(m);
+            CUDA_TRY(lane, cudaMemcpyAsync(dX, xy.data(), 2 * mAl * 8, cudaMemcpyHostToDevice, lane->stream));
+            CUDA_TRY(lane, launchSamplePointsDev(tGrid, dX, dY, int(m), dV, dIn, lane->stream));
+            CUDA_TRY(lane, cudaMemcpyAsync(val.data(), dV, m * 4, cudaMemcpyDeviceToHost, lane->stream));
+            CUDA_TRY(lane, cudaMemcpyAsync(in.data(), dIn, m, cudaMemcpyDeviceToHost, lane->stream));
+            CUDA_TRY(lane, cudaStreamSynchronize(lane->stream));
+            launches++;
+            h2d += int64_t(2 * mAl * 8);
+            d2h += int64_t(m * 5);
+            for (size_t k = 0; k < m; k++) if (in[k]) airT[need[k]] = val[k];      // the map's value, its flag included
+        }
+        // the stations' dew point: Crit3DMeteoPoint::getMeteoPointValueH(airDewTemperature) (meteoPoint.cpp:967-972)
+        std::vector<int> have;
+        std::vector<float> tdew(n, kNoData);
+        for (int i = 0; i < n; i++) {
+            tdew[i] = tDewFromRelHumHost(st->value[i], airT[i]);
+            if (!(fabs(double(tdew[i]) - double(kNoData)) < kEpsilon)) have.push_back(i);      // checkAndPassDataToInterpolation: valid values only
+        }
+        SubStations dew(st, have, tdew.data());
+        pb_dem_step stepLocal{};
+        std::vector<uint8_t> wrong(std::max<size_t>(have.size(), 1), 0);
+        std::vector<float> resid(std::max<size_t>(have.size(), 1), kNoData);
+        if (v.step) {
+            stepLocal = *v.step;
+            stepLocal.wrongSpatial = v.step->wrongSpatial ? wrong.data() : nullptr;
+            stepLocal.residual = v.step->residual ? resid.data() : nullptr;
+        }
+        int rc = pb_interpolation_dem(lane, &dew.st, v.qualitySettings, v.settings, PB_VAR_AIR_DEW_TEMPERATURE, dem, proxyGrids,
+                                      nProxyGrids, 0, -1, 1, out, v.step ? &stepLocal : nullptr);
+        account();
+        if (rc != PB_OK) return rc;
+        if (v.step) {
+            if (v.step->wrongSpatial) { memset(v.step->wrongSpatial, 0, n); for (size_t k = 0; k < have.size(); k++) v.step->wrongSpatial[have[k]] = wrong[k]; }
+            if (v.step->residual) { for (int i = 0; i < n; i++) v.step->residual[i] = kNoData; for (size_t k = 0; k < have.size(); k++) v.step->residual[have[k]] = resid[k]; }
+        }
+        // computeRelativeHumidityMap (meteoMaps.cpp:301-321): in place over the dew-point map (a cell reads its own two inputs)
+        lane->hMinMax[0] = 0xffffffffu; lane->hMinMax[1] = 0u; lane->hMinMax[2] = 0u; lane->hMinMax[3] = 0u;
+        CUDA_TRY(lane, cudaMemcpyAsync(lane->dMinMax, lane->hMinMax, 4 * sizeof(unsigned), cudaMemcpyHostToDevice, lane->stream));
+        CUDA_TRY(lane, launchRelativeHumidityMapDev(lane->dMapT.p, eDem.h.flag, lane->dOut.p, eDem.h.flag, (long long)nCellsDem,
+                                                   eDem.h.flag, lane->dOut.p, lane->dMinMax, lane->stream));
+        CUDA_TRY(lane, cudaMemcpyAsync(lane->hMinMax, lane->dMinMax, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, lane->stream));
+        launches++;
+        if (v.out && (v.out->data || v.out->rows)) {
+            const int rows = eDem.h.nrRows, cols = eDem.h.nrCols;
+            if (v.out->data)
+                CUDA_TRY(lane, cudaMemcpyAsync(v.out->data, lane->dOut.p, nCellsDem * 4, cudaMemcpyDeviceToHost, lane->stream));
+            else
+                for (int r = 0; r < rows; r++)
+                    CUDA_TRY(lane, cudaMemcpyAsync(v.out->rows[r], lane->dOut.p + size_t(r) * cols, size_t(cols) * 4, cudaMemcpyDeviceToHost,
+                                                   lane->stream));
+            d2h += int64_t(nCellsDem * 4);
+        }
+        CUDA_TRY(lane, cudaStreamSynchronize(lane->stream));
+        if (lane->hMinMax[0] == 0xffffffffu) { out->minimum = kNoData; out->maximum = kNoData; }
+        else { out->minimum = keyToFloatS(lane->hMinMax[0]); out->maximum = keyToFloatS(lane->hMinMax[1]); }
+    } else {
+        const int deviceOnly = !(v.out && (v.out->data || v.out->rows));
+        int rc = pb_interpolation_dem(lane, v.meteo, v.qualitySettings, v.settings, v.variable, dem, proxyGrids, nProxyGrids, 0, -1,
+                                      deviceOnly, out, v.step);
+        account();
+        if (rc != PB_OK && rc != PB_ERR_NO_VALID_CELL) return rc;
+        if (v.variable == PB_VAR_AIR_TEMPERATURE) {
+            // mapHourlyTair of this hour, kept for the humidity chain
+            CUDA_TRY(lane, lane->dMapT.reserve(nCellsDem));
+            CUDA_TRY(lane, cudaMemcpyAsync(lane->dMapT.p, lane->dOut.p, nCellsDem * 4, cudaMemcpyDeviceToDevice, lane->stream));
+            tMapValid = true;
+        }
+        if (rc == PB_ERR_NO_VALID_CELL) {
+            if (g && v.cellValue) for (int c = 0; c < g->nCells; c++) v.cellValue[c] = kNoData;
+            return rc;
+        }
+    }
+    if (g && v.cellValue) {
+        mapGrid.data = lane->dOut.p;
+        int rc = aggregateLaneMap(lane, *g, mapGrid, v.aggrMethod, v.cellValue);
+        if (rc) return rc;
+        launches++;
+        d2h += int64_t(g->nCells) * 4;
+    }
+    return PB_OK;
+}
+
+}  // namespace
+
+extern "C" int pb_meteo_grid_step_batch(pb_context* ctx, pb_meteo_grid_hour* hours, int nHours, pb_raster_id dem,
+                                        const pb_raster_id* proxyGrids, int nProxyGrids, int32_t aggregation, int nLanes)
+{
+    PB_NVTX_RANGE();
+    if (!ctx) return PB_ERR_INVALID;
+    if (nHours < 0 || (nHours > 0 && !hours)) return fail(ctx, PB_ERR_INVALID, "null argument");
+    if (nHours == 0) return PB_OK;
+    if (dem < 0 || dem >= (int)ctx->rasters.size() || !ctx->rasters[dem].used) return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
+    const AggregationGeometry* g = nullptr;
+    if (aggregation >= 0) {
+        if (aggregation >= (int)ctx->aggregations.size() || !ctx->aggregations[aggregation].used)
+            return fail(ctx, PB_ERR_INVALID, "bad aggregation id");
+        g = &ctx->aggregations[aggregation];
+    }
+    cudaSetDevice(ctx->device);
+    if (nLanes <= 0) nLanes = 4;
+    nLanes = std::min(std::min(nLanes, nHours), 16);
+    int rc = ensureValidList(ctx, ctx->rasters[dem]);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    while ((int)ctx->lanes.size() < nLanes) {
+        pb_context* lane = nullptr;
+        rc = pb_create(ctx->device, &lane);
+        if (rc) return fail(ctx, rc, "could not create a lane context");
+        ctx->lanes.push_back(lane);
+    }
+    for (int l = 0; l < nLanes; l++) {
+        pb_context* lane = ctx->lanes[l];
+        lane->rasters = ctx->rasters;                       // same ids, same device memory
+        for (auto& e : lane->rasters) e.borrowed = true;
+        lane->outInitRaster = -1;
+        lane->parent = ctx;
+        lane->reserveSms = nLanes > 1 ? laneReserveSms() : 0;
+    }
+    ctx->lastRaster = nullptr;
+    std::atomic<int> next(0);
+    std::vector<int> launches(nLanes, 0);
+    std::vector<int64_t> h2d(nLanes, 0), d2h(nLanes, 0);
+    auto work = [&](int l) {
+        pb_context* lane = ctx->lanes[l];
+        cudaSetDevice(lane->device);
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= nHours) break;
+            pb_meteo_grid_hour& hour = hours[i];
+            bool tMapValid = false;
+            for (int k = 0; k < hour.nVars; k++) {
+                pb_meteo_grid_var& v = hour.vars[k];
+                v.status = meteoGridVar(lane, v, dem, proxyGrids, nProxyGrids, g, tMapValid, launches[l], h2d[l], d2h[l]);
+            }
+        }
+    };
+    const auto tBatch = std::chrono::steady_clock::now();
+    std::vector<std::thread> threads;
+    for (int l = 1; l < nLanes; l++) threads.emplace_back(work, l);
+    work(0);
+    for (auto& th : threads) th.join();
+    stageReport("pb_meteo_grid_step_batch", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tBatch).count(), nLanes);
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    int firstError = PB_OK;
+    std::string firstMsg;
+    for (int l = 0; l < nLanes; l++) {
+        pb_context* lane = ctx->lanes[l];
+        cudaStreamSynchronize(lane->stream);
+        for (auto& e : lane->rasters) e = RasterEntry();    // views only: nothing to release
+        lane->rasters.clear();
+        ctx->timing.launches += launches[l];
+        ctx->timing.h2d_bytes += h2d[l];
+        ctx->timing.d2h_bytes += d2h[l];
+    }
+    for (int i = 0; i < nHours; i++)
+        for (int k = 0; k < hours[i].nVars; k++) {
+            const int st = hours[i].vars[k].status;
+            if (st != PB_OK && st != PB_ERR_NO_VALID_CELL && firstError == PB_OK) firstError = st;
+        }
+    if (firstError != PB_OK) return fail(ctx, firstError, "a variable of the batch failed (see the variables' status)");
+    return PB_OK;
+}
+

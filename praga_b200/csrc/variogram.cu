@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "context.cuh"
+#include "nvtx.cuh"
 
 namespace {
 
@@ -106,6 +107,7 @@ extern "C" {
 int pb_kriging_empirical_variogram(const double* pos, const double* val, int n, int nBins, double maxDistance, float* binDist,
                                    float* binSemiVar, int32_t* binCount, double* maxDistanceUsed)
 {
+    PB_NVTX_RANGE();
     if (!pos || !val || n < 2 || nBins < 1 || !binDist || !binSemiVar || !binCount) return PB_ERR_INVALID;
     if (!(maxDistance > 0)) {       // default: half the diagonal of the stations' bounding box
         double x0 = pos[0], x1 = x0, y0 = pos[1], y1 = y0;
@@ -150,6 +152,7 @@ int pb_kriging_empirical_variogram(const double* pos, const double* val, int n, 
 int pb_kriging_fit_variogram(const float* binDist, const float* binSemiVar, const int32_t* binCount, int nBins, int mode,
                              double* range, double* nugget, double* sill, double* slope, int* modeOut, double* weightedSse)
 {
+    PB_NVTX_RANGE();
     if (!binDist || !binSemiVar || nBins < 2 || !range || !nugget || !sill || !slope) return PB_ERR_INVALID;
     if (mode != 0 && mode != PB_KRIGING_SPHERICAL && mode != PB_KRIGING_EXPONENTIAL && mode != PB_KRIGING_GAUSSIAN &&
         mode != PB_KRIGING_LINEAR)

@@ -75,6 +75,8 @@ def load_library():
                                          P(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int, P(A.pb_raster_out), P(A.pb_dem_step)]
     lib.pb_interpolation_dem_batch.argtypes = [C.c_void_p, P(A.pb_dem_batch_item), C.c_int, C.c_int32, P(C.c_int32), C.c_int, C.c_int,
                                                C.c_int, C.c_int, C.c_int]
+    lib.pb_meteo_grid_step_batch.argtypes = [C.c_void_p, P(A.pb_meteo_grid_hour), C.c_int, C.c_int32, P(C.c_int32), C.c_int, C.c_int32,
+                                             C.c_int]
     lib.pb_kriging_setup.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_int, P(C.c_int32)]
     lib.pb_kriging_free.argtypes = [C.c_void_p, C.c_int32]
@@ -120,7 +122,7 @@ def load_library():
     lib.pb_measure_fp64_peak.argtypes = [C.c_void_p, P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
                  "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series", "pb_dem_step", "pb_dem_batch_item",
-                 "pb_macro_area"):
+                 "pb_macro_area", "pb_meteo_grid_var", "pb_meteo_grid_hour"):
         got, want = lib.pb_abi_sizeof(name.encode()), C.sizeof(getattr(A, name))
         if got != want:
             raise PragaB200Error(A.PB_ERR_INVALID, f"ABI mismatch for {name}: library {got} B, binding {want} B")
@@ -187,6 +189,11 @@ class Engine:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.pb_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_blocking_sync(self, blocking=True):
+        """host threads sleep instead of spinning while they wait for the device (more waiting threads than cores)"""
+        self.lib.pb_set_blocking_sync.argtypes = [C.c_void_p, C.c_int]
+        return self.lib.pb_set_blocking_sync(self.h, int(blocking)) == A.PB_OK
 
     def timing(self):
         t = A.pb_timing()
@@ -519,6 +526,70 @@ class Engine:
                             n_valid=o.nValid, wrong_spatial=wrong.astype(bool), residual=res if cross_validate else None,
                             stats={k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_} if cross_validate else None,
                             kh_series=[(series.kh[j], series.error[j]) for j in range(series.n)]))
+        return out
+
+    def meteo_grid_step_batch(self, hours, dem_id, shape, proxy_ids=(), aggregation_id=-1, n_cells=0, lanes=0, cross_validate=False):
+        """pb_meteo_grid_step_batch: the hourly driver kept on the device (PragaProject::interpolationMeteoGrid with
+        getMeteoGridUpscaleFromDem(), pragaProject.cpp:2951-2990). hours: list of lists of dicts with keys meteo, settings,
+        variable and optionally quality_settings, use_dew_point, air_temperature, aggr_method (default average), want_raster.
+        Returns the same nesting of dicts(status, ok, cells, grid, min, max, n_valid, wrong_spatial, residual, stats)."""
+        nh = len(hours)
+        harr = (A.pb_meteo_grid_hour * max(1, nh))()
+        keep, res = [], []
+        for i, hour in enumerate(hours):
+            varr = (A.pb_meteo_grid_var * max(1, len(hour)))()
+            hres = []
+            for k, u in enumerate(hour):
+                meteo = u["meteo"]
+                st = meteo.as_pb()
+                o = A.pb_raster_out()
+                grid = None
+                if u.get("want_raster"):
+                    grid = np.empty(shape, dtype=np.float32)
+                    o.data = A.fptr(grid)
+                cells = np.empty(max(1, n_cells), dtype=np.float32) if aggregation_id >= 0 else None
+                wrong = np.zeros(meteo.n, dtype=np.uint8)
+                resid = np.empty(meteo.n, dtype=np.float32)
+                stats, step = A.pb_cv_stats(), A.pb_dem_step()
+                step.wrongSpatial = A.u8ptr(wrong)
+                if cross_validate:
+                    step.residual = A.fptr(resid)
+                    step.stats = C.pointer(stats)
+                v = varr[k]
+                v.meteo = C.pointer(st)
+                v.settings = C.pointer(u["settings"])
+                if u.get("quality_settings") is not None:
+                    v.qualitySettings = C.pointer(u["quality_settings"])
+                v.variable = u["variable"]
+                v.useDewPoint = int(bool(u.get("use_dew_point")))
+                air = None
+                if u.get("air_temperature") is not None:
+                    air = np.ascontiguousarray(u["air_temperature"], dtype=np.float32)
+                    v.airTemperature = A.fptr(air)
+                v.aggrMethod = u.get("aggr_method", A.PB_AGGR_AVERAGE)
+                if cells is not None:
+                    v.cellValue = A.fptr(cells)
+                v.out = C.pointer(o)
+                v.step = C.pointer(step)
+                keep.append((meteo, st, o, air, wrong, resid, stats, step))
+                hres.append(dict(cells=cells, grid=grid, out=o, wrong=wrong, resid=resid, stats=stats))
+            harr[i].vars = varr
+            harr[i].nVars = len(hour)
+            keep.append(varr)
+            res.append((varr, hres))
+        ids = (C.c_int32 * max(1, len(proxy_ids)))(*proxy_ids)
+        rc = self.lib.pb_meteo_grid_step_batch(self.h, harr, nh, dem_id, ids, len(proxy_ids), aggregation_id, lanes)
+        self._check(rc, allow=(A.PB_ERR_NO_VALID_CELL,))
+        out = []
+        for varr, hres in res:
+            row = []
+            for k, r in enumerate(hres):
+                o = r["out"]
+                row.append(dict(status=varr[k].status, ok=varr[k].status == A.PB_OK, cells=r["cells"], grid=r["grid"], min=o.minimum,
+                                max=o.maximum, n_valid=o.nValid, wrong_spatial=r["wrong"].astype(bool),
+                                residual=r["resid"] if cross_validate else None,
+                                stats={f: getattr(r["stats"], f) for f, _ in A.pb_cv_stats._fields_} if cross_validate else None))
+            out.append(row)
         return out
 
     def pre_interpolation_batch(self, stations, values, settings, variable, points_range=None):

@@ -16,8 +16,8 @@ from bench import HourlyBatchWorkload, WORKLOADS  # noqa: E402
 eng = pb.Engine(0)
 wl = HourlyBatchWorkload(eng, WORKLOADS["c5"], 0, 1, 8)
 out = {}
-for k in range(3):
-    st, var = wl._step_inputs(k)
+t_st, rh_st, own_t, p_st = wl._hour_inputs(0)
+for st, var in ((t_st, A.airTemperature), (rh_st, A.airRelHumidity), (p_st, A.precipitation)):
     acc = {}
     for rep in range(6):
         s, sq = wl._settings(var)
