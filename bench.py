@@ -317,6 +317,8 @@ class IdwWorkload:
             return False
         import ctypes as C
         self._C, self.shim = C, binding.load_shim()
+        if self.shim.shim_session_set_device(int(os.environ.get("LOCAL_RANK", "0"))) != A.PB_OK:      # one GPU per rank
+            return False
         d = self.dem.as_pb()
         g = (A.pb_raster * 2)()
         g[0], g[1] = d, self.urban.as_pb()

@@ -49,6 +49,7 @@ def load_shim():
     lib.shim_session_output.argtypes = [C.c_void_p, P(A.pb_raster_out)]
     lib.shim_session_poke_dem.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]
     lib.shim_session_poke_dem.restype = None
+    lib.shim_session_set_device.argtypes = [C.c_int]
     lib.shim_session_timing.argtypes = [P(A.pb_timing)]
     lib.shim_session_cache.argtypes = [C.c_int]
     lib.shim_session_cache.restype = None

@@ -302,6 +302,7 @@ void shim_session_poke_dem(void* session, int row, int col, float value, int ann
     ss->dem.value[row][col] = value;
     if (announce) pragab200::invalidate(&ss->dem);
 }
+int shim_session_set_device(int device) { return pragab200::setDevice(device) ? PB_OK : PB_ERR_INVALID; }
 int shim_session_timing(pb_timing* t) { return pragab200::lastTiming(t) ? PB_OK : PB_ERR_INVALID; }
 void shim_session_cache(int enabled) { pragab200::setRasterCache(enabled != 0); }
 void shim_session_close(void* session)
