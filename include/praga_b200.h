@@ -547,6 +547,43 @@ int pb_topographic_index(pb_context* ctx, pb_raster_id dem, const float* windowW
 int pb_raster_sample_points(pb_context* ctx, pb_raster_id raster, const double* x, const double* y, int n, float* value,
                             uint8_t* inGrid);
 
+/* --- solar radiation maps: radiation::computeRadiationDEM (agrolib/solarRadiation/solarRadiation.cpp:1045-1069)
+ * = for every valid DEM cell computeRadiationDemPoint (:946-981) -> computeRadiationRsun (:700-834): sun position (NREL SOLPOS,
+ * solPos.cpp / sunPosition.cpp), shadowing by the DEM (computeShadow :543-604), real-sky split of the transmissivity
+ * (separateTransmissivity_Erbs_Reindl :634-690) or the Linke clear-sky model (:343-392), irradiance on the cell's slope / aspect
+ * (getBeamInclined, getDiffuseInclined_Muneer, getReflectedIrradiance) — then gis::updateMinMaxRasterGrid of the maps
+ * (updateRadiationMaps :1072-1089). The transmissivity map is what Project::interpolateDemRadiation (agrolib/project/project.cpp:
+ * 3382-3437) grids from the stations' atmTransmissivity with this engine; lat / lon / slope / aspect are the static maps of
+ * Crit3DRadiationMaps (gis::computeLatLonMaps, gis::computeSlopeAspectMaps), uploaded once. All maps are resident rasters with
+ * the DEM's geometry. The time is the LOCAL time (the host applies isUTC / timeZone like computeRadiationRsun :714-719).
+ * Linke / albedo: the scalar the reference ends up with for an in-grid cell — the fixed value, the month's for PARAM_MODE_MONTHLY
+ * (Linke), PB_NODATA for the map modes, whose accessors only ever read OUT-of-grid cells (radiationSettings.cpp:131-133, :179-181).
+ * With shadowing off the reference reads an uninitialised TsunPosition::shadow (:744-750, :801); here it is false. */
+typedef struct pb_radiation_settings {
+    int32_t realSky, realSkyAlgorithm /* 0 total transmissivity, 1 Linke */, shadowing;
+    int32_t tiltMode /* 1 fixed, 2 dem */, linkeMode, albedoMode /* 0 fixed, 1 map, 2 monthly */;
+    float linke, albedo, tilt, aspect, clearSky;
+    float demMaximum;              /* dem.maximum (gis::updateMinMaxRasterGrid): bound of the shadow march */
+    int32_t timeZone;
+    int32_t year, month, day, secondsOfDay;
+} pb_radiation_settings;
+typedef struct pb_radiation_maps {
+    pb_raster_id dem, lat, lon, slope, aspect, transmissivity;
+} pb_radiation_maps;
+typedef struct pb_radiation_out {
+    pb_raster_out* sunElevation;   /* each may be NULL or have data / rows NULL: not downloaded; minimum / maximum always set */
+    pb_raster_out* beam;
+    pb_raster_out* diffuse;
+    pb_raster_out* reflected;
+    pb_raster_out* global;
+    int32_t keepResident;          /* != 0: the five maps stay resident, ids[] (same order) to be released with pb_raster_free */
+    pb_raster_id ids[5];
+} pb_radiation_out;
+int pb_compute_radiation_dem(pb_context* ctx, const pb_radiation_settings* s, const pb_radiation_maps* maps, pb_radiation_out* out);
+/* the map the last raster call of this context left on the device (pb_*_device forms, deviceOnly) as a resident raster with
+ * the header of `like` (the DEM): e.g. the gridded transmissivity map handed to pb_compute_radiation_dem without a PCIe trip */
+int pb_raster_from_last_output(pb_context* ctx, pb_raster_id like, pb_raster_id* id);
+
 /* --- ESRI float grids (.hdr + .flt), the on-disk format at either end of the path, streamed between
  * the file and HBM through pinned staging (no pageable full-size copy):
  *   pb_raster_read_esri_header <- gis::readEsriGridHeader (agrolib/gis/gisIO.cpp:118-193)

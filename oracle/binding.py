@@ -406,6 +406,27 @@ class Oracle:
         f(A.fptr(rh), A.fptr(t), rh.shape[0], A.fptr(out))
         return out
 
+    def compute_radiation_dem(self, settings, dem, transmissivity, utm_zone=32, start_latitude=44.5, threads=0, shim=None):
+        """radiation::computeRadiationDEM on the reference's objects (reference oracle only). Returns dict with the static maps the
+        reference derives from the DEM (lat, lon, slope, aspect), the five output maps, minmax[10], demMaximum, seconds.
+        shim: the loaded libpraga_shim_test.so -> the same driver with pragab200::computeRadiationDEM in place of the reference's."""
+        assert self.kind == "reference"
+        lib = _load(REF_LIB, "ref")
+        P = C.POINTER
+        fn = lib.ref_compute_radiation_dem if shim is None else shim.shim_compute_radiation_dem
+        fn.argtypes = [P(A.pb_radiation_settings), C.c_int, C.c_double, P(A.pb_raster), P(A.pb_raster)] + \
+            [P(C.c_float)] * 11 + [C.c_int, P(C.c_double)]
+        d, tr = dem.as_pb(), transmissivity.as_pb()
+        names = ("lat", "lon", "slope", "aspect", "sunElevation", "beam", "diffuse", "reflected", "global")
+        arrs = {k: np.empty(dem.shape, dtype=np.float32) for k in names}
+        mm = np.empty(10, dtype=np.float32)
+        dmax = C.c_float(0)
+        sec = C.c_double(0)
+        rc = fn(C.byref(settings), utm_zone, start_latitude, C.byref(d), C.byref(tr),
+                                           *[A.fptr(arrs[k]) for k in names], A.fptr(mm), C.byref(dmax), threads, C.byref(sec))
+        arrs.update(ok=rc == A.PB_OK, minmax=mm, dem_maximum=dmax.value, seconds=sec.value)
+        return arrs
+
     def relative_humidity_map(self, air_t, dew_t):
         a, b = air_t.as_pb(), dew_t.as_pb()
         out = np.empty(air_t.shape, dtype=np.float32)

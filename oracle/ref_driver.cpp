@@ -24,6 +24,8 @@
 #include <math.h>
 #include <string.h>
 #include <chrono>
+#include "solarRadiation.h"
+#include "radiationSettings.h"
 #include <string>
 #include <vector>
 
@@ -1191,3 +1193,78 @@ extern "C" int ref_topographic_index(const pb_raster* dem, const float* windowWi
     out->nValid = int64_t(DEM.header->nrRows) * DEM.header->nrCols;
     return ok ? PB_OK : PB_ERR_INVALID;
 }
+
+/* radiation::computeRadiationDEM (solarRadiation.cpp:1045-1069) on the reference's own objects: Crit3DRadiationSettings,
+ * Crit3DRadiationMaps(dem, gisSettings) (the constructor derives the static lat / lon / slope / aspect maps from the DEM with
+ * gis::computeLatLonMaps / computeSlopeAspectMaps; they are returned so that the GPU side is fed the same inputs), the
+ * transmissivity map given. s carries the LOCAL time (gisSettings.isUTC = false). Every output array holds nrRows * nrCols
+ * floats; minmax = {min, max} of sunElevation, beam, diffuse, reflected, global as updateRadiationMaps leaves them. */
+typedef bool (*RadiationDemFn)(Crit3DRadiationSettings*, const gis::Crit3DRasterGrid&, Crit3DRadiationMaps*, const Crit3DTime&, bool);
+static int radiationDemDriver(RadiationDemFn compute, const pb_radiation_settings* s, int utmZone, double startLatitude, const pb_raster* dem,
+                              const pb_raster* transmissivity, float* lat, float* lon, float* slope, float* aspect,
+                              float* sunElevation, float* beam, float* diffuse, float* reflected, float* global,
+                              float* minmax, float* demMaximum, int nThreads, double* elapsed_s)
+{
+    gis::Crit3DRasterGrid demGrid;
+    fillGrid(demGrid, *dem);
+    gis::updateMinMaxRasterGrid(&demGrid);
+    if (demMaximum) *demMaximum = demGrid.maximum;
+    gis::Crit3DGisSettings gisSettings;
+    gisSettings.utmZone = utmZone;
+    gisSettings.isUTC = false;
+    gisSettings.timeZone = s->timeZone;
+    gisSettings.startLocation.latitude = startLatitude;
+    Crit3DRadiationSettings rad;
+    rad.setGisSettings(&gisSettings);
+    rad.setRealSky(s->realSky != 0);
+    rad.setRealSkyAlgorithm(TradiationRealSkyAlgorithm(s->realSkyAlgorithm));
+    rad.setShadowing(s->shadowing != 0);
+    rad.setTiltMode(TtiltMode(s->tiltMode));
+    rad.setLinkeMode(PARAM_MODE_FIXED);
+    rad.setAlbedoMode(PARAM_MODE_FIXED);
+    rad.setLinkeDefault(s->linke);
+    rad.setAlbedo(s->albedo);
+    rad.setTilt(s->tilt);
+    rad.setAspect(s->aspect);
+    rad.setClearSky(s->clearSky);
+    Crit3DRadiationMaps maps(demGrid, gisSettings);
+    const int rows = demGrid.header->nrRows, cols = demGrid.header->nrCols;
+    auto copyGrid = [&](const gis::Crit3DRasterGrid* g, float* dst) {
+        if (!dst) return;
+        for (int r = 0; r < rows; r++) memcpy(dst + size_t(r) * cols, g->value[r], sizeof(float) * cols);
+    };
+    copyGrid(maps.latMap, lat);
+    copyGrid(maps.lonMap, lon);
+    copyGrid(maps.slopeMap, slope);
+    copyGrid(maps.aspectMap, aspect);
+    for (int r = 0; r < rows; r++)
+        for (int c = 0; c < cols; c++)
+            maps.transmissivityMap->value[r][c] = transmissivity->data ? transmissivity->data[size_t(r) * cols + c] : transmissivity->rows[r][c];
+    Crit3DTime myTime(Crit3DDate(s->day, s->month, s->year), s->secondsOfDay);
+    if (nThreads > 0) omp_set_num_threads(nThreads);
+    auto t0 = std::chrono::steady_clock::now();
+    const bool ok = compute(&rad, demGrid, &maps, myTime, nThreads != 1);
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
+    copyGrid(maps.sunElevationMap, sunElevation);
+    copyGrid(maps.beamRadiationMap, beam);
+    copyGrid(maps.diffuseRadiationMap, diffuse);
+    copyGrid(maps.reflectedRadiationMap, reflected);
+    copyGrid(maps.globalRadiationMap, global);
+    if (minmax) {
+        const gis::Crit3DRasterGrid* gs[5] = {maps.sunElevationMap, maps.beamRadiationMap, maps.diffuseRadiationMap, maps.reflectedRadiationMap,
+                                              maps.globalRadiationMap};
+        for (int k = 0; k < 5; k++) { minmax[2 * k] = gs[k]->minimum; minmax[2 * k + 1] = gs[k]->maximum; }
+    }
+    return ok ? PB_OK : PB_ERR_INVALID;
+}
+
+extern "C" int ref_compute_radiation_dem(const pb_radiation_settings* s, int utmZone, double startLatitude, const pb_raster* dem,
+                                         const pb_raster* transmissivity, float* lat, float* lon, float* slope, float* aspect,
+                                         float* sunElevation, float* beam, float* diffuse, float* reflected, float* global,
+                                         float* minmax, float* demMaximum, int nThreads, double* elapsed_s)
+{
+    return radiationDemDriver(radiation::computeRadiationDEM, s, utmZone, startLatitude, dem, transmissivity, lat, lon, slope, aspect,
+                              sunElevation, beam, diffuse, reflected, global, minmax, demMaximum, nThreads, elapsed_s);
+}
+

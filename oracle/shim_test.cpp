@@ -313,4 +313,17 @@ void shim_session_close(void* session)
     delete ss;
 }
 
+/* pragab200::computeRadiationDEM on the reference's own Crit3DRadiationSettings / Crit3DRadiationMaps objects (same driver as
+ * ref_compute_radiation_dem, the drop-in in place of radiation::computeRadiationDEM) */
+int shim_compute_radiation_dem(const pb_radiation_settings* s, int utmZone, double startLatitude, const pb_raster* dem,
+                               const pb_raster* transmissivity, float* lat, float* lon, float* slope, float* aspect, float* sunElevation,
+                               float* beam, float* diffuse, float* reflected, float* global, float* minmax, float* demMaximum, int nThreads,
+                               double* elapsed_s)
+{
+    const int rc = radiationDemDriver(pragab200::computeRadiationDEM, s, utmZone, startLatitude, dem, transmissivity, lat, lon, slope, aspect,
+                                      sunElevation, beam, diffuse, reflected, global, minmax, demMaximum, nThreads, elapsed_s);
+    pragab200::invalidateAll();          // the driver's grids die with this call
+    return rc;
+}
+
 }  // extern "C"

@@ -142,6 +142,33 @@ class pb_meteo_grid_hour(C.Structure):
     _fields_ = [("vars", C.POINTER(pb_meteo_grid_var)), ("nVars", C.c_int32), ("reserved", C.c_int32)]
 
 
+class pb_radiation_settings(C.Structure):
+    _fields_ = [("realSky", C.c_int32), ("realSkyAlgorithm", C.c_int32), ("shadowing", C.c_int32), ("tiltMode", C.c_int32),
+                ("linkeMode", C.c_int32), ("albedoMode", C.c_int32), ("linke", C.c_float), ("albedo", C.c_float), ("tilt", C.c_float),
+                ("aspect", C.c_float), ("clearSky", C.c_float), ("demMaximum", C.c_float), ("timeZone", C.c_int32),
+                ("year", C.c_int32), ("month", C.c_int32), ("day", C.c_int32), ("secondsOfDay", C.c_int32)]
+
+
+class pb_radiation_maps(C.Structure):
+    _fields_ = [("dem", C.c_int32), ("lat", C.c_int32), ("lon", C.c_int32), ("slope", C.c_int32), ("aspect", C.c_int32),
+                ("transmissivity", C.c_int32)]
+
+
+class pb_radiation_out(C.Structure):
+    _fields_ = [("sunElevation", C.POINTER(pb_raster_out)), ("beam", C.POINTER(pb_raster_out)), ("diffuse", C.POINTER(pb_raster_out)),
+                ("reflected", C.POINTER(pb_raster_out)), ("global_", C.POINTER(pb_raster_out)), ("keepResident", C.c_int32),
+                ("ids", C.c_int32 * 5)]
+
+
+def default_radiation_settings(year, month, day, seconds_of_day, time_zone=1):
+    """Crit3DRadiationSettings::initialize() defaults (radiationSettings.cpp:41-72) + the local time of the step"""
+    s = pb_radiation_settings()
+    s.realSky, s.realSkyAlgorithm, s.shadowing, s.tiltMode = 1, 1, 1, 2
+    s.linke, s.albedo, s.clearSky = 4.0, 0.2, 0.75
+    s.timeZone, s.year, s.month, s.day, s.secondsOfDay = time_zone, year, month, day, seconds_of_day
+    return s
+
+
 class pb_macro_area(C.Structure):
     _fields_ = [("nMeteoPoints", C.c_int32), ("reserved", C.c_int32), ("meteoPoints", C.POINTER(C.c_int32)),
                 ("nAreaCells", C.c_int64), ("areaCellsDEM", C.POINTER(C.c_float)),

@@ -29,6 +29,7 @@ SOURCES = {
     "station_space.cu": ["-fmad=false"],
     "glocal.cu": ["-fmad=false"],
     "raster_ops.cu": ["-fmad=false"],
+    "radiation.cu": ["-fmad=false"],
     "raster_io.cu": [],
     "kriging.cu": [],
     "kriging_tc.cu": [],

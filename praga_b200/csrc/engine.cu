@@ -1319,6 +1319,32 @@ int pb_raster_free(pb_context* ctx, pb_raster_id id)
     return PB_OK;
 }
 
+int pb_raster_from_last_output(pb_context* ctx, pb_raster_id like, pb_raster_id* id)
+{
+    PB_NVTX_RANGE();
+    if (!ctx) return PB_ERR_INVALID;
+    if (!id || like < 0 || like >= (int)ctx->rasters.size() || !ctx->rasters[like].used) return fail(ctx, PB_ERR_INVALID, "bad raster id");
+    cudaSetDevice(ctx->device);
+    const size_t n = ctx->rasters[like].n;
+    if (!ctx->dOut.p || ctx->dOut.cap < n) return fail(ctx, PB_ERR_INVALID, "no output map of that size on the device");
+    int slot = -1;
+    for (size_t i = 0; i < ctx->rasters.size(); i++) if (!ctx->rasters[i].used) { slot = (int)i; break; }
+    if (slot < 0) { ctx->rasters.emplace_back(); slot = (int)ctx->rasters.size() - 1; }
+    void* d = nullptr;
+    CUDA_TRY(ctx, ctx->pool.acquire(n * sizeof(float), &d));
+    RasterEntry& e = ctx->rasters[slot];
+    e = RasterEntry();
+    e.d = static_cast<float*>(d);
+    e.h = ctx->rasters[like].h;
+    e.n = n;
+    e.used = true;
+    if (ctx->outInitRaster == slot) ctx->outInitRaster = -1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(e.d, ctx->dOut.p, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *id = slot;
+    return PB_OK;
+}
+
 int pb_raster_valid_cells(pb_context* ctx, pb_raster_id id, int64_t* nValid)
 {
     PB_NVTX_RANGE();
@@ -2090,6 +2116,9 @@ extern "C" size_t pb_abi_sizeof(const char* name)
     if (!strcmp(name, "pb_dem_step")) return sizeof(pb_dem_step);
     if (!strcmp(name, "pb_dem_batch_item")) return sizeof(pb_dem_batch_item);
     if (!strcmp(name, "pb_macro_area")) return sizeof(pb_macro_area);
+    if (!strcmp(name, "pb_radiation_settings")) return sizeof(pb_radiation_settings);
+    if (!strcmp(name, "pb_radiation_maps")) return sizeof(pb_radiation_maps);
+    if (!strcmp(name, "pb_radiation_out")) return sizeof(pb_radiation_out);
     if (!strcmp(name, "pb_meteo_grid_var")) return sizeof(pb_meteo_grid_var);
     if (!strcmp(name, "pb_meteo_grid_hour")) return sizeof(pb_meteo_grid_hour);
     return 0;

@@ -77,6 +77,8 @@ def load_library():
                                                C.c_int, C.c_int, C.c_int]
     lib.pb_meteo_grid_step_batch.argtypes = [C.c_void_p, P(A.pb_meteo_grid_hour), C.c_int, C.c_int32, P(C.c_int32), C.c_int, C.c_int32,
                                              C.c_int]
+    lib.pb_compute_radiation_dem.argtypes = [C.c_void_p, P(A.pb_radiation_settings), P(A.pb_radiation_maps), P(A.pb_radiation_out)]
+    lib.pb_raster_from_last_output.argtypes = [C.c_void_p, C.c_int32, P(C.c_int32)]
     lib.pb_kriging_setup.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_int, P(C.c_int32)]
     lib.pb_kriging_free.argtypes = [C.c_void_p, C.c_int32]
@@ -122,7 +124,8 @@ def load_library():
     lib.pb_measure_fp64_peak.argtypes = [C.c_void_p, P(C.c_float)]
     for name in ("pb_raster_header", "pb_raster", "pb_stations", "pb_proxy", "pb_settings", "pb_raster_out",
                  "pb_cv_stats", "pb_timing", "pb_cv_points", "pb_kh_series", "pb_dem_step", "pb_dem_batch_item",
-                 "pb_macro_area", "pb_meteo_grid_var", "pb_meteo_grid_hour"):
+                 "pb_macro_area", "pb_meteo_grid_var", "pb_meteo_grid_hour", "pb_radiation_settings", "pb_radiation_maps",
+                 "pb_radiation_out"):
         got, want = lib.pb_abi_sizeof(name.encode()), C.sizeof(getattr(A, name))
         if got != want:
             raise PragaB200Error(A.PB_ERR_INVALID, f"ABI mismatch for {name}: library {got} B, binding {want} B")
@@ -591,6 +594,34 @@ class Engine:
                                 stats={f: getattr(r["stats"], f) for f, _ in A.pb_cv_stats._fields_} if cross_validate else None))
             out.append(row)
         return out
+
+    def compute_radiation_dem(self, settings, dem_id, lat_id, lon_id, slope_id, aspect_id, transmissivity_id, shape, want_host=True,
+                              keep=False):
+        """radiation::computeRadiationDEM (solarRadiation.cpp:1045-1069). Returns dict name -> (grid or None, min, max) for
+        sunElevation, beam, diffuse, reflected, global (+ "ids" when keep)."""
+        maps = A.pb_radiation_maps(dem_id, lat_id, lon_id, slope_id, aspect_id, transmissivity_id)
+        names = ("sunElevation", "beam", "diffuse", "reflected", "global")
+        outs, grids = [], []
+        ro = A.pb_radiation_out()
+        for k, nme in enumerate(names):
+            o = A.pb_raster_out()
+            g = np.empty(shape, dtype=np.float32) if want_host else None
+            if g is not None:
+                o.data = A.fptr(g)
+            outs.append(o)
+            grids.append(g)
+            setattr(ro, "global_" if nme == "global" else nme, C.pointer(o))
+        ro.keepResident = int(keep)
+        self._check(self.lib.pb_compute_radiation_dem(self.h, C.byref(settings), C.byref(maps), C.byref(ro)))
+        res = {nme: (grids[k], outs[k].minimum, outs[k].maximum) for k, nme in enumerate(names)}
+        if keep:
+            res["ids"] = [ro.ids[k] for k in range(5)]
+        return res
+
+    def raster_from_last_output(self, like_id):
+        rid = C.c_int32(-1)
+        self._check(self.lib.pb_raster_from_last_output(self.h, like_id, C.byref(rid)))
+        return rid.value
 
     def pre_interpolation_batch(self, stations, values, settings, variable, points_range=None):
         """T time steps sharing the station set. values: (T, n). Returns (detrended (T, n), keep (T, n), [settings] * T)."""

@@ -9,6 +9,7 @@
 #include "furtherMathFunctions.h"
 #include "interpolation.h"
 #include "interpolationConstants.h"
+#include "solarRadiation.h"
 
 #include "../../include/praga_b200.h"
 
@@ -899,6 +900,75 @@ bool krigingRaster(gis::Crit3DRasterGrid& raster, gis::Crit3DRasterGrid* estimat
     if (failed(ctx, rc)) return false;
     gis::updateMinMaxRasterGrid(estimateGrid);
     if (rmseGrid) gis::updateMinMaxRasterGrid(rmseGrid);
+    return true;
+}
+
+/* radiation::computeRadiationDEM (agrolib/solarRadiation/solarRadiation.cpp:1045-1069) */
+bool computeRadiationDEM(Crit3DRadiationSettings* radSettings, const gis::Crit3DRasterGrid& dem, Crit3DRadiationMaps* radiationMaps,
+                         const Crit3DTime& myTime, bool /*isParallelComputing*/)
+{
+    if (radSettings->getAlgorithm() != RADIATION_ALGORITHM_RSUN) return false;
+    pb_context* ctx = context();
+    if (!ctx) return false;
+    // computeRadiationRsun :714-719
+    Crit3DTime localTime = myTime;
+    if (radSettings->gisSettings->isUTC) localTime = myTime.addSeconds(radSettings->gisSettings->timeZone * 3600);
+    pb_radiation_settings s;
+    memset(&s, 0, sizeof(s));
+    s.realSky = radSettings->getRealSky();
+    s.realSkyAlgorithm = int(radSettings->getRealSkyAlgorithm());
+    s.shadowing = radSettings->getShadowing();
+    s.tiltMode = int(radSettings->getTiltMode());
+    s.linkeMode = int(radSettings->getLinkeMode());
+    s.albedoMode = int(radSettings->getAlbedoMode());
+    // the scalars the reference ends up with for an in-grid cell (computeRadiationDemPoint :958-964): monthly or default Linke;
+    // the map accessors only read OUT-of-grid cells (radiationSettings.cpp:131-133, :179-181), i.e. NODATA for every DEM cell
+    if (radSettings->getLinkeMode() == PARAM_MODE_MONTHLY) s.linke = radSettings->getLinke(localTime.date.month - 1);
+    else s.linke = radSettings->getLinkeMode() == PARAM_MODE_FIXED ? radSettings->getLinkeDefault() : float(NODATA);
+    s.albedo = radSettings->getAlbedoMode() == PARAM_MODE_FIXED ? radSettings->getAlbedo() : float(NODATA);
+    s.tilt = radSettings->getTilt();
+    s.aspect = radSettings->getAspect();
+    s.clearSky = radSettings->getClearSky();
+    s.demMaximum = dem.maximum;
+    s.timeZone = radSettings->gisSettings->timeZone;
+    s.year = localTime.date.year; s.month = localTime.date.month; s.day = localTime.date.day;
+    s.secondsOfDay = localTime.time;
+    // resident copies: the DEM and the four static maps are cached across time steps, the transmissivity map changes every step
+    // (its fingerprint differs: uploaded again)
+    pb_radiation_maps maps;
+    const gis::Crit3DRasterGrid* in[6] = {&dem, radiationMaps->latMap, radiationMaps->lonMap, radiationMaps->slopeMap, radiationMaps->aspectMap,
+                                          radiationMaps->transmissivityMap};
+    pb_raster_id ids[6];
+    std::vector<pb_raster_id> temporaries;
+    for (int k = 0; k < 6; k++) {
+        if (!in[k] || !in[k]->isLoaded) { g_error = "a radiation input map is not loaded"; return false; }
+        bool tmp = false;
+        if (!residentId(ctx, in[k], rasterOf(*in[k]), &ids[k], &tmp)) return false;
+        if (tmp) temporaries.push_back(ids[k]);
+    }
+    maps.dem = ids[0]; maps.lat = ids[1]; maps.lon = ids[2]; maps.slope = ids[3]; maps.aspect = ids[4]; maps.transmissivity = ids[5];
+    gis::Crit3DRasterGrid* outGrid[5] = {radiationMaps->sunElevationMap, radiationMaps->beamRadiationMap, radiationMaps->diffuseRadiationMap,
+                                         radiationMaps->reflectedRadiationMap, radiationMaps->globalRadiationMap};
+    pb_raster_out outs[5];
+    memset(outs, 0, sizeof(outs));
+    for (int k = 0; k < 5; k++) outs[k].rows = outGrid[k]->value;
+    pb_radiation_out ro;
+    memset(&ro, 0, sizeof(ro));
+    ro.sunElevation = &outs[0]; ro.beam = &outs[1]; ro.diffuse = &outs[2]; ro.reflected = &outs[3]; ro.global = &outs[4];
+    const int rc = pb_compute_radiation_dem(ctx, &s, &maps, &ro);
+    const bool bad = failed(ctx, rc);
+    for (pb_raster_id t : temporaries) pb_raster_free(ctx, t);
+    if (bad) return false;
+    // updateRadiationMaps (:1072-1089)
+    gis::updateMinMaxRasterGrid(radiationMaps->transmissivityMap);
+    for (int k = 0; k < 5; k++) {
+        outGrid[k]->minimum = outs[k].minimum;
+        outGrid[k]->maximum = outs[k].maximum;
+        if (!outGrid[k]->colorScale->isFixedRange()) outGrid[k]->colorScale->setRange(outs[k].minimum, outs[k].maximum);
+        outGrid[k]->setMapTime(myTime);
+    }
+    radiationMaps->transmissivityMap->setMapTime(myTime);
+    radiationMaps->setComputed(true);
     return true;
 }
 

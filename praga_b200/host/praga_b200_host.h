@@ -19,6 +19,7 @@
  *   pragab200::krigingVariogram / krigingSetWeight / krigingResult / krigingRMSE / krigingFreeMemory
  *                                             <- agrolib/interpolation/kriging.h:4-15
  *   pragab200::krigingRaster                  (new: the reference never wired kriging into a raster loop)
+ *   pragab200::computeRadiationDEM            <- agrolib/solarRadiation/solarRadiation.h (.cpp:1045-1069)
  * A GPU failure returns false (there is no CPU fallback); pragab200::lastError() gives the message.
  */
 #ifndef PRAGA_B200_HOST_H
@@ -32,6 +33,7 @@
 #include "meteoPoint.h"
 #include "interpolationSettings.h"
 #include "interpolationPoint.h"
+#include "solarRadiation.h"
 
 #include "../../include/praga_b200.h"
 
@@ -120,6 +122,13 @@ bool krigingEstimateVariogram(float* myDist, float* mySemiVar, int sizeMyVar, in
                               double* myNugget, double* myRange, double* mySlope, TkrigingMode* myMode, int nrPointData);
 /* batched form: estimate and RMSE for every valid cell (cell centres) of `raster` with the current system */
 bool krigingRaster(gis::Crit3DRasterGrid& raster, gis::Crit3DRasterGrid* estimateGrid, gis::Crit3DRasterGrid* rmseGrid);
+
+/* radiation::computeRadiationDEM (agrolib/solarRadiation/solarRadiation.h, .cpp:1045-1069): same signature and side effects
+ * (the five maps of radiationMaps, their minimum / maximum / mapTime, setComputed). The DEM and the static lat / lon / slope /
+ * aspect maps stay resident (raster cache above). dem.maximum must be up to date (gis::updateMinMaxRasterGrid), as the
+ * reference's shadow march needs it too. */
+bool computeRadiationDEM(Crit3DRadiationSettings* radSettings, const gis::Crit3DRasterGrid& dem, Crit3DRadiationMaps* radiationMaps,
+                         const Crit3DTime& myTime, bool isParallelComputing);
 
 }  // namespace pragab200
 

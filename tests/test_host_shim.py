@@ -319,3 +319,22 @@ def test_shim_session_keeps_rasters_resident_and_notices_changes(shim, ref):
         assert np.array_equal(gg, gg2)
     finally:
         sess.close()
+
+
+def test_shim_compute_radiation_dem(shim, ref):
+    """pragab200::computeRadiationDEM in place of radiation::computeRadiationDEM on the reference's own Crit3DRadiationSettings /
+    Crit3DRadiationMaps objects: the five maps, their min / max."""
+    from test_radiation import transmissivity_map
+    dem = syn.make_dem(110, 120, seed=13, cell_size=100.0)
+    dem.data[dem.data != np.float32(dem.flag)] *= np.float32(2.0)
+    tr = transmissivity_map(dem)
+    s = A.default_radiation_settings(2023, 2, 3, 9 * 3600 + 900, time_zone=1)
+    want = ref.compute_radiation_dem(s, dem, tr)
+    got = ref.compute_radiation_dem(s, dem, tr, shim=shim)
+    assert want["ok"] and got["ok"]
+    flag = np.float32(dem.flag)
+    for nme in ("sunElevation", "beam", "diffuse", "reflected", "global"):
+        assert np.array_equal(got[nme] == flag, want[nme] == flag)
+        m = want[nme] != flag
+        assert np.abs(got[nme][m].astype(np.float64) - want[nme][m]).max() <= TOL, nme
+    assert np.abs(got["minmax"] - want["minmax"]).max() <= TOL
