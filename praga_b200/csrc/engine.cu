@@ -266,7 +266,7 @@ int stageShepardStations(pb_context* ctx, const pb_stations* st, const pb_settin
     const unsigned nrPoints = unsigned(st->n), minPointsNr = 8;
     R0 = float(sqrt((minPointsNr * s->pointsBoundingBoxArea) / (float(3.1415926535898) * nrPoints)));
     const size_t offXd = 0, offYd = offXd + nAl * 8, offX = offYd + nAl * 8, offY = offX + nAl * 4, offV = offY + nAl * 4,
-                 total = offV + nAl * 4 + 16;
+                 offZ = offV + nAl * 4, total = offZ + nAl * 4 + 16;
     CUDA_TRY(ctx, ctx->hStations.reserve(total));
     CUDA_TRY(ctx, ctx->dStations.reserve(total));
     unsigned char* h = ctx->hStations.p;
@@ -275,11 +275,13 @@ int stageShepardStations(pb_context* ctx, const pb_stations* st, const pb_settin
     float* px = reinterpret_cast<float*>(h + offX);
     float* py = reinterpret_cast<float*>(h + offY);
     float* pv = reinterpret_cast<float*>(h + offV);
+    float* pz = reinterpret_cast<float*>(h + offZ);
     for (size_t k = 0; k < n; k++) {
         const int i = use[k];
         xd[k] = st->x[i]; yd[k] = st->y[i];
         px[k] = float(st->x[i]); py[k] = float(st->y[i]);
         pv[k] = st->value[i];
+        pz[k] = float(st->z[i]);
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dStations.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
     ctx->timing.h2d_bytes += (int64_t)total;
@@ -289,6 +291,7 @@ int stageShepardStations(pb_context* ctx, const pb_stations* st, const pb_settin
     ss.x = reinterpret_cast<const float*>(d + offX);
     ss.y = reinterpret_cast<const float*>(d + offY);
     ss.value = reinterpret_cast<const float*>(d + offV);
+    ss.z = reinterpret_cast<const float*>(d + offZ);
     ss.n = int(n);
     return PB_OK;
 }
@@ -449,8 +452,6 @@ int buildLocalModel(pb_context* ctx, const pb_settings* s, int variable, int nSt
             return fail(ctx, PB_ERR_INVALID, "local detrending needs useLocalDetrending and a detrending variable");
         if (!s->useMultipleDetrending)
             return fail(ctx, PB_ERR_UNSUPPORTED, "local detrending without multiple detrending is outside the hot-path scope (DESIGN.md)");
-        if (s->method != PB_METHOD_IDW && s->method != PB_METHOD_SHEPARD_MODIFIED)
-            return fail(ctx, PB_ERR_UNSUPPORTED, "local detrending runs with idw or shepard_modified on the GPU path (shepard: DESIGN.md)");
     }
     if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending runs through pb_glocal_detrending_fitting / pb_glocal_detrending_raster (macro areas needed)");
     if (!s->hasPointsRange && !range)     // setMultipleDetrendingHeightTemperatureRange returns false (:1508)
@@ -464,6 +465,7 @@ int buildLocalModel(pb_context* ctx, const pb_settings* s, int variable, int nSt
     const float ratioMinPoints = 1.2f;
     m.minPoints = unsigned(s->minPointsLocalDetrending * ratioMinPoints);
     m.thr80 = unsigned(m.minPoints * 0.8);
+    m.bboxArea = s->pointsBoundingBoxArea;
     m.shepardRadius = nStations > 0 ? float(sqrt((m.minPoints * s->pointsBoundingBoxArea) / (float(3.141592653589793238462643383) * unsigned(nStations)))) : 0.f;
     m.clampMode = clampModeOf(variable);
     m.rainfallThreshold = s->rainfallThreshold;
@@ -981,8 +983,6 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
     ShepardStations ss{};
     float shepardR0 = 0.f;
     const bool shepardMethod = !local && s->method != PB_METHOD_IDW;
-    if (shepardMethod && usesTopographicDistance(s, variable))
-        return fail(ctx, PB_ERR_UNSUPPORTED, "the Shepard estimators run without topographic distance on the GPU path");
     if (!precZero && !local) {
         if (shepardMethod) rc = stageShepardStations(ctx, st, s, true, ss, shepardR0);
         else rc = stageStations(ctx, st, s, true, ds, m.valueOffset);
@@ -1041,8 +1041,13 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
         if (nTargets > 0) { ctx->hMinMax[0] = 0x80000000u; ctx->hMinMax[1] = 0x80000000u; }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dMinMax, ctx->hMinMax, 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
     } else if (shepardMethod) {
+        // computeDistances adds the topographic distance before any estimator (interpolation.cpp:226-251): the march needs the
+        // whole resident DEM also for a row band
+        ShepardTd std_{};
+        std_.kh = usesTopographicDistance(s, variable) ? s->topoDist_Kh : 0;
+        std_.dem = dg;
         CUDA_TRY(ctx, launchShepardRaster(ss, m, dg, shepardR0, s->method == PB_METHOD_SHEPARD_MODIFIED, dem.validIdx + t0,
-                                          nTargets, ctx->dOut.p, ctx->dMinMax, ctx->stream));
+                                          nTargets, ctx->dOut.p, ctx->dMinMax, ctx->stream, &std_));
     } else if (usesTopographicDistance(s, variable)) {
         // the march needs the whole DEM (a ray reaches any station): `dem` is the full resident raster also for a row band
         CUDA_TRY(ctx, launchIdwTdRaster(ds, ds.z, m, dg, s->topoDist_Kh, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax,
@@ -1755,7 +1760,6 @@ static int interpolatePointsImpl(pb_context* ctx, const pb_stations* st, const p
     ShepardStations ss{};
     float shepardR0 = 0.f;
     const bool shepardMethod = s->method != PB_METHOD_IDW;
-    if (shepardMethod && td) return fail(ctx, PB_ERR_UNSUPPORTED, "the Shepard estimators run without topographic distance on the GPU path");
     if (shepardMethod && s->method == PB_METHOD_SHEPARD_MODIFIED && s->useLocalDetrending)
         return fail(ctx, PB_ERR_UNSUPPORTED, "modified Shepard with the local radius is not on the GPU path");
     if (shepardMethod) rc = stageShepardStations(ctx, st, s, excludeSupplemental != 0, ss, shepardR0);
@@ -1772,11 +1776,18 @@ static int interpolatePointsImpl(pb_context* ctx, const pb_stations* st, const p
         CUDA_TRY(ctx, cudaMemcpyAsync(d + offP, proxyValues, size_t(m) * mod.nProxy * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (td) CUDA_TRY(ctx, cudaMemcpyAsync(d + offZ, z, size_t(m) * 4, cudaMemcpyHostToDevice, ctx->stream));
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    if (shepardMethod)
+    if (shepardMethod) {
+        ShepardTd std_{};
+        if (td) {
+            std_.kh = s->topoDist_Kh;
+            std_.dem = devGridOf(ctx->rasters[demId]);
+            std_.tz = reinterpret_cast<const float*>(d + offZ);
+        }
         CUDA_TRY(ctx, launchShepardPoints(ss, mod, shepardR0, s->method == PB_METHOD_SHEPARD_MODIFIED,
                                           reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                           reinterpret_cast<const double*>(d + offP), m, reinterpret_cast<float*>(d + offO),
-                                          ctx->stream));
+                                          ctx->stream, &std_));
+    }
     else if (td)
         CUDA_TRY(ctx, launchIdwTdPoints(ds, ds.z, mod, devGridOf(ctx->rasters[demId]), s->topoDist_Kh,
                                         reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),

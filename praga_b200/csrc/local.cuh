@@ -15,10 +15,11 @@ struct LocalModel {
     unsigned thr80;                // unsigned(minPoints * 0.8)         (:1152)
     float candRadius;              // radius of the per-cell candidate list of the ring search (0 = scan all stations)
     float shepardRadius;           // computeShepardInitialRadius(bboxArea, S, minPoints) when S <= minPoints (:1098)
+    float bboxArea;                // getPointsBoundingBoxArea(): shepardSearchNeighbour over the subset (:812)
     int clampMode;
     float rainfallThreshold;
     int useDoNotRetrend, useRetrendOnly;
-    int method;                    // PB_METHOD_IDW or PB_METHOD_SHEPARD_MODIFIED (interpolate :2513-2530; the demo's default estimator)
+    int method;                    // PB_METHOD_IDW / _SHEPARD / _SHEPARD_MODIFIED (interpolate :2513-2530; modified = the demo's default)
     uint8_t selectedActive[PB_MAX_PROXY];
     int kind[PB_MAX_PROXY];
     float stdDevThreshold[PB_MAX_PROXY];

@@ -252,6 +252,102 @@ __device__ float localFinish(const LocalModel& m, const LocalStations& st, const
                 if (w.flg[k] & 1) r += ((w.X[k] * w.X[k] * (1.0 + w.Y[k])) * inv) * double(w.val[k]);
             result = float(r);
         }
+    } else if (m.method == PB_METHOD_SHEPARD) {
+        // shepardIdw (:871-945) behind shepardSearchNeighbour (:806-868) over the subset: the vector is the points still in
+        // myPoints (flag bit 0), a point computeDistances excludes has distance 0. At most 10 points survive, so every lane
+        // of the group carries the whole estimate (group-uniform, nothing shared is written). Equal distances: subset order.
+        constexpr int kMinPts = 5, kMaxPts = 10;      // SHEPARD_MIN_NRPOINTS / SHEPARD_MAX_NRPOINTS
+        unsigned nrPoints = 0;
+        for (int k = 0; k < n; k++) nrPoints += (w.flg[k] & 1) ? 1u : 0u;
+        result = kNoData;
+        if (nrPoints > 0) {
+            // computeShepardInitialRadius(getPointsBoundingBoxArea(), inputPoints.size(), SHEPARD_AVG_NRPOINTS = 8) (:800-803)
+            const float R0 = sqrtf((8u * m.bboxArea) / (float(3.1415926535898) * nrPoints));
+            float d10[kMaxPts], d5[kMinPts];
+            int i10[kMaxPts], i5[kMinPts];
+            int n10 = 0, n5 = 0, cnt = 0;
+            auto insert = [](float* dd, int* ii, int& cntIn, int K, float d, int i) {
+                if (cntIn == K && !(d < dd[K - 1])) return;
+                int pos = cntIn < K ? cntIn : K - 1;
+                while (pos > 0 && d < dd[pos - 1]) { dd[pos] = dd[pos - 1]; ii[pos] = ii[pos - 1]; pos--; }
+                dd[pos] = d; ii[pos] = i;
+                if (cntIn < K) cntIn++;
+            };
+            for (int k = 0; k < n; k++) {
+                if (!(w.flg[k] & 1)) continue;
+                float d = w.d[k];
+                if (excludeSupplemental && !checkLapseRateCodeDev(st.code[w.idx[k]], useCode, false)) d = 0.f;
+                const bool sortable = !(fabs(double(d)) < kEpsilon);      // sortPointsByDistance drops |d| < EPSILON (:134)
+                if (sortable) insert(d5, i5, n5, kMinPts, d, k);
+                if (d <= R0 && d > 0.f) {
+                    cnt++;
+                    if (sortable) insert(d10, i10, n10, kMaxPts, d, k);
+                }
+            }
+            float sd[kMaxPts];
+            int si[kMaxPts];
+            int kk = 0;
+            float radius = kNoData;
+            if (cnt < kMinPts) {
+                kk = n5;
+                for (int q = 0; q < kk; q++) { sd[q] = d5[q]; si[q] = i5[q]; }
+                if (kk > 0) radius = d5[kk - 1] + float(kEpsilon);
+            } else if (cnt > kMaxPts) {
+                kk = n10;
+                for (int q = 0; q < kk; q++) { sd[q] = d10[q]; si[q] = i10[q]; }
+                radius = d10[kk - 1] + float(kEpsilon);
+            } else {
+                kk = n10;                           // the neighbourhood itself, in subset order
+                for (int q = 0; q < kk; q++) { sd[q] = d10[q]; si[q] = i10[q]; }
+                for (int a = 1; a < kk; a++) {
+                    const float vd = sd[a];
+                    const int vi = si[a];
+                    int b = a;
+                    while (b > 0 && si[b - 1] > vi) { sd[b] = sd[b - 1]; si[b] = si[b - 1]; b--; }
+                    sd[b] = vd; si[b] = vi;
+                }
+                radius = R0;
+            }
+            if (kk > 0) {
+                double S[kMaxPts], T[kMaxPts], px[kMaxPts], py[kMaxPts];
+                for (int q = 0; q < kk; q++) { px[q] = st.xd[w.idx[si[q]]]; py[q] = st.yd[w.idx[si[q]]]; S[q] = 0.; T[q] = 0.; }
+                double weightSum = 0.;
+                const double radius_3 = double(radius) / 3.;
+                const double radius_27_4 = 6.75 / double(radius);
+                for (int q = 0; q < kk; q++) {
+                    const float d = sd[q];
+                    if (d > 0.f) {
+                        if (double(d) <= radius_3) S[q] = double(1.f / d);
+                        else if (d <= radius) {
+                            const double tmp = double((d / radius) - 1.f);
+                            S[q] = radius_27_4 * tmp * tmp;
+                        } else S[q] = 0.;
+                        weightSum += S[q];
+                    }
+                }
+                if (weightSum != 0.) {
+                    const double X = double(xf), Y = double(yf);
+                    for (int a = 0; a < kk; a++) {
+                        double tt = 0.;
+                        for (int b = 0; b < kk; b++)
+                            if (a != b) {
+                                const double cosine = ((X - px[a]) * (X - px[b]) + (Y - py[a]) * (Y - py[b])) / double(sd[a] * sd[b]);
+                                tt += S[b] * (1. - cosine);
+                            }
+                        tt /= weightSum;
+                        T[a] = tt;
+                    }
+                    double wsum = 0.;
+                    for (int a = 0; a < kk; a++) {
+                        T[a] = S[a] * S[a] * (1. + T[a]);
+                        wsum += T[a];
+                    }
+                    double r = 0.;
+                    for (int a = 0; a < kk; a++) r += (T[a] / wsum) * double(w.val[si[a]]);
+                    result = float(r);
+                }
+            }
+        }
     } else {
         double sum = 0, sumWeights = 0;
         for (int k = 0; k < n; k++) {

@@ -12,12 +12,23 @@ struct ShepardStations {
     const double* xd;
     const double* yd;
     const float* value;
+    const float* z;                // float(point->z): topographic distance only
     int n;
 };
 
+// topographic distance of computeDistances (interpolation.cpp:226-251) in front of the Shepard estimators: kh != 0 and the DEM
+// the ray march samples; tz = the targets' elevation in the point form (raster form: the DEM value of the cell)
+struct ShepardTd {
+    int kh;                        // 0: planar distances only
+    DevGrid dem;
+    const float* tz;
+};
+
 cudaError_t launchShepardRaster(const ShepardStations& st, const DevModel& m, const DevGrid& dem, float R0, bool modified,
-                                const int* validIdx, int nTargets, float* out, unsigned* minmax, cudaStream_t s);
+                                const int* validIdx, int nTargets, float* out, unsigned* minmax, cudaStream_t s,
+                                const ShepardTd* td = nullptr);
 cudaError_t launchShepardPoints(const ShepardStations& st, const DevModel& m, float R0, bool modified, const float* tx,
-                                const float* ty, const double* tproxy, int nTargets, float* out, cudaStream_t s);
+                                const float* ty, const double* tproxy, int nTargets, float* out, cudaStream_t s,
+                                const ShepardTd* td = nullptr);
 
 }  // namespace pb

@@ -14,6 +14,7 @@
 // reference's std::sort leaves them unspecified).
 #include "epilogue.cuh"
 #include "shepard.cuh"
+#include "td_device.cuh"
 
 namespace pb {
 
@@ -47,24 +48,25 @@ __device__ __forceinline__ unsigned orderedKeyS(float f)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-template <bool POINTS, bool MODIFIED>
+template <bool POINTS, bool MODIFIED, bool TD>
 __global__ void __launch_bounds__(128)
 shepard_kernel(ShepardStations st, DevModel m, DevGrid dem, float R0, const int* __restrict__ validIdx, int nTargets,
                const float* __restrict__ tx, const float* __restrict__ ty, const double* __restrict__ tproxy,
-               float* __restrict__ out, unsigned* __restrict__ minmax)
+               float* __restrict__ out, unsigned* __restrict__ minmax, ShepardTd td)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     float vmin = INFINITY, vmax = -INFINITY;
     if (t < nTargets) {
-        float x, y;
+        float x, y, z = 0.f;
         int cell;
-        if (POINTS) { cell = t; x = tx[t]; y = ty[t]; }
+        if (POINTS) { cell = t; x = tx[t]; y = ty[t]; if (TD) z = td.tz[t]; }
         else {
             cell = validIdx[t];
             const int row = cell / dem.nrCols, col = cell - row * dem.nrCols;
             // getUtmXYFromRowColSinglePrecision(header, ...), gis.cpp:799-804
             x = float(dem.llx + dem.cellSize * double(col) + 0.5);
             y = float(dem.lly + dem.cellSize * double(dem.nrRows - row) - 0.5);
+            if (TD) z = dem.data[cell];          // interpolate(..., myX, myY, myZ = the DEM value, ...) (interpolationCmd.cpp:379-388)
         }
 
         float result = kNoData;
@@ -78,8 +80,14 @@ shepard_kernel(ShepardStations st, DevModel m, DevGrid dem, float R0, const int*
                 const float dx = __ldg(st.x + i) - x, dy = __ldg(st.y + i) - y;
                 const float d2 = dx * dx + dy * dy;
                 const float w5 = n5 == kMinPts ? all5[kMinPts - 1].d : INFINITY;
-                if (d2 > R0sq && d2 > w5 * w5 * 1.000001f) continue;
-                const float d = sqrtf(d2);
+                // (with topographic distance the total distance is >= the planar one for kh >= 0: the planar test still rules out)
+                if ((!TD || td.kh >= 0) && d2 > R0sq && d2 > w5 * w5 * 1.000001f) continue;
+                float d = sqrtf(d2);
+                if (TD) {
+                    // computeDistances :226-251: distance += kh * topographicDistance(x, y, z, point x, y, z, distance, DEM)
+                    const float topo = topographicDistanceDev(td.dem, x, y, z, __ldg(st.x + i), __ldg(st.y + i), __ldg(st.z + i), d);
+                    d += (td.kh * topo);
+                }
                 if (!(fabs(double(d)) < kEpsilon)) insertNear(all5, n5, d, i);       // sortPointsByDistance drops |d| < EPSILON
                 if (d <= R0 && d > 0.f) {
                     cnt++;
@@ -221,28 +229,42 @@ shepard_kernel(ShepardStations st, DevModel m, DevGrid dem, float R0, const int*
 }  // namespace
 
 cudaError_t launchShepardRaster(const ShepardStations& st, const DevModel& m, const DevGrid& dem, float R0, bool modified,
-                                const int* validIdx, int nTargets, float* out, unsigned* minmax, cudaStream_t s)
+                                const int* validIdx, int nTargets, float* out, unsigned* minmax, cudaStream_t s, const ShepardTd* td)
 {
     if (nTargets <= 0) return cudaSuccess;
     const int grid = (nTargets + 127) / 128;
-    if (modified)
-        shepard_kernel<false, true><<<grid, 128, 0, s>>>(st, m, dem, R0, validIdx, nTargets, nullptr, nullptr, nullptr, out, minmax);
+    const bool useTd = td && td->kh != 0;
+    const ShepardTd t = useTd ? *td : ShepardTd{};
+    if (useTd) {
+        if (modified)
+            shepard_kernel<false, true, true><<<grid, 128, 0, s>>>(st, m, dem, R0, validIdx, nTargets, nullptr, nullptr, nullptr, out, minmax, t);
+        else
+            shepard_kernel<false, false, true><<<grid, 128, 0, s>>>(st, m, dem, R0, validIdx, nTargets, nullptr, nullptr, nullptr, out, minmax, t);
+    } else if (modified)
+        shepard_kernel<false, true, false><<<grid, 128, 0, s>>>(st, m, dem, R0, validIdx, nTargets, nullptr, nullptr, nullptr, out, minmax, t);
     else
-        shepard_kernel<false, false><<<grid, 128, 0, s>>>(st, m, dem, R0, validIdx, nTargets, nullptr, nullptr, nullptr, out, minmax);
+        shepard_kernel<false, false, false><<<grid, 128, 0, s>>>(st, m, dem, R0, validIdx, nTargets, nullptr, nullptr, nullptr, out, minmax, t);
     return cudaGetLastError();
 }
 
 cudaError_t launchShepardPoints(const ShepardStations& st, const DevModel& m, float R0, bool modified, const float* tx,
-                                const float* ty, const double* tproxy, int nTargets, float* out, cudaStream_t s)
+                                const float* ty, const double* tproxy, int nTargets, float* out, cudaStream_t s, const ShepardTd* td)
 {
     if (nTargets <= 0) return cudaSuccess;
     const int grid = (nTargets + 127) / 128;
     DevGrid none{};
     none.flag = kNoData;
-    if (modified)
-        shepard_kernel<true, true><<<grid, 128, 0, s>>>(st, m, none, R0, nullptr, nTargets, tx, ty, tproxy, out, nullptr);
+    const bool useTd = td && td->kh != 0;
+    const ShepardTd t = useTd ? *td : ShepardTd{};
+    if (useTd) {
+        if (modified)
+            shepard_kernel<true, true, true><<<grid, 128, 0, s>>>(st, m, none, R0, nullptr, nTargets, tx, ty, tproxy, out, nullptr, t);
+        else
+            shepard_kernel<true, false, true><<<grid, 128, 0, s>>>(st, m, none, R0, nullptr, nTargets, tx, ty, tproxy, out, nullptr, t);
+    } else if (modified)
+        shepard_kernel<true, true, false><<<grid, 128, 0, s>>>(st, m, none, R0, nullptr, nTargets, tx, ty, tproxy, out, nullptr, t);
     else
-        shepard_kernel<true, false><<<grid, 128, 0, s>>>(st, m, none, R0, nullptr, nTargets, tx, ty, tproxy, out, nullptr);
+        shepard_kernel<true, false, false><<<grid, 128, 0, s>>>(st, m, none, R0, nullptr, nTargets, tx, ty, tproxy, out, nullptr, t);
     return cudaGetLastError();
 }
 

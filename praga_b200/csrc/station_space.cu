@@ -11,6 +11,8 @@
 #include <chrono>
 #include <string>
 #include <thread>
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "classic.cuh"
@@ -84,7 +86,8 @@ struct UploadBatch {
 int shepardLoo(pb_context* ctx, const pb_settings* sp, int variable, int nS, const double* sx, const double* sy, const double* sz,
                const float* sval, const int* scode, int nT, const float* tx, const float* ty, const float* tproxy /* nT * max(P,1) */,
                const int* tcode, const uint8_t* tinside, const float* tobs, int excludeOutsideDem, int excludeSupplemental,
-               float* residual, float* estimate)
+               float* residual, float* estimate, const uint8_t* sactive = nullptr, const float* tz = nullptr,
+               pb_raster_id demId = -1)
 {
     const int P = sp->nProxy;
     const size_t Pp = std::max(P, 1);
@@ -97,9 +100,11 @@ int shepardLoo(pb_context* ctx, const pb_settings* sp, int variable, int nS, con
     st.value = val.data();
     st.lapseRateCode = code.data();
     st.proxyValues = proxy.data();              // interpolate() never reads the points' own proxy values
+    st.isActive = sactive;
     std::vector<double> pv(size_t(nT) * Pp);
     for (size_t k = 0; k < pv.size(); k++) pv[k] = double(tproxy[k]);
-    int rc = pb_interpolate_points(ctx, &st, sp, variable, tx, ty, pv.data(), nT, 0, est.data());
+    // (tz / demId: the topographic distance of computeDistances, read only when the settings switch it on with kh != 0)
+    int rc = pb_interpolate_points_td(ctx, &st, sp, variable, tx, ty, tz, pv.data(), nT, 0, demId, est.data());
     if (rc) return rc;
     const bool isPrec = varIsPrec(variable);
     for (int j = 0; j < nT; j++) {
@@ -173,13 +178,14 @@ bool getCombination(const pb_settings& s, int indexHeight, int k, uint8_t* activ
 }
 
 // goldenSectionSearch (interpolation.cpp:2297-2335) over f(kh) = MAE at kh = int(khFloat), read from the table
-double goldenSection(const float* maeOfKh, int maxKh, double a, double b, pb_kh_series* series)
+template <class MaeOfKh>
+double goldenSection(MaeOfKh maeOfKh, int maxKh, double a, double b, pb_kh_series* series)
 {
     const double GOLDEN = 1.6180339887499;      // GOLDEN_SECTION, commonConstants.h:258
     auto f = [&](double khFloat) -> double {
         int kh = int(khFloat);
         kh = std::max(0, std::min(kh, maxKh));
-        return double(maeOfKh[kh]);
+        return double(maeOfKh(kh));
     };
     auto add = [&](float kh, float err) {
         if (series && series->n < PB_MAX_KH_SERIES) { series->kh[series->n] = kh; series->error[series->n] = err; series->n++; }
@@ -253,11 +259,9 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     if ((optimal || useTD) && n == 0) return PB_OK;
     if (useTD && (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used))
         return fail(ctx, PB_ERR_INVALID, "topographic-distance optimisation needs the resident DEM (getCurrentDEM())");
-    if (useTD && s->method != PB_METHOD_IDW)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "leave-one-out for the kh search runs the idw estimator only");
-    if (optimal && s->method != PB_METHOD_IDW && useTD)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "the Shepard estimators run without topographic distance on the GPU path");
-    const bool shepardCv = optimal && s->method != PB_METHOD_IDW;
+    // Shepard estimators: the leave-one-out of optimalDetrending and of the kh search goes through the K8 point form, one
+    // call per (combination, kh) the searches actually visit
+    const bool shepardCv = (optimal || useTD) && s->method != PB_METHOD_IDW;
 
     // interpolation points = survivors of multiple detrending (points with NODATA proxies are erased, :2230); the meteo
     // points the leave-one-out walks stay ALL stations
@@ -317,7 +321,7 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     }
     const int NP = (int)problems.size();
     const int maxKh = std::max(0, s->topoDist_maxKh);
-    const int nKh = useTD ? maxKh + 1 : 1;
+    const int nKh = (useTD && !shepardCv) ? maxKh + 1 : 1;
 
     // ---- stage everything once: sources = interpolation points (m), targets = meteo points (n) ----
     const size_t Pp = std::max(P, 1);
@@ -330,7 +334,8 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     add(size_t(NP) * nKh * n, 4);                            // residuals
     add(size_t(NP) * nKh, 4);                                // mae
     add(nKh, 4);                                             // kh list
-    if (useTD) add(size_t(n) * m, 4);                        // target-to-station topographic distances
+    const bool topoTable = useTD && !shepardCv;              // the Shepard form marches inside its own kernel
+    if (topoTable) add(size_t(n) * m, 4);                    // target-to-station topographic distances
     CUDA_TRY(ctx, ctx->dScratch.reserve(bytes + 4096));
     unsigned char* d = ctx->dScratch.p;
     float* dX = carve<float>(d, m);
@@ -353,7 +358,7 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     float* dWork = carve<float>(d, size_t(m) * NP);
     float* dResidual = carve<float>(d, size_t(NP) * nKh * n);
     float* dMae = carve<float>(d, size_t(NP) * nKh);
-    float* dTopo = useTD ? carve<float>(d, size_t(n) * m) : nullptr;
+    float* dTopo = topoTable ? carve<float>(d, size_t(n) * m) : nullptr;
 
     std::vector<float> hx(m), hy(m), hzf(m), hproxy(m * Pp, kNoData), hval(m);
     std::vector<double> hz(m);
@@ -403,7 +408,7 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     CUDA_TRY(ctx, up(tInside, gin.data(), n));
     CUDA_TRY(ctx, up(dProblems, problems.data(), sizeof(ClassicProblem) * NP));
     std::vector<int> khList(nKh);
-    for (int k = 0; k < nKh; k++) khList[k] = useTD ? k : 0;
+    for (int k = 0; k < nKh; k++) khList[k] = topoTable ? k : 0;
     CUDA_TRY(ctx, up(dKh, khList.data(), nKh * 4));
     CUDA_TRY(ctx, batch.flush(ctx, stream));
     memset(&ctx->timing, 0, sizeof(ctx->timing));
@@ -434,37 +439,46 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     // ---- leave-one-out tables ----
     std::vector<float> mae;
     std::vector<float> hWork;                 // host copy of the detrended values of every problem (Shepard cross-validation)
-    auto runLoo = [&](int excludeOutsideDem) -> int {
-        if (shepardCv) {
-            // one K8 point-form call per combination over that combination's detrended points and regression fields
+    // Shepard estimators: MAE of combination p at kh, computed when a search asks for it (one K8 point-form call over that
+    // combination's detrended points and regression fields) and kept
+    std::map<std::tuple<int, int, int>, float> shepardMae;
+    int shepardRc = PB_OK;
+    auto shepardMaeAt = [&](int p, int kh, int excludeOutsideDem) -> float {
+        if (shepardRc) return kNoData;
+        const auto key = std::make_tuple(p, kh, excludeOutsideDem);
+        auto it = shepardMae.find(key);
+        if (it != shepardMae.end()) return it->second;
+        if (hWork.empty()) {
             hWork.resize(size_t(m) * NP);
-            CUDA_TRY(ctx, cudaMemcpyAsync(hWork.data(), dWork, hWork.size() * 4, cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(ctx, cudaStreamSynchronize(stream));
-            mae.assign(size_t(NP) * nKh, kNoData);
-            std::vector<double> sxd(m), syd(m);
-            for (int k = 0; k < m; k++) { sxd[k] = st->x[ip[k]]; syd[k] = st->y[ip[k]]; }
-            std::vector<float> col(m), res(n);
-            pb_timing acc = ctx->timing;
-            for (int p = 0; p < NP; p++) {
-                pb_settings sp = *s;
-                for (int i = 0; i < P; i++) {
-                    applyWrites(sp.proxy[i], problems[p].proxy[i]);
-                    sp.currentActive[i] = problems[p].active[i];
-                    sp.currentSignificant[i] = problems[p].significant[i];
-                }
-                sp.currentUseThermalInversion = problems[p].useThermalInversion;
-                for (int k = 0; k < m; k++) col[k] = hWork[size_t(k) * NP + p];
-                int rc = shepardLoo(ctx, &sp, variable, m, sxd.data(), syd.data(), hz.data(), col.data(), hcode.data(), n, gx.data(),
-                                    gy.data(), gproxy.data(), gcode.data(), gin.data(), gobs.data(), excludeOutsideDem, 1, res.data(),
-                                    nullptr);
-                if (rc) return rc;
-                acc.launches += ctx->timing.launches;
-                acc.kernel_ms += ctx->timing.kernel_ms;
-                mae[p] = cvMaeHost(res.data(), gobs.data(), n);
-            }
-            ctx->timing = acc;
-            return PB_OK;
+            shepardRc = cudaMemcpyAsync(hWork.data(), dWork, hWork.size() * 4, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+                        cudaStreamSynchronize(stream) == cudaSuccess ? PB_OK : fail(ctx, PB_ERR_CUDA, "download of the detrended points");
+            if (shepardRc) return kNoData;
         }
+        std::vector<double> sxd(m), syd(m);
+        for (int k = 0; k < m; k++) { sxd[k] = st->x[ip[k]]; syd[k] = st->y[ip[k]]; }
+        std::vector<float> col(m), res(n);
+        pb_settings sp = *s;
+        if (classic)
+            for (int i = 0; i < P; i++) {
+                applyWrites(sp.proxy[i], problems[p].proxy[i]);
+                sp.currentActive[i] = problems[p].active[i];
+                sp.currentSignificant[i] = problems[p].significant[i];
+            }
+        if (classic) sp.currentUseThermalInversion = problems[p].useThermalInversion;
+        sp.topoDist_Kh = kh;
+        for (int k = 0; k < m; k++) col[k] = hWork[size_t(k) * NP + p];
+        const pb_timing acc = ctx->timing;
+        shepardRc = shepardLoo(ctx, &sp, variable, m, sxd.data(), syd.data(), hz.data(), col.data(), hcode.data(), n, gx.data(),
+                               gy.data(), gproxy.data(), gcode.data(), gin.data(), gobs.data(), excludeOutsideDem, 1, res.data(),
+                               nullptr, hact.data(), gzf.data(), useTD ? demId : -1);
+        if (shepardRc) return kNoData;
+        ctx->timing.launches += acc.launches;
+        ctx->timing.kernel_ms += acc.kernel_ms;
+        const float v = cvMaeHost(res.data(), gobs.data(), n);
+        shepardMae[key] = v;
+        return v;
+    };
+    auto runLoo = [&](int excludeOutsideDem) -> int {
         LooSetup ls{};
         ls.nS = m; ls.nT = n; ls.nProxy = P; ls.nProblems = NP; ls.nKh = nKh;
         ls.useLapseRateCode = s->useLapseRateCode;
@@ -494,7 +508,7 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
         return PB_OK;
     };
 
-    if (useTD) {
+    if (topoTable) {
         const DevGrid dem = devGridOfRaster(ctx->rasters[demId]);
         CUDA_TRY(ctx, launchTopoMatrix(tX, tY, tZf, n, dX, dY, dZf, m, dem, dTopo, stream));
         ctx->timing.launches++;
@@ -502,7 +516,38 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
 
     int best = 0;
     std::vector<int> khOf(NP, s->topoDist_Kh);
-    if (optimal || useTD) {
+    if (shepardCv) {
+        // the same searches as below, the table replaced by shepardMaeAt
+        const int excl = cv ? cv->excludeOutsideDem : 0;
+        if (useTD)
+            for (int p = 0; p < NP; p++) {
+                pb_kh_series tmp{};
+                khOf[p] = int(goldenSection([&](int kh) { return shepardMaeAt(p, kh, 1); }, maxKh, 0., double(maxKh), &tmp));
+            }
+        if (optimal) {
+            float minError = kNoData;
+            int bestCombinationIndex = 0;
+            best = -1;
+            for (int p = 0; p < NP; p++) {
+                const int kh = useTD ? std::max(0, std::min(khOf[p], maxKh)) : 0;
+                const float avgError = shepardMaeAt(p, kh, excl);
+                if (!isEqualF(avgError, kNoData) && (isEqualF(minError, kNoData) || avgError < minError)) {
+                    minError = avgError;
+                    bestCombinationIndex = comboId[p];
+                    best = p;
+                }
+            }
+            if (best < 0) {
+                for (int p = 0; p < NP; p++) if (comboId[p] == bestCombinationIndex) best = p;
+                if (best < 0) best = 0;
+            }
+        }
+        if (useTD) {
+            if (khSeries) khSeries->n = 0;
+            s->topoDist_Kh = int(goldenSection([&](int kh) { return shepardMaeAt(best, kh, 1); }, maxKh, 0., double(maxKh), khSeries));
+        }
+        if (shepardRc) return shepardRc;
+    } else if (optimal || useTD) {
         // topographicDistanceOptimize runs computeResiduals(..., excludeOutsideDem = true, excludeSupplemental = true)
         int rc = runLoo(useTD ? 1 : (cv ? cv->excludeOutsideDem : 0));
         if (rc) return rc;
@@ -510,7 +555,8 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
         if (useTD)
             for (int p = 0; p < NP; p++) {
                 pb_kh_series tmp{};
-                const double bestKh = goldenSection(&maeTd[size_t(p) * nKh], maxKh, 0., double(maxKh), &tmp);
+                const float* row = &maeTd[size_t(p) * nKh];
+                const double bestKh = goldenSection([row](int kh) { return row[kh]; }, maxKh, 0., double(maxKh), &tmp);
                 khOf[p] = int(bestKh);
             }
         if (optimal) {
@@ -542,7 +588,8 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
         if (useTD) {
             // the search preInterpolation runs last, on the final points (:2493-2496): same table row, series kept
             if (khSeries) khSeries->n = 0;
-            const double bestKh = goldenSection(&maeTd[size_t(best) * nKh], maxKh, 0., double(maxKh), khSeries);
+            const float* row = &maeTd[size_t(best) * nKh];
+            const double bestKh = goldenSection([row](int kh) { return row[kh]; }, maxKh, 0., double(maxKh), khSeries);
             s->topoDist_Kh = int(bestKh);
         }
     }
@@ -618,8 +665,6 @@ int exactLoo(pb_context* ctx, const LooArrays& a, const pb_settings* s, int vari
     if (useTD && (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used))
         return fail(ctx, PB_ERR_INVALID, "topographic distance needs the resident DEM (getCurrentDEM())");
     const bool shepardMethod = s->method != PB_METHOD_IDW;
-    if (shepardMethod && useTD)
-        return fail(ctx, PB_ERR_UNSUPPORTED, "the Shepard estimators run without topographic distance on the GPU path");
     if (shepardMethod && (residual || estimate)) {
         if (a.sxd.size() != size_t(nS)) return fail(ctx, PB_ERR_INVALID, "Shepard leave-one-out needs the f64 station coordinates");
         if (nb) {       // the neighbourhood statistics do not depend on the estimator: device pass first, then the estimates
@@ -628,7 +673,7 @@ int exactLoo(pb_context* ctx, const LooArrays& a, const pb_settings* s, int vari
         }
         return shepardLoo(ctx, s, variable, nS, a.sxd.data(), a.syd.data(), a.sz.data(), a.sval.data(), a.scode.data(), nT,
                           a.tx.data(), a.ty.data(), a.tproxy.data(), a.tcode.data(), a.tin.data(), a.tobs.data(), excludeOutsideDem,
-                          excludeSupplemental, residual, estimate);
+                          excludeSupplemental, residual, estimate, nullptr, a.tz.data(), useTD ? demId : -1);
     }
     size_t bytes = 0;
     auto add = [&](size_t count, size_t size) { bytes += (count * size + 255) / 256 * 256; };

@@ -180,15 +180,26 @@ def test_local_residuals_modified_shepard(engine, ref):
     assert stats_r["n"] == stats_g["n"] and abs(stats_r["meanAbsoluteError"] - stats_g["meanAbsoluteError"]) <= TOL
 
 
-def test_local_detrending_plain_shepard_is_rejected(engine):
-    import praga_b200 as pb
-    dem = syn.make_dem(20, 20)
-    st = syn.make_stations(dem, 50, proxies=(dem,))
-    s = local_settings(st, use_urban=False)
+@pytest.mark.parametrize("area_scale", [1.0, 0.012, 0.004])
+def test_local_detrending_plain_shepard(engine, ref, area_scale):
+    """shepardIdw behind shepardSearchNeighbour over each cell's subset (interpolation.cpp:806-945). The initial radius comes
+    from getPointsBoundingBoxArea() and the SUBSET size: with the stations' real bounding box every selected station lies
+    inside it (the 10-nearest branch); smaller areas reach the 5..10 and the 5-nearest branches too."""
+    dem = syn.make_dem(90, 100, cell_size=5000.0)
+    urban = syn.make_urban(90, 100, cell_size=5000.0)
+    st = syn.make_stations(dem, 1900, proxies=(dem, urban), seed=21, supplemental_frac=0.1)
+    s = shepard_local(st)
     s.method = A.shepard
-    with pytest.raises(pb.PragaB200Error) as e:
-        engine.local_detrending_raster(st, s, A.airTemperature, dem, (dem,))
-    assert e.value.status == A.PB_ERR_UNSUPPORTED
+    s.useLapseRateCode = 1
+    s.pointsBoundingBoxArea = float(np.float32(s.pointsBoundingBoxArea * area_scale))
+    err, exact = compare(engine, ref, st, s, A.airTemperature, dem, (dem, urban))
+    print(f"area x{area_scale}: max |gpu-ref| = {err:.2e}, bit-identical cells: {100 * exact:.1f} %")
+    assert exact >= 0.999
+    if area_scale == 1.0:
+        res_r, stats_r = ref.compute_residuals(st, s, A.airTemperature, st.value, local=True)
+        res_g, stats_g = engine.compute_residuals(st, s, A.airTemperature, st.value, local=True)
+        assert np.array_equal(res_r == np.float32(-9999), res_g == np.float32(-9999))
+        assert np.abs(res_r.astype(np.float64) - res_g.astype(np.float64)).max() <= TOL
 
 
 def test_pipeline_and_fused_schedules_give_the_same_bits(engine, monkeypatch):

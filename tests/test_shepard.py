@@ -36,6 +36,9 @@ def scenario(case, rows=70, cols=90, n=160):
         var, grids = A.airTemperature, (dem, urban)
     s.method = method
     s.pointsBoundingBoxArea = bbox_area(st)
+    if "_td" in case:           # computeDistances adds kh * topographicDistance in front of the estimator (interpolation.cpp:226-251)
+        s.useTD = 1
+        s.topoDist_Kh = 9 if "humidity" in case else 4
     if "clustered" in case:     # > 10 points inside the initial radius around the cluster: the 10-nearest branch
         rng = np.random.default_rng(4)
         k = st.n // 2
@@ -46,7 +49,8 @@ def scenario(case, rows=70, cols=90, n=160):
 
 
 CASES = ["shepard_humidity", "modified_humidity", "shepard_sparse", "modified_sparse", "shepard_clustered_humidity",
-         "modified_clustered_humidity", "shepard_detrended", "modified_detrended_codes"]
+         "modified_clustered_humidity", "shepard_detrended", "modified_detrended_codes",
+         "shepard_humidity_td", "modified_humidity_td", "modified_sparse_humidity_td", "modified_detrended_codes_td"]
 
 
 def prepared(ref, case):
@@ -67,8 +71,12 @@ def test_port_reproduces_reference_shepard(ref, port, case):  # noqa: F811
     assert np.array_equal(a[1], b[1]), f"max diff {np.abs(a[1] - b[1]).max()}"
     x, y, z = st.x.astype(np.float32), st.y.astype(np.float32), st.z.astype(np.float32)
     pv = st.proxy_values.astype(np.float64)
-    pa = ref.interpolate_points(st, clone(s), var, x, y, z, pv)
-    pb_ = port.interpolate_points(st, clone(s), var, x, y, z, pv)
+    if "_td" in case:
+        pa = ref.interpolate_points_td(st, clone(s), var, x, y, z, pv, dem)
+        pb_ = port.interpolate_points_td(st, clone(s), var, x, y, z, pv, dem)
+    else:
+        pa = ref.interpolate_points(st, clone(s), var, x, y, z, pv)
+        pb_ = port.interpolate_points(st, clone(s), var, x, y, z, pv)
     assert np.array_equal(pa, pb_)
 
 
@@ -108,10 +116,20 @@ def test_gpu_shepard_raster_and_points(engine, ref, case):
     # leave-one-out at the stations (computeResiduals' inner call)
     x, y, z = st.x.astype(np.float32), st.y.astype(np.float32), st.z.astype(np.float32)
     pv = st.proxy_values.astype(np.float64)
-    pr = ref.interpolate_points(st, clone(s), var, x, y, z, pv)
-    pg = engine.interpolate_points(st, clone(s), var, x, y, pv)
+    if "_td" in case:
+        pr = ref.interpolate_points_td(st, clone(s), var, x, y, z, pv, dem)
+        dem_id = engine.upload(dem)
+        try:
+            pg = engine.interpolate_points(st, clone(s), var, x, y, pv, z=z, dem_id=dem_id)
+        finally:
+            engine.free(dem_id)
+    else:
+        pr = ref.interpolate_points(st, clone(s), var, x, y, z, pv)
+        pg = engine.interpolate_points(st, clone(s), var, x, y, pv)
     assert np.array_equal(pr == np.float32(A.NODATA), pg == np.float32(A.NODATA))
     assert np.abs(pr.astype(np.float64) - pg.astype(np.float64)).max() <= 1e-4
+    if "_td" in case:           # (computeResiduals with topographic distance: test_spatial_quality / test_station_space)
+        return
     res_r, stats_r = ref.compute_residuals(st, clone(s), var, st.value)
     res_g, stats_g = engine.compute_residuals(st, clone(s), var, st.value)
     assert np.abs(res_r.astype(np.float64) - res_g.astype(np.float64)).max() <= 1e-4

@@ -13,7 +13,7 @@ from test_station_space import scenario
 
 CASES = ["classic_inversion", "classic_codes", "optimal", "optimal_codes_warm_valley", "classic_pressure",
          "td_humidity", "classic_td_kh64", "multiple_td", "humidity_plain", "wind", "radiation", "transmissivity",
-         "optimal_modified_shepard", "classic_shepard_codes"]
+         "optimal_modified_shepard", "classic_shepard_codes", "classic_td_kh64_modified_shepard"]
 
 
 def sq_scenario(case, n=150, seed=19):
@@ -93,7 +93,7 @@ def test_gpu_spatial_quality_many_seeds(engine, ref):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["classic_td_kh64", "optimal_codes_warm_valley", "td_humidity", "optimal_modified_shepard_codes",
-                                  "classic_shepard_inversion"])
+                                  "classic_shepard_inversion", "classic_td_kh64_shepard", "optimal_td_kh64_modified_shepard"])
 def test_gpu_exact_residuals_identical(engine, ref, port, case):  # noqa: F811
     """pb_compute_residuals_exact against computeResiduals with the fitted settings (topographic distance included)."""
     dem, urban, st, s, var = scenario(case)

@@ -57,7 +57,9 @@ def scenario(case, n=150, seed=19):
 CPU_CASES = ["classic_inversion", "classic_warm_valley", "classic_noinv", "classic_codes", "classic_pressure",
              "optimal", "optimal_inversion", "optimal_codes_warm_valley", "optimal_noinv",
              "td_humidity", "classic_td_kh64", "optimal_td_kh64", "multiple_td",
-             "optimal_shepard", "optimal_modified_shepard_codes_warm_valley", "optimal_modified_shepard_inversion"]
+             "optimal_shepard", "optimal_modified_shepard_codes_warm_valley", "optimal_modified_shepard_inversion",
+             # Shepard estimators behind the kh search (computeDistances adds the topographic distance before any estimator)
+             "classic_td_kh64_shepard", "optimal_td_kh64_modified_shepard_inversion"]
 
 
 def run_oracle(orc, case):
