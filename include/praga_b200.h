@@ -287,8 +287,14 @@ int pb_local_detrending_raster_device(pb_context* ctx, const pb_stations* st, co
  *       cell is set to NODATA), interpolate() over the area's stations, out[cell] (+)= value * weight. Areas are applied in
  *       index order (the reference's order when isParallelComputing is off; with OpenMP it is unordered, same sum up to
  *       float rounding). Returns PB_ERR_NO_VALID_CELL where the reference returns false (an interpolate() gave NODATA); the
- *       grid is still written. out->minimum / maximum as gis::updateMinMaxRasterGrid would set them. Topographic distance
- *       inside macro areas is not on the GPU path (PB_ERR_UNSUPPORTED).
+ *       grid is still written. out->minimum / maximum as gis::updateMinMaxRasterGrid would set them.
+ *   pb_glocal_detrending_raster_td <- the same with settings.useTD: macroAreaDetrending then ends with
+ *       topographicDistanceOptimize over the AREA's meteo points (interpolation.cpp:1811-1826: golden-section search of kh on
+ *       the leave-one-out MAE, computeResiduals(..., excludeOutsideDem = true, excludeSupplemental = true)) and the area's
+ *       cells are gridded with distance + kh * topographicDistance (computeDistances :226-251). meteo = what
+ *       pb_compute_residuals_glocal takes (one entry per Crit3DMeteoPoint, indexed by area.meteoPoints); cells = a
+ *       pb_macro_areas_upload id or -1 for the areas' host cells; areaKh (nAreas, may be NULL) receives each area's kh.
+ *       Without the meteo points a TD call fails with PB_ERR_INVALID.
  *   pb_compute_residuals_glocal  <- Project::computeResidualsAndStatisticsGlocalDetrending (project.cpp:6525-6565) over
  *       computeResidualsGlocalDetrending (agrolib/interpolation/spatialControl.cpp:231-302), areas already fitted: meteo =
  *       one entry per Crit3DMeteoPoint (position, lapse code, proxy values; meteo->isActive = active), area.meteoPoints index
@@ -323,6 +329,20 @@ int pb_glocal_detrending_raster_resident(pb_context* ctx, const pb_stations* st,
 int pb_compute_residuals_glocal(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
                                 const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
                                 int excludeOutsideDem, int excludeSupplemental, float* residual);
+/* topographic distance inside macro areas (settings.useTD): the meteo points of the per-area kh search, the resident DEM of
+ * the ray march */
+typedef struct pb_glocal_meteo {
+    const pb_stations* meteo;      /* one entry per Crit3DMeteoPoint (isActive = active) */
+    const float* observed;         /* currentValue; NULL: meteo->value */
+    const pb_cv_points* cv;        /* isInsideDem; may be NULL */
+} pb_glocal_meteo;
+int pb_glocal_detrending_raster_td(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
+                                   int nAreas, pb_macro_areas_id cells, const pb_glocal_meteo* meteo, pb_raster_id dem,
+                                   const pb_raster_id* proxyGrids, int nProxyGrids, int deviceOnly, pb_raster_out* out,
+                                   int32_t* areaKh);
+int pb_compute_residuals_glocal_td(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
+                                   const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
+                                   pb_raster_id dem, int excludeOutsideDem, int excludeSupplemental, float* residual);
 
 /* --- interpolate() at explicit targets (agrolib/interpolation/interpolation.h:77-79, .cpp:2502-2560) -------
  * The building block of computeResiduals (spatialControl.cpp:97-155): x, y are the f32 target coordinates,

@@ -368,8 +368,10 @@ class Oracle:
         rc = self._f("glocal_detrending_fitting")(C.byref(st), C.byref(settings), variable, areas.arr, areas.n)
         return rc == A.PB_OK
 
-    def glocal_detrending_raster(self, stations, settings, variable, areas, dem, proxy_grids=(), threads=1):
-        """gridding part of Project::interpolationDemGlocalDetrending (project.cpp:3283-3375).
+    def glocal_detrending_raster(self, stations, settings, variable, areas, dem, proxy_grids=(), threads=1, meteo=None,
+                                 observed=None):
+        """gridding part of Project::interpolationDemGlocalDetrending (project.cpp:3283-3375). meteo (+ observed): Project::meteoPoints,
+        which macroAreaDetrending's kh search walks when settings.useTD is on (reference only).
         Returns (ok, grid, min, max, nValid, seconds)."""
         st = stations.as_pb()
         d = dem.as_pb()
@@ -380,6 +382,18 @@ class Oracle:
         o = A.pb_raster_out()
         o.data = A.fptr(out)
         sec = C.c_double(0)
+        if meteo is not None:
+            mp = meteo.as_pb()
+            gm = A.pb_glocal_meteo()
+            gm.meteo = C.pointer(mp)
+            obs = None if observed is None else np.ascontiguousarray(observed, dtype=np.float32)
+            if obs is not None:
+                gm.observed = A.fptr(obs)
+            fn = self.lib.ref_glocal_detrending_raster_td
+            fn.restype = C.c_int
+            rc = fn(C.byref(st), C.byref(settings), C.c_int(variable), areas.arr, C.c_int(areas.n), C.byref(gm), C.byref(d), grids,
+                    C.c_int(len(proxy_grids)), C.c_int(threads), C.byref(o), C.byref(sec))
+            return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid, sec.value
         rc = self._f("glocal_detrending_raster")(C.byref(st), C.byref(settings), variable, areas.arr, areas.n, C.byref(d), grids,
                                                  len(proxy_grids), threads, C.byref(o), C.byref(sec))
         return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid, sec.value

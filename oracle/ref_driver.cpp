@@ -945,9 +945,28 @@ int ref_glocal_detrending_fitting(const pb_stations* st, pb_settings* s, int var
  * setMultipleDetrendingHeightTemperatureRange, the loop over macro areas. Every call inside is the reference's own code
  * (macroAreaDetrending, getUtmXYFromRowCol, getSignificantProxyValuesXY, interpolate). updateMinMaxRasterGrid is what the
  * callers of interpolationDemMain run on the result. */
+static int glocalRasterDriver(const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas,
+                              const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int nThreads,
+                              pb_raster_out* out, double* elapsed_s, const pb_glocal_meteo* gm);
+
 int ref_glocal_detrending_raster(const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas,
                                  const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int nThreads,
                                  pb_raster_out* out, double* elapsed_s)
+{
+    return glocalRasterDriver(st, s, variable, areas, nAreas, dem, proxyGrids, nProxyGrids, nThreads, out, elapsed_s, nullptr);
+}
+
+/* the same with Project::meteoPoints filled (what macroAreaDetrending's kh search walks when settings.useTD is on) */
+int ref_glocal_detrending_raster_td(const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas,
+                                    const pb_glocal_meteo* gm, const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids,
+                                    int nThreads, pb_raster_out* out, double* elapsed_s)
+{
+    return glocalRasterDriver(st, s, variable, areas, nAreas, dem, proxyGrids, nProxyGrids, nThreads, out, elapsed_s, gm);
+}
+
+static int glocalRasterDriver(const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas,
+                              const pb_raster* dem, const pb_raster* proxyGrids, int nProxyGrids, int nThreads,
+                              pb_raster_out* out, double* elapsed_s, const pb_glocal_meteo* gm)
 {
     Scenario sc;
     buildSettings(sc, *s, proxyGrids, nProxyGrids);
@@ -960,6 +979,7 @@ int ref_glocal_detrending_raster(const pb_stations* st, pb_settings* s, int vari
     Crit3DInterpolationSettings& interpolationSettings = sc.settings;
     if (!getUseDetrendingVar(myVar) || !interpolationSettings.getUseGlocalDetrending()) return PB_ERR_INVALID;
     std::vector<Crit3DMeteoPoint> meteoPoints;
+    if (gm && gm->meteo) buildMeteoPoints(meteoPoints, gm->meteo, gm->observed, gm->cv);
     std::vector<Crit3DInterpolationDataPoint>& interpolationPoints = sc.points;
     Crit3DMeteoSettings* meteoSettings = &sc.meteoSettings;
     gis::Crit3DRasterGrid* myRaster = &outGrid;

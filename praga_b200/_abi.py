@@ -113,6 +113,10 @@ class pb_cv_points(C.Structure):
                 ("excludeOutsideDem", C.c_int32), ("reserved", C.c_int32), ("suspectProxyValues", C.POINTER(C.c_float))]
 
 
+class pb_glocal_meteo(C.Structure):
+    _fields_ = [("meteo", C.POINTER(pb_stations)), ("observed", C.POINTER(C.c_float)), ("cv", C.POINTER(pb_cv_points))]
+
+
 PB_AGGR_AVERAGE, PB_AGGR_MEDIAN, PB_AGGR_STDDEV, PB_AGGR_PREVAILING, PB_AGGR_CENTER = 1, 2, 3, 7, 9
 PB_MAX_KH_SERIES = 64
 

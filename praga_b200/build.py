@@ -35,7 +35,7 @@ SOURCES = {
     "kriging_tc.cu": [],
     "variogram.cu": [],
 }
-HEADERS = ["common.cuh", "epilogue.cuh", "context.cuh", "local.cuh", "local_device.cuh", "nvtx.cuh", "td_device.cuh", "pre.cuh", "multiple_detrend.cuh", "detrend_device.cuh", "kriging.cuh", "classic.cuh", "shepard.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
+HEADERS = ["common.cuh", "epilogue.cuh", "context.cuh", "local.cuh", "local_device.cuh", "nvtx.cuh", "td_device.cuh", "kh_search.cuh", "pre.cuh", "multiple_detrend.cuh", "detrend_device.cuh", "kriging.cuh", "classic.cuh", "shepard.cuh", os.path.join("..", "..", "include", "praga_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "context.cuh"
+#include "kh_search.cuh"
 #include "pre.cuh"
 #include "shepard.cuh"
 #include "nvtx.cuh"
@@ -48,6 +49,10 @@ bool varUsesTd(int v);
 cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const float* tx, const float* ty, const double* tproxy,
                             int nTargets, float* out, cudaStream_t s);
 cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);
+// td_kernels.cu
+cudaError_t launchIdwTdPoints(const DevStations& st, const float* sz, const DevModel& m, const DevGrid& dem, int kh,
+                              const float* tx, const float* ty, const float* tz, const double* tproxy, int nTargets, float* out,
+                              cudaStream_t s);
 
 // which proxies getSignificantProxyValuesXY looks up (active && significant, grid loaded)
 struct GlocalLookup {
@@ -80,14 +85,14 @@ __device__ __forceinline__ void glocalRowCol(float idxf, int nrCols, int& row, i
 // getSignificantProxyValuesXY and interpolate), the significant proxies' values
 __global__ void __launch_bounds__(256)
 glocal_targets_kernel(const float* __restrict__ cells, int nCells, DevGrid dem, GlocalLookup lk, float* __restrict__ tx,
-                      float* __restrict__ ty, double* __restrict__ pv, unsigned char* __restrict__ state)
+                      float* __restrict__ ty, float* __restrict__ tz, double* __restrict__ pv, unsigned char* __restrict__ state)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     int row, col;
     glocalRowCol(cells[2 * c], dem.nrCols, row, col);
     unsigned char st = CELL_SKIP;
-    float xf = 0.f, yf = 0.f;
+    float xf = 0.f, yf = 0.f, zf = 0.f;
     double v[PB_MAX_PROXY];
 #pragma unroll
     for (int i = 0; i < PB_MAX_PROXY; i++) v[i] = -9999.;
@@ -98,6 +103,7 @@ glocal_targets_kernel(const float* __restrict__ cells, int nCells, DevGrid dem, 
             const double y = dem.lly + dem.cellSize * (dem.nrRows - row - 0.5);
             xf = float(x);
             yf = float(y);
+            zf = z;                                  // interpolate(..., x, y, z = DEM.value[row][col], ...) (project.cpp:3340, 3356)
             bool complete = true;
 #pragma unroll
             for (int i = 0; i < PB_MAX_PROXY; i++)
@@ -112,6 +118,7 @@ glocal_targets_kernel(const float* __restrict__ cells, int nCells, DevGrid dem, 
     }
     tx[c] = xf;
     ty[c] = yf;
+    tz[c] = zf;
     state[c] = st;
     for (int i = 0; i < lk.nProxy; i++) pv[(size_t)c * lk.nProxy + i] = v[i];
 }
@@ -329,13 +336,86 @@ void secondHeightRangeCall(pb_settings& s)
         }
 }
 
+// the area's active meteo points, in the area's order, as the targets of a leave-one-out (computeResiduals skips the others)
+struct AreaMeteo {
+    std::vector<int> who;
+    std::vector<double> x, y, z;
+    std::vector<float> val, proxy;
+    std::vector<int32_t> code;
+    std::vector<uint8_t> inside;
+    pb_stations mp{};
+    pb_cv_points cva{};
+};
+
+int areaMeteoPoints(pb_context* ctx, const pb_macro_area& A, const pb_stations* meteo, const float* obs, const pb_cv_points* cv,
+                    AreaMeteo& o)
+{
+    const int P = std::max(meteo->nProxy, 0);
+    for (int i = 0; i < A.nMeteoPoints; i++) {
+        const int j = A.meteoPoints[i];
+        if (j < 0 || j >= meteo->n) return fail(ctx, PB_ERR_INVALID, "macro area meteo point out of range");
+        if (meteo->isActive && !meteo->isActive[j]) continue;
+        o.who.push_back(j);
+    }
+    const size_t m = o.who.size();
+    o.x.resize(m); o.y.resize(m); o.z.resize(m); o.val.resize(m); o.code.resize(m);
+    o.proxy.assign(std::max<size_t>(m * P, 1), kNoData);
+    o.inside.assign(std::max<size_t>(m, 1), 1);
+    for (size_t q = 0; q < m; q++) {
+        const int j = o.who[q];
+        o.x[q] = meteo->x[j]; o.y[q] = meteo->y[j]; o.z[q] = meteo->z[j];
+        o.val[q] = obs[j];
+        o.code[q] = meteo->lapseRateCode ? meteo->lapseRateCode[j] : PB_LAPSE_PRIMARY;
+        if (cv && cv->isInsideDem) o.inside[q] = cv->isInsideDem[j];
+        for (int p = 0; p < P; p++) o.proxy[q * P + p] = meteo->proxyValues[size_t(j) * P + p];
+    }
+    o.mp = pb_stations{};
+    o.mp.n = int(m);
+    o.mp.nProxy = meteo->nProxy;
+    o.mp.x = o.x.data(); o.mp.y = o.y.data(); o.mp.z = o.z.data();
+    o.mp.value = o.val.data();
+    o.mp.lapseRateCode = o.code.data();
+    o.mp.proxyValues = o.proxy.data();
+    o.cva = pb_cv_points{};
+    o.cva.isInsideDem = o.inside.data();
+    return PB_OK;
+}
+
+// topographicDistanceOptimize at the end of macroAreaDetrending (:1811-1826): golden-section search of kh over the
+// leave-one-out MAE of the AREA's meteo points against the area's detrended stations (computeResiduals(..., true, true)), each
+// visited kh one exact leave-one-out launch. sub.s.topoDist_Kh receives the result.
+int areaKhSearch(pb_context* ctx, const AreaMeteo& am, AreaStations& sub, int variable, pb_raster_id demId, pb_timing& sum)
+{
+    const int maxKh = std::max(0, sub.s.topoDist_maxKh);
+    const int m = am.mp.n;
+    std::vector<float> res(std::max(m, 1));
+    std::vector<float> table(size_t(maxKh) + 1, 0.f);
+    std::vector<uint8_t> known(size_t(maxKh) + 1, 0);
+    int rc = PB_OK;
+    auto f = [&](int kh) -> float {
+        if (m == 0 || sub.st.n == 0) return kNoData;        // computeErrorCrossValidation over nothing (:323-324)
+        if (rc) return kNoData;
+        if (known[kh]) return table[kh];
+        sub.s.topoDist_Kh = kh;
+        rc = pb_compute_residuals_exact(ctx, &am.mp, am.val.data(), &am.cva, &sub.st, &sub.s, variable, demId, 1, 1, res.data());
+        if (rc) return kNoData;
+        sum.kernel_ms += ctx->timing.kernel_ms; sum.total_ms += ctx->timing.total_ms; sum.launches += ctx->timing.launches;
+        known[kh] = 1;
+        table[kh] = cvMaeHost(res.data(), am.val.data(), m);
+        return table[kh];
+    };
+    pb_kh_series series{};
+    const double best = goldenSection(f, maxKh, 0., double(maxKh), &series);
+    if (rc) return rc;
+    sub.s.topoDist_Kh = int(best);
+    return PB_OK;
+}
+
 // glocalDetrendingFitting on the device: every area with stations is one unit of the batched preInterpolation kernel
 int glocalFit(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas)
 {
     if (!varUsesDetrending(variable) || !s->useMultipleDetrending) return PB_OK;      // preInterpolation :2464-2467
     if (s->useLocalDetrending) return fail(ctx, PB_ERR_INVALID, "glocal and local detrending are exclusive (project.cpp:3546-3552)");
-    if (s->useTD && varUsesTd(variable))
-        return fail(ctx, PB_ERR_UNSUPPORTED, "topographic distance inside macro areas is not on the GPU path (DESIGN.md)");
     if (!s->hasPointsRange) return fail(ctx, PB_ERR_FIT, "couldn't set temperature ranges for height proxy (points range not set)");
     pb_settings s0 = *s;
     s0.useGlocalDetrending = 0;
@@ -443,7 +523,7 @@ int pb_glocal_detrending_fitting(pb_context* ctx, const pb_stations* st, pb_sett
 
 static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas, int nAreas,
                             const ResidentMacroAreas* resident, pb_raster_id demId, const pb_raster_id* proxyGrids, int nProxyGrids,
-                            int deviceOnly, pb_raster_out* out)
+                            int deviceOnly, pb_raster_out* out, const pb_glocal_meteo* gm = nullptr, int32_t* areaKh = nullptr)
 {
     if (!st || !s || !out || (!areas && nAreas > 0) || nAreas < 0) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
@@ -455,6 +535,10 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
         return fail(ctx, PB_ERR_INVALID, "dem id is not a live raster");
     if (!deviceOnly && !out->data && !out->rows) return fail(ctx, PB_ERR_INVALID, "output has neither data nor rows");
     if (resident && int(resident->firstFloat.size()) != nAreas + 1) return fail(ctx, PB_ERR_INVALID, "resident cells describe other areas");
+    // topographic distance: macroAreaDetrending searches kh per area over the area's METEO points (:1811-1826)
+    const bool useTD = s->useTD && varUsesTd(variable);
+    if (useTD && (!gm || !gm->meteo))
+        return fail(ctx, PB_ERR_INVALID, "topographic distance inside macro areas needs the meteo points (pb_glocal_detrending_raster_td)");
     cudaEventRecord(ctx->ev[0], ctx->stream);
     for (int i = 0; i < s->nProxy; i++) { s->currentActive[i] = s->selectedActive[i]; s->currentSignificant[i] = 0; }
     s->currentUseThermalInversion = s->selectedUseThermalInversion;
@@ -479,10 +563,22 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
     // synchronisation between the areas
     std::vector<AreaStations> subs(nAreas);
     std::vector<size_t> stOff(nAreas + 1, 0);
+    pb_timing khTiming{};
     for (int a = 0; a < nAreas; a++) {
-        if (areas[a].nAreaCells / 2 > 0) macroAreaDetrendingHost(areas[a], *s, st, subs[a]);
+        if (areas[a].nAreaCells / 2 > 0) {
+            macroAreaDetrendingHost(areas[a], *s, st, subs[a]);
+            if (useTD) {
+                // (the searches run before anything of the raster is staged: they go through the shared scratch buffers)
+                AreaMeteo am;
+                rc = areaMeteoPoints(ctx, areas[a], gm->meteo, gm->observed ? gm->observed : gm->meteo->value, gm->cv, am);
+                if (!rc) rc = areaKhSearch(ctx, am, subs[a], variable, demId, khTiming);
+                if (rc) return rc;
+            }
+        }
+        if (areaKh) areaKh[a] = (useTD && areas[a].nAreaCells / 2 > 0) ? subs[a].s.topoDist_Kh : 0;
         stOff[a + 1] = stOff[a] + (areas[a].nAreaCells / 2 > 0 ? idwStationsStagingBytes(subs[a].st.n) : 0);
     }
+    if (useTD) { memset(&ctx->timing, 0, sizeof(ctx->timing)); ctx->timing.launches = khTiming.launches; }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));           // nothing in flight may still read the staging buffer
     CUDA_TRY(ctx, ctx->hStations.reserve(stOff[nAreas] + 256));
     CUDA_TRY(ctx, ctx->dStations.reserve(stOff[nAreas] + 256));
@@ -502,8 +598,8 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
 
     const int P = std::max(s->nProxy, 0);
     const size_t mAl = (size_t(maxCells) + 3) / 4 * 4;
-    const size_t offCells = 0, offX = offCells + (resident ? 0 : mAl * 8), offY = offX + mAl * 4, offRes = offY + mAl * 4,
-                 offPv = offRes + mAl * 4, offState = offPv + mAl * 8 * std::max(P, 1), offFlag = (offState + mAl + 15) / 16 * 16,
+    const size_t offCells = 0, offX = offCells + (resident ? 0 : mAl * 8), offY = offX + mAl * 4, offZ = offY + mAl * 4,
+                 offRes = offZ + mAl * 4, offPv = offRes + mAl * 4, offState = offPv + mAl * 8 * std::max(P, 1), offFlag = (offState + mAl + 15) / 16 * 16,
                  total = offFlag + 16;
     CUDA_TRY(ctx, ctx->dScratch.reserve(total));
     unsigned char* d = ctx->dScratch.p;
@@ -533,8 +629,8 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
         }
         const int grid = (nCells + 255) / 256;
         glocal_targets_kernel<<<grid, 256, 0, ctx->stream>>>(dCells, nCells, dg, lk, reinterpret_cast<float*>(d + offX),
-                                                             reinterpret_cast<float*>(d + offY), reinterpret_cast<double*>(d + offPv),
-                                                             d + offState);
+                                                             reinterpret_cast<float*>(d + offY), reinterpret_cast<float*>(d + offZ),
+                                                             reinterpret_cast<double*>(d + offPv), d + offState);
         CUDA_TRY(ctx, cudaGetLastError());
         if (shepardMethod) {
             // shepardIdw / modifiedShepardIdw over the area's points: neighbourhood radius from the settings' bounding box and
@@ -544,11 +640,20 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
             float R0 = 0.f;
             rc = stageShepardStationsFor(ctx, &subs[a].st, &subs[a].s, true, ss, R0);
             if (rc) return rc;
+            ShepardTd std_{};
+            std_.kh = useTD ? subs[a].s.topoDist_Kh : 0;
+            std_.dem = dg;
+            std_.tz = reinterpret_cast<const float*>(d + offZ);
             CUDA_TRY(ctx, launchShepardPoints(ss, mods[a], R0, s->method == PB_METHOD_SHEPARD_MODIFIED,
                                               reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                               reinterpret_cast<const double*>(d + offPv), nCells,
-                                              reinterpret_cast<float*>(d + offRes), ctx->stream));
-        } else
+                                              reinterpret_cast<float*>(d + offRes), ctx->stream, &std_));
+        } else if (useTD && subs[a].s.topoDist_Kh != 0)
+            CUDA_TRY(ctx, launchIdwTdPoints(dss[a], dss[a].z, mods[a], dg, subs[a].s.topoDist_Kh,
+                                            reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
+                                            reinterpret_cast<const float*>(d + offZ), reinterpret_cast<const double*>(d + offPv),
+                                            nCells, reinterpret_cast<float*>(d + offRes), ctx->stream));
+        else
         CUDA_TRY(ctx, launchIdwPoints(dss[a], mods[a], reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                       reinterpret_cast<const double*>(d + offPv), nCells, reinterpret_cast<float*>(d + offRes),
                                       ctx->stream));
@@ -622,6 +727,24 @@ int pb_glocal_detrending_raster_resident(pb_context* ctx, const pb_stations* st,
                             out);
 }
 
+/* the same with topographic distance: the per-area kh search needs the meteo points; cells < 0 = the areas' host cells */
+int pb_glocal_detrending_raster_td(pb_context* ctx, const pb_stations* st, pb_settings* s, int variable, pb_macro_area* areas,
+                                   int nAreas, pb_macro_areas_id cells, const pb_glocal_meteo* meteo, pb_raster_id demId,
+                                   const pb_raster_id* proxyGrids, int nProxyGrids, int deviceOnly, pb_raster_out* out,
+                                   int32_t* areaKh)
+{
+    PB_NVTX_RANGE();
+    if (!ctx) return PB_ERR_INVALID;
+    const ResidentMacroAreas* resident = nullptr;
+    if (cells >= 0) {
+        if (cells >= (int)ctx->macroAreas.size() || !ctx->macroAreas[cells].used)
+            return fail(ctx, PB_ERR_INVALID, "macro areas id is not live");
+        resident = &ctx->macroAreas[cells];
+    }
+    return glocalRasterImpl(ctx, st, s, variable, areas, nAreas, resident, demId, proxyGrids, nProxyGrids, deviceOnly, out, meteo,
+                            areaKh);
+}
+
 int pb_macro_areas_upload(pb_context* ctx, const pb_macro_area* areas, int nAreas, pb_macro_areas_id* id)
 {
     PB_NVTX_RANGE();
@@ -661,71 +784,68 @@ int pb_macro_areas_free(pb_context* ctx, pb_macro_areas_id id)
     return PB_OK;
 }
 
-int pb_compute_residuals_glocal(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
-                                const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
-                                int excludeOutsideDem, int excludeSupplemental, float* residual)
+static int residualsGlocalImpl(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
+                               const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
+                               pb_raster_id demId, int excludeOutsideDem, int excludeSupplemental, float* residual)
 {
-    PB_NVTX_RANGE();
-    if (!ctx) return PB_ERR_INVALID;
     if (!meteo || !points || !s || !residual || (!areas && nAreas > 0)) return fail(ctx, PB_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->device);
     if (!s->hasPointsRange || !s->useMultipleDetrending)        // setMultipleDetrendingHeightTemperatureRange false (project.cpp:3069)
         return fail(ctx, PB_ERR_FIT, "couldn't set temperature ranges for height proxy");
-    if (s->useTD && varUsesTd(variable))
-        return fail(ctx, PB_ERR_UNSUPPORTED, "topographic distance inside macro areas is not on the GPU path (DESIGN.md)");
+    const bool useTD = s->useTD && varUsesTd(variable);
+    if (useTD && (demId < 0 || demId >= (int)ctx->rasters.size() || !ctx->rasters[demId].used))
+        return fail(ctx, PB_ERR_INVALID, "topographic distance inside macro areas needs the resident DEM (pb_compute_residuals_glocal_td)");
     for (int i = 0; i < meteo->n; i++) residual[i] = kNoData;
     const float* obs = observed ? observed : meteo->value;
-    const int P = std::max(meteo->nProxy, 0);
     pb_timing sum{};
     for (int k = 0; k < nAreas; k++) {
         const pb_macro_area& A = areas[k];
         if (A.nAreaCells <= 0 || A.nMeteoPoints <= 0) continue;
         AreaStations sub;
         macroAreaDetrendingHost(A, *s, points, sub);
-        // the area's active meteo points, in the area's order
-        std::vector<int> who;
-        for (int i = 0; i < A.nMeteoPoints; i++) {
-            const int j = A.meteoPoints[i];
-            if (j < 0 || j >= meteo->n) return fail(ctx, PB_ERR_INVALID, "macro area meteo point out of range");
-            if (meteo->isActive && !meteo->isActive[j]) continue;
-            who.push_back(j);
+        AreaMeteo am;
+        int rc = areaMeteoPoints(ctx, A, meteo, obs, cv, am);
+        if (rc) return rc;
+        if (useTD) {            // macroAreaDetrending ends with the area's kh search (:1811-1826)
+            rc = areaKhSearch(ctx, am, sub, variable, demId, sum);
+            if (rc) return rc;
         }
-        if (who.empty()) continue;
-        const size_t m = who.size();
-        std::vector<double> x(m), y(m), z(m);
-        std::vector<float> val(m), proxy(std::max<size_t>(m * P, 1)), res(m);
-        std::vector<int32_t> code(m);
-        std::vector<uint8_t> inside(m, 1);
-        for (size_t q = 0; q < m; q++) {
-            const int j = who[q];
-            x[q] = meteo->x[j]; y[q] = meteo->y[j]; z[q] = meteo->z[j];
-            val[q] = obs[j];
-            code[q] = meteo->lapseRateCode ? meteo->lapseRateCode[j] : PB_LAPSE_PRIMARY;
-            if (cv && cv->isInsideDem) inside[q] = cv->isInsideDem[j];
-            for (int p = 0; p < P; p++) proxy[q * P + p] = meteo->proxyValues[size_t(j) * P + p];
-        }
-        pb_stations mp{};
-        mp.n = int(m);
-        mp.nProxy = meteo->nProxy;
-        mp.x = x.data(); mp.y = y.data(); mp.z = z.data();
-        mp.value = val.data();
-        mp.lapseRateCode = code.data();
-        mp.proxyValues = proxy.data();
-        pb_cv_points cva{};
-        cva.isInsideDem = inside.data();
-        int rc = pb_compute_residuals_exact(ctx, &mp, val.data(), &cva, &sub.st, &sub.s, variable, -1, excludeOutsideDem,
-                                            excludeSupplemental, res.data());
+        if (am.who.empty()) continue;
+        const size_t m = am.who.size();
+        std::vector<float> res(m);
+        rc = pb_compute_residuals_exact(ctx, &am.mp, am.val.data(), &am.cva, &sub.st, &sub.s, variable, useTD ? demId : -1,
+                                        excludeOutsideDem, excludeSupplemental, res.data());
         if (rc) return rc;
         sum.kernel_ms += ctx->timing.kernel_ms; sum.total_ms += ctx->timing.total_ms; sum.launches += ctx->timing.launches;
         for (size_t q = 0; q < m; q++) {
             if (isEqualF(res[q], kNoData)) continue;
-            float& r = residual[who[q]];
+            float& r = residual[am.who[q]];
             if (isEqualF(r, kNoData)) r = res[q] * 1.f;
             else r += res[q] * 1.f;
         }
     }
     ctx->timing = sum;
     return PB_OK;
+}
+
+int pb_compute_residuals_glocal(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
+                                const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
+                                int excludeOutsideDem, int excludeSupplemental, float* residual)
+{
+    PB_NVTX_RANGE();
+    if (!ctx) return PB_ERR_INVALID;
+    return residualsGlocalImpl(ctx, meteo, observed, cv, points, s, variable, areas, nAreas, -1, excludeOutsideDem,
+                               excludeSupplemental, residual);
+}
+
+int pb_compute_residuals_glocal_td(pb_context* ctx, const pb_stations* meteo, const float* observed, const pb_cv_points* cv,
+                                   const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
+                                   pb_raster_id dem, int excludeOutsideDem, int excludeSupplemental, float* residual)
+{
+    PB_NVTX_RANGE();
+    if (!ctx) return PB_ERR_INVALID;
+    return residualsGlocalImpl(ctx, meteo, observed, cv, points, s, variable, areas, nAreas, dem, excludeOutsideDem,
+                               excludeSupplemental, residual);
 }
 
 }  // extern "C"

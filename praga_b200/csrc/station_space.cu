@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "classic.cuh"
+#include "kh_search.cuh"
 #include "context.cuh"
 #include "nvtx.cuh"
 
@@ -126,21 +127,6 @@ int shepardLoo(pb_context* ctx, const pb_settings* sp, int variable, int nS, con
     return PB_OK;
 }
 
-// computeErrorCrossValidation (spatialControl.cpp:305-328) + statistics::meanAbsoluteError (statistics.cpp:201-220) on the host
-float cvMaeHost(const float* residual, const float* observed, int n)
-{
-    double sum = 0.;
-    long cnt = 0;
-    for (int j = 0; j < n; j++) {
-        const float value = observed[j], res = residual[j];
-        if (value != kNoData && res != kNoData) {
-            const float e = value - res;
-            if (e != kNoData) { sum += fabs(double(value - e)); cnt++; }
-        }
-    }
-    return cnt == 0 ? kNoData : float(sum / double(cnt));
-}
-
 void applyWrites(pb_proxy& dst, const ClassicProxyState& p)
 {
     if (p.written & CF_SLOPE) dst.regressionSlope = p.slope;
@@ -175,41 +161,6 @@ bool getCombination(const pb_settings& s, int indexHeight, int k, uint8_t* activ
     for (int i = 0; i < s.nProxy; i++) active[i] = (bit(i) && s.selectedActive[i]) ? 1 : 0;
     useInversion = (bit(digits - 1) && s.selectedUseThermalInversion) ? 1 : 0;
     return true;
-}
-
-// goldenSectionSearch (interpolation.cpp:2297-2335) over f(kh) = MAE at kh = int(khFloat), read from the table
-template <class MaeOfKh>
-double goldenSection(MaeOfKh maeOfKh, int maxKh, double a, double b, pb_kh_series* series)
-{
-    const double GOLDEN = 1.6180339887499;      // GOLDEN_SECTION, commonConstants.h:258
-    auto f = [&](double khFloat) -> double {
-        int kh = int(khFloat);
-        kh = std::max(0, std::min(kh, maxKh));
-        return double(maeOfKh(kh));
-    };
-    auto add = [&](float kh, float err) {
-        if (series && series->n < PB_MAX_KH_SERIES) { series->kh[series->n] = kh; series->error[series->n] = err; series->n++; }
-    };
-    const double tol = 1;
-    double x1 = b - (b - a) / GOLDEN;
-    double x2 = a + (b - a) / GOLDEN;
-    int counter = 0;
-    while (fabs(b - a) > tol && counter < 100) {
-        counter++;
-        if (f(x1) < f(x2)) {
-            b = x2;
-            x2 = x1;
-            x1 = b - (b - a) / GOLDEN;
-            add(float(x1), float(f(x1)));
-        } else {
-            a = x1;
-            x1 = x2;
-            x2 = a + (b - a) / GOLDEN;
-            add(float(x2), float(f(x2)));
-        }
-    }
-    add(float((a + b) / 2), float(f((a + b) / 2)));
-    return (a + b) / 2;
 }
 
 }  // namespace

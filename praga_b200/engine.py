@@ -104,6 +104,12 @@ def load_library():
     lib.pb_glocal_detrending_raster_resident.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area),
                                                          C.c_int, C.c_int32, C.c_int32, P(C.c_int32), C.c_int, C.c_int,
                                                          P(A.pb_raster_out)]
+    lib.pb_glocal_detrending_raster_td.argtypes = [C.c_void_p, P(A.pb_stations), P(A.pb_settings), C.c_int, P(A.pb_macro_area),
+                                                   C.c_int, C.c_int32, P(A.pb_glocal_meteo), C.c_int32, P(C.c_int32), C.c_int,
+                                                   C.c_int, P(A.pb_raster_out), P(C.c_int32)]
+    lib.pb_compute_residuals_glocal_td.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), P(A.pb_cv_points), P(A.pb_stations),
+                                                   P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int, C.c_int32, C.c_int,
+                                                   C.c_int, P(C.c_float)]
     lib.pb_macro_areas_upload.argtypes = [C.c_void_p, P(A.pb_macro_area), C.c_int, P(C.c_int32)]
     lib.pb_macro_areas_free.argtypes = [C.c_void_p, C.c_int32]
     lib.pb_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -654,16 +660,33 @@ class Engine:
         self._check(self.lib.pb_macro_areas_free(self.h, mid))
 
     def glocal_detrending_raster(self, stations, settings, variable, areas, dem_id, shape, proxy_ids=(), device_only=False,
-                                 cells_id=None, out=None):
+                                 cells_id=None, out=None, meteo=None, observed=None, inside_dem=None, area_kh=None):
         """gridding part of Project::interpolationDemGlocalDetrending (project.cpp:3283-3375). cells_id: macro_areas_upload id.
-        Returns (ok, grid or None, min, max, nValid); ok False where the reference returns false."""
+        meteo (+ observed, inside_dem): the meteo points of the per-area kh search when settings.useTD is on; area_kh: an
+        int32 array (n areas) receiving each area's kh. Returns (ok, grid or None, min, max, nValid); ok False where the
+        reference returns false."""
         st = stations.as_pb()
         ids = (C.c_int32 * max(1, len(proxy_ids)))(*proxy_ids)
         grid = None if device_only else (out if out is not None else np.empty(shape, dtype=np.float32))
         o = A.pb_raster_out()
         if grid is not None:
             o.data = A.fptr(grid)
-        if cells_id is None:
+        if meteo is not None:
+            mp = meteo.as_pb()
+            gm, cv = A.pb_glocal_meteo(), A.pb_cv_points()
+            gm.meteo = C.pointer(mp)
+            obs = None if observed is None else np.ascontiguousarray(observed, dtype=np.float32)
+            if obs is not None:
+                gm.observed = A.fptr(obs)
+            ins = None if inside_dem is None else np.ascontiguousarray(inside_dem, dtype=np.uint8)
+            if ins is not None:
+                cv.isInsideDem = A.u8ptr(ins)
+                gm.cv = C.pointer(cv)
+            rc = self.lib.pb_glocal_detrending_raster_td(self.h, C.byref(st), C.byref(settings), variable, areas.arr, areas.n,
+                                                         -1 if cells_id is None else cells_id, C.byref(gm), dem_id, ids,
+                                                         len(proxy_ids), int(device_only), C.byref(o),
+                                                         None if area_kh is None else A.iptr(area_kh))
+        elif cells_id is None:
             rc = self.lib.pb_glocal_detrending_raster(self.h, C.byref(st), C.byref(settings), variable, areas.arr, areas.n, dem_id, ids,
                                                       len(proxy_ids), int(device_only), C.byref(o))
         else:
@@ -673,7 +696,7 @@ class Engine:
         return rc == A.PB_OK, grid, o.minimum, o.maximum, o.nValid
 
     def compute_residuals_glocal(self, meteo, observed, points, settings, variable, areas, exclude_outside_dem=True,
-                                 exclude_supplemental=True, inside_dem=None):
+                                 exclude_supplemental=True, inside_dem=None, dem_id=None):
         """computeResidualsAndStatisticsGlocalDetrending (project.cpp:6525-6565) over computeResidualsGlocalDetrending
         (spatialControl.cpp:231-302); the areas carry their fit."""
         mp, pt = meteo.as_pb(), points.as_pb()
@@ -683,6 +706,11 @@ class Engine:
         if ins is not None:
             cv.isInsideDem = A.u8ptr(ins)
         res = np.empty(meteo.n, dtype=np.float32)
+        if dem_id is not None:      # topographic distance inside the macro areas: the resident DEM of the ray march
+            self._check(self.lib.pb_compute_residuals_glocal_td(self.h, C.byref(mp), A.fptr(obs), C.byref(cv), C.byref(pt),
+                                                                C.byref(settings), variable, areas.arr, areas.n, dem_id,
+                                                                int(exclude_outside_dem), int(exclude_supplemental), A.fptr(res)))
+            return res
         self._check(self.lib.pb_compute_residuals_glocal(self.h, C.byref(mp), A.fptr(obs), C.byref(cv), C.byref(pt), C.byref(settings),
                                                          variable, areas.arr, areas.n, int(exclude_outside_dem),
                                                          int(exclude_supplemental), A.fptr(res)))

@@ -187,10 +187,10 @@ def test_gpu_glocal_rejects_what_it_does_not_cover(engine):
     dem_id = engine.upload(dem)
     try:
         s_td = clone(s)
-        s_td.useTD = 1          # topographic distance inside macro areas: not on the GPU path, never silently ignored
+        s_td.useTD = 1          # topographic distance inside macro areas needs the meteo points of the kh search: never silently ignored
         with pytest.raises(pb.PragaB200Error) as e:
             engine.glocal_detrending_raster(st.copy(), s_td, A.airTemperature, areas(), dem_id, dem.shape, (dem_id, dem_id))
-        assert e.value.status == A.PB_ERR_UNSUPPORTED
+        assert e.value.status == A.PB_ERR_INVALID
         s_off = clone(s)
         s_off.useGlocalDetrending = 0
         with pytest.raises(pb.PragaB200Error) as e:
@@ -198,3 +198,73 @@ def test_gpu_glocal_rejects_what_it_does_not_cover(engine):
         assert e.value.status == A.PB_ERR_INVALID
     finally:
         engine.free(dem_id)
+
+
+# ---- topographic distance inside macro areas: macroAreaDetrending ends with the area's own kh search over the area's meteo
+# points (interpolation.cpp:1811-1826), the area's cells are gridded with distance + kh * topographicDistance
+TD_CASES = ["two_piece", "lapse_codes", "modified_shepard", "shepard_lapse_codes"]
+
+
+def td_scenario(case):
+    dem, urban, st, s, areas = scenario(case)
+    s.useTD = 1
+    s.topoDist_maxKh = 24
+    return dem, urban, st, s, areas
+
+
+def test_reference_glocal_td_differs_from_plain(ref):
+    """sanity: with useTD the reference's grid changes (some area ends on kh != 0)."""
+    dem, urban, st, s, areas = td_scenario("two_piece")
+    ok, grid_td, *_ = ref.glocal_detrending_raster(st.copy(), clone(s), A.airTemperature, areas(), dem, (dem, urban), threads=1,
+                                                   meteo=st, observed=st.value)
+    s.useTD = 0
+    ok0, grid_0, *_ = ref.glocal_detrending_raster(st.copy(), clone(s), A.airTemperature, areas(), dem, (dem, urban), threads=1)
+    assert ok and ok0
+    assert np.abs(grid_td - grid_0).max() > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", TD_CASES)
+def test_gpu_glocal_topographic_distance(engine, ref, case):
+    import praga_b200 as pb
+    dem, urban, st, s, areas = td_scenario(case)
+    a_r, s_r = areas(), clone(s)
+    ok_r, grid_r, mn_r, mx_r, nv_r, _ = ref.glocal_detrending_raster(st.copy(), s_r, A.airTemperature, a_r, dem, (dem, urban),
+                                                                     threads=1, meteo=st, observed=st.value)
+    dem_id, urb_id = engine.upload(dem), engine.upload(urban)
+    try:
+        a_g, s_g = areas(), clone(s)
+        kh = np.full(a_g.n, -1, dtype=np.int32)
+        ok_g, grid_g, mn_g, mx_g, nv_g = engine.glocal_detrending_raster(st.copy(), s_g, A.airTemperature, a_g, dem_id, dem.shape,
+                                                                         (dem_id, urb_id), meteo=st, observed=st.value, area_kh=kh)
+        print("kh per area:", kh.tolist())
+        assert ok_g == ok_r and nv_g == nv_r
+        assert a_g.fits() == a_r.fits(), "area fits differ"
+        assert settings_equal(s_r, s_g), describe_diff(s_r, s_g)
+        assert (kh > 0).any(), "no area searched its way to kh != 0: the case does not exercise the ray march"
+        nod_r = (grid_r == np.float32(dem.flag)) | (grid_r == np.float32(A.NODATA))
+        nod_g = (grid_g == np.float32(dem.flag)) | (grid_g == np.float32(A.NODATA))
+        assert np.array_equal(nod_r, nod_g), "NODATA masks differ"
+        err = np.abs(grid_g.astype(np.float64) - grid_r.astype(np.float64))[~nod_r].max()
+        assert err <= 1e-4, err
+        assert abs(mn_g - mn_r) <= 1e-4 and abs(mx_g - mx_r) <= 1e-4
+        # resident cells: same bits
+        cid = engine.macro_areas_upload(a_g)
+        try:
+            a_c = areas()
+            ok_c, grid_c, *_ = engine.glocal_detrending_raster(st.copy(), clone(s), A.airTemperature, a_c, dem_id, dem.shape,
+                                                               (dem_id, urb_id), cells_id=cid, meteo=st, observed=st.value)
+            assert ok_c == ok_g and np.array_equal(grid_c, grid_g)
+        finally:
+            engine.macro_areas_free(cid)
+        # leave-one-out: macroAreaDetrending (kh search included) then interpolate() with the area's kh
+        ok2, res_r = ref.compute_residuals_glocal(st, st.value, st, clone(s_r), A.airTemperature, a_r, dem)
+        res_g = engine.compute_residuals_glocal(st, st.value, st, clone(s_g), A.airTemperature, a_g, dem_id=dem_id)
+        assert ok2 and np.array_equal(res_r, res_g), np.abs(res_r - res_g).max()
+        # without the meteo points the call refuses instead of skipping the search
+        with pytest.raises(pb.PragaB200Error) as e:
+            engine.glocal_detrending_raster(st.copy(), clone(s), A.airTemperature, areas(), dem_id, dem.shape, (dem_id, urb_id))
+        assert e.value.status == A.PB_ERR_INVALID
+    finally:
+        engine.free(dem_id)
+        engine.free(urb_id)
