@@ -344,6 +344,17 @@ int pb_compute_residuals_glocal_td(pb_context* ctx, const pb_stations* meteo, co
                                    const pb_stations* points, pb_settings* s, int variable, const pb_macro_area* areas, int nAreas,
                                    pb_raster_id dem, int excludeOutsideDem, int excludeSupplemental, float* residual);
 
+/* --- precomputed topographic-distance maps of the points: Crit3DMeteoPoint::topographicDistance (meteo/meteoPoint.h:121),
+ * one raster per meteo point written by gis::topographicDistanceMap (gis/gis.cpp:1650-1675) and loaded by
+ * Project::loadTopographicDistanceMaps (project/project.cpp:2368-2430); passDataToInterpolation hands the pointer to the
+ * interpolation point (interpolation/spatialControl.cpp:529). computeDistances (interpolation.cpp:232-247) then reads the
+ * map at the target's cell where the target lies inside it and only marches through the DEM where the map holds NODATA.
+ * pointIndex[k] = Crit3DInterpolationDataPoint::index of the point (matched against pb_stations.index, or the position
+ * when that is NULL), maps[k] = a resident raster (pb_raster_upload / pb_raster_read_esri / pb_topographic_distance_map
+ * with keep), or -1 to drop the point's map; n = 0 drops all. Every call with topographic distance on this context
+ * (rasters, points, leave-one-out, kh search, macro areas) consults the registry; freeing a raster drops it. */
+int pb_set_topographic_distance_maps(pb_context* ctx, const int32_t* pointIndex, const pb_raster_id* maps, int n);
+
 /* --- interpolate() at explicit targets (agrolib/interpolation/interpolation.h:77-79, .cpp:2502-2560) -------
  * The building block of computeResiduals (spatialControl.cpp:97-155): x, y are the f32 target coordinates,
  * proxyValues holds m * settings.nProxy doubles (the targets' own proxy values, NODATA where missing).

@@ -301,6 +301,20 @@ class Oracle:
                     stats={k: getattr(stats, k) for k, _ in A.pb_cv_stats._fields_} if cross_validate else None,
                     kh_series=[(series.kh[i], series.error[i]) for i in range(series.n)])
 
+    def set_topographic_distance_maps(self, point_index=(), maps=()):
+        """Crit3DMeteoPoint::topographicDistance of the points (reference only): maps = Raster objects; no arguments = drop all."""
+        fn = self.lib.ref_set_topographic_distance_maps
+        fn.restype = C.c_int
+        n = len(point_index)
+        if n == 0:
+            fn(None, None, C.c_int(0))
+            return
+        idx = (C.c_int32 * n)(*[int(i) for i in point_index])
+        arr = (A.pb_raster * n)()
+        for k, g in enumerate(maps):
+            arr[k] = g.as_pb()
+        fn(idx, arr, C.c_int(n))
+
     def interpolate_points(self, stations, settings, variable, x, y, z, proxy_values, exclude_supplemental=False):
         x = np.ascontiguousarray(x, dtype=np.float32)
         y = np.ascontiguousarray(y, dtype=np.float32)

@@ -27,6 +27,7 @@
 #include "solarRadiation.h"
 #include "radiationSettings.h"
 #include <string>
+#include <map>
 #include <vector>
 
 #include "commonConstants.h"
@@ -287,6 +288,15 @@ void exportSettings(Scenario& sc, pb_settings& s)
     s.nFitFunctions = int(funcs.size());
 }
 
+// Crit3DMeteoPoint::topographicDistance of the test scenario (Project::loadTopographicDistanceMaps, project.cpp:2368-2430),
+// keyed by point index; set through ref_set_topographic_distance_maps
+std::map<int, gis::Crit3DRasterGrid*> g_tdMaps;
+gis::Crit3DRasterGrid* tdMapOf(int index)
+{
+    auto it = g_tdMaps.find(index);
+    return it == g_tdMaps.end() ? nullptr : it->second;
+}
+
 void buildPoints(Scenario& sc, const pb_stations& st)
 {
     sc.points.resize(st.n);
@@ -296,6 +306,7 @@ void buildPoints(Scenario& sc, const pb_stations& st)
         p.point->utm.y = st.y[i];
         p.point->z = st.z[i];
         p.index = st.index ? st.index[i] : i;
+        p.topographicDistance = tdMapOf(p.index);        // passDataToInterpolation, spatialControl.cpp:529
         p.isActive = st.isActive ? st.isActive[i] != 0 : true;
         p.value = st.value[i];
         p.regressionWeight = st.regressionWeight ? st.regressionWeight[i] : float(NODATA);
@@ -319,6 +330,26 @@ void copyOut(const gis::Crit3DRasterGrid& g, pb_raster_out* out)
 extern "C" {
 
 int ref_max_threads(void) { return omp_get_max_threads(); }
+
+/* the points' precomputed topographic-distance maps (what Project::loadTopographicDistanceMaps leaves in
+ * Crit3DMeteoPoint::topographicDistance): every driver below hands them to its points; n = 0 drops all */
+int ref_set_topographic_distance_maps(const int32_t* pointIndex, const pb_raster* maps, int n)
+{
+    if (n <= 0) {
+        for (auto& kv : g_tdMaps) delete kv.second;
+        g_tdMaps.clear();
+        return PB_OK;
+    }
+    for (int k = 0; k < n; k++) {
+        auto it = g_tdMaps.find(pointIndex[k]);
+        if (it != g_tdMaps.end()) { delete it->second; g_tdMaps.erase(it); }
+        if (!maps[k].data && !maps[k].rows) continue;
+        gis::Crit3DRasterGrid* g = new gis::Crit3DRasterGrid();
+        fillGrid(*g, maps[k]);
+        g_tdMaps[pointIndex[k]] = g;
+    }
+    return PB_OK;
+}
 
 /* interpolationRaster, verbatim reference code. nThreads <= 0: all cores (the reference forces that anyway,
  * interpolationCmd.cpp:362-367; OMP_NUM_THREADS / omp_set_num_threads before the call is how we time 1 thread).
@@ -390,6 +421,7 @@ int ref_pre_interpolation_ex(pb_stations* st, pb_settings* s, int variable, cons
     for (int i = 0; i < st->n; i++) {
         sc.points[i].index = i;
         mp[i].active = true;
+        mp[i].topographicDistance = tdMapOf(i);
         mp[i].quality = quality::accepted;
         mp[i].currentValue = (cv && cv->currentValue) ? cv->currentValue[i] : st->value[i];
         mp[i].point.utm.x = st->x[i];
@@ -433,6 +465,7 @@ int ref_spatial_quality_control(const pb_stations* st, pb_settings* s, int varia
     std::vector<Crit3DMeteoPoint> mp(st->n);
     for (int i = 0; i < st->n; i++) {
         mp[i].active = true;
+        mp[i].topographicDistance = tdMapOf(i);
         mp[i].quality = quality::accepted;
         mp[i].currentValue = (cv && cv->currentValue) ? cv->currentValue[i] : st->value[i];
         mp[i].point.utm.x = st->x[i];
@@ -468,6 +501,7 @@ int ref_interpolation_dem(const pb_stations* meteo, pb_settings* sq, pb_settings
     std::vector<Crit3DMeteoPoint> mp(meteo->n);
     for (int i = 0; i < meteo->n; i++) {
         mp[i].active = true;
+        mp[i].topographicDistance = tdMapOf(i);
         mp[i].quality = quality::accepted;
         mp[i].currentValue = meteo->value[i];
         mp[i].point.utm.x = meteo->x[i];
@@ -911,6 +945,7 @@ void buildMeteoPoints(std::vector<Crit3DMeteoPoint>& mp, const pb_stations* mete
     mp.resize(meteo->n);
     for (int i = 0; i < meteo->n; i++) {
         mp[i].active = meteo->isActive ? meteo->isActive[i] != 0 : true;
+        mp[i].topographicDistance = tdMapOf(i);
         mp[i].quality = quality::accepted;
         mp[i].currentValue = observed ? observed[i] : meteo->value[i];
         mp[i].point.utm.x = meteo->x[i];

@@ -286,7 +286,8 @@ class Raster:
 class Stations:
     """SoA of std::vector<Crit3DInterpolationDataPoint> (interpolationPoint.h:14-31)."""
 
-    def __init__(self, x, y, z, value, proxy_values=None, lapse_rate_code=None, is_active=None, regression_weight=None):
+    def __init__(self, x, y, z, value, proxy_values=None, lapse_rate_code=None, is_active=None, regression_weight=None,
+                 index=None):
         self.x = np.ascontiguousarray(x, dtype=np.float64)
         self.y = np.ascontiguousarray(y, dtype=np.float64)
         self.z = np.ascontiguousarray(z, dtype=np.float64)
@@ -300,6 +301,8 @@ class Stations:
         self.is_active = None if is_active is None else np.ascontiguousarray(is_active, dtype=np.uint8)
         self.regression_weight = (None if regression_weight is None
                                   else np.ascontiguousarray(regression_weight, dtype=np.float32))
+        # Crit3DInterpolationDataPoint::index (the meteo point behind the interpolation point); None = the position
+        self.index = None if index is None else np.ascontiguousarray(index, dtype=np.int32)
 
     @property
     def n(self):
@@ -307,14 +310,15 @@ class Stations:
 
     def copy(self):
         return Stations(self.x, self.y, self.z, self.value.copy(), self.proxy_values, self.lapse_rate_code,
-                        self.is_active, self.regression_weight)
+                        self.is_active, self.regression_weight, self.index)
 
     def subset(self, keep):
         keep = np.asarray(keep, dtype=bool)
         return Stations(self.x[keep], self.y[keep], self.z[keep], self.value[keep], self.proxy_values[keep],
                         None if self.lapse_rate_code is None else self.lapse_rate_code[keep],
                         None if self.is_active is None else self.is_active[keep],
-                        None if self.regression_weight is None else self.regression_weight[keep])
+                        None if self.regression_weight is None else self.regression_weight[keep],
+                        None if self.index is None else self.index[keep])
 
     def as_pb(self):
         st = pb_stations()
@@ -330,4 +334,7 @@ class Stations:
             st.isActive = u8ptr(self.is_active)
         if self.proxy_values.size:
             st.proxyValues = fptr(self.proxy_values)
+        if self.index is not None:
+            self.index = np.ascontiguousarray(self.index, dtype=np.int32)
+            st.index = iptr(self.index)
         return st

@@ -73,7 +73,8 @@ cudaError_t launchClassicDetrend(const ClassicSetup& cs, const ClassicStations& 
                                  cudaStream_t s);
 cudaError_t launchClassicGather(const float* work, int n, int NP, int problem, float* out, cudaStream_t s);
 cudaError_t launchTopoMatrix(const float* tx, const float* ty, const float* tz, int nT, const float* sx, const float* sy,
-                             const float* sz, int nS, const DevGrid& dem, float* topo, cudaStream_t s);
+                             const float* sz, int nS, const DevGrid& dem, float* topo, cudaStream_t s,
+                             const DevGrid* tdMaps = nullptr);
 cudaError_t launchLooExact(const LooSetup& ls, const LooTargets& t, const float* sx, const float* sy, const float* work,
                            const ClassicProblem* problems, const float* topo, const int* khList, float* residual, cudaStream_t s,
                            float* estimate = nullptr);

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include "classic.cuh"
 #include "epilogue.cuh"
+#include "td_device.cuh"
 
 namespace pb {
 
@@ -610,46 +611,19 @@ __global__ void classic_gather_kernel(const float* __restrict__ work, int n, int
     if (i < n) out[i] = work[(size_t)i * NP + problem];
 }
 
-// gis::topographicDistance, gis/gis.cpp:1595-1647 (same code as td_kernels.cu: the march is a chain of f32 additions)
-__device__ __forceinline__ float topoDistancePair(const DevGrid& dem, float x1, float y1, float z1, float x2, float y2, float z2,
-                                                  float distance)
-{
-    const float stepMeter = float(dem.cellSize);
-    if (distance < stepMeter) return 0.f;
-    const int nrStep = int(distance / stepMeter);
-    float Xi, Yi, Zi, Xf, Yf;
-    if (z1 < z2) { Xi = x1; Yi = y1; Zi = z1; Xf = x2; Yf = y2; }
-    else { Xi = x2; Yi = y2; Zi = z2; Xf = x1; Yf = y1; }
-    const float dx = (Xf - Xi) / float(nrStep);
-    const float dy = (Yf - Yi) / float(nrStep);
-    float x = Xi, y = Yi, maxDeltaZ = 0.f;
-    for (int i = 1; i <= nrStep; i++) {
-        x = x + dx;
-        y = y + dy;
-        const int r = int((double(y) - dem.lly) * dem.invCellSize);
-        const int row = (dem.nrRows - 1) - r;
-        const int col = int((double(x) - dem.llx) * dem.invCellSize);
-        float demValue = dem.flag;
-        if (unsigned(row) < unsigned(dem.nrRows) && unsigned(col) < unsigned(dem.nrCols))
-            demValue = __ldg(dem.data + (size_t)row * dem.nrCols + col);
-        if (!isEqualF(demValue, dem.flag))
-            if (demValue > Zi) maxDeltaZ = (maxDeltaZ > demValue - Zi) ? maxDeltaZ : demValue - Zi;
-    }
-    return maxDeltaZ;
-}
-
 // topo[j * nS + i] = topographicDistance(target j -> station i) as computeDistances :244-247 calls it
 __global__ void __launch_bounds__(128) topo_matrix_kernel(const float* __restrict__ tx, const float* __restrict__ ty,
                                                           const float* __restrict__ tz, int nT, const float* __restrict__ sx,
                                                           const float* __restrict__ sy, const float* __restrict__ sz, int nS,
-                                                          DevGrid dem, float* __restrict__ topo)
+                                                          DevGrid dem, float* __restrict__ topo,
+                                                          const DevGrid* __restrict__ tdMaps)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= (long long)nT * nS) return;
     const int j = int(k / nS), i = int(k - (long long)j * nS);
     const float dx = sx[i] - tx[j], dy = sy[i] - ty[j];
     const float d = sqrtf(dx * dx + dy * dy);
-    topo[k] = topoDistancePair(dem, tx[j], ty[j], tz[j], sx[i], sy[i], sz[i], d);
+    topo[k] = topographicDistanceCachedDev(tdMaps, i, dem, tx[j], ty[j], tz[j], sx[i], sy[i], sz[i], d);
 }
 
 // retrend, classic branch (interpolation.cpp:1316-1347) with the problem's fitted proxies
@@ -887,11 +861,11 @@ cudaError_t launchClassicGather(const float* work, int n, int NP, int problem, f
 }
 
 cudaError_t launchTopoMatrix(const float* tx, const float* ty, const float* tz, int nT, const float* sx, const float* sy,
-                             const float* sz, int nS, const DevGrid& dem, float* topo, cudaStream_t s)
+                             const float* sz, int nS, const DevGrid& dem, float* topo, cudaStream_t s, const DevGrid* tdMaps)
 {
     if (nT <= 0 || nS <= 0) return cudaSuccess;
     const long long total = (long long)nT * nS;
-    topo_matrix_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(tx, ty, tz, nT, sx, sy, sz, nS, dem, topo);
+    topo_matrix_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(tx, ty, tz, nT, sx, sy, sz, nS, dem, topo, tdMaps);
     return cudaGetLastError();
 }
 

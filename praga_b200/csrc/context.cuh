@@ -3,6 +3,7 @@
 #pragma once
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -205,6 +206,10 @@ struct pb_context {
     std::mutex rasterMutex;                     // parent: guards lastRaster
     cudaEvent_t lastRaster = nullptr;           // parent: completion of the raster kernel launched last by any lane
     cudaEvent_t evRaster = nullptr;             // lane: completion of this lane's last raster kernel
+    // Crit3DMeteoPoint::topographicDistance: point index -> resident raster (pb_set_topographic_distance_maps), and the
+    // descriptors of the stations staged by the current call
+    std::unordered_map<int32_t, pb_raster_id> tdMaps;
+    pb::DevBuf<unsigned char> dTdMaps;
     pb::DevBuf<float> dMapT;                    // a lane's air temperature map of the hour (pb_meteo_grid_step_batch)
     pb::DevBuf<float> dAgg;                     // a lane's aggregation scratch (one float per point) + cell values
 };
@@ -214,6 +219,11 @@ namespace pb {
 int failCtx(pb_context* ctx, int code, const std::string& msg);     // engine.cu
 int ensureValidList(pb_context* ctx, RasterEntry& e);               // engine.cu
 int ensureRowStart(pb_context* ctx, RasterEntry& e);                // engine.cu
+// engine.cu: descriptors of the precomputed topographic-distance maps of n staged stations (pointIndex[k] = the station's
+// Crit3DInterpolationDataPoint::index), uploaded on ctx->stream; *out = nullptr when none of them has a map
+int stageTdMapsFor(pb_context* ctx, const int32_t* pointIndex, int n, const DevGrid** out);
+// the same for the stations the IDW / Shepard staging keeps (excludeSupplemental filter, same order)
+int stageTdMaps(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, const DevGrid** out);
 
 }  // namespace pb
 

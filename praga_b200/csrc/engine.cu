@@ -33,10 +33,11 @@ cudaError_t launchIdwPoints(const DevStations& st, const DevModel& m, const floa
 cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);
 // td_kernels.cu
 cudaError_t launchIdwTdRaster(const DevStations& st, const float* sz, const DevModel& m, const DevGrid& dem, int kh,
-                              const int* validIdx, int nTargets, float* out, unsigned* minmax, cudaStream_t s);
+                              const int* validIdx, int nTargets, float* out, unsigned* minmax, cudaStream_t s,
+                              const DevGrid* tdMaps = nullptr);
 cudaError_t launchIdwTdPoints(const DevStations& st, const float* sz, const DevModel& m, const DevGrid& dem, int kh,
                               const float* tx, const float* ty, const float* tz, const double* tproxy, int nTargets, float* out,
-                              cudaStream_t s);
+                              cudaStream_t s, const DevGrid* tdMaps = nullptr);
 cudaError_t launchRowStart(const int* validIdx, long long total, int nrRows, int nrCols, long long* rowStart, cudaStream_t s);
 cudaError_t launchFillValid(float* out, const int* validIdx, int n, float v, cudaStream_t s);
 // peaks.cu
@@ -294,6 +295,47 @@ int stageShepardStations(pb_context* ctx, const pb_stations* st, const pb_settin
     ss.z = reinterpret_cast<const float*>(d + offZ);
     ss.n = int(n);
     return PB_OK;
+}
+
+int stageTdMapsForImpl(pb_context* ctx, const int32_t* pointIndex, int n, const DevGrid** out)
+{
+    *out = nullptr;
+    const pb_context* owner = ctx->parent ? ctx->parent : ctx;      // a lane reads its parent's registry (and rasters)
+    if (owner->tdMaps.empty() || n <= 0) return PB_OK;
+    std::vector<DevGrid> g(n);
+    bool any = false;
+    for (int k = 0; k < n; k++) {
+        g[k] = DevGrid{};
+        auto it = owner->tdMaps.find(pointIndex[k]);
+        if (it == owner->tdMaps.end()) continue;
+        const pb_raster_id id = it->second;
+        if (id < 0 || id >= (int)owner->rasters.size() || !owner->rasters[id].used)
+            return fail(ctx, PB_ERR_INVALID, "a registered topographic-distance map is no longer a live raster");
+        g[k] = devGridOf(owner->rasters[id]);
+        any = true;
+    }
+    if (!any) return PB_OK;
+    CUDA_TRY(ctx, ctx->dTdMaps.reserve(size_t(n) * sizeof(DevGrid)));
+    // (pageable source: the call returns once the descriptors sit in the driver's staging buffer)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dTdMaps.p, g.data(), size_t(n) * sizeof(DevGrid), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->timing.h2d_bytes += (int64_t)(size_t(n) * sizeof(DevGrid));
+    *out = reinterpret_cast<const DevGrid*>(ctx->dTdMaps.p);
+    return PB_OK;
+}
+
+int stageTdMapsImpl(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, const DevGrid** out)
+{
+    *out = nullptr;
+    const pb_context* owner = ctx->parent ? ctx->parent : ctx;
+    if (owner->tdMaps.empty()) return PB_OK;
+    std::vector<int32_t> idx;
+    idx.reserve(st->n);
+    for (int i = 0; i < st->n; i++) {
+        const int code = st->lapseRateCode ? st->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+        if (excludeSupplemental && !checkLapseRateCode(code, s->useLapseRateCode != 0, false)) continue;
+        idx.push_back(st->index ? st->index[i] : i);
+    }
+    return stageTdMapsForImpl(ctx, idx.data(), int(idx.size()), out);
 }
 
 constexpr size_t kStageSlotBytes = size_t(8) << 20;
@@ -1046,12 +1088,19 @@ int rasterCore(pb_context* ctx, const pb_stations* st, const pb_settings* s, int
         ShepardTd std_{};
         std_.kh = usesTopographicDistance(s, variable) ? s->topoDist_Kh : 0;
         std_.dem = dg;
+        if (std_.kh != 0) {
+            rc = stageTdMapsImpl(ctx, st, s, true, &std_.maps);
+            if (rc) return rc;
+        }
         CUDA_TRY(ctx, launchShepardRaster(ss, m, dg, shepardR0, s->method == PB_METHOD_SHEPARD_MODIFIED, dem.validIdx + t0,
                                           nTargets, ctx->dOut.p, ctx->dMinMax, ctx->stream, &std_));
     } else if (usesTopographicDistance(s, variable)) {
         // the march needs the whole DEM (a ray reaches any station): `dem` is the full resident raster also for a row band
+        const DevGrid* tdMaps = nullptr;
+        rc = stageTdMapsImpl(ctx, st, s, true, &tdMaps);
+        if (rc) return rc;
         CUDA_TRY(ctx, launchIdwTdRaster(ds, ds.z, m, dg, s->topoDist_Kh, dem.validIdx + t0, nTargets, ctx->dOut.p, ctx->dMinMax,
-                                        ctx->stream));
+                                        ctx->stream, tdMaps));
     } else {
         pb_context* par = ctx->parent;
         if (par && ctx->reserveSms > 0) {
@@ -1183,6 +1232,14 @@ int stageAllStations(pb_context* ctx, const pb_stations* st, LocalStations& ds) 
 void applyPreFitToSettings(const pb_settings& s, const LocalModel& m, const PreFit& f, pb_settings& o)
 {
     applyPreFit(s, m, f, nullptr, true, o);
+}
+int stageTdMapsFor(pb_context* ctx, const int32_t* pointIndex, int n, const DevGrid** out)
+{
+    return stageTdMapsForImpl(ctx, pointIndex, n, out);
+}
+int stageTdMaps(pb_context* ctx, const pb_stations* st, const pb_settings* s, bool excludeSupplemental, const DevGrid** out)
+{
+    return stageTdMapsImpl(ctx, st, s, excludeSupplemental, out);
 }
 int ensureValidList(pb_context* ctx, RasterEntry& e) { return ensureValidListImpl(ctx, e); }
 int ensureRowStart(pb_context* ctx, RasterEntry& e) { return ensureRowStartImpl(ctx, e); }
@@ -1321,6 +1378,26 @@ int pb_raster_free(pb_context* ctx, pb_raster_id id)
     cudaStreamSynchronize(ctx->stream);
     freeEntry(ctx, ctx->rasters[id]);
     if (ctx->outInitRaster == id) ctx->outInitRaster = -1;
+    for (auto it = ctx->tdMaps.begin(); it != ctx->tdMaps.end();)       // a freed map no longer belongs to its point
+        if (it->second == id) it = ctx->tdMaps.erase(it);
+        else ++it;
+    return PB_OK;
+}
+
+/* Crit3DMeteoPoint::topographicDistance of the points (Project::loadTopographicDistanceMaps); see include/praga_b200.h */
+int pb_set_topographic_distance_maps(pb_context* ctx, const int32_t* pointIndex, const pb_raster_id* maps, int n)
+{
+    PB_NVTX_RANGE();
+    if (!ctx) return PB_ERR_INVALID;
+    if (n > 0 && (!pointIndex || !maps)) return fail(ctx, PB_ERR_INVALID, "null argument");
+    if (n <= 0) { ctx->tdMaps.clear(); return PB_OK; }
+    for (int k = 0; k < n; k++)
+        if (maps[k] >= 0 && (maps[k] >= (int)ctx->rasters.size() || !ctx->rasters[maps[k]].used))
+            return fail(ctx, PB_ERR_INVALID, "topographic-distance map is not a live raster");
+    for (int k = 0; k < n; k++) {
+        if (maps[k] < 0) ctx->tdMaps.erase(pointIndex[k]);
+        else ctx->tdMaps[pointIndex[k]] = maps[k];
+    }
     return PB_OK;
 }
 
@@ -1782,17 +1859,23 @@ static int interpolatePointsImpl(pb_context* ctx, const pb_stations* st, const p
             std_.kh = s->topoDist_Kh;
             std_.dem = devGridOf(ctx->rasters[demId]);
             std_.tz = reinterpret_cast<const float*>(d + offZ);
+            rc = stageTdMapsImpl(ctx, st, s, excludeSupplemental != 0, &std_.maps);
+            if (rc) return rc;
         }
         CUDA_TRY(ctx, launchShepardPoints(ss, mod, shepardR0, s->method == PB_METHOD_SHEPARD_MODIFIED,
                                           reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                           reinterpret_cast<const double*>(d + offP), m, reinterpret_cast<float*>(d + offO),
                                           ctx->stream, &std_));
     }
-    else if (td)
+    else if (td) {
+        const DevGrid* tdMaps = nullptr;
+        rc = stageTdMapsImpl(ctx, st, s, excludeSupplemental != 0, &tdMaps);
+        if (rc) return rc;
         CUDA_TRY(ctx, launchIdwTdPoints(ds, ds.z, mod, devGridOf(ctx->rasters[demId]), s->topoDist_Kh,
                                         reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                         reinterpret_cast<const float*>(d + offZ), reinterpret_cast<const double*>(d + offP), m,
-                                        reinterpret_cast<float*>(d + offO), ctx->stream));
+                                        reinterpret_cast<float*>(d + offO), ctx->stream, tdMaps));
+    }
     else
         CUDA_TRY(ctx, launchIdwPoints(ds, mod, reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                       reinterpret_cast<const double*>(d + offP), m, reinterpret_cast<float*>(d + offO), ctx->stream));

@@ -52,7 +52,7 @@ cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);
 // td_kernels.cu
 cudaError_t launchIdwTdPoints(const DevStations& st, const float* sz, const DevModel& m, const DevGrid& dem, int kh,
                               const float* tx, const float* ty, const float* tz, const double* tproxy, int nTargets, float* out,
-                              cudaStream_t s);
+                              cudaStream_t s, const DevGrid* tdMaps = nullptr);
 
 // which proxies getSignificantProxyValuesXY looks up (active && significant, grid loaded)
 struct GlocalLookup {
@@ -644,16 +644,23 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
             std_.kh = useTD ? subs[a].s.topoDist_Kh : 0;
             std_.dem = dg;
             std_.tz = reinterpret_cast<const float*>(d + offZ);
+            if (std_.kh != 0) {
+                rc = stageTdMaps(ctx, &subs[a].st, &subs[a].s, true, &std_.maps);
+                if (rc) return rc;
+            }
             CUDA_TRY(ctx, launchShepardPoints(ss, mods[a], R0, s->method == PB_METHOD_SHEPARD_MODIFIED,
                                               reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                               reinterpret_cast<const double*>(d + offPv), nCells,
                                               reinterpret_cast<float*>(d + offRes), ctx->stream, &std_));
-        } else if (useTD && subs[a].s.topoDist_Kh != 0)
+        } else if (useTD && subs[a].s.topoDist_Kh != 0) {
+            const DevGrid* tdMaps = nullptr;        // (restaged per area: the copy is ordered behind the previous area's kernel)
+            rc = stageTdMaps(ctx, &subs[a].st, &subs[a].s, true, &tdMaps);
+            if (rc) return rc;
             CUDA_TRY(ctx, launchIdwTdPoints(dss[a], dss[a].z, mods[a], dg, subs[a].s.topoDist_Kh,
                                             reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                             reinterpret_cast<const float*>(d + offZ), reinterpret_cast<const double*>(d + offPv),
-                                            nCells, reinterpret_cast<float*>(d + offRes), ctx->stream));
-        else
+                                            nCells, reinterpret_cast<float*>(d + offRes), ctx->stream, tdMaps));
+        } else
         CUDA_TRY(ctx, launchIdwPoints(dss[a], mods[a], reinterpret_cast<const float*>(d + offX), reinterpret_cast<const float*>(d + offY),
                                       reinterpret_cast<const double*>(d + offPv), nCells, reinterpret_cast<float*>(d + offRes),
                                       ctx->stream));

@@ -22,6 +22,7 @@ struct ShepardTd {
     int kh;                        // 0: planar distances only
     DevGrid dem;
     const float* tz;
+    const DevGrid* maps;           // the stations' precomputed maps (td_device.cuh), nullptr = none
 };
 
 cudaError_t launchShepardRaster(const ShepardStations& st, const DevModel& m, const DevGrid& dem, float R0, bool modified,

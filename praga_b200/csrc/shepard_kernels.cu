@@ -85,7 +85,7 @@ shepard_kernel(ShepardStations st, DevModel m, DevGrid dem, float R0, const int*
                 float d = sqrtf(d2);
                 if (TD) {
                     // computeDistances :226-251: distance += kh * topographicDistance(x, y, z, point x, y, z, distance, DEM)
-                    const float topo = topographicDistanceDev(td.dem, x, y, z, __ldg(st.x + i), __ldg(st.y + i), __ldg(st.z + i), d);
+                    const float topo = topographicDistanceCachedDev(td.maps, i, td.dem, x, y, z, __ldg(st.x + i), __ldg(st.y + i), __ldg(st.z + i), d);
                     d += (td.kh * topo);
                 }
                 if (!(fabs(double(d)) < kEpsilon)) insertNear(all5, n5, d, i);       // sortPointsByDistance drops |d| < EPSILON

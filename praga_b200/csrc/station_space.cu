@@ -88,7 +88,7 @@ int shepardLoo(pb_context* ctx, const pb_settings* sp, int variable, int nS, con
                const float* sval, const int* scode, int nT, const float* tx, const float* ty, const float* tproxy /* nT * max(P,1) */,
                const int* tcode, const uint8_t* tinside, const float* tobs, int excludeOutsideDem, int excludeSupplemental,
                float* residual, float* estimate, const uint8_t* sactive = nullptr, const float* tz = nullptr,
-               pb_raster_id demId = -1)
+               pb_raster_id demId = -1, const int32_t* sindex = nullptr)
 {
     const int P = sp->nProxy;
     const size_t Pp = std::max(P, 1);
@@ -102,6 +102,7 @@ int shepardLoo(pb_context* ctx, const pb_settings* sp, int variable, int nS, con
     st.lapseRateCode = code.data();
     st.proxyValues = proxy.data();              // interpolate() never reads the points' own proxy values
     st.isActive = sactive;
+    st.index = sindex;
     std::vector<double> pv(size_t(nT) * Pp);
     for (size_t k = 0; k < pv.size(); k++) pv[k] = double(tproxy[k]);
     // (tz / demId: the topographic distance of computeDistances, read only when the settings switch it on with kh != 0)
@@ -390,6 +391,8 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
     // ---- leave-one-out tables ----
     std::vector<float> mae;
     std::vector<float> hWork;                 // host copy of the detrended values of every problem (Shepard cross-validation)
+    std::vector<int32_t> ipIndex(m);          // Crit3DInterpolationDataPoint::index: the points' precomputed topographic-distance maps
+    for (int k = 0; k < m; k++) ipIndex[k] = st->index ? st->index[ip[k]] : ip[k];
     // Shepard estimators: MAE of combination p at kh, computed when a search asks for it (one K8 point-form call over that
     // combination's detrended points and regression fields) and kept
     std::map<std::tuple<int, int, int>, float> shepardMae;
@@ -421,7 +424,7 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
         const pb_timing acc = ctx->timing;
         shepardRc = shepardLoo(ctx, &sp, variable, m, sxd.data(), syd.data(), hz.data(), col.data(), hcode.data(), n, gx.data(),
                                gy.data(), gproxy.data(), gcode.data(), gin.data(), gobs.data(), excludeOutsideDem, 1, res.data(),
-                               nullptr, hact.data(), gzf.data(), useTD ? demId : -1);
+                               nullptr, hact.data(), gzf.data(), useTD ? demId : -1, ipIndex.data());
         if (shepardRc) return kNoData;
         ctx->timing.launches += acc.launches;
         ctx->timing.kernel_ms += acc.kernel_ms;
@@ -461,7 +464,10 @@ extern "C" int pb_pre_interpolation_ex(pb_context* ctx, pb_stations* st, pb_sett
 
     if (topoTable) {
         const DevGrid dem = devGridOfRaster(ctx->rasters[demId]);
-        CUDA_TRY(ctx, launchTopoMatrix(tX, tY, tZf, n, dX, dY, dZf, m, dem, dTopo, stream));
+        const DevGrid* tdMaps = nullptr;
+        int rcm = stageTdMapsFor(ctx, ipIndex.data(), m, &tdMaps);
+        if (rcm) return rcm;
+        CUDA_TRY(ctx, launchTopoMatrix(tX, tY, tZf, n, dX, dY, dZf, m, dem, dTopo, stream, tdMaps));
         ctx->timing.launches++;
     }
 
@@ -590,6 +596,7 @@ struct LooArrays {
     std::vector<double> sz;
     std::vector<int> scode;
     std::vector<double> sxd, syd;           // the Shepard estimators take the direction cosines from the f64 coordinates
+    std::vector<int32_t> sindex;            // Crit3DInterpolationDataPoint::index: the points' precomputed topographic-distance maps
 };
 
 // problem = what the settings say about classic detrending (current combination + the proxies' regression fields)
@@ -624,7 +631,8 @@ int exactLoo(pb_context* ctx, const LooArrays& a, const pb_settings* s, int vari
         }
         return shepardLoo(ctx, s, variable, nS, a.sxd.data(), a.syd.data(), a.sz.data(), a.sval.data(), a.scode.data(), nT,
                           a.tx.data(), a.ty.data(), a.tproxy.data(), a.tcode.data(), a.tin.data(), a.tobs.data(), excludeOutsideDem,
-                          excludeSupplemental, residual, estimate, nullptr, a.tz.data(), useTD ? demId : -1);
+                          excludeSupplemental, residual, estimate, nullptr, a.tz.data(), useTD ? demId : -1,
+                          a.sindex.size() == size_t(nS) ? a.sindex.data() : nullptr);
     }
     size_t bytes = 0;
     auto add = [&](size_t count, size_t size) { bytes += (count * size + 255) / 256 * 256; };
@@ -675,7 +683,12 @@ int exactLoo(pb_context* ctx, const LooArrays& a, const pb_settings* s, int vari
     CUDA_TRY(ctx, up(dKh, &kh, 4));
     CUDA_TRY(ctx, batch.flush(ctx, stream));
     if (useTD) {
-        CUDA_TRY(ctx, launchTopoMatrix(tX, tY, tZ, nT, sX, sY, sZf, nS, devGridOfRaster(ctx->rasters[demId]), dTopo, stream));
+        const DevGrid* tdMaps = nullptr;
+        if (a.sindex.size() == size_t(nS)) {
+            int rcm = stageTdMapsFor(ctx, a.sindex.data(), nS, &tdMaps);
+            if (rcm) return rcm;
+        }
+        CUDA_TRY(ctx, launchTopoMatrix(tX, tY, tZ, nT, sX, sY, sZf, nS, devGridOfRaster(ctx->rasters[demId]), dTopo, stream, tdMaps));
         ctx->timing.launches++;
     }
     if (residual || estimate) {
@@ -783,8 +796,10 @@ void fillTargets(LooArrays& a, const pb_stations* st, const std::vector<int>& tI
 void fillSources(LooArrays& a, const pb_stations* pts, const uint8_t* keep)
 {
     a.sx.clear(); a.sy.clear(); a.szf.clear(); a.sval.clear(); a.sz.clear(); a.scode.clear(); a.sxd.clear(); a.syd.clear();
+    a.sindex.clear();
     for (int i = 0; i < pts->n; i++) {
         if (keep && !keep[i]) continue;
+        a.sindex.push_back(pts->index ? pts->index[i] : i);
         a.sxd.push_back(pts->x[i]);
         a.syd.push_back(pts->y[i]);
         a.sx.push_back(float(pts->x[i]));
@@ -800,18 +815,19 @@ void fillSources(LooArrays& a, const pb_stations* pts, const uint8_t* keep)
 struct SubStations {
     std::vector<double> x, y, z;
     std::vector<float> value, weight, proxy;
-    std::vector<int32_t> code;
+    std::vector<int32_t> code, index;
     pb_stations st{};
     SubStations(const pb_stations* src, const std::vector<int>& idx, const float* values)
     {
         const size_t n = idx.size(), P = size_t(std::max(src->nProxy, 0));
-        x.resize(n); y.resize(n); z.resize(n); value.resize(n); code.resize(n);
+        x.resize(n); y.resize(n); z.resize(n); value.resize(n); code.resize(n); index.resize(n);
         proxy.resize(n * std::max<size_t>(P, 1));
         for (size_t k = 0; k < n; k++) {
             const int i = idx[k];
             x[k] = src->x[i]; y[k] = src->y[i]; z[k] = src->z[i];
             value[k] = values[i];
             code[k] = src->lapseRateCode ? src->lapseRateCode[i] : PB_LAPSE_PRIMARY;
+            index[k] = src->index ? src->index[i] : i;      // the view keeps the points' identity
             for (size_t q = 0; q < P; q++) proxy[k * P + q] = src->proxyValues[size_t(i) * P + q];
         }
         st.n = int(n);
@@ -820,6 +836,7 @@ struct SubStations {
         st.value = value.data();
         st.lapseRateCode = code.data();
         st.proxyValues = proxy.data();
+        st.index = index.data();
     }
 };
 

@@ -34,4 +34,30 @@ __device__ __forceinline__ float topographicDistanceDev(const DevGrid& dem, floa
     return maxDeltaZ;
 }
 
+// computeDistances (interpolation.cpp:226-251) in front of the march: the point's precomputed map
+// (Crit3DInterpolationDataPoint::topographicDistance, written by gis::topographicDistanceMap gis.cpp:1650-1675 and loaded
+// by Project::loadTopographicDistanceMaps project.cpp:2368-2430) where the target lies inside it; NODATA there (or no map)
+// => topographicDistance() on the current DEM. maps: one descriptor per staged station, data == nullptr = no map.
+__device__ __forceinline__ float topographicDistanceCachedDev(const DevGrid* __restrict__ maps, int i, const DevGrid& dem, float x1,
+                                                              float y1, float z1, float x2, float y2, float z2, float distance)
+{
+    if (maps) {
+        const DevGrid& g = maps[i];
+        if (g.data) {
+            const double x = double(x1), y = double(y1);
+            // isOutOfGridXY (gis.cpp:840-845), getRowColFromXY (:735-739)
+            const bool out = (x < g.llx) || (y < g.lly) || (x >= (g.llx + g.nrCols * g.cellSize)) || (y >= (g.lly + g.nrRows * g.cellSize));
+            if (!out) {
+                const int row = (g.nrRows - 1) - int(floor((y - g.lly) * g.invCellSize));
+                const int col = int(floor((x - g.llx) * g.invCellSize));
+                if (unsigned(row) < unsigned(g.nrRows) && unsigned(col) < unsigned(g.nrCols)) {
+                    const float topo = __ldg(g.data + (size_t)row * g.nrCols + col);
+                    if (!isEqualF(topo, kNoData)) return topo;
+                }
+            }
+        }
+    }
+    return topographicDistanceDev(dem, x1, y1, z1, x2, y2, z2, distance);
+}
+
 }  // namespace pb

@@ -5,7 +5,8 @@
 // DEM cell each step samples, so it is reproduced operation by operation (this TU is built with -fmad=false) and the
 // weights are summed in f64 in station order like inverseDistanceWeighted (:1031-1051): the result is bit-identical.
 // One thread per target; the DEM stays in L2 (the march of neighbouring targets touches neighbouring cells).
-// Per-station precomputed TD rasters (Crit3DInterpolationDataPoint::topographicDistance) are not part of this path.
+// Per-station precomputed TD rasters (Crit3DInterpolationDataPoint::topographicDistance, pb_set_topographic_distance_maps)
+// are read in front of the march like computeDistances does (td_device.cuh).
 #include "epilogue.cuh"
 #include "td_device.cuh"
 
@@ -21,7 +22,8 @@ template <bool POINTS>
 __global__ void __launch_bounds__(128)
 idw_td_kernel(DevStations st, const float* __restrict__ sz, DevModel m, DevGrid dem, int kh, const int* __restrict__ validIdx,
               int nTargets, const float* __restrict__ tx, const float* __restrict__ ty, const float* __restrict__ tz,
-              const double* __restrict__ tproxy, float* __restrict__ out, unsigned* __restrict__ minmax)
+              const double* __restrict__ tproxy, float* __restrict__ out, unsigned* __restrict__ minmax,
+              const DevGrid* __restrict__ tdMaps)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     float vmin = INFINITY, vmax = -INFINITY;
@@ -42,7 +44,7 @@ idw_td_kernel(DevStations st, const float* __restrict__ sz, DevModel m, DevGrid 
             const float px = st.x[i], py = st.y[i];
             const float dx = px - x, dy = py - y;
             float d = sqrtf(dx * dx + dy * dy);
-            const float topo = topographicDistanceDev(dem, x, y, z, px, py, sz[i], d);
+            const float topo = topographicDistanceCachedDev(tdMaps, i, dem, x, y, z, px, py, sz[i], d);
             d += (kh * topo);
             if (d > 0.f) {
                 const double dk = double(d) / 10000.;
@@ -85,21 +87,22 @@ idw_td_kernel(DevStations st, const float* __restrict__ sz, DevModel m, DevGrid 
 }
 
 cudaError_t launchIdwTdRaster(const DevStations& st, const float* sz, const DevModel& m, const DevGrid& dem, int kh,
-                              const int* validIdx, int nTargets, float* out, unsigned* minmax, cudaStream_t s)
+                              const int* validIdx, int nTargets, float* out, unsigned* minmax, cudaStream_t s,
+                              const DevGrid* tdMaps)
 {
     if (nTargets <= 0) return cudaSuccess;
     idw_td_kernel<false><<<(nTargets + 127) / 128, 128, 0, s>>>(st, sz, m, dem, kh, validIdx, nTargets, nullptr, nullptr, nullptr,
-                                                               nullptr, out, minmax);
+                                                               nullptr, out, minmax, tdMaps);
     return cudaGetLastError();
 }
 
 cudaError_t launchIdwTdPoints(const DevStations& st, const float* sz, const DevModel& m, const DevGrid& dem, int kh,
                               const float* tx, const float* ty, const float* tz, const double* tproxy, int nTargets, float* out,
-                              cudaStream_t s)
+                              cudaStream_t s, const DevGrid* tdMaps)
 {
     if (nTargets <= 0) return cudaSuccess;
     idw_td_kernel<true><<<(nTargets + 127) / 128, 128, 0, s>>>(st, sz, m, dem, kh, nullptr, nTargets, tx, ty, tz, tproxy, out,
-                                                              nullptr);
+                                                              nullptr, tdMaps);
     return cudaGetLastError();
 }
 

@@ -110,6 +110,7 @@ def load_library():
     lib.pb_compute_residuals_glocal_td.argtypes = [C.c_void_p, P(A.pb_stations), P(C.c_float), P(A.pb_cv_points), P(A.pb_stations),
                                                    P(A.pb_settings), C.c_int, P(A.pb_macro_area), C.c_int, C.c_int32, C.c_int,
                                                    C.c_int, P(C.c_float)]
+    lib.pb_set_topographic_distance_maps.argtypes = [C.c_void_p, P(C.c_int32), P(C.c_int32), C.c_int]
     lib.pb_macro_areas_upload.argtypes = [C.c_void_p, P(A.pb_macro_area), C.c_int, P(C.c_int32)]
     lib.pb_macro_areas_free.argtypes = [C.c_void_p, C.c_int32]
     lib.pb_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -282,6 +283,17 @@ class Engine:
         rc = self._check(fn(self.h, C.byref(st), C.byref(settings), variable, dem_id, ids, len(proxy_ids), row_begin,
                             row_end, C.byref(o)), allow=(A.PB_ERR_NO_VALID_CELL,))
         return rc == A.PB_OK, out, o.minimum, o.maximum, o.nValid
+
+    def set_topographic_distance_maps(self, point_index=(), map_ids=()):
+        """Crit3DMeteoPoint::topographicDistance (Project::loadTopographicDistanceMaps, project.cpp:2368-2430): the points'
+        precomputed maps as resident raster ids, keyed by Crit3DInterpolationDataPoint::index; no arguments = drop all."""
+        n = len(point_index)
+        if n == 0:
+            self._check(self.lib.pb_set_topographic_distance_maps(self.h, None, None, 0))
+            return
+        idx = (C.c_int32 * n)(*[int(i) for i in point_index])
+        ids = (C.c_int32 * n)(*[int(i) for i in map_ids])
+        self._check(self.lib.pb_set_topographic_distance_maps(self.h, idx, ids, n))
 
     # ---- interpolate() at explicit targets (interpolation.cpp:2502) ----
     def interpolate_points(self, stations, settings, variable, x, y, proxy_values, exclude_supplemental=False, z=None,
