@@ -493,7 +493,10 @@ int buildLocalModel(pb_context* ctx, const pb_settings* s, int variable, int nSt
         if (!useDetrendingVar(variable) || !s->useLocalDetrending)      // project.cpp:3155
             return fail(ctx, PB_ERR_INVALID, "local detrending needs useLocalDetrending and a detrending variable");
         if (!s->useMultipleDetrending)
-            return fail(ctx, PB_ERR_UNSUPPORTED, "local detrending without multiple detrending is outside the hot-path scope (DESIGN.md)");
+            // (the reference's settings dialog switches multiple detrending on with local detrending,
+            // project/dialogInterpolation.cpp:251-268: only a hand-edited .ini reaches this combination; there the classic
+            // regression state would leak from cell to cell in OpenMP schedule order, so there is no single reference answer)
+            return fail(ctx, PB_ERR_UNSUPPORTED, "local detrending needs multiple detrending (as the reference's settings dialog enforces)");
     }
     if (s->useGlocalDetrending) return fail(ctx, PB_ERR_UNSUPPORTED, "glocal detrending runs through pb_glocal_detrending_fitting / pb_glocal_detrending_raster (macro areas needed)");
     if (!s->hasPointsRange && !range)     // setMultipleDetrendingHeightTemperatureRange returns false (:1508)

@@ -66,52 +66,80 @@ __device__ __forceinline__ void blockMinMax(float v, bool valid, unsigned* minma
     }
 }
 
-// relHumFromTdew(float Td, float T), meteo.cpp:301-315. The reference evaluates pow(exp(a), esp); exp(a * esp) is the same
-// number to ~1e-15 relative (far inside the float result's half ulp except at rounding ties, and the parity bar is 1e-4)
-// at a quarter of the FP64 instructions, which is what bounds this map.
-__device__ __forceinline__ float relHumFromTdewDev(float Td, float T)
+// isEqual(float, float) = fabs(double(a) - double(b)) < EPSILON (basicMath.cpp) without FP64 on the fast side: the float
+// difference is the correctly rounded exact difference, so it only disagrees with the double test inside a hair of EPSILON;
+// there (never in practice) the double test decides. The HBM-bound map kernels below run six of these per cell.
+__device__ __forceinline__ bool isEqualQ(float a, float b)
 {
-    if (isEqualF(Td, kNoData) || isEqualF(T, kNoData)) return kNoData;
-    const double d = 237.3;
-    const double c = 17.2693882;
-    const double esp = 1 / (double(T) + d);
-    // c T / (T + d) as c T esp: one FP64 division per cell instead of two (same ~1e-16 argument as above)
-    double rh = exp(((c * double(Td)) - ((c * double(T)) * esp) * (double(Td) + d)) * esp);
-    rh *= 100;
-    if (rh > 100) return 100;
-    return fmaxf(1.f, float(rh));
+    const float diff = fabsf(a - b);
+    if (diff < 0.99e-5f) return true;
+    if (diff > 1.01e-5f) return false;
+    return isEqualF(a, b);
 }
 
-// four cells per thread (128-bit loads / stores when the buffers allow it), scalar tail
+// relHumFromTdew(float Td, float T), meteo.cpp:301-315: rh = 100 pow(exp(c Td - (c T / (T + d)) (Td + d)), 1 / (T + d)).
+// The exponent collapses algebraically to a = c d (Td - T) / (T + d)^2 (the two products cancel term by term), which has no
+// cancellation left: a is taken in FP64 (a handful of instructions, one division), split into a float head and tail, and
+// the exponential is FP32: exp(a) = expf(hi) (1 + lo). Against the reference's FP64 pow(exp()) the map agrees to ~1e-5 in
+// RH units (expf is good to 1 ulp, 6e-8 of at most 100; the parity bar is 1e-4) at a tenth of the FP64 instructions, which
+// is what bounded this map (0.12-0.14 of the HBM roofline).
+__device__ __forceinline__ float relHumFromTdewDev(float Td, float T)
+{
+    if (isEqualQ(Td, kNoData) || isEqualQ(T, kNoData)) return kNoData;
+    const double d = 237.3;
+    const double c = 17.2693882;
+    const double td = double(T) + d;
+    // 1 / (T + d)^2: FP32 reciprocal as the seed, one Newton step in FP64 (relative error ~4e-15; an IEEE division would
+    // cost as much as everything else here together)
+    const double q = td * td;
+    const double x0 = double(1.f / float(q));
+    const double x1 = fma(x0, fma(-q, x0, 1.0), x0);
+    const double a = ((c * d) * (double(Td) - double(T))) * x1;
+    const float hi = float(a);
+    const float lo = fabsf(hi) < 80.f ? float(a - double(hi)) : 0.f;
+    const float e = expf(hi);
+    const float rh = fmaf(e, lo, e) * 100.f;
+    if (rh > 100.f) return 100.f;
+    return fmaxf(1.f, rh);
+}
+
+// four cells per thread and iteration (128-bit loads / stores), grid-stride over the map, scalar tail; min / max leave the CTA
+// as ONE atomic pair (a pair per warp on the same two words serialises in L2: 1.5 M atomics cost more than the 1.2 GB of traffic)
 __global__ void __launch_bounds__(256) relative_humidity_map_kernel(const float* __restrict__ airT, float flagT,
                                                                     const float* __restrict__ dewT, float flagTd, long long n,
                                                                     float outFlag, float* __restrict__ out,
                                                                     unsigned* __restrict__ minmax)
 {
-    const long long k0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    float tv[4], dv[4], ov[4];
-    const bool full = k0 + 3 < n;
-    if (full) {
-        *reinterpret_cast<float4*>(tv) = *reinterpret_cast<const float4*>(airT + k0);
-        *reinterpret_cast<float4*>(dv) = *reinterpret_cast<const float4*>(dewT + k0);
-    } else {
-        for (int q = 0; q < 4; q++) { tv[q] = (k0 + q < n) ? airT[k0 + q] : flagT; dv[q] = (k0 + q < n) ? dewT[k0 + q] : flagTd; }
-    }
     float vmin = INFINITY, vmax = -INFINITY;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long k0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; k0 < n; k0 += stride) {
+        float tv[4], dv[4], ov[4];
+        const bool full = k0 + 3 < n;
+        if (full) {
+            *reinterpret_cast<float4*>(tv) = __ldcs(reinterpret_cast<const float4*>(airT + k0));
+            *reinterpret_cast<float4*>(dv) = __ldcs(reinterpret_cast<const float4*>(dewT + k0));
+        } else {
+            for (int q = 0; q < 4; q++) { tv[q] = (k0 + q < n) ? airT[k0 + q] : flagT; dv[q] = (k0 + q < n) ? dewT[k0 + q] : flagTd; }
+        }
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        float o = outFlag;
-        if (!isEqualF(tv[q], flagT) && !isEqualF(dv[q], flagTd)) o = relHumFromTdewDev(dv[q], tv[q]);
-        ov[q] = o;
-        if (k0 + q < n && !isEqualF(o, outFlag) && !isEqualF(o, kNoData)) { vmin = fminf(vmin, o); vmax = fmaxf(vmax, o); }
+        for (int q = 0; q < 4; q++) {
+            float o = outFlag;
+            if (!isEqualQ(tv[q], flagT) && !isEqualQ(dv[q], flagTd)) o = relHumFromTdewDev(dv[q], tv[q]);
+            ov[q] = o;
+            if (k0 + q < n && !isEqualQ(o, outFlag) && !isEqualQ(o, kNoData)) { vmin = fminf(vmin, o); vmax = fmaxf(vmax, o); }
+        }
+        if (full) *reinterpret_cast<float4*>(out + k0) = *reinterpret_cast<const float4*>(ov);
+        else for (int q = 0; q < 4; q++) if (k0 + q < n) out[k0 + q] = ov[q];
     }
-    if (full) *reinterpret_cast<float4*>(out + k0) = *reinterpret_cast<const float4*>(ov);
-    else for (int q = 0; q < 4; q++) if (k0 + q < n) out[k0 + q] = ov[q];
     for (int o = 16; o; o >>= 1) {
         vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
         vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
-    if ((threadIdx.x & 31) == 0) {
+    __shared__ float smin[8], smax[8];
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = vmin; smax[threadIdx.x >> 5] = vmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { vmin = fminf(vmin, smin[w]); vmax = fmaxf(vmax, smax[w]); }
         if (vmin != INFINITY) atomicMin(&minmax[0], orderedKeyR(vmin));
         if (vmax != -INFINITY) atomicMax(&minmax[1], orderedKeyR(vmax));
     }
@@ -133,7 +161,7 @@ __global__ void __launch_bounds__(256) thermal_consistency_kernel(const float* _
     int cnt = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++)
-        if (!isEqualF(a[q], flagMax) && !isEqualF(b[q], flagMin) && b[q] > a[q]) {
+        if (!isEqualQ(a[q], flagMax) && !isEqualQ(b[q], flagMin) && b[q] > a[q]) {
             b[q] = a[q] - 0.1f;
             cnt++;
         }
@@ -298,6 +326,82 @@ __device__ void heapSortAscending(float* v, int n)
     }
 }
 
+// rank-k value (0-based, ascending) of the valid entries of z[0..n) and the value of rank k + 1 (= the same value when it
+// repeats, else the smallest larger one; the rank-k value again when k is the last rank), by a 4-pass radix select over the
+// order-preserving keys: the two neighbours sorting::percentile (mathFunctions/statistics.cpp) interpolates between, without
+// sorting. One warp, all lanes return the same pair. hist = 256 counters of this warp in shared memory.
+__device__ __forceinline__ unsigned orderedKeyA(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float keyToFloatA(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ void warpSelectPair(const float* __restrict__ z, int n, int k, unsigned* hist, float& vk, float& vk1)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned prefix = 0u, mask = 0u;
+    int cntEq = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int b = lane; b < 256; b += 32) hist[b] = 0u;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const float v = z[i];
+            if (v != kNoData) {
+                const unsigned key = orderedKeyA(v);
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+        }
+        __syncwarp();
+        // lane l owns bins 8l .. 8l+7
+        unsigned own[8], sum = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { own[j] = hist[lane * 8 + j]; sum += own[j]; }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned excl = incl - sum;
+        const bool mine = unsigned(k) >= excl && unsigned(k) < incl;
+        int bin = 0, before = 0, inBin = 0;
+        if (mine) {
+            unsigned run = excl;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (unsigned(k) >= run && unsigned(k) < run + own[j]) { bin = lane * 8 + j; before = int(run); inBin = int(own[j]); }
+                run += own[j];
+            }
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        const int src = __ffs(who) - 1;
+        bin = __shfl_sync(0xffffffffu, bin, src);
+        before = __shfl_sync(0xffffffffu, before, src);
+        inBin = __shfl_sync(0xffffffffu, inBin, src);
+        k -= before;
+        prefix |= unsigned(bin) << shift;
+        mask |= 255u << shift;
+        cntEq = inBin;
+        __syncwarp();
+    }
+    vk = keyToFloatA(prefix);
+    if (k + 1 < cntEq) { vk1 = vk; return; }
+    unsigned best = 0xffffffffu;
+    for (int i = lane; i < n; i += 32) {
+        const float v = z[i];
+        if (v != kNoData) {
+            const unsigned key = orderedKeyA(v);
+            if (key > prefix && key < best) best = key;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    vk1 = best == 0xffffffffu ? vk : keyToFloatA(best);
+}
+
 __global__ void __launch_bounds__(256)
 spatial_aggregate_kernel(DevGrid raster, const double* __restrict__ px, const double* __restrict__ py,
                          const long long* __restrict__ first, const int* __restrict__ maxNr, int nCells, int method,
@@ -324,6 +428,32 @@ spatial_aggregate_kernel(DevGrid raster, const double* __restrict__ px, const do
     }
     for (int o = 16; o; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
     __syncwarp();
+    if (method == PB_AGGR_MEDIAN) {
+        // sorting::percentile(validValues, 50) (mathFunctions/statistics.cpp): the whole warp selects the two neighbours of the
+        // rank instead of sorting the list
+        __shared__ unsigned histAll[8][256];
+        unsigned* hist = histAll[threadIdx.x >> 5];
+        float result = kNoData;
+        int m = 0;
+        for (int i = lane; i < n; i += 32) m += z[i] != kNoData;
+        for (int o = 16; o; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+        if (n > 0 && (double(valid) / double(maxNr[cell])) > 0 && m >= 3) {       // MINIMUM_PERCENTILE_DATA
+            const double rank = m * double(50.0 / 100.f) - 1.0;
+            float lo, hi;
+            if (rank < 0.0) { warpSelectPair(z, n, 0, hist, lo, hi); result = lo; }
+            else {
+                const int low = int(rank);
+                if (low >= m - 1) { warpSelectPair(z, n, m - 1, hist, lo, hi); result = lo; }
+                else {
+                    warpSelectPair(z, n, low, hist, lo, hi);
+                    const double frac = rank - low;
+                    result = float(lo + frac * (hi - lo));
+                }
+            }
+        }
+        if (lane == 0) value[cell] = result;
+        return;
+    }
     if (lane != 0) return;
     float result = kNoData;
     // (validValues / aggregationPointsMaxNr) > (GRID_MIN_COVERAGE / 100), GRID_MIN_COVERAGE = 0 (meteoGrid.h:8)
@@ -346,21 +476,6 @@ spatial_aggregate_kernel(DevGrid raster, const double* __restrict__ px, const do
                     if (v != kNoData) { const float d = v - mean; squareDiff += d * d; }
                 }
                 result = sqrtf(squareDiff / (m - 1));
-            }
-        } else if (method == PB_AGGR_MEDIAN) {
-            for (int i = 0; i < n; i++) { const float v = z[i]; if (v != kNoData) z[m++] = v; }
-            if (m >= 3) {                                   // MINIMUM_PERCENTILE_DATA
-                heapSortAscending(z, m);
-                const double rank = m * double(50.0 / 100.f) - 1.0;
-                if (rank < 0.0) result = z[0];
-                else {
-                    const int low = int(rank);
-                    if (low >= m - 1) result = z[m - 1];
-                    else {
-                        const double frac = rank - low;
-                        result = float(z[low] + frac * (z[low + 1] - z[low]));
-                    }
-                }
             }
         }
     }
@@ -570,10 +685,21 @@ cudaError_t launchSpatialAggregateDev(const DevGrid& raster, const AggregationGe
     spatial_aggregate_kernel<<<nb, 256, 0, s>>>(raster, g.x, g.y, g.first, g.maxNr, g.nCells, method, scratch, value);
     return cudaGetLastError();
 }
+// grid of the grid-stride map kernels: 8 CTAs of 256 threads per SM (a full SM), never more than the map needs
+static unsigned mapGridBlocks(long long n)
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return (unsigned)std::max<long long>(1, std::min<long long>((n + 1023) / 1024, (long long)sms * 8));
+}
 cudaError_t launchRelativeHumidityMapDev(const float* airT, float flagT, const float* dewT, float flagTd, long long n, float outFlag,
                                          float* out, unsigned* minmax, cudaStream_t s)
 {
-    relative_humidity_map_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(airT, flagT, dewT, flagTd, n, outFlag, out, minmax);
+    relative_humidity_map_kernel<<<mapGridBlocks(n), 256, 0, s>>>(airT, flagT, dewT, flagTd, n, outFlag, out, minmax);
     return cudaGetLastError();
 }
 cudaError_t launchSamplePointsDev(const DevGrid& g, const double* x, const double* y, int n, float* value, unsigned char* inGrid,
@@ -629,9 +755,8 @@ int pb_relative_humidity_map(pb_context* ctx, pb_raster_id airT, pb_raster_id de
     if (rc) return rc;
     cudaEventRecord(ctx->ev[1], ctx->stream);
     // emptyGrid(): every cell = the output's own flag; the output header is the air temperature map's
-    relative_humidity_map_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, ctx->stream>>>(t->d, t->h.flag, td->d, td->h.flag, n, t->h.flag,
-                                                                                     dOut, ctx->dMinMax);
-    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, pb::launchRelativeHumidityMapDev(t->d, t->h.flag, td->d, td->h.flag, (long long)n, t->h.flag, dOut, ctx->dMinMax,
+                                                   ctx->stream));
     ctx->timing.launches++;
     cudaEventRecord(ctx->ev[2], ctx->stream);
     if (out) out->nValid = n;
