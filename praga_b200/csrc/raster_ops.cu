@@ -79,28 +79,24 @@ __device__ __forceinline__ bool isEqualQ(float a, float b)
 
 // relHumFromTdew(float Td, float T), meteo.cpp:301-315: rh = 100 pow(exp(c Td - (c T / (T + d)) (Td + d)), 1 / (T + d)).
 // The exponent collapses algebraically to a = c d (Td - T) / (T + d)^2 (the two products cancel term by term), which has no
-// cancellation left: a is taken in FP64 (a handful of instructions, one division), split into a float head and tail, and
-// the exponential is FP32: exp(a) = expf(hi) (1 + lo). Against the reference's FP64 pow(exp()) the map agrees to ~1e-5 in
-// RH units (expf is good to 1 ulp, 6e-8 of at most 100; the parity bar is 1e-4) at a tenth of the FP64 instructions, which
-// is what bounded this map (0.12-0.14 of the HBM roofline).
+// cancellation left: a is taken in FP64 (a handful of instructions, the reciprocal from the FP64 seed instruction + one Newton
+// step), rounded to float once and the exponential is FP32. Error against the reference's FP64 pow(exp()): the rounding of a
+// (6e-8 |a|, i.e. at most 2e-6 RH units at rh = 37) + expf (1-2 ulp of a value <= 100: 1e-5); the parity bar is 1e-4.
+// Conversions and special functions share one quarter-rate pipe: this form needs five of them per cell.
 __device__ __forceinline__ float relHumFromTdewDev(float Td, float T)
 {
     if (isEqualQ(Td, kNoData) || isEqualQ(T, kNoData)) return kNoData;
     const double d = 237.3;
     const double c = 17.2693882;
     const double td = double(T) + d;
-    // 1 / (T + d)^2: FP32 reciprocal as the seed, one Newton step in FP64 (relative error ~4e-15; an IEEE division would
-    // cost as much as everything else here together)
     const double q = td * td;
-    const double x0 = double(1.f / float(q));
-    const double x1 = fma(x0, fma(-q, x0, 1.0), x0);
+    double x0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(q));           // ~20 bits
+    const double x1 = fma(x0, fma(-q, x0, 1.0), x0);                  // ~40 bits
     const double a = ((c * d) * (double(Td) - double(T))) * x1;
-    const float hi = float(a);
-    const float lo = fabsf(hi) < 80.f ? float(a - double(hi)) : 0.f;
-    const float e = expf(hi);
-    const float rh = fmaf(e, lo, e) * 100.f;
+    const float rh = expf(float(a)) * 100.f;
     if (rh > 100.f) return 100.f;
-    return fmaxf(1.f, rh);
+    return fmaxf(1.f, rh);       // (NaN inputs: fmaxf returns 1 like std::max(1.f, NaN))
 }
 
 // four cells per thread and iteration (128-bit loads / stores), grid-stride over the map, scalar tail; min / max leave the CTA

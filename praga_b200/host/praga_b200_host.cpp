@@ -183,6 +183,39 @@ void flattenPoints(const std::vector<Crit3DInterpolationDataPoint>& pts, int nPr
     f.st.isActive = f.active.data(); f.st.proxyValues = f.proxy.data(); f.st.index = f.index.data();
 }
 
+// Project::meteoPoints as the C ABI takes them (pb_compute_residuals_glocal, pb_glocal_meteo): one entry per
+// Crit3DMeteoPoint; only active, accepted points are cross-validated
+struct FlatMeteo {
+    std::vector<double> x, y, z;
+    std::vector<float> value, proxy;
+    std::vector<int32_t> code;
+    std::vector<uint8_t> active, inside;
+    pb_stations st;
+    pb_cv_points cv;
+};
+
+void flattenMeteo(const std::vector<Crit3DMeteoPoint>& meteoPoints, int P, FlatMeteo& f)
+{
+    const int n = int(meteoPoints.size());
+    f.x.resize(n); f.y.resize(n); f.z.resize(n); f.value.resize(n); f.code.resize(n); f.active.resize(n); f.inside.resize(n);
+    f.proxy.assign(size_t(n) * std::max(P, 1), float(NODATA));
+    for (int i = 0; i < n; i++) {
+        const Crit3DMeteoPoint& m = meteoPoints[i];
+        f.x[i] = m.point.utm.x; f.y[i] = m.point.utm.y; f.z[i] = m.point.z;
+        f.value[i] = m.currentValue;
+        f.code[i] = int(m.lapseRateCode);
+        f.active[i] = m.active && m.quality == quality::accepted;
+        f.inside[i] = m.isInsideDem;
+        for (int k = 0; k < P && k < int(m.proxyValues.size()); k++) f.proxy[size_t(i) * P + k] = m.proxyValues[k];
+    }
+    memset(&f.st, 0, sizeof(f.st));
+    f.st.n = n; f.st.nProxy = P;
+    f.st.x = f.x.data(); f.st.y = f.y.data(); f.st.z = f.z.data(); f.st.value = f.value.data(); f.st.lapseRateCode = f.code.data();
+    f.st.isActive = f.active.data(); f.st.proxyValues = f.proxy.data();
+    memset(&f.cv, 0, sizeof(f.cv));
+    f.cv.isInsideDem = f.inside.data();
+}
+
 /* ---- resident raster cache -----------------------------------------------------------------------------------------
  * The reference keeps its DEM and proxy grids loaded for the whole session (Project::loadDEM / loadProxyGrids) and every
  * time step grids onto them; the drop-in therefore keeps one device copy per (device, grid): key = the grid's row-pointer
@@ -272,6 +305,49 @@ bool residentId(pb_context* ctx, const gis::Crit3DRasterGrid* owner, const pb_ra
     return true;
 }
 
+/* The points' precomputed topographic-distance maps (Crit3DInterpolationDataPoint::topographicDistance, copied from
+ * Crit3DMeteoPoint::topographicDistance by passDataToInterpolation, spatialControl.cpp:529) registered with the engine for the
+ * duration of one call: each map becomes a resident raster through the cache above, keyed by the point's index. */
+struct TdMapScope {
+    pb_context* ctx;
+    std::vector<pb_raster_id> temporaries;
+    bool registered = false, ok = true;
+    explicit TdMapScope(pb_context* c) : ctx(c) {}
+    void add(std::vector<int32_t>& index, std::vector<pb_raster_id>& ids, int pointIndex, const gis::Crit3DRasterGrid* map)
+    {
+        if (!ok || map == nullptr || !map->isLoaded || map->value == nullptr) return;
+        pb_raster_id id = -1;
+        bool tmp = false;
+        if (!residentId(ctx, map, rasterOf(*map), &id, &tmp)) { ok = false; return; }
+        if (tmp) temporaries.push_back(id);
+        index.push_back(pointIndex);
+        ids.push_back(id);
+    }
+    bool commit(const std::vector<int32_t>& index, const std::vector<pb_raster_id>& ids)
+    {
+        if (!ok) return false;
+        if (index.empty()) return true;
+        registered = true;
+        // (a map evicted from the raster cache while the others were uploaded is no longer live: the call fails here instead of
+        // silently marching; pragab200::setRasterCache raises the limit)
+        if (failed(ctx, pb_set_topographic_distance_maps(ctx, index.data(), ids.data(), int(index.size())))) { ok = false; return false; }
+        return true;
+    }
+    bool fromPoints(const std::vector<Crit3DInterpolationDataPoint>& pts, bool useTD)
+    {
+        if (!useTD) return true;
+        std::vector<int32_t> index;
+        std::vector<pb_raster_id> ids;
+        for (const auto& p : pts) add(index, ids, p.index, p.topographicDistance);
+        return commit(index, ids);
+    }
+    ~TdMapScope()
+    {
+        if (registered) pb_set_topographic_distance_maps(ctx, nullptr, nullptr, 0);
+        for (pb_raster_id t : temporaries) pb_raster_free(ctx, t);
+    }
+};
+
 bool rasterCall(bool local, std::vector<Crit3DInterpolationDataPoint>& points, Crit3DInterpolationSettings& settings,
                 Crit3DMeteoSettings* meteoSettings, gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster,
                 meteoVariable variable)
@@ -307,6 +383,8 @@ bool rasterCall(bool local, std::vector<Crit3DInterpolationDataPoint>& points, C
         ok = residentId(ctx, nullptr, grids[g], &ids[g], &tmp);
         if (ok && tmp) temporaries.push_back(ids[g]);
     }
+    TdMapScope tdMaps(ctx);
+    if (ok) ok = tdMaps.fromPoints(points, s.useTD != 0);
     int rc = PB_ERR_CUDA;
     if (ok)
         rc = local ? pb_local_detrending_raster_resident(ctx, &fp.st, &s, int(variable), demId, ids, int(grids.size()), 0, -1, &out)
@@ -528,6 +606,8 @@ bool preInterpolation(std::vector<Crit3DInterpolationDataPoint>& myPoints, Crit3
     else s.climateLapseRate = 0.f;
     FlatPoints fp;
     flattenPoints(myPoints, s.nProxy, fp);
+    TdMapScope tdMaps(ctx);
+    if (!tdMaps.fromPoints(myPoints, s.useTD != 0)) { errorStr = g_error; return false; }
     const int n = fp.st.n;
     // the meteo point behind each interpolation point: Crit3DInterpolationDataPoint::index (passDataToInterpolation :516)
     std::vector<float> current(n);
@@ -581,7 +661,8 @@ bool preInterpolation(std::vector<Crit3DInterpolationDataPoint>& myPoints, Crit3
 
 bool interpolationRasterGlocalDetrending(std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
                                          Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
-                                         gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster, meteoVariable variable)
+                                         gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster, meteoVariable variable,
+                                         const std::vector<Crit3DMeteoPoint>* meteoPoints)
 {
     if (!getUseDetrendingVar(variable) || !interpolationSettings.getUseGlocalDetrending()) return false;     // project.cpp:3264
     interpolationSettings.setCurrentCombination(interpolationSettings.getSelectedCombination());               // :3279-3280
@@ -611,8 +692,23 @@ bool interpolationRasterGlocalDetrending(std::vector<Crit3DInterpolationDataPoin
     pb_raster_out out;
     memset(&out, 0, sizeof(out));
     out.rows = outputGrid->value;
-    const int rc = pb_glocal_detrending_raster(ctx, &fp.st, &s, int(variable), fa.a.data(), int(fa.a.size()), demId, ids.data(),
-                                               int(ids.size()), 0, &out);
+    int rc;
+    if (s.useTD && meteoPoints != nullptr) {
+        // macroAreaDetrending's kh search walks Project::meteoPoints (interpolation.cpp:1811-1826)
+        FlatMeteo fm;
+        flattenMeteo(*meteoPoints, s.nProxy, fm);
+        pb_glocal_meteo gm;
+        memset(&gm, 0, sizeof(gm));
+        gm.meteo = &fm.st;
+        gm.observed = fm.value.data();
+        gm.cv = &fm.cv;
+        TdMapScope tdMaps(ctx);
+        if (!tdMaps.fromPoints(interpolationPoints, true)) { release(); return false; }
+        rc = pb_glocal_detrending_raster_td(ctx, &fp.st, &s, int(variable), fa.a.data(), int(fa.a.size()), -1, &gm, demId, ids.data(),
+                                            int(ids.size()), 0, &out, nullptr);
+    } else
+        rc = pb_glocal_detrending_raster(ctx, &fp.st, &s, int(variable), fa.a.data(), int(fa.a.size()), demId, ids.data(),
+                                         int(ids.size()), 0, &out);
     release();
     if (rc != PB_OK && rc != PB_ERR_NO_VALID_CELL) { failed(ctx, rc); return false; }
     pb_kh_series kh;
@@ -644,30 +740,23 @@ bool computeResidualsGlocalDetrending(meteoVariable myVar, const Crit3DMacroArea
     flattenArea(myArea, s.nProxy, A, pts, cells);
     if (A.nAreaCells <= 0) { A.nAreaCells = 2; static const float one[2] = {0.f, 1.f}; A.areaCellsDEM = one; }   // this call never reads the cells
     // one Crit3DMeteoPoint per entry: position, lapse code, proxy values, current value; only accepted points are cross-validated
-    const int n = int(meteoPoints.size()), P = s.nProxy;
-    std::vector<double> x(n), y(n), z(n);
-    std::vector<float> val(n), proxy(size_t(n) * std::max(P, 1), float(NODATA)), res(n);
-    std::vector<int32_t> code(n);
-    std::vector<uint8_t> active(n), inside(n);
-    for (int i = 0; i < n; i++) {
-        const Crit3DMeteoPoint& m = meteoPoints[i];
-        x[i] = m.point.utm.x; y[i] = m.point.utm.y; z[i] = m.point.z;
-        val[i] = m.currentValue;
-        code[i] = int(m.lapseRateCode);
-        active[i] = m.active && m.quality == quality::accepted;
-        inside[i] = m.isInsideDem;
-        for (int k = 0; k < P && k < int(m.proxyValues.size()); k++) proxy[size_t(i) * P + k] = m.proxyValues[k];
-    }
-    pb_stations mp;
-    memset(&mp, 0, sizeof(mp));
-    mp.n = n; mp.nProxy = P;
-    mp.x = x.data(); mp.y = y.data(); mp.z = z.data(); mp.value = val.data(); mp.lapseRateCode = code.data();
-    mp.isActive = active.data(); mp.proxyValues = proxy.data();
-    pb_cv_points cv;
-    memset(&cv, 0, sizeof(cv));
-    cv.isInsideDem = inside.data();
-    if (failed(ctx, pb_compute_residuals_glocal(ctx, &mp, val.data(), &cv, &fp.st, &s, int(myVar), &A, 1, excludeOutsideDem,
-                                                excludeSupplemental, res.data())))
+    const int n = int(meteoPoints.size());
+    FlatMeteo fm;
+    flattenMeteo(meteoPoints, s.nProxy, fm);
+    std::vector<float> res(n);
+    gis::Crit3DRasterGrid* dem = interpolationSettings.getCurrentDEM();
+    if (s.useTD && dem != nullptr && dem->isLoaded) {
+        TdMapScope tdMaps(ctx);
+        pb_raster_id demId = -1;
+        bool tmp = false;
+        if (!residentId(ctx, dem, rasterOf(*dem), &demId, &tmp)) return false;
+        if (tmp) tdMaps.temporaries.push_back(demId);
+        if (!tdMaps.fromPoints(interpolationPoints, true)) return false;
+        if (failed(ctx, pb_compute_residuals_glocal_td(ctx, &fm.st, fm.value.data(), &fm.cv, &fp.st, &s, int(myVar), &A, 1, demId,
+                                                       excludeOutsideDem, excludeSupplemental, res.data())))
+            return false;
+    } else if (failed(ctx, pb_compute_residuals_glocal(ctx, &fm.st, fm.value.data(), &fm.cv, &fp.st, &s, int(myVar), &A, 1,
+                                                       excludeOutsideDem, excludeSupplemental, res.data())))
         return false;
     for (int i = 0; i < n; i++) {
         if (isEqual(res[i], NODATA)) continue;
@@ -690,8 +779,19 @@ bool computeResiduals(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoP
     if (!flattenSettings(interpolationSettings, meteoSettings, s, grids, nullptr)) return false;
     FlatPoints fp;
     flattenPoints(interpolationPoints, s.nProxy, fp);
+    // topographic distance (computeDistances :226-251): the current DEM resident, the points' precomputed maps registered
+    gis::Crit3DRasterGrid* dem = interpolationSettings.getCurrentDEM();
+    const bool td = s.useTD && !s.useLocalDetrending && dem != nullptr && dem->isLoaded;
+    TdMapScope tdMaps(ctx);
+    pb_raster_id demId = -1;
+    bool demTemporary = false;
+    if (td) {
+        if (!residentId(ctx, dem, rasterOf(*dem), &demId, &demTemporary)) return false;
+        if (demTemporary) tdMaps.temporaries.push_back(demId);
+        if (!tdMaps.fromPoints(interpolationPoints, true)) return false;
+    }
     // targets = the meteo points that computeResiduals would evaluate (spatialControl.cpp:113-121)
-    std::vector<float> x, y, est;
+    std::vector<float> x, y, z, est;
     std::vector<double> pv;
     std::vector<size_t> who;
     for (size_t i = 0; i < meteoPoints.size(); i++) {
@@ -703,12 +803,16 @@ bool computeResiduals(meteoVariable myVar, std::vector<Crit3DMeteoPoint>& meteoP
         who.push_back(i);
         x.push_back(float(meteoPoints[i].point.utm.x));
         y.push_back(float(meteoPoints[i].point.utm.y));
+        z.push_back(float(meteoPoints[i].point.z));
         std::vector<double> v = meteoPoints[i].getProxyValues();
         for (int k = 0; k < s.nProxy; k++) pv.push_back(k < int(v.size()) ? v[k] : double(NODATA));
     }
     est.resize(who.size());
     if (!who.empty()) {
-        const int rc = pb_interpolate_points(ctx, &fp.st, &s, int(myVar), x.data(), y.data(), pv.data(), int(who.size()), 0, est.data());
+        const int rc = td ? pb_interpolate_points_td(ctx, &fp.st, &s, int(myVar), x.data(), y.data(), z.data(), pv.data(),
+                                                     int(who.size()), 0, demId, est.data())
+                          : pb_interpolate_points(ctx, &fp.st, &s, int(myVar), x.data(), y.data(), pv.data(), int(who.size()), 0,
+                                                  est.data());
         if (failed(ctx, rc)) return false;
     }
     for (size_t k = 0; k < who.size(); k++) {

@@ -74,7 +74,9 @@ bool interpolationRasterLocalDetrending(std::vector<Crit3DInterpolationDataPoint
  * Returns false where the reference does (an interpolate() inside an area gave NODATA). */
 bool interpolationRasterGlocalDetrending(std::vector<Crit3DInterpolationDataPoint>& interpolationPoints,
                                          Crit3DInterpolationSettings& interpolationSettings, Crit3DMeteoSettings* meteoSettings,
-                                         gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster, meteoVariable variable);
+                                         gis::Crit3DRasterGrid* outputGrid, gis::Crit3DRasterGrid& raster, meteoVariable variable,
+                                         const std::vector<Crit3DMeteoPoint>* meteoPoints = nullptr /* Project::meteoPoints: needed
+                                         when the settings use topographic distance (the per-area kh search walks them) */);
 
 /* same signature and side effects as the reference (residuals are ADDED to meteoPoints[].residual, one area per call) */
 bool computeResidualsGlocalDetrending(meteoVariable myVar, const Crit3DMacroArea& myArea, int elevationPos,

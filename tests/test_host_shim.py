@@ -338,3 +338,33 @@ def test_shim_compute_radiation_dem(shim, ref):
         m = want[nme] != flag
         assert np.abs(got[nme][m].astype(np.float64) - want[nme][m]).max() <= TOL, nme
     assert np.abs(got["minmax"] - want["minmax"]).max() <= TOL
+
+
+def test_shim_registers_the_points_topographic_distance_maps(shim, ref):
+    """Crit3DInterpolationDataPoint::topographicDistance (what passDataToInterpolation copies from the meteo points) reaches
+    the engine through the shim: the maps are uploaded through the raster cache and registered for the call."""
+    from test_td_maps import humidity_case, make_maps
+    from test_oracle_port import clone
+    dem, st, s, var = humidity_case()
+    maps = make_maps(ref, dem, st)
+    idx = sorted(maps)
+    plain = ref.interpolation_raster(st, clone(s), var, dem, ())[1]
+    ref.set_topographic_distance_maps(idx, [maps[i] for i in idx])
+    arr = (A.pb_raster * len(idx))()
+    for k, i in enumerate(idx):
+        arr[k] = maps[i].as_pb()
+    shim.ref_set_topographic_distance_maps.restype = C.c_int
+    shim.ref_set_topographic_distance_maps((C.c_int32 * len(idx))(*idx), arr, C.c_int(len(idx)))      # the harness' own point builder
+    try:
+        okc, gc, mnc, mxc, _, _ = ref.interpolation_raster(st, clone(s), var, dem, ())
+        okg, gg, mng, mxg, err = shim_raster(shim, st, clone(s), var, dem, ())
+    finally:
+        ref.set_topographic_distance_maps()
+        shim.ref_set_topographic_distance_maps(None, None, C.c_int(0))
+    assert okg == okc, err
+    assert np.array_equal(gg == np.float32(dem.flag), gc == np.float32(dem.flag))
+    assert np.abs(gg.astype(np.float64) - gc).max() <= TOL
+    assert np.abs(gc - plain).max() > 1e-2          # the maps mattered
+    # and without maps the same call marches
+    okg2, gg2, *_ = shim_raster(shim, st, clone(s), var, dem, ())
+    assert okg2 and np.abs(gg2.astype(np.float64) - plain).max() <= TOL
