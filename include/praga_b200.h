@@ -504,6 +504,9 @@ int pb_kriging_setup(pb_context* ctx, const double* pos, const double* val, int 
                      double sill, double slope, int flags, pb_kriging_id* id);
 int pb_kriging_free(pb_context* ctx, pb_kriging_id id);
 int pb_kriging_uses_tensor_path(pb_context* ctx, pb_kriging_id id);      /* 1 tensor, 0 FP64 direct, -1 bad id */
+/* measurement aid (no reference counterpart): tcgen05 MMAs of 2 * 256 * 256 * 16 flop issued for this system since the last
+   call (the variance kernel skips K stages out of the variogram range); resets the counter */
+int pb_kriging_mma_count(pb_context* ctx, pb_kriging_id id, unsigned long long* count);
 int pb_kriging_points(pb_context* ctx, pb_kriging_id id, const double* xy, int m, double* result, double* rmse /* may be NULL */);
 int pb_kriging_raster(pb_context* ctx, pb_kriging_id id, pb_raster_id dem, int rowBegin, int rowEnd,
                       pb_raster_out* estimate, pb_raster_out* rmse /* may be NULL */);

@@ -100,36 +100,89 @@ kriging_estimate_kernel(KrigingParams k, const double* __restrict__ pos, const d
 // the estimate on the tensor path (no D column is kept): the FP64 pipe bounds this kernel, so the pair loop is stripped to
 // what the sum needs. h = d2 * rsqrt(d2) (1-2 ulp instead of the correctly rounded sqrt), h / range as a multiplication by the
 // reciprocal, and the spherical model folded to gamma = nugget + h (A - B d2): 17 FP64 instructions per pair instead of
-// ~40. The differences are ~1e-16 relative on gamma (the estimate's cancellation, 6e4 : 1, leaves them at ~1e-11).
+// ~40. The differences are ~1e-16 relative on gamma.
+// Bounded model (spherical): gamma = sill beyond the range, so with S = sum_j u_j (0 up to rounding: the unbiasedness row of V)
+//   estimate = u_n + sum_j u_j gamma_j = (u_n + sill S) + sum_{j: |p - s_j| < range} u_j (gamma_j - sill)
+// and only the stations inside the range contribute. The cells of a CTA are one run of the valid-cell list (neighbours in
+// a raster row): stations farther than the range from the CTA's bounding box are dropped for the whole CTA by an ORDERED
+// compaction into the shared-memory tile (station order is kept, so the sum is deterministic): at C4 (range 200 km in a
+// 1000 km box) ~1/8 of the pairs are left. Unbounded models (exponential, Gaussian) keep every station.
 template <int MODE>
 __global__ void __launch_bounds__(kEstThreads)
-kriging_estimate_fast_kernel(KrigingParams k, const double* __restrict__ pos, const double* __restrict__ u, KrigingTargets t,
-                             long long c0, int m, double* __restrict__ est)
+kriging_estimate_fast_kernel(KrigingParams k, const double* __restrict__ pos, const double* __restrict__ u, double sumU,
+                             KrigingTargets t, long long c0, int m, double* __restrict__ est)
 {
+    constexpr bool kBounded = MODE == PB_KRIGING_SPHERICAL;
+    constexpr int kWarps = kEstThreads / 32;
     __shared__ double sx[kEstTile], sy[kEstTile], su[kEstTile];
-    const int c = blockIdx.x * kEstThreads + threadIdx.x;
+    __shared__ double sBox[4][kWarps];
+    __shared__ int sWarpCnt[kWarps];
+    const int c = blockIdx.x * kEstThreads + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool valid = c < m;
     double x = 0, y = 0;
-    if (c < m) targetXY(t, c0 + c, x, y);
+    if (valid) targetXY(t, c0 + c, x, y);
     const double invR = 1.0 / k.range, range2 = k.range * k.range, sill = k.nugget + k.sillNugget;
     const double sphA = 1.5 * k.sillNugget * invR, sphB = 0.5 * k.sillNugget * invR * invR * invR;
-    double acc0 = 0, acc1 = 0;
-    for (int j0 = 0; j0 < k.n; j0 += kEstTile) {
-        const int nj = min(kEstTile, k.n - j0);
-        __syncthreads();
-        for (int j = threadIdx.x; j < nj; j += kEstThreads) {
-            sx[j] = pos[2 * (j0 + j)];
-            sy[j] = pos[2 * (j0 + j) + 1];
-            su[j] = u[j0 + j];
+    double bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
+    if (kBounded) {
+        bx0 = valid ? x : 1e300; bx1 = valid ? x : -1e300; by0 = valid ? y : 1e300; by1 = valid ? y : -1e300;
+        for (int o = 16; o > 0; o >>= 1) {
+            bx0 = fmin(bx0, __shfl_xor_sync(~0u, bx0, o));
+            bx1 = fmax(bx1, __shfl_xor_sync(~0u, bx1, o));
+            by0 = fmin(by0, __shfl_xor_sync(~0u, by0, o));
+            by1 = fmax(by1, __shfl_xor_sync(~0u, by1, o));
         }
+        if (lane == 0) { sBox[0][warp] = bx0; sBox[1][warp] = bx1; sBox[2][warp] = by0; sBox[3][warp] = by1; }
         __syncthreads();
-        if (c < m) {
+        for (int w = 0; w < kWarps; w++) {
+            bx0 = fmin(bx0, sBox[0][w]); bx1 = fmax(bx1, sBox[1][w]);
+            by0 = fmin(by0, sBox[2][w]); by1 = fmax(by1, sBox[3][w]);
+        }
+    }
+    double acc0 = 0, acc1 = 0;
+    int j0 = 0;
+    while (j0 < k.n) {
+        // fill the tile with the next (up to kEstTile) stations that can be inside the range of a cell of this CTA
+        int cnt = 0;
+        __syncthreads();                                // the previous tile has been consumed
+        while (j0 < k.n && cnt + kEstThreads <= kEstTile) {
+            const int j = j0 + threadIdx.x;
+            bool keep = false;
+            double px = 0, py = 0;
+            if (j < k.n) {
+                px = pos[2 * j];
+                py = pos[2 * j + 1];
+                if (kBounded) {
+                    const double ex = fmax(fmax(bx0 - px, px - bx1), 0.), ey = fmax(fmax(by0 - py, py - by1), 0.);
+                    keep = ex * ex + ey * ey < range2;
+                } else keep = true;
+            }
+            const unsigned b = __ballot_sync(~0u, keep);
+            if (lane == 0) sWarpCnt[warp] = __popc(b);
+            __syncthreads();
+            int base = cnt, tot = 0;
+            for (int w = 0; w < kWarps; w++) {
+                if (w < warp) base += sWarpCnt[w];
+                tot += sWarpCnt[w];
+            }
+            if (keep) {
+                const int idx = base + __popc(b & ((1u << lane) - 1u));
+                sx[idx] = px;
+                sy[idx] = py;
+                su[idx] = u[j];
+            }
+            cnt += tot;
+            j0 += kEstThreads;
+            __syncthreads();                            // sWarpCnt is rewritten by the next chunk; the tile is visible
+        }
+        if (valid) {
 #pragma unroll 4
-            for (int j = 0; j < nj; j++) {
+            for (int j = 0; j < cnt; j++) {
                 const double dx = sx[j] - x, dy = sy[j] - y;
                 const double d2 = dx * dx + dy * dy;
                 const double h = d2 > 0. ? d2 * rsqrt(d2) : 0.;
                 double g;
-                if (MODE == PB_KRIGING_SPHERICAL) g = (d2 < range2) ? k.nugget + h * (sphA - sphB * d2) : sill;
+                if (MODE == PB_KRIGING_SPHERICAL) g = (d2 < range2) ? h * (sphA - sphB * d2) - k.sillNugget : 0.;   // gamma - sill
                 else if (MODE == PB_KRIGING_EXPONENTIAL) g = k.nugget + k.sillNugget * (1. - exp(-3. * (h * invR)));
                 else g = k.nugget + k.sillNugget * (1. - exp(-4. * (d2 * invR * invR)));
                 if (j & 1) acc1 += su[j] * g;         // two accumulators: the dependent add chain is the latency floor
@@ -137,7 +190,7 @@ kriging_estimate_fast_kernel(KrigingParams k, const double* __restrict__ pos, co
             }
         }
     }
-    if (c < m) est[c] = (acc0 + acc1) + u[k.n];
+    if (valid) est[c] = (acc0 + acc1) + (kBounded ? u[k.n] + sill * sumU : u[k.n]);
 }
 
 // direct variance: q_c = sum_i D[i][c] * (sum_j A[i][j] D[j][c]), i < n, j <= n. 64 x 64 output tile, K step 16,
@@ -305,6 +358,29 @@ static void invertLower(const std::vector<double>& L, std::vector<double>& M, in
     }
 }
 
+// k-d ordering of the stations (tensor path, bounded model): recursive bisection along the longer side of the bounding
+// box, split points at multiples of 32, so that every K stage of the variance kernel (32 consecutive stations) is a spatially
+// compact leaf. The whitened quantities |y|^2 and z.y are invariant under a permutation of the stations (C' = P C P^T),
+// so the order is free; a compact stage that lies out of every cell's range is skipped by the kernel (kriging_tc.cu).
+static void kdOrder(const double* pos, int* idx, int lo, int hi)
+{
+    if (hi - lo <= kTcBK) return;
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int i = lo; i < hi; i++) {
+        x0 = std::min(x0, pos[2 * idx[i]]); x1 = std::max(x1, pos[2 * idx[i]]);
+        y0 = std::min(y0, pos[2 * idx[i] + 1]); y1 = std::max(y1, pos[2 * idx[i] + 1]);
+    }
+    const int axis = (x1 - x0 >= y1 - y0) ? 0 : 1;
+    const int leaves = (hi - lo + kTcBK - 1) / kTcBK;
+    const int mid = lo + (leaves / 2) * kTcBK;
+    std::nth_element(idx + lo, idx + mid, idx + hi, [&](int a, int b) {
+        const double va = pos[2 * a + axis], vb = pos[2 * b + axis];
+        return va < vb || (va == vb && a < b);
+    });
+    kdOrder(pos, idx, lo, mid);
+    kdOrder(pos, idx, mid, hi);
+}
+
 void krigingFree(KrigingSystem* k)
 {
     if (!k) return;
@@ -314,6 +390,8 @@ void krigingFree(KrigingSystem* k)
     if (k->dMhi) cudaFree(k->dMhi);
     if (k->dMlo) cudaFree(k->dMlo);
     if (k->dZ) cudaFree(k->dZ);
+    if (k->dKbBox) cudaFree(k->dKbBox);
+    if (k->dMmaCount) cudaFree(k->dMmaCount);
     if (k->dWork) cudaFree(k->dWork);
     delete k;
 }
@@ -362,11 +440,11 @@ int evaluate(pb_context* ctx, KrigingSystem* k, const KrigingTargets& t, long lo
         if (dD || k->params.mode == PB_KRIGING_LINEAR)
             kriging_estimate_kernel<<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, t, c0, mc, dEst, dD, (int)ldD);
         else if (k->params.mode == PB_KRIGING_SPHERICAL)
-            kriging_estimate_fast_kernel<PB_KRIGING_SPHERICAL><<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, t, c0, mc, dEst);
+            kriging_estimate_fast_kernel<PB_KRIGING_SPHERICAL><<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, k->sumU, t, c0, mc, dEst);
         else if (k->params.mode == PB_KRIGING_EXPONENTIAL)
-            kriging_estimate_fast_kernel<PB_KRIGING_EXPONENTIAL><<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, t, c0, mc, dEst);
+            kriging_estimate_fast_kernel<PB_KRIGING_EXPONENTIAL><<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, k->sumU, t, c0, mc, dEst);
         else
-            kriging_estimate_fast_kernel<PB_KRIGING_GAUSSIAN><<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, t, c0, mc, dEst);
+            kriging_estimate_fast_kernel<PB_KRIGING_GAUSSIAN><<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, k->sumU, t, c0, mc, dEst);
         ctx->timing.launches++;
         if (wantRmse) {
             if (k->tensor) {
@@ -409,17 +487,40 @@ int pb_kriging_setup(pb_context* ctx, const double* pos, const double* val, int 
     k->params.slope = slope;
     k->params.sill = nugget + (sill - nugget);          // the value the reference's bounded models reach (:171)
     const int dim = n + 1;
-    std::vector<double> G(size_t(n) * n);
-#pragma omp parallel for schedule(dynamic, 16)
-    for (int i = 0; i < n; i++)
-        for (int j = i; j < n; j++) {
-            const double dx = pos[i * 2] - pos[j * 2], dy = pos[i * 2 + 1] - pos[j * 2 + 1];
-            const double g = variogramHost(k->params, sqrt(dx * dx + dy * dy));
-            G[size_t(i) * n + j] = g;
-            G[size_t(j) * n + i] = g;
-        }
-    std::vector<double> u(dim);
     bool tensor = !(flags & PB_KRIGING_FLAG_FP64_DIRECT) && k->params.mode != PB_KRIGING_LINEAR;
+    // tensor path, bounded model: stations in k-d order (kdOrder); the exact path keeps the caller's order (it eliminates in
+    // the reference's order)
+    std::vector<double> posK, valK;
+    const double* posIn = pos;
+    const double* valIn = val;
+    const bool reorder = tensor && k->params.mode == PB_KRIGING_SPHERICAL && n > kTcBK;
+    if (reorder) {
+        std::vector<int> idx(n);
+        for (int i = 0; i < n; i++) idx[i] = i;
+        kdOrder(pos, idx.data(), 0, n);
+        posK.resize(size_t(2) * n);
+        valK.resize(n);
+        for (int i = 0; i < n; i++) {
+            posK[2 * i] = pos[2 * idx[i]];
+            posK[2 * i + 1] = pos[2 * idx[i] + 1];
+            valK[i] = val[idx[i]];
+        }
+        pos = posK.data();
+        val = valK.data();
+    }
+    std::vector<double> G(size_t(n) * n);
+    auto buildG = [&]() {
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int i = 0; i < n; i++)
+            for (int j = i; j < n; j++) {
+                const double dx = pos[i * 2] - pos[j * 2], dy = pos[i * 2 + 1] - pos[j * 2 + 1];
+                const double g = variogramHost(k->params, sqrt(dx * dx + dy * dy));
+                G[size_t(i) * n + j] = g;
+                G[size_t(j) * n + i] = g;
+            }
+    };
+    buildG();
+    std::vector<double> u(dim);
     std::vector<double> M;
     if (tensor) {
         // covariance form: C = sill - Gamma = L L^T
@@ -461,11 +562,16 @@ int pb_kriging_setup(pb_context* ctx, const double* pos, const double* val, int 
                 u[j] = s;
             }
             u[n] = u2;
-            int rc = krigingUploadWhitened(*k, M, z, zz);
+            int rc = krigingUploadWhitened(*k, M, z, zz, pos);
             if (rc != 0) { krigingFree(k); return fail(ctx, PB_ERR_CUDA, "kriging: upload of the whitened system failed"); }
         }
     }
     if (!tensor) {
+        if (reorder) {          // the whitened system was rejected: back to the caller's station order
+            pos = posIn;
+            val = valIn;
+            buildG();
+        }
         std::vector<double> V(size_t(dim) * dim, 0.), I(size_t(dim) * dim);
         for (int i = 0; i < n; i++) {
             memcpy(&V[size_t(i) * dim], &G[size_t(i) * n], sizeof(double) * n);
@@ -489,6 +595,8 @@ int pb_kriging_setup(pb_context* ctx, const double* pos, const double* val, int 
         }
     }
     k->tensor = tensor;
+    k->sumU = 0;
+    for (int j = 0; j < n; j++) k->sumU += u[j];
     if (cudaMalloc(&k->dPos, sizeof(double) * 2 * n) != cudaSuccess || cudaMalloc(&k->dU, sizeof(double) * dim) != cudaSuccess ||
         cudaMemcpy(k->dPos, pos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(k->dU, u.data(), sizeof(double) * dim, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -522,6 +630,22 @@ int pb_kriging_uses_tensor_path(pb_context* ctx, pb_kriging_id id)
     PB_NVTX_RANGE();
     KrigingSystem* k = ctx ? systemOf(ctx, id) : nullptr;
     return k ? (k->tensor ? 1 : 0) : -1;
+}
+
+/* measurement aid: tensor-core MMAs (M = 256, N = 256, K = 16: 2 * 256 * 256 * 16 flop each) the variance kernel has issued
+   for this system since the last call; the counter is reset. 0 on the FP64 direct path. */
+int pb_kriging_mma_count(pb_context* ctx, pb_kriging_id id, unsigned long long* count)
+{
+    if (!ctx || !count) return PB_ERR_INVALID;
+    KrigingSystem* k = systemOf(ctx, id);
+    if (!k) return fail(ctx, PB_ERR_INVALID, "kriging: unknown system id");
+    *count = 0;
+    if (!k->dMmaCount) return PB_OK;
+    cudaSetDevice(ctx->device);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(count, k->dMmaCount, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(ctx, cudaMemset(k->dMmaCount, 0, sizeof(unsigned long long)));
+    return PB_OK;
 }
 
 /* krigingSetWeight + krigingResult + krigingRMSE (kriging.cpp:211-295) for m target points (x0, y0, x1, y1, ...) */

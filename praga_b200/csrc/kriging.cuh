@@ -43,15 +43,19 @@ struct KrigingSystem {
     unsigned char* dMhi = nullptr;     // tiles[(it * nKb + kb) * 2 + piece][kTcTileBytes]   (dMlo unused: pieces are interleaved)
     unsigned char* dMlo = nullptr;
     float* dZ = nullptr;               // z = M 1, padded to nPad
+    unsigned long long* dMmaCount = nullptr;   // tcgen05 MMAs (256 x 256 x 16) issued by the pair kernel since the last read
+    double* dKbBox = nullptr;          // per K stage (32 stations): xmin, xmax, ymin, ymax (+inf / -inf for padding stages)
     float2* dPosF = nullptr;           // not owned separately (inside dZ allocation)
     int nPad = 0, nIt = 0, nKb = 0;
     double zz = 0;                     // |z|^2
+    double sumU = 0;                   // sum_j u_j, j < n (0 up to rounding)
     unsigned char* dWork = nullptr;
     size_t workBytes = 0;
 };
 
 void krigingFree(KrigingSystem* k);
-int krigingUploadWhitened(KrigingSystem& k, const std::vector<double>& M, const std::vector<double>& z, double zz);
+int krigingUploadWhitened(KrigingSystem& k, const std::vector<double>& M, const std::vector<double>& z, double zz,
+                          const double* pos);
 cudaError_t launchKrigingVarianceTc(const KrigingSystem& k, const KrigingTargets& t, long long c0, int m, double* q,
                                     cudaStream_t s);
 cudaError_t launchFill(float* out, long long n, float v, cudaStream_t s);     // idw_kernels.cu

@@ -21,6 +21,7 @@
 //     tiles of stage s+1.. while the tensor core works on stage s; nobody waits for an MMA except to reuse its buffers;
 //   epilogue per pass: tcgen05.ld, thread = cell (TMEM lane), per-thread sums of y^2 and z*y, no cross-lane reduction.
 #include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 
 #include "kriging.cuh"
@@ -86,6 +87,8 @@ __host__ __device__ inline size_t tileOffset(int r, int k) { return size_t(r >> 
 
 struct TcParams {
     int n, nPad, nKb, mode;
+    int skip;         // bounded model: K stages out of every cell's range are skipped (pair kernel)
+    int dbg;          // PB_KRIGING_DBG (timing experiments only: 1 = generators idle, 2 = no MMAs, 4 = no epilogue reads)
     float range, invRange, sn;  // sn = sill - nugget
     double sill, zz;
 };
@@ -355,6 +358,540 @@ kriging_variance_tc_kernel(TcParams p, const double* __restrict__ pos, const uns
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair form (tcgen05 cta_group::2): the default for the variance contraction
+// ---------------------------------------------------------------------------------------------------------
+// The single-CTA kernel above regenerates the covariance tile A 4.5 times on average (once per pass of 256 stations i:
+// 512 TMEM columns = 2 M tiles x 256) and its M = N = 128 MMAs read 8 KiB of operands from shared memory per 64 tensor
+// clocks, i.e. the whole shared-memory bandwidth, while 16 generator warps store A through the same port: ncu showed the
+// tensor pipe 56 % active. Here two CTAs of a cluster (one TPC) run ONE MMA of M = 256 (128 cells from each CTA), N = 256:
+//   * each CTA generates the A rows of its own 128 cells only and keeps HALF of the B rows (stations i) of every N block:
+//     per 128 tensor clocks a CTA's shared memory feeds 4 KiB of A + 4 KiB of B, half of the single-CTA rate;
+//   * each CTA's TMEM holds 128 cells x 512 columns = a pass of 512 stations i: A is generated 2.5 times instead of 4.5;
+//   * the L2 -> SM stream of L^-1 stays at 32 KiB per stage per SM (every loaded tile still serves 256 cells).
+// Roles per CTA: warps 0-15 generators + epilogue (thread = (cell, quarter of the stage's K range / of the pass's columns)),
+// warp 16 B loader (this CTA's halves of the L^-1 tiles by bulk async copies), warp 17: in the leader CTA (cluster rank 0)
+// the MMA issuer, in the peer a relay that forwards "my B halves have landed" to the leader, warp 18 the stations'
+// coordinates of each stage (loaded ahead of the wait for the stage). The MMA issuer is lane 0 of its warp; a
+// warp-convergent form with the issuing lane picked by elect.sync (no ELECT / R2UR.BROADCAST waterfall around every
+// UTCHMMA) measured 10 % slower (PB_KRIGING_DBG=8 selects it).
+// A ring of three A stages + ten separate B tiles was tried and is slower (10.6 vs 7.9 ms without stage skipping): the
+// issuer then waits on and commits to twice as many barriers per stage.
+// Cross-CTA signalling: generator warps of both CTAs arrive on the LEADER's aFull (fence.proxy.async by every writer, then
+// one arrive per warp), tcgen05.commit multicasts mmaDone / passDone to both CTAs, the epilogue warps of both
+// CTAs arrive on the leader's tmemFree.
+constexpr int kPrCells = 128;                                   // cells per CTA = one M tile; the pair's MMA has M = 256
+constexpr int kPrN = 256;                                       // MMA N: stations i per MMA, 128 rows of B in each CTA
+constexpr int kPrPass = 512;                                    // stations i per pass = the 512 TMEM columns of each CTA
+constexpr int kPrStages = 4;                                    // ring of K = 32 stages
+constexpr int kPrStageA = 2 * kTcTileBytes;                     // hi, lo of this CTA's 128 cells: 16 KiB
+constexpr int kPrBTile = 2 * kTcTileBytes;                      // this CTA's 128 rows of one N block, hi + lo: 16 KiB
+constexpr int kPrStageBytes = kPrStageA + (kPrPass / kPrN) * kPrBTile;     // 48 KiB
+constexpr int kPrGenWarps = 16;
+constexpr int kPrGenThreads = kPrGenWarps * 32;                 // 4 threads per cell
+constexpr int kPrThreads = kPrGenThreads + 96;                  // + B loader, MMA issuer / relay, station-coordinate warp
+constexpr int kPrSmem = kPrStages * kPrStageBytes + kPrStages * kTcBK * 8 + kPrPass * 4 + 2 * 3 * kPrCells * 8 + 1024;
+constexpr int kPrMaxPasses = 64;
+constexpr int kPrMaxKb = 1024;                                  // K stages the active list can hold (n <= 32768)
+constexpr uint32_t kIdescPair = (1u << 4) | (uint32_t(kPrN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    // relaxed arrive (as CUTLASS after fence_barrier_init): .release would put a MEMBAR.ALL.GPU in front of both syncs
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank)
+{
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t clusterAddr)
+{
+    // default semantics (release at CTA scope) as in CUTLASS' ClusterBarrier::arrive(cta_id): the data the leader's MMA reads
+    // from this CTA was made visible to the async proxy by fence.proxy.async in the writing threads; .release.cluster would
+    // put a MEMBAR.ALL.GPU in front of every arrive (measured: half of the kernel's stall samples)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(clusterAddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dstSmem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dstSmem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmemD),
+        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma2_commit(uint64_t* bar)
+{
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+// warp-convergent forms: every lane executes them, one elected lane issues
+__device__ __forceinline__ void umma2_f16_elect(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmemD),
+        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_elect(uint64_t* bar)
+{
+    const uint16_t mask = 3;
+    asm volatile(
+        "{\n"
+        ".reg .pred e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ void pair_gen_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPrThreads, 1)
+kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const unsigned char* __restrict__ Mt,
+                             const float* __restrict__ z, const double* __restrict__ kbBox, KrigingTargets t, long long c0, int m,
+                             double* __restrict__ q, unsigned long long* __restrict__ mmaCount)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // stage s: [A: hi, lo of this CTA's 128 cells][B: N block 0 hi, lo, N block 1 hi, lo of this CTA's 128 stations i]
+    float2* sRel = reinterpret_cast<float2*>(smem + kPrStages * kPrStageBytes);       // [stage][kTcBK]
+    float* sZ = reinterpret_cast<float*>(sRel + kPrStages * kTcBK);                   // [kPrPass]
+    double* sRed = reinterpret_cast<double*>(sZ + kPrPass);                           // [2 sums][3 partials][kPrCells]
+    __shared__ __align__(8) uint64_t relFull[kPrStages], aFull[kPrStages], bFull[kPrStages], bPeer[kPrStages], mmaDone[kPrStages],
+        passDone, tmemFree;
+    __shared__ uint32_t tmemBase;
+    __shared__ double sCenter[2];
+    __shared__ double sBoxPart[8][4];
+    __shared__ unsigned short sList[kPrMaxKb];      // K stages (32 stations j) that can be inside the range of a cell of the pair
+    __shared__ int sNAct;
+    __shared__ unsigned short sPassStages[kPrMaxPasses];   // active stages of each pass = list entries below the end of its K range
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const long long tile0 = (long long)blockIdx.x * kPrCells;
+    if (tid == 0) {
+        for (int s = 0; s < kPrStages; s++) {
+            mbar_init(&relFull[s], 32);
+            mbar_init(&aFull[s], 2 * kPrGenWarps);      // leader only: one arrival per generator warp of either CTA
+            mbar_init(&bFull[s], 1);
+            mbar_init(&bPeer[s], 1);                    // leader only: the peer's relay
+            mbar_init(&mmaDone[s], 1);
+        }
+        mbar_init(&passDone, 1);
+        mbar_init(&tmemFree, 2 * kPrGenWarps);          // leader only
+        mbar_fence_init();
+        // centre of the CTA's cells: its first target (an empty peer CTA of the last pair takes the last target)
+        const long long cc = c0 + (tile0 < m ? tile0 : (long long)m - 1);
+        double cx, cy;
+        if (t.xy) { cx = t.xy[2 * cc]; cy = t.xy[2 * cc + 1]; }
+        else {
+            const int cell = t.validIdx[cc];
+            const int row = cell / t.grid.nrCols, col = cell - row * t.grid.nrCols;
+            cx = t.grid.llx + t.grid.cellSize * (col + 0.5);
+            cy = t.grid.lly + t.grid.cellSize * (t.grid.nrRows - row - 0.5);
+        }
+        sCenter[0] = cx;
+        sCenter[1] = cy;
+    }
+    // ---- K stages of this PAIR of CTAs: with a bounded model (p.skip) c_j = 0 beyond the range, so a stage whose 32 stations
+    // (spatially compact after the host's k-d ordering) all lie farther than the range from the pair's 256 cells contributes
+    // nothing to y = L^-1 c: it is neither generated, loaded nor multiplied. Both CTAs build the same ascending list.
+    {
+        const long long pairBase = (long long)(blockIdx.x & ~1u) * kPrCells;
+        if (tid < 2 * kPrCells) {
+            const long long ci = pairBase + tid;
+            double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+            if (p.skip && ci < m) {
+                double x, y;
+                if (t.xy) { x = t.xy[2 * (c0 + ci)]; y = t.xy[2 * (c0 + ci) + 1]; }
+                else {
+                    const int cell = t.validIdx[c0 + ci];
+                    const int row = cell / t.grid.nrCols, col = cell - row * t.grid.nrCols;
+                    x = t.grid.llx + t.grid.cellSize * (col + 0.5);
+                    y = t.grid.lly + t.grid.cellSize * (t.grid.nrRows - row - 0.5);
+                }
+                x0 = x1 = x;
+                y0 = y1 = y;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                x0 = fmin(x0, __shfl_xor_sync(~0u, x0, o));
+                x1 = fmax(x1, __shfl_xor_sync(~0u, x1, o));
+                y0 = fmin(y0, __shfl_xor_sync(~0u, y0, o));
+                y1 = fmax(y1, __shfl_xor_sync(~0u, y1, o));
+            }
+            if (lane == 0) { sBoxPart[warp][0] = x0; sBoxPart[warp][1] = x1; sBoxPart[warp][2] = y0; sBoxPart[warp][3] = y1; }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+            for (int w = 0; w < 8; w++) {
+                x0 = fmin(x0, sBoxPart[w][0]); x1 = fmax(x1, sBoxPart[w][1]);
+                y0 = fmin(y0, sBoxPart[w][2]); y1 = fmax(y1, sBoxPart[w][3]);
+            }
+            const double reach = double(p.range) * (1. + 1e-6), reach2 = reach * reach;
+            int cnt = 0;
+            for (int base = 0; base < p.nKb; base += 32) {
+                const int kb = base + lane;
+                bool act = false;
+                if (kb < p.nKb) {
+                    if (!p.skip) act = true;
+                    else {
+                        const double bx0 = kbBox[4 * kb], bx1 = kbBox[4 * kb + 1], by0 = kbBox[4 * kb + 2], by1 = kbBox[4 * kb + 3];
+                        const double ex = fmax(fmax(x0 - bx1, bx0 - x1), 0.), ey = fmax(fmax(y0 - by1, by0 - y1), 0.);
+                        act = ex * ex + ey * ey < reach2;          // an empty (padding) stage has bx0 = +inf: never active
+                    }
+                }
+                const unsigned b = __ballot_sync(~0u, act);
+                if (act) sList[cnt + __popc(b & ((1u << lane) - 1u))] = (unsigned short)kb;
+                cnt += __popc(b);
+            }
+            if (lane == 0) sNAct = cnt;
+            __syncwarp();
+            for (int pass = lane; pass < (p.nPad + kPrPass - 1) / kPrPass; pass += 32) {
+                const int i0p = pass * kPrPass;
+                const int nNb = min(kPrPass / kPrN, (p.nPad - i0p) / kPrN);
+                const int kbEnd = min(p.nKb, (i0p + nNb * kPrN) / kTcBK);
+                int c = 0;
+                while (c < cnt && sList[c] < kbEnd) c++;
+                sPassStages[pass] = (unsigned short)c;
+            }
+        }
+    }
+    if (warp == 0) {
+        tmem_alloc2(&tmemBase, 512);
+        tmem_relinquish2();
+    }
+    tc_fence_before();
+    cluster_sync_all();                                  // barriers of both CTAs initialised before any remote arrive; sList visible
+    tc_fence_after();
+    const uint32_t tmem = tmemBase;
+    const double cx = sCenter[0], cy = sCenter[1];
+    const double invRangeD = 1.0 / double(p.range);
+    const int nPasses = (p.nPad + kPrPass - 1) / kPrPass;
+    const int nAct = sNAct;
+
+    if (warp == kPrGenWarps) {
+        // ------------------------------------------------------------ B loader: this CTA's halves of the L^-1 tiles
+        if (lane == 0) {
+            uint32_t it = 0;
+            int idxEnd = 0;
+            for (int pass = 0; pass < nPasses; pass++) {
+                const int i0p = pass * kPrPass;
+                const int nNb = min(kPrPass / kPrN, (p.nPad - i0p) / kPrN);
+                const int kbEnd = min(p.nKb, (i0p + nNb * kPrN) / kTcBK);
+                while (idxEnd < nAct && sList[idxEnd] < kbEnd) idxEnd++;
+                for (int idx = 0; idx < idxEnd; idx++, it++) {
+                    const int kb = sList[idx], j0 = kb * kTcBK;
+                    const int s = it % kPrStages;
+                    const uint32_t u = it / kPrStages;
+                    if (u > 0) mbar_wait(&mmaDone[s], (u - 1) & 1);        // the MMAs that read this stage's buffers are done
+                    unsigned char* sB = smem + s * kPrStageBytes + kPrStageA;
+                    int cnt = 0;
+                    for (int nb = 0; nb < nNb; nb++) cnt += (j0 <= i0p + nb * kPrN + kPrN - 1);
+                    mbar_expect_tx(&bFull[s], uint32_t(cnt) * kPrBTile);
+                    for (int nb = 0; nb < nNb; nb++)
+                        if (j0 <= i0p + nb * kPrN + kPrN - 1) {
+                            const size_t itile = size_t(i0p / kTcNT + 2 * nb) + rank;      // this CTA's 128 rows of the N block
+                            bulk_g2s(sB + size_t(nb) * kPrBTile, Mt + (itile * p.nKb + kb) * kPrBTile, kPrBTile, &bFull[s]);
+                        }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kPrGenWarps + 2) {
+        // ------------------------------------------------------------ station coordinates of each stage
+        uint32_t it = 0;
+        int idxEnd = 0;
+        for (int pass = 0; pass < nPasses; pass++) {
+            const int i0p = pass * kPrPass;
+            const int nNb = min(kPrPass / kPrN, (p.nPad - i0p) / kPrN);
+            const int kbEnd = min(p.nKb, (i0p + nNb * kPrN) / kTcBK);
+            while (idxEnd < nAct && sList[idxEnd] < kbEnd) idxEnd++;
+            for (int idx = 0; idx < idxEnd; idx++, it++) {
+                const int kb = sList[idx];
+                const int s = it % kPrStages;
+                const uint32_t u = it / kPrStages;
+                const int j = kb * kTcBK + lane;
+                // coordinates in units of the range, pairs of stations as {x0, x1, y0, y1}; padding stations sit far away
+                const float rx = (j < p.n) ? float((pos[2 * j] - cx) * invRangeD) : 1e12f;
+                const float ry = (j < p.n) ? float((pos[2 * j + 1] - cy) * invRangeD) : 1e12f;
+                if (u > 0) mbar_wait(&mmaDone[s], (u - 1) & 1);            // the generators have read the stage's previous use
+                float* relS = reinterpret_cast<float*>(sRel + s * kTcBK) + (lane >> 1) * 4 + (lane & 1);
+                relS[0] = rx;
+                relS[2] = ry;
+                mbar_arrive(&relFull[s]);
+            }
+        }
+    } else if (warp == kPrGenWarps + 1) {
+        uint32_t it = 0, ep = 0, nMma = 0;
+        int idxEnd = 0;
+        if (rank != 0) {
+            // -------------------------------------------------------- relay (peer CTA): my B halves of the stage are in place
+            if (lane == 0) {
+                const uint32_t bPeerLeader = mapa_shared(smem_u32(&bPeer[0]), 0);
+                for (int pass = 0; pass < nPasses; pass++) {
+                    const int i0p = pass * kPrPass;
+                    const int nNb = min(kPrPass / kPrN, (p.nPad - i0p) / kPrN);
+                    const int kbEnd = min(p.nKb, (i0p + nNb * kPrN) / kTcBK);
+                    while (idxEnd < nAct && sList[idxEnd] < kbEnd) idxEnd++;
+                    for (int idx = 0; idx < idxEnd; idx++, it++) {
+                        const int s = it % kPrStages;
+                        mbar_wait(&bFull[s], (it / kPrStages) & 1);
+                        mbar_arrive_cluster(bPeerLeader + uint32_t(s) * 8u);
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // -------------------------------------------------------- MMA issuer (leader CTA), warp-convergent
+            for (int pass = 0; pass < nPasses; pass++) {
+                const int i0p = pass * kPrPass;
+                const int nNb = min(kPrPass / kPrN, (p.nPad - i0p) / kPrN);
+                const int kbEnd = min(p.nKb, (i0p + nNb * kPrN) / kTcBK);
+                while (idxEnd < nAct && sList[idxEnd] < kbEnd) idxEnd++;
+                if (idxEnd == 0) continue;                                  // no station of this pass's K range is near: y = 0
+                if (ep > 0) {
+                    if (lane == 0) mbar_wait(&tmemFree, (ep - 1) & 1);     // both CTAs' epilogues have read the accumulators
+                    __syncwarp();
+                    tc_fence_after();
+                }
+                ep++;
+                for (int idx = 0; idx < idxEnd; idx++, it++) {
+                    const int kb = sList[idx], j0 = kb * kTcBK;
+                    const int s = it % kPrStages;
+                    const uint32_t ph = (it / kPrStages) & 1;
+                    if (lane == 0) {
+                        mbar_wait(&aFull[s], ph);
+                        mbar_wait(&bFull[s], ph);
+                        mbar_wait(&bPeer[s], ph);
+                    }
+                    __syncwarp();
+                    tc_fence_after();
+                    if (!(p.dbg & 8)) {
+                        if (lane == 0) {
+                            const uint32_t sa = smem_u32(smem + s * kPrStageBytes), sb = sa + kPrStageA;
+                            const uint32_t aHi = sa, aLo = sa + kTcTileBytes;
+                            for (int nb = 0; nb < nNb; nb++) {
+                                if (!(j0 <= i0p + nb * kPrN + kPrN - 1)) continue;
+                                nMma += 3 * (kTcBK / 16);
+                                const uint32_t bHi = sb + uint32_t(nb) * kPrBTile, bLo = bHi + kTcTileBytes;
+                                const uint32_t d = tmem + uint32_t(nb * kPrN);
+#pragma unroll
+                                for (int ks = 0; ks < kTcBK / 16; ks++) {
+                                    const uint32_t o = ks * 256;
+                                    umma2_f16(d, umma_desc(aHi + o), umma_desc(bHi + o), kIdescPair, (idx > 0 || ks > 0) ? 1u : 0u);
+                                    umma2_f16(d, umma_desc(aHi + o), umma_desc(bLo + o), kIdescPair, 1u);
+                                    umma2_f16(d, umma_desc(aLo + o), umma_desc(bHi + o), kIdescPair, 1u);
+                                }
+                            }
+                            umma2_commit(&mmaDone[s]);
+                            if (idx == idxEnd - 1) umma2_commit(&passDone);
+                        }
+                        __syncwarp();
+                        continue;
+                    }
+                    if (!(p.dbg & 2)) {
+                        const uint32_t sa = smem_u32(smem + s * kPrStageBytes), sb = sa + kPrStageA;
+                        const uint32_t aHi = sa, aLo = sa + kTcTileBytes;
+                        for (int nb = 0; nb < nNb; nb++) {
+                            if (!(j0 <= i0p + nb * kPrN + kPrN - 1)) continue;
+                            const uint32_t bHi = sb + uint32_t(nb) * kPrBTile, bLo = bHi + kTcTileBytes;
+                            const uint32_t d = tmem + uint32_t(nb * kPrN);
+#pragma unroll
+                            for (int ks = 0; ks < kTcBK / 16; ks++) {
+                                const uint32_t o = ks * 256;
+                                umma2_f16_elect(d, umma_desc(aHi + o), umma_desc(bHi + o), kIdescPair, (idx > 0 || ks > 0) ? 1u : 0u);
+                                umma2_f16_elect(d, umma_desc(aHi + o), umma_desc(bLo + o), kIdescPair, 1u);
+                                umma2_f16_elect(d, umma_desc(aLo + o), umma_desc(bHi + o), kIdescPair, 1u);
+                            }
+                        }
+                    }
+                    umma2_commit_elect(&mmaDone[s]);                        // frees the stage in both CTAs
+                    if (idx == idxEnd - 1) umma2_commit_elect(&passDone);
+                }
+            }
+            // issued M = 256, N = 256, K = 16 MMAs of this pair (bench.py: executed tensor flops next to the algorithmic ones)
+            if (lane == 0 && mmaCount && nMma) atomicAdd(mmaCount, (unsigned long long)nMma);
+        }
+    } else {
+        // ------------------------------------------------------------ generators: four threads per cell (= MMA row = TMEM lane)
+        const int r = (warp & 3) * 32 + lane;             // a warp reads the TMEM lanes 32 (warp % 4) ..
+        const int kq = warp >> 2;                         // quarter of the stage's K range / of the pass's columns
+        const long long cidx = tile0 + r;
+        const bool valid = cidx < m;
+        float xr = 0.f, yr = 0.f;
+        if (valid) {
+            double x, y;
+            if (t.xy) { x = t.xy[2 * (c0 + cidx)]; y = t.xy[2 * (c0 + cidx) + 1]; }
+            else {
+                const int cell = t.validIdx[c0 + cidx];
+                const int row = cell / t.grid.nrCols, col = cell - row * t.grid.nrCols;
+                x = t.grid.llx + t.grid.cellSize * (col + 0.5);
+                y = t.grid.lly + t.grid.cellSize * (t.grid.nrRows - row - 0.5);
+            }
+            xr = float((x - cx) * invRangeD);
+            yr = float((y - cy) * invRangeD);
+        }
+        double accY2 = 0., accZY = 0.;
+        uint32_t it = 0;
+        const uint32_t laneBase = uint32_t((warp & 3) * 32) << 16;
+        const uint32_t aFullLeader = mapa_shared(smem_u32(&aFull[0]), 0), tmemFreeLeader = mapa_shared(smem_u32(&tmemFree), 0);
+        const f32x2 nxr2 = pack2(-xr, -xr), nyr2 = pack2(-yr, -yr);
+        const f32x2 one2 = pack2(1.f, 1.f), negOne2 = pack2(-1.f, -1.f), sn2 = pack2(p.sn, p.sn), hsn2 = pack2(0.5f * p.sn, 0.5f * p.sn);
+        const int k0 = kq * 8;
+        const size_t offA = tileOffset(r, k0);
+        // one stage of A: the generators do not need to know which stations it holds (their coordinates arrive in sRel)
+        auto genStage = [&]() {
+            {
+                const int s = it % kPrStages;
+                const uint32_t u = it / kPrStages;
+                if (u > 0) mbar_wait(&mmaDone[s], (u - 1) & 1);            // A[s] is free again
+                mbar_wait(&relFull[s], u & 1);
+                unsigned char* sA = smem + s * kPrStageBytes;
+                const ulonglong2* rel = reinterpret_cast<const ulonglong2*>(sRel + s * kTcBK) + (k0 >> 1);     // [pair] = {x0 x1, y0 y1}
+                if (!(p.dbg & 1)) {
+                __half2 hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const ulonglong2 sxy = rel[e];
+                    const f32x2 dx = add2(sxy.x, nxr2), dy = add2(sxy.y, nyr2);
+                    const f32x2 t2p = fma2(dx, dx, mul2(dy, dy));          // (h / range)^2
+                    float ta, tb, c0v, c1v;
+                    unpack2(t2p, ta, tb);
+                    if (MODE == PB_KRIGING_SPHERICAL) {
+                        // sn (1 - 1.5 t + 0.5 t^3) = sn (1 - t)^2 (1 + t / 2), t clamped to 1: exactly 0 beyond the range
+                        const f32x2 tt = pack2(fminf(sqrt_approx(ta), 1.f), fminf(sqrt_approx(tb), 1.f));
+                        const f32x2 um = fma2(tt, negOne2, one2);
+                        const f32x2 c = mul2(mul2(um, um), fma2(tt, hsn2, sn2));
+                        unpack2(c, c0v, c1v);
+                    } else if (MODE == PB_KRIGING_EXPONENTIAL) {
+                        c0v = p.sn * ex2_approx(-4.328085123f * sqrt_approx(ta));      // exp(-3 t)
+                        c1v = p.sn * ex2_approx(-4.328085123f * sqrt_approx(tb));
+                    } else {
+                        c0v = p.sn * ex2_approx(-5.770780164f * ta);                   // exp(-4 t^2)
+                        c1v = p.sn * ex2_approx(-5.770780164f * tb);
+                    }
+                    const __half2 h2 = __floats2half2_rn(c0v, c1v);
+                    const float2 back = __half22float2(h2);
+                    hi[e] = h2;
+                    lo[e] = __floats2half2_rn(c0v - back.x, c1v - back.y);
+                }
+                *reinterpret_cast<uint4*>(sA + offA) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(sA + kTcTileBytes + offA) = *reinterpret_cast<const uint4*>(lo);
+                }
+                fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(aFullLeader + uint32_t(s) * 8u);
+                it++;
+            }
+        };
+        // active stages of a pass = list entries below the end of its K range
+        auto stagesOf = [&](int pass) { return pass < nPasses ? int(sPassStages[pass]) : 0; };
+        uint32_t ep = 0;
+        int carried = 0;                        // stages of this pass already generated while the previous pass drained
+        for (int pass = 0; pass < nPasses; pass++) {
+            const int i0p = pass * kPrPass;
+            const int nNb = min(kPrPass / kPrN, (p.nPad - i0p) / kPrN);
+            const int nSt = stagesOf(pass);
+            if (nSt == 0) continue;                                         // nothing near in this pass's K range: y = 0
+            for (int k = carried; k < nSt; k++) genStage();
+            // run ahead: the first stages of the next pass are generated while the tensor core drains this one (their ring
+            // slots are freed by this pass's MMAs; the issuer holds the next pass's MMAs back until tmemFree), so the
+            // pipeline is full again as soon as the epilogue below has released the accumulators
+            carried = min(kPrStages - 1, stagesOf(pass + 1));
+            for (int k = 0; k < carried; k++) genStage();
+            // ---- epilogue of the pass: columns = stations i of this pass, a quarter for each of the four threads of a cell ----
+            sZ[tid] = (i0p + tid < p.nPad) ? z[i0p + tid] : 0.f;          // kPrGenThreads == kPrPass
+            mbar_wait(&passDone, ep & 1);
+            ep++;
+            // the first N block has columns only if the pass's first active stage reaches it (its K range ends 256 earlier)
+            const bool hasNb0 = int(sList[0]) * kTcBK <= i0p + kPrN - 1;
+            tc_fence_after();
+            pair_gen_bar_sync();
+            const int nCb = nNb * kPrN / 32;
+            for (int cb = kq; cb < nCb && !(p.dbg & 4); cb += 4) {
+                if (cb < kPrN / 32 && !hasNb0) continue;
+                uint32_t v[32];
+                tmem_ld32(tmem + laneBase + uint32_t(cb * 32), v);
+                float y2 = 0.f, zy = 0.f;
+                const float4* z4 = reinterpret_cast<const float4*>(sZ + cb * 32);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const float4 zz4 = z4[e];
+                    const float y0 = __uint_as_float(v[4 * e]), y1 = __uint_as_float(v[4 * e + 1]);
+                    const float y2_ = __uint_as_float(v[4 * e + 2]), y3 = __uint_as_float(v[4 * e + 3]);
+                    y2 = fmaf(y0, y0, y2); zy = fmaf(zz4.x, y0, zy);
+                    y2 = fmaf(y1, y1, y2); zy = fmaf(zz4.y, y1, zy);
+                    y2 = fmaf(y2_, y2_, y2); zy = fmaf(zz4.z, y2_, zy);
+                    y2 = fmaf(y3, y3, y2); zy = fmaf(zz4.w, y3, zy);
+                }
+                accY2 += double(y2);
+                accZY += double(zy);
+            }
+            tc_fence_before();
+            pair_gen_bar_sync();                // sZ is rewritten for the next pass; every warp's TMEM reads are complete
+            if (lane == 0) mbar_arrive_cluster(tmemFreeLeader);
+        }
+        if (kq > 0) { sRed[(kq - 1) * kPrCells + r] = accY2; sRed[(3 + kq - 1) * kPrCells + r] = accZY; }
+        pair_gen_bar_sync();
+        if (kq == 0 && valid) {
+            const double y2 = accY2 + sRed[r] + sRed[kPrCells + r] + sRed[2 * kPrCells + r];
+            const double zy = accZY + sRed[3 * kPrCells + r] + sRed[4 * kPrCells + r] + sRed[5 * kPrCells + r];
+            q[cidx] = p.sill - (y2 - zy * (zy - 1.) / p.zz);      // = sum_i weight_i D_i of krigingRMSE
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                         // nobody leaves while the peer can still signal or read this CTA
+    if (warp == 0) tmem_dealloc2(tmem, 512);
+}
+
 // CUDA-core check of the same whitened formulation from the same pre-tiled FP16 pieces (tests / debugging only:
 // PB_KRIGING_SIMPLE=1). One thread per target, O(n^2) covariance evaluations: small systems only.
 __global__ void kriging_variance_simple_kernel(TcParams p, const double* __restrict__ pos, const unsigned char* __restrict__ Mt,
@@ -394,10 +931,11 @@ __global__ void kriging_variance_simple_kernel(TcParams p, const double* __restr
 // ---------------------------------------------------------------------------------------------------------
 // host: split M into FP16 hi/lo pieces, pre-tiled in the canonical UMMA layout; upload with z
 // ---------------------------------------------------------------------------------------------------------
-int krigingUploadWhitened(KrigingSystem& k, const std::vector<double>& M, const std::vector<double>& z, double zz)
+int krigingUploadWhitened(KrigingSystem& k, const std::vector<double>& M, const std::vector<double>& z, double zz,
+                          const double* pos)
 {
     const int n = k.n;
-    const int nPad = (n + kTcNT - 1) / kTcNT * kTcNT;
+    const int nPad = (n + 2 * kTcNT - 1) / (2 * kTcNT) * (2 * kTcNT);     // whole N blocks of the CTA-pair kernel
     const int nIt = nPad / kTcNT, nKb = nPad / kTcBK;
     double maxAbs = 0;
     for (double v : M) maxAbs = std::max(maxAbs, fabs(v));
@@ -427,6 +965,20 @@ int krigingUploadWhitened(KrigingSystem& k, const std::vector<double>& M, const 
         }
     std::vector<float> zf(nPad, 0.f);
     for (int i = 0; i < n; i++) zf[i] = float(z[i]);
+    // bounding box of every K stage's stations (kriging.cu kdOrder makes them compact); padding stages are empty
+    std::vector<double> box(size_t(4) * nKb);
+    for (int kb = 0; kb < nKb; kb++) {
+        double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+        for (int j = kb * kTcBK; j < std::min(n, (kb + 1) * kTcBK); j++) {
+            x0 = std::min(x0, pos[2 * j]); x1 = std::max(x1, pos[2 * j]);
+            y0 = std::min(y0, pos[2 * j + 1]); y1 = std::max(y1, pos[2 * j + 1]);
+        }
+        box[4 * kb] = x0; box[4 * kb + 1] = x1; box[4 * kb + 2] = y0; box[4 * kb + 3] = y1;
+    }
+    if (cudaMalloc(&k.dKbBox, sizeof(double) * box.size()) != cudaSuccess) return 2;
+    if (cudaMemcpy(k.dKbBox, box.data(), sizeof(double) * box.size(), cudaMemcpyHostToDevice) != cudaSuccess) return 2;
+    if (cudaMalloc(&k.dMmaCount, sizeof(unsigned long long)) != cudaSuccess) return 2;
+    if (cudaMemset(k.dMmaCount, 0, sizeof(unsigned long long)) != cudaSuccess) return 2;
     if (cudaMalloc(&k.dMhi, bytes) != cudaSuccess) return 2;
     if (cudaMalloc(&k.dZ, sizeof(float) * nPad) != cudaSuccess) return 2;
     if (cudaMemcpy(k.dMhi, blob.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return 2;
@@ -451,23 +1003,44 @@ cudaError_t launchKrigingVarianceTc(const KrigingSystem& k, const KrigingTargets
     p.sn = float(k.params.sillNugget);
     p.sill = k.params.sill;
     p.zz = k.zz;
+    static const int dbg = getenv("PB_KRIGING_DBG") ? atoi(getenv("PB_KRIGING_DBG")) : 0;
+    p.dbg = dbg;
     static const bool simple = getenv("PB_KRIGING_SIMPLE") && atoi(getenv("PB_KRIGING_SIMPLE")) != 0;
     if (simple) {
         kriging_variance_simple_kernel<<<(m + 127) / 128, 128, 0, s>>>(p, k.dPos, k.dMhi, k.dZ, t, c0, m, q);
         return cudaGetLastError();
     }
-    const int grid = (m + kTcCells - 1) / kTcCells;
-    auto launch = [&](auto kernel) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-        if (e != cudaSuccess) return e;
-        kernel<<<grid, kTcThreads, kTcSmem, s>>>(p, k.dPos, k.dMhi, k.dZ, t, c0, m, q);
-        return cudaSuccess;
-    };
+    static const bool envSingle = getenv("PB_KRIGING_SINGLE_CTA") && atoi(getenv("PB_KRIGING_SINGLE_CTA")) != 0;
+    static const bool noSkip = getenv("PB_KRIGING_NOSKIP") && atoi(getenv("PB_KRIGING_NOSKIP")) != 0;
+    const bool single = envSingle || k.nKb > kPrMaxKb || (k.nPad + kPrPass - 1) / kPrPass > kPrMaxPasses;
+    p.skip = (p.mode == PB_KRIGING_SPHERICAL && !noSkip) ? 1 : 0;
     cudaError_t e;
-    switch (p.mode) {
-    case PB_KRIGING_SPHERICAL: e = launch(kriging_variance_tc_kernel<PB_KRIGING_SPHERICAL>); break;
-    case PB_KRIGING_EXPONENTIAL: e = launch(kriging_variance_tc_kernel<PB_KRIGING_EXPONENTIAL>); break;
-    default: e = launch(kriging_variance_tc_kernel<PB_KRIGING_GAUSSIAN>); break;
+    if (single) {
+        const int grid = (m + kTcCells - 1) / kTcCells;
+        auto launch = [&](auto kernel) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+            if (e != cudaSuccess) return e;
+            kernel<<<grid, kTcThreads, kTcSmem, s>>>(p, k.dPos, k.dMhi, k.dZ, t, c0, m, q);
+            return cudaSuccess;
+        };
+        switch (p.mode) {
+        case PB_KRIGING_SPHERICAL: e = launch(kriging_variance_tc_kernel<PB_KRIGING_SPHERICAL>); break;
+        case PB_KRIGING_EXPONENTIAL: e = launch(kriging_variance_tc_kernel<PB_KRIGING_EXPONENTIAL>); break;
+        default: e = launch(kriging_variance_tc_kernel<PB_KRIGING_GAUSSIAN>); break;
+        }
+    } else {
+        const int grid = 2 * ((m + 2 * kPrCells - 1) / (2 * kPrCells));      // whole CTA pairs (__cluster_dims__(2, 1, 1))
+        auto launch = [&](auto kernel) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrSmem);
+            if (e != cudaSuccess) return e;
+            kernel<<<grid, kPrThreads, kPrSmem, s>>>(p, k.dPos, k.dMhi, k.dZ, k.dKbBox, t, c0, m, q, k.dMmaCount);
+            return cudaSuccess;
+        };
+        switch (p.mode) {
+        case PB_KRIGING_SPHERICAL: e = launch(kriging_variance_pair_kernel<PB_KRIGING_SPHERICAL>); break;
+        case PB_KRIGING_EXPONENTIAL: e = launch(kriging_variance_pair_kernel<PB_KRIGING_EXPONENTIAL>); break;
+        default: e = launch(kriging_variance_pair_kernel<PB_KRIGING_GAUSSIAN>); break;
+        }
     }
     if (e != cudaSuccess) return e;
     return cudaGetLastError();

@@ -83,6 +83,7 @@ def load_library():
                                      C.c_double, C.c_double, C.c_int, P(C.c_int32)]
     lib.pb_kriging_free.argtypes = [C.c_void_p, C.c_int32]
     lib.pb_kriging_uses_tensor_path.argtypes = [C.c_void_p, C.c_int32]
+    lib.pb_kriging_mma_count.argtypes = [C.c_void_p, C.c_int32, P(C.c_ulonglong)]
     lib.pb_kriging_points.argtypes = [C.c_void_p, C.c_int32, P(C.c_double), C.c_int, P(C.c_double), P(C.c_double)]
     lib.pb_kriging_raster.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_int, P(A.pb_raster_out),
                                       P(A.pb_raster_out)]
@@ -395,6 +396,12 @@ class Engine:
 
     def kriging_uses_tensor_path(self, kid):
         return self.lib.pb_kriging_uses_tensor_path(self.h, kid) == 1
+
+    def kriging_mma_count(self, kid):
+        """tensor-core MMAs (2 * 256 * 256 * 16 flop each) issued for this system since the last call (measurement aid)"""
+        n = C.c_ulonglong(0)
+        self._check(self.lib.pb_kriging_mma_count(self.h, kid, C.byref(n)))
+        return int(n.value)
 
     def kriging_points(self, kid, xy, want_rmse=True):
         """krigingSetWeight + krigingResult + krigingRMSE (kriging.cpp:211-295) at m points."""

@@ -110,3 +110,54 @@ def test_kriging_raster_matches_points(engine, ref):
     assert np.abs(rm[rows, cols] - want_rm).max() <= TOL
     engine.kriging_free(kid)
     engine.free(did)
+
+
+def test_kriging_c4_raster_tile_with_skipped_stages(engine, ref):
+    """The C4 system on raster tiles, where the variance kernel skips K stages: a pair of CTAs covers 256 neighbouring cells
+    and multiplies only the stages (32 stations, k-d ordered on the host) that can be inside the variogram range of one of
+    them. A 40 x 40 window of 100 m cells in the middle of the 1000 km box and one in its corner, every cell against the
+    reference's krigingSetWeight / krigingResult / krigingRMSE; the counter of issued MMAs proves that stages were skipped."""
+    n = 2000
+    rng = np.random.default_rng(1)
+    pos = np.stack([syn.LLX + rng.random(n) * 1.0e6, syn.LLY + rng.random(n) * 1.0e6], axis=1)
+    val = rng.normal(12.0, 3.0, n)
+    kid = engine.kriging_setup(pos, val, A.KRIGING_SPHERICAL, 2.0e5, 0.1, 4.0, 0.0)
+    assert engine.kriging_uses_tensor_path(kid) == 1
+    for (ox, oy) in ((4.7e5, 5.1e5), (0.0, 0.0)):
+        data = np.full((40, 40), 100.0, dtype=np.float32)
+        data[3, 5:9] = -9999.0
+        dem = A.Raster(data, syn.LLX + ox, syn.LLY + oy, 100.0, -9999.0)
+        did = engine.upload(dem)
+        engine.kriging_mma_count(kid)
+        est, rm, nv = engine.kriging_raster(kid, did, dem.shape)
+        mma = engine.kriging_mma_count(kid)
+        rows, cols = np.nonzero(data != np.float32(-9999.0))
+        assert nv == rows.size
+        xy = np.stack([dem.llx + 100.0 * (cols + 0.5), dem.lly + 100.0 * (40 - rows - 0.5)], axis=1)
+        sel = np.random.default_rng(5).choice(rows.size, 160, replace=False)
+        ok, want, want_rm, _, _ = ref.kriging_points(pos, val, A.KRIGING_SPHERICAL, 2.0e5, 0.1, 4.0, 0.0, xy[sel])
+        assert ok
+        e1 = np.abs(est[rows[sel], cols[sel]] - want).max()
+        e2 = np.abs(rm[rows[sel], cols[sel]] - want_rm).max()
+        dense = 1728 * ((nv + 255) // 256)              # MMAs of the unskipped lower triangle (n padded to 2048) per 256 cells
+        print(f"window at ({ox:.0f}, {oy:.0f}): estimate {e1:.2e} rmse {e2:.2e}, MMAs {mma} of {dense}")
+        assert e1 <= TOL and e2 <= TOL
+        assert 0 < mma < 0.5 * dense
+        engine.free(did)
+    engine.kriging_free(kid)
+
+
+def test_kriging_targets_out_of_every_range(engine, ref):
+    """targets farther than the range from every station: all weights come from the unbiasedness constraint alone; the
+    variance kernel skips every stage (y = 0) and must still return the reference's numbers."""
+    pos, val, _ = scenario(300, 1, seed=11)
+    xy = np.stack([np.full(40, 5.0e5 + 9.0e5) + np.arange(40) * 50.0, np.full(40, 4.8e6 + 1.0e5)], axis=1)
+    ok, want, want_rm, _, _ = ref.kriging_points(pos, val, A.KRIGING_SPHERICAL, 8.0e4, 0.2, 4.0, 0.0, xy)
+    assert ok
+    kid = engine.kriging_setup(pos, val, A.KRIGING_SPHERICAL, 8.0e4, 0.2, 4.0, 0.0)
+    assert engine.kriging_uses_tensor_path(kid) == 1
+    engine.kriging_mma_count(kid)
+    got, got_rm = engine.kriging_points(kid, xy)
+    assert engine.kriging_mma_count(kid) == 0
+    engine.kriging_free(kid)
+    assert np.abs(got - want).max() <= TOL and np.abs(got_rm - want_rm).max() <= TOL
