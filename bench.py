@@ -34,6 +34,14 @@ import sys
 import threading
 import time
 
+# One process per GPU: torchrun pins every rank to OMP_NUM_THREADS=1 unless the variable is set, which leaves the host side
+# of a step (scatter of the 16 MB output grid into the caller's float** rows, station staging) on one core per rank while
+# the others idle. Every rank takes its share of the node's cores instead; must happen before libgomp is loaded.
+_WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+if _WORLD > 1 and os.environ.get("PB_BENCH_KEEP_OMP") is None:
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _WORLD))
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")       # idle OpenMP workers sleep: the cores belong to the lane threads
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -657,7 +665,10 @@ class HourlyBatchWorkload:
                      A.precipitation: syn.make_stations(self.dem, n, proxies=grids, variable="precipitation")}
         self.rank, self.world = rank, world
         # 4 lanes measured best on one B200 (the raster kernels of the lanes run one after the other; more lanes only queue)
-        self.lanes = int(os.environ.get("PB_BENCH_LANES", "4"))
+        # with several ranks on one node every rank's lane threads + its own thread should fit the rank's share of the cores
+        # (they wait for the device by spinning; oversubscribed spinning threads were what collapsed c5 at 8 GPUs in r01)
+        share = max(1, (os.cpu_count() or 1) // max(1, world))
+        self.lanes = int(os.environ.get("PB_BENCH_LANES", str(max(1, min(4, share - 1)))))
         self.geom = self._geometry()
         self.n_cells = self.geom[3].size
         self.gpu = getattr(eng, "h", None) is not None
@@ -935,7 +946,18 @@ def get_oracle():
     return binding.Oracle(kind), kind
 
 
+BLOCKING_SYNC_FOR = set()          # workloads that run with blocking synchronisation (filled by main)
+
+
 def run_workload(name, eng, torch, dist, rank, world, steps, warmup, sampler, flush, want_cpu):
+    eng.set_blocking_sync(name in BLOCKING_SYNC_FOR)
+    try:
+        return _run_workload(name, eng, torch, dist, rank, world, steps, warmup, sampler, flush, want_cpu)
+    finally:
+        eng.set_blocking_sync(False)
+
+
+def _run_workload(name, eng, torch, dist, rank, world, steps, warmup, sampler, flush, want_cpu):
     """one workload through the contract: W untimed warm-up steps, K timed steps (CUDA events on the launching stream, L2
     flushed between iterations), barrier + synchronize on both sides, max over ranks; then the same K steps end to end."""
     n_total = warmup + steps
@@ -1162,9 +1184,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = pb.Engine(local_rank)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    if world * 5 > (os.cpu_count() or 1):
-        # more waiting host threads (ranks x lanes of the batch driver + the ranks' own) than cores: sleep, do not spin
-        eng.set_blocking_sync(True)
+    # c5 only (run_workload): with more waiting host threads (ranks x lanes of the batch driver + the ranks' own) than cores
+    # the lane threads sleep in their synchronisations instead of spinning; the single-threaded workloads keep spinning
+    # (a blocking wake-up sits inside every device-timed step: it cost c2 0.35 ms per step at 8 ranks)
+    lanes_c5 = int(os.environ.get("PB_BENCH_LANES", str(max(1, min(4, max(1, (os.cpu_count() or 1) // world) - 1)))))
+    blocking_for_c5 = world * (lanes_c5 + 1) > (os.cpu_count() or 1)
+    if blocking_for_c5:
+        BLOCKING_SYNC_FOR.add("c5")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     sampler = None

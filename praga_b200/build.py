@@ -83,6 +83,8 @@ def build(force=False, verbose=False):
         cmd = [nvcc] + ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp,-O2", "-ccbin", "/usr/bin/g++"]
         if verbose:
             cmd += ["-Xptxas", "-v"]
+        if os.environ.get("PB_DEBUG"):
+            cmd += ["-DPB_DEBUG_ASSERTS"]          # device-side capacity asserts (common.cuh PB_DEV_ASSERT)
         cmd += extra + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False

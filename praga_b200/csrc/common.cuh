@@ -4,6 +4,22 @@
 #include <stdint.h>
 #include "../../include/praga_b200.h"
 
+// Device-side capacity checks (tile / scratch / ring sizes), compiled in with -DPB_DEBUG_ASSERTS (PB_DEBUG=1 python -m
+// praga_b200.build --force): compute-sanitizer is not available on the GPU pool, so the engine carries its own bounds checks.
+// A failed check prints the site and traps: the launch ends with an error that the C ABI reports as PB_ERR_CUDA.
+#ifdef PB_DEBUG_ASSERTS
+#include <stdio.h>
+#define PB_DEV_ASSERT(cond)                                                                                          \
+    do {                                                                                                             \
+        if (!(cond)) {                                                                                               \
+            printf("praga_b200 device assert: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, blockIdx.x, threadIdx.x); \
+            __trap();                                                                                                \
+        }                                                                                                            \
+    } while (0)
+#else
+#define PB_DEV_ASSERT(cond) ((void)0)
+#endif
+
 namespace pb {
 
 constexpr float kNoData = -9999.f;           // NODATA, agrolib/mathFunctions/commonConstants.h:31

@@ -205,6 +205,7 @@ idw_kernel(DevStations st, DevModel m, DevGrid dem, const int* __restrict__ vali
     const int nTiles = st.nPadded / kTileStations;
     const int usedPadded = (st.n + kChunk - 1) / kChunk * kChunk;     // stations rounded up to whole accumulation chunks
     constexpr int C = 2 * P;
+    PB_DEV_ASSERT(st.nPadded % kTileStations == 0 && st.n <= st.nPadded);
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -395,6 +396,8 @@ idw_persistent_kernel(DevStations st, DevModel m, DevGrid dem, const int* __rest
     const int nTiles = st.nPadded / kTileStations;
     const int usedPadded = (st.n + kChunk - 1) / kChunk * kChunk;
     constexpr int C = 2 * P;
+    // every station tile is resident: the launch sized the dynamic shared memory for nPadded stations
+    PB_DEV_ASSERT(st.nPadded % kTileStations == 0 && st.nPadded <= kResidentMaxStations && st.n <= st.nPadded);
 
     if (tid == 0) {
         mbar_init(&bar, 1);

@@ -23,6 +23,7 @@
 #include <omp.h>
 #include <string.h>
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -392,6 +393,10 @@ void krigingFree(KrigingSystem* k)
     if (k->dZ) cudaFree(k->dZ);
     if (k->dKbBox) cudaFree(k->dKbBox);
     if (k->dMmaCount) cudaFree(k->dMmaCount);
+    if (k->sDn) {
+        cudaStreamDestroy(k->sDn);
+        for (auto& e : k->evDn) cudaEventDestroy(e);
+    }
     if (k->dWork) cudaFree(k->dWork);
     delete k;
 }
@@ -418,7 +423,7 @@ KrigingSystem* systemOf(pb_context* ctx, pb_kriging_id id)
 
 // run estimate + variance over targets [0, m) in chunks; results to host doubles (points) or device grids (raster)
 int evaluate(pb_context* ctx, KrigingSystem* k, const KrigingTargets& t, long long m, bool wantRmse, double* dOutEst,
-             double* dOutRmse, float* gridEst, float* gridRmse)
+             double* dOutRmse, float* gridEst, float* gridRmse, const std::function<int(long long)>& afterChunk = nullptr)
 {
     const int chunk = k->tensor ? kTcChunk : 8192;
     const size_t ldD = chunk;
@@ -461,6 +466,10 @@ int evaluate(pb_context* ctx, KrigingSystem* k, const KrigingTargets& t, long lo
                                                                           dOutRmse, gridEst, gridRmse);
         ctx->timing.launches++;
         CUDA_TRY(ctx, cudaGetLastError());
+        if (afterChunk) {
+            const int rc = afterChunk(c0 + mc);      // the kernels of the targets [0, c0 + mc) are in the stream
+            if (rc) return rc;
+        }
     }
     return PB_OK;
 }
@@ -719,27 +728,67 @@ int pb_kriging_raster(pb_context* ctx, pb_kriging_id id, pb_raster_id demId, int
     t.grid.nrRows = dem.h.nrRows; t.grid.nrCols = dem.h.nrCols;
     t.grid.llx = dem.h.llx; t.grid.lly = dem.h.lly; t.grid.cellSize = dem.h.cellSize; t.grid.invCellSize = dem.h.invCellSize;
     t.grid.flag = dem.h.flag;
-    cudaEventRecord(ctx->ev[1], ctx->stream);
-    rc = evaluate(ctx, k, t, t1 - t0, rmse != nullptr, nullptr, nullptr, gEst, gRm);
-    cudaEventRecord(ctx->ev[2], ctx->stream);
-    if (rc) return rc;
+    // the rows of both grids come down chunk by chunk on a second stream while the following chunks are evaluated: a chunk's
+    // rows are copied once the NEXT chunk's kernels are in the compute stream (a copy into pageable memory blocks the host)
     pb_raster_out* outs[2] = {estimate, rmse};
     float* grids[2] = {gEst, gRm};
     const int cols = dem.h.nrCols;
-    for (int g = 0; g < 2; g++) {
-        pb_raster_out* o = outs[g];
-        if (!o) continue;
-        o->nValid = t1 - t0;
-        if (o->data) {
-            CUDA_TRY(ctx, cudaMemcpyAsync(o->data + size_t(rowBegin) * cols, grids[g] + size_t(rowBegin) * cols,
-                                          sizeof(float) * size_t(rowEnd - rowBegin) * cols, cudaMemcpyDeviceToHost, ctx->stream));
-            ctx->timing.d2h_bytes += (int64_t)(sizeof(float) * size_t(rowEnd - rowBegin) * cols);
-        } else if (o->rows) {
-            for (int r = rowBegin; r < rowEnd; r++)
-                CUDA_TRY(ctx, cudaMemcpyAsync(o->rows[r], grids[g] + size_t(r) * cols, sizeof(float) * cols,
-                                              cudaMemcpyDeviceToHost, ctx->stream));
-            ctx->timing.d2h_bytes += (int64_t)(sizeof(float) * size_t(rowEnd - rowBegin) * cols);
+    const bool toHost = (estimate->data || estimate->rows) || (rmse && (rmse->data || rmse->rows));
+    if (toHost) {
+        rc = ensureRowStart(ctx, dem);
+        if (rc) return rc;
+        if (!k->sDn) {
+            CUDA_TRY(ctx, cudaStreamCreateWithFlags(&k->sDn, cudaStreamNonBlocking));
+            for (auto& e : k->evDn) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
+    }
+    auto copyRows = [&](int ra, int rb) -> int {
+        if (ra >= rb) return PB_OK;
+        for (int g = 0; g < 2; g++) {
+            pb_raster_out* o = outs[g];
+            if (!o) continue;
+            if (o->data) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(o->data + size_t(ra) * cols, grids[g] + size_t(ra) * cols,
+                                              sizeof(float) * size_t(rb - ra) * cols, cudaMemcpyDeviceToHost, k->sDn));
+            } else if (o->rows) {
+                for (int r = ra; r < rb; r++)
+                    CUDA_TRY(ctx, cudaMemcpyAsync(o->rows[r], grids[g] + size_t(r) * cols, sizeof(float) * cols,
+                                                  cudaMemcpyDeviceToHost, k->sDn));
+            } else continue;
+            ctx->timing.d2h_bytes += (int64_t)(sizeof(float) * size_t(rb - ra) * cols);
+        }
+        return PB_OK;
+    };
+    int rowCopied = rowBegin, rowPending = rowBegin, nChunk = 0;       // rows [rowCopied, rowPending) wait for evDn[(nChunk - 1) & 1]
+    auto afterChunk = [&](long long done) -> int {
+        // rows whose cells are all among the first `done` targets of the band
+        const long long* rs = dem.rowStart.data();
+        int rTo = int(std::upper_bound(rs + rowPending, rs + rowEnd + 1, t0 + done) - rs) - 1;
+        if (t0 + done >= t1) rTo = rowEnd;
+        if (rowPending > rowCopied) {           // the previous chunk's rows: its event was recorded before this chunk's kernels
+            CUDA_TRY(ctx, cudaStreamWaitEvent(k->sDn, k->evDn[(nChunk - 1) & 1], 0));
+            const int rc2 = copyRows(rowCopied, rowPending);
+            if (rc2) return rc2;
+            rowCopied = rowPending;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(k->evDn[nChunk & 1], ctx->stream));
+        rowPending = std::max(rowPending, rTo);
+        nChunk++;
+        return PB_OK;
+    };
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    rc = evaluate(ctx, k, t, t1 - t0, rmse != nullptr, nullptr, nullptr, gEst, gRm,
+                  toHost ? std::function<int(long long)>(afterChunk) : std::function<int(long long)>());
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (rc) { if (k->sDn) cudaStreamSynchronize(k->sDn); return rc; }
+    for (int g = 0; g < 2; g++)
+        if (outs[g]) outs[g]->nValid = t1 - t0;
+    if (toHost) {
+        if (nChunk > 0) CUDA_TRY(ctx, cudaStreamWaitEvent(k->sDn, k->evDn[(nChunk - 1) & 1], 0));
+        else CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));          // no valid cell: only the fill kernel ran
+        rc = copyRows(rowCopied, rowEnd);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaStreamSynchronize(k->sDn));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->timing.kernel_ms, ctx->ev[1], ctx->ev[2]);

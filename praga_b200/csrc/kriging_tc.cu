@@ -592,6 +592,7 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
                 if (act) sList[cnt + __popc(b & ((1u << lane) - 1u))] = (unsigned short)kb;
                 cnt += __popc(b);
             }
+            PB_DEV_ASSERT(cnt <= kPrMaxKb && (p.nPad + kPrPass - 1) / kPrPass <= kPrMaxPasses && p.nPad % kPrN == 0);
             if (lane == 0) sNAct = cnt;
             __syncwarp();
             for (int pass = lane; pass < (p.nPad + kPrPass - 1) / kPrPass; pass += 32) {

@@ -210,6 +210,7 @@ local_select_kernel(const LocalModel* __restrict__ mp, LocalStations st, DevGrid
             const int n = localSelect<G>(m, st, xy, xf, yf, gw, kRecCap, rec + recWorkOff(), kRecCap, nullptr, w, localRadius, list,
                                          nList, kCandCap, listRadius);
             int nE = 0, flags = 0;
+            PB_DEV_ASSERT(nList <= kSelListCap);
             if (n > kRecCap) flags = CELL_OVERFLOW;
             else if (hasElev) {
                 bool isValid;
@@ -364,6 +365,7 @@ local_descent_kernel(const LocalModel* __restrict__ mp, unsigned char* __restric
             int* sHdr = reinterpret_cast<int*>(sb + P::offHdr);
             const WorkPtrs rw = carve(rec + recWorkOff(), kRecCap);
             const int nE = h.nE;
+            PB_DEV_ASSERT(nE <= kFitCap && slot < P::NSLOT);      // the selection kernel sent larger fits to the overflow list
             for (int j = lane; j < nE; j += 32) { sX[j] = rw.X[j]; sY[j] = rw.Y[j]; sW[j] = rw.W[j]; }
             if (lane == 0) { sHdr[0] = int(t); sHdr[1] = nE; sHdr[2] = nGuess; sHdr[3] = 0; }
             {
@@ -408,6 +410,7 @@ local_descent_kernel(const LocalModel* __restrict__ mp, unsigned char* __restric
                 stVolatile(ep, 0u);                                   // consumed: the position may be written again
                 slot = int((e >> 5) & 0x7ffu);
                 guess = int(e & 31u);
+                PB_DEV_ASSERT(slot < P::NSLOT && guess < nGuess);
                 unsigned char* sb = smem + size_t(slot) * P::slotBytes;
                 X = reinterpret_cast<const double*>(sb);
                 Y = X + kFitCap;
