@@ -20,6 +20,7 @@
 //     warp 9 = MMA issuer (one elected lane, tcgen05.mma + tcgen05.commit on the stage's mbarrier), warps 0-7 generate the A
 //     tiles of stage s+1.. while the tensor core works on stage s; nobody waits for an MMA except to reuse its buffers;
 //   epilogue per pass: tcgen05.ld, thread = cell (TMEM lane), per-thread sums of y^2 and z*y, no cross-lane reduction.
+#include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
 #include <string.h>
@@ -367,11 +368,16 @@ kriging_variance_tc_kernel(TcParams p, const double* __restrict__ pos, const uns
 // tensor pipe 56 % active. Here two CTAs of a cluster (one TPC) run ONE MMA of M = 256 (128 cells from each CTA), N = 256:
 //   * each CTA generates the A rows of its own 128 cells only and keeps HALF of the B rows (stations i) of every N block:
 //     per 128 tensor clocks a CTA's shared memory feeds 4 KiB of A + 4 KiB of B, half of the single-CTA rate;
-//   * each CTA's TMEM holds 128 cells x 512 columns = a pass of 512 stations i: A is generated 2.5 times instead of 4.5;
-//   * the L2 -> SM stream of L^-1 stays at 32 KiB per stage per SM (every loaded tile still serves 256 cells).
-// Roles per CTA: warps 0-15 generators + epilogue (thread = (cell, quarter of the stage's K range / of the pass's columns)),
-// warp 16 B loader (this CTA's halves of the L^-1 tiles by bulk async copies), warp 17: in the leader CTA (cluster rank 0)
-// the MMA issuer, in the peer a relay that forwards "my B halves have landed" to the leader, warp 18 the stations'
+//   * the L2 -> SM stream of L^-1 stays at 16 KiB per (stage, N block) per SM (every loaded tile still serves 256 cells);
+//   * a pass is ONE N block (256 stations i = 256 TMEM columns per CTA) and the ring has three 32 KiB stages, so that TWO
+//     pairs are resident on a TPC (2 x 256 TMEM columns, 2 x 105 KiB of shared memory, 2 x 352 threads): while one pair
+//     drains a pass, reads its accumulators (epilogue) or starts up, the other one keeps the tensor cores busy. With the
+//     512-column passes of the first pair kernel (one pair per TPC, A regenerated 2.5 instead of 4.5 times) the dense
+//     contraction took 7.8 ms on the 925k-cell probe and the skipping one 3.2; two resident pairs: 7.7 and 3.0 ms, although A
+//     is regenerated as often as in the single-CTA kernel (the generators are not what bounds it any more).
+// Roles per CTA: warps 0-7 generators + epilogue (thread = (cell, half of the stage's K range / of the pass's columns)),
+// warp 8 B loader (this CTA's halves of the L^-1 tiles by bulk async copies), warp 9: in the leader CTA (cluster rank 0)
+// the MMA issuer, in the peer a relay that forwards "my B halves have landed" to the leader, warp 10 the stations'
 // coordinates of each stage (loaded ahead of the wait for the stage). The MMA issuer is lane 0 of its warp; a
 // warp-convergent form with the issuing lane picked by elect.sync (no ELECT / R2UR.BROADCAST waterfall around every
 // UTCHMMA) measured 10 % slower (PB_KRIGING_DBG=8 selects it).
@@ -382,16 +388,21 @@ kriging_variance_tc_kernel(TcParams p, const double* __restrict__ pos, const uns
 // CTAs arrive on the leader's tmemFree.
 constexpr int kPrCells = 128;                                   // cells per CTA = one M tile; the pair's MMA has M = 256
 constexpr int kPrN = 256;                                       // MMA N: stations i per MMA, 128 rows of B in each CTA
-constexpr int kPrPass = 512;                                    // stations i per pass = the 512 TMEM columns of each CTA
-constexpr int kPrStages = 4;                                    // ring of K = 32 stages
+constexpr int kPrPass = 256;                                    // stations i per pass = TMEM columns a CTA allocates: one N block, so that
+                                                                // TWO pairs fit a TPC (2 x 256 of the 512 columns, 2 x 104 KiB of shared memory)
+constexpr int kPrStages = 3;                                    // ring of K = 32 stages
 constexpr int kPrStageA = 2 * kTcTileBytes;                     // hi, lo of this CTA's 128 cells: 16 KiB
 constexpr int kPrBTile = 2 * kTcTileBytes;                      // this CTA's 128 rows of one N block, hi + lo: 16 KiB
 constexpr int kPrStageBytes = kPrStageA + (kPrPass / kPrN) * kPrBTile;     // 48 KiB
-constexpr int kPrGenWarps = 16;
-constexpr int kPrGenThreads = kPrGenWarps * 32;                 // 4 threads per cell
+constexpr int kPrGenWarps = 8;
+constexpr int kPrGenThreads = kPrGenWarps * 32;
+constexpr int kPrKSplit = kPrGenThreads / kPrCells;             // threads per cell: each a slice of the stage's K range / of the pass's columns
+constexpr int kPrGenK = kTcBK / kPrKSplit;                      // K columns a generator thread writes per stage (groups of 8)
 constexpr int kPrThreads = kPrGenThreads + 96;                  // + B loader, MMA issuer / relay, station-coordinate warp
-constexpr int kPrSmem = kPrStages * kPrStageBytes + kPrStages * kTcBK * 8 + kPrPass * 4 + 2 * 3 * kPrCells * 8 + 1024;
-constexpr int kPrMaxPasses = 64;
+constexpr int kPrSmem = kPrStages * kPrStageBytes + kPrStages * kTcBK * 8 + kPrPass * 4 + 2 * (kPrKSplit - 1) * kPrCells * 8 + 1024;
+static_assert(kPrGenThreads == kPrPass, "the generators reload z with one element per thread");
+static_assert((kPrPass & (kPrPass - 1)) == 0 && kPrPass >= 32 && kPrPass <= 512, "TMEM allocations are powers of two");
+constexpr int kPrMaxPasses = 128;
 constexpr int kPrMaxKb = 1024;                                  // K stages the active list can hold (n <= 32768)
 constexpr uint32_t kIdescPair = (1u << 4) | (uint32_t(kPrN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
 
@@ -491,10 +502,10 @@ __device__ __forceinline__ float ex2_approx(float x)
 {
     float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 }
-__device__ __forceinline__ void pair_gen_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void pair_gen_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kPrGenThreads) : "memory"); }
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPrThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPrThreads, 2)
 kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const unsigned char* __restrict__ Mt,
                              const float* __restrict__ z, const double* __restrict__ kbBox, KrigingTargets t, long long c0, int m,
                              double* __restrict__ q, unsigned long long* __restrict__ mmaCount)
@@ -503,7 +514,7 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
     // stage s: [A: hi, lo of this CTA's 128 cells][B: N block 0 hi, lo, N block 1 hi, lo of this CTA's 128 stations i]
     float2* sRel = reinterpret_cast<float2*>(smem + kPrStages * kPrStageBytes);       // [stage][kTcBK]
     float* sZ = reinterpret_cast<float*>(sRel + kPrStages * kTcBK);                   // [kPrPass]
-    double* sRed = reinterpret_cast<double*>(sZ + kPrPass);                           // [2 sums][3 partials][kPrCells]
+    double* sRed = reinterpret_cast<double*>(sZ + kPrPass);                           // [2 sums][kPrKSplit - 1 partials][kPrCells]
     __shared__ __align__(8) uint64_t relFull[kPrStages], aFull[kPrStages], bFull[kPrStages], bPeer[kPrStages], mmaDone[kPrStages],
         passDone, tmemFree;
     __shared__ uint32_t tmemBase;
@@ -606,7 +617,7 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
         }
     }
     if (warp == 0) {
-        tmem_alloc2(&tmemBase, 512);
+        tmem_alloc2(&tmemBase, kPrPass);
         tmem_relinquish2();
     }
     tc_fence_before();
@@ -762,9 +773,9 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
             if (lane == 0 && mmaCount && nMma) atomicAdd(mmaCount, (unsigned long long)nMma);
         }
     } else {
-        // ------------------------------------------------------------ generators: four threads per cell (= MMA row = TMEM lane)
+        // ------------------------------------------------------------ generators: kPrKSplit threads per cell (= MMA row = TMEM lane)
         const int r = (warp & 3) * 32 + lane;             // a warp reads the TMEM lanes 32 (warp % 4) ..
-        const int kq = warp >> 2;                         // quarter of the stage's K range / of the pass's columns
+        const int kq = warp >> 2;                         // slice of the stage's K range / of the pass's columns
         const long long cidx = tile0 + r;
         const bool valid = cidx < m;
         float xr = 0.f, yr = 0.f;
@@ -786,8 +797,8 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
         const uint32_t aFullLeader = mapa_shared(smem_u32(&aFull[0]), 0), tmemFreeLeader = mapa_shared(smem_u32(&tmemFree), 0);
         const f32x2 nxr2 = pack2(-xr, -xr), nyr2 = pack2(-yr, -yr);
         const f32x2 one2 = pack2(1.f, 1.f), negOne2 = pack2(-1.f, -1.f), sn2 = pack2(p.sn, p.sn), hsn2 = pack2(0.5f * p.sn, 0.5f * p.sn);
-        const int k0 = kq * 8;
-        const size_t offA = tileOffset(r, k0);
+        const int k0 = kq * kPrGenK;
+        const size_t offA = tileOffset(r, k0);         // + g * 128 for the g-th group of 8 K columns
         // one stage of A: the generators do not need to know which stations it holds (their coordinates arrive in sRel)
         auto genStage = [&]() {
             {
@@ -798,10 +809,12 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
                 unsigned char* sA = smem + s * kPrStageBytes;
                 const ulonglong2* rel = reinterpret_cast<const ulonglong2*>(sRel + s * kTcBK) + (k0 >> 1);     // [pair] = {x0 x1, y0 y1}
                 if (!(p.dbg & 1)) {
+#pragma unroll
+                for (int g = 0; g < kPrGenK / 8; g++) {
                 __half2 hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    const ulonglong2 sxy = rel[e];
+                    const ulonglong2 sxy = rel[4 * g + e];
                     const f32x2 dx = add2(sxy.x, nxr2), dy = add2(sxy.y, nyr2);
                     const f32x2 t2p = fma2(dx, dx, mul2(dy, dy));          // (h / range)^2
                     float ta, tb, c0v, c1v;
@@ -824,8 +837,9 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
                     hi[e] = h2;
                     lo[e] = __floats2half2_rn(c0v - back.x, c1v - back.y);
                 }
-                *reinterpret_cast<uint4*>(sA + offA) = *reinterpret_cast<const uint4*>(hi);
-                *reinterpret_cast<uint4*>(sA + kTcTileBytes + offA) = *reinterpret_cast<const uint4*>(lo);
+                *reinterpret_cast<uint4*>(sA + offA + g * 128) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(sA + kTcTileBytes + offA + g * 128) = *reinterpret_cast<const uint4*>(lo);
+                }
                 }
                 fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -848,7 +862,7 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
             // pipeline is full again as soon as the epilogue below has released the accumulators
             carried = min(kPrStages - 1, stagesOf(pass + 1));
             for (int k = 0; k < carried; k++) genStage();
-            // ---- epilogue of the pass: columns = stations i of this pass, a quarter for each of the four threads of a cell ----
+            // ---- epilogue of the pass: columns = stations i of this pass, a slice for each of the threads of a cell ----
             sZ[tid] = (i0p + tid < p.nPad) ? z[i0p + tid] : 0.f;          // kPrGenThreads == kPrPass
             mbar_wait(&passDone, ep & 1);
             ep++;
@@ -857,7 +871,7 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
             tc_fence_after();
             pair_gen_bar_sync();
             const int nCb = nNb * kPrN / 32;
-            for (int cb = kq; cb < nCb && !(p.dbg & 4); cb += 4) {
+            for (int cb = kq; cb < nCb && !(p.dbg & 4); cb += kPrKSplit) {
                 if (cb < kPrN / 32 && !hasNb0) continue;
                 uint32_t v[32];
                 tmem_ld32(tmem + laneBase + uint32_t(cb * 32), v);
@@ -880,17 +894,18 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
             pair_gen_bar_sync();                // sZ is rewritten for the next pass; every warp's TMEM reads are complete
             if (lane == 0) mbar_arrive_cluster(tmemFreeLeader);
         }
-        if (kq > 0) { sRed[(kq - 1) * kPrCells + r] = accY2; sRed[(3 + kq - 1) * kPrCells + r] = accZY; }
+        if (kq > 0) { sRed[(kq - 1) * kPrCells + r] = accY2; sRed[(kPrKSplit - 1 + kq - 1) * kPrCells + r] = accZY; }
         pair_gen_bar_sync();
         if (kq == 0 && valid) {
-            const double y2 = accY2 + sRed[r] + sRed[kPrCells + r] + sRed[2 * kPrCells + r];
-            const double zy = accZY + sRed[3 * kPrCells + r] + sRed[4 * kPrCells + r] + sRed[5 * kPrCells + r];
+            double y2 = accY2, zy = accZY;
+#pragma unroll
+            for (int h = 0; h < kPrKSplit - 1; h++) { y2 += sRed[h * kPrCells + r]; zy += sRed[(kPrKSplit - 1 + h) * kPrCells + r]; }
             q[cidx] = p.sill - (y2 - zy * (zy - 1.) / p.zz);      // = sum_i weight_i D_i of krigingRMSE
         }
     }
     tc_fence_before();
     cluster_sync_all();                         // nobody leaves while the peer can still signal or read this CTA
-    if (warp == 0) tmem_dealloc2(tmem, 512);
+    if (warp == 0) tmem_dealloc2(tmem, kPrPass);
 }
 
 // CUDA-core check of the same whitened formulation from the same pre-tiled FP16 pieces (tests / debugging only:
@@ -1034,6 +1049,18 @@ cudaError_t launchKrigingVarianceTc(const KrigingSystem& k, const KrigingTargets
         auto launch = [&](auto kernel) -> cudaError_t {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrSmem);
             if (e != cudaSuccess) return e;
+            // two CTAs per SM (two pairs per TPC): the whole L1 / shared-memory array as shared memory
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            // PB_KRIGING_PAD_SMEM=90000 pads the dynamic shared memory so that only ONE CTA fits an SM (A/B of the co-residency:
+            // 3.0 -> 3.85 ms on tools/bench_kriging.py; cudaOccupancyMaxActiveClusters reports 74 clusters for this kernel either
+            // way, the hardware places two pairs per TPC when they fit)
+            static const int padSmem = getenv("PB_KRIGING_PAD_SMEM") ? atoi(getenv("PB_KRIGING_PAD_SMEM")) : 0;
+            if (padSmem) {
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrSmem + padSmem);
+                kernel<<<grid, kPrThreads, kPrSmem + padSmem, s>>>(p, k.dPos, k.dMhi, k.dZ, k.dKbBox, t, c0, m, q, k.dMmaCount);
+                return cudaSuccess;
+            }
             kernel<<<grid, kPrThreads, kPrSmem, s>>>(p, k.dPos, k.dMhi, k.dZ, k.dKbBox, t, c0, m, q, k.dMmaCount);
             return cudaSuccess;
         };
