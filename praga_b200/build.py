@@ -21,7 +21,7 @@ SOURCES = {
     "idw_kernels.cu": [],
     "peaks.cu": [],
     "local_kernels.cu": ["-fmad=false"],
-    "local_pipeline.cu": ["-fmad=false", "-DPB_LM_UNROLL=2"],
+    "local_pipeline.cu": ["-fmad=false", "-DPB_LM_UNROLL=3"],
     "pre_kernels.cu": ["-fmad=false"],
     "td_kernels.cu": ["-fmad=false"],
     "classic_kernels.cu": ["-fmad=false"],

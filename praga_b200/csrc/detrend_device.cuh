@@ -201,6 +201,26 @@ __device__ __forceinline__ double lmPointJacobian(double x, const double* p0, co
     return f0;
 }
 
+// branch-free form for the lane-per-descent loops: a quotient outside the fast division's exponent range only raises `slow`
+// (the caller redoes the whole pass over the data with lmPointJacobian). Without the fix-up branch the body of the data loop
+// is one basic block, so the points of an unrolled loop interleave.
+template <int F>
+__device__ __forceinline__ double lmPointJacobianFast(double x, const double* p0, const double* up, const double* rs, double sp2,
+                                                      const double* dl, const double* rdl, double* P, bool& slow)
+{
+    constexpr int N = Fit<F>::N;
+    const double f0 = Fit<F>::eval(x, p0);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        double q[N];
+#pragma unroll
+        for (int c = 0; c < N; c++) q[c] = (c < k) ? ((F != PB_FIT_PIECEWISE_TWO && c == 2) ? sp2 : rs[c]) : p0[c];
+        q[k] = up[k];
+        P[k] = divFast(Fit<F>::eval(x, q) - f0, dl[k], rdl[k], slow);
+    }
+    return f0;
+}
+
 // one Levenberg-Marquardt iteration; true when the descent is over (the reference's do-while condition turned false)
 template <int F, bool SCORED = false>
 __device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__ pmin, const double* __restrict__ pmax,
@@ -231,11 +251,12 @@ __device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__
 #pragma unroll
         for (int j = 0; j < N; j++) a[i][j] = 0;
     }
+    bool anySlow = false;
 #pragma unroll kLmUnroll
     for (int j = 0; j < nData; j++) {
         const double x = X[j], y = Y[j], w = W[j];
         double P[N], WP[N];
-        const double f0 = lmPointJacobian<F>(x, p0, up, rs, s.p[2], dl, rdl, P);
+        const double f0 = lmPointJacobianFast<F>(x, p0, up, rs, s.p[2], dl, rdl, P, anySlow);
 #pragma unroll
         for (int k = 0; k < N; k++) WP[k] = w * P[k];
 #pragma unroll
@@ -243,6 +264,30 @@ __device__ __forceinline__ bool lmIter(LmState<F>& s, const double* __restrict__
 #pragma unroll
             for (int c = i; c < N; c++) a[i][c] += (P[i] * WP[c]);
             g[i] += P[i] * w * (y - f0);
+        }
+    }
+    if (anySlow) {
+        // a quotient left the fast division's exponent range (subnormal / huge): the pass again with the plain division where
+        // it is needed, same terms in the same order
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            g[i] = 0;
+#pragma unroll
+            for (int j = 0; j < N; j++) a[i][j] = 0;
+        }
+#pragma unroll 1
+        for (int j = 0; j < nData; j++) {
+            const double x = X[j], y = Y[j], w = W[j];
+            double P[N], WP[N];
+            const double f0 = lmPointJacobian<F>(x, p0, up, rs, s.p[2], dl, rdl, P);
+#pragma unroll
+            for (int k = 0; k < N; k++) WP[k] = w * P[k];
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+#pragma unroll
+                for (int c = i; c < N; c++) a[i][c] += (P[i] * WP[c]);
+                g[i] += P[i] * w * (y - f0);
+            }
         }
     }
 #pragma unroll
