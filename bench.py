@@ -34,14 +34,6 @@ import sys
 import threading
 import time
 
-# One process per GPU: torchrun pins every rank to OMP_NUM_THREADS=1 unless the variable is set, which leaves the host side
-# of a step (scatter of the 16 MB output grid into the caller's float** rows, station staging) on one core per rank while
-# the others idle. Every rank takes its share of the node's cores instead; must happen before libgomp is loaded.
-_WORLD = int(os.environ.get("WORLD_SIZE", "1"))
-if _WORLD > 1 and os.environ.get("PB_BENCH_KEEP_OMP") is None:
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _WORLD))
-    os.environ.setdefault("OMP_WAIT_POLICY", "passive")       # idle OpenMP workers sleep: the cores belong to the lane threads
-
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -1168,6 +1160,8 @@ def main():
         # the reference arm runs on rank 0 alone and gets every host core
         share = 1 if args.impl == "reference" else world
         os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // share))
+        if args.impl != "reference":
+            os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # idle OpenMP workers sleep: the cores belong to the lane threads
 
     if args.impl == "reference":
         run_reference(args, rank)
