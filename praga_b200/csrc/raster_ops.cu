@@ -410,7 +410,8 @@ spatial_aggregate_kernel(DevGrid raster, const double* __restrict__ px, const do
     const int n = int(first[cell + 1] - p0);
     float* z = scratch + p0;
     int valid = 0;
-    for (int i = lane; i < n; i += 32) {
+#pragma unroll 4
+    for (int i = lane; i < n; i += 32) {           // independent iterations: four samples' loads in flight per lane
         const double x = px[p0 + i], y = py[p0 + i];
         const int r = int((y - raster.lly) * raster.invCellSize);
         const int row = (raster.nrRows - 1) - r;
@@ -450,32 +451,50 @@ spatial_aggregate_kernel(DevGrid raster, const double* __restrict__ px, const do
         if (lane == 0) value[cell] = result;
         return;
     }
-    if (lane != 0) return;
+    // average / standard deviation (meteoGrid.cpp:1201-1233; statistics::mean / standardDeviation): float sums over the samples
+    // in LIST ORDER. The warp reads 32 samples at a time (every lane the ones it wrote above: coalesced, independent loads)
+    // and takes them into the running sum in list order through shuffles; a dropped sample adds +0, which leaves a float
+    // sum unchanged. All lanes carry the same sum. (One lane walking the list alone re-read every sample from L2, one
+    // dependent load per add: 0.28 ms for the 1600 cells of the hourly batch.)
     float result = kNoData;
     // (validValues / aggregationPointsMaxNr) > (GRID_MIN_COVERAGE / 100), GRID_MIN_COVERAGE = 0 (meteoGrid.h:8)
     if (n > 0 && (double(valid) / double(maxNr[cell])) > 0) {
-        // validValues: z != NODATA, as floats, in list order
+        float sum = 0.f;
         int m = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const float v = i < n ? z[i] : kNoData;
+            const bool ok = v != kNoData;
+            m += __popc(__ballot_sync(0xffffffffu, ok));
+            const float a = ok ? v : 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; k++) sum += __shfl_sync(0xffffffffu, a, k);
+        }
         if (method == PB_AGGR_AVERAGE) {
-            float sum = 0.f;
-            for (int i = 0; i < n; i++) { const float v = z[i]; if (double(v) != -9999.) { if (v != kNoData) sum += v; m++; } }
-            // statistics::mean(float*, n): the NODATA test is redundant here (they were dropped above)
             if (m > 0) result = sum / float(m);
-        } else if (method == PB_AGGR_STDDEV) {
-            float sum = 0.f;
-            for (int i = 0; i < n; i++) { const float v = z[i]; if (v != kNoData) { sum += v; m++; } }
-            if (m > 1) {
-                const float mean = sum / float(m);
-                float squareDiff = 0.f;
-                for (int i = 0; i < n; i++) {
-                    const float v = z[i];
-                    if (v != kNoData) { const float d = v - mean; squareDiff += d * d; }
-                }
-                result = sqrtf(squareDiff / (m - 1));
+        } else if (method == PB_AGGR_STDDEV && m > 1) {
+            const float mean = sum / float(m);
+            float squareDiff = 0.f;
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                const float v = i < n ? z[i] : kNoData;
+                const float d = v - mean;
+                const float a = v != kNoData ? d * d : 0.f;
+#pragma unroll
+                for (int k = 0; k < 32; k++) squareDiff += __shfl_sync(0xffffffffu, a, k);
             }
+            result = sqrtf(squareDiff / (m - 1));
         }
     }
-    value[cell] = result;
+    if (lane == 0) value[cell] = result;
+}
+
+static cudaError_t launchAggregatePair(const DevGrid& raster, const double* px, const double* py, const long long* first,
+                                       const int* maxNr, int nCells, int method, float* scratch, float* value, cudaStream_t s)
+{
+    const unsigned nb = (unsigned)((size_t(nCells) * 32 + 255) / 256);
+    spatial_aggregate_kernel<<<nb, 256, 0, s>>>(raster, px, py, first, maxNr, nCells, method, scratch, value);
+    return cudaGetLastError();
 }
 
 // values of a resident raster at explicit points: Crit3DRasterGrid::getRowCol (gis.cpp:485-492) + gis::isOutOfGridRowCol
@@ -677,9 +696,7 @@ namespace pb {
 cudaError_t launchSpatialAggregateDev(const DevGrid& raster, const AggregationGeometry& g, int method, float* scratch, float* value,
                                       cudaStream_t s)
 {
-    const unsigned nb = (unsigned)((size_t(g.nCells) * 32 + 255) / 256);
-    spatial_aggregate_kernel<<<nb, 256, 0, s>>>(raster, g.x, g.y, g.first, g.maxNr, g.nCells, method, scratch, value);
-    return cudaGetLastError();
+    return launchAggregatePair(raster, g.x, g.y, g.first, g.maxNr, g.nCells, method, scratch, value, s);
 }
 // grid of the grid-stride map kernels: 8 CTAs of 256 threads per SM (a full SM), never more than the map needs
 static unsigned mapGridBlocks(long long n)
@@ -938,9 +955,7 @@ int pb_spatial_aggregate_meteo_grid(pb_context* ctx, pb_raster_id rasterId, pb_a
     memset(&ctx->timing, 0, sizeof(ctx->timing));
     AggregationGeometry& g = ctx->aggregations[aggId];
     cudaEventRecord(ctx->ev[1], ctx->stream);
-    const unsigned nb = (unsigned)((size_t(g.nCells) * 32 + 255) / 256);
-    spatial_aggregate_kernel<<<nb, 256, 0, ctx->stream>>>(gridOf(*src), g.x, g.y, g.first, g.maxNr, g.nCells, method, g.scratch, g.value);
-    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, launchAggregatePair(gridOf(*src), g.x, g.y, g.first, g.maxNr, g.nCells, method, g.scratch, g.value, ctx->stream));
     ctx->timing.launches++;
     cudaEventRecord(ctx->ev[2], ctx->stream);
     CUDA_TRY(ctx, cudaMemcpyAsync(value, g.value, size_t(g.nCells) * 4, cudaMemcpyDeviceToHost, ctx->stream));
