@@ -50,3 +50,13 @@ out = {"lanes": wl.lanes, "step_us": t1 - t0, "some_kernel_running_us": cov1, "t
 print(json.dumps(out))
 if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
     prof.export_chrome_trace(os.path.join(ROOT, "gpurun_out", "c5_trace.json"))
+# per-kernel launch count and mean duration
+import re  # noqa: E402
+per = {}
+for a, b, n in spans:
+    m = re.search(r"(\w+)(<[^>]*>)?\(", n)
+    k = (m.group(1) if m else n)[:40]
+    c = per.setdefault(k, [0, 0.0])
+    c[0] += 1
+    c[1] += b - a
+print(json.dumps({"mean_us_by_kernel": {k: [v[0], round(v[1] / v[0], 1)] for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])[:12]}}))
