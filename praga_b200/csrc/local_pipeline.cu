@@ -461,10 +461,11 @@ local_descent_kernel(const LocalModel* __restrict__ mp, unsigned char* __restric
 // ---------------------------------------------------------------------------------------------------------------------
 // C: pick + the rest of multipleDetrendingMain + estimate. One group of 4 lanes per cell working on the cell's record.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kFinThreads = 256;
+constexpr int kFinThreads = 256;     // 4 CTAs per SM (64 registers): the kernel waits on the records' loads, occupancy beats registers
+                                     // (2 CTAs at 128 registers: 169.8 ms on the 3.7M-cell probe, 3: 168.0, 4: 163.8, 6: 170.6)
 
 template <int F>
-__global__ void __launch_bounds__(kFinThreads)
+__global__ void __launch_bounds__(kFinThreads, 4)
 local_finish_kernel(const LocalModel* __restrict__ mp, LocalStations st, DevGrid dem, unsigned char* __restrict__ records,
                     size_t recStride, int nCells, float* __restrict__ out, unsigned* __restrict__ minmax)
 {
