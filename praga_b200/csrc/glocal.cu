@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "context.cuh"
+#include "epilogue.cuh"
 #include "kh_search.cuh"
 #include "pre.cuh"
 #include "shepard.cuh"
@@ -141,6 +142,129 @@ glocal_blend_kernel(const float* __restrict__ cells, int nCells, int nrCols, con
     const double prod = interpolatedValue * double(cells[2 * c + 1]);
     const float cur = *cell;
     *cell = isEqualF(cur, kNoData) ? float(prod) : float(double(cur) + prod);
+}
+
+// One macro area in ONE launch (plain idw, no topographic distance): thread = an entry of the area's (cell, weight) list.
+// glocal_targets_kernel + the K1 point form + glocal_blend_kernel cost three launches and 28 B of scratch traffic per entry
+// for ~140 station pairs of arithmetic; here the entry is decoded, its significant proxies are looked up, the area's stations
+// (shared memory, <= kGlocalTile per pass) are gridded with K1's weight (rsqrt(d2)^3: the 1/10000 scale cancels in the ratio),
+// FP32 over chunks of 32 stations and FP64 across chunks, a station ON the cell takes the exact loop of the reference
+// (f32 distance, f64 weights, d > 0), then retrend / clamp with the area's model and the blend of project.cpp:3361-3369.
+// Areas are launched in index order on one stream, a cell occurs once per area: the blend order is the reference's.
+constexpr int kGlocalTile = 512;          // stations per shared-memory pass (K1's packed tile: {x, x, y, y} + {v, v})
+struct GlocalEntry {                       // one (cell, weight) entry of an area, decoded
+    int row, col;
+    bool live, complete;
+    float xf, yf;
+    double pv[PB_MAX_PROXY];
+};
+__device__ __forceinline__ void glocalDecode(const float* __restrict__ cells, int c, int nCells, const DevGrid& dem, const GlocalLookup& lk,
+                                             GlocalEntry& e)
+{
+    e.row = e.col = 0;
+    e.live = false;
+    e.complete = true;
+    e.xf = e.yf = 0.f;
+#pragma unroll
+    for (int i = 0; i < PB_MAX_PROXY; i++) e.pv[i] = -9999.;
+    if (c >= nCells) return;
+    glocalRowCol(cells[2 * c], dem.nrCols, e.row, e.col);
+    if (unsigned(e.row) >= unsigned(dem.nrRows) || unsigned(e.col) >= unsigned(dem.nrCols)) return;
+    const float z = __ldg(dem.data + (size_t)e.row * dem.nrCols + e.col);
+    if (isEqualF(z, dem.flag)) return;
+    e.live = true;
+    e.xf = float(dem.llx + dem.cellSize * (e.col + 0.5));
+    e.yf = float(dem.lly + dem.cellSize * (dem.nrRows - e.row - 0.5));
+#pragma unroll
+    for (int i = 0; i < PB_MAX_PROXY; i++)
+        if (i < lk.nProxy && lk.slot[i] >= 0) {
+            const DevGrid& g = lk.grid[lk.slot[i]];
+            const float gv = glocalGridValueXY(g, double(e.xf), double(e.yf));
+            if (gv != g.flag) e.pv[i] = double(gv);
+            else e.complete = false;
+        }
+}
+__device__ __forceinline__ void glocalFinish(const float* __restrict__ cells, int c, const GlocalEntry& e, const DevGrid& dem,
+                                             const DevStations& st, const DevModel& m, double SW, double SWV, float* __restrict__ out,
+                                             int* __restrict__ notOk)
+{
+    if (!e.live) return;
+    float* cell = out + (size_t)e.row * dem.nrCols + e.col;
+    if (!e.complete) { *cell = kNoData; return; }             // an incomplete proxy set leaves NODATA (:3350-3354)
+    float result;
+    if (m.useRetrendOnly) result = 0.f;
+    else {
+        if (!(SW <= 1.0e300) || !(fabs(SWV) <= 1.0e300)) {
+            // a station on the cell (inf / NaN sums): computeDistances + inverseDistanceWeighted in the reference's arithmetic
+            // (:208-256, :1031-1051); DevStations::val is centred on the host
+            SW = 0.;
+            SWV = 0.;
+            for (int i = 0; i < st.n; i++) {
+                const float dx = st.x[i] - e.xf, dy = st.y[i] - e.yf;
+                const float d = sqrtf(dx * dx + dy * dy);
+                if (d > 0.f) {
+                    const double dk = double(d) / 10000.;
+                    const double w = 1.0 / (dk * dk * dk);
+                    SW += w;
+                    SWV += double(st.val[i]) * w;
+                }
+            }
+        }
+        result = SW > 0. ? float(SWV / SW + m.valueOffset) : kNoData;
+    }
+    const double interpolatedValue = double(finishEstimate(m, result, e.pv));
+    if (fabs(interpolatedValue - (-9999.)) < kEpsilon) *notOk = 1;
+    const double prod = interpolatedValue * double(cells[2 * c + 1]);
+    const float cur = *cell;
+    *cell = isEqualF(cur, kNoData) ? float(prod) : float(double(cur) + prod);
+}
+
+__global__ void __launch_bounds__(256)
+glocal_area_kernel(const float* __restrict__ cells, int nCells, DevGrid dem, GlocalLookup lk, DevStations st, DevModel m,
+                   float* __restrict__ out, int* __restrict__ notOk)
+{
+    __shared__ float4 sxy[kGlocalTile];
+    __shared__ float2 sv[kGlocalTile];
+    // two neighbouring entries per thread: K1's packed FP32x2 station loop
+    const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    GlocalEntry ea, eb;
+    glocalDecode(cells, c0, nCells, dem, lk, ea);
+    glocalDecode(cells, c0 + 1, nCells, dem, lk, eb);
+    const bool work = (ea.live && ea.complete) || (eb.live && eb.complete);
+    const f32x2 nx = pack2(-ea.xf, -eb.xf), ny = pack2(-ea.yf, -eb.yf);
+    double SWa = 0., SWVa = 0., SWb = 0., SWVb = 0.;
+    const int used = (st.n + 31) / 32 * 32;                 // the padding of the packed tile weighs +0
+    for (int j0 = 0; j0 < used; j0 += kGlocalTile) {
+        const int nj = min(kGlocalTile, used - j0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < nj; j += blockDim.x) { sxy[j] = st.xy[j0 + j]; sv[j] = st.v[j0 + j]; }
+        __syncthreads();
+        if (work && !m.useRetrendOnly) {
+            for (int b = 0; b < nj; b += 32) {
+                f32x2 sw = pack2(0.f, 0.f), swv = pack2(0.f, 0.f);
+#pragma unroll 8
+                for (int j = b; j < b + 32; j++) {
+                    const float4 pxy = sxy[j];
+                    const float2 pvv = sv[j];
+                    const f32x2 dx = add2(pack2(pxy.x, pxy.y), nx), dy = add2(pack2(pxy.z, pxy.w), ny);
+                    const f32x2 d2 = fma2(dx, dx, mul2(dy, dy));
+                    float a, bq;
+                    unpack2(d2, a, bq);
+                    const f32x2 r = pack2(rsqrt_approx(a), rsqrt_approx(bq));
+                    const f32x2 w = mul2(mul2(r, r), r);
+                    sw = add2(sw, w);
+                    swv = fma2(w, pack2(pvv.x, pvv.y), swv);
+                }
+                float a, bq, va, vb;
+                unpack2(sw, a, bq);
+                unpack2(swv, va, vb);
+                SWa += double(a); SWb += double(bq);
+                SWVa += double(va); SWVb += double(vb);
+            }
+        }
+    }
+    glocalFinish(cells, c0, ea, dem, st, m, SWa, SWVa, out, notOk);
+    glocalFinish(cells, c0 + 1, eb, dem, st, m, SWb, SWVb, out, notOk);
 }
 
 __device__ __forceinline__ unsigned orderedKeyG(float f)
@@ -628,6 +752,13 @@ static int glocalRasterImpl(pb_context* ctx, const pb_stations* st, pb_settings*
             dCells = reinterpret_cast<const float*>(d + offCells);
         }
         const int grid = (nCells + 255) / 256;
+        static const bool noFuse = getenv("PB_GLOCAL_NO_FUSE") != nullptr;
+        if (!shepardMethod && !(useTD && subs[a].s.topoDist_Kh != 0) && !noFuse) {
+            glocal_area_kernel<<<(nCells + 511) / 512, 256, 0, ctx->stream>>>(dCells, nCells, dg, lk, dss[a], mods[a], ctx->dOut.p, dNotOk);
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->timing.launches++;
+            continue;
+        }
         glocal_targets_kernel<<<grid, 256, 0, ctx->stream>>>(dCells, nCells, dg, lk, reinterpret_cast<float*>(d + offX),
                                                              reinterpret_cast<float*>(d + offY), reinterpret_cast<float*>(d + offZ),
                                                              reinterpret_cast<double*>(d + offPv), d + offState);
