@@ -393,14 +393,18 @@ __device__ __forceinline__ double lmWarpSse(const double* p /* clamped */, const
     double sse = 0;
     for (int base = 0; base < nData; base += 32) {
         const int j = base + lane;
+        double term = 0.;                                  // lanes past the last point add +0: the sum keeps its bits
         if (j < nData) {
             const double error = Y[j] - Fit<F>::eval(X[j], p);
             const double w = W[j];
-            sm[lane] = error * error * w * w;
+            term = error * error * w * w;
         }
+        sm[lane] = term;
         __syncwarp();
-        const int cnt = min(32, nData - base);
-        for (int l = 0; l < cnt; l++) sse += sm[l];      // every lane: the same ordered sum (broadcast reads)
+        // every lane: the same ordered sum (broadcast reads); a fixed trip count, so the 32 loads are in flight at once and
+        // only the chain of additions is serial
+#pragma unroll
+        for (int l = 0; l < 32; l++) sse += sm[l];
         __syncwarp();
     }
     return sse;
@@ -452,12 +456,16 @@ __device__ __noinline__ void lmElevationWarp(const double* __restrict__ pmin, co
                 }
 #pragma unroll
                 for (int i = 0; i < N; i++) sm[(NA + i) * kLmWarpStride + lane] = P[i] * w * (y - f0);
+            } else {
+                // past the last point: the terms are +0 (a sum keeps its bits), so the accumulation below has a fixed trip count
+#pragma unroll
+                for (int t = 0; t < NA + N; t++) sm[t * kLmWarpStride + lane] = 0.;
             }
             __syncwarp();
-            const int cnt = min(32, nData - base);
             if (lane < NA + N) {
                 const double* src = sm + lane * kLmWarpStride;
-                for (int l = 0; l < cnt; l++) acc += src[l];
+#pragma unroll
+                for (int l = 0; l < 32; l++) acc += src[l];      // 32 loads in flight, only the additions are serial
             }
             __syncwarp();
         }
@@ -880,13 +888,15 @@ __device__ __noinline__ void lmOthersWarp(double (*pmin)[2], double (*pmax)[2], 
         double n = 0;
         for (int base = 0; base < nData; base += 32) {
             const int j = base + lane;
+            double term = 0.;                   // +0 past the last point
             if (j < nData) {
                 const double e = Y[j] - fsum(j, q);
-                sm[lane] = e * e * W[j] * W[j];
+                term = e * e * W[j] * W[j];
             }
+            sm[lane] = term;
             __syncwarp();
-            const int cnt = min(32, nData - base);
-            for (int l = 0; l < cnt; l++) n += sm[l];
+#pragma unroll
+            for (int l = 0; l < 32; l++) n += sm[l];
             __syncwarp();
         }
         return n;
@@ -929,12 +939,15 @@ __device__ __noinline__ void lmOthersWarp(double (*pmin)[2], double (*pmax)[2], 
                 }
 #pragma unroll
                 for (int i = 0; i < MT; i++) sm[(NA + i) * kLmWarpStride + lane] = P[i] * W[j] * (Y[j] - f0);
+            } else {
+#pragma unroll
+                for (int t = 0; t < NA + MT; t++) sm[t * kLmWarpStride + lane] = 0.;      // +0 past the last point
             }
             __syncwarp();
-            const int cnt = min(32, nData - base);
             if (lane < NA + MT) {
                 const double* src = sm + lane * kLmWarpStride;
-                for (int l = 0; l < cnt; l++) acc += src[l];
+#pragma unroll
+                for (int l = 0; l < 32; l++) acc += src[l];
             }
             __syncwarp();
         }
