@@ -62,7 +62,8 @@ __device__ __forceinline__ void targetXY(const KrigingTargets& t, long long c, d
 }
 
 constexpr int kEstThreads = 128;
-constexpr int kEstTile = 1024;      // stations per shared-memory tile (x, y, u: 24 KiB)
+constexpr int kEstTile = 384;       // stations per shared-memory tile (x, y, u: 9 KiB: an estimate CTA fits an SM beside the two
+                                    // 105 KiB CTAs of the variance kernel, see evaluate())
 
 // estimate_c = sum_j u_j gamma(|p_c - s_j|) + u_n ; optionally stores D[j][c] (direct variance path)
 __global__ void __launch_bounds__(kEstThreads)
@@ -393,6 +394,11 @@ void krigingFree(KrigingSystem* k)
     if (k->dZ) cudaFree(k->dZ);
     if (k->dKbBox) cudaFree(k->dKbBox);
     if (k->dMmaCount) cudaFree(k->dMmaCount);
+    if (k->sEst) {
+        cudaStreamDestroy(k->sEst);
+        for (auto& e : k->evEst) cudaEventDestroy(e);
+        for (auto& e : k->evFin) cudaEventDestroy(e);
+    }
     if (k->sDn) {
         cudaStreamDestroy(k->sDn);
         for (auto& e : k->evDn) cudaEventDestroy(e);
@@ -428,7 +434,7 @@ int evaluate(pb_context* ctx, KrigingSystem* k, const KrigingTargets& t, long lo
     const int chunk = k->tensor ? kTcChunk : 8192;
     const size_t ldD = chunk;
     const size_t needD = (!k->tensor && wantRmse) ? size_t(k->n + 1) * ldD * sizeof(double) : 0;
-    const size_t need = needD + 2 * size_t(chunk) * sizeof(double);
+    const size_t need = needD + 3 * size_t(chunk) * sizeof(double);          // two estimate buffers + the variance's
     if (k->workBytes < need) {
         if (k->dWork) cudaFree(k->dWork);
         k->dWork = nullptr;
@@ -436,21 +442,58 @@ int evaluate(pb_context* ctx, KrigingSystem* k, const KrigingTargets& t, long lo
         CUDA_TRY(ctx, cudaMalloc(&k->dWork, need));
         k->workBytes = need;
     }
-    double* dEst = reinterpret_cast<double*>(k->dWork);
-    double* dQ = dEst + chunk;
+    // tensor path with the variance wanted: the estimate of chunk c + 1 (FP64 pipe, its own low-priority stream) runs beside
+    // the variance kernel of chunk c (tensor + FP32 pipes): two estimate buffers, events both ways
+    const bool overlap = k->tensor && wantRmse && m > chunk && !getenv("PB_KRIGING_NO_OVERLAP");
+    double* dEstBuf[2] = {reinterpret_cast<double*>(k->dWork), reinterpret_cast<double*>(k->dWork) + chunk};
+    double* dQ = dEstBuf[1] + chunk;
     double* dD = needD ? dQ + chunk : nullptr;
-    for (long long c0 = 0; c0 < m; c0 += chunk) {
-        const int mc = (int)std::min<long long>(chunk, m - c0);
+    if (overlap && !k->sEst) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&k->sEst, cudaStreamNonBlocking, least));
+        for (auto& e : k->evEst) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : k->evFin) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t sE = overlap ? k->sEst : ctx->stream;
+    if (overlap) {                                     // the estimate stream starts behind whatever precedes this call
+        CUDA_TRY(ctx, cudaEventRecord(k->evFin[0], ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(sE, k->evFin[0], 0));
+    }
+    auto launchEstimate = [&](long long c0, int mc, double* dEst) -> int {
         const int estGrid = (mc + kEstThreads - 1) / kEstThreads;
         if (dD || k->params.mode == PB_KRIGING_LINEAR)
-            kriging_estimate_kernel<<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, t, c0, mc, dEst, dD, (int)ldD);
+            kriging_estimate_kernel<<<estGrid, kEstThreads, 0, sE>>>(k->params, k->dPos, k->dU, t, c0, mc, dEst, dD, (int)ldD);
         else if (k->params.mode == PB_KRIGING_SPHERICAL)
-            kriging_estimate_fast_kernel<PB_KRIGING_SPHERICAL><<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, k->sumU, t, c0, mc, dEst);
+            kriging_estimate_fast_kernel<PB_KRIGING_SPHERICAL><<<estGrid, kEstThreads, 0, sE>>>(k->params, k->dPos, k->dU, k->sumU, t, c0, mc, dEst);
         else if (k->params.mode == PB_KRIGING_EXPONENTIAL)
-            kriging_estimate_fast_kernel<PB_KRIGING_EXPONENTIAL><<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, k->sumU, t, c0, mc, dEst);
+            kriging_estimate_fast_kernel<PB_KRIGING_EXPONENTIAL><<<estGrid, kEstThreads, 0, sE>>>(k->params, k->dPos, k->dU, k->sumU, t, c0, mc, dEst);
         else
-            kriging_estimate_fast_kernel<PB_KRIGING_GAUSSIAN><<<estGrid, kEstThreads, 0, ctx->stream>>>(k->params, k->dPos, k->dU, k->sumU, t, c0, mc, dEst);
+            kriging_estimate_fast_kernel<PB_KRIGING_GAUSSIAN><<<estGrid, kEstThreads, 0, sE>>>(k->params, k->dPos, k->dU, k->sumU, t, c0, mc, dEst);
         ctx->timing.launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return PB_OK;
+    };
+    long long nChunk = 0;
+    if (overlap) {
+        const int rc = launchEstimate(0, (int)std::min<long long>(chunk, m), dEstBuf[0]);
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaEventRecord(k->evEst[0], sE));
+    }
+    for (long long c0 = 0; c0 < m; c0 += chunk, nChunk++) {
+        const int mc = (int)std::min<long long>(chunk, m - c0);
+        double* dEst = dEstBuf[overlap ? (nChunk & 1) : 0];
+        if (!overlap) {
+            const int rc = launchEstimate(c0, mc, dEst);
+            if (rc) return rc;
+        } else if (c0 + chunk < m) {
+            // the next chunk's estimate: its buffer was read by the finish kernel of chunk nChunk - 1
+            const int nb = int((nChunk + 1) & 1);
+            if (nChunk >= 1) CUDA_TRY(ctx, cudaStreamWaitEvent(sE, k->evFin[nb], 0));
+            const int rc = launchEstimate(c0 + chunk, (int)std::min<long long>(chunk, m - c0 - chunk), dEstBuf[nb]);
+            if (rc) return rc;
+            CUDA_TRY(ctx, cudaEventRecord(k->evEst[nb], sE));
+        }
         if (wantRmse) {
             if (k->tensor) {
                 CUDA_TRY(ctx, launchKrigingVarianceTc(*k, t, c0, mc, dQ, ctx->stream));
@@ -462,10 +505,12 @@ int evaluate(pb_context* ctx, KrigingSystem* k, const KrigingTargets& t, long lo
                 ctx->timing.launches++;
             }
         }
+        if (overlap) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, k->evEst[nChunk & 1], 0));
         kriging_finish_kernel<<<(mc + 255) / 256, 256, 0, ctx->stream>>>(t, c0, mc, dEst, wantRmse ? dQ : nullptr, dOutEst,
                                                                           dOutRmse, gridEst, gridRmse);
         ctx->timing.launches++;
         CUDA_TRY(ctx, cudaGetLastError());
+        if (overlap) CUDA_TRY(ctx, cudaEventRecord(k->evFin[nChunk & 1], ctx->stream));
         if (afterChunk) {
             const int rc = afterChunk(c0 + mc);      // the kernels of the targets [0, c0 + mc) are in the stream
             if (rc) return rc;

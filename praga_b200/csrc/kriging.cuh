@@ -49,6 +49,8 @@ struct KrigingSystem {
     int nPad = 0, nIt = 0, nKb = 0;
     double zz = 0;                     // |z|^2
     double sumU = 0;                   // sum_j u_j, j < n (0 up to rounding)
+    cudaStream_t sEst = nullptr;       // estimate stream + events of evaluate()'s estimate / variance overlap
+    cudaEvent_t evEst[2] = {nullptr, nullptr}, evFin[2] = {nullptr, nullptr};
     cudaStream_t sDn = nullptr;        // download stream + events of pb_kriging_raster's chunk pipeline
     cudaEvent_t evDn[2] = {nullptr, nullptr};
     unsigned char* dWork = nullptr;
