@@ -6,6 +6,12 @@
 // Formulation (kriging.cu header): y = M c with M = L^-1 (lower triangular, C = sill - Gamma = L L^T) and
 // c_j = sill - gamma(|p - s_j|);  sum_i weight_i D_i = sill - (|y|^2 - (z.y)(z.y - 1) / |z|^2),  z = M 1.
 //
+// Two kernels share the formulation, the operand layouts and the generator arithmetic:
+//   kriging_variance_pair_kernel  (default, further down): a cluster of two CTAs per tile, tcgen05 cta_group::2, one N block per
+//                                  pass, two pairs resident per TPC, K stages out of the variogram range skipped;
+//   kriging_variance_tc_kernel    (round 1, PB_KRIGING_SINGLE_CTA=1 or systems too large for the pair kernel's stage list): one
+//                                  CTA per 256 cells, described first.
+//
 // GEMM mapping: D[cell][i] = sum_j A[cell][j] * B[i][j]
 //   A (2 M tiles x 128 cells x K): c values GENERATED on the fly by 8 generator warps (thread = cell; FP32 variogram of
 //     centred FP32 distances), split into FP16 hi + lo, written to shared memory in the canonical K-major no-swizzle UMMA
