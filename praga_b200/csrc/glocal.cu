@@ -234,6 +234,7 @@ glocal_area_kernel(const float* __restrict__ cells, int nCells, DevGrid dem, Glo
     const f32x2 nx = pack2(-ea.xf, -eb.xf), ny = pack2(-ea.yf, -eb.yf);
     double SWa = 0., SWVa = 0., SWb = 0., SWVb = 0.;
     const int used = (st.n + 31) / 32 * 32;                 // the padding of the packed tile weighs +0
+    PB_DEV_ASSERT(used <= st.nPadded);
     for (int j0 = 0; j0 < used; j0 += kGlocalTile) {
         const int nj = min(kGlocalTile, used - j0);
         __syncthreads();

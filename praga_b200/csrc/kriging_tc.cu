@@ -657,6 +657,7 @@ kriging_variance_pair_kernel(TcParams p, const double* __restrict__ pos, const u
                     for (int nb = 0; nb < nNb; nb++)
                         if (j0 <= i0p + nb * kPrN + kPrN - 1) {
                             const size_t itile = size_t(i0p / kTcNT + 2 * nb) + rank;      // this CTA's 128 rows of the N block
+                            PB_DEV_ASSERT(itile < size_t(p.nPad / kTcNT) && kb < p.nKb);
                             bulk_g2s(sB + size_t(nb) * kPrBTile, Mt + (itile * p.nKb + kb) * kPrBTile, kPrBTile, &bFull[s]);
                         }
                 }

@@ -408,6 +408,7 @@ spatial_aggregate_kernel(DevGrid raster, const double* __restrict__ px, const do
     if (cell >= nCells) return;
     const long long p0 = first[cell];
     const int n = int(first[cell + 1] - p0);
+    PB_DEV_ASSERT(n >= 0 && p0 >= 0);
     float* z = scratch + p0;
     int valid = 0;
 #pragma unroll 4
