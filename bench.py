@@ -381,7 +381,7 @@ class IdwWorkload:
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at C2 from the ncu --set full capture
                 # profiles/r01_idw_c2b.ncu_summary.json (46.9 MB + 10.2 MB; algorithmic 12 B/cell = 44.4 MB + the 14.8 MB
                 # valid-cell list); other workloads: not captured
-                "traffic": 57.09e6 if self.name == "c2" else None,
+                "traffic": 56.70e6 if self.name == "c2" else None,   # dram read + write, ncu --set full (profiles/r02_idw_c2.ncu_summary.json)
                 "kernel": self.kernel, "kernel_ms_per_launch": kernel_s * 1e3,
                 "algorithmic": f"11 flop x {S} stations x {int(cells_per_launch)} cells per launch (SURVEY.md 8d)",
                 "peak_source": "FFMA2 chain measured live on this GPU by the builder's own micro-kernel (pb_measure_pipe_peaks): "
@@ -436,7 +436,7 @@ class IdwWorkload:
 
 class LocalDetrendingWorkload:
     """c3: K2. unit = a band of rows of the 10k x 10k raster; ranks take different bands (row-band sharding)."""
-    kernel = "pb::local_detrending_kernel (selection + Levenberg-Marquardt fits + estimate)"
+    kernel = "pb::local_descent_kernel<0,11,1> (+ pb::local_select_kernel, pb::local_finish_kernel<0>: the three-kernel pipeline)"
     # FP64 flop per cell executed by the LM fits + estimate at this station density, counted with ncu
     # (thread-level DADD + DMUL + 2 DFMA of profiles/r01_local_k2e_flops.csv / 453 823 cells; data dependent)
     FP64_FLOP_PER_CELL = 3.64e5
